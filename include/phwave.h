@@ -1,0 +1,118 @@
+/* phwave.h - C ABI of libphwave.so: the B200-native hot path of FinbarArgus/portHamiltonian_FEM.
+ *
+ * The reference has no FFI of its own: its only seam is the Python function
+ *     wave_2D_solve(...)          fenics_projects/wave_eqn/wave_2D.py:15-20 (returns at :1032)
+ * whose body asks dolfin/PETSc to (a) mesh + build dof maps (:92-285), (b) assemble the operators of
+ * the forms (:449-595), (c) per step assemble a right-hand side and LU-solve (:787-854), (d) assemble
+ * energy functionals (:876-927).  This header is the boundary a maintainer binds instead (ctypes stub
+ * in INTEGRATION.md); each entry point names the reference region it replaces.
+ *
+ * Conventions: plain C, no exceptions cross the ABI, every function returns 0 on success and a
+ * negative phw_status otherwise (text via phw_last_error(), thread-local).  All buffers are owned by
+ * the caller; the library copies what it keeps.  Vector arguments are in the *user numbering*
+ * (vertex ids as given; edge ids = unique (lo,hi) vertex pairs in lexicographic order) and may be host
+ * or device pointers (resolved with cudaPointerGetAttributes).  A handle is bound to one device and
+ * one stream and is not thread-safe.
+ */
+#ifndef PHWAVE_H
+#define PHWAVE_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct phw_mesh_s*   phw_mesh_t;
+typedef struct phw_solver_s* phw_solver_t;
+
+enum phw_status { PHW_OK = 0, PHW_EINVAL = -1, PHW_ECUDA = -2, PHW_ENOMEM = -3, PHW_ESTATE = -4, PHW_ENOCONV = -5 };
+
+/* time integration schemes, wave_2D.py:295-324 */
+enum phw_scheme { PHW_EE = 0, PHW_IE = 1, PHW_SE = 2, PHW_SM = 3, PHW_EH = 4, PHW_SV = 5 };
+/* boundary tags, wave_2D.py:266-280 */
+enum phw_tag { PHW_TAG_LEFT = 0, PHW_TAG_TOP = 1, PHW_TAG_RIGHT = 2, PHW_TAG_GENERAL = 3, PHW_TAG_NONE = 4 };
+/* input signal of the left port / the voltage source */
+enum phw_input {
+    PHW_IN_SINE_WINDOW = 0, /* (t<t_stop) ? amp*sin(omega t) : 0   wave_2D.py:384,433,444 */
+    PHW_IN_SINE        = 1, /* amp*sin(omega t)                    wave_2D.py:380 (casimir)   */
+    PHW_IN_COSINE      = 2, /* amp*cos(omega t)                    wave_2D.py:376 (analytical time factor) */
+    PHW_IN_PASSIVITY   = 3  /* (t<t_stop) ? amp*sin(omega t) : (t<t_ctrl) ? 0 : -gain*x0_prev   control_input.py:12-18 */
+};
+enum phw_which { PHW_P = 0, PHW_Q = 1 };
+
+typedef struct phw_params {
+    int32_t scheme;          /* phw_scheme */
+    int32_t strong;          /* 0 weak / 1 strong Dirichlet (wave_2D.py:413-422) */
+    int32_t interconnection; /* 0 none / 1 'IC' three-state lumped model (wave_2D.py:148-166,528-577) */
+    int32_t casimir;         /* 1: impedance top/right boundaries (wave_2D.py:327-351) */
+    int32_t analytical;      /* 1: analytical diagnostics -> 12 output columns (wave_2D.py:929-965) */
+    int32_t input_kind;      /* phw_input */
+    double dt, K_wave, rho;
+    double in_amp, in_omega, in_t_stop, in_t_ctrl, in_gain;
+    double Bl_em, R1_em, R2_em, K_em, m_em, L_em;   /* wave_2D.py:153-158 */
+    double H_init;           /* wave_2D.py:746,769,771 (computed by the caller with phw_energy) */
+    double an_omega, an_xLength, an_yLength, an_xPoint, an_yPoint;  /* analytical case constants */
+    double tol;              /* relative residual of the mass / block solves (default 1e-13) */
+    int32_t max_iter;        /* iteration cap per solve (default 200) */
+    int32_t flags;           /* bit0: disable first-same-as-last reuse in SV; bit1: synchronous error checks */
+} phw_params;
+
+typedef struct phw_stats {
+    int64_t steps, solves_p, solves_q, solves_block, iters_p, iters_q, iters_block;
+    double  max_rel_residual;   /* largest accepted ||b - A x|| / ||b|| */
+    double  device_ms;          /* CUDA-event time of the last phw_run */
+    int64_t kernel_launches;    /* launches issued by the last phw_run */
+    int64_t bytes_model;        /* algorithmic bytes of the last phw_run ("bytes model") */
+    double  lam_min_q, lam_max_q, skew_bound;
+} phw_stats;
+
+const char* phw_last_error(void);
+int phw_version(void);
+
+/* ---- mesh connectivity + patch layout: replaces mesh.topology / FunctionSpace dofmaps / MeshFunction
+ *      markers (wave_2D.py:126,168-220,266-285).  Host-only, no GPU needed. ---- */
+int phw_mesh_create(int64_t n_vertices, const double* vertices_xy, int64_t n_cells, const int32_t* cells,
+                    int32_t patch_cells, phw_mesh_t* out);
+int phw_mesh_sizes(phw_mesh_t m, int64_t* n_vertices, int64_t* n_cells, int64_t* n_edges,
+                   int64_t* n_boundary_edges, int64_t* n_patches);
+/* edges [n_edges,2], cell_edges [n_cells,3], cell_edge_sign [n_cells,3] (+1/-1); any pointer may be NULL */
+int phw_mesh_get_edges(phw_mesh_t m, int32_t* edges, int32_t* cell_edges, int8_t* cell_edge_sign);
+/* boundary edges: ids [n_b], sign of the adjacent cell [n_b] (+1: global normal is outward) */
+int phw_mesh_get_boundary(phw_mesh_t m, int32_t* edge_ids, int8_t* sign);
+/* tags [n_b] (phw_tag) and optional left-port weights [n_b] = (1/|e|) int_e g_L ds  (NULL -> 1) */
+int phw_mesh_set_boundary(phw_mesh_t m, const int32_t* tags, const double* port_weight);
+/* layout introspection for tests: permutations new->old for vertices/edges, cell->patch */
+int phw_mesh_get_numbering(phw_mesh_t m, int32_t* vertex_new2old, int32_t* edge_new2old, int32_t* cell_patch);
+/* per-patch counts [n_patches,6]: own cells, edge-op cells, vertex-op cells, owned vertices, owned edges, ghosts(v+e) */
+int phw_mesh_get_patch_counts(phw_mesh_t m, int32_t* counts);
+int phw_mesh_destroy(phw_mesh_t m);
+
+/* ---- solver: replaces assemble(a)/assemble(b)/solve/assemble(energy) of wave_2D.py:579-595,787-982 ---- */
+int phw_solver_create(phw_mesh_t m, const phw_params* prm, int32_t device, void* cuda_stream, phw_solver_t* out);
+int phw_solver_destroy(phw_solver_t s);
+int phw_set_state(phw_solver_t s, const double* p, const double* q, const double* x3);   /* u_m, wave_2D.py:738,768 */
+int phw_get_state(phw_solver_t s, double* p, double* q, double* x3);
+/* run n_steps of the loop wave_2D.py:787-982 on the device; H_rows [n_steps, 8|12] host or device */
+int phw_run(phw_solver_t s, int64_t n_steps, double* H_rows);
+int phw_get_stats(phw_solver_t s, phw_stats* out);
+int phw_synchronize(phw_solver_t s);
+
+/* ---- kernel-level entry points (parity tests, profiling) ---- */
+/* y[Ne] = D p = (C - N) p            weak coupling block of wave_2D.py:468-472,479-483,503-518 */
+int phw_apply_D(phw_solver_t s, const double* p, double* y);
+/* y[Nv] = D^T q */
+int phw_apply_DT(phw_solver_t s, const double* q, double* y);
+/* y = M_p x (which=PHW_P) or M_q x (PHW_Q):  (p v_p dx) / dot(q, v_q) dx blocks */
+int phw_mass_matvec(phw_solver_t s, int32_t which, const double* x, double* y);
+/* x = M^-1 b to params.tol; *iters receives the iteration count (may be NULL) */
+int phw_mass_solve(phw_solver_t s, int32_t which, const double* b, double* x, int32_t* iters);
+/* parts2[0] = 0.5 p^T M_p p / rho, parts2[1] = 0.5 K q^T M_q q of the current state (wave_2D.py:746,769,882,907) */
+int phw_energy(phw_solver_t s, double* parts2);
+/* H_init of wave_2D.py:746,769,771 (subtracted in the energy-residual column) */
+int phw_set_H_init(phw_solver_t s, double H_init);
+/* b_L^T q of the current state: integral of q.n over the left port (wave_2D.py:534,546,622-631) */
+int phw_port_flux(phw_solver_t s, double* flux);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

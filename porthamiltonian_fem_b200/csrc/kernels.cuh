@@ -1,0 +1,429 @@
+// kernels.cuh - sm_100a kernels of the port-Hamiltonian wave hot path (P1 x RT1, fp64).
+//
+// Two "row" kernel families evaluate, patch by patch and entirely from shared memory,
+//   vertex rows:  val_v = cM (M_p x_p)_v + cD (D^T x_q)_v + cB (B_top x_p)_v
+//   edge rows:    val_e = cM (M_q x_q)_e + cD (D x_p)_e   + cB (B_right x_q)_e
+// i.e. every block of the reference's mixed system  [[M_p, dt K D^T], [-dt/rho D, M_q]]
+// (wave_2D.py:449-518; casimir boundary blocks :327-351), followed by a fused epilogue:
+//   STORE  y = val                      -> right-hand sides  (replaces assemble(b), wave_2D.py:814,849)
+//   CHEB   x+ = x + c1 (x - x-) + c2 P^-1 (b - val), accumulating ||b - val||^2
+//                                        -> one Chebyshev iteration (replaces solve(A, x, b), :820,854)
+//   DOT    sum += x . val                -> quadratic energy forms (replaces assemble(scalar), :882,907)
+// A patch = owned dof ranges + halo cells (layout.hpp).  Stage 1 stages the local input values in
+// shared memory (owned range: coalesced; ghosts: gathered), stage 2 computes the three per-cell
+// contributions into shared memory (cell records and geometry streamed once, coalesced), stage 3
+// sums the contributions of each owned dof in a fixed order (deterministic; no atomics on data) and
+// applies the epilogue with coalesced global traffic.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "layout.hpp"
+
+namespace phw {
+
+constexpr int NT = 512;   // threads per CTA of the row kernels
+
+struct SolveCtl {
+    int k, done, cur, pad;
+    double rho, rr, bb, racc, bacc, maxres;
+    long long iters, solves;
+};
+
+// device-resident control block: everything the step loop needs between kernels lives here, so the
+// host only enqueues work and never reads anything back (wave_2D.py:787-982 loop state).
+struct Ctl {
+    double t, bE, inpE, H_em, H_wave, disp, pleft, u_now, h1, pad0;
+    double x[3], xm[3], xt2, xi1;
+    double flux[4];
+    double red[8];
+    long long step;
+    long long nonconv;
+    SolveCtl sc[3];
+    unsigned int counters[8];
+};
+
+struct DevMesh {
+    int npatch, nv, ne;
+    const PatchHdr* hdr;
+    const uint4* rec;
+    const double* area;
+    const double* g0; const double* g1; const double* g2;
+    const int* ghost_v; const int* ghost_e;
+    const uint32_t* eadj;
+    const uint32_t* vadj_off;
+    const uint16_t* vadj;
+};
+
+struct TriBuf { double* b[3]; };
+
+enum { EPI_STORE = 0, EPI_CHEB = 1, EPI_DOT = 2 };
+enum { MODE_OP = 0, MODE_DIAG = 1 };
+
+struct RowArgs {
+    DevMesh m;
+    const double* xp;        // vertex input (nullptr -> taken from tp.b[cur])
+    const double* xq;        // edge input
+    TriBuf tp, tq;           // Chebyshev buffers of the p and q unknowns
+    double cM, cD, cB;
+    // STORE
+    double* y;
+    // CHEB
+    const double* b;
+    const double* pinv;
+    double cheb_d, cheb_c;   // centre and focal distance of the spectrum ellipse
+    double tol2, weight;
+    int which;               // SolveCtl index
+    int use_cheb_input;      // 1: the row's own unknown is read from the TriBuf[cur]
+    int coupled_from_tribuf; // 1: the *other* field is also read from its TriBuf[cur] (block solve)
+    int finalize;            // 1: this launch closes the iteration (advance k, rotate, test convergence)
+    int max_iter;
+    // DOT
+    int red_slot;            // ctl->red[red_slot] receives the sum (scaled by dot_scale)
+    double dot_scale;
+    int dot_accumulate;
+    double* partials;        // [npatch*2] scratch
+    Ctl* ctl;
+    int counter_id;
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// deterministic block reduction of two values; result valid in thread 0
+__device__ __forceinline__ void block_sum2(double& a, double& b, double* red /* >= 2*32 doubles */) {
+    a = warp_sum(a); b = warp_sum(b);
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) { red[w] = a; red[32 + w] = b; }
+    __syncthreads();
+    if (w == 0) {
+        int nw = (blockDim.x + 31) >> 5;
+        a = (l < nw) ? red[l] : 0.0;
+        b = (l < nw) ? red[32 + l] : 0.0;
+        a = warp_sum(a); b = warp_sum(b);
+    }
+}
+
+// Chebyshev coefficients for iteration k given rho_{k-1} (Saad, Iterative Methods, Alg. 12.1;
+// ellipse version: Manteuffel 1977).  x_{k+1} = x_k + c1 (x_k - x_{k-1}) + c2 P^-1 r_k.
+__device__ __forceinline__ void cheb_coeffs(int k, double rho_prev, double d, double c, double& c1, double& c2, double& rho_k) {
+    if (k == 0 || c <= 0.0) { c1 = 0.0; c2 = 1.0 / d; rho_k = c / d; return; }
+    double sigma1 = d / c;
+    rho_k = 1.0 / (2.0 * sigma1 - rho_prev);
+    c1 = rho_k * rho_prev;
+    c2 = 2.0 * rho_k / c;
+}
+
+// ------------------------------------------------------------------------------------------------
+// last-block epilogue shared by the row kernels: deterministic sum of the per-patch partials and the
+// iteration control of the Chebyshev solve
+// ------------------------------------------------------------------------------------------------
+template <int EPI>
+__device__ void finish_launch(const RowArgs& a, double* red) {
+    __shared__ bool is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int prev = atomicAdd(&a.ctl->counters[a.counter_id], 1u);
+        is_last = (prev == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    double s0 = 0.0, s1 = 0.0;
+    for (int p = threadIdx.x; p < a.m.npatch; p += blockDim.x) {
+        s0 += __ldcg(&a.partials[2 * p]);
+        s1 += __ldcg(&a.partials[2 * p + 1]);
+    }
+    block_sum2(s0, s1, red);
+    if (threadIdx.x == 0) {
+        Ctl* ctl = a.ctl;
+        ctl->counters[a.counter_id] = 0;
+        if (EPI == EPI_DOT) {
+            double v = s0 * a.dot_scale;
+            ctl->red[a.red_slot] = a.dot_accumulate ? ctl->red[a.red_slot] + v : v;
+        } else if (EPI == EPI_CHEB) {
+            SolveCtl& sc = ctl->sc[a.which];
+            double rr = sc.racc + s0 * a.weight;
+            double bb = sc.bacc + s1 * a.weight;
+            if (!a.finalize) { sc.racc = rr; sc.bacc = bb; }
+            else {
+                sc.racc = 0.0; sc.bacc = 0.0;
+                sc.rr = rr; sc.bb = bb;
+                double c1, c2, rho_k;
+                cheb_coeffs(sc.k, sc.rho, a.cheb_d, a.cheb_c, c1, c2, rho_k);
+                sc.rho = rho_k;
+                sc.k += 1;
+                sc.cur = (sc.cur + 1) % 3;
+                sc.iters += 1;
+                if (rr <= a.tol2 * bb) {
+                    sc.done = 1;
+                    double rel = (bb > 0.0) ? sqrt(rr / bb) : 0.0;
+                    if (rel > sc.maxres) sc.maxres = rel;
+                } else if (sc.k >= a.max_iter) {
+                    sc.done = 1;
+                    ctl->nonconv += 1;
+                    double rel = (bb > 0.0) ? sqrt(rr / bb) : 0.0;
+                    if (rel > sc.maxres) sc.maxres = rel;
+                }
+            }
+        }
+        __threadfence();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// vertex rows
+// ------------------------------------------------------------------------------------------------
+template <int EPI, int MODE, bool HAS_M, bool HAS_D, bool CAS>
+__global__ void __launch_bounds__(NT, 2) vertex_rows_k(const RowArgs a) {
+    extern __shared__ double smem[];
+    __shared__ double red[64];
+    const DevMesh& m = a.m;
+    int cur = 0, k = 0;
+    double c1 = 0.0, c2 = 0.0;
+    if (EPI == EPI_CHEB) {
+        const SolveCtl& sc = a.ctl->sc[a.which];
+        if (sc.done) return;
+        cur = sc.cur; k = sc.k;
+        double rk;
+        cheb_coeffs(k, sc.rho, a.cheb_d, a.cheb_c, c1, c2, rk);
+    }
+    const double* xp = a.xp;
+    const double* xq = a.xq;
+    if (EPI == EPI_CHEB) {
+        if (a.use_cheb_input) xp = a.tp.b[cur];
+        if (a.coupled_from_tribuf) xq = a.tq.b[cur];
+    }
+    double acc0 = 0.0, acc1 = 0.0;
+    for (int P = blockIdx.x; P < m.npatch; P += gridDim.x) {
+        const PatchHdr h = m.hdr[P];
+        const int nlv = h.v_cnt + h.gv_cnt, nle = h.e_cnt + h.ge_cnt;
+        double* sp = smem;                         // [nlv]
+        double* sq = sp + ((nlv + 1) & ~1);        // [nle] (only if HAS_D)
+        double* sc3 = HAS_D ? sq + ((nle + 1) & ~1) : sq;   // [3*n_vcells]
+        // ---- stage 1: local inputs
+        if (MODE == MODE_OP && (HAS_M || CAS || EPI != EPI_STORE)) {
+            for (int i = threadIdx.x; i < h.v_cnt; i += NT) sp[i] = xp[h.v_start + i];
+            for (int i = threadIdx.x; i < h.gv_cnt; i += NT) sp[h.v_cnt + i] = xp[m.ghost_v[h.gv_off + i]];
+        }
+        if (HAS_D && MODE == MODE_OP) {
+            for (int i = threadIdx.x; i < h.e_cnt; i += NT) sq[i] = xq[h.e_start + i];
+            for (int i = threadIdx.x; i < h.ge_cnt; i += NT) sq[h.e_cnt + i] = xq[m.ghost_e[h.ge_off + i]];
+        }
+        __syncthreads();
+        // ---- stage 2: per-cell contributions to its three vertices
+        for (int lc = threadIdx.x; lc < h.n_vcells; lc += NT) {
+            const uint4 r = __ldg(&m.rec[h.cell_off + lc]);
+            double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+            if (HAS_M || CAS) {
+                const double A = __ldg(&m.area[h.cell_off + lc]);
+                if (MODE == MODE_DIAG) {
+                    v0 = v1 = v2 = a.cM * A * (1.0 / 6.0);
+                    if (CAS) {
+                        const uint32_t fl = r.y >> 16;
+                        if (fl & 1u) { const double d = a.cB * sqrt(48.0 * A * __ldg(&m.g0[h.cell_off + lc])) * (1.0 / 3.0); v1 += d; v2 += d; }
+                        if (fl & 2u) { const double d = a.cB * sqrt(48.0 * A * __ldg(&m.g1[h.cell_off + lc])) * (1.0 / 3.0); v0 += d; v2 += d; }
+                        if (fl & 4u) { const double d = a.cB * sqrt(48.0 * A * __ldg(&m.g2[h.cell_off + lc])) * (1.0 / 3.0); v0 += d; v1 += d; }
+                    }
+                } else {
+                    const double x0 = sp[r.x & 0xFFFFu], x1 = sp[r.x >> 16], x2 = sp[r.y & 0xFFFFu];
+                    if (HAS_M) {
+                        const double w = a.cM * A * (1.0 / 12.0), s = x0 + x1 + x2;
+                        v0 = w * (s + x0); v1 = w * (s + x1); v2 = w * (s + x2);
+                    }
+                    if (CAS) {
+                        const uint32_t fl = r.y >> 16;
+                        if (fl & 7u) {   // impedance top side: P1 edge mass |e|/6 [2 1; 1 2]  (wave_2D.py:330,476)
+                            const double gg[3] = {__ldg(&m.g0[h.cell_off + lc]), __ldg(&m.g1[h.cell_off + lc]), __ldg(&m.g2[h.cell_off + lc])};
+                            const double xx[3] = {x0, x1, x2};
+                            double vv[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+                            for (int i = 0; i < 3; ++i)
+                                if (fl & (1u << i)) {
+                                    const double len = sqrt(48.0 * A * gg[i]);
+                                    const int j = (i + 1) % 3, kk = (i + 2) % 3;
+                                    vv[j] += a.cB * len * (1.0 / 6.0) * (2.0 * xx[j] + xx[kk]);
+                                    vv[kk] += a.cB * len * (1.0 / 6.0) * (2.0 * xx[kk] + xx[j]);
+                                }
+                            v0 += vv[0]; v1 += vv[1]; v2 += vv[2];
+                        }
+                    }
+                }
+            }
+            if (HAS_D && MODE == MODE_OP) {
+                const uint32_t e0 = r.z & 0xFFFFu, e1 = r.z >> 16, e2 = r.w & 0xFFFFu;
+                const double t0 = (e0 & 0x8000u) ? -sq[e0 & 0x3FFFu] : sq[e0 & 0x3FFFu];
+                const double t1 = (e1 & 0x8000u) ? -sq[e1 & 0x3FFFu] : sq[e1 & 0x3FFFu];
+                const double t2 = (e2 & 0x8000u) ? -sq[e2 & 0x3FFFu] : sq[e2 & 0x3FFFu];
+                const double common = a.cD * (t0 + t1 + t2) * (1.0 / 3.0);
+                double d0 = common, d1 = common, d2 = common;
+                // zero-flux sides: -(1/2) s_e q_e at both end vertices of edge i (the vertices != i)
+                if (e0 & 0x4000u) { const double hq = 0.5 * a.cD * t0; d1 -= hq; d2 -= hq; }
+                if (e1 & 0x4000u) { const double hq = 0.5 * a.cD * t1; d0 -= hq; d2 -= hq; }
+                if (e2 & 0x4000u) { const double hq = 0.5 * a.cD * t2; d0 -= hq; d1 -= hq; }
+                v0 += d0; v1 += d1; v2 += d2;
+            }
+            sc3[3 * lc] = v0; sc3[3 * lc + 1] = v1; sc3[3 * lc + 2] = v2;
+        }
+        __syncthreads();
+        // ---- stage 3: owned rows, fixed summation order, fused epilogue
+        for (int lv = threadIdx.x; lv < h.v_cnt; lv += NT) {
+            const int gid = h.v_start + lv;
+            const uint32_t o0 = m.vadj_off[gid], o1 = m.vadj_off[gid + 1];
+            double val = 0.0;
+            for (uint32_t o = o0; o < o1; ++o) {
+                const uint32_t code = m.vadj[o];
+                val += sc3[3 * (code >> 2) + (code & 3u)];
+            }
+            if (EPI == EPI_STORE) {
+                a.y[gid] = val;
+            } else if (EPI == EPI_CHEB) {
+                const double bv = a.b[gid], pv = a.pinv[gid], xc = sp[lv];
+                const double r_ = bv - val;
+                double xn = xc + c2 * pv * r_;
+                if (k > 0) xn += c1 * (xc - a.tp.b[(cur + 2) % 3][gid]);
+                a.tp.b[(cur + 1) % 3][gid] = xn;
+                acc0 += pv * r_ * r_;
+                acc1 += pv * bv * bv;
+            } else {
+                acc0 += sp[lv] * val;
+            }
+        }
+        __syncthreads();
+        if (EPI != EPI_STORE) {
+            double s0 = acc0, s1 = acc1;
+            block_sum2(s0, s1, red);
+            if (threadIdx.x == 0) { a.partials[2 * P] = s0; a.partials[2 * P + 1] = s1; }
+            acc0 = acc1 = 0.0;
+        }
+    }
+    if (EPI != EPI_STORE) finish_launch<EPI>(a, red);
+}
+
+// ------------------------------------------------------------------------------------------------
+// edge rows
+// ------------------------------------------------------------------------------------------------
+template <int EPI, int MODE, bool HAS_M, bool HAS_D, bool CAS>
+__global__ void __launch_bounds__(NT, 2) edge_rows_k(const RowArgs a) {
+    extern __shared__ double smem[];
+    __shared__ double red[64];
+    const DevMesh& m = a.m;
+    int cur = 0, k = 0;
+    double c1 = 0.0, c2 = 0.0;
+    if (EPI == EPI_CHEB) {
+        const SolveCtl& sc = a.ctl->sc[a.which];
+        if (sc.done) return;
+        cur = sc.cur; k = sc.k;
+        double rk;
+        cheb_coeffs(k, sc.rho, a.cheb_d, a.cheb_c, c1, c2, rk);
+    }
+    const double* xp = a.xp;
+    const double* xq = a.xq;
+    if (EPI == EPI_CHEB) {
+        if (a.use_cheb_input) xq = a.tq.b[cur];
+        if (a.coupled_from_tribuf) xp = a.tp.b[cur];
+    }
+    double acc0 = 0.0, acc1 = 0.0;
+    for (int P = blockIdx.x; P < m.npatch; P += gridDim.x) {
+        const PatchHdr h = m.hdr[P];
+        const int nlv = h.v_cnt + h.gv_cnt, nle = h.e_cnt + h.ge_cnt;
+        double* sq = smem;                          // [nle]
+        double* sp = sq + ((nle + 1) & ~1);         // [nlv] (only if HAS_D)
+        double* sc3 = HAS_D ? sp + ((nlv + 1) & ~1) : sp;   // [3*n_ecells]
+        if (MODE == MODE_OP && (HAS_M || CAS || EPI != EPI_STORE)) {
+            for (int i = threadIdx.x; i < h.e_cnt; i += NT) sq[i] = xq[h.e_start + i];
+            for (int i = threadIdx.x; i < h.ge_cnt; i += NT) sq[h.e_cnt + i] = xq[m.ghost_e[h.ge_off + i]];
+        }
+        if (HAS_D && MODE == MODE_OP) {
+            for (int i = threadIdx.x; i < h.v_cnt; i += NT) sp[i] = xp[h.v_start + i];
+            for (int i = threadIdx.x; i < h.gv_cnt; i += NT) sp[h.v_cnt + i] = xp[m.ghost_v[h.gv_off + i]];
+        }
+        __syncthreads();
+        for (int lc = threadIdx.x; lc < h.n_ecells; lc += NT) {
+            const uint4 r = __ldg(&m.rec[h.cell_off + lc]);
+            const uint32_t e0 = r.z & 0xFFFFu, e1 = r.z >> 16, e2 = r.w & 0xFFFFu;
+            const double s0 = (e0 & 0x8000u) ? -1.0 : 1.0, s1 = (e1 & 0x8000u) ? -1.0 : 1.0, s2 = (e2 & 0x8000u) ? -1.0 : 1.0;
+            double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+            if (HAS_M || CAS) {
+                const double g0 = __ldg(&m.g0[h.cell_off + lc]), g1 = __ldg(&m.g1[h.cell_off + lc]), g2 = __ldg(&m.g2[h.cell_off + lc]);
+                const double S = g0 + g1 + g2;
+                if (MODE == MODE_DIAG) {
+                    v0 = a.cM * (3.0 * S - 4.0 * g0); v1 = a.cM * (3.0 * S - 4.0 * g1); v2 = a.cM * (3.0 * S - 4.0 * g2);
+                    if (CAS) {
+                        const uint32_t fl = (r.y >> 16) >> 3;
+                        if (fl & 7u) {
+                            const double A = __ldg(&m.area[h.cell_off + lc]);
+                            if (fl & 1u) v0 += a.cB * rsqrt(48.0 * A * g0);
+                            if (fl & 2u) v1 += a.cB * rsqrt(48.0 * A * g1);
+                            if (fl & 4u) v2 += a.cB * rsqrt(48.0 * A * g2);
+                        }
+                    }
+                } else {
+                    const double q0 = sq[e0 & 0x3FFFu], q1 = sq[e1 & 0x3FFFu], q2 = sq[e2 & 0x3FFFu];
+                    if (HAS_M) {
+                        // RT1 element mass from the metric: m_ii = 3S - 4 g_i, m_ij = S - 4 g_k (unsigned basis)
+                        const double t0 = s0 * q0, t1 = s1 * q1, t2 = s2 * q2;
+                        const double ST = S * (t0 + t1 + t2);
+                        v0 = a.cM * s0 * (ST + 2.0 * S * t0 - 4.0 * (g0 * t0 + g2 * t1 + g1 * t2));
+                        v1 = a.cM * s1 * (ST + 2.0 * S * t1 - 4.0 * (g2 * t0 + g1 * t1 + g0 * t2));
+                        v2 = a.cM * s2 * (ST + 2.0 * S * t2 - 4.0 * (g1 * t0 + g0 * t1 + g2 * t2));
+                    }
+                    if (CAS) {
+                        const uint32_t fl = (r.y >> 16) >> 3;
+                        if (fl & 7u) {   // impedance right side: <phi_e.n, phi_e.n> = 1/|e|   (wave_2D.py:350,482)
+                            const double A = __ldg(&m.area[h.cell_off + lc]);
+                            if (fl & 1u) v0 += a.cB * q0 * rsqrt(48.0 * A * g0);
+                            if (fl & 2u) v1 += a.cB * q1 * rsqrt(48.0 * A * g1);
+                            if (fl & 4u) v2 += a.cB * q2 * rsqrt(48.0 * A * g2);
+                        }
+                    }
+                }
+            }
+            if (HAS_D && MODE == MODE_OP) {
+                const double p0 = sp[r.x & 0xFFFFu], p1 = sp[r.x >> 16], p2 = sp[r.y & 0xFFFFu];
+                const double third = (p0 + p1 + p2) * (1.0 / 3.0);
+                double d0 = third, d1 = third, d2 = third;
+                if (e0 & 0x4000u) d0 -= 0.5 * (p1 + p2);
+                if (e1 & 0x4000u) d1 -= 0.5 * (p0 + p2);
+                if (e2 & 0x4000u) d2 -= 0.5 * (p0 + p1);
+                v0 += a.cD * s0 * d0; v1 += a.cD * s1 * d1; v2 += a.cD * s2 * d2;
+            }
+            sc3[3 * lc] = v0; sc3[3 * lc + 1] = v1; sc3[3 * lc + 2] = v2;
+        }
+        __syncthreads();
+        for (int le = threadIdx.x; le < h.e_cnt; le += NT) {
+            const int gid = h.e_start + le;
+            const uint32_t adj = m.eadj[gid];
+            const uint32_t ca = adj & 0xFFFFu, cb = adj >> 16;
+            double val = sc3[3 * (ca >> 2) + (ca & 3u)];
+            if (cb != 0xFFFFu) val += sc3[3 * (cb >> 2) + (cb & 3u)];
+            if (EPI == EPI_STORE) {
+                a.y[gid] = val;
+            } else if (EPI == EPI_CHEB) {
+                const double bv = a.b[gid], pv = a.pinv[gid], xc = sq[le];
+                const double r_ = bv - val;
+                double xn = xc + c2 * pv * r_;
+                if (k > 0) xn += c1 * (xc - a.tq.b[(cur + 2) % 3][gid]);
+                a.tq.b[(cur + 1) % 3][gid] = xn;
+                acc0 += pv * r_ * r_;
+                acc1 += pv * bv * bv;
+            } else {
+                acc0 += sq[le] * val;
+            }
+        }
+        __syncthreads();
+        if (EPI != EPI_STORE) {
+            double t0 = acc0, t1 = acc1;
+            block_sum2(t0, t1, red);
+            if (threadIdx.x == 0) { a.partials[2 * P] = t0; a.partials[2 * P + 1] = t1; }
+            acc0 = acc1 = 0.0;
+        }
+    }
+    if (EPI != EPI_STORE) finish_launch<EPI>(a, red);
+}
+
+}  // namespace phw

@@ -1,0 +1,331 @@
+// layout.cpp - see layout.hpp.  Pure host C++ (compiled by nvcc's host compiler), no CUDA calls.
+#include "layout.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <numeric>
+
+namespace phw {
+
+namespace {
+
+// Hilbert curve index of a point on a 2^16 x 2^16 lattice.
+inline uint32_t hilbert_d(uint32_t x, uint32_t y) {
+    uint32_t d = 0;
+    for (uint32_t s = 1u << 15; s > 0; s >>= 1) {
+        uint32_t rx = (x & s) ? 1u : 0u, ry = (y & s) ? 1u : 0u;
+        d += s * s * ((3u * rx) ^ ry);
+        if (ry == 0) {
+            if (rx == 1) { x = 65535u - x; y = 65535u - y; }
+            std::swap(x, y);
+        }
+    }
+    return d;
+}
+
+// stable LSD radix sort of (key32, value32) pairs, two 16-bit passes
+void radix_sort_pairs(std::vector<uint32_t>& key, std::vector<int32_t>& val) {
+    const size_t n = key.size();
+    std::vector<uint32_t> k2(n);
+    std::vector<int32_t> v2(n);
+    std::vector<size_t> hist(65537);
+    for (int pass = 0; pass < 2; ++pass) {
+        const int sh = 16 * pass;
+        std::fill(hist.begin(), hist.end(), 0);
+        for (size_t i = 0; i < n; ++i) hist[((key[i] >> sh) & 0xFFFFu) + 1]++;
+        for (size_t b = 0; b < 65536; ++b) hist[b + 1] += hist[b];
+        for (size_t i = 0; i < n; ++i) {
+            size_t dst = hist[(key[i] >> sh) & 0xFFFFu]++;
+            k2[dst] = key[i];
+            v2[dst] = val[i];
+        }
+        key.swap(k2);
+        val.swap(v2);
+    }
+}
+
+}  // namespace
+
+std::string Layout::build(int64_t nv_, const double* vxy, int64_t nc_, const int32_t* cells_, int32_t patch_cells_) {
+    if (nv_ <= 0 || nc_ <= 0 || !vxy || !cells_) return "empty mesh";
+    if (nv_ > (int64_t)1 << 30 || nc_ > (int64_t)1 << 30) return "mesh too large for int32 indexing";
+    if (patch_cells_ < 16 || patch_cells_ > 8192) return "patch_cells must be in [16, 8192]";
+    nv = nv_; nc = nc_; patch_cells = patch_cells_;
+    vtx.assign(vxy, vxy + 2 * nv);
+    cells.assign(cells_, cells_ + 3 * nc);
+    // ---- 1. orient cells counter-clockwise
+    for (int64_t c = 0; c < nc; ++c) {
+        int32_t* v = &cells[3 * c];
+        for (int i = 0; i < 3; ++i)
+            if (v[i] < 0 || v[i] >= nv) return "cell vertex index out of range";
+        const double* a = &vtx[2 * (int64_t)v[0]]; const double* b = &vtx[2 * (int64_t)v[1]]; const double* d = &vtx[2 * (int64_t)v[2]];
+        double area2 = (b[0] - a[0]) * (d[1] - a[1]) - (b[1] - a[1]) * (d[0] - a[0]);
+        if (area2 == 0.0) return "degenerate cell";
+        if (area2 < 0) std::swap(v[1], v[2]);
+    }
+    // ---- 2. edges: unique (lo,hi) pairs in lexicographic order; local edge i joins v[i+1], v[i+2]
+    {
+        std::vector<int64_t> start(nv + 1, 0);
+        for (int64_t h = 0; h < 3 * nc; ++h) {
+            int64_t c = h / 3; int i = (int)(h % 3);
+            int32_t a = cells[3 * c + (i + 1) % 3], b = cells[3 * c + (i + 2) % 3];
+            start[std::min(a, b) + 1]++;
+        }
+        for (int64_t v = 0; v < nv; ++v) start[v + 1] += start[v];
+        std::vector<int64_t> pos(start.begin(), start.end() - 1);
+        std::vector<int32_t> bhi(3 * nc);
+        std::vector<int64_t> bhe(3 * nc);
+        for (int64_t h = 0; h < 3 * nc; ++h) {
+            int64_t c = h / 3; int i = (int)(h % 3);
+            int32_t a = cells[3 * c + (i + 1) % 3], b = cells[3 * c + (i + 2) % 3];
+            int64_t p = pos[std::min(a, b)]++;
+            bhi[p] = std::max(a, b);
+            bhe[p] = h;
+        }
+        cell_edges.assign(3 * nc, -1);
+        cell_sign.assign(3 * nc, 0);
+        edges.clear();
+        edges.reserve(3 * nc + 2 * nv);
+        std::vector<int32_t> ecount;
+        ecount.reserve(3 * nc / 2 + nv);
+        std::vector<std::pair<int32_t, int64_t>> tmp;
+        for (int64_t lo = 0; lo < nv; ++lo) {
+            int64_t s = start[lo], e = start[lo + 1];
+            if (s == e) continue;
+            tmp.clear();
+            for (int64_t k = s; k < e; ++k) tmp.emplace_back(bhi[k], bhe[k]);
+            std::sort(tmp.begin(), tmp.end());
+            int32_t prev = -1;
+            for (auto& t : tmp) {
+                if (t.first != prev) {
+                    edges.push_back((int32_t)lo);
+                    edges.push_back(t.first);
+                    ecount.push_back(0);
+                    prev = t.first;
+                }
+                int32_t eid = (int32_t)(edges.size() / 2 - 1);
+                int64_t h = t.second;
+                cell_edges[h] = eid;
+                int64_t c = h / 3; int i = (int)(h % 3);
+                int32_t a = cells[3 * c + (i + 1) % 3], b = cells[3 * c + (i + 2) % 3];
+                cell_sign[h] = (a < b) ? 1 : -1;
+                if (++ecount.back() > 2) return "non-manifold edge (more than two adjacent cells)";
+            }
+        }
+        ne = (int64_t)edges.size() / 2;
+        edges.shrink_to_fit();
+        // boundary edges: one adjacent cell
+        bedge.clear();
+        for (int64_t e = 0; e < ne; ++e)
+            if (ecount[e] == 1) bedge.push_back((int32_t)e);
+        nb = (int64_t)bedge.size();
+        std::vector<int8_t> esign(ne, 0);
+        for (int64_t h = 0; h < 3 * nc; ++h) esign[cell_edges[h]] += cell_sign[h];
+        bsign.resize(nb);
+        for (int64_t k = 0; k < nb; ++k) bsign[k] = esign[bedge[k]];
+        btag.assign(nb, 4);
+        bweight.assign(nb, 1.0);
+        boundary_set = false;
+    }
+    // ---- 3. Hilbert order of cell centroids -> patches
+    std::vector<int32_t> order(nc);
+    {
+        double xmin = std::numeric_limits<double>::max(), xmax = -xmin, ymin = xmin, ymax = -xmin;
+        for (int64_t v = 0; v < nv; ++v) {
+            xmin = std::min(xmin, vtx[2 * v]); xmax = std::max(xmax, vtx[2 * v]);
+            ymin = std::min(ymin, vtx[2 * v + 1]); ymax = std::max(ymax, vtx[2 * v + 1]);
+        }
+        double ext = std::max(xmax - xmin, ymax - ymin);
+        if (!(ext > 0)) return "mesh has zero extent";
+        double sc = 65535.0 / ext;
+        std::vector<uint32_t> key(nc);
+        for (int64_t c = 0; c < nc; ++c) {
+            const int32_t* v = &cells[3 * c];
+            double cx = (vtx[2 * (int64_t)v[0]] + vtx[2 * (int64_t)v[1]] + vtx[2 * (int64_t)v[2]]) / 3.0;
+            double cy = (vtx[2 * (int64_t)v[0] + 1] + vtx[2 * (int64_t)v[1] + 1] + vtx[2 * (int64_t)v[2] + 1]) / 3.0;
+            uint32_t qx = (uint32_t)std::min(65535.0, std::max(0.0, (cx - xmin) * sc));
+            uint32_t qy = (uint32_t)std::min(65535.0, std::max(0.0, (cy - ymin) * sc));
+            key[c] = hilbert_d(qx, qy);
+            order[c] = (int32_t)c;
+        }
+        radix_sort_pairs(key, order);
+    }
+    npatch = (int32_t)((nc + patch_cells - 1) / patch_cells);
+    cell_patch.assign(nc, 0);
+    std::vector<int64_t> own_off(npatch + 1);
+    for (int32_t p = 0; p <= npatch; ++p) own_off[p] = (int64_t)p * nc / npatch;
+    for (int32_t p = 0; p < npatch; ++p)
+        for (int64_t k = own_off[p]; k < own_off[p + 1]; ++k) cell_patch[order[k]] = p;
+    // ---- 4. dof ownership = lowest adjacent patch; renumber so owned ranges are contiguous
+    v_owner.assign(nv, std::numeric_limits<int32_t>::max());
+    e_owner.assign(ne, std::numeric_limits<int32_t>::max());
+    for (int64_t c = 0; c < nc; ++c) {
+        int32_t p = cell_patch[c];
+        for (int i = 0; i < 3; ++i) {
+            int32_t& ov = v_owner[cells[3 * c + i]]; ov = std::min(ov, p);
+            int32_t& oe = e_owner[cell_edges[3 * c + i]]; oe = std::min(oe, p);
+        }
+    }
+    for (int64_t v = 0; v < nv; ++v)
+        if (v_owner[v] == std::numeric_limits<int32_t>::max()) return "unreferenced vertex in mesh";
+    auto renumber = [&](const std::vector<int32_t>& owner, int64_t n, std::vector<int32_t>& new2old,
+                        std::vector<int32_t>& old2new, std::vector<int32_t>& pstart) {
+        pstart.assign(npatch + 1, 0);
+        for (int64_t i = 0; i < n; ++i) pstart[owner[i] + 1]++;
+        for (int32_t p = 0; p < npatch; ++p) pstart[p + 1] += pstart[p];
+        std::vector<int32_t> pos(pstart.begin(), pstart.end() - 1);
+        new2old.resize(n); old2new.resize(n);
+        for (int64_t i = 0; i < n; ++i) {
+            int32_t d = pos[owner[i]]++;
+            new2old[d] = (int32_t)i;
+            old2new[i] = d;
+        }
+    };
+    std::vector<int32_t> vstart, estart;
+    renumber(v_owner, nv, v_new2old, v_old2new, vstart);
+    renumber(e_owner, ne, e_new2old, e_old2new, estart);
+    // ---- 5. halo cells: (patch, cell, type) type 0 = adjacent to an owned edge, 1 = only to an owned vertex
+    std::vector<uint64_t> halo;
+    for (int64_t c = 0; c < nc; ++c) {
+        int32_t pc = cell_patch[c];
+        for (int i = 0; i < 3; ++i) {
+            int32_t pe = e_owner[cell_edges[3 * c + i]];
+            if (pe != pc) halo.push_back(((uint64_t)pe << 33) | ((uint64_t)c << 1) | 0u);
+            int32_t pv = v_owner[cells[3 * c + i]];
+            if (pv != pc) halo.push_back(((uint64_t)pv << 33) | ((uint64_t)c << 1) | 1u);
+        }
+    }
+    std::sort(halo.begin(), halo.end());
+    {   // unique on (patch, cell), keeping the smallest type
+        size_t w = 0;
+        for (size_t r = 0; r < halo.size(); ++r)
+            if (w == 0 || (halo[r] >> 1) != (halo[w - 1] >> 1)) halo[w++] = halo[r];
+        halo.resize(w);
+    }
+    // ---- 6. per-patch local numbering, cell lists, adjacency
+    hdr.assign(npatch, PatchHdr{});
+    pcell_user.clear(); pc_lv.clear(); pc_le.clear(); ghost_v.clear(); ghost_e.clear();
+    pcell_user.reserve(nc + halo.size());
+    eadj.assign(ne, 0xFFFFFFFFu);
+    vadj_off.assign(nv + 1, 0);
+    vadj.clear();
+    vadj.reserve(3 * nc + 3 * halo.size());
+    std::vector<int32_t> lv_of(nv, -1), le_of(ne, -1);
+    std::vector<int32_t> gv_tmp, ge_tmp, cl;
+    std::vector<uint32_t> vcnt;
+    max_lv = max_le = max_cells = 0;
+    size_t hpos = 0;
+    for (int32_t p = 0; p < npatch; ++p) {
+        PatchHdr& H = hdr[p];
+        H.cell_off = (int32_t)pcell_user.size();
+        H.n_own = (int32_t)(own_off[p + 1] - own_off[p]);
+        H.v_start = vstart[p]; H.v_cnt = vstart[p + 1] - vstart[p];
+        H.e_start = estart[p]; H.e_cnt = estart[p + 1] - estart[p];
+        cl.clear();
+        for (int64_t k = own_off[p]; k < own_off[p + 1]; ++k) cl.push_back(order[k]);
+        size_t h0 = hpos;
+        while (hpos < halo.size() && (int32_t)(halo[hpos] >> 33) == p) ++hpos;
+        for (size_t r = h0; r < hpos; ++r)
+            if ((halo[r] & 1u) == 0) cl.push_back((int32_t)((halo[r] >> 1) & 0xFFFFFFFFu));
+        H.n_ecells = (int32_t)cl.size();
+        for (size_t r = h0; r < hpos; ++r)
+            if ((halo[r] & 1u) == 1) cl.push_back((int32_t)((halo[r] >> 1) & 0xFFFFFFFFu));
+        H.n_vcells = (int32_t)cl.size();
+        // ghosts
+        gv_tmp.clear(); ge_tmp.clear();
+        for (int32_t c : cl)
+            for (int i = 0; i < 3; ++i) {
+                int32_t v = cells[3 * (int64_t)c + i];
+                if (v_owner[v] != p && lv_of[v] < 0) { lv_of[v] = 0; gv_tmp.push_back(v_old2new[v]); }
+                int32_t e = cell_edges[3 * (int64_t)c + i];
+                if (e_owner[e] != p && le_of[e] < 0) { le_of[e] = 0; ge_tmp.push_back(e_old2new[e]); }
+            }
+        std::sort(gv_tmp.begin(), gv_tmp.end());
+        std::sort(ge_tmp.begin(), ge_tmp.end());
+        H.gv_off = (int32_t)ghost_v.size(); H.gv_cnt = (int32_t)gv_tmp.size();
+        H.ge_off = (int32_t)ghost_e.size(); H.ge_cnt = (int32_t)ge_tmp.size();
+        for (size_t k = 0; k < gv_tmp.size(); ++k) { lv_of[v_new2old[gv_tmp[k]]] = H.v_cnt + (int32_t)k; ghost_v.push_back(gv_tmp[k]); }
+        for (size_t k = 0; k < ge_tmp.size(); ++k) { le_of[e_new2old[ge_tmp[k]]] = H.e_cnt + (int32_t)k; ghost_e.push_back(ge_tmp[k]); }
+        int32_t nlv = H.v_cnt + H.gv_cnt, nle = H.e_cnt + H.ge_cnt;
+        if (nlv >= 65536 || nle >= 16384 || H.n_vcells >= 16383)
+            return "patch too large for 16-bit local indices; reduce patch_cells";
+        max_lv = std::max(max_lv, nlv); max_le = std::max(max_le, nle); max_cells = std::max(max_cells, H.n_vcells);
+        // records + adjacency
+        vcnt.assign(H.v_cnt + 1, 0);
+        for (size_t lc = 0; lc < cl.size(); ++lc) {
+            int64_t c = cl[lc];
+            pcell_user.push_back((int32_t)c);
+            for (int i = 0; i < 3; ++i) {
+                int32_t v = cells[3 * c + i], e = cell_edges[3 * c + i];
+                int32_t lv = (v_owner[v] == p) ? v_old2new[v] - H.v_start : lv_of[v];
+                int32_t le = (e_owner[e] == p) ? e_old2new[e] - H.e_start : le_of[e];
+                pc_lv.push_back((uint16_t)lv);
+                pc_le.push_back((uint16_t)le);
+                if (v_owner[v] == p) vcnt[lv + 1]++;
+                if (e_owner[e] == p) {
+                    if ((int32_t)lc >= H.n_ecells) return "internal: owned edge adjacent to a vertex-halo cell";
+                    uint32_t& a = eadj[e_old2new[e]];
+                    uint32_t code = (uint32_t)(lc * 4 + i);
+                    if ((a & 0xFFFFu) == 0xFFFFu) a = (a & 0xFFFF0000u) | code;
+                    else if ((a >> 16) == 0xFFFFu) a = (a & 0xFFFFu) | (code << 16);
+                    else return "internal: edge with more than two adjacent patch cells";
+                }
+            }
+        }
+        // vertex CSR (entries ascending in lc)
+        for (int32_t k = 0; k < H.v_cnt; ++k) vcnt[k + 1] += vcnt[k];
+        size_t base = vadj.size();
+        vadj.resize(base + vcnt[H.v_cnt]);
+        for (int32_t k = 0; k < H.v_cnt; ++k) vadj_off[H.v_start + k] = (uint32_t)(base + vcnt[k]);
+        std::vector<uint32_t> fill(vcnt.begin(), vcnt.end() - 1);
+        for (size_t lc = 0; lc < cl.size(); ++lc) {
+            int64_t c = cl[lc];
+            for (int i = 0; i < 3; ++i) {
+                int32_t v = cells[3 * c + i];
+                if (v_owner[v] == p) {
+                    int32_t lv = v_old2new[v] - H.v_start;
+                    vadj[base + fill[lv]++] = (uint16_t)(lc * 4 + i);
+                }
+            }
+        }
+        // reset scratch
+        for (int32_t g : gv_tmp) lv_of[v_new2old[g]] = -1;
+        for (int32_t g : ge_tmp) le_of[e_new2old[g]] = -1;
+    }
+    vadj_off[nv] = (uint32_t)vadj.size();
+    if (vadj.size() >= ((size_t)1 << 32)) return "vertex adjacency exceeds 32-bit offsets";
+    return "";
+}
+
+void Layout::make_records(bool strong, bool casimir, std::vector<CellRec>& rec) const {
+    // per-edge boundary tag (-1 interior)
+    std::vector<int8_t> etag(ne, -1);
+    for (int64_t k = 0; k < nb; ++k) etag[bedge[k]] = (int8_t)btag[k];
+    const size_t npc = pcell_user.size();
+    rec.resize(npc);
+    for (size_t k = 0; k < npc; ++k) {
+        int64_t c = pcell_user[k];
+        uint32_t le[3], lv[3], flags = 0;
+        for (int i = 0; i < 3; ++i) {
+            int32_t e = cell_edges[3 * c + i];
+            lv[i] = pc_lv[3 * k + i];
+            le[i] = pc_le[3 * k + i];
+            if (cell_sign[3 * c + i] < 0) le[i] |= 0x8000u;
+            int8_t t = etag[e];
+            if (t >= 0) {
+                bool nterm = strong ? true : (t == 1 || t == 3);
+                if (nterm) le[i] |= 0x4000u;
+                if (casimir && t == 1) flags |= (1u << i);
+                if (casimir && t == 2) flags |= (1u << (3 + i));
+            }
+        }
+        rec[k].x = lv[0] | (lv[1] << 16);
+        rec[k].y = lv[2] | (flags << 16);
+        rec[k].z = le[0] | (le[1] << 16);
+        rec[k].w = le[2];
+    }
+}
+
+}  // namespace phw

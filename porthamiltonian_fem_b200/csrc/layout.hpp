@@ -1,0 +1,68 @@
+// layout.hpp - host-side mesh connectivity and patch layout (no CUDA dependency).
+//
+// Replaces what dolfin builds behind `FunctionSpace(mesh, MixedElement([P1, RT, ...]))`,
+// `MeshFunction(...).mark` and `FacetNormal` (reference wave_2D.py:168-220,266-285): dof maps of the
+// P1 (vertex) and RT1 (edge) spaces, edge orientation signs and boundary tags - re-organised for the
+// GPU as *patches*: runs of cells contiguous along a Hilbert curve, each owning a contiguous range of
+// vertex- and edge-dofs, with one layer of halo cells so that every owned row can be evaluated inside
+// one thread block from shared memory (owner-computes, deterministic, no global atomics).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace phw {
+
+// 16-byte per-(patch,cell) record.  Local ids index the patch's local vertex/edge arrays:
+// [owned (contiguous global range) | ghosts].
+//   x = lv0 | lv1<<16          y = lv2 | flags<<16
+//   z = le0 | le1<<16          w = le2
+// le bits: 0..13 local edge id, bit 14: "N-term" edge (zero-flux boundary side, wave_2D.py:465-472
+// ds(1), ds(3); every boundary edge in the strong form), bit 15: orientation sign is -1.
+// flags bits (y>>16): 0..2 slot i lies on the impedance top side (casimir, tag 1),
+//                     3..5 slot i lies on the impedance right side (casimir, tag 2).
+struct CellRec { uint32_t x, y, z, w; };
+
+struct PatchHdr {
+    int32_t cell_off;   // first entry in the patch-cell arrays
+    int32_t n_own;      // own cells
+    int32_t n_ecells;   // cells processed by edge-row operators (own + E-halo)
+    int32_t n_vcells;   // cells processed by vertex-row operators (all)
+    int32_t v_start, v_cnt, gv_off, gv_cnt;   // owned vertex range (new numbering), ghost list
+    int32_t e_start, e_cnt, ge_off, ge_cnt;   // owned edge range, ghost list
+};
+
+struct Layout {
+    int64_t nv = 0, nc = 0, ne = 0, nb = 0;
+    int32_t patch_cells = 0, npatch = 0;
+    std::vector<double>  vtx;          // [nv,2] user order
+    std::vector<int32_t> cells;        // [nc,3] user order, CCW
+    std::vector<int32_t> edges;        // [ne,2] (lo,hi), canonical order
+    std::vector<int32_t> cell_edges;   // [nc,3]
+    std::vector<int8_t>  cell_sign;    // [nc,3]
+    std::vector<int32_t> bedge;        // [nb] boundary edge ids (ascending)
+    std::vector<int8_t>  bsign;        // [nb]
+    std::vector<int32_t> btag;         // [nb] phw_tag (default NONE)
+    std::vector<double>  bweight;      // [nb] left-port weights (default 1)
+    bool boundary_set = false;
+
+    std::vector<int32_t> cell_patch;   // [nc] user cell -> patch
+    std::vector<int32_t> v_new2old, v_old2new, e_new2old, e_old2new;
+    std::vector<int32_t> v_owner, e_owner;     // by old id
+
+    std::vector<PatchHdr> hdr;
+    std::vector<int32_t> pcell_user;   // [npc] user cell id of every patch cell
+    std::vector<uint16_t> pc_lv;       // [npc,3] local vertex ids
+    std::vector<uint16_t> pc_le;       // [npc,3] local edge ids (no flag bits)
+    std::vector<int32_t> ghost_v, ghost_e;     // new ids
+    std::vector<uint32_t> eadj;        // [ne] by new id: (lc*4+slot) | (lc*4+slot)<<16, 0xFFFF = none
+    std::vector<uint32_t> vadj_off;    // [nv+1] by new id
+    std::vector<uint16_t> vadj;        // lc*4+slot
+    int32_t max_lv = 0, max_le = 0, max_cells = 0;
+
+    std::string build(int64_t nv_, const double* vxy, int64_t nc_, const int32_t* cells_, int32_t patch_cells_);
+    // cell records with boundary flag bits for the given formulation
+    void make_records(bool strong, bool casimir, std::vector<CellRec>& rec) const;
+};
+
+}  // namespace phw

@@ -1,0 +1,1159 @@
+// phwave.cu - C ABI (include/phwave.h) + device-resident time loop of the port-Hamiltonian wave solver.
+//
+// Reference being replaced: fenics_projects/wave_eqn/wave_2D.py (setup :92-641, loop :787-982).
+// The host side of this file only *enqueues* kernels on one stream; all loop state (time, lumped ODE
+// state, energies, Chebyshev iteration control) lives in a device-resident control block (Ctl), so the
+// step loop never returns to the host.  See DESIGN.md for the data layout and per-kernel byte model.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/phwave.h"
+#include "kernels.cuh"
+#include "layout.hpp"
+
+using namespace phw;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            char buf_[512];                                                                        \
+            snprintf(buf_, sizeof buf_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return fail(PHW_ECUDA, buf_);                                                          \
+        }                                                                                          \
+    } while (0)
+
+struct phw_mesh_s { Layout L; };
+
+// ================================================================================================
+// small kernels
+// ================================================================================================
+namespace phw {
+
+// per-(patch,cell) geometry: area and the RT1 metric g_i = |e_i|^2 / (48 |K|); also the element-wise
+// generalized eigenvalue range of (M_K, diag M_K), which bounds the spectrum of the Jacobi-scaled RT1
+// mass matrix (Wathen 1987) - the Chebyshev interval.
+__global__ void geom_k(int npc, const int* __restrict__ pcell_user, const int* __restrict__ cells,
+                       const double* __restrict__ vtx, double* area, double* g0, double* g1, double* g2,
+                       unsigned long long* lam_minmax) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    double lmin = 1.0, lmax = 1.0;
+    if (k < npc) {
+        int c = pcell_user[k];
+        int a = cells[3 * c], b = cells[3 * c + 1], d = cells[3 * c + 2];
+        double ax = vtx[2 * a], ay = vtx[2 * a + 1], bx = vtx[2 * b], by = vtx[2 * b + 1], dx = vtx[2 * d], dy = vtx[2 * d + 1];
+        double A = 0.5 * fabs((bx - ax) * (dy - ay) - (by - ay) * (dx - ax));
+        double l0 = (dx - bx) * (dx - bx) + (dy - by) * (dy - by);   // edge 0 joins v1, v2
+        double l1 = (ax - dx) * (ax - dx) + (ay - dy) * (ay - dy);   // edge 1 joins v2, v0
+        double l2 = (bx - ax) * (bx - ax) + (by - ay) * (by - ay);   // edge 2 joins v0, v1
+        double inv = 1.0 / (48.0 * A);
+        double G0 = l0 * inv, G1 = l1 * inv, G2 = l2 * inv, S = G0 + G1 + G2;
+        area[k] = A; g0[k] = G0; g1[k] = G1; g2[k] = G2;
+        double m00 = 3 * S - 4 * G0, m11 = 3 * S - 4 * G1, m22 = 3 * S - 4 * G2;
+        double m01 = S - 4 * G2, m02 = S - 4 * G1, m12 = S - 4 * G0;
+        double ea = m01 / sqrt(m00 * m11), eb = m02 / sqrt(m00 * m22), ec = m12 / sqrt(m11 * m22);
+        double p = ea * ea + eb * eb + ec * ec, q = 2.0 * ea * eb * ec;
+        if (p > 1e-30) {
+            double arg = 0.5 * q * pow(3.0 / p, 1.5);
+            arg = fmin(1.0, fmax(-1.0, arg));
+            double phi = acos(arg) / 3.0, amp = 2.0 * sqrt(p / 3.0);
+            lmax = 1.0 + amp * cos(phi);
+            lmin = 1.0 + amp * cos(phi + 2.0943951023931953);
+        }
+    }
+    // positive doubles order like their bit patterns
+    for (int o = 16; o > 0; o >>= 1) {
+        lmin = fmin(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
+        lmax = fmax(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&lam_minmax[0], (unsigned long long)__double_as_longlong(lmin));
+        atomicMax(&lam_minmax[1], (unsigned long long)__double_as_longlong(lmax));
+    }
+}
+
+__global__ void invert_k(int n, double* d) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) d[i] = (d[i] != 0.0) ? 1.0 / d[i] : 0.0;
+}
+__global__ void gather_k(int n, double* dst, const double* src, const int* map) {   // dst[i] = src[map[i]]
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[map[i]];
+}
+__global__ void scatter_k(int n, double* dst, const double* src, const int* map) {  // dst[map[i]] = src[i]
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[map[i]] = src[i];
+}
+// y += a * x      (x optionally = the current Chebyshev buffer of solve `which`)
+__global__ void axpy_k(int n, double* y, double a, const double* x, TriBuf tb, const Ctl* ctl, int which) {
+    const double* xs = x ? x : tb.b[ctl->sc[which].cur];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) y[i] += a * xs[i];
+}
+// w = y + a * x
+__global__ void waxpy_k(int n, double* w, const double* y, double a, const double* x, TriBuf tb, const Ctl* ctl, int which) {
+    const double* xs = x ? x : tb.b[ctl->sc[which].cur];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) w[i] = y[i] + a * xs[i];
+}
+// buf[cur] += coef(device) * w
+__global__ void axpy_dev_k(int n, TriBuf tb, const Ctl* ctl, int which, const double* coef, const double* w) {
+    double* y = tb.b[ctl->sc[which].cur];
+    const double a = *coef;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) y[i] += a * w[i];
+}
+__global__ void copy_from_tb_k(int n, double* dst, TriBuf tb, const Ctl* ctl, int which) {
+    const double* xs = tb.b[ctl->sc[which].cur];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = xs[i];
+}
+__global__ void copy_to_tb_k(int n, TriBuf tb, const Ctl* ctl, int which, const double* src) {
+    double* xs = tb.b[ctl->sc[which].cur];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) xs[i] = src ? src[i] : 0.0;
+}
+
+// port flux  b_L^T q = int_{Gamma_0} (q.n) g_L ds   (wave_2D.py:534,546,622-631), single CTA, fixed order
+__global__ void flux_k(int nport, const int* __restrict__ pe, const double* __restrict__ bl, const double* q,
+                       TriBuf tb, Ctl* ctl, int which, int slot) {
+    __shared__ double red[64];
+    const double* qs = q ? q : tb.b[ctl->sc[which].cur];
+    double s = 0.0, z = 0.0;
+    for (int i = threadIdx.x; i < nport; i += blockDim.x) s += bl[i] * qs[pe[i]];
+    block_sum2(s, z, red);
+    if (threadIdx.x == 0) ctl->flux[slot] = s;
+}
+// b[e] -= coef * b_L[e] * p_left   on the port edges (the ds(0) term of the q rows, wave_2D.py:469,480,504,515)
+__global__ void port_rhs_k(int nport, const int* __restrict__ pe, const double* __restrict__ bl, double* b, double coef, const Ctl* ctl) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nport) b[pe[i]] -= coef * bl[i] * ctl->pleft;
+}
+__global__ void solve_begin_k(Ctl* ctl, int which) {
+    SolveCtl& sc = ctl->sc[which];
+    sc.k = 0; sc.done = 0; sc.racc = 0.0; sc.bacc = 0.0; sc.rho = 0.0; sc.solves += 1;
+}
+
+struct ScalarPrm {
+    double dt, K, rho, c2;
+    double A[3][3];
+    double m_em, L_em, K_em;
+    int input_kind;
+    double in_amp, in_omega, in_t_stop, in_t_ctrl, in_gain;
+    double H_init;
+    int ncol, ic;
+    double w_old, w_new;   // energy-flux weights of b_L^T q_m and b_L^T q_new (wave_2D.py:603-615)
+};
+
+__device__ double input_value(const ScalarPrm& s, double t, double x0_prev) {
+    switch (s.input_kind) {
+        case PHW_IN_SINE_WINDOW: return (t < s.in_t_stop) ? s.in_amp * sin(s.in_omega * t) : 0.0;
+        case PHW_IN_SINE: return s.in_amp * sin(s.in_omega * t);
+        case PHW_IN_COSINE: return s.in_amp * cos(s.in_omega * t);
+        case PHW_IN_PASSIVITY:
+            if (t < s.in_t_stop) return s.in_amp * sin(s.in_omega * t);
+            if (t < s.in_t_ctrl) return 0.0;
+            return -s.in_gain * x0_prev;
+    }
+    return 0.0;
+}
+
+__device__ void solve3(double M[3][3], double r[3], double x[3]) {   // Gaussian elimination, partial pivoting
+    int idx[3] = {0, 1, 2};
+    for (int c = 0; c < 3; ++c) {
+        int piv = c;
+        for (int r_ = c + 1; r_ < 3; ++r_)
+            if (fabs(M[idx[r_]][c]) > fabs(M[idx[piv]][c])) piv = r_;
+        int t = idx[c]; idx[c] = idx[piv]; idx[piv] = t;
+        for (int r_ = c + 1; r_ < 3; ++r_) {
+            double f = M[idx[r_]][c] / M[idx[c]][c];
+            for (int cc = c; cc < 3; ++cc) M[idx[r_]][cc] -= f * M[idx[c]][cc];
+            r[idx[r_]] -= f * r[idx[c]];
+        }
+    }
+    for (int c = 2; c >= 0; --c) {
+        double s = r[idx[c]];
+        for (int cc = c + 1; cc < 3; ++cc) s -= M[idx[c]][cc] * x[cc];
+        x[c] = s / M[idx[c]][c];
+    }
+}
+
+enum ScalarOp {
+    S_BEGIN_1SUB = 0,   // t += dt; p_left = g(t) | u = u(t)          wave_2D.py:790-808
+    S_SV_STAGE1,        // p_left(t_n) | lumped half step for x2         :812-820 with :530-534
+    S_SV_MID,           // first boundary-energy half, t += dt, new input :830-843
+    S_ODE_SE,           // lumped rows of symplectic Euler                :552-556
+    S_ODE_SV,           // lumped rows of Stormer-Verlet stage 2          :538-546
+    S_SM_PLEFT,         // p_left = rho x1_m / m for the explicit part of the SM q rows
+    S_ODE_SM,           // bordered 3x3 solve of the implicit-midpoint lumped rows   :562-572
+    S_END_1SUB,         // energies + H_array row for one-sub-step schemes :876-927,967-979
+    S_END_SV,
+    S_END_EH,
+    S_EH_BEGIN
+};
+
+__global__ void scalar_k(Ctl* ctl, const ScalarPrm s, int op, double* Hrows, double aux0, double aux1) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    Ctl& c = *ctl;
+    const double dt = s.dt;
+    switch (op) {
+        case S_BEGIN_1SUB:
+        case S_EH_BEGIN:
+            c.t += dt;
+            if (s.ic) { c.u_now = input_value(s, c.t, c.x[0]); }
+            else c.pleft = input_value(s, c.t, 0.0);
+            break;
+        case S_SV_STAGE1:
+            if (s.ic) {
+                for (int i = 0; i < 3; ++i) c.xm[i] = c.x[i];
+                // F_temp_em (wave_2D.py:530-534): only x[2] implicit; only x_temp[2] is used afterwards.
+                // row 2: (x2 - x2m)/(dt/2) = A20 x0m + A21 x1m + A22 x2
+                c.xt2 = (c.xm[2] + 0.5 * dt * (s.A[2][0] * c.xm[0] + s.A[2][1] * c.xm[1])) / (1.0 - 0.5 * dt * s.A[2][2]);
+                c.pleft = s.rho * c.xm[1] / s.m_em;                                  // :392
+            } else c.pleft = input_value(s, c.t, 0.0);
+            break;
+        case S_SV_MID:
+            if (!s.ic) c.bE += 0.5 * dt * s.c2 * c.flux[0] * c.pleft;               // :622,830
+            c.t += dt;                                                               // :833-834
+            if (s.ic) c.u_now = input_value(s, c.t, c.xm[0]);
+            else c.pleft = input_value(s, c.t, 0.0);
+            break;
+        case S_ODE_SE: {
+            for (int i = 0; i < 3; ++i) c.xm[i] = c.x[i];
+            double M[3][3], r[3], x[3];
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j) M[i][j] = (i == j ? 1.0 : 0.0) - (j < 2 ? dt * s.A[i][j] : 0.0);
+            const double f[3] = {c.u_now, s.K * c.flux[0], 0.0};
+            for (int i = 0; i < 3; ++i) r[i] = c.xm[i] + dt * (s.A[i][2] * c.xm[2] + f[i]);
+            solve3(M, r, x);
+            for (int i = 0; i < 3; ++i) c.x[i] = x[i];
+            c.pleft = s.rho * c.x[1] / s.m_em;                                       // :397
+        } break;
+        case S_ODE_SV: {
+            double M[3][3], r[3], x[3];
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j) M[i][j] = (i == j ? 1.0 : 0.0) - (j < 2 ? 0.5 * dt * s.A[i][j] : 0.0);
+            r[0] = c.xm[0] + dt * (0.5 * (s.A[0][0] * c.xm[0] + s.A[0][1] * c.xm[1]) + s.A[0][2] * c.xt2 + c.u_now);
+            r[1] = c.xm[1] + dt * (0.5 * (s.A[1][0] * c.xm[0] + s.A[1][1] * c.xm[1]) + s.A[1][2] * c.xt2 + s.K * c.flux[0]);
+            r[2] = c.xt2 + dt * 0.5 * s.A[2][2] * c.xt2;
+            solve3(M, r, x);
+            for (int i = 0; i < 3; ++i) c.x[i] = x[i];
+            c.pleft = s.rho * c.x[1] / s.m_em;                                       // :393
+        } break;
+        case S_SM_PLEFT:
+            for (int i = 0; i < 3; ++i) c.xm[i] = c.x[i];
+            c.pleft = s.rho * c.xm[1] / s.m_em;
+            break;
+        case S_ODE_SM: {
+            // unknown xi = (x+ - x-)/dt ; v_q = vhat_q - 0.5 dt (xi1/m) w_q, aux0 = b_L^T w_q (constant), flux[2] = b_L^T vhat_q
+            const double th = 0.5;
+            double M[3][3], r[3], xi[3];
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j) M[i][j] = (i == j ? 1.0 : 0.0) - th * dt * s.A[i][j];
+            M[1][1] += th * th * dt * dt * s.K * aux0 / s.m_em;
+            const double f[3] = {c.u_now, s.K * (c.flux[0] + th * dt * c.flux[2]), 0.0};
+            for (int i = 0; i < 3; ++i) r[i] = s.A[i][0] * c.xm[0] + s.A[i][1] * c.xm[1] + s.A[i][2] * c.xm[2] + f[i];
+            solve3(M, r, xi);
+            for (int i = 0; i < 3; ++i) c.x[i] = c.xm[i] + dt * xi[i];
+            c.xi1 = -th * dt * xi[1] / s.m_em;     // coefficient of w in v = vhat + xi1 * w
+        } break;
+        case S_END_1SUB:
+        case S_END_SV:
+        case S_END_EH: {
+            double H_wave = c.red[0] + c.red[1];
+            double E, H;
+            if (!s.ic) {
+                if (op == S_END_1SUB) {
+                    c.bE += dt * s.c2 * (s.w_old * c.flux[0] + s.w_new * c.flux[1]) * c.pleft + dt * s.c2 * (c.red[2] + c.red[3]);   // :631-641
+                } else if (op == S_END_SV) {
+                    c.bE += 0.5 * dt * s.c2 * c.flux[0] * c.pleft;                   // :625,880
+                } else {
+                    // EH: q0_ = q_m, q1_ = q_temp = q_m + dt v_q1 ; flux[1] = b_L^T v_q1     :617-628
+                    c.bE += 0.5 * dt * s.c2 * (2.0 * c.flux[0] + dt * c.flux[1]) * c.pleft;
+                }
+                E = H_wave + c.bE - s.H_init;                                        // :884
+                H = H_wave;
+            } else {
+                if (op == S_END_SV) {
+                    c.inpE += 0.5 * dt * c.u_now * c.xm[0] / s.L_em + 0.5 * dt * c.u_now * c.x[0] / s.L_em;          // :828,892,903
+                    c.bE += 0.5 * dt * s.c2 * c.flux[0] * s.rho * (c.xm[1] + c.x[1]) / s.m_em;                        // :622-628
+                } else if (s.w_new == 0.0) {   // SE
+                    c.inpE += dt * c.u_now * c.x[0] / s.L_em;                                                         // :894
+                    c.bE += dt * s.c2 * c.flux[0] * s.rho * c.x[1] / s.m_em;                                          // :631,398
+                } else {                       // SM
+                    c.inpE += 0.5 * dt * c.u_now * (c.xm[0] + c.x[0]) / s.L_em;                                      // :898
+                    c.bE += dt * s.c2 * (s.w_old * c.flux[0] + s.w_new * c.flux[1]) * 0.5 * s.rho * (c.xm[1] + c.x[1]) / s.m_em;   // :631,401
+                }
+                c.H_em = 0.5 * (c.x[0] * c.x[0] / s.L_em + c.x[1] * c.x[1] / s.m_em + s.K_em * c.x[2] * c.x[2]);       // :911
+                E = -c.inpE + H_wave + c.H_em - s.H_init;                                                              // :914
+                H = H_wave + c.H_em;
+                c.disp = c.x[2];                                                                                       // :921
+            }
+            c.H_wave = H_wave;
+            if (Hrows) {
+                double* row = Hrows + c.step * s.ncol;                               // :1011-1030
+                row[0] = c.t; row[1] = H; row[2] = E; row[3] = c.disp; row[4] = c.bE; row[5] = c.inpE; row[6] = c.H_em; row[7] = H_wave;
+            }
+            c.step += 1;
+        } break;
+    }
+}
+
+}  // namespace phw
+
+// ================================================================================================
+// solver object
+// ================================================================================================
+struct phw_solver_s {
+    phw_mesh_s* mesh = nullptr;
+    phw_params prm{};
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int nv = 0, ne = 0, npatch = 0, npc = 0, nport = 0;
+    std::vector<void*> allocs;
+    DevMesh dm{};
+    int *d_v_new2old = nullptr, *d_e_new2old = nullptr;
+    int* d_port_e = nullptr; double* d_port_bl = nullptr;
+    double *p = nullptr, *q = nullptr, *bp = nullptr, *bq = nullptr, *tmp_p = nullptr, *tmp_q = nullptr;
+    double *pinv_p = nullptr, *pinv_q = nullptr, *wp = nullptr, *wq = nullptr;
+    double *io_v = nullptr, *io_e = nullptr, *io_v2 = nullptr, *io_e2 = nullptr;
+    TriBuf tp{}, tq{};
+    double* partials = nullptr;
+    Ctl* ctl = nullptr;
+    double* dH = nullptr; int64_t dH_rows = 0;
+    ScalarPrm sp{};
+    double lam_min_q = 0.5, lam_max_q = 2.0, skew_bound = 0.0, blw = 0.0;
+    double cheb_d[3] = {1.25, 1.25, 1.25}, cheb_c[3] = {0.75, 0.75, 0.75};
+    size_t smem_v = 0, smem_e = 0, smem_vd = 0, smem_ed = 0;
+    int grid_rows = 0, sm_count = 148;
+    int64_t launches = 0;
+    bool have_vq = false;      // Stormer-Verlet first-same-as-last: v_q of the previous step is valid
+    phw_stats stats{};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int ncol = 8;
+
+    template <class T> int dalloc(T** ptr, size_t n) {
+        void* d = nullptr;
+        cudaError_t e = cudaMalloc(&d, std::max<size_t>(n, 1) * sizeof(T));
+        if (e != cudaSuccess) return fail(PHW_ENOMEM, std::string("cudaMalloc failed: ") + cudaGetErrorString(e));
+        allocs.push_back(d);
+        *ptr = (T*)d;
+        return 0;
+    }
+    template <class T> int upload(T** ptr, const std::vector<T>& h) {
+        int rc = dalloc(ptr, h.size());
+        if (rc) return rc;
+        if (!h.empty()) CU(cudaMemcpyAsync(*ptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, stream));
+        return 0;
+    }
+};
+
+namespace {
+
+inline int nblk(int n, int bs = 256) { return (n + bs - 1) / bs; }
+inline int vec_grid(phw_solver_s* s, int n) { return std::max(1, std::min(nblk(n), s->sm_count * 8)); }
+
+// ---- typed launchers for the row kernels -------------------------------------------------------
+template <int EPI, int MODE, bool HAS_M, bool HAS_D, bool CAS>
+int launch_vertex(phw_solver_s* s, const RowArgs& a) {
+    size_t sm = HAS_D ? s->smem_vd : s->smem_v;
+    auto kern = vertex_rows_k<EPI, MODE, HAS_M, HAS_D, CAS>;
+    static bool configured = false;
+    if (!configured) { CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); configured = true; }
+    kern<<<s->grid_rows, NT, sm, s->stream>>>(a);
+    s->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+template <int EPI, int MODE, bool HAS_M, bool HAS_D, bool CAS>
+int launch_edge(phw_solver_s* s, const RowArgs& a) {
+    size_t sm = HAS_D ? s->smem_ed : s->smem_e;
+    auto kern = edge_rows_k<EPI, MODE, HAS_M, HAS_D, CAS>;
+    static bool configured = false;
+    if (!configured) { CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); configured = true; }
+    kern<<<s->grid_rows, NT, sm, s->stream>>>(a);
+    s->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+RowArgs base_args(phw_solver_s* s) {
+    RowArgs a{};
+    a.m = s->dm; a.tp = s->tp; a.tq = s->tq;
+    a.partials = s->partials; a.ctl = s->ctl;
+    a.tol2 = s->prm.tol * s->prm.tol; a.max_iter = s->prm.max_iter; a.weight = 1.0;
+    a.dot_scale = 1.0;
+    return a;
+}
+
+// y_v = cD (D^T xq)_v [+ cB (B_top xp)_v]          (explicit part of the p rows)
+int op_vertex_store(phw_solver_s* s, const double* xp, const double* xq, double cM, double cD, double cB, double* y) {
+    RowArgs a = base_args(s);
+    a.xp = xp; a.xq = xq; a.cM = cM; a.cD = cD; a.cB = cB; a.y = y;
+    const bool cas = s->prm.casimir && cB != 0.0;
+    if (cM != 0.0 && cD == 0.0) return cas ? launch_vertex<EPI_STORE, MODE_OP, true, false, true>(s, a) : launch_vertex<EPI_STORE, MODE_OP, true, false, false>(s, a);
+    if (cM == 0.0) return cas ? launch_vertex<EPI_STORE, MODE_OP, false, true, true>(s, a) : launch_vertex<EPI_STORE, MODE_OP, false, true, false>(s, a);
+    return cas ? launch_vertex<EPI_STORE, MODE_OP, true, true, true>(s, a) : launch_vertex<EPI_STORE, MODE_OP, true, true, false>(s, a);
+}
+int op_edge_store(phw_solver_s* s, const double* xp, const double* xq, double cM, double cD, double cB, double* y) {
+    RowArgs a = base_args(s);
+    a.xp = xp; a.xq = xq; a.cM = cM; a.cD = cD; a.cB = cB; a.y = y;
+    const bool cas = s->prm.casimir && cB != 0.0;
+    if (cM != 0.0 && cD == 0.0) return cas ? launch_edge<EPI_STORE, MODE_OP, true, false, true>(s, a) : launch_edge<EPI_STORE, MODE_OP, true, false, false>(s, a);
+    if (cM == 0.0) return cas ? launch_edge<EPI_STORE, MODE_OP, false, true, true>(s, a) : launch_edge<EPI_STORE, MODE_OP, false, true, false>(s, a);
+    return cas ? launch_edge<EPI_STORE, MODE_OP, true, true, true>(s, a) : launch_edge<EPI_STORE, MODE_OP, true, true, false>(s, a);
+}
+// ctl->red[slot] (+)= scale * x^T (cM M + cB B) x
+int op_vertex_dot(phw_solver_s* s, const double* xp, double cM, double cB, int slot, double scale, int counter) {
+    RowArgs a = base_args(s);
+    a.xp = xp; a.cM = cM; a.cB = cB; a.red_slot = slot; a.dot_scale = scale; a.counter_id = counter;
+    if (cB != 0.0) return (cM != 0.0) ? launch_vertex<EPI_DOT, MODE_OP, true, false, true>(s, a) : launch_vertex<EPI_DOT, MODE_OP, false, false, true>(s, a);
+    return launch_vertex<EPI_DOT, MODE_OP, true, false, false>(s, a);
+}
+int op_edge_dot(phw_solver_s* s, const double* xq, double cM, double cB, int slot, double scale, int counter) {
+    RowArgs a = base_args(s);
+    a.xq = xq; a.cM = cM; a.cB = cB; a.red_slot = slot; a.dot_scale = scale; a.counter_id = counter;
+    if (cB != 0.0) return (cM != 0.0) ? launch_edge<EPI_DOT, MODE_OP, true, false, true>(s, a) : launch_edge<EPI_DOT, MODE_OP, false, false, true>(s, a);
+    return launch_edge<EPI_DOT, MODE_OP, true, false, false>(s, a);
+}
+
+int solve_begin(phw_solver_s* s, int which) {
+    solve_begin_k<<<1, 1, 0, s->stream>>>(s->ctl, which);
+    s->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// Chebyshev solve of M_p x = bp (which = 0) or M_q x = bq (which = 1); warm start = tribuf[cur]
+int solve_mass(phw_solver_s* s, int which, int n_launch) {
+    int rc = solve_begin(s, which);
+    if (rc) return rc;
+    RowArgs a = base_args(s);
+    a.which = which; a.use_cheb_input = 1; a.finalize = 1; a.cM = 1.0; a.counter_id = which;
+    a.cheb_d = s->cheb_d[which]; a.cheb_c = s->cheb_c[which];
+    for (int it = 0; it < n_launch; ++it) {
+        if (which == PHW_P) { a.b = s->bp; a.pinv = s->pinv_p; rc = launch_vertex<EPI_CHEB, MODE_OP, true, false, false>(s, a); }
+        else { a.b = s->bq; a.pinv = s->pinv_q; rc = launch_edge<EPI_CHEB, MODE_OP, true, false, false>(s, a); }
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+// Chebyshev (ellipse) solve of the coupled block system
+//   M_p v_p + th dt K (D^T v_q + B_top v_p) = bp ;  M_q v_q - th dt/rho (D v_p - B_right v_q) = bq
+int solve_block(phw_solver_s* s, double theta, int n_launch) {
+    int rc = solve_begin(s, 2);
+    if (rc) return rc;
+    const double dt = s->prm.dt, K = s->prm.K_wave, rho = s->prm.rho;
+    RowArgs a = base_args(s);
+    a.which = 2; a.use_cheb_input = 1; a.coupled_from_tribuf = 1; a.cM = 1.0;
+    a.cheb_d = s->cheb_d[2]; a.cheb_c = s->cheb_c[2];
+    const bool cas = s->prm.casimir != 0;
+    for (int it = 0; it < n_launch; ++it) {
+        RowArgs av = a;
+        av.b = s->bp; av.pinv = s->pinv_p; av.cD = theta * dt * K; av.cB = cas ? theta * dt * K : 0.0; av.finalize = 0; av.weight = 1.0 / K; av.counter_id = 2;
+        rc = cas ? launch_vertex<EPI_CHEB, MODE_OP, true, true, true>(s, av) : launch_vertex<EPI_CHEB, MODE_OP, true, true, false>(s, av);
+        if (rc) return rc;
+        RowArgs ae = a;
+        ae.b = s->bq; ae.pinv = s->pinv_q; ae.cD = -theta * dt / rho; ae.cB = cas ? theta * dt / rho : 0.0; ae.finalize = 1; ae.weight = rho; ae.counter_id = 3;
+        rc = cas ? launch_edge<EPI_CHEB, MODE_OP, true, true, true>(s, ae) : launch_edge<EPI_CHEB, MODE_OP, true, true, false>(s, ae);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+int scalar(phw_solver_s* s, int op, double aux0 = 0.0, double aux1 = 0.0) {
+    scalar_k<<<1, 32, 0, s->stream>>>(s->ctl, s->sp, op, s->dH, aux0, aux1);
+    s->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+int flux(phw_solver_s* s, const double* q, int which, int slot) {
+    flux_k<<<1, 256, 0, s->stream>>>(s->nport, s->d_port_e, s->d_port_bl, q, s->tq, s->ctl, which, slot);
+    s->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+int axpy(phw_solver_s* s, int n, double* y, double a, const double* x, TriBuf tb, int which) {
+    axpy_k<<<vec_grid(s, n), 256, 0, s->stream>>>(n, y, a, x, tb, s->ctl, which);
+    s->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+int waxpy(phw_solver_s* s, int n, double* w, const double* y, double a, const double* x, TriBuf tb, int which) {
+    waxpy_k<<<vec_grid(s, n), 256, 0, s->stream>>>(n, w, y, a, x, tb, s->ctl, which);
+    s->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// b_p = -K (D^T qsrc [+ B_top psrc])          (explicit part of the p rows, velocity form)
+int rhs_p(phw_solver_s* s, const double* qsrc, const double* psrc) {
+    const double K = s->prm.K_wave;
+    return op_vertex_store(s, psrc, qsrc, 0.0, -K, s->prm.casimir ? -K : 0.0, s->bp);
+}
+// b_q = (1/rho) (D psrc - b_L p_left [- B_right qsrc])
+int rhs_q(phw_solver_s* s, const double* psrc, const double* qsrc) {
+    const double ir = 1.0 / s->prm.rho;
+    int rc = op_edge_store(s, psrc, qsrc, 0.0, ir, s->prm.casimir ? -ir : 0.0, s->bq);
+    if (rc) return rc;
+    if (!s->prm.strong && s->nport > 0) {
+        port_rhs_k<<<nblk(s->nport), 256, 0, s->stream>>>(s->nport, s->d_port_e, s->d_port_bl, s->bq, ir, s->ctl);
+        s->launches++;
+        CU(cudaGetLastError());
+    }
+    return 0;
+}
+int energy(phw_solver_s* s) {
+    int rc = op_vertex_dot(s, s->p, 1.0, 0.0, 0, 0.5 / s->prm.rho, 4);
+    if (rc) return rc;
+    return op_edge_dot(s, s->q, 1.0, 0.0, 1, 0.5 * s->prm.K_wave, 5);
+}
+
+int n_iter_launch(phw_solver_s* s) { return s->prm.max_iter; }
+
+// ---- one time step of each scheme (wave_2D.py:787-982) ------------------------------------------
+int step(phw_solver_s* s) {
+    const double dt = s->prm.dt;
+    const int nv = s->nv, ne = s->ne;
+    const bool ic = s->prm.interconnection != 0;
+    const int NL = n_iter_launch(s);
+    int rc = 0;
+#define RC(x) do { rc = (x); if (rc) return rc; } while (0)
+    switch (s->prm.scheme) {
+        case PHW_EE:
+            RC(scalar(s, S_BEGIN_1SUB));
+            RC(flux(s, s->q, 1, 0));
+            RC(rhs_p(s, s->q, s->p)); RC(solve_mass(s, PHW_P, NL));
+            RC(rhs_q(s, s->p, s->q)); RC(solve_mass(s, PHW_Q, NL));
+            RC(axpy(s, nv, s->p, dt, nullptr, s->tp, 0));
+            RC(axpy(s, ne, s->q, dt, nullptr, s->tq, 1));
+            RC(energy(s));
+            RC(scalar(s, S_END_1SUB));
+            break;
+        case PHW_SE:
+            RC(scalar(s, S_BEGIN_1SUB));
+            RC(flux(s, s->q, 1, 0));
+            RC(rhs_p(s, s->q, s->p)); RC(solve_mass(s, PHW_P, NL));
+            RC(axpy(s, nv, s->p, dt, nullptr, s->tp, 0));
+            if (ic) RC(scalar(s, S_ODE_SE));
+            RC(rhs_q(s, s->p, s->q)); RC(solve_mass(s, PHW_Q, NL));
+            RC(axpy(s, ne, s->q, dt, nullptr, s->tq, 1));
+            RC(energy(s));
+            RC(scalar(s, S_END_1SUB));
+            break;
+        case PHW_SV:
+            RC(scalar(s, S_SV_STAGE1));
+            if (!s->have_vq || (s->prm.flags & 1)) { RC(rhs_q(s, s->p, s->q)); RC(solve_mass(s, PHW_Q, NL)); }
+            RC(axpy(s, ne, s->q, 0.5 * dt, nullptr, s->tq, 1));       // q_temp
+            RC(flux(s, s->q, 1, 0));
+            RC(scalar(s, S_SV_MID));
+            RC(rhs_p(s, s->q, s->p)); RC(solve_mass(s, PHW_P, NL));
+            RC(axpy(s, nv, s->p, dt, nullptr, s->tp, 0));
+            if (ic) RC(scalar(s, S_ODE_SV));
+            RC(rhs_q(s, s->p, s->q)); RC(solve_mass(s, PHW_Q, NL));
+            RC(axpy(s, ne, s->q, 0.5 * dt, nullptr, s->tq, 1));
+            s->have_vq = true;
+            RC(energy(s));
+            RC(scalar(s, S_END_SV));
+            break;
+        case PHW_EH:
+            RC(scalar(s, S_EH_BEGIN));
+            RC(flux(s, s->q, 1, 0));
+            RC(rhs_p(s, s->q, s->p)); RC(solve_mass(s, PHW_P, NL));
+            RC(rhs_q(s, s->p, s->q)); RC(solve_mass(s, PHW_Q, NL));
+            RC(flux(s, nullptr, 1, 1));                               // b_L^T v_q1
+            RC(waxpy(s, nv, s->tmp_p, s->p, 0.5 * dt, nullptr, s->tp, 0));   // 0.5 (p_m + p_temp)
+            RC(waxpy(s, ne, s->tmp_q, s->q, 0.5 * dt, nullptr, s->tq, 1));
+            RC(rhs_p(s, s->tmp_q, s->tmp_p)); RC(solve_mass(s, PHW_P, NL));
+            RC(rhs_q(s, s->tmp_p, s->tmp_q)); RC(solve_mass(s, PHW_Q, NL));
+            RC(axpy(s, nv, s->p, dt, nullptr, s->tp, 0));
+            RC(axpy(s, ne, s->q, dt, nullptr, s->tq, 1));
+            RC(energy(s));
+            RC(scalar(s, S_END_EH));
+            break;
+        case PHW_IE:
+        case PHW_SM: {
+            const double theta = (s->prm.scheme == PHW_IE) ? 1.0 : 0.5;
+            RC(scalar(s, S_BEGIN_1SUB));
+            RC(flux(s, s->q, 1, 0));
+            if (ic) RC(scalar(s, S_SM_PLEFT));
+            RC(rhs_p(s, s->q, s->p));
+            RC(rhs_q(s, s->p, s->q));
+            RC(solve_block(s, theta, NL));
+            if (ic) {
+                RC(flux(s, nullptr, 2, 2));                            // b_L^T vhat_q
+                RC(scalar(s, S_ODE_SM, s->blw));
+                axpy_dev_k<<<vec_grid(s, nv), 256, 0, s->stream>>>(nv, s->tp, s->ctl, 2, &s->ctl->xi1, s->wp);
+                axpy_dev_k<<<vec_grid(s, ne), 256, 0, s->stream>>>(ne, s->tq, s->ctl, 2, &s->ctl->xi1, s->wq);
+                s->launches += 2;
+                CU(cudaGetLastError());
+            }
+            if (s->prm.casimir) {
+                // boundary energy of the impedance sides uses the midpoint averages (wave_2D.py:633-634)
+                RC(waxpy(s, nv, s->tmp_p, s->p, 0.5 * dt, nullptr, s->tp, 2));
+                RC(waxpy(s, ne, s->tmp_q, s->q, 0.5 * dt, nullptr, s->tq, 2));
+                RC(op_vertex_dot(s, s->tmp_p, 0.0, 1.0, 2, 1.0, 6));
+                RC(op_edge_dot(s, s->tmp_q, 0.0, 1.0, 3, 1.0, 7));
+            }
+            RC(axpy(s, nv, s->p, dt, nullptr, s->tp, 2));
+            RC(axpy(s, ne, s->q, dt, nullptr, s->tq, 2));
+            RC(flux(s, s->q, 1, 1));
+            RC(energy(s));
+            RC(scalar(s, S_END_1SUB));
+        } break;
+        default:
+            return fail(PHW_EINVAL, "unknown scheme");
+    }
+#undef RC
+    return 0;
+}
+
+bool is_device_ptr(const void* p) {
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+// user-numbering vector (host or device) -> internal numbering device vector
+int import_vec(phw_solver_s* s, const double* src, double* dst, int n, const int* d_new2old, double* stage) {
+    const double* dsrc = src;
+    if (!is_device_ptr(src)) {
+        CU(cudaMemcpyAsync(stage, src, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+        dsrc = stage;
+    }
+    gather_k<<<nblk(n), 256, 0, s->stream>>>(n, dst, dsrc, d_new2old);
+    CU(cudaGetLastError());
+    return 0;
+}
+int export_vec(phw_solver_s* s, const double* src, double* dst, int n, const int* d_new2old, double* stage) {
+    if (is_device_ptr(dst)) {
+        scatter_k<<<nblk(n), 256, 0, s->stream>>>(n, dst, src, d_new2old);
+        CU(cudaGetLastError());
+    } else {
+        scatter_k<<<nblk(n), 256, 0, s->stream>>>(n, stage, src, d_new2old);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(dst, stage, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+    }
+    return 0;
+}
+
+// minimise the Chebyshev convergence factor over ellipses through the corner (delta, mu) of the
+// rectangle [alpha,beta] x i[-mu,mu] that contains the field of values of the Jacobi-scaled block operator
+void ellipse_for_rectangle(double alpha, double beta, double mu, double& d, double& c) {
+    d = 0.5 * (alpha + beta);
+    const double delta = 0.5 * (beta - alpha);
+    if (mu <= 0.0) { c = delta; return; }
+    double best = 1e300, best_c = delta;
+    for (int i = 1; i <= 4000; ++i) {
+        // semi-axis a >= delta ; b from delta^2/a^2 + mu^2/b^2 = 1
+        double a = delta * (1.0 + 4.0 * i / 4000.0 * (mu / delta + 0.05));
+        double t = 1.0 - delta * delta / (a * a);
+        if (t <= 0.0) continue;
+        double b = mu / std::sqrt(t);
+        if (a >= d) continue;
+        double c2 = a * a - b * b;
+        double cc = std::sqrt(std::fabs(c2));
+        double rate;
+        if (c2 >= 0.0) rate = (a + b) / (d + std::sqrt(d * d - c2));
+        else continue;   // keep real foci
+        if (rate < best) { best = rate; best_c = cc; }
+    }
+    c = best_c;
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+const char* phw_last_error(void) { return g_err.c_str(); }
+int phw_version(void) { return 100; }
+
+int phw_mesh_create(int64_t n_vertices, const double* vertices_xy, int64_t n_cells, const int32_t* cells,
+                    int32_t patch_cells, phw_mesh_t* out) {
+    if (!out) return fail(PHW_EINVAL, "out is NULL");
+    phw_mesh_s* m = new (std::nothrow) phw_mesh_s();
+    if (!m) return fail(PHW_ENOMEM, "out of host memory");
+    std::string err;
+    try {
+        err = m->L.build(n_vertices, vertices_xy, n_cells, cells, patch_cells > 0 ? patch_cells : 2048);
+    } catch (const std::bad_alloc&) {
+        delete m;
+        return fail(PHW_ENOMEM, "out of host memory while building the mesh layout");
+    }
+    if (!err.empty()) { delete m; return fail(PHW_EINVAL, err); }
+    *out = m;
+    return PHW_OK;
+}
+
+int phw_mesh_sizes(phw_mesh_t m, int64_t* nv, int64_t* nc, int64_t* ne, int64_t* nb, int64_t* np) {
+    if (!m) return fail(PHW_EINVAL, "mesh is NULL");
+    if (nv) *nv = m->L.nv;
+    if (nc) *nc = m->L.nc;
+    if (ne) *ne = m->L.ne;
+    if (nb) *nb = m->L.nb;
+    if (np) *np = m->L.npatch;
+    return PHW_OK;
+}
+
+int phw_mesh_get_edges(phw_mesh_t m, int32_t* edges, int32_t* cell_edges, int8_t* cell_edge_sign) {
+    if (!m) return fail(PHW_EINVAL, "mesh is NULL");
+    if (edges) memcpy(edges, m->L.edges.data(), m->L.edges.size() * sizeof(int32_t));
+    if (cell_edges) memcpy(cell_edges, m->L.cell_edges.data(), m->L.cell_edges.size() * sizeof(int32_t));
+    if (cell_edge_sign) memcpy(cell_edge_sign, m->L.cell_sign.data(), m->L.cell_sign.size());
+    return PHW_OK;
+}
+
+int phw_mesh_get_boundary(phw_mesh_t m, int32_t* edge_ids, int8_t* sign) {
+    if (!m) return fail(PHW_EINVAL, "mesh is NULL");
+    if (edge_ids) memcpy(edge_ids, m->L.bedge.data(), m->L.bedge.size() * sizeof(int32_t));
+    if (sign) memcpy(sign, m->L.bsign.data(), m->L.bsign.size());
+    return PHW_OK;
+}
+
+int phw_mesh_set_boundary(phw_mesh_t m, const int32_t* tags, const double* port_weight) {
+    if (!m || !tags) return fail(PHW_EINVAL, "mesh or tags is NULL");
+    for (int64_t k = 0; k < m->L.nb; ++k) {
+        if (tags[k] < 0 || tags[k] > 4) return fail(PHW_EINVAL, "boundary tag out of range [0,4]");
+        m->L.btag[k] = tags[k];
+        m->L.bweight[k] = port_weight ? port_weight[k] : 1.0;
+    }
+    m->L.boundary_set = true;
+    return PHW_OK;
+}
+
+int phw_mesh_get_numbering(phw_mesh_t m, int32_t* v_new2old, int32_t* e_new2old, int32_t* cell_patch) {
+    if (!m) return fail(PHW_EINVAL, "mesh is NULL");
+    if (v_new2old) memcpy(v_new2old, m->L.v_new2old.data(), m->L.v_new2old.size() * sizeof(int32_t));
+    if (e_new2old) memcpy(e_new2old, m->L.e_new2old.data(), m->L.e_new2old.size() * sizeof(int32_t));
+    if (cell_patch) memcpy(cell_patch, m->L.cell_patch.data(), m->L.cell_patch.size() * sizeof(int32_t));
+    return PHW_OK;
+}
+
+int phw_mesh_get_patch_counts(phw_mesh_t m, int32_t* counts) {
+    if (!m || !counts) return fail(PHW_EINVAL, "mesh or counts is NULL");
+    for (int32_t p = 0; p < m->L.npatch; ++p) {
+        const PatchHdr& h = m->L.hdr[p];
+        int32_t* c = counts + 6 * (int64_t)p;
+        c[0] = h.n_own; c[1] = h.n_ecells; c[2] = h.n_vcells; c[3] = h.v_cnt; c[4] = h.e_cnt; c[5] = h.gv_cnt + h.ge_cnt;
+    }
+    return PHW_OK;
+}
+
+int phw_mesh_destroy(phw_mesh_t m) { delete m; return PHW_OK; }
+
+int phw_solver_destroy(phw_solver_t s) {
+    if (!s) return PHW_OK;
+    cudaSetDevice(s->device);
+    for (void* d : s->allocs) cudaFree(d);
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    delete s;
+    return PHW_OK;
+}
+
+int phw_synchronize(phw_solver_t s) {
+    if (!s) return fail(PHW_EINVAL, "solver is NULL");
+    CU(cudaStreamSynchronize(s->stream));
+    return PHW_OK;
+}
+
+static int setup_solver(phw_solver_s* s) {
+    const Layout& L = s->mesh->L;
+    const phw_params& P = s->prm;
+    s->nv = (int)L.nv; s->ne = (int)L.ne; s->npatch = L.npatch; s->npc = (int)L.pcell_user.size();
+    cudaDeviceProp prop{};
+    CU(cudaGetDeviceProperties(&prop, s->device));
+    s->sm_count = prop.multiProcessorCount;
+    CU(cudaEventCreate(&s->ev0));
+    CU(cudaEventCreate(&s->ev1));
+    int rc;
+#define RC(x) do { rc = (x); if (rc) return rc; } while (0)
+    // ---- mesh SoA
+    std::vector<CellRec> rec;
+    L.make_records(P.strong != 0, P.casimir != 0, rec);
+    PatchHdr* d_hdr; uint4* d_rec; int *d_gv, *d_ge; uint32_t *d_eadj, *d_voff; uint16_t* d_vadj;
+    RC(s->upload(&d_hdr, L.hdr));
+    {
+        RC(s->dalloc(&d_rec, rec.size()));
+        CU(cudaMemcpyAsync(d_rec, rec.data(), rec.size() * sizeof(CellRec), cudaMemcpyHostToDevice, s->stream));
+    }
+    RC(s->upload(&d_gv, L.ghost_v)); RC(s->upload(&d_ge, L.ghost_e));
+    RC(s->upload(&d_eadj, L.eadj)); RC(s->upload(&d_voff, L.vadj_off)); RC(s->upload(&d_vadj, L.vadj));
+    RC(s->upload(&s->d_v_new2old, L.v_new2old)); RC(s->upload(&s->d_e_new2old, L.e_new2old));
+    double *d_area, *d_g0, *d_g1, *d_g2;
+    RC(s->dalloc(&d_area, s->npc)); RC(s->dalloc(&d_g0, s->npc)); RC(s->dalloc(&d_g1, s->npc)); RC(s->dalloc(&d_g2, s->npc));
+    {   // one-time GPU geometry pass (replaces the per-cell Jacobians FFC kernels recompute at every assemble)
+        int *d_pcu, *d_cells; double* d_vtx; unsigned long long* d_mm;
+        RC(s->upload(&d_pcu, L.pcell_user)); RC(s->upload(&d_cells, L.cells)); RC(s->upload(&d_vtx, L.vtx));
+        RC(s->dalloc(&d_mm, 2));
+        unsigned long long init[2];
+        double one = 1.0;
+        memcpy(&init[0], &one, 8); memcpy(&init[1], &one, 8);
+        CU(cudaMemcpyAsync(d_mm, init, sizeof init, cudaMemcpyHostToDevice, s->stream));
+        geom_k<<<nblk(s->npc), 256, 0, s->stream>>>(s->npc, d_pcu, d_cells, d_vtx, d_area, d_g0, d_g1, d_g2, d_mm);
+        CU(cudaGetLastError());
+        unsigned long long out[2];
+        CU(cudaMemcpyAsync(out, d_mm, sizeof out, cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+        memcpy(&s->lam_min_q, &out[0], 8); memcpy(&s->lam_max_q, &out[1], 8);
+    }
+    s->dm.npatch = s->npatch; s->dm.nv = s->nv; s->dm.ne = s->ne;
+    s->dm.hdr = d_hdr; s->dm.rec = d_rec; s->dm.area = d_area; s->dm.g0 = d_g0; s->dm.g1 = d_g1; s->dm.g2 = d_g2;
+    s->dm.ghost_v = d_gv; s->dm.ghost_e = d_ge; s->dm.eadj = d_eadj; s->dm.vadj_off = d_voff; s->dm.vadj = d_vadj;
+    // ---- port (left boundary, tag 0): b_L[e] = sign * weight   (flux-normalised RT1: <phi_e.n, g_L> = sign * mean(g_L))
+    {
+        std::vector<int32_t> pe; std::vector<double> bl;
+        for (int64_t k = 0; k < L.nb; ++k)
+            if (L.btag[k] == PHW_TAG_LEFT) { pe.push_back(L.e_old2new[L.bedge[k]]); bl.push_back(L.bsign[k] * L.bweight[k]); }
+        s->nport = (int)pe.size();
+        RC(s->upload(&s->d_port_e, pe)); RC(s->upload(&s->d_port_bl, bl));
+    }
+    // ---- vectors
+    const size_t nv = s->nv, ne = s->ne;
+    RC(s->dalloc(&s->p, nv)); RC(s->dalloc(&s->q, ne)); RC(s->dalloc(&s->bp, nv)); RC(s->dalloc(&s->bq, ne));
+    RC(s->dalloc(&s->tmp_p, nv)); RC(s->dalloc(&s->tmp_q, ne)); RC(s->dalloc(&s->pinv_p, nv)); RC(s->dalloc(&s->pinv_q, ne));
+    RC(s->dalloc(&s->io_v, nv)); RC(s->dalloc(&s->io_e, ne)); RC(s->dalloc(&s->io_v2, nv)); RC(s->dalloc(&s->io_e2, ne));
+    for (int i = 0; i < 3; ++i) { RC(s->dalloc(&s->tp.b[i], nv)); RC(s->dalloc(&s->tq.b[i], ne)); }
+    RC(s->dalloc(&s->partials, 2 * (size_t)s->npatch));
+    RC(s->dalloc(&s->ctl, 1));
+    for (double* v : {s->p, s->bp, s->tmp_p, s->tp.b[0], s->tp.b[1], s->tp.b[2], s->io_v, s->io_v2}) CU(cudaMemsetAsync(v, 0, nv * 8, s->stream));
+    for (double* v : {s->q, s->bq, s->tmp_q, s->tq.b[0], s->tq.b[1], s->tq.b[2], s->io_e, s->io_e2}) CU(cudaMemsetAsync(v, 0, ne * 8, s->stream));
+    CU(cudaMemsetAsync(s->ctl, 0, sizeof(Ctl), s->stream));
+    // ---- shared-memory budgets and grid
+    auto ev = [](int x) { return (size_t)((x + 1) & ~1); };
+    s->smem_v = (ev(L.max_lv) + 3 * (size_t)L.max_cells) * 8;
+    s->smem_vd = (ev(L.max_lv) + ev(L.max_le) + 3 * (size_t)L.max_cells) * 8;
+    s->smem_e = (ev(L.max_le) + 3 * (size_t)L.max_cells) * 8;
+    s->smem_ed = s->smem_vd;
+    if (s->smem_vd > 200 * 1024) return fail(PHW_EINVAL, "patch does not fit in shared memory; reduce patch_cells");
+    s->grid_rows = std::max(1, std::min(s->npatch, 2 * s->sm_count));
+    // ---- scalar parameters
+    ScalarPrm& sp = s->sp;
+    sp.dt = P.dt; sp.K = P.K_wave; sp.rho = P.rho; sp.c2 = P.K_wave / P.rho;
+    {   // A_em = (J - R) diag(1/L, 1/m, K_em)      wave_2D.py:160-166
+        const double J[3][3] = {{0, P.Bl_em, 0}, {-P.Bl_em, 0, -1}, {0, 1, 0}};
+        const double R[3] = {P.R1_em, P.R2_em, 0.0};
+        const double cv[3] = {P.L_em != 0 ? 1.0 / P.L_em : 0.0, P.m_em != 0 ? 1.0 / P.m_em : 0.0, P.K_em};
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) sp.A[i][j] = (J[i][j] - (i == j ? R[i] : 0.0)) * cv[j];
+    }
+    sp.m_em = P.m_em; sp.L_em = P.L_em; sp.K_em = P.K_em;
+    sp.input_kind = P.input_kind; sp.in_amp = P.in_amp; sp.in_omega = P.in_omega; sp.in_t_stop = P.in_t_stop;
+    sp.in_t_ctrl = P.in_t_ctrl; sp.in_gain = P.in_gain; sp.H_init = P.H_init;
+    s->ncol = P.analytical ? 12 : 8;
+    sp.ncol = s->ncol; sp.ic = P.interconnection;
+    switch (P.scheme) {   // q1_ of wave_2D.py:603-615
+        case PHW_EE: case PHW_SE: sp.w_old = 1.0; sp.w_new = 0.0; break;
+        case PHW_IE: sp.w_old = 0.0; sp.w_new = 1.0; break;
+        case PHW_SM: sp.w_old = 0.5; sp.w_new = 0.5; break;
+        default: sp.w_old = 1.0; sp.w_new = 0.0;
+    }
+    // ---- Jacobi diagonals (inverse) of the solved blocks
+    const bool implicit = (P.scheme == PHW_IE || P.scheme == PHW_SM);
+    const double theta = (P.scheme == PHW_IE) ? 1.0 : 0.5;
+    {
+        RowArgs a = base_args(s);
+        a.cM = 1.0; a.y = s->pinv_p;
+        a.cB = (implicit && P.casimir) ? theta * P.dt * P.K_wave : 0.0;
+        RC((a.cB != 0.0) ? (launch_vertex<EPI_STORE, MODE_DIAG, true, false, true>(s, a)) : (launch_vertex<EPI_STORE, MODE_DIAG, true, false, false>(s, a)));
+        a.y = s->pinv_q;
+        a.cB = (implicit && P.casimir) ? theta * P.dt / P.rho : 0.0;
+        RC((a.cB != 0.0) ? (launch_edge<EPI_STORE, MODE_DIAG, true, false, true>(s, a)) : (launch_edge<EPI_STORE, MODE_DIAG, true, false, false>(s, a)));
+        invert_k<<<nblk(s->nv), 256, 0, s->stream>>>(s->nv, s->pinv_p);
+        invert_k<<<nblk(s->ne), 256, 0, s->stream>>>(s->ne, s->pinv_q);
+        CU(cudaGetLastError());
+    }
+    // ---- Chebyshev intervals.  P1: element bound [1/2, 2] (Wathen); RT1: element bounds from geom_k.
+    s->cheb_d[0] = 1.25; s->cheb_c[0] = 0.75;
+    s->cheb_d[1] = 0.5 * (s->lam_min_q + s->lam_max_q); s->cheb_c[1] = 0.5 * (s->lam_max_q - s->lam_min_q);
+#undef RC
+    return 0;
+}
+
+// largest singular value of P_q^-1/2 D P_p^-1/2 by power iteration on the device (setup only)
+static int estimate_skew(phw_solver_s* s, double* sigma) {
+    const int nv = s->nv, ne = s->ne;
+    std::vector<double> h(nv), dp(nv), dq(ne), y(ne);
+    std::vector<double> hp(nv), hq(ne);
+    CU(cudaMemcpyAsync(dp.data(), s->pinv_p, nv * 8, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaMemcpyAsync(dq.data(), s->pinv_q, ne * 8, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    unsigned long long seed = 88172645463325252ull;
+    for (int i = 0; i < nv; ++i) { seed ^= seed << 13; seed ^= seed >> 7; seed ^= seed << 17; h[i] = (double)(seed % 2000001) / 1000000.0 - 1.0; }
+    double lam = 0.0;
+    int rc;
+    for (int it = 0; it < 40; ++it) {
+        // z = P_p^-1/2 h ; y = D z ; y <- P_q^-1 y ; w = D^T y ; h' = P_p^-1/2 w
+        for (int i = 0; i < nv; ++i) hp[i] = h[i] * std::sqrt(dp[i]);
+        CU(cudaMemcpyAsync(s->io_v, hp.data(), nv * 8, cudaMemcpyHostToDevice, s->stream));
+        rc = op_edge_store(s, s->io_v, nullptr, 0.0, 1.0, 0.0, s->io_e); if (rc) return rc;
+        CU(cudaMemcpyAsync(y.data(), s->io_e, ne * 8, cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+        for (int i = 0; i < ne; ++i) hq[i] = y[i] * dq[i];
+        CU(cudaMemcpyAsync(s->io_e, hq.data(), ne * 8, cudaMemcpyHostToDevice, s->stream));
+        rc = op_vertex_store(s, nullptr, s->io_e, 0.0, 1.0, 0.0, s->io_v); if (rc) return rc;
+        CU(cudaMemcpyAsync(hp.data(), s->io_v, nv * 8, cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+        double nrm = 0.0;
+        for (int i = 0; i < nv; ++i) { hp[i] *= std::sqrt(dp[i]); nrm += hp[i] * hp[i]; }
+        nrm = std::sqrt(nrm);
+        if (nrm == 0.0) break;
+        double hn = 0.0;
+        for (int i = 0; i < nv; ++i) hn += h[i] * h[i];
+        lam = nrm / std::sqrt(hn);
+        for (int i = 0; i < nv; ++i) h[i] = hp[i] / nrm;
+    }
+    *sigma = std::sqrt(lam);
+    return 0;
+}
+
+int phw_solver_create(phw_mesh_t m, const phw_params* prm, int32_t device, void* cuda_stream, phw_solver_t* out) {
+    if (!m || !prm || !out) return fail(PHW_EINVAL, "NULL argument");
+    if (!m->L.boundary_set) return fail(PHW_ESTATE, "phw_mesh_set_boundary must be called before phw_solver_create");
+    if (prm->scheme < 0 || prm->scheme > 5) return fail(PHW_EINVAL, "unknown scheme");
+    if (!(prm->dt > 0) || !(prm->K_wave > 0) || !(prm->rho > 0)) return fail(PHW_EINVAL, "dt, K_wave, rho must be positive");
+    if (prm->interconnection && !(prm->scheme == PHW_SE || prm->scheme == PHW_SV || prm->scheme == PHW_SM))
+        return fail(PHW_EINVAL, "only SE, SV and SM time int schemes implemented for interconnection model");
+    if (prm->interconnection && prm->strong) return fail(PHW_EINVAL, "can only do interconnection model with weak boundary conditions");
+    if (prm->casimir && prm->scheme != PHW_SM) return fail(PHW_EINVAL, "casimir control requires the SM scheme");
+    if (prm->strong) return fail(PHW_EINVAL, "strong Dirichlet form is not implemented in the device path yet");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(PHW_ECUDA, "no CUDA device available (libphwave has no CPU fallback)"); }
+    if (device < 0 || device >= ndev) return fail(PHW_EINVAL, "device index out of range");
+    CU(cudaSetDevice(device));
+    phw_solver_s* s = new (std::nothrow) phw_solver_s();
+    if (!s) return fail(PHW_ENOMEM, "out of host memory");
+    s->mesh = m; s->prm = *prm; s->device = device; s->stream = (cudaStream_t)cuda_stream;
+    if (!(s->prm.tol > 0)) s->prm.tol = 1e-13;
+    if (s->prm.max_iter <= 0) s->prm.max_iter = 200;
+    int rc = setup_solver(s);
+    if (rc) { std::string keep = g_err; phw_solver_destroy(s); g_err = keep; return rc; }
+    const bool implicit = (prm->scheme == PHW_IE || prm->scheme == PHW_SM);
+    if (implicit) {
+        const double theta = (prm->scheme == PHW_IE) ? 1.0 : 0.5;
+        double sigma = 0.0;
+        rc = estimate_skew(s, &sigma);
+        if (rc) { std::string keep = g_err; phw_solver_destroy(s); g_err = keep; return rc; }
+        s->skew_bound = 1.05 * theta * prm->dt * std::sqrt(prm->K_wave / prm->rho) * sigma;
+        double lo = std::min(0.5, s->lam_min_q), hi = std::max(2.0, s->lam_max_q);
+        ellipse_for_rectangle(lo, hi, s->skew_bound, s->cheb_d[2], s->cheb_c[2]);
+        if (prm->interconnection) {
+            // w = B^-1 [0; b_L]: constant column of the bordered system (lumped x1 <-> port edges), solved once
+            rc = s->dalloc(&s->wp, s->nv); if (!rc) rc = s->dalloc(&s->wq, s->ne);
+            if (rc) { std::string keep = g_err; phw_solver_destroy(s); g_err = keep; return rc; }
+            std::vector<double> bl(s->ne, 0.0);
+            const Layout& L = m->L;
+            for (int64_t k = 0; k < L.nb; ++k)
+                if (L.btag[k] == PHW_TAG_LEFT) bl[L.e_old2new[L.bedge[k]]] = L.bsign[k] * L.bweight[k];
+            cudaMemcpyAsync(s->bq, bl.data(), (size_t)s->ne * 8, cudaMemcpyHostToDevice, s->stream);
+            cudaMemsetAsync(s->bp, 0, (size_t)s->nv * 8, s->stream);
+            double tol_keep = s->prm.tol;
+            s->prm.tol = std::min(tol_keep, 1e-14);
+            rc = solve_block(s, theta, s->prm.max_iter);
+            s->prm.tol = tol_keep;
+            if (!rc) {
+                copy_from_tb_k<<<vec_grid(s, s->nv), 256, 0, s->stream>>>(s->nv, s->wp, s->tp, s->ctl, 2);
+                copy_from_tb_k<<<vec_grid(s, s->ne), 256, 0, s->stream>>>(s->ne, s->wq, s->tq, s->ctl, 2);
+                flux_k<<<1, 256, 0, s->stream>>>(s->nport, s->d_port_e, s->d_port_bl, s->wq, s->tq, s->ctl, 2, 3);
+                double f3 = 0.0;
+                cudaMemcpyAsync(&f3, &s->ctl->flux[3], 8, cudaMemcpyDeviceToHost, s->stream);
+                cudaStreamSynchronize(s->stream);
+                s->blw = f3;
+                // reset warm starts and counters
+                for (int i = 0; i < 3; ++i) { cudaMemsetAsync(s->tp.b[i], 0, (size_t)s->nv * 8, s->stream); cudaMemsetAsync(s->tq.b[i], 0, (size_t)s->ne * 8, s->stream); }
+                cudaMemsetAsync(s->ctl, 0, sizeof(Ctl), s->stream);
+            }
+            if (rc || cudaGetLastError() != cudaSuccess) { phw_solver_destroy(s); return fail(PHW_ECUDA, "bordered-column setup solve failed"); }
+        }
+    }
+    CU(cudaStreamSynchronize(s->stream));
+    s->launches = 0;
+    *out = s;
+    return PHW_OK;
+}
+
+int phw_set_state(phw_solver_t s, const double* p, const double* q, const double* x3) {
+    if (!s) return fail(PHW_EINVAL, "solver is NULL");
+    CU(cudaSetDevice(s->device));
+    int rc;
+    if (p) { rc = import_vec(s, p, s->p, s->nv, s->d_v_new2old, s->io_v); if (rc) return rc; }
+    if (q) { rc = import_vec(s, q, s->q, s->ne, s->d_e_new2old, s->io_e); if (rc) return rc; }
+    if (x3) {
+        double h[3];
+        if (is_device_ptr(x3)) CU(cudaMemcpyAsync(h, x3, 24, cudaMemcpyDeviceToHost, s->stream));
+        else memcpy(h, x3, 24);
+        CU(cudaStreamSynchronize(s->stream));
+        CU(cudaMemcpyAsync(&s->ctl->x[0], h, 24, cudaMemcpyHostToDevice, s->stream));
+    }
+    s->have_vq = false;
+    CU(cudaStreamSynchronize(s->stream));
+    return PHW_OK;
+}
+
+int phw_get_state(phw_solver_t s, double* p, double* q, double* x3) {
+    if (!s) return fail(PHW_EINVAL, "solver is NULL");
+    CU(cudaSetDevice(s->device));
+    int rc;
+    if (p) { rc = export_vec(s, s->p, p, s->nv, s->d_v_new2old, s->io_v); if (rc) return rc; }
+    if (q) { rc = export_vec(s, s->q, q, s->ne, s->d_e_new2old, s->io_e); if (rc) return rc; }
+    if (x3) {
+        double h[3];
+        CU(cudaMemcpyAsync(h, &s->ctl->x[0], 24, cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+        if (is_device_ptr(x3)) CU(cudaMemcpy(x3, h, 24, cudaMemcpyHostToDevice));
+        else memcpy(x3, h, 24);
+    }
+    CU(cudaStreamSynchronize(s->stream));
+    return PHW_OK;
+}
+
+int phw_run(phw_solver_t s, int64_t n_steps, double* H_rows) {
+    if (!s || n_steps < 0) return fail(PHW_EINVAL, "bad arguments");
+    CU(cudaSetDevice(s->device));
+    if (n_steps > s->dH_rows) {
+        double* d = nullptr;
+        int rc = s->dalloc(&d, (size_t)n_steps * s->ncol);
+        if (rc) return rc;
+        s->dH = d; s->dH_rows = n_steps;
+    }
+    if (n_steps > 0) CU(cudaMemsetAsync(s->dH, 0, (size_t)n_steps * s->ncol * 8, s->stream));
+    // row index restarts at 0 for every run; iteration statistics are per run
+    Ctl hc;
+    CU(cudaMemcpyAsync(&hc, s->ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    hc.step = 0; hc.nonconv = 0;
+    for (int i = 0; i < 3; ++i) { hc.sc[i].iters = 0; hc.sc[i].solves = 0; hc.sc[i].maxres = 0.0; }
+    CU(cudaMemcpyAsync(s->ctl, &hc, sizeof(Ctl), cudaMemcpyHostToDevice, s->stream));
+    s->launches = 0;
+    CU(cudaEventRecord(s->ev0, s->stream));
+    for (int64_t n = 0; n < n_steps; ++n) {
+        int rc = step(s);
+        if (rc) return rc;
+        if ((s->prm.flags & 2) && cudaStreamSynchronize(s->stream) != cudaSuccess) return fail(PHW_ECUDA, "kernel failure inside step loop");
+    }
+    CU(cudaEventRecord(s->ev1, s->stream));
+    if (H_rows && n_steps > 0) {
+        if (is_device_ptr(H_rows)) CU(cudaMemcpyAsync(H_rows, s->dH, (size_t)n_steps * s->ncol * 8, cudaMemcpyDeviceToDevice, s->stream));
+        else CU(cudaMemcpyAsync(H_rows, s->dH, (size_t)n_steps * s->ncol * 8, cudaMemcpyDeviceToHost, s->stream));
+    }
+    CU(cudaStreamSynchronize(s->stream));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+    CU(cudaMemcpy(&hc, s->ctl, sizeof(Ctl), cudaMemcpyDeviceToHost));
+    phw_stats& st = s->stats;
+    st.steps = n_steps;
+    st.solves_p = hc.sc[0].solves; st.solves_q = hc.sc[1].solves; st.solves_block = hc.sc[2].solves;
+    st.iters_p = hc.sc[0].iters; st.iters_q = hc.sc[1].iters; st.iters_block = hc.sc[2].iters;
+    st.max_rel_residual = std::max(hc.sc[0].maxres, std::max(hc.sc[1].maxres, hc.sc[2].maxres));
+    st.device_ms = ms;
+    st.kernel_launches = s->launches;
+    st.lam_min_q = s->lam_min_q; st.lam_max_q = s->lam_max_q; st.skew_bound = s->skew_bound;
+    {   // algorithmic bytes: per cell 40 B skew apply, 28/60 B mass apply; per dof 8 B per vector pass
+        const double nc = (double)s->mesh->L.nc, nv = s->nv, ne = s->ne;
+        const double it_p = (double)st.iters_p + (double)st.iters_block, it_q = (double)st.iters_q + (double)st.iters_block;
+        const double rhs = (double)(st.solves_p + st.solves_q + 2 * st.solves_block) * 40.0 * nc;
+        double bytes = rhs + it_p * (28.0 * nc + 3 * 8.0 * nv) + it_q * (60.0 * nc + 3 * 8.0 * ne) + (double)n_steps * 88.0 * nc;
+        bytes += (double)st.iters_block * 2 * 40.0 * nc;
+        st.bytes_model = (int64_t)bytes;
+    }
+    if (hc.nonconv > 0) {
+        char buf[160];
+        snprintf(buf, sizeof buf, "%lld solves hit max_iter without reaching tol (max relative residual %.3e)", (long long)hc.nonconv, st.max_rel_residual);
+        return fail(PHW_ENOCONV, buf);
+    }
+    return PHW_OK;
+}
+
+int phw_get_stats(phw_solver_t s, phw_stats* out) {
+    if (!s || !out) return fail(PHW_EINVAL, "NULL argument");
+    *out = s->stats;
+    return PHW_OK;
+}
+
+// ---- kernel-level entry points ------------------------------------------------------------------
+int phw_apply_D(phw_solver_t s, const double* p, double* y) {
+    if (!s || !p || !y) return fail(PHW_EINVAL, "NULL argument");
+    CU(cudaSetDevice(s->device));
+    int rc = import_vec(s, p, s->io_v2, s->nv, s->d_v_new2old, s->io_v); if (rc) return rc;
+    rc = op_edge_store(s, s->io_v2, nullptr, 0.0, 1.0, 0.0, s->io_e2); if (rc) return rc;
+    return export_vec(s, s->io_e2, y, s->ne, s->d_e_new2old, s->io_e);
+}
+int phw_apply_DT(phw_solver_t s, const double* q, double* y) {
+    if (!s || !q || !y) return fail(PHW_EINVAL, "NULL argument");
+    CU(cudaSetDevice(s->device));
+    int rc = import_vec(s, q, s->io_e2, s->ne, s->d_e_new2old, s->io_e); if (rc) return rc;
+    rc = op_vertex_store(s, nullptr, s->io_e2, 0.0, 1.0, 0.0, s->io_v2); if (rc) return rc;
+    return export_vec(s, s->io_v2, y, s->nv, s->d_v_new2old, s->io_v);
+}
+int phw_mass_matvec(phw_solver_t s, int32_t which, const double* x, double* y) {
+    if (!s || !x || !y) return fail(PHW_EINVAL, "NULL argument");
+    CU(cudaSetDevice(s->device));
+    int rc;
+    if (which == PHW_P) {
+        rc = import_vec(s, x, s->io_v2, s->nv, s->d_v_new2old, s->io_v); if (rc) return rc;
+        rc = op_vertex_store(s, s->io_v2, nullptr, 1.0, 0.0, 0.0, s->tmp_p); if (rc) return rc;
+        return export_vec(s, s->tmp_p, y, s->nv, s->d_v_new2old, s->io_v);
+    } else if (which == PHW_Q) {
+        rc = import_vec(s, x, s->io_e2, s->ne, s->d_e_new2old, s->io_e); if (rc) return rc;
+        rc = op_edge_store(s, nullptr, s->io_e2, 1.0, 0.0, 0.0, s->tmp_q); if (rc) return rc;
+        return export_vec(s, s->tmp_q, y, s->ne, s->d_e_new2old, s->io_e);
+    }
+    return fail(PHW_EINVAL, "which must be PHW_P or PHW_Q");
+}
+int phw_mass_solve(phw_solver_t s, int32_t which, const double* b, double* x, int32_t* iters) {
+    if (!s || !b || !x) return fail(PHW_EINVAL, "NULL argument");
+    if (which != PHW_P && which != PHW_Q) return fail(PHW_EINVAL, "which must be PHW_P or PHW_Q");
+    CU(cudaSetDevice(s->device));
+    const int n = which == PHW_P ? s->nv : s->ne;
+    int rc = import_vec(s, b, which == PHW_P ? s->bp : s->bq, n, which == PHW_P ? s->d_v_new2old : s->d_e_new2old, which == PHW_P ? s->io_v : s->io_e);
+    if (rc) return rc;
+    TriBuf tb = which == PHW_P ? s->tp : s->tq;
+    copy_to_tb_k<<<vec_grid(s, n), 256, 0, s->stream>>>(n, tb, s->ctl, which, nullptr);   // cold start
+    CU(cudaGetLastError());
+    long long it0 = 0, it1 = 0;
+    CU(cudaMemcpyAsync(&it0, &s->ctl->sc[which].iters, 8, cudaMemcpyDeviceToHost, s->stream));
+    rc = solve_mass(s, which, s->prm.max_iter); if (rc) return rc;
+    double* out = which == PHW_P ? s->tmp_p : s->tmp_q;
+    copy_from_tb_k<<<vec_grid(s, n), 256, 0, s->stream>>>(n, out, tb, s->ctl, which);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(&it1, &s->ctl->sc[which].iters, 8, cudaMemcpyDeviceToHost, s->stream));
+    rc = export_vec(s, out, x, n, which == PHW_P ? s->d_v_new2old : s->d_e_new2old, which == PHW_P ? s->io_v : s->io_e);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(s->stream));
+    if (iters) *iters = (int32_t)(it1 - it0);
+    s->have_vq = false;
+    return PHW_OK;
+}
+int phw_energy(phw_solver_t s, double* parts2) {
+    if (!s || !parts2) return fail(PHW_EINVAL, "NULL argument");
+    CU(cudaSetDevice(s->device));
+    int rc = energy(s); if (rc) return rc;
+    CU(cudaMemcpyAsync(parts2, &s->ctl->red[0], 16, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return PHW_OK;
+}
+int phw_set_H_init(phw_solver_t s, double H_init) {
+    if (!s) return fail(PHW_EINVAL, "solver is NULL");
+    s->prm.H_init = H_init;
+    s->sp.H_init = H_init;
+    return PHW_OK;
+}
+int phw_port_flux(phw_solver_t s, double* out) {
+    if (!s || !out) return fail(PHW_EINVAL, "NULL argument");
+    CU(cudaSetDevice(s->device));
+    int rc = flux(s, s->q, 1, 3); if (rc) return rc;
+    CU(cudaMemcpyAsync(out, &s->ctl->flux[3], 8, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return PHW_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,227 @@
+"""Drop-in for the reference solver call: ``wave_2D_solve`` (reference
+``fenics_projects/wave_eqn/wave_2D.py:15-20,1032``) with the same positional/keyword arguments, the
+same printed messages on invalid case combinations (``print`` + ``quit()``, :63-83,148-151) and the
+same ``(H_array, numCells)`` return value (:1011-1032).  Behind it there is no dolfin/PETSc: the mesh
+goes to libphwave.so (C ABI, include/phwave.h) and the whole time loop runs on the GPU.
+
+Extra keyword arguments (defaults keep the reference behaviour): ``mesh=(vertices, cells)`` to bypass
+the built-in generator (the reference calls mshr, :93-119), ``mesh_kind``, ``device``, ``patch_cells``,
+``tol``, ``lumped`` (dict overriding the hard-coded constants of :153-158), ``return_state``.
+"""
+import os
+import time
+
+import numpy as np
+
+from . import _lib
+from .mesh import generate_mesh
+from .solver import Mesh, Solver, tag_boundary_edges, port_weights
+
+_DEFAULT_LUMPED = dict(Bl_em=5.0, R1_em=0.0, R2_em=0.0, K_em=5.0, m_em=0.15, L_em=0.1)   # wave_2D.py:153-158
+
+
+def _quit(msg):
+    print(msg)
+    raise SystemExit
+
+
+def wave_2D_solve(tFinal, numSteps, outputDir,
+                  nx, xLength, yLength,
+                  domainShape='R', timeIntScheme='SV', dirichletImp='weak',
+                  K_wave=1, rho=1, BOUNDARYPLOT=False, interConnection=None,
+                  analytical=False, saveP=True, controlType=None,
+                  input_stop_t=None, control_start_t=None, basis_order=(1, 1),
+                  mesh=None, mesh_kind='structured', device=0, patch_cells=None, tol=1e-13,
+                  lumped=None, return_state=False, verbose=True):
+    """Solve the 2D port-Hamiltonian wave equation; see the reference docstring (wave_2D.py:22-51).
+
+    Returns (H_array [numSteps, 8 | 12], numCells)."""
+    rank = 0
+    # ---- check case combinations (wave_2D.py:63-83) ----
+    if controlType == 'lqr':
+        _quit('lqr no longer implemented')
+    if controlType == 'passivity':
+        if interConnection != 'IC':
+            _quit('passivity control only implemented for IC interconnection')
+    if controlType == 'casimir':
+        if interConnection is not None:
+            _quit('casimir control not implemented for IC interconnection')
+    if analytical:
+        if not domainShape == 'R':
+            _quit('analytical solution for rectangle domain only')
+    if interConnection == 'IC':
+        if not dirichletImp == 'weak':
+            _quit('can only do interconnection model with weak boundary conditions')
+    BOUNDARYPLOT = False                                               # wave_2D.py:86
+    tic = time.time()
+    if rank == 0 and verbose:
+        print('Started solving for case: {}, {}, {} '.format(domainShape, timeIntScheme, dirichletImp))
+    if domainShape not in ('R', 'S_1C'):
+        _quit('domainShape \"{}\" hasn\'t been created'.format(domainShape))
+    if interConnection == 'IC' and timeIntScheme not in ['SV', 'SE', 'SM']:
+        _quit('only SE, SV and SM time int schemes implemented for interconnection model')
+    if timeIntScheme not in _lib.SCHEMES:
+        _quit('time integration scheme {} not implemented'.format(timeIntScheme))
+    if dirichletImp not in ('weak', 'strong'):
+        _quit('dirichlet implementation {} not implemented'.format(dirichletImp))
+    if tuple(basis_order) != (1, 1):
+        raise NotImplementedError('the device path implements the P1/RT1 pair; basis_order={} is not available yet'.format(basis_order))
+    if controlType == 'casimir' and timeIntScheme != 'SM':
+        raise NotImplementedError('casimir control is only defined for the SM scheme (wave_2D.py:615)')
+    if controlType == 'passivity' and timeIntScheme in ['SV', 'EH']:
+        raise NotImplementedError('passivity control is only wired for one-sub-step schemes (wave_2D.py:844)')
+
+    # ---- mesh (wave_2D.py:92-128) ----
+    if mesh is None:
+        mesh = generate_mesh(domainShape, nx, xLength, yLength, kind=mesh_kind)
+    vertices, cells = mesh
+    if patch_cells is None:
+        patch_cells = 2048 if len(cells) >= 200000 else max(64, min(2048, len(cells) // 256))
+    m = Mesh(vertices, cells, patch_cells=patch_cells)
+    numCells = m.n_cells
+    if rank == 0 and verbose:
+        print('number of cells = {}'.format(numCells))
+
+    dt_value = tFinal / numSteps                                       # wave_2D.py:131
+    c = np.sqrt(K_wave / rho)
+    prm = _lib.PhwParams()
+    prm.scheme = _lib.SCHEMES[timeIntScheme]
+    prm.strong = 1 if dirichletImp == 'strong' else 0
+    prm.interconnection = 1 if interConnection == 'IC' else 0
+    prm.casimir = 1 if controlType == 'casimir' else 0
+    prm.analytical = 0                                                 # diagnostics columns are filled below
+    prm.dt, prm.K_wave, prm.rho = dt_value, float(K_wave), float(rho)
+    prm.tol, prm.max_iter, prm.flags = float(tol), 200, 0
+    lp = dict(_DEFAULT_LUMPED)
+    if lumped:
+        lp.update(lumped)
+    for k, v in lp.items():
+        setattr(prm, k, float(v))
+
+    # ---- boundary markers and data (wave_2D.py:226-285,326-444) ----
+    tags = tag_boundary_edges(m, domainShape, xLength, yLength)
+    weights = None
+    omega = 0.0
+    if analytical:
+        omega = c * np.sqrt(np.pi ** 2 / (4 * xLength ** 2) + 4 * np.pi ** 2 / yLength ** 2)           # cSqrtConst :375
+        weights = port_weights(m, tags, lambda x, y: rho * omega * np.sin(2 * np.pi * y / yLength + np.pi / 2))
+        prm.input_kind, prm.in_amp, prm.in_omega = _lib.IN_COSINE, 1.0, omega                         # :376
+    elif interConnection == 'IC':
+        if controlType == 'passivity':
+            prm.input_kind = _lib.IN_PASSIVITY                                                         # control_input.py:12-18
+            prm.in_amp, prm.in_omega, prm.in_gain = 10.0, 8 * np.pi, 100.0
+            prm.in_t_stop, prm.in_t_ctrl = float(input_stop_t), float(control_start_t)
+        else:
+            prm.input_kind, prm.in_amp, prm.in_omega, prm.in_t_stop = _lib.IN_SINE_WINDOW, 5.0, 8 * np.pi, 0.25   # :433,444
+    elif controlType == 'casimir':
+        prm.input_kind, prm.in_amp, prm.in_omega = _lib.IN_SINE, 3.0, 8 * np.pi                        # :380
+    else:
+        prm.input_kind, prm.in_amp, prm.in_omega, prm.in_t_stop = _lib.IN_SINE_WINDOW, 10.0, 8 * np.pi, 0.25    # :384
+    m.set_boundary(tags, weights)
+
+    solver = Solver(m, prm, device=device)
+
+    # ---- initial conditions (wave_2D.py:732-771) ----
+    H_init = 0.0
+    X, Y = m.vertices[:, 0], m.vertices[:, 1]
+    p_space = None
+    if analytical:
+        p_space = rho * omega * np.sin(np.pi * X / (2 * xLength) + np.pi / 2) * np.sin(2 * np.pi * Y / yLength + np.pi / 2)
+        solver.set_state(p=p_space, q=np.zeros(m.n_edges), x3=np.zeros(3))
+        Hp, Hq = solver.energy_parts()
+        H_init = Hp                                                     # :746 (q_m = 0)
+    elif controlType == 'passivity':
+        edges = m.edges()[0]
+        p0 = np.sin(4 * np.pi * X / xLength)                            # :759-763
+        mid = 0.5 * (m.vertices[edges[:, 0]] + m.vertices[edges[:, 1]])
+        tang = m.vertices[edges[:, 1]] - m.vertices[edges[:, 0]]
+        q0 = np.sin(4 * np.pi * mid[:, 0] / xLength) * tang[:, 1]       # RT1 dof = |e| q(mid).n_e, n_e = (t_y, -t_x)/|e|
+        solver.set_state(p=p0, q=q0, x3=np.zeros(3))
+        Hp, Hq = solver.energy_parts()
+        # :769  rho (1/2 p^T M_p p + 1/2 c^2 q^T M_q q)   (deliberately not the H_wave formula of :882)
+        H_init = rho * (rho * Hp) + rho * (Hq / K_wave) * (K_wave / rho)
+    solver.set_H_init(H_init)
+
+    # ---- time loop on the device (wave_2D.py:787-982) ----
+    ncol = 12 if analytical else 8
+    H_array = np.zeros((numSteps, ncol))
+    if not analytical:
+        H8 = solver.run(numSteps)
+        H_array[:, :8] = H8
+    else:
+        diag = _AnalyticalDiagnostics(m, p_space, omega)
+        diag.set_space(lambda x, y: rho * omega * np.sin(np.pi * x / (2 * xLength) + np.pi / 2) * np.sin(2 * np.pi * y / yLength + np.pi / 2))
+        for n in range(numSteps):
+            H_array[n, :8] = solver.run(1)[0]
+            p_h, _, _ = solver.get_state()
+            H_array[n, 8:12] = diag.evaluate(p_h, H_array[n, 0])
+    stats = solver.stats()
+    totalTime = time.time() - tic
+    if rank == 0 and verbose:
+        print('{}, {}, {} Simulation finished in {} seconds'.format(domainShape, timeIntScheme, dirichletImp, totalTime))
+    if return_state:
+        p, q, x = solver.get_state()
+        solver.close()
+        return H_array, numCells, dict(p=p, q=q, x=x, stats=stats, mesh=m)
+    solver.close()
+    m.close()
+    return H_array, numCells
+
+
+class _AnalyticalDiagnostics:
+    """Columns 8-11 of the analytical cases (wave_2D.py:929-965): dolfin ``errornorm`` (both fields
+    interpolated into P_{k+3}, here P4, then the exact L2 norm of the difference), nodal max error and the
+    point probe at (0.155, 0.189).  Host-side for now (device diagnostics kernel is 'next')."""
+
+    def __init__(self, mesh, p_space_vertices, omega, xPoint=0.155, yPoint=0.189):
+        self.omega = omega
+        self.cells = mesh.cells.astype(np.int64)
+        V = mesh.vertices[self.cells]
+        # P4 equispaced nodes in barycentric coordinates
+        k = 4
+        nodes = np.array([(i / k, j / k) for j in range(k + 1) for i in range(k + 1 - j)])
+        lam = np.stack([1 - nodes[:, 0] - nodes[:, 1], nodes[:, 0], nodes[:, 1]], axis=1)
+        self.lam = lam
+        xy = np.einsum('nj,cjd->cnd', lam, V)
+        # exact spatial factor at the P4 nodes: same closed form as the initial condition (wave_2D.py:741)
+        self.exact_vertices = p_space_vertices
+        self._xy = xy
+        self.area = 0.5 * np.abs((V[:, 1, 0] - V[:, 0, 0]) * (V[:, 2, 1] - V[:, 0, 1]) - (V[:, 1, 1] - V[:, 0, 1]) * (V[:, 2, 0] - V[:, 0, 0]))
+        # reference P4 mass matrix by exact quadrature
+        def mono(x, y):
+            return np.stack([x ** a * y ** b for b in range(k + 1) for a in range(k + 1 - b)], axis=-1)
+        gx, gw = np.polynomial.legendre.leggauss(6)
+        u, wu = 0.5 * (gx + 1), 0.5 * gw
+        U, W2 = np.meshgrid(u, u, indexing='ij')
+        qx, qy = U.ravel(), (W2 * (1 - U)).ravel()
+        qw = 2.0 * (np.outer(wu, wu) * (1 - U)).ravel()
+        tab = np.linalg.solve(mono(nodes[:, 0], nodes[:, 1]).T, mono(qx, qy).T).T
+        self.mass_ref = np.einsum('qi,qj,q->ij', tab, tab, qw)
+        self.exact_nodes = None
+        # point probe
+        P = np.array([xPoint, yPoint])
+        T = np.stack([V[:, 1] - V[:, 0], V[:, 2] - V[:, 0]], axis=2)
+        rhs = P[None, :] - V[:, 0]
+        det = T[:, 0, 0] * T[:, 1, 1] - T[:, 0, 1] * T[:, 1, 0]
+        l1 = (rhs[:, 0] * T[:, 1, 1] - rhs[:, 1] * T[:, 0, 1]) / det
+        l2 = (T[:, 0, 0] * rhs[:, 1] - T[:, 1, 0] * rhs[:, 0]) / det
+        l0 = 1 - l1 - l2
+        inside = np.nonzero((l0 >= -1e-12) & (l1 >= -1e-12) & (l2 >= -1e-12))[0]
+        self.pt_cell = int(inside[0]) if inside.size else -1
+        if self.pt_cell >= 0:
+            self.pt_lam = np.array([l0[self.pt_cell], l1[self.pt_cell], l2[self.pt_cell]])
+
+    def set_space(self, fn):
+        self.exact_nodes = fn(self._xy[..., 0], self._xy[..., 1])
+
+    def evaluate(self, p_h, t):
+        if self.exact_nodes is None:
+            raise RuntimeError('set_space must be called first')
+        ct = np.cos(t * self.omega)
+        e = self.exact_nodes * ct - p_h[self.cells] @ self.lam.T
+        err_L2 = np.sqrt(np.sum(np.einsum('ci,ij,cj->c', e, self.mass_ref, e) * self.area))
+        err_max = np.abs(self.exact_vertices * ct - p_h).max()
+        if self.pt_cell >= 0:
+            vc = self.cells[self.pt_cell]
+            return err_L2, err_max, float(p_h[vc] @ self.pt_lam), float((self.exact_vertices[vc] * ct) @ self.pt_lam)
+        return err_L2, err_max, 0.0, 0.0
