@@ -1,0 +1,246 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark of the hot path (contract: see the task statement / DESIGN.md "Measurement").
+
+Workload (BASELINE.json configs[3], fits one B200): refined synthetic rectangle 1.0 x 0.25, Nx x Ny quads split
+in two -> 25.0 M cells, 50.0 M dofs (P1 vertices + RT1 edges), weak form, symplectic Euler, K=3, rho=2,
+dt=2e-5, input g(t) = 10 sin(8 pi t).  One "step" = one time step of the loop wave_2D.py:787-982.
+metric = dof-updates/s = N_dof * steps / seconds.
+
+  value : device-timed (CUDA events on the solver's stream inside phw_run, state resident in HBM)
+  e2e   : same K steps through the host-buffer C-ABI path (phw_set_state from pinned host memory ->
+          phw_run -> H_array rows + phw_get_state back to the host), wall clock
+  roofline : Chebyshev M_q solve kernel (the dominant kernel), algorithmic bytes / its CUDA-event time
+  cpu_baseline : the CPU oracle (oracle/, scipy splu factor-once) on a down-scaled mesh of the same family
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+K_WAVE, RHO = 3.0, 2.0
+FULL_NX, FULL_NY = 7072, 1768
+DT_FULL = 2e-5
+
+
+def clocks_sampler(stop, out, dev):
+    q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+    while not stop.is_set():
+        try:
+            r = subprocess.run(['nvidia-smi', '-i', str(dev), '--query-gpu=' + q, '--format=csv,noheader,nounits'],
+                               capture_output=True, text=True, timeout=5)
+            f = [x.strip() for x in r.stdout.strip().split(',')]
+            if len(f) >= 6:
+                out.append(f)
+        except Exception:
+            pass
+        stop.wait(0.2)
+
+
+def summarize_clocks(samples):
+    if not samples:
+        return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': []}
+    sm = sorted(int(s[0]) for s in samples if s[0].isdigit())
+    mx = [int(s[1]) for s in samples if s[1].isdigit()]
+    reasons = []
+    for idx, name in [(2, 'hw_slowdown'), (3, 'hw_thermal_slowdown'), (4, 'sw_thermal_slowdown'), (5, 'sw_power_cap')]:
+        if any(s[idx].lower().startswith('active') for s in samples):
+            reasons.append(name)
+    return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons}
+
+
+def cpu_oracle_rate(nx, ny, steps, refactor):
+    """dof-updates/s of the CPU oracle (SE, weak, wave only) on an nx x ny x 2 mesh of the same family."""
+    from oracle.wave_2D_oracle import wave_2D_solve_oracle
+    from porthamiltonian_fem_b200.mesh import rectangle_structured
+    mesh = rectangle_structured(nx, ny, 1.0, 0.25)
+    dt = DT_FULL * FULL_NX / nx                       # same CFL ratio as the full-size run
+    timing = {}
+    wave_2D_solve_oracle(dt * steps, steps, mesh, 1.0, 0.25, timeIntScheme='SE', K_wave=K_WAVE, rho=RHO,
+                         refactor_every_solve=refactor, timing=timing)
+    n_dof = timing['n_dof']
+    return n_dof * steps / timing['loop_seconds'], n_dof, timing['loop_seconds']
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's CPU algorithm (oracle port, re-factorising at every solve call the way
+    dolfin's solve(A, x, b) does) on a bounded sample of the workload, timed on the host cores."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    nx, ny = 221, 55
+    steps = max(1, args.steps)
+    t0 = time.time()
+    for _ in range(min(args.warmup, 1)):
+        cpu_oracle_rate(nx, ny, 1, True)
+    rate, n_dof, secs = cpu_oracle_rate(nx, ny, steps, True)
+    line = {
+        'metric': 'dof-updates/sec (fp64)', 'value': rate, 'unit': 'dof-updates/s', 'impl': 'reference', 'n_gpus': args.gpus,
+        'steps': steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * secs / steps, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': 'SE weak P1/RT1 wave on a structured rectangle; CPU sample {}x{}x2 cells ({} dofs) of the '
+                               '7072x1768x2 workload, same CFL ratio'.format(nx, ny, n_dof)},
+        'cpu_baseline': {'value': rate, 'unit': 'dof-updates/s', 'cores': 1, 'kind': 'port',
+                         'sample': '{} steps on {}x{}x2 cells, scipy SuperLU re-factorised at every solve (dolfin solve(A,x,b) '
+                                   'behaviour); the real dolfin/PETSc stack is not installable here'.format(steps, nx, ny)},
+        'e2e': {'value': rate, 'unit': 'dof-updates/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'wall_s': time.time() - t0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200')
+    ap.add_argument('--nx', type=int, default=FULL_NX)
+    ap.add_argument('--ny', type=int, default=FULL_NY)
+    ap.add_argument('--scheme', default='SE')
+    ap.add_argument('--patch-cells', type=int, default=2048)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--tol', type=float, default=1e-13)
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device (no CPU fallback)')
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    from porthamiltonian_fem_b200 import _lib
+    from porthamiltonian_fem_b200.mesh import rectangle_structured
+    from porthamiltonian_fem_b200.solver import Mesh, Solver, tag_boundary_edges
+
+    # ---- setup (not timed): mesh, layout, device SoA.  Weak scaling: every rank owns one slab of the size below.
+    t_setup = time.time()
+    vertices, cells = rectangle_structured(args.nx, args.ny, 1.0, 0.25)
+    m = Mesh(vertices, cells, patch_cells=args.patch_cells)
+    m.set_boundary(tag_boundary_edges(m, 'R', 1.0, 0.25))
+    dt = DT_FULL * FULL_NX / args.nx
+    prm = _lib.PhwParams()
+    prm.scheme, prm.dt, prm.K_wave, prm.rho = _lib.SCHEMES[args.scheme], dt, K_WAVE, RHO
+    prm.input_kind, prm.in_amp, prm.in_omega, prm.in_t_stop = _lib.IN_SINE, 10.0, 8 * np.pi, 1e30
+    prm.tol, prm.max_iter, prm.flags = args.tol, 200, 4
+    solver = Solver(m, prm, device=local_rank)
+    n_dof = m.n_vertices + m.n_edges
+    setup_s = time.time() - t_setup
+    del vertices, cells
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up
+    barrier()
+    solver.run(args.warmup)
+    barrier()
+    # ---- timed region: K steps, device events inside phw_run on the solver's stream
+    samples, stop = [], threading.Event()
+    th = threading.Thread(target=clocks_sampler, args=(stop, samples, local_rank), daemon=True)
+    th.start()
+    barrier()
+    t0 = time.perf_counter()
+    H = solver.run(args.steps)
+    barrier()
+    wall = time.perf_counter() - t0
+    stop.set()
+    th.join(timeout=2)
+    st = solver.stats()
+    dev_s = st['device_ms'] * 1e-3
+    if world > 1:
+        tt = torch.tensor([dev_s], dtype=torch.float64, device='cuda')
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dev_s = float(tt.item())
+    value = world * n_dof * args.steps / dev_s
+
+    # ---- end-to-end through host buffers (pinned), copies inside the timed region
+    p_host = torch.zeros(m.n_vertices, dtype=torch.float64).pin_memory()
+    q_host = torch.zeros(m.n_edges, dtype=torch.float64).pin_memory()
+    x_host = np.zeros(3)
+    H_host = torch.zeros((args.steps, 8), dtype=torch.float64).pin_memory()
+    p_np, q_np = p_host.numpy(), q_host.numpy()
+    lib = _lib.load()
+    _lib.check(lib.phw_get_state(solver.handle, p_np.ctypes.data, q_np.ctypes.data, x_host.ctypes.data))
+    barrier()
+    t0 = time.perf_counter()
+    _lib.check(lib.phw_set_state(solver.handle, p_np.ctypes.data, q_np.ctypes.data, x_host.ctypes.data))
+    _lib.check(lib.phw_run(solver.handle, args.steps, H_host.numpy().ctypes.data))
+    _lib.check(lib.phw_get_state(solver.handle, p_np.ctypes.data, q_np.ctypes.data, x_host.ctypes.data))
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([e2e_s], dtype=torch.float64, device='cuda')
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt.item())
+    st2 = solver.stats()
+    e2e_value = world * n_dof * args.steps / e2e_s
+    h2d = (n_dof * 8 + 24) / args.steps
+    d2h = (n_dof * 8 + 24 + args.steps * 8 * 8) / args.steps
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        except Exception:
+            pass
+        peak = float(peaks.get('hbm_gbs', 6650.0))
+        peak_src = 'measured (MEASURED_PEAKS.json hbm_gbs)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s (B200_PROFILING.md)'
+        # dominant kernel: cooperative Chebyshev solve of M_q; algorithmic bytes = 96 B/cell/iteration
+        nc = m.n_cells
+        it_q = st['iters_q']
+        q_bytes = 96.0 * nc * it_q
+        achieved = q_bytes / (st['ms_solve_q'] * 1e-3) / 1e9 if st['ms_solve_q'] > 0 else None
+        line = {
+            'metric': 'dof-updates/sec (fp64, device-timed)', 'value': value, 'unit': 'dof-updates/s',
+            'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dev_s / args.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': '{} weak P1/RT1 wave, structured rectangle {}x{}x2 = {} cells, {} dofs per GPU, dt={:g}; '
+                                   'state vectors ({:.0f} MB each) exceed L2, no flush needed'.format(
+                                       args.scheme, args.nx, args.ny, nc, n_dof, dt, 8e-6 * m.n_edges),
+                       'dofs_per_gpu': n_dof, 'patch_cells': args.patch_cells, 'tol': args.tol,
+                       'iters_per_solve_p': st['iters_p'] / max(1, st['solves_p']), 'iters_per_solve_q': st['iters_q'] / max(1, st['solves_q']),
+                       'max_rel_residual': st['max_rel_residual'], 'setup_seconds': setup_s},
+            'e2e': {'value': e2e_value, 'unit': 'dof-updates/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                    'seconds': e2e_s},
+            'gpu_launches': int(st['kernel_launches']),
+            'clocks': summarize_clocks(samples),
+            'roofline': {'bound': 'hbm', 'kernel': 'solve_coop_k<1> (Chebyshev M_q solve, all iterations in one cooperative launch)',
+                         'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': (achieved / peak) if achieved else None,
+                         'traffic': None, 'peak_source': peak_src,
+                         'bytes_per_launch': q_bytes / max(1, st['solves_q']), 'ms_per_launch': st['ms_solve_q'] / max(1, st['solves_q']),
+                         'whole_loop_model_gbs': st['bytes_model'] / dev_s / 1e9, 'kernel_share_of_step': st['ms_solve_q'] / st['device_ms']},
+            'wall_s_timed_region': wall,
+        }
+        if not args.no_cpu_baseline:
+            try:
+                rate, nd, secs = cpu_oracle_rate(442, 110, 10, False)
+                line['cpu_baseline'] = {'value': rate, 'unit': 'dof-updates/s', 'cores': 1, 'kind': 'port',
+                                        'sample': '10 SE steps on a 442x110x2-cell mesh ({} dofs) of the same family, CPU oracle '
+                                                  '(scipy SuperLU, factor once), {:.1f} s'.format(nd, secs)}
+            except Exception as ex:   # the bench line must still be printed
+                line['cpu_baseline'] = {'value': None, 'unit': 'dof-updates/s', 'cores': 1, 'kind': 'port', 'sample': 'failed: %r' % (ex,)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

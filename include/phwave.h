@@ -53,7 +53,8 @@ typedef struct phw_params {
     double an_omega, an_xLength, an_yLength, an_xPoint, an_yPoint;  /* analytical case constants */
     double tol;              /* relative residual of the mass / block solves (default 1e-13) */
     int32_t max_iter;        /* iteration cap per solve (default 200) */
-    int32_t flags;           /* bit0: disable first-same-as-last reuse in SV; bit1: synchronous error checks */
+    int32_t flags;           /* bit0: disable first-same-as-last reuse in SV; bit1: synchronous error checks;
+                                bit2: CUDA-event timing of every solve kernel; bit3: force the multi-launch solve path */
 } phw_params;
 
 typedef struct phw_stats {
@@ -63,6 +64,7 @@ typedef struct phw_stats {
     int64_t kernel_launches;    /* launches issued by the last phw_run */
     int64_t bytes_model;        /* algorithmic bytes of the last phw_run ("bytes model") */
     double  lam_min_q, lam_max_q, skew_bound;
+    double  ms_solve_p, ms_solve_q, ms_solve_block;   /* summed CUDA-event time of the solve kernels (flags bit2) */
 } phw_stats;
 
 const char* phw_last_error(void);

@@ -37,7 +37,8 @@ class PhwStats(ctypes.Structure):
                 ('solves_block', ctypes.c_int64), ('iters_p', ctypes.c_int64), ('iters_q', ctypes.c_int64),
                 ('iters_block', ctypes.c_int64), ('max_rel_residual', ctypes.c_double),
                 ('device_ms', ctypes.c_double), ('kernel_launches', ctypes.c_int64), ('bytes_model', ctypes.c_int64),
-                ('lam_min_q', ctypes.c_double), ('lam_max_q', ctypes.c_double), ('skew_bound', ctypes.c_double)]
+                ('lam_min_q', ctypes.c_double), ('lam_max_q', ctypes.c_double), ('skew_bound', ctypes.c_double),
+                ('ms_solve_p', ctypes.c_double), ('ms_solve_q', ctypes.c_double), ('ms_solve_block', ctypes.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -17,6 +17,7 @@
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 #include "layout.hpp"
 
 namespace phw {
@@ -117,88 +118,25 @@ __device__ __forceinline__ void cheb_coeffs(int k, double rho_prev, double d, do
     c2 = 2.0 * rho_k / c;
 }
 
-// ------------------------------------------------------------------------------------------------
-// last-block epilogue shared by the row kernels: deterministic sum of the per-patch partials and the
-// iteration control of the Chebyshev solve
-// ------------------------------------------------------------------------------------------------
-template <int EPI>
-__device__ void finish_launch(const RowArgs& a, double* red) {
-    __shared__ bool is_last;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned int prev = atomicAdd(&a.ctl->counters[a.counter_id], 1u);
-        is_last = (prev == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-    double s0 = 0.0, s1 = 0.0;
-    for (int p = threadIdx.x; p < a.m.npatch; p += blockDim.x) {
-        s0 += __ldcg(&a.partials[2 * p]);
-        s1 += __ldcg(&a.partials[2 * p + 1]);
-    }
-    block_sum2(s0, s1, red);
-    if (threadIdx.x == 0) {
-        Ctl* ctl = a.ctl;
-        ctl->counters[a.counter_id] = 0;
-        if (EPI == EPI_DOT) {
-            double v = s0 * a.dot_scale;
-            ctl->red[a.red_slot] = a.dot_accumulate ? ctl->red[a.red_slot] + v : v;
-        } else if (EPI == EPI_CHEB) {
-            SolveCtl& sc = ctl->sc[a.which];
-            double rr = sc.racc + s0 * a.weight;
-            double bb = sc.bacc + s1 * a.weight;
-            if (!a.finalize) { sc.racc = rr; sc.bacc = bb; }
-            else {
-                sc.racc = 0.0; sc.bacc = 0.0;
-                sc.rr = rr; sc.bb = bb;
-                double c1, c2, rho_k;
-                cheb_coeffs(sc.k, sc.rho, a.cheb_d, a.cheb_c, c1, c2, rho_k);
-                sc.rho = rho_k;
-                sc.k += 1;
-                sc.cur = (sc.cur + 1) % 3;
-                sc.iters += 1;
-                if (rr <= a.tol2 * bb) {
-                    sc.done = 1;
-                    double rel = (bb > 0.0) ? sqrt(rr / bb) : 0.0;
-                    if (rel > sc.maxres) sc.maxres = rel;
-                } else if (sc.k >= a.max_iter) {
-                    sc.done = 1;
-                    ctl->nonconv += 1;
-                    double rel = (bb > 0.0) ? sqrt(rr / bb) : 0.0;
-                    if (rel > sc.maxres) sc.maxres = rel;
-                }
-            }
-        }
-        __threadfence();
-    }
-}
+
+// resolved per-launch (or per-iteration) pointers and Chebyshev coefficients
+struct PassIO {
+    const double* xp;      // vertex input
+    const double* xq;      // edge input
+    const double* xprev;   // previous iterate of the row's own unknown (CHEB, k > 0)
+    double* xnew;          // next iterate (CHEB)
+    double c1, c2;
+    int use_prev;
+};
+
+__device__ __forceinline__ double* tb_sel(const TriBuf& t, int i) { return i == 0 ? t.b[0] : (i == 1 ? t.b[1] : t.b[2]); }
 
 // ------------------------------------------------------------------------------------------------
-// vertex rows
+// vertex rows: all patches of this block
 // ------------------------------------------------------------------------------------------------
 template <int EPI, int MODE, bool HAS_M, bool HAS_D, bool CAS>
-__global__ void __launch_bounds__(NT, 2) vertex_rows_k(const RowArgs a) {
-    extern __shared__ double smem[];
-    __shared__ double red[64];
+__device__ __forceinline__ void vertex_pass(const RowArgs& a, const PassIO& io, double* smem, double& acc0, double& acc1) {
     const DevMesh& m = a.m;
-    int cur = 0, k = 0;
-    double c1 = 0.0, c2 = 0.0;
-    if (EPI == EPI_CHEB) {
-        const SolveCtl& sc = a.ctl->sc[a.which];
-        if (sc.done) return;
-        cur = sc.cur; k = sc.k;
-        double rk;
-        cheb_coeffs(k, sc.rho, a.cheb_d, a.cheb_c, c1, c2, rk);
-    }
-    const double* xp = a.xp;
-    const double* xq = a.xq;
-    if (EPI == EPI_CHEB) {
-        if (a.use_cheb_input) xp = a.tp.b[cur];
-        if (a.coupled_from_tribuf) xq = a.tq.b[cur];
-    }
-    double acc0 = 0.0, acc1 = 0.0;
     for (int P = blockIdx.x; P < m.npatch; P += gridDim.x) {
         const PatchHdr h = m.hdr[P];
         const int nlv = h.v_cnt + h.gv_cnt, nle = h.e_cnt + h.ge_cnt;
@@ -207,12 +145,12 @@ __global__ void __launch_bounds__(NT, 2) vertex_rows_k(const RowArgs a) {
         double* sc3 = HAS_D ? sq + ((nle + 1) & ~1) : sq;   // [3*n_vcells]
         // ---- stage 1: local inputs
         if (MODE == MODE_OP && (HAS_M || CAS || EPI != EPI_STORE)) {
-            for (int i = threadIdx.x; i < h.v_cnt; i += NT) sp[i] = xp[h.v_start + i];
-            for (int i = threadIdx.x; i < h.gv_cnt; i += NT) sp[h.v_cnt + i] = xp[m.ghost_v[h.gv_off + i]];
+            for (int i = threadIdx.x; i < h.v_cnt; i += NT) sp[i] = io.xp[h.v_start + i];
+            for (int i = threadIdx.x; i < h.gv_cnt; i += NT) sp[h.v_cnt + i] = io.xp[m.ghost_v[h.gv_off + i]];
         }
         if (HAS_D && MODE == MODE_OP) {
-            for (int i = threadIdx.x; i < h.e_cnt; i += NT) sq[i] = xq[h.e_start + i];
-            for (int i = threadIdx.x; i < h.ge_cnt; i += NT) sq[h.e_cnt + i] = xq[m.ghost_e[h.ge_off + i]];
+            for (int i = threadIdx.x; i < h.e_cnt; i += NT) sq[i] = io.xq[h.e_start + i];
+            for (int i = threadIdx.x; i < h.ge_cnt; i += NT) sq[h.e_cnt + i] = io.xq[m.ghost_e[h.ge_off + i]];
         }
         __syncthreads();
         // ---- stage 2: per-cell contributions to its three vertices
@@ -284,9 +222,9 @@ __global__ void __launch_bounds__(NT, 2) vertex_rows_k(const RowArgs a) {
             } else if (EPI == EPI_CHEB) {
                 const double bv = a.b[gid], pv = a.pinv[gid], xc = sp[lv];
                 const double r_ = bv - val;
-                double xn = xc + c2 * pv * r_;
-                if (k > 0) xn += c1 * (xc - a.tp.b[(cur + 2) % 3][gid]);
-                a.tp.b[(cur + 1) % 3][gid] = xn;
+                double xn = xc + io.c2 * pv * r_;
+                if (io.use_prev) xn += io.c1 * (xc - io.xprev[gid]);
+                io.xnew[gid] = xn;
                 acc0 += pv * r_ * r_;
                 acc1 += pv * bv * bv;
             } else {
@@ -294,40 +232,15 @@ __global__ void __launch_bounds__(NT, 2) vertex_rows_k(const RowArgs a) {
             }
         }
         __syncthreads();
-        if (EPI != EPI_STORE) {
-            double s0 = acc0, s1 = acc1;
-            block_sum2(s0, s1, red);
-            if (threadIdx.x == 0) { a.partials[2 * P] = s0; a.partials[2 * P + 1] = s1; }
-            acc0 = acc1 = 0.0;
-        }
     }
-    if (EPI != EPI_STORE) finish_launch<EPI>(a, red);
 }
 
 // ------------------------------------------------------------------------------------------------
-// edge rows
+// edge rows: all patches of this block
 // ------------------------------------------------------------------------------------------------
 template <int EPI, int MODE, bool HAS_M, bool HAS_D, bool CAS>
-__global__ void __launch_bounds__(NT, 2) edge_rows_k(const RowArgs a) {
-    extern __shared__ double smem[];
-    __shared__ double red[64];
+__device__ __forceinline__ void edge_pass(const RowArgs& a, const PassIO& io, double* smem, double& acc0, double& acc1) {
     const DevMesh& m = a.m;
-    int cur = 0, k = 0;
-    double c1 = 0.0, c2 = 0.0;
-    if (EPI == EPI_CHEB) {
-        const SolveCtl& sc = a.ctl->sc[a.which];
-        if (sc.done) return;
-        cur = sc.cur; k = sc.k;
-        double rk;
-        cheb_coeffs(k, sc.rho, a.cheb_d, a.cheb_c, c1, c2, rk);
-    }
-    const double* xp = a.xp;
-    const double* xq = a.xq;
-    if (EPI == EPI_CHEB) {
-        if (a.use_cheb_input) xq = a.tq.b[cur];
-        if (a.coupled_from_tribuf) xp = a.tp.b[cur];
-    }
-    double acc0 = 0.0, acc1 = 0.0;
     for (int P = blockIdx.x; P < m.npatch; P += gridDim.x) {
         const PatchHdr h = m.hdr[P];
         const int nlv = h.v_cnt + h.gv_cnt, nle = h.e_cnt + h.ge_cnt;
@@ -335,12 +248,12 @@ __global__ void __launch_bounds__(NT, 2) edge_rows_k(const RowArgs a) {
         double* sp = sq + ((nle + 1) & ~1);         // [nlv] (only if HAS_D)
         double* sc3 = HAS_D ? sp + ((nlv + 1) & ~1) : sp;   // [3*n_ecells]
         if (MODE == MODE_OP && (HAS_M || CAS || EPI != EPI_STORE)) {
-            for (int i = threadIdx.x; i < h.e_cnt; i += NT) sq[i] = xq[h.e_start + i];
-            for (int i = threadIdx.x; i < h.ge_cnt; i += NT) sq[h.e_cnt + i] = xq[m.ghost_e[h.ge_off + i]];
+            for (int i = threadIdx.x; i < h.e_cnt; i += NT) sq[i] = io.xq[h.e_start + i];
+            for (int i = threadIdx.x; i < h.ge_cnt; i += NT) sq[h.e_cnt + i] = io.xq[m.ghost_e[h.ge_off + i]];
         }
         if (HAS_D && MODE == MODE_OP) {
-            for (int i = threadIdx.x; i < h.v_cnt; i += NT) sp[i] = xp[h.v_start + i];
-            for (int i = threadIdx.x; i < h.gv_cnt; i += NT) sp[h.v_cnt + i] = xp[m.ghost_v[h.gv_off + i]];
+            for (int i = threadIdx.x; i < h.v_cnt; i += NT) sp[i] = io.xp[h.v_start + i];
+            for (int i = threadIdx.x; i < h.gv_cnt; i += NT) sp[h.v_cnt + i] = io.xp[m.ghost_v[h.gv_off + i]];
         }
         __syncthreads();
         for (int lc = threadIdx.x; lc < h.n_ecells; lc += NT) {
@@ -406,9 +319,9 @@ __global__ void __launch_bounds__(NT, 2) edge_rows_k(const RowArgs a) {
             } else if (EPI == EPI_CHEB) {
                 const double bv = a.b[gid], pv = a.pinv[gid], xc = sq[le];
                 const double r_ = bv - val;
-                double xn = xc + c2 * pv * r_;
-                if (k > 0) xn += c1 * (xc - a.tq.b[(cur + 2) % 3][gid]);
-                a.tq.b[(cur + 1) % 3][gid] = xn;
+                double xn = xc + io.c2 * pv * r_;
+                if (io.use_prev) xn += io.c1 * (xc - io.xprev[gid]);
+                io.xnew[gid] = xn;
                 acc0 += pv * r_ * r_;
                 acc1 += pv * bv * bv;
             } else {
@@ -416,14 +329,168 @@ __global__ void __launch_bounds__(NT, 2) edge_rows_k(const RowArgs a) {
             }
         }
         __syncthreads();
-        if (EPI != EPI_STORE) {
-            double t0 = acc0, t1 = acc1;
-            block_sum2(t0, t1, red);
-            if (threadIdx.x == 0) { a.partials[2 * P] = t0; a.partials[2 * P + 1] = t1; }
-            acc0 = acc1 = 0.0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// last-block epilogue of the multi-launch path: deterministic sum of the per-block partials and the
+// iteration control of the Chebyshev solve
+// ------------------------------------------------------------------------------------------------
+template <int EPI>
+__device__ void finish_launch(const RowArgs& a, double acc0, double acc1, double* red) {
+    __shared__ bool is_last;
+    block_sum2(acc0, acc1, red);
+    if (threadIdx.x == 0) {
+        a.partials[2 * blockIdx.x] = acc0; a.partials[2 * blockIdx.x + 1] = acc1;
+        __threadfence();
+        unsigned int prev = atomicAdd(&a.ctl->counters[a.counter_id], 1u);
+        is_last = (prev == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    double s0 = 0.0, s1 = 0.0;
+    for (int p = threadIdx.x; p < (int)gridDim.x; p += blockDim.x) {
+        s0 += __ldcg(&a.partials[2 * p]);
+        s1 += __ldcg(&a.partials[2 * p + 1]);
+    }
+    block_sum2(s0, s1, red);
+    if (threadIdx.x == 0) {
+        Ctl* ctl = a.ctl;
+        ctl->counters[a.counter_id] = 0;
+        if (EPI == EPI_DOT) {
+            double v = s0 * a.dot_scale;
+            ctl->red[a.red_slot] = a.dot_accumulate ? ctl->red[a.red_slot] + v : v;
+        } else if (EPI == EPI_CHEB) {
+            SolveCtl& sc = ctl->sc[a.which];
+            double rr = sc.racc + s0 * a.weight;
+            double bb = sc.bacc + s1 * a.weight;
+            if (!a.finalize) { sc.racc = rr; sc.bacc = bb; }
+            else {
+                sc.racc = 0.0; sc.bacc = 0.0;
+                sc.rr = rr; sc.bb = bb;
+                double c1, c2, rho_k;
+                cheb_coeffs(sc.k, sc.rho, a.cheb_d, a.cheb_c, c1, c2, rho_k);
+                sc.rho = rho_k;
+                sc.k += 1;
+                sc.cur = (sc.cur + 1) % 3;
+                sc.iters += 1;
+                const bool conv = rr <= a.tol2 * bb;
+                if (conv || sc.k >= a.max_iter) {
+                    sc.done = 1;
+                    if (!conv) ctl->nonconv += 1;
+                    double rel = (bb > 0.0) ? sqrt(rr / bb) : 0.0;
+                    if (rel > sc.maxres) sc.maxres = rel;
+                }
+            }
         }
     }
-    if (EPI != EPI_STORE) finish_launch<EPI>(a, red);
+}
+
+template <int EPI>
+__device__ __forceinline__ bool resolve_io(const RowArgs& a, bool vertex, PassIO& io) {
+    io.xp = a.xp; io.xq = a.xq; io.xprev = nullptr; io.xnew = nullptr; io.c1 = 0.0; io.c2 = 0.0; io.use_prev = 0;
+    if (EPI == EPI_CHEB) {
+        const SolveCtl& sc = a.ctl->sc[a.which];
+        if (sc.done) return false;
+        const int cur = sc.cur, k = sc.k;
+        double rk;
+        cheb_coeffs(k, sc.rho, a.cheb_d, a.cheb_c, io.c1, io.c2, rk);
+        io.use_prev = (k > 0);
+        const TriBuf& own = vertex ? a.tp : a.tq;
+        const TriBuf& oth = vertex ? a.tq : a.tp;
+        if (vertex) { io.xp = tb_sel(own, cur); if (a.coupled_from_tribuf) io.xq = tb_sel(oth, cur); }
+        else        { io.xq = tb_sel(own, cur); if (a.coupled_from_tribuf) io.xp = tb_sel(oth, cur); }
+        io.xprev = tb_sel(own, (cur + 2) % 3);
+        io.xnew = tb_sel(own, (cur + 1) % 3);
+    }
+    return true;
+}
+
+template <int EPI, int MODE, bool HAS_M, bool HAS_D, bool CAS>
+__global__ void __launch_bounds__(NT, 2) vertex_rows_k(const RowArgs a) {
+    extern __shared__ double smem[];
+    __shared__ double red[64];
+    PassIO io;
+    if (!resolve_io<EPI>(a, true, io)) return;
+    double acc0 = 0.0, acc1 = 0.0;
+    vertex_pass<EPI, MODE, HAS_M, HAS_D, CAS>(a, io, smem, acc0, acc1);
+    if (EPI != EPI_STORE) finish_launch<EPI>(a, acc0, acc1, red);
+}
+
+template <int EPI, int MODE, bool HAS_M, bool HAS_D, bool CAS>
+__global__ void __launch_bounds__(NT, 2) edge_rows_k(const RowArgs a) {
+    extern __shared__ double smem[];
+    __shared__ double red[64];
+    PassIO io;
+    if (!resolve_io<EPI>(a, false, io)) return;
+    double acc0 = 0.0, acc1 = 0.0;
+    edge_pass<EPI, MODE, HAS_M, HAS_D, CAS>(a, io, smem, acc0, acc1);
+    if (EPI != EPI_STORE) finish_launch<EPI>(a, acc0, acc1, red);
+}
+
+// ------------------------------------------------------------------------------------------------
+// persistent cooperative solve: the whole Chebyshev iteration loop of one linear solve in ONE launch.
+// WHICH = 0: M_p x = b_p, 1: M_q x = b_q, 2: coupled block system (implicit schemes).  One grid-wide
+// barrier per iteration; the residual norm is reduced deterministically (per-block partials, summed in
+// the same order by every block) so all blocks take the same stop decision without host involvement.
+// ------------------------------------------------------------------------------------------------
+template <int WHICH, bool CAS>
+__global__ void __launch_bounds__(NT, 2) solve_coop_k(const RowArgs av, const RowArgs ae) {
+    extern __shared__ double smem[];
+    __shared__ double red[64];
+    __shared__ double bc[2];
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    const RowArgs& a0 = (WHICH == 1) ? ae : av;
+    SolveCtl& sc = a0.ctl->sc[a0.which];
+    int k = 0, cur = sc.cur;
+    double rho = 0.0, rr = 0.0, bb = 0.0;
+    bool conv = false;
+    double* partials = a0.partials;
+    while (true) {
+        PassIO iov, ioe;
+        double c1, c2, rho_k;
+        cheb_coeffs(k, rho, a0.cheb_d, a0.cheb_c, c1, c2, rho_k);
+        const int nxt = (cur + 1) % 3, prv = (cur + 2) % 3;
+        iov.xp = tb_sel(av.tp, cur); iov.xq = tb_sel(av.tq, cur); iov.xprev = tb_sel(av.tp, prv); iov.xnew = tb_sel(av.tp, nxt);
+        ioe.xp = iov.xp; ioe.xq = iov.xq; ioe.xprev = tb_sel(av.tq, prv); ioe.xnew = tb_sel(av.tq, nxt);
+        iov.c1 = ioe.c1 = c1; iov.c2 = ioe.c2 = c2; iov.use_prev = ioe.use_prev = (k > 0);
+        double r0 = 0.0, b0 = 0.0;
+        if (WHICH == 0 || WHICH == 2) {
+            double a0_ = 0.0, a1_ = 0.0;
+            vertex_pass<EPI_CHEB, MODE_OP, true, WHICH == 2, CAS>(av, iov, smem, a0_, a1_);
+            r0 += av.weight * a0_; b0 += av.weight * a1_;
+        }
+        if (WHICH == 1 || WHICH == 2) {
+            double a0_ = 0.0, a1_ = 0.0;
+            edge_pass<EPI_CHEB, MODE_OP, true, WHICH == 2, CAS>(ae, ioe, smem, a0_, a1_);
+            r0 += ae.weight * a0_; b0 += ae.weight * a1_;
+        }
+        block_sum2(r0, b0, red);
+        double* part = partials + (size_t)(k & 1) * 2 * gridDim.x;
+        if (threadIdx.x == 0) { part[2 * blockIdx.x] = r0; part[2 * blockIdx.x + 1] = b0; }
+        grid.sync();
+        if (threadIdx.x < 32) {
+            double s0 = 0.0, s1 = 0.0;
+            for (int i = threadIdx.x; i < (int)gridDim.x; i += 32) { s0 += __ldcg(&part[2 * i]); s1 += __ldcg(&part[2 * i + 1]); }
+            s0 = warp_sum(s0); s1 = warp_sum(s1);
+            if (threadIdx.x == 0) { bc[0] = s0; bc[1] = s1; }
+        }
+        __syncthreads();
+        rr = bc[0]; bb = bc[1];
+        __syncthreads();
+        rho = rho_k; k += 1; cur = nxt;
+        conv = rr <= a0.tol2 * bb;
+        if (conv || k >= a0.max_iter) break;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        sc.cur = cur; sc.k = k; sc.done = 1; sc.rr = rr; sc.bb = bb; sc.rho = rho;
+        sc.iters += k; sc.solves += 1;
+        if (!conv) a0.ctl->nonconv += 1;
+        double rel = (bb > 0.0) ? sqrt(rr / bb) : 0.0;
+        if (rel > sc.maxres) sc.maxres = rel;
+    }
 }
 
 }  // namespace phw

@@ -330,6 +330,8 @@ struct phw_solver_s {
     size_t smem_v = 0, smem_e = 0, smem_vd = 0, smem_ed = 0;
     int grid_rows = 0, sm_count = 148;
     int64_t launches = 0;
+    bool coop = false;
+    std::vector<cudaEvent_t> prof_ev; std::vector<int> prof_which;
     bool have_vq = false;      // Stormer-Verlet first-same-as-last: v_q of the previous step is valid
     phw_stats stats{};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -420,6 +422,33 @@ int op_edge_dot(phw_solver_s* s, const double* xq, double cM, double cB, int slo
     return launch_edge<EPI_DOT, MODE_OP, true, false, false>(s, a);
 }
 
+// one cooperative launch = one complete Chebyshev solve
+template <int WHICH, bool CAS>
+int launch_coop(phw_solver_s* s, const RowArgs& av, const RowArgs& ae) {
+    auto kern = solve_coop_k<WHICH, CAS>;
+    const size_t sm = (WHICH == 0) ? s->smem_v : (WHICH == 1 ? s->smem_e : s->smem_vd);
+    static bool configured = false;
+    if (!configured) { CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); configured = true; }
+    int occ = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, sm));
+    if (occ < 1) return fail(PHW_ECUDA, "cooperative solve kernel does not fit on an SM");
+    const int grid = std::max(1, std::min(s->npatch, occ * s->sm_count));
+    void* args[] = {(void*)&av, (void*)&ae};
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    const bool prof = (s->prm.flags & 4) && s->prof_ev.size() < 2 * 8192;
+    if (prof) {
+        CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+        CU(cudaEventRecord(e0, s->stream));
+    }
+    CU(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(NT), args, sm, s->stream));
+    if (prof) {
+        CU(cudaEventRecord(e1, s->stream));
+        s->prof_ev.push_back(e0); s->prof_ev.push_back(e1); s->prof_which.push_back(WHICH);
+    }
+    s->launches++;
+    return 0;
+}
+
 int solve_begin(phw_solver_s* s, int which) {
     solve_begin_k<<<1, 1, 0, s->stream>>>(s->ctl, which);
     s->launches++;
@@ -429,11 +458,17 @@ int solve_begin(phw_solver_s* s, int which) {
 
 // Chebyshev solve of M_p x = bp (which = 0) or M_q x = bq (which = 1); warm start = tribuf[cur]
 int solve_mass(phw_solver_s* s, int which, int n_launch) {
-    int rc = solve_begin(s, which);
-    if (rc) return rc;
+    int rc;
     RowArgs a = base_args(s);
     a.which = which; a.use_cheb_input = 1; a.finalize = 1; a.cM = 1.0; a.counter_id = which;
     a.cheb_d = s->cheb_d[which]; a.cheb_c = s->cheb_c[which];
+    if (s->coop) {
+        a.b = which == PHW_P ? s->bp : s->bq;
+        a.pinv = which == PHW_P ? s->pinv_p : s->pinv_q;
+        return which == PHW_P ? launch_coop<0, false>(s, a, a) : launch_coop<1, false>(s, a, a);
+    }
+    rc = solve_begin(s, which);
+    if (rc) return rc;
     for (int it = 0; it < n_launch; ++it) {
         if (which == PHW_P) { a.b = s->bp; a.pinv = s->pinv_p; rc = launch_vertex<EPI_CHEB, MODE_OP, true, false, false>(s, a); }
         else { a.b = s->bq; a.pinv = s->pinv_q; rc = launch_edge<EPI_CHEB, MODE_OP, true, false, false>(s, a); }
@@ -445,13 +480,20 @@ int solve_mass(phw_solver_s* s, int which, int n_launch) {
 // Chebyshev (ellipse) solve of the coupled block system
 //   M_p v_p + th dt K (D^T v_q + B_top v_p) = bp ;  M_q v_q - th dt/rho (D v_p - B_right v_q) = bq
 int solve_block(phw_solver_s* s, double theta, int n_launch) {
-    int rc = solve_begin(s, 2);
-    if (rc) return rc;
+    int rc;
     const double dt = s->prm.dt, K = s->prm.K_wave, rho = s->prm.rho;
     RowArgs a = base_args(s);
     a.which = 2; a.use_cheb_input = 1; a.coupled_from_tribuf = 1; a.cM = 1.0;
     a.cheb_d = s->cheb_d[2]; a.cheb_c = s->cheb_c[2];
     const bool cas = s->prm.casimir != 0;
+    if (s->coop) {
+        RowArgs av = a, ae = a;
+        av.b = s->bp; av.pinv = s->pinv_p; av.cD = theta * dt * K; av.cB = cas ? theta * dt * K : 0.0; av.weight = 1.0 / K;
+        ae.b = s->bq; ae.pinv = s->pinv_q; ae.cD = -theta * dt / rho; ae.cB = cas ? theta * dt / rho : 0.0; ae.weight = rho;
+        return cas ? launch_coop<2, true>(s, av, ae) : launch_coop<2, false>(s, av, ae);
+    }
+    rc = solve_begin(s, 2);
+    if (rc) return rc;
     for (int it = 0; it < n_launch; ++it) {
         RowArgs av = a;
         av.b = s->bp; av.pinv = s->pinv_p; av.cD = theta * dt * K; av.cB = cas ? theta * dt * K : 0.0; av.finalize = 0; av.weight = 1.0 / K; av.counter_id = 2;
@@ -822,7 +864,12 @@ static int setup_solver(phw_solver_s* s) {
     RC(s->dalloc(&s->tmp_p, nv)); RC(s->dalloc(&s->tmp_q, ne)); RC(s->dalloc(&s->pinv_p, nv)); RC(s->dalloc(&s->pinv_q, ne));
     RC(s->dalloc(&s->io_v, nv)); RC(s->dalloc(&s->io_e, ne)); RC(s->dalloc(&s->io_v2, nv)); RC(s->dalloc(&s->io_e2, ne));
     for (int i = 0; i < 3; ++i) { RC(s->dalloc(&s->tp.b[i], nv)); RC(s->dalloc(&s->tq.b[i], ne)); }
-    RC(s->dalloc(&s->partials, 2 * (size_t)s->npatch));
+    RC(s->dalloc(&s->partials, 2 * (size_t)s->npatch + 8192));
+    {
+        int coop_attr = 0;
+        CU(cudaDeviceGetAttribute(&coop_attr, cudaDevAttrCooperativeLaunch, s->device));
+        s->coop = coop_attr != 0 && !(P.flags & 8);
+    }
     RC(s->dalloc(&s->ctl, 1));
     for (double* v : {s->p, s->bp, s->tmp_p, s->tp.b[0], s->tp.b[1], s->tp.b[2], s->io_v, s->io_v2}) CU(cudaMemsetAsync(v, 0, nv * 8, s->stream));
     for (double* v : {s->q, s->bq, s->tmp_q, s->tq.b[0], s->tq.b[1], s->tq.b[2], s->io_e, s->io_e2}) CU(cudaMemsetAsync(v, 0, ne * 8, s->stream));
@@ -1057,6 +1104,14 @@ int phw_run(phw_solver_t s, int64_t n_steps, double* H_rows) {
     st.device_ms = ms;
     st.kernel_launches = s->launches;
     st.lam_min_q = s->lam_min_q; st.lam_max_q = s->lam_max_q; st.skew_bound = s->skew_bound;
+    st.ms_solve_p = st.ms_solve_q = st.ms_solve_block = 0.0;
+    for (size_t i = 0; i < s->prof_which.size(); ++i) {
+        float t = 0.f;
+        cudaEventElapsedTime(&t, s->prof_ev[2 * i], s->prof_ev[2 * i + 1]);
+        (s->prof_which[i] == 0 ? st.ms_solve_p : (s->prof_which[i] == 1 ? st.ms_solve_q : st.ms_solve_block)) += t;
+        cudaEventDestroy(s->prof_ev[2 * i]); cudaEventDestroy(s->prof_ev[2 * i + 1]);
+    }
+    s->prof_ev.clear(); s->prof_which.clear();
     {   // algorithmic bytes: per cell 40 B skew apply, 28/60 B mass apply; per dof 8 B per vector pass
         const double nc = (double)s->mesh->L.nc, nv = s->nv, ne = s->ne;
         const double it_p = (double)st.iters_p + (double)st.iters_block, it_q = (double)st.iters_q + (double)st.iters_block;
