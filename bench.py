@@ -109,6 +109,7 @@ def main():
     ap.add_argument('--patch-cells', type=int, default=2048)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--tol', type=float, default=1e-13)
+    ap.add_argument('--extrap', type=int, default=2)
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference_arm(args)
@@ -131,14 +132,23 @@ def main():
     t_setup = time.time()
     vertices, cells = rectangle_structured(args.nx, args.ny, 1.0, 0.25)
     m = Mesh(vertices, cells, patch_cells=args.patch_cells)
-    m.set_boundary(tag_boundary_edges(m, 'R', 1.0, 0.25))
+    # state and left datum of the reference's 'analytical' case (wave_2D.py:375-377,734-738): a standing wave that
+    # populates every dof, so each step updates a fully non-trivial field
+    xL, yL = 1.0, 0.25
+    omega = np.sqrt(K_WAVE / RHO) * np.sqrt(np.pi ** 2 / (4 * xL ** 2) + 4 * np.pi ** 2 / yL ** 2)
+    tags = tag_boundary_edges(m, 'R', xL, yL)
+    from porthamiltonian_fem_b200.solver import port_weights
+    m.set_boundary(tags, port_weights(m, tags, lambda x, y: RHO * omega * np.sin(2 * np.pi * y / yL + np.pi / 2)))
     dt = DT_FULL * FULL_NX / args.nx
     prm = _lib.PhwParams()
     prm.scheme, prm.dt, prm.K_wave, prm.rho = _lib.SCHEMES[args.scheme], dt, K_WAVE, RHO
-    prm.input_kind, prm.in_amp, prm.in_omega, prm.in_t_stop = _lib.IN_SINE, 10.0, 8 * np.pi, 1e30
-    prm.tol, prm.max_iter, prm.flags = args.tol, 200, 4
+    prm.input_kind, prm.in_amp, prm.in_omega = _lib.IN_COSINE, 1.0, omega
+    prm.tol, prm.max_iter, prm.flags, prm.extrap_order = args.tol, 200, 4, args.extrap
     solver = Solver(m, prm, device=local_rank)
     n_dof = m.n_vertices + m.n_edges
+    p0 = RHO * omega * np.sin(np.pi * vertices[:, 0] / (2 * xL) + np.pi / 2) * np.sin(2 * np.pi * vertices[:, 1] / yL + np.pi / 2)
+    solver.set_state(p=p0, q=np.zeros(m.n_edges), x3=np.zeros(3))
+    del p0
     setup_s = time.time() - t_setup
     del vertices, cells
 
@@ -212,10 +222,10 @@ def main():
             'metric': 'dof-updates/sec (fp64, device-timed)', 'value': value, 'unit': 'dof-updates/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dev_s / args.steps,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': '{} weak P1/RT1 wave, structured rectangle {}x{}x2 = {} cells, {} dofs per GPU, dt={:g}; '
+            'config': {'workload': '{} weak P1/RT1 wave, analytical standing-wave state and left datum (wave_2D.py:375-377,734), structured rectangle {}x{}x2 = {} cells, {} dofs per GPU, dt={:g}; '
                                    'state vectors ({:.0f} MB each) exceed L2, no flush needed'.format(
                                        args.scheme, args.nx, args.ny, nc, n_dof, dt, 8e-6 * m.n_edges),
-                       'dofs_per_gpu': n_dof, 'patch_cells': args.patch_cells, 'tol': args.tol,
+                       'dofs_per_gpu': n_dof, 'patch_cells': args.patch_cells, 'tol': args.tol, 'extrap_order': args.extrap,
                        'iters_per_solve_p': st['iters_p'] / max(1, st['solves_p']), 'iters_per_solve_q': st['iters_q'] / max(1, st['solves_q']),
                        'max_rel_residual': st['max_rel_residual'], 'setup_seconds': setup_s},
             'e2e': {'value': e2e_value, 'unit': 'dof-updates/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
@@ -226,7 +236,9 @@ def main():
                          'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': (achieved / peak) if achieved else None,
                          'traffic': None, 'peak_source': peak_src,
                          'bytes_per_launch': q_bytes / max(1, st['solves_q']), 'ms_per_launch': st['ms_solve_q'] / max(1, st['solves_q']),
-                         'whole_loop_model_gbs': st['bytes_model'] / dev_s / 1e9, 'kernel_share_of_step': st['ms_solve_q'] / st['device_ms']},
+                         'whole_loop_model_gbs': st['bytes_model'] / dev_s / 1e9, 'whole_loop_model_frac': st['bytes_model'] / dev_s / 1e9 / peak,
+                         'kernel_share_of_step': st['ms_solve_q'] / st['device_ms'], 'solve_p_share_of_step': st['ms_solve_p'] / st['device_ms'],
+                         'ms_per_iter_q': st['ms_solve_q'] / max(1, st['iters_q']), 'ms_per_iter_p': st['ms_solve_p'] / max(1, st['iters_p'])},
             'wall_s_timed_region': wall,
         }
         if not args.no_cpu_baseline:

@@ -53,6 +53,8 @@ typedef struct phw_params {
     double an_omega, an_xLength, an_yLength, an_xPoint, an_yPoint;  /* analytical case constants */
     double tol;              /* relative residual of the mass / block solves (default 1e-13) */
     int32_t max_iter;        /* iteration cap per solve (default 200) */
+    int32_t extrap_order;    /* initial guess of each solve = polynomial extrapolation of that solve's previous
+                                solutions: 0 last solution, 1 linear, 2 quadratic (default choice of the host code), 3 cubic */
     int32_t flags;           /* bit0: disable first-same-as-last reuse in SV; bit1: synchronous error checks;
                                 bit2: CUDA-event timing of every solve kernel; bit3: force the multi-launch solve path */
 } phw_params;

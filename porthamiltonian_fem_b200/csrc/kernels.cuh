@@ -46,12 +46,13 @@ struct Ctl {
 struct DevMesh {
     int npatch, nv, ne;
     const PatchHdr* hdr;
-    const uint4* rec;
+    const uint2* recv;   // vertex half of the cell record: lv0|lv1<<16, lv2|flags<<16
+    const uint2* rece;   // edge half: le0|le1<<16, le2
     const double* area;
     const double* g0; const double* g1; const double* g2;
     const int* ghost_v; const int* ghost_e;
     const uint32_t* eadj;
-    const uint32_t* vadj_off;
+    const uint32_t* vslice_off;
     const uint16_t* vadj;
 };
 
@@ -71,6 +72,7 @@ struct RowArgs {
     // CHEB
     const double* b;
     const double* pinv;
+    const double* mdiag;     // pure P1 mass diagonal sum_K |K|/6 (nullptr: use 1/pinv)
     double cheb_d, cheb_c;   // centre and focal distance of the spectrum ellipse
     double tol2, weight;
     int which;               // SolveCtl index
@@ -137,12 +139,15 @@ __device__ __forceinline__ double* tb_sel(const TriBuf& t, int i) { return i == 
 template <int EPI, int MODE, bool HAS_M, bool HAS_D, bool CAS>
 __device__ __forceinline__ void vertex_pass(const RowArgs& a, const PassIO& io, double* smem, double& acc0, double& acc1) {
     const DevMesh& m = a.m;
+    // pure P1 mass rows: (M_p x)_v = sum_K (|K|/12) sum(x_K) + x_v * diag_v / 2, diag_v = sum_K |K|/6 = 1/pinv_v,
+    // so one value per cell suffices (a.pinv must be set)
+    constexpr bool ONEVAL = HAS_M && !HAS_D && !CAS && MODE == MODE_OP;
     for (int P = blockIdx.x; P < m.npatch; P += gridDim.x) {
         const PatchHdr h = m.hdr[P];
         const int nlv = h.v_cnt + h.gv_cnt, nle = h.e_cnt + h.ge_cnt;
         double* sp = smem;                         // [nlv]
         double* sq = sp + ((nlv + 1) & ~1);        // [nle] (only if HAS_D)
-        double* sc3 = HAS_D ? sq + ((nle + 1) & ~1) : sq;   // [3*n_vcells]
+        double* sc3 = HAS_D ? sq + ((nle + 1) & ~1) : sq;   // [CW*n_vcells]
         // ---- stage 1: local inputs
         if (MODE == MODE_OP && (HAS_M || CAS || EPI != EPI_STORE)) {
             for (int i = threadIdx.x; i < h.v_cnt; i += NT) sp[i] = io.xp[h.v_start + i];
@@ -154,27 +159,45 @@ __device__ __forceinline__ void vertex_pass(const RowArgs& a, const PassIO& io, 
         }
         __syncthreads();
         // ---- stage 2: per-cell contributions to its three vertices
-        for (int lc = threadIdx.x; lc < h.n_vcells; lc += NT) {
-            const uint4 r = __ldg(&m.rec[h.cell_off + lc]);
+        if (ONEVAL) {
+            // batched: issue the loads of U cells before consuming them (memory-level parallelism)
+            constexpr int U = 3;
+            for (int base = threadIdx.x; base < h.n_vcells; base += U * NT) {
+                uint2 rvb[U]; double Ab[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int lc = base + u * NT;
+                    if (lc < h.n_vcells) { rvb[u] = __ldg(&m.recv[h.cell_off + lc]); Ab[u] = __ldg(&m.area[h.cell_off + lc]); }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int lc = base + u * NT;
+                    if (lc < h.n_vcells)
+                        sc3[lc] = a.cM * Ab[u] * (1.0 / 12.0) * (sp[rvb[u].x & 0xFFFFu] + sp[rvb[u].x >> 16] + sp[rvb[u].y & 0xFFFFu]);
+                }
+            }
+        }
+        for (int lc = threadIdx.x; lc < (ONEVAL ? 0 : h.n_vcells); lc += NT) {
+            const uint2 rv = __ldg(&m.recv[h.cell_off + lc]);
             double v0 = 0.0, v1 = 0.0, v2 = 0.0;
             if (HAS_M || CAS) {
                 const double A = __ldg(&m.area[h.cell_off + lc]);
                 if (MODE == MODE_DIAG) {
                     v0 = v1 = v2 = a.cM * A * (1.0 / 6.0);
                     if (CAS) {
-                        const uint32_t fl = r.y >> 16;
+                        const uint32_t fl = rv.y >> 16;
                         if (fl & 1u) { const double d = a.cB * sqrt(48.0 * A * __ldg(&m.g0[h.cell_off + lc])) * (1.0 / 3.0); v1 += d; v2 += d; }
                         if (fl & 2u) { const double d = a.cB * sqrt(48.0 * A * __ldg(&m.g1[h.cell_off + lc])) * (1.0 / 3.0); v0 += d; v2 += d; }
                         if (fl & 4u) { const double d = a.cB * sqrt(48.0 * A * __ldg(&m.g2[h.cell_off + lc])) * (1.0 / 3.0); v0 += d; v1 += d; }
                     }
                 } else {
-                    const double x0 = sp[r.x & 0xFFFFu], x1 = sp[r.x >> 16], x2 = sp[r.y & 0xFFFFu];
+                    const double x0 = sp[rv.x & 0xFFFFu], x1 = sp[rv.x >> 16], x2 = sp[rv.y & 0xFFFFu];
                     if (HAS_M) {
                         const double w = a.cM * A * (1.0 / 12.0), s = x0 + x1 + x2;
                         v0 = w * (s + x0); v1 = w * (s + x1); v2 = w * (s + x2);
                     }
                     if (CAS) {
-                        const uint32_t fl = r.y >> 16;
+                        const uint32_t fl = rv.y >> 16;
                         if (fl & 7u) {   // impedance top side: P1 edge mass |e|/6 [2 1; 1 2]  (wave_2D.py:330,476)
                             const double gg[3] = {__ldg(&m.g0[h.cell_off + lc]), __ldg(&m.g1[h.cell_off + lc]), __ldg(&m.g2[h.cell_off + lc])};
                             const double xx[3] = {x0, x1, x2};
@@ -193,7 +216,8 @@ __device__ __forceinline__ void vertex_pass(const RowArgs& a, const PassIO& io, 
                 }
             }
             if (HAS_D && MODE == MODE_OP) {
-                const uint32_t e0 = r.z & 0xFFFFu, e1 = r.z >> 16, e2 = r.w & 0xFFFFu;
+                const uint2 re = __ldg(&m.rece[h.cell_off + lc]);
+                const uint32_t e0 = re.x & 0xFFFFu, e1 = re.x >> 16, e2 = re.y & 0xFFFFu;
                 const double t0 = (e0 & 0x8000u) ? -sq[e0 & 0x3FFFu] : sq[e0 & 0x3FFFu];
                 const double t1 = (e1 & 0x8000u) ? -sq[e1 & 0x3FFFu] : sq[e1 & 0x3FFFu];
                 const double t2 = (e2 & 0x8000u) ? -sq[e2 & 0x3FFFu] : sq[e2 & 0x3FFFu];
@@ -208,26 +232,48 @@ __device__ __forceinline__ void vertex_pass(const RowArgs& a, const PassIO& io, 
             sc3[3 * lc] = v0; sc3[3 * lc + 1] = v1; sc3[3 * lc + 2] = v2;
         }
         __syncthreads();
-        // ---- stage 3: owned rows, fixed summation order, fused epilogue
-        for (int lv = threadIdx.x; lv < h.v_cnt; lv += NT) {
-            const int gid = h.v_start + lv;
-            const uint32_t o0 = m.vadj_off[gid], o1 = m.vadj_off[gid + 1];
-            double val = 0.0;
-            for (uint32_t o = o0; o < o1; ++o) {
-                const uint32_t code = m.vadj[o];
-                val += sc3[3 * (code >> 2) + (code & 3u)];
+        // ---- stage 3: owned rows (sliced-ELL adjacency, 8 codes per 16-byte load, warp-uniform trip count),
+        //      fixed summation order, fused epilogue; streaming operands are requested before the reduction
+        const int vround = (h.v_cnt + 31) & ~31;
+        const uint4* adj4 = reinterpret_cast<const uint4*>(m.vadj);
+        for (int lv = threadIdx.x; lv < vround; lv += NT) {
+            const uint32_t o0 = m.vslice_off[h.vs_off + (lv >> 5)], o1 = m.vslice_off[h.vs_off + (lv >> 5) + 1];
+            const bool live = lv < h.v_cnt;
+            const int gid = h.v_start + (live ? lv : 0);
+            double bv = 0.0, pv = 0.0, xpv = 0.0, dgv = 0.0;
+            if (EPI == EPI_CHEB && live) {
+                bv = a.b[gid]; pv = a.pinv[gid];
+                if (io.use_prev) xpv = io.xprev[gid];
+                if (ONEVAL && a.mdiag) dgv = a.mdiag[gid];
             }
+            if (EPI != EPI_CHEB && ONEVAL && live) dgv = a.mdiag[gid];
+            double val = 0.0;
+            const uint32_t nchunk = (o1 - o0) >> 8;            // 32 lanes * 8 codes per chunk
+            for (uint32_t k = 0; k < nchunk; ++k) {
+                const uint4 cd = __ldg(&adj4[(o0 >> 3) + k * 32 + (lv & 31)]);
+                const uint32_t w4[4] = {cd.x, cd.y, cd.z, cd.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t c0 = w4[j] & 0xFFFFu, c1 = w4[j] >> 16;
+                    if (c0 != 0xFFFFu) val += ONEVAL ? sc3[c0 >> 2] : sc3[3 * (c0 >> 2) + (c0 & 3u)];
+                    if (c1 != 0xFFFFu) val += ONEVAL ? sc3[c1 >> 2] : sc3[3 * (c1 >> 2) + (c1 & 3u)];
+                }
+            }
+            if (!live) continue;
             if (EPI == EPI_STORE) {
+                if (ONEVAL) val += 0.5 * a.cM * sp[lv] * dgv;
                 a.y[gid] = val;
             } else if (EPI == EPI_CHEB) {
-                const double bv = a.b[gid], pv = a.pinv[gid], xc = sp[lv];
+                const double xc = sp[lv];
+                if (ONEVAL) val += 0.5 * a.cM * xc * (a.mdiag ? dgv : 1.0 / pv);
                 const double r_ = bv - val;
                 double xn = xc + io.c2 * pv * r_;
-                if (io.use_prev) xn += io.c1 * (xc - io.xprev[gid]);
+                if (io.use_prev) xn += io.c1 * (xc - xpv);
                 io.xnew[gid] = xn;
                 acc0 += pv * r_ * r_;
                 acc1 += pv * bv * bv;
             } else {
+                if (ONEVAL) val += 0.5 * a.cM * sp[lv] * dgv;
                 acc0 += sp[lv] * val;
             }
         }
@@ -257,8 +303,10 @@ __device__ __forceinline__ void edge_pass(const RowArgs& a, const PassIO& io, do
         }
         __syncthreads();
         for (int lc = threadIdx.x; lc < h.n_ecells; lc += NT) {
-            const uint4 r = __ldg(&m.rec[h.cell_off + lc]);
-            const uint32_t e0 = r.z & 0xFFFFu, e1 = r.z >> 16, e2 = r.w & 0xFFFFu;
+            const uint2 re = __ldg(&m.rece[h.cell_off + lc]);
+            uint2 rv = make_uint2(0u, 0u);
+            if (HAS_D || CAS) rv = __ldg(&m.recv[h.cell_off + lc]);
+            const uint32_t e0 = re.x & 0xFFFFu, e1 = re.x >> 16, e2 = re.y & 0xFFFFu;
             const double s0 = (e0 & 0x8000u) ? -1.0 : 1.0, s1 = (e1 & 0x8000u) ? -1.0 : 1.0, s2 = (e2 & 0x8000u) ? -1.0 : 1.0;
             double v0 = 0.0, v1 = 0.0, v2 = 0.0;
             if (HAS_M || CAS) {
@@ -267,7 +315,7 @@ __device__ __forceinline__ void edge_pass(const RowArgs& a, const PassIO& io, do
                 if (MODE == MODE_DIAG) {
                     v0 = a.cM * (3.0 * S - 4.0 * g0); v1 = a.cM * (3.0 * S - 4.0 * g1); v2 = a.cM * (3.0 * S - 4.0 * g2);
                     if (CAS) {
-                        const uint32_t fl = (r.y >> 16) >> 3;
+                        const uint32_t fl = (rv.y >> 16) >> 3;
                         if (fl & 7u) {
                             const double A = __ldg(&m.area[h.cell_off + lc]);
                             if (fl & 1u) v0 += a.cB * rsqrt(48.0 * A * g0);
@@ -286,7 +334,7 @@ __device__ __forceinline__ void edge_pass(const RowArgs& a, const PassIO& io, do
                         v2 = a.cM * s2 * (ST + 2.0 * S * t2 - 4.0 * (g1 * t0 + g0 * t1 + g2 * t2));
                     }
                     if (CAS) {
-                        const uint32_t fl = (r.y >> 16) >> 3;
+                        const uint32_t fl = (rv.y >> 16) >> 3;
                         if (fl & 7u) {   // impedance right side: <phi_e.n, phi_e.n> = 1/|e|   (wave_2D.py:350,482)
                             const double A = __ldg(&m.area[h.cell_off + lc]);
                             if (fl & 1u) v0 += a.cB * q0 * rsqrt(48.0 * A * g0);
@@ -297,7 +345,7 @@ __device__ __forceinline__ void edge_pass(const RowArgs& a, const PassIO& io, do
                 }
             }
             if (HAS_D && MODE == MODE_OP) {
-                const double p0 = sp[r.x & 0xFFFFu], p1 = sp[r.x >> 16], p2 = sp[r.y & 0xFFFFu];
+                const double p0 = sp[rv.x & 0xFFFFu], p1 = sp[rv.x >> 16], p2 = sp[rv.y & 0xFFFFu];
                 const double third = (p0 + p1 + p2) * (1.0 / 3.0);
                 double d0 = third, d1 = third, d2 = third;
                 if (e0 & 0x4000u) d0 -= 0.5 * (p1 + p2);
@@ -311,16 +359,18 @@ __device__ __forceinline__ void edge_pass(const RowArgs& a, const PassIO& io, do
         for (int le = threadIdx.x; le < h.e_cnt; le += NT) {
             const int gid = h.e_start + le;
             const uint32_t adj = m.eadj[gid];
+            double bv = 0.0, pv = 0.0, xpv = 0.0;
+            if (EPI == EPI_CHEB) { bv = a.b[gid]; pv = a.pinv[gid]; if (io.use_prev) xpv = io.xprev[gid]; }
             const uint32_t ca = adj & 0xFFFFu, cb = adj >> 16;
             double val = sc3[3 * (ca >> 2) + (ca & 3u)];
             if (cb != 0xFFFFu) val += sc3[3 * (cb >> 2) + (cb & 3u)];
             if (EPI == EPI_STORE) {
                 a.y[gid] = val;
             } else if (EPI == EPI_CHEB) {
-                const double bv = a.b[gid], pv = a.pinv[gid], xc = sq[le];
+                const double xc = sq[le];
                 const double r_ = bv - val;
                 double xn = xc + io.c2 * pv * r_;
-                if (io.use_prev) xn += io.c1 * (xc - io.xprev[gid]);
+                if (io.use_prev) xn += io.c1 * (xc - xpv);
                 io.xnew[gid] = xn;
                 acc0 += pv * r_ * r_;
                 acc1 += pv * bv * bv;

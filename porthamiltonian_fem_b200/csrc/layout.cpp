@@ -170,22 +170,37 @@ std::string Layout::build(int64_t nv_, const double* vxy, int64_t nc_, const int
     }
     for (int64_t v = 0; v < nv; ++v)
         if (v_owner[v] == std::numeric_limits<int32_t>::max()) return "unreferenced vertex in mesh";
-    auto renumber = [&](const std::vector<int32_t>& owner, int64_t n, std::vector<int32_t>& new2old,
-                        std::vector<int32_t>& old2new, std::vector<int32_t>& pstart) {
+    v_degree.assign(nv, 0);
+    for (int64_t h = 0; h < 3 * nc; ++h) v_degree[cells[h]]++;
+    // new id = rank by (owner, -degree, old id): stable counting sorts, least significant key first
+    auto renumber = [&](const std::vector<int32_t>& owner, const std::vector<int32_t>* degree, int64_t n,
+                        std::vector<int32_t>& new2old, std::vector<int32_t>& old2new, std::vector<int32_t>& pstart) {
+        std::vector<int32_t> order(n);
+        if (degree) {
+            int32_t dmax = 0;
+            for (int64_t i = 0; i < n; ++i) dmax = std::max(dmax, (*degree)[i]);
+            std::vector<int64_t> cnt(dmax + 2, 0);
+            for (int64_t i = 0; i < n; ++i) cnt[dmax - (*degree)[i] + 1]++;
+            for (int32_t d = 0; d <= dmax; ++d) cnt[d + 1] += cnt[d];
+            for (int64_t i = 0; i < n; ++i) order[cnt[dmax - (*degree)[i]]++] = (int32_t)i;
+        } else {
+            for (int64_t i = 0; i < n; ++i) order[i] = (int32_t)i;
+        }
         pstart.assign(npatch + 1, 0);
         for (int64_t i = 0; i < n; ++i) pstart[owner[i] + 1]++;
         for (int32_t p = 0; p < npatch; ++p) pstart[p + 1] += pstart[p];
         std::vector<int32_t> pos(pstart.begin(), pstart.end() - 1);
         new2old.resize(n); old2new.resize(n);
-        for (int64_t i = 0; i < n; ++i) {
+        for (int64_t k = 0; k < n; ++k) {
+            int32_t i = order[k];
             int32_t d = pos[owner[i]]++;
-            new2old[d] = (int32_t)i;
+            new2old[d] = i;
             old2new[i] = d;
         }
     };
     std::vector<int32_t> vstart, estart;
-    renumber(v_owner, nv, v_new2old, v_old2new, vstart);
-    renumber(e_owner, ne, e_new2old, e_old2new, estart);
+    renumber(v_owner, &v_degree, nv, v_new2old, v_old2new, vstart);
+    renumber(e_owner, nullptr, ne, e_new2old, e_old2new, estart);
     // ---- 5. halo cells: (patch, cell, type) type 0 = adjacent to an owned edge, 1 = only to an owned vertex
     std::vector<uint64_t> halo;
     for (int64_t c = 0; c < nc; ++c) {
@@ -209,9 +224,10 @@ std::string Layout::build(int64_t nv_, const double* vxy, int64_t nc_, const int
     pcell_user.clear(); pc_lv.clear(); pc_le.clear(); ghost_v.clear(); ghost_e.clear();
     pcell_user.reserve(nc + halo.size());
     eadj.assign(ne, 0xFFFFFFFFu);
-    vadj_off.assign(nv + 1, 0);
+    vslice_off.clear();
+    vslice_off.push_back(0);
     vadj.clear();
-    vadj.reserve(3 * nc + 3 * halo.size());
+    vadj.reserve(4 * nc + 4 * halo.size());
     std::vector<int32_t> lv_of(nv, -1), le_of(ne, -1);
     std::vector<int32_t> gv_tmp, ge_tmp, cl;
     std::vector<uint32_t> vcnt;
@@ -274,19 +290,28 @@ std::string Layout::build(int64_t nv_, const double* vxy, int64_t nc_, const int
                 }
             }
         }
-        // vertex CSR (entries ascending in lc)
-        for (int32_t k = 0; k < H.v_cnt; ++k) vcnt[k + 1] += vcnt[k];
+        // vertex adjacency as sliced ELL (entries of a vertex ascending in lc -> fixed summation order)
+        H.vs_off = (int32_t)(vslice_off.size() - 1);
+        const int32_t nslice = (H.v_cnt + 31) / 32;
         size_t base = vadj.size();
-        vadj.resize(base + vcnt[H.v_cnt]);
-        for (int32_t k = 0; k < H.v_cnt; ++k) vadj_off[H.v_start + k] = (uint32_t)(base + vcnt[k]);
-        std::vector<uint32_t> fill(vcnt.begin(), vcnt.end() - 1);
+        std::vector<size_t> sbase(nslice + 1, 0);
+        for (int32_t sl = 0; sl < nslice; ++sl) {
+            uint32_t w = 0;
+            for (int32_t k = 32 * sl; k < std::min(32 * (sl + 1), H.v_cnt); ++k) w = std::max(w, vcnt[k + 1]);
+            w = (w + 7u) & ~7u;                    // chunks of 8 codes = one 16-byte load per vertex
+            sbase[sl + 1] = sbase[sl] + (size_t)w * 32;
+            vslice_off.push_back((uint32_t)(base + sbase[sl + 1]));
+        }
+        vadj.resize(base + sbase[nslice], (uint16_t)0xFFFFu);
+        std::vector<uint32_t> fill(H.v_cnt, 0);
         for (size_t lc = 0; lc < cl.size(); ++lc) {
             int64_t c = cl[lc];
             for (int i = 0; i < 3; ++i) {
                 int32_t v = cells[3 * c + i];
                 if (v_owner[v] == p) {
                     int32_t lv = v_old2new[v] - H.v_start;
-                    vadj[base + fill[lv]++] = (uint16_t)(lc * 4 + i);
+                    const uint32_t j = fill[lv]++;
+                    vadj[base + sbase[lv / 32] + ((size_t)(j / 8) * 32 + (lv % 32)) * 8 + (j % 8)] = (uint16_t)(lc * 4 + i);
                 }
             }
         }
@@ -294,7 +319,6 @@ std::string Layout::build(int64_t nv_, const double* vxy, int64_t nc_, const int
         for (int32_t g : gv_tmp) lv_of[v_new2old[g]] = -1;
         for (int32_t g : ge_tmp) le_of[e_new2old[g]] = -1;
     }
-    vadj_off[nv] = (uint32_t)vadj.size();
     if (vadj.size() >= ((size_t)1 << 32)) return "vertex adjacency exceeds 32-bit offsets";
     return "";
 }

@@ -21,7 +21,7 @@ namespace phw {
 // ds(1), ds(3); every boundary edge in the strong form), bit 15: orientation sign is -1.
 // flags bits (y>>16): 0..2 slot i lies on the impedance top side (casimir, tag 1),
 //                     3..5 slot i lies on the impedance right side (casimir, tag 2).
-struct CellRec { uint32_t x, y, z, w; };
+struct CellRec { uint32_t x, y, z, w; };   // (x,y) = vertex half, (z,w) = edge half; stored as two uint2 arrays on the device
 
 struct PatchHdr {
     int32_t cell_off;   // first entry in the patch-cell arrays
@@ -30,6 +30,8 @@ struct PatchHdr {
     int32_t n_vcells;   // cells processed by vertex-row operators (all)
     int32_t v_start, v_cnt, gv_off, gv_cnt;   // owned vertex range (new numbering), ghost list
     int32_t e_start, e_cnt, ge_off, ge_cnt;   // owned edge range, ghost list
+    int32_t vs_off;     // first 32-vertex slice of this patch in vslice_off
+    int32_t pad[3];
 };
 
 struct Layout {
@@ -56,8 +58,13 @@ struct Layout {
     std::vector<uint16_t> pc_le;       // [npc,3] local edge ids (no flag bits)
     std::vector<int32_t> ghost_v, ghost_e;     // new ids
     std::vector<uint32_t> eadj;        // [ne] by new id: (lc*4+slot) | (lc*4+slot)<<16, 0xFFFF = none
-    std::vector<uint32_t> vadj_off;    // [nv+1] by new id
-    std::vector<uint16_t> vadj;        // lc*4+slot
+    // vertex -> (cell,slot) adjacency as sliced ELL: owned vertices are sorted by degree inside a patch and
+    // grouped in slices of 32; slice s stores ceil(width_s/8) chunks, chunk k holding 8 codes (lc*4+slot,
+    // 0xFFFF = padding) for each of the 32 vertices: [chunk][lane][8] -> one coalesced 16-byte load per vertex
+    // and chunk, warp-uniform trip count.
+    std::vector<uint32_t> vslice_off;  // [n_slices+1] offsets into vadj
+    std::vector<uint16_t> vadj;
+    std::vector<int32_t> v_degree;     // [nv] by old id
     int32_t max_lv = 0, max_le = 0, max_cells = 0;
 
     std::string build(int64_t nv_, const double* vxy, int64_t nc_, const int32_t* cells_, int32_t patch_cells_);

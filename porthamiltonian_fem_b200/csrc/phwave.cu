@@ -108,6 +108,19 @@ __global__ void axpy_dev_k(int n, TriBuf tb, const Ctl* ctl, int which, const do
     const double a = *coef;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) y[i] += a * w[i];
 }
+// x0 = sum_j c_j hist_j : polynomial extrapolation of the previous solutions of the same solve site,
+// written into the current Chebyshev buffer (initial guess only - the accepted solution still has to meet tol)
+__global__ void predict_k(int n, TriBuf tb, const Ctl* ctl, int which, const double* h0, const double* h1, const double* h2,
+                          const double* h3, double c0, double c1, double c2, double c3, int m) {
+    double* x = tb.b[ctl->sc[which].cur];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        double v = c0 * h0[i];
+        if (m > 1) v += c1 * h1[i];
+        if (m > 2) v += c2 * h2[i];
+        if (m > 3) v += c3 * h3[i];
+        x[i] = v;
+    }
+}
 __global__ void copy_from_tb_k(int n, double* dst, TriBuf tb, const Ctl* ctl, int which) {
     const double* xs = tb.b[ctl->sc[which].cur];
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = xs[i];
@@ -318,7 +331,7 @@ struct phw_solver_s {
     int *d_v_new2old = nullptr, *d_e_new2old = nullptr;
     int* d_port_e = nullptr; double* d_port_bl = nullptr;
     double *p = nullptr, *q = nullptr, *bp = nullptr, *bq = nullptr, *tmp_p = nullptr, *tmp_q = nullptr;
-    double *pinv_p = nullptr, *pinv_q = nullptr, *wp = nullptr, *wq = nullptr;
+    double *pinv_p = nullptr, *pinv_q = nullptr, *mdiag_p = nullptr, *wp = nullptr, *wq = nullptr;
     double *io_v = nullptr, *io_e = nullptr, *io_v2 = nullptr, *io_e2 = nullptr;
     TriBuf tp{}, tq{};
     double* partials = nullptr;
@@ -327,9 +340,12 @@ struct phw_solver_s {
     ScalarPrm sp{};
     double lam_min_q = 0.5, lam_max_q = 2.0, skew_bound = 0.0, blw = 0.0;
     double cheb_d[3] = {1.25, 1.25, 1.25}, cheb_c[3] = {0.75, 0.75, 0.75};
-    size_t smem_v = 0, smem_e = 0, smem_vd = 0, smem_ed = 0;
+    size_t smem_v = 0, smem_v1 = 0, smem_e = 0, smem_vd = 0, smem_ed = 0;
     int grid_rows = 0, sm_count = 148;
     int64_t launches = 0;
+    struct Hist { double* h[4] = {nullptr, nullptr, nullptr, nullptr}; int count = 0, head = 0; };
+    Hist hist[2][2];           // [field p/q][solve site]
+    int extrap = 2, n_sites = 1;
     bool coop = false;
     std::vector<cudaEvent_t> prof_ev; std::vector<int> prof_which;
     bool have_vq = false;      // Stormer-Verlet first-same-as-last: v_q of the previous step is valid
@@ -361,7 +377,7 @@ inline int vec_grid(phw_solver_s* s, int n) { return std::max(1, std::min(nblk(n
 // ---- typed launchers for the row kernels -------------------------------------------------------
 template <int EPI, int MODE, bool HAS_M, bool HAS_D, bool CAS>
 int launch_vertex(phw_solver_s* s, const RowArgs& a) {
-    size_t sm = HAS_D ? s->smem_vd : s->smem_v;
+    size_t sm = HAS_D ? s->smem_vd : ((HAS_M && !CAS && MODE == MODE_OP) ? s->smem_v1 : s->smem_v);
     auto kern = vertex_rows_k<EPI, MODE, HAS_M, HAS_D, CAS>;
     static bool configured = false;
     if (!configured) { CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); configured = true; }
@@ -388,6 +404,7 @@ RowArgs base_args(phw_solver_s* s) {
     a.partials = s->partials; a.ctl = s->ctl;
     a.tol2 = s->prm.tol * s->prm.tol; a.max_iter = s->prm.max_iter; a.weight = 1.0;
     a.dot_scale = 1.0;
+    a.mdiag = s->mdiag_p;   // vertex M-only rows use the pure P1 mass diagonal
     return a;
 }
 
@@ -426,7 +443,7 @@ int op_edge_dot(phw_solver_s* s, const double* xq, double cM, double cB, int slo
 template <int WHICH, bool CAS>
 int launch_coop(phw_solver_s* s, const RowArgs& av, const RowArgs& ae) {
     auto kern = solve_coop_k<WHICH, CAS>;
-    const size_t sm = (WHICH == 0) ? s->smem_v : (WHICH == 1 ? s->smem_e : s->smem_vd);
+    const size_t sm = (WHICH == 0) ? s->smem_v1 : (WHICH == 1 ? s->smem_e : s->smem_vd);
     static bool configured = false;
     if (!configured) { CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); configured = true; }
     int occ = 0;
@@ -462,6 +479,7 @@ int solve_mass(phw_solver_s* s, int which, int n_launch) {
     RowArgs a = base_args(s);
     a.which = which; a.use_cheb_input = 1; a.finalize = 1; a.cM = 1.0; a.counter_id = which;
     a.cheb_d = s->cheb_d[which]; a.cheb_c = s->cheb_c[which];
+    if (!(s->prm.casimir && (s->prm.scheme == PHW_IE || s->prm.scheme == PHW_SM))) a.mdiag = nullptr;   // pinv_p is then exactly 1/mdiag_p
     if (s->coop) {
         a.b = which == PHW_P ? s->bp : s->bq;
         a.pinv = which == PHW_P ? s->pinv_p : s->pinv_q;
@@ -557,20 +575,67 @@ int energy(phw_solver_s* s) {
 
 int n_iter_launch(phw_solver_s* s) { return s->prm.max_iter; }
 
+// initial guess of a solve from the history of its site (field 0 = p unknown, 1 = q unknown)
+int predict(phw_solver_s* s, int field, int site, int which) {
+    phw_solver_s::Hist& H = s->hist[field][site];
+    const int order = s->extrap + 1;
+    const int m = std::min(H.count, order);
+    if (m <= 0 || !H.h[0]) return 0;
+    static const double C[4][4] = {{1, 0, 0, 0}, {2, -1, 0, 0}, {3, -3, 1, 0}, {4, -6, 4, -1}};
+    const double* hp[4];
+    for (int j = 0; j < 4; ++j) hp[j] = H.h[((H.head - j) % order + order) % order];
+    const int n = field == 0 ? s->nv : s->ne;
+    predict_k<<<vec_grid(s, n), 256, 0, s->stream>>>(n, field == 0 ? s->tp : s->tq, s->ctl, which, hp[0], hp[1], hp[2], hp[3],
+                                                      C[m - 1][0], C[m - 1][1], C[m - 1][2], C[m - 1][3], m);
+    s->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+int remember(phw_solver_s* s, int field, int site, int which) {
+    phw_solver_s::Hist& H = s->hist[field][site];
+    if (!H.h[0]) return 0;
+    const int order = s->extrap + 1;
+    H.head = (H.head + 1) % order;
+    H.count = std::min(H.count + 1, order);
+    const int n = field == 0 ? s->nv : s->ne;
+    copy_from_tb_k<<<vec_grid(s, n), 256, 0, s->stream>>>(n, H.h[H.head], field == 0 ? s->tp : s->tq, s->ctl, which);
+    s->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+int solve_site(phw_solver_s* s, int which, int site) {
+    int rc = predict(s, which, site, which);
+    if (rc) return rc;
+    rc = solve_mass(s, which, s->prm.max_iter);
+    if (rc) return rc;
+    return remember(s, which, site, which);
+}
+int solve_block_site(phw_solver_s* s, double theta) {
+    int rc = predict(s, 0, 0, 2); if (rc) return rc;
+    rc = predict(s, 1, 0, 2); if (rc) return rc;
+    rc = solve_block(s, theta, s->prm.max_iter); if (rc) return rc;
+    rc = remember(s, 0, 0, 2); if (rc) return rc;
+    return remember(s, 1, 0, 2);
+}
+void reset_history(phw_solver_s* s) {
+    for (int f = 0; f < 2; ++f)
+        for (int k = 0; k < 2; ++k) { s->hist[f][k].count = 0; s->hist[f][k].head = 0; }
+    s->have_vq = false;
+}
+
 // ---- one time step of each scheme (wave_2D.py:787-982) ------------------------------------------
 int step(phw_solver_s* s) {
     const double dt = s->prm.dt;
     const int nv = s->nv, ne = s->ne;
     const bool ic = s->prm.interconnection != 0;
-    const int NL = n_iter_launch(s);
     int rc = 0;
 #define RC(x) do { rc = (x); if (rc) return rc; } while (0)
     switch (s->prm.scheme) {
         case PHW_EE:
             RC(scalar(s, S_BEGIN_1SUB));
             RC(flux(s, s->q, 1, 0));
-            RC(rhs_p(s, s->q, s->p)); RC(solve_mass(s, PHW_P, NL));
-            RC(rhs_q(s, s->p, s->q)); RC(solve_mass(s, PHW_Q, NL));
+            RC(rhs_p(s, s->q, s->p)); RC(solve_site(s, PHW_P, 0));
+            RC(rhs_q(s, s->p, s->q)); RC(solve_site(s, PHW_Q, 0));
             RC(axpy(s, nv, s->p, dt, nullptr, s->tp, 0));
             RC(axpy(s, ne, s->q, dt, nullptr, s->tq, 1));
             RC(energy(s));
@@ -579,24 +644,24 @@ int step(phw_solver_s* s) {
         case PHW_SE:
             RC(scalar(s, S_BEGIN_1SUB));
             RC(flux(s, s->q, 1, 0));
-            RC(rhs_p(s, s->q, s->p)); RC(solve_mass(s, PHW_P, NL));
+            RC(rhs_p(s, s->q, s->p)); RC(solve_site(s, PHW_P, 0));
             RC(axpy(s, nv, s->p, dt, nullptr, s->tp, 0));
             if (ic) RC(scalar(s, S_ODE_SE));
-            RC(rhs_q(s, s->p, s->q)); RC(solve_mass(s, PHW_Q, NL));
+            RC(rhs_q(s, s->p, s->q)); RC(solve_site(s, PHW_Q, 0));
             RC(axpy(s, ne, s->q, dt, nullptr, s->tq, 1));
             RC(energy(s));
             RC(scalar(s, S_END_1SUB));
             break;
         case PHW_SV:
             RC(scalar(s, S_SV_STAGE1));
-            if (!s->have_vq || (s->prm.flags & 1)) { RC(rhs_q(s, s->p, s->q)); RC(solve_mass(s, PHW_Q, NL)); }
+            if (!s->have_vq || (s->prm.flags & 1)) { RC(rhs_q(s, s->p, s->q)); RC(solve_site(s, PHW_Q, 0)); }
             RC(axpy(s, ne, s->q, 0.5 * dt, nullptr, s->tq, 1));       // q_temp
             RC(flux(s, s->q, 1, 0));
             RC(scalar(s, S_SV_MID));
-            RC(rhs_p(s, s->q, s->p)); RC(solve_mass(s, PHW_P, NL));
+            RC(rhs_p(s, s->q, s->p)); RC(solve_site(s, PHW_P, 0));
             RC(axpy(s, nv, s->p, dt, nullptr, s->tp, 0));
             if (ic) RC(scalar(s, S_ODE_SV));
-            RC(rhs_q(s, s->p, s->q)); RC(solve_mass(s, PHW_Q, NL));
+            RC(rhs_q(s, s->p, s->q)); RC(solve_site(s, PHW_Q, 0));
             RC(axpy(s, ne, s->q, 0.5 * dt, nullptr, s->tq, 1));
             s->have_vq = true;
             RC(energy(s));
@@ -605,13 +670,13 @@ int step(phw_solver_s* s) {
         case PHW_EH:
             RC(scalar(s, S_EH_BEGIN));
             RC(flux(s, s->q, 1, 0));
-            RC(rhs_p(s, s->q, s->p)); RC(solve_mass(s, PHW_P, NL));
-            RC(rhs_q(s, s->p, s->q)); RC(solve_mass(s, PHW_Q, NL));
+            RC(rhs_p(s, s->q, s->p)); RC(solve_site(s, PHW_P, 0));
+            RC(rhs_q(s, s->p, s->q)); RC(solve_site(s, PHW_Q, 0));
             RC(flux(s, nullptr, 1, 1));                               // b_L^T v_q1
             RC(waxpy(s, nv, s->tmp_p, s->p, 0.5 * dt, nullptr, s->tp, 0));   // 0.5 (p_m + p_temp)
             RC(waxpy(s, ne, s->tmp_q, s->q, 0.5 * dt, nullptr, s->tq, 1));
-            RC(rhs_p(s, s->tmp_q, s->tmp_p)); RC(solve_mass(s, PHW_P, NL));
-            RC(rhs_q(s, s->tmp_p, s->tmp_q)); RC(solve_mass(s, PHW_Q, NL));
+            RC(rhs_p(s, s->tmp_q, s->tmp_p)); RC(solve_site(s, PHW_P, 1));
+            RC(rhs_q(s, s->tmp_p, s->tmp_q)); RC(solve_site(s, PHW_Q, 1));
             RC(axpy(s, nv, s->p, dt, nullptr, s->tp, 0));
             RC(axpy(s, ne, s->q, dt, nullptr, s->tq, 1));
             RC(energy(s));
@@ -625,7 +690,7 @@ int step(phw_solver_s* s) {
             if (ic) RC(scalar(s, S_SM_PLEFT));
             RC(rhs_p(s, s->q, s->p));
             RC(rhs_q(s, s->p, s->q));
-            RC(solve_block(s, theta, NL));
+            RC(solve_block_site(s, theta));
             if (ic) {
                 RC(flux(s, nullptr, 2, 2));                            // b_L^T vhat_q
                 RC(scalar(s, S_ODE_SM, s->blw));
@@ -821,14 +886,16 @@ static int setup_solver(phw_solver_s* s) {
     // ---- mesh SoA
     std::vector<CellRec> rec;
     L.make_records(P.strong != 0, P.casimir != 0, rec);
-    PatchHdr* d_hdr; uint4* d_rec; int *d_gv, *d_ge; uint32_t *d_eadj, *d_voff; uint16_t* d_vadj;
+    PatchHdr* d_hdr; uint2 *d_recv, *d_rece; int *d_gv, *d_ge; uint32_t *d_eadj, *d_voff; uint16_t* d_vadj;
     RC(s->upload(&d_hdr, L.hdr));
     {
-        RC(s->dalloc(&d_rec, rec.size()));
-        CU(cudaMemcpyAsync(d_rec, rec.data(), rec.size() * sizeof(CellRec), cudaMemcpyHostToDevice, s->stream));
+        std::vector<uint2> hv(rec.size()), he(rec.size());
+        for (size_t k = 0; k < rec.size(); ++k) { hv[k] = make_uint2(rec[k].x, rec[k].y); he[k] = make_uint2(rec[k].z, rec[k].w); }
+        RC(s->upload(&d_recv, hv)); RC(s->upload(&d_rece, he));
+        CU(cudaStreamSynchronize(s->stream));
     }
     RC(s->upload(&d_gv, L.ghost_v)); RC(s->upload(&d_ge, L.ghost_e));
-    RC(s->upload(&d_eadj, L.eadj)); RC(s->upload(&d_voff, L.vadj_off)); RC(s->upload(&d_vadj, L.vadj));
+    RC(s->upload(&d_eadj, L.eadj)); RC(s->upload(&d_voff, L.vslice_off)); RC(s->upload(&d_vadj, L.vadj));
     RC(s->upload(&s->d_v_new2old, L.v_new2old)); RC(s->upload(&s->d_e_new2old, L.e_new2old));
     double *d_area, *d_g0, *d_g1, *d_g2;
     RC(s->dalloc(&d_area, s->npc)); RC(s->dalloc(&d_g0, s->npc)); RC(s->dalloc(&d_g1, s->npc)); RC(s->dalloc(&d_g2, s->npc));
@@ -848,8 +915,8 @@ static int setup_solver(phw_solver_s* s) {
         memcpy(&s->lam_min_q, &out[0], 8); memcpy(&s->lam_max_q, &out[1], 8);
     }
     s->dm.npatch = s->npatch; s->dm.nv = s->nv; s->dm.ne = s->ne;
-    s->dm.hdr = d_hdr; s->dm.rec = d_rec; s->dm.area = d_area; s->dm.g0 = d_g0; s->dm.g1 = d_g1; s->dm.g2 = d_g2;
-    s->dm.ghost_v = d_gv; s->dm.ghost_e = d_ge; s->dm.eadj = d_eadj; s->dm.vadj_off = d_voff; s->dm.vadj = d_vadj;
+    s->dm.hdr = d_hdr; s->dm.recv = d_recv; s->dm.rece = d_rece; s->dm.area = d_area; s->dm.g0 = d_g0; s->dm.g1 = d_g1; s->dm.g2 = d_g2;
+    s->dm.ghost_v = d_gv; s->dm.ghost_e = d_ge; s->dm.eadj = d_eadj; s->dm.vslice_off = d_voff; s->dm.vadj = d_vadj;
     // ---- port (left boundary, tag 0): b_L[e] = sign * weight   (flux-normalised RT1: <phi_e.n, g_L> = sign * mean(g_L))
     {
         std::vector<int32_t> pe; std::vector<double> bl;
@@ -861,7 +928,7 @@ static int setup_solver(phw_solver_s* s) {
     // ---- vectors
     const size_t nv = s->nv, ne = s->ne;
     RC(s->dalloc(&s->p, nv)); RC(s->dalloc(&s->q, ne)); RC(s->dalloc(&s->bp, nv)); RC(s->dalloc(&s->bq, ne));
-    RC(s->dalloc(&s->tmp_p, nv)); RC(s->dalloc(&s->tmp_q, ne)); RC(s->dalloc(&s->pinv_p, nv)); RC(s->dalloc(&s->pinv_q, ne));
+    RC(s->dalloc(&s->tmp_p, nv)); RC(s->dalloc(&s->tmp_q, ne)); RC(s->dalloc(&s->pinv_p, nv)); RC(s->dalloc(&s->pinv_q, ne)); RC(s->dalloc(&s->mdiag_p, nv));
     RC(s->dalloc(&s->io_v, nv)); RC(s->dalloc(&s->io_e, ne)); RC(s->dalloc(&s->io_v2, nv)); RC(s->dalloc(&s->io_e2, ne));
     for (int i = 0; i < 3; ++i) { RC(s->dalloc(&s->tp.b[i], nv)); RC(s->dalloc(&s->tq.b[i], ne)); }
     RC(s->dalloc(&s->partials, 2 * (size_t)s->npatch + 8192));
@@ -871,12 +938,22 @@ static int setup_solver(phw_solver_s* s) {
         s->coop = coop_attr != 0 && !(P.flags & 8);
     }
     RC(s->dalloc(&s->ctl, 1));
+    s->extrap = (P.extrap_order < 0) ? 0 : std::min(P.extrap_order, 3);
+    s->n_sites = (P.scheme == PHW_EH) ? 2 : 1;
+    if (s->extrap > 0 || true) {
+        for (int site = 0; site < s->n_sites; ++site)
+            for (int j = 0; j <= s->extrap; ++j) {
+                RC(s->dalloc(&s->hist[0][site].h[j], nv));
+                RC(s->dalloc(&s->hist[1][site].h[j], ne));
+            }
+    }
     for (double* v : {s->p, s->bp, s->tmp_p, s->tp.b[0], s->tp.b[1], s->tp.b[2], s->io_v, s->io_v2}) CU(cudaMemsetAsync(v, 0, nv * 8, s->stream));
     for (double* v : {s->q, s->bq, s->tmp_q, s->tq.b[0], s->tq.b[1], s->tq.b[2], s->io_e, s->io_e2}) CU(cudaMemsetAsync(v, 0, ne * 8, s->stream));
     CU(cudaMemsetAsync(s->ctl, 0, sizeof(Ctl), s->stream));
     // ---- shared-memory budgets and grid
     auto ev = [](int x) { return (size_t)((x + 1) & ~1); };
     s->smem_v = (ev(L.max_lv) + 3 * (size_t)L.max_cells) * 8;
+    s->smem_v1 = (ev(L.max_lv) + (size_t)L.max_cells) * 8;
     s->smem_vd = (ev(L.max_lv) + ev(L.max_le) + 3 * (size_t)L.max_cells) * 8;
     s->smem_e = (ev(L.max_le) + 3 * (size_t)L.max_cells) * 8;
     s->smem_ed = s->smem_vd;
@@ -908,7 +985,9 @@ static int setup_solver(phw_solver_s* s) {
     const double theta = (P.scheme == PHW_IE) ? 1.0 : 0.5;
     {
         RowArgs a = base_args(s);
-        a.cM = 1.0; a.y = s->pinv_p;
+        a.cM = 1.0; a.cB = 0.0; a.y = s->mdiag_p;
+        RC((launch_vertex<EPI_STORE, MODE_DIAG, true, false, false>(s, a)));
+        a.y = s->pinv_p;
         a.cB = (implicit && P.casimir) ? theta * P.dt * P.K_wave : 0.0;
         RC((a.cB != 0.0) ? (launch_vertex<EPI_STORE, MODE_DIAG, true, false, true>(s, a)) : (launch_vertex<EPI_STORE, MODE_DIAG, true, false, false>(s, a)));
         a.y = s->pinv_q;
@@ -1041,7 +1120,7 @@ int phw_set_state(phw_solver_t s, const double* p, const double* q, const double
         CU(cudaStreamSynchronize(s->stream));
         CU(cudaMemcpyAsync(&s->ctl->x[0], h, 24, cudaMemcpyHostToDevice, s->stream));
     }
-    s->have_vq = false;
+    reset_history(s);
     CU(cudaStreamSynchronize(s->stream));
     return PHW_OK;
 }
@@ -1185,7 +1264,7 @@ int phw_mass_solve(phw_solver_t s, int32_t which, const double* b, double* x, in
     if (rc) return rc;
     CU(cudaStreamSynchronize(s->stream));
     if (iters) *iters = (int32_t)(it1 - it0);
-    s->have_vq = false;
+    reset_history(s);
     return PHW_OK;
 }
 int phw_energy(phw_solver_t s, double* parts2) {
