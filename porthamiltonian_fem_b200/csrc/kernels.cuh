@@ -22,7 +22,8 @@
 
 namespace phw {
 
-constexpr int NT = 512;   // threads per CTA of the row kernels
+constexpr int NT_ROWS = 512;   // threads per CTA of the row kernels
+constexpr int NT_COOP_P = 256;  // threads per CTA of the persistent M_p solve (more, smaller CTAs hide the per-stage latencies)
 
 struct SolveCtl {
     int k, done, cur, pad;
@@ -136,7 +137,7 @@ __device__ __forceinline__ double* tb_sel(const TriBuf& t, int i) { return i == 
 // ------------------------------------------------------------------------------------------------
 // vertex rows: all patches of this block
 // ------------------------------------------------------------------------------------------------
-template <int EPI, int MODE, bool HAS_M, bool HAS_D, bool CAS>
+template <int EPI, int MODE, bool HAS_M, bool HAS_D, bool CAS, int NT>
 __device__ __forceinline__ void vertex_pass(const RowArgs& a, const PassIO& io, double* smem, double& acc0, double& acc1) {
     const DevMesh& m = a.m;
     // pure P1 mass rows: (M_p x)_v = sum_K (|K|/12) sum(x_K) + x_v * diag_v / 2, diag_v = sum_K |K|/6 = 1/pinv_v,
@@ -284,7 +285,7 @@ __device__ __forceinline__ void vertex_pass(const RowArgs& a, const PassIO& io, 
 // ------------------------------------------------------------------------------------------------
 // edge rows: all patches of this block
 // ------------------------------------------------------------------------------------------------
-template <int EPI, int MODE, bool HAS_M, bool HAS_D, bool CAS>
+template <int EPI, int MODE, bool HAS_M, bool HAS_D, bool CAS, int NT>
 __device__ __forceinline__ void edge_pass(const RowArgs& a, const PassIO& io, double* smem, double& acc0, double& acc1) {
     const DevMesh& m = a.m;
     for (int P = blockIdx.x; P < m.npatch; P += gridDim.x) {
@@ -458,24 +459,24 @@ __device__ __forceinline__ bool resolve_io(const RowArgs& a, bool vertex, PassIO
 }
 
 template <int EPI, int MODE, bool HAS_M, bool HAS_D, bool CAS>
-__global__ void __launch_bounds__(NT, 2) vertex_rows_k(const RowArgs a) {
+__global__ void __launch_bounds__(NT_ROWS, 2) vertex_rows_k(const RowArgs a) {
     extern __shared__ double smem[];
     __shared__ double red[64];
     PassIO io;
     if (!resolve_io<EPI>(a, true, io)) return;
     double acc0 = 0.0, acc1 = 0.0;
-    vertex_pass<EPI, MODE, HAS_M, HAS_D, CAS>(a, io, smem, acc0, acc1);
+    vertex_pass<EPI, MODE, HAS_M, HAS_D, CAS, NT_ROWS>(a, io, smem, acc0, acc1);
     if (EPI != EPI_STORE) finish_launch<EPI>(a, acc0, acc1, red);
 }
 
 template <int EPI, int MODE, bool HAS_M, bool HAS_D, bool CAS>
-__global__ void __launch_bounds__(NT, 2) edge_rows_k(const RowArgs a) {
+__global__ void __launch_bounds__(NT_ROWS, 2) edge_rows_k(const RowArgs a) {
     extern __shared__ double smem[];
     __shared__ double red[64];
     PassIO io;
     if (!resolve_io<EPI>(a, false, io)) return;
     double acc0 = 0.0, acc1 = 0.0;
-    edge_pass<EPI, MODE, HAS_M, HAS_D, CAS>(a, io, smem, acc0, acc1);
+    edge_pass<EPI, MODE, HAS_M, HAS_D, CAS, NT_ROWS>(a, io, smem, acc0, acc1);
     if (EPI != EPI_STORE) finish_launch<EPI>(a, acc0, acc1, red);
 }
 
@@ -485,8 +486,8 @@ __global__ void __launch_bounds__(NT, 2) edge_rows_k(const RowArgs a) {
 // barrier per iteration; the residual norm is reduced deterministically (per-block partials, summed in
 // the same order by every block) so all blocks take the same stop decision without host involvement.
 // ------------------------------------------------------------------------------------------------
-template <int WHICH, bool CAS>
-__global__ void __launch_bounds__(NT, 2) solve_coop_k(const RowArgs av, const RowArgs ae) {
+template <int WHICH, bool CAS, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) solve_coop_k(const RowArgs av, const RowArgs ae) {
     extern __shared__ double smem[];
     __shared__ double red[64];
     __shared__ double bc[2];
@@ -509,12 +510,12 @@ __global__ void __launch_bounds__(NT, 2) solve_coop_k(const RowArgs av, const Ro
         double r0 = 0.0, b0 = 0.0;
         if (WHICH == 0 || WHICH == 2) {
             double a0_ = 0.0, a1_ = 0.0;
-            vertex_pass<EPI_CHEB, MODE_OP, true, WHICH == 2, CAS>(av, iov, smem, a0_, a1_);
+            vertex_pass<EPI_CHEB, MODE_OP, true, WHICH == 2, CAS, NT>(av, iov, smem, a0_, a1_);
             r0 += av.weight * a0_; b0 += av.weight * a1_;
         }
         if (WHICH == 1 || WHICH == 2) {
             double a0_ = 0.0, a1_ = 0.0;
-            edge_pass<EPI_CHEB, MODE_OP, true, WHICH == 2, CAS>(ae, ioe, smem, a0_, a1_);
+            edge_pass<EPI_CHEB, MODE_OP, true, WHICH == 2, CAS, NT>(ae, ioe, smem, a0_, a1_);
             r0 += ae.weight * a0_; b0 += ae.weight * a1_;
         }
         block_sum2(r0, b0, red);

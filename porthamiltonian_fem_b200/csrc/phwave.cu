@@ -381,7 +381,7 @@ int launch_vertex(phw_solver_s* s, const RowArgs& a) {
     auto kern = vertex_rows_k<EPI, MODE, HAS_M, HAS_D, CAS>;
     static bool configured = false;
     if (!configured) { CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); configured = true; }
-    kern<<<s->grid_rows, NT, sm, s->stream>>>(a);
+    kern<<<s->grid_rows, NT_ROWS, sm, s->stream>>>(a);
     s->launches++;
     CU(cudaGetLastError());
     return 0;
@@ -392,7 +392,7 @@ int launch_edge(phw_solver_s* s, const RowArgs& a) {
     auto kern = edge_rows_k<EPI, MODE, HAS_M, HAS_D, CAS>;
     static bool configured = false;
     if (!configured) { CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); configured = true; }
-    kern<<<s->grid_rows, NT, sm, s->stream>>>(a);
+    kern<<<s->grid_rows, NT_ROWS, sm, s->stream>>>(a);
     s->launches++;
     CU(cudaGetLastError());
     return 0;
@@ -442,7 +442,9 @@ int op_edge_dot(phw_solver_s* s, const double* xq, double cM, double cB, int slo
 // one cooperative launch = one complete Chebyshev solve
 template <int WHICH, bool CAS>
 int launch_coop(phw_solver_s* s, const RowArgs& av, const RowArgs& ae) {
-    auto kern = solve_coop_k<WHICH, CAS>;
+    constexpr int NT = (WHICH == 0) ? NT_COOP_P : NT_ROWS;
+    constexpr int MINB = (WHICH == 0) ? 6 : 2;
+    auto kern = solve_coop_k<WHICH, CAS, NT, MINB>;
     const size_t sm = (WHICH == 0) ? s->smem_v1 : (WHICH == 1 ? s->smem_e : s->smem_vd);
     static bool configured = false;
     if (!configured) { CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); configured = true; }
