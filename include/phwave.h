@@ -76,6 +76,12 @@ int phw_version(void);
  *      markers (wave_2D.py:126,168-220,266-285).  Host-only, no GPU needed. ---- */
 int phw_mesh_create(int64_t n_vertices, const double* vertices_xy, int64_t n_cells, const int32_t* cells,
                     int32_t patch_cells, phw_mesh_t* out);
+/* partitioned run: the local mesh of one rank (own cells + one halo layer); vertex_external[n_vertices] /
+ * edge_external[n_edges] flag the dofs owned by another rank (edge ids = the canonical numbering above).
+ * Replaces dolfin's MPI mesh distribution (run_main_wave_2D_mpi.sh:1, wave_2D.py:54-61). */
+int phw_mesh_create_partitioned(int64_t n_vertices, const double* vertices_xy, int64_t n_cells, const int32_t* cells,
+                                int32_t patch_cells, const uint8_t* vertex_external, int64_t n_edges,
+                                const uint8_t* edge_external, phw_mesh_t* out);
 int phw_mesh_sizes(phw_mesh_t m, int64_t* n_vertices, int64_t* n_cells, int64_t* n_edges,
                    int64_t* n_boundary_edges, int64_t* n_patches);
 /* edges [n_edges,2], cell_edges [n_cells,3], cell_edge_sign [n_cells,3] (+1/-1); any pointer may be NULL */
@@ -99,6 +105,22 @@ int phw_get_state(phw_solver_t s, double* p, double* q, double* x3);
 int phw_run(phw_solver_t s, int64_t n_steps, double* H_rows);
 int phw_get_stats(phw_solver_t s, phw_stats* out);
 int phw_synchronize(phw_solver_t s);
+
+/* ---- multi-GPU (one process per GPU on one node).  The exchange arena of every rank (Chebyshev buffers +
+ *      mailbox) is shared through CUDA IPC; halo values and residual norms then travel as peer-memory stores
+ *      issued from inside the persistent solve kernel.  Replaces PETSc's ghost updates / parallel solves. ---- */
+/* 64-byte cudaIpcMemHandle of this rank's arena + its local vector lengths (to be all-gathered by the caller) */
+int phw_comm_arena_handle(phw_solver_t s, void* handle64, int64_t* n_vertices_local, int64_t* n_edges_local);
+/* user (local mesh) dof indices -> positions inside this rank's device vectors (what a neighbour must write to) */
+int phw_comm_internal_index(phw_solver_t s, int32_t which, int64_t n, const int32_t* user_idx, int32_t* internal_idx);
+/* handles64 [world][64], peer_nv/peer_ne [world]; per neighbour k: owned dofs to push (local user ids) and the
+ * position of each of them in the neighbour's vectors (from its phw_comm_internal_index) */
+int phw_comm_setup(phw_solver_t s, int32_t rank, int32_t world, const void* handles64, const int64_t* peer_nv,
+                   const int64_t* peer_ne, int32_t n_nb, const int32_t* nb_rank,
+                   const int64_t* n_send_v, const int32_t* const* send_v_user, const int32_t* const* send_v_remote,
+                   const int64_t* n_send_e, const int32_t* const* send_e_user, const int32_t* const* send_e_remote);
+/* global spectral bounds of the Jacobi-scaled RT1 mass matrix (all ranks must iterate with the same interval) */
+int phw_set_cheb_bounds(phw_solver_t s, double lam_min_q, double lam_max_q);
 
 /* ---- kernel-level entry points (parity tests, profiling) ---- */
 /* y[Ne] = D p = (C - N) p            weak coupling block of wave_2D.py:468-472,479-483,503-518 */

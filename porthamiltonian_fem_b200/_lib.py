@@ -49,6 +49,7 @@ SIGNATURES = {
     'phw_last_error': (ctypes.c_char_p, []),
     'phw_version': (ctypes.c_int, []),
     'phw_mesh_create': (ctypes.c_int, [ctypes.c_int64, c_f64p, ctypes.c_int64, c_i32p, ctypes.c_int32, ctypes.POINTER(ctypes.c_void_p)]),
+    'phw_mesh_create_partitioned': (ctypes.c_int, [ctypes.c_int64, c_f64p, ctypes.c_int64, c_i32p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]),
     'phw_mesh_sizes': (ctypes.c_int, [ctypes.c_void_p, c_i64p, c_i64p, c_i64p, c_i64p, c_i64p]),
     'phw_mesh_get_edges': (ctypes.c_int, [ctypes.c_void_p, c_i32p, c_i32p, c_i8p]),
     'phw_mesh_get_boundary': (ctypes.c_int, [ctypes.c_void_p, c_i32p, c_i8p]),
@@ -63,6 +64,11 @@ SIGNATURES = {
     'phw_run': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]),
     'phw_get_stats': (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(PhwStats)]),
     'phw_synchronize': (ctypes.c_int, [ctypes.c_void_p]),
+    'phw_comm_arena_handle': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_i64p, c_i64p]),
+    'phw_comm_internal_index': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, c_i32p, c_i32p]),
+    'phw_comm_setup': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, c_i64p, c_i64p, ctypes.c_int32, c_i32p,
+                                      c_i64p, ctypes.POINTER(c_i32p), ctypes.POINTER(c_i32p), c_i64p, ctypes.POINTER(c_i32p), ctypes.POINTER(c_i32p)]),
+    'phw_set_cheb_bounds': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double, ctypes.c_double]),
     'phw_apply_D': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     'phw_apply_DT': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     'phw_mass_matvec': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]),

@@ -40,6 +40,9 @@ struct Ctl {
     double red[8];
     long long step;
     long long nonconv;
+    unsigned long long comm_seq;     // number of inter-GPU exchanges done (identical on every rank)
+    int comm_dead, comm_pad;
+    double xch[2][4];                // globally reduced values of the current exchange
     SolveCtl sc[3];
     unsigned int counters[8];
 };
@@ -58,6 +61,68 @@ struct DevMesh {
 };
 
 struct TriBuf { double* b[3]; };
+
+// ---- multi-GPU: peer-memory halo exchange + all-reduce fused into the persistent solve ----
+constexpr int MAX_RANKS = 8;
+struct Mailbox {                       // lives at the start of every rank's exchange arena (peer-mapped)
+    unsigned long long flag[MAX_RANKS];        // flag[r] = last exchange sequence number rank r has published here
+    double part[2][MAX_RANKS][4];              // per-rank partial sums, double-buffered by sequence parity
+};
+struct PeerComm {
+    int rank, world, n_nb, pad;
+    int nb_rank[MAX_RANKS];
+    double* nb_tp[MAX_RANKS][3];               // neighbour's Chebyshev buffers (peer pointers)
+    double* nb_tq[MAX_RANKS][3];
+    const int* send_v_loc[MAX_RANKS]; const int* send_v_rem[MAX_RANKS]; int n_send_v[MAX_RANKS];
+    const int* send_e_loc[MAX_RANKS]; const int* send_e_rem[MAX_RANKS]; int n_send_e[MAX_RANKS];
+    Mailbox* mbox[MAX_RANKS];                  // every rank's mailbox (own one included)
+    long long timeout_cycles;
+};
+
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+
+// all-reduce (sum, rank order => identical bits on every rank) of n <= 4 doubles through the peer mailboxes.
+// Called by ONE thread per rank.  Every rank calls it the same number of times (seq is the call count).
+__device__ inline void peer_allreduce(const PeerComm& pc, Ctl* ctl, double* vals, int n) {
+    const unsigned long long seq = ctl->comm_seq + 1;
+    ctl->comm_seq = seq;
+    if (pc.world <= 1) return;
+    const int par = (int)(seq & 1ull);
+    for (int r = 0; r < pc.world; ++r)
+        for (int i = 0; i < n; ++i) pc.mbox[r]->part[par][pc.rank][i] = vals[i];
+    __threadfence_system();
+    for (int r = 0; r < pc.world; ++r) *((volatile unsigned long long*)&pc.mbox[r]->flag[pc.rank]) = seq;
+    Mailbox* mine = pc.mbox[pc.rank];
+    if (!ctl->comm_dead) {
+        const long long t0 = clock64();
+        for (int r = 0; r < pc.world; ++r) {
+            while (ld_volatile_u64(&mine->flag[r]) < seq) {
+                if (clock64() - t0 > pc.timeout_cycles) { ctl->comm_dead = 1; break; }
+            }
+            if (ctl->comm_dead) break;
+        }
+    }
+    __threadfence_system();
+    for (int i = 0; i < n; ++i) {
+        double sacc = 0.0;
+        for (int r = 0; r < pc.world; ++r) sacc += *((volatile double*)&mine->part[par][r][i]);
+        vals[i] = sacc;
+    }
+}
+
+// small single-block kernel: all-reduce ctl->red[first..first+n) or ctl->flux[first..] across ranks
+__global__ void allreduce_k(PeerComm pc, Ctl* ctl, int what, int first, int n) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double* v = (what == 0) ? &ctl->red[first] : &ctl->flux[first];
+    double tmp[4];
+    for (int i = 0; i < n; ++i) tmp[i] = v[i];
+    peer_allreduce(pc, ctl, tmp, n);
+    for (int i = 0; i < n; ++i) v[i] = tmp[i];
+}
 
 enum { EPI_STORE = 0, EPI_CHEB = 1, EPI_DOT = 2 };
 enum { MODE_OP = 0, MODE_DIAG = 1 };
@@ -487,7 +552,7 @@ __global__ void __launch_bounds__(NT_ROWS, 2) edge_rows_k(const RowArgs a) {
 // the same order by every block) so all blocks take the same stop decision without host involvement.
 // ------------------------------------------------------------------------------------------------
 template <int WHICH, bool CAS, int NT, int MINB>
-__global__ void __launch_bounds__(NT, MINB) solve_coop_k(const RowArgs av, const RowArgs ae) {
+__global__ void __launch_bounds__(NT, MINB) solve_coop_k(const RowArgs av, const RowArgs ae, const PeerComm pc) {
     extern __shared__ double smem[];
     __shared__ double red[64];
     __shared__ double bc[2];
@@ -531,6 +596,31 @@ __global__ void __launch_bounds__(NT, MINB) solve_coop_k(const RowArgs av, const
         __syncthreads();
         rr = bc[0]; bb = bc[1];
         __syncthreads();
+        if (pc.world > 1) {
+            // (1) push the new iterate of the dofs my neighbours hold as external, straight into their buffers
+            const int gtid = blockIdx.x * NT + threadIdx.x, gsz = gridDim.x * NT;
+            for (int nb = 0; nb < pc.n_nb; ++nb) {
+                if (WHICH == 0 || WHICH == 2) {
+                    const double* src = iov.xnew; double* dst = pc.nb_tp[nb][nxt];
+                    for (int i = gtid; i < pc.n_send_v[nb]; i += gsz) dst[pc.send_v_rem[nb][i]] = src[pc.send_v_loc[nb][i]];
+                }
+                if (WHICH == 1 || WHICH == 2) {
+                    const double* src = ioe.xnew; double* dst = pc.nb_tq[nb][nxt];
+                    for (int i = gtid; i < pc.n_send_e[nb]; i += gsz) dst[pc.send_e_rem[nb][i]] = src[pc.send_e_loc[nb][i]];
+                }
+            }
+            __threadfence_system();
+            grid.sync();
+            // (2) one thread publishes this rank's residual norms + "iterate pushed" flag and waits for the others
+            if (blockIdx.x == 0 && threadIdx.x == 0) {
+                double v2[2] = {rr, bb};
+                peer_allreduce(pc, a0.ctl, v2, 2);
+                a0.ctl->xch[k & 1][0] = v2[0]; a0.ctl->xch[k & 1][1] = v2[1];
+                __threadfence();
+            }
+            grid.sync();
+            rr = __ldcg(&a0.ctl->xch[k & 1][0]); bb = __ldcg(&a0.ctl->xch[k & 1][1]);
+        }
         rho = rho_k; k += 1; cur = nxt;
         conv = rr <= a0.tol2 * bb;
         if (conv || k >= a0.max_iter) break;

@@ -48,7 +48,8 @@ void radix_sort_pairs(std::vector<uint32_t>& key, std::vector<int32_t>& val) {
 
 }  // namespace
 
-std::string Layout::build(int64_t nv_, const double* vxy, int64_t nc_, const int32_t* cells_, int32_t patch_cells_) {
+std::string Layout::build(int64_t nv_, const double* vxy, int64_t nc_, const int32_t* cells_, int32_t patch_cells_,
+                          const uint8_t* v_ext, int64_t ne_expected, const uint8_t* e_ext) {
     if (nv_ <= 0 || nc_ <= 0 || !vxy || !cells_) return "empty mesh";
     if (nv_ > (int64_t)1 << 30 || nc_ > (int64_t)1 << 30) return "mesh too large for int32 indexing";
     if (patch_cells_ < 16 || patch_cells_ > 8192) return "patch_cells must be in [16, 8192]";
@@ -170,6 +171,10 @@ std::string Layout::build(int64_t nv_, const double* vxy, int64_t nc_, const int
     }
     for (int64_t v = 0; v < nv; ++v)
         if (v_owner[v] == std::numeric_limits<int32_t>::max()) return "unreferenced vertex in mesh";
+    if (e_ext && ne_expected != ne) return "edge_external has the wrong length (edge numbering mismatch)";
+    // dofs owned by another rank belong to the virtual patch `npatch`: numbered last, never a row here
+    if (v_ext) for (int64_t v = 0; v < nv; ++v) if (v_ext[v]) v_owner[v] = npatch;
+    if (e_ext) for (int64_t e = 0; e < ne; ++e) if (e_ext[e]) e_owner[e] = npatch;
     v_degree.assign(nv, 0);
     for (int64_t h = 0; h < 3 * nc; ++h) v_degree[cells[h]]++;
     // new id = rank by (owner, -degree, old id): stable counting sorts, least significant key first
@@ -186,9 +191,9 @@ std::string Layout::build(int64_t nv_, const double* vxy, int64_t nc_, const int
         } else {
             for (int64_t i = 0; i < n; ++i) order[i] = (int32_t)i;
         }
-        pstart.assign(npatch + 1, 0);
+        pstart.assign(npatch + 2, 0);
         for (int64_t i = 0; i < n; ++i) pstart[owner[i] + 1]++;
-        for (int32_t p = 0; p < npatch; ++p) pstart[p + 1] += pstart[p];
+        for (int32_t p = 0; p <= npatch; ++p) pstart[p + 1] += pstart[p];
         std::vector<int32_t> pos(pstart.begin(), pstart.end() - 1);
         new2old.resize(n); old2new.resize(n);
         for (int64_t k = 0; k < n; ++k) {
@@ -201,15 +206,16 @@ std::string Layout::build(int64_t nv_, const double* vxy, int64_t nc_, const int
     std::vector<int32_t> vstart, estart;
     renumber(v_owner, &v_degree, nv, v_new2old, v_old2new, vstart);
     renumber(e_owner, nullptr, ne, e_new2old, e_old2new, estart);
+    nv_owned = vstart[npatch]; ne_owned = estart[npatch];
     // ---- 5. halo cells: (patch, cell, type) type 0 = adjacent to an owned edge, 1 = only to an owned vertex
     std::vector<uint64_t> halo;
     for (int64_t c = 0; c < nc; ++c) {
         int32_t pc = cell_patch[c];
         for (int i = 0; i < 3; ++i) {
             int32_t pe = e_owner[cell_edges[3 * c + i]];
-            if (pe != pc) halo.push_back(((uint64_t)pe << 33) | ((uint64_t)c << 1) | 0u);
+            if (pe != pc && pe != npatch) halo.push_back(((uint64_t)pe << 33) | ((uint64_t)c << 1) | 0u);
             int32_t pv = v_owner[cells[3 * c + i]];
-            if (pv != pc) halo.push_back(((uint64_t)pv << 33) | ((uint64_t)c << 1) | 1u);
+            if (pv != pc && pv != npatch) halo.push_back(((uint64_t)pv << 33) | ((uint64_t)c << 1) | 1u);
         }
     }
     std::sort(halo.begin(), halo.end());

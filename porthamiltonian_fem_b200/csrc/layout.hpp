@@ -67,7 +67,10 @@ struct Layout {
     std::vector<int32_t> v_degree;     // [nv] by old id
     int32_t max_lv = 0, max_le = 0, max_cells = 0;
 
-    std::string build(int64_t nv_, const double* vxy, int64_t nc_, const int32_t* cells_, int32_t patch_cells_);
+    int64_t nv_owned = 0, ne_owned = 0;   // external (other-rank) dofs are numbered after the owned ones
+    // v_ext / e_ext (optional, by user id): 1 = dof owned by another rank (never a row of this rank)
+    std::string build(int64_t nv_, const double* vxy, int64_t nc_, const int32_t* cells_, int32_t patch_cells_,
+                      const uint8_t* v_ext = nullptr, int64_t ne_expected = -1, const uint8_t* e_ext = nullptr);
     // cell records with boundary flag bits for the given formulation
     void make_records(bool strong, bool casimir, std::vector<CellRec>& rec) const;
 };

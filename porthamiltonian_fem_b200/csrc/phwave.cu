@@ -343,6 +343,9 @@ struct phw_solver_s {
     size_t smem_v = 0, smem_v1 = 0, smem_e = 0, smem_vd = 0, smem_ed = 0;
     int grid_rows = 0, sm_count = 148;
     int64_t launches = 0;
+    PeerComm pc{};
+    void* arena = nullptr; size_t arena_bytes = 0;
+    std::vector<void*> peer_arenas;
     struct Hist { double* h[4] = {nullptr, nullptr, nullptr, nullptr}; int count = 0, head = 0; };
     Hist hist[2][2];           // [field p/q][solve site]
     int extrap = 2, n_sites = 1;
@@ -452,7 +455,7 @@ int launch_coop(phw_solver_s* s, const RowArgs& av, const RowArgs& ae) {
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, sm));
     if (occ < 1) return fail(PHW_ECUDA, "cooperative solve kernel does not fit on an SM");
     const int grid = std::max(1, std::min(s->npatch, occ * s->sm_count));
-    void* args[] = {(void*)&av, (void*)&ae};
+    void* args[] = {(void*)&av, (void*)&ae, (void*)&s->pc};
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     const bool prof = (s->prm.flags & 4) && s->prof_ev.size() < 2 * 8192;
     if (prof) {
@@ -527,6 +530,14 @@ int solve_block(phw_solver_s* s, double theta, int n_launch) {
     return 0;
 }
 
+// sum ctl->red[first..first+n) (what = 0) or ctl->flux[...] (what = 1) over all ranks (no-op on one GPU)
+int allreduce(phw_solver_s* s, int what, int first, int n) {
+    if (s->pc.world <= 1) return 0;
+    allreduce_k<<<1, 32, 0, s->stream>>>(s->pc, s->ctl, what, first, n);
+    s->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
 int scalar(phw_solver_s* s, int op, double aux0 = 0.0, double aux1 = 0.0) {
     scalar_k<<<1, 32, 0, s->stream>>>(s->ctl, s->sp, op, s->dH, aux0, aux1);
     s->launches++;
@@ -537,7 +548,7 @@ int flux(phw_solver_s* s, const double* q, int which, int slot) {
     flux_k<<<1, 256, 0, s->stream>>>(s->nport, s->d_port_e, s->d_port_bl, q, s->tq, s->ctl, which, slot);
     s->launches++;
     CU(cudaGetLastError());
-    return 0;
+    return allreduce(s, 1, slot, 1);      // only the rank holding the port contributes
 }
 int axpy(phw_solver_s* s, int n, double* y, double a, const double* x, TriBuf tb, int which) {
     axpy_k<<<vec_grid(s, n), 256, 0, s->stream>>>(n, y, a, x, tb, s->ctl, which);
@@ -572,7 +583,9 @@ int rhs_q(phw_solver_s* s, const double* psrc, const double* qsrc) {
 int energy(phw_solver_s* s) {
     int rc = op_vertex_dot(s, s->p, 1.0, 0.0, 0, 0.5 / s->prm.rho, 4);
     if (rc) return rc;
-    return op_edge_dot(s, s->q, 1.0, 0.0, 1, 0.5 * s->prm.K_wave, 5);
+    rc = op_edge_dot(s, s->q, 1.0, 0.0, 1, 0.5 * s->prm.K_wave, 5);
+    if (rc) return rc;
+    return allreduce(s, 0, 0, 2);
 }
 
 int n_iter_launch(phw_solver_s* s) { return s->prm.max_iter; }
@@ -802,6 +815,25 @@ int phw_mesh_create(int64_t n_vertices, const double* vertices_xy, int64_t n_cel
     return PHW_OK;
 }
 
+int phw_mesh_create_partitioned(int64_t n_vertices, const double* vertices_xy, int64_t n_cells, const int32_t* cells,
+                                int32_t patch_cells, const uint8_t* vertex_external, int64_t n_edges,
+                                const uint8_t* edge_external, phw_mesh_t* out) {
+    if (!out || !vertex_external || !edge_external) return fail(PHW_EINVAL, "NULL argument");
+    phw_mesh_s* m = new (std::nothrow) phw_mesh_s();
+    if (!m) return fail(PHW_ENOMEM, "out of host memory");
+    std::string err;
+    try {
+        err = m->L.build(n_vertices, vertices_xy, n_cells, cells, patch_cells > 0 ? patch_cells : 2048,
+                         vertex_external, n_edges, edge_external);
+    } catch (const std::bad_alloc&) {
+        delete m;
+        return fail(PHW_ENOMEM, "out of host memory while building the mesh layout");
+    }
+    if (!err.empty()) { delete m; return fail(PHW_EINVAL, err); }
+    *out = m;
+    return PHW_OK;
+}
+
 int phw_mesh_sizes(phw_mesh_t m, int64_t* nv, int64_t* nc, int64_t* ne, int64_t* nb, int64_t* np) {
     if (!m) return fail(PHW_EINVAL, "mesh is NULL");
     if (nv) *nv = m->L.nv;
@@ -861,6 +893,8 @@ int phw_mesh_destroy(phw_mesh_t m) { delete m; return PHW_OK; }
 int phw_solver_destroy(phw_solver_t s) {
     if (!s) return PHW_OK;
     cudaSetDevice(s->device);
+    for (size_t r = 0; r < s->peer_arenas.size(); ++r)
+        if (s->peer_arenas[r] && s->peer_arenas[r] != s->arena) cudaIpcCloseMemHandle(s->peer_arenas[r]);
     for (void* d : s->allocs) cudaFree(d);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
@@ -932,7 +966,21 @@ static int setup_solver(phw_solver_s* s) {
     RC(s->dalloc(&s->p, nv)); RC(s->dalloc(&s->q, ne)); RC(s->dalloc(&s->bp, nv)); RC(s->dalloc(&s->bq, ne));
     RC(s->dalloc(&s->tmp_p, nv)); RC(s->dalloc(&s->tmp_q, ne)); RC(s->dalloc(&s->pinv_p, nv)); RC(s->dalloc(&s->pinv_q, ne)); RC(s->dalloc(&s->mdiag_p, nv));
     RC(s->dalloc(&s->io_v, nv)); RC(s->dalloc(&s->io_e, ne)); RC(s->dalloc(&s->io_v2, nv)); RC(s->dalloc(&s->io_e2, ne));
-    for (int i = 0; i < 3; ++i) { RC(s->dalloc(&s->tp.b[i], nv)); RC(s->dalloc(&s->tq.b[i], ne)); }
+    {   // exchange arena: [Mailbox | tp0 tp1 tp2 | tq0 tq1 tq2] in ONE allocation so that a single CUDA IPC handle
+        // lets the neighbouring ranks write halo values and partial sums straight into it (peer memory over NVLink)
+        const size_t head = 4096, nvp = (nv + 31) & ~(size_t)31, nep = (ne + 31) & ~(size_t)31;
+        s->arena_bytes = head + 3 * (nvp + nep) * sizeof(double);
+        char* base = nullptr;
+        RC(s->dalloc(&base, s->arena_bytes));
+        s->arena = base;
+        CU(cudaMemsetAsync(base, 0, s->arena_bytes, s->stream));
+        double* d0 = (double*)(base + head);
+        for (int i = 0; i < 3; ++i) { s->tp.b[i] = d0 + i * nvp; s->tq.b[i] = d0 + 3 * nvp + i * nep; }
+        s->pc = PeerComm{};
+        s->pc.rank = 0; s->pc.world = 1; s->pc.n_nb = 0;
+        s->pc.mbox[0] = (Mailbox*)base;
+        s->pc.timeout_cycles = 20000000000LL;
+    }
     RC(s->dalloc(&s->partials, 2 * (size_t)s->npatch + 8192));
     {
         int coop_attr = 0;
@@ -1109,6 +1157,100 @@ int phw_solver_create(phw_mesh_t m, const phw_params* prm, int32_t device, void*
     return PHW_OK;
 }
 
+// ---- multi-GPU plumbing (one process per GPU; handles travel through the caller's torch.distributed) ----
+int phw_comm_arena_handle(phw_solver_t s, void* handle64, int64_t* n_vertices_local, int64_t* n_edges_local) {
+    if (!s || !handle64) return fail(PHW_EINVAL, "NULL argument");
+    CU(cudaSetDevice(s->device));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, s->arena));
+    memcpy(handle64, &h, 64);
+    if (n_vertices_local) *n_vertices_local = s->nv;
+    if (n_edges_local) *n_edges_local = s->ne;
+    return PHW_OK;
+}
+
+int phw_comm_internal_index(phw_solver_t s, int32_t which, int64_t n, const int32_t* user_idx, int32_t* internal_idx) {
+    if (!s || (n > 0 && (!user_idx || !internal_idx))) return fail(PHW_EINVAL, "NULL argument");
+    const std::vector<int32_t>& o2n = (which == PHW_P) ? s->mesh->L.v_old2new : s->mesh->L.e_old2new;
+    for (int64_t i = 0; i < n; ++i) {
+        if (user_idx[i] < 0 || (size_t)user_idx[i] >= o2n.size()) return fail(PHW_EINVAL, "index out of range");
+        internal_idx[i] = o2n[user_idx[i]];
+    }
+    return PHW_OK;
+}
+
+int phw_comm_setup(phw_solver_t s, int32_t rank, int32_t world, const void* handles64, const int64_t* peer_nv,
+                   const int64_t* peer_ne, int32_t n_nb, const int32_t* nb_rank,
+                   const int64_t* n_send_v, const int32_t* const* send_v_user, const int32_t* const* send_v_remote,
+                   const int64_t* n_send_e, const int32_t* const* send_e_user, const int32_t* const* send_e_remote) {
+    if (!s || !handles64 || !peer_nv || !peer_ne) return fail(PHW_EINVAL, "NULL argument");
+    if (world < 1 || world > MAX_RANKS || rank < 0 || rank >= world || n_nb < 0 || n_nb >= MAX_RANKS)
+        return fail(PHW_EINVAL, "rank/world/neighbour count out of range (at most 8 ranks)");
+    if (!s->coop) return fail(PHW_ESTATE, "multi-GPU runs need the cooperative solve path");
+    if (s->prm.scheme == PHW_IE || s->prm.scheme == PHW_SM) return fail(PHW_EINVAL, "implicit schemes are not available in partitioned runs yet");
+    CU(cudaSetDevice(s->device));
+    PeerComm pc = s->pc;
+    pc.rank = rank; pc.world = world; pc.n_nb = n_nb;
+    s->peer_arenas.assign(world, nullptr);
+    const size_t head = 4096;
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) { s->peer_arenas[r] = s->arena; }
+        else {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, (const char*)handles64 + 64 * (size_t)r, 64);
+            void* ptr = nullptr;
+            CU(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+            s->peer_arenas[r] = ptr;
+        }
+        pc.mbox[r] = (Mailbox*)s->peer_arenas[r];
+    }
+    const Layout& L = s->mesh->L;
+    for (int k = 0; k < n_nb; ++k) {
+        const int r = nb_rank[k];
+        if (r < 0 || r >= world || r == rank) return fail(PHW_EINVAL, "bad neighbour rank");
+        pc.nb_rank[k] = r;
+        const size_t nvp = ((size_t)peer_nv[r] + 31) & ~(size_t)31, nep = ((size_t)peer_ne[r] + 31) & ~(size_t)31;
+        double* d0 = (double*)((char*)s->peer_arenas[r] + head);
+        for (int i = 0; i < 3; ++i) { pc.nb_tp[k][i] = d0 + i * nvp; pc.nb_tq[k][i] = d0 + 3 * nvp + i * nep; }
+        std::vector<int32_t> loc;
+        int rc;
+        int32_t* d;
+        loc.resize(n_send_v[k]);
+        for (int64_t i = 0; i < n_send_v[k]; ++i) {
+            const int32_t u = send_v_user[k][i];
+            if (u < 0 || u >= L.nv || L.v_old2new[u] >= L.nv_owned) return fail(PHW_EINVAL, "send list contains a vertex this rank does not own");
+            if (send_v_remote[k][i] < 0 || send_v_remote[k][i] >= peer_nv[r]) return fail(PHW_EINVAL, "remote vertex index out of range");
+            loc[i] = L.v_old2new[u];
+        }
+        rc = s->upload(&d, loc); if (rc) return rc; pc.send_v_loc[k] = d;
+        loc.assign(send_v_remote[k], send_v_remote[k] + n_send_v[k]);
+        rc = s->upload(&d, loc); if (rc) return rc; pc.send_v_rem[k] = d;
+        pc.n_send_v[k] = (int)n_send_v[k];
+        loc.resize(n_send_e[k]);
+        for (int64_t i = 0; i < n_send_e[k]; ++i) {
+            const int32_t u = send_e_user[k][i];
+            if (u < 0 || u >= L.ne || L.e_old2new[u] >= L.ne_owned) return fail(PHW_EINVAL, "send list contains an edge this rank does not own");
+            if (send_e_remote[k][i] < 0 || send_e_remote[k][i] >= peer_ne[r]) return fail(PHW_EINVAL, "remote edge index out of range");
+            loc[i] = L.e_old2new[u];
+        }
+        rc = s->upload(&d, loc); if (rc) return rc; pc.send_e_loc[k] = d;
+        loc.assign(send_e_remote[k], send_e_remote[k] + n_send_e[k]);
+        rc = s->upload(&d, loc); if (rc) return rc; pc.send_e_rem[k] = d;
+        pc.n_send_e[k] = (int)n_send_e[k];
+    }
+    CU(cudaStreamSynchronize(s->stream));
+    s->pc = pc;
+    return PHW_OK;
+}
+
+int phw_set_cheb_bounds(phw_solver_t s, double lam_min_q, double lam_max_q) {
+    if (!s || !(lam_min_q > 0) || !(lam_max_q >= lam_min_q)) return fail(PHW_EINVAL, "bad bounds");
+    s->lam_min_q = lam_min_q; s->lam_max_q = lam_max_q;
+    s->cheb_d[1] = 0.5 * (lam_min_q + lam_max_q); s->cheb_c[1] = 0.5 * (lam_max_q - lam_min_q);
+    return PHW_OK;
+}
+
 int phw_set_state(phw_solver_t s, const double* p, const double* q, const double* x3) {
     if (!s) return fail(PHW_EINVAL, "solver is NULL");
     CU(cudaSetDevice(s->device));
@@ -1201,6 +1343,7 @@ int phw_run(phw_solver_t s, int64_t n_steps, double* H_rows) {
         bytes += (double)st.iters_block * 2 * 40.0 * nc;
         st.bytes_model = (int64_t)bytes;
     }
+    if (hc.comm_dead) return fail(PHW_ECUDA, "inter-GPU exchange timed out (a peer rank stopped responding)");
     if (hc.nonconv > 0) {
         char buf[160];
         snprintf(buf, sizeof buf, "%lld solves hit max_iter without reaching tol (max relative residual %.3e)", (long long)hc.nonconv, st.max_rel_residual);
@@ -1211,6 +1354,7 @@ int phw_run(phw_solver_t s, int64_t n_steps, double* H_rows) {
 
 int phw_get_stats(phw_solver_t s, phw_stats* out) {
     if (!s || !out) return fail(PHW_EINVAL, "NULL argument");
+    s->stats.lam_min_q = s->lam_min_q; s->stats.lam_max_q = s->lam_max_q; s->stats.skew_bound = s->skew_bound;
     *out = s->stats;
     return PHW_OK;
 }

@@ -11,16 +11,26 @@ TAG_LEFT, TAG_TOP, TAG_RIGHT, TAG_GENERAL, TAG_NONE = 0, 1, 2, 3, 4
 class Mesh:
     """Connectivity + patch layout of a triangle mesh (phw_mesh_*; host only, no GPU needed)."""
 
-    def __init__(self, vertices, cells, patch_cells=2048):
+    def __init__(self, vertices, cells, patch_cells=2048, vertex_external=None, edge_external=None):
         self.lib = _lib.load()
         self.vertices = np.ascontiguousarray(vertices, dtype=np.float64)
         self.cells = np.ascontiguousarray(cells, dtype=np.int32)
         if self.vertices.ndim != 2 or self.vertices.shape[1] != 2 or self.cells.ndim != 2 or self.cells.shape[1] != 3:
             raise ValueError('vertices must be [Nv,2], cells must be [Nc,3]')
         h = ctypes.c_void_p()
-        _lib.check(self.lib.phw_mesh_create(self.vertices.shape[0], self.vertices.ctypes.data_as(_lib.c_f64p),
-                                            self.cells.shape[0], self.cells.ctypes.data_as(_lib.c_i32p),
-                                            int(patch_cells), ctypes.byref(h)))
+        if vertex_external is None:
+            _lib.check(self.lib.phw_mesh_create(self.vertices.shape[0], self.vertices.ctypes.data_as(_lib.c_f64p),
+                                                self.cells.shape[0], self.cells.ctypes.data_as(_lib.c_i32p),
+                                                int(patch_cells), ctypes.byref(h)))
+        else:   # local mesh of one rank of a partitioned run
+            ve = np.ascontiguousarray(vertex_external, dtype=np.uint8)
+            ee = np.ascontiguousarray(edge_external, dtype=np.uint8)
+            if ve.shape[0] != self.vertices.shape[0]:
+                raise ValueError('one external flag per vertex expected')
+            _lib.check(self.lib.phw_mesh_create_partitioned(
+                self.vertices.shape[0], self.vertices.ctypes.data_as(_lib.c_f64p), self.cells.shape[0],
+                self.cells.ctypes.data_as(_lib.c_i32p), int(patch_cells), ve.ctypes.data, ee.shape[0], ee.ctypes.data,
+                ctypes.byref(h)))
         self.handle = h
         s = [ctypes.c_int64() for _ in range(5)]
         _lib.check(self.lib.phw_mesh_sizes(h, *[ctypes.byref(x) for x in s]))
@@ -212,3 +222,71 @@ class Solver:
             self.close()
         except Exception:
             pass
+
+
+def setup_peer_exchange(solver, part, dist, rank, world):
+    """Wire the peer-memory halo exchange of a partitioned run (one process per GPU).
+
+    `part` is a partition.LocalPart, `dist` an initialised torch.distributed (any backend; only object
+    collectives are used here - the data path itself is peer-memory stores issued by the solve kernel)."""
+    from . import partition as pt
+    lib = solver.lib
+    # 1. identical Chebyshev interval on every rank
+    st = solver.stats()
+    lam = [None] * world
+    dist.all_gather_object(lam, (st['lam_min_q'], st['lam_max_q']))
+    _lib.check(lib.phw_set_cheb_bounds(solver.handle, min(x[0] for x in lam), max(x[1] for x in lam)))
+    # 2. where my external dofs live in my vectors, and which global dofs they are
+    need = {}
+    for nb, lists in part.recv.items():
+        need[nb] = {}
+        for kind, idx in lists.items():
+            idx = np.ascontiguousarray(idx, dtype=np.int32)
+            internal = np.empty_like(idx)
+            _lib.check(lib.phw_comm_internal_index(solver.handle, 0 if kind == 'v' else 1, idx.shape[0],
+                                                   idx.ctypes.data_as(_lib.c_i32p), internal.ctypes.data_as(_lib.c_i32p)))
+            gid = (part.vertex_gid if kind == 'v' else part.edge_gid)[idx]
+            need[nb][kind] = (gid, internal)
+    allneed = [None] * world
+    dist.all_gather_object(allneed, need)
+    # 3. arena handles and local sizes
+    handle = (ctypes.c_char * 64)()
+    nvl, nel = ctypes.c_int64(), ctypes.c_int64()
+    _lib.check(lib.phw_comm_arena_handle(solver.handle, handle, ctypes.byref(nvl), ctypes.byref(nel)))
+    allh = [None] * world
+    dist.all_gather_object(allh, (bytes(handle), int(nvl.value), int(nel.value)))
+    handles = b''.join(x[0] for x in allh)
+    peer_nv = np.array([x[1] for x in allh], dtype=np.int64)
+    peer_ne = np.array([x[2] for x in allh], dtype=np.int64)
+    # 4. send lists: what each other rank asked me for
+    nbs = sorted(r for r in range(world) if r != rank and (rank in allneed[r] or r in part.recv))
+    keep = []
+    n_send = {'v': [], 'e': []}
+    loc_ptrs = {'v': [], 'e': []}
+    rem_ptrs = {'v': [], 'e': []}
+    for nb in nbs:
+        asked = allneed[nb].get(rank, {})
+        for kind in ('v', 'e'):
+            if kind in asked:
+                gids, remote = asked[kind]
+                loc = np.ascontiguousarray(pt.needed_by(gids, part, kind), dtype=np.int32)
+                rem = np.ascontiguousarray(remote, dtype=np.int32)
+            else:
+                loc = np.zeros(0, dtype=np.int32)
+                rem = np.zeros(0, dtype=np.int32)
+            keep += [loc, rem]
+            n_send[kind].append(loc.shape[0])
+            loc_ptrs[kind].append(loc.ctypes.data_as(_lib.c_i32p))
+            rem_ptrs[kind].append(rem.ctypes.data_as(_lib.c_i32p))
+    n = len(nbs)
+    PtrArr = _lib.c_i32p * max(n, 1)
+    nb_arr = np.array(nbs, dtype=np.int32) if n else np.zeros(1, dtype=np.int32)
+    nsv = np.array(n_send['v'] or [0], dtype=np.int64)
+    nse = np.array(n_send['e'] or [0], dtype=np.int64)
+    _lib.check(lib.phw_comm_setup(
+        solver.handle, rank, world, handles, peer_nv.ctypes.data_as(_lib.c_i64p), peer_ne.ctypes.data_as(_lib.c_i64p),
+        n, nb_arr.ctypes.data_as(_lib.c_i32p),
+        nsv.ctypes.data_as(_lib.c_i64p), PtrArr(*loc_ptrs['v']) if n else PtrArr(), PtrArr(*rem_ptrs['v']) if n else PtrArr(),
+        nse.ctypes.data_as(_lib.c_i64p), PtrArr(*loc_ptrs['e']) if n else PtrArr(), PtrArr(*rem_ptrs['e']) if n else PtrArr()))
+    dist.barrier()
+    return dict(neighbours=nbs, send_v=n_send['v'], send_e=n_send['e'])

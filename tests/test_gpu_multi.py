@@ -1,0 +1,82 @@
+"""Multi-GPU parity (needs >= 2 CUDA devices; run with `gpurun --gpus 2`): the mesh-partitioned run with
+peer-memory halo exchange must reproduce the single-domain CPU oracle on the owned dofs of every rank."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+pytestmark = pytest.mark.gpu
+K_WAVE, RHO = 3.0, 2.0
+
+
+def _ngpu():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+def _worker(rank, world, port, scheme, q):
+    import torch
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from oracle.wave_2D_oracle import wave_2D_solve_oracle
+        from porthamiltonian_fem_b200 import _lib, partition as pt
+        from porthamiltonian_fem_b200.mesh import rectangle_delaunay
+        from porthamiltonian_fem_b200.solver import Mesh, Solver, tag_boundary_edges, setup_peer_exchange
+        mesh = rectangle_delaunay(48, 12, seed=9)
+        steps, tF = 40, 0.02
+        Ho, _, so = wave_2D_solve_oracle(tF, steps, mesh, 1.0, 0.25, timeIntScheme=scheme, K_wave=K_WAVE, rho=RHO, return_state=True)
+        part = pt.build_local_part(mesh[0], mesh[1], pt.slab_cell_ranks(mesh[0], mesh[1], world), rank)
+        m = Mesh(part.vertices, part.cells, patch_cells=96, vertex_external=part.vertex_external, edge_external=part.edge_external)
+        m.set_boundary(tag_boundary_edges(m, 'R', 1.0, 0.25))
+        prm = _lib.PhwParams()
+        prm.scheme, prm.dt, prm.K_wave, prm.rho = _lib.SCHEMES[scheme], tF / steps, K_WAVE, RHO
+        prm.input_kind, prm.in_amp, prm.in_omega, prm.in_t_stop = _lib.IN_SINE_WINDOW, 10.0, 8 * np.pi, 0.25
+        prm.tol, prm.max_iter, prm.extrap_order = 1e-13, 200, 2
+        s = Solver(m, prm, device=rank)
+        info = setup_peer_exchange(s, part, dist, rank, world)
+        H = s.run(steps)
+        p, qv, _ = s.get_state()
+        ov, oe = part.vertex_owner == rank, part.edge_owner == rank
+        topo_edges = so['topo'].edges
+        # oracle edge ids of my local edges (through global vertex ids)
+        ep = np.linalg.norm(p[ov] - so['p'][part.vertex_gid[ov]]) / np.linalg.norm(so['p'])
+        eq = np.linalg.norm(qv[oe] - so['q'][part.edge_gid[oe]]) / np.linalg.norm(so['q'])
+        # external copies must equal the owners' values too (halo pushed after the last iteration + local axpy)
+        epx = np.abs(p - so['p'][part.vertex_gid]).max() / np.abs(so['p']).max()
+        eH = np.abs(H - Ho).max() / np.abs(Ho).max()
+        q.put((rank, ep, eq, epx, eH, info))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('scheme', ['SE', 'SV'])
+def test_two_gpu_partitioned_run_matches_oracle(scheme):
+    if _ngpu() < 2:
+        pytest.skip('needs 2 GPUs')
+    import torch.multiprocessing as mp
+    sck = socket.socket()
+    sck.bind(('127.0.0.1', 0))
+    port = sck.getsockname()[1]
+    sck.close()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, scheme, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ep, eq, epx, eH, info in res:
+        assert ep < 1e-10 and eq < 1e-10 and epx < 1e-10 and eH < 1e-10, (rank, ep, eq, epx, eH, info)
