@@ -128,16 +128,23 @@ def main():
     from porthamiltonian_fem_b200.mesh import rectangle_structured
     from porthamiltonian_fem_b200.solver import Mesh, Solver, tag_boundary_edges
 
-    # ---- setup (not timed): mesh, layout, device SoA.  Weak scaling: every rank owns one slab of the size below.
+    # ---- setup (not timed): mesh, layout, device SoA.  Weak scaling: every rank owns one slab of nx x ny quads of a
+    # global rectangle (world x 1.0) x 0.25 partitioned into x-slabs; halo values travel as peer-memory stores.
     t_setup = time.time()
-    vertices, cells = rectangle_structured(args.nx, args.ny, 1.0, 0.25)
-    m = Mesh(vertices, cells, patch_cells=args.patch_cells)
+    from porthamiltonian_fem_b200 import partition as pt
+    from porthamiltonian_fem_b200.solver import port_weights, setup_peer_exchange
+    part = pt.structured_slab_part(args.nx, args.ny, world, rank, 1.0, 0.25)
+    vertices = part.vertices
+    if world > 1:
+        m = Mesh(part.vertices, part.cells, patch_cells=args.patch_cells, vertex_external=part.vertex_external,
+                 edge_external=part.edge_external)
+    else:
+        m = Mesh(part.vertices, part.cells, patch_cells=args.patch_cells)
     # state and left datum of the reference's 'analytical' case (wave_2D.py:375-377,734-738): a standing wave that
     # populates every dof, so each step updates a fully non-trivial field
-    xL, yL = 1.0, 0.25
+    xL, yL = 1.0 * world, 0.25
     omega = np.sqrt(K_WAVE / RHO) * np.sqrt(np.pi ** 2 / (4 * xL ** 2) + 4 * np.pi ** 2 / yL ** 2)
     tags = tag_boundary_edges(m, 'R', xL, yL)
-    from porthamiltonian_fem_b200.solver import port_weights
     m.set_boundary(tags, port_weights(m, tags, lambda x, y: RHO * omega * np.sin(2 * np.pi * y / yL + np.pi / 2)))
     dt = DT_FULL * FULL_NX / args.nx
     prm = _lib.PhwParams()
@@ -145,12 +152,20 @@ def main():
     prm.input_kind, prm.in_amp, prm.in_omega = _lib.IN_COSINE, 1.0, omega
     prm.tol, prm.max_iter, prm.flags, prm.extrap_order = args.tol, 200, 4, args.extrap
     solver = Solver(m, prm, device=local_rank)
-    n_dof = m.n_vertices + m.n_edges
+    n_dof_local = int((part.vertex_owner == rank).sum() + (part.edge_owner == rank).sum())
+    n_cells_local = int(part.cell_owned.sum())
+    if world > 1:
+        setup_peer_exchange(solver, part, dist, rank, world)
+        tt = torch.tensor([n_dof_local, n_cells_local], dtype=torch.int64, device='cuda')
+        dist.all_reduce(tt)
+        n_dof, n_cells_total = int(tt[0].item()), int(tt[1].item())
+    else:
+        n_dof, n_cells_total = n_dof_local, n_cells_local
     p0 = RHO * omega * np.sin(np.pi * vertices[:, 0] / (2 * xL) + np.pi / 2) * np.sin(2 * np.pi * vertices[:, 1] / yL + np.pi / 2)
     solver.set_state(p=p0, q=np.zeros(m.n_edges), x3=np.zeros(3))
     del p0
     setup_s = time.time() - t_setup
-    del vertices, cells
+    del vertices
 
     def barrier():
         torch.cuda.synchronize()
@@ -179,7 +194,7 @@ def main():
         tt = torch.tensor([dev_s], dtype=torch.float64, device='cuda')
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dev_s = float(tt.item())
-    value = world * n_dof * args.steps / dev_s
+    value = n_dof * args.steps / dev_s
 
     # ---- end-to-end through host buffers (pinned), copies inside the timed region
     p_host = torch.zeros(m.n_vertices, dtype=torch.float64).pin_memory()
@@ -201,9 +216,10 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s = float(tt.item())
     st2 = solver.stats()
-    e2e_value = world * n_dof * args.steps / e2e_s
-    h2d = (n_dof * 8 + 24) / args.steps
-    d2h = (n_dof * 8 + 24 + args.steps * 8 * 8) / args.steps
+    e2e_value = n_dof * args.steps / e2e_s
+    nloc = m.n_vertices + m.n_edges
+    h2d = world * (nloc * 8 + 24) / args.steps
+    d2h = world * (nloc * 8 + 24 + args.steps * 8 * 8) / args.steps
 
     if rank == 0:
         peaks = {}
@@ -214,7 +230,7 @@ def main():
         peak = float(peaks.get('hbm_gbs', 6650.0))
         peak_src = 'measured (MEASURED_PEAKS.json hbm_gbs)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s (B200_PROFILING.md)'
         # dominant kernel: cooperative Chebyshev solve of M_q; algorithmic bytes = 96 B/cell/iteration
-        nc = m.n_cells
+        nc = n_cells_local
         it_q = st['iters_q']
         q_bytes = 96.0 * nc * it_q
         achieved = q_bytes / (st['ms_solve_q'] * 1e-3) / 1e9 if st['ms_solve_q'] > 0 else None
@@ -222,10 +238,10 @@ def main():
             'metric': 'dof-updates/sec (fp64, device-timed)', 'value': value, 'unit': 'dof-updates/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dev_s / args.steps,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': '{} weak P1/RT1 wave, analytical standing-wave state and left datum (wave_2D.py:375-377,734), structured rectangle {}x{}x2 = {} cells, {} dofs per GPU, dt={:g}; '
+            'config': {'workload': '{} weak P1/RT1 wave, analytical standing-wave state and left datum (wave_2D.py:375-377,734), structured rectangle {}x{}x2 = {} cells and {} dofs per GPU ({} dofs in total, x-slab partition, peer-memory halo exchange), dt={:g}; '
                                    'state vectors ({:.0f} MB each) exceed L2, no flush needed'.format(
-                                       args.scheme, args.nx, args.ny, nc, n_dof, dt, 8e-6 * m.n_edges),
-                       'dofs_per_gpu': n_dof, 'patch_cells': args.patch_cells, 'tol': args.tol, 'extrap_order': args.extrap,
+                                       args.scheme, args.nx, args.ny, nc, n_dof_local, n_dof, dt, 8e-6 * m.n_edges),
+                       'dofs_per_gpu': n_dof_local, 'dofs_total': n_dof, 'patch_cells': args.patch_cells, 'tol': args.tol, 'extrap_order': args.extrap,
                        'iters_per_solve_p': st['iters_p'] / max(1, st['solves_p']), 'iters_per_solve_q': st['iters_q'] / max(1, st['solves_q']),
                        'max_rel_residual': st['max_rel_residual'], 'setup_seconds': setup_s},
             'e2e': {'value': e2e_value, 'unit': 'dof-updates/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,

@@ -1,0 +1,37 @@
+"""Same comparison as the reference's test_case_check.py (:80-126): max absolute / relative-percent difference of
+the Hamiltonian (column 1), the energy residual (column 2) and, for analytical cases, the L2 error (column 8)
+between a run and its ground truth; FAIL above 1e-5 % (1e-7 % for the analytical error)."""
+import os
+
+import numpy as np
+
+
+def check_cases(caseName, caseArray):
+    from main_wave_2D import sub_dir_name
+    outputDir = os.path.join('test_output', caseName)
+    all_ok = True
+    for caseVec in caseArray:
+        subDir = sub_dir_name(caseVec)
+        data_array = np.load(os.path.join(outputDir, subDir, 'H_array.npy'))
+        gt_array = np.load(os.path.join(outputDir, 'ground_truth', subDir, 'H_array.npy'))
+        analytical = caseVec[4] == 'analytical'
+        eps = 1e-10
+        hamDiff = max(abs(data_array[:, 1] - gt_array[:, 1]))
+        resDiff = max(abs(data_array[:, 2] - gt_array[:, 2]))
+        hamDiffPerc = 100 * max(abs((data_array[:, 1] - gt_array[:, 1]) / (abs(gt_array[:, 1]) + eps)))
+        resDiffPerc = 100 * max(abs((data_array[:, 2] - gt_array[:, 2]) / (abs(gt_array[:, 2]) + eps)))
+        ok = not (hamDiffPerc > 1e-5 or resDiffPerc > 1e-5)
+        if analytical:
+            analyticDiff = max(abs(data_array[:, 8] - gt_array[:, 8]))
+            analyticDiffPerc = 100 * max(abs((data_array[:, 8] - gt_array[:, 8]) / (abs(gt_array[:, 8]) + eps)))
+            ok = ok and not analyticDiffPerc > 1e-7
+        print('{} test {}'.format(subDir, 'passed' if ok else 'FAILED'))
+        print('Hamiltonian max diff    : {}%'.format(hamDiffPerc))
+        print('Energy res max diff     : {}%'.format(resDiffPerc))
+        print('Hamiltonian total diff  : {}'.format(hamDiff))
+        print('Energy res total diff   : {}'.format(resDiff))
+        if analytical:
+            print('analytic diff of        : {}%'.format(analyticDiffPerc))
+            print('analytic total diff of  : {}'.format(analyticDiff))
+        all_ok = all_ok and ok
+    return all_ok
