@@ -90,6 +90,9 @@ int phw_mesh_get_edges(phw_mesh_t m, int32_t* edges, int32_t* cell_edges, int8_t
 int phw_mesh_get_boundary(phw_mesh_t m, int32_t* edge_ids, int8_t* sign);
 /* tags [n_b] (phw_tag) and optional left-port weights [n_b] = (1/|e|) int_e g_L ds  (NULL -> 1) */
 int phw_mesh_set_boundary(phw_mesh_t m, const int32_t* tags, const double* port_weight);
+/* strong Dirichlet rows (DirichletBC(U.sub(0), ...), wave_2D.py:413-422): vertex ids and value weights w, the
+ * prescribed value being w * g(t) (w = 1 or the analytical left profile on the left side, 0 on the right side) */
+int phw_mesh_set_dirichlet(phw_mesh_t m, int64_t n, const int32_t* vertex_ids, const double* weights);
 /* layout introspection for tests: permutations new->old for vertices/edges, cell->patch */
 int phw_mesh_get_numbering(phw_mesh_t m, int32_t* vertex_new2old, int32_t* edge_new2old, int32_t* cell_patch);
 /* per-patch counts [n_patches,6]: own cells, edge-op cells, vertex-op cells, owned vertices, owned edges, ghosts(v+e) */

@@ -139,6 +139,7 @@ struct RowArgs {
     const double* b;
     const double* pinv;
     const double* mdiag;     // pure P1 mass diagonal sum_K |K|/6 (nullptr: use 1/pinv)
+    double xscale;           // > 0 (strong Dirichlet rows): stop test ||r|| <= tol (||b|| + sqrt(xscale) ||x||_M), needs mdiag
     double cheb_d, cheb_c;   // centre and focal distance of the spectrum ellipse
     double tol2, weight;
     int which;               // SolveCtl index
@@ -310,7 +311,7 @@ __device__ __forceinline__ void vertex_pass(const RowArgs& a, const PassIO& io, 
             if (EPI == EPI_CHEB && live) {
                 bv = a.b[gid]; pv = a.pinv[gid];
                 if (io.use_prev) xpv = io.xprev[gid];
-                if (ONEVAL && a.mdiag) dgv = a.mdiag[gid];
+                if ((ONEVAL || a.xscale > 0.0) && a.mdiag) dgv = a.mdiag[gid];
             }
             if (EPI != EPI_CHEB && ONEVAL && live) dgv = a.mdiag[gid];
             double val = 0.0;
@@ -337,7 +338,7 @@ __device__ __forceinline__ void vertex_pass(const RowArgs& a, const PassIO& io, 
                 if (io.use_prev) xn += io.c1 * (xc - xpv);
                 io.xnew[gid] = xn;
                 acc0 += pv * r_ * r_;
-                acc1 += pv * bv * bv;
+                acc1 += pv * bv * bv + a.xscale * dgv * xc * xc;
             } else {
                 if (ONEVAL) val += 0.5 * a.cM * sp[lv] * dgv;
                 acc0 += sp[lv] * val;

@@ -47,6 +47,8 @@ struct Layout {
     std::vector<int32_t> btag;         // [nb] phw_tag (default NONE)
     std::vector<double>  bweight;      // [nb] left-port weights (default 1)
     bool boundary_set = false;
+    std::vector<int32_t> dir_vertex;   // strong Dirichlet rows (user vertex ids) and their value weights
+    std::vector<double>  dir_weight;   // value = weight * g(t)  (0 for the homogeneous right side)
 
     std::vector<int32_t> cell_patch;   // [nc] user cell -> patch
     std::vector<int32_t> v_new2old, v_old2new, e_new2old, e_old2new;

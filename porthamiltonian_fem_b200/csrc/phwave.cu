@@ -145,6 +145,18 @@ __global__ void port_rhs_k(int nport, const int* __restrict__ pe, const double* 
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < nport) b[pe[i]] -= coef * bl[i] * ctl->pleft;
 }
+// strong Dirichlet rows (wave_2D.py:413-422, bc.apply :593-595,817,852): the new p value is prescribed, so the
+// velocity unknown of a constrained vertex is (w g(t) - p_old)/dt; its row is frozen by a zero Jacobi weight
+__global__ void dirichlet_set_k(int n, const int* __restrict__ idx, const double* __restrict__ w, TriBuf tb, const Ctl* ctl,
+                                int which, const double* p, double inv_dt) {
+    double* x = tb.b[ctl->sc[which].cur];
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[idx[i]] = (w[i] * ctl->pleft - p[idx[i]]) * inv_dt;
+}
+__global__ void zero_at_k(int n, const int* __restrict__ idx, double* v) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[idx[i]] = 0.0;
+}
 __global__ void solve_begin_k(Ctl* ctl, int which) {
     SolveCtl& sc = ctl->sc[which];
     sc.k = 0; sc.done = 0; sc.racc = 0.0; sc.bacc = 0.0; sc.rho = 0.0; sc.solves += 1;
@@ -330,6 +342,7 @@ struct phw_solver_s {
     DevMesh dm{};
     int *d_v_new2old = nullptr, *d_e_new2old = nullptr;
     int* d_port_e = nullptr; double* d_port_bl = nullptr;
+    int n_dir = 0; int* d_dir_idx = nullptr; double* d_dir_w = nullptr;
     double *p = nullptr, *q = nullptr, *bp = nullptr, *bq = nullptr, *tmp_p = nullptr, *tmp_q = nullptr;
     double *pinv_p = nullptr, *pinv_q = nullptr, *mdiag_p = nullptr, *wp = nullptr, *wq = nullptr;
     double *io_v = nullptr, *io_e = nullptr, *io_v2 = nullptr, *io_e2 = nullptr;
@@ -408,6 +421,7 @@ RowArgs base_args(phw_solver_s* s) {
     a.tol2 = s->prm.tol * s->prm.tol; a.max_iter = s->prm.max_iter; a.weight = 1.0;
     a.dot_scale = 1.0;
     a.mdiag = s->mdiag_p;   // vertex M-only rows use the pure P1 mass diagonal
+    a.xscale = s->prm.strong ? 4.0 : 0.0;
     return a;
 }
 
@@ -484,7 +498,7 @@ int solve_mass(phw_solver_s* s, int which, int n_launch) {
     RowArgs a = base_args(s);
     a.which = which; a.use_cheb_input = 1; a.finalize = 1; a.cM = 1.0; a.counter_id = which;
     a.cheb_d = s->cheb_d[which]; a.cheb_c = s->cheb_c[which];
-    if (!(s->prm.casimir && (s->prm.scheme == PHW_IE || s->prm.scheme == PHW_SM))) a.mdiag = nullptr;   // pinv_p is then exactly 1/mdiag_p
+    if (!s->prm.strong && !(s->prm.casimir && (s->prm.scheme == PHW_IE || s->prm.scheme == PHW_SM))) a.mdiag = nullptr;   // pinv_p is then exactly 1/mdiag_p
     if (s->coop) {
         a.b = which == PHW_P ? s->bp : s->bq;
         a.pinv = which == PHW_P ? s->pinv_p : s->pinv_q;
@@ -618,9 +632,17 @@ int remember(phw_solver_s* s, int field, int site, int which) {
     CU(cudaGetLastError());
     return 0;
 }
+int dirichlet_preset(phw_solver_s* s, int which_ctl) {
+    if (!s->prm.strong || s->n_dir == 0) return 0;
+    dirichlet_set_k<<<nblk(s->n_dir), 256, 0, s->stream>>>(s->n_dir, s->d_dir_idx, s->d_dir_w, s->tp, s->ctl, which_ctl, s->p, 1.0 / s->prm.dt);
+    s->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
 int solve_site(phw_solver_s* s, int which, int site) {
     int rc = predict(s, which, site, which);
     if (rc) return rc;
+    if (which == PHW_P) { rc = dirichlet_preset(s, PHW_P); if (rc) return rc; }
     rc = solve_mass(s, which, s->prm.max_iter);
     if (rc) return rc;
     return remember(s, which, site, which);
@@ -628,6 +650,7 @@ int solve_site(phw_solver_s* s, int which, int site) {
 int solve_block_site(phw_solver_s* s, double theta) {
     int rc = predict(s, 0, 0, 2); if (rc) return rc;
     rc = predict(s, 1, 0, 2); if (rc) return rc;
+    rc = dirichlet_preset(s, 2); if (rc) return rc;
     rc = solve_block(s, theta, s->prm.max_iter); if (rc) return rc;
     rc = remember(s, 0, 0, 2); if (rc) return rc;
     return remember(s, 1, 0, 2);
@@ -870,6 +893,15 @@ int phw_mesh_set_boundary(phw_mesh_t m, const int32_t* tags, const double* port_
     return PHW_OK;
 }
 
+int phw_mesh_set_dirichlet(phw_mesh_t m, int64_t n, const int32_t* vertex_ids, const double* weights) {
+    if (!m || (n > 0 && (!vertex_ids || !weights))) return fail(PHW_EINVAL, "NULL argument");
+    for (int64_t k = 0; k < n; ++k)
+        if (vertex_ids[k] < 0 || vertex_ids[k] >= m->L.nv) return fail(PHW_EINVAL, "Dirichlet vertex id out of range");
+    m->L.dir_vertex.assign(vertex_ids, vertex_ids + n);
+    m->L.dir_weight.assign(weights, weights + n);
+    return PHW_OK;
+}
+
 int phw_mesh_get_numbering(phw_mesh_t m, int32_t* v_new2old, int32_t* e_new2old, int32_t* cell_patch) {
     if (!m) return fail(PHW_EINVAL, "mesh is NULL");
     if (v_new2old) memcpy(v_new2old, m->L.v_new2old.data(), m->L.v_new2old.size() * sizeof(int32_t));
@@ -1047,6 +1079,16 @@ static int setup_solver(phw_solver_s* s) {
         invert_k<<<nblk(s->ne), 256, 0, s->stream>>>(s->ne, s->pinv_q);
         CU(cudaGetLastError());
     }
+    if (P.strong) {
+        std::vector<int32_t> di; std::vector<double> dw;
+        for (size_t k = 0; k < L.dir_vertex.size(); ++k) { di.push_back(L.v_old2new[L.dir_vertex[k]]); dw.push_back(L.dir_weight[k]); }
+        s->n_dir = (int)di.size();
+        RC(s->upload(&s->d_dir_idx, di)); RC(s->upload(&s->d_dir_w, dw));
+        if (s->n_dir > 0) {
+            zero_at_k<<<nblk(s->n_dir), 256, 0, s->stream>>>(s->n_dir, s->d_dir_idx, s->pinv_p);
+            CU(cudaGetLastError());
+        }
+    }
     // ---- Chebyshev intervals.  P1: element bound [1/2, 2] (Wathen); RT1: element bounds from geom_k.
     s->cheb_d[0] = 1.25; s->cheb_c[0] = 0.75;
     s->cheb_d[1] = 0.5 * (s->lam_min_q + s->lam_max_q); s->cheb_c[1] = 0.5 * (s->lam_max_q - s->lam_min_q);
@@ -1100,7 +1142,6 @@ int phw_solver_create(phw_mesh_t m, const phw_params* prm, int32_t device, void*
         return fail(PHW_EINVAL, "only SE, SV and SM time int schemes implemented for interconnection model");
     if (prm->interconnection && prm->strong) return fail(PHW_EINVAL, "can only do interconnection model with weak boundary conditions");
     if (prm->casimir && prm->scheme != PHW_SM) return fail(PHW_EINVAL, "casimir control requires the SM scheme");
-    if (prm->strong) return fail(PHW_EINVAL, "strong Dirichlet form is not implemented in the device path yet");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(PHW_ECUDA, "no CUDA device available (libphwave has no CPU fallback)"); }

@@ -66,6 +66,12 @@ class Mesh:
         _lib.check(self.lib.phw_mesh_set_boundary(self.handle, tags.ctypes.data_as(_lib.c_i32p), w))
         self.tags = tags
 
+    def set_dirichlet(self, vertex_ids, weights):
+        vertex_ids = np.ascontiguousarray(vertex_ids, dtype=np.int32)
+        weights = np.ascontiguousarray(weights, dtype=np.float64)
+        _lib.check(self.lib.phw_mesh_set_dirichlet(self.handle, vertex_ids.shape[0], vertex_ids.ctypes.data_as(_lib.c_i32p),
+                                                   weights.ctypes.data_as(_lib.c_f64p)))
+
     def numbering(self):
         v = np.empty(self.n_vertices, dtype=np.int32)
         e = np.empty(self.n_edges, dtype=np.int32)

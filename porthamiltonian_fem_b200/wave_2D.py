@@ -118,6 +118,17 @@ def wave_2D_solve(tFinal, numSteps, outputDir,
     else:
         prm.input_kind, prm.in_amp, prm.in_omega, prm.in_t_stop = _lib.IN_SINE_WINDOW, 10.0, 8 * np.pi, 0.25    # :384
     m.set_boundary(tags, weights)
+    if dirichletImp == 'strong':
+        # DirichletBC(U.sub(0), pLeftBoundary1, forced_boundary) / DirichletBC(U.sub(0), 0, fixed_boundary)  (:413-420)
+        ids, _ = m.boundary()
+        edges = m.edges()[0]
+        left_v = np.unique(edges[ids[tags == 0]].ravel())
+        right_v = np.unique(edges[ids[tags == 2]].ravel())
+        if analytical:
+            left_w = rho * omega * np.sin(2 * np.pi * m.vertices[left_v, 1] / yLength + np.pi / 2)
+        else:
+            left_w = np.ones(left_v.shape[0])
+        m.set_dirichlet(np.concatenate([left_v, right_v]), np.concatenate([left_w, np.zeros(right_v.shape[0])]))
 
     solver = Solver(m, prm, device=device)
 

@@ -96,6 +96,12 @@ CASES = [
     ('SV_wave', 34, 8, 120, 0.06, dict(timeIntScheme='SV')),
     ('IE_wave', 34, 8, 120, 0.06, dict(timeIntScheme='IE')),
     ('SM_wave', 34, 8, 120, 0.06, dict(timeIntScheme='SM')),
+    ('SV_strong', 34, 8, 120, 0.06, dict(timeIntScheme='SV', dirichletImp='strong')),
+    ('SE_strong', 34, 8, 120, 0.06, dict(timeIntScheme='SE', dirichletImp='strong')),
+    ('EH_strong', 34, 8, 120, 0.06, dict(timeIntScheme='EH', dirichletImp='strong')),
+    ('SM_strong', 34, 8, 120, 0.06, dict(timeIntScheme='SM', dirichletImp='strong')),
+    ('IE_strong', 34, 8, 120, 0.06, dict(timeIntScheme='IE', dirichletImp='strong')),
+    ('SV_strong_analytical', 40, 10, 60, 0.03, dict(timeIntScheme='SV', dirichletImp='strong', analytical=True)),
     ('SE_IC', 52, 13, 100, 0.1, dict(timeIntScheme='SE', interConnection='IC')),
     ('SV_IC', 52, 13, 100, 0.1, dict(timeIntScheme='SV', interConnection='IC')),
     ('SM_IC', 52, 13, 100, 0.1, dict(timeIntScheme='SM', interConnection='IC')),
