@@ -136,6 +136,13 @@ int phw_mass_matvec(phw_solver_t s, int32_t which, const double* x, double* y);
 int phw_mass_solve(phw_solver_t s, int32_t which, const double* b, double* x, int32_t* iters);
 /* parts2[0] = 0.5 p^T M_p p / rho, parts2[1] = 0.5 K q^T M_q q of the current state (wave_2D.py:746,769,882,907) */
 int phw_energy(phw_solver_t s, double* parts2);
+/* analytical diagnostics (wave_2D.py:929-965), required when params.analytical = 1: exact solution
+ * amp sin(kx x + pi/2) sin(ky y + pi/2) cos(omega t) (:741), reference P4 mass matrix [15x15] and barycentric node
+ * coordinates [15x3] of the degree-(k+3) space errornorm interpolates into (:956), exact spatial factor at the
+ * vertices [n_vertices] (:958), point probe = 3 vertex ids (-1 = none) + barycentric weights (:946-950) */
+int phw_set_analytical(phw_solver_t s, double amp, double kx, double ky, double omega, const double* mass_ref225,
+                       const double* lam_nodes45, const double* exact_vertices, const int32_t* pt_vertices3,
+                       const double* pt_lam3);
 /* H_init of wave_2D.py:746,769,771 (subtracted in the energy-residual column) */
 int phw_set_H_init(phw_solver_t s, double H_init);
 /* b_L^T q of the current state: integral of q.n over the left port (wave_2D.py:534,546,622-631) */

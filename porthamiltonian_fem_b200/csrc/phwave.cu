@@ -162,6 +162,66 @@ __global__ void solve_begin_k(Ctl* ctl, int which) {
     sc.k = 0; sc.done = 0; sc.racc = 0.0; sc.bacc = 0.0; sc.rho = 0.0; sc.solves += 1;
 }
 
+// ---- analytical diagnostics (wave_2D.py:929-965) -------------------------------------------------------------
+struct AnalyticPrm {
+    double amp, kx, ky, omega;          // exact p = amp sin(kx x + pi/2) sin(ky y + pi/2) cos(omega t)   (:741)
+    double lam[15][3];                  // barycentric coordinates of the P4 (degree k+3) nodes
+    int pt_v[3]; double pt_lam[3];      // point probe: internal vertex ids + barycentric weights (:946-950)
+};
+__constant__ double c_mass_ref[225];    // reference P4 mass matrix (|K| = 1)
+
+// errornorm: || I_4 p_exact - p_h ||_L2^2 summed over the cells (both fields interpolated into P_{k+3}, :956)
+__global__ void diag_cells_k(int nc, const int* __restrict__ cells_new, const double* __restrict__ vtx_new, const double* __restrict__ p,
+                             const AnalyticPrm ap, const Ctl* ctl, double* partial) {
+    __shared__ double red[64];
+    const double ct = cos(ctl->t * ap.omega);
+    double acc = 0.0, z = 0.0;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += gridDim.x * blockDim.x) {
+        const int a = cells_new[3 * c], b = cells_new[3 * c + 1], d = cells_new[3 * c + 2];
+        const double ax = vtx_new[2 * a], ay = vtx_new[2 * a + 1], bx = vtx_new[2 * b], by = vtx_new[2 * b + 1], dx = vtx_new[2 * d], dy = vtx_new[2 * d + 1];
+        const double pa = p[a], pb = p[b], pd = p[d];
+        const double area = 0.5 * fabs((bx - ax) * (dy - ay) - (by - ay) * (dx - ax));
+        double e[15];
+#pragma unroll
+        for (int n = 0; n < 15; ++n) {
+            const double l0 = ap.lam[n][0], l1 = ap.lam[n][1], l2 = ap.lam[n][2];
+            const double x = l0 * ax + l1 * bx + l2 * dx, y = l0 * ay + l1 * by + l2 * dy;
+            e[n] = ap.amp * sin(ap.kx * x + 1.5707963267948966) * sin(ap.ky * y + 1.5707963267948966) * ct - (l0 * pa + l1 * pb + l2 * pd);
+        }
+        double qf = 0.0;
+        for (int i = 0; i < 15; ++i) {
+            double row = 0.0;
+            for (int j = 0; j < 15; ++j) row += c_mass_ref[15 * i + j] * e[j];
+            qf += e[i] * row;
+        }
+        acc += area * qf;
+    }
+    block_sum2(acc, z, red);
+    if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
+// nodal max error (:958), point probe (:949-950) and the final sum of the cell partials
+__global__ void diag_finish_k(int nv, int nblk_cells, const double* __restrict__ exact_v, const double* __restrict__ p, const AnalyticPrm ap,
+                              Ctl* ctl, const double* partial) {
+    __shared__ double red[64];
+    const double ct = cos(ctl->t * ap.omega);
+    double mx = 0.0;
+    for (int i = threadIdx.x; i < nv; i += blockDim.x) mx = fmax(mx, fabs(exact_v[i] * ct - p[i]));
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double m2 = 0.0;
+        for (int w = 0; w < (int)(blockDim.x + 31) / 32; ++w) m2 = fmax(m2, red[w]);
+        double s = 0.0;
+        for (int b = 0; b < nblk_cells; ++b) s += partial[b];
+        ctl->red[4] = sqrt(s);
+        ctl->red[5] = m2;
+        double ph = 0.0, pe = 0.0;
+        for (int k = 0; k < 3; ++k) if (ap.pt_v[k] >= 0) { ph += ap.pt_lam[k] * p[ap.pt_v[k]]; pe += ap.pt_lam[k] * exact_v[ap.pt_v[k]] * ct; }
+        ctl->red[6] = ph; ctl->red[7] = pe;
+    }
+}
+
 struct ScalarPrm {
     double dt, K, rho, c2;
     double A[3][3];
@@ -321,6 +381,7 @@ __global__ void scalar_k(Ctl* ctl, const ScalarPrm s, int op, double* Hrows, dou
             if (Hrows) {
                 double* row = Hrows + c.step * s.ncol;                               // :1011-1030
                 row[0] = c.t; row[1] = H; row[2] = E; row[3] = c.disp; row[4] = c.bE; row[5] = c.inpE; row[6] = c.H_em; row[7] = H_wave;
+                if (s.ncol == 12) { row[8] = c.red[4]; row[9] = c.red[5]; row[10] = c.red[6]; row[11] = c.red[7]; }    // :1027-1030
             }
             c.step += 1;
         } break;
@@ -343,6 +404,7 @@ struct phw_solver_s {
     int *d_v_new2old = nullptr, *d_e_new2old = nullptr;
     int* d_port_e = nullptr; double* d_port_bl = nullptr;
     int n_dir = 0; int* d_dir_idx = nullptr; double* d_dir_w = nullptr;
+    bool an_ready = false; AnalyticPrm an{}; int* d_cells_new = nullptr; double *d_vtx_new = nullptr, *d_exact_v = nullptr, *d_diag_part = nullptr;
     double *p = nullptr, *q = nullptr, *bp = nullptr, *bq = nullptr, *tmp_p = nullptr, *tmp_q = nullptr;
     double *pinv_p = nullptr, *pinv_q = nullptr, *mdiag_p = nullptr, *wp = nullptr, *wq = nullptr;
     double *io_v = nullptr, *io_e = nullptr, *io_v2 = nullptr, *io_e2 = nullptr;
@@ -362,6 +424,7 @@ struct phw_solver_s {
     struct Hist { double* h[4] = {nullptr, nullptr, nullptr, nullptr}; int count = 0, head = 0; };
     Hist hist[2][2];           // [field p/q][solve site]
     int extrap = 2, n_sites = 1;
+    bool in_step = false;
     bool coop = false;
     std::vector<cudaEvent_t> prof_ev; std::vector<int> prof_which;
     bool have_vq = false;      // Stormer-Verlet first-same-as-last: v_q of the previous step is valid
@@ -599,6 +662,13 @@ int energy(phw_solver_s* s) {
     if (rc) return rc;
     rc = op_edge_dot(s, s->q, 1.0, 0.0, 1, 0.5 * s->prm.K_wave, 5);
     if (rc) return rc;
+    if (s->prm.analytical && s->an_ready && s->in_step) {
+        const int nb = 4 * s->sm_count;
+        diag_cells_k<<<nb, 256, 0, s->stream>>>((int)s->mesh->L.nc, s->d_cells_new, s->d_vtx_new, s->p, s->an, s->ctl, s->d_diag_part);
+        diag_finish_k<<<1, 1024, 0, s->stream>>>(s->nv, nb, s->d_exact_v, s->p, s->an, s->ctl, s->d_diag_part);
+        s->launches += 2;
+        CU(cudaGetLastError());
+    }
     return allreduce(s, 0, 0, 2);
 }
 
@@ -1346,8 +1416,11 @@ int phw_run(phw_solver_t s, int64_t n_steps, double* H_rows) {
     CU(cudaMemcpyAsync(s->ctl, &hc, sizeof(Ctl), cudaMemcpyHostToDevice, s->stream));
     s->launches = 0;
     CU(cudaEventRecord(s->ev0, s->stream));
+    if (s->prm.analytical && !s->an_ready) return fail(PHW_ESTATE, "analytical run: call phw_set_analytical before phw_run");
     for (int64_t n = 0; n < n_steps; ++n) {
+        s->in_step = true;
         int rc = step(s);
+        s->in_step = false;
         if (rc) return rc;
         if ((s->prm.flags & 2) && cudaStreamSynchronize(s->stream) != cudaSuccess) return fail(PHW_ECUDA, "kernel failure inside step loop");
     }
@@ -1462,6 +1535,40 @@ int phw_energy(phw_solver_t s, double* parts2) {
     CU(cudaStreamSynchronize(s->stream));
     return PHW_OK;
 }
+int phw_set_analytical(phw_solver_t s, double amp, double kx, double ky, double omega, const double* mass_ref225,
+                       const double* lam_nodes45, const double* exact_vertices, const int32_t* pt_vertices3,
+                       const double* pt_lam3) {
+    if (!s || !mass_ref225 || !lam_nodes45 || !exact_vertices || !pt_vertices3 || !pt_lam3) return fail(PHW_EINVAL, "NULL argument");
+    if (s->pc.world > 1) return fail(PHW_EINVAL, "analytical diagnostics are not available in partitioned runs");
+    CU(cudaSetDevice(s->device));
+    const Layout& L = s->mesh->L;
+    AnalyticPrm& a = s->an;
+    a.amp = amp; a.kx = kx; a.ky = ky; a.omega = omega;
+    for (int n = 0; n < 15; ++n) for (int k = 0; k < 3; ++k) a.lam[n][k] = lam_nodes45[3 * n + k];
+    for (int k = 0; k < 3; ++k) {
+        a.pt_v[k] = pt_vertices3[k] >= 0 ? L.v_old2new[pt_vertices3[k]] : -1;
+        a.pt_lam[k] = pt_lam3[k];
+    }
+    CU(cudaMemcpyToSymbol(c_mass_ref, mass_ref225, 225 * sizeof(double)));
+    if (!s->d_cells_new) {
+        std::vector<int32_t> cn(3 * (size_t)L.nc);
+        for (size_t h = 0; h < cn.size(); ++h) cn[h] = L.v_old2new[L.cells[h]];
+        std::vector<double> vn(2 * (size_t)L.nv), ev((size_t)L.nv);
+        for (int64_t v = 0; v < L.nv; ++v) {
+            const int32_t nw = L.v_old2new[v];
+            vn[2 * (size_t)nw] = L.vtx[2 * v]; vn[2 * (size_t)nw + 1] = L.vtx[2 * v + 1];
+            ev[nw] = exact_vertices[v];
+        }
+        int rc = s->upload(&s->d_cells_new, cn); if (rc) return rc;
+        rc = s->upload(&s->d_vtx_new, vn); if (rc) return rc;
+        rc = s->upload(&s->d_exact_v, ev); if (rc) return rc;
+        rc = s->dalloc(&s->d_diag_part, 4 * (size_t)s->sm_count); if (rc) return rc;
+        CU(cudaStreamSynchronize(s->stream));
+    }
+    s->an_ready = true;
+    return PHW_OK;
+}
+
 int phw_set_H_init(phw_solver_t s, double H_init) {
     if (!s) return fail(PHW_EINVAL, "solver is NULL");
     s->prm.H_init = H_init;
