@@ -24,6 +24,7 @@ namespace phw {
 
 constexpr int NT_ROWS = 512;   // threads per CTA of the row kernels
 constexpr int NT_COOP_P = 256;  // threads per CTA of the persistent M_p solve (more, smaller CTAs hide the per-stage latencies)
+constexpr int NT_COOP_Q = 384;  // M_q solve: 2 CTAs/SM (shared-memory bound) x 384 threads leaves 85 registers per thread for batched loads
 
 struct SolveCtl {
     int k, done, cur, pad;
@@ -369,7 +370,38 @@ __device__ __forceinline__ void edge_pass(const RowArgs& a, const PassIO& io, do
             for (int i = threadIdx.x; i < h.gv_cnt; i += NT) sp[h.v_cnt + i] = io.xp[m.ghost_v[h.gv_off + i]];
         }
         __syncthreads();
-        for (int lc = threadIdx.x; lc < h.n_ecells; lc += NT) {
+        constexpr bool MONLY = HAS_M && !HAS_D && !CAS && MODE == MODE_OP && EPI == EPI_CHEB;
+        if (MONLY) {
+            // pure RT1 mass rows: issue the loads of U cells before consuming them (memory-level parallelism)
+            constexpr int U = 2;
+            for (int base = threadIdx.x; base < h.n_ecells; base += U * NT) {
+                uint2 reb[U]; double gb[U][3];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int lc = base + u * NT;
+                    if (lc < h.n_ecells) {
+                        reb[u] = __ldg(&m.rece[h.cell_off + lc]);
+                        gb[u][0] = __ldg(&m.g0[h.cell_off + lc]); gb[u][1] = __ldg(&m.g1[h.cell_off + lc]); gb[u][2] = __ldg(&m.g2[h.cell_off + lc]);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int lc = base + u * NT;
+                    if (lc < h.n_ecells) {
+                        const uint32_t e0 = reb[u].x & 0xFFFFu, e1 = reb[u].x >> 16, e2 = reb[u].y & 0xFFFFu;
+                        const double g0 = gb[u][0], g1 = gb[u][1], g2 = gb[u][2], S = g0 + g1 + g2;
+                        const double q0 = sq[e0 & 0x3FFFu], q1 = sq[e1 & 0x3FFFu], q2 = sq[e2 & 0x3FFFu];
+                        const double s0 = (e0 & 0x8000u) ? -1.0 : 1.0, s1 = (e1 & 0x8000u) ? -1.0 : 1.0, s2 = (e2 & 0x8000u) ? -1.0 : 1.0;
+                        const double t0 = s0 * q0, t1 = s1 * q1, t2 = s2 * q2;
+                        const double ST = S * (t0 + t1 + t2);
+                        sc3[3 * lc] = a.cM * s0 * (ST + 2.0 * S * t0 - 4.0 * (g0 * t0 + g2 * t1 + g1 * t2));
+                        sc3[3 * lc + 1] = a.cM * s1 * (ST + 2.0 * S * t1 - 4.0 * (g2 * t0 + g1 * t1 + g0 * t2));
+                        sc3[3 * lc + 2] = a.cM * s2 * (ST + 2.0 * S * t2 - 4.0 * (g1 * t0 + g0 * t1 + g2 * t2));
+                    }
+                }
+            }
+        }
+        for (int lc = threadIdx.x; lc < (MONLY ? 0 : h.n_ecells); lc += NT) {
             const uint2 re = __ldg(&m.rece[h.cell_off + lc]);
             uint2 rv = make_uint2(0u, 0u);
             if (HAS_D || CAS) rv = __ldg(&m.recv[h.cell_off + lc]);
@@ -423,7 +455,39 @@ __device__ __forceinline__ void edge_pass(const RowArgs& a, const PassIO& io, do
             sc3[3 * lc] = v0; sc3[3 * lc + 1] = v1; sc3[3 * lc + 2] = v2;
         }
         __syncthreads();
-        for (int le = threadIdx.x; le < h.e_cnt; le += NT) {
+        if (MONLY) {
+            constexpr int U3 = 2;
+            for (int base = threadIdx.x; base < h.e_cnt; base += U3 * NT) {
+                uint32_t adjb[U3]; double bvb[U3], pvb[U3], xpb[U3];
+#pragma unroll
+                for (int u = 0; u < U3; ++u) {
+                    const int le = base + u * NT;
+                    if (le < h.e_cnt) {
+                        const int gid = h.e_start + le;
+                        adjb[u] = __ldg(&m.eadj[gid]); bvb[u] = __ldg(&a.b[gid]); pvb[u] = __ldg(&a.pinv[gid]);
+                        xpb[u] = io.use_prev ? io.xprev[gid] : 0.0;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U3; ++u) {
+                    const int le = base + u * NT;
+                    if (le < h.e_cnt) {
+                        const int gid = h.e_start + le;
+                        const uint32_t ca = adjb[u] & 0xFFFFu, cb = adjb[u] >> 16;
+                        double val = sc3[3 * (ca >> 2) + (ca & 3u)];
+                        if (cb != 0xFFFFu) val += sc3[3 * (cb >> 2) + (cb & 3u)];
+                        const double xc = sq[le];
+                        const double r_ = bvb[u] - val;
+                        double xn = xc + io.c2 * pvb[u] * r_;
+                        if (io.use_prev) xn += io.c1 * (xc - xpb[u]);
+                        io.xnew[gid] = xn;
+                        acc0 += pvb[u] * r_ * r_;
+                        acc1 += pvb[u] * bvb[u] * bvb[u];
+                    }
+                }
+            }
+        }
+        for (int le = threadIdx.x; le < (MONLY ? 0 : h.e_cnt); le += NT) {
             const int gid = h.e_start + le;
             const uint32_t adj = m.eadj[gid];
             double bv = 0.0, pv = 0.0, xpv = 0.0;

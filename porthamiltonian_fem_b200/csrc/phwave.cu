@@ -522,7 +522,7 @@ int op_edge_dot(phw_solver_s* s, const double* xq, double cM, double cB, int slo
 // one cooperative launch = one complete Chebyshev solve
 template <int WHICH, bool CAS>
 int launch_coop(phw_solver_s* s, const RowArgs& av, const RowArgs& ae) {
-    constexpr int NT = (WHICH == 0) ? NT_COOP_P : NT_ROWS;
+    constexpr int NT = (WHICH == 0) ? NT_COOP_P : (WHICH == 1 ? NT_COOP_Q : NT_ROWS);
     constexpr int MINB = (WHICH == 0) ? 6 : 2;
     auto kern = solve_coop_k<WHICH, CAS, NT, MINB>;
     const size_t sm = (WHICH == 0) ? s->smem_v1 : (WHICH == 1 ? s->smem_e : s->smem_vd);
