@@ -82,6 +82,12 @@ int phw_mesh_create(int64_t n_vertices, const double* vertices_xy, int64_t n_cel
 int phw_mesh_create_partitioned(int64_t n_vertices, const double* vertices_xy, int64_t n_cells, const int32_t* cells,
                                 int32_t patch_cells, const uint8_t* vertex_external, int64_t n_edges,
                                 const uint8_t* edge_external, phw_mesh_t* out);
+/* batched parameter sweep (BASELINE.json configs[4]; the reference runs its cases one after the other,
+ * main_wave_2D.py:144): the mesh holds n_groups disjoint copies of one domain, cell_group[n_cells] names the copy
+ * (= case) of every cell.  All cases advance in the same kernels; per-case physics via
+ * phw_solver_set_group_params.  H_rows of phw_run becomes [n_groups][n_steps][8]. */
+int phw_mesh_create_grouped(int64_t n_vertices, const double* vertices_xy, int64_t n_cells, const int32_t* cells,
+                            int32_t patch_cells, const int32_t* cell_group, int32_t n_groups, phw_mesh_t* out);
 int phw_mesh_sizes(phw_mesh_t m, int64_t* n_vertices, int64_t* n_cells, int64_t* n_edges,
                    int64_t* n_boundary_edges, int64_t* n_patches);
 /* edges [n_edges,2], cell_edges [n_cells,3], cell_edge_sign [n_cells,3] (+1/-1); any pointer may be NULL */
@@ -102,6 +108,10 @@ int phw_mesh_destroy(phw_mesh_t m);
 /* ---- solver: replaces assemble(a)/assemble(b)/solve/assemble(energy) of wave_2D.py:579-595,787-982 ---- */
 int phw_solver_create(phw_mesh_t m, const phw_params* prm, int32_t device, void* cuda_stream, phw_solver_t* out);
 int phw_solver_destroy(phw_solver_t s);
+/* per-case K_wave[n], rho[n] and lumped constants lumped6[n][6] = (Bl, R1, R2, K_em, m_em, L_em) (wave_2D.py:153-158) */
+int phw_solver_set_group_params(phw_solver_t s, int32_t n_groups, const double* K_wave, const double* rho, const double* lumped6);
+/* lumped states of every case: x3_all[n_groups][3] */
+int phw_get_group_states(phw_solver_t s, double* x3_all);
 int phw_set_state(phw_solver_t s, const double* p, const double* q, const double* x3);   /* u_m, wave_2D.py:738,768 */
 int phw_get_state(phw_solver_t s, double* p, double* q, double* x3);
 /* run n_steps of the loop wave_2D.py:787-982 on the device; H_rows [n_steps, 8|12] host or device */

@@ -50,6 +50,7 @@ SIGNATURES = {
     'phw_version': (ctypes.c_int, []),
     'phw_mesh_create': (ctypes.c_int, [ctypes.c_int64, c_f64p, ctypes.c_int64, c_i32p, ctypes.c_int32, ctypes.POINTER(ctypes.c_void_p)]),
     'phw_mesh_create_partitioned': (ctypes.c_int, [ctypes.c_int64, c_f64p, ctypes.c_int64, c_i32p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]),
+    'phw_mesh_create_grouped': (ctypes.c_int, [ctypes.c_int64, c_f64p, ctypes.c_int64, c_i32p, ctypes.c_int32, c_i32p, ctypes.c_int32, ctypes.POINTER(ctypes.c_void_p)]),
     'phw_mesh_sizes': (ctypes.c_int, [ctypes.c_void_p, c_i64p, c_i64p, c_i64p, c_i64p, c_i64p]),
     'phw_mesh_get_edges': (ctypes.c_int, [ctypes.c_void_p, c_i32p, c_i32p, c_i8p]),
     'phw_mesh_get_boundary': (ctypes.c_int, [ctypes.c_void_p, c_i32p, c_i8p]),
@@ -60,6 +61,8 @@ SIGNATURES = {
     'phw_mesh_destroy': (ctypes.c_int, [ctypes.c_void_p]),
     'phw_solver_create': (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(PhwParams), ctypes.c_int32, ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]),
     'phw_solver_destroy': (ctypes.c_int, [ctypes.c_void_p]),
+    'phw_solver_set_group_params': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, c_f64p, c_f64p, c_f64p]),
+    'phw_get_group_states': (ctypes.c_int, [ctypes.c_void_p, c_f64p]),
     'phw_set_state': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     'phw_get_state': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     'phw_run': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]),

@@ -140,6 +140,8 @@ struct RowArgs {
     const double* b;
     const double* pinv;
     const double* mdiag;     // pure P1 mass diagonal sum_K |K|/6 (nullptr: use 1/pinv)
+    const double* gscale;    // batched runs: per-group factor applied to cD (nullptr: 1)
+    double* wpart;           // batched runs, DOT: per-(patch, warp) partial sums [npatch][NT/32] (nullptr: block reduction)
     double xscale;           // > 0 (strong Dirichlet rows): stop test ||r|| <= tol (||b|| + sqrt(xscale) ||x||_M), needs mdiag
     double cheb_d, cheb_c;   // centre and focal distance of the spectrum ellipse
     double tol2, weight;
@@ -212,6 +214,7 @@ __device__ __forceinline__ void vertex_pass(const RowArgs& a, const PassIO& io, 
     constexpr bool ONEVAL = HAS_M && !HAS_D && !CAS && MODE == MODE_OP;
     for (int P = blockIdx.x; P < m.npatch; P += gridDim.x) {
         const PatchHdr h = m.hdr[P];
+        const double cD = (HAS_D && a.gscale) ? a.cD * a.gscale[h.group] : a.cD;
         const int nlv = h.v_cnt + h.gv_cnt, nle = h.e_cnt + h.ge_cnt;
         double* sp = smem;                         // [nlv]
         double* sq = sp + ((nlv + 1) & ~1);        // [nle] (only if HAS_D)
@@ -289,12 +292,12 @@ __device__ __forceinline__ void vertex_pass(const RowArgs& a, const PassIO& io, 
                 const double t0 = (e0 & 0x8000u) ? -sq[e0 & 0x3FFFu] : sq[e0 & 0x3FFFu];
                 const double t1 = (e1 & 0x8000u) ? -sq[e1 & 0x3FFFu] : sq[e1 & 0x3FFFu];
                 const double t2 = (e2 & 0x8000u) ? -sq[e2 & 0x3FFFu] : sq[e2 & 0x3FFFu];
-                const double common = a.cD * (t0 + t1 + t2) * (1.0 / 3.0);
+                const double common = cD * (t0 + t1 + t2) * (1.0 / 3.0);
                 double d0 = common, d1 = common, d2 = common;
                 // zero-flux sides: -(1/2) s_e q_e at both end vertices of edge i (the vertices != i)
-                if (e0 & 0x4000u) { const double hq = 0.5 * a.cD * t0; d1 -= hq; d2 -= hq; }
-                if (e1 & 0x4000u) { const double hq = 0.5 * a.cD * t1; d0 -= hq; d2 -= hq; }
-                if (e2 & 0x4000u) { const double hq = 0.5 * a.cD * t2; d0 -= hq; d1 -= hq; }
+                if (e0 & 0x4000u) { const double hq = 0.5 * cD * t0; d1 -= hq; d2 -= hq; }
+                if (e1 & 0x4000u) { const double hq = 0.5 * cD * t1; d0 -= hq; d2 -= hq; }
+                if (e2 & 0x4000u) { const double hq = 0.5 * cD * t2; d0 -= hq; d1 -= hq; }
                 v0 += d0; v1 += d1; v2 += d2;
             }
             sc3[3 * lc] = v0; sc3[3 * lc + 1] = v1; sc3[3 * lc + 2] = v2;
@@ -345,6 +348,11 @@ __device__ __forceinline__ void vertex_pass(const RowArgs& a, const PassIO& io, 
                 acc0 += sp[lv] * val;
             }
         }
+        if (EPI == EPI_DOT && a.wpart) {   // batched runs: per-(patch, warp) partials, reduced per group afterwards
+            const double w0 = warp_sum(acc0);
+            if ((threadIdx.x & 31) == 0) a.wpart[(size_t)P * (NT / 32) + (threadIdx.x >> 5)] = w0;
+            acc0 = 0.0;
+        }
         __syncthreads();
     }
 }
@@ -357,6 +365,7 @@ __device__ __forceinline__ void edge_pass(const RowArgs& a, const PassIO& io, do
     const DevMesh& m = a.m;
     for (int P = blockIdx.x; P < m.npatch; P += gridDim.x) {
         const PatchHdr h = m.hdr[P];
+        const double cD = (HAS_D && a.gscale) ? a.cD * a.gscale[h.group] : a.cD;
         const int nlv = h.v_cnt + h.gv_cnt, nle = h.e_cnt + h.ge_cnt;
         double* sq = smem;                          // [nle]
         double* sp = sq + ((nle + 1) & ~1);         // [nlv] (only if HAS_D)
@@ -450,7 +459,7 @@ __device__ __forceinline__ void edge_pass(const RowArgs& a, const PassIO& io, do
                 if (e0 & 0x4000u) d0 -= 0.5 * (p1 + p2);
                 if (e1 & 0x4000u) d1 -= 0.5 * (p0 + p2);
                 if (e2 & 0x4000u) d2 -= 0.5 * (p0 + p1);
-                v0 += a.cD * s0 * d0; v1 += a.cD * s1 * d1; v2 += a.cD * s2 * d2;
+                v0 += cD * s0 * d0; v1 += cD * s1 * d1; v2 += cD * s2 * d2;
             }
             sc3[3 * lc] = v0; sc3[3 * lc + 1] = v1; sc3[3 * lc + 2] = v2;
         }
@@ -508,6 +517,11 @@ __device__ __forceinline__ void edge_pass(const RowArgs& a, const PassIO& io, do
             } else {
                 acc0 += sq[le] * val;
             }
+        }
+        if (EPI == EPI_DOT && a.wpart) {
+            const double w0 = warp_sum(acc0);
+            if ((threadIdx.x & 31) == 0) a.wpart[(size_t)P * (NT / 32) + (threadIdx.x >> 5)] = w0;
+            acc0 = 0.0;
         }
         __syncthreads();
     }
@@ -596,7 +610,7 @@ __global__ void __launch_bounds__(NT_ROWS, 2) vertex_rows_k(const RowArgs a) {
     if (!resolve_io<EPI>(a, true, io)) return;
     double acc0 = 0.0, acc1 = 0.0;
     vertex_pass<EPI, MODE, HAS_M, HAS_D, CAS, NT_ROWS>(a, io, smem, acc0, acc1);
-    if (EPI != EPI_STORE) finish_launch<EPI>(a, acc0, acc1, red);
+    if (EPI != EPI_STORE && !(EPI == EPI_DOT && a.wpart)) finish_launch<EPI>(a, acc0, acc1, red);
 }
 
 template <int EPI, int MODE, bool HAS_M, bool HAS_D, bool CAS>
@@ -607,7 +621,7 @@ __global__ void __launch_bounds__(NT_ROWS, 2) edge_rows_k(const RowArgs a) {
     if (!resolve_io<EPI>(a, false, io)) return;
     double acc0 = 0.0, acc1 = 0.0;
     edge_pass<EPI, MODE, HAS_M, HAS_D, CAS, NT_ROWS>(a, io, smem, acc0, acc1);
-    if (EPI != EPI_STORE) finish_launch<EPI>(a, acc0, acc1, red);
+    if (EPI != EPI_STORE && !(EPI == EPI_DOT && a.wpart)) finish_launch<EPI>(a, acc0, acc1, red);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -49,11 +49,19 @@ void radix_sort_pairs(std::vector<uint32_t>& key, std::vector<int32_t>& val) {
 }  // namespace
 
 std::string Layout::build(int64_t nv_, const double* vxy, int64_t nc_, const int32_t* cells_, int32_t patch_cells_,
-                          const uint8_t* v_ext, int64_t ne_expected, const uint8_t* e_ext) {
+                          const uint8_t* v_ext, int64_t ne_expected, const uint8_t* e_ext,
+                          const int32_t* cell_group, int32_t n_groups_) {
     if (nv_ <= 0 || nc_ <= 0 || !vxy || !cells_) return "empty mesh";
     if (nv_ > (int64_t)1 << 30 || nc_ > (int64_t)1 << 30) return "mesh too large for int32 indexing";
     if (patch_cells_ < 16 || patch_cells_ > 8192) return "patch_cells must be in [16, 8192]";
     nv = nv_; nc = nc_; patch_cells = patch_cells_;
+    n_groups = (cell_group && n_groups_ > 1) ? n_groups_ : 1;
+    cell_group_v.clear();
+    if (n_groups > 1) {
+        cell_group_v.assign(cell_group, cell_group + nc);
+        for (int64_t c = 0; c < nc; ++c)
+            if (cell_group[c] < 0 || cell_group[c] >= n_groups) return "cell group id out of range";
+    }
     vtx.assign(vxy, vxy + 2 * nv);
     cells.assign(cells_, cells_ + 3 * nc);
     // ---- 1. orient cells counter-clockwise
@@ -153,10 +161,29 @@ std::string Layout::build(int64_t nv_, const double* vxy, int64_t nc_, const int
         }
         radix_sort_pairs(key, order);
     }
-    npatch = (int32_t)((nc + patch_cells - 1) / patch_cells);
+    // batched runs: group-major order (stable), patches never straddle two groups
+    std::vector<int64_t> gcell_off(n_groups + 1, 0);
+    if (n_groups > 1) {
+        for (int64_t c = 0; c < nc; ++c) gcell_off[cell_group_v[c] + 1]++;
+        for (int32_t g = 0; g < n_groups; ++g) gcell_off[g + 1] += gcell_off[g];
+        std::vector<int64_t> pos(gcell_off.begin(), gcell_off.end() - 1);
+        std::vector<int32_t> o2(nc);
+        for (int64_t k = 0; k < nc; ++k) o2[pos[cell_group_v[order[k]]]++] = order[k];
+        order.swap(o2);
+    } else {
+        gcell_off[1] = nc;
+    }
+    std::vector<int64_t> own_off(1, 0);
+    std::vector<int32_t> patch_group;
+    group_patch_off.assign(n_groups + 1, 0);
+    for (int32_t g = 0; g < n_groups; ++g) {
+        const int64_t ng = gcell_off[g + 1] - gcell_off[g];
+        const int32_t npg = (int32_t)((ng + patch_cells - 1) / patch_cells);
+        for (int32_t p = 1; p <= npg; ++p) { own_off.push_back(gcell_off[g] + (int64_t)p * ng / npg); patch_group.push_back(g); }
+        group_patch_off[g + 1] = group_patch_off[g] + npg;
+    }
+    npatch = (int32_t)patch_group.size();
     cell_patch.assign(nc, 0);
-    std::vector<int64_t> own_off(npatch + 1);
-    for (int32_t p = 0; p <= npatch; ++p) own_off[p] = (int64_t)p * nc / npatch;
     for (int32_t p = 0; p < npatch; ++p)
         for (int64_t k = own_off[p]; k < own_off[p + 1]; ++k) cell_patch[order[k]] = p;
     // ---- 4. dof ownership = lowest adjacent patch; renumber so owned ranges are contiguous
@@ -242,6 +269,7 @@ std::string Layout::build(int64_t nv_, const double* vxy, int64_t nc_, const int
     for (int32_t p = 0; p < npatch; ++p) {
         PatchHdr& H = hdr[p];
         H.cell_off = (int32_t)pcell_user.size();
+        H.group = patch_group[p];
         H.n_own = (int32_t)(own_off[p + 1] - own_off[p]);
         H.v_start = vstart[p]; H.v_cnt = vstart[p + 1] - vstart[p];
         H.e_start = estart[p]; H.e_cnt = estart[p + 1] - estart[p];

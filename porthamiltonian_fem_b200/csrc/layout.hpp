@@ -31,7 +31,8 @@ struct PatchHdr {
     int32_t v_start, v_cnt, gv_off, gv_cnt;   // owned vertex range (new numbering), ghost list
     int32_t e_start, e_cnt, ge_off, ge_cnt;   // owned edge range, ghost list
     int32_t vs_off;     // first 32-vertex slice of this patch in vslice_off
-    int32_t pad[3];
+    int32_t group;      // case index of a batched (replicated-mesh) run, 0 otherwise
+    int32_t pad[2];
 };
 
 struct Layout {
@@ -72,7 +73,11 @@ struct Layout {
     int64_t nv_owned = 0, ne_owned = 0;   // external (other-rank) dofs are numbered after the owned ones
     // v_ext / e_ext (optional, by user id): 1 = dof owned by another rank (never a row of this rank)
     std::string build(int64_t nv_, const double* vxy, int64_t nc_, const int32_t* cells_, int32_t patch_cells_,
-                      const uint8_t* v_ext = nullptr, int64_t ne_expected = -1, const uint8_t* e_ext = nullptr);
+                      const uint8_t* v_ext = nullptr, int64_t ne_expected = -1, const uint8_t* e_ext = nullptr,
+                      const int32_t* cell_group = nullptr, int32_t n_groups_ = 1);
+    int32_t n_groups = 1;
+    std::vector<int32_t> group_patch_off;   // [n_groups+1] patches of a group are contiguous
+    std::vector<int32_t> cell_group_v;      // [nc] (empty when n_groups == 1)
     // cell records with boundary flag bits for the given formulation
     void make_records(bool strong, bool casimir, std::vector<CellRec>& rec) const;
 };

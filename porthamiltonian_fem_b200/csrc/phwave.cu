@@ -131,19 +131,34 @@ __global__ void copy_to_tb_k(int n, TriBuf tb, const Ctl* ctl, int which, const 
 }
 
 // port flux  b_L^T q = int_{Gamma_0} (q.n) g_L ds   (wave_2D.py:534,546,622-631), single CTA, fixed order
-__global__ void flux_k(int nport, const int* __restrict__ pe, const double* __restrict__ bl, const double* q,
+// one block per group (case of a batched run; a single group otherwise)
+__global__ void flux_k(const int* __restrict__ port_goff, const int* __restrict__ pe, const double* __restrict__ bl, const double* q,
                        TriBuf tb, Ctl* ctl, int which, int slot) {
     __shared__ double red[64];
     const double* qs = q ? q : tb.b[ctl->sc[which].cur];
+    const int g = blockIdx.x;
     double s = 0.0, z = 0.0;
-    for (int i = threadIdx.x; i < nport; i += blockDim.x) s += bl[i] * qs[pe[i]];
+    for (int i = port_goff[g] + threadIdx.x; i < port_goff[g + 1]; i += blockDim.x) s += bl[i] * qs[pe[i]];
     block_sum2(s, z, red);
-    if (threadIdx.x == 0) ctl->flux[slot] = s;
+    if (threadIdx.x == 0) ctl[g].flux[slot] = s;
 }
 // b[e] -= coef * b_L[e] * p_left   on the port edges (the ds(0) term of the q rows, wave_2D.py:469,480,504,515)
-__global__ void port_rhs_k(int nport, const int* __restrict__ pe, const double* __restrict__ bl, double* b, double coef, const Ctl* ctl) {
+__global__ void port_rhs_k(int nport, const int* __restrict__ pe, const double* __restrict__ bl, const int* __restrict__ pg,
+                           const double* __restrict__ gcoef, double* b, double coef, const Ctl* ctl) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < nport) b[pe[i]] -= coef * bl[i] * ctl->pleft;
+    if (i < nport) {
+        const int g = pg[i];
+        b[pe[i]] -= coef * (gcoef ? gcoef[g] : 1.0) * bl[i] * ctl[g].pleft;
+    }
+}
+// batched runs: ctl[g].red[slot] = scale * gscale[g] * sum of the (patch, warp) partials of group g
+__global__ void group_reduce_k(const double* __restrict__ wpart, int nw, const int* __restrict__ gpoff, const double* __restrict__ gscale,
+                               double scale, Ctl* ctl, int slot) {
+    const int g = blockIdx.x;
+    double s = 0.0;
+    for (int i = gpoff[g] * nw + threadIdx.x; i < gpoff[g + 1] * nw; i += 32) s += wpart[i];
+    s = warp_sum(s);
+    if (threadIdx.x == 0) ctl[g].red[slot] = scale * (gscale ? gscale[g] : 1.0) * s;
 }
 // strong Dirichlet rows (wave_2D.py:413-422, bc.apply :593-595,817,852): the new p value is prescribed, so the
 // velocity unknown of a constrained vertex is (w g(t) - p_old)/dt; its row is frozen by a zero Jacobi weight
@@ -280,9 +295,12 @@ enum ScalarOp {
     S_EH_BEGIN
 };
 
-__global__ void scalar_k(Ctl* ctl, const ScalarPrm s, int op, double* Hrows, double aux0, double aux1) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    Ctl& c = *ctl;
+__global__ void scalar_k(Ctl* ctl, const ScalarPrm* __restrict__ prms, int n_groups, int op, double* Hrows, long long rows_per_group,
+                         double aux0, double aux1) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_groups) return;
+    Ctl& c = ctl[g];
+    const ScalarPrm s = prms[g];
     const double dt = s.dt;
     switch (op) {
         case S_BEGIN_1SUB:
@@ -379,7 +397,7 @@ __global__ void scalar_k(Ctl* ctl, const ScalarPrm s, int op, double* Hrows, dou
             }
             c.H_wave = H_wave;
             if (Hrows) {
-                double* row = Hrows + c.step * s.ncol;                               // :1011-1030
+                double* row = Hrows + ((long long)g * rows_per_group + c.step) * s.ncol;   // :1011-1030
                 row[0] = c.t; row[1] = H; row[2] = E; row[3] = c.disp; row[4] = c.bE; row[5] = c.inpE; row[6] = c.H_em; row[7] = H_wave;
                 if (s.ncol == 12) { row[8] = c.red[4]; row[9] = c.red[5]; row[10] = c.red[6]; row[11] = c.red[7]; }    // :1027-1030
             }
@@ -411,8 +429,11 @@ struct phw_solver_s {
     TriBuf tp{}, tq{};
     double* partials = nullptr;
     Ctl* ctl = nullptr;
-    double* dH = nullptr; int64_t dH_rows = 0;
+    double* dH = nullptr; int64_t dH_rows = 0; int64_t run_rows = 0;
     ScalarPrm sp{};
+    int G = 1; ScalarPrm* d_sp = nullptr; std::vector<ScalarPrm> h_sp;
+    int *d_port_goff = nullptr, *d_port_group = nullptr, *d_gpoff = nullptr;
+    double *d_gK = nullptr, *d_ginvrho = nullptr, *wpart = nullptr;
     double lam_min_q = 0.5, lam_max_q = 2.0, skew_bound = 0.0, blw = 0.0;
     double cheb_d[3] = {1.25, 1.25, 1.25}, cheb_c[3] = {0.75, 0.75, 0.75};
     size_t smem_v = 0, smem_v1 = 0, smem_e = 0, smem_vd = 0, smem_ed = 0;
@@ -482,6 +503,8 @@ RowArgs base_args(phw_solver_s* s) {
     a.m = s->dm; a.tp = s->tp; a.tq = s->tq;
     a.partials = s->partials; a.ctl = s->ctl;
     a.tol2 = s->prm.tol * s->prm.tol; a.max_iter = s->prm.max_iter; a.weight = 1.0;
+    // batched runs test the aggregated residual of all cases: tighten it so that every case of comparable amplitude meets tol
+    if (s->G > 1) a.tol2 /= 100.0 * s->G;
     a.dot_scale = 1.0;
     a.mdiag = s->mdiag_p;   // vertex M-only rows use the pure P1 mass diagonal
     a.xscale = s->prm.strong ? 4.0 : 0.0;
@@ -489,16 +512,18 @@ RowArgs base_args(phw_solver_s* s) {
 }
 
 // y_v = cD (D^T xq)_v [+ cB (B_top xp)_v]          (explicit part of the p rows)
-int op_vertex_store(phw_solver_s* s, const double* xp, const double* xq, double cM, double cD, double cB, double* y) {
+int op_vertex_store(phw_solver_s* s, const double* xp, const double* xq, double cM, double cD, double cB, double* y, const double* gscale = nullptr) {
     RowArgs a = base_args(s);
+    a.gscale = gscale;
     a.xp = xp; a.xq = xq; a.cM = cM; a.cD = cD; a.cB = cB; a.y = y;
     const bool cas = s->prm.casimir && cB != 0.0;
     if (cM != 0.0 && cD == 0.0) return cas ? launch_vertex<EPI_STORE, MODE_OP, true, false, true>(s, a) : launch_vertex<EPI_STORE, MODE_OP, true, false, false>(s, a);
     if (cM == 0.0) return cas ? launch_vertex<EPI_STORE, MODE_OP, false, true, true>(s, a) : launch_vertex<EPI_STORE, MODE_OP, false, true, false>(s, a);
     return cas ? launch_vertex<EPI_STORE, MODE_OP, true, true, true>(s, a) : launch_vertex<EPI_STORE, MODE_OP, true, true, false>(s, a);
 }
-int op_edge_store(phw_solver_s* s, const double* xp, const double* xq, double cM, double cD, double cB, double* y) {
+int op_edge_store(phw_solver_s* s, const double* xp, const double* xq, double cM, double cD, double cB, double* y, const double* gscale = nullptr) {
     RowArgs a = base_args(s);
+    a.gscale = gscale;
     a.xp = xp; a.xq = xq; a.cM = cM; a.cD = cD; a.cB = cB; a.y = y;
     const bool cas = s->prm.casimir && cB != 0.0;
     if (cM != 0.0 && cD == 0.0) return cas ? launch_edge<EPI_STORE, MODE_OP, true, false, true>(s, a) : launch_edge<EPI_STORE, MODE_OP, true, false, false>(s, a);
@@ -509,12 +534,14 @@ int op_edge_store(phw_solver_s* s, const double* xp, const double* xq, double cM
 int op_vertex_dot(phw_solver_s* s, const double* xp, double cM, double cB, int slot, double scale, int counter) {
     RowArgs a = base_args(s);
     a.xp = xp; a.cM = cM; a.cB = cB; a.red_slot = slot; a.dot_scale = scale; a.counter_id = counter;
+    if (s->G > 1) a.wpart = s->wpart;
     if (cB != 0.0) return (cM != 0.0) ? launch_vertex<EPI_DOT, MODE_OP, true, false, true>(s, a) : launch_vertex<EPI_DOT, MODE_OP, false, false, true>(s, a);
     return launch_vertex<EPI_DOT, MODE_OP, true, false, false>(s, a);
 }
 int op_edge_dot(phw_solver_s* s, const double* xq, double cM, double cB, int slot, double scale, int counter) {
     RowArgs a = base_args(s);
     a.xq = xq; a.cM = cM; a.cB = cB; a.red_slot = slot; a.dot_scale = scale; a.counter_id = counter;
+    if (s->G > 1) a.wpart = s->wpart;
     if (cB != 0.0) return (cM != 0.0) ? launch_edge<EPI_DOT, MODE_OP, true, false, true>(s, a) : launch_edge<EPI_DOT, MODE_OP, false, false, true>(s, a);
     return launch_edge<EPI_DOT, MODE_OP, true, false, false>(s, a);
 }
@@ -616,13 +643,13 @@ int allreduce(phw_solver_s* s, int what, int first, int n) {
     return 0;
 }
 int scalar(phw_solver_s* s, int op, double aux0 = 0.0, double aux1 = 0.0) {
-    scalar_k<<<1, 32, 0, s->stream>>>(s->ctl, s->sp, op, s->dH, aux0, aux1);
+    scalar_k<<<nblk(s->G, 64), 64, 0, s->stream>>>(s->ctl, s->d_sp, s->G, op, s->dH, (long long)s->run_rows, aux0, aux1);
     s->launches++;
     CU(cudaGetLastError());
     return 0;
 }
 int flux(phw_solver_s* s, const double* q, int which, int slot) {
-    flux_k<<<1, 256, 0, s->stream>>>(s->nport, s->d_port_e, s->d_port_bl, q, s->tq, s->ctl, which, slot);
+    flux_k<<<s->G, s->G > 1 ? 32 : 256, 0, s->stream>>>(s->d_port_goff, s->d_port_e, s->d_port_bl, q, s->tq, s->ctl, which, slot);
     s->launches++;
     CU(cudaGetLastError());
     return allreduce(s, 1, slot, 1);      // only the rank holding the port contributes
@@ -643,21 +670,33 @@ int waxpy(phw_solver_s* s, int n, double* w, const double* y, double a, const do
 // b_p = -K (D^T qsrc [+ B_top psrc])          (explicit part of the p rows, velocity form)
 int rhs_p(phw_solver_s* s, const double* qsrc, const double* psrc) {
     const double K = s->prm.K_wave;
+    if (s->G > 1) return op_vertex_store(s, psrc, qsrc, 0.0, -1.0, 0.0, s->bp, s->d_gK);
     return op_vertex_store(s, psrc, qsrc, 0.0, -K, s->prm.casimir ? -K : 0.0, s->bp);
 }
 // b_q = (1/rho) (D psrc - b_L p_left [- B_right qsrc])
 int rhs_q(phw_solver_s* s, const double* psrc, const double* qsrc) {
-    const double ir = 1.0 / s->prm.rho;
-    int rc = op_edge_store(s, psrc, qsrc, 0.0, ir, s->prm.casimir ? -ir : 0.0, s->bq);
+    const double ir = (s->G > 1) ? 1.0 : 1.0 / s->prm.rho;
+    int rc = (s->G > 1) ? op_edge_store(s, psrc, qsrc, 0.0, 1.0, 0.0, s->bq, s->d_ginvrho)
+                        : op_edge_store(s, psrc, qsrc, 0.0, ir, s->prm.casimir ? -ir : 0.0, s->bq);
     if (rc) return rc;
     if (!s->prm.strong && s->nport > 0) {
-        port_rhs_k<<<nblk(s->nport), 256, 0, s->stream>>>(s->nport, s->d_port_e, s->d_port_bl, s->bq, ir, s->ctl);
+        port_rhs_k<<<nblk(s->nport), 256, 0, s->stream>>>(s->nport, s->d_port_e, s->d_port_bl, s->d_port_group,
+                                                          s->G > 1 ? s->d_ginvrho : nullptr, s->bq, ir, s->ctl);
         s->launches++;
         CU(cudaGetLastError());
     }
     return 0;
 }
 int energy(phw_solver_s* s) {
+    if (s->G > 1) {   // batched: per-(patch, warp) partials -> one reduction block per case
+        int rc = op_vertex_dot(s, s->p, 1.0, 0.0, 0, 1.0, 4); if (rc) return rc;
+        group_reduce_k<<<s->G, 32, 0, s->stream>>>(s->wpart, NT_ROWS / 32, s->d_gpoff, s->d_ginvrho, 0.5, s->ctl, 0);
+        rc = op_edge_dot(s, s->q, 1.0, 0.0, 1, 1.0, 5); if (rc) return rc;
+        group_reduce_k<<<s->G, 32, 0, s->stream>>>(s->wpart, NT_ROWS / 32, s->d_gpoff, s->d_gK, 0.5, s->ctl, 1);
+        s->launches += 2;
+        CU(cudaGetLastError());
+        return 0;
+    }
     int rc = op_vertex_dot(s, s->p, 1.0, 0.0, 0, 0.5 / s->prm.rho, 4);
     if (rc) return rc;
     rc = op_edge_dot(s, s->q, 1.0, 0.0, 1, 0.5 * s->prm.K_wave, 5);
@@ -927,6 +966,23 @@ int phw_mesh_create_partitioned(int64_t n_vertices, const double* vertices_xy, i
     return PHW_OK;
 }
 
+int phw_mesh_create_grouped(int64_t n_vertices, const double* vertices_xy, int64_t n_cells, const int32_t* cells,
+                            int32_t patch_cells, const int32_t* cell_group, int32_t n_groups, phw_mesh_t* out) {
+    if (!out || !cell_group || n_groups < 1) return fail(PHW_EINVAL, "bad arguments");
+    phw_mesh_s* m = new (std::nothrow) phw_mesh_s();
+    if (!m) return fail(PHW_ENOMEM, "out of host memory");
+    std::string err;
+    try {
+        err = m->L.build(n_vertices, vertices_xy, n_cells, cells, patch_cells > 0 ? patch_cells : 2048, nullptr, -1, nullptr, cell_group, n_groups);
+    } catch (const std::bad_alloc&) {
+        delete m;
+        return fail(PHW_ENOMEM, "out of host memory while building the mesh layout");
+    }
+    if (!err.empty()) { delete m; return fail(PHW_EINVAL, err); }
+    *out = m;
+    return PHW_OK;
+}
+
 int phw_mesh_sizes(phw_mesh_t m, int64_t* nv, int64_t* nc, int64_t* ne, int64_t* nb, int64_t* np) {
     if (!m) return fail(PHW_EINVAL, "mesh is NULL");
     if (nv) *nv = m->L.nv;
@@ -1010,6 +1066,18 @@ int phw_synchronize(phw_solver_t s) {
     return PHW_OK;
 }
 
+static bool implicit_scheme(int scheme) { return scheme == PHW_IE || scheme == PHW_SM; }
+static void fill_physics(ScalarPrm& sp, double dt, double K, double rho, double Bl, double R1, double R2, double K_em, double m_em, double L_em) {
+    sp.dt = dt; sp.K = K; sp.rho = rho; sp.c2 = K / rho;
+    // A_em = (J - R) diag(1/L, 1/m, K_em)      wave_2D.py:160-166
+    const double J[3][3] = {{0, Bl, 0}, {-Bl, 0, -1}, {0, 1, 0}};
+    const double R[3] = {R1, R2, 0.0};
+    const double cv[3] = {L_em != 0 ? 1.0 / L_em : 0.0, m_em != 0 ? 1.0 / m_em : 0.0, K_em};
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) sp.A[i][j] = (J[i][j] - (i == j ? R[i] : 0.0)) * cv[j];
+    sp.m_em = m_em; sp.L_em = L_em; sp.K_em = K_em;
+}
+
 static int setup_solver(phw_solver_s* s) {
     const Layout& L = s->mesh->L;
     const phw_params& P = s->prm;
@@ -1057,11 +1125,29 @@ static int setup_solver(phw_solver_s* s) {
     s->dm.ghost_v = d_gv; s->dm.ghost_e = d_ge; s->dm.eadj = d_eadj; s->dm.vslice_off = d_voff; s->dm.vadj = d_vadj;
     // ---- port (left boundary, tag 0): b_L[e] = sign * weight   (flux-normalised RT1: <phi_e.n, g_L> = sign * mean(g_L))
     {
-        std::vector<int32_t> pe; std::vector<double> bl;
+        s->G = L.n_groups;
+        std::vector<int32_t> egroup;
+        if (s->G > 1) {
+            egroup.assign(L.ne, 0);
+            for (int64_t h = 0; h < 3 * L.nc; ++h) egroup[L.cell_edges[h]] = L.cell_group_v[h / 3];
+        }
+        std::vector<int32_t> pe, pg, goff(s->G + 1, 0); std::vector<double> bl;
+        std::vector<int64_t> ks;
         for (int64_t k = 0; k < L.nb; ++k)
-            if (L.btag[k] == PHW_TAG_LEFT) { pe.push_back(L.e_old2new[L.bedge[k]]); bl.push_back(L.bsign[k] * L.bweight[k]); }
+            if (L.btag[k] == PHW_TAG_LEFT) { ks.push_back(k); goff[(s->G > 1 ? egroup[L.bedge[k]] : 0) + 1]++; }
+        for (int g = 0; g < s->G; ++g) goff[g + 1] += goff[g];
+        pe.resize(ks.size()); pg.resize(ks.size()); bl.resize(ks.size());
+        std::vector<int32_t> pos(goff.begin(), goff.end() - 1);
+        for (int64_t k : ks) {
+            const int g = s->G > 1 ? egroup[L.bedge[k]] : 0;
+            const int d = pos[g]++;
+            pe[d] = L.e_old2new[L.bedge[k]]; pg[d] = g; bl[d] = L.bsign[k] * L.bweight[k];
+        }
         s->nport = (int)pe.size();
         RC(s->upload(&s->d_port_e, pe)); RC(s->upload(&s->d_port_bl, bl));
+        RC(s->upload(&s->d_port_goff, goff)); RC(s->upload(&s->d_port_group, pg));
+        RC(s->upload(&s->d_gpoff, L.group_patch_off));
+        if (s->G > 1) RC(s->dalloc(&s->wpart, (size_t)L.npatch * (NT_ROWS / 32)));
     }
     // ---- vectors
     const size_t nv = s->nv, ne = s->ne;
@@ -1089,7 +1175,7 @@ static int setup_solver(phw_solver_s* s) {
         CU(cudaDeviceGetAttribute(&coop_attr, cudaDevAttrCooperativeLaunch, s->device));
         s->coop = coop_attr != 0 && !(P.flags & 8);
     }
-    RC(s->dalloc(&s->ctl, 1));
+    RC(s->dalloc(&s->ctl, (size_t)s->G));
     s->extrap = (P.extrap_order < 0) ? 0 : std::min(P.extrap_order, 3);
     s->n_sites = (P.scheme == PHW_EH) ? 2 : 1;
     if (s->extrap > 0 || true) {
@@ -1101,7 +1187,7 @@ static int setup_solver(phw_solver_s* s) {
     }
     for (double* v : {s->p, s->bp, s->tmp_p, s->tp.b[0], s->tp.b[1], s->tp.b[2], s->io_v, s->io_v2}) CU(cudaMemsetAsync(v, 0, nv * 8, s->stream));
     for (double* v : {s->q, s->bq, s->tmp_q, s->tq.b[0], s->tq.b[1], s->tq.b[2], s->io_e, s->io_e2}) CU(cudaMemsetAsync(v, 0, ne * 8, s->stream));
-    CU(cudaMemsetAsync(s->ctl, 0, sizeof(Ctl), s->stream));
+    CU(cudaMemsetAsync(s->ctl, 0, sizeof(Ctl) * (size_t)s->G, s->stream));
     // ---- shared-memory budgets and grid
     auto ev = [](int x) { return (size_t)((x + 1) & ~1); };
     s->smem_v = (ev(L.max_lv) + 3 * (size_t)L.max_cells) * 8;
@@ -1113,15 +1199,7 @@ static int setup_solver(phw_solver_s* s) {
     s->grid_rows = std::max(1, std::min(s->npatch, 2 * s->sm_count));
     // ---- scalar parameters
     ScalarPrm& sp = s->sp;
-    sp.dt = P.dt; sp.K = P.K_wave; sp.rho = P.rho; sp.c2 = P.K_wave / P.rho;
-    {   // A_em = (J - R) diag(1/L, 1/m, K_em)      wave_2D.py:160-166
-        const double J[3][3] = {{0, P.Bl_em, 0}, {-P.Bl_em, 0, -1}, {0, 1, 0}};
-        const double R[3] = {P.R1_em, P.R2_em, 0.0};
-        const double cv[3] = {P.L_em != 0 ? 1.0 / P.L_em : 0.0, P.m_em != 0 ? 1.0 / P.m_em : 0.0, P.K_em};
-        for (int i = 0; i < 3; ++i)
-            for (int j = 0; j < 3; ++j) sp.A[i][j] = (J[i][j] - (i == j ? R[i] : 0.0)) * cv[j];
-    }
-    sp.m_em = P.m_em; sp.L_em = P.L_em; sp.K_em = P.K_em;
+    fill_physics(sp, P.dt, P.K_wave, P.rho, P.Bl_em, P.R1_em, P.R2_em, P.K_em, P.m_em, P.L_em);
     sp.input_kind = P.input_kind; sp.in_amp = P.in_amp; sp.in_omega = P.in_omega; sp.in_t_stop = P.in_t_stop;
     sp.in_t_ctrl = P.in_t_ctrl; sp.in_gain = P.in_gain; sp.H_init = P.H_init;
     s->ncol = P.analytical ? 12 : 8;
@@ -1131,6 +1209,14 @@ static int setup_solver(phw_solver_s* s) {
         case PHW_IE: sp.w_old = 0.0; sp.w_new = 1.0; break;
         case PHW_SM: sp.w_old = 0.5; sp.w_new = 0.5; break;
         default: sp.w_old = 1.0; sp.w_new = 0.0;
+    }
+    s->h_sp.assign(s->G, sp);
+    RC(s->upload(&s->d_sp, s->h_sp));
+    if (s->G > 1) {
+        if (implicit_scheme(P.scheme) || P.strong || P.analytical || P.casimir)
+            return fail(PHW_EINVAL, "batched (grouped) runs support the explicit weak-form schemes only");
+        std::vector<double> gk(s->G, P.K_wave), gir(s->G, 1.0 / P.rho);
+        RC(s->upload(&s->d_gK, gk)); RC(s->upload(&s->d_ginvrho, gir));
     }
     // ---- Jacobi diagonals (inverse) of the solved blocks
     const bool implicit = (P.scheme == PHW_IE || P.scheme == PHW_SM);
@@ -1250,7 +1336,7 @@ int phw_solver_create(phw_mesh_t m, const phw_params* prm, int32_t device, void*
             if (!rc) {
                 copy_from_tb_k<<<vec_grid(s, s->nv), 256, 0, s->stream>>>(s->nv, s->wp, s->tp, s->ctl, 2);
                 copy_from_tb_k<<<vec_grid(s, s->ne), 256, 0, s->stream>>>(s->ne, s->wq, s->tq, s->ctl, 2);
-                flux_k<<<1, 256, 0, s->stream>>>(s->nport, s->d_port_e, s->d_port_bl, s->wq, s->tq, s->ctl, 2, 3);
+                flux_k<<<1, 256, 0, s->stream>>>(s->d_port_goff, s->d_port_e, s->d_port_bl, s->wq, s->tq, s->ctl, 2, 3);
                 double f3 = 0.0;
                 cudaMemcpyAsync(&f3, &s->ctl->flux[3], 8, cudaMemcpyDeviceToHost, s->stream);
                 cudaStreamSynchronize(s->stream);
@@ -1362,6 +1448,35 @@ int phw_set_cheb_bounds(phw_solver_t s, double lam_min_q, double lam_max_q) {
     return PHW_OK;
 }
 
+int phw_solver_set_group_params(phw_solver_t s, int32_t n_groups, const double* K_wave, const double* rho, const double* lumped6) {
+    if (!s || !K_wave || !rho || !lumped6) return fail(PHW_EINVAL, "NULL argument");
+    if (n_groups != s->G) return fail(PHW_EINVAL, "n_groups does not match the mesh");
+    if (s->G < 2) return fail(PHW_ESTATE, "the mesh has a single group: use phw_params");
+    CU(cudaSetDevice(s->device));
+    std::vector<double> gk(s->G), gir(s->G);
+    for (int g = 0; g < s->G; ++g) {
+        if (!(K_wave[g] > 0) || !(rho[g] > 0)) return fail(PHW_EINVAL, "K_wave and rho must be positive");
+        const double* l = lumped6 + 6 * (size_t)g;   // Bl, R1, R2, K_em, m_em, L_em   (wave_2D.py:153-158)
+        fill_physics(s->h_sp[g], s->prm.dt, K_wave[g], rho[g], l[0], l[1], l[2], l[3], l[4], l[5]);
+        gk[g] = K_wave[g]; gir[g] = 1.0 / rho[g];
+    }
+    CU(cudaMemcpyAsync(s->d_sp, s->h_sp.data(), s->h_sp.size() * sizeof(ScalarPrm), cudaMemcpyHostToDevice, s->stream));
+    CU(cudaMemcpyAsync(s->d_gK, gk.data(), gk.size() * 8, cudaMemcpyHostToDevice, s->stream));
+    CU(cudaMemcpyAsync(s->d_ginvrho, gir.data(), gir.size() * 8, cudaMemcpyHostToDevice, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return PHW_OK;
+}
+
+int phw_get_group_states(phw_solver_t s, double* x3_all) {
+    if (!s || !x3_all) return fail(PHW_EINVAL, "NULL argument");
+    CU(cudaSetDevice(s->device));
+    std::vector<Ctl> hcs(s->G);
+    CU(cudaMemcpyAsync(hcs.data(), s->ctl, sizeof(Ctl) * (size_t)s->G, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    for (int g = 0; g < s->G; ++g) for (int i = 0; i < 3; ++i) x3_all[3 * g + i] = hcs[g].x[i];
+    return PHW_OK;
+}
+
 int phw_set_state(phw_solver_t s, const double* p, const double* q, const double* x3) {
     if (!s) return fail(PHW_EINVAL, "solver is NULL");
     CU(cudaSetDevice(s->device));
@@ -1373,7 +1488,7 @@ int phw_set_state(phw_solver_t s, const double* p, const double* q, const double
         if (is_device_ptr(x3)) CU(cudaMemcpyAsync(h, x3, 24, cudaMemcpyDeviceToHost, s->stream));
         else memcpy(h, x3, 24);
         CU(cudaStreamSynchronize(s->stream));
-        CU(cudaMemcpyAsync(&s->ctl->x[0], h, 24, cudaMemcpyHostToDevice, s->stream));
+        for (int g = 0; g < s->G; ++g) CU(cudaMemcpyAsync(&s->ctl[g].x[0], h, 24, cudaMemcpyHostToDevice, s->stream));
     }
     reset_history(s);
     CU(cudaStreamSynchronize(s->stream));
@@ -1400,20 +1515,24 @@ int phw_get_state(phw_solver_t s, double* p, double* q, double* x3) {
 int phw_run(phw_solver_t s, int64_t n_steps, double* H_rows) {
     if (!s || n_steps < 0) return fail(PHW_EINVAL, "bad arguments");
     CU(cudaSetDevice(s->device));
-    if (n_steps > s->dH_rows) {
+    const size_t nrow = (size_t)n_steps * (size_t)s->G;
+    if ((int64_t)nrow > s->dH_rows) {
         double* d = nullptr;
-        int rc = s->dalloc(&d, (size_t)n_steps * s->ncol);
+        int rc = s->dalloc(&d, nrow * s->ncol);
         if (rc) return rc;
-        s->dH = d; s->dH_rows = n_steps;
+        s->dH = d; s->dH_rows = (int64_t)nrow;
     }
-    if (n_steps > 0) CU(cudaMemsetAsync(s->dH, 0, (size_t)n_steps * s->ncol * 8, s->stream));
+    s->run_rows = n_steps;
+    if (n_steps > 0) CU(cudaMemsetAsync(s->dH, 0, nrow * s->ncol * 8, s->stream));
     // row index restarts at 0 for every run; iteration statistics are per run
-    Ctl hc;
-    CU(cudaMemcpyAsync(&hc, s->ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, s->stream));
+    std::vector<Ctl> hcs(s->G);
+    CU(cudaMemcpyAsync(hcs.data(), s->ctl, sizeof(Ctl) * (size_t)s->G, cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
-    hc.step = 0; hc.nonconv = 0;
-    for (int i = 0; i < 3; ++i) { hc.sc[i].iters = 0; hc.sc[i].solves = 0; hc.sc[i].maxres = 0.0; }
-    CU(cudaMemcpyAsync(s->ctl, &hc, sizeof(Ctl), cudaMemcpyHostToDevice, s->stream));
+    for (auto& g : hcs) { g.step = 0; g.nonconv = 0; }
+    for (int i = 0; i < 3; ++i) { hcs[0].sc[i].iters = 0; hcs[0].sc[i].solves = 0; hcs[0].sc[i].maxres = 0.0; }
+    CU(cudaMemcpyAsync(s->ctl, hcs.data(), sizeof(Ctl) * (size_t)s->G, cudaMemcpyHostToDevice, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    Ctl hc;
     s->launches = 0;
     CU(cudaEventRecord(s->ev0, s->stream));
     if (s->prm.analytical && !s->an_ready) return fail(PHW_ESTATE, "analytical run: call phw_set_analytical before phw_run");
@@ -1426,8 +1545,8 @@ int phw_run(phw_solver_t s, int64_t n_steps, double* H_rows) {
     }
     CU(cudaEventRecord(s->ev1, s->stream));
     if (H_rows && n_steps > 0) {
-        if (is_device_ptr(H_rows)) CU(cudaMemcpyAsync(H_rows, s->dH, (size_t)n_steps * s->ncol * 8, cudaMemcpyDeviceToDevice, s->stream));
-        else CU(cudaMemcpyAsync(H_rows, s->dH, (size_t)n_steps * s->ncol * 8, cudaMemcpyDeviceToHost, s->stream));
+        if (is_device_ptr(H_rows)) CU(cudaMemcpyAsync(H_rows, s->dH, nrow * s->ncol * 8, cudaMemcpyDeviceToDevice, s->stream));
+        else CU(cudaMemcpyAsync(H_rows, s->dH, nrow * s->ncol * 8, cudaMemcpyDeviceToHost, s->stream));
     }
     CU(cudaStreamSynchronize(s->stream));
     float ms = 0.f;
@@ -1573,6 +1692,10 @@ int phw_set_H_init(phw_solver_t s, double H_init) {
     if (!s) return fail(PHW_EINVAL, "solver is NULL");
     s->prm.H_init = H_init;
     s->sp.H_init = H_init;
+    for (auto& g : s->h_sp) g.H_init = H_init;
+    CU(cudaSetDevice(s->device));
+    CU(cudaMemcpyAsync(s->d_sp, s->h_sp.data(), s->h_sp.size() * sizeof(ScalarPrm), cudaMemcpyHostToDevice, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
     return PHW_OK;
 }
 int phw_port_flux(phw_solver_t s, double* out) {

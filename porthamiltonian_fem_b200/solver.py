@@ -11,14 +11,20 @@ TAG_LEFT, TAG_TOP, TAG_RIGHT, TAG_GENERAL, TAG_NONE = 0, 1, 2, 3, 4
 class Mesh:
     """Connectivity + patch layout of a triangle mesh (phw_mesh_*; host only, no GPU needed)."""
 
-    def __init__(self, vertices, cells, patch_cells=2048, vertex_external=None, edge_external=None):
+    def __init__(self, vertices, cells, patch_cells=2048, vertex_external=None, edge_external=None, cell_group=None, n_groups=1):
         self.lib = _lib.load()
         self.vertices = np.ascontiguousarray(vertices, dtype=np.float64)
         self.cells = np.ascontiguousarray(cells, dtype=np.int32)
         if self.vertices.ndim != 2 or self.vertices.shape[1] != 2 or self.cells.ndim != 2 or self.cells.shape[1] != 3:
             raise ValueError('vertices must be [Nv,2], cells must be [Nc,3]')
         h = ctypes.c_void_p()
-        if vertex_external is None:
+        self.n_groups = int(n_groups) if cell_group is not None else 1
+        if cell_group is not None:   # batched sweep: disjoint copies of one domain, one case per copy
+            cg = np.ascontiguousarray(cell_group, dtype=np.int32)
+            _lib.check(self.lib.phw_mesh_create_grouped(self.vertices.shape[0], self.vertices.ctypes.data_as(_lib.c_f64p),
+                                                        self.cells.shape[0], self.cells.ctypes.data_as(_lib.c_i32p),
+                                                        int(patch_cells), cg.ctypes.data_as(_lib.c_i32p), self.n_groups, ctypes.byref(h)))
+        elif vertex_external is None:
             _lib.check(self.lib.phw_mesh_create(self.vertices.shape[0], self.vertices.ctypes.data_as(_lib.c_f64p),
                                                 self.cells.shape[0], self.cells.ctypes.data_as(_lib.c_i32p),
                                                 int(patch_cells), ctypes.byref(h)))
@@ -169,9 +175,22 @@ class Solver:
         _lib.check(self.lib.phw_get_state(self.handle, p.ctypes.data, q.ctypes.data, x.ctypes.data))
         return p, q, x
 
+    def set_group_params(self, K_wave, rho, lumped6):
+        K_wave = np.ascontiguousarray(K_wave, dtype=np.float64)
+        rho = np.ascontiguousarray(rho, dtype=np.float64)
+        lumped6 = np.ascontiguousarray(lumped6, dtype=np.float64)
+        _lib.check(self.lib.phw_solver_set_group_params(self.handle, K_wave.shape[0], K_wave.ctypes.data_as(_lib.c_f64p),
+                                                        rho.ctypes.data_as(_lib.c_f64p), lumped6.ctypes.data_as(_lib.c_f64p)))
+
+    def group_states(self):
+        x = np.empty((self.mesh.n_groups, 3))
+        _lib.check(self.lib.phw_get_group_states(self.handle, x.ctypes.data_as(_lib.c_f64p)))
+        return x
+
     def run(self, n_steps, out=None):
         if out is None:
-            out = np.zeros((n_steps, self.ncol))
+            G = getattr(self.mesh, 'n_groups', 1)
+            out = np.zeros((n_steps, self.ncol)) if G == 1 else np.zeros((G, n_steps, self.ncol))
         _lib.check(self.lib.phw_run(self.handle, int(n_steps), _lib.ptr(out)))
         return out
 

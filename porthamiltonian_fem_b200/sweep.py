@@ -1,0 +1,72 @@
+"""Batched parameter / control sweep (BASELINE.json configs[4]): many independent coupled wave + lumped cases on the
+same mesh, advanced together by the same kernels.
+
+The reference runs its case list one case after the other (main_wave_2D.py:144, one ``wave_2D_solve`` call each).
+Here the mesh is replicated once per case as disjoint components of ONE device mesh ("groups"), so a single set of
+launches per step serves every case; only scalars differ between cases (K_wave, rho and the lumped constants of
+wave_2D.py:153-158), which the kernels look up per patch / per port edge.  There is no coupling and no collective
+between cases; on several GPUs each rank simply takes a contiguous shard of the case list.
+"""
+import numpy as np
+
+from . import _lib
+from .mesh import generate_mesh
+from .solver import Mesh, Solver, tag_boundary_edges
+
+LUMPED_KEYS = ('Bl_em', 'R1_em', 'R2_em', 'K_em', 'm_em', 'L_em')
+DEFAULT_LUMPED = dict(Bl_em=5.0, R1_em=0.0, R2_em=0.0, K_em=5.0, m_em=0.15, L_em=0.1)
+
+
+def replicate_mesh(vertices, cells, n_copies):
+    nv = vertices.shape[0]
+    V = np.tile(np.asarray(vertices, dtype=np.float64), (n_copies, 1))
+    C = (np.asarray(cells, dtype=np.int64)[None, :, :] + (np.arange(n_copies, dtype=np.int64) * nv)[:, None, None]).reshape(-1, 3)
+    group = np.repeat(np.arange(n_copies, dtype=np.int32), cells.shape[0])
+    return V, C.astype(np.int32), group
+
+
+def sweep_cases(n_cases, seed=1234):
+    """The parameter set of SURVEY.md 8d config 5 (numpy default_rng(1234))."""
+    rng = np.random.default_rng(seed)
+    return [dict(K_wave=rng.uniform(1, 5), rho=rng.uniform(1, 3), R1_em=rng.uniform(0, 1), R2_em=rng.uniform(0, 1),
+                 L_em=rng.uniform(0.05, 0.2), m_em=rng.uniform(0.1, 0.3), K_em=rng.uniform(2, 10), Bl_em=rng.uniform(2, 8))
+            for _ in range(n_cases)]
+
+
+def wave_sweep_solve(tFinal, numSteps, nx, xLength, yLength, cases, domainShape='R', timeIntScheme='SV',
+                     mesh=None, device=0, patch_cells=None, tol=1e-13, extrap_order=2, return_solver=False):
+    """Run len(cases) independent 'IC' cases (weak form, explicit scheme) at once.
+
+    Returns (H_arrays [n_cases, numSteps, 8], numCells) - H_arrays[i] is what wave_2D_solve would return for case i."""
+    if timeIntScheme not in ('SV', 'SE'):
+        raise ValueError('the sweep runs the interconnected model: SV or SE')
+    if mesh is None:
+        mesh = generate_mesh(domainShape, nx, xLength, yLength)
+    B = len(cases)
+    V, C, group = replicate_mesh(mesh[0], mesh[1], B)
+    if patch_cells is None:
+        patch_cells = max(64, min(2048, len(mesh[1])))
+    m = Mesh(V, C, patch_cells=patch_cells, cell_group=group, n_groups=B)
+    m.set_boundary(tag_boundary_edges(m, domainShape, xLength, yLength))
+    prm = _lib.PhwParams()
+    prm.scheme, prm.interconnection = _lib.SCHEMES[timeIntScheme], 1
+    prm.dt, prm.K_wave, prm.rho = tFinal / numSteps, 1.0, 1.0
+    for k, v in DEFAULT_LUMPED.items():
+        setattr(prm, k, v)
+    prm.input_kind, prm.in_amp, prm.in_omega, prm.in_t_stop = _lib.IN_SINE_WINDOW, 5.0, 8 * np.pi, 0.25     # wave_2D.py:433
+    prm.tol, prm.max_iter, prm.extrap_order = float(tol), 400, int(extrap_order)
+    solver = Solver(m, prm, device=device)
+    K = np.array([c.get('K_wave', 1.0) for c in cases], dtype=np.float64)
+    rho = np.array([c.get('rho', 1.0) for c in cases], dtype=np.float64)
+    lum = np.array([[c.get(k, DEFAULT_LUMPED[k]) for k in LUMPED_KEYS] for c in cases], dtype=np.float64)
+    if B > 1:
+        solver.set_group_params(K, rho, lum)
+    H = solver.run(numSteps)
+    if B == 1:
+        H = H[None]
+    numCells = len(mesh[1])
+    if return_solver:
+        return H, numCells, solver
+    solver.close()
+    m.close()
+    return H, numCells

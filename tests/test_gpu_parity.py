@@ -176,3 +176,23 @@ def test_golden_exact_entries_on_gpu():
     assert abs(H[0, 3] + 1.046651205470e-08) < 2e-20
     assert abs(H[0, 5] - 7.890733406804e-08) < 2e-19
     assert abs(H[0, 6] - 7.890733434191e-08) < 2e-19
+
+
+def test_batched_sweep_matches_per_case_oracle():
+    """BASELINE configs[4]: independent cases with different wave speed and lumped constants in one batched run."""
+    from porthamiltonian_fem_b200.sweep import wave_sweep_solve, sweep_cases, LUMPED_KEYS, DEFAULT_LUMPED
+    mesh = rectangle_structured(26, 6, 1.0, 0.25)
+    cases = sweep_cases(7)
+    cases[3] = dict(K_wave=3.0, rho=2.0)                       # the paper constants among them
+    H, nc, solver = wave_sweep_solve(0.06, 60, 0, 1.0, 0.25, cases, mesh=mesh, patch_cells=96, return_solver=True)
+    xs = solver.group_states()
+    assert H.shape == (7, 60, 8)
+    for i, c in enumerate(cases):
+        lum = {k: c.get(k, DEFAULT_LUMPED[k]) for k in LUMPED_KEYS}
+        Ho, _, so = wave_2D_solve_oracle(0.06, 60, mesh, 1.0, 0.25, timeIntScheme='SV', interConnection='IC',
+                                         K_wave=c['K_wave'], rho=c['rho'], lumped=lum, return_state=True)
+        scale = np.abs(Ho[:, 1:]).max()
+        assert np.abs(H[i][:, 1:] - Ho[:, 1:]).max() < 1e-10 * scale, i
+        assert np.array_equal(H[i][:, 0], Ho[:, 0])
+        assert rel(xs[i], so['x']) < TOL_STATE
+    solver.close()
