@@ -566,11 +566,10 @@ __device__ void finish_launch(const RowArgs& a, double acc0, double acc1, double
                 sc.rr = rr; sc.bb = bb;
                 double c1, c2, rho_k;
                 cheb_coeffs(sc.k, sc.rho, a.cheb_d, a.cheb_c, c1, c2, rho_k);
-                sc.rho = rho_k;
-                sc.k += 1;
-                sc.cur = (sc.cur + 1) % 3;
-                sc.iters += 1;
                 const bool conv = rr <= a.tol2 * bb;
+                sc.k += 1;
+                sc.iters += 1;
+                if (!conv) { sc.rho = rho_k; sc.cur = (sc.cur + 1) % 3; }   // on convergence keep the verified iterate x_k
                 if (conv || sc.k >= a.max_iter) {
                     sc.done = 1;
                     if (!conv) ctl->nonconv += 1;
@@ -700,9 +699,14 @@ __global__ void __launch_bounds__(NT, MINB) solve_coop_k(const RowArgs av, const
             grid.sync();
             rr = __ldcg(&a0.ctl->xch[k & 1][0]); bb = __ldcg(&a0.ctl->xch[k & 1][1]);
         }
-        rho = rho_k; k += 1; cur = nxt;
+        // the residual just measured belongs to x_k (buffer `cur`), not to the x_{k+1} produced in the same pass:
+        // a Chebyshev iterate can be exact for the components present while its successor is not (the momentum
+        // term), so on convergence the verified iterate x_k is the one that is returned.
         conv = rr <= a0.tol2 * bb;
-        if (conv || k >= a0.max_iter) break;
+        k += 1;
+        if (conv) break;
+        rho = rho_k; cur = nxt;
+        if (k >= a0.max_iter) break;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         sc.cur = cur; sc.k = k; sc.done = 1; sc.rr = rr; sc.bb = bb; sc.rho = rho;

@@ -504,7 +504,7 @@ RowArgs base_args(phw_solver_s* s) {
     a.partials = s->partials; a.ctl = s->ctl;
     a.tol2 = s->prm.tol * s->prm.tol; a.max_iter = s->prm.max_iter; a.weight = 1.0;
     // batched runs test the aggregated residual of all cases: tighten it so that every case of comparable amplitude meets tol
-    if (s->G > 1) a.tol2 /= 100.0 * s->G;
+    if (s->G > 1) { const double t = std::max(s->prm.tol / std::sqrt((double)s->G), 1e-14); a.tol2 = std::min(a.tol2, t * t); }
     a.dot_scale = 1.0;
     a.mdiag = s->mdiag_p;   // vertex M-only rows use the pure P1 mass diagonal
     a.xscale = s->prm.strong ? 4.0 : 0.0;

@@ -196,3 +196,27 @@ def test_batched_sweep_matches_per_case_oracle():
         assert np.array_equal(H[i][:, 0], Ho[:, 0])
         assert rel(xs[i], so['x']) < TOL_STATE
     solver.close()
+
+
+def test_mass_solve_port_rhs_on_square_cells():
+    """Regression: on square cells the port vector b_L is an eigenvector of the Jacobi-scaled RT1 mass matrix at the
+    centre of the Chebyshev interval, so the first iterate is exact while the second is not; the accepted iterate must be
+    the one whose residual was verified."""
+    for Nx, Ny, pc in [(68, 17, 128), (136, 34, 2048)]:
+        v, c = rectangle_structured(Nx, Ny)
+        m, s = make_solver(v, c, 'R', 1.0, 0.25, pc)
+        topo = fem.Topology(v, c)
+        ops = fem.assemble_wave_operators(topo, fem.tag_boundary(topo, 'R', 1.0, 0.25))
+        x, it = s.mass_solve(_lib.PHW_Q, ops['b_L'])
+        assert rel(x, spla.spsolve(ops['M_q'].tocsc(), ops['b_L'])) < 1e-11, (Nx, Ny, it)
+
+
+@pytest.mark.parametrize('scheme', ['SE', 'SV', 'EE'])
+def test_time_loop_parity_config1_size(scheme):
+    mesh = rectangle_structured(136, 34, 1.0, 0.25)
+    steps, tF = 150, 0.075
+    Ho, _, so = wave_2D_solve_oracle(tF, steps, mesh, 1.0, 0.25, K_wave=K_WAVE, rho=RHO, timeIntScheme=scheme, return_state=True)
+    Hg, _, sg = wave_2D_solve(tF, steps, '/tmp', 0, 1.0, 0.25, K_wave=K_WAVE, rho=RHO, mesh=mesh, timeIntScheme=scheme,
+                              return_state=True, verbose=False)
+    assert rel(sg['p'], so['p']) < TOL_STATE and rel(sg['q'], so['q']) < TOL_STATE
+    assert np.abs(Hg[:, 1:] - Ho[:, 1:]).max() < 1e-10 * np.abs(Ho[:, 1:]).max()
