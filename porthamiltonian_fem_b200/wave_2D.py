@@ -6,7 +6,9 @@ goes to libphwave.so (C ABI, include/phwave.h) and the whole time loop runs on t
 
 Extra keyword arguments (defaults keep the reference behaviour): ``mesh=(vertices, cells)`` to bypass
 the built-in generator (the reference calls mshr, :93-119), ``mesh_kind``, ``device``, ``patch_cells``,
-``tol``, ``lumped`` (dict overriding the hard-coded constants of :153-158), ``return_state``.
+``tol``, ``lumped`` (dict overriding the hard-coded constants of :153-158), ``return_state``, ``save_every``
+(with ``saveP``: write p every that many steps to ``<outputDir>/p.xdmf``; default ``None`` = no field output, because a
+per-step device-to-host copy would dominate the run).
 """
 import os
 import time
@@ -31,7 +33,7 @@ def wave_2D_solve(tFinal, numSteps, outputDir,
                   K_wave=1, rho=1, BOUNDARYPLOT=False, interConnection=None,
                   analytical=False, saveP=True, controlType=None,
                   input_stop_t=None, control_start_t=None, basis_order=(1, 1),
-                  mesh=None, mesh_kind='structured', device=0, patch_cells=None, tol=1e-13, extrap_order=2,
+                  mesh=None, mesh_kind='structured', device=0, patch_cells=None, tol=1e-13, extrap_order=2, save_every=None,
                   lumped=None, return_state=False, verbose=True):
     """Solve the 2D port-Hamiltonian wave equation; see the reference docstring (wave_2D.py:22-51).
 
@@ -166,7 +168,23 @@ def wave_2D_solve(tFinal, numSteps, outputDir,
         _lib.check(solver.lib.phw_set_analytical(solver.handle, float(rho * omega), float(np.pi / (2 * xLength)), float(2 * np.pi / yLength),
                                                  float(omega), mass.ctypes.data_as(_lib.c_f64p), lam.ctypes.data_as(_lib.c_f64p),
                                                  ev.ctypes.data_as(_lib.c_f64p), pt_v.ctypes.data_as(_lib.c_i32p), pt_l.ctypes.data_as(_lib.c_f64p)))
-    H_array = solver.run(numSteps)
+    if saveP and save_every and outputDir:
+        # field output (the reference writes p to p.xdmf at every step, wave_2D.py:646-651,865-866).  h5py is not
+        # available, so the heavy data goes to raw little-endian binaries referenced from an XDMF file (ParaView
+        # reads Format="Binary"); the time loop runs in chunks of `save_every` steps between snapshots.
+        from .field_output import XdmfBinaryWriter
+        writer = XdmfBinaryWriter(outputDir, 'p', m.vertices, m.cells)
+        H_array = np.zeros((numSteps, solver.ncol))
+        done = 0
+        while done < numSteps:
+            n = min(int(save_every), numSteps - done)
+            H_array[done:done + n] = solver.run(n)
+            done += n
+            p_h, _, _ = solver.get_state()
+            writer.write(p_h, H_array[done - 1, 0])
+        writer.close()
+    else:
+        H_array = solver.run(numSteps)
     stats = solver.stats()
     totalTime = time.time() - tic
     if rank == 0 and verbose:

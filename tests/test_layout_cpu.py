@@ -129,3 +129,19 @@ def test_reference_argument_checks():
                dict(analytical=True, domainShape='S_1C'), dict(timeIntScheme='XX')]:
         with pytest.raises(SystemExit):
             wave_2D_solve(0.1, 2, '/tmp', 4, 1.0, 0.25, verbose=False, **kw)
+
+
+def test_xdmf_binary_writer(tmp_path):
+    import xml.etree.ElementTree as ET
+    from porthamiltonian_fem_b200.field_output import XdmfBinaryWriter
+    v, c = rectangle_structured(3, 2)
+    w = XdmfBinaryWriter(str(tmp_path), 'p', v, c)
+    for k in range(3):
+        w.write(np.full(v.shape[0], float(k)), 0.1 * (k + 1))
+    w.close()
+    root = ET.parse(str(tmp_path / 'p.xdmf')).getroot()
+    grids = root.findall('./Domain/Grid/Grid')
+    assert len(grids) == 3 and grids[2].find('Time').attrib['Value'] == repr(0.1 * 3)
+    vals = np.fromfile(str(tmp_path / 'p_values.bin'), dtype='<f8').reshape(3, -1)
+    assert np.all(vals[2] == 2.0) and vals.shape[1] == v.shape[0]
+    assert np.array_equal(np.fromfile(str(tmp_path / 'p_topology.bin'), dtype='<i4').reshape(-1, 3), c)
