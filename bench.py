@@ -279,11 +279,22 @@ def main():
             pass
         peak = float(peaks.get('hbm_gbs', 6650.0))
         peak_src = 'measured (MEASURED_PEAKS.json hbm_gbs)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s (B200_PROFILING.md)'
-        # dominant kernel: cooperative Chebyshev solve of M_q; algorithmic bytes = 96 B/cell/iteration
+        # the two solve kernels take ~85 % of the step; the one with the larger share of the timed region is reported as
+        # the dominant kernel.  Algorithmic bytes per cell and Chebyshev iteration: 40 (M_p), 96 (M_q).
+        # traffic = DRAM bytes of one launch from the committed ncu --set full capture (profiles/r1_ncu_full_solve_kernels.txt:
+        # 54 B (M_p) and 99 B (M_q) per cell and iteration), scaled to this run's iterations per launch.
         nc = n_cells_local
-        it_q = st['iters_q']
-        q_bytes = 96.0 * nc * it_q
-        achieved = q_bytes / (st['ms_solve_q'] * 1e-3) / 1e9 if st['ms_solve_q'] > 0 else None
+        kern = {}
+        for key, name, alg, ncu_b, it, ms, solves in (
+                ('p', 'solve_coop_k<0> (Chebyshev M_p solve, all iterations in one cooperative launch)', 40.0, 54.0, st['iters_p'], st['ms_solve_p'], st['solves_p']),
+                ('q', 'solve_coop_k<1> (Chebyshev M_q solve, all iterations in one cooperative launch)', 96.0, 99.0, st['iters_q'], st['ms_solve_q'], st['solves_q'])):
+            ach = alg * nc * it / (ms * 1e-3) / 1e9 if ms > 0 else None
+            kern[key] = {'kernel': name, 'achieved': ach, 'frac': (ach / peak) if ach else None, 'share_of_step': ms / st['device_ms'],
+                         'bytes_per_launch': alg * nc * it / max(1, solves), 'ms_per_launch': ms / max(1, solves),
+                         'ms_per_iteration': ms / max(1, it), 'traffic': ncu_b * nc * it / max(1, solves)}
+        dom = kern['p'] if kern['p']['share_of_step'] >= kern['q']['share_of_step'] else kern['q']
+        oth = kern['q'] if dom is kern['p'] else kern['p']
+        achieved = dom['achieved']
         line = {
             'metric': 'dof-updates/sec (fp64, device-timed)', 'value': value, 'unit': 'dof-updates/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dev_s / args.steps,
@@ -298,13 +309,12 @@ def main():
                     'seconds': e2e_s},
             'gpu_launches': int(st['kernel_launches']),
             'clocks': summarize_clocks(samples),
-            'roofline': {'bound': 'hbm', 'kernel': 'solve_coop_k<1> (Chebyshev M_q solve, all iterations in one cooperative launch)',
-                         'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': (achieved / peak) if achieved else None,
-                         'traffic': None, 'peak_source': peak_src,
-                         'bytes_per_launch': q_bytes / max(1, st['solves_q']), 'ms_per_launch': st['ms_solve_q'] / max(1, st['solves_q']),
+            'roofline': {'bound': 'hbm', 'kernel': dom['kernel'], 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                         'frac': dom['frac'], 'traffic': dom['traffic'], 'peak_source': peak_src,
+                         'bytes_per_launch': dom['bytes_per_launch'], 'ms_per_launch': dom['ms_per_launch'],
+                         'kernel_share_of_step': dom['share_of_step'], 'second_kernel': oth,
                          'whole_loop_model_gbs': st['bytes_model'] / dev_s / 1e9, 'whole_loop_model_frac': st['bytes_model'] / dev_s / 1e9 / peak,
-                         'kernel_share_of_step': st['ms_solve_q'] / st['device_ms'], 'solve_p_share_of_step': st['ms_solve_p'] / st['device_ms'],
-                         'ms_per_iter_q': st['ms_solve_q'] / max(1, st['iters_q']), 'ms_per_iter_p': st['ms_solve_p'] / max(1, st['iters_p'])},
+                         'ms_per_iter_q': kern['q']['ms_per_iteration'], 'ms_per_iter_p': kern['p']['ms_per_iteration']},
             'wall_s_timed_region': wall,
         }
         if not args.no_cpu_baseline:
