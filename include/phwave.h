@@ -153,6 +153,24 @@ int phw_energy(phw_solver_t s, double* parts2);
 int phw_set_analytical(phw_solver_t s, double amp, double kx, double ky, double omega, const double* mass_ref225,
                        const double* lam_nodes45, const double* exact_vertices, const int32_t* pt_vertices3,
                        const double* pt_lam3);
+/* ---- higher-order element pairs P_k x RT_k, k <= 3 (basis_order of wave_2D.py:15-20,174-175): the operators of the
+ *      forms :449-526 are assembled once by the host (porthamiltonian_fem_b200/fem_ho.py) and handed over as CSR
+ *      matrices (int32 indices): M_p [n_p x n_p], M_q [n_q x n_q], D = C - N [n_q x n_p], D^T [n_p x n_q], port vector
+ *      b_L [n_q], element-wise (Wathen) bounds of the Jacobi-scaled mass spectra.  Explicit weak-form schemes, with or
+ *      without the lumped model.  State vectors are in the caller's dof numbering. ---- */
+int phw_ho_create(const phw_params* prm, int32_t device, void* cuda_stream, int64_t n_p, int64_t n_q,
+                  const int32_t* Mp_indptr, const int32_t* Mp_idx, const double* Mp_val,
+                  const int32_t* Mq_indptr, const int32_t* Mq_idx, const double* Mq_val,
+                  const int32_t* D_indptr, const int32_t* D_idx, const double* D_val,
+                  const int32_t* DT_indptr, const int32_t* DT_idx, const double* DT_val,
+                  const double* b_L, double lam_min_p, double lam_max_p, double lam_min_q, double lam_max_q,
+                  phw_solver_t* out);
+/* analytical diagnostics of a higher-order run (wave_2D.py:929-965): cell_dofs [n_cells x ndp], tabulation T [nn x ndp]
+ * of the P_k basis at the P_{k+3} nodes, reference mass matrix [nn x nn], exact spatial factor at those nodes
+ * [n_cells x nn] and at the P_k dofs [n_p], cell areas, point probe as (dof, weight) pairs */
+int phw_ho_set_analytical(phw_solver_t s, double omega, int32_t n_cells, int32_t ndp, int32_t nn, const int32_t* cell_dofs,
+                          const double* T, const double* mass_ref, const double* exact_nodes, const double* area,
+                          const double* exact_dofs, int32_t nprobe, const int32_t* probe_dofs, const double* probe_w);
 /* H_init of wave_2D.py:746,769,771 (subtracted in the energy-residual column) */
 int phw_set_H_init(phw_solver_t s, double H_init);
 /* b_L^T q of the current state: integral of q.n over the left port (wave_2D.py:534,546,622-631) */

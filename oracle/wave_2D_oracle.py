@@ -90,12 +90,20 @@ def wave_2D_solve_oracle(tFinal, numSteps, mesh, xLength, yLength,
     mesh passed in.  Returns (H_array, numCells) or, with return_state, also a dict holding the
     final p, q, x (oracle numbering = fem.Topology numbering)."""
     _check_case(domainShape, timeIntScheme, dirichletImp, interConnection, analytical, controlType)
-    if tuple(basis_order) != (1, 1):
-        raise NotImplementedError('oracle: only the P1/RT1 pair is restated (higher orders: SURVEY 8f-1)')
     vertices, cells = mesh
     topo = fem.Topology(vertices, cells)
     tags = fem.tag_boundary(topo, domainShape, xLength, yLength)
     nv, ne = topo.n_vertices, topo.n_edges
+    high_order = tuple(basis_order) != (1, 1)
+    if high_order:
+        # basis_order of wave_2D.py:15-20,174-175: P_k x RT_k spaces, same forms; nv / ne below are then the numbers of
+        # P / RT dofs.  Restated for the weak form without control (the variants the reference runs at higher order:
+        # main_wave_2D.py:53-114, run_test_cases.py:30-31,44-46).
+        if dirichletImp != 'weak' or controlType is not None:
+            raise NotImplementedError('oracle: higher-order pairs are restated for the weak form without control')
+        from . import fem_ho
+        spaces = fem_ho.SpacesHO(topo, int(basis_order[0]), int(basis_order[1]))
+        nv, ne = spaces.n_p, spaces.n_q
     IC = interConnection == 'IC'
     strong = dirichletImp == 'strong'
     casimir = controlType == 'casimir'
@@ -119,7 +127,10 @@ def wave_2D_solve_oracle(tFinal, numSteps, mesh, xLength, yLength,
             g_time = lambda t: 3 * np.sin(8 * np.pi * t)                                      # :380
         else:
             g_time = lambda t: 10 * np.sin(8 * np.pi * t) if t < 0.25 else 0.0               # :384
-    ops = fem.assemble_wave_operators(topo, tags, left_weight=left_weight)
+    if high_order:
+        ops = spaces.assemble(tags, left_weight=left_weight)
+    else:
+        ops = fem.assemble_wave_operators(topo, tags, left_weight=left_weight)
     Mp, Mq, bL = ops['M_p'], ops['M_q'], ops['b_L']
     if strong:
         # (phi, grad psi) = -(div phi, psi) + <phi.n, psi>_whole boundary; keep the quadrature-assembled G
@@ -248,12 +259,15 @@ def wave_2D_solve_oracle(tFinal, numSteps, mesh, xLength, yLength,
     q_m = np.zeros(ne)
     x_m = np.zeros(3)
     H_init = 0.0
-    X, Y = topo.vertices[:, 0], topo.vertices[:, 1]
+    X, Y = (spaces.p_coords[:, 0], spaces.p_coords[:, 1]) if high_order else (topo.vertices[:, 0], topo.vertices[:, 1])
     if analytical:
         p_space = rho_val * omega * np.sin(np.pi * X / (2 * xLength) + np.pi / 2) * np.sin(2 * np.pi * Y / yLength + np.pi / 2)
         p_m = p_space.copy()
         H_init = 0.5 * p_m @ (Mp @ p_m) / rho_val                                        # :746
-        diag = _AnalyticalDiagnostics(topo, rho_val, omega, xLength, yLength)
+        if high_order:
+            diag = fem_ho.AnalyticalDiagnosticsHO(spaces, rho_val, omega, xLength, yLength)
+        else:
+            diag = _AnalyticalDiagnostics(topo, rho_val, omega, xLength, yLength)
     elif controlType == 'passivity':
         p_m = np.sin(4 * np.pi * X / xLength)                                            # :759-763
         mid = 0.5 * (topo.vertices[topo.edges[:, 0]] + topo.vertices[topo.edges[:, 1]])
@@ -393,7 +407,8 @@ def wave_2D_solve_oracle(tFinal, numSteps, mesh, xLength, yLength,
         timing['loop_seconds'] = time.perf_counter() - tic
         timing['n_dof'] = ntot
     if return_state:
-        return H_array, topo.n_cells, dict(p=p_m, q=q_m, x=x_m, topo=topo, tags=tags, ops=ops)
+        return H_array, topo.n_cells, dict(p=p_m, q=q_m, x=x_m, topo=topo, tags=tags, ops=ops,
+                                           spaces=spaces if high_order else None)
     return H_array, topo.n_cells
 
 

@@ -717,4 +717,84 @@ __global__ void __launch_bounds__(NT, MINB) solve_coop_k(const RowArgs av, const
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// higher-order pairs (P_k x RT_k, k <= 3): the operators are assembled once on the host (fem_ho.py) and applied as
+// CSR matrices; same epilogues and the same persistent cooperative Chebyshev solve as the matrix-free path.
+// ------------------------------------------------------------------------------------------------
+struct Csr { int n_rows; const int* indptr; const int* idx; const double* val; };
+
+__device__ __forceinline__ double csr_row(const Csr& A, int r, const double* __restrict__ x) {
+    double v = 0.0;
+    const int j1 = A.indptr[r + 1];
+    for (int j = A.indptr[r]; j < j1; ++j) v += A.val[j] * x[A.idx[j]];
+    return v;
+}
+// y = alpha A x
+__global__ void csr_store_k(Csr A, const double* x, double alpha, double* y) {
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < A.n_rows; r += gridDim.x * blockDim.x) y[r] = alpha * csr_row(A, r, x);
+}
+// ctl->red[slot] = scale x^T A x   (single block, fixed order)
+__global__ void csr_dot_k(Csr A, const double* x, double scale, Ctl* ctl, int slot) {
+    __shared__ double red[64];
+    double s = 0.0, z = 0.0;
+    for (int r = threadIdx.x; r < A.n_rows; r += blockDim.x) s += x[r] * csr_row(A, r, x);
+    block_sum2(s, z, red);
+    if (threadIdx.x == 0) ctl->red[slot] = scale * s;
+}
+struct CsrSolveArgs {
+    Csr A; TriBuf tb; const double* b; const double* pinv; double cheb_d, cheb_c, tol2; int max_iter, which;
+    double* partials; Ctl* ctl;
+};
+__global__ void __launch_bounds__(256) solve_coop_csr_k(const CsrSolveArgs a) {
+    __shared__ double red[64];
+    __shared__ double bc[2];
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    SolveCtl& sc = a.ctl->sc[a.which];
+    int k = 0, cur = sc.cur;
+    double rho = 0.0, rr = 0.0, bb = 0.0;
+    bool conv = false;
+    while (true) {
+        double c1, c2, rho_k;
+        cheb_coeffs(k, rho, a.cheb_d, a.cheb_c, c1, c2, rho_k);
+        const int nxt = (cur + 1) % 3, prv = (cur + 2) % 3;
+        const double* x = tb_sel(a.tb, cur); const double* xp = tb_sel(a.tb, prv); double* xn = tb_sel(a.tb, nxt);
+        double r0 = 0.0, b0 = 0.0;
+        for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < a.A.n_rows; r += gridDim.x * blockDim.x) {
+            const double val = csr_row(a.A, r, x), bv = a.b[r], pv = a.pinv[r], xc = x[r];
+            const double res = bv - val;
+            double v = xc + c2 * pv * res;
+            if (k > 0) v += c1 * (xc - xp[r]);
+            xn[r] = v;
+            r0 += pv * res * res; b0 += pv * bv * bv;
+        }
+        block_sum2(r0, b0, red);
+        double* part = a.partials + (size_t)(k & 1) * 2 * gridDim.x;
+        if (threadIdx.x == 0) { part[2 * blockIdx.x] = r0; part[2 * blockIdx.x + 1] = b0; }
+        grid.sync();
+        if (threadIdx.x < 32) {
+            double s0 = 0.0, s1 = 0.0;
+            for (int i = threadIdx.x; i < (int)gridDim.x; i += 32) { s0 += __ldcg(&part[2 * i]); s1 += __ldcg(&part[2 * i + 1]); }
+            s0 = warp_sum(s0); s1 = warp_sum(s1);
+            if (threadIdx.x == 0) { bc[0] = s0; bc[1] = s1; }
+        }
+        __syncthreads();
+        rr = bc[0]; bb = bc[1];
+        __syncthreads();
+        conv = rr <= a.tol2 * bb;
+        k += 1;
+        if (conv) break;
+        rho = rho_k; cur = nxt;
+        if (k >= a.max_iter) break;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        sc.cur = cur; sc.k = k; sc.done = 1; sc.rr = rr; sc.bb = bb; sc.rho = rho;
+        sc.iters += k; sc.solves += 1;
+        if (!conv) a.ctl->nonconv += 1;
+        double rel = (bb > 0.0) ? sqrt(rr / bb) : 0.0;
+        if (rel > sc.maxres) sc.maxres = rel;
+    }
+}
+
 }  // namespace phw

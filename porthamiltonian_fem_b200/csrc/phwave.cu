@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <numeric>
 #include <string>
 #include <vector>
 
@@ -237,6 +238,56 @@ __global__ void diag_finish_k(int nv, int nblk_cells, const double* __restrict__
     }
 }
 
+// higher-order analytical diagnostics: generic P_k -> P_{k+3} tabulation, data in global memory
+__global__ void diag_cells_ho_k(int nc, int ndp, int nn, const int* __restrict__ cell_dofs, const double* __restrict__ T,
+                                const double* __restrict__ mass, const double* __restrict__ exact_nodes,
+                                const double* __restrict__ area, const double* __restrict__ p, double omega, const Ctl* ctl,
+                                double* partial) {
+    __shared__ double red[64];
+    const double ct = cos(ctl->t * omega);
+    double acc = 0.0, z = 0.0;
+    double e[28], pl[10];
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += gridDim.x * blockDim.x) {
+        for (int j = 0; j < ndp; ++j) pl[j] = p[cell_dofs[(size_t)c * ndp + j]];
+        for (int n = 0; n < nn; ++n) {
+            double ph = 0.0;
+            for (int j = 0; j < ndp; ++j) ph += T[n * ndp + j] * pl[j];
+            e[n] = exact_nodes[(size_t)c * nn + n] * ct - ph;
+        }
+        double qf = 0.0;
+        for (int i = 0; i < nn; ++i) {
+            double row = 0.0;
+            for (int j = 0; j < nn; ++j) row += mass[i * nn + j] * e[j];
+            qf += e[i] * row;
+        }
+        acc += area[c] * qf;
+    }
+    block_sum2(acc, z, red);
+    if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
+__global__ void diag_finish_ho_k(int np, int nblk_cells, const double* __restrict__ exact_dofs, const double* __restrict__ p,
+                                 double omega, int nprobe, const int* __restrict__ probe_dofs, const double* __restrict__ probe_w,
+                                 Ctl* ctl, const double* partial) {
+    __shared__ double red[64];
+    const double ct = cos(ctl->t * omega);
+    double mx = 0.0;
+    for (int i = threadIdx.x; i < np; i += blockDim.x) mx = fmax(mx, fabs(exact_dofs[i] * ct - p[i]));
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double m2 = 0.0;
+        for (int w = 0; w < (int)(blockDim.x + 31) / 32; ++w) m2 = fmax(m2, red[w]);
+        double s = 0.0;
+        for (int b = 0; b < nblk_cells; ++b) s += partial[b];
+        ctl->red[4] = sqrt(s);
+        ctl->red[5] = m2;
+        double ph = 0.0, pe = 0.0;
+        for (int k = 0; k < nprobe; ++k) { ph += probe_w[k] * p[probe_dofs[k]]; pe += probe_w[k] * exact_dofs[probe_dofs[k]] * ct; }
+        ctl->red[6] = ph; ctl->red[7] = pe;
+    }
+}
+
 struct ScalarPrm {
     double dt, K, rho, c2;
     double A[3][3];
@@ -445,6 +496,10 @@ struct phw_solver_s {
     struct Hist { double* h[4] = {nullptr, nullptr, nullptr, nullptr}; int count = 0, head = 0; };
     Hist hist[2][2];           // [field p/q][solve site]
     int extrap = 2, n_sites = 1;
+    bool ho = false; Csr hMp{}, hMq{}, hD{}, hDT{};
+    int ho_nc = 0, ho_ndp = 0, ho_nn = 0, ho_nprobe = 0; double ho_omega = 0.0;
+    int *ho_cell_dofs = nullptr, *ho_probe_dofs = nullptr;
+    double *ho_T = nullptr, *ho_mass = nullptr, *ho_exact_nodes = nullptr, *ho_area = nullptr, *ho_exact_dofs = nullptr, *ho_probe_w = nullptr;
     bool in_step = false;
     bool coop = false;
     std::vector<cudaEvent_t> prof_ev; std::vector<int> prof_which;
@@ -585,6 +640,20 @@ int solve_begin(phw_solver_s* s, int which) {
 // Chebyshev solve of M_p x = bp (which = 0) or M_q x = bq (which = 1); warm start = tribuf[cur]
 int solve_mass(phw_solver_s* s, int which, int n_launch) {
     int rc;
+    if (s->ho) {
+        CsrSolveArgs a{};
+        a.A = which == PHW_P ? s->hMp : s->hMq; a.tb = which == PHW_P ? s->tp : s->tq;
+        a.b = which == PHW_P ? s->bp : s->bq; a.pinv = which == PHW_P ? s->pinv_p : s->pinv_q;
+        a.cheb_d = s->cheb_d[which]; a.cheb_c = s->cheb_c[which]; a.tol2 = s->prm.tol * s->prm.tol;
+        a.max_iter = s->prm.max_iter; a.which = which; a.partials = s->partials; a.ctl = s->ctl;
+        int occ = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, solve_coop_csr_k, 256, 0));
+        const int grid = std::max(1, std::min(nblk(a.A.n_rows), std::min(occ, 4) * s->sm_count));
+        void* args[] = {(void*)&a};
+        CU(cudaLaunchCooperativeKernel((void*)solve_coop_csr_k, dim3(grid), dim3(256), args, 0, s->stream));
+        s->launches++;
+        return 0;
+    }
     RowArgs a = base_args(s);
     a.which = which; a.use_cheb_input = 1; a.finalize = 1; a.cM = 1.0; a.counter_id = which;
     a.cheb_d = s->cheb_d[which]; a.cheb_c = s->cheb_c[which];
@@ -670,14 +739,27 @@ int waxpy(phw_solver_s* s, int n, double* w, const double* y, double a, const do
 // b_p = -K (D^T qsrc [+ B_top psrc])          (explicit part of the p rows, velocity form)
 int rhs_p(phw_solver_s* s, const double* qsrc, const double* psrc) {
     const double K = s->prm.K_wave;
+    if (s->ho) {
+        csr_store_k<<<vec_grid(s, s->nv), 256, 0, s->stream>>>(s->hDT, qsrc, -K, s->bp);
+        s->launches++;
+        CU(cudaGetLastError());
+        return 0;
+    }
     if (s->G > 1) return op_vertex_store(s, psrc, qsrc, 0.0, -1.0, 0.0, s->bp, s->d_gK);
     return op_vertex_store(s, psrc, qsrc, 0.0, -K, s->prm.casimir ? -K : 0.0, s->bp);
 }
 // b_q = (1/rho) (D psrc - b_L p_left [- B_right qsrc])
 int rhs_q(phw_solver_s* s, const double* psrc, const double* qsrc) {
     const double ir = (s->G > 1) ? 1.0 : 1.0 / s->prm.rho;
-    int rc = (s->G > 1) ? op_edge_store(s, psrc, qsrc, 0.0, 1.0, 0.0, s->bq, s->d_ginvrho)
+    int rc = 0;
+    if (s->ho) {
+        csr_store_k<<<vec_grid(s, s->ne), 256, 0, s->stream>>>(s->hD, psrc, ir, s->bq);
+        s->launches++;
+        CU(cudaGetLastError());
+    } else {
+        rc = (s->G > 1) ? op_edge_store(s, psrc, qsrc, 0.0, 1.0, 0.0, s->bq, s->d_ginvrho)
                         : op_edge_store(s, psrc, qsrc, 0.0, ir, s->prm.casimir ? -ir : 0.0, s->bq);
+    }
     if (rc) return rc;
     if (!s->prm.strong && s->nport > 0) {
         port_rhs_k<<<nblk(s->nport), 256, 0, s->stream>>>(s->nport, s->d_port_e, s->d_port_bl, s->d_port_group,
@@ -688,6 +770,21 @@ int rhs_q(phw_solver_s* s, const double* psrc, const double* qsrc) {
     return 0;
 }
 int energy(phw_solver_s* s) {
+    if (s->ho) {
+        csr_dot_k<<<1, 1024, 0, s->stream>>>(s->hMp, s->p, 0.5 / s->prm.rho, s->ctl, 0);
+        csr_dot_k<<<1, 1024, 0, s->stream>>>(s->hMq, s->q, 0.5 * s->prm.K_wave, s->ctl, 1);
+        s->launches += 2;
+        if (s->prm.analytical && s->an_ready && s->in_step) {
+            const int nb = 2 * s->sm_count;
+            diag_cells_ho_k<<<nb, 128, 0, s->stream>>>(s->ho_nc, s->ho_ndp, s->ho_nn, s->ho_cell_dofs, s->ho_T, s->ho_mass, s->ho_exact_nodes,
+                                                     s->ho_area, s->p, s->ho_omega, s->ctl, s->d_diag_part);
+            diag_finish_ho_k<<<1, 1024, 0, s->stream>>>(s->nv, nb, s->ho_exact_dofs, s->p, s->ho_omega, s->ho_nprobe, s->ho_probe_dofs,
+                                                        s->ho_probe_w, s->ctl, s->d_diag_part);
+            s->launches += 2;
+        }
+        CU(cudaGetLastError());
+        return 0;
+    }
     if (s->G > 1) {   // batched: per-(patch, warp) partials -> one reduction block per case
         int rc = op_vertex_dot(s, s->p, 1.0, 0.0, 0, 1.0, 4); if (rc) return rc;
         group_reduce_k<<<s->G, 32, 0, s->stream>>>(s->wpart, NT_ROWS / 32, s->d_gpoff, s->d_ginvrho, 0.5, s->ctl, 0);
@@ -1078,6 +1175,76 @@ static void fill_physics(ScalarPrm& sp, double dt, double K, double rho, double 
     sp.m_em = m_em; sp.L_em = L_em; sp.K_em = K_em;
 }
 
+// state / work vectors, exchange arena, control blocks (shared by the matrix-free and the CSR path)
+static int setup_vectors(phw_solver_s* s) {
+    const phw_params& P = s->prm;
+    int rc;
+#define RC(x) do { rc = (x); if (rc) return rc; } while (0)
+    // ---- vectors
+    const size_t nv = s->nv, ne = s->ne;
+    RC(s->dalloc(&s->p, nv)); RC(s->dalloc(&s->q, ne)); RC(s->dalloc(&s->bp, nv)); RC(s->dalloc(&s->bq, ne));
+    RC(s->dalloc(&s->tmp_p, nv)); RC(s->dalloc(&s->tmp_q, ne)); RC(s->dalloc(&s->pinv_p, nv)); RC(s->dalloc(&s->pinv_q, ne)); RC(s->dalloc(&s->mdiag_p, nv));
+    RC(s->dalloc(&s->io_v, nv)); RC(s->dalloc(&s->io_e, ne)); RC(s->dalloc(&s->io_v2, nv)); RC(s->dalloc(&s->io_e2, ne));
+    {   // exchange arena: [Mailbox | tp0 tp1 tp2 | tq0 tq1 tq2] in ONE allocation so that a single CUDA IPC handle
+        // lets the neighbouring ranks write halo values and partial sums straight into it (peer memory over NVLink)
+        const size_t head = 4096, nvp = (nv + 31) & ~(size_t)31, nep = (ne + 31) & ~(size_t)31;
+        s->arena_bytes = head + 3 * (nvp + nep) * sizeof(double);
+        char* base = nullptr;
+        RC(s->dalloc(&base, s->arena_bytes));
+        s->arena = base;
+        CU(cudaMemsetAsync(base, 0, s->arena_bytes, s->stream));
+        double* d0 = (double*)(base + head);
+        for (int i = 0; i < 3; ++i) { s->tp.b[i] = d0 + i * nvp; s->tq.b[i] = d0 + 3 * nvp + i * nep; }
+        s->pc = PeerComm{};
+        s->pc.rank = 0; s->pc.world = 1; s->pc.n_nb = 0;
+        s->pc.mbox[0] = (Mailbox*)base;
+        s->pc.timeout_cycles = 20000000000LL;
+    }
+    RC(s->dalloc(&s->partials, 2 * (size_t)s->npatch + 8192));
+    {
+        int coop_attr = 0;
+        CU(cudaDeviceGetAttribute(&coop_attr, cudaDevAttrCooperativeLaunch, s->device));
+        s->coop = coop_attr != 0 && !(P.flags & 8);
+    }
+    RC(s->dalloc(&s->ctl, (size_t)s->G));
+    s->extrap = (P.extrap_order < 0) ? 0 : std::min(P.extrap_order, 3);
+    s->n_sites = (P.scheme == PHW_EH) ? 2 : 1;
+    if (s->extrap > 0 || true) {
+        for (int site = 0; site < s->n_sites; ++site)
+            for (int j = 0; j <= s->extrap; ++j) {
+                RC(s->dalloc(&s->hist[0][site].h[j], nv));
+                RC(s->dalloc(&s->hist[1][site].h[j], ne));
+            }
+    }
+    for (double* v : {s->p, s->bp, s->tmp_p, s->tp.b[0], s->tp.b[1], s->tp.b[2], s->io_v, s->io_v2}) CU(cudaMemsetAsync(v, 0, nv * 8, s->stream));
+    for (double* v : {s->q, s->bq, s->tmp_q, s->tq.b[0], s->tq.b[1], s->tq.b[2], s->io_e, s->io_e2}) CU(cudaMemsetAsync(v, 0, ne * 8, s->stream));
+    CU(cudaMemsetAsync(s->ctl, 0, sizeof(Ctl) * (size_t)s->G, s->stream));
+    return 0;
+#undef RC
+}
+static int setup_scalars(phw_solver_s* s) {
+    const phw_params& P = s->prm;
+    int rc;
+#define RC(x) do { rc = (x); if (rc) return rc; } while (0)
+    // ---- scalar parameters
+    ScalarPrm& sp = s->sp;
+    fill_physics(sp, P.dt, P.K_wave, P.rho, P.Bl_em, P.R1_em, P.R2_em, P.K_em, P.m_em, P.L_em);
+    sp.input_kind = P.input_kind; sp.in_amp = P.in_amp; sp.in_omega = P.in_omega; sp.in_t_stop = P.in_t_stop;
+    sp.in_t_ctrl = P.in_t_ctrl; sp.in_gain = P.in_gain; sp.H_init = P.H_init;
+    s->ncol = P.analytical ? 12 : 8;
+    sp.ncol = s->ncol; sp.ic = P.interconnection;
+    switch (P.scheme) {   // q1_ of wave_2D.py:603-615
+        case PHW_EE: case PHW_SE: sp.w_old = 1.0; sp.w_new = 0.0; break;
+        case PHW_IE: sp.w_old = 0.0; sp.w_new = 1.0; break;
+        case PHW_SM: sp.w_old = 0.5; sp.w_new = 0.5; break;
+        default: sp.w_old = 1.0; sp.w_new = 0.0;
+    }
+    s->h_sp.assign(s->G, sp);
+    RC(s->upload(&s->d_sp, s->h_sp));
+    return 0;
+#undef RC
+}
+
 static int setup_solver(phw_solver_s* s) {
     const Layout& L = s->mesh->L;
     const phw_params& P = s->prm;
@@ -1149,45 +1316,9 @@ static int setup_solver(phw_solver_s* s) {
         RC(s->upload(&s->d_gpoff, L.group_patch_off));
         if (s->G > 1) RC(s->dalloc(&s->wpart, (size_t)L.npatch * (NT_ROWS / 32)));
     }
-    // ---- vectors
+    RC(setup_vectors(s));
     const size_t nv = s->nv, ne = s->ne;
-    RC(s->dalloc(&s->p, nv)); RC(s->dalloc(&s->q, ne)); RC(s->dalloc(&s->bp, nv)); RC(s->dalloc(&s->bq, ne));
-    RC(s->dalloc(&s->tmp_p, nv)); RC(s->dalloc(&s->tmp_q, ne)); RC(s->dalloc(&s->pinv_p, nv)); RC(s->dalloc(&s->pinv_q, ne)); RC(s->dalloc(&s->mdiag_p, nv));
-    RC(s->dalloc(&s->io_v, nv)); RC(s->dalloc(&s->io_e, ne)); RC(s->dalloc(&s->io_v2, nv)); RC(s->dalloc(&s->io_e2, ne));
-    {   // exchange arena: [Mailbox | tp0 tp1 tp2 | tq0 tq1 tq2] in ONE allocation so that a single CUDA IPC handle
-        // lets the neighbouring ranks write halo values and partial sums straight into it (peer memory over NVLink)
-        const size_t head = 4096, nvp = (nv + 31) & ~(size_t)31, nep = (ne + 31) & ~(size_t)31;
-        s->arena_bytes = head + 3 * (nvp + nep) * sizeof(double);
-        char* base = nullptr;
-        RC(s->dalloc(&base, s->arena_bytes));
-        s->arena = base;
-        CU(cudaMemsetAsync(base, 0, s->arena_bytes, s->stream));
-        double* d0 = (double*)(base + head);
-        for (int i = 0; i < 3; ++i) { s->tp.b[i] = d0 + i * nvp; s->tq.b[i] = d0 + 3 * nvp + i * nep; }
-        s->pc = PeerComm{};
-        s->pc.rank = 0; s->pc.world = 1; s->pc.n_nb = 0;
-        s->pc.mbox[0] = (Mailbox*)base;
-        s->pc.timeout_cycles = 20000000000LL;
-    }
-    RC(s->dalloc(&s->partials, 2 * (size_t)s->npatch + 8192));
-    {
-        int coop_attr = 0;
-        CU(cudaDeviceGetAttribute(&coop_attr, cudaDevAttrCooperativeLaunch, s->device));
-        s->coop = coop_attr != 0 && !(P.flags & 8);
-    }
-    RC(s->dalloc(&s->ctl, (size_t)s->G));
-    s->extrap = (P.extrap_order < 0) ? 0 : std::min(P.extrap_order, 3);
-    s->n_sites = (P.scheme == PHW_EH) ? 2 : 1;
-    if (s->extrap > 0 || true) {
-        for (int site = 0; site < s->n_sites; ++site)
-            for (int j = 0; j <= s->extrap; ++j) {
-                RC(s->dalloc(&s->hist[0][site].h[j], nv));
-                RC(s->dalloc(&s->hist[1][site].h[j], ne));
-            }
-    }
-    for (double* v : {s->p, s->bp, s->tmp_p, s->tp.b[0], s->tp.b[1], s->tp.b[2], s->io_v, s->io_v2}) CU(cudaMemsetAsync(v, 0, nv * 8, s->stream));
-    for (double* v : {s->q, s->bq, s->tmp_q, s->tq.b[0], s->tq.b[1], s->tq.b[2], s->io_e, s->io_e2}) CU(cudaMemsetAsync(v, 0, ne * 8, s->stream));
-    CU(cudaMemsetAsync(s->ctl, 0, sizeof(Ctl) * (size_t)s->G, s->stream));
+    (void)nv; (void)ne;
     // ---- shared-memory budgets and grid
     auto ev = [](int x) { return (size_t)((x + 1) & ~1); };
     s->smem_v = (ev(L.max_lv) + 3 * (size_t)L.max_cells) * 8;
@@ -1197,21 +1328,7 @@ static int setup_solver(phw_solver_s* s) {
     s->smem_ed = s->smem_vd;
     if (s->smem_vd > 200 * 1024) return fail(PHW_EINVAL, "patch does not fit in shared memory; reduce patch_cells");
     s->grid_rows = std::max(1, std::min(s->npatch, 2 * s->sm_count));
-    // ---- scalar parameters
-    ScalarPrm& sp = s->sp;
-    fill_physics(sp, P.dt, P.K_wave, P.rho, P.Bl_em, P.R1_em, P.R2_em, P.K_em, P.m_em, P.L_em);
-    sp.input_kind = P.input_kind; sp.in_amp = P.in_amp; sp.in_omega = P.in_omega; sp.in_t_stop = P.in_t_stop;
-    sp.in_t_ctrl = P.in_t_ctrl; sp.in_gain = P.in_gain; sp.H_init = P.H_init;
-    s->ncol = P.analytical ? 12 : 8;
-    sp.ncol = s->ncol; sp.ic = P.interconnection;
-    switch (P.scheme) {   // q1_ of wave_2D.py:603-615
-        case PHW_EE: case PHW_SE: sp.w_old = 1.0; sp.w_new = 0.0; break;
-        case PHW_IE: sp.w_old = 0.0; sp.w_new = 1.0; break;
-        case PHW_SM: sp.w_old = 0.5; sp.w_new = 0.5; break;
-        default: sp.w_old = 1.0; sp.w_new = 0.0;
-    }
-    s->h_sp.assign(s->G, sp);
-    RC(s->upload(&s->d_sp, s->h_sp));
+    RC(setup_scalars(s));
     if (s->G > 1) {
         if (implicit_scheme(P.scheme) || P.strong || P.analytical || P.casimir)
             return fail(PHW_EINVAL, "batched (grouped) runs support the explicit weak-form schemes only");
@@ -1369,6 +1486,7 @@ int phw_comm_arena_handle(phw_solver_t s, void* handle64, int64_t* n_vertices_lo
 
 int phw_comm_internal_index(phw_solver_t s, int32_t which, int64_t n, const int32_t* user_idx, int32_t* internal_idx) {
     if (!s || (n > 0 && (!user_idx || !internal_idx))) return fail(PHW_EINVAL, "NULL argument");
+    if (s->ho) return fail(PHW_ESTATE, "not available for higher-order solvers");
     const std::vector<int32_t>& o2n = (which == PHW_P) ? s->mesh->L.v_old2new : s->mesh->L.e_old2new;
     for (int64_t i = 0; i < n; ++i) {
         if (user_idx[i] < 0 || (size_t)user_idx[i] >= o2n.size()) return fail(PHW_EINVAL, "index out of range");
@@ -1384,6 +1502,7 @@ int phw_comm_setup(phw_solver_t s, int32_t rank, int32_t world, const void* hand
     if (!s || !handles64 || !peer_nv || !peer_ne) return fail(PHW_EINVAL, "NULL argument");
     if (world < 1 || world > MAX_RANKS || rank < 0 || rank >= world || n_nb < 0 || n_nb >= MAX_RANKS)
         return fail(PHW_EINVAL, "rank/world/neighbour count out of range (at most 8 ranks)");
+    if (s->ho) return fail(PHW_EINVAL, "partitioned runs are not available for higher-order solvers");
     if (!s->coop) return fail(PHW_ESTATE, "multi-GPU runs need the cooperative solve path");
     if (s->prm.scheme == PHW_IE || s->prm.scheme == PHW_SM) return fail(PHW_EINVAL, "implicit schemes are not available in partitioned runs yet");
     CU(cudaSetDevice(s->device));
@@ -1569,7 +1688,7 @@ int phw_run(phw_solver_t s, int64_t n_steps, double* H_rows) {
     }
     s->prof_ev.clear(); s->prof_which.clear();
     {   // algorithmic bytes: per cell 40 B skew apply, 28/60 B mass apply; per dof 8 B per vector pass
-        const double nc = (double)s->mesh->L.nc, nv = s->nv, ne = s->ne;
+        const double nc = s->mesh ? (double)s->mesh->L.nc : 0.0, nv = s->nv, ne = s->ne;
         const double it_p = (double)st.iters_p + (double)st.iters_block, it_q = (double)st.iters_q + (double)st.iters_block;
         const double rhs = (double)(st.solves_p + st.solves_q + 2 * st.solves_block) * 40.0 * nc;
         double bytes = rhs + it_p * (28.0 * nc + 3 * 8.0 * nv) + it_q * (60.0 * nc + 3 * 8.0 * ne) + (double)n_steps * 88.0 * nc;
@@ -1595,6 +1714,7 @@ int phw_get_stats(phw_solver_t s, phw_stats* out) {
 // ---- kernel-level entry points ------------------------------------------------------------------
 int phw_apply_D(phw_solver_t s, const double* p, double* y) {
     if (!s || !p || !y) return fail(PHW_EINVAL, "NULL argument");
+    if (s->ho) return fail(PHW_ESTATE, "kernel-level entry points are for the matrix-free (P1/RT1) solver");
     CU(cudaSetDevice(s->device));
     int rc = import_vec(s, p, s->io_v2, s->nv, s->d_v_new2old, s->io_v); if (rc) return rc;
     rc = op_edge_store(s, s->io_v2, nullptr, 0.0, 1.0, 0.0, s->io_e2); if (rc) return rc;
@@ -1602,6 +1722,7 @@ int phw_apply_D(phw_solver_t s, const double* p, double* y) {
 }
 int phw_apply_DT(phw_solver_t s, const double* q, double* y) {
     if (!s || !q || !y) return fail(PHW_EINVAL, "NULL argument");
+    if (s->ho) return fail(PHW_ESTATE, "kernel-level entry points are for the matrix-free (P1/RT1) solver");
     CU(cudaSetDevice(s->device));
     int rc = import_vec(s, q, s->io_e2, s->ne, s->d_e_new2old, s->io_e); if (rc) return rc;
     rc = op_vertex_store(s, nullptr, s->io_e2, 0.0, 1.0, 0.0, s->io_v2); if (rc) return rc;
@@ -1609,6 +1730,7 @@ int phw_apply_DT(phw_solver_t s, const double* q, double* y) {
 }
 int phw_mass_matvec(phw_solver_t s, int32_t which, const double* x, double* y) {
     if (!s || !x || !y) return fail(PHW_EINVAL, "NULL argument");
+    if (s->ho) return fail(PHW_ESTATE, "kernel-level entry points are for the matrix-free (P1/RT1) solver");
     CU(cudaSetDevice(s->device));
     int rc;
     if (which == PHW_P) {
@@ -1624,6 +1746,7 @@ int phw_mass_matvec(phw_solver_t s, int32_t which, const double* x, double* y) {
 }
 int phw_mass_solve(phw_solver_t s, int32_t which, const double* b, double* x, int32_t* iters) {
     if (!s || !b || !x) return fail(PHW_EINVAL, "NULL argument");
+    if (s->ho) return fail(PHW_ESTATE, "kernel-level entry points are for the matrix-free (P1/RT1) solver");
     if (which != PHW_P && which != PHW_Q) return fail(PHW_EINVAL, "which must be PHW_P or PHW_Q");
     CU(cudaSetDevice(s->device));
     const int n = which == PHW_P ? s->nv : s->ne;
@@ -1658,6 +1781,7 @@ int phw_set_analytical(phw_solver_t s, double amp, double kx, double ky, double 
                        const double* lam_nodes45, const double* exact_vertices, const int32_t* pt_vertices3,
                        const double* pt_lam3) {
     if (!s || !mass_ref225 || !lam_nodes45 || !exact_vertices || !pt_vertices3 || !pt_lam3) return fail(PHW_EINVAL, "NULL argument");
+    if (s->ho) return fail(PHW_ESTATE, "use phw_ho_set_analytical for higher-order solvers");
     if (s->pc.world > 1) return fail(PHW_EINVAL, "analytical diagnostics are not available in partitioned runs");
     CU(cudaSetDevice(s->device));
     const Layout& L = s->mesh->L;
@@ -1684,6 +1808,107 @@ int phw_set_analytical(phw_solver_t s, double amp, double kx, double ky, double 
         rc = s->dalloc(&s->d_diag_part, 4 * (size_t)s->sm_count); if (rc) return rc;
         CU(cudaStreamSynchronize(s->stream));
     }
+    s->an_ready = true;
+    return PHW_OK;
+}
+
+// ---- higher-order pairs: solver on host-assembled CSR operators ----------------------------------------------
+static int upload_csr(phw_solver_s* s, int64_t n_rows, const int32_t* indptr, const int32_t* idx, const double* val, Csr* out) {
+    if (!indptr || !idx || !val || n_rows <= 0) return fail(PHW_EINVAL, "bad CSR matrix");
+    std::vector<int32_t> ip(indptr, indptr + n_rows + 1), ix(idx, idx + indptr[n_rows]);
+    std::vector<double> v(val, val + indptr[n_rows]);
+    int *d_ip, *d_ix; double* d_v;
+    int rc = s->upload(&d_ip, ip); if (rc) return rc;
+    rc = s->upload(&d_ix, ix); if (rc) return rc;
+    rc = s->upload(&d_v, v); if (rc) return rc;
+    CU(cudaStreamSynchronize(s->stream));
+    out->n_rows = (int)n_rows; out->indptr = d_ip; out->idx = d_ix; out->val = d_v;
+    return 0;
+}
+
+int phw_ho_create(const phw_params* prm, int32_t device, void* cuda_stream, int64_t n_p, int64_t n_q,
+                  const int32_t* Mp_indptr, const int32_t* Mp_idx, const double* Mp_val,
+                  const int32_t* Mq_indptr, const int32_t* Mq_idx, const double* Mq_val,
+                  const int32_t* D_indptr, const int32_t* D_idx, const double* D_val,
+                  const int32_t* DT_indptr, const int32_t* DT_idx, const double* DT_val,
+                  const double* b_L, double lam_min_p, double lam_max_p, double lam_min_q, double lam_max_q,
+                  phw_solver_t* out) {
+    if (!prm || !out || !b_L) return fail(PHW_EINVAL, "NULL argument");
+    if (prm->scheme < 0 || prm->scheme > 5) return fail(PHW_EINVAL, "unknown scheme");
+    if (prm->scheme == PHW_IE || prm->scheme == PHW_SM || prm->strong || prm->casimir)
+        return fail(PHW_EINVAL, "higher-order pairs: explicit weak-form schemes only (EE, SE, EH, SV)");
+    if (prm->interconnection && !(prm->scheme == PHW_SE || prm->scheme == PHW_SV))
+        return fail(PHW_EINVAL, "only SE, SV and SM time int schemes implemented for interconnection model");
+    if (!(lam_min_p > 0) || !(lam_min_q > 0) || lam_max_p < lam_min_p || lam_max_q < lam_min_q) return fail(PHW_EINVAL, "bad spectral bounds");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(PHW_ECUDA, "no CUDA device available (libphwave has no CPU fallback)"); }
+    if (device < 0 || device >= ndev) return fail(PHW_EINVAL, "device index out of range");
+    CU(cudaSetDevice(device));
+    phw_solver_s* s = new (std::nothrow) phw_solver_s();
+    if (!s) return fail(PHW_ENOMEM, "out of host memory");
+    s->mesh = nullptr; s->prm = *prm; s->device = device; s->stream = (cudaStream_t)cuda_stream; s->ho = true;
+    if (!(s->prm.tol > 0)) s->prm.tol = 1e-13;
+    if (s->prm.max_iter <= 0) s->prm.max_iter = 1000;
+    s->nv = (int)n_p; s->ne = (int)n_q; s->npatch = 0; s->G = 1;
+    auto bail = [&](int rc) { std::string keep = g_err; phw_solver_destroy(s); g_err = keep; return rc; };
+    cudaDeviceProp prop{};
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail(fail(PHW_ECUDA, "cudaGetDeviceProperties failed"));
+    s->sm_count = prop.multiProcessorCount;
+    if (cudaEventCreate(&s->ev0) != cudaSuccess || cudaEventCreate(&s->ev1) != cudaSuccess) return bail(fail(PHW_ECUDA, "event creation failed"));
+    int rc = setup_vectors(s); if (rc) return bail(rc);
+    if (!s->coop) return bail(fail(PHW_ECUDA, "cooperative launch is required"));
+    rc = setup_scalars(s); if (rc) return bail(rc);
+    rc = upload_csr(s, n_p, Mp_indptr, Mp_idx, Mp_val, &s->hMp); if (rc) return bail(rc);
+    rc = upload_csr(s, n_q, Mq_indptr, Mq_idx, Mq_val, &s->hMq); if (rc) return bail(rc);
+    rc = upload_csr(s, n_q, D_indptr, D_idx, D_val, &s->hD); if (rc) return bail(rc);
+    rc = upload_csr(s, n_p, DT_indptr, DT_idx, DT_val, &s->hDT); if (rc) return bail(rc);
+    {   // Jacobi weights from the CSR diagonals, identity numbering, port list = non-zeros of b_L
+        std::vector<double> pp(n_p, 0.0), pq(n_q, 0.0);
+        for (int64_t r = 0; r < n_p; ++r) for (int j = Mp_indptr[r]; j < Mp_indptr[r + 1]; ++j) if (Mp_idx[j] == r) pp[r] = 1.0 / Mp_val[j];
+        for (int64_t r = 0; r < n_q; ++r) for (int j = Mq_indptr[r]; j < Mq_indptr[r + 1]; ++j) if (Mq_idx[j] == r) pq[r] = 1.0 / Mq_val[j];
+        if (cudaMemcpyAsync(s->pinv_p, pp.data(), n_p * 8, cudaMemcpyHostToDevice, s->stream) != cudaSuccess ||
+            cudaMemcpyAsync(s->pinv_q, pq.data(), n_q * 8, cudaMemcpyHostToDevice, s->stream) != cudaSuccess) return bail(fail(PHW_ECUDA, "memcpy failed"));
+        std::vector<int32_t> idv(n_p), ide(n_q), pe, pg, goff(2, 0), gpoff(2, 0);
+        std::iota(idv.begin(), idv.end(), 0); std::iota(ide.begin(), ide.end(), 0);
+        std::vector<double> bl;
+        for (int64_t r = 0; r < n_q; ++r) if (b_L[r] != 0.0) { pe.push_back((int32_t)r); bl.push_back(b_L[r]); pg.push_back(0); }
+        goff[1] = (int32_t)pe.size();
+        s->nport = (int)pe.size();
+        rc = s->upload(&s->d_v_new2old, idv); if (rc) return bail(rc);
+        rc = s->upload(&s->d_e_new2old, ide); if (rc) return bail(rc);
+        rc = s->upload(&s->d_port_e, pe); if (rc) return bail(rc);
+        rc = s->upload(&s->d_port_bl, bl); if (rc) return bail(rc);
+        rc = s->upload(&s->d_port_goff, goff); if (rc) return bail(rc);
+        rc = s->upload(&s->d_port_group, pg); if (rc) return bail(rc);
+        rc = s->upload(&s->d_gpoff, gpoff); if (rc) return bail(rc);
+        if (cudaStreamSynchronize(s->stream) != cudaSuccess) return bail(fail(PHW_ECUDA, "sync failed"));
+    }
+    s->cheb_d[0] = 0.5 * (lam_min_p + lam_max_p); s->cheb_c[0] = 0.5 * (lam_max_p - lam_min_p);
+    s->cheb_d[1] = 0.5 * (lam_min_q + lam_max_q); s->cheb_c[1] = 0.5 * (lam_max_q - lam_min_q);
+    s->lam_min_q = lam_min_q; s->lam_max_q = lam_max_q;
+    s->launches = 0;
+    *out = s;
+    return PHW_OK;
+}
+
+int phw_ho_set_analytical(phw_solver_t s, double omega, int32_t n_cells, int32_t ndp, int32_t nn, const int32_t* cell_dofs,
+                          const double* T, const double* mass_ref, const double* exact_nodes, const double* area,
+                          const double* exact_dofs, int32_t nprobe, const int32_t* probe_dofs, const double* probe_w) {
+    if (!s || !s->ho || !cell_dofs || !T || !mass_ref || !exact_nodes || !area || !exact_dofs) return fail(PHW_EINVAL, "bad arguments");
+    if (ndp > 10 || nn > 28 || nprobe > 10 || nprobe < 0) return fail(PHW_EINVAL, "tabulation sizes exceed P3 -> P6");
+    CU(cudaSetDevice(s->device));
+    s->ho_nc = n_cells; s->ho_ndp = ndp; s->ho_nn = nn; s->ho_nprobe = nprobe; s->ho_omega = omega;
+    int rc;
+    rc = s->upload(&s->ho_cell_dofs, std::vector<int32_t>(cell_dofs, cell_dofs + (size_t)n_cells * ndp)); if (rc) return rc;
+    rc = s->upload(&s->ho_T, std::vector<double>(T, T + (size_t)nn * ndp)); if (rc) return rc;
+    rc = s->upload(&s->ho_mass, std::vector<double>(mass_ref, mass_ref + (size_t)nn * nn)); if (rc) return rc;
+    rc = s->upload(&s->ho_exact_nodes, std::vector<double>(exact_nodes, exact_nodes + (size_t)n_cells * nn)); if (rc) return rc;
+    rc = s->upload(&s->ho_area, std::vector<double>(area, area + n_cells)); if (rc) return rc;
+    rc = s->upload(&s->ho_exact_dofs, std::vector<double>(exact_dofs, exact_dofs + s->nv)); if (rc) return rc;
+    rc = s->upload(&s->ho_probe_dofs, std::vector<int32_t>(probe_dofs, probe_dofs + nprobe)); if (rc) return rc;
+    rc = s->upload(&s->ho_probe_w, std::vector<double>(probe_w, probe_w + nprobe)); if (rc) return rc;
+    if (!s->d_diag_part) { rc = s->dalloc(&s->d_diag_part, 4 * (size_t)s->sm_count); if (rc) return rc; }
+    CU(cudaStreamSynchronize(s->stream));
     s->an_ready = true;
     return PHW_OK;
 }

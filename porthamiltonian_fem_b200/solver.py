@@ -315,3 +315,39 @@ def setup_peer_exchange(solver, part, dist, rank, world):
         nse.ctypes.data_as(_lib.c_i64p), PtrArr(*loc_ptrs['e']) if n else PtrArr(), PtrArr(*rem_ptrs['e']) if n else PtrArr()))
     dist.barrier()
     return dict(neighbours=nbs, send_v=n_send['v'], send_e=n_send['e'])
+
+
+class _DofCounts:
+    """minimal stand-in for Mesh in solvers that are not tied to a libphwave mesh handle"""
+
+    def __init__(self, n_p, n_q):
+        self.n_vertices, self.n_edges, self.n_groups = int(n_p), int(n_q), 1
+        self.handle = None
+
+
+class HighOrderSolver(Solver):
+    """Solver for the P_k x RT_k pairs, k <= 3, on host-assembled CSR operators (phw_ho_create)."""
+
+    def __init__(self, spaces, ops, params, bounds_p, bounds_q, device=0):
+        self.lib = _lib.load()
+        self.spaces = spaces
+        self.mesh = _DofCounts(spaces.np_dofs, spaces.nq_dofs)
+        self.params = params
+        keep = []
+
+        def csr(M):
+            M = M.tocsr()
+            M.sort_indices()
+            ip = np.ascontiguousarray(M.indptr, dtype=np.int32)
+            ix = np.ascontiguousarray(M.indices, dtype=np.int32)
+            v = np.ascontiguousarray(M.data, dtype=np.float64)
+            keep.extend([ip, ix, v])
+            return ip.ctypes.data_as(_lib.c_i32p), ix.ctypes.data_as(_lib.c_i32p), v.ctypes.data_as(_lib.c_f64p)
+        bL = np.ascontiguousarray(ops['b_L'], dtype=np.float64)
+        h = ctypes.c_void_p()
+        _lib.check(self.lib.phw_ho_create(ctypes.byref(params), int(device), None, spaces.np_dofs, spaces.nq_dofs,
+                                          *csr(ops['M_p']), *csr(ops['M_q']), *csr(ops['D']), *csr(ops['D'].T),
+                                          bL.ctypes.data_as(_lib.c_f64p), bounds_p[0], bounds_p[1], bounds_q[0], bounds_q[1],
+                                          ctypes.byref(h)))
+        self.handle = h
+        self.ncol = 12 if params.analytical else 8

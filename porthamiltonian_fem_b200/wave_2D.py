@@ -67,7 +67,9 @@ def wave_2D_solve(tFinal, numSteps, outputDir,
     if dirichletImp not in ('weak', 'strong'):
         _quit('dirichlet implementation {} not implemented'.format(dirichletImp))
     if tuple(basis_order) != (1, 1):
-        raise NotImplementedError('the device path implements the P1/RT1 pair; basis_order={} is not available yet'.format(basis_order))
+        return _solve_high_order(tFinal, numSteps, outputDir, nx, xLength, yLength, domainShape, timeIntScheme, dirichletImp,
+                                 K_wave, rho, interConnection, analytical, controlType, tuple(basis_order), mesh, mesh_kind,
+                                 device, tol, extrap_order, lumped, return_state, verbose, tic)
     if controlType == 'casimir' and timeIntScheme != 'SM':
         raise NotImplementedError('casimir control is only defined for the SM scheme (wave_2D.py:615)')
     if controlType == 'passivity' and timeIntScheme in ['SV', 'EH']:
@@ -256,3 +258,109 @@ class _AnalyticalDiagnostics:
             vc = self.cells[self.pt_cell]
             return err_L2, err_max, float(p_h[vc] @ self.pt_lam), float((self.exact_vertices[vc] * ct) @ self.pt_lam)
         return err_L2, err_max, 0.0, 0.0
+
+
+def _solve_high_order(tFinal, numSteps, outputDir, nx, xLength, yLength, domainShape, timeIntScheme, dirichletImp, K_wave, rho,
+                      interConnection, analytical, controlType, basis_order, mesh, mesh_kind, device, tol, extrap_order, lumped,
+                      return_state, verbose, tic):
+    """basis_order != (1,1) (wave_2D.py:174-175,202-203): host-assembled operators (fem_ho.py) + CSR device kernels."""
+    from .fem_ho import HighOrderSpaces, LagrangeRef, tri_rule
+    from .solver import HighOrderSolver
+    if dirichletImp != 'weak' or controlType is not None or timeIntScheme in ('IE', 'SM'):
+        raise NotImplementedError('higher-order pairs are available for the explicit weak-form schemes (EE, SE, EH, SV)')
+    if mesh is None:
+        mesh = generate_mesh(domainShape, nx, xLength, yLength, kind=mesh_kind)
+    S = HighOrderSpaces(mesh[0], mesh[1], basis_order[0], basis_order[1])
+    if verbose:
+        print('number of cells = {}'.format(S.nc))
+    # facet markers (wave_2D.py:226-280) on the boundary edges
+    be = S.boundary_edges
+    pa, pb = S.vertices[S.edges[be, 0]], S.vertices[S.edges[be, 1]]
+    pm = 0.5 * (pa + pb)
+    tol_g = 1e-12
+    xin = 0.0 if domainShape == 'R' else -0.10
+
+    def on(pred):
+        return pred(pa) & pred(pb) & pred(pm)
+    tags = np.full(be.shape[0], 4, dtype=np.int64)
+    tags[on(lambda p: np.abs(p[:, 0] - xin) < tol_g)] = 0
+    if domainShape == 'R':
+        tags[on(lambda p: np.abs(p[:, 1] - yLength) < tol_g)] = 1
+    tags[on(lambda p: np.abs(p[:, 0] - xLength) < tol_g)] = 2
+    if domainShape == 'R':
+        tags[on(lambda p: np.abs(p[:, 1]) < tol_g)] = 3
+    else:
+        ylo, yhi = xLength / 2 - yLength / 2, xLength / 2 + yLength / 2
+        tags[on(lambda p: (np.abs(p[:, 1]) < tol_g) | (np.abs(p[:, 1] - xLength) < tol_g) | (np.abs(p[:, 1] - ylo) < tol_g) |
+                (np.abs(p[:, 1] - yhi) < tol_g) | (np.abs(p[:, 0]) < tol_g))] = 3
+    c = np.sqrt(K_wave / rho)
+    omega = c * np.sqrt(np.pi ** 2 / (4 * xLength ** 2) + 4 * np.pi ** 2 / yLength ** 2)
+    left_w = (lambda x, y: rho * omega * np.sin(2 * np.pi * y / yLength + np.pi / 2)) if analytical else None
+    ops = S.assemble({int(e): int(t) for e, t in zip(be, tags)}, left_weight=left_w)
+    bp, bq = S.jacobi_bounds(ops)
+    prm = _lib.PhwParams()
+    prm.scheme = _lib.SCHEMES[timeIntScheme]
+    prm.interconnection = 1 if interConnection == 'IC' else 0
+    prm.analytical = 1 if analytical else 0
+    prm.dt, prm.K_wave, prm.rho = tFinal / numSteps, float(K_wave), float(rho)
+    prm.tol, prm.max_iter, prm.extrap_order = float(tol), 2000, int(extrap_order)
+    lp = dict(_DEFAULT_LUMPED)
+    if lumped:
+        lp.update(lumped)
+    for k, v in lp.items():
+        setattr(prm, k, float(v))
+    if analytical:
+        prm.input_kind, prm.in_amp, prm.in_omega = _lib.IN_COSINE, 1.0, omega
+    elif interConnection == 'IC':
+        prm.input_kind, prm.in_amp, prm.in_omega, prm.in_t_stop = _lib.IN_SINE_WINDOW, 5.0, 8 * np.pi, 0.25
+    else:
+        prm.input_kind, prm.in_amp, prm.in_omega, prm.in_t_stop = _lib.IN_SINE_WINDOW, 10.0, 8 * np.pi, 0.25
+    solver = HighOrderSolver(S, ops, prm, bp, bq, device=device)
+    H_init = 0.0
+    if analytical:
+        space = lambda x, y: rho * omega * np.sin(np.pi * x / (2 * xLength) + np.pi / 2) * np.sin(2 * np.pi * y / yLength + np.pi / 2)
+        p0 = S.interpolate_p(space)
+        solver.set_state(p=p0, q=np.zeros(S.nq_dofs), x3=np.zeros(3))
+        H_init = solver.energy_parts()[0]
+        solver.set_H_init(H_init)
+        # errornorm tabulations: P_k -> P_{k+3} (wave_2D.py:956), probe point (0.155, 0.189) (:946-950)
+        kk = S.kp + 3
+        hi = LagrangeRef(kk)
+        T = S.lag.tabulate(hi.nodes_bary)                                  # [nn, ndp]
+        bary, wq = tri_rule(8)
+        tab = hi.tabulate(bary)
+        mass = np.einsum('qi,qj,q->ij', tab, tab, wq)
+        xy = np.einsum('nj,cjd->cnd', hi.nodes_bary, S.V)
+        exact_nodes = space(xy[..., 0], xy[..., 1])
+        P = np.array([0.155, 0.189])
+        Tm = np.stack([S.V[:, 1] - S.V[:, 0], S.V[:, 2] - S.V[:, 0]], axis=2)
+        rhs = P[None, :] - S.V[:, 0]
+        det = Tm[:, 0, 0] * Tm[:, 1, 1] - Tm[:, 0, 1] * Tm[:, 1, 0]
+        l1 = (rhs[:, 0] * Tm[:, 1, 1] - rhs[:, 1] * Tm[:, 0, 1]) / det
+        l2 = (Tm[:, 0, 0] * rhs[:, 1] - Tm[:, 1, 0] * rhs[:, 0]) / det
+        l0 = 1 - l1 - l2
+        inside = np.nonzero((l0 >= -1e-12) & (l1 >= -1e-12) & (l2 >= -1e-12))[0]
+        if inside.size:
+            pc = int(inside[0])
+            pw = S.lag.tabulate(np.array([[l0[pc], l1[pc], l2[pc]]]))[0]
+            pd = S.cell_dofs_p[pc].astype(np.int32)
+        else:
+            pw, pd = np.zeros(0), np.zeros(0, dtype=np.int32)
+        cd = np.ascontiguousarray(S.cell_dofs_p, dtype=np.int32)
+        arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (T, mass, exact_nodes, S.area, p0, pw)]
+        pd = np.ascontiguousarray(pd, dtype=np.int32)
+        _lib.check(solver.lib.phw_ho_set_analytical(solver.handle, float(omega), S.nc, S.ndp, hi.nodes_bary.shape[0],
+                                                    cd.ctypes.data_as(_lib.c_i32p), arrs[0].ctypes.data_as(_lib.c_f64p),
+                                                    arrs[1].ctypes.data_as(_lib.c_f64p), arrs[2].ctypes.data_as(_lib.c_f64p),
+                                                    arrs[3].ctypes.data_as(_lib.c_f64p), arrs[4].ctypes.data_as(_lib.c_f64p),
+                                                    int(pd.shape[0]), pd.ctypes.data_as(_lib.c_i32p), arrs[5].ctypes.data_as(_lib.c_f64p)))
+    H_array = solver.run(numSteps)
+    stats = solver.stats()
+    if verbose:
+        print('{}, {}, {} Simulation finished in {} seconds'.format(domainShape, timeIntScheme, dirichletImp, time.time() - tic))
+    if return_state:
+        p, q, x = solver.get_state()
+        solver.close()
+        return H_array, S.nc, dict(p=p, q=q, x=x, stats=stats, spaces=S, ops=ops)
+    solver.close()
+    return H_array, S.nc
