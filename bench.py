@@ -158,6 +158,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--tol', type=float, default=1e-13)
     ap.add_argument('--extrap', type=int, default=2)
+    ap.add_argument('--debug-residuals', action='store_true', help='print the residual history of the last M_p / M_q solve to stderr')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference_arm(args)
@@ -239,6 +240,9 @@ def main():
     stop.set()
     th.join(timeout=2)
     st = solver.stats()
+    if args.debug_residuals and rank == 0:
+        for w, nm in ((0, 'M_p'), (1, 'M_q')):
+            sys.stderr.write('residual history {}: {}\n'.format(nm, ' '.join('%.1e' % r for r in solver.residual_history(w))))
     dev_s = st['device_ms'] * 1e-3
     if world > 1:
         tt = torch.tensor([dev_s], dtype=torch.float64, device='cuda')

@@ -46,6 +46,7 @@ struct Ctl {
     double xch[2][4];                // globally reduced values of the current exchange
     SolveCtl sc[3];
     unsigned int counters[8];
+    double reshist[3][48];           // ||r_k||^2 / ||b||^2 of the first 48 iterations of the most recent solve (diagnostics)
 };
 
 struct DevMesh {
@@ -203,6 +204,12 @@ struct PassIO {
 
 __device__ __forceinline__ double* tb_sel(const TriBuf& t, int i) { return i == 0 ? t.b[0] : (i == 1 ? t.b[1] : t.b[2]); }
 
+// patch headers are double-buffered in shared memory: the header of the CTA's next patch is fetched while the current
+// patch is processed (no exposed header load at the top of a patch)
+__device__ __forceinline__ void load_hdr_smem(PatchHdr* dst, const PatchHdr* src) {
+    if (threadIdx.x < 16) reinterpret_cast<int*>(dst)[threadIdx.x] = __ldg(reinterpret_cast<const int*>(src) + threadIdx.x);
+}
+
 // ------------------------------------------------------------------------------------------------
 // vertex rows: all patches of this block
 // ------------------------------------------------------------------------------------------------
@@ -212,14 +219,23 @@ __device__ __forceinline__ void vertex_pass(const RowArgs& a, const PassIO& io, 
     // pure P1 mass rows: (M_p x)_v = sum_K (|K|/12) sum(x_K) + x_v * diag_v / 2, diag_v = sum_K |K|/6 = 1/pinv_v,
     // so one value per cell suffices (a.pinv must be set)
     constexpr bool ONEVAL = HAS_M && !HAS_D && !CAS && MODE == MODE_OP;
-    for (int P = blockIdx.x; P < m.npatch; P += gridDim.x) {
-        const PatchHdr h = m.hdr[P];
+    __shared__ PatchHdr s_hdr[2];
+    if (blockIdx.x < m.npatch) load_hdr_smem(&s_hdr[0], &m.hdr[blockIdx.x]);
+    __syncthreads();
+    int it = 0;
+    for (int P = blockIdx.x; P < m.npatch; P += gridDim.x, ++it) {
+        const PatchHdr& h = s_hdr[it & 1];
+        const int Pn = P + gridDim.x;
+        if (Pn < m.npatch) load_hdr_smem(&s_hdr[(it + 1) & 1], &m.hdr[Pn]);
         const double cD = (HAS_D && a.gscale) ? a.cD * a.gscale[h.group] : a.cD;
         const int nlv = h.v_cnt + h.gv_cnt, nle = h.e_cnt + h.ge_cnt;
-        double* sp = smem;                         // [nlv]
+        const int nsl = (h.v_cnt + 31) >> 5;
+        uint32_t* s_off = reinterpret_cast<uint32_t*>(smem);   // [nsl + 1] slice offsets of the sliced-ELL adjacency
+        double* sp = smem + ((nsl + 2) >> 1);      // [nlv]
         double* sq = sp + ((nlv + 1) & ~1);        // [nle] (only if HAS_D)
         double* sc3 = HAS_D ? sq + ((nle + 1) & ~1) : sq;   // [CW*n_vcells]
         // ---- stage 1: local inputs
+        for (int i = threadIdx.x; i <= nsl; i += NT) s_off[i] = __ldg(&m.vslice_off[h.vs_off + i]);
         if (MODE == MODE_OP && (HAS_M || CAS || EPI != EPI_STORE)) {
             for (int i = threadIdx.x; i < h.v_cnt; i += NT) sp[i] = io.xp[h.v_start + i];
             for (int i = threadIdx.x; i < h.gv_cnt; i += NT) sp[h.v_cnt + i] = io.xp[m.ghost_v[h.gv_off + i]];
@@ -308,7 +324,7 @@ __device__ __forceinline__ void vertex_pass(const RowArgs& a, const PassIO& io, 
         const int vround = (h.v_cnt + 31) & ~31;
         const uint4* adj4 = reinterpret_cast<const uint4*>(m.vadj);
         for (int lv = threadIdx.x; lv < vround; lv += NT) {
-            const uint32_t o0 = m.vslice_off[h.vs_off + (lv >> 5)], o1 = m.vslice_off[h.vs_off + (lv >> 5) + 1];
+            const uint32_t o0 = s_off[lv >> 5], o1 = s_off[(lv >> 5) + 1];
             const bool live = lv < h.v_cnt;
             const int gid = h.v_start + (live ? lv : 0);
             double bv = 0.0, pv = 0.0, xpv = 0.0, dgv = 0.0;
@@ -363,8 +379,14 @@ __device__ __forceinline__ void vertex_pass(const RowArgs& a, const PassIO& io, 
 template <int EPI, int MODE, bool HAS_M, bool HAS_D, bool CAS, int NT>
 __device__ __forceinline__ void edge_pass(const RowArgs& a, const PassIO& io, double* smem, double& acc0, double& acc1) {
     const DevMesh& m = a.m;
-    for (int P = blockIdx.x; P < m.npatch; P += gridDim.x) {
-        const PatchHdr h = m.hdr[P];
+    __shared__ PatchHdr s_hdr[2];
+    if (blockIdx.x < m.npatch) load_hdr_smem(&s_hdr[0], &m.hdr[blockIdx.x]);
+    __syncthreads();
+    int it = 0;
+    for (int P = blockIdx.x; P < m.npatch; P += gridDim.x, ++it) {
+        const PatchHdr& h = s_hdr[it & 1];
+        const int Pn = P + gridDim.x;
+        if (Pn < m.npatch) load_hdr_smem(&s_hdr[(it + 1) & 1], &m.hdr[Pn]);
         const double cD = (HAS_D && a.gscale) ? a.cD * a.gscale[h.group] : a.cD;
         const int nlv = h.v_cnt + h.gv_cnt, nle = h.e_cnt + h.ge_cnt;
         double* sq = smem;                          // [nle]
@@ -703,6 +725,7 @@ __global__ void __launch_bounds__(NT, MINB) solve_coop_k(const RowArgs av, const
         // a Chebyshev iterate can be exact for the components present while its successor is not (the momentum
         // term), so on convergence the verified iterate x_k is the one that is returned.
         conv = rr <= a0.tol2 * bb;
+        if (blockIdx.x == 0 && threadIdx.x == 0 && k < 48) a0.ctl->reshist[a0.which][k] = (bb > 0.0) ? rr / bb : 0.0;
         k += 1;
         if (conv) break;
         rho = rho_k; cur = nxt;

@@ -337,6 +337,7 @@ std::string Layout::build(int64_t nv_, const double* vxy, int64_t nc_, const int
             vslice_off.push_back((uint32_t)(base + sbase[sl + 1]));
         }
         vadj.resize(base + sbase[nslice], (uint16_t)0xFFFFu);
+        H.adj_off = (int32_t)(uint32_t)base; H.adj_cnt = (int32_t)sbase[nslice];
         std::vector<uint32_t> fill(H.v_cnt, 0);
         for (size_t lc = 0; lc < cl.size(); ++lc) {
             int64_t c = cl[lc];

@@ -32,7 +32,8 @@ struct PatchHdr {
     int32_t e_start, e_cnt, ge_off, ge_cnt;   // owned edge range, ghost list
     int32_t vs_off;     // first 32-vertex slice of this patch in vslice_off
     int32_t group;      // case index of a batched (replicated-mesh) run, 0 otherwise
-    int32_t pad[2];
+    int32_t adj_off;    // first uint16 code of this patch in vadj (uint32 bits) and number of codes: the patch's adjacency
+    int32_t adj_cnt;    // is one contiguous range, so the next patch can be prefetched without reading vslice_off
 };
 
 struct Layout {

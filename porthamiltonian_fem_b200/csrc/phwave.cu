@@ -1157,6 +1157,15 @@ int phw_solver_destroy(phw_solver_t s) {
     return PHW_OK;
 }
 
+int phw_residual_history(phw_solver_t s, int32_t which, int32_t n, double* rel, int32_t* n_it) {
+    if (!s || which < 0 || which > 2 || n < 0 || n > 48 || !rel) return fail(PHW_EINVAL, "phw_residual_history: bad arguments");
+    CU(cudaStreamSynchronize(s->stream));
+    Ctl h;
+    CU(cudaMemcpy(&h, s->ctl, sizeof(Ctl), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < n; ++k) rel[k] = std::sqrt(h.reshist[which][k]);
+    if (n_it) *n_it = h.sc[which].k;
+    return 0;
+}
 int phw_synchronize(phw_solver_t s) {
     if (!s) return fail(PHW_EINVAL, "solver is NULL");
     CU(cudaStreamSynchronize(s->stream));
@@ -1321,9 +1330,10 @@ static int setup_solver(phw_solver_s* s) {
     (void)nv; (void)ne;
     // ---- shared-memory budgets and grid
     auto ev = [](int x) { return (size_t)((x + 1) & ~1); };
-    s->smem_v = (ev(L.max_lv) + 3 * (size_t)L.max_cells) * 8;
-    s->smem_v1 = (ev(L.max_lv) + (size_t)L.max_cells) * 8;
-    s->smem_vd = (ev(L.max_lv) + ev(L.max_le) + 3 * (size_t)L.max_cells) * 8;
+    const size_t soff = ((size_t)(L.max_lv + 31) / 32 + 4) / 2 + 1;   // slice offsets staged by the vertex rows (uint32, in doubles)
+    s->smem_v = (soff + ev(L.max_lv) + 3 * (size_t)L.max_cells) * 8;
+    s->smem_v1 = (soff + ev(L.max_lv) + (size_t)L.max_cells) * 8;
+    s->smem_vd = (soff + ev(L.max_lv) + ev(L.max_le) + 3 * (size_t)L.max_cells) * 8;
     s->smem_e = (ev(L.max_le) + 3 * (size_t)L.max_cells) * 8;
     s->smem_ed = s->smem_vd;
     if (s->smem_vd > 200 * 1024) return fail(PHW_EINVAL, "patch does not fit in shared memory; reduce patch_cells");

@@ -199,6 +199,13 @@ class Solver:
         _lib.check(self.lib.phw_get_stats(self.handle, ctypes.byref(st)))
         return st.as_dict()
 
+    def residual_history(self, which, n=48):
+        """relative residuals of the iterations of the most recent solve of kind `which` (diagnostics)"""
+        out = np.zeros(n)
+        nit = ctypes.c_int32(0)
+        _lib.check(self.lib.phw_residual_history(self.handle, int(which), int(n), out.ctypes.data_as(_lib.c_f64p), ctypes.byref(nit)))
+        return out[:min(n, nit.value)]
+
     def set_H_init(self, v):
         _lib.check(self.lib.phw_set_H_init(self.handle, float(v)))
 
