@@ -56,7 +56,9 @@ typedef struct phw_params {
     int32_t extrap_order;    /* initial guess of each solve = polynomial extrapolation of that solve's previous
                                 solutions: 0 last solution, 1 linear, 2 quadratic (default choice of the host code), 3 cubic */
     int32_t flags;           /* bit0: disable first-same-as-last reuse in SV; bit1: synchronous error checks;
-                                bit2: CUDA-event timing of every solve kernel; bit3: force the multi-launch solve path */
+                                bit2: CUDA-event timing of every solve kernel; bit3: force the multi-launch solve path;
+                                bit4: two-sweep mass solves (two Chebyshev iterations per pass over the data, csrc/kernels2.cuh;
+                                single GPU, weak form, explicit schemes; default off - see DESIGN.md section 10) */
 } phw_params;
 
 typedef struct phw_stats {

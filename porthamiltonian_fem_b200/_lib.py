@@ -104,8 +104,8 @@ def load(rebuild_if_stale=True):
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB
-    if rebuild_if_stale and (not os.path.exists(path) or _build.needs_build()):
+    path = os.environ.get('PHW_LIB', _build.LIB)     # tuning variants of the same sources (profiles/), default: the in-tree build
+    if path == _build.LIB and rebuild_if_stale and (not os.path.exists(path) or _build.needs_build()):
         try:
             _build.build()
         except Exception:

@@ -20,11 +20,35 @@
 #include <cooperative_groups.h>
 #include "layout.hpp"
 
+// loads in flight per thread in the batched stages (memory-level parallelism vs registers)
+#ifndef PHW_U_VCELLS
+#define PHW_U_VCELLS 3
+#endif
+#ifndef PHW_U_ECELLS
+#define PHW_U_ECELLS 2
+#endif
+#ifndef PHW_U_EROWS
+#define PHW_U_EROWS 2
+#endif
+
+#ifndef PHW_NT_P
+#define PHW_NT_P 256
+#endif
+#ifndef PHW_NT_Q
+#define PHW_NT_Q 384
+#endif
+#ifndef PHW_MINB_P
+#define PHW_MINB_P 6
+#endif
+#ifndef PHW_MINB_Q
+#define PHW_MINB_Q 2
+#endif
+
 namespace phw {
 
 constexpr int NT_ROWS = 512;   // threads per CTA of the row kernels
-constexpr int NT_COOP_P = 256;  // threads per CTA of the persistent M_p solve (more, smaller CTAs hide the per-stage latencies)
-constexpr int NT_COOP_Q = 384;  // M_q solve: 2 CTAs/SM (shared-memory bound) x 384 threads leaves 85 registers per thread for batched loads
+constexpr int NT_COOP_P = PHW_NT_P;  // threads per CTA of the persistent M_p solve (more, smaller CTAs hide the per-stage latencies)
+constexpr int NT_COOP_Q = PHW_NT_Q;  // M_q solve: 2 CTAs/SM (shared-memory bound) x 384 threads leaves 85 registers per thread for batched loads
 
 struct SolveCtl {
     int k, done, cur, pad;
@@ -62,7 +86,7 @@ struct DevMesh {
     const uint16_t* vadj;
 };
 
-struct TriBuf { double* b[3]; };
+struct TriBuf { double* b[4]; };   // rotating Chebyshev iterates (the one-sweep kernels use the first three)
 
 // ---- multi-GPU: peer-memory halo exchange + all-reduce fused into the persistent solve ----
 constexpr int MAX_RANKS = 8;
@@ -248,7 +272,7 @@ __device__ __forceinline__ void vertex_pass(const RowArgs& a, const PassIO& io, 
         // ---- stage 2: per-cell contributions to its three vertices
         if (ONEVAL) {
             // batched: issue the loads of U cells before consuming them (memory-level parallelism)
-            constexpr int U = 3;
+            constexpr int U = PHW_U_VCELLS;
             for (int base = threadIdx.x; base < h.n_vcells; base += U * NT) {
                 uint2 rvb[U]; double Ab[U];
 #pragma unroll
@@ -404,7 +428,7 @@ __device__ __forceinline__ void edge_pass(const RowArgs& a, const PassIO& io, do
         constexpr bool MONLY = HAS_M && !HAS_D && !CAS && MODE == MODE_OP && EPI == EPI_CHEB;
         if (MONLY) {
             // pure RT1 mass rows: issue the loads of U cells before consuming them (memory-level parallelism)
-            constexpr int U = 2;
+            constexpr int U = PHW_U_ECELLS;
             for (int base = threadIdx.x; base < h.n_ecells; base += U * NT) {
                 uint2 reb[U]; double gb[U][3];
 #pragma unroll
@@ -487,7 +511,7 @@ __device__ __forceinline__ void edge_pass(const RowArgs& a, const PassIO& io, do
         }
         __syncthreads();
         if (MONLY) {
-            constexpr int U3 = 2;
+            constexpr int U3 = PHW_U_EROWS;
             for (int base = threadIdx.x; base < h.e_cnt; base += U3 * NT) {
                 uint32_t adjb[U3]; double bvb[U3], pvb[U3], xpb[U3];
 #pragma unroll

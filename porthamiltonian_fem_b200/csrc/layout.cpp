@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <numeric>
@@ -204,19 +205,33 @@ std::string Layout::build(int64_t nv_, const double* vxy, int64_t nc_, const int
     if (e_ext) for (int64_t e = 0; e < ne; ++e) if (e_ext[e]) e_owner[e] = npatch;
     v_degree.assign(nv, 0);
     for (int64_t h = 0; h < 3 * nc; ++h) v_degree[cells[h]]++;
-    // new id = rank by (owner, -degree, old id): stable counting sorts, least significant key first
-    auto renumber = [&](const std::vector<int32_t>& owner, const std::vector<int32_t>* degree, int64_t n,
-                        std::vector<int32_t>& new2old, std::vector<int32_t>& old2new, std::vector<int32_t>& pstart) {
-        std::vector<int32_t> order(n);
-        if (degree) {
+    // new id = rank by (owner, first touch along the owner patch's cell order): dofs that are used together by neighbouring
+    // cells get neighbouring local ids, which keeps the shared-memory gathers of a warp on distinct banks (a degree sort
+    // would make the sliced-ELL adjacency a little tighter on irregular meshes but scatters the ids: ~3-way bank conflicts).
+    // PHW_DEGREE_SORT=1 restores the degree-sorted vertex numbering (A/B only).
+    static const bool degree_sort = [] { const char* e = getenv("PHW_DEGREE_SORT"); return e && atoi(e) != 0; }();
+    auto renumber = [&](const std::vector<int32_t>& owner, const std::vector<int32_t>& cell_dofs, const std::vector<int32_t>* degree,
+                        int64_t n, std::vector<int32_t>& new2old, std::vector<int32_t>& old2new, std::vector<int32_t>& pstart) {
+        std::vector<int32_t> ord(n);
+        if (degree && degree_sort) {
             int32_t dmax = 0;
             for (int64_t i = 0; i < n; ++i) dmax = std::max(dmax, (*degree)[i]);
             std::vector<int64_t> cnt(dmax + 2, 0);
             for (int64_t i = 0; i < n; ++i) cnt[dmax - (*degree)[i] + 1]++;
             for (int32_t d = 0; d <= dmax; ++d) cnt[d + 1] += cnt[d];
-            for (int64_t i = 0; i < n; ++i) order[cnt[dmax - (*degree)[i]]++] = (int32_t)i;
+            for (int64_t i = 0; i < n; ++i) ord[cnt[dmax - (*degree)[i]]++] = (int32_t)i;
         } else {
-            for (int64_t i = 0; i < n; ++i) order[i] = (int32_t)i;
+            std::vector<uint8_t> seen(n, 0);
+            int64_t w = 0;
+            for (int64_t k = 0; k < nc; ++k) {
+                const int64_t c = order[k];
+                const int32_t pc = cell_patch[c];
+                for (int i = 0; i < 3; ++i) {
+                    const int32_t d = cell_dofs[3 * c + i];
+                    if (!seen[d] && owner[d] == pc) { seen[d] = 1; ord[w++] = d; }
+                }
+            }
+            for (int64_t i = 0; i < n; ++i) if (!seen[i]) ord[w++] = (int32_t)i;   // dofs of other ranks (virtual patch npatch)
         }
         pstart.assign(npatch + 2, 0);
         for (int64_t i = 0; i < n; ++i) pstart[owner[i] + 1]++;
@@ -224,15 +239,15 @@ std::string Layout::build(int64_t nv_, const double* vxy, int64_t nc_, const int
         std::vector<int32_t> pos(pstart.begin(), pstart.end() - 1);
         new2old.resize(n); old2new.resize(n);
         for (int64_t k = 0; k < n; ++k) {
-            int32_t i = order[k];
+            int32_t i = ord[k];
             int32_t d = pos[owner[i]]++;
             new2old[d] = i;
             old2new[i] = d;
         }
     };
     std::vector<int32_t> vstart, estart;
-    renumber(v_owner, &v_degree, nv, v_new2old, v_old2new, vstart);
-    renumber(e_owner, nullptr, ne, e_new2old, e_old2new, estart);
+    renumber(v_owner, cells, &v_degree, nv, v_new2old, v_old2new, vstart);
+    renumber(e_owner, cell_edges, nullptr, ne, e_new2old, e_old2new, estart);
     nv_owned = vstart[npatch]; ne_owned = estart[npatch];
     // ---- 5. halo cells: (patch, cell, type) type 0 = adjacent to an owned edge, 1 = only to an owned vertex
     std::vector<uint64_t> halo;
@@ -355,6 +370,134 @@ std::string Layout::build(int64_t nv_, const double* vxy, int64_t nc_, const int
         for (int32_t g : ge_tmp) le_of[e_new2old[g]] = -1;
     }
     if (vadj.size() >= ((size_t)1 << 32)) return "vertex adjacency exceeds 32-bit offsets";
+    return "";
+}
+
+std::string Layout::build_ring2(int kind, Ring2& R) const {
+    const bool vk = (kind == 0);
+    const int64_t nd = vk ? nv : ne;
+    const std::vector<int32_t>& cd = vk ? cells : cell_edges;          // [nc,3] dofs of a cell (user numbering)
+    const std::vector<int32_t>& old2new = vk ? v_old2new : e_old2new;
+    const std::vector<int32_t>& new2old = vk ? v_new2old : e_new2old;
+    const uint32_t id_limit = vk ? 65535u : 32767u;
+    // dof -> cells, each list ascending in the user cell id: every patch sums the contributions of a row in this
+    // order, so a row recomputed by a neighbouring patch (G1 rows) gets bit-identical values
+    std::vector<int64_t> off(nd + 1, 0);
+    for (int64_t h = 0; h < 3 * nc; ++h) off[cd[h] + 1]++;
+    for (int64_t d = 0; d < nd; ++d) off[d + 1] += off[d];
+    std::vector<int32_t> d2c(3 * nc);
+    {
+        std::vector<int64_t> pos(off.begin(), off.end() - 1);
+        for (int64_t c = 0; c < nc; ++c)
+            for (int i = 0; i < 3; ++i) d2c[pos[cd[3 * c + i]]++] = (int32_t)c;
+    }
+    R = Ring2{};
+    R.hdr.assign(npatch, Ring2Hdr{});
+    R.slice_off.push_back(0);
+    std::vector<int32_t> mark_c(nc, -1), lc_of(nc, 0), mark_d(nd, -1), lid(nd, 0);
+    std::vector<int32_t> cl, g1, g2;
+    std::vector<uint32_t> deg;
+    for (int32_t p = 0; p < npatch; ++p) {
+        const PatchHdr& H0 = hdr[p];
+        Ring2Hdr& H = R.hdr[p];
+        H.group = H0.group;
+        H.d_start = vk ? H0.v_start : H0.e_start;
+        H.d_cnt = vk ? H0.v_cnt : H0.e_cnt;
+        auto owned = [&](int32_t nw) { return nw >= H.d_start && nw < H.d_start + H.d_cnt; };
+        cl.clear(); g1.clear(); g2.clear();
+        for (int32_t r = 0; r < H.d_cnt; ++r) {
+            const int32_t d = new2old[H.d_start + r];
+            for (int64_t k = off[d]; k < off[d + 1]; ++k) {
+                const int32_t c = d2c[k];
+                if (mark_c[c] != p) { mark_c[c] = p; lc_of[c] = (int32_t)cl.size(); cl.push_back(c); }
+            }
+        }
+        H.n_c1 = (int32_t)cl.size();
+        for (int32_t k = 0; k < H.n_c1; ++k)
+            for (int i = 0; i < 3; ++i) {
+                const int32_t d = cd[3 * (int64_t)cl[k] + i], nw = old2new[d];
+                if (!owned(nw) && mark_d[d] != p) { mark_d[d] = p; g1.push_back(nw); }
+            }
+        std::sort(g1.begin(), g1.end());
+        for (int32_t g : g1) {
+            const int32_t d = new2old[g];
+            for (int64_t k = off[d]; k < off[d + 1]; ++k) {
+                const int32_t c = d2c[k];
+                if (mark_c[c] != p) { mark_c[c] = p; lc_of[c] = (int32_t)cl.size(); cl.push_back(c); }
+            }
+        }
+        H.n_c2 = (int32_t)cl.size();
+        for (int32_t k = H.n_c1; k < H.n_c2; ++k)
+            for (int i = 0; i < 3; ++i) {
+                const int32_t d = cd[3 * (int64_t)cl[k] + i], nw = old2new[d];
+                if (!owned(nw) && mark_d[d] != p) { mark_d[d] = p; g2.push_back(nw); }
+            }
+        std::sort(g2.begin(), g2.end());
+        H.g_off = (int32_t)R.ghost.size(); H.g1_cnt = (int32_t)g1.size(); H.g2_cnt = (int32_t)g2.size();
+        for (size_t k = 0; k < g1.size(); ++k) { lid[new2old[g1[k]]] = H.d_cnt + (int32_t)k; R.ghost.push_back(g1[k]); }
+        for (size_t k = 0; k < g2.size(); ++k) { lid[new2old[g2[k]]] = H.d_cnt + H.g1_cnt + (int32_t)k; R.ghost.push_back(g2[k]); }
+        const int32_t nr = H.d_cnt + H.g1_cnt, nl = nr + H.g2_cnt;
+        if ((uint32_t)nl >= id_limit || H.n_c2 >= 16383) return "two-sweep patch too large for 16-bit local indices; reduce patch_cells";
+        R.max_ld = std::max(R.max_ld, nl); R.max_rows = std::max(R.max_rows, nr); R.max_c2 = std::max(R.max_c2, H.n_c2);
+        // cell records
+        H.cell_off = (int32_t)R.pcell_user.size();
+        for (int32_t k = 0; k < H.n_c2; ++k) {
+            const int64_t c = cl[k];
+            R.pcell_user.push_back((int32_t)c);
+            uint32_t l[3];
+            for (int i = 0; i < 3; ++i) {
+                const int32_t d = cd[3 * c + i], nw = old2new[d];
+                l[i] = (uint32_t)(owned(nw) ? nw - H.d_start : lid[d]);
+                if (!vk && cell_sign[3 * c + i] < 0) l[i] |= 0x8000u;
+            }
+            R.rec.push_back(l[0] | (l[1] << 16));
+            R.rec.push_back(l[2]);
+        }
+        // rows [D0 | G1] and their adjacency
+        H.row_off = (int32_t)R.row_gid.size();
+        for (int32_t r = 0; r < nr; ++r) R.row_gid.push_back(r < H.d_cnt ? H.d_start + r : g1[r - H.d_cnt]);
+        auto slot_of = [&](int32_t c, int32_t d) { for (int i = 0; i < 3; ++i) if (cd[3 * (int64_t)c + i] == d) return i; return 0; };
+        if (vk) {
+            H.vs_off = (int32_t)(R.slice_off.size() - 1);
+            const int32_t nslice = (nr + 31) / 32;
+            const size_t base = R.adj.size();
+            std::vector<size_t> sbase(nslice + 1, 0);
+            deg.assign(nr, 0);
+            for (int32_t r = 0; r < nr; ++r) { const int32_t d = new2old[R.row_gid[H.row_off + r]]; deg[r] = (uint32_t)(off[d + 1] - off[d]); }
+            for (int32_t sl = 0; sl < nslice; ++sl) {
+                uint32_t w = 0;
+                for (int32_t k = 32 * sl; k < std::min(32 * (sl + 1), nr); ++k) w = std::max(w, deg[k]);
+                w = (w + 7u) & ~7u;
+                sbase[sl + 1] = sbase[sl] + (size_t)w * 32;
+                R.slice_off.push_back((uint32_t)(base + sbase[sl + 1]));
+            }
+            R.adj.resize(base + sbase[nslice], (uint16_t)0xFFFFu);
+            H.adj_off = (int32_t)(uint32_t)base; H.adj_cnt = (int32_t)sbase[nslice];
+            for (int32_t r = 0; r < nr; ++r) {
+                const int32_t d = new2old[R.row_gid[H.row_off + r]];
+                uint32_t j = 0;
+                for (int64_t k = off[d]; k < off[d + 1]; ++k, ++j) {
+                    const int32_t c = d2c[k];
+                    R.adj[base + sbase[r / 32] + ((size_t)(j / 8) * 32 + (r % 32)) * 8 + (j % 8)] = (uint16_t)(lc_of[c] * 4 + slot_of(c, d));
+                }
+            }
+        } else {
+            for (int32_t r = 0; r < nr; ++r) {
+                const int32_t d = new2old[R.row_gid[H.row_off + r]];
+                uint32_t a = 0xFFFFFFFFu;
+                int j = 0;
+                for (int64_t k = off[d]; k < off[d + 1]; ++k, ++j) {
+                    const int32_t c = d2c[k];
+                    const uint32_t code = (uint32_t)(lc_of[c] * 4 + slot_of(c, d));
+                    if (j == 0) a = (a & 0xFFFF0000u) | code;
+                    else if (j == 1) a = (a & 0xFFFFu) | (code << 16);
+                    else return "internal: edge with more than two cells";
+                }
+                R.eadj.push_back(a);
+            }
+        }
+    }
+    if (R.adj.size() >= ((size_t)1 << 32) || R.pcell_user.size() >= ((size_t)1 << 31)) return "two-sweep layout exceeds 32-bit offsets";
     return "";
 }
 

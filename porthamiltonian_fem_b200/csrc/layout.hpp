@@ -36,6 +36,30 @@ struct PatchHdr {
     int32_t adj_cnt;    // is one contiguous range, so the next patch can be prefetched without reading vslice_off
 };
 
+// ---- two-sweep patches (temporal blocking of the Chebyshev mass solves): for one dof kind (vertices or edges) a patch
+// holds its owned dofs D0, the cells C1 touching D0, the other dofs G1 of those cells, the further cells C2 \ C1 touching
+// G1 and their remaining dofs G2.  With x_k on D0+G1+G2 in shared memory a CTA computes x_{k+1} on D0+G1 (all cells of
+// those rows are in C2) and then x_{k+2} on D0 (cells C1) - two Chebyshev iterations per pass over the data.
+struct Ring2Hdr {
+    int32_t cell_off, n_c1, n_c2;      // patch cells [C1 | C2 \ C1] in the ring-2 cell arrays
+    int32_t d_start, d_cnt;            // owned dof range (new numbering) = rows of the second sweep
+    int32_t g_off, g1_cnt, g2_cnt;     // ghost list [G1 | G2] (new ids, each part ascending); first-sweep rows = [D0 | G1]
+    int32_t row_off;                   // first row of this patch in the per-row arrays (replicated pinv, edge adjacency)
+    int32_t vs_off, adj_off, adj_cnt;  // vertex kind: sliced-ELL adjacency of the rows [D0 | G1]
+    int32_t group, pad[3];
+};
+struct Ring2 {
+    std::vector<Ring2Hdr> hdr;
+    std::vector<int32_t> pcell_user;   // [npc] user cell id of every patch cell
+    std::vector<uint32_t> rec;         // [npc,2] cell records: x = l0 | l1<<16, y = l2 (edge kind: bit 15 = orientation sign -1)
+    std::vector<int32_t> ghost;
+    std::vector<int32_t> row_gid;      // [n_rows] new global id of every first-sweep row
+    std::vector<uint32_t> slice_off;   // vertex kind (same sliced-ELL format as Layout::vadj)
+    std::vector<uint16_t> adj;
+    std::vector<uint32_t> eadj;        // edge kind: [n_rows] two (cell, slot) codes per row
+    int32_t max_ld = 0, max_rows = 0, max_c2 = 0;
+};
+
 struct Layout {
     int64_t nv = 0, nc = 0, ne = 0, nb = 0;
     int32_t patch_cells = 0, npatch = 0;
@@ -81,6 +105,8 @@ struct Layout {
     std::vector<int32_t> cell_group_v;      // [nc] (empty when n_groups == 1)
     // cell records with boundary flag bits for the given formulation
     void make_records(bool strong, bool casimir, std::vector<CellRec>& rec) const;
+    // two-sweep patches of the vertex (kind 0) or edge (kind 1) rows; returns "" or an error message
+    std::string build_ring2(int kind, Ring2& R) const;
 };
 
 }  // namespace phw

@@ -15,6 +15,7 @@
 
 #include "../../include/phwave.h"
 #include "kernels.cuh"
+#include "kernels2.cuh"
 #include "layout.hpp"
 
 using namespace phw;
@@ -57,7 +58,8 @@ __global__ void geom_k(int npc, const int* __restrict__ pcell_user, const int* _
         double l2 = (bx - ax) * (bx - ax) + (by - ay) * (by - ay);   // edge 2 joins v0, v1
         double inv = 1.0 / (48.0 * A);
         double G0 = l0 * inv, G1 = l1 * inv, G2 = l2 * inv, S = G0 + G1 + G2;
-        area[k] = A; g0[k] = G0; g1[k] = G1; g2[k] = G2;
+        if (area) area[k] = A;
+        if (g0) { g0[k] = G0; g1[k] = G1; g2[k] = G2; }
         double m00 = 3 * S - 4 * G0, m11 = 3 * S - 4 * G1, m22 = 3 * S - 4 * G2;
         double m01 = S - 4 * G2, m02 = S - 4 * G1, m12 = S - 4 * G0;
         double ea = m01 / sqrt(m00 * m11), eb = m02 / sqrt(m00 * m22), ec = m12 / sqrt(m11 * m22);
@@ -502,6 +504,10 @@ struct phw_solver_s {
     double *ho_T = nullptr, *ho_mass = nullptr, *ho_exact_nodes = nullptr, *ho_area = nullptr, *ho_exact_dofs = nullptr, *ho_probe_w = nullptr;
     bool in_step = false;
     bool coop = false;
+    bool two_sweep = false;     // mass solves run two Chebyshev iterations per pass (kernels2.cuh)
+    Ring2Dev r2[2]{};
+    size_t smem2[2] = {0, 0};
+    int *d_cells_user = nullptr; double* d_vtx_user = nullptr; unsigned long long* d_mm = nullptr;
     std::vector<cudaEvent_t> prof_ev; std::vector<int> prof_which;
     bool have_vq = false;      // Stormer-Verlet first-same-as-last: v_q of the previous step is valid
     phw_stats stats{};
@@ -605,7 +611,7 @@ int op_edge_dot(phw_solver_s* s, const double* xq, double cM, double cB, int slo
 template <int WHICH, bool CAS>
 int launch_coop(phw_solver_s* s, const RowArgs& av, const RowArgs& ae) {
     constexpr int NT = (WHICH == 0) ? NT_COOP_P : (WHICH == 1 ? NT_COOP_Q : NT_ROWS);
-    constexpr int MINB = (WHICH == 0) ? 6 : 2;
+    constexpr int MINB = (WHICH == 0) ? PHW_MINB_P : PHW_MINB_Q;
     auto kern = solve_coop_k<WHICH, CAS, NT, MINB>;
     const size_t sm = (WHICH == 0) ? s->smem_v1 : (WHICH == 1 ? s->smem_e : s->smem_vd);
     static bool configured = false;
@@ -628,6 +634,62 @@ int launch_coop(phw_solver_s* s, const RowArgs& av, const RowArgs& ae) {
     }
     s->launches++;
     return 0;
+}
+
+// one cooperative launch = one complete two-sweep Chebyshev solve of M_p (KIND 0) or M_q (KIND 1)
+template <int KIND, int NT, int MINB>
+int launch_coop2_cfg(phw_solver_s* s) {
+    auto kern = solve2_coop_k<KIND, NT, MINB>;
+    const size_t sm = s->smem2[KIND];
+    static bool configured = false;
+    if (!configured) { CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); configured = true; }
+    int occ = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, sm));
+    if (occ < 1) return fail(PHW_ECUDA, "two-sweep solve kernel does not fit on an SM");
+    const int grid = std::max(1, std::min(s->npatch, occ * s->sm_count));
+    Solve2Args a{};
+    a.m = s->r2[KIND];
+    const TriBuf& tb = (KIND == 0) ? s->tp : s->tq;
+    for (int i = 0; i < 4; ++i) a.buf[i] = tb.b[i];
+    a.b = (KIND == 0) ? s->bp : s->bq;
+    a.cheb_d = s->cheb_d[KIND]; a.cheb_c = s->cheb_c[KIND];
+    a.tol2 = s->prm.tol * s->prm.tol;
+    if (s->G > 1) { const double t = std::max(s->prm.tol / std::sqrt((double)s->G), 1e-14); a.tol2 = std::min(a.tol2, t * t); }
+    a.max_iter = s->prm.max_iter; a.which = KIND; a.partials = s->partials; a.ctl = s->ctl;
+    void* args[] = {(void*)&a};
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    const bool prof = (s->prm.flags & 4) && s->prof_ev.size() < 2 * 8192;
+    if (prof) {
+        CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+        CU(cudaEventRecord(e0, s->stream));
+    }
+    CU(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(NT), args, sm, s->stream));
+    if (prof) {
+        CU(cudaEventRecord(e1, s->stream));
+        s->prof_ev.push_back(e0); s->prof_ev.push_back(e1); s->prof_which.push_back(KIND);
+    }
+    s->launches++;
+    return 0;
+}
+template <int KIND>
+int launch_coop2(phw_solver_s* s) {
+    static const int cfg = [] { const char* e = getenv(KIND == 0 ? "PHW_P2_CFG" : "PHW_Q2_CFG"); return e ? atoi(e) : 0; }();
+    if (KIND == 0) {
+        switch (cfg) {
+            case 1: return launch_coop2_cfg<KIND, 256, 6>(s);
+            case 2: return launch_coop2_cfg<KIND, 512, 3>(s);
+            case 3: return launch_coop2_cfg<KIND, 128, 12>(s);
+            case 4: return launch_coop2_cfg<KIND, 1024, 1>(s);
+            default: return launch_coop2_cfg<KIND, 256, 5>(s);
+        }
+    }
+    switch (cfg) {
+        case 1: return launch_coop2_cfg<KIND, 512, 2>(s);
+        case 2: return launch_coop2_cfg<KIND, 256, 4>(s);
+        case 3: return launch_coop2_cfg<KIND, 1024, 1>(s);
+        case 4: return launch_coop2_cfg<KIND, 384, 3>(s);
+        default: return launch_coop2_cfg<KIND, 384, 2>(s);
+    }
 }
 
 int solve_begin(phw_solver_s* s, int which) {
@@ -654,6 +716,7 @@ int solve_mass(phw_solver_s* s, int which, int n_launch) {
         s->launches++;
         return 0;
     }
+    if (s->two_sweep) return which == PHW_P ? launch_coop2<0>(s) : launch_coop2<1>(s);
     RowArgs a = base_args(s);
     a.which = which; a.use_cheb_input = 1; a.finalize = 1; a.cM = 1.0; a.counter_id = which;
     a.cheb_d = s->cheb_d[which]; a.cheb_c = s->cheb_c[which];
@@ -1197,19 +1260,20 @@ static int setup_vectors(phw_solver_s* s) {
     {   // exchange arena: [Mailbox | tp0 tp1 tp2 | tq0 tq1 tq2] in ONE allocation so that a single CUDA IPC handle
         // lets the neighbouring ranks write halo values and partial sums straight into it (peer memory over NVLink)
         const size_t head = 4096, nvp = (nv + 31) & ~(size_t)31, nep = (ne + 31) & ~(size_t)31;
-        s->arena_bytes = head + 3 * (nvp + nep) * sizeof(double);
+        s->arena_bytes = head + 4 * (nvp + nep) * sizeof(double);   // [.. | tp3 | tq3]: fourth iterate buffers of the two-sweep solves
         char* base = nullptr;
         RC(s->dalloc(&base, s->arena_bytes));
         s->arena = base;
         CU(cudaMemsetAsync(base, 0, s->arena_bytes, s->stream));
         double* d0 = (double*)(base + head);
         for (int i = 0; i < 3; ++i) { s->tp.b[i] = d0 + i * nvp; s->tq.b[i] = d0 + 3 * nvp + i * nep; }
+        s->tp.b[3] = d0 + 3 * (nvp + nep); s->tq.b[3] = s->tp.b[3] + nvp;
         s->pc = PeerComm{};
         s->pc.rank = 0; s->pc.world = 1; s->pc.n_nb = 0;
         s->pc.mbox[0] = (Mailbox*)base;
         s->pc.timeout_cycles = 20000000000LL;
     }
-    RC(s->dalloc(&s->partials, 2 * (size_t)s->npatch + 8192));
+    RC(s->dalloc(&s->partials, 2 * (size_t)s->npatch + 16384));
     {
         int coop_attr = 0;
         CU(cudaDeviceGetAttribute(&coop_attr, cudaDevAttrCooperativeLaunch, s->device));
@@ -1285,6 +1349,7 @@ static int setup_solver(phw_solver_s* s) {
         int *d_pcu, *d_cells; double* d_vtx; unsigned long long* d_mm;
         RC(s->upload(&d_pcu, L.pcell_user)); RC(s->upload(&d_cells, L.cells)); RC(s->upload(&d_vtx, L.vtx));
         RC(s->dalloc(&d_mm, 2));
+        s->d_cells_user = d_cells; s->d_vtx_user = d_vtx; s->d_mm = d_mm;
         unsigned long long init[2];
         double one = 1.0;
         memcpy(&init[0], &one, 8); memcpy(&init[1], &one, 8);
@@ -1371,6 +1436,42 @@ static int setup_solver(phw_solver_s* s) {
             zero_at_k<<<nblk(s->n_dir), 256, 0, s->stream>>>(s->n_dir, s->d_dir_idx, s->pinv_p);
             CU(cudaGetLastError());
         }
+    }
+    // ---- two-sweep patches of the mass solves (kernels2.cuh): single GPU, weak form (pinv_p is then exactly the
+    //      inverse of the P1 mass diagonal), explicit schemes
+    s->two_sweep = s->coop && (P.flags & 16) && !P.strong && !implicit && L.nv_owned == L.nv && L.ne_owned == L.ne;
+    for (int kind = 0; kind < 2 && s->two_sweep; ++kind) {
+        Ring2 R;
+        if (!L.build_ring2(kind, R).empty()) { s->two_sweep = false; break; }   // patches too large for one more ring
+        const size_t soff2 = ((size_t)(R.max_rows + 31) / 32 + 4) / 2 + 1;
+        s->smem2[kind] = (kind == 0) ? (soff2 + ev(R.max_ld) + (size_t)R.max_c2) * 8 : (ev(R.max_ld) + 3 * (size_t)R.max_c2) * 8;
+        if (s->smem2[kind] > 200 * 1024) { s->two_sweep = false; break; }
+        Ring2Dev& d = s->r2[kind];
+        d.npatch = s->npatch;
+        Ring2Hdr* d_h; uint32_t* d_rec; int *d_gh, *d_pcu2, *d_rg; double* d_pinv2;
+        const int npc2 = (int)R.pcell_user.size(), nrows = (int)R.row_gid.size();
+        RC(s->upload(&d_h, R.hdr)); RC(s->upload(&d_rec, R.rec)); RC(s->upload(&d_gh, R.ghost));
+        RC(s->upload(&d_pcu2, R.pcell_user)); RC(s->upload(&d_rg, R.row_gid));
+        RC(s->dalloc(&d_pinv2, nrows));
+        d.hdr = d_h; d.rec = reinterpret_cast<const uint2*>(d_rec); d.ghost = d_gh; d.pinv = d_pinv2;
+        double *ga = nullptr, *gb = nullptr, *gc = nullptr;
+        RC(s->dalloc(&ga, npc2));
+        if (kind == 1) { RC(s->dalloc(&gb, npc2)); RC(s->dalloc(&gc, npc2)); }
+        geom_k<<<nblk(npc2), 256, 0, s->stream>>>(npc2, d_pcu2, s->d_cells_user, s->d_vtx_user, kind == 0 ? ga : nullptr,
+                                                   kind == 1 ? ga : nullptr, gb, gc, s->d_mm);
+        gather_k<<<nblk(nrows), 256, 0, s->stream>>>(nrows, d_pinv2, kind == 0 ? s->pinv_p : s->pinv_q, d_rg);
+        CU(cudaGetLastError());
+        d.g0 = ga; d.g1 = gb; d.g2 = gc;
+        if (kind == 0) {
+            uint32_t* d_so; uint16_t* d_adj;
+            RC(s->upload(&d_so, R.slice_off)); RC(s->upload(&d_adj, R.adj));
+            d.slice_off = d_so; d.adj = d_adj;
+        } else {
+            uint32_t* d_ea;
+            RC(s->upload(&d_ea, R.eadj));
+            d.eadj = d_ea;
+        }
+        CU(cudaStreamSynchronize(s->stream));   // the host vectors of R go out of scope
     }
     // ---- Chebyshev intervals.  P1: element bound [1/2, 2] (Wathen); RT1: element bounds from geom_k.
     s->cheb_d[0] = 1.25; s->cheb_c[0] = 0.75;
@@ -1567,6 +1668,7 @@ int phw_comm_setup(phw_solver_t s, int32_t rank, int32_t world, const void* hand
     }
     CU(cudaStreamSynchronize(s->stream));
     s->pc = pc;
+    if (world > 1) s->two_sweep = false;   // the peer exchange is fused into the one-sweep kernel
     return PHW_OK;
 }
 

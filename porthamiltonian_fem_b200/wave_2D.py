@@ -34,7 +34,7 @@ def wave_2D_solve(tFinal, numSteps, outputDir,
                   analytical=False, saveP=True, controlType=None,
                   input_stop_t=None, control_start_t=None, basis_order=(1, 1),
                   mesh=None, mesh_kind='structured', device=0, patch_cells=None, tol=1e-13, extrap_order=2, save_every=None,
-                  lumped=None, return_state=False, verbose=True):
+                  lumped=None, return_state=False, verbose=True, solver_flags=0):
     """Solve the 2D port-Hamiltonian wave equation; see the reference docstring (wave_2D.py:22-51).
 
     Returns (H_array [numSteps, 8 | 12], numCells)."""
@@ -95,7 +95,7 @@ def wave_2D_solve(tFinal, numSteps, outputDir,
     prm.casimir = 1 if controlType == 'casimir' else 0
     prm.analytical = 1 if analytical else 0
     prm.dt, prm.K_wave, prm.rho = dt_value, float(K_wave), float(rho)
-    prm.tol, prm.max_iter, prm.flags, prm.extrap_order = float(tol), 200, 0, int(extrap_order)
+    prm.tol, prm.max_iter, prm.flags, prm.extrap_order = float(tol), 200, int(solver_flags), int(extrap_order)
     lp = dict(_DEFAULT_LUMPED)
     if lumped:
         lp.update(lumped)
