@@ -157,7 +157,8 @@ def main():
     ap.add_argument('--patch-cells', type=int, default=2048)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--tol', type=float, default=1e-13)
-    ap.add_argument('--extrap', type=int, default=2)
+    ap.add_argument('--extrap', type=int, default=3)
+    ap.add_argument('--phase', type=float, default=0.25, help='phase omega*t0 / pi of the standing wave the run starts from (0: the t = 0 state of wave_2D.py:734)')
     ap.add_argument('--two-sweep', action='store_true', help='two Chebyshev iterations per pass in the mass solves (csrc/kernels2.cuh; A/B)')
     ap.add_argument('--debug-residuals', action='store_true', help='print the residual history of the last M_p / M_q solve to stderr')
     args = ap.parse_args()
@@ -213,9 +214,27 @@ def main():
         n_dof, n_cells_total = int(tt[0].item()), int(tt[1].item())
     else:
         n_dof, n_cells_total = n_dof_local, n_cells_local
-    p0 = RHO * omega * np.sin(np.pi * vertices[:, 0] / (2 * xL) + np.pi / 2) * np.sin(2 * np.pi * vertices[:, 1] / yL + np.pi / 2)
-    solver.set_state(p=p0, q=np.zeros(m.n_edges), x3=np.zeros(3))
-    del p0
+    # exact standing wave p = P(x,y) cos(w t), q = -(1/(rho w)) grad P sin(w t) of the analytical case at phase w t0: p nodal, q as RT1
+    # edge fluxes (3-point Gauss on every edge).  At w t0 = 0 this is the reference's initial state (q = 0); the default pi/4 is
+    # a generic instant of the run, where both fields and both velocities are O(1) of their amplitudes.
+    phase = np.pi * args.phase
+    p0 = RHO * omega * np.cos(np.pi * vertices[:, 0] / (2 * xL)) * np.cos(2 * np.pi * vertices[:, 1] / yL) * np.cos(phase)
+    q0 = np.zeros(m.n_edges)
+    if args.phase != 0.0:
+        edges = m.edges()[0]
+        a, b = vertices[edges[:, 0]], vertices[edges[:, 1]]
+        tx, ty = b[:, 0] - a[:, 0], b[:, 1] - a[:, 1]
+        kx, ky = np.pi / (2 * xL), 2 * np.pi / yL
+        for gp, gw in zip((0.5 - np.sqrt(0.15), 0.5, 0.5 + np.sqrt(0.15)), (5.0 / 18, 8.0 / 18, 5.0 / 18)):
+            x, y = a[:, 0] + gp * tx, a[:, 1] + gp * ty
+            qx = kx * np.sin(kx * x) * np.cos(ky * y)
+            qy = ky * np.cos(kx * x) * np.sin(ky * y)
+            q0 += gw * (qx * ty - qy * tx)              # q . (|e| n_e), n_e = tangent (lo -> hi) rotated by -90 degrees
+        q0 *= np.sin(phase)
+        del edges, a, b, tx, ty, x, y, qx, qy
+    solver.set_state(p=p0, q=q0, x3=np.zeros(3))
+    solver.set_time(phase / omega)
+    del p0, q0
     setup_s = time.time() - t_setup
     del vertices
 
@@ -304,10 +323,10 @@ def main():
             'metric': 'dof-updates/sec (fp64, device-timed)', 'value': value, 'unit': 'dof-updates/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dev_s / args.steps,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': '{} weak P1/RT1 wave, analytical standing-wave state and left datum (wave_2D.py:375-377,734), structured rectangle {}x{}x2 = {} cells and {} dofs per GPU ({} dofs in total, x-slab partition, peer-memory halo exchange), dt={:g}; '
+            'config': {'workload': '{} weak P1/RT1 wave, exact standing wave of the analytical case at phase w*t0 = ' + '%.3g' % args.phase + ' pi with its left datum (wave_2D.py:375-377,734), structured rectangle {}x{}x2 = {} cells and {} dofs per GPU ({} dofs in total, x-slab partition, peer-memory halo exchange), dt={:g}; '
                                    'state vectors ({:.0f} MB each) exceed L2, no flush needed'.format(
                                        args.scheme, args.nx, args.ny, nc, n_dof_local, n_dof, dt, 8e-6 * m.n_edges),
-                       'dofs_per_gpu': n_dof_local, 'dofs_total': n_dof, 'patch_cells': args.patch_cells, 'tol': args.tol, 'extrap_order': args.extrap,
+                       'dofs_per_gpu': n_dof_local, 'dofs_total': n_dof, 'patch_cells': args.patch_cells, 'phase_over_pi': args.phase, 'two_sweep': bool(args.two_sweep), 'tol': args.tol, 'extrap_order': args.extrap,
                        'iters_per_solve_p': st['iters_p'] / max(1, st['solves_p']), 'iters_per_solve_q': st['iters_q'] / max(1, st['solves_q']),
                        'max_rel_residual': st['max_rel_residual'], 'setup_seconds': setup_s},
             'e2e': {'value': e2e_value, 'unit': 'dof-updates/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,

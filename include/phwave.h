@@ -120,6 +120,8 @@ int phw_get_state(phw_solver_t s, double* p, double* q, double* x3);
 int phw_run(phw_solver_t s, int64_t n_steps, double* H_rows);
 int phw_get_stats(phw_solver_t s, phw_stats* out);
 int phw_synchronize(phw_solver_t s);
+/* simulation clock (t of wave_2D.py:790-799,833-834; 0 after creation): restart / continue a run from a stored state */
+int phw_set_time(phw_solver_t s, double t);
 /* diagnostics: relative residuals ||b - A x_k|| / ||b||, k = 0..n-1 (n <= 48), of the most recent solve of kind
  * `which` (PHW_P, PHW_Q, 2 = block system) and its iteration count; entries beyond it are stale */
 int phw_residual_history(phw_solver_t s, int32_t which, int32_t n, double* rel_residuals, int32_t* n_iterations);

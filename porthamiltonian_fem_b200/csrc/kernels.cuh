@@ -38,7 +38,7 @@
 #define PHW_NT_Q 384
 #endif
 #ifndef PHW_MINB_P
-#define PHW_MINB_P 6
+#define PHW_MINB_P 4
 #endif
 #ifndef PHW_MINB_Q
 #define PHW_MINB_Q 2
@@ -47,7 +47,7 @@
 namespace phw {
 
 constexpr int NT_ROWS = 512;   // threads per CTA of the row kernels
-constexpr int NT_COOP_P = PHW_NT_P;  // threads per CTA of the persistent M_p solve (more, smaller CTAs hide the per-stage latencies)
+constexpr int NT_COOP_P = PHW_NT_P;  // threads per CTA of the persistent M_p solve: 256 x 4 CTAs/SM (64 registers; 6 CTAs x 40 registers spill into L2)
 constexpr int NT_COOP_Q = PHW_NT_Q;  // M_q solve: 2 CTAs/SM (shared-memory bound) x 384 threads leaves 85 registers per thread for batched loads
 
 struct SolveCtl {

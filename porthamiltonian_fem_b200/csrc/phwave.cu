@@ -1726,6 +1726,14 @@ int phw_set_state(phw_solver_t s, const double* p, const double* q, const double
     return PHW_OK;
 }
 
+int phw_set_time(phw_solver_t s, double t) {
+    if (!s) return fail(PHW_EINVAL, "solver is NULL");
+    CU(cudaSetDevice(s->device));
+    for (int g = 0; g < s->G; ++g) CU(cudaMemcpyAsync(&s->ctl[g].t, &t, sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return PHW_OK;
+}
+
 int phw_get_state(phw_solver_t s, double* p, double* q, double* x3) {
     if (!s) return fail(PHW_EINVAL, "solver is NULL");
     CU(cudaSetDevice(s->device));

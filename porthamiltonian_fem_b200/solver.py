@@ -199,6 +199,9 @@ class Solver:
         _lib.check(self.lib.phw_get_stats(self.handle, ctypes.byref(st)))
         return st.as_dict()
 
+    def set_time(self, t):
+        _lib.check(self.lib.phw_set_time(self.handle, float(t)))
+
     def residual_history(self, which, n=48):
         """relative residuals of the iterations of the most recent solve of kind `which` (diagnostics)"""
         out = np.zeros(n)

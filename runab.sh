@@ -1,5 +1,7 @@
-run() { echo "== $* $EXTRA"; env "$@" bash runb.sh $EXTRA; }
-EXTRA="--one-sweep" run PHW_DEGREE_SORT=0
-EXTRA="--one-sweep" run PHW_DEGREE_SORT=1
-EXTRA="" run PHW_DEGREE_SORT=0
-EXTRA="" run PHW_DEGREE_SORT=1
+run() { echo "== $*"; bash runb.sh "$@"; }
+run --phase 0 --extrap 2
+run --phase 0
+run
+run --phase 0.5
+run --debug-residuals
+run --scheme SV
