@@ -1,2 +1,2 @@
 N=$1; shift
-python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 8 --extrap 3 --no-cpu-baseline "$@" 2>&1 | tail -3
+python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 8 --no-cpu-baseline "$@" 2>&1 | tail -3
