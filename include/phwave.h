@@ -58,7 +58,8 @@ typedef struct phw_params {
     int32_t flags;           /* bit0: disable first-same-as-last reuse in SV; bit1: synchronous error checks;
                                 bit2: CUDA-event timing of every solve kernel; bit3: force the multi-launch solve path;
                                 bit4: two-sweep mass solves (two Chebyshev iterations per pass over the data, csrc/kernels2.cuh;
-                                single GPU, weak form, explicit schemes; default off - see DESIGN.md section 10) */
+                                single GPU, weak form, explicit schemes; default off - see DESIGN.md section 10);
+                                bit5: cell-based instead of assembled (ELL) rows in the M_p solve */
 } phw_params;
 
 typedef struct phw_stats {

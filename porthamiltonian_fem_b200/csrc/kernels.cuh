@@ -43,6 +43,12 @@
 #ifndef PHW_MINB_Q
 #define PHW_MINB_Q 2
 #endif
+#ifndef PHW_NT_ELL
+#define PHW_NT_ELL 256
+#endif
+#ifndef PHW_MINB_ELL
+#define PHW_MINB_ELL 4
+#endif
 
 namespace phw {
 
@@ -84,6 +90,9 @@ struct DevMesh {
     const uint32_t* eadj;
     const uint32_t* vslice_off;
     const uint16_t* vadj;
+    // assembled P1 mass rows (sliced ELL, layout.hpp): neighbour local ids + weights (|K1| + |K2|) / 12
+    const uint32_t* ell_ioff; const uint32_t* ell_woff;
+    const uint16_t* ell_ids; const double* ell_w;
 };
 
 struct TriBuf { double* b[4]; };   // rotating Chebyshev iterates (the one-sweep kernels use the first three)
@@ -398,6 +407,69 @@ __device__ __forceinline__ void vertex_pass(const RowArgs& a, const PassIO& io, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// vertex rows of the pure P1 mass solve in assembled form: (M_p x)_v = d_v x_v + sum_w m_vw x_w, d_v = sum_w m_vw, with the sliced-ELL
+// rows of layout.hpp (weights m_vw = (|K1| + |K2|) / 12).  Same rows, same bounds and the same DRAM bytes as the cell-based
+// pass (ids 16 B + weights 8 B x degree per vertex instead of cell records + areas + adjacency), but one shared-memory
+// stage instead of two: no per-cell buffer, one barrier less, about half the shared-memory wavefronts.
+// ------------------------------------------------------------------------------------------------
+template <int NT>
+__device__ __forceinline__ void vertex_ell_pass(const RowArgs& a, const PassIO& io, double* smem, double& acc0, double& acc1) {
+    const DevMesh& m = a.m;
+    __shared__ PatchHdr s_hdr[2];
+    if (blockIdx.x < m.npatch) load_hdr_smem(&s_hdr[0], &m.hdr[blockIdx.x]);
+    __syncthreads();
+    const uint4* ids4 = reinterpret_cast<const uint4*>(m.ell_ids);
+    int it = 0;
+    for (int P = blockIdx.x; P < m.npatch; P += gridDim.x, ++it) {
+        const PatchHdr& h = s_hdr[it & 1];
+        if (P + (int)gridDim.x < m.npatch) load_hdr_smem(&s_hdr[(it + 1) & 1], &m.hdr[P + gridDim.x]);
+        const int nsl = (h.v_cnt + 31) >> 5;
+        uint32_t* s_io = reinterpret_cast<uint32_t*>(smem);   // [nsl + 1] id offsets
+        uint32_t* s_wo = s_io + (nsl + 1);                     // [nsl + 1] weight offsets
+        double* sx = smem + (nsl + 2);                         // [v_cnt + gv_cnt]
+        for (int i = threadIdx.x; i <= nsl; i += NT) { s_io[i] = __ldg(&m.ell_ioff[h.vs_off + i]); s_wo[i] = __ldg(&m.ell_woff[h.vs_off + i]); }
+        for (int i = threadIdx.x; i < h.v_cnt; i += NT) sx[i] = io.xp[h.v_start + i];
+        for (int i = threadIdx.x; i < h.gv_cnt; i += NT) sx[h.v_cnt + i] = io.xp[__ldg(&m.ghost_v[h.gv_off + i])];
+        __syncthreads();
+        for (int lv = threadIdx.x; lv < h.v_cnt; lv += NT) {
+            const int sl = lv >> 5, lane = lv & 31;
+            const uint32_t io0 = s_io[sl], wo0 = s_wo[sl];
+            const int W = (int)((s_wo[sl + 1] - wo0) >> 5);
+            const int gid = h.v_start + lv;
+            const double bv = __ldg(&a.b[gid]);
+            const double xpv = io.use_prev ? io.xprev[gid] : 0.0;
+            const double* __restrict__ wrow = m.ell_w + wo0 + lane;
+            double val = 0.0, dsum = 0.0;
+            for (int c = 0; 8 * c < W; ++c) {
+                const uint4 cd = __ldg(&ids4[(io0 >> 3) + c * 32 + lane]);
+                const uint32_t w4[4] = {cd.x, cd.y, cd.z, cd.w};
+                double wv[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) wv[j] = (8 * c + j < W) ? __ldg(&wrow[(8 * c + j) * 32]) : 0.0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    val += wv[2 * j] * sx[w4[j] & 0xFFFFu];
+                    val += wv[2 * j + 1] * sx[w4[j] >> 16];
+                    dsum += wv[2 * j] + wv[2 * j + 1];
+                }
+            }
+            // the P1 mass diagonal is the sum of the row's off-diagonal entries (sum_K |K|/6 = sum_w (|K1|+|K2|)/12), so
+            // neither the diagonal nor the Jacobi weight has to be read
+            const double xc = sx[lv];
+            const double pv = 1.0 / dsum;
+            val += dsum * xc;
+            const double r_ = bv - val;
+            double xn = xc + io.c2 * pv * r_;
+            if (io.use_prev) xn += io.c1 * (xc - xpv);
+            io.xnew[gid] = xn;
+            acc0 += pv * r_ * r_;
+            acc1 += pv * bv * bv;
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // edge rows: all patches of this block
 // ------------------------------------------------------------------------------------------------
 template <int EPI, int MODE, bool HAS_M, bool HAS_D, bool CAS, int NT>
@@ -675,7 +747,7 @@ __global__ void __launch_bounds__(NT_ROWS, 2) edge_rows_k(const RowArgs a) {
 // barrier per iteration; the residual norm is reduced deterministically (per-block partials, summed in
 // the same order by every block) so all blocks take the same stop decision without host involvement.
 // ------------------------------------------------------------------------------------------------
-template <int WHICH, bool CAS, int NT, int MINB>
+template <int WHICH, bool CAS, int NT, int MINB, bool ELL = false>
 __global__ void __launch_bounds__(NT, MINB) solve_coop_k(const RowArgs av, const RowArgs ae, const PeerComm pc) {
     extern __shared__ double smem[];
     __shared__ double red[64];
@@ -699,7 +771,8 @@ __global__ void __launch_bounds__(NT, MINB) solve_coop_k(const RowArgs av, const
         double r0 = 0.0, b0 = 0.0;
         if (WHICH == 0 || WHICH == 2) {
             double a0_ = 0.0, a1_ = 0.0;
-            vertex_pass<EPI_CHEB, MODE_OP, true, WHICH == 2, CAS, NT>(av, iov, smem, a0_, a1_);
+            if (ELL && WHICH == 0) vertex_ell_pass<NT>(av, iov, smem, a0_, a1_);
+            else vertex_pass<EPI_CHEB, MODE_OP, true, WHICH == 2, CAS, NT>(av, iov, smem, a0_, a1_);
             r0 += av.weight * a0_; b0 += av.weight * a1_;
         }
         if (WHICH == 1 || WHICH == 2) {

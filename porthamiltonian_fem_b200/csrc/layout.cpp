@@ -205,11 +205,11 @@ std::string Layout::build(int64_t nv_, const double* vxy, int64_t nc_, const int
     if (e_ext) for (int64_t e = 0; e < ne; ++e) if (e_ext[e]) e_owner[e] = npatch;
     v_degree.assign(nv, 0);
     for (int64_t h = 0; h < 3 * nc; ++h) v_degree[cells[h]]++;
-    // new id = rank by (owner, first touch along the owner patch's cell order): dofs that are used together by neighbouring
-    // cells get neighbouring local ids, which keeps the shared-memory gathers of a warp on distinct banks (a degree sort
-    // would make the sliced-ELL adjacency a little tighter on irregular meshes but scatters the ids: ~3-way bank conflicts).
-    // PHW_DEGREE_SORT=1 restores the degree-sorted vertex numbering (A/B only).
-    static const bool degree_sort = [] { const char* e = getenv("PHW_DEGREE_SORT"); return e && atoi(e) != 0; }();
+    // new id = rank by (owner, key): edges by first touch along the owner patch's cell order (spatially coherent local ids and
+    // ghost lists), vertices by descending degree (uniform 32-row slices keep the sliced-ELL structures tight: the ELL mass rows
+    // then carry no padding on meshes with mixed degrees); PHW_DEGREE_SORT=0 numbers the vertices by first touch too (A/B:
+    // neutral for the cell-based kernels, profiles/r1b_ab_first_touch_numbering.txt).
+    static const bool degree_sort = [] { const char* e = getenv("PHW_DEGREE_SORT"); return !e || atoi(e) != 0; }();
     auto renumber = [&](const std::vector<int32_t>& owner, const std::vector<int32_t>& cell_dofs, const std::vector<int32_t>* degree,
                         int64_t n, std::vector<int32_t>& new2old, std::vector<int32_t>& old2new, std::vector<int32_t>& pstart) {
         std::vector<int32_t> ord(n);
@@ -274,6 +274,7 @@ std::string Layout::build(int64_t nv_, const double* vxy, int64_t nc_, const int
     eadj.assign(ne, 0xFFFFFFFFu);
     vslice_off.clear();
     vslice_off.push_back(0);
+    ell_ioff.assign(1, 0); ell_woff.assign(1, 0); ell_ids.clear(); ell_pair.clear();
     vadj.clear();
     vadj.reserve(4 * nc + 4 * halo.size());
     std::vector<int32_t> lv_of(nv, -1), le_of(ne, -1);
@@ -365,11 +366,65 @@ std::string Layout::build(int64_t nv_, const double* vxy, int64_t nc_, const int
                 }
             }
         }
+        // ---- ELL rows of the assembled P1 mass matrix for the owned vertices: local ids of the neighbour vertices and, per
+        //      entry, the (<= 2) patch cells shared with that neighbour (the weight (|K1| + |K2|) / 12 is filled on the device)
+        {
+            std::vector<uint32_t> rstart(H.v_cnt + 1, 0), rfill(H.v_cnt, 0);
+            for (int32_t lv = 0; lv < H.v_cnt; ++lv) rstart[lv + 1] = rstart[lv] + vcnt[lv + 1];
+            std::vector<uint16_t> rcode(rstart[H.v_cnt]);
+            for (size_t lc = 0; lc < cl.size(); ++lc)
+                for (int i = 0; i < 3; ++i) {
+                    const int32_t v = cells[3 * (int64_t)cl[lc] + i];
+                    if (v_owner[v] == p) { const int32_t lv = v_old2new[v] - H.v_start; rcode[rstart[lv] + rfill[lv]++] = (uint16_t)(lc * 4 + i); }
+                }
+            const size_t pcb = (size_t)H.cell_off;
+            std::vector<uint16_t> nid((size_t)H.v_cnt * 16);
+            std::vector<uint32_t> npair((size_t)H.v_cnt * 16), ncnt(H.v_cnt, 0);
+            for (int32_t lv = 0; lv < H.v_cnt; ++lv) {
+                uint32_t cnt = 0;
+                for (uint32_t k = rstart[lv]; k < rstart[lv + 1]; ++k) {
+                    const uint32_t lc = rcode[k] >> 2, slot = rcode[k] & 3u;
+                    for (int t = 1; t <= 2; ++t) {
+                        const uint16_t o = pc_lv[3 * (pcb + lc) + (slot + t) % 3];
+                        uint32_t j = 0;
+                        while (j < cnt && nid[(size_t)lv * 16 + j] != o) ++j;
+                        if (j < cnt) npair[(size_t)lv * 16 + j] = (npair[(size_t)lv * 16 + j] & 0xFFFFu) | (lc << 16);
+                        else {
+                            if (cnt >= 16) return "vertex with more than 16 neighbours: not supported by the ELL mass rows";
+                            nid[(size_t)lv * 16 + cnt] = o; npair[(size_t)lv * 16 + cnt] = lc | 0xFFFF0000u; ++cnt;
+                        }
+                    }
+                }
+                ncnt[lv] = cnt;
+            }
+            const size_t ibase = ell_ids.size(), wbase = ell_pair.size();
+            size_t ioff = 0, woff = 0;
+            for (int32_t sl = 0; sl < nslice; ++sl) {
+                uint32_t w = 0;
+                for (int32_t k = 32 * sl; k < std::min(32 * (sl + 1), H.v_cnt); ++k) w = std::max(w, ncnt[k]);
+                const uint32_t nch = (w + 7u) / 8u;
+                ell_ids.resize(ibase + ioff + (size_t)nch * 256, 0);
+                ell_pair.resize(wbase + woff + (size_t)w * 32, 0xFFFFFFFFu);
+                for (int32_t k = 32 * sl; k < 32 * (sl + 1); ++k) {
+                    const int lane = k % 32;
+                    for (uint32_t j = 0; j < nch * 8; ++j) {
+                        const bool valid = k < H.v_cnt && j < ncnt[k];
+                        // padding points at the row itself (or at 0) with weight zero: no predicate in the kernel
+                        ell_ids[ibase + ioff + ((size_t)(j / 8) * 32 + lane) * 8 + (j % 8)] = valid ? nid[(size_t)k * 16 + j] : (uint16_t)(k < H.v_cnt ? k : 0);
+                        if (j < w && valid) ell_pair[wbase + woff + (size_t)j * 32 + lane] = npair[(size_t)k * 16 + j];
+                    }
+                }
+                ioff += (size_t)nch * 256; woff += (size_t)w * 32;
+                ell_ioff.push_back((uint32_t)(ibase + ioff));
+                ell_woff.push_back((uint32_t)(wbase + woff));
+            }
+        }
         // reset scratch
         for (int32_t g : gv_tmp) lv_of[v_new2old[g]] = -1;
         for (int32_t g : ge_tmp) le_of[e_new2old[g]] = -1;
     }
-    if (vadj.size() >= ((size_t)1 << 32)) return "vertex adjacency exceeds 32-bit offsets";
+    if (vadj.size() >= ((size_t)1 << 32) || ell_ids.size() >= ((size_t)1 << 32) || ell_pair.size() >= ((size_t)1 << 32))
+        return "vertex adjacency exceeds 32-bit offsets";
     return "";
 }
 

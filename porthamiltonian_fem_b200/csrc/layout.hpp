@@ -92,6 +92,12 @@ struct Layout {
     // and chunk, warp-uniform trip count.
     std::vector<uint32_t> vslice_off;  // [n_slices+1] offsets into vadj
     std::vector<uint16_t> vadj;
+    // assembled P1 mass rows of the owned vertices as sliced ELL (same 32-row slices): ell_ids = local ids of the neighbour
+    // vertices, chunks of 8 as in vadj (padding = the row itself); ell_pair = per entry [k][lane] the two patch cells shared
+    // with that neighbour (lcA | lcB << 16, 0xFFFF none; 0xFFFFFFFF = padding) from which the device fills the weights
+    std::vector<uint32_t> ell_ioff, ell_woff;   // [n_slices+1]
+    std::vector<uint16_t> ell_ids;
+    std::vector<uint32_t> ell_pair;
     std::vector<int32_t> v_degree;     // [nv] by old id
     int32_t max_lv = 0, max_le = 0, max_cells = 0;
 

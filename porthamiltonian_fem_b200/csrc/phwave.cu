@@ -83,6 +83,26 @@ __global__ void geom_k(int npc, const int* __restrict__ pcell_user, const int* _
     }
 }
 
+// weights of the ELL mass rows: m_vw = (|K1| + |K2|) / 12 from the patch's own area array (one block per patch)
+__global__ void ell_weights_k(int npatch, const PatchHdr* __restrict__ hdr, const uint32_t* __restrict__ woff,
+                              const uint32_t* __restrict__ pair, const double* __restrict__ area, double* __restrict__ w) {
+    for (int P = blockIdx.x; P < npatch; P += gridDim.x) {
+        const PatchHdr h = hdr[P];
+        const int nsl = (h.v_cnt + 31) >> 5;
+        const uint32_t e0 = woff[h.vs_off], e1 = woff[h.vs_off + nsl];
+        for (uint32_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+            const uint32_t pr = pair[e];
+            double v = 0.0;
+            if (pr != 0xFFFFFFFFu) {
+                v = area[h.cell_off + (pr & 0xFFFFu)];
+                if ((pr >> 16) != 0xFFFFu) v += area[h.cell_off + (pr >> 16)];
+                v *= (1.0 / 12.0);
+            }
+            w[e] = v;
+        }
+    }
+}
+
 __global__ void invert_k(int n, double* d) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) d[i] = (d[i] != 0.0) ? 1.0 / d[i] : 0.0;
@@ -504,6 +524,8 @@ struct phw_solver_s {
     double *ho_T = nullptr, *ho_mass = nullptr, *ho_exact_nodes = nullptr, *ho_area = nullptr, *ho_exact_dofs = nullptr, *ho_probe_w = nullptr;
     bool in_step = false;
     bool coop = false;
+    bool ell_p = false;         // M_p solve on the assembled ELL rows (vertex_ell_pass)
+    size_t smem_ell = 0;
     bool two_sweep = false;     // mass solves run two Chebyshev iterations per pass (kernels2.cuh)
     Ring2Dev r2[2]{};
     size_t smem2[2] = {0, 0};
@@ -608,12 +630,12 @@ int op_edge_dot(phw_solver_s* s, const double* xq, double cM, double cB, int slo
 }
 
 // one cooperative launch = one complete Chebyshev solve
-template <int WHICH, bool CAS>
+template <int WHICH, bool CAS, bool ELL = false>
 int launch_coop(phw_solver_s* s, const RowArgs& av, const RowArgs& ae) {
-    constexpr int NT = (WHICH == 0) ? NT_COOP_P : (WHICH == 1 ? NT_COOP_Q : NT_ROWS);
-    constexpr int MINB = (WHICH == 0) ? PHW_MINB_P : PHW_MINB_Q;
-    auto kern = solve_coop_k<WHICH, CAS, NT, MINB>;
-    const size_t sm = (WHICH == 0) ? s->smem_v1 : (WHICH == 1 ? s->smem_e : s->smem_vd);
+    constexpr int NT = (WHICH == 0) ? (ELL ? PHW_NT_ELL : NT_COOP_P) : (WHICH == 1 ? NT_COOP_Q : NT_ROWS);
+    constexpr int MINB = (WHICH == 0) ? (ELL ? PHW_MINB_ELL : PHW_MINB_P) : PHW_MINB_Q;
+    auto kern = solve_coop_k<WHICH, CAS, NT, MINB, ELL>;
+    const size_t sm = (WHICH == 0) ? (ELL ? s->smem_ell : s->smem_v1) : (WHICH == 1 ? s->smem_e : s->smem_vd);
     static bool configured = false;
     if (!configured) { CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); configured = true; }
     int occ = 0;
@@ -724,6 +746,7 @@ int solve_mass(phw_solver_s* s, int which, int n_launch) {
     if (s->coop) {
         a.b = which == PHW_P ? s->bp : s->bq;
         a.pinv = which == PHW_P ? s->pinv_p : s->pinv_q;
+        if (which == PHW_P && s->ell_p && a.mdiag == nullptr) return launch_coop<0, false, true>(s, a, a);   // pinv_p = 1 / diag(M_p) exactly
         return which == PHW_P ? launch_coop<0, false>(s, a, a) : launch_coop<1, false>(s, a, a);
     }
     rc = solve_begin(s, which);
@@ -1364,6 +1387,15 @@ static int setup_solver(phw_solver_s* s) {
     s->dm.npatch = s->npatch; s->dm.nv = s->nv; s->dm.ne = s->ne;
     s->dm.hdr = d_hdr; s->dm.recv = d_recv; s->dm.rece = d_rece; s->dm.area = d_area; s->dm.g0 = d_g0; s->dm.g1 = d_g1; s->dm.g2 = d_g2;
     s->dm.ghost_v = d_gv; s->dm.ghost_e = d_ge; s->dm.eadj = d_eadj; s->dm.vslice_off = d_voff; s->dm.vadj = d_vadj;
+    {   // assembled P1 mass rows (ELL): structure from the layout, weights from the device areas
+        uint32_t *d_io, *d_wo, *d_pair; uint16_t* d_ids; double* d_w;
+        RC(s->upload(&d_io, L.ell_ioff)); RC(s->upload(&d_wo, L.ell_woff)); RC(s->upload(&d_ids, L.ell_ids)); RC(s->upload(&d_pair, L.ell_pair));
+        RC(s->dalloc(&d_w, L.ell_pair.size()));
+        ell_weights_k<<<std::max(1, std::min(s->npatch, 8 * s->sm_count)), 256, 0, s->stream>>>(s->npatch, d_hdr, d_wo, d_pair, d_area, d_w);
+        CU(cudaGetLastError());
+        s->dm.ell_ioff = d_io; s->dm.ell_woff = d_wo; s->dm.ell_ids = d_ids; s->dm.ell_w = d_w;
+        CU(cudaStreamSynchronize(s->stream));
+    }
     // ---- port (left boundary, tag 0): b_L[e] = sign * weight   (flux-normalised RT1: <phi_e.n, g_L> = sign * mean(g_L))
     {
         s->G = L.n_groups;
@@ -1401,6 +1433,8 @@ static int setup_solver(phw_solver_s* s) {
     s->smem_vd = (soff + ev(L.max_lv) + ev(L.max_le) + 3 * (size_t)L.max_cells) * 8;
     s->smem_e = (ev(L.max_le) + 3 * (size_t)L.max_cells) * 8;
     s->smem_ed = s->smem_vd;
+    s->smem_ell = ((size_t)(L.max_lv + 31) / 32 + 4 + ev(L.max_lv)) * 8;
+    s->ell_p = !(P.flags & 32);
     if (s->smem_vd > 200 * 1024) return fail(PHW_EINVAL, "patch does not fit in shared memory; reduce patch_cells");
     s->grid_rows = std::max(1, std::min(s->npatch, 2 * s->sm_count));
     RC(setup_scalars(s));
