@@ -842,30 +842,63 @@ __global__ void __launch_bounds__(NT, MINB) solve_coop_k(const RowArgs av, const
 // higher-order pairs (P_k x RT_k, k <= 3): the operators are assembled once on the host (fem_ho.py) and applied as
 // CSR matrices; same epilogues and the same persistent cooperative Chebyshev solve as the matrix-free path.
 // ------------------------------------------------------------------------------------------------
-struct Csr { int n_rows; const int* indptr; const int* idx; const double* val; };
+struct Csr { int n_rows; const int* indptr; const int* idx; const double* val; int lanes; };   // lanes: threads per row (4..32)
 
-__device__ __forceinline__ double csr_row(const Csr& A, int r, const double* __restrict__ x) {
+// one row of A x by a group of L consecutive lanes (L | 32): the lanes stride over the row's entries (coalesced 8 L-byte
+// segments of val / 4 L-byte segments of idx) and combine with a butterfly, so every lane of the group returns the sum -
+// in a fixed order, independent of the launch configuration
+template <int L>
+__device__ __forceinline__ double csr_row_group(const Csr& A, int r, const double* __restrict__ x, int sub) {
     double v = 0.0;
-    const int j1 = A.indptr[r + 1];
-    for (int j = A.indptr[r]; j < j1; ++j) v += A.val[j] * x[A.idx[j]];
+    const int j1 = __ldg(&A.indptr[r + 1]);
+    for (int j = __ldg(&A.indptr[r]) + sub; j < j1; j += L) v += __ldg(&A.val[j]) * x[__ldg(&A.idx[j])];
+#pragma unroll
+    for (int o = L / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
 // y = alpha A x
-__global__ void csr_store_k(Csr A, const double* x, double alpha, double* y) {
-    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < A.n_rows; r += gridDim.x * blockDim.x) y[r] = alpha * csr_row(A, r, x);
+template <int L>
+__global__ void __launch_bounds__(256) csr_store_k(Csr A, const double* x, double alpha, double* y) {
+    const int sub = threadIdx.x % L, g = (blockIdx.x * blockDim.x + threadIdx.x) / L, ng = gridDim.x * blockDim.x / L;
+    const int nround = (A.n_rows + ng - 1) / ng;
+    for (int i = 0; i < nround; ++i) {          // whole warps stay converged for the shuffles
+        const int r = g + i * ng;
+        const double v = csr_row_group<L>(A, r < A.n_rows ? r : A.n_rows - 1, x, sub);
+        if (r < A.n_rows && sub == 0) y[r] = alpha * v;
+    }
 }
-// ctl->red[slot] = scale x^T A x   (single block, fixed order)
-__global__ void csr_dot_k(Csr A, const double* x, double scale, Ctl* ctl, int slot) {
+// ctl->red[slot] = scale x^T A x: per-block partials, summed in block order by the last block to finish
+template <int L>
+__global__ void __launch_bounds__(256) csr_dot_k(Csr A, const double* x, double scale, Ctl* ctl, int slot, double* partials, int counter_id) {
     __shared__ double red[64];
+    __shared__ bool is_last;
+    const int sub = threadIdx.x % L, g = (blockIdx.x * blockDim.x + threadIdx.x) / L, ng = gridDim.x * blockDim.x / L;
+    const int nround = (A.n_rows + ng - 1) / ng;
     double s = 0.0, z = 0.0;
-    for (int r = threadIdx.x; r < A.n_rows; r += blockDim.x) s += x[r] * csr_row(A, r, x);
+    for (int i = 0; i < nround; ++i) {
+        const int r = g + i * ng;
+        const double v = csr_row_group<L>(A, r < A.n_rows ? r : A.n_rows - 1, x, sub);
+        if (r < A.n_rows && sub == 0) s += x[r] * v;
+    }
     block_sum2(s, z, red);
-    if (threadIdx.x == 0) ctl->red[slot] = scale * s;
+    if (threadIdx.x == 0) {
+        partials[blockIdx.x] = s;
+        __threadfence();
+        is_last = (atomicAdd(&ctl->counters[counter_id], 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    double t = 0.0; z = 0.0;
+    for (int p = threadIdx.x; p < (int)gridDim.x; p += blockDim.x) t += __ldcg(&partials[p]);
+    block_sum2(t, z, red);
+    if (threadIdx.x == 0) { ctl->counters[counter_id] = 0; ctl->red[slot] = scale * t; }
 }
 struct CsrSolveArgs {
     Csr A; TriBuf tb; const double* b; const double* pinv; double cheb_d, cheb_c, tol2; int max_iter, which;
     double* partials; Ctl* ctl;
 };
+template <int L>
 __global__ void __launch_bounds__(256) solve_coop_csr_k(const CsrSolveArgs a) {
     __shared__ double red[64];
     __shared__ double bc[2];
@@ -875,19 +908,27 @@ __global__ void __launch_bounds__(256) solve_coop_csr_k(const CsrSolveArgs a) {
     int k = 0, cur = sc.cur;
     double rho = 0.0, rr = 0.0, bb = 0.0;
     bool conv = false;
+    const int sub = threadIdx.x % L, g = (blockIdx.x * blockDim.x + threadIdx.x) / L, ng = gridDim.x * blockDim.x / L;
+    const int nround = (a.A.n_rows + ng - 1) / ng;
     while (true) {
         double c1, c2, rho_k;
         cheb_coeffs(k, rho, a.cheb_d, a.cheb_c, c1, c2, rho_k);
         const int nxt = (cur + 1) % 3, prv = (cur + 2) % 3;
         const double* x = tb_sel(a.tb, cur); const double* xp = tb_sel(a.tb, prv); double* xn = tb_sel(a.tb, nxt);
         double r0 = 0.0, b0 = 0.0;
-        for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < a.A.n_rows; r += gridDim.x * blockDim.x) {
-            const double val = csr_row(a.A, r, x), bv = a.b[r], pv = a.pinv[r], xc = x[r];
-            const double res = bv - val;
-            double v = xc + c2 * pv * res;
-            if (k > 0) v += c1 * (xc - xp[r]);
-            xn[r] = v;
-            r0 += pv * res * res; b0 += pv * bv * bv;
+        for (int i = 0; i < nround; ++i) {
+            const int r = g + i * ng;
+            const bool live = r < a.A.n_rows;
+            double bv = 0.0, pv = 0.0, xc = 0.0, xpv = 0.0;
+            if (live && sub == 0) { bv = a.b[r]; pv = a.pinv[r]; xc = x[r]; if (k > 0) xpv = xp[r]; }   // requested before the row sum
+            const double val = csr_row_group<L>(a.A, live ? r : a.A.n_rows - 1, x, sub);
+            if (live && sub == 0) {
+                const double res = bv - val;
+                double v = xc + c2 * pv * res;
+                if (k > 0) v += c1 * (xc - xpv);
+                xn[r] = v;
+                r0 += pv * res * res; b0 += pv * bv * bv;
+            }
         }
         block_sum2(r0, b0, red);
         double* part = a.partials + (size_t)(k & 1) * 2 * gridDim.x;
@@ -903,6 +944,7 @@ __global__ void __launch_bounds__(256) solve_coop_csr_k(const CsrSolveArgs a) {
         rr = bc[0]; bb = bc[1];
         __syncthreads();
         conv = rr <= a.tol2 * bb;
+        if (blockIdx.x == 0 && threadIdx.x == 0 && k < 48) a.ctl->reshist[a.which][k] = (bb > 0.0) ? rr / bb : 0.0;
         k += 1;
         if (conv) break;
         rho = rho_k; cur = nxt;

@@ -581,6 +581,28 @@ int launch_edge(phw_solver_s* s, const RowArgs& a) {
     return 0;
 }
 
+// ---- CSR operators of the higher-order pairs: a group of `lanes` threads per row
+inline int csr_grid(phw_solver_s* s, const Csr& A) { return std::max(1, std::min(nblk(A.n_rows * A.lanes), s->sm_count * 8)); }
+void csr_store(phw_solver_s* s, const Csr& A, const double* x, double alpha, double* y) {
+    const int g = csr_grid(s, A);
+    switch (A.lanes) {
+        case 4: csr_store_k<4><<<g, 256, 0, s->stream>>>(A, x, alpha, y); break;
+        case 8: csr_store_k<8><<<g, 256, 0, s->stream>>>(A, x, alpha, y); break;
+        case 16: csr_store_k<16><<<g, 256, 0, s->stream>>>(A, x, alpha, y); break;
+        default: csr_store_k<32><<<g, 256, 0, s->stream>>>(A, x, alpha, y);
+    }
+}
+void csr_dot(phw_solver_s* s, const Csr& A, const double* x, double scale, int slot, int counter) {
+    const int g = csr_grid(s, A);
+    double* part = s->partials + 8192 + 2048 * (size_t)slot;     // beyond the partials of the solves
+    switch (A.lanes) {
+        case 4: csr_dot_k<4><<<g, 256, 0, s->stream>>>(A, x, scale, s->ctl, slot, part, counter); break;
+        case 8: csr_dot_k<8><<<g, 256, 0, s->stream>>>(A, x, scale, s->ctl, slot, part, counter); break;
+        case 16: csr_dot_k<16><<<g, 256, 0, s->stream>>>(A, x, scale, s->ctl, slot, part, counter); break;
+        default: csr_dot_k<32><<<g, 256, 0, s->stream>>>(A, x, scale, s->ctl, slot, part, counter);
+    }
+}
+
 RowArgs base_args(phw_solver_s* s) {
     RowArgs a{};
     a.m = s->dm; a.tp = s->tp; a.tq = s->tq;
@@ -730,11 +752,14 @@ int solve_mass(phw_solver_s* s, int which, int n_launch) {
         a.b = which == PHW_P ? s->bp : s->bq; a.pinv = which == PHW_P ? s->pinv_p : s->pinv_q;
         a.cheb_d = s->cheb_d[which]; a.cheb_c = s->cheb_c[which]; a.tol2 = s->prm.tol * s->prm.tol;
         a.max_iter = s->prm.max_iter; a.which = which; a.partials = s->partials; a.ctl = s->ctl;
+        void* kern = a.A.lanes == 4 ? (void*)solve_coop_csr_k<4> : a.A.lanes == 8 ? (void*)solve_coop_csr_k<8>
+                   : a.A.lanes == 16 ? (void*)solve_coop_csr_k<16> : (void*)solve_coop_csr_k<32>;
         int occ = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, solve_coop_csr_k, 256, 0));
-        const int grid = std::max(1, std::min(nblk(a.A.n_rows), std::min(occ, 4) * s->sm_count));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0));
+        const int want = nblk(a.A.n_rows * a.A.lanes);
+        const int grid = std::max(1, std::min(want, std::min(occ, 4) * s->sm_count));
         void* args[] = {(void*)&a};
-        CU(cudaLaunchCooperativeKernel((void*)solve_coop_csr_k, dim3(grid), dim3(256), args, 0, s->stream));
+        CU(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(256), args, 0, s->stream));
         s->launches++;
         return 0;
     }
@@ -826,7 +851,7 @@ int waxpy(phw_solver_s* s, int n, double* w, const double* y, double a, const do
 int rhs_p(phw_solver_s* s, const double* qsrc, const double* psrc) {
     const double K = s->prm.K_wave;
     if (s->ho) {
-        csr_store_k<<<vec_grid(s, s->nv), 256, 0, s->stream>>>(s->hDT, qsrc, -K, s->bp);
+        csr_store(s, s->hDT, qsrc, -K, s->bp);
         s->launches++;
         CU(cudaGetLastError());
         return 0;
@@ -839,7 +864,7 @@ int rhs_q(phw_solver_s* s, const double* psrc, const double* qsrc) {
     const double ir = (s->G > 1) ? 1.0 : 1.0 / s->prm.rho;
     int rc = 0;
     if (s->ho) {
-        csr_store_k<<<vec_grid(s, s->ne), 256, 0, s->stream>>>(s->hD, psrc, ir, s->bq);
+        csr_store(s, s->hD, psrc, ir, s->bq);
         s->launches++;
         CU(cudaGetLastError());
     } else {
@@ -857,8 +882,8 @@ int rhs_q(phw_solver_s* s, const double* psrc, const double* qsrc) {
 }
 int energy(phw_solver_s* s) {
     if (s->ho) {
-        csr_dot_k<<<1, 1024, 0, s->stream>>>(s->hMp, s->p, 0.5 / s->prm.rho, s->ctl, 0);
-        csr_dot_k<<<1, 1024, 0, s->stream>>>(s->hMq, s->q, 0.5 * s->prm.K_wave, s->ctl, 1);
+        csr_dot(s, s->hMp, s->p, 0.5 / s->prm.rho, 0, 6);
+        csr_dot(s, s->hMq, s->q, 0.5 * s->prm.K_wave, 1, 7);
         s->launches += 2;
         if (s->prm.analytical && s->an_ready && s->in_step) {
             const int nb = 2 * s->sm_count;
@@ -1977,6 +2002,8 @@ static int upload_csr(phw_solver_s* s, int64_t n_rows, const int32_t* indptr, co
     rc = s->upload(&d_v, v); if (rc) return rc;
     CU(cudaStreamSynchronize(s->stream));
     out->n_rows = (int)n_rows; out->indptr = d_ip; out->idx = d_ix; out->val = d_v;
+    const double avg = (double)indptr[n_rows] / (double)n_rows;     // threads per row ~ entries per row / 2
+    out->lanes = avg <= 8 ? 4 : (avg <= 16 ? 8 : (avg <= 40 ? 16 : 32));
     return 0;
 }
 
