@@ -106,6 +106,9 @@ int phw_mesh_set_dirichlet(phw_mesh_t m, int64_t n, const int32_t* vertex_ids, c
 int phw_mesh_get_numbering(phw_mesh_t m, int32_t* vertex_new2old, int32_t* edge_new2old, int32_t* cell_patch);
 /* per-patch counts [n_patches,6]: own cells, edge-op cells, vertex-op cells, owned vertices, owned edges, ghosts(v+e) */
 int phw_mesh_get_patch_counts(phw_mesh_t m, int32_t* counts);
+/* host-only structural invariants of the patch layout, the assembled (ELL) mass rows and the two-sweep patches
+ * (tests; small meshes) */
+int phw_mesh_self_check(phw_mesh_t m);
 int phw_mesh_destroy(phw_mesh_t m);
 
 /* ---- solver: replaces assemble(a)/assemble(b)/solve/assemble(energy) of wave_2D.py:579-595,787-982 ---- */

@@ -57,6 +57,7 @@ SIGNATURES = {
     'phw_mesh_set_boundary': (ctypes.c_int, [ctypes.c_void_p, c_i32p, c_f64p]),
     'phw_mesh_set_dirichlet': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, c_i32p, c_f64p]),
     'phw_mesh_get_numbering': (ctypes.c_int, [ctypes.c_void_p, c_i32p, c_i32p, c_i32p]),
+    'phw_mesh_self_check': (ctypes.c_int, [ctypes.c_void_p]),
     'phw_mesh_get_patch_counts': (ctypes.c_int, [ctypes.c_void_p, c_i32p]),
     'phw_mesh_destroy': (ctypes.c_int, [ctypes.c_void_p]),
     'phw_solver_create': (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(PhwParams), ctypes.c_int32, ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]),

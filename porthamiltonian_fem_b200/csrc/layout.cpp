@@ -556,6 +556,110 @@ std::string Layout::build_ring2(int kind, Ring2& R) const {
     return "";
 }
 
+std::string Layout::self_check() const {
+    auto err = [](const std::string& what, int64_t p, int64_t i) { return what + " (patch " + std::to_string(p) + ", item " + std::to_string(i) + ")"; };
+    // ---- every dof is a row of exactly one patch; owned ranges tile the numbering
+    int64_t vsum = 0, esum = 0;
+    for (int32_t p = 0; p < npatch; ++p) {
+        const PatchHdr& H = hdr[p];
+        if (H.v_start != vsum || H.e_start != esum) return err("owned ranges are not contiguous", p, 0);
+        vsum += H.v_cnt; esum += H.e_cnt;
+    }
+    if (vsum != nv_owned || esum != ne_owned) return "owned ranges do not cover the owned dofs";
+    // ---- ELL mass rows: neighbours of a vertex = the other vertices of its cells; the shared cells contain both
+    for (int32_t p = 0; p < npatch; ++p) {
+        const PatchHdr& H = hdr[p];
+        const int32_t nsl = (H.v_cnt + 31) / 32;
+        auto gid_of = [&](uint32_t lv) { return (int32_t)lv < H.v_cnt ? H.v_start + (int32_t)lv : ghost_v[H.gv_off + (int32_t)lv - H.v_cnt]; };
+        for (int32_t lv = 0; lv < H.v_cnt; ++lv) {
+            const int32_t sl = lv / 32, lane = lv % 32;
+            const uint32_t io0 = ell_ioff[H.vs_off + sl], wo0 = ell_woff[H.vs_off + sl];
+            const uint32_t W = (ell_woff[H.vs_off + sl + 1] - wo0) / 32;
+            const int32_t v_old = v_new2old[H.v_start + lv];
+            std::vector<int32_t> expect;       // user ids of the neighbours, from the global cell list
+            for (int32_t k = 0; k < H.n_vcells; ++k) {
+                const int32_t c = pcell_user[H.cell_off + k];
+                for (int i = 0; i < 3; ++i)
+                    if (cells[3 * (int64_t)c + i] == v_old) { expect.push_back(cells[3 * (int64_t)c + (i + 1) % 3]); expect.push_back(cells[3 * (int64_t)c + (i + 2) % 3]); }
+            }
+            std::sort(expect.begin(), expect.end());
+            expect.erase(std::unique(expect.begin(), expect.end()), expect.end());
+            std::vector<int32_t> got;
+            for (uint32_t k = 0; k < W; ++k) {
+                const uint32_t pr = ell_pair[wo0 + k * 32 + lane];
+                const uint16_t id = ell_ids[io0 + ((size_t)(k / 8) * 32 + lane) * 8 + (k % 8)];
+                if (pr == 0xFFFFFFFFu) { if (id != lv) return err("ELL padding does not point at its own row", p, lv); continue; }
+                const int32_t w_old = v_new2old[gid_of(id)];
+                got.push_back(w_old);
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t lc = h == 0 ? (pr & 0xFFFFu) : (pr >> 16);
+                    if (lc == 0xFFFFu) { if (h == 0) return err("ELL entry without a cell", p, lv); continue; }
+                    if ((int32_t)lc >= H.n_vcells) return err("ELL cell index out of range", p, lv);
+                    const int32_t c = pcell_user[H.cell_off + lc];
+                    int hit = 0;
+                    for (int i = 0; i < 3; ++i) hit += (cells[3 * (int64_t)c + i] == v_old) + 2 * (cells[3 * (int64_t)c + i] == w_old);
+                    if (hit != 3) return err("ELL cell does not contain both vertices", p, lv);
+                }
+            }
+            std::sort(got.begin(), got.end());
+            if (got != expect) return err("ELL neighbours differ from the cell connectivity", p, lv);
+        }
+        (void)nsl;
+    }
+    // ---- two-sweep patches of both kinds
+    for (int kind = 0; kind < 2; ++kind) {
+        Ring2 R;
+        const std::string e = build_ring2(kind, R);
+        if (!e.empty()) continue;                    // too large for one more ring: the solver falls back, nothing to check
+        const std::vector<int32_t>& cd = kind == 0 ? cells : cell_edges;
+        const std::vector<int32_t>& new2old = kind == 0 ? v_new2old : e_new2old;
+        const uint32_t mask = kind == 0 ? 0xFFFFu : 0x7FFFu;
+        for (int32_t p = 0; p < npatch; ++p) {
+            const Ring2Hdr& H = R.hdr[p];
+            const int32_t nr = H.d_cnt + H.g1_cnt, nl = nr + H.g2_cnt;
+            auto gid_of = [&](int32_t l) { return l < H.d_cnt ? H.d_start + l : R.ghost[H.g_off + l - H.d_cnt]; };
+            if (H.n_c1 > H.n_c2) return err("ring-2: C1 is not a prefix of C2", p, kind);
+            for (int32_t k = 0; k < H.n_c2; ++k) {
+                const int32_t c = R.pcell_user[H.cell_off + k];
+                const uint32_t l[3] = {R.rec[2 * (size_t)(H.cell_off + k)] & 0xFFFFu, R.rec[2 * (size_t)(H.cell_off + k)] >> 16, R.rec[2 * (size_t)(H.cell_off + k) + 1] & 0xFFFFu};
+                for (int i = 0; i < 3; ++i) {
+                    const int32_t li = (int32_t)(l[i] & mask);
+                    if (li >= nl) return err("ring-2: local id out of range", p, k);
+                    if (k < H.n_c1 && li >= nr) return err("ring-2: a C1 cell uses a dof outside D0+G1", p, k);
+                    if (new2old[gid_of(li)] != cd[3 * (int64_t)c + i]) return err("ring-2: cell record does not match the mesh", p, k);
+                    if (kind == 1 && ((l[i] & 0x8000u) != 0) != (cell_sign[3 * (int64_t)c + i] < 0)) return err("ring-2: orientation sign", p, k);
+                }
+            }
+            // rows [D0 | G1]: the adjacency lists exactly the cells of the mesh that contain the dof, all inside C2 (C1 for D0)
+            for (int32_t r = 0; r < nr; ++r) {
+                const int32_t d_old = new2old[R.row_gid[H.row_off + r]];
+                if (R.row_gid[H.row_off + r] != gid_of(r)) return err("ring-2: row numbering", p, r);
+                std::vector<uint32_t> codes;
+                if (kind == 0) {
+                    const uint32_t o0 = R.slice_off[H.vs_off + r / 32], o1 = R.slice_off[H.vs_off + r / 32 + 1];
+                    for (uint32_t j = 0; j < (o1 - o0) / 32; ++j) {
+                        const uint16_t c = R.adj[o0 + ((size_t)(j / 8) * 32 + (r % 32)) * 8 + (j % 8)];
+                        if (c != 0xFFFFu) codes.push_back(c);
+                    }
+                } else {
+                    const uint32_t a = R.eadj[H.row_off + r];
+                    if ((a & 0xFFFFu) != 0xFFFFu) codes.push_back(a & 0xFFFFu);
+                    if ((a >> 16) != 0xFFFFu) codes.push_back(a >> 16);
+                }
+                int64_t in_mesh = 0;
+                for (int64_t h = 0; h < 3 * nc; ++h) in_mesh += (cd[h] == d_old);   // small test meshes only
+                if ((int64_t)codes.size() != in_mesh) return err("ring-2: a row misses cells", p, r);
+                for (uint32_t c : codes) {
+                    const int32_t lc = (int32_t)(c >> 2);
+                    if (lc >= H.n_c2 || (r < H.d_cnt && lc >= H.n_c1)) return err("ring-2: row cell outside its sweep", p, r);
+                    if (cd[3 * (int64_t)R.pcell_user[H.cell_off + lc] + (c & 3u)] != d_old) return err("ring-2: adjacency slot", p, r);
+                }
+            }
+        }
+    }
+    return "";
+}
+
 void Layout::make_records(bool strong, bool casimir, std::vector<CellRec>& rec) const {
     // per-edge boundary tag (-1 interior)
     std::vector<int8_t> etag(ne, -1);

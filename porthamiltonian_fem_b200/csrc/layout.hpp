@@ -113,6 +113,8 @@ struct Layout {
     void make_records(bool strong, bool casimir, std::vector<CellRec>& rec) const;
     // two-sweep patches of the vertex (kind 0) or edge (kind 1) rows; returns "" or an error message
     std::string build_ring2(int kind, Ring2& R) const;
+    // structural invariants of the patch layout, the ELL mass rows and the two-sweep patches (host-only; tests)
+    std::string self_check() const;
 };
 
 }  // namespace phw

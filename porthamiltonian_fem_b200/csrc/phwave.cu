@@ -1254,6 +1254,14 @@ int phw_mesh_get_patch_counts(phw_mesh_t m, int32_t* counts) {
     return PHW_OK;
 }
 
+int phw_mesh_self_check(phw_mesh_t m) {
+    if (!m) return fail(PHW_EINVAL, "mesh is NULL");
+    if (m->L.nc > 200000) return fail(PHW_EINVAL, "phw_mesh_self_check is quadratic in places: meshes up to 200 000 cells");
+    const std::string e = m->L.self_check();
+    if (!e.empty()) return fail(PHW_ESTATE, "layout self check failed: " + e);
+    return PHW_OK;
+}
+
 int phw_mesh_destroy(phw_mesh_t m) { delete m; return PHW_OK; }
 
 int phw_solver_destroy(phw_solver_t s) {

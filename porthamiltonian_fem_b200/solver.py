@@ -86,6 +86,10 @@ class Mesh:
                                                    e.ctypes.data_as(_lib.c_i32p), c.ctypes.data_as(_lib.c_i32p)))
         return v, e, c
 
+    def self_check(self):
+        """structural invariants of the layout (host-only); raises PhwError with the first violation"""
+        _lib.check(self.lib.phw_mesh_self_check(self.handle))
+
     def patch_counts(self):
         c = np.empty((self.n_patches, 6), dtype=np.int32)
         _lib.check(self.lib.phw_mesh_get_patch_counts(self.handle, c.ctypes.data_as(_lib.c_i32p)))

@@ -145,3 +145,19 @@ def test_xdmf_binary_writer(tmp_path):
     vals = np.fromfile(str(tmp_path / 'p_values.bin'), dtype='<f8').reshape(3, -1)
     assert np.all(vals[2] == 2.0) and vals.shape[1] == v.shape[0]
     assert np.array_equal(np.fromfile(str(tmp_path / 'p_topology.bin'), dtype='<i4').reshape(-1, 3), c)
+
+
+@pytest.mark.parametrize('name,make,pc', [
+    ('structured_34x8_pc64', lambda: rectangle_structured(34, 8), 64),
+    ('structured_20x20_pc128', lambda: rectangle_structured(20, 20, 1.0, 1.0), 128),
+    ('delaunay_40x10_pc100', lambda: rectangle_delaunay(40, 10, seed=4), 100),
+    ('s1c_20_pc96', lambda: square_one_channel(20), 96),
+    ('single_patch', lambda: rectangle_structured(6, 3), 4096),
+    ('tiny_2x1', lambda: rectangle_structured(2, 1), 16),
+])
+def test_layout_self_check_ell_rows_and_two_sweep_patches(name, make, pc):
+    """ELL mass rows (neighbour lists, shared cells) and ring-2 patches (C1 prefix, rows complete inside their sweep,
+    records / signs / adjacency consistent with the mesh) - the structures behind vertex_ell_pass and kernels2.cuh."""
+    v, c = make()
+    m = Mesh(v, c, patch_cells=pc)
+    m.self_check()
