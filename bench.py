@@ -158,6 +158,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--tol', type=float, default=1e-13)
     ap.add_argument('--extrap', type=int, default=3)
+    ap.add_argument('--extrap-q', type=int, default=0, help='extrapolation order of the q solves (0: same as --extrap)')
     ap.add_argument('--phase', type=float, default=0.25, help='phase omega*t0 / pi of the standing wave the run starts from (0: the t = 0 state of wave_2D.py:734)')
     ap.add_argument('--two-sweep', action='store_true', help='two Chebyshev iterations per pass in the mass solves (csrc/kernels2.cuh; A/B)')
     ap.add_argument('--cell-rows', action='store_true', help='cell-based instead of assembled (ELL) rows in the M_p solve (A/B)')
@@ -205,6 +206,7 @@ def main():
     prm.scheme, prm.dt, prm.K_wave, prm.rho = _lib.SCHEMES[args.scheme], dt, K_WAVE, RHO
     prm.input_kind, prm.in_amp, prm.in_omega = _lib.IN_COSINE, 1.0, omega
     prm.tol, prm.max_iter, prm.flags, prm.extrap_order = args.tol, 200, 4 | (16 if args.two_sweep else 0) | (32 if args.cell_rows else 0), args.extrap
+    prm.extrap_order_q = args.extrap_q
     solver = Solver(m, prm, device=local_rank)
     n_dof_local = int((part.vertex_owner == rank).sum() + (part.edge_owner == rank).sum())
     n_cells_local = int(part.cell_owned.sum())
@@ -324,9 +326,9 @@ def main():
             'metric': 'dof-updates/sec (fp64, device-timed)', 'value': value, 'unit': 'dof-updates/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dev_s / args.steps,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': '{} weak P1/RT1 wave, exact standing wave of the analytical case at phase w*t0 = ' + '%.3g' % args.phase + ' pi with its left datum (wave_2D.py:375-377,734), structured rectangle {}x{}x2 = {} cells and {} dofs per GPU ({} dofs in total, x-slab partition, peer-memory halo exchange), dt={:g}; '
+            'config': {'workload': '{} weak P1/RT1 wave, exact standing wave of the analytical case at phase w*t0 = {:.3g} pi with its left datum (wave_2D.py:375-377,734), structured rectangle {}x{}x2 = {} cells and {} dofs per GPU ({} dofs in total, x-slab partition, peer-memory halo exchange), dt={:g}; '
                                    'state vectors ({:.0f} MB each) exceed L2, no flush needed'.format(
-                                       args.scheme, args.nx, args.ny, nc, n_dof_local, n_dof, dt, 8e-6 * m.n_edges),
+                                       args.scheme, args.phase, args.nx, args.ny, nc, n_dof_local, n_dof, dt, 8e-6 * m.n_edges),
                        'dofs_per_gpu': n_dof_local, 'dofs_total': n_dof, 'patch_cells': args.patch_cells, 'phase_over_pi': args.phase, 'two_sweep': bool(args.two_sweep), 'tol': args.tol, 'extrap_order': args.extrap,
                        'iters_per_solve_p': st['iters_p'] / max(1, st['solves_p']), 'iters_per_solve_q': st['iters_q'] / max(1, st['solves_q']),
                        'max_rel_residual': st['max_rel_residual'], 'setup_seconds': setup_s},

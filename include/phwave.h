@@ -54,12 +54,13 @@ typedef struct phw_params {
     double tol;              /* relative residual of the mass / block solves (default 1e-13) */
     int32_t max_iter;        /* iteration cap per solve (default 200) */
     int32_t extrap_order;    /* initial guess of each solve = polynomial extrapolation of that solve's previous
-                                solutions: 0 last solution, 1 linear, 2 quadratic (default choice of the host code), 3 cubic */
+                                solutions: 0 last solution, 1 linear, 2 quadratic (default choice of the host code), 3 cubic ... 5 */
     int32_t flags;           /* bit0: disable first-same-as-last reuse in SV; bit1: synchronous error checks;
                                 bit2: CUDA-event timing of every solve kernel; bit3: force the multi-launch solve path;
                                 bit4: two-sweep mass solves (two Chebyshev iterations per pass over the data, csrc/kernels2.cuh;
                                 single GPU, weak form, explicit schemes; default off - see DESIGN.md section 10);
                                 bit5: cell-based instead of assembled (ELL) rows in the M_p solve */
+    int32_t extrap_order_q;  /* extrapolation order of the q (and block) solves; 0: same as extrap_order.  Orders up to 5 */
 } phw_params;
 
 typedef struct phw_stats {

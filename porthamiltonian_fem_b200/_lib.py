@@ -29,7 +29,8 @@ class PhwParams(ctypes.Structure):
                 ('H_init', ctypes.c_double),
                 ('an_omega', ctypes.c_double), ('an_xLength', ctypes.c_double), ('an_yLength', ctypes.c_double),
                 ('an_xPoint', ctypes.c_double), ('an_yPoint', ctypes.c_double),
-                ('tol', ctypes.c_double), ('max_iter', ctypes.c_int32), ('extrap_order', ctypes.c_int32), ('flags', ctypes.c_int32)]
+                ('tol', ctypes.c_double), ('max_iter', ctypes.c_int32), ('extrap_order', ctypes.c_int32), ('flags', ctypes.c_int32),
+                ('extrap_order_q', ctypes.c_int32)]
 
 
 class PhwStats(ctypes.Structure):

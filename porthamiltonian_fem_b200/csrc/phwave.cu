@@ -133,14 +133,14 @@ __global__ void axpy_dev_k(int n, TriBuf tb, const Ctl* ctl, int which, const do
 }
 // x0 = sum_j c_j hist_j : polynomial extrapolation of the previous solutions of the same solve site,
 // written into the current Chebyshev buffer (initial guess only - the accepted solution still has to meet tol)
-__global__ void predict_k(int n, TriBuf tb, const Ctl* ctl, int which, const double* h0, const double* h1, const double* h2,
-                          const double* h3, double c0, double c1, double c2, double c3, int m) {
+struct PredictArgs { const double* h[6]; double c[6]; int m; };
+__global__ void predict_k(int n, TriBuf tb, const Ctl* ctl, int which, PredictArgs pa) {
     double* x = tb.b[ctl->sc[which].cur];
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        double v = c0 * h0[i];
-        if (m > 1) v += c1 * h1[i];
-        if (m > 2) v += c2 * h2[i];
-        if (m > 3) v += c3 * h3[i];
+        double v = pa.c[0] * pa.h[0][i];
+#pragma unroll
+        for (int j = 1; j < 6; ++j)
+            if (j < pa.m) v += pa.c[j] * pa.h[j][i];
         x[i] = v;
     }
 }
@@ -515,9 +515,10 @@ struct phw_solver_s {
     PeerComm pc{};
     void* arena = nullptr; size_t arena_bytes = 0;
     std::vector<void*> peer_arenas;
-    struct Hist { double* h[4] = {nullptr, nullptr, nullptr, nullptr}; int count = 0, head = 0; };
+    struct Hist { double* h[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; int count = 0, head = 0; };
     Hist hist[2][2];           // [field p/q][solve site]
     int extrap = 2, n_sites = 1;
+    int extrap_f[2] = {2, 2};  // extrapolation order of the p / q solves
     bool ho = false; Csr hMp{}, hMq{}, hD{}, hDT{};
     int ho_nc = 0, ho_ndp = 0, ho_nn = 0, ho_nprobe = 0; double ho_omega = 0.0;
     int *ho_cell_dofs = nullptr, *ho_probe_dofs = nullptr;
@@ -924,15 +925,20 @@ int n_iter_launch(phw_solver_s* s) { return s->prm.max_iter; }
 // initial guess of a solve from the history of its site (field 0 = p unknown, 1 = q unknown)
 int predict(phw_solver_s* s, int field, int site, int which) {
     phw_solver_s::Hist& H = s->hist[field][site];
-    const int order = s->extrap + 1;
+    const int order = s->extrap_f[field] + 1;
     const int m = std::min(H.count, order);
     if (m <= 0 || !H.h[0]) return 0;
-    static const double C[4][4] = {{1, 0, 0, 0}, {2, -1, 0, 0}, {3, -3, 1, 0}, {4, -6, 4, -1}};
-    const double* hp[4];
-    for (int j = 0; j < 4; ++j) hp[j] = H.h[((H.head - j) % order + order) % order];
+    // extrapolation through the last m solutions: c_j = (-1)^j binom(m, j + 1)
+    PredictArgs pa{};
+    pa.m = m;
+    double binom = 1.0;
+    for (int j = 0; j < m; ++j) {
+        binom = binom * (double)(m - j) / (double)(j + 1);
+        pa.c[j] = (j % 2 == 0) ? binom : -binom;
+        pa.h[j] = H.h[((H.head - j) % order + order) % order];
+    }
     const int n = field == 0 ? s->nv : s->ne;
-    predict_k<<<vec_grid(s, n), 256, 0, s->stream>>>(n, field == 0 ? s->tp : s->tq, s->ctl, which, hp[0], hp[1], hp[2], hp[3],
-                                                      C[m - 1][0], C[m - 1][1], C[m - 1][2], C[m - 1][3], m);
+    predict_k<<<vec_grid(s, n), 256, 0, s->stream>>>(n, field == 0 ? s->tp : s->tq, s->ctl, which, pa);
     s->launches++;
     CU(cudaGetLastError());
     return 0;
@@ -940,7 +946,7 @@ int predict(phw_solver_s* s, int field, int site, int which) {
 int remember(phw_solver_s* s, int field, int site, int which) {
     phw_solver_s::Hist& H = s->hist[field][site];
     if (!H.h[0]) return 0;
-    const int order = s->extrap + 1;
+    const int order = s->extrap_f[field] + 1;
     H.head = (H.head + 1) % order;
     H.count = std::min(H.count + 1, order);
     const int n = field == 0 ? s->nv : s->ne;
@@ -1336,14 +1342,14 @@ static int setup_vectors(phw_solver_s* s) {
         s->coop = coop_attr != 0 && !(P.flags & 8);
     }
     RC(s->dalloc(&s->ctl, (size_t)s->G));
-    s->extrap = (P.extrap_order < 0) ? 0 : std::min(P.extrap_order, 3);
+    // initial guesses: extrapolation order of the p solves (extrap_order) and of the q solves (extrap_order_q, 0 = the same)
+    s->extrap = (P.extrap_order < 0) ? 0 : std::min(P.extrap_order, 5);
+    s->extrap_f[0] = s->extrap;
+    s->extrap_f[1] = (P.extrap_order_q > 0) ? std::min(P.extrap_order_q, 5) : s->extrap;
     s->n_sites = (P.scheme == PHW_EH) ? 2 : 1;
-    if (s->extrap > 0 || true) {
-        for (int site = 0; site < s->n_sites; ++site)
-            for (int j = 0; j <= s->extrap; ++j) {
-                RC(s->dalloc(&s->hist[0][site].h[j], nv));
-                RC(s->dalloc(&s->hist[1][site].h[j], ne));
-            }
+    for (int site = 0; site < s->n_sites; ++site) {
+        for (int j = 0; j <= s->extrap_f[0]; ++j) RC(s->dalloc(&s->hist[0][site].h[j], nv));
+        for (int j = 0; j <= s->extrap_f[1]; ++j) RC(s->dalloc(&s->hist[1][site].h[j], ne));
     }
     for (double* v : {s->p, s->bp, s->tmp_p, s->tp.b[0], s->tp.b[1], s->tp.b[2], s->io_v, s->io_v2}) CU(cudaMemsetAsync(v, 0, nv * 8, s->stream));
     for (double* v : {s->q, s->bq, s->tmp_q, s->tq.b[0], s->tq.b[1], s->tq.b[2], s->io_e, s->io_e2}) CU(cudaMemsetAsync(v, 0, ne * 8, s->stream));
