@@ -22,7 +22,8 @@ struct Ring2Dev {
     const double* g0; const double* g1; const double* g2;   // vertex kind: g0 = cell area, g1 = g2 = nullptr
     const int* ghost;
     const double* pinv;          // [n_rows] Jacobi weights replicated per first-sweep row (contiguous per patch)
-    const uint32_t* slice_off; const uint16_t* adj;         // vertex kind
+    const uint32_t* ell_ioff; const uint32_t* ell_woff;     // vertex kind: assembled mass rows of [D0 | G1] (sliced ELL)
+    const uint16_t* ell_ids; const double* ell_w;
     const uint32_t* eadj;                                   // edge kind
 };
 
@@ -193,121 +194,110 @@ __device__ __forceinline__ void edge_pass2(const Solve2Args& a, const Pass2IO& i
 }
 
 // ------------------------------------------------------------------------------------------------
-// vertex rows (M_p): (M_p x)_v = sum_K |K|/12 (x_K0 + x_K1 + x_K2) + x_v / (2 pinv_v)   (pinv_v = 1 / sum_K |K|/6)
+// vertex rows (M_p) on the assembled sliced-ELL rows of the ring-2 patch (layout.hpp): (M_p x)_v = d_v x_v + sum_w m_vw x_w,
+// d_v = sum_w m_vw.  Sweep 1 reads the rows of [D0 | G1] from global memory and parks those of D0 (ids + weights, 64 B per
+// row) and b in shared memory; sweep 2 runs entirely from shared memory.  DRAM per pass (two iterations): the ELL rows of
+// D0+G1 once, x_k, b, x_{k-1} once, two iterate writes.
 // ------------------------------------------------------------------------------------------------
 template <int NT>
-__device__ __forceinline__ double vertex_row_sum(const uint4* __restrict__ adj4, const uint32_t o0, const uint32_t o1, const int r,
-                                                 const double* __restrict__ sc) {
-    double val = 0.0;
-    const uint32_t nchunk = (o1 - o0) >> 8;
-    for (uint32_t k = 0; k < nchunk; ++k) {
-        const uint4 cd = __ldg(&adj4[(o0 >> 3) + k * 32 + (r & 31)]);
-        const uint32_t w4[4] = {cd.x, cd.y, cd.z, cd.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const uint32_t c0 = w4[j] & 0xFFFFu, c1 = w4[j] >> 16;
-            if (c0 != 0xFFFFu) val += sc[c0 >> 2];
-            if (c1 != 0xFFFFu) val += sc[c1 >> 2];
-        }
-    }
-    return val;
-}
-
-template <int NT>
-__device__ __forceinline__ void vertex_pass2(const Solve2Args& a, const Pass2IO& io, double* smem, double& rr0, double& rr1, double& bb) {
+__device__ __forceinline__ void vertex_ell_pass2(const Solve2Args& a, const Pass2IO& io, double* smem, double& rr0, double& rr1, double& bb) {
     const Ring2Dev& m = a.m;
     __shared__ Ring2Hdr s_hdr[2];
     if (blockIdx.x < m.npatch) load_hdr2_smem(&s_hdr[0], &m.hdr[blockIdx.x]);
     __syncthreads();
-    const uint4* adj4 = reinterpret_cast<const uint4*>(m.adj);
+    const uint4* ids4 = reinterpret_cast<const uint4*>(m.ell_ids);
     int it = 0;
     for (int P = blockIdx.x; P < m.npatch; P += gridDim.x, ++it) {
         const Ring2Hdr& h = s_hdr[it & 1];
         if (P + (int)gridDim.x < m.npatch) load_hdr2_smem(&s_hdr[(it + 1) & 1], &m.hdr[P + gridDim.x]);
-        const int n0 = h.d_cnt, nr = n0 + h.g1_cnt, ng = h.g1_cnt + h.g2_cnt;
-        const int nsl = (nr + 31) >> 5;
-        uint32_t* s_off = reinterpret_cast<uint32_t*>(smem);   // [nsl + 1]
-        double* sx = smem + ((nsl + 2) >> 1);                   // [n0 + ng]
-        double* sc = sx + ((n0 + ng + 1) & ~1);                 // [n_c2]
-        for (int i = threadIdx.x; i <= nsl; i += NT) s_off[i] = __ldg(&m.slice_off[h.vs_off + i]);
+        const int n0 = h.d_cnt, nr = n0 + h.g1_cnt, ng = h.g1_cnt + h.g2_cnt, nl = n0 + ng;
+        const int nsl = (nr + 31) >> 5, nsl0 = (n0 + 31) >> 5;
+        const uint32_t iobase = __ldg(&m.ell_ioff[h.vs_off]), wobase = __ldg(&m.ell_woff[h.vs_off]);
+        const uint32_t wcount0 = __ldg(&m.ell_woff[h.vs_off + nsl0]) - wobase;
+        uint32_t* s_io = reinterpret_cast<uint32_t*>(smem);   // [nsl + 1]
+        uint32_t* s_wo = s_io + (nsl + 1);                     // [nsl + 1]
+        double* sx = smem + ((nsl + 3) & ~1);                  // [nl]  x_k (even offset: the ids below are read as uint4)
+        double* sx1 = sx + ((nl + 1) & ~1);                    // [nr]  x_{k+1}
+        double* sb = sx1 + ((nr + 1) & ~1);                    // [n0]  b on D0
+        double* sw = sb + ((n0 + 1) & ~1);                     // weights of the D0 slices (slice layout kept)
+        uint4* sid4 = reinterpret_cast<uint4*>(sw + wcount0);  // ids of the D0 slices (wcount0 is a multiple of 32)
+        for (int i = threadIdx.x; i <= nsl; i += NT) { s_io[i] = __ldg(&m.ell_ioff[h.vs_off + i]); s_wo[i] = __ldg(&m.ell_woff[h.vs_off + i]); }
         for (int i = threadIdx.x; i < n0; i += NT) sx[i] = io.xk[h.d_start + i];
         for (int i = threadIdx.x; i < ng; i += NT) sx[n0 + i] = io.xk[__ldg(&m.ghost[h.g_off + i])];
         __syncthreads();
-        // ---- sweep 1, cells C2
-        {
-            constexpr int U = 3;
-            for (int base = threadIdx.x; base < h.n_c2; base += U * NT) {
-                uint2 rvb[U]; double Ab[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int lc = base + u * NT;
-                    if (lc < h.n_c2) { rvb[u] = __ldg(&m.rec[h.cell_off + lc]); Ab[u] = __ldg(&m.g0[h.cell_off + lc]); }
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int lc = base + u * NT;
-                    if (lc < h.n_c2) sc[lc] = Ab[u] * (1.0 / 12.0) * (sx[rvb[u].x & 0xFFFFu] + sx[rvb[u].x >> 16] + sx[rvb[u].y & 0xFFFFu]);
-                }
-            }
-        }
-        __syncthreads();
-        // ---- sweep 1, rows [D0 | G1]
+        // ---- sweep 1: rows [D0 | G1] from global memory
         const int rround = (nr + 31) & ~31;
         for (int r = threadIdx.x; r < rround; r += NT) {
-            const uint32_t o0 = s_off[r >> 5], o1 = s_off[(r >> 5) + 1];
-            const bool live = r < nr;
-            int gid = 0; double bv = 0.0, pv = 0.0, xpv = 0.0;
+            const int sl = r >> 5, lane = r & 31;
+            const uint32_t io0 = s_io[sl], wo0 = s_wo[sl];
+            const int W = (int)((s_wo[sl + 1] - wo0) >> 5);
+            const bool live = r < nr, keep = sl < nsl0;
+            int gid = 0; double bv = 0.0, xpv = 0.0;
             if (live) {
                 gid = (r < n0) ? h.d_start + r : __ldg(&m.ghost[h.g_off + r - n0]);
-                pv = __ldg(&m.pinv[h.row_off + r]); bv = __ldg(&a.b[gid]);
+                bv = __ldg(&a.b[gid]);
                 if (io.use_prev) xpv = io.xprev[gid];
             }
-            double val = vertex_row_sum<NT>(adj4, o0, o1, r, sc);
+            const double* __restrict__ wrow = m.ell_w + wo0 + lane;
+            double val = 0.0, dsum = 0.0;
+            for (int c = 0; 8 * c < W; ++c) {
+                const uint4 cd = __ldg(&ids4[(io0 >> 3) + c * 32 + lane]);
+                const uint32_t w4[4] = {cd.x, cd.y, cd.z, cd.w};
+                double wv[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) wv[j] = (8 * c + j < W) ? __ldg(&wrow[(8 * c + j) * 32]) : 0.0;
+                if (keep) {
+                    sid4[((io0 - iobase) >> 3) + c * 32 + lane] = cd;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (8 * c + j < W) sw[(wo0 - wobase) + (8 * c + j) * 32 + lane] = wv[j];
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    val += wv[2 * j] * sx[w4[j] & 0xFFFFu];
+                    val += wv[2 * j + 1] * sx[w4[j] >> 16];
+                    dsum += wv[2 * j] + wv[2 * j + 1];
+                }
+            }
             if (!live) continue;
             const double xc = sx[r];
-            val += 0.5 * xc / pv;
+            const double pv = 1.0 / dsum;
+            val += dsum * xc;
             const double res = bv - val;
             double xn = xc + io.c2a * pv * res;
             if (io.use_prev) xn += io.c1a * (xc - xpv);
-            sx[r] = xn;
+            sx1[r] = xn;
             if (r < n0) {
                 io.x1[gid] = xn;
+                sb[r] = bv;
                 rr0 += pv * res * res;
                 bb += pv * bv * bv;
             }
         }
         __syncthreads();
-        // ---- sweep 2, cells C1
-        {
-            constexpr int U = 3;
-            for (int base = threadIdx.x; base < h.n_c1; base += U * NT) {
-                uint2 rvb[U]; double Ab[U];
+        // ---- sweep 2: rows D0 from shared memory
+        for (int r = threadIdx.x; r < n0; r += NT) {
+            const int sl = r >> 5, lane = r & 31;
+            const uint32_t io0 = s_io[sl] - iobase, wo0 = s_wo[sl] - wobase;
+            const int W = (int)((s_wo[sl + 1] - s_wo[sl]) >> 5);
+            double val = 0.0, dsum = 0.0;
+            for (int c = 0; 8 * c < W; ++c) {
+                const uint4 cd = sid4[(io0 >> 3) + c * 32 + lane];
+                const uint32_t w4[4] = {cd.x, cd.y, cd.z, cd.w};
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int lc = base + u * NT;
-                    if (lc < h.n_c1) { rvb[u] = __ldg(&m.rec[h.cell_off + lc]); Ab[u] = __ldg(&m.g0[h.cell_off + lc]); }
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int lc = base + u * NT;
-                    if (lc < h.n_c1) sc[lc] = Ab[u] * (1.0 / 12.0) * (sx[rvb[u].x & 0xFFFFu] + sx[rvb[u].x >> 16] + sx[rvb[u].y & 0xFFFFu]);
+                for (int j = 0; j < 4; ++j) {
+                    const double w0 = (8 * c + 2 * j < W) ? sw[wo0 + (8 * c + 2 * j) * 32 + lane] : 0.0;
+                    const double w1 = (8 * c + 2 * j + 1 < W) ? sw[wo0 + (8 * c + 2 * j + 1) * 32 + lane] : 0.0;
+                    val += w0 * sx1[w4[j] & 0xFFFFu];
+                    val += w1 * sx1[w4[j] >> 16];
+                    dsum += w0 + w1;
                 }
             }
-        }
-        __syncthreads();
-        // ---- sweep 2, rows D0
-        const int r0round = (n0 + 31) & ~31;
-        for (int r = threadIdx.x; r < r0round; r += NT) {
-            const uint32_t o0 = s_off[r >> 5], o1 = s_off[(r >> 5) + 1];
-            const bool live = r < n0;
-            double bv = 0.0, pv = 0.0, xk = 0.0;
-            if (live) { pv = __ldg(&m.pinv[h.row_off + r]); bv = __ldg(&a.b[h.d_start + r]); xk = io.xk[h.d_start + r]; }
-            double val = vertex_row_sum<NT>(adj4, o0, o1, r, sc);
-            if (!live) continue;
-            const double x1 = sx[r];
-            val += 0.5 * x1 / pv;
-            const double res = bv - val;
-            io.x2[h.d_start + r] = x1 + io.c2b * pv * res + io.c1b * (x1 - xk);
+            const double x1 = sx1[r];
+            const double pv = 1.0 / dsum;
+            val += dsum * x1;
+            const double res = sb[r] - val;
+            io.x2[h.d_start + r] = x1 + io.c2b * pv * res + io.c1b * (x1 - sx[r]);
             rr1 += pv * res * res;
         }
         __syncthreads();
@@ -348,7 +338,7 @@ __global__ void __launch_bounds__(NT, MINB) solve2_coop_k(const Solve2Args a) {
         io.xk = sel4(a.buf, cur); io.x1 = sel4(a.buf, (cur + 1) & 3); io.x2 = sel4(a.buf, (cur + 2) & 3); io.xprev = sel4(a.buf, (cur + 3) & 3);
         io.use_prev = (k > 0);
         double r0 = 0.0, r1 = 0.0, b0 = 0.0;
-        if (KIND == 0) vertex_pass2<NT>(a, io, smem, r0, r1, b0);
+        if (KIND == 0) vertex_ell_pass2<NT>(a, io, smem, r0, r1, b0);
         else edge_pass2<NT>(a, io, smem, r0, r1, b0);
         block_sum3(r0, r1, b0, red);
         double* part = a.partials + (size_t)(pass & 1) * 3 * gridDim.x;

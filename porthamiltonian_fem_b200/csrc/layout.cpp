@@ -449,6 +449,7 @@ std::string Layout::build_ring2(int kind, Ring2& R) const {
     R = Ring2{};
     R.hdr.assign(npatch, Ring2Hdr{});
     R.slice_off.push_back(0);
+    R.ell_ioff.push_back(0); R.ell_woff.push_back(0);
     std::vector<int32_t> mark_c(nc, -1), lc_of(nc, 0), mark_d(nd, -1), lid(nd, 0);
     std::vector<int32_t> cl, g1, g2;
     std::vector<uint32_t> deg;
@@ -536,6 +537,55 @@ std::string Layout::build_ring2(int kind, Ring2& R) const {
                     R.adj[base + sbase[r / 32] + ((size_t)(j / 8) * 32 + (r % 32)) * 8 + (j % 8)] = (uint16_t)(lc_of[c] * 4 + slot_of(c, d));
                 }
             }
+            // assembled mass rows (ELL) of [D0 | G1]
+            std::vector<uint16_t> nid((size_t)nr * 16);
+            std::vector<uint32_t> npair((size_t)nr * 16), ncnt(nr, 0);
+            for (int32_t r = 0; r < nr; ++r) {
+                const int32_t d = new2old[R.row_gid[H.row_off + r]];
+                uint32_t cnt = 0;
+                for (int64_t k = off[d]; k < off[d + 1]; ++k) {
+                    const int32_t c = d2c[k];
+                    const int i = slot_of(c, d);
+                    for (int t = 1; t <= 2; ++t) {
+                        const int32_t o_old = cd[3 * (int64_t)c + (i + t) % 3], o_new = old2new[o_old];
+                        const uint16_t o = (uint16_t)(owned(o_new) ? o_new - H.d_start : lid[o_old]);
+                        uint32_t j = 0;
+                        while (j < cnt && nid[(size_t)r * 16 + j] != o) ++j;
+                        if (j < cnt) npair[(size_t)r * 16 + j] = (npair[(size_t)r * 16 + j] & 0xFFFFu) | ((uint32_t)lc_of[c] << 16);
+                        else {
+                            if (cnt >= 16) return "vertex with more than 16 neighbours: not supported by the ELL mass rows";
+                            nid[(size_t)r * 16 + cnt] = o; npair[(size_t)r * 16 + cnt] = (uint32_t)lc_of[c] | 0xFFFF0000u; ++cnt;
+                        }
+                    }
+                }
+                ncnt[r] = cnt;
+            }
+            const size_t ibase = R.ell_ids.size(), wbase = R.ell_pair.size();
+            size_t ioff = 0, woff = 0, ioff0 = 0, woff0 = 0;
+            const int32_t nslice0 = (H.d_cnt + 31) / 32;
+            for (int32_t sl = 0; sl < nslice; ++sl) {
+                uint32_t w = 0;
+                for (int32_t k = 32 * sl; k < std::min(32 * (sl + 1), nr); ++k) w = std::max(w, ncnt[k]);
+                const uint32_t nch = (w + 7u) / 8u;
+                R.ell_ids.resize(ibase + ioff + (size_t)nch * 256, 0);
+                R.ell_pair.resize(wbase + woff + (size_t)w * 32, 0xFFFFFFFFu);
+                for (int32_t k = 32 * sl; k < 32 * (sl + 1); ++k) {
+                    const int lane = k % 32;
+                    for (uint32_t j = 0; j < nch * 8; ++j) {
+                        const bool valid = k < nr && j < ncnt[k];
+                        R.ell_ids[ibase + ioff + ((size_t)(j / 8) * 32 + lane) * 8 + (j % 8)] = valid ? nid[(size_t)k * 16 + j] : (uint16_t)(k < nr ? k : 0);
+                        if (j < w && valid) R.ell_pair[wbase + woff + (size_t)j * 32 + lane] = npair[(size_t)k * 16 + j];
+                    }
+                }
+                ioff += (size_t)nch * 256; woff += (size_t)w * 32;
+                if (sl + 1 == nslice0) { ioff0 = ioff; woff0 = woff; }
+                R.ell_ioff.push_back((uint32_t)(ibase + ioff));
+                R.ell_woff.push_back((uint32_t)(wbase + woff));
+            }
+            // shared memory of vertex_ell_pass2 (doubles): offsets | x_k [nl] | x_{k+1} [nr] | b [n0] | weights + ids of the D0 slices
+            auto ev2 = [](int64_t x) { return (x + 1) & ~(int64_t)1; };
+            const int64_t need = ((nslice + 3) & ~1) + ev2(nl) + ev2(nr) + ev2(H.d_cnt) + (int64_t)woff0 + (int64_t)(ioff0 + 3) / 4 + 2;
+            R.max_smem_ell = std::max(R.max_smem_ell, need);
         } else {
             for (int32_t r = 0; r < nr; ++r) {
                 const int32_t d = new2old[R.row_gid[H.row_off + r]];
@@ -552,7 +602,8 @@ std::string Layout::build_ring2(int kind, Ring2& R) const {
             }
         }
     }
-    if (R.adj.size() >= ((size_t)1 << 32) || R.pcell_user.size() >= ((size_t)1 << 31)) return "two-sweep layout exceeds 32-bit offsets";
+    if (R.adj.size() >= ((size_t)1 << 32) || R.pcell_user.size() >= ((size_t)1 << 31) || R.ell_ids.size() >= ((size_t)1 << 32) ||
+        R.ell_pair.size() >= ((size_t)1 << 32)) return "two-sweep layout exceeds 32-bit offsets";
     return "";
 }
 
@@ -645,6 +696,36 @@ std::string Layout::self_check() const {
                     const uint32_t a = R.eadj[H.row_off + r];
                     if ((a & 0xFFFFu) != 0xFFFFu) codes.push_back(a & 0xFFFFu);
                     if ((a >> 16) != 0xFFFFu) codes.push_back(a >> 16);
+                }
+                if (kind == 0) {   // assembled mass row: neighbours = the other vertices of the row's cells; pair cells contain both
+                    const int32_t sl = r / 32, lane = r % 32;
+                    const uint32_t io0 = R.ell_ioff[H.vs_off + sl], wo0 = R.ell_woff[H.vs_off + sl];
+                    const uint32_t W = (R.ell_woff[H.vs_off + sl + 1] - wo0) / 32;
+                    std::vector<int32_t> expect, got;
+                    for (int64_t c = 0; c < nc; ++c)
+                        for (int i = 0; i < 3; ++i)
+                            if (cd[3 * c + i] == d_old) { expect.push_back(cd[3 * c + (i + 1) % 3]); expect.push_back(cd[3 * c + (i + 2) % 3]); }
+                    std::sort(expect.begin(), expect.end());
+                    expect.erase(std::unique(expect.begin(), expect.end()), expect.end());
+                    for (uint32_t k = 0; k < W; ++k) {
+                        const uint32_t pr = R.ell_pair[wo0 + k * 32 + lane];
+                        const uint16_t id = R.ell_ids[io0 + ((size_t)(k / 8) * 32 + lane) * 8 + (k % 8)];
+                        if (pr == 0xFFFFFFFFu) { if (id != r) return err("ring-2 ELL padding", p, r); continue; }
+                        if ((int32_t)id >= nl || (r < H.d_cnt && (int32_t)id >= nr)) return err("ring-2 ELL neighbour outside its sweep", p, r);
+                        const int32_t w_old = new2old[gid_of(id)];
+                        got.push_back(w_old);
+                        for (int hh = 0; hh < 2; ++hh) {
+                            const uint32_t lc = hh == 0 ? (pr & 0xFFFFu) : (pr >> 16);
+                            if (lc == 0xFFFFu) continue;
+                            if ((int32_t)lc >= H.n_c2) return err("ring-2 ELL cell out of range", p, r);
+                            const int32_t c = R.pcell_user[H.cell_off + lc];
+                            int hit = 0;
+                            for (int i = 0; i < 3; ++i) hit += (cd[3 * (int64_t)c + i] == d_old) + 2 * (cd[3 * (int64_t)c + i] == w_old);
+                            if (hit != 3) return err("ring-2 ELL cell does not contain both vertices", p, r);
+                        }
+                    }
+                    std::sort(got.begin(), got.end());
+                    if (got != expect) return err("ring-2 ELL neighbours differ from the mesh", p, r);
                 }
                 int64_t in_mesh = 0;
                 for (int64_t h = 0; h < 3 * nc; ++h) in_mesh += (cd[h] == d_old);   // small test meshes only

@@ -57,6 +57,12 @@ struct Ring2 {
     std::vector<uint32_t> slice_off;   // vertex kind (same sliced-ELL format as Layout::vadj)
     std::vector<uint16_t> adj;
     std::vector<uint32_t> eadj;        // edge kind: [n_rows] two (cell, slot) codes per row
+    // vertex kind: assembled P1 mass rows of [D0 | G1] as sliced ELL (same slices as slice_off; ids = ring-2 local ids,
+    // entries of a row in ascending user cell id so that recomputed halo rows are bit-identical to their owners')
+    std::vector<uint32_t> ell_ioff, ell_woff;
+    std::vector<uint16_t> ell_ids;
+    std::vector<uint32_t> ell_pair;
+    int64_t max_smem_ell = 0;          // doubles of shared memory the ELL two-sweep pass needs for the largest patch
     int32_t max_ld = 0, max_rows = 0, max_c2 = 0;
 };
 

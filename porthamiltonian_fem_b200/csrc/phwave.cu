@@ -103,6 +103,25 @@ __global__ void ell_weights_k(int npatch, const PatchHdr* __restrict__ hdr, cons
     }
 }
 
+__global__ void ell2_weights_k(int npatch, const Ring2Hdr* __restrict__ hdr, const uint32_t* __restrict__ woff,
+                               const uint32_t* __restrict__ pair, const double* __restrict__ area, double* __restrict__ w) {
+    for (int P = blockIdx.x; P < npatch; P += gridDim.x) {
+        const Ring2Hdr h = hdr[P];
+        const int nsl = (h.d_cnt + h.g1_cnt + 31) >> 5;
+        const uint32_t e0 = woff[h.vs_off], e1 = woff[h.vs_off + nsl];
+        for (uint32_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+            const uint32_t pr = pair[e];
+            double v = 0.0;
+            if (pr != 0xFFFFFFFFu) {
+                v = area[h.cell_off + (pr & 0xFFFFu)];
+                if ((pr >> 16) != 0xFFFFu) v += area[h.cell_off + (pr >> 16)];
+                v *= (1.0 / 12.0);
+            }
+            w[e] = v;
+        }
+    }
+}
+
 __global__ void invert_k(int n, double* d) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) d[i] = (d[i] != 0.0) ? 1.0 / d[i] : 0.0;
@@ -721,11 +740,11 @@ int launch_coop2(phw_solver_s* s) {
     static const int cfg = [] { const char* e = getenv(KIND == 0 ? "PHW_P2_CFG" : "PHW_Q2_CFG"); return e ? atoi(e) : 0; }();
     if (KIND == 0) {
         switch (cfg) {
-            case 1: return launch_coop2_cfg<KIND, 256, 6>(s);
-            case 2: return launch_coop2_cfg<KIND, 512, 3>(s);
-            case 3: return launch_coop2_cfg<KIND, 128, 12>(s);
-            case 4: return launch_coop2_cfg<KIND, 1024, 1>(s);
-            default: return launch_coop2_cfg<KIND, 256, 5>(s);
+            case 1: return launch_coop2_cfg<KIND, 256, 2>(s);
+            case 2: return launch_coop2_cfg<KIND, 384, 2>(s);
+            case 3: return launch_coop2_cfg<KIND, 1024, 1>(s);
+            case 4: return launch_coop2_cfg<KIND, 256, 3>(s);
+            default: return launch_coop2_cfg<KIND, 512, 2>(s);
         }
     }
     switch (cfg) {
@@ -1517,7 +1536,8 @@ static int setup_solver(phw_solver_s* s) {
         Ring2 R;
         if (!L.build_ring2(kind, R).empty()) { s->two_sweep = false; break; }   // patches too large for one more ring
         const size_t soff2 = ((size_t)(R.max_rows + 31) / 32 + 4) / 2 + 1;
-        s->smem2[kind] = (kind == 0) ? (soff2 + ev(R.max_ld) + (size_t)R.max_c2) * 8 : (ev(R.max_ld) + 3 * (size_t)R.max_c2) * 8;
+        s->smem2[kind] = (kind == 0) ? (size_t)R.max_smem_ell * 8 : (ev(R.max_ld) + 3 * (size_t)R.max_c2) * 8;
+        (void)soff2;
         if (s->smem2[kind] > 200 * 1024) { s->two_sweep = false; break; }
         Ring2Dev& d = s->r2[kind];
         d.npatch = s->npatch;
@@ -1536,9 +1556,12 @@ static int setup_solver(phw_solver_s* s) {
         CU(cudaGetLastError());
         d.g0 = ga; d.g1 = gb; d.g2 = gc;
         if (kind == 0) {
-            uint32_t* d_so; uint16_t* d_adj;
-            RC(s->upload(&d_so, R.slice_off)); RC(s->upload(&d_adj, R.adj));
-            d.slice_off = d_so; d.adj = d_adj;
+            uint32_t *d_io, *d_wo, *d_pair; uint16_t* d_ids; double* d_w;
+            RC(s->upload(&d_io, R.ell_ioff)); RC(s->upload(&d_wo, R.ell_woff)); RC(s->upload(&d_ids, R.ell_ids)); RC(s->upload(&d_pair, R.ell_pair));
+            RC(s->dalloc(&d_w, R.ell_pair.size()));
+            ell2_weights_k<<<std::max(1, std::min(s->npatch, 8 * s->sm_count)), 256, 0, s->stream>>>(s->npatch, d_h, d_wo, d_pair, ga, d_w);
+            CU(cudaGetLastError());
+            d.ell_ioff = d_io; d.ell_woff = d_wo; d.ell_ids = d_ids; d.ell_w = d_w;
         } else {
             uint32_t* d_ea;
             RC(s->upload(&d_ea, R.eadj));

@@ -1,5 +1,5 @@
-run() { echo "== $*"; bash runb.sh "$@" --debug-residuals; }
-run --extrap-q 4
-run --extrap-q 5
-run --extrap 4 --extrap-q 5
-run --extrap 5 --extrap-q 5
+run() { echo "== $*"; env "$@" bash runb.sh --two-sweep; }
+run PHW_P2_CFG=0
+run PHW_P2_CFG=1
+run PHW_P2_CFG=2
+run PHW_P2_CFG=4
