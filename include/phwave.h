@@ -59,7 +59,8 @@ typedef struct phw_params {
                                 bit2: CUDA-event timing of every solve kernel; bit3: force the multi-launch solve path;
                                 bit4: two-sweep mass solves (two Chebyshev iterations per pass over the data, csrc/kernels2.cuh;
                                 single GPU, weak form, explicit schemes; default off - see DESIGN.md section 10);
-                                bit5: cell-based instead of assembled (ELL) rows in the M_p solve */
+                                bit5: cell-based instead of assembled (ELL) rows in the M_p solve;
+                                bit6: ELL rows read directly from global memory instead of staged by cp.async */
     int32_t extrap_order_q;  /* extrapolation order of the q (and block) solves; 0: same as extrap_order.  Orders up to 5 */
 } phw_params;
 
@@ -129,6 +130,9 @@ int phw_synchronize(phw_solver_t s);
 int phw_set_time(phw_solver_t s, double t);
 /* diagnostics: relative residuals ||b - A x_k|| / ||b||, k = 0..n-1 (n <= 48), of the most recent solve of kind
  * `which` (PHW_P, PHW_Q, 2 = block system) and its iteration count; entries beyond it are stale */
+/* diagnostics: a pass that only streams what one iteration of the ELL M_p solve reads and writes, patch by patch, with
+ * `threads` per CTA and `ctas_per_sm` resident CTAs: the bandwidth the memory system delivers for this layout */
+int phw_stream_probe(phw_solver_t s, int32_t threads, int32_t ctas_per_sm, int32_t reps, double* ms_per_pass, double* bytes_per_pass);
 int phw_residual_history(phw_solver_t s, int32_t which, int32_t n, double* rel_residuals, int32_t* n_iterations);
 
 /* ---- multi-GPU (one process per GPU on one node).  The exchange arena of every rank (Chebyshev buffers +

@@ -87,6 +87,7 @@ SIGNATURES = {
     'phw_ho_set_analytical': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, c_i32p,
                                              c_f64p, c_f64p, c_f64p, c_f64p, c_f64p, ctypes.c_int32, c_i32p, c_f64p]),
     'phw_set_time': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double]),
+    'phw_stream_probe': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, c_f64p, c_f64p]),
     'phw_residual_history': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, c_f64p, c_i32p]),
     'phw_set_H_init': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double]),
     'phw_port_flux': (ctypes.c_int, [ctypes.c_void_p, c_f64p]),

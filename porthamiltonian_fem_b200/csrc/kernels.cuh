@@ -49,6 +49,12 @@
 #ifndef PHW_MINB_ELL
 #define PHW_MINB_ELL 4
 #endif
+#ifndef PHW_NT_ELLS
+#define PHW_NT_ELLS 512
+#endif
+#ifndef PHW_MINB_ELLS
+#define PHW_MINB_ELLS 2
+#endif
 
 namespace phw {
 
@@ -240,7 +246,19 @@ __device__ __forceinline__ double* tb_sel(const TriBuf& t, int i) { return i == 
 // patch headers are double-buffered in shared memory: the header of the CTA's next patch is fetched while the current
 // patch is processed (no exposed header load at the top of a patch)
 __device__ __forceinline__ void load_hdr_smem(PatchHdr* dst, const PatchHdr* src) {
-    if (threadIdx.x < 16) reinterpret_cast<int*>(dst)[threadIdx.x] = __ldg(reinterpret_cast<const int*>(src) + threadIdx.x);
+    if (threadIdx.x < 20) reinterpret_cast<int*>(dst)[threadIdx.x] = __ldg(reinterpret_cast<const int*>(src) + threadIdx.x);
+}
+
+// asynchronous global -> shared copies (LDGSTS): the data of a whole patch is put in flight at once without holding
+// registers; completion is awaited with cp_async_wait_all() before the block-wide barrier
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -466,6 +484,94 @@ __device__ __forceinline__ void vertex_ell_pass(const RowArgs& a, const PassIO& 
             acc1 += pv * bv * bv;
         }
         __syncthreads();
+    }
+}
+
+// The same rows with every stream of the patch staged in shared memory by asynchronous copies: ids and weights (two
+// contiguous blocks), b and x_{k-1} (owned range) are requested for the WHOLE patch before anything is consumed, so a
+// patch costs one memory latency instead of one per 256-row round; rows then run from shared memory.
+template <int NT>
+__device__ __forceinline__ void vertex_ell_pass_staged(const RowArgs& a, const PassIO& io, double* smem, double& acc0, double& acc1) {
+    const DevMesh& m = a.m;
+    __shared__ PatchHdr s_hdr[2];
+    if (blockIdx.x < m.npatch) load_hdr_smem(&s_hdr[0], &m.hdr[blockIdx.x]);
+    __syncthreads();
+    int it = 0;
+    for (int P = blockIdx.x; P < m.npatch; P += gridDim.x, ++it) {
+        const PatchHdr& h = s_hdr[it & 1];
+        if (P + (int)gridDim.x < m.npatch) load_hdr_smem(&s_hdr[(it + 1) & 1], &m.hdr[P + gridDim.x]);
+        const int nsl = (h.v_cnt + 31) >> 5, nlv = h.v_cnt + h.gv_cnt;
+        const uint32_t i0 = (uint32_t)h.ell_i0, in = (uint32_t)h.ell_in, w0 = (uint32_t)h.ell_w0, wn = (uint32_t)h.ell_wn;
+        uint32_t* s_io = reinterpret_cast<uint32_t*>(smem);
+        uint32_t* s_wo = s_io + (nsl + 1);
+        double* sx = smem + ((nsl + 3) & ~1);
+        double* sb = sx + ((nlv + 1) & ~1);
+        double* sxp = sb + ((h.v_cnt + 1) & ~1);
+        double* sw = sxp + ((h.v_cnt + 1) & ~1);
+        uint4* sid4 = reinterpret_cast<uint4*>(sw + wn);
+        {   // whole-patch requests
+            const uint4* gi = reinterpret_cast<const uint4*>(m.ell_ids + i0);
+            for (uint32_t i = threadIdx.x; i < (in >> 3); i += NT) cp_async16(&sid4[i], &gi[i]);
+            const double2* gw = reinterpret_cast<const double2*>(m.ell_w + w0);
+            double2* sw2 = reinterpret_cast<double2*>(sw);
+            for (uint32_t i = threadIdx.x; i < (wn >> 1); i += NT) cp_async16(&sw2[i], &gw[i]);
+            for (int i = threadIdx.x; i < h.v_cnt; i += NT) cp_async8(&sb[i], &a.b[h.v_start + i]);
+            if (io.use_prev)
+                for (int i = threadIdx.x; i < h.v_cnt; i += NT) cp_async8(&sxp[i], &io.xprev[h.v_start + i]);
+        }
+        for (int i = threadIdx.x; i <= nsl; i += NT) { s_io[i] = __ldg(&m.ell_ioff[h.vs_off + i]) - i0; s_wo[i] = __ldg(&m.ell_woff[h.vs_off + i]) - w0; }
+        for (int i = threadIdx.x; i < h.v_cnt; i += NT) sx[i] = io.xp[h.v_start + i];
+        for (int i = threadIdx.x; i < h.gv_cnt; i += NT) sx[h.v_cnt + i] = io.xp[__ldg(&m.ghost_v[h.gv_off + i])];
+        cp_async_wait_all();
+        __syncthreads();
+        for (int lv = threadIdx.x; lv < h.v_cnt; lv += NT) {
+            const int sl = lv >> 5, lane = lv & 31;
+            const uint32_t io0 = s_io[sl], wo0 = s_wo[sl];
+            const int W = (int)((s_wo[sl + 1] - wo0) >> 5);
+            double val = 0.0, dsum = 0.0;
+            for (int c = 0; 8 * c < W; ++c) {
+                const uint4 cd = sid4[(io0 >> 3) + c * 32 + lane];
+                const uint32_t w4[4] = {cd.x, cd.y, cd.z, cd.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const double wa = (8 * c + 2 * j < W) ? sw[wo0 + (8 * c + 2 * j) * 32 + lane] : 0.0;
+                    const double wb = (8 * c + 2 * j + 1 < W) ? sw[wo0 + (8 * c + 2 * j + 1) * 32 + lane] : 0.0;
+                    val += wa * sx[w4[j] & 0xFFFFu];
+                    val += wb * sx[w4[j] >> 16];
+                    dsum += wa + wb;
+                }
+            }
+            const double xc = sx[lv], bv = sb[lv];
+            const double pv = 1.0 / dsum;
+            val += dsum * xc;
+            const double r_ = bv - val;
+            double xn = xc + io.c2 * pv * r_;
+            if (io.use_prev) xn += io.c1 * (xc - sxp[lv]);
+            io.xnew[h.v_start + lv] = xn;
+            acc0 += pv * r_ * r_;
+            acc1 += pv * bv * bv;
+        }
+        __syncthreads();
+    }
+}
+
+// diagnostics: reads exactly the streams of one ELL M_p iteration patch by patch (ids, weights, b, x_prev, x owned) and
+// writes one value per owned vertex - no shared memory, no barriers, no dependent loads: the bandwidth the memory system
+// delivers for this layout and access order, to compare the solve kernels with (phw_stream_probe)
+template <int NT>
+__global__ void __launch_bounds__(NT) stream_probe_k(DevMesh m, const double* __restrict__ b, const double* __restrict__ xprev,
+                                                       const double* __restrict__ x, double* __restrict__ out) {
+    for (int P = blockIdx.x; P < m.npatch; P += gridDim.x) {
+        const PatchHdr h = m.hdr[P];
+        double acc = 0.0;
+        const uint4* gi = reinterpret_cast<const uint4*>(m.ell_ids + (uint32_t)h.ell_i0);
+        for (uint32_t i = threadIdx.x; i < ((uint32_t)h.ell_in >> 3); i += NT) { const uint4 v = __ldg(&gi[i]); acc += (double)(v.x ^ v.y ^ v.z ^ v.w); }
+        const double2* gw = reinterpret_cast<const double2*>(m.ell_w + (uint32_t)h.ell_w0);
+        for (uint32_t i = threadIdx.x; i < ((uint32_t)h.ell_wn >> 1); i += NT) { const double2 v = __ldg(&gw[i]); acc += v.x + v.y; }
+        for (int i = threadIdx.x; i < h.v_cnt; i += NT) {
+            const int g = h.v_start + i;
+            out[g] = acc + __ldg(&b[g]) + __ldg(&xprev[g]) + __ldg(&x[g]);
+        }
     }
 }
 
@@ -747,7 +853,7 @@ __global__ void __launch_bounds__(NT_ROWS, 2) edge_rows_k(const RowArgs a) {
 // barrier per iteration; the residual norm is reduced deterministically (per-block partials, summed in
 // the same order by every block) so all blocks take the same stop decision without host involvement.
 // ------------------------------------------------------------------------------------------------
-template <int WHICH, bool CAS, int NT, int MINB, bool ELL = false>
+template <int WHICH, bool CAS, int NT, int MINB, int ELL = 0>
 __global__ void __launch_bounds__(NT, MINB) solve_coop_k(const RowArgs av, const RowArgs ae, const PeerComm pc) {
     extern __shared__ double smem[];
     __shared__ double red[64];
@@ -771,7 +877,8 @@ __global__ void __launch_bounds__(NT, MINB) solve_coop_k(const RowArgs av, const
         double r0 = 0.0, b0 = 0.0;
         if (WHICH == 0 || WHICH == 2) {
             double a0_ = 0.0, a1_ = 0.0;
-            if (ELL && WHICH == 0) vertex_ell_pass<NT>(av, iov, smem, a0_, a1_);
+            if (ELL == 2 && WHICH == 0) vertex_ell_pass_staged<NT>(av, iov, smem, a0_, a1_);
+            else if (ELL == 1 && WHICH == 0) vertex_ell_pass<NT>(av, iov, smem, a0_, a1_);
             else vertex_pass<EPI_CHEB, MODE_OP, true, WHICH == 2, CAS, NT>(av, iov, smem, a0_, a1_);
             r0 += av.weight * a0_; b0 += av.weight * a1_;
         }

@@ -281,6 +281,7 @@ std::string Layout::build(int64_t nv_, const double* vxy, int64_t nc_, const int
     std::vector<int32_t> gv_tmp, ge_tmp, cl;
     std::vector<uint32_t> vcnt;
     max_lv = max_le = max_cells = 0;
+    max_smem_ell = 0;
     size_t hpos = 0;
     for (int32_t p = 0; p < npatch; ++p) {
         PatchHdr& H = hdr[p];
@@ -418,6 +419,11 @@ std::string Layout::build(int64_t nv_, const double* vxy, int64_t nc_, const int
                 ell_ioff.push_back((uint32_t)(ibase + ioff));
                 ell_woff.push_back((uint32_t)(wbase + woff));
             }
+            H.ell_i0 = (int32_t)(uint32_t)ibase; H.ell_in = (int32_t)ioff;
+            H.ell_w0 = (int32_t)(uint32_t)wbase; H.ell_wn = (int32_t)woff;
+            // shared memory of the staged pass (doubles): slice offsets | x [nlv] | b, x_prev [v_cnt] | weights | ids
+            auto ev2 = [](int64_t x) { return (x + 1) & ~(int64_t)1; };
+            max_smem_ell = std::max(max_smem_ell, (int64_t)((nslice + 3) & ~1) + ev2(nlv) + 2 * ev2(H.v_cnt) + (int64_t)woff + (int64_t)(ioff + 3) / 4 + 2);
         }
         // reset scratch
         for (int32_t g : gv_tmp) lv_of[v_new2old[g]] = -1;

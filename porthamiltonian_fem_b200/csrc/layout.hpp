@@ -33,8 +33,11 @@ struct PatchHdr {
     int32_t vs_off;     // first 32-vertex slice of this patch in vslice_off
     int32_t group;      // case index of a batched (replicated-mesh) run, 0 otherwise
     int32_t adj_off;    // first uint16 code of this patch in vadj (uint32 bits) and number of codes: the patch's adjacency
-    int32_t adj_cnt;    // is one contiguous range, so the next patch can be prefetched without reading vslice_off
+    int32_t adj_cnt;    // is one contiguous range
+    int32_t ell_i0, ell_in;   // ELL mass rows of the patch: first id code / number of codes in ell_ids (uint32 bits),
+    int32_t ell_w0, ell_wn;   // first weight / number of weights in ell_w: two contiguous, 16-byte aligned blocks
 };
+static_assert(sizeof(PatchHdr) == 80, "PatchHdr is loaded as 20 ints");
 
 // ---- two-sweep patches (temporal blocking of the Chebyshev mass solves): for one dof kind (vertices or edges) a patch
 // holds its owned dofs D0, the cells C1 touching D0, the other dofs G1 of those cells, the further cells C2 \ C1 touching
@@ -106,6 +109,7 @@ struct Layout {
     std::vector<uint32_t> ell_pair;
     std::vector<int32_t> v_degree;     // [nv] by old id
     int32_t max_lv = 0, max_le = 0, max_cells = 0;
+    int64_t max_smem_ell = 0;          // doubles of shared memory vertex_ell_pass needs with all streams of a patch staged
 
     int64_t nv_owned = 0, ne_owned = 0;   // external (other-rank) dofs are numbered after the owned ones
     // v_ext / e_ext (optional, by user id): 1 = dof owned by another rank (never a row of this rank)

@@ -545,7 +545,8 @@ struct phw_solver_s {
     bool in_step = false;
     bool coop = false;
     bool ell_p = false;         // M_p solve on the assembled ELL rows (vertex_ell_pass)
-    size_t smem_ell = 0;
+    bool ell_staged = false;    // ... with all streams of a patch staged in shared memory by cp.async
+    size_t smem_ell = 0, smem_ells = 0;
     bool two_sweep = false;     // mass solves run two Chebyshev iterations per pass (kernels2.cuh)
     Ring2Dev r2[2]{};
     size_t smem2[2] = {0, 0};
@@ -672,12 +673,12 @@ int op_edge_dot(phw_solver_s* s, const double* xq, double cM, double cB, int slo
 }
 
 // one cooperative launch = one complete Chebyshev solve
-template <int WHICH, bool CAS, bool ELL = false>
+template <int WHICH, bool CAS, int ELL = 0>
 int launch_coop(phw_solver_s* s, const RowArgs& av, const RowArgs& ae) {
-    constexpr int NT = (WHICH == 0) ? (ELL ? PHW_NT_ELL : NT_COOP_P) : (WHICH == 1 ? NT_COOP_Q : NT_ROWS);
-    constexpr int MINB = (WHICH == 0) ? (ELL ? PHW_MINB_ELL : PHW_MINB_P) : PHW_MINB_Q;
+    constexpr int NT = (WHICH == 0) ? (ELL == 2 ? PHW_NT_ELLS : (ELL == 1 ? PHW_NT_ELL : NT_COOP_P)) : (WHICH == 1 ? NT_COOP_Q : NT_ROWS);
+    constexpr int MINB = (WHICH == 0) ? (ELL == 2 ? PHW_MINB_ELLS : (ELL == 1 ? PHW_MINB_ELL : PHW_MINB_P)) : PHW_MINB_Q;
     auto kern = solve_coop_k<WHICH, CAS, NT, MINB, ELL>;
-    const size_t sm = (WHICH == 0) ? (ELL ? s->smem_ell : s->smem_v1) : (WHICH == 1 ? s->smem_e : s->smem_vd);
+    const size_t sm = (WHICH == 0) ? (ELL == 2 ? s->smem_ells : (ELL == 1 ? s->smem_ell : s->smem_v1)) : (WHICH == 1 ? s->smem_e : s->smem_vd);
     static bool configured = false;
     if (!configured) { CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); configured = true; }
     int occ = 0;
@@ -791,7 +792,8 @@ int solve_mass(phw_solver_s* s, int which, int n_launch) {
     if (s->coop) {
         a.b = which == PHW_P ? s->bp : s->bq;
         a.pinv = which == PHW_P ? s->pinv_p : s->pinv_q;
-        if (which == PHW_P && s->ell_p && a.mdiag == nullptr) return launch_coop<0, false, true>(s, a, a);   // pinv_p = 1 / diag(M_p) exactly
+        if (which == PHW_P && s->ell_p && a.mdiag == nullptr)      // pinv_p = 1 / diag(M_p) exactly
+            return (s->ell_staged && s->smem_ells <= 110 * 1024) ? launch_coop<0, false, 2>(s, a, a) : launch_coop<0, false, 1>(s, a, a);
         return which == PHW_P ? launch_coop<0, false>(s, a, a) : launch_coop<1, false>(s, a, a);
     }
     rc = solve_begin(s, which);
@@ -1301,6 +1303,31 @@ int phw_solver_destroy(phw_solver_t s) {
     return PHW_OK;
 }
 
+int phw_stream_probe(phw_solver_t s, int32_t threads, int32_t ctas_per_sm, int32_t reps, double* ms_per_pass, double* bytes_per_pass) {
+    if (!s || !ms_per_pass || !bytes_per_pass || reps < 1) return fail(PHW_EINVAL, "phw_stream_probe: bad arguments");
+    if (s->ho) return fail(PHW_ESTATE, "not available for higher-order solvers");
+    CU(cudaSetDevice(s->device));
+    const int grid = std::max(1, std::min(s->npatch, ctas_per_sm * s->sm_count));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    for (int r = 0; r < reps + 1; ++r) {
+        if (r == 1) CU(cudaEventRecord(e0, s->stream));
+        if (threads == 128) stream_probe_k<128><<<grid, 128, 0, s->stream>>>(s->dm, s->bp, s->tp.b[1], s->tp.b[0], s->tp.b[2]);
+        else if (threads == 512) stream_probe_k<512><<<grid, 512, 0, s->stream>>>(s->dm, s->bp, s->tp.b[1], s->tp.b[0], s->tp.b[2]);
+        else if (threads == 1024) stream_probe_k<1024><<<grid, 1024, 0, s->stream>>>(s->dm, s->bp, s->tp.b[1], s->tp.b[0], s->tp.b[2]);
+        else stream_probe_k<256><<<grid, 256, 0, s->stream>>>(s->dm, s->bp, s->tp.b[1], s->tp.b[0], s->tp.b[2]);
+    }
+    CU(cudaEventRecord(e1, s->stream));
+    CU(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    const Layout& L = s->mesh->L;
+    *ms_per_pass = ms / reps;
+    *bytes_per_pass = 2.0 * (double)L.ell_ids.size() + 8.0 * (double)L.ell_pair.size() + 4.0 * 8.0 * (double)L.nv_owned;
+    return PHW_OK;
+}
+
 int phw_residual_history(phw_solver_t s, int32_t which, int32_t n, double* rel, int32_t* n_it) {
     if (!s || which < 0 || which > 2 || n < 0 || n > 48 || !rel) return fail(PHW_EINVAL, "phw_residual_history: bad arguments");
     CU(cudaStreamSynchronize(s->stream));
@@ -1493,6 +1520,8 @@ static int setup_solver(phw_solver_s* s) {
     s->smem_ed = s->smem_vd;
     s->smem_ell = ((size_t)(L.max_lv + 31) / 32 + 4 + ev(L.max_lv)) * 8;
     s->ell_p = !(P.flags & 32);
+    s->smem_ells = (size_t)L.max_smem_ell * 8;
+    s->ell_staged = !(P.flags & 64);
     if (s->smem_vd > 200 * 1024) return fail(PHW_EINVAL, "patch does not fit in shared memory; reduce patch_cells");
     s->grid_rows = std::max(1, std::min(s->npatch, 2 * s->sm_count));
     RC(setup_scalars(s));

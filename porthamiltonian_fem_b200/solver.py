@@ -206,6 +206,12 @@ class Solver:
     def set_time(self, t):
         _lib.check(self.lib.phw_set_time(self.handle, float(t)))
 
+    def stream_probe(self, threads=256, ctas_per_sm=8, reps=10):
+        """(ms, bytes) of a pass that only streams the data of one ELL M_p iteration (diagnostics)"""
+        ms, nb = ctypes.c_double(0), ctypes.c_double(0)
+        _lib.check(self.lib.phw_stream_probe(self.handle, int(threads), int(ctas_per_sm), int(reps), ctypes.byref(ms), ctypes.byref(nb)))
+        return ms.value, nb.value
+
     def residual_history(self, which, n=48):
         """relative residuals of the iterations of the most recent solve of kind `which` (diagnostics)"""
         out = np.zeros(n)
