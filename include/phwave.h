@@ -60,7 +60,8 @@ typedef struct phw_params {
                                 bit4: two-sweep mass solves (two Chebyshev iterations per pass over the data, csrc/kernels2.cuh;
                                 single GPU, weak form, explicit schemes; default off - see DESIGN.md section 10);
                                 bit5: cell-based instead of assembled (ELL) rows in the M_p solve;
-                                bit6: ELL rows read directly from global memory instead of staged by cp.async */
+                                bit6: ELL rows of the M_p solve staged in shared memory by cp.async (whole patch in flight;
+                                A/B: slower than the direct loads) */
     int32_t extrap_order_q;  /* extrapolation order of the q (and block) solves; 0: same as extrap_order.  Orders up to 5 */
 } phw_params;
 

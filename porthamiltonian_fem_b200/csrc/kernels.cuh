@@ -946,6 +946,255 @@ __global__ void __launch_bounds__(NT, MINB) solve_coop_k(const RowArgs av, const
 
 
 // ------------------------------------------------------------------------------------------------
+// lean single-GPU variant of the ELL M_p solve: the same iteration as solve_coop_k<0,..,ELL>, with a compact argument block
+// and a register-light row loop, so that more threads fit on an SM (the streams need the parallelism: phw_stream_probe)
+// ------------------------------------------------------------------------------------------------
+struct EllSolveArgs {
+    int npatch;
+    const PatchHdr* hdr;
+    const uint32_t* ell_ioff; const uint32_t* ell_woff; const uint16_t* ell_ids; const double* ell_w;
+    const int* ghost_v;
+    const double* b;
+    double* buf[3];
+    double cheb_d, cheb_c, tol2;
+    int max_iter, which;
+    double* partials; Ctl* ctl;
+};
+
+template <int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) solve_ell_coop_k(const __grid_constant__ EllSolveArgs a) {
+    extern __shared__ double smem[];
+    __shared__ double red[64];
+    __shared__ double bc[2];
+    __shared__ PatchHdr s_hdr[2];
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    SolveCtl& sc = a.ctl->sc[a.which];
+    int k = 0, cur = sc.cur;
+    double rho = 0.0, rr = 0.0, bb = 0.0;
+    bool conv = false;
+    const uint4* ids4 = reinterpret_cast<const uint4*>(a.ell_ids);
+    while (true) {
+        double c1, c2, rho_k;
+        cheb_coeffs(k, rho, a.cheb_d, a.cheb_c, c1, c2, rho_k);
+        const int nxt = (cur + 1) % 3, prv = (cur + 2) % 3;
+        const double* __restrict__ xk = cur == 0 ? a.buf[0] : (cur == 1 ? a.buf[1] : a.buf[2]);
+        const double* __restrict__ xprev = prv == 0 ? a.buf[0] : (prv == 1 ? a.buf[1] : a.buf[2]);
+        double* __restrict__ xnew = nxt == 0 ? a.buf[0] : (nxt == 1 ? a.buf[1] : a.buf[2]);
+        double r0 = 0.0, b0 = 0.0;
+        if (blockIdx.x < a.npatch) load_hdr_smem(&s_hdr[0], &a.hdr[blockIdx.x]);
+        __syncthreads();
+        int it = 0;
+        for (int P = blockIdx.x; P < a.npatch; P += gridDim.x, ++it) {
+            const PatchHdr& h = s_hdr[it & 1];
+            if (P + (int)gridDim.x < a.npatch) load_hdr_smem(&s_hdr[(it + 1) & 1], &a.hdr[P + gridDim.x]);
+            const int nsl = (h.v_cnt + 31) >> 5;
+            uint32_t* s_io = reinterpret_cast<uint32_t*>(smem);
+            uint32_t* s_wo = s_io + (nsl + 1);
+            double* sx = smem + (nsl + 2);
+            for (int i = threadIdx.x; i <= nsl; i += NT) { s_io[i] = __ldg(&a.ell_ioff[h.vs_off + i]); s_wo[i] = __ldg(&a.ell_woff[h.vs_off + i]); }
+            for (int i = threadIdx.x; i < h.v_cnt; i += NT) sx[i] = xk[h.v_start + i];
+            for (int i = threadIdx.x; i < h.gv_cnt; i += NT) sx[h.v_cnt + i] = xk[__ldg(&a.ghost_v[h.gv_off + i])];
+            __syncthreads();
+            for (int lv = threadIdx.x; lv < h.v_cnt; lv += NT) {
+                const int sl = lv >> 5, lane = lv & 31;
+                const uint32_t wo0 = s_wo[sl];
+                const int W = (int)((s_wo[sl + 1] - wo0) >> 5);
+                const uint4* idp = ids4 + (s_io[sl] >> 3) + lane;
+                const double* __restrict__ wrow = a.ell_w + wo0 + lane;
+                const int gid = h.v_start + lv;
+                const double bv = __ldg(&a.b[gid]);
+                const double xpv = (k > 0) ? xprev[gid] : 0.0;
+                double val = 0.0, dsum = 0.0;
+                for (int c = 0; 8 * c < W; ++c) {
+                    const uint4 cd = __ldg(idp + c * 32);
+                    const int kk = 8 * c;
+                    {
+                        const double w0 = (kk + 0 < W) ? __ldg(&wrow[(kk + 0) * 32]) : 0.0, w1 = (kk + 1 < W) ? __ldg(&wrow[(kk + 1) * 32]) : 0.0;
+                        const double w2 = (kk + 2 < W) ? __ldg(&wrow[(kk + 2) * 32]) : 0.0, w3 = (kk + 3 < W) ? __ldg(&wrow[(kk + 3) * 32]) : 0.0;
+                        val += w0 * sx[cd.x & 0xFFFFu]; val += w1 * sx[cd.x >> 16]; val += w2 * sx[cd.y & 0xFFFFu]; val += w3 * sx[cd.y >> 16];
+                        dsum += (w0 + w1) + (w2 + w3);
+                    }
+                    if (kk + 4 < W) {
+                        const double w0 = __ldg(&wrow[(kk + 4) * 32]), w1 = (kk + 5 < W) ? __ldg(&wrow[(kk + 5) * 32]) : 0.0;
+                        const double w2 = (kk + 6 < W) ? __ldg(&wrow[(kk + 6) * 32]) : 0.0, w3 = (kk + 7 < W) ? __ldg(&wrow[(kk + 7) * 32]) : 0.0;
+                        val += w0 * sx[cd.z & 0xFFFFu]; val += w1 * sx[cd.z >> 16]; val += w2 * sx[cd.w & 0xFFFFu]; val += w3 * sx[cd.w >> 16];
+                        dsum += (w0 + w1) + (w2 + w3);
+                    }
+                }
+                const double xc = sx[lv];
+                const double pv = 1.0 / dsum;
+                val += dsum * xc;
+                const double r_ = bv - val;
+                double xn = xc + c2 * pv * r_;
+                if (k > 0) xn += c1 * (xc - xpv);
+                xnew[gid] = xn;
+                r0 += pv * r_ * r_;
+                b0 += pv * bv * bv;
+            }
+            __syncthreads();
+        }
+        block_sum2(r0, b0, red);
+        double* part = a.partials + (size_t)(k & 1) * 2 * gridDim.x;
+        if (threadIdx.x == 0) { part[2 * blockIdx.x] = r0; part[2 * blockIdx.x + 1] = b0; }
+        grid.sync();
+        if (threadIdx.x < 32) {
+            double s0 = 0.0, s1 = 0.0;
+            for (int i = threadIdx.x; i < (int)gridDim.x; i += 32) { s0 += __ldcg(&part[2 * i]); s1 += __ldcg(&part[2 * i + 1]); }
+            s0 = warp_sum(s0); s1 = warp_sum(s1);
+            if (threadIdx.x == 0) { bc[0] = s0; bc[1] = s1; }
+        }
+        __syncthreads();
+        rr = bc[0]; bb = bc[1];
+        __syncthreads();
+        conv = rr <= a.tol2 * bb;
+        if (blockIdx.x == 0 && threadIdx.x == 0 && k < 48) a.ctl->reshist[a.which][k] = (bb > 0.0) ? rr / bb : 0.0;
+        k += 1;
+        if (conv) break;
+        rho = rho_k; cur = nxt;
+        if (k >= a.max_iter) break;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        sc.cur = cur; sc.k = k; sc.done = 1; sc.rr = rr; sc.bb = bb; sc.rho = rho;
+        sc.iters += k; sc.solves += 1;
+        if (!conv) a.ctl->nonconv += 1;
+        double rel = (bb > 0.0) ? sqrt(rr / bb) : 0.0;
+        if (rel > sc.maxres) sc.maxres = rel;
+    }
+}
+
+// lean single-GPU variant of the cell-based M_q solve (same iteration as solve_coop_k<1>): compact arguments, restrict-
+// qualified streams, nothing of the multi-GPU exchange in the loop
+struct MqSolveArgs {
+    int npatch;
+    const PatchHdr* hdr;
+    const uint2* rece; const double* g0; const double* g1; const double* g2;
+    const int* ghost_e; const uint32_t* eadj;
+    const double* b; const double* pinv;
+    double* buf[3];
+    double cheb_d, cheb_c, tol2;
+    int max_iter, which;
+    double* partials; Ctl* ctl;
+};
+
+template <int NT, int MINB, int UC, int UR>
+__global__ void __launch_bounds__(NT, MINB) solve_mq_coop_k(const __grid_constant__ MqSolveArgs a) {
+    extern __shared__ double smem[];
+    __shared__ double red[64];
+    __shared__ double bc[2];
+    __shared__ PatchHdr s_hdr[2];
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    SolveCtl& sc = a.ctl->sc[a.which];
+    int k = 0, cur = sc.cur;
+    double rho = 0.0, rr = 0.0, bb = 0.0;
+    bool conv = false;
+    while (true) {
+        double c1, c2, rho_k;
+        cheb_coeffs(k, rho, a.cheb_d, a.cheb_c, c1, c2, rho_k);
+        const int nxt = (cur + 1) % 3, prv = (cur + 2) % 3;
+        const double* __restrict__ xk = cur == 0 ? a.buf[0] : (cur == 1 ? a.buf[1] : a.buf[2]);
+        const double* __restrict__ xprev = prv == 0 ? a.buf[0] : (prv == 1 ? a.buf[1] : a.buf[2]);
+        double* __restrict__ xnew = nxt == 0 ? a.buf[0] : (nxt == 1 ? a.buf[1] : a.buf[2]);
+        double r0 = 0.0, b0 = 0.0;
+        if (blockIdx.x < a.npatch) load_hdr_smem(&s_hdr[0], &a.hdr[blockIdx.x]);
+        __syncthreads();
+        int it = 0;
+        for (int P = blockIdx.x; P < a.npatch; P += gridDim.x, ++it) {
+            const PatchHdr& h = s_hdr[it & 1];
+            if (P + (int)gridDim.x < a.npatch) load_hdr_smem(&s_hdr[(it + 1) & 1], &a.hdr[P + gridDim.x]);
+            const int nle = h.e_cnt + h.ge_cnt;
+            double* __restrict__ sq = smem;
+            double* __restrict__ sc3 = sq + ((nle + 1) & ~1);
+            for (int i = threadIdx.x; i < h.e_cnt; i += NT) sq[i] = xk[h.e_start + i];
+            for (int i = threadIdx.x; i < h.ge_cnt; i += NT) sq[h.e_cnt + i] = xk[__ldg(&a.ghost_e[h.ge_off + i])];
+            __syncthreads();
+            for (int base = threadIdx.x; base < h.n_ecells; base += UC * NT) {
+                uint2 reb[UC]; double gb[UC][3];
+#pragma unroll
+                for (int u = 0; u < UC; ++u) {
+                    const int lc = base + u * NT;
+                    if (lc < h.n_ecells) {
+                        reb[u] = __ldg(&a.rece[h.cell_off + lc]);
+                        gb[u][0] = __ldg(&a.g0[h.cell_off + lc]); gb[u][1] = __ldg(&a.g1[h.cell_off + lc]); gb[u][2] = __ldg(&a.g2[h.cell_off + lc]);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < UC; ++u) {
+                    const int lc = base + u * NT;
+                    if (lc < h.n_ecells) {
+                        const uint32_t e0 = reb[u].x & 0xFFFFu, e1 = reb[u].x >> 16, e2 = reb[u].y & 0xFFFFu;
+                        const double g0 = gb[u][0], g1 = gb[u][1], g2 = gb[u][2], S = g0 + g1 + g2;
+                        const double s0 = (e0 & 0x8000u) ? -1.0 : 1.0, s1 = (e1 & 0x8000u) ? -1.0 : 1.0, s2 = (e2 & 0x8000u) ? -1.0 : 1.0;
+                        const double t0 = s0 * sq[e0 & 0x3FFFu], t1 = s1 * sq[e1 & 0x3FFFu], t2 = s2 * sq[e2 & 0x3FFFu];
+                        const double ST = S * (t0 + t1 + t2);
+                        sc3[3 * lc] = s0 * (ST + 2.0 * S * t0 - 4.0 * (g0 * t0 + g2 * t1 + g1 * t2));
+                        sc3[3 * lc + 1] = s1 * (ST + 2.0 * S * t1 - 4.0 * (g2 * t0 + g1 * t1 + g0 * t2));
+                        sc3[3 * lc + 2] = s2 * (ST + 2.0 * S * t2 - 4.0 * (g1 * t0 + g0 * t1 + g2 * t2));
+                    }
+                }
+            }
+            __syncthreads();
+            for (int base = threadIdx.x; base < h.e_cnt; base += UR * NT) {
+                uint32_t adjb[UR]; double bvb[UR], pvb[UR], xpb[UR];
+#pragma unroll
+                for (int u = 0; u < UR; ++u) {
+                    const int le = base + u * NT;
+                    if (le < h.e_cnt) {
+                        const int gid = h.e_start + le;
+                        adjb[u] = __ldg(&a.eadj[gid]); bvb[u] = __ldg(&a.b[gid]); pvb[u] = __ldg(&a.pinv[gid]);
+                        xpb[u] = (k > 0) ? xprev[gid] : 0.0;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < UR; ++u) {
+                    const int le = base + u * NT;
+                    if (le < h.e_cnt) {
+                        const uint32_t ca = adjb[u] & 0xFFFFu, cb = adjb[u] >> 16;
+                        double val = sc3[3 * (ca >> 2) + (ca & 3u)];
+                        if (cb != 0xFFFFu) val += sc3[3 * (cb >> 2) + (cb & 3u)];
+                        const double xc = sq[le];
+                        const double r_ = bvb[u] - val;
+                        double xn = xc + c2 * pvb[u] * r_;
+                        if (k > 0) xn += c1 * (xc - xpb[u]);
+                        xnew[h.e_start + le] = xn;
+                        r0 += pvb[u] * r_ * r_;
+                        b0 += pvb[u] * bvb[u] * bvb[u];
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        block_sum2(r0, b0, red);
+        double* part = a.partials + (size_t)(k & 1) * 2 * gridDim.x;
+        if (threadIdx.x == 0) { part[2 * blockIdx.x] = r0; part[2 * blockIdx.x + 1] = b0; }
+        grid.sync();
+        if (threadIdx.x < 32) {
+            double s0 = 0.0, s1 = 0.0;
+            for (int i = threadIdx.x; i < (int)gridDim.x; i += 32) { s0 += __ldcg(&part[2 * i]); s1 += __ldcg(&part[2 * i + 1]); }
+            s0 = warp_sum(s0); s1 = warp_sum(s1);
+            if (threadIdx.x == 0) { bc[0] = s0; bc[1] = s1; }
+        }
+        __syncthreads();
+        rr = bc[0]; bb = bc[1];
+        __syncthreads();
+        conv = rr <= a.tol2 * bb;
+        if (blockIdx.x == 0 && threadIdx.x == 0 && k < 48) a.ctl->reshist[a.which][k] = (bb > 0.0) ? rr / bb : 0.0;
+        k += 1;
+        if (conv) break;
+        rho = rho_k; cur = nxt;
+        if (k >= a.max_iter) break;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        sc.cur = cur; sc.k = k; sc.done = 1; sc.rr = rr; sc.bb = bb; sc.rho = rho;
+        sc.iters += k; sc.solves += 1;
+        if (!conv) a.ctl->nonconv += 1;
+        double rel = (bb > 0.0) ? sqrt(rr / bb) : 0.0;
+        if (rel > sc.maxres) sc.maxres = rel;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // higher-order pairs (P_k x RT_k, k <= 3): the operators are assembled once on the host (fem_ho.py) and applied as
 // CSR matrices; same epilogues and the same persistent cooperative Chebyshev solve as the matrix-free path.
 // ------------------------------------------------------------------------------------------------

@@ -757,6 +757,74 @@ int launch_coop2(phw_solver_s* s) {
     }
 }
 
+// lean single-GPU ELL M_p solve
+template <int NT, int MINB>
+int launch_ell_lean(phw_solver_s* s) {
+    auto kern = solve_ell_coop_k<NT, MINB>;
+    static bool configured = false;
+    if (!configured) { CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); configured = true; }
+    int occ = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, s->smem_ell));
+    if (occ < 1) return fail(PHW_ECUDA, "ELL solve kernel does not fit on an SM");
+    const int grid = std::max(1, std::min(s->npatch, occ * s->sm_count));
+    EllSolveArgs a{};
+    a.npatch = s->npatch; a.hdr = s->dm.hdr; a.ell_ioff = s->dm.ell_ioff; a.ell_woff = s->dm.ell_woff; a.ell_ids = s->dm.ell_ids; a.ell_w = s->dm.ell_w;
+    a.ghost_v = s->dm.ghost_v; a.b = s->bp;
+    for (int i = 0; i < 3; ++i) a.buf[i] = s->tp.b[i];
+    a.cheb_d = s->cheb_d[0]; a.cheb_c = s->cheb_c[0];
+    a.tol2 = s->prm.tol * s->prm.tol;
+    if (s->G > 1) { const double t = std::max(s->prm.tol / std::sqrt((double)s->G), 1e-14); a.tol2 = std::min(a.tol2, t * t); }
+    a.max_iter = s->prm.max_iter; a.which = 0; a.partials = s->partials; a.ctl = s->ctl;
+    void* args[] = {(void*)&a};
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    const bool prof = (s->prm.flags & 4) && s->prof_ev.size() < 2 * 8192;
+    if (prof) {
+        CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+        CU(cudaEventRecord(e0, s->stream));
+    }
+    CU(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(NT), args, s->smem_ell, s->stream));
+    if (prof) {
+        CU(cudaEventRecord(e1, s->stream));
+        s->prof_ev.push_back(e0); s->prof_ev.push_back(e1); s->prof_which.push_back(0);
+    }
+    s->launches++;
+    return 0;
+}
+
+// lean single-GPU cell-based M_q solve
+template <int NT, int MINB, int UC, int UR>
+int launch_mq_lean(phw_solver_s* s) {
+    auto kern = solve_mq_coop_k<NT, MINB, UC, UR>;
+    static bool configured = false;
+    if (!configured) { CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); configured = true; }
+    int occ = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, s->smem_e));
+    if (occ < 1) return fail(PHW_ECUDA, "M_q solve kernel does not fit on an SM");
+    const int grid = std::max(1, std::min(s->npatch, occ * s->sm_count));
+    MqSolveArgs a{};
+    a.npatch = s->npatch; a.hdr = s->dm.hdr; a.rece = s->dm.rece; a.g0 = s->dm.g0; a.g1 = s->dm.g1; a.g2 = s->dm.g2;
+    a.ghost_e = s->dm.ghost_e; a.eadj = s->dm.eadj; a.b = s->bq; a.pinv = s->pinv_q;
+    for (int i = 0; i < 3; ++i) a.buf[i] = s->tq.b[i];
+    a.cheb_d = s->cheb_d[1]; a.cheb_c = s->cheb_c[1];
+    a.tol2 = s->prm.tol * s->prm.tol;
+    if (s->G > 1) { const double t = std::max(s->prm.tol / std::sqrt((double)s->G), 1e-14); a.tol2 = std::min(a.tol2, t * t); }
+    a.max_iter = s->prm.max_iter; a.which = 1; a.partials = s->partials; a.ctl = s->ctl;
+    void* args[] = {(void*)&a};
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    const bool prof = (s->prm.flags & 4) && s->prof_ev.size() < 2 * 8192;
+    if (prof) {
+        CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+        CU(cudaEventRecord(e0, s->stream));
+    }
+    CU(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(NT), args, s->smem_e, s->stream));
+    if (prof) {
+        CU(cudaEventRecord(e1, s->stream));
+        s->prof_ev.push_back(e0); s->prof_ev.push_back(e1); s->prof_which.push_back(1);
+    }
+    s->launches++;
+    return 0;
+}
+
 int solve_begin(phw_solver_s* s, int which) {
     solve_begin_k<<<1, 1, 0, s->stream>>>(s->ctl, which);
     s->launches++;
@@ -792,6 +860,30 @@ int solve_mass(phw_solver_s* s, int which, int n_launch) {
     if (s->coop) {
         a.b = which == PHW_P ? s->bp : s->bq;
         a.pinv = which == PHW_P ? s->pinv_p : s->pinv_q;
+        if (which == PHW_P && s->ell_p && a.mdiag == nullptr && s->pc.world <= 1 && !s->ell_staged) {
+            static const int cfg = [] { const char* e = getenv("PHW_ELL_CFG"); return e ? atoi(e) : 0; }();
+            switch (cfg) {
+                case 1: return launch_ell_lean<256, 6>(s);
+                case 2: return launch_ell_lean<256, 8>(s);
+                case 3: return launch_ell_lean<512, 3>(s);
+                case 4: return launch_ell_lean<128, 12>(s);
+                case 5: return launch_ell_lean<256, 5>(s);
+                case 9: break;
+                default: return launch_ell_lean<256, 4>(s);
+            }
+        }
+        if (which == PHW_Q && s->pc.world <= 1 && !(s->prm.flags & 128)) {
+            static const int cfg = [] { const char* e = getenv("PHW_MQ_CFG"); return e ? atoi(e) : 0; }();
+            switch (cfg) {
+                case 1: return launch_mq_lean<384, 2, 3, 3>(s);
+                case 2: return launch_mq_lean<512, 2, 2, 2>(s);
+                case 3: return launch_mq_lean<384, 2, 2, 4>(s);
+                case 4: return launch_mq_lean<320, 2, 3, 3>(s);
+                case 5: return launch_mq_lean<384, 2, 1, 1>(s);
+                case 9: break;
+                default: return launch_mq_lean<384, 2, 2, 2>(s);
+            }
+        }
         if (which == PHW_P && s->ell_p && a.mdiag == nullptr)      // pinv_p = 1 / diag(M_p) exactly
             return (s->ell_staged && s->smem_ells <= 110 * 1024) ? launch_coop<0, false, 2>(s, a, a) : launch_coop<0, false, 1>(s, a, a);
         return which == PHW_P ? launch_coop<0, false>(s, a, a) : launch_coop<1, false>(s, a, a);
@@ -1521,7 +1613,7 @@ static int setup_solver(phw_solver_s* s) {
     s->smem_ell = ((size_t)(L.max_lv + 31) / 32 + 4 + ev(L.max_lv)) * 8;
     s->ell_p = !(P.flags & 32);
     s->smem_ells = (size_t)L.max_smem_ell * 8;
-    s->ell_staged = !(P.flags & 64);
+    s->ell_staged = (P.flags & 64) != 0;
     if (s->smem_vd > 200 * 1024) return fail(PHW_EINVAL, "patch does not fit in shared memory; reduce patch_cells");
     s->grid_rows = std::max(1, std::min(s->npatch, 2 * s->sm_count));
     RC(setup_scalars(s));

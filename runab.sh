@@ -1,5 +1,6 @@
-run() { echo "== $*"; env "$@" bash runb.sh --two-sweep; }
-run PHW_P2_CFG=0
-run PHW_P2_CFG=1
-run PHW_P2_CFG=2
-run PHW_P2_CFG=4
+run() { echo "== $*"; env "$@" bash runb.sh; }
+run PHW_MQ_CFG=0
+run PHW_MQ_CFG=5
+run PHW_MQ_CFG=1
+run PHW_MQ_CFG=2
+run PHW_MQ_CFG=4
