@@ -143,6 +143,11 @@ def run_sweep_bench(args):
         dist.destroy_process_group()
 
 
+# DRAM bytes per cell and Chebyshev iteration of the two solve kernels, from the committed `ncu --set full` captures
+# (profiles/r1b_ncu_full_lean_solves.txt: dram__bytes_read.sum + dram__bytes_write.sum of one launch / cells / iterations)
+P_NCU_BYTES, Q_NCU_BYTES = 48.0, 99.0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--workload', default='mesh50m', choices=['mesh50m', 'sweep'])
@@ -315,12 +320,14 @@ def main():
         # the two solve kernels take ~85 % of the step; the one with the larger share of the timed region is reported as
         # the dominant kernel.  Algorithmic bytes per cell and Chebyshev iteration: 40 (M_p), 96 (M_q).
         # traffic = DRAM bytes of one launch from the committed ncu --set full capture (profiles/r1_ncu_full_solve_kernels.txt:
-        # 54 B (M_p) and 99 B (M_q) per cell and iteration), scaled to this run's iterations per launch.
+        # P_NCU_BYTES (M_p) and Q_NCU_BYTES (M_q) per cell and iteration), scaled to this run's iterations per launch.
         nc = n_cells_local
         kern = {}
         for key, name, alg, ncu_b, it, ms, solves in (
-                ('p', 'solve_coop_k<0> (Chebyshev M_p solve, all iterations in one cooperative launch)', 40.0, 54.0, st['iters_p'], st['ms_solve_p'], st['solves_p']),
-                ('q', 'solve_coop_k<1> (Chebyshev M_q solve, all iterations in one cooperative launch)', 96.0, 99.0, st['iters_q'], st['ms_solve_q'], st['solves_q'])):
+                ('p', ('solve_ell_coop_k' if world == 1 and not (args.cell_rows or args.two_sweep or args.ell_staged) else 'solve_coop_k<0>') +
+                 ' (Chebyshev M_p solve, all iterations in one cooperative launch)', 40.0, P_NCU_BYTES, st['iters_p'], st['ms_solve_p'], st['solves_p']),
+                ('q', ('solve_mq_coop_k' if world == 1 and not args.two_sweep else 'solve_coop_k<1>') +
+                 ' (Chebyshev M_q solve, all iterations in one cooperative launch)', 96.0, Q_NCU_BYTES, st['iters_q'], st['ms_solve_q'], st['solves_q'])):
             ach = alg * nc * it / (ms * 1e-3) / 1e9 if ms > 0 else None
             kern[key] = {'kernel': name, 'achieved': ach, 'frac': (ach / peak) if ach else None, 'share_of_step': ms / st['device_ms'],
                          'bytes_per_launch': alg * nc * it / max(1, solves), 'ms_per_launch': ms / max(1, solves),

@@ -58,7 +58,13 @@
 
 namespace phw {
 
-constexpr int NT_ROWS = 512;   // threads per CTA of the row kernels
+#ifndef PHW_NT_ROWS
+#define PHW_NT_ROWS 512
+#endif
+#ifndef PHW_MINB_ROWS
+#define PHW_MINB_ROWS 2
+#endif
+constexpr int NT_ROWS = PHW_NT_ROWS;   // threads per CTA of the row kernels
 constexpr int NT_COOP_P = PHW_NT_P;  // threads per CTA of the persistent M_p solve: 256 x 4 CTAs/SM (64 registers; 6 CTAs x 40 registers spill into L2)
 constexpr int NT_COOP_Q = PHW_NT_Q;  // M_q solve: 2 CTAs/SM (shared-memory bound) x 384 threads leaves 85 registers per thread for batched loads
 
@@ -826,7 +832,7 @@ __device__ __forceinline__ bool resolve_io(const RowArgs& a, bool vertex, PassIO
 }
 
 template <int EPI, int MODE, bool HAS_M, bool HAS_D, bool CAS>
-__global__ void __launch_bounds__(NT_ROWS, 2) vertex_rows_k(const RowArgs a) {
+__global__ void __launch_bounds__(NT_ROWS, PHW_MINB_ROWS) vertex_rows_k(const __grid_constant__ RowArgs a) {
     extern __shared__ double smem[];
     __shared__ double red[64];
     PassIO io;
@@ -837,7 +843,7 @@ __global__ void __launch_bounds__(NT_ROWS, 2) vertex_rows_k(const RowArgs a) {
 }
 
 template <int EPI, int MODE, bool HAS_M, bool HAS_D, bool CAS>
-__global__ void __launch_bounds__(NT_ROWS, 2) edge_rows_k(const RowArgs a) {
+__global__ void __launch_bounds__(NT_ROWS, PHW_MINB_ROWS) edge_rows_k(const __grid_constant__ RowArgs a) {
     extern __shared__ double smem[];
     __shared__ double red[64];
     PassIO io;
@@ -854,7 +860,8 @@ __global__ void __launch_bounds__(NT_ROWS, 2) edge_rows_k(const RowArgs a) {
 // the same order by every block) so all blocks take the same stop decision without host involvement.
 // ------------------------------------------------------------------------------------------------
 template <int WHICH, bool CAS, int NT, int MINB, int ELL = 0>
-__global__ void __launch_bounds__(NT, MINB) solve_coop_k(const RowArgs av, const RowArgs ae, const PeerComm pc) {
+__global__ void __launch_bounds__(NT, MINB) solve_coop_k(const __grid_constant__ RowArgs av, const __grid_constant__ RowArgs ae,
+                                                         const __grid_constant__ PeerComm pc) {
     extern __shared__ double smem[];
     __shared__ double red[64];
     __shared__ double bc[2];

@@ -320,7 +320,7 @@ __device__ __forceinline__ void block_sum3(double& a, double& b, double& c, doub
 
 // KIND = 0: vertex rows (M_p), 1: edge rows (M_q).  One grid-wide barrier per pass (= two iterations).
 template <int KIND, int NT, int MINB>
-__global__ void __launch_bounds__(NT, MINB) solve2_coop_k(const Solve2Args a) {
+__global__ void __launch_bounds__(NT, MINB) solve2_coop_k(const __grid_constant__ Solve2Args a) {
     extern __shared__ double smem[];
     __shared__ double red[96];
     __shared__ double bc[3];

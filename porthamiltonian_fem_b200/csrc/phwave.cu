@@ -1615,7 +1615,7 @@ static int setup_solver(phw_solver_s* s) {
     s->smem_ells = (size_t)L.max_smem_ell * 8;
     s->ell_staged = (P.flags & 64) != 0;
     if (s->smem_vd > 200 * 1024) return fail(PHW_EINVAL, "patch does not fit in shared memory; reduce patch_cells");
-    s->grid_rows = std::max(1, std::min(s->npatch, 2 * s->sm_count));
+    s->grid_rows = std::max(1, std::min(s->npatch, PHW_MINB_ROWS * s->sm_count));
     RC(setup_scalars(s));
     if (s->G > 1) {
         if (implicit_scheme(P.scheme) || P.strong || P.analytical || P.casimir)
