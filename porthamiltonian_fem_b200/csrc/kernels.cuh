@@ -1075,7 +1075,7 @@ __global__ void __launch_bounds__(NT, MINB) solve_ell_coop_k(const __grid_consta
 struct MqSolveArgs {
     int npatch;
     const PatchHdr* hdr;
-    const uint2* rece; const double* g0; const double* g1; const double* g2;
+    const uint4* cellq;          // [npc][2] packed edge-row cell records: {rece.x, rece.y, g0} {g1, g2}: one 32-byte stream
     const int* ghost_e; const uint32_t* eadj;
     const double* b; const double* pinv;
     double* buf[3];
@@ -1117,21 +1117,20 @@ __global__ void __launch_bounds__(NT, MINB) solve_mq_coop_k(const __grid_constan
             for (int i = threadIdx.x; i < h.ge_cnt; i += NT) sq[h.e_cnt + i] = xk[__ldg(&a.ghost_e[h.ge_off + i])];
             __syncthreads();
             for (int base = threadIdx.x; base < h.n_ecells; base += UC * NT) {
-                uint2 reb[UC]; double gb[UC][3];
+                uint4 qa[UC], qb[UC];
 #pragma unroll
                 for (int u = 0; u < UC; ++u) {
                     const int lc = base + u * NT;
-                    if (lc < h.n_ecells) {
-                        reb[u] = __ldg(&a.rece[h.cell_off + lc]);
-                        gb[u][0] = __ldg(&a.g0[h.cell_off + lc]); gb[u][1] = __ldg(&a.g1[h.cell_off + lc]); gb[u][2] = __ldg(&a.g2[h.cell_off + lc]);
-                    }
+                    if (lc < h.n_ecells) { qa[u] = __ldg(&a.cellq[2 * (size_t)(h.cell_off + lc)]); qb[u] = __ldg(&a.cellq[2 * (size_t)(h.cell_off + lc) + 1]); }
                 }
 #pragma unroll
                 for (int u = 0; u < UC; ++u) {
                     const int lc = base + u * NT;
                     if (lc < h.n_ecells) {
-                        const uint32_t e0 = reb[u].x & 0xFFFFu, e1 = reb[u].x >> 16, e2 = reb[u].y & 0xFFFFu;
-                        const double g0 = gb[u][0], g1 = gb[u][1], g2 = gb[u][2], S = g0 + g1 + g2;
+                        const uint32_t e0 = qa[u].x & 0xFFFFu, e1 = qa[u].x >> 16, e2 = qa[u].y & 0xFFFFu;
+                        const double g0 = __hiloint2double((int)qa[u].w, (int)qa[u].z);
+                        const double g1 = __hiloint2double((int)qb[u].y, (int)qb[u].x), g2 = __hiloint2double((int)qb[u].w, (int)qb[u].z);
+                        const double S = g0 + g1 + g2;
                         const double s0 = (e0 & 0x8000u) ? -1.0 : 1.0, s1 = (e1 & 0x8000u) ? -1.0 : 1.0, s2 = (e2 & 0x8000u) ? -1.0 : 1.0;
                         const double t0 = s0 * sq[e0 & 0x3FFFu], t1 = s1 * sq[e1 & 0x3FFFu], t2 = s2 * sq[e2 & 0x3FFFu];
                         const double ST = S * (t0 + t1 + t2);

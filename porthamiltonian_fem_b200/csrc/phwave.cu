@@ -122,6 +122,17 @@ __global__ void ell2_weights_k(int npatch, const Ring2Hdr* __restrict__ hdr, con
     }
 }
 
+// packed edge-row cell records of the lean M_q solve: {rece.x, rece.y, g0} {g1, g2}
+__global__ void pack_cellq_k(int npc, const uint2* __restrict__ rece, const double* __restrict__ g0, const double* __restrict__ g1,
+                             const double* __restrict__ g2, uint4* __restrict__ out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= npc) return;
+    const uint2 r = rece[k];
+    const double a = g0[k], b = g1[k], c = g2[k];
+    out[2 * (size_t)k] = make_uint4(r.x, r.y, (unsigned)__double2loint(a), (unsigned)__double2hiint(a));
+    out[2 * (size_t)k + 1] = make_uint4((unsigned)__double2loint(b), (unsigned)__double2hiint(b), (unsigned)__double2loint(c), (unsigned)__double2hiint(c));
+}
+
 __global__ void invert_k(int n, double* d) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) d[i] = (d[i] != 0.0) ? 1.0 / d[i] : 0.0;
@@ -550,6 +561,7 @@ struct phw_solver_s {
     bool two_sweep = false;     // mass solves run two Chebyshev iterations per pass (kernels2.cuh)
     Ring2Dev r2[2]{};
     size_t smem2[2] = {0, 0};
+    uint4* d_cellq = nullptr;
     int *d_cells_user = nullptr; double* d_vtx_user = nullptr; unsigned long long* d_mm = nullptr;
     std::vector<cudaEvent_t> prof_ev; std::vector<int> prof_which;
     bool have_vq = false;      // Stormer-Verlet first-same-as-last: v_q of the previous step is valid
@@ -802,7 +814,7 @@ int launch_mq_lean(phw_solver_s* s) {
     if (occ < 1) return fail(PHW_ECUDA, "M_q solve kernel does not fit on an SM");
     const int grid = std::max(1, std::min(s->npatch, occ * s->sm_count));
     MqSolveArgs a{};
-    a.npatch = s->npatch; a.hdr = s->dm.hdr; a.rece = s->dm.rece; a.g0 = s->dm.g0; a.g1 = s->dm.g1; a.g2 = s->dm.g2;
+    a.npatch = s->npatch; a.hdr = s->dm.hdr; a.cellq = s->d_cellq;
     a.ghost_e = s->dm.ghost_e; a.eadj = s->dm.eadj; a.b = s->bq; a.pinv = s->pinv_q;
     for (int i = 0; i < 3; ++i) a.buf[i] = s->tq.b[i];
     a.cheb_d = s->cheb_d[1]; a.cheb_c = s->cheb_c[1];
@@ -875,13 +887,14 @@ int solve_mass(phw_solver_s* s, int which, int n_launch) {
         if (which == PHW_Q && s->pc.world <= 1 && !(s->prm.flags & 128)) {
             static const int cfg = [] { const char* e = getenv("PHW_MQ_CFG"); return e ? atoi(e) : 0; }();
             switch (cfg) {
-                case 1: return launch_mq_lean<384, 2, 3, 3>(s);
-                case 2: return launch_mq_lean<512, 2, 2, 2>(s);
-                case 3: return launch_mq_lean<384, 2, 2, 4>(s);
-                case 4: return launch_mq_lean<320, 2, 3, 3>(s);
-                case 5: return launch_mq_lean<384, 2, 1, 1>(s);
+                case 1: return launch_mq_lean<384, 2, 2, 2>(s);
+                case 2: return launch_mq_lean<512, 2, 1, 2>(s);
+                case 3: return launch_mq_lean<512, 2, 2, 1>(s);
+                case 4: return launch_mq_lean<448, 2, 2, 2>(s);
+                case 5: return launch_mq_lean<576, 2, 2, 2>(s);
+                case 6: return launch_mq_lean<512, 2, 1, 1>(s);
                 case 9: break;
-                default: return launch_mq_lean<384, 2, 2, 2>(s);
+                default: return launch_mq_lean<512, 2, 2, 2>(s);
             }
         }
         if (which == PHW_P && s->ell_p && a.mdiag == nullptr)      // pinv_p = 1 / diag(M_p) exactly
@@ -1564,6 +1577,11 @@ static int setup_solver(phw_solver_s* s) {
     s->dm.npatch = s->npatch; s->dm.nv = s->nv; s->dm.ne = s->ne;
     s->dm.hdr = d_hdr; s->dm.recv = d_recv; s->dm.rece = d_rece; s->dm.area = d_area; s->dm.g0 = d_g0; s->dm.g1 = d_g1; s->dm.g2 = d_g2;
     s->dm.ghost_v = d_gv; s->dm.ghost_e = d_ge; s->dm.eadj = d_eadj; s->dm.vslice_off = d_voff; s->dm.vadj = d_vadj;
+    {   // packed cell records of the lean M_q solve
+        RC(s->dalloc(&s->d_cellq, 2 * (size_t)s->npc));
+        pack_cellq_k<<<nblk(s->npc), 256, 0, s->stream>>>(s->npc, d_rece, d_g0, d_g1, d_g2, s->d_cellq);
+        CU(cudaGetLastError());
+    }
     {   // assembled P1 mass rows (ELL): structure from the layout, weights from the device areas
         uint32_t *d_io, *d_wo, *d_pair; uint16_t* d_ids; double* d_w;
         RC(s->upload(&d_io, L.ell_ioff)); RC(s->upload(&d_wo, L.ell_woff)); RC(s->upload(&d_ids, L.ell_ids)); RC(s->upload(&d_pair, L.ell_pair));
