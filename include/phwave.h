@@ -61,7 +61,8 @@ typedef struct phw_params {
                                 single GPU, weak form, explicit schemes; default off - see DESIGN.md section 10);
                                 bit5: cell-based instead of assembled (ELL) rows in the M_p solve;
                                 bit6: ELL rows of the M_p solve staged in shared memory by cp.async (whole patch in flight;
-                                A/B: slower than the direct loads) */
+                                A/B: slower than the direct loads);
+                                bit7: generic instead of lean kernels for the M_q solve and the energy reductions */
     int32_t extrap_order_q;  /* extrapolation order of the q (and block) solves; 0: same as extrap_order.  Orders up to 5 */
 } phw_params;
 

@@ -1201,6 +1201,149 @@ __global__ void __launch_bounds__(NT, MINB) solve_mq_coop_k(const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------------
+// lean energy reductions (replace assemble(scalar) of H_wave, wave_2D.py:882,907):  red[slot] = scale x^T M x  on the assembled
+// ELL rows (M_p) / the packed cell records (M_q); per-block partials, summed in block order by the last block to finish
+// ------------------------------------------------------------------------------------------------
+struct DotArgs {
+    int npatch;
+    const PatchHdr* hdr;
+    const uint32_t* ell_ioff; const uint32_t* ell_woff; const uint16_t* ell_ids; const double* ell_w;   // M_p
+    const uint4* cellq; const uint32_t* eadj;                                                           // M_q
+    const int* ghost;
+    const double* x;
+    double scale;
+    int slot, counter_id;
+    double* partials; Ctl* ctl;
+};
+
+__device__ __forceinline__ void dot_finish(const DotArgs& a, double acc, double* red) {
+    __shared__ bool is_last;
+    double z = 0.0;
+    block_sum2(acc, z, red);
+    if (threadIdx.x == 0) {
+        a.partials[blockIdx.x] = acc;
+        __threadfence();
+        is_last = (atomicAdd(&a.ctl->counters[a.counter_id], 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    double t = 0.0; z = 0.0;
+    for (int p = threadIdx.x; p < (int)gridDim.x; p += blockDim.x) t += __ldcg(&a.partials[p]);
+    block_sum2(t, z, red);
+    if (threadIdx.x == 0) { a.ctl->counters[a.counter_id] = 0; a.ctl->red[a.slot] = a.scale * t; }
+}
+
+template <int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) dot_ell_k(const __grid_constant__ DotArgs a) {
+    extern __shared__ double smem[];
+    __shared__ double red[64];
+    __shared__ PatchHdr s_hdr[2];
+    const uint4* ids4 = reinterpret_cast<const uint4*>(a.ell_ids);
+    const double* __restrict__ x = a.x;
+    double acc = 0.0;
+    if (blockIdx.x < a.npatch) load_hdr_smem(&s_hdr[0], &a.hdr[blockIdx.x]);
+    __syncthreads();
+    int it = 0;
+    for (int P = blockIdx.x; P < a.npatch; P += gridDim.x, ++it) {
+        const PatchHdr& h = s_hdr[it & 1];
+        if (P + (int)gridDim.x < a.npatch) load_hdr_smem(&s_hdr[(it + 1) & 1], &a.hdr[P + gridDim.x]);
+        const int nsl = (h.v_cnt + 31) >> 5;
+        uint32_t* s_io = reinterpret_cast<uint32_t*>(smem);
+        uint32_t* s_wo = s_io + (nsl + 1);
+        double* sx = smem + (nsl + 2);
+        for (int i = threadIdx.x; i <= nsl; i += NT) { s_io[i] = __ldg(&a.ell_ioff[h.vs_off + i]); s_wo[i] = __ldg(&a.ell_woff[h.vs_off + i]); }
+        for (int i = threadIdx.x; i < h.v_cnt; i += NT) sx[i] = x[h.v_start + i];
+        for (int i = threadIdx.x; i < h.gv_cnt; i += NT) sx[h.v_cnt + i] = x[__ldg(&a.ghost[h.gv_off + i])];
+        __syncthreads();
+        for (int lv = threadIdx.x; lv < h.v_cnt; lv += NT) {
+            const int sl = lv >> 5, lane = lv & 31;
+            const uint32_t wo0 = s_wo[sl];
+            const int W = (int)((s_wo[sl + 1] - wo0) >> 5);
+            const uint4* idp = ids4 + (s_io[sl] >> 3) + lane;
+            const double* __restrict__ wrow = a.ell_w + wo0 + lane;
+            double val = 0.0, dsum = 0.0;
+            for (int c = 0; 8 * c < W; ++c) {
+                const uint4 cd = __ldg(idp + c * 32);
+                const int kk = 8 * c;
+                {
+                    const double w0 = (kk + 0 < W) ? __ldg(&wrow[(kk + 0) * 32]) : 0.0, w1 = (kk + 1 < W) ? __ldg(&wrow[(kk + 1) * 32]) : 0.0;
+                    const double w2 = (kk + 2 < W) ? __ldg(&wrow[(kk + 2) * 32]) : 0.0, w3 = (kk + 3 < W) ? __ldg(&wrow[(kk + 3) * 32]) : 0.0;
+                    val += w0 * sx[cd.x & 0xFFFFu]; val += w1 * sx[cd.x >> 16]; val += w2 * sx[cd.y & 0xFFFFu]; val += w3 * sx[cd.y >> 16];
+                    dsum += (w0 + w1) + (w2 + w3);
+                }
+                if (kk + 4 < W) {
+                    const double w0 = __ldg(&wrow[(kk + 4) * 32]), w1 = (kk + 5 < W) ? __ldg(&wrow[(kk + 5) * 32]) : 0.0;
+                    const double w2 = (kk + 6 < W) ? __ldg(&wrow[(kk + 6) * 32]) : 0.0, w3 = (kk + 7 < W) ? __ldg(&wrow[(kk + 7) * 32]) : 0.0;
+                    val += w0 * sx[cd.z & 0xFFFFu]; val += w1 * sx[cd.z >> 16]; val += w2 * sx[cd.w & 0xFFFFu]; val += w3 * sx[cd.w >> 16];
+                    dsum += (w0 + w1) + (w2 + w3);
+                }
+            }
+            const double xc = sx[lv];
+            acc += xc * (val + dsum * xc);
+        }
+        __syncthreads();
+    }
+    dot_finish(a, acc, red);
+}
+
+template <int NT, int MINB, int UC>
+__global__ void __launch_bounds__(NT, MINB) dot_mq_k(const __grid_constant__ DotArgs a) {
+    extern __shared__ double smem[];
+    __shared__ double red[64];
+    __shared__ PatchHdr s_hdr[2];
+    const double* __restrict__ x = a.x;
+    double acc = 0.0;
+    if (blockIdx.x < a.npatch) load_hdr_smem(&s_hdr[0], &a.hdr[blockIdx.x]);
+    __syncthreads();
+    int it = 0;
+    for (int P = blockIdx.x; P < a.npatch; P += gridDim.x, ++it) {
+        const PatchHdr& h = s_hdr[it & 1];
+        if (P + (int)gridDim.x < a.npatch) load_hdr_smem(&s_hdr[(it + 1) & 1], &a.hdr[P + gridDim.x]);
+        const int nle = h.e_cnt + h.ge_cnt;
+        double* __restrict__ sq = smem;
+        double* __restrict__ sc3 = sq + ((nle + 1) & ~1);
+        for (int i = threadIdx.x; i < h.e_cnt; i += NT) sq[i] = x[h.e_start + i];
+        for (int i = threadIdx.x; i < h.ge_cnt; i += NT) sq[h.e_cnt + i] = x[__ldg(&a.ghost[h.ge_off + i])];
+        __syncthreads();
+        for (int base = threadIdx.x; base < h.n_ecells; base += UC * NT) {
+            uint4 qa[UC], qb[UC];
+#pragma unroll
+            for (int u = 0; u < UC; ++u) {
+                const int lc = base + u * NT;
+                if (lc < h.n_ecells) { qa[u] = __ldg(&a.cellq[2 * (size_t)(h.cell_off + lc)]); qb[u] = __ldg(&a.cellq[2 * (size_t)(h.cell_off + lc) + 1]); }
+            }
+#pragma unroll
+            for (int u = 0; u < UC; ++u) {
+                const int lc = base + u * NT;
+                if (lc < h.n_ecells) {
+                    const uint32_t e0 = qa[u].x & 0xFFFFu, e1 = qa[u].x >> 16, e2 = qa[u].y & 0xFFFFu;
+                    const double g0 = __hiloint2double((int)qa[u].w, (int)qa[u].z);
+                    const double g1 = __hiloint2double((int)qb[u].y, (int)qb[u].x), g2 = __hiloint2double((int)qb[u].w, (int)qb[u].z);
+                    const double S = g0 + g1 + g2;
+                    const double s0 = (e0 & 0x8000u) ? -1.0 : 1.0, s1 = (e1 & 0x8000u) ? -1.0 : 1.0, s2 = (e2 & 0x8000u) ? -1.0 : 1.0;
+                    const double t0 = s0 * sq[e0 & 0x3FFFu], t1 = s1 * sq[e1 & 0x3FFFu], t2 = s2 * sq[e2 & 0x3FFFu];
+                    const double ST = S * (t0 + t1 + t2);
+                    sc3[3 * lc] = s0 * (ST + 2.0 * S * t0 - 4.0 * (g0 * t0 + g2 * t1 + g1 * t2));
+                    sc3[3 * lc + 1] = s1 * (ST + 2.0 * S * t1 - 4.0 * (g2 * t0 + g1 * t1 + g0 * t2));
+                    sc3[3 * lc + 2] = s2 * (ST + 2.0 * S * t2 - 4.0 * (g1 * t0 + g0 * t1 + g2 * t2));
+                }
+            }
+        }
+        __syncthreads();
+        for (int le = threadIdx.x; le < h.e_cnt; le += NT) {
+            const uint32_t adj = __ldg(&a.eadj[h.e_start + le]);
+            const uint32_t ca = adj & 0xFFFFu, cb = adj >> 16;
+            double val = sc3[3 * (ca >> 2) + (ca & 3u)];
+            if (cb != 0xFFFFu) val += sc3[3 * (cb >> 2) + (cb & 3u)];
+            acc += sq[le] * val;
+        }
+        __syncthreads();
+    }
+    dot_finish(a, acc, red);
+}
+
+// ------------------------------------------------------------------------------------------------
 // higher-order pairs (P_k x RT_k, k <= 3): the operators are assembled once on the host (fem_ho.py) and applied as
 // CSR matrices; same epilogues and the same persistent cooperative Chebyshev solve as the matrix-free path.
 // ------------------------------------------------------------------------------------------------

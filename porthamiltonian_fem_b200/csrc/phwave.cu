@@ -884,7 +884,7 @@ int solve_mass(phw_solver_s* s, int which, int n_launch) {
                 default: return launch_ell_lean<256, 4>(s);
             }
         }
-        if (which == PHW_Q && s->pc.world <= 1 && !(s->prm.flags & 128)) {
+        if (which == PHW_Q && s->pc.world <= 1 && !(s->prm.flags & 128)) {   // flags bit 7: generic kernels everywhere
             static const int cfg = [] { const char* e = getenv("PHW_MQ_CFG"); return e ? atoi(e) : 0; }();
             switch (cfg) {
                 case 1: return launch_mq_lean<384, 2, 2, 2>(s);
@@ -1032,10 +1032,30 @@ int energy(phw_solver_s* s) {
         CU(cudaGetLastError());
         return 0;
     }
-    int rc = op_vertex_dot(s, s->p, 1.0, 0.0, 0, 0.5 / s->prm.rho, 4);
-    if (rc) return rc;
-    rc = op_edge_dot(s, s->q, 1.0, 0.0, 1, 0.5 * s->prm.K_wave, 5);
-    if (rc) return rc;
+    int rc = 0;
+    if (!(s->prm.flags & 128)) {   // lean reductions on the ELL rows / packed cell records
+        DotArgs a{};
+        a.npatch = s->npatch; a.hdr = s->dm.hdr; a.partials = s->partials + 8192; a.ctl = s->ctl;
+        a.ell_ioff = s->dm.ell_ioff; a.ell_woff = s->dm.ell_woff; a.ell_ids = s->dm.ell_ids; a.ell_w = s->dm.ell_w;
+        a.ghost = s->dm.ghost_v; a.x = s->p; a.scale = 0.5 / s->prm.rho; a.slot = 0; a.counter_id = 4;
+        static bool conf = false;
+        if (!conf) {
+            CU(cudaFuncSetAttribute(dot_ell_k<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            CU(cudaFuncSetAttribute(dot_mq_k<512, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            conf = true;
+        }
+        dot_ell_k<256, 4><<<std::max(1, std::min(s->npatch, 4 * s->sm_count)), 256, s->smem_ell, s->stream>>>(a);
+        a.cellq = s->d_cellq; a.eadj = s->dm.eadj; a.ghost = s->dm.ghost_e; a.x = s->q; a.scale = 0.5 * s->prm.K_wave; a.slot = 1; a.counter_id = 5;
+        a.partials = s->partials + 8192 + 2048;
+        dot_mq_k<512, 2, 2><<<std::max(1, std::min(s->npatch, 2 * s->sm_count)), 512, s->smem_e, s->stream>>>(a);
+        s->launches += 2;
+        CU(cudaGetLastError());
+    } else {
+        rc = op_vertex_dot(s, s->p, 1.0, 0.0, 0, 0.5 / s->prm.rho, 4);
+        if (rc) return rc;
+        rc = op_edge_dot(s, s->q, 1.0, 0.0, 1, 0.5 * s->prm.K_wave, 5);
+        if (rc) return rc;
+    }
     if (s->prm.analytical && s->an_ready && s->in_step) {
         const int nb = 4 * s->sm_count;
         diag_cells_k<<<nb, 256, 0, s->stream>>>((int)s->mesh->L.nc, s->d_cells_new, s->d_vtx_new, s->p, s->an, s->ctl, s->d_diag_part);
