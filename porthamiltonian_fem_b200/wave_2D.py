@@ -33,7 +33,7 @@ def wave_2D_solve(tFinal, numSteps, outputDir,
                   K_wave=1, rho=1, BOUNDARYPLOT=False, interConnection=None,
                   analytical=False, saveP=True, controlType=None,
                   input_stop_t=None, control_start_t=None, basis_order=(1, 1),
-                  mesh=None, mesh_kind='structured', device=0, patch_cells=None, tol=1e-13, extrap_order=2, save_every=None,
+                  mesh=None, mesh_kind='structured', device=0, patch_cells=None, tol=1e-13, extrap_order=3, save_every=None,
                   lumped=None, return_state=False, verbose=True, solver_flags=0):
     """Solve the 2D port-Hamiltonian wave equation; see the reference docstring (wave_2D.py:22-51).
 

@@ -257,3 +257,30 @@ def test_two_sweep_time_loop_parity(scheme, ic):
     assert rel(sg['p'], so['p']) < TOL_STATE and rel(sg['q'], so['q']) < TOL_STATE
     assert np.abs(Hg[:, 1:] - Ho[:, 1:]).max() < 1e-10 * np.abs(Ho[:, 1:]).max()
     assert sg['stats']['max_rel_residual'] <= 1e-13
+
+
+def test_edge_cases_empty_run_tiny_meshes_and_restart():
+    """n_steps = 0, a two-cell mesh, a one-patch mesh with the smallest patch size, and restart through
+    phw_get_state / phw_set_state / phw_set_time: two half runs reproduce one full run."""
+    v, c = rectangle_structured(1, 1)
+    m, s = make_solver(v, c, 'R', 1.0, 0.25, 16, scheme='SV')
+    assert s.run(0).shape == (0, 8)
+    H = s.run(3)
+    Ho, _ = wave_2D_solve_oracle(3e-3, 3, (v, c), 1.0, 0.25, K_wave=K_WAVE, rho=RHO, timeIntScheme='SV')
+    assert np.abs(H[:, 1:] - Ho[:, 1:]).max() <= 1e-10 * max(np.abs(Ho[:, 1:]).max(), 1e-300)
+    # restart: 40 steps == 20 + (state, clock, accumulators carried over by the caller) + 20
+    v, c = rectangle_delaunay(30, 8, seed=11)
+    m, s = make_solver(v, c, 'R', 1.0, 0.25, 80, scheme='SE')
+    H_full = s.run(40)
+    p_full, q_full, _ = s.get_state()
+    m2, s2 = make_solver(v, c, 'R', 1.0, 0.25, 80, scheme='SE')
+    H_a = s2.run(20)
+    p, q, x = s2.get_state()
+    m3, s3 = make_solver(v, c, 'R', 1.0, 0.25, 80, scheme='SE')
+    s3.set_state(p=p, q=q, x3=x)
+    s3.set_time(H_a[-1, 0])
+    H_b = s3.run(20)
+    p_b, q_b, _ = s3.get_state()
+    assert rel(p_b, p_full) < 1e-10 and rel(q_b, q_full) < 1e-10
+    assert np.allclose(H_b[:, 0], H_full[20:, 0], rtol=0, atol=1e-15)
+    assert np.abs(H_b[:, 7] - H_full[20:, 7]).max() < 1e-10 * np.abs(H_full[:, 7]).max()      # H_wave depends on the state only
