@@ -16,6 +16,7 @@
 // applies the epilogue with coalesced global traffic.
 #pragma once
 #include <cstdint>
+#include <type_traits>
 #include <cuda_runtime.h>
 #include <cooperative_groups.h>
 #include "layout.hpp"
@@ -88,6 +89,7 @@ struct Ctl {
     double xch[2][4];                // globally reduced values of the current exchange
     SolveCtl sc[3];
     unsigned int counters[8];
+    unsigned int gbar[4];            // arrival counter of grid_barrier (zeroed by the host before each cooperative launch)
     double reshist[3][48];           // ||r_k||^2 / ||b||^2 of the first 48 iterations of the most recent solve (diagnostics)
 };
 
@@ -952,8 +954,51 @@ __global__ void __launch_bounds__(NT, MINB) solve_coop_k(const __grid_constant__
 }
 
 
+// grid-wide barrier for co-resident grids (cooperative launch): one arrival per CTA on a monotonically increasing counter
+// (zeroed by the host before the launch).  Back-to-back cooperative_groups grid syncs cost ~40 us each in these kernels
+// (592 CTAs of 256 threads, measured); this barrier ~1 us - which is what makes the inter-GPU exchange, with its two extra
+// barriers per iteration, affordable in the lean kernels.
+__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int& epoch) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        epoch += gridDim.x;
+        __threadfence();
+        atomicAdd(bar, 1u);
+        while (*((volatile unsigned int*)bar) < epoch) { }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// one inter-GPU exchange of a Chebyshev iteration, called by all threads of all CTAs after the grid-wide
+// reduction: push the new iterate of the interface dofs into the neighbours' buffer `nxt`, all-reduce the residual norms
+template <int NT>
+__device__ __forceinline__ void peer_exchange_iter(const PeerComm& pc, Ctl* ctl, unsigned int& epoch, bool vertex_field,
+                                                   const double* xnew, int nxt, int k, double& rr, double& bb) {
+    const int gtid = blockIdx.x * NT + threadIdx.x, gsz = gridDim.x * NT;
+    for (int nb = 0; nb < pc.n_nb; ++nb) {
+        if (vertex_field) {
+            double* dst = pc.nb_tp[nb][nxt];
+            for (int i = gtid; i < pc.n_send_v[nb]; i += gsz) dst[pc.send_v_rem[nb][i]] = xnew[pc.send_v_loc[nb][i]];
+        } else {
+            double* dst = pc.nb_tq[nb][nxt];
+            for (int i = gtid; i < pc.n_send_e[nb]; i += gsz) dst[pc.send_e_rem[nb][i]] = xnew[pc.send_e_loc[nb][i]];
+        }
+    }
+    __threadfence_system();
+    grid_barrier(&ctl->gbar[0], epoch);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        double v2[2] = {rr, bb};
+        peer_allreduce(pc, ctl, v2, 2);
+        ctl->xch[k & 1][0] = v2[0]; ctl->xch[k & 1][1] = v2[1];
+        __threadfence();
+    }
+    grid_barrier(&ctl->gbar[0], epoch);
+    rr = __ldcg(&ctl->xch[k & 1][0]); bb = __ldcg(&ctl->xch[k & 1][1]);
+}
+
 // ------------------------------------------------------------------------------------------------
-// lean single-GPU variant of the ELL M_p solve: the same iteration as solve_coop_k<0,..,ELL>, with a compact argument block
+// lean variant of the ELL M_p solve (MULTI: with the inter-GPU exchange): the same iteration as solve_coop_k<0,..,ELL>, with a compact argument block
 // and a register-light row loop, so that more threads fit on an SM (the streams need the parallelism: phw_stream_probe)
 // ------------------------------------------------------------------------------------------------
 struct EllSolveArgs {
@@ -968,26 +1013,27 @@ struct EllSolveArgs {
     double* partials; Ctl* ctl;
 };
 
-template <int NT, int MINB>
-__global__ void __launch_bounds__(NT, MINB) solve_ell_coop_k(const __grid_constant__ EllSolveArgs a) {
+template <int NT, int MINB, bool MULTI>
+__global__ void __launch_bounds__(NT, MINB) solve_ell_coop_k(const __grid_constant__ EllSolveArgs a, const __grid_constant__ PeerComm pc) {
     extern __shared__ double smem[];
     __shared__ double red[64];
     __shared__ double bc[2];
     __shared__ PatchHdr s_hdr[2];
-    namespace cg = cooperative_groups;
-    cg::grid_group grid = cg::this_grid();
     SolveCtl& sc = a.ctl->sc[a.which];
     int k = 0, cur = sc.cur;
     double rho = 0.0, rr = 0.0, bb = 0.0;
     bool conv = false;
+    unsigned int epoch = 0;
     const uint4* ids4 = reinterpret_cast<const uint4*>(a.ell_ids);
     while (true) {
         double c1, c2, rho_k;
         cheb_coeffs(k, rho, a.cheb_d, a.cheb_c, c1, c2, rho_k);
         const int nxt = (cur + 1) % 3, prv = (cur + 2) % 3;
-        const double* __restrict__ xk = cur == 0 ? a.buf[0] : (cur == 1 ? a.buf[1] : a.buf[2]);
-        const double* __restrict__ xprev = prv == 0 ? a.buf[0] : (prv == 1 ? a.buf[1] : a.buf[2]);
-        double* __restrict__ xnew = nxt == 0 ? a.buf[0] : (nxt == 1 ? a.buf[1] : a.buf[2]);
+        typedef typename std::conditional<MULTI, const double*, const double* __restrict__>::type xin_t;   // peers write these buffers
+        typedef typename std::conditional<MULTI, double*, double* __restrict__>::type xout_t;
+        xin_t xk = cur == 0 ? a.buf[0] : (cur == 1 ? a.buf[1] : a.buf[2]);
+        xin_t xprev = prv == 0 ? a.buf[0] : (prv == 1 ? a.buf[1] : a.buf[2]);
+        xout_t xnew = nxt == 0 ? a.buf[0] : (nxt == 1 ? a.buf[1] : a.buf[2]);
         double r0 = 0.0, b0 = 0.0;
         if (blockIdx.x < a.npatch) load_hdr_smem(&s_hdr[0], &a.hdr[blockIdx.x]);
         __syncthreads();
@@ -1044,7 +1090,7 @@ __global__ void __launch_bounds__(NT, MINB) solve_ell_coop_k(const __grid_consta
         block_sum2(r0, b0, red);
         double* part = a.partials + (size_t)(k & 1) * 2 * gridDim.x;
         if (threadIdx.x == 0) { part[2 * blockIdx.x] = r0; part[2 * blockIdx.x + 1] = b0; }
-        grid.sync();
+        grid_barrier(&a.ctl->gbar[0], epoch);
         if (threadIdx.x < 32) {
             double s0 = 0.0, s1 = 0.0;
             for (int i = threadIdx.x; i < (int)gridDim.x; i += 32) { s0 += __ldcg(&part[2 * i]); s1 += __ldcg(&part[2 * i + 1]); }
@@ -1054,6 +1100,7 @@ __global__ void __launch_bounds__(NT, MINB) solve_ell_coop_k(const __grid_consta
         __syncthreads();
         rr = bc[0]; bb = bc[1];
         __syncthreads();
+        if (MULTI) peer_exchange_iter<NT>(pc, a.ctl, epoch, true, xnew, nxt, k, rr, bb);
         conv = rr <= a.tol2 * bb;
         if (blockIdx.x == 0 && threadIdx.x == 0 && k < 48) a.ctl->reshist[a.which][k] = (bb > 0.0) ? rr / bb : 0.0;
         k += 1;
@@ -1070,8 +1117,8 @@ __global__ void __launch_bounds__(NT, MINB) solve_ell_coop_k(const __grid_consta
     }
 }
 
-// lean single-GPU variant of the cell-based M_q solve (same iteration as solve_coop_k<1>): compact arguments, restrict-
-// qualified streams, nothing of the multi-GPU exchange in the loop
+// lean variant of the cell-based M_q solve (same iteration as solve_coop_k<1>; MULTI: with the inter-GPU exchange): compact
+// arguments, restrict-qualified streams, packed cell records
 struct MqSolveArgs {
     int npatch;
     const PatchHdr* hdr;
@@ -1084,25 +1131,26 @@ struct MqSolveArgs {
     double* partials; Ctl* ctl;
 };
 
-template <int NT, int MINB, int UC, int UR>
-__global__ void __launch_bounds__(NT, MINB) solve_mq_coop_k(const __grid_constant__ MqSolveArgs a) {
+template <int NT, int MINB, int UC, int UR, bool MULTI>
+__global__ void __launch_bounds__(NT, MINB) solve_mq_coop_k(const __grid_constant__ MqSolveArgs a, const __grid_constant__ PeerComm pc) {
     extern __shared__ double smem[];
     __shared__ double red[64];
     __shared__ double bc[2];
     __shared__ PatchHdr s_hdr[2];
-    namespace cg = cooperative_groups;
-    cg::grid_group grid = cg::this_grid();
     SolveCtl& sc = a.ctl->sc[a.which];
     int k = 0, cur = sc.cur;
     double rho = 0.0, rr = 0.0, bb = 0.0;
     bool conv = false;
+    unsigned int epoch = 0;
     while (true) {
         double c1, c2, rho_k;
         cheb_coeffs(k, rho, a.cheb_d, a.cheb_c, c1, c2, rho_k);
         const int nxt = (cur + 1) % 3, prv = (cur + 2) % 3;
-        const double* __restrict__ xk = cur == 0 ? a.buf[0] : (cur == 1 ? a.buf[1] : a.buf[2]);
-        const double* __restrict__ xprev = prv == 0 ? a.buf[0] : (prv == 1 ? a.buf[1] : a.buf[2]);
-        double* __restrict__ xnew = nxt == 0 ? a.buf[0] : (nxt == 1 ? a.buf[1] : a.buf[2]);
+        typedef typename std::conditional<MULTI, const double*, const double* __restrict__>::type xin_t;   // peers write these buffers
+        typedef typename std::conditional<MULTI, double*, double* __restrict__>::type xout_t;
+        xin_t xk = cur == 0 ? a.buf[0] : (cur == 1 ? a.buf[1] : a.buf[2]);
+        xin_t xprev = prv == 0 ? a.buf[0] : (prv == 1 ? a.buf[1] : a.buf[2]);
+        xout_t xnew = nxt == 0 ? a.buf[0] : (nxt == 1 ? a.buf[1] : a.buf[2]);
         double r0 = 0.0, b0 = 0.0;
         if (blockIdx.x < a.npatch) load_hdr_smem(&s_hdr[0], &a.hdr[blockIdx.x]);
         __syncthreads();
@@ -1174,7 +1222,7 @@ __global__ void __launch_bounds__(NT, MINB) solve_mq_coop_k(const __grid_constan
         block_sum2(r0, b0, red);
         double* part = a.partials + (size_t)(k & 1) * 2 * gridDim.x;
         if (threadIdx.x == 0) { part[2 * blockIdx.x] = r0; part[2 * blockIdx.x + 1] = b0; }
-        grid.sync();
+        grid_barrier(&a.ctl->gbar[0], epoch);
         if (threadIdx.x < 32) {
             double s0 = 0.0, s1 = 0.0;
             for (int i = threadIdx.x; i < (int)gridDim.x; i += 32) { s0 += __ldcg(&part[2 * i]); s1 += __ldcg(&part[2 * i + 1]); }
@@ -1184,6 +1232,7 @@ __global__ void __launch_bounds__(NT, MINB) solve_mq_coop_k(const __grid_constan
         __syncthreads();
         rr = bc[0]; bb = bc[1];
         __syncthreads();
+        if (MULTI) peer_exchange_iter<NT>(pc, a.ctl, epoch, false, xnew, nxt, k, rr, bb);
         conv = rr <= a.tol2 * bb;
         if (blockIdx.x == 0 && threadIdx.x == 0 && k < 48) a.ctl->reshist[a.which][k] = (bb > 0.0) ? rr / bb : 0.0;
         k += 1;

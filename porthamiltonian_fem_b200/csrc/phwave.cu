@@ -772,9 +772,10 @@ int launch_coop2(phw_solver_s* s) {
 // lean single-GPU ELL M_p solve
 template <int NT, int MINB>
 int launch_ell_lean(phw_solver_s* s) {
-    auto kern = solve_ell_coop_k<NT, MINB>;
-    static bool configured = false;
-    if (!configured) { CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); configured = true; }
+    void* kern = s->pc.world > 1 ? (void*)solve_ell_coop_k<NT, MINB, true> : (void*)solve_ell_coop_k<NT, MINB, false>;
+    CU(cudaMemsetAsync(&s->ctl->gbar[0], 0, sizeof(unsigned int), s->stream));
+    static bool configured[2] = {false, false};
+    if (!configured[s->pc.world > 1]) { CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); configured[s->pc.world > 1] = true; }
     int occ = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, s->smem_ell));
     if (occ < 1) return fail(PHW_ECUDA, "ELL solve kernel does not fit on an SM");
@@ -787,14 +788,14 @@ int launch_ell_lean(phw_solver_s* s) {
     a.tol2 = s->prm.tol * s->prm.tol;
     if (s->G > 1) { const double t = std::max(s->prm.tol / std::sqrt((double)s->G), 1e-14); a.tol2 = std::min(a.tol2, t * t); }
     a.max_iter = s->prm.max_iter; a.which = 0; a.partials = s->partials; a.ctl = s->ctl;
-    void* args[] = {(void*)&a};
+    void* args[] = {(void*)&a, (void*)&s->pc};
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     const bool prof = (s->prm.flags & 4) && s->prof_ev.size() < 2 * 8192;
     if (prof) {
         CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
         CU(cudaEventRecord(e0, s->stream));
     }
-    CU(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(NT), args, s->smem_ell, s->stream));
+    CU(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(NT), args, s->smem_ell, s->stream));
     if (prof) {
         CU(cudaEventRecord(e1, s->stream));
         s->prof_ev.push_back(e0); s->prof_ev.push_back(e1); s->prof_which.push_back(0);
@@ -806,9 +807,10 @@ int launch_ell_lean(phw_solver_s* s) {
 // lean single-GPU cell-based M_q solve
 template <int NT, int MINB, int UC, int UR>
 int launch_mq_lean(phw_solver_s* s) {
-    auto kern = solve_mq_coop_k<NT, MINB, UC, UR>;
-    static bool configured = false;
-    if (!configured) { CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); configured = true; }
+    void* kern = s->pc.world > 1 ? (void*)solve_mq_coop_k<NT, MINB, UC, UR, true> : (void*)solve_mq_coop_k<NT, MINB, UC, UR, false>;
+    CU(cudaMemsetAsync(&s->ctl->gbar[0], 0, sizeof(unsigned int), s->stream));
+    static bool configured[2] = {false, false};
+    if (!configured[s->pc.world > 1]) { CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); configured[s->pc.world > 1] = true; }
     int occ = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, s->smem_e));
     if (occ < 1) return fail(PHW_ECUDA, "M_q solve kernel does not fit on an SM");
@@ -821,14 +823,14 @@ int launch_mq_lean(phw_solver_s* s) {
     a.tol2 = s->prm.tol * s->prm.tol;
     if (s->G > 1) { const double t = std::max(s->prm.tol / std::sqrt((double)s->G), 1e-14); a.tol2 = std::min(a.tol2, t * t); }
     a.max_iter = s->prm.max_iter; a.which = 1; a.partials = s->partials; a.ctl = s->ctl;
-    void* args[] = {(void*)&a};
+    void* args[] = {(void*)&a, (void*)&s->pc};
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     const bool prof = (s->prm.flags & 4) && s->prof_ev.size() < 2 * 8192;
     if (prof) {
         CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
         CU(cudaEventRecord(e0, s->stream));
     }
-    CU(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(NT), args, s->smem_e, s->stream));
+    CU(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(NT), args, s->smem_e, s->stream));
     if (prof) {
         CU(cudaEventRecord(e1, s->stream));
         s->prof_ev.push_back(e0); s->prof_ev.push_back(e1); s->prof_which.push_back(1);
@@ -872,7 +874,7 @@ int solve_mass(phw_solver_s* s, int which, int n_launch) {
     if (s->coop) {
         a.b = which == PHW_P ? s->bp : s->bq;
         a.pinv = which == PHW_P ? s->pinv_p : s->pinv_q;
-        if (which == PHW_P && s->ell_p && a.mdiag == nullptr && s->pc.world <= 1 && !s->ell_staged) {
+        if (which == PHW_P && s->ell_p && a.mdiag == nullptr && !s->ell_staged) {
             static const int cfg = [] { const char* e = getenv("PHW_ELL_CFG"); return e ? atoi(e) : 0; }();
             switch (cfg) {
                 case 1: return launch_ell_lean<256, 6>(s);
@@ -884,7 +886,7 @@ int solve_mass(phw_solver_s* s, int which, int n_launch) {
                 default: return launch_ell_lean<256, 4>(s);
             }
         }
-        if (which == PHW_Q && s->pc.world <= 1 && !(s->prm.flags & 128)) {   // flags bit 7: generic kernels everywhere
+        if (which == PHW_Q && !(s->prm.flags & 128)) {   // flags bit 7: generic kernels everywhere
             static const int cfg = [] { const char* e = getenv("PHW_MQ_CFG"); return e ? atoi(e) : 0; }();
             switch (cfg) {
                 case 1: return launch_mq_lean<384, 2, 2, 2>(s);
