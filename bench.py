@@ -159,7 +159,7 @@ def main():
     ap.add_argument('--nx', type=int, default=FULL_NX)
     ap.add_argument('--ny', type=int, default=FULL_NY)
     ap.add_argument('--scheme', default='SE')
-    ap.add_argument('--patch-cells', type=int, default=2048)
+    ap.add_argument('--patch-cells', type=int, default=0, help='cells per patch (0: 2048, or 1024 with --pipe so that two stages fit in shared memory)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--tol', type=float, default=1e-13)
     ap.add_argument('--extrap', type=int, default=3)
@@ -168,9 +168,12 @@ def main():
     ap.add_argument('--two-sweep', action='store_true', help='two Chebyshev iterations per pass in the mass solves (csrc/kernels2.cuh; A/B)')
     ap.add_argument('--ell-staged', action='store_true', help='ELL rows of the M_p solve staged in shared memory by cp.async (A/B)')
     ap.add_argument('--cell-rows', action='store_true', help='cell-based instead of assembled (ELL) rows in the M_p solve (A/B)')
+    ap.add_argument('--pipe', default='', help="bulk-copy pipelined mass solves (csrc/kernels_pipe.cuh; A/B): 'pq' both, 'p' or 'q' one of them")
     ap.add_argument('--stream-probe', action='store_true', help='print the bandwidth of a pure streaming pass over the ELL M_p data (diagnostics)')
     ap.add_argument('--debug-residuals', action='store_true', help='print the residual history of the last M_p / M_q solve to stderr')
     args = ap.parse_args()
+    if args.patch_cells <= 0:
+        args.patch_cells = 1024 if 'q' in args.pipe else 2048
     if args.impl == 'reference':
         return run_reference_arm(args)
     if args.workload == 'sweep':
@@ -212,7 +215,7 @@ def main():
     prm = _lib.PhwParams()
     prm.scheme, prm.dt, prm.K_wave, prm.rho = _lib.SCHEMES[args.scheme], dt, K_WAVE, RHO
     prm.input_kind, prm.in_amp, prm.in_omega = _lib.IN_COSINE, 1.0, omega
-    prm.tol, prm.max_iter, prm.flags, prm.extrap_order = args.tol, 200, 4 | (16 if args.two_sweep else 0) | (32 if args.cell_rows else 0) | (64 if args.ell_staged else 0), args.extrap
+    prm.tol, prm.max_iter, prm.flags, prm.extrap_order = args.tol, 200, 4 | (16 if args.two_sweep else 0) | (32 if args.cell_rows else 0) | (64 if args.ell_staged else 0) | (256 if 'q' in args.pipe else 0) | (512 if 'p' in args.pipe else 0), args.extrap
     prm.extrap_order_q = args.extrap_q
     solver = Solver(m, prm, device=local_rank)
     n_dof_local = int((part.vertex_owner == rank).sum() + (part.edge_owner == rank).sum())
@@ -322,11 +325,12 @@ def main():
         # traffic = DRAM bytes of one launch from the committed ncu --set full capture (profiles/r1_ncu_full_solve_kernels.txt:
         # P_NCU_BYTES (M_p) and Q_NCU_BYTES (M_q) per cell and iteration), scaled to this run's iterations per launch.
         nc = n_cells_local
+        paths = int(st.get('kernel_paths', 0))      # phw_path bits: 1 lean M_p, 2 lean M_q, 4 pipelined M_p, 8 pipelined M_q
         kern = {}
         for key, name, alg, ncu_b, it, ms, solves in (
-                ('p', ('solve_ell_coop_k' if world == 1 and not (args.cell_rows or args.two_sweep or args.ell_staged) else 'solve_coop_k<0>') +
+                ('p', ('solve_ell_pipe_k' if paths & 4 else 'solve_ell_coop_k' if paths & 1 else 'solve2_coop_k<0>' if args.two_sweep else 'solve_coop_k<0>') +
                  ' (Chebyshev M_p solve, all iterations in one cooperative launch)', 40.0, P_NCU_BYTES, st['iters_p'], st['ms_solve_p'], st['solves_p']),
-                ('q', ('solve_mq_coop_k' if world == 1 and not args.two_sweep else 'solve_coop_k<1>') +
+                ('q', ('solve_mq_pipe_k' if paths & 8 else 'solve_mq_coop_k' if paths & 2 else 'solve2_coop_k<1>' if args.two_sweep else 'solve_coop_k<1>') +
                  ' (Chebyshev M_q solve, all iterations in one cooperative launch)', 96.0, Q_NCU_BYTES, st['iters_q'], st['ms_solve_q'], st['solves_q'])):
             ach = alg * nc * it / (ms * 1e-3) / 1e9 if ms > 0 else None
             kern[key] = {'kernel': name, 'achieved': ach, 'frac': (ach / peak) if ach else None, 'share_of_step': ms / st['device_ms'],
@@ -342,7 +346,7 @@ def main():
             'config': {'workload': '{} weak P1/RT1 wave, exact standing wave of the analytical case at phase w*t0 = {:.3g} pi with its left datum (wave_2D.py:375-377,734), structured rectangle {}x{}x2 = {} cells and {} dofs per GPU ({} dofs in total, x-slab partition, peer-memory halo exchange), dt={:g}; '
                                    'state vectors ({:.0f} MB each) exceed L2, no flush needed'.format(
                                        args.scheme, args.phase, args.nx, args.ny, nc, n_dof_local, n_dof, dt, 8e-6 * m.n_edges),
-                       'dofs_per_gpu': n_dof_local, 'dofs_total': n_dof, 'patch_cells': args.patch_cells, 'phase_over_pi': args.phase, 'two_sweep': bool(args.two_sweep), 'tol': args.tol, 'extrap_order': args.extrap,
+                       'dofs_per_gpu': n_dof_local, 'dofs_total': n_dof, 'patch_cells': args.patch_cells, 'phase_over_pi': args.phase, 'two_sweep': bool(args.two_sweep), 'pipe': args.pipe, 'tol': args.tol, 'extrap_order': args.extrap,
                        'iters_per_solve_p': st['iters_p'] / max(1, st['solves_p']), 'iters_per_solve_q': st['iters_q'] / max(1, st['solves_q']),
                        'max_rel_residual': st['max_rel_residual'], 'setup_seconds': setup_s},
             'e2e': {'value': e2e_value, 'unit': 'dof-updates/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,

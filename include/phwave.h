@@ -62,7 +62,14 @@ typedef struct phw_params {
                                 bit5: cell-based instead of assembled (ELL) rows in the M_p solve;
                                 bit6: ELL rows of the M_p solve staged in shared memory by cp.async (whole patch in flight;
                                 A/B: slower than the direct loads);
-                                bit7: generic instead of lean kernels for the M_q solve and the energy reductions */
+                                bit7: generic instead of lean kernels for the M_q solve and the energy reductions;
+                                bit8: bulk-copy pipelined M_q solve (csrc/kernels_pipe.cuh: every stream of the CTA's next patch
+                                is fetched by cp.async.bulk into a second shared-memory stage while the current patch is computed;
+                                one GPU; needs patches of <= ~1000 cells so that two stages fit - phw_solver_create fails otherwise);
+                                bit9: the same for the ELL M_p solve;
+                                bit10: the generic cooperative kernels (block solve of IE/SM/casimir, strong form, partitioned and
+                                higher-order CSR solves, two-sweep solves) synchronise the grid with the one-atomic-per-CTA barrier
+                                of the lean kernels instead of cooperative-groups grid syncs */
     int32_t extrap_order_q;  /* extrapolation order of the q (and block) solves; 0: same as extrap_order.  Orders up to 5 */
 } phw_params;
 
@@ -74,7 +81,9 @@ typedef struct phw_stats {
     int64_t bytes_model;        /* algorithmic bytes of the last phw_run ("bytes model") */
     double  lam_min_q, lam_max_q, skew_bound;
     double  ms_solve_p, ms_solve_q, ms_solve_block;   /* summed CUDA-event time of the solve kernels (flags bit2) */
+    int64_t kernel_paths;       /* phw_path bits: which variants of the mass-solve kernels the last phw_run launched */
 } phw_stats;
+enum phw_path { PHW_PATH_LEAN_P = 1, PHW_PATH_LEAN_Q = 2, PHW_PATH_PIPE_P = 4, PHW_PATH_PIPE_Q = 8 };
 
 const char* phw_last_error(void);
 int phw_version(void);
@@ -110,6 +119,9 @@ int phw_mesh_set_dirichlet(phw_mesh_t m, int64_t n, const int32_t* vertex_ids, c
 int phw_mesh_get_numbering(phw_mesh_t m, int32_t* vertex_new2old, int32_t* edge_new2old, int32_t* cell_patch);
 /* per-patch counts [n_patches,6]: own cells, edge-op cells, vertex-op cells, owned vertices, owned edges, ghosts(v+e) */
 int phw_mesh_get_patch_counts(phw_mesh_t m, int32_t* counts);
+/* dynamic shared memory (bytes) the bulk-copy pipelined M_p (bytes2[0]) and M_q (bytes2[1]) solves need for this layout
+ * (phw_params.flags bits 9 / 8; they are available when the figure is <= 227 KB - 1 KB).  Host-only. */
+int phw_mesh_pipe_smem(phw_mesh_t m, int64_t* bytes2);
 /* host-only structural invariants of the patch layout, the assembled (ELL) mass rows and the two-sweep patches
  * (tests; small meshes) */
 int phw_mesh_self_check(phw_mesh_t m);

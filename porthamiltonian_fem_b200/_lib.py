@@ -39,7 +39,8 @@ class PhwStats(ctypes.Structure):
                 ('iters_block', ctypes.c_int64), ('max_rel_residual', ctypes.c_double),
                 ('device_ms', ctypes.c_double), ('kernel_launches', ctypes.c_int64), ('bytes_model', ctypes.c_int64),
                 ('lam_min_q', ctypes.c_double), ('lam_max_q', ctypes.c_double), ('skew_bound', ctypes.c_double),
-                ('ms_solve_p', ctypes.c_double), ('ms_solve_q', ctypes.c_double), ('ms_solve_block', ctypes.c_double)]
+                ('ms_solve_p', ctypes.c_double), ('ms_solve_q', ctypes.c_double), ('ms_solve_block', ctypes.c_double),
+                ('kernel_paths', ctypes.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -60,6 +61,7 @@ SIGNATURES = {
     'phw_mesh_get_numbering': (ctypes.c_int, [ctypes.c_void_p, c_i32p, c_i32p, c_i32p]),
     'phw_mesh_self_check': (ctypes.c_int, [ctypes.c_void_p]),
     'phw_mesh_get_patch_counts': (ctypes.c_int, [ctypes.c_void_p, c_i32p]),
+    'phw_mesh_pipe_smem': (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64)]),
     'phw_mesh_destroy': (ctypes.c_int, [ctypes.c_void_p]),
     'phw_solver_create': (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(PhwParams), ctypes.c_int32, ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]),
     'phw_solver_destroy': (ctypes.c_int, [ctypes.c_void_p]),

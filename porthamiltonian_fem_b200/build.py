@@ -7,10 +7,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libphwave.so')
 SOURCES = ['phwave.cu', 'layout.cpp']
-HEADERS = ['kernels.cuh', 'layout.hpp', os.path.join('..', '..', 'include', 'phwave.h')]
+HEADERS = ['kernels.cuh', 'kernels2.cuh', 'kernels_pipe.cuh', 'layout.hpp', os.path.join('..', '..', 'include', 'phwave.h')]
 NVCC_FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
-              '-Xcompiler', '-fPIC,-O3,-fopenmp', '-shared', '--use_fast_math=false']
-NVCC_FLAGS = [f for f in NVCC_FLAGS if not f.startswith('--use_fast_math')]
+              '-Xcompiler', '-fPIC,-O3,-fopenmp', '-shared']
 
 
 def nvcc_path():

@@ -205,6 +205,7 @@ struct RowArgs {
     double* partials;        // [npatch*2] scratch
     Ctl* ctl;
     int counter_id;
+    int gbar;                // 1: cooperative kernels synchronise the grid with grid_barrier (ctl->gbar[0] zeroed before the launch)
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -855,6 +856,26 @@ __global__ void __launch_bounds__(NT_ROWS, PHW_MINB_ROWS) edge_rows_k(const __gr
     if (EPI != EPI_STORE && !(EPI == EPI_DOT && a.wpart)) finish_launch<EPI>(a, acc0, acc1, red);
 }
 
+// grid-wide barrier for co-resident grids (cooperative launch): one arrival per CTA on a monotonically increasing counter
+// (zeroed by the host before the launch).  Back-to-back cooperative_groups grid syncs cost ~40 us each in these kernels
+// (592 CTAs of 256 threads, measured); this barrier ~1 us - which is what makes the inter-GPU exchange, with its two extra
+// barriers per iteration, affordable in the lean kernels.
+__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int& epoch) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        epoch += gridDim.x;
+        __threadfence();
+        atomicAdd(bar, 1u);
+        while (*((volatile unsigned int*)bar) < epoch) { }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// the generic cooperative kernels use the same barrier when RowArgs::gbar is set (phw_params.flags bit 10), else a
+// cooperative-groups grid sync
+#define PHW_GRID_SYNC(args_) do { if ((args_).gbar) grid_barrier(&(args_).ctl->gbar[0], epoch); else grid.sync(); } while (0)
+
 // ------------------------------------------------------------------------------------------------
 // persistent cooperative solve: the whole Chebyshev iteration loop of one linear solve in ONE launch.
 // WHICH = 0: M_p x = b_p, 1: M_q x = b_q, 2: coupled block system (implicit schemes).  One grid-wide
@@ -874,6 +895,7 @@ __global__ void __launch_bounds__(NT, MINB) solve_coop_k(const __grid_constant__
     int k = 0, cur = sc.cur;
     double rho = 0.0, rr = 0.0, bb = 0.0;
     bool conv = false;
+    unsigned int epoch = 0;
     double* partials = a0.partials;
     while (true) {
         PassIO iov, ioe;
@@ -899,7 +921,7 @@ __global__ void __launch_bounds__(NT, MINB) solve_coop_k(const __grid_constant__
         block_sum2(r0, b0, red);
         double* part = partials + (size_t)(k & 1) * 2 * gridDim.x;
         if (threadIdx.x == 0) { part[2 * blockIdx.x] = r0; part[2 * blockIdx.x + 1] = b0; }
-        grid.sync();
+        PHW_GRID_SYNC(a0);
         if (threadIdx.x < 32) {
             double s0 = 0.0, s1 = 0.0;
             for (int i = threadIdx.x; i < (int)gridDim.x; i += 32) { s0 += __ldcg(&part[2 * i]); s1 += __ldcg(&part[2 * i + 1]); }
@@ -923,7 +945,7 @@ __global__ void __launch_bounds__(NT, MINB) solve_coop_k(const __grid_constant__
                 }
             }
             __threadfence_system();
-            grid.sync();
+            PHW_GRID_SYNC(a0);
             // (2) one thread publishes this rank's residual norms + "iterate pushed" flag and waits for the others
             if (blockIdx.x == 0 && threadIdx.x == 0) {
                 double v2[2] = {rr, bb};
@@ -931,7 +953,7 @@ __global__ void __launch_bounds__(NT, MINB) solve_coop_k(const __grid_constant__
                 a0.ctl->xch[k & 1][0] = v2[0]; a0.ctl->xch[k & 1][1] = v2[1];
                 __threadfence();
             }
-            grid.sync();
+            PHW_GRID_SYNC(a0);
             rr = __ldcg(&a0.ctl->xch[k & 1][0]); bb = __ldcg(&a0.ctl->xch[k & 1][1]);
         }
         // the residual just measured belongs to x_k (buffer `cur`), not to the x_{k+1} produced in the same pass:
@@ -953,22 +975,6 @@ __global__ void __launch_bounds__(NT, MINB) solve_coop_k(const __grid_constant__
     }
 }
 
-
-// grid-wide barrier for co-resident grids (cooperative launch): one arrival per CTA on a monotonically increasing counter
-// (zeroed by the host before the launch).  Back-to-back cooperative_groups grid syncs cost ~40 us each in these kernels
-// (592 CTAs of 256 threads, measured); this barrier ~1 us - which is what makes the inter-GPU exchange, with its two extra
-// barriers per iteration, affordable in the lean kernels.
-__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int& epoch) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        epoch += gridDim.x;
-        __threadfence();
-        atomicAdd(bar, 1u);
-        while (*((volatile unsigned int*)bar) < epoch) { }
-        __threadfence();
-    }
-    __syncthreads();
-}
 
 // one inter-GPU exchange of a Chebyshev iteration, called by all threads of all CTAs after the grid-wide
 // reduction: push the new iterate of the interface dofs into the neighbours' buffer `nxt`, all-reduce the residual norms
@@ -1451,6 +1457,7 @@ __global__ void __launch_bounds__(256) csr_dot_k(Csr A, const double* x, double 
 struct CsrSolveArgs {
     Csr A; TriBuf tb; const double* b; const double* pinv; double cheb_d, cheb_c, tol2; int max_iter, which;
     double* partials; Ctl* ctl;
+    int gbar;
 };
 template <int L>
 __global__ void __launch_bounds__(256) solve_coop_csr_k(const CsrSolveArgs a) {
@@ -1462,6 +1469,7 @@ __global__ void __launch_bounds__(256) solve_coop_csr_k(const CsrSolveArgs a) {
     int k = 0, cur = sc.cur;
     double rho = 0.0, rr = 0.0, bb = 0.0;
     bool conv = false;
+    unsigned int epoch = 0;
     const int sub = threadIdx.x % L, g = (blockIdx.x * blockDim.x + threadIdx.x) / L, ng = gridDim.x * blockDim.x / L;
     const int nround = (a.A.n_rows + ng - 1) / ng;
     while (true) {
@@ -1487,7 +1495,7 @@ __global__ void __launch_bounds__(256) solve_coop_csr_k(const CsrSolveArgs a) {
         block_sum2(r0, b0, red);
         double* part = a.partials + (size_t)(k & 1) * 2 * gridDim.x;
         if (threadIdx.x == 0) { part[2 * blockIdx.x] = r0; part[2 * blockIdx.x + 1] = b0; }
-        grid.sync();
+        PHW_GRID_SYNC(a);
         if (threadIdx.x < 32) {
             double s0 = 0.0, s1 = 0.0;
             for (int i = threadIdx.x; i < (int)gridDim.x; i += 32) { s0 += __ldcg(&part[2 * i]); s1 += __ldcg(&part[2 * i + 1]); }

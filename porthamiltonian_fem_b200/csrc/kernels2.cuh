@@ -35,6 +35,7 @@ struct Solve2Args {
     int max_iter, which;
     double* partials;            // [2][3 * gridDim.x]
     Ctl* ctl;
+    int gbar;                    // 1: grid_barrier instead of cooperative-groups grid syncs (phw_params.flags bit 10)
 };
 
 __device__ __forceinline__ double* sel4(double* const (&b)[4], int i) { return i == 0 ? b[0] : (i == 1 ? b[1] : (i == 2 ? b[2] : b[3])); }
@@ -330,6 +331,7 @@ __global__ void __launch_bounds__(NT, MINB) solve2_coop_k(const __grid_constant_
     int k = 0, cur = sc.cur & 3, pass = 0;
     double rho = 0.0, rr = 0.0, bbv = 0.0;
     bool conv = false;
+    unsigned int epoch = 0;
     while (true) {
         Pass2IO io;
         double rho_a, rho_b;
@@ -343,7 +345,7 @@ __global__ void __launch_bounds__(NT, MINB) solve2_coop_k(const __grid_constant_
         block_sum3(r0, r1, b0, red);
         double* part = a.partials + (size_t)(pass & 1) * 3 * gridDim.x;
         if (threadIdx.x == 0) { part[3 * blockIdx.x] = r0; part[3 * blockIdx.x + 1] = r1; part[3 * blockIdx.x + 2] = b0; }
-        grid.sync();
+        PHW_GRID_SYNC(a);
         if (threadIdx.x < 32) {
             double s0 = 0.0, s1 = 0.0, s2 = 0.0;
             for (int i = threadIdx.x; i < (int)gridDim.x; i += 32) { s0 += __ldcg(&part[3 * i]); s1 += __ldcg(&part[3 * i + 1]); s2 += __ldcg(&part[3 * i + 2]); }

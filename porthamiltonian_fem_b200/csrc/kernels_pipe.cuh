@@ -1,0 +1,461 @@
+// kernels_pipe.cuh - bulk-copy pipelined variants of the two Chebyshev mass solves (sm_100a).
+//
+// The lean solve kernels (kernels.cuh: solve_ell_coop_k, solve_mq_coop_k) are bound by the number of independent request
+// streams an SM keeps in flight, not by the layout (phw_stream_probe): every patch goes through
+// load -> barrier -> compute -> barrier phases and only the loads of the resident CTAs overlap.  Here ALL contiguous
+// streams of a patch (cell records or ELL rows, b, x_{k-1}, the owned range of x_k, Jacobi weights, adjacency codes)
+// are fetched by the copy engine: one thread issues 1-D bulk copies (cp.async.bulk.shared::cluster.global, the TMA path
+// without a tensor map) that complete on an mbarrier, into the OTHER of two shared-memory stages while the CTA computes
+// the current patch entirely from shared memory.  The irregular part (ghost values, <= 10 % of a patch) is gathered by
+// 8-byte LDGSTS copies one patch ahead, from an index list that itself arrived by bulk copy with the previous stage.
+// Per SM one stage (50-100 KB) is always in flight, independent of registers and resident warps.
+//
+// Bulk copies need 16-byte aligned addresses and sizes.  The owned ranges start at arbitrary dof ids, so a stream of n
+// elements starting at global element `start` lands in shared memory shifted by (start mod 2) [doubles] or (start mod 4)
+// [32-bit words]: the aligned middle part travels as one bulk copy, the (<= 1 / <= 3) elements before and after it as
+// single LDGSTS copies - nothing outside the range is ever read.
+//
+// Same iteration, same accepted iterate and the same deterministic reductions as the lean kernels (wave_2D.py:820,854).
+#pragma once
+#include "kernels.cuh"
+
+namespace phw {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// wait for the phase with the given parity; a wait that exceeds ~2 s flags the run (ctl->nonconv) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity, Ctl* ctl) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) {
+            if ((threadIdx.x & 31) == 0) atomicAdd((unsigned long long*)&ctl->nonconv, 1ull << 32);
+            return;
+        }
+    }
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+// orders generic-proxy accesses (ld/st) against the async-proxy accesses of the bulk copies, both ways
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// ---- streams of doubles: element i of the range [start, start + n) lives at s[(start & 1) + i]
+__device__ __forceinline__ uint32_t f64s_bytes(int start, int n) {
+    const int m = n - (start & 1);
+    return m > 0 ? (uint32_t)(m & ~1) * 8u : 0u;
+}
+__device__ __forceinline__ void f64s_bulk(double* s, const double* g, int start, int n, unsigned long long* bar) {
+    const int head = start & 1;
+    const uint32_t bytes = f64s_bytes(start, n);
+    if (bytes) bulk_g2s(s + 2 * head, g + start + head, bytes, bar);
+}
+// j = 0: the element before the aligned part, j = 1: the element after it (each by one thread)
+__device__ __forceinline__ void f64s_fix(double* s, const double* g, int start, int n, int j) {
+    const int head = start & 1, m = n - head;
+    if (j == 0) { if (head && n > 0) cp_async8(&s[head], &g[start]); }
+    else if (m > 0 && (m & 1)) cp_async8(&s[head + n - 1], &g[start + n - 1]);
+}
+// ---- streams of 32-bit words: element i lives at s[(start & 3) + i]
+__device__ __forceinline__ int u32s_head(int start, int n) { const int h = (4 - (start & 3)) & 3; return h < n ? h : n; }
+__device__ __forceinline__ uint32_t u32s_bytes(int start, int n) { return n > 0 ? (uint32_t)((n - u32s_head(start, n)) & ~3) * 4u : 0u; }
+__device__ __forceinline__ void u32s_bulk(uint32_t* s, const uint32_t* g, int start, int n, unsigned long long* bar) {
+    if (n <= 0) return;
+    const int head = u32s_head(start, n);
+    const uint32_t bytes = u32s_bytes(start, n);
+    if (bytes) bulk_g2s(s + (start & 3) + head, g + start + head, bytes, bar);
+}
+// j = 0..2: the elements before the aligned part, j = 3..5: those after it
+__device__ __forceinline__ void u32s_fix(uint32_t* s, const uint32_t* g, int start, int n, int j) {
+    if (n <= 0) return;
+    const int head = u32s_head(start, n), nb = (n - head) & ~3;
+    const int e = (j < 3) ? j : head + nb + (j - 3);
+    const bool ok = (j < 3) ? (j < head) : (e < n);
+    if (ok) cp_async4(&s[(start & 3) + e], &g[start + e]);
+}
+
+// patch headers of a CTA's next patches are kept in a ring of four in shared memory (loaded three patches ahead)
+__device__ __forceinline__ void load_hdr_smem_at(PatchHdr* dst, const PatchHdr* src, int first_thread) {
+    const int t = (int)threadIdx.x - first_thread;
+    if (t >= 0 && t < 20) reinterpret_cast<int*>(dst)[t] = __ldg(reinterpret_cast<const int*>(src) + t);
+}
+
+// grid-wide barrier of the pipelined kernels: grid_barrier plus the proxy fences that order the iterate written with
+// ordinary stores before the barrier against the bulk copies that read it after the barrier
+__device__ __forceinline__ void grid_barrier_px(unsigned int* bar, unsigned int& epoch) {
+    fence_proxy_async();
+    grid_barrier(bar, epoch);
+    fence_proxy_async();
+}
+
+// ------------------------------------------------------------------------------------------------
+// M_q solve (cell-based rows on the packed 32-byte cell records).  Stage = [x_k local | cell records | b | pinv |
+// x_{k-1} | eadj]; besides the two stages: the per-cell contributions (3 doubles per cell) and two ghost-index lists.
+// ------------------------------------------------------------------------------------------------
+struct MqPipeArgs {
+    int npatch;
+    const PatchHdr* hdr;
+    const uint4* cellq;
+    const int* ghost_e; const uint32_t* eadj;
+    const double* b; const double* pinv;
+    double* buf[3];
+    double cheb_d, cheb_c, tol2;
+    int max_iter, which;
+    double* partials; Ctl* ctl;
+    // carve-up of the dynamic shared memory (bytes, multiples of 16; sized for the largest patch by the host)
+    uint32_t off_cells, off_b, off_pinv, off_xprev, off_eadj, stage_bytes, off_sc3, off_gidx, gidx_bytes;
+};
+
+// put everything patch `hn` needs in flight into `stage` (all threads call this; thread 0 issues the bulk copies).
+// gidx_this: ghost index list of this patch in shared memory (nullptr: read it from global memory - first patch of an
+// iteration); hn2 / gidx_next: the patch after `hn` and the list slot its ghost indices go to (nullptr: none).
+template <int NT>
+__device__ __forceinline__ void mq_issue(const MqPipeArgs& a, unsigned char* stage, const uint32_t* gidx_this, uint32_t* gidx_next,
+                                         const PatchHdr& hn, const PatchHdr* hn2, const double* xk, const double* xprev,
+                                         bool use_prev, unsigned long long* bar) {
+    double* sq = reinterpret_cast<double*>(stage);
+    double* sb = reinterpret_cast<double*>(stage + a.off_b);
+    double* spv = reinterpret_cast<double*>(stage + a.off_pinv);
+    double* sxp = reinterpret_cast<double*>(stage + a.off_xprev);
+    uint32_t* sea = reinterpret_cast<uint32_t*>(stage + a.off_eadj);
+    const int es = hn.e_start, ec = hn.e_cnt;
+    const uint32_t* gh = reinterpret_cast<const uint32_t*>(a.ghost_e);
+    if (threadIdx.x == 0) {
+        const uint32_t cell_bytes = (uint32_t)hn.n_ecells * 32u;
+        uint32_t bytes = f64s_bytes(es, ec) * (use_prev ? 4u : 3u) + cell_bytes + u32s_bytes(es, ec);
+        if (hn2) bytes += u32s_bytes(hn2->ge_off, hn2->ge_cnt);
+        mbar_arrive_expect_tx(bar, bytes);
+        if (cell_bytes) bulk_g2s(stage + a.off_cells, a.cellq + 2 * (size_t)hn.cell_off, cell_bytes, bar);
+        f64s_bulk(sq, xk, es, ec, bar);
+        f64s_bulk(sb, a.b, es, ec, bar);
+        f64s_bulk(spv, a.pinv, es, ec, bar);
+        if (use_prev) f64s_bulk(sxp, xprev, es, ec, bar);
+        u32s_bulk(sea, a.eadj, es, ec, bar);
+        if (hn2) u32s_bulk(gidx_next, gh, hn2->ge_off, hn2->ge_cnt, bar);
+    }
+    const int lane = (int)threadIdx.x - (NT - 32);      // the last warp copies the unaligned ends of the streams
+    if (lane >= 0) {
+        if (lane < 2) f64s_fix(sq, xk, es, ec, lane);
+        else if (lane < 4) f64s_fix(sb, a.b, es, ec, lane - 2);
+        else if (lane < 6) f64s_fix(spv, a.pinv, es, ec, lane - 4);
+        else if (lane < 8) { if (use_prev) f64s_fix(sxp, xprev, es, ec, lane - 6); }
+        else if (lane < 14) u32s_fix(sea, a.eadj, es, ec, lane - 8);
+        else if (lane < 20) { if (hn2) u32s_fix(gidx_next, gh, hn2->ge_off, hn2->ge_cnt, lane - 14); }
+    }
+    double* sg = sq + (es & 1) + ec;                     // ghost values follow the owned range
+    if (gidx_this) {
+        const uint32_t* gi = gidx_this + (hn.ge_off & 3);
+        for (int i = threadIdx.x; i < hn.ge_cnt; i += NT) cp_async8(&sg[i], &xk[gi[i]]);
+    } else {
+        for (int i = threadIdx.x; i < hn.ge_cnt; i += NT) cp_async8(&sg[i], &xk[__ldg(&a.ghost_e[hn.ge_off + i])]);
+    }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT, 1) solve_mq_pipe_k(const __grid_constant__ MqPipeArgs a) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    __shared__ double red[64];
+    __shared__ double bc[2];
+    __shared__ PatchHdr s_hdr[4];
+    __shared__ __align__(8) unsigned long long full[2];
+    SolveCtl& sc = a.ctl->sc[a.which];
+    int k = 0, cur = sc.cur;
+    double rho = 0.0, rr = 0.0, bb = 0.0;
+    bool conv = false;
+    unsigned int epoch = 0;
+    unsigned int seq = 0;       // patches this CTA has processed so far: stage = seq & 1, mbarrier parity = (seq >> 1) & 1
+    if (threadIdx.x == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_fence_init(); }
+    __syncthreads();
+    double* sc3 = reinterpret_cast<double*>(smraw + a.off_sc3);
+    const int n_my = ((int)blockIdx.x < a.npatch) ? (a.npatch - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    while (true) {
+        double c1, c2, rho_k;
+        cheb_coeffs(k, rho, a.cheb_d, a.cheb_c, c1, c2, rho_k);
+        const int nxt = (cur + 1) % 3, prv = (cur + 2) % 3;
+        const double* xk = cur == 0 ? a.buf[0] : (cur == 1 ? a.buf[1] : a.buf[2]);
+        const double* xprev = prv == 0 ? a.buf[0] : (prv == 1 ? a.buf[1] : a.buf[2]);
+        double* xnew = nxt == 0 ? a.buf[0] : (nxt == 1 ? a.buf[1] : a.buf[2]);
+        const bool use_prev = k > 0;
+        double r0 = 0.0, b0 = 0.0;
+        for (int j = 0; j < 3 && j < n_my; ++j) load_hdr_smem_at(&s_hdr[j], &a.hdr[blockIdx.x + j * gridDim.x], 32 * j);
+        __syncthreads();
+        if (n_my > 0)
+            mq_issue<NT>(a, smraw + (seq & 1u) * a.stage_bytes, nullptr,
+                         reinterpret_cast<uint32_t*>(smraw + a.off_gidx + ((seq + 1u) & 1u) * a.gidx_bytes),
+                         s_hdr[0], n_my > 1 ? &s_hdr[1] : nullptr, xk, xprev, use_prev, &full[seq & 1u]);
+        for (int it = 0; it < n_my; ++it, ++seq) {
+            const unsigned int s = seq & 1u;
+            cp_async_wait_all();
+            mbar_wait(&full[s], (seq >> 1) & 1u, a.ctl);
+            __syncthreads();
+            const PatchHdr& h = s_hdr[it & 3];
+            if (it + 3 < n_my) load_hdr_smem_at(&s_hdr[(it + 3) & 3], &a.hdr[blockIdx.x + (it + 3) * gridDim.x], 64);
+            if (it + 1 < n_my)
+                mq_issue<NT>(a, smraw + (s ^ 1u) * a.stage_bytes,
+                             reinterpret_cast<const uint32_t*>(smraw + a.off_gidx + (s ^ 1u) * a.gidx_bytes),
+                             reinterpret_cast<uint32_t*>(smraw + a.off_gidx + s * a.gidx_bytes),
+                             s_hdr[(it + 1) & 3], it + 2 < n_my ? &s_hdr[(it + 2) & 3] : nullptr, xk, xprev, use_prev, &full[s ^ 1u]);
+            const unsigned char* stage = smraw + s * a.stage_bytes;
+            const double* sq = reinterpret_cast<const double*>(stage) + (h.e_start & 1);
+            const uint4* scell = reinterpret_cast<const uint4*>(stage + a.off_cells);
+            for (int lc = threadIdx.x; lc < h.n_ecells; lc += NT) {
+                const uint4 qa = scell[2 * lc], qb = scell[2 * lc + 1];
+                const uint32_t e0 = qa.x & 0xFFFFu, e1 = qa.x >> 16, e2 = qa.y & 0xFFFFu;
+                const double g0 = __hiloint2double((int)qa.w, (int)qa.z);
+                const double g1 = __hiloint2double((int)qb.y, (int)qb.x), g2 = __hiloint2double((int)qb.w, (int)qb.z);
+                const double S = g0 + g1 + g2;
+                const double s0 = (e0 & 0x8000u) ? -1.0 : 1.0, s1 = (e1 & 0x8000u) ? -1.0 : 1.0, s2 = (e2 & 0x8000u) ? -1.0 : 1.0;
+                const double t0 = s0 * sq[e0 & 0x3FFFu], t1 = s1 * sq[e1 & 0x3FFFu], t2 = s2 * sq[e2 & 0x3FFFu];
+                const double ST = S * (t0 + t1 + t2);
+                sc3[3 * lc] = s0 * (ST + 2.0 * S * t0 - 4.0 * (g0 * t0 + g2 * t1 + g1 * t2));
+                sc3[3 * lc + 1] = s1 * (ST + 2.0 * S * t1 - 4.0 * (g2 * t0 + g1 * t1 + g0 * t2));
+                sc3[3 * lc + 2] = s2 * (ST + 2.0 * S * t2 - 4.0 * (g1 * t0 + g0 * t1 + g2 * t2));
+            }
+            __syncthreads();
+            const double* sb = reinterpret_cast<const double*>(stage + a.off_b) + (h.e_start & 1);
+            const double* spv = reinterpret_cast<const double*>(stage + a.off_pinv) + (h.e_start & 1);
+            const double* sxp = reinterpret_cast<const double*>(stage + a.off_xprev) + (h.e_start & 1);
+            const uint32_t* sea = reinterpret_cast<const uint32_t*>(stage + a.off_eadj) + (h.e_start & 3);
+            for (int le = threadIdx.x; le < h.e_cnt; le += NT) {
+                const uint32_t adj = sea[le];
+                const uint32_t ca = adj & 0xFFFFu, cb = adj >> 16;
+                const double bv = sb[le], pv = spv[le];
+                double val = sc3[3 * (ca >> 2) + (ca & 3u)];
+                if (cb != 0xFFFFu) val += sc3[3 * (cb >> 2) + (cb & 3u)];
+                const double xc = sq[le];
+                const double r_ = bv - val;
+                double xn = xc + c2 * pv * r_;
+                if (use_prev) xn += c1 * (xc - sxp[le]);
+                xnew[h.e_start + le] = xn;
+                r0 += pv * r_ * r_;
+                b0 += pv * bv * bv;
+            }
+        }
+        __syncthreads();
+        block_sum2(r0, b0, red);
+        double* part = a.partials + (size_t)(k & 1) * 2 * gridDim.x;
+        if (threadIdx.x == 0) { part[2 * blockIdx.x] = r0; part[2 * blockIdx.x + 1] = b0; }
+        grid_barrier_px(&a.ctl->gbar[0], epoch);
+        if (threadIdx.x < 32) {
+            double s0 = 0.0, s1 = 0.0;
+            for (int i = threadIdx.x; i < (int)gridDim.x; i += 32) { s0 += __ldcg(&part[2 * i]); s1 += __ldcg(&part[2 * i + 1]); }
+            s0 = warp_sum(s0); s1 = warp_sum(s1);
+            if (threadIdx.x == 0) { bc[0] = s0; bc[1] = s1; }
+        }
+        __syncthreads();
+        rr = bc[0]; bb = bc[1];
+        __syncthreads();
+        conv = rr <= a.tol2 * bb;
+        if (blockIdx.x == 0 && threadIdx.x == 0 && k < 48) a.ctl->reshist[a.which][k] = (bb > 0.0) ? rr / bb : 0.0;
+        k += 1;
+        if (conv) break;
+        rho = rho_k; cur = nxt;
+        if (k >= a.max_iter) break;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        sc.cur = cur; sc.k = k; sc.done = 1; sc.rr = rr; sc.bb = bb; sc.rho = rho;
+        sc.iters += k; sc.solves += 1;
+        if (!conv) a.ctl->nonconv += 1;
+        double rel = (bb > 0.0) ? sqrt(rr / bb) : 0.0;
+        if (rel > sc.maxres) sc.maxres = rel;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// M_p solve on the assembled sliced-ELL rows.  Stage = [slice offsets (ids | weights) | x_k local | b | x_{k-1} |
+// weights | ids]; plus two ghost-index lists.
+// ------------------------------------------------------------------------------------------------
+struct EllPipeArgs {
+    int npatch;
+    const PatchHdr* hdr;
+    const uint32_t* ell_ioff; const uint32_t* ell_woff; const uint16_t* ell_ids; const double* ell_w;
+    const int* ghost_v;
+    const double* b;
+    double* buf[3];
+    double cheb_d, cheb_c, tol2;
+    int max_iter, which;
+    double* partials; Ctl* ctl;
+    uint32_t off_wo, off_x, off_b, off_xprev, off_w, off_ids, stage_bytes, off_gidx, gidx_bytes;
+};
+
+template <int NT>
+__device__ __forceinline__ void ell_issue(const EllPipeArgs& a, unsigned char* stage, const uint32_t* gidx_this, uint32_t* gidx_next,
+                                          const PatchHdr& hn, const PatchHdr* hn2, const double* xk, const double* xprev,
+                                          bool use_prev, unsigned long long* bar) {
+    uint32_t* s_io = reinterpret_cast<uint32_t*>(stage);
+    uint32_t* s_wo = reinterpret_cast<uint32_t*>(stage + a.off_wo);
+    double* sx = reinterpret_cast<double*>(stage + a.off_x);
+    double* sb = reinterpret_cast<double*>(stage + a.off_b);
+    double* sxp = reinterpret_cast<double*>(stage + a.off_xprev);
+    const int vs = hn.v_start, vc = hn.v_cnt;
+    const uint32_t* gh = reinterpret_cast<const uint32_t*>(a.ghost_v);
+    if (threadIdx.x == 0) {
+        const uint32_t id_bytes = (uint32_t)hn.ell_in * 2u, w_bytes = (uint32_t)hn.ell_wn * 8u;
+        uint32_t bytes = f64s_bytes(vs, vc) * (use_prev ? 3u : 2u) + id_bytes + w_bytes;
+        if (hn2) bytes += u32s_bytes(hn2->gv_off, hn2->gv_cnt);
+        mbar_arrive_expect_tx(bar, bytes);
+        if (w_bytes) bulk_g2s(stage + a.off_w, a.ell_w + (uint32_t)hn.ell_w0, w_bytes, bar);
+        if (id_bytes) bulk_g2s(stage + a.off_ids, a.ell_ids + (uint32_t)hn.ell_i0, id_bytes, bar);
+        f64s_bulk(sx, xk, vs, vc, bar);
+        f64s_bulk(sb, a.b, vs, vc, bar);
+        if (use_prev) f64s_bulk(sxp, xprev, vs, vc, bar);
+        if (hn2) u32s_bulk(gidx_next, gh, hn2->gv_off, hn2->gv_cnt, bar);
+    }
+    const int lane = (int)threadIdx.x - (NT - 32);
+    if (lane >= 0) {
+        if (lane < 2) f64s_fix(sx, xk, vs, vc, lane);
+        else if (lane < 4) f64s_fix(sb, a.b, vs, vc, lane - 2);
+        else if (lane < 6) { if (use_prev) f64s_fix(sxp, xprev, vs, vc, lane - 4); }
+        else if (lane < 12) { if (hn2) u32s_fix(gidx_next, gh, hn2->gv_off, hn2->gv_cnt, lane - 6); }
+    }
+    // slice offsets of the patch (raw; the patch bases ell_i0 / ell_w0 are subtracted where they are used)
+    const int nsl = (vc + 31) >> 5;
+    for (int i = threadIdx.x; i <= nsl; i += NT) { cp_async4(&s_io[i], &a.ell_ioff[hn.vs_off + i]); cp_async4(&s_wo[i], &a.ell_woff[hn.vs_off + i]); }
+    double* sg = sx + (vs & 1) + vc;
+    if (gidx_this) {
+        const uint32_t* gi = gidx_this + (hn.gv_off & 3);
+        for (int i = threadIdx.x; i < hn.gv_cnt; i += NT) cp_async8(&sg[i], &xk[gi[i]]);
+    } else {
+        for (int i = threadIdx.x; i < hn.gv_cnt; i += NT) cp_async8(&sg[i], &xk[__ldg(&a.ghost_v[hn.gv_off + i])]);
+    }
+}
+
+template <int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) solve_ell_pipe_k(const __grid_constant__ EllPipeArgs a) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    __shared__ double red[64];
+    __shared__ double bc[2];
+    __shared__ PatchHdr s_hdr[4];
+    __shared__ __align__(8) unsigned long long full[2];
+    SolveCtl& sc = a.ctl->sc[a.which];
+    int k = 0, cur = sc.cur;
+    double rho = 0.0, rr = 0.0, bb = 0.0;
+    bool conv = false;
+    unsigned int epoch = 0;
+    unsigned int seq = 0;
+    if (threadIdx.x == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_fence_init(); }
+    __syncthreads();
+    const int n_my = ((int)blockIdx.x < a.npatch) ? (a.npatch - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    while (true) {
+        double c1, c2, rho_k;
+        cheb_coeffs(k, rho, a.cheb_d, a.cheb_c, c1, c2, rho_k);
+        const int nxt = (cur + 1) % 3, prv = (cur + 2) % 3;
+        const double* xk = cur == 0 ? a.buf[0] : (cur == 1 ? a.buf[1] : a.buf[2]);
+        const double* xprev = prv == 0 ? a.buf[0] : (prv == 1 ? a.buf[1] : a.buf[2]);
+        double* xnew = nxt == 0 ? a.buf[0] : (nxt == 1 ? a.buf[1] : a.buf[2]);
+        const bool use_prev = k > 0;
+        double r0 = 0.0, b0 = 0.0;
+        for (int j = 0; j < 3 && j < n_my; ++j) load_hdr_smem_at(&s_hdr[j], &a.hdr[blockIdx.x + j * gridDim.x], 32 * j);
+        __syncthreads();
+        if (n_my > 0)
+            ell_issue<NT>(a, smraw + (seq & 1u) * a.stage_bytes, nullptr,
+                          reinterpret_cast<uint32_t*>(smraw + a.off_gidx + ((seq + 1u) & 1u) * a.gidx_bytes),
+                          s_hdr[0], n_my > 1 ? &s_hdr[1] : nullptr, xk, xprev, use_prev, &full[seq & 1u]);
+        for (int it = 0; it < n_my; ++it, ++seq) {
+            const unsigned int s = seq & 1u;
+            cp_async_wait_all();
+            mbar_wait(&full[s], (seq >> 1) & 1u, a.ctl);
+            __syncthreads();
+            const PatchHdr& h = s_hdr[it & 3];
+            if (it + 3 < n_my) load_hdr_smem_at(&s_hdr[(it + 3) & 3], &a.hdr[blockIdx.x + (it + 3) * gridDim.x], 64);
+            if (it + 1 < n_my)
+                ell_issue<NT>(a, smraw + (s ^ 1u) * a.stage_bytes,
+                              reinterpret_cast<const uint32_t*>(smraw + a.off_gidx + (s ^ 1u) * a.gidx_bytes),
+                              reinterpret_cast<uint32_t*>(smraw + a.off_gidx + s * a.gidx_bytes),
+                              s_hdr[(it + 1) & 3], it + 2 < n_my ? &s_hdr[(it + 2) & 3] : nullptr, xk, xprev, use_prev, &full[s ^ 1u]);
+            const unsigned char* stage = smraw + s * a.stage_bytes;
+            const uint32_t* s_io = reinterpret_cast<const uint32_t*>(stage);
+            const uint32_t* s_wo = reinterpret_cast<const uint32_t*>(stage + a.off_wo);
+            const double* sx = reinterpret_cast<const double*>(stage + a.off_x) + (h.v_start & 1);
+            const double* sb = reinterpret_cast<const double*>(stage + a.off_b) + (h.v_start & 1);
+            const double* sxp = reinterpret_cast<const double*>(stage + a.off_xprev) + (h.v_start & 1);
+            const double* sw = reinterpret_cast<const double*>(stage + a.off_w);
+            const uint4* sid4 = reinterpret_cast<const uint4*>(stage + a.off_ids);
+            const uint32_t i0 = (uint32_t)h.ell_i0, w0 = (uint32_t)h.ell_w0;
+            for (int lv = threadIdx.x; lv < h.v_cnt; lv += NT) {
+                const int sl = lv >> 5, lane = lv & 31;
+                const uint32_t io0 = s_io[sl] - i0, wo0 = s_wo[sl] - w0;
+                const int W = (int)((s_wo[sl + 1] - w0 - wo0) >> 5);
+                double val = 0.0, dsum = 0.0;
+                for (int c = 0; 8 * c < W; ++c) {
+                    const uint4 cd = sid4[(io0 >> 3) + c * 32 + lane];
+                    const uint32_t w4[4] = {cd.x, cd.y, cd.z, cd.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const double wa = (8 * c + 2 * j < W) ? sw[wo0 + (8 * c + 2 * j) * 32 + lane] : 0.0;
+                        const double wb = (8 * c + 2 * j + 1 < W) ? sw[wo0 + (8 * c + 2 * j + 1) * 32 + lane] : 0.0;
+                        val += wa * sx[w4[j] & 0xFFFFu];
+                        val += wb * sx[w4[j] >> 16];
+                        dsum += wa + wb;
+                    }
+                }
+                // the P1 mass diagonal is the sum of the row's off-diagonal entries, so neither it nor the Jacobi weight is read
+                const double xc = sx[lv], bv = sb[lv];
+                const double pv = 1.0 / dsum;
+                val += dsum * xc;
+                const double r_ = bv - val;
+                double xn = xc + c2 * pv * r_;
+                if (use_prev) xn += c1 * (xc - sxp[lv]);
+                xnew[h.v_start + lv] = xn;
+                r0 += pv * r_ * r_;
+                b0 += pv * bv * bv;
+            }
+        }
+        __syncthreads();
+        block_sum2(r0, b0, red);
+        double* part = a.partials + (size_t)(k & 1) * 2 * gridDim.x;
+        if (threadIdx.x == 0) { part[2 * blockIdx.x] = r0; part[2 * blockIdx.x + 1] = b0; }
+        grid_barrier_px(&a.ctl->gbar[0], epoch);
+        if (threadIdx.x < 32) {
+            double s0 = 0.0, s1 = 0.0;
+            for (int i = threadIdx.x; i < (int)gridDim.x; i += 32) { s0 += __ldcg(&part[2 * i]); s1 += __ldcg(&part[2 * i + 1]); }
+            s0 = warp_sum(s0); s1 = warp_sum(s1);
+            if (threadIdx.x == 0) { bc[0] = s0; bc[1] = s1; }
+        }
+        __syncthreads();
+        rr = bc[0]; bb = bc[1];
+        __syncthreads();
+        conv = rr <= a.tol2 * bb;
+        if (blockIdx.x == 0 && threadIdx.x == 0 && k < 48) a.ctl->reshist[a.which][k] = (bb > 0.0) ? rr / bb : 0.0;
+        k += 1;
+        if (conv) break;
+        rho = rho_k; cur = nxt;
+        if (k >= a.max_iter) break;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        sc.cur = cur; sc.k = k; sc.done = 1; sc.rr = rr; sc.bb = bb; sc.rho = rho;
+        sc.iters += k; sc.solves += 1;
+        if (!conv) a.ctl->nonconv += 1;
+        double rel = (bb > 0.0) ? sqrt(rr / bb) : 0.0;
+        if (rel > sc.maxres) sc.maxres = rel;
+    }
+}
+
+}  // namespace phw

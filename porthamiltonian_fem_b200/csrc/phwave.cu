@@ -16,6 +16,7 @@
 #include "../../include/phwave.h"
 #include "kernels.cuh"
 #include "kernels2.cuh"
+#include "kernels_pipe.cuh"
 #include "layout.hpp"
 
 using namespace phw;
@@ -562,6 +563,10 @@ struct phw_solver_s {
     Ring2Dev r2[2]{};
     size_t smem2[2] = {0, 0};
     uint4* d_cellq = nullptr;
+    bool pipe_q = false, pipe_p = false;   // bulk-copy pipelined mass solves (kernels_pipe.cuh; flags bits 8 / 9)
+    MqPipeArgs pq{}; EllPipeArgs pp{};     // their shared-memory carve-ups (sized for the largest patch)
+    size_t smem_pq = 0, smem_pp = 0;
+    int64_t kernel_paths = 0;              // PHW_PATH_* bits of the solve kernels launched since the last phw_run began
     int *d_cells_user = nullptr; double* d_vtx_user = nullptr; unsigned long long* d_mm = nullptr;
     std::vector<cudaEvent_t> prof_ev; std::vector<int> prof_which;
     bool have_vq = false;      // Stormer-Verlet first-same-as-last: v_q of the previous step is valid
@@ -646,6 +651,7 @@ RowArgs base_args(phw_solver_s* s) {
     a.dot_scale = 1.0;
     a.mdiag = s->mdiag_p;   // vertex M-only rows use the pure P1 mass diagonal
     a.xscale = s->prm.strong ? 4.0 : 0.0;
+    a.gbar = (s->prm.flags & 1024) ? 1 : 0;
     return a;
 }
 
@@ -698,6 +704,7 @@ int launch_coop(phw_solver_s* s, const RowArgs& av, const RowArgs& ae) {
     if (occ < 1) return fail(PHW_ECUDA, "cooperative solve kernel does not fit on an SM");
     const int grid = std::max(1, std::min(s->npatch, occ * s->sm_count));
     void* args[] = {(void*)&av, (void*)&ae, (void*)&s->pc};
+    if (av.gbar) CU(cudaMemsetAsync(&s->ctl->gbar[0], 0, sizeof(unsigned int), s->stream));
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     const bool prof = (s->prm.flags & 4) && s->prof_ev.size() < 2 * 8192;
     if (prof) {
@@ -733,6 +740,8 @@ int launch_coop2_cfg(phw_solver_s* s) {
     a.tol2 = s->prm.tol * s->prm.tol;
     if (s->G > 1) { const double t = std::max(s->prm.tol / std::sqrt((double)s->G), 1e-14); a.tol2 = std::min(a.tol2, t * t); }
     a.max_iter = s->prm.max_iter; a.which = KIND; a.partials = s->partials; a.ctl = s->ctl;
+    a.gbar = (s->prm.flags & 1024) ? 1 : 0;
+    if (a.gbar) CU(cudaMemsetAsync(&s->ctl->gbar[0], 0, sizeof(unsigned int), s->stream));
     void* args[] = {(void*)&a};
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     const bool prof = (s->prm.flags & 4) && s->prof_ev.size() < 2 * 8192;
@@ -839,6 +848,81 @@ int launch_mq_lean(phw_solver_s* s) {
     return 0;
 }
 
+// bulk-copy pipelined M_q solve (kernels_pipe.cuh): 1024 threads, one CTA per SM, two shared-memory stages
+int launch_mq_pipe(phw_solver_s* s) {
+    constexpr int NT = 1024;
+    void* kern = (void*)solve_mq_pipe_k<NT>;
+    CU(cudaMemsetAsync(&s->ctl->gbar[0], 0, sizeof(unsigned int), s->stream));
+    static bool configured = false;
+    if (!configured) { CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024)); configured = true; }
+    int occ = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, s->smem_pq));
+    if (occ < 1) return fail(PHW_ECUDA, "pipelined M_q solve kernel does not fit on an SM");
+    const int grid = std::max(1, std::min(s->npatch, occ * s->sm_count));
+    MqPipeArgs a = s->pq;
+    a.npatch = s->npatch; a.hdr = s->dm.hdr; a.cellq = s->d_cellq;
+    a.ghost_e = s->dm.ghost_e; a.eadj = s->dm.eadj; a.b = s->bq; a.pinv = s->pinv_q;
+    for (int i = 0; i < 3; ++i) a.buf[i] = s->tq.b[i];
+    a.cheb_d = s->cheb_d[1]; a.cheb_c = s->cheb_c[1];
+    a.tol2 = s->prm.tol * s->prm.tol;
+    if (s->G > 1) { const double t = std::max(s->prm.tol / std::sqrt((double)s->G), 1e-14); a.tol2 = std::min(a.tol2, t * t); }
+    a.max_iter = s->prm.max_iter; a.which = 1; a.partials = s->partials; a.ctl = s->ctl;
+    void* args[] = {(void*)&a};
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    const bool prof = (s->prm.flags & 4) && s->prof_ev.size() < 2 * 8192;
+    if (prof) {
+        CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+        CU(cudaEventRecord(e0, s->stream));
+    }
+    CU(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(NT), args, s->smem_pq, s->stream));
+    if (prof) {
+        CU(cudaEventRecord(e1, s->stream));
+        s->prof_ev.push_back(e0); s->prof_ev.push_back(e1); s->prof_which.push_back(1);
+    }
+    s->launches++;
+    s->kernel_paths |= PHW_PATH_PIPE_Q;
+    return 0;
+}
+
+// bulk-copy pipelined ELL M_p solve: two CTAs of 512 threads per SM when two pairs of stages fit, else one of 1024
+template <int NT, int MINB>
+int launch_ell_pipe_cfg(phw_solver_s* s) {
+    void* kern = (void*)solve_ell_pipe_k<NT, MINB>;
+    CU(cudaMemsetAsync(&s->ctl->gbar[0], 0, sizeof(unsigned int), s->stream));
+    static bool configured = false;
+    if (!configured) { CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024)); configured = true; }
+    int occ = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, s->smem_pp));
+    if (occ < 1) return fail(PHW_ECUDA, "pipelined M_p solve kernel does not fit on an SM");
+    const int grid = std::max(1, std::min(s->npatch, std::min(occ, MINB) * s->sm_count));
+    EllPipeArgs a = s->pp;
+    a.npatch = s->npatch; a.hdr = s->dm.hdr; a.ell_ioff = s->dm.ell_ioff; a.ell_woff = s->dm.ell_woff; a.ell_ids = s->dm.ell_ids; a.ell_w = s->dm.ell_w;
+    a.ghost_v = s->dm.ghost_v; a.b = s->bp;
+    for (int i = 0; i < 3; ++i) a.buf[i] = s->tp.b[i];
+    a.cheb_d = s->cheb_d[0]; a.cheb_c = s->cheb_c[0];
+    a.tol2 = s->prm.tol * s->prm.tol;
+    if (s->G > 1) { const double t = std::max(s->prm.tol / std::sqrt((double)s->G), 1e-14); a.tol2 = std::min(a.tol2, t * t); }
+    a.max_iter = s->prm.max_iter; a.which = 0; a.partials = s->partials; a.ctl = s->ctl;
+    void* args[] = {(void*)&a};
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    const bool prof = (s->prm.flags & 4) && s->prof_ev.size() < 2 * 8192;
+    if (prof) {
+        CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+        CU(cudaEventRecord(e0, s->stream));
+    }
+    CU(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(NT), args, s->smem_pp, s->stream));
+    if (prof) {
+        CU(cudaEventRecord(e1, s->stream));
+        s->prof_ev.push_back(e0); s->prof_ev.push_back(e1); s->prof_which.push_back(0);
+    }
+    s->launches++;
+    s->kernel_paths |= PHW_PATH_PIPE_P;
+    return 0;
+}
+int launch_ell_pipe(phw_solver_s* s) {
+    return (2 * (s->smem_pp + 2048) <= 227 * 1024) ? launch_ell_pipe_cfg<512, 2>(s) : launch_ell_pipe_cfg<1024, 1>(s);
+}
+
 int solve_begin(phw_solver_s* s, int which) {
     solve_begin_k<<<1, 1, 0, s->stream>>>(s->ctl, which);
     s->launches++;
@@ -855,6 +939,8 @@ int solve_mass(phw_solver_s* s, int which, int n_launch) {
         a.b = which == PHW_P ? s->bp : s->bq; a.pinv = which == PHW_P ? s->pinv_p : s->pinv_q;
         a.cheb_d = s->cheb_d[which]; a.cheb_c = s->cheb_c[which]; a.tol2 = s->prm.tol * s->prm.tol;
         a.max_iter = s->prm.max_iter; a.which = which; a.partials = s->partials; a.ctl = s->ctl;
+        a.gbar = (s->prm.flags & 1024) ? 1 : 0;
+        if (a.gbar) CU(cudaMemsetAsync(&s->ctl->gbar[0], 0, sizeof(unsigned int), s->stream));
         void* kern = a.A.lanes == 4 ? (void*)solve_coop_csr_k<4> : a.A.lanes == 8 ? (void*)solve_coop_csr_k<8>
                    : a.A.lanes == 16 ? (void*)solve_coop_csr_k<16> : (void*)solve_coop_csr_k<32>;
         int occ = 0;
@@ -874,7 +960,10 @@ int solve_mass(phw_solver_s* s, int which, int n_launch) {
     if (s->coop) {
         a.b = which == PHW_P ? s->bp : s->bq;
         a.pinv = which == PHW_P ? s->pinv_p : s->pinv_q;
+        if (which == PHW_Q && s->pipe_q && s->pc.world <= 1) return launch_mq_pipe(s);
+        if (which == PHW_P && s->pipe_p && s->pc.world <= 1 && s->ell_p && a.mdiag == nullptr) return launch_ell_pipe(s);
         if (which == PHW_P && s->ell_p && a.mdiag == nullptr && !s->ell_staged) {
+            s->kernel_paths |= PHW_PATH_LEAN_P;
             static const int cfg = [] { const char* e = getenv("PHW_ELL_CFG"); return e ? atoi(e) : 0; }();
             switch (cfg) {
                 case 1: return launch_ell_lean<256, 6>(s);
@@ -887,6 +976,7 @@ int solve_mass(phw_solver_s* s, int which, int n_launch) {
             }
         }
         if (which == PHW_Q && !(s->prm.flags & 128)) {   // flags bit 7: generic kernels everywhere
+            s->kernel_paths |= PHW_PATH_LEAN_Q;
             static const int cfg = [] { const char* e = getenv("PHW_MQ_CFG"); return e ? atoi(e) : 0; }();
             switch (cfg) {
                 case 1: return launch_mq_lean<384, 2, 2, 2>(s);
@@ -1408,6 +1498,16 @@ int phw_mesh_get_patch_counts(phw_mesh_t m, int32_t* counts) {
     return PHW_OK;
 }
 
+static void pipe_carve(const Layout& L, MqPipeArgs& cq, EllPipeArgs& cp, size_t& smem_pq, size_t& smem_pp);
+int phw_mesh_pipe_smem(phw_mesh_t m, int64_t* bytes2) {
+    if (!m || !bytes2) return fail(PHW_EINVAL, "mesh or bytes2 is NULL");
+    MqPipeArgs cq{}; EllPipeArgs cp{};
+    size_t sq = 0, sp = 0;
+    pipe_carve(m->L, cq, cp, sq, sp);
+    bytes2[0] = (int64_t)sp; bytes2[1] = (int64_t)sq;
+    return PHW_OK;
+}
+
 int phw_mesh_self_check(phw_mesh_t m) {
     if (!m) return fail(PHW_EINVAL, "mesh is NULL");
     if (m->L.nc > 200000) return fail(PHW_EINVAL, "phw_mesh_self_check is quadratic in places: meshes up to 200 000 cells");
@@ -1553,6 +1653,45 @@ static int setup_scalars(phw_solver_s* s) {
 #undef RC
 }
 
+// shared-memory carve-up of the bulk-copy pipelined mass solves (kernels_pipe.cuh) for the largest patch of a layout:
+// offsets inside a stage, stage size, and the dynamic shared memory each kernel needs (two stages + scratch)
+constexpr size_t PIPE_SMEM_LIMIT = 227 * 1024 - 1024;   // 227 KB per CTA minus the kernels' static shared memory
+static void pipe_carve(const Layout& L, MqPipeArgs& cq, EllPipeArgs& cp, size_t& smem_pq, size_t& smem_pp) {
+    int max_ec = 0, max_ecells = 0, max_ge = 0, max_vc = 0, max_gv = 0, max_wn = 0, max_in = 0;
+    for (const PatchHdr& h : L.hdr) {
+        max_ec = std::max(max_ec, h.e_cnt); max_ecells = std::max(max_ecells, h.n_ecells); max_ge = std::max(max_ge, h.ge_cnt);
+        max_vc = std::max(max_vc, h.v_cnt); max_gv = std::max(max_gv, h.gv_cnt); max_wn = std::max(max_wn, h.ell_wn); max_in = std::max(max_in, h.ell_in);
+    }
+    auto r16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
+    {   // M_q: stage = [x_k local | cell records | b | pinv | x_{k-1} | eadj], then the cell contributions and two ghost lists
+        size_t o = r16(((size_t)L.max_le + 2) * 8);
+        cq.off_cells = (uint32_t)o; o += (size_t)max_ecells * 32;
+        cq.off_b = (uint32_t)o; o += r16(((size_t)max_ec + 2) * 8);
+        cq.off_pinv = (uint32_t)o; o += r16(((size_t)max_ec + 2) * 8);
+        cq.off_xprev = (uint32_t)o; o += r16(((size_t)max_ec + 2) * 8);
+        cq.off_eadj = (uint32_t)o; o += r16(((size_t)max_ec + 8) * 4);
+        cq.stage_bytes = (uint32_t)((o + 127) & ~(size_t)127);
+        cq.off_sc3 = 2 * cq.stage_bytes;
+        cq.off_gidx = cq.off_sc3 + (uint32_t)r16((size_t)max_ecells * 24);
+        cq.gidx_bytes = (uint32_t)r16(((size_t)max_ge + 8) * 4);
+        smem_pq = (size_t)cq.off_gidx + 2 * cq.gidx_bytes;
+    }
+    {   // M_p: stage = [slice offsets ids | slice offsets weights | x_k local | b | x_{k-1} | weights | ids], then two ghost lists
+        const size_t nslw = r16(((size_t)(max_vc + 31) / 32 + 2) * 4);
+        size_t o = nslw;
+        cp.off_wo = (uint32_t)o; o += nslw;
+        cp.off_x = (uint32_t)o; o += r16(((size_t)L.max_lv + 2) * 8);
+        cp.off_b = (uint32_t)o; o += r16(((size_t)max_vc + 2) * 8);
+        cp.off_xprev = (uint32_t)o; o += r16(((size_t)max_vc + 2) * 8);
+        cp.off_w = (uint32_t)o; o += r16((size_t)max_wn * 8);
+        cp.off_ids = (uint32_t)o; o += r16((size_t)max_in * 2);
+        cp.stage_bytes = (uint32_t)((o + 127) & ~(size_t)127);
+        cp.off_gidx = 2 * cp.stage_bytes;
+        cp.gidx_bytes = (uint32_t)r16(((size_t)max_gv + 8) * 4);
+        smem_pp = (size_t)cp.off_gidx + 2 * cp.gidx_bytes;
+    }
+}
+
 static int setup_solver(phw_solver_s* s) {
     const Layout& L = s->mesh->L;
     const phw_params& P = s->prm;
@@ -1655,6 +1794,18 @@ static int setup_solver(phw_solver_s* s) {
     s->smem_ells = (size_t)L.max_smem_ell * 8;
     s->ell_staged = (P.flags & 64) != 0;
     if (s->smem_vd > 200 * 1024) return fail(PHW_EINVAL, "patch does not fit in shared memory; reduce patch_cells");
+    // ---- bulk-copy pipelined mass solves (flags bits 8 / 9): two stages holding every stream of the largest patch
+    if (s->coop && (P.flags & (256 | 512))) {
+        pipe_carve(L, s->pq, s->pp, s->smem_pq, s->smem_pp);
+        if (P.flags & 256) {
+            if (s->smem_pq > PIPE_SMEM_LIMIT) return fail(PHW_EINVAL, "pipelined M_q solve (flags bit 8): two stages of the largest patch exceed the shared memory of an SM; use patch_cells <= 1024");
+            s->pipe_q = true;
+        }
+        if ((P.flags & 512) && s->ell_p) {
+            if (s->smem_pp > PIPE_SMEM_LIMIT) return fail(PHW_EINVAL, "pipelined M_p solve (flags bit 9): two stages of the largest patch exceed the shared memory of an SM; reduce patch_cells");
+            s->pipe_p = true;
+        }
+    }
     s->grid_rows = std::max(1, std::min(s->npatch, PHW_MINB_ROWS * s->sm_count));
     RC(setup_scalars(s));
     if (s->G > 1) {
@@ -1774,6 +1925,12 @@ static int estimate_skew(phw_solver_s* s, double* sigma) {
     return 0;
 }
 
+// A/B knob: PHW_FLAGS_OR=<int> is OR-ed into phw_params.flags of every solver (e.g. run the whole test suite with a kernel variant)
+static int env_flags() {
+    static const int f = [] { const char* e = getenv("PHW_FLAGS_OR"); return e ? atoi(e) : 0; }();
+    return f;
+}
+
 int phw_solver_create(phw_mesh_t m, const phw_params* prm, int32_t device, void* cuda_stream, phw_solver_t* out) {
     if (!m || !prm || !out) return fail(PHW_EINVAL, "NULL argument");
     if (!m->L.boundary_set) return fail(PHW_ESTATE, "phw_mesh_set_boundary must be called before phw_solver_create");
@@ -1791,6 +1948,7 @@ int phw_solver_create(phw_mesh_t m, const phw_params* prm, int32_t device, void*
     phw_solver_s* s = new (std::nothrow) phw_solver_s();
     if (!s) return fail(PHW_ENOMEM, "out of host memory");
     s->mesh = m; s->prm = *prm; s->device = device; s->stream = (cudaStream_t)cuda_stream;
+    s->prm.flags |= env_flags();
     if (!(s->prm.tol > 0)) s->prm.tol = 1e-13;
     if (s->prm.max_iter <= 0) s->prm.max_iter = 200;
     int rc = setup_solver(s);
@@ -2030,6 +2188,7 @@ int phw_run(phw_solver_t s, int64_t n_steps, double* H_rows) {
     CU(cudaStreamSynchronize(s->stream));
     Ctl hc;
     s->launches = 0;
+    s->kernel_paths = 0;
     CU(cudaEventRecord(s->ev0, s->stream));
     if (s->prm.analytical && !s->an_ready) return fail(PHW_ESTATE, "analytical run: call phw_set_analytical before phw_run");
     for (int64_t n = 0; n < n_steps; ++n) {
@@ -2055,6 +2214,7 @@ int phw_run(phw_solver_t s, int64_t n_steps, double* H_rows) {
     st.max_rel_residual = std::max(hc.sc[0].maxres, std::max(hc.sc[1].maxres, hc.sc[2].maxres));
     st.device_ms = ms;
     st.kernel_launches = s->launches;
+    st.kernel_paths = s->kernel_paths;
     st.lam_min_q = s->lam_min_q; st.lam_max_q = s->lam_max_q; st.skew_bound = s->skew_bound;
     st.ms_solve_p = st.ms_solve_q = st.ms_solve_block = 0.0;
     for (size_t i = 0; i < s->prof_which.size(); ++i) {
@@ -2084,6 +2244,7 @@ int phw_run(phw_solver_t s, int64_t n_steps, double* H_rows) {
 int phw_get_stats(phw_solver_t s, phw_stats* out) {
     if (!s || !out) return fail(PHW_EINVAL, "NULL argument");
     s->stats.lam_min_q = s->lam_min_q; s->stats.lam_max_q = s->lam_max_q; s->stats.skew_bound = s->skew_bound;
+    s->stats.kernel_paths = s->kernel_paths;
     *out = s->stats;
     return PHW_OK;
 }
@@ -2226,6 +2387,7 @@ int phw_ho_create(const phw_params* prm, int32_t device, void* cuda_stream, int6
     phw_solver_s* s = new (std::nothrow) phw_solver_s();
     if (!s) return fail(PHW_ENOMEM, "out of host memory");
     s->mesh = nullptr; s->prm = *prm; s->device = device; s->stream = (cudaStream_t)cuda_stream; s->ho = true;
+    s->prm.flags |= env_flags();
     if (!(s->prm.tol > 0)) s->prm.tol = 1e-13;
     if (s->prm.max_iter <= 0) s->prm.max_iter = 1000;
     s->nv = (int)n_p; s->ne = (int)n_q; s->npatch = 0; s->G = 1;

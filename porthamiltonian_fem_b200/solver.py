@@ -95,6 +95,12 @@ class Mesh:
         _lib.check(self.lib.phw_mesh_get_patch_counts(self.handle, c.ctypes.data_as(_lib.c_i32p)))
         return c
 
+    def pipe_smem(self):
+        """dynamic shared memory (bytes) of the bulk-copy pipelined (M_p, M_q) solves for this layout (flags bits 9 / 8)"""
+        b = (ctypes.c_int64 * 2)()
+        _lib.check(self.lib.phw_mesh_pipe_smem(self.handle, b))
+        return int(b[0]), int(b[1])
+
     def close(self):
         if getattr(self, 'handle', None):
             self.lib.phw_mesh_destroy(self.handle)

@@ -34,7 +34,7 @@ def sweep_cases(n_cases, seed=1234):
 
 
 def wave_sweep_solve(tFinal, numSteps, nx, xLength, yLength, cases, domainShape='R', timeIntScheme='SV',
-                     mesh=None, device=0, patch_cells=None, tol=1e-13, extrap_order=2, return_solver=False):
+                     mesh=None, device=0, patch_cells=None, tol=1e-13, extrap_order=2, return_solver=False, solver_flags=0):
     """Run len(cases) independent 'IC' cases (weak form, explicit scheme) at once.
 
     Returns (H_arrays [n_cases, numSteps, 8], numCells) - H_arrays[i] is what wave_2D_solve would return for case i."""
@@ -54,7 +54,7 @@ def wave_sweep_solve(tFinal, numSteps, nx, xLength, yLength, cases, domainShape=
     for k, v in DEFAULT_LUMPED.items():
         setattr(prm, k, v)
     prm.input_kind, prm.in_amp, prm.in_omega, prm.in_t_stop = _lib.IN_SINE_WINDOW, 5.0, 8 * np.pi, 0.25     # wave_2D.py:433
-    prm.tol, prm.max_iter, prm.extrap_order = float(tol), 400, int(extrap_order)
+    prm.tol, prm.max_iter, prm.extrap_order, prm.flags = float(tol), 400, int(extrap_order), int(solver_flags)
     solver = Solver(m, prm, device=device)
     K = np.array([c.get('K_wave', 1.0) for c in cases], dtype=np.float64)
     rho = np.array([c.get('rho', 1.0) for c in cases], dtype=np.float64)

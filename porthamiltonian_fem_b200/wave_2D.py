@@ -69,7 +69,7 @@ def wave_2D_solve(tFinal, numSteps, outputDir,
     if tuple(basis_order) != (1, 1):
         return _solve_high_order(tFinal, numSteps, outputDir, nx, xLength, yLength, domainShape, timeIntScheme, dirichletImp,
                                  K_wave, rho, interConnection, analytical, controlType, tuple(basis_order), mesh, mesh_kind,
-                                 device, tol, extrap_order, lumped, return_state, verbose, tic)
+                                 device, tol, extrap_order, lumped, return_state, verbose, tic, solver_flags)
     if controlType == 'casimir' and timeIntScheme != 'SM':
         raise NotImplementedError('casimir control is only defined for the SM scheme (wave_2D.py:615)')
     if controlType == 'passivity' and timeIntScheme in ['SV', 'EH']:
@@ -262,7 +262,7 @@ class _AnalyticalDiagnostics:
 
 def _solve_high_order(tFinal, numSteps, outputDir, nx, xLength, yLength, domainShape, timeIntScheme, dirichletImp, K_wave, rho,
                       interConnection, analytical, controlType, basis_order, mesh, mesh_kind, device, tol, extrap_order, lumped,
-                      return_state, verbose, tic):
+                      return_state, verbose, tic, solver_flags=0):
     """basis_order != (1,1) (wave_2D.py:174-175,202-203): host-assembled operators (fem_ho.py) + CSR device kernels."""
     from .fem_ho import HighOrderSpaces, LagrangeRef, tri_rule
     from .solver import HighOrderSolver
@@ -303,7 +303,7 @@ def _solve_high_order(tFinal, numSteps, outputDir, nx, xLength, yLength, domainS
     prm.interconnection = 1 if interConnection == 'IC' else 0
     prm.analytical = 1 if analytical else 0
     prm.dt, prm.K_wave, prm.rho = tFinal / numSteps, float(K_wave), float(rho)
-    prm.tol, prm.max_iter, prm.extrap_order = float(tol), 2000, int(extrap_order)
+    prm.tol, prm.max_iter, prm.extrap_order, prm.flags = float(tol), 2000, int(extrap_order), int(solver_flags)
     lp = dict(_DEFAULT_LUMPED)
     if lumped:
         lp.update(lumped)

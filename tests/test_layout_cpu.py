@@ -161,3 +161,19 @@ def test_layout_self_check_ell_rows_and_two_sweep_patches(name, make, pc):
     v, c = make()
     m = Mesh(v, c, patch_cells=pc)
     m.self_check()
+
+
+def test_pipelined_solve_shared_memory_budget_is_host_computable():
+    """phw_mesh_pipe_smem (host-only): the bulk-copy pipelined solves (flags bits 8 / 9) need two stages of the largest
+    patch; 1024-cell patches fit the 227 KB of an SM, 2048-cell patches do not (M_q)."""
+    v, c = rectangle_structured(400, 100)
+    limit = 227 * 1024 - 1024
+    m = Mesh(v, c, patch_cells=1024)
+    sp, sq = m.pipe_smem()
+    assert 0 < sp <= limit // 2 and 0 < sq <= limit
+    assert sp % 16 == 0 and sq % 16 == 0
+    m.close()
+    m = Mesh(v, c, patch_cells=2048)
+    sp2, sq2 = m.pipe_smem()
+    assert sq2 > limit and sp2 > sp
+    m.close()
