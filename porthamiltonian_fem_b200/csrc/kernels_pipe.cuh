@@ -46,13 +46,17 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, uint32_t 
         : "memory");
     return ok != 0;
 }
-// wait for the phase with the given parity; a wait that exceeds ~2 s flags the run (ctl->nonconv) instead of hanging the GPU
+// wait for the phase with the given parity.  A wait that exceeds ~0.5 s marks the run as failed (high word of ctl->nonconv,
+// reported by phw_run as PHW_ENOCONV) and every later wait of the launch gives up at once, so a protocol error ends in a
+// wrong-result error instead of a hung GPU
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity, Ctl* ctl) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
+    unsigned int spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) {
-            if ((threadIdx.x & 31) == 0) atomicAdd((unsigned long long*)&ctl->nonconv, 1ull << 32);
+        if ((++spins & 255u) == 0u && (*((volatile long long*)&ctl->nonconv) >> 32) != 0) return;
+        if (clock64() - t0 > 1000000000LL) {
+            atomicAdd((unsigned long long*)&ctl->nonconv, 1ull << 32);
             return;
         }
     }

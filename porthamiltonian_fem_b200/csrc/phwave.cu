@@ -2233,6 +2233,7 @@ int phw_run(phw_solver_t s, int64_t n_steps, double* H_rows) {
         st.bytes_model = (int64_t)bytes;
     }
     if (hc.comm_dead) return fail(PHW_ECUDA, "inter-GPU exchange timed out (a peer rank stopped responding)");
+    if ((hc.nonconv >> 32) != 0) return fail(PHW_ECUDA, "pipelined solve: a bulk-copy stage did not arrive (mbarrier wait timed out)");
     if (hc.nonconv > 0) {
         char buf[160];
         snprintf(buf, sizeof buf, "%lld solves hit max_iter without reaching tol (max relative residual %.3e)", (long long)hc.nonconv, st.max_rel_residual);
@@ -2302,9 +2303,12 @@ int phw_mass_solve(phw_solver_t s, int32_t which, const double* b, double* x, in
     CU(cudaMemcpyAsync(&it1, &s->ctl->sc[which].iters, 8, cudaMemcpyDeviceToHost, s->stream));
     rc = export_vec(s, out, x, n, which == PHW_P ? s->d_v_new2old : s->d_e_new2old, which == PHW_P ? s->io_v : s->io_e);
     if (rc) return rc;
+    long long nonconv = 0;
+    CU(cudaMemcpyAsync(&nonconv, &s->ctl->nonconv, 8, cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
     if (iters) *iters = (int32_t)(it1 - it0);
     reset_history(s);
+    if ((nonconv >> 32) != 0) return fail(PHW_ECUDA, "pipelined solve: a bulk-copy stage did not arrive (mbarrier wait timed out)");
     return PHW_OK;
 }
 int phw_energy(phw_solver_t s, double* parts2) {
