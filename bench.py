@@ -168,7 +168,7 @@ def main():
     ap.add_argument('--two-sweep', action='store_true', help='two Chebyshev iterations per pass in the mass solves (csrc/kernels2.cuh; A/B)')
     ap.add_argument('--ell-staged', action='store_true', help='ELL rows of the M_p solve staged in shared memory by cp.async (A/B)')
     ap.add_argument('--cell-rows', action='store_true', help='cell-based instead of assembled (ELL) rows in the M_p solve (A/B)')
-    ap.add_argument('--pipe', default='', help="bulk-copy pipelined mass solves (csrc/kernels_pipe.cuh; A/B): 'pq' both, 'p' or 'q' one of them")
+    ap.add_argument('--pipe', default='', help="bulk-copy pipelined kernels (csrc/kernels_pipe.cuh; A/B): any of 'p' (M_p solve), 'q' (M_q solve), 'e' (fused H_wave reduction), 'r' (right-hand sides)")
     ap.add_argument('--stream-probe', action='store_true', help='print the bandwidth of a pure streaming pass over the ELL M_p data (diagnostics)')
     ap.add_argument('--debug-residuals', action='store_true', help='print the residual history of the last M_p / M_q solve to stderr')
     args = ap.parse_args()
@@ -215,7 +215,7 @@ def main():
     prm = _lib.PhwParams()
     prm.scheme, prm.dt, prm.K_wave, prm.rho = _lib.SCHEMES[args.scheme], dt, K_WAVE, RHO
     prm.input_kind, prm.in_amp, prm.in_omega = _lib.IN_COSINE, 1.0, omega
-    prm.tol, prm.max_iter, prm.flags, prm.extrap_order = args.tol, 200, 4 | (16 if args.two_sweep else 0) | (32 if args.cell_rows else 0) | (64 if args.ell_staged else 0) | (256 if 'q' in args.pipe else 0) | (512 if 'p' in args.pipe else 0), args.extrap
+    prm.tol, prm.max_iter, prm.flags, prm.extrap_order = args.tol, 200, 4 | (16 if args.two_sweep else 0) | (32 if args.cell_rows else 0) | (64 if args.ell_staged else 0) | (256 if 'q' in args.pipe else 0) | (512 if 'p' in args.pipe else 0) | (2048 if 'e' in args.pipe else 0) | (4096 if 'r' in args.pipe else 0), args.extrap
     prm.extrap_order_q = args.extrap_q
     solver = Solver(m, prm, device=local_rank)
     n_dof_local = int((part.vertex_owner == rank).sum() + (part.edge_owner == rank).sum())

@@ -140,7 +140,7 @@ struct MqPipeArgs {
 // put everything patch `hn` needs in flight into `stage` (all threads call this; thread 0 issues the bulk copies).
 // gidx_this: ghost index list of this patch in shared memory (nullptr: read it from global memory - first patch of an
 // iteration); hn2 / gidx_next: the patch after `hn` and the list slot its ghost indices go to (nullptr: none).
-template <int NT>
+template <int NT, bool DIAG>
 __device__ __forceinline__ void mq_issue(const MqPipeArgs& a, unsigned char* stage, const uint32_t* gidx_this, uint32_t* gidx_next,
                                          const PatchHdr& hn, const PatchHdr* hn2, const double* xk, const double* xprev,
                                          bool use_prev, unsigned long long* bar) {
@@ -153,13 +153,13 @@ __device__ __forceinline__ void mq_issue(const MqPipeArgs& a, unsigned char* sta
     const uint32_t* gh = reinterpret_cast<const uint32_t*>(a.ghost_e);
     if (threadIdx.x == 0) {
         const uint32_t cell_bytes = (uint32_t)hn.n_ecells * 32u;
-        uint32_t bytes = f64s_bytes(es, ec) * (use_prev ? 4u : 3u) + cell_bytes + u32s_bytes(es, ec);
+        uint32_t bytes = f64s_bytes(es, ec) * ((use_prev ? 3u : 2u) + (DIAG ? 0u : 1u)) + cell_bytes + u32s_bytes(es, ec);
         if (hn2) bytes += u32s_bytes(hn2->ge_off, hn2->ge_cnt);
         mbar_arrive_expect_tx(bar, bytes);
         if (cell_bytes) bulk_g2s(stage + a.off_cells, a.cellq + 2 * (size_t)hn.cell_off, cell_bytes, bar);
         f64s_bulk(sq, xk, es, ec, bar);
         f64s_bulk(sb, a.b, es, ec, bar);
-        f64s_bulk(spv, a.pinv, es, ec, bar);
+        if (!DIAG) f64s_bulk(spv, a.pinv, es, ec, bar);
         if (use_prev) f64s_bulk(sxp, xprev, es, ec, bar);
         u32s_bulk(sea, a.eadj, es, ec, bar);
         if (hn2) u32s_bulk(gidx_next, gh, hn2->ge_off, hn2->ge_cnt, bar);
@@ -168,7 +168,7 @@ __device__ __forceinline__ void mq_issue(const MqPipeArgs& a, unsigned char* sta
     if (lane >= 0) {
         if (lane < 2) f64s_fix(sq, xk, es, ec, lane);
         else if (lane < 4) f64s_fix(sb, a.b, es, ec, lane - 2);
-        else if (lane < 6) f64s_fix(spv, a.pinv, es, ec, lane - 4);
+        else if (lane < 6) { if (!DIAG) f64s_fix(spv, a.pinv, es, ec, lane - 4); }
         else if (lane < 8) { if (use_prev) f64s_fix(sxp, xprev, es, ec, lane - 6); }
         else if (lane < 14) u32s_fix(sea, a.eadj, es, ec, lane - 8);
         else if (lane < 20) { if (hn2) u32s_fix(gidx_next, gh, hn2->ge_off, hn2->ge_cnt, lane - 14); }
@@ -182,7 +182,9 @@ __device__ __forceinline__ void mq_issue(const MqPipeArgs& a, unsigned char* sta
     }
 }
 
-template <int NT>
+// DIAG: the Jacobi weight 1 / diag(M_q)_e is recomputed from the (<= 2) cell records of the edge, which are in shared memory
+// anyway (diag contribution of slot i of a cell: 3 S - 4 g_i), instead of being streamed (12 of 99 B per cell and iteration)
+template <int NT, bool DIAG>
 __global__ void __launch_bounds__(NT, 1) solve_mq_pipe_k(const __grid_constant__ MqPipeArgs a) {
     extern __shared__ __align__(128) unsigned char smraw[];
     __shared__ double red[64];
@@ -211,7 +213,7 @@ __global__ void __launch_bounds__(NT, 1) solve_mq_pipe_k(const __grid_constant__
         for (int j = 0; j < 3 && j < n_my; ++j) load_hdr_smem_at(&s_hdr[j], &a.hdr[blockIdx.x + j * gridDim.x], 32 * j);
         __syncthreads();
         if (n_my > 0)
-            mq_issue<NT>(a, smraw + (seq & 1u) * a.stage_bytes, nullptr,
+            mq_issue<NT, DIAG>(a, smraw + (seq & 1u) * a.stage_bytes, nullptr,
                          reinterpret_cast<uint32_t*>(smraw + a.off_gidx + ((seq + 1u) & 1u) * a.gidx_bytes),
                          s_hdr[0], n_my > 1 ? &s_hdr[1] : nullptr, xk, xprev, use_prev, &full[seq & 1u]);
         for (int it = 0; it < n_my; ++it, ++seq) {
@@ -222,7 +224,7 @@ __global__ void __launch_bounds__(NT, 1) solve_mq_pipe_k(const __grid_constant__
             const PatchHdr& h = s_hdr[it & 3];
             if (it + 3 < n_my) load_hdr_smem_at(&s_hdr[(it + 3) & 3], &a.hdr[blockIdx.x + (it + 3) * gridDim.x], 64);
             if (it + 1 < n_my)
-                mq_issue<NT>(a, smraw + (s ^ 1u) * a.stage_bytes,
+                mq_issue<NT, DIAG>(a, smraw + (s ^ 1u) * a.stage_bytes,
                              reinterpret_cast<const uint32_t*>(smraw + a.off_gidx + (s ^ 1u) * a.gidx_bytes),
                              reinterpret_cast<uint32_t*>(smraw + a.off_gidx + s * a.gidx_bytes),
                              s_hdr[(it + 1) & 3], it + 2 < n_my ? &s_hdr[(it + 2) & 3] : nullptr, xk, xprev, use_prev, &full[s ^ 1u]);
@@ -247,12 +249,20 @@ __global__ void __launch_bounds__(NT, 1) solve_mq_pipe_k(const __grid_constant__
             const double* spv = reinterpret_cast<const double*>(stage + a.off_pinv) + (h.e_start & 1);
             const double* sxp = reinterpret_cast<const double*>(stage + a.off_xprev) + (h.e_start & 1);
             const uint32_t* sea = reinterpret_cast<const uint32_t*>(stage + a.off_eadj) + (h.e_start & 3);
+            const double* sgeo = reinterpret_cast<const double*>(stage + a.off_cells);
             for (int le = threadIdx.x; le < h.e_cnt; le += NT) {
                 const uint32_t adj = sea[le];
                 const uint32_t ca = adj & 0xFFFFu, cb = adj >> 16;
-                const double bv = sb[le], pv = spv[le];
+                const double bv = sb[le];
                 double val = sc3[3 * (ca >> 2) + (ca & 3u)];
                 if (cb != 0xFFFFu) val += sc3[3 * (cb >> 2) + (cb & 3u)];
+                double pv;
+                if (DIAG) {
+                    const double* ra = sgeo + 4 * (ca >> 2);          // record as doubles: [ids | g0 | g1 | g2]
+                    double dg = 3.0 * (ra[1] + ra[2] + ra[3]) - 4.0 * ra[1 + (ca & 3u)];
+                    if (cb != 0xFFFFu) { const double* rb = sgeo + 4 * (cb >> 2); dg += 3.0 * (rb[1] + rb[2] + rb[3]) - 4.0 * rb[1 + (cb & 3u)]; }
+                    pv = 1.0 / dg;
+                } else pv = spv[le];
                 const double xc = sq[le];
                 const double r_ = bv - val;
                 double xn = xc + c2 * pv * r_;
@@ -459,6 +469,350 @@ __global__ void __launch_bounds__(NT, MINB) solve_ell_pipe_k(const __grid_consta
         if (!conv) a.ctl->nonconv += 1;
         double rel = (bb > 0.0) ? sqrt(rr / bb) : 0.0;
         if (rel > sc.maxres) sc.maxres = rel;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// H_wave in ONE pipelined pass (replaces the two assemble(scalar) calls of wave_2D.py:882,907): both quadratic forms are
+// sums of cell-local forms over the OWN cells of every patch,
+//   p^T M_p p = sum_K |K|/12 (sum_i p_i^2 + (sum_i p_i)^2),     q^T M_q q = sum_K t^T M_K t,  t_i = s_i q_i,
+// so no row gather (adjacency codes, per-cell contribution buffer) and no halo cells are needed: 64 B per cell
+// (vertex ids 8, area 8, edge ids + metric 32, p 4, q 12) instead of the 88 B of the two row-based reductions.
+// Stage = [p local | q local | vertex-id records | areas | edge records]; two ghost lists per field.
+// ------------------------------------------------------------------------------------------------
+struct EnergyPipeArgs {
+    int npatch;
+    const PatchHdr* hdr;
+    const uint2* recv; const double* area; const uint4* cellq;
+    const int* ghost_v; const int* ghost_e;
+    const double* p; const double* q;
+    double scale_p, scale_q;         // red[0] = scale_p * p^T M_p p, red[1] = scale_q * q^T M_q q
+    int counter_id;
+    double* partials; Ctl* ctl;
+    uint32_t off_q, off_recv, off_area, off_cells, stage_bytes, off_gv, gv_bytes, off_ge, ge_bytes;
+};
+
+template <int NT>
+__device__ __forceinline__ void en_issue(const EnergyPipeArgs& a, unsigned char* stage, const uint32_t* gv_this, const uint32_t* ge_this,
+                                         uint32_t* gv_next, uint32_t* ge_next, const PatchHdr& hn, const PatchHdr* hn2,
+                                         unsigned long long* bar) {
+    double* sp = reinterpret_cast<double*>(stage);
+    double* sq = reinterpret_cast<double*>(stage + a.off_q);
+    double* srv = reinterpret_cast<double*>(stage + a.off_recv);
+    double* sar = reinterpret_cast<double*>(stage + a.off_area);
+    const double* grecv = reinterpret_cast<const double*>(a.recv);
+    const uint32_t* ghv = reinterpret_cast<const uint32_t*>(a.ghost_v);
+    const uint32_t* ghe = reinterpret_cast<const uint32_t*>(a.ghost_e);
+    const int vs = hn.v_start, vc = hn.v_cnt, es = hn.e_start, ec = hn.e_cnt, co = hn.cell_off, no = hn.n_own;
+    if (threadIdx.x == 0) {
+        const uint32_t cell_bytes = (uint32_t)no * 32u;
+        uint32_t bytes = f64s_bytes(vs, vc) + f64s_bytes(es, ec) + 2u * f64s_bytes(co, no) + cell_bytes;
+        if (hn2) bytes += u32s_bytes(hn2->gv_off, hn2->gv_cnt) + u32s_bytes(hn2->ge_off, hn2->ge_cnt);
+        mbar_arrive_expect_tx(bar, bytes);
+        if (cell_bytes) bulk_g2s(stage + a.off_cells, a.cellq + 2 * (size_t)co, cell_bytes, bar);
+        f64s_bulk(sq, a.q, es, ec, bar);
+        f64s_bulk(sp, a.p, vs, vc, bar);
+        f64s_bulk(srv, grecv, co, no, bar);
+        f64s_bulk(sar, a.area, co, no, bar);
+        if (hn2) { u32s_bulk(gv_next, ghv, hn2->gv_off, hn2->gv_cnt, bar); u32s_bulk(ge_next, ghe, hn2->ge_off, hn2->ge_cnt, bar); }
+    }
+    const int lane = (int)threadIdx.x - (NT - 32);
+    if (lane >= 0) {
+        if (lane < 2) f64s_fix(sp, a.p, vs, vc, lane);
+        else if (lane < 4) f64s_fix(sq, a.q, es, ec, lane - 2);
+        else if (lane < 6) f64s_fix(srv, grecv, co, no, lane - 4);
+        else if (lane < 8) f64s_fix(sar, a.area, co, no, lane - 6);
+        else if (lane < 14) { if (hn2) u32s_fix(gv_next, ghv, hn2->gv_off, hn2->gv_cnt, lane - 8); }
+        else if (lane < 20) { if (hn2) u32s_fix(ge_next, ghe, hn2->ge_off, hn2->ge_cnt, lane - 14); }
+    }
+    double* sgp = sp + (vs & 1) + vc;
+    double* sgq = sq + (es & 1) + ec;
+    if (gv_this) {
+        const uint32_t* gi = gv_this + (hn.gv_off & 3);
+        for (int i = threadIdx.x; i < hn.gv_cnt; i += NT) cp_async8(&sgp[i], &a.p[gi[i]]);
+        const uint32_t* gj = ge_this + (hn.ge_off & 3);
+        for (int i = threadIdx.x; i < hn.ge_cnt; i += NT) cp_async8(&sgq[i], &a.q[gj[i]]);
+    } else {
+        for (int i = threadIdx.x; i < hn.gv_cnt; i += NT) cp_async8(&sgp[i], &a.p[__ldg(&a.ghost_v[hn.gv_off + i])]);
+        for (int i = threadIdx.x; i < hn.ge_cnt; i += NT) cp_async8(&sgq[i], &a.q[__ldg(&a.ghost_e[hn.ge_off + i])]);
+    }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT, 1) energy_pipe_k(const __grid_constant__ EnergyPipeArgs a) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    __shared__ double red[64];
+    __shared__ PatchHdr s_hdr[4];
+    __shared__ __align__(8) unsigned long long full[2];
+    __shared__ bool is_last;
+    if (threadIdx.x == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_fence_init(); }
+    const int n_my = ((int)blockIdx.x < a.npatch) ? (a.npatch - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    for (int j = 0; j < 3 && j < n_my; ++j) load_hdr_smem_at(&s_hdr[j], &a.hdr[blockIdx.x + j * gridDim.x], 32 * j);
+    __syncthreads();
+    double accp = 0.0, accq = 0.0;
+    auto gv_slot = [&](unsigned int i) { return reinterpret_cast<uint32_t*>(smraw + a.off_gv + (i & 1u) * a.gv_bytes); };
+    auto ge_slot = [&](unsigned int i) { return reinterpret_cast<uint32_t*>(smraw + a.off_ge + (i & 1u) * a.ge_bytes); };
+    if (n_my > 0)
+        en_issue<NT>(a, smraw, nullptr, nullptr, gv_slot(1), ge_slot(1), s_hdr[0], n_my > 1 ? &s_hdr[1] : nullptr, &full[0]);
+    for (int it = 0; it < n_my; ++it) {
+        const unsigned int s = (unsigned int)it & 1u;
+        cp_async_wait_all();
+        mbar_wait(&full[s], ((unsigned int)it >> 1) & 1u, a.ctl);
+        __syncthreads();
+        const PatchHdr& h = s_hdr[it & 3];
+        if (it + 3 < n_my) load_hdr_smem_at(&s_hdr[(it + 3) & 3], &a.hdr[blockIdx.x + (it + 3) * gridDim.x], 64);
+        if (it + 1 < n_my)
+            en_issue<NT>(a, smraw + (s ^ 1u) * a.stage_bytes, gv_slot(it + 1), ge_slot(it + 1), gv_slot(it + 2), ge_slot(it + 2),
+                         s_hdr[(it + 1) & 3], it + 2 < n_my ? &s_hdr[(it + 2) & 3] : nullptr, &full[s ^ 1u]);
+        const unsigned char* stage = smraw + s * a.stage_bytes;
+        const double* sp = reinterpret_cast<const double*>(stage) + (h.v_start & 1);
+        const double* sq = reinterpret_cast<const double*>(stage + a.off_q) + (h.e_start & 1);
+        const uint2* srv = reinterpret_cast<const uint2*>(stage + a.off_recv) + (h.cell_off & 1);
+        const double* sar = reinterpret_cast<const double*>(stage + a.off_area) + (h.cell_off & 1);
+        const uint4* scell = reinterpret_cast<const uint4*>(stage + a.off_cells);
+        for (int lc = threadIdx.x; lc < h.n_own; lc += NT) {
+            const uint2 rv = srv[lc];
+            const double p0 = sp[rv.x & 0xFFFFu], p1 = sp[rv.x >> 16], p2 = sp[rv.y & 0xFFFFu];
+            const double ps = p0 + p1 + p2;
+            accp += sar[lc] * (p0 * p0 + p1 * p1 + p2 * p2 + ps * ps);
+            const uint4 qa = scell[2 * lc], qb = scell[2 * lc + 1];
+            const uint32_t e0 = qa.x & 0xFFFFu, e1 = qa.x >> 16, e2 = qa.y & 0xFFFFu;
+            const double g0 = __hiloint2double((int)qa.w, (int)qa.z);
+            const double g1 = __hiloint2double((int)qb.y, (int)qb.x), g2 = __hiloint2double((int)qb.w, (int)qb.z);
+            const double S = g0 + g1 + g2;
+            const double s0 = (e0 & 0x8000u) ? -1.0 : 1.0, s1 = (e1 & 0x8000u) ? -1.0 : 1.0, s2 = (e2 & 0x8000u) ? -1.0 : 1.0;
+            const double t0 = s0 * sq[e0 & 0x3FFFu], t1 = s1 * sq[e1 & 0x3FFFu], t2 = s2 * sq[e2 & 0x3FFFu];
+            const double ST = S * (t0 + t1 + t2);
+            accq += t0 * (ST + 2.0 * S * t0 - 4.0 * (g0 * t0 + g2 * t1 + g1 * t2))
+                  + t1 * (ST + 2.0 * S * t1 - 4.0 * (g2 * t0 + g1 * t1 + g0 * t2))
+                  + t2 * (ST + 2.0 * S * t2 - 4.0 * (g1 * t0 + g0 * t1 + g2 * t2));
+        }
+    }
+    __syncthreads();
+    block_sum2(accp, accq, red);
+    if (threadIdx.x == 0) {
+        a.partials[2 * blockIdx.x] = accp; a.partials[2 * blockIdx.x + 1] = accq;
+        __threadfence();
+        is_last = (atomicAdd(&a.ctl->counters[a.counter_id], 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    double tp = 0.0, tq = 0.0;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += NT) { tp += __ldcg(&a.partials[2 * b]); tq += __ldcg(&a.partials[2 * b + 1]); }
+    block_sum2(tp, tq, red);
+    if (threadIdx.x == 0) { a.ctl->counters[a.counter_id] = 0; a.ctl->red[0] = a.scale_p * tp; a.ctl->red[1] = a.scale_q * tq; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// right-hand sides (replace assemble(b), wave_2D.py:814,849), pipelined:  y_e = cD (D x_p)_e  and  y_v = cD (D^T x_q)_v.
+// Same per-cell contributions and the same fixed summation order as edge_rows_k / vertex_rows_k <STORE, HAS_D>.
+// ------------------------------------------------------------------------------------------------
+struct RhsPipeArgs {
+    int npatch;
+    const PatchHdr* hdr;
+    const uint2* recv; const uint2* rece;
+    const int* ghost;                 // ghost list of the INPUT field (vertices for the edge rows, edges for the vertex rows)
+    const uint32_t* eadj;             // edge rows: (cell, slot) codes of every owned edge
+    const uint32_t* vslice_off; const uint16_t* vadj;   // vertex rows: sliced-ELL adjacency
+    const double* x;                  // input field
+    double* y;                        // output rows
+    double cD;
+    Ctl* ctl;
+    uint32_t off_a, off_b, off_c, stage_bytes, off_sc3, off_gidx, gidx_bytes;
+};
+
+// edge rows.  Stage = [x_p local | vertex-id records | edge-id records | eadj]
+template <int NT>
+__device__ __forceinline__ void rhs_e_issue(const RhsPipeArgs& a, unsigned char* stage, const uint32_t* gidx_this, uint32_t* gidx_next,
+                                            const PatchHdr& hn, const PatchHdr* hn2, unsigned long long* bar) {
+    double* sp = reinterpret_cast<double*>(stage);
+    double* srv = reinterpret_cast<double*>(stage + a.off_a);
+    double* sre = reinterpret_cast<double*>(stage + a.off_b);
+    uint32_t* sea = reinterpret_cast<uint32_t*>(stage + a.off_c);
+    const double* grv = reinterpret_cast<const double*>(a.recv);
+    const double* gre = reinterpret_cast<const double*>(a.rece);
+    const uint32_t* gh = reinterpret_cast<const uint32_t*>(a.ghost);
+    const int vs = hn.v_start, vc = hn.v_cnt, es = hn.e_start, ec = hn.e_cnt, co = hn.cell_off, ncl = hn.n_ecells;
+    if (threadIdx.x == 0) {
+        uint32_t bytes = f64s_bytes(vs, vc) + 2u * f64s_bytes(co, ncl) + u32s_bytes(es, ec);
+        if (hn2) bytes += u32s_bytes(hn2->gv_off, hn2->gv_cnt);
+        mbar_arrive_expect_tx(bar, bytes);
+        f64s_bulk(srv, grv, co, ncl, bar);
+        f64s_bulk(sre, gre, co, ncl, bar);
+        f64s_bulk(sp, a.x, vs, vc, bar);
+        u32s_bulk(sea, a.eadj, es, ec, bar);
+        if (hn2) u32s_bulk(gidx_next, gh, hn2->gv_off, hn2->gv_cnt, bar);
+    }
+    const int lane = (int)threadIdx.x - (NT - 32);
+    if (lane >= 0) {
+        if (lane < 2) f64s_fix(sp, a.x, vs, vc, lane);
+        else if (lane < 4) f64s_fix(srv, grv, co, ncl, lane - 2);
+        else if (lane < 6) f64s_fix(sre, gre, co, ncl, lane - 4);
+        else if (lane < 12) u32s_fix(sea, a.eadj, es, ec, lane - 6);
+        else if (lane < 18) { if (hn2) u32s_fix(gidx_next, gh, hn2->gv_off, hn2->gv_cnt, lane - 12); }
+    }
+    double* sg = sp + (vs & 1) + vc;
+    if (gidx_this) {
+        const uint32_t* gi = gidx_this + (hn.gv_off & 3);
+        for (int i = threadIdx.x; i < hn.gv_cnt; i += NT) cp_async8(&sg[i], &a.x[gi[i]]);
+    } else {
+        for (int i = threadIdx.x; i < hn.gv_cnt; i += NT) cp_async8(&sg[i], &a.x[__ldg(&a.ghost[hn.gv_off + i])]);
+    }
+}
+
+template <int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) rhs_edge_pipe_k(const __grid_constant__ RhsPipeArgs a) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    __shared__ PatchHdr s_hdr[4];
+    __shared__ __align__(8) unsigned long long full[2];
+    if (threadIdx.x == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_fence_init(); }
+    const int n_my = ((int)blockIdx.x < a.npatch) ? (a.npatch - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    for (int j = 0; j < 3 && j < n_my; ++j) load_hdr_smem_at(&s_hdr[j], &a.hdr[blockIdx.x + j * gridDim.x], 32 * j);
+    __syncthreads();
+    double* sc3 = reinterpret_cast<double*>(smraw + a.off_sc3);
+    auto g_slot = [&](unsigned int i) { return reinterpret_cast<uint32_t*>(smraw + a.off_gidx + (i & 1u) * a.gidx_bytes); };
+    const double cD = a.cD;
+    if (n_my > 0) rhs_e_issue<NT>(a, smraw, nullptr, g_slot(1), s_hdr[0], n_my > 1 ? &s_hdr[1] : nullptr, &full[0]);
+    for (int it = 0; it < n_my; ++it) {
+        const unsigned int s = (unsigned int)it & 1u;
+        cp_async_wait_all();
+        mbar_wait(&full[s], ((unsigned int)it >> 1) & 1u, a.ctl);
+        __syncthreads();
+        const PatchHdr& h = s_hdr[it & 3];
+        if (it + 3 < n_my) load_hdr_smem_at(&s_hdr[(it + 3) & 3], &a.hdr[blockIdx.x + (it + 3) * gridDim.x], 64);
+        if (it + 1 < n_my)
+            rhs_e_issue<NT>(a, smraw + (s ^ 1u) * a.stage_bytes, g_slot(it + 1), g_slot(it + 2), s_hdr[(it + 1) & 3],
+                            it + 2 < n_my ? &s_hdr[(it + 2) & 3] : nullptr, &full[s ^ 1u]);
+        const unsigned char* stage = smraw + s * a.stage_bytes;
+        const double* sp = reinterpret_cast<const double*>(stage) + (h.v_start & 1);
+        const uint2* srv = reinterpret_cast<const uint2*>(stage + a.off_a) + (h.cell_off & 1);
+        const uint2* sre = reinterpret_cast<const uint2*>(stage + a.off_b) + (h.cell_off & 1);
+        const uint32_t* sea = reinterpret_cast<const uint32_t*>(stage + a.off_c) + (h.e_start & 3);
+        for (int lc = threadIdx.x; lc < h.n_ecells; lc += NT) {
+            const uint2 re = sre[lc], rv = srv[lc];
+            const uint32_t e0 = re.x & 0xFFFFu, e1 = re.x >> 16, e2 = re.y & 0xFFFFu;
+            const double s0 = (e0 & 0x8000u) ? -1.0 : 1.0, s1 = (e1 & 0x8000u) ? -1.0 : 1.0, s2 = (e2 & 0x8000u) ? -1.0 : 1.0;
+            const double p0 = sp[rv.x & 0xFFFFu], p1 = sp[rv.x >> 16], p2 = sp[rv.y & 0xFFFFu];
+            const double third = (p0 + p1 + p2) * (1.0 / 3.0);
+            double d0 = third, d1 = third, d2 = third;
+            if (e0 & 0x4000u) d0 -= 0.5 * (p1 + p2);      // zero-flux sides: -(1/2) (p_a + p_b) at the edge's end vertices
+            if (e1 & 0x4000u) d1 -= 0.5 * (p0 + p2);
+            if (e2 & 0x4000u) d2 -= 0.5 * (p0 + p1);
+            double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+            v0 += cD * s0 * d0; v1 += cD * s1 * d1; v2 += cD * s2 * d2;
+            sc3[3 * lc] = v0; sc3[3 * lc + 1] = v1; sc3[3 * lc + 2] = v2;
+        }
+        __syncthreads();
+        for (int le = threadIdx.x; le < h.e_cnt; le += NT) {
+            const uint32_t adj = sea[le];
+            const uint32_t ca = adj & 0xFFFFu, cb = adj >> 16;
+            double val = sc3[3 * (ca >> 2) + (ca & 3u)];
+            if (cb != 0xFFFFu) val += sc3[3 * (cb >> 2) + (cb & 3u)];
+            a.y[h.e_start + le] = val;
+        }
+    }
+}
+
+// vertex rows.  Stage = [slice offsets | x_q local | edge-id records | adjacency codes of the patch]
+template <int NT>
+__device__ __forceinline__ void rhs_v_issue(const RhsPipeArgs& a, unsigned char* stage, const uint32_t* gidx_this, uint32_t* gidx_next,
+                                            const PatchHdr& hn, const PatchHdr* hn2, unsigned long long* bar) {
+    uint32_t* s_off = reinterpret_cast<uint32_t*>(stage);
+    double* sq = reinterpret_cast<double*>(stage + a.off_a);
+    double* sre = reinterpret_cast<double*>(stage + a.off_b);
+    const double* gre = reinterpret_cast<const double*>(a.rece);
+    const uint32_t* gh = reinterpret_cast<const uint32_t*>(a.ghost);
+    const int es = hn.e_start, ec = hn.e_cnt, co = hn.cell_off, ncl = hn.n_vcells;
+    if (threadIdx.x == 0) {
+        const uint32_t adj_bytes = (uint32_t)hn.adj_cnt * 2u;
+        uint32_t bytes = f64s_bytes(es, ec) + f64s_bytes(co, ncl) + adj_bytes;
+        if (hn2) bytes += u32s_bytes(hn2->ge_off, hn2->ge_cnt);
+        mbar_arrive_expect_tx(bar, bytes);
+        if (adj_bytes) bulk_g2s(stage + a.off_c, a.vadj + (uint32_t)hn.adj_off, adj_bytes, bar);
+        f64s_bulk(sre, gre, co, ncl, bar);
+        f64s_bulk(sq, a.x, es, ec, bar);
+        if (hn2) u32s_bulk(gidx_next, gh, hn2->ge_off, hn2->ge_cnt, bar);
+    }
+    const int lane = (int)threadIdx.x - (NT - 32);
+    if (lane >= 0) {
+        if (lane < 2) f64s_fix(sq, a.x, es, ec, lane);
+        else if (lane < 4) f64s_fix(sre, gre, co, ncl, lane - 2);
+        else if (lane < 10) { if (hn2) u32s_fix(gidx_next, gh, hn2->ge_off, hn2->ge_cnt, lane - 4); }
+    }
+    const int nsl = (hn.v_cnt + 31) >> 5;
+    for (int i = threadIdx.x; i <= nsl; i += NT) cp_async4(&s_off[i], &a.vslice_off[hn.vs_off + i]);
+    double* sg = sq + (es & 1) + ec;
+    if (gidx_this) {
+        const uint32_t* gi = gidx_this + (hn.ge_off & 3);
+        for (int i = threadIdx.x; i < hn.ge_cnt; i += NT) cp_async8(&sg[i], &a.x[gi[i]]);
+    } else {
+        for (int i = threadIdx.x; i < hn.ge_cnt; i += NT) cp_async8(&sg[i], &a.x[__ldg(&a.ghost[hn.ge_off + i])]);
+    }
+}
+
+template <int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) rhs_vertex_pipe_k(const __grid_constant__ RhsPipeArgs a) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    __shared__ PatchHdr s_hdr[4];
+    __shared__ __align__(8) unsigned long long full[2];
+    if (threadIdx.x == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_fence_init(); }
+    const int n_my = ((int)blockIdx.x < a.npatch) ? (a.npatch - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    for (int j = 0; j < 3 && j < n_my; ++j) load_hdr_smem_at(&s_hdr[j], &a.hdr[blockIdx.x + j * gridDim.x], 32 * j);
+    __syncthreads();
+    double* sc3 = reinterpret_cast<double*>(smraw + a.off_sc3);
+    auto g_slot = [&](unsigned int i) { return reinterpret_cast<uint32_t*>(smraw + a.off_gidx + (i & 1u) * a.gidx_bytes); };
+    const double cD = a.cD;
+    if (n_my > 0) rhs_v_issue<NT>(a, smraw, nullptr, g_slot(1), s_hdr[0], n_my > 1 ? &s_hdr[1] : nullptr, &full[0]);
+    for (int it = 0; it < n_my; ++it) {
+        const unsigned int s = (unsigned int)it & 1u;
+        cp_async_wait_all();
+        mbar_wait(&full[s], ((unsigned int)it >> 1) & 1u, a.ctl);
+        __syncthreads();
+        const PatchHdr& h = s_hdr[it & 3];
+        if (it + 3 < n_my) load_hdr_smem_at(&s_hdr[(it + 3) & 3], &a.hdr[blockIdx.x + (it + 3) * gridDim.x], 64);
+        if (it + 1 < n_my)
+            rhs_v_issue<NT>(a, smraw + (s ^ 1u) * a.stage_bytes, g_slot(it + 1), g_slot(it + 2), s_hdr[(it + 1) & 3],
+                            it + 2 < n_my ? &s_hdr[(it + 2) & 3] : nullptr, &full[s ^ 1u]);
+        const unsigned char* stage = smraw + s * a.stage_bytes;
+        const uint32_t* s_off = reinterpret_cast<const uint32_t*>(stage);
+        const double* sq = reinterpret_cast<const double*>(stage + a.off_a) + (h.e_start & 1);
+        const uint2* sre = reinterpret_cast<const uint2*>(stage + a.off_b) + (h.cell_off & 1);
+        const uint4* sadj4 = reinterpret_cast<const uint4*>(stage + a.off_c);
+        for (int lc = threadIdx.x; lc < h.n_vcells; lc += NT) {
+            const uint2 re = sre[lc];
+            const uint32_t e0 = re.x & 0xFFFFu, e1 = re.x >> 16, e2 = re.y & 0xFFFFu;
+            const double t0 = (e0 & 0x8000u) ? -sq[e0 & 0x3FFFu] : sq[e0 & 0x3FFFu];
+            const double t1 = (e1 & 0x8000u) ? -sq[e1 & 0x3FFFu] : sq[e1 & 0x3FFFu];
+            const double t2 = (e2 & 0x8000u) ? -sq[e2 & 0x3FFFu] : sq[e2 & 0x3FFFu];
+            const double common = cD * (t0 + t1 + t2) * (1.0 / 3.0);
+            double d0 = common, d1 = common, d2 = common;
+            // zero-flux sides: -(1/2) s_e q_e at both end vertices of edge i (the vertices != i)
+            if (e0 & 0x4000u) { const double hq = 0.5 * cD * t0; d1 -= hq; d2 -= hq; }
+            if (e1 & 0x4000u) { const double hq = 0.5 * cD * t1; d0 -= hq; d2 -= hq; }
+            if (e2 & 0x4000u) { const double hq = 0.5 * cD * t2; d0 -= hq; d1 -= hq; }
+            double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+            v0 += d0; v1 += d1; v2 += d2;
+            sc3[3 * lc] = v0; sc3[3 * lc + 1] = v1; sc3[3 * lc + 2] = v2;
+        }
+        __syncthreads();
+        const uint32_t adj0 = (uint32_t)h.adj_off;
+        for (int lv = threadIdx.x; lv < h.v_cnt; lv += NT) {
+            const uint32_t o0 = s_off[lv >> 5] - adj0, o1 = s_off[(lv >> 5) + 1] - adj0;
+            double val = 0.0;
+            const uint32_t nchunk = (o1 - o0) >> 8;            // 32 lanes * 8 codes per chunk
+            for (uint32_t k = 0; k < nchunk; ++k) {
+                const uint4 cd = sadj4[(o0 >> 3) + k * 32 + (lv & 31)];
+                const uint32_t w4[4] = {cd.x, cd.y, cd.z, cd.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t c0 = w4[j] & 0xFFFFu, c1 = w4[j] >> 16;
+                    if (c0 != 0xFFFFu) val += sc3[3 * (c0 >> 2) + (c0 & 3u)];
+                    if (c1 != 0xFFFFu) val += sc3[3 * (c1 >> 2) + (c1 & 3u)];
+                }
+            }
+            a.y[h.v_start + lv] = val;
+        }
     }
 }
 

@@ -566,6 +566,8 @@ struct phw_solver_s {
     bool pipe_q = false, pipe_p = false;   // bulk-copy pipelined mass solves (kernels_pipe.cuh; flags bits 8 / 9)
     MqPipeArgs pq{}; EllPipeArgs pp{};     // their shared-memory carve-ups (sized for the largest patch)
     size_t smem_pq = 0, smem_pp = 0;
+    bool pipe_en = false; EnergyPipeArgs pe{}; size_t smem_pe = 0;   // fused pipelined H_wave reduction (flags bit 11)
+    bool pipe_rhs = false; RhsPipeArgs pre{}, prv{}; size_t smem_pre = 0, smem_prv = 0;   // pipelined right-hand sides (flags bit 12)
     int64_t kernel_paths = 0;              // PHW_PATH_* bits of the solve kernels launched since the last phw_run began
     int *d_cells_user = nullptr; double* d_vtx_user = nullptr; unsigned long long* d_mm = nullptr;
     std::vector<cudaEvent_t> prof_ev; std::vector<int> prof_which;
@@ -655,12 +657,38 @@ RowArgs base_args(phw_solver_s* s) {
     return a;
 }
 
+// bulk-copy pipelined right-hand sides (kernels_pipe.cuh): y_e = cD (D x_p)_e / y_v = cD (D^T x_q)_v
+template <bool VERTEX, int NT, int MINB>
+int launch_rhs_pipe_cfg(phw_solver_s* s, const double* x, double cD, double* y) {
+    auto kern = VERTEX ? rhs_vertex_pipe_k<NT, MINB> : rhs_edge_pipe_k<NT, MINB>;
+    const size_t sm = VERTEX ? s->smem_prv : s->smem_pre;
+    static bool configured = false;
+    if (!configured) { CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024)); configured = true; }
+    RhsPipeArgs a = VERTEX ? s->prv : s->pre;
+    a.npatch = s->npatch; a.hdr = s->dm.hdr; a.recv = s->dm.recv; a.rece = s->dm.rece;
+    a.ghost = VERTEX ? s->dm.ghost_e : s->dm.ghost_v; a.eadj = s->dm.eadj; a.vslice_off = s->dm.vslice_off; a.vadj = s->dm.vadj;
+    a.x = x; a.y = y; a.cD = cD; a.ctl = s->ctl;
+    kern<<<std::max(1, std::min(s->npatch, MINB * s->sm_count)), NT, sm, s->stream>>>(a);
+    s->launches++;
+    s->kernel_paths |= PHW_PATH_PIPE_RHS;
+    CU(cudaGetLastError());
+    return 0;
+}
+template <bool VERTEX>
+int launch_rhs_pipe(phw_solver_s* s, const double* x, double cD, double* y) {
+    const size_t sm = VERTEX ? s->smem_prv : s->smem_pre;
+    if (3 * (sm + 2048) <= 227 * 1024) return launch_rhs_pipe_cfg<VERTEX, 384, 3>(s, x, cD, y);
+    if (2 * (sm + 2048) <= 227 * 1024) return launch_rhs_pipe_cfg<VERTEX, 512, 2>(s, x, cD, y);
+    return launch_rhs_pipe_cfg<VERTEX, 1024, 1>(s, x, cD, y);
+}
+
 // y_v = cD (D^T xq)_v [+ cB (B_top xp)_v]          (explicit part of the p rows)
 int op_vertex_store(phw_solver_s* s, const double* xp, const double* xq, double cM, double cD, double cB, double* y, const double* gscale = nullptr) {
     RowArgs a = base_args(s);
     a.gscale = gscale;
     a.xp = xp; a.xq = xq; a.cM = cM; a.cD = cD; a.cB = cB; a.y = y;
     const bool cas = s->prm.casimir && cB != 0.0;
+    if (s->pipe_rhs && s->pc.world <= 1 && cM == 0.0 && cB == 0.0 && !gscale) return launch_rhs_pipe<true>(s, xq, cD, y);
     if (cM != 0.0 && cD == 0.0) return cas ? launch_vertex<EPI_STORE, MODE_OP, true, false, true>(s, a) : launch_vertex<EPI_STORE, MODE_OP, true, false, false>(s, a);
     if (cM == 0.0) return cas ? launch_vertex<EPI_STORE, MODE_OP, false, true, true>(s, a) : launch_vertex<EPI_STORE, MODE_OP, false, true, false>(s, a);
     return cas ? launch_vertex<EPI_STORE, MODE_OP, true, true, true>(s, a) : launch_vertex<EPI_STORE, MODE_OP, true, true, false>(s, a);
@@ -670,6 +698,7 @@ int op_edge_store(phw_solver_s* s, const double* xp, const double* xq, double cM
     a.gscale = gscale;
     a.xp = xp; a.xq = xq; a.cM = cM; a.cD = cD; a.cB = cB; a.y = y;
     const bool cas = s->prm.casimir && cB != 0.0;
+    if (s->pipe_rhs && s->pc.world <= 1 && cM == 0.0 && cB == 0.0 && !gscale) return launch_rhs_pipe<false>(s, xp, cD, y);
     if (cM != 0.0 && cD == 0.0) return cas ? launch_edge<EPI_STORE, MODE_OP, true, false, true>(s, a) : launch_edge<EPI_STORE, MODE_OP, true, false, false>(s, a);
     if (cM == 0.0) return cas ? launch_edge<EPI_STORE, MODE_OP, false, true, true>(s, a) : launch_edge<EPI_STORE, MODE_OP, false, true, false>(s, a);
     return cas ? launch_edge<EPI_STORE, MODE_OP, true, true, true>(s, a) : launch_edge<EPI_STORE, MODE_OP, true, true, false>(s, a);
@@ -851,10 +880,14 @@ int launch_mq_lean(phw_solver_s* s) {
 // bulk-copy pipelined M_q solve (kernels_pipe.cuh): 1024 threads, one CTA per SM, two shared-memory stages
 int launch_mq_pipe(phw_solver_s* s) {
     constexpr int NT = 1024;
-    void* kern = (void*)solve_mq_pipe_k<NT>;
+    // Jacobi weights recomputed from the cell records unless pinv_q carries a boundary term (implicit casimir) - or PHW_MQ_PIPE_DIAG=0 (A/B)
+    static const int diag_env = [] { const char* e = getenv("PHW_MQ_PIPE_DIAG"); return e ? atoi(e) : 1; }();
+    const bool implicit = (s->prm.scheme == PHW_IE || s->prm.scheme == PHW_SM);
+    const bool diag = diag_env != 0 && !(implicit && s->prm.casimir);
+    void* kern = diag ? (void*)solve_mq_pipe_k<NT, true> : (void*)solve_mq_pipe_k<NT, false>;
     CU(cudaMemsetAsync(&s->ctl->gbar[0], 0, sizeof(unsigned int), s->stream));
-    static bool configured = false;
-    if (!configured) { CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024)); configured = true; }
+    static bool configured[2] = {false, false};
+    if (!configured[diag]) { CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024)); configured[diag] = true; }
     int occ = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, s->smem_pq));
     if (occ < 1) return fail(PHW_ECUDA, "pipelined M_q solve kernel does not fit on an SM");
@@ -1125,7 +1158,20 @@ int energy(phw_solver_s* s) {
         return 0;
     }
     int rc = 0;
-    if (!(s->prm.flags & 128)) {   // lean reductions on the ELL rows / packed cell records
+    if (s->pipe_en && s->pc.world <= 1) {   // both forms in one bulk-copy pipelined pass over the own cells (kernels_pipe.cuh)
+        constexpr int NT = 1024;
+        static bool conf = false;
+        if (!conf) { CU(cudaFuncSetAttribute(energy_pipe_k<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024)); conf = true; }
+        EnergyPipeArgs a = s->pe;
+        a.npatch = s->npatch; a.hdr = s->dm.hdr; a.recv = s->dm.recv; a.area = s->dm.area; a.cellq = s->d_cellq;
+        a.ghost_v = s->dm.ghost_v; a.ghost_e = s->dm.ghost_e; a.p = s->p; a.q = s->q;
+        a.scale_p = 0.5 / s->prm.rho / 12.0; a.scale_q = 0.5 * s->prm.K_wave; a.counter_id = 4;
+        a.partials = s->partials + 8192 + 4096; a.ctl = s->ctl;
+        energy_pipe_k<NT><<<std::max(1, std::min(s->npatch, s->sm_count)), NT, s->smem_pe, s->stream>>>(a);
+        s->launches += 1;
+        s->kernel_paths |= PHW_PATH_PIPE_ENERGY;
+        CU(cudaGetLastError());
+    } else if (!(s->prm.flags & 128)) {   // lean reductions on the ELL rows / packed cell records
         DotArgs a{};
         a.npatch = s->npatch; a.hdr = s->dm.hdr; a.partials = s->partials + 8192; a.ctl = s->ctl;
         a.ell_ioff = s->dm.ell_ioff; a.ell_woff = s->dm.ell_woff; a.ell_ids = s->dm.ell_ids; a.ell_w = s->dm.ell_w;
@@ -1498,13 +1544,14 @@ int phw_mesh_get_patch_counts(phw_mesh_t m, int32_t* counts) {
     return PHW_OK;
 }
 
-static void pipe_carve(const Layout& L, MqPipeArgs& cq, EllPipeArgs& cp, size_t& smem_pq, size_t& smem_pp);
-int phw_mesh_pipe_smem(phw_mesh_t m, int64_t* bytes2) {
-    if (!m || !bytes2) return fail(PHW_EINVAL, "mesh or bytes2 is NULL");
-    MqPipeArgs cq{}; EllPipeArgs cp{};
-    size_t sq = 0, sp = 0;
-    pipe_carve(m->L, cq, cp, sq, sp);
-    bytes2[0] = (int64_t)sp; bytes2[1] = (int64_t)sq;
+static void pipe_carve(const Layout& L, MqPipeArgs& cq, EllPipeArgs& cp, size_t& smem_pq, size_t& smem_pp, EnergyPipeArgs* ce = nullptr, size_t* smem_pe = nullptr,
+                       RhsPipeArgs* re = nullptr, size_t* smem_re = nullptr, RhsPipeArgs* rv = nullptr, size_t* smem_rv = nullptr);
+int phw_mesh_pipe_smem(phw_mesh_t m, int64_t* bytes5) {
+    if (!m || !bytes5) return fail(PHW_EINVAL, "mesh or bytes5 is NULL");
+    MqPipeArgs cq{}; EllPipeArgs cp{}; EnergyPipeArgs ce{}; RhsPipeArgs re{}, rv{};
+    size_t sq = 0, sp = 0, se = 0, sre = 0, srv = 0;
+    pipe_carve(m->L, cq, cp, sq, sp, &ce, &se, &re, &sre, &rv, &srv);
+    bytes5[0] = (int64_t)sp; bytes5[1] = (int64_t)sq; bytes5[2] = (int64_t)se; bytes5[3] = (int64_t)sre; bytes5[4] = (int64_t)srv;
     return PHW_OK;
 }
 
@@ -1656,11 +1703,13 @@ static int setup_scalars(phw_solver_s* s) {
 // shared-memory carve-up of the bulk-copy pipelined mass solves (kernels_pipe.cuh) for the largest patch of a layout:
 // offsets inside a stage, stage size, and the dynamic shared memory each kernel needs (two stages + scratch)
 constexpr size_t PIPE_SMEM_LIMIT = 227 * 1024 - 1024;   // 227 KB per CTA minus the kernels' static shared memory
-static void pipe_carve(const Layout& L, MqPipeArgs& cq, EllPipeArgs& cp, size_t& smem_pq, size_t& smem_pp) {
-    int max_ec = 0, max_ecells = 0, max_ge = 0, max_vc = 0, max_gv = 0, max_wn = 0, max_in = 0;
+static void pipe_carve(const Layout& L, MqPipeArgs& cq, EllPipeArgs& cp, size_t& smem_pq, size_t& smem_pp, EnergyPipeArgs* ce, size_t* smem_pe,
+                       RhsPipeArgs* re, size_t* smem_re, RhsPipeArgs* rv, size_t* smem_rv) {
+    int max_ec = 0, max_ecells = 0, max_ge = 0, max_vc = 0, max_gv = 0, max_wn = 0, max_in = 0, max_own = 0, max_adj = 0;
     for (const PatchHdr& h : L.hdr) {
         max_ec = std::max(max_ec, h.e_cnt); max_ecells = std::max(max_ecells, h.n_ecells); max_ge = std::max(max_ge, h.ge_cnt);
         max_vc = std::max(max_vc, h.v_cnt); max_gv = std::max(max_gv, h.gv_cnt); max_wn = std::max(max_wn, h.ell_wn); max_in = std::max(max_in, h.ell_in);
+        max_own = std::max(max_own, h.n_own); max_adj = std::max(max_adj, h.adj_cnt);
     }
     auto r16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
     {   // M_q: stage = [x_k local | cell records | b | pinv | x_{k-1} | eadj], then the cell contributions and two ghost lists
@@ -1689,6 +1738,41 @@ static void pipe_carve(const Layout& L, MqPipeArgs& cq, EllPipeArgs& cp, size_t&
         cp.off_gidx = 2 * cp.stage_bytes;
         cp.gidx_bytes = (uint32_t)r16(((size_t)max_gv + 8) * 4);
         smem_pp = (size_t)cp.off_gidx + 2 * cp.gidx_bytes;
+    }
+    if (ce && smem_pe) {   // fused energy: stage = [p local | q local | vertex-id records | areas | edge records], two ghost lists per field
+        size_t o = r16(((size_t)L.max_lv + 2) * 8);
+        ce->off_q = (uint32_t)o; o += r16(((size_t)L.max_le + 2) * 8);
+        ce->off_recv = (uint32_t)o; o += r16(((size_t)max_own + 2) * 8);
+        ce->off_area = (uint32_t)o; o += r16(((size_t)max_own + 2) * 8);
+        ce->off_cells = (uint32_t)o; o += (size_t)max_own * 32;
+        ce->stage_bytes = (uint32_t)((o + 127) & ~(size_t)127);
+        ce->off_gv = 2 * ce->stage_bytes;
+        ce->gv_bytes = (uint32_t)r16(((size_t)max_gv + 8) * 4);
+        ce->off_ge = ce->off_gv + 2 * ce->gv_bytes;
+        ce->ge_bytes = (uint32_t)r16(((size_t)max_ge + 8) * 4);
+        *smem_pe = (size_t)ce->off_ge + 2 * ce->ge_bytes;
+    }
+    if (re && smem_re) {   // edge-row right-hand side: stage = [x_p local | vertex-id records | edge-id records | eadj], then contributions, ghost lists
+        size_t o = r16(((size_t)L.max_lv + 2) * 8);
+        re->off_a = (uint32_t)o; o += r16(((size_t)max_ecells + 2) * 8);
+        re->off_b = (uint32_t)o; o += r16(((size_t)max_ecells + 2) * 8);
+        re->off_c = (uint32_t)o; o += r16(((size_t)max_ec + 8) * 4);
+        re->stage_bytes = (uint32_t)((o + 127) & ~(size_t)127);
+        re->off_sc3 = 2 * re->stage_bytes;
+        re->off_gidx = re->off_sc3 + (uint32_t)r16((size_t)max_ecells * 24);
+        re->gidx_bytes = (uint32_t)r16(((size_t)max_gv + 8) * 4);
+        *smem_re = (size_t)re->off_gidx + 2 * re->gidx_bytes;
+    }
+    if (rv && smem_rv) {   // vertex-row right-hand side: stage = [slice offsets | x_q local | edge-id records | adjacency codes]
+        size_t o = r16(((size_t)(max_vc + 31) / 32 + 2) * 4);
+        rv->off_a = (uint32_t)o; o += r16(((size_t)L.max_le + 2) * 8);
+        rv->off_b = (uint32_t)o; o += r16(((size_t)L.max_cells + 2) * 8);
+        rv->off_c = (uint32_t)o; o += r16((size_t)max_adj * 2);
+        rv->stage_bytes = (uint32_t)((o + 127) & ~(size_t)127);
+        rv->off_sc3 = 2 * rv->stage_bytes;
+        rv->off_gidx = rv->off_sc3 + (uint32_t)r16((size_t)L.max_cells * 24);
+        rv->gidx_bytes = (uint32_t)r16(((size_t)max_ge + 8) * 4);
+        *smem_rv = (size_t)rv->off_gidx + 2 * rv->gidx_bytes;
     }
 }
 
@@ -1795,8 +1879,18 @@ static int setup_solver(phw_solver_s* s) {
     s->ell_staged = (P.flags & 64) != 0;
     if (s->smem_vd > 200 * 1024) return fail(PHW_EINVAL, "patch does not fit in shared memory; reduce patch_cells");
     // ---- bulk-copy pipelined mass solves (flags bits 8 / 9): two stages holding every stream of the largest patch
+    if (P.flags & (256 | 512 | 2048 | 4096)) {
+        pipe_carve(L, s->pq, s->pp, s->smem_pq, s->smem_pp, &s->pe, &s->smem_pe, &s->pre, &s->smem_pre, &s->prv, &s->smem_prv);
+        if ((P.flags & 4096) && L.n_groups == 1 && !P.casimir && L.nv_owned == L.nv && L.ne_owned == L.ne) {
+            if (std::max(s->smem_pre, s->smem_prv) > PIPE_SMEM_LIMIT) return fail(PHW_EINVAL, "pipelined right-hand sides (flags bit 12): two stages of the largest patch exceed the shared memory of an SM; reduce patch_cells");
+            s->pipe_rhs = true;
+        }
+        if ((P.flags & 2048) && L.n_groups == 1 && L.nv_owned == L.nv && L.ne_owned == L.ne) {
+            if (s->smem_pe > PIPE_SMEM_LIMIT) return fail(PHW_EINVAL, "pipelined energy reduction (flags bit 11): two stages of the largest patch exceed the shared memory of an SM; reduce patch_cells");
+            s->pipe_en = true;
+        }
+    }
     if (s->coop && (P.flags & (256 | 512))) {
-        pipe_carve(L, s->pq, s->pp, s->smem_pq, s->smem_pp);
         if (P.flags & 256) {
             if (s->smem_pq > PIPE_SMEM_LIMIT) return fail(PHW_EINVAL, "pipelined M_q solve (flags bit 8): two stages of the largest patch exceed the shared memory of an SM; use patch_cells <= 1024");
             s->pipe_q = true;

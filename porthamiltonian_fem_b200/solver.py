@@ -96,10 +96,11 @@ class Mesh:
         return c
 
     def pipe_smem(self):
-        """dynamic shared memory (bytes) of the bulk-copy pipelined (M_p, M_q) solves for this layout (flags bits 9 / 8)"""
-        b = (ctypes.c_int64 * 2)()
+        """dynamic shared memory (bytes) of the bulk-copy pipelined kernels for this layout:
+        (M_p solve, M_q solve, energy reduction, edge-row rhs, vertex-row rhs) - flags bits 9, 8, 11, 12, 12"""
+        b = (ctypes.c_int64 * 5)()
         _lib.check(self.lib.phw_mesh_pipe_smem(self.handle, b))
-        return int(b[0]), int(b[1])
+        return tuple(int(x) for x in b)
 
     def close(self):
         if getattr(self, 'handle', None):

@@ -15,7 +15,10 @@ from test_gpu_parity import make_solver, rel, K_WAVE, RHO, TOL_STATE
 
 pytestmark = pytest.mark.gpu
 PIPE = 256 | 512
-PATH_PIPE_P, PATH_PIPE_Q = 4, 8
+ENERGY = 2048
+RHS = 4096
+PATH_PIPE_P, PATH_PIPE_Q, PATH_PIPE_ENERGY, PATH_PIPE_RHS = 4, 8, 16, 32
+ALL_PIPE = PIPE | ENERGY | RHS
 
 MESHES = [
     ('structured_34x8_pc64', lambda: rectangle_structured(34, 8), 'R', 1.0, 0.25, 64),
@@ -55,6 +58,79 @@ def test_pipelined_mass_solves_match_oracle_and_lean_kernels(name, make, shape, 
     assert np.all(z == 0.0)
 
 
+@pytest.mark.parametrize('name,make,shape,xL,yL,pc', MESHES)
+def test_pipelined_energy_reduction_matches_oracle(name, make, shape, xL, yL, pc):
+    """flags bit 11: both quadratic forms of H_wave in one pipelined pass over the own cells of every patch"""
+    v, c = make()
+    m, s = make_solver(v, c, shape, xL, yL, pc, flags=ENERGY)
+    topo = fem.Topology(v, c)
+    ops = fem.assemble_wave_operators(topo, fem.tag_boundary(topo, shape, xL, yL))
+    rng = np.random.default_rng(23)
+    for _ in range(2):
+        p = rng.standard_normal(topo.n_vertices)
+        q = rng.standard_normal(topo.n_edges)
+        s.set_state(p=p, q=q, x3=np.zeros(3))
+        Hp, Hq = s.energy_parts()
+        assert abs(Hp - 0.5 * p @ (ops['M_p'] @ p) / RHO) < 1e-12 * abs(Hp)
+        assert abs(Hq - 0.5 * K_WAVE * q @ (ops['M_q'] @ q)) < 1e-12 * abs(Hq)
+    assert s.stats()['kernel_paths'] & PATH_PIPE_ENERGY
+
+
+@pytest.mark.parametrize('name,make,shape,xL,yL,pc', MESHES)
+def test_pipelined_right_hand_sides_match_oracle(name, make, shape, xL, yL, pc):
+    """flags bit 12: D p and D^T q (assemble(b), wave_2D.py:814,849) through the pipelined row kernels"""
+    v, c = make()
+    m, s = make_solver(v, c, shape, xL, yL, pc, flags=RHS)
+    topo = fem.Topology(v, c)
+    ops = fem.assemble_wave_operators(topo, fem.tag_boundary(topo, shape, xL, yL))
+    rng = np.random.default_rng(29)
+    for _ in range(2):
+        p = rng.standard_normal(topo.n_vertices)
+        q = rng.standard_normal(topo.n_edges)
+        assert rel(s.apply_D(p), ops['D'] @ p) < 1e-13
+        assert rel(s.apply_DT(q), ops['D'].T @ q) < 1e-13
+    assert s.stats()['kernel_paths'] & PATH_PIPE_RHS
+    m0, s0 = make_solver(v, c, shape, xL, yL, pc)
+    assert rel(s.apply_D(p), s0.apply_D(p)) < 1e-14 and rel(s.apply_DT(q), s0.apply_DT(q)) < 1e-14   # same summation order
+
+
+def test_pipelined_right_hand_sides_strong_form():
+    mesh = rectangle_delaunay(120, 30, seed=6)
+    kw = dict(timeIntScheme='SV', dirichletImp='strong')
+    Ho, _, so = wave_2D_solve_oracle(0.03, 60, mesh, 1.0, 0.25, K_wave=K_WAVE, rho=RHO, return_state=True, **kw)
+    Hg, _, sg = wave_2D_solve(0.03, 60, '/tmp', 0, 1.0, 0.25, K_wave=K_WAVE, rho=RHO, mesh=mesh, patch_cells=48,
+                              return_state=True, verbose=False, solver_flags=RHS | ENERGY | 256, **kw)
+    assert sg['stats']['kernel_paths'] & PATH_PIPE_RHS
+    assert rel(sg['p'], so['p']) < TOL_STATE and rel(sg['q'], so['q']) < TOL_STATE
+    assert np.abs(Hg[:, 1:] - Ho[:, 1:]).max() < 1e-10 * np.abs(Ho[:, 1:]).max()
+
+
+@pytest.mark.parametrize('mq_diag', ['1', '0'])
+def test_pipelined_mq_solve_with_and_without_streamed_jacobi_weights(mq_diag, monkeypatch):
+    """PHW_MQ_PIPE_DIAG (A/B knob, read once per process - so this test runs the solver in a child process)"""
+    import subprocess, sys, os, textwrap
+    code = textwrap.dedent("""
+        import numpy as np, scipy.sparse.linalg as spla
+        from oracle import fem
+        from porthamiltonian_fem_b200 import _lib
+        from porthamiltonian_fem_b200.mesh import rectangle_delaunay
+        from test_gpu_parity import make_solver, rel
+        v, c = rectangle_delaunay(200, 50, seed=9)
+        m, s = make_solver(v, c, 'R', 1.0, 0.25, 80, flags=256)
+        topo = fem.Topology(v, c)
+        ops = fem.assemble_wave_operators(topo, fem.tag_boundary(topo, 'R', 1.0, 0.25))
+        bq = np.random.default_rng(5).standard_normal(topo.n_edges)
+        xq, it = s.mass_solve(_lib.PHW_Q, bq)
+        assert s.stats()['kernel_paths'] & 8
+        assert rel(xq, spla.spsolve(ops['M_q'].tocsc(), bq)) < 1e-11
+        print('ok', it)
+    """)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PHW_MQ_PIPE_DIAG=mq_diag, PYTHONPATH=root + os.pathsep + os.path.join(root, 'tests'))
+    r = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and 'ok' in r.stdout, r.stdout + r.stderr
+
+
 @pytest.mark.parametrize('scheme,ic', [('SE', None), ('SV', 'IC'), ('EH', None)])
 def test_pipelined_time_loop_parity(scheme, ic):
     mesh = rectangle_delaunay(120, 30, seed=5)
@@ -62,8 +138,9 @@ def test_pipelined_time_loop_parity(scheme, ic):
     kw = dict(timeIntScheme=scheme, interConnection=ic)
     Ho, _, so = wave_2D_solve_oracle(tF, steps, mesh, 1.0, 0.25, K_wave=K_WAVE, rho=RHO, return_state=True, **kw)
     Hg, _, sg = wave_2D_solve(tF, steps, '/tmp', 0, 1.0, 0.25, K_wave=K_WAVE, rho=RHO, mesh=mesh, patch_cells=48,
-                              return_state=True, verbose=False, solver_flags=PIPE, **kw)
-    assert sg['stats']['kernel_paths'] & (PATH_PIPE_P | PATH_PIPE_Q) == (PATH_PIPE_P | PATH_PIPE_Q)
+                              return_state=True, verbose=False, solver_flags=ALL_PIPE, **kw)
+    want = PATH_PIPE_P | PATH_PIPE_Q | PATH_PIPE_ENERGY | PATH_PIPE_RHS
+    assert sg['stats']['kernel_paths'] & want == want
     assert rel(sg['p'], so['p']) < TOL_STATE and rel(sg['q'], so['q']) < TOL_STATE
     assert np.abs(Hg[:, 1:] - Ho[:, 1:]).max() < 1e-10 * np.abs(Ho[:, 1:]).max()
     assert sg['stats']['max_rel_residual'] <= 1e-13

@@ -169,11 +169,11 @@ def test_pipelined_solve_shared_memory_budget_is_host_computable():
     v, c = rectangle_structured(400, 100)
     limit = 227 * 1024 - 1024
     m = Mesh(v, c, patch_cells=1024)
-    sp, sq = m.pipe_smem()
-    assert 0 < sp <= limit // 2 and 0 < sq <= limit
-    assert sp % 16 == 0 and sq % 16 == 0
+    sp, sq, se, sre, srv = m.pipe_smem()
+    assert 0 < sp <= limit // 2 and 0 < sq <= limit and 0 < se <= limit and 0 < sre <= limit // 2 and 0 < srv <= limit // 2
+    assert all(x % 16 == 0 for x in (sp, sq, se, sre, srv))
     m.close()
     m = Mesh(v, c, patch_cells=2048)
-    sp2, sq2 = m.pipe_smem()
+    sp2, sq2 = m.pipe_smem()[:2]
     assert sq2 > limit and sp2 > sp
     m.close()
