@@ -149,6 +149,35 @@ P_NCU_BYTES, Q_NCU_BYTES = 48.0, 99.0
 
 
 def main():
+    """Runs the benchmark; if the pipelined configuration fails on one GPU (a CUDA error poisons the process), the lean
+    configuration is measured in a fresh process instead and the line says so (config.fallback)."""
+    try:
+        return run_bench()
+    except SystemExit:
+        raise
+    except Exception as ex:
+        def argval(name, default):
+            return sys.argv[sys.argv.index(name) + 1] if name in sys.argv and sys.argv.index(name) + 1 < len(sys.argv) else default
+        if argval('--pipe', 'auto') == 'none' or int(os.environ.get('WORLD_SIZE', '1')) != 1 or argval('--impl', 'b200') != 'b200' \
+                or argval('--workload', 'mesh50m') != 'mesh50m' or os.environ.get('PHW_BENCH_NO_FALLBACK'):
+            raise
+        sys.stderr.write('bench.py: pipelined configuration failed ({!r}); measuring the lean configuration in a fresh process\n'.format(ex))
+        argv = [a for a in sys.argv[1:]]
+        if '--pipe' in argv:
+            i = argv.index('--pipe'); del argv[i:i + 2]
+        r = subprocess.run([sys.executable, os.path.abspath(__file__)] + argv + ['--pipe', 'none'], capture_output=True, text=True)
+        sys.stderr.write(r.stderr[-2000:])
+        for ln in r.stdout.splitlines():
+            if ln.startswith('{'):
+                d = json.loads(ln)
+                d.setdefault('config', {})['fallback'] = 'pipelined run failed: {}'.format(str(ex)[:200])
+                print(json.dumps(d))
+            elif ln.strip():
+                print(ln)
+        return r.returncode
+
+
+def run_bench():
     ap = argparse.ArgumentParser()
     ap.add_argument('--workload', default='mesh50m', choices=['mesh50m', 'sweep'])
     ap.add_argument('--cases', type=int, default=1024)
@@ -168,10 +197,15 @@ def main():
     ap.add_argument('--two-sweep', action='store_true', help='two Chebyshev iterations per pass in the mass solves (csrc/kernels2.cuh; A/B)')
     ap.add_argument('--ell-staged', action='store_true', help='ELL rows of the M_p solve staged in shared memory by cp.async (A/B)')
     ap.add_argument('--cell-rows', action='store_true', help='cell-based instead of assembled (ELL) rows in the M_p solve (A/B)')
-    ap.add_argument('--pipe', default='', help="bulk-copy pipelined kernels (csrc/kernels_pipe.cuh; A/B): any of 'p' (M_p solve), 'q' (M_q solve), 'e' (fused H_wave reduction), 'r' (right-hand sides)")
+    ap.add_argument('--pipe', default='auto', help="'auto' (default): 'pqer' on one GPU, 'none' on several (the pipelined kernels carry no inter-GPU exchange yet); 'none': lean kernels; " +
+                    "bulk-copy pipelined kernels (csrc/kernels_pipe.cuh; A/B): any of 'p' (M_p solve), 'q' (M_q solve), 'e' (fused H_wave reduction), 'r' (right-hand sides)")
     ap.add_argument('--stream-probe', action='store_true', help='print the bandwidth of a pure streaming pass over the ELL M_p data (diagnostics)')
     ap.add_argument('--debug-residuals', action='store_true', help='print the residual history of the last M_p / M_q solve to stderr')
     args = ap.parse_args()
+    if args.pipe == 'auto':
+        args.pipe = 'pqer' if int(os.environ.get('WORLD_SIZE', '1')) == 1 else 'none'
+    if args.pipe == 'none':
+        args.pipe = ''
     if args.patch_cells <= 0:
         args.patch_cells = 1024 if 'q' in args.pipe else 2048
     if args.impl == 'reference':
@@ -363,10 +397,12 @@ def main():
         }
         if not args.no_cpu_baseline:
             try:
-                rate, nd, secs = cpu_oracle_rate(442, 110, 10, False)
+                t_cpu = time.time()
+                rate, nd, secs = cpu_oracle_rate(442, 110, 40, False)
                 line['cpu_baseline'] = {'value': rate, 'unit': 'dof-updates/s', 'cores': 1, 'kind': 'port',
-                                        'sample': '10 SE steps on a 442x110x2-cell mesh ({} dofs) of the same family, CPU oracle '
-                                                  '(scipy SuperLU, factor once), {:.1f} s'.format(nd, secs)}
+                                        'sample': '40 SE steps on a 442x110x2-cell mesh ({} dofs) of the same family, CPU oracle '
+                                                  '(scipy SuperLU, factor once: {:.1f} s in the step loop, {:.1f} s with assembly and '
+                                                  'factorisation)'.format(nd, secs, time.time() - t_cpu)}
             except Exception as ex:   # the bench line must still be printed
                 line['cpu_baseline'] = {'value': None, 'unit': 'dof-updates/s', 'cores': 1, 'kind': 'port', 'sample': 'failed: %r' % (ex,)}
         print(json.dumps(line))

@@ -33,6 +33,10 @@ class PhwParams(ctypes.Structure):
                 ('extrap_order_q', ctypes.c_int32)]
 
 
+# phw_params.flags: bulk-copy pipelined M_q / M_p solves, fused energy reduction, right-hand sides (include/phwave.h)
+FLAGS_PIPELINED = 256 | 512 | 2048 | 4096
+
+
 class PhwStats(ctypes.Structure):
     _fields_ = [('steps', ctypes.c_int64), ('solves_p', ctypes.c_int64), ('solves_q', ctypes.c_int64),
                 ('solves_block', ctypes.c_int64), ('iters_p', ctypes.c_int64), ('iters_q', ctypes.c_int64),

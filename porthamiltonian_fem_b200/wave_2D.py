@@ -6,7 +6,8 @@ goes to libphwave.so (C ABI, include/phwave.h) and the whole time loop runs on t
 
 Extra keyword arguments (defaults keep the reference behaviour): ``mesh=(vertices, cells)`` to bypass
 the built-in generator (the reference calls mshr, :93-119), ``mesh_kind``, ``device``, ``patch_cells``,
-``tol``, ``lumped`` (dict overriding the hard-coded constants of :153-158), ``return_state``, ``save_every``
+``tol``, ``lumped`` (dict overriding the hard-coded constants of :153-158), ``solver_flags`` (phw_params.flags; default:
+pipelined kernels for meshes of >= 200 000 cells, lean kernels below), ``return_state``, ``save_every``
 (with ``saveP``: write p every that many steps to ``<outputDir>/p.xdmf``; default ``None`` = no field output, because a
 per-step device-to-host copy would dominate the run).
 """
@@ -34,7 +35,7 @@ def wave_2D_solve(tFinal, numSteps, outputDir,
                   analytical=False, saveP=True, controlType=None,
                   input_stop_t=None, control_start_t=None, basis_order=(1, 1),
                   mesh=None, mesh_kind='structured', device=0, patch_cells=None, tol=1e-13, extrap_order=3, save_every=None,
-                  lumped=None, return_state=False, verbose=True, solver_flags=0):
+                  lumped=None, return_state=False, verbose=True, solver_flags=None):
     """Solve the 2D port-Hamiltonian wave equation; see the reference docstring (wave_2D.py:22-51).
 
     Returns (H_array [numSteps, 8 | 12], numCells)."""
@@ -69,7 +70,7 @@ def wave_2D_solve(tFinal, numSteps, outputDir,
     if tuple(basis_order) != (1, 1):
         return _solve_high_order(tFinal, numSteps, outputDir, nx, xLength, yLength, domainShape, timeIntScheme, dirichletImp,
                                  K_wave, rho, interConnection, analytical, controlType, tuple(basis_order), mesh, mesh_kind,
-                                 device, tol, extrap_order, lumped, return_state, verbose, tic, solver_flags)
+                                 device, tol, extrap_order, lumped, return_state, verbose, tic, solver_flags or 0)
     if controlType == 'casimir' and timeIntScheme != 'SM':
         raise NotImplementedError('casimir control is only defined for the SM scheme (wave_2D.py:615)')
     if controlType == 'passivity' and timeIntScheme in ['SV', 'EH']:
@@ -79,8 +80,13 @@ def wave_2D_solve(tFinal, numSteps, outputDir,
     if mesh is None:
         mesh = generate_mesh(domainShape, nx, xLength, yLength, kind=mesh_kind)
     vertices, cells = mesh
+    # meshes far beyond the caches run the bulk-copy pipelined kernels (csrc/kernels_pipe.cuh; flags bits 8, 9, 11, 12), which need
+    # patches of <= ~1000 cells so that two shared-memory stages fit; small (cache-resident) meshes keep the lean kernels
+    big = len(cells) >= 200000
+    if solver_flags is None:
+        solver_flags = (_lib.FLAGS_PIPELINED if big and (patch_cells is None or patch_cells <= 1024) else 0)
     if patch_cells is None:
-        patch_cells = 2048 if len(cells) >= 200000 else max(64, min(2048, len(cells) // 256))
+        patch_cells = (1024 if solver_flags & 256 else 2048) if big else max(64, min(2048, len(cells) // 256))
     m = Mesh(vertices, cells, patch_cells=patch_cells)
     numCells = m.n_cells
     if rank == 0 and verbose:

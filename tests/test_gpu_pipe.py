@@ -189,3 +189,16 @@ def test_custom_grid_barrier_batched_sweep():
         Ho, _, _ = wave_2D_solve_oracle(0.04, 40, mesh, 1.0, 0.25, timeIntScheme='SV', interConnection='IC',
                                         K_wave=c['K_wave'], rho=c['rho'], lumped=lum, return_state=True)
         assert np.abs(H[i][:, 1:] - Ho[:, 1:]).max() < 1e-10 * np.abs(Ho[:, 1:]).max(), i
+
+
+def test_drop_in_default_on_a_large_mesh_runs_the_pipelined_kernels():
+    """wave_2D_solve without solver_flags on >= 200 000 cells: 1024-cell patches + all pipelined kernels; parity as everywhere"""
+    mesh = rectangle_structured(640, 160)                      # 204 800 cells, 410 k dofs
+    steps, tF = 8, 0.0016
+    Ho, _, so = wave_2D_solve_oracle(tF, steps, mesh, 1.0, 0.25, K_wave=K_WAVE, rho=RHO, return_state=True, timeIntScheme='SE')
+    Hg, nc, sg = wave_2D_solve(tF, steps, '/tmp', 0, 1.0, 0.25, K_wave=K_WAVE, rho=RHO, mesh=mesh, timeIntScheme='SE',
+                               return_state=True, verbose=False)
+    want = PATH_PIPE_P | PATH_PIPE_Q | PATH_PIPE_ENERGY | PATH_PIPE_RHS
+    assert nc == 204800 and sg['stats']['kernel_paths'] & want == want
+    assert rel(sg['p'], so['p']) < TOL_STATE and rel(sg['q'], so['q']) < TOL_STATE
+    assert np.abs(Hg[:, 1:] - Ho[:, 1:]).max() < 1e-10 * np.abs(Ho[:, 1:]).max()
