@@ -9,5 +9,5 @@ tail -4 gpurun_out/r1h_gpu_suite.log
 tail -c 400 gpurun_out/r1h_bench_default.log
 ( time timeout 70 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r1h_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline ) > gpurun_out/r1h_ncu_list.log 2>&1
 tail -2 gpurun_out/r1h_ncu_list.log
-( time timeout 70 ncu --set full --clock-control none --import-source on -k regex:solve_.*pipe_k -c 2 -o gpurun_out/r1h_pipe_solves python bench.py --steps 1 --warmup 0 --no-cpu-baseline ) > gpurun_out/r1h_ncu_full.log 2>&1
+( time timeout 45 ncu --set full --clock-control none --import-source on -k regex:solve_.*pipe_k -c 2 -o gpurun_out/r1h_pipe_solves python bench.py --steps 1 --warmup 0 --no-cpu-baseline ) > gpurun_out/r1h_ncu_full.log 2>&1
 tail -2 gpurun_out/r1h_ncu_full.log
