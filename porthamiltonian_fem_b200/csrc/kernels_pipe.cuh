@@ -46,20 +46,30 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, uint32_t 
         : "memory");
     return ok != 0;
 }
-// wait for the phase with the given parity.  A wait that exceeds ~0.5 s marks the run as failed (high word of ctl->nonconv,
-// reported by phw_run as PHW_ENOCONV) and every later wait of the launch gives up at once, so a protocol error ends in a
-// wrong-result error instead of a hung GPU
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity, Ctl* ctl) {
-    if (mbar_try_wait(bar, parity)) return;
+// wait for the phase with the given parity; false if the stage did not arrive.  A wait that exceeds ~5 s (never seen; a stage
+// lands within microseconds) marks the run as failed in the high word of ctl->nonconv, which phw_run / phw_mass_solve report
+// as an error, and every later wait of the run gives up at once.  The callers then skip the patch (pipe_alive), so that a
+// protocol error ends in a clean error code - not in a hung GPU and not in loads from indices that never arrived.
+__device__ __forceinline__ bool mbar_wait(unsigned long long* bar, uint32_t parity, Ctl* ctl) {
+    if (mbar_try_wait(bar, parity)) return true;
     const long long t0 = clock64();
     unsigned int spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if ((++spins & 255u) == 0u && (*((volatile long long*)&ctl->nonconv) >> 32) != 0) return;
-        if (clock64() - t0 > 1000000000LL) {
+        if ((spins++ & 63u) == 0u && (*((volatile long long*)&ctl->nonconv) >> 32) != 0) return false;
+        if (clock64() - t0 > 10000000000LL) {
             atomicAdd((unsigned long long*)&ctl->nonconv, 1ull << 32);
-            return;
+            return false;
         }
     }
+    return true;
+}
+// top-of-patch protocol of every pipelined kernel: own gathers done, bulk copies landed, visible to the whole CTA.
+// Returns false (for all threads of the CTA alike) if the stage must not be used.
+__device__ __forceinline__ bool pipe_stage_ready(unsigned long long* bar, uint32_t parity, Ctl* ctl, int* s_dead) {
+    cp_async_wait_all();
+    if (!mbar_wait(bar, parity, ctl)) *s_dead = 1;
+    __syncthreads();
+    return *s_dead == 0;
 }
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, unsigned long long* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -191,13 +201,14 @@ __global__ void __launch_bounds__(NT, 1) solve_mq_pipe_k(const __grid_constant__
     __shared__ double bc[2];
     __shared__ PatchHdr s_hdr[4];
     __shared__ __align__(8) unsigned long long full[2];
+    __shared__ int s_dead;       // a stage did not arrive (see mbar_wait): the CTA stops touching the stages
     SolveCtl& sc = a.ctl->sc[a.which];
     int k = 0, cur = sc.cur;
     double rho = 0.0, rr = 0.0, bb = 0.0;
     bool conv = false;
     unsigned int epoch = 0;
     unsigned int seq = 0;       // patches this CTA has processed so far: stage = seq & 1, mbarrier parity = (seq >> 1) & 1
-    if (threadIdx.x == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_fence_init(); }
+    if (threadIdx.x == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_fence_init(); s_dead = 0; }
     __syncthreads();
     double* sc3 = reinterpret_cast<double*>(smraw + a.off_sc3);
     const int n_my = ((int)blockIdx.x < a.npatch) ? (a.npatch - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
@@ -218,9 +229,7 @@ __global__ void __launch_bounds__(NT, 1) solve_mq_pipe_k(const __grid_constant__
                          s_hdr[0], n_my > 1 ? &s_hdr[1] : nullptr, xk, xprev, use_prev, &full[seq & 1u]);
         for (int it = 0; it < n_my; ++it, ++seq) {
             const unsigned int s = seq & 1u;
-            cp_async_wait_all();
-            mbar_wait(&full[s], (seq >> 1) & 1u, a.ctl);
-            __syncthreads();
+            if (!pipe_stage_ready(&full[s], (seq >> 1) & 1u, a.ctl, &s_dead)) continue;
             const PatchHdr& h = s_hdr[it & 3];
             if (it + 3 < n_my) load_hdr_smem_at(&s_hdr[(it + 3) & 3], &a.hdr[blockIdx.x + (it + 3) * gridDim.x], 64);
             if (it + 1 < n_my)
@@ -368,13 +377,14 @@ __global__ void __launch_bounds__(NT, MINB) solve_ell_pipe_k(const __grid_consta
     __shared__ double bc[2];
     __shared__ PatchHdr s_hdr[4];
     __shared__ __align__(8) unsigned long long full[2];
+    __shared__ int s_dead;       // a stage did not arrive (see mbar_wait): the CTA stops touching the stages
     SolveCtl& sc = a.ctl->sc[a.which];
     int k = 0, cur = sc.cur;
     double rho = 0.0, rr = 0.0, bb = 0.0;
     bool conv = false;
     unsigned int epoch = 0;
     unsigned int seq = 0;
-    if (threadIdx.x == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_fence_init(); }
+    if (threadIdx.x == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_fence_init(); s_dead = 0; }
     __syncthreads();
     const int n_my = ((int)blockIdx.x < a.npatch) ? (a.npatch - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     while (true) {
@@ -394,9 +404,7 @@ __global__ void __launch_bounds__(NT, MINB) solve_ell_pipe_k(const __grid_consta
                           s_hdr[0], n_my > 1 ? &s_hdr[1] : nullptr, xk, xprev, use_prev, &full[seq & 1u]);
         for (int it = 0; it < n_my; ++it, ++seq) {
             const unsigned int s = seq & 1u;
-            cp_async_wait_all();
-            mbar_wait(&full[s], (seq >> 1) & 1u, a.ctl);
-            __syncthreads();
+            if (!pipe_stage_ready(&full[s], (seq >> 1) & 1u, a.ctl, &s_dead)) continue;
             const PatchHdr& h = s_hdr[it & 3];
             if (it + 3 < n_my) load_hdr_smem_at(&s_hdr[(it + 3) & 3], &a.hdr[blockIdx.x + (it + 3) * gridDim.x], 64);
             if (it + 1 < n_my)
@@ -544,8 +552,9 @@ __global__ void __launch_bounds__(NT, 1) energy_pipe_k(const __grid_constant__ E
     __shared__ double red[64];
     __shared__ PatchHdr s_hdr[4];
     __shared__ __align__(8) unsigned long long full[2];
+    __shared__ int s_dead;       // a stage did not arrive (see mbar_wait): the CTA stops touching the stages
     __shared__ bool is_last;
-    if (threadIdx.x == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_fence_init(); }
+    if (threadIdx.x == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_fence_init(); s_dead = 0; }
     const int n_my = ((int)blockIdx.x < a.npatch) ? (a.npatch - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     for (int j = 0; j < 3 && j < n_my; ++j) load_hdr_smem_at(&s_hdr[j], &a.hdr[blockIdx.x + j * gridDim.x], 32 * j);
     __syncthreads();
@@ -556,9 +565,7 @@ __global__ void __launch_bounds__(NT, 1) energy_pipe_k(const __grid_constant__ E
         en_issue<NT>(a, smraw, nullptr, nullptr, gv_slot(1), ge_slot(1), s_hdr[0], n_my > 1 ? &s_hdr[1] : nullptr, &full[0]);
     for (int it = 0; it < n_my; ++it) {
         const unsigned int s = (unsigned int)it & 1u;
-        cp_async_wait_all();
-        mbar_wait(&full[s], ((unsigned int)it >> 1) & 1u, a.ctl);
-        __syncthreads();
+        if (!pipe_stage_ready(&full[s], ((unsigned int)it >> 1) & 1u, a.ctl, &s_dead)) continue;
         const PatchHdr& h = s_hdr[it & 3];
         if (it + 3 < n_my) load_hdr_smem_at(&s_hdr[(it + 3) & 3], &a.hdr[blockIdx.x + (it + 3) * gridDim.x], 64);
         if (it + 1 < n_my)
@@ -666,7 +673,8 @@ __global__ void __launch_bounds__(NT, MINB) rhs_edge_pipe_k(const __grid_constan
     extern __shared__ __align__(128) unsigned char smraw[];
     __shared__ PatchHdr s_hdr[4];
     __shared__ __align__(8) unsigned long long full[2];
-    if (threadIdx.x == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_fence_init(); }
+    __shared__ int s_dead;       // a stage did not arrive (see mbar_wait): the CTA stops touching the stages
+    if (threadIdx.x == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_fence_init(); s_dead = 0; }
     const int n_my = ((int)blockIdx.x < a.npatch) ? (a.npatch - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     for (int j = 0; j < 3 && j < n_my; ++j) load_hdr_smem_at(&s_hdr[j], &a.hdr[blockIdx.x + j * gridDim.x], 32 * j);
     __syncthreads();
@@ -676,9 +684,7 @@ __global__ void __launch_bounds__(NT, MINB) rhs_edge_pipe_k(const __grid_constan
     if (n_my > 0) rhs_e_issue<NT>(a, smraw, nullptr, g_slot(1), s_hdr[0], n_my > 1 ? &s_hdr[1] : nullptr, &full[0]);
     for (int it = 0; it < n_my; ++it) {
         const unsigned int s = (unsigned int)it & 1u;
-        cp_async_wait_all();
-        mbar_wait(&full[s], ((unsigned int)it >> 1) & 1u, a.ctl);
-        __syncthreads();
+        if (!pipe_stage_ready(&full[s], ((unsigned int)it >> 1) & 1u, a.ctl, &s_dead)) continue;
         const PatchHdr& h = s_hdr[it & 3];
         if (it + 3 < n_my) load_hdr_smem_at(&s_hdr[(it + 3) & 3], &a.hdr[blockIdx.x + (it + 3) * gridDim.x], 64);
         if (it + 1 < n_my)
@@ -756,7 +762,8 @@ __global__ void __launch_bounds__(NT, MINB) rhs_vertex_pipe_k(const __grid_const
     extern __shared__ __align__(128) unsigned char smraw[];
     __shared__ PatchHdr s_hdr[4];
     __shared__ __align__(8) unsigned long long full[2];
-    if (threadIdx.x == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_fence_init(); }
+    __shared__ int s_dead;       // a stage did not arrive (see mbar_wait): the CTA stops touching the stages
+    if (threadIdx.x == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_fence_init(); s_dead = 0; }
     const int n_my = ((int)blockIdx.x < a.npatch) ? (a.npatch - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     for (int j = 0; j < 3 && j < n_my; ++j) load_hdr_smem_at(&s_hdr[j], &a.hdr[blockIdx.x + j * gridDim.x], 32 * j);
     __syncthreads();
@@ -766,9 +773,7 @@ __global__ void __launch_bounds__(NT, MINB) rhs_vertex_pipe_k(const __grid_const
     if (n_my > 0) rhs_v_issue<NT>(a, smraw, nullptr, g_slot(1), s_hdr[0], n_my > 1 ? &s_hdr[1] : nullptr, &full[0]);
     for (int it = 0; it < n_my; ++it) {
         const unsigned int s = (unsigned int)it & 1u;
-        cp_async_wait_all();
-        mbar_wait(&full[s], ((unsigned int)it >> 1) & 1u, a.ctl);
-        __syncthreads();
+        if (!pipe_stage_ready(&full[s], ((unsigned int)it >> 1) & 1u, a.ctl, &s_dead)) continue;
         const PatchHdr& h = s_hdr[it & 3];
         if (it + 3 < n_my) load_hdr_smem_at(&s_hdr[(it + 3) & 3], &a.hdr[blockIdx.x + (it + 3) * gridDim.x], 64);
         if (it + 1 < n_my)
