@@ -194,8 +194,11 @@ __device__ __forceinline__ void mq_issue(const MqPipeArgs& a, unsigned char* sta
 
 // DIAG: the Jacobi weight 1 / diag(M_q)_e is recomputed from the (<= 2) cell records of the edge, which are in shared memory
 // anyway (diag contribution of slot i of a cell: 3 S - 4 g_i), instead of being streamed (12 of 99 B per cell and iteration)
-template <int NT, bool DIAG>
-__global__ void __launch_bounds__(NT, 1) solve_mq_pipe_k(const __grid_constant__ MqPipeArgs a) {
+// MULTI: with the inter-GPU exchange of the lean kernels after the grid-wide reduction (peer_exchange_iter: interface values pushed
+// into the neighbours' iterate buffers, residual norms all-reduced through the mailboxes).  External dofs are never part of an owned
+// range, so only the ghost gathers (ordinary LDGSTS loads, behind the barrier's fence) read what the peers wrote.
+template <int NT, bool DIAG, bool MULTI>
+__global__ void __launch_bounds__(NT, 1) solve_mq_pipe_k(const __grid_constant__ MqPipeArgs a, const __grid_constant__ PeerComm pc) {
     extern __shared__ __align__(128) unsigned char smraw[];
     __shared__ double red[64];
     __shared__ double bc[2];
@@ -295,6 +298,7 @@ __global__ void __launch_bounds__(NT, 1) solve_mq_pipe_k(const __grid_constant__
         __syncthreads();
         rr = bc[0]; bb = bc[1];
         __syncthreads();
+        if (MULTI) { peer_exchange_iter<NT>(pc, a.ctl, epoch, false, xnew, nxt, k, rr, bb); fence_proxy_async(); }
         conv = rr <= a.tol2 * bb;
         if (blockIdx.x == 0 && threadIdx.x == 0 && k < 48) a.ctl->reshist[a.which][k] = (bb > 0.0) ? rr / bb : 0.0;
         k += 1;
@@ -370,8 +374,8 @@ __device__ __forceinline__ void ell_issue(const EllPipeArgs& a, unsigned char* s
     }
 }
 
-template <int NT, int MINB>
-__global__ void __launch_bounds__(NT, MINB) solve_ell_pipe_k(const __grid_constant__ EllPipeArgs a) {
+template <int NT, int MINB, bool MULTI>
+__global__ void __launch_bounds__(NT, MINB) solve_ell_pipe_k(const __grid_constant__ EllPipeArgs a, const __grid_constant__ PeerComm pc) {
     extern __shared__ __align__(128) unsigned char smraw[];
     __shared__ double red[64];
     __shared__ double bc[2];
@@ -464,6 +468,7 @@ __global__ void __launch_bounds__(NT, MINB) solve_ell_pipe_k(const __grid_consta
         __syncthreads();
         rr = bc[0]; bb = bc[1];
         __syncthreads();
+        if (MULTI) { peer_exchange_iter<NT>(pc, a.ctl, epoch, true, xnew, nxt, k, rr, bb); fence_proxy_async(); }
         conv = rr <= a.tol2 * bb;
         if (blockIdx.x == 0 && threadIdx.x == 0 && k < 48) a.ctl->reshist[a.which][k] = (bb > 0.0) ? rr / bb : 0.0;
         k += 1;

@@ -885,10 +885,12 @@ int launch_mq_pipe(phw_solver_s* s) {
     static const int diag_env = [] { const char* e = getenv("PHW_MQ_PIPE_DIAG"); return e ? atoi(e) : 0; }();
     const bool implicit = (s->prm.scheme == PHW_IE || s->prm.scheme == PHW_SM);
     const bool diag = diag_env != 0 && !(implicit && s->prm.casimir);
-    void* kern = diag ? (void*)solve_mq_pipe_k<NT, true> : (void*)solve_mq_pipe_k<NT, false>;
+    const bool multi = s->pc.world > 1;
+    void* kern = multi ? (void*)solve_mq_pipe_k<NT, false, true> : (diag ? (void*)solve_mq_pipe_k<NT, true, false> : (void*)solve_mq_pipe_k<NT, false, false>);
     CU(cudaMemsetAsync(&s->ctl->gbar[0], 0, sizeof(unsigned int), s->stream));
-    static bool configured[2] = {false, false};
-    if (!configured[diag]) { CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024)); configured[diag] = true; }
+    static bool configured[3] = {false, false, false};
+    const int ci = multi ? 2 : (diag ? 1 : 0);
+    if (!configured[ci]) { CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024)); configured[ci] = true; }
     int occ = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, s->smem_pq));
     if (occ < 1) return fail(PHW_ECUDA, "pipelined M_q solve kernel does not fit on an SM");
@@ -901,7 +903,7 @@ int launch_mq_pipe(phw_solver_s* s) {
     a.tol2 = s->prm.tol * s->prm.tol;
     if (s->G > 1) { const double t = std::max(s->prm.tol / std::sqrt((double)s->G), 1e-14); a.tol2 = std::min(a.tol2, t * t); }
     a.max_iter = s->prm.max_iter; a.which = 1; a.partials = s->partials; a.ctl = s->ctl;
-    void* args[] = {(void*)&a};
+    void* args[] = {(void*)&a, (void*)&s->pc};
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     const bool prof = (s->prm.flags & 4) && s->prof_ev.size() < 2 * 8192;
     if (prof) {
@@ -921,10 +923,11 @@ int launch_mq_pipe(phw_solver_s* s) {
 // bulk-copy pipelined ELL M_p solve: two CTAs of 512 threads per SM when two pairs of stages fit, else one of 1024
 template <int NT, int MINB>
 int launch_ell_pipe_cfg(phw_solver_s* s) {
-    void* kern = (void*)solve_ell_pipe_k<NT, MINB>;
+    const bool multi = s->pc.world > 1;
+    void* kern = multi ? (void*)solve_ell_pipe_k<NT, MINB, true> : (void*)solve_ell_pipe_k<NT, MINB, false>;
     CU(cudaMemsetAsync(&s->ctl->gbar[0], 0, sizeof(unsigned int), s->stream));
-    static bool configured = false;
-    if (!configured) { CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024)); configured = true; }
+    static bool configured[2] = {false, false};
+    if (!configured[multi]) { CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024)); configured[multi] = true; }
     int occ = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, s->smem_pp));
     if (occ < 1) return fail(PHW_ECUDA, "pipelined M_p solve kernel does not fit on an SM");
@@ -937,7 +940,7 @@ int launch_ell_pipe_cfg(phw_solver_s* s) {
     a.tol2 = s->prm.tol * s->prm.tol;
     if (s->G > 1) { const double t = std::max(s->prm.tol / std::sqrt((double)s->G), 1e-14); a.tol2 = std::min(a.tol2, t * t); }
     a.max_iter = s->prm.max_iter; a.which = 0; a.partials = s->partials; a.ctl = s->ctl;
-    void* args[] = {(void*)&a};
+    void* args[] = {(void*)&a, (void*)&s->pc};
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     const bool prof = (s->prm.flags & 4) && s->prof_ev.size() < 2 * 8192;
     if (prof) {
@@ -994,8 +997,11 @@ int solve_mass(phw_solver_s* s, int which, int n_launch) {
     if (s->coop) {
         a.b = which == PHW_P ? s->bp : s->bq;
         a.pinv = which == PHW_P ? s->pinv_p : s->pinv_q;
-        if (which == PHW_Q && s->pipe_q && s->pc.world <= 1) return launch_mq_pipe(s);
-        if (which == PHW_P && s->pipe_p && s->pc.world <= 1 && s->ell_p && a.mdiag == nullptr) return launch_ell_pipe(s);
+        // partitioned runs: the pipelined solves with the exchange are opt-in (PHW_PIPE_MULTI=1) until they have run on 2+ GPUs
+        static const bool pipe_multi = [] { const char* e = getenv("PHW_PIPE_MULTI"); return e && atoi(e) != 0; }();
+        const bool pipe_ok = s->pc.world <= 1 || pipe_multi;
+        if (which == PHW_Q && s->pipe_q && pipe_ok) return launch_mq_pipe(s);
+        if (which == PHW_P && s->pipe_p && pipe_ok && s->ell_p && a.mdiag == nullptr) return launch_ell_pipe(s);
         if (which == PHW_P && s->ell_p && a.mdiag == nullptr && !s->ell_staged) {
             s->kernel_paths |= PHW_PATH_LEAN_P;
             static const int cfg = [] { const char* e = getenv("PHW_ELL_CFG"); return e ? atoi(e) : 0; }();

@@ -21,11 +21,13 @@ def _ngpu():
         return 0
 
 
-def _worker(rank, world, port, scheme, q):
+def _worker(rank, world, port, scheme, q, flags=0):
     import torch
     import torch.distributed as dist
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
+    if flags & 768:
+        os.environ['PHW_PIPE_MULTI'] = '1'          # pipelined solves with the inter-GPU exchange (opt-in, csrc/kernels_pipe.cuh)
     torch.cuda.set_device(rank)
     dist.init_process_group('gloo', rank=rank, world_size=world)
     try:
@@ -42,7 +44,7 @@ def _worker(rank, world, port, scheme, q):
         prm = _lib.PhwParams()
         prm.scheme, prm.dt, prm.K_wave, prm.rho = _lib.SCHEMES[scheme], tF / steps, K_WAVE, RHO
         prm.input_kind, prm.in_amp, prm.in_omega, prm.in_t_stop = _lib.IN_SINE_WINDOW, 10.0, 8 * np.pi, 0.25
-        prm.tol, prm.max_iter, prm.extrap_order = 1e-13, 200, 2
+        prm.tol, prm.max_iter, prm.extrap_order, prm.flags = 1e-13, 200, 2, int(flags)
         s = Solver(m, prm, device=rank)
         info = setup_peer_exchange(s, part, dist, rank, world)
         H = s.run(steps)
@@ -60,8 +62,8 @@ def _worker(rank, world, port, scheme, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('scheme', ['SE', 'SV'])
-def test_two_gpu_partitioned_run_matches_oracle(scheme):
+@pytest.mark.parametrize('scheme,flags', [('SE', 0), ('SV', 0), ('SE', 768), ('SV', 768)])
+def test_two_gpu_partitioned_run_matches_oracle(scheme, flags):
     if _ngpu() < 2:
         pytest.skip('needs 2 GPUs')
     import torch.multiprocessing as mp
@@ -71,7 +73,7 @@ def test_two_gpu_partitioned_run_matches_oracle(scheme):
     sck.close()
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, scheme, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, scheme, q, flags)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=240) for _ in procs]
