@@ -66,6 +66,8 @@ def _worker(rank, world, port, scheme, q, flags=0):
 def test_two_gpu_partitioned_run_matches_oracle(scheme, flags):
     if _ngpu() < 2:
         pytest.skip('needs 2 GPUs')
+    if flags & 768 and not os.environ.get('PHW_TEST_PIPE_MULTI'):
+        pytest.skip('pipelined solves with the inter-GPU exchange: opt-in until they have run on 2 GPUs (set PHW_TEST_PIPE_MULTI=1)')
     import torch.multiprocessing as mp
     sck = socket.socket()
     sck.bind(('127.0.0.1', 0))
