@@ -10,7 +10,12 @@ reproducible) here, so the solver accepts *any* conforming triangle mesh as
 * ``square_one_channel``    - the 'S_1C' domain of wave_2D.py:97-119 (unit square plus inlet
   channel, locally refined near the inlet);
 * ``generate_mesh``         - maps the reference's ``(domainShape, nx, xLength, yLength)`` to
-  one of the above with a comparable cell count (mshr gives ~1.46 nx^2 cells on 1 x 0.25).
+  one of the above with a comparable cell count (mshr gives ~1.46 nx^2 cells on 1 x 0.25);
+* ``load_mesh`` / ``save_mesh`` - triangulations from / to files: ``.npz`` (arrays ``vertices``, ``cells``), a pair of
+  ``.npy`` files, or the XDMF + raw-binary / inline-XML layout dolfin's ``XDMFFile.write(mesh)`` family uses for
+  triangle meshes (``Topology`` ``Triangle`` + ``Geometry`` ``XY``; HDF5 heavy data needs h5py, which this image
+  lacks - such files are rejected with a clear message).  Lets a mesh produced by mshr on another machine
+  (``wave_2D.py:93-119``) run here unchanged: ``wave_2D_solve(..., mesh=load_mesh(path))``.
 """
 import numpy as np
 
@@ -130,3 +135,65 @@ def generate_mesh(domainShape, nx, xLength, yLength, kind='structured', seed=0):
         return square_one_channel(N, xLength, yLength)
     print('domainShape \"{}\" hasn\'t been created'.format(domainShape))
     raise SystemExit
+
+
+def _check_mesh(vertices, cells):
+    vertices = np.ascontiguousarray(vertices, dtype=np.float64)
+    cells = np.ascontiguousarray(cells)
+    if vertices.ndim != 2 or vertices.shape[1] not in (2, 3) or cells.ndim != 2 or cells.shape[1] != 3:
+        raise ValueError('a mesh is (vertices [Nv,2], cells [Nc,3]); got {} and {}'.format(vertices.shape, cells.shape))
+    if vertices.shape[1] == 3:
+        if np.abs(vertices[:, 2]).max(initial=0.0) > 0:
+            raise ValueError('only planar meshes (z = 0) are supported')
+        vertices = np.ascontiguousarray(vertices[:, :2])
+    if cells.size and (cells.min() < 0 or cells.max() >= vertices.shape[0]):
+        raise ValueError('cell vertex index out of range')
+    return vertices, cells.astype(np.int32)
+
+
+def save_mesh(path, vertices, cells):
+    """Write ``path`` (.npz) with the arrays ``vertices`` and ``cells``."""
+    vertices, cells = _check_mesh(vertices, cells)
+    np.savez(path, vertices=vertices, cells=cells)
+
+
+def load_mesh(path, cells_path=None):
+    """(vertices, cells) from ``.npz`` | (``vertices.npy``, ``cells.npy``) | ``.xdmf`` (Triangle topology, XY geometry with
+    inline XML or raw-binary heavy data)."""
+    import os
+    ext = os.path.splitext(path)[1].lower()
+    if ext == '.npz':
+        with np.load(path) as z:
+            return _check_mesh(z['vertices'], z['cells'])
+    if ext == '.npy':
+        if cells_path is None:
+            raise ValueError('load_mesh(vertices.npy, cells.npy): the cells file is missing')
+        return _check_mesh(np.load(path), np.load(cells_path))
+    if ext == '.xdmf':
+        import xml.etree.ElementTree as ET
+        root = ET.parse(path).getroot()
+        grid = next((g for g in root.iter('Grid') if g.find('Topology') is not None and g.find('Geometry') is not None), None)
+        if grid is None:
+            raise ValueError('{}: no Grid with Topology and Geometry'.format(path))
+        topo, geom = grid.find('Topology'), grid.find('Geometry')
+        if topo.get('TopologyType', topo.get('Type', '')).lower() != 'triangle':
+            raise ValueError('{}: only Triangle topologies are supported'.format(path))
+
+        def read_item(item, dtype):
+            dims = [int(x) for x in item.get('Dimensions').split()]
+            fmt = item.get('Format', 'XML').upper()
+            text = (item.text or '').strip()
+            if fmt == 'XML':
+                return np.array(text.split(), dtype=dtype).reshape(dims)
+            if fmt == 'BINARY':
+                prec = int(item.get('Precision', '8' if dtype == np.float64 else '4'))
+                kind = {('f', 8): np.float64, ('f', 4): np.float32, ('i', 8): np.int64, ('i', 4): np.int32}[('f' if dtype == np.float64 else 'i', prec)]
+                raw = np.fromfile(os.path.join(os.path.dirname(os.path.abspath(path)), text), dtype=kind,
+                                  count=int(np.prod(dims)), offset=int(item.get('Seek', '0')))
+                return raw.reshape(dims).astype(dtype)
+            raise ValueError('{}: heavy data in {} format needs h5py, which is not available here; re-export the mesh as .npz '
+                             '(numpy.savez(path, vertices=mesh.coordinates(), cells=mesh.cells()))'.format(path, fmt))
+        cells = read_item(topo.find('DataItem'), np.int64)
+        vertices = read_item(geom.find('DataItem'), np.float64)
+        return _check_mesh(vertices, cells)
+    raise ValueError('unknown mesh file type {!r} (use .npz, .npy + .npy or .xdmf)'.format(ext))

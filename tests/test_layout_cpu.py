@@ -177,3 +177,44 @@ def test_pipelined_solve_shared_memory_budget_is_host_computable():
     sp2, sq2 = m.pipe_smem()[:2]
     assert sq2 > limit and sp2 > sp
     m.close()
+
+
+def test_mesh_files_round_trip(tmp_path):
+    """load_mesh: .npz, .npy pair, XDMF with inline-XML and raw-binary heavy data (the stand-in for reading an mshr mesh
+    written by dolfin on another machine, wave_2D.py:93-119); HDF5 heavy data is rejected with a clear message."""
+    from porthamiltonian_fem_b200.mesh import save_mesh, load_mesh
+    v, c = rectangle_delaunay(12, 3, seed=2)
+    save_mesh(str(tmp_path / 'm.npz'), v, c)
+    v2, c2 = load_mesh(str(tmp_path / 'm.npz'))
+    assert np.array_equal(v, v2) and np.array_equal(c, c2) and c2.dtype == np.int32
+    np.save(tmp_path / 'v.npy', v)
+    np.save(tmp_path / 'c.npy', c.astype(np.int64))
+    v3, c3 = load_mesh(str(tmp_path / 'v.npy'), str(tmp_path / 'c.npy'))
+    assert np.array_equal(v, v3) and np.array_equal(c, c3)
+    # XDMF, inline XML, 3-component geometry with z = 0 (what dolfin writes for 2D meshes in some versions)
+    xml = ('<?xml version="1.0"?><Xdmf Version="3.0"><Domain><Grid Name="mesh" GridType="Uniform">'
+           '<Topology NumberOfElements="{nc}" TopologyType="Triangle" NodesPerElement="3"><DataItem Dimensions="{nc} 3" NumberType="UInt" Format="XML">{cells}</DataItem></Topology>'
+           '<Geometry GeometryType="XYZ"><DataItem Dimensions="{nv} 3" Format="XML">{verts}</DataItem></Geometry></Grid></Domain></Xdmf>')
+    v3d = np.concatenate([v, np.zeros((v.shape[0], 1))], axis=1)
+    (tmp_path / 'a.xdmf').write_text(xml.format(nc=c.shape[0], nv=v.shape[0], cells=' '.join(map(str, c.ravel())),
+                                                verts=' '.join(repr(float(x)) for x in v3d.ravel())))
+    v4, c4 = load_mesh(str(tmp_path / 'a.xdmf'))
+    assert np.array_equal(v, v4) and np.array_equal(c, c4)
+    # XDMF, raw binary heavy data
+    c.astype(np.int32).tofile(tmp_path / 'b_cells.bin')
+    v.tofile(tmp_path / 'b_verts.bin')
+    xmlb = ('<?xml version="1.0"?><Xdmf Version="3.0"><Domain><Grid Name="mesh" GridType="Uniform">'
+            '<Topology TopologyType="Triangle"><DataItem Dimensions="{nc} 3" NumberType="Int" Precision="4" Format="Binary">b_cells.bin</DataItem></Topology>'
+            '<Geometry GeometryType="XY"><DataItem Dimensions="{nv} 2" NumberType="Float" Precision="8" Format="Binary">b_verts.bin</DataItem></Geometry></Grid></Domain></Xdmf>')
+    (tmp_path / 'b.xdmf').write_text(xmlb.format(nc=c.shape[0], nv=v.shape[0]))
+    v5, c5 = load_mesh(str(tmp_path / 'b.xdmf'))
+    assert np.array_equal(v, v5) and np.array_equal(c, c5)
+    (tmp_path / 'h.xdmf').write_text(xmlb.replace('Format="Binary"', 'Format="HDF"').format(nc=c.shape[0], nv=v.shape[0]))
+    with pytest.raises(ValueError, match='h5py'):
+        load_mesh(str(tmp_path / 'h.xdmf'))
+    with pytest.raises(ValueError):
+        load_mesh(str(tmp_path / 'm.txt'))
+    # the loaded mesh goes through the layout builder like a generated one
+    m = Mesh(v4, c4, patch_cells=32)
+    assert m.n_cells == c.shape[0]
+    m.close()
