@@ -33,6 +33,33 @@ def slab_cell_ranks(vertices, cells, world, xmin=None, xmax=None):
     return np.clip(r, 0, world - 1)
 
 
+def rcb_cell_ranks(vertices, cells, world):
+    """Recursive coordinate bisection of the cell centroids into `world` parts (any world >= 1, not only powers of two):
+    the partition for general domains (the reference relies on dolfin's graph partitioner, which - like
+    metis.h - is not available here).  A part with n ranks is cut along its longer bounding-box axis at the weighted median
+    that gives floor(n/2) : ceil(n/2) of its cells to the two halves; ties are broken by cell index, so the result is
+    deterministic.  Returns the rank of every cell."""
+    cells = np.asarray(cells, dtype=np.int64)
+    cen = np.asarray(vertices, dtype=np.float64)[cells].mean(axis=1)
+    rank = np.zeros(cells.shape[0], dtype=np.int64)
+
+    def split(idx, r0, n):
+        if n <= 1 or idx.size == 0:
+            rank[idx] = r0
+            return
+        lo = cen[idx].min(axis=0)
+        hi = cen[idx].max(axis=0)
+        axis = 0 if (hi[0] - lo[0]) >= (hi[1] - lo[1]) else 1
+        order = idx[np.lexsort((idx, cen[idx, axis]))]
+        n_left = n // 2
+        k = (idx.size * n_left) // n
+        split(order[:k], r0, n_left)
+        split(order[k:], r0 + n_left, n - n_left)
+
+    split(np.arange(cells.shape[0], dtype=np.int64), 0, int(world))
+    return rank
+
+
 class LocalPart:
     """What one rank needs: local mesh, global ids, ownership flags, exchange lists (local user numbering)."""
     pass

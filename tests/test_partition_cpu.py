@@ -16,10 +16,14 @@ from porthamiltonian_fem_b200 import partition as pt
 
 
 @pytest.mark.parametrize('world', [2, 3, 4])
-@pytest.mark.parametrize('mesh', ['structured', 'delaunay'])
+@pytest.mark.parametrize('mesh', ['structured', 'delaunay', 's1c_rcb', 'delaunay_rcb'])
 def test_partition_invariants(world, mesh):
-    v, c = rectangle_structured(24, 6) if mesh == 'structured' else rectangle_delaunay(24, 6, seed=2)
-    cr = pt.slab_cell_ranks(v, c, world)
+    if mesh == 's1c_rcb':
+        from porthamiltonian_fem_b200.mesh import square_one_channel
+        v, c = square_one_channel(20)
+    else:
+        v, c = rectangle_structured(24, 6) if mesh == 'structured' else rectangle_delaunay(24, 6, seed=2)
+    cr = pt.rcb_cell_ranks(v, c, world) if mesh.endswith('_rcb') else pt.slab_cell_ranks(v, c, world)
     parts = [pt.build_local_part(v, c, cr, r) for r in range(world)]
     NV, NE = parts[0].n_global_vertices, parts[0].n_global_edges
     # every dof is owned by exactly one rank, and every rank holds all cells touching its owned dofs
@@ -39,6 +43,23 @@ def test_partition_invariants(world, mesh):
                 own = (parts[nb].vertex_owner if kind == 'v' else parts[nb].edge_owner)[loc]
                 assert np.all(own == nb)
                 assert np.all(np.diff(gid) > 0)
+
+
+@pytest.mark.parametrize('world', [1, 2, 3, 5, 8])
+def test_rcb_partition_is_balanced_and_compact(world):
+    """recursive coordinate bisection (general domains): balanced to one cell per cut, deterministic, and
+    on the unit square with the inlet channel every part is a compact box-like region (few neighbours)"""
+    from porthamiltonian_fem_b200.mesh import square_one_channel
+    v, c = square_one_channel(20)
+    cr = pt.rcb_cell_ranks(v, c, world)
+    counts = np.bincount(cr, minlength=world)
+    assert counts.sum() == len(c) and counts.min() >= len(c) // world - world and counts.max() <= -(-len(c) // world) + world
+    assert np.array_equal(cr, pt.rcb_cell_ranks(v, c, world))
+    if world > 1:
+        parts = [pt.build_local_part(v, c, cr, r) for r in range(world)]
+        assert max(len(p.recv) for p in parts) <= 7            # MAX_RANKS - 1 neighbours fit the device exchange tables
+        halo = sum(int((~p.cell_owned).sum()) for p in parts)
+        assert halo < 0.6 * len(c)                             # one halo layer around compact parts stays a fraction of the mesh
 
 
 def test_structured_slab_shortcut_matches_general_partition():
