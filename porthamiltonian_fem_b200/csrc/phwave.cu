@@ -17,6 +17,7 @@
 #include "kernels.cuh"
 #include "kernels2.cuh"
 #include "kernels_pipe.cuh"
+#include "kernels_pipe2.cuh"
 #include "layout.hpp"
 
 using namespace phw;
@@ -567,6 +568,7 @@ struct phw_solver_s {
     MqPipeArgs pq{}; EllPipeArgs pp{};     // their shared-memory carve-ups (sized for the largest patch)
     size_t smem_pq = 0, smem_pp = 0;
     bool pipe_en = false; EnergyPipeArgs pe{}; size_t smem_pe = 0;   // fused pipelined H_wave reduction (flags bit 11)
+    bool pipe2_q = false; Mq2PipeArgs pq2{}; size_t smem_pq2 = 0;     // pipelined two-sweep M_q solve (experimental, flags bit 13)
     bool pipe_rhs = false; RhsPipeArgs pre{}, prv{}; size_t smem_pre = 0, smem_prv = 0;   // pipelined right-hand sides (flags bit 12)
     int64_t kernel_paths = 0;              // PHW_PATH_* bits of the solve kernels launched since the last phw_run began
     int *d_cells_user = nullptr; double* d_vtx_user = nullptr; unsigned long long* d_mm = nullptr;
@@ -986,6 +988,41 @@ int launch_ell_pipe(phw_solver_s* s) {
     return l2_persist_window(s, s->bp, (size_t)s->nv * sizeof(double), false);
 }
 
+// pipelined two-sweep M_q solve (kernels_pipe2.cuh; experimental)
+int launch_mq_pipe2(phw_solver_s* s) {
+    constexpr int NT = 1024;
+    void* kern = (void*)solve2_mq_pipe_k<NT>;
+    CU(cudaMemsetAsync(&s->ctl->gbar[0], 0, sizeof(unsigned int), s->stream));
+    static bool configured = false;
+    if (!configured) { CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048)); configured = true; }
+    int occ = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, s->smem_pq2));
+    if (occ < 1) return fail(PHW_ECUDA, "pipelined two-sweep M_q solve kernel does not fit on an SM");
+    const int grid = std::max(1, std::min(s->npatch, occ * s->sm_count));
+    Mq2PipeArgs a = s->pq2;
+    a.m = s->r2[1];
+    for (int i = 0; i < 4; ++i) a.buf[i] = s->tq.b[i];
+    a.b = s->bq;
+    a.cheb_d = s->cheb_d[1]; a.cheb_c = s->cheb_c[1];
+    a.tol2 = s->prm.tol * s->prm.tol;
+    a.max_iter = s->prm.max_iter; a.which = 1; a.partials = s->partials; a.ctl = s->ctl;
+    void* args[] = {(void*)&a};
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    const bool prof = (s->prm.flags & 4) && s->prof_ev.size() < 2 * 8192;
+    if (prof) {
+        CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+        CU(cudaEventRecord(e0, s->stream));
+    }
+    CU(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(NT), args, s->smem_pq2, s->stream));
+    if (prof) {
+        CU(cudaEventRecord(e1, s->stream));
+        s->prof_ev.push_back(e0); s->prof_ev.push_back(e1); s->prof_which.push_back(1);
+    }
+    s->launches++;
+    s->kernel_paths |= PHW_PATH_PIPE2_Q;
+    return 0;
+}
+
 int solve_begin(phw_solver_s* s, int which) {
     solve_begin_k<<<1, 1, 0, s->stream>>>(s->ctl, which);
     s->launches++;
@@ -1015,6 +1052,7 @@ int solve_mass(phw_solver_s* s, int which, int n_launch) {
         s->launches++;
         return 0;
     }
+    if (which == PHW_Q && s->pipe2_q && s->coop && s->pc.world <= 1) return launch_mq_pipe2(s);
     if (s->two_sweep) return which == PHW_P ? launch_coop2<0>(s) : launch_coop2<1>(s);
     RowArgs a = base_args(s);
     a.which = which; a.use_cheb_input = 1; a.finalize = 1; a.cM = 1.0; a.counter_id = which;
@@ -1575,14 +1613,18 @@ int phw_mesh_get_patch_counts(phw_mesh_t m, int32_t* counts) {
     return PHW_OK;
 }
 
+static size_t pipe2_carve(const Ring2& R, Mq2PipeArgs& c);
 static void pipe_carve(const Layout& L, MqPipeArgs& cq, EllPipeArgs& cp, size_t& smem_pq, size_t& smem_pp, EnergyPipeArgs* ce = nullptr, size_t* smem_pe = nullptr,
                        RhsPipeArgs* re = nullptr, size_t* smem_re = nullptr, RhsPipeArgs* rv = nullptr, size_t* smem_rv = nullptr);
-int phw_mesh_pipe_smem(phw_mesh_t m, int64_t* bytes5) {
-    if (!m || !bytes5) return fail(PHW_EINVAL, "mesh or bytes5 is NULL");
+int phw_mesh_pipe_smem(phw_mesh_t m, int64_t* bytes6) {
+    if (!m || !bytes6) return fail(PHW_EINVAL, "mesh or bytes6 is NULL");
     MqPipeArgs cq{}; EllPipeArgs cp{}; EnergyPipeArgs ce{}; RhsPipeArgs re{}, rv{};
     size_t sq = 0, sp = 0, se = 0, sre = 0, srv = 0;
     pipe_carve(m->L, cq, cp, sq, sp, &ce, &se, &re, &sre, &rv, &srv);
-    bytes5[0] = (int64_t)sp; bytes5[1] = (int64_t)sq; bytes5[2] = (int64_t)se; bytes5[3] = (int64_t)sre; bytes5[4] = (int64_t)srv;
+    bytes6[0] = (int64_t)sp; bytes6[1] = (int64_t)sq; bytes6[2] = (int64_t)se; bytes6[3] = (int64_t)sre; bytes6[4] = (int64_t)srv;
+    bytes6[5] = 0;
+    Ring2 R;
+    if (m->L.n_groups == 1 && m->L.build_ring2(1, R).empty()) { Mq2PipeArgs c2{}; bytes6[5] = (int64_t)pipe2_carve(R, c2); }
     return PHW_OK;
 }
 
@@ -1807,6 +1849,29 @@ static void pipe_carve(const Layout& L, MqPipeArgs& cq, EllPipeArgs& cp, size_t&
     }
 }
 
+// shared-memory carve-up of the pipelined two-sweep M_q solve (kernels_pipe2.cuh) for the largest ring-2 patch
+static size_t pipe2_carve(const Ring2& R, Mq2PipeArgs& c) {
+    int max_ng = 0, max_n0 = 0;
+    for (const Ring2Hdr& h : R.hdr) { max_ng = std::max(max_ng, h.g1_cnt + h.g2_cnt); max_n0 = std::max(max_n0, h.d_cnt); }
+    auto r16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
+    const size_t rowd = r16(((size_t)R.max_rows + 2) * 8), celld = r16(((size_t)R.max_c2 + 2) * 8);
+    size_t o = r16(((size_t)R.max_ld + 2) * 8);
+    c.off_xprev = (uint32_t)o; o += rowd;
+    c.off_b = (uint32_t)o; o += rowd;
+    c.off_pinv = (uint32_t)o; o += rowd;
+    c.off_eadj = (uint32_t)o; o += r16(((size_t)R.max_rows + 8) * 4);
+    c.off_rec = (uint32_t)o; o += celld;
+    c.off_g0 = (uint32_t)o; o += celld;
+    c.off_g1 = (uint32_t)o; o += celld;
+    c.off_g2 = (uint32_t)o; o += celld;
+    c.stage_bytes = (uint32_t)((o + 127) & ~(size_t)127);
+    c.off_sc3 = 2 * c.stage_bytes;
+    c.off_xk0 = c.off_sc3 + (uint32_t)r16((size_t)R.max_c2 * 24);
+    c.off_gidx = c.off_xk0 + (uint32_t)r16((size_t)max_n0 * 8);
+    c.gidx_bytes = (uint32_t)r16(((size_t)max_ng + 8) * 4);
+    return (size_t)c.off_gidx + 2 * c.gidx_bytes;
+}
+
 static int setup_solver(phw_solver_s* s) {
     const Layout& L = s->mesh->L;
     const phw_params& P = s->prm;
@@ -1968,14 +2033,23 @@ static int setup_solver(phw_solver_s* s) {
     }
     // ---- two-sweep patches of the mass solves (kernels2.cuh): single GPU, weak form (pinv_p is then exactly the
     //      inverse of the P1 mass diagonal), explicit schemes
-    s->two_sweep = s->coop && (P.flags & 16) && !P.strong && !implicit && L.nv_owned == L.nv && L.ne_owned == L.ne;
-    for (int kind = 0; kind < 2 && s->two_sweep; ++kind) {
+    const bool ring2_ok = s->coop && !P.strong && !implicit && L.nv_owned == L.nv && L.ne_owned == L.ne;
+    s->two_sweep = ring2_ok && (P.flags & 16);
+    bool want_pipe2 = ring2_ok && (P.flags & 8192) && L.n_groups == 1;
+    for (int kind = 0; kind < 2 && (s->two_sweep || want_pipe2); ++kind) {
+        if (!s->two_sweep && kind == 0) continue;                               // the pipelined two-sweep solve exists for M_q only
         Ring2 R;
-        if (!L.build_ring2(kind, R).empty()) { s->two_sweep = false; break; }   // patches too large for one more ring
+        if (!L.build_ring2(kind, R).empty()) { s->two_sweep = false; want_pipe2 = false; break; }   // patches too large for one more ring
+        if (kind == 1 && want_pipe2) {   // shared-memory carve-up of solve2_mq_pipe_k for the largest ring-2 patch
+            s->smem_pq2 = pipe2_carve(R, s->pq2);
+            if (s->smem_pq2 > PIPE_SMEM_LIMIT - 1024)   // this kernel has 1.2 KB of static shared memory
+                return fail(PHW_EINVAL, "pipelined two-sweep M_q solve (flags bit 13): two stages of the largest ring-2 patch exceed the shared memory of an SM; use patch_cells <= 768");
+            s->pipe2_q = true;
+        }
         const size_t soff2 = ((size_t)(R.max_rows + 31) / 32 + 4) / 2 + 1;
         s->smem2[kind] = (kind == 0) ? (size_t)R.max_smem_ell * 8 : (ev(R.max_ld) + 3 * (size_t)R.max_c2) * 8;
         (void)soff2;
-        if (s->smem2[kind] > 200 * 1024) { s->two_sweep = false; break; }
+        if (s->smem2[kind] > 200 * 1024) { s->two_sweep = false; if (!s->pipe2_q) break; }
         Ring2Dev& d = s->r2[kind];
         d.npatch = s->npatch;
         Ring2Hdr* d_h; uint32_t* d_rec; int *d_gh, *d_pcu2, *d_rg; double* d_pinv2;
@@ -2208,7 +2282,7 @@ int phw_comm_setup(phw_solver_t s, int32_t rank, int32_t world, const void* hand
     }
     CU(cudaStreamSynchronize(s->stream));
     s->pc = pc;
-    if (world > 1) s->two_sweep = false;   // the peer exchange is fused into the one-sweep kernel
+    if (world > 1) { s->two_sweep = false; s->pipe2_q = false; }   // the peer exchange is fused into the one-sweep kernels
     return PHW_OK;
 }
 

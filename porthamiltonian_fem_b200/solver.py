@@ -97,8 +97,8 @@ class Mesh:
 
     def pipe_smem(self):
         """dynamic shared memory (bytes) of the bulk-copy pipelined kernels for this layout:
-        (M_p solve, M_q solve, energy reduction, edge-row rhs, vertex-row rhs) - flags bits 9, 8, 11, 12, 12"""
-        b = (ctypes.c_int64 * 5)()
+        (M_p solve, M_q solve, energy reduction, edge-row rhs, vertex-row rhs, two-sweep M_q solve) - flags bits 9, 8, 11, 12, 12, 13"""
+        b = (ctypes.c_int64 * 6)()
         _lib.check(self.lib.phw_mesh_pipe_smem(self.handle, b))
         return tuple(int(x) for x in b)
 
