@@ -199,7 +199,7 @@ def run_bench():
     ap.add_argument('--ell-staged', action='store_true', help='ELL rows of the M_p solve staged in shared memory by cp.async (A/B)')
     ap.add_argument('--cell-rows', action='store_true', help='cell-based instead of assembled (ELL) rows in the M_p solve (A/B)')
     ap.add_argument('--pipe', default='auto', help="'auto' (default): 'pqer' on one GPU, 'none' on several (the pipelined kernels carry no inter-GPU exchange yet); 'none': lean kernels; " +
-                    "bulk-copy pipelined kernels (csrc/kernels_pipe.cuh; A/B): any of 'p' (M_p solve), 'q' (M_q solve), 'e' (fused H_wave reduction), 'r' (right-hand sides), '2' (EXPERIMENTAL pipelined two-sweep M_q solve, 768-cell patches)")
+                    "bulk-copy pipelined kernels (csrc/kernels_pipe.cuh; A/B): any of 'p' (M_p solve), 'q' (M_q solve), 'e' (fused H_wave reduction), 'r' (right-hand sides), 'Q' / 'P' (EXPERIMENTAL pipelined two-sweep M_q / M_p solves, 768-cell patches)")
     ap.add_argument('--stream-probe', action='store_true', help='print the bandwidth of a pure streaming pass over the ELL M_p data (diagnostics)')
     ap.add_argument('--debug-residuals', action='store_true', help='print the residual history of the last M_p / M_q solve to stderr')
     args = ap.parse_args()
@@ -208,7 +208,7 @@ def run_bench():
     if args.pipe == 'none':
         args.pipe = ''
     if args.patch_cells <= 0:
-        args.patch_cells = 768 if '2' in args.pipe else (1024 if 'q' in args.pipe else 2048)
+        args.patch_cells = 768 if ('Q' in args.pipe or 'P' in args.pipe) else (1024 if 'q' in args.pipe else 2048)
     if args.impl == 'reference':
         return run_reference_arm(args)
     if args.workload == 'sweep':
@@ -250,7 +250,7 @@ def run_bench():
     prm = _lib.PhwParams()
     prm.scheme, prm.dt, prm.K_wave, prm.rho = _lib.SCHEMES[args.scheme], dt, K_WAVE, RHO
     prm.input_kind, prm.in_amp, prm.in_omega = _lib.IN_COSINE, 1.0, omega
-    prm.tol, prm.max_iter, prm.flags, prm.extrap_order = args.tol, 200, 4 | (16 if args.two_sweep else 0) | (32 if args.cell_rows else 0) | (64 if args.ell_staged else 0) | (256 if 'q' in args.pipe else 0) | (512 if 'p' in args.pipe else 0) | (2048 if 'e' in args.pipe else 0) | (4096 if 'r' in args.pipe else 0) | (8192 if '2' in args.pipe else 0), args.extrap
+    prm.tol, prm.max_iter, prm.flags, prm.extrap_order = args.tol, 200, 4 | (16 if args.two_sweep else 0) | (32 if args.cell_rows else 0) | (64 if args.ell_staged else 0) | (256 if 'q' in args.pipe else 0) | (512 if 'p' in args.pipe else 0) | (2048 if 'e' in args.pipe else 0) | (4096 if 'r' in args.pipe else 0) | (8192 if 'Q' in args.pipe else 0) | (16384 if 'P' in args.pipe else 0), args.extrap
     prm.extrap_order_q = args.extrap_q
     solver = Solver(m, prm, device=local_rank)
     n_dof_local = int((part.vertex_owner == rank).sum() + (part.edge_owner == rank).sum())
@@ -363,7 +363,7 @@ def run_bench():
         paths = int(st.get('kernel_paths', 0))      # phw_path bits: 1 lean M_p, 2 lean M_q, 4 pipelined M_p, 8 pipelined M_q
         kern = {}
         for key, name, alg, ncu_b, it, ms, solves in (
-                ('p', ('solve_ell_pipe_k' if paths & 4 else 'solve_ell_coop_k' if paths & 1 else 'solve2_coop_k<0>' if args.two_sweep else 'solve_coop_k<0>') +
+                ('p', ('solve2_ell_pipe_k' if paths & 128 else 'solve_ell_pipe_k' if paths & 4 else 'solve_ell_coop_k' if paths & 1 else 'solve2_coop_k<0>' if args.two_sweep else 'solve_coop_k<0>') +
                  ' (Chebyshev M_p solve, all iterations in one cooperative launch)', 40.0, P_NCU_BYTES, st['iters_p'], st['ms_solve_p'], st['solves_p']),
                 ('q', ('solve2_mq_pipe_k' if paths & 64 else 'solve_mq_pipe_k' if paths & 8 else 'solve_mq_coop_k' if paths & 2 else 'solve2_coop_k<1>' if args.two_sweep else 'solve_coop_k<1>') +
                  ' (Chebyshev M_q solve, all iterations in one cooperative launch)', 96.0, Q_NCU_BYTES, st['iters_q'], st['ms_solve_q'], st['solves_q'])):

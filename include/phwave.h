@@ -74,7 +74,8 @@ typedef struct phw_params {
                                 patch (64 instead of 88 B per cell; one GPU, unbatched runs);
                                 bit12: bulk-copy pipelined right-hand sides D p / D^T q (one GPU, unbatched, no casimir terms);
                                 bit13: EXPERIMENTAL - pipelined two-sweep M_q solve (csrc/kernels_pipe2.cuh: two iterations per
-                                pass over a ring-2 patch staged by bulk copies; patches of <= ~768 cells; not yet run on a GPU) */
+                                pass over a ring-2 patch staged by bulk copies; patches of <= ~768 cells; not yet run on a GPU);
+                                bit14: EXPERIMENTAL - the same for the ELL M_p solve */
     int32_t extrap_order_q;  /* extrapolation order of the q (and block) solves; 0: same as extrap_order.  Orders up to 5 */
 } phw_params;
 
@@ -88,7 +89,7 @@ typedef struct phw_stats {
     double  ms_solve_p, ms_solve_q, ms_solve_block;   /* summed CUDA-event time of the solve kernels (flags bit2) */
     int64_t kernel_paths;       /* phw_path bits: which variants of the mass-solve kernels the last phw_run launched */
 } phw_stats;
-enum phw_path { PHW_PATH_LEAN_P = 1, PHW_PATH_LEAN_Q = 2, PHW_PATH_PIPE_P = 4, PHW_PATH_PIPE_Q = 8, PHW_PATH_PIPE_ENERGY = 16, PHW_PATH_PIPE_RHS = 32, PHW_PATH_PIPE2_Q = 64 };
+enum phw_path { PHW_PATH_LEAN_P = 1, PHW_PATH_LEAN_Q = 2, PHW_PATH_PIPE_P = 4, PHW_PATH_PIPE_Q = 8, PHW_PATH_PIPE_ENERGY = 16, PHW_PATH_PIPE_RHS = 32, PHW_PATH_PIPE2_Q = 64, PHW_PATH_PIPE2_P = 128 };
 
 const char* phw_last_error(void);
 int phw_version(void);
@@ -129,6 +130,8 @@ int phw_mesh_get_patch_counts(phw_mesh_t m, int32_t* counts);
  * (phw_params.flags bits 9, 8, 11, 12, 12, 13; a variant is available when its figure is <= 227 KB - 1 KB (- 2 KB for the
  * last one)).  Host-only. */
 int phw_mesh_pipe_smem(phw_mesh_t m, int64_t* bytes6);
+/* the same for the experimental pipelined two-sweep solves: bytes2 = {M_p (flags bit 14), M_q (bit 13)}; 0: no ring-2 patches */
+int phw_mesh_pipe2_smem(phw_mesh_t m, int64_t* bytes2);
 /* host-only structural invariants of the patch layout, the assembled (ELL) mass rows and the two-sweep patches
  * (tests; small meshes) */
 int phw_mesh_self_check(phw_mesh_t m);

@@ -66,6 +66,7 @@ SIGNATURES = {
     'phw_mesh_self_check': (ctypes.c_int, [ctypes.c_void_p]),
     'phw_mesh_get_patch_counts': (ctypes.c_int, [ctypes.c_void_p, c_i32p]),
     'phw_mesh_pipe_smem': (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64)]),
+    'phw_mesh_pipe2_smem': (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64)]),
     'phw_mesh_destroy': (ctypes.c_int, [ctypes.c_void_p]),
     'phw_solver_create': (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(PhwParams), ctypes.c_int32, ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]),
     'phw_solver_destroy': (ctypes.c_int, [ctypes.c_void_p]),

@@ -47,7 +47,7 @@ struct Pass2IO {
 };
 
 __device__ __forceinline__ void load_hdr2_smem(Ring2Hdr* dst, const Ring2Hdr* src) {
-    if (threadIdx.x < 16) reinterpret_cast<int*>(dst)[threadIdx.x] = __ldg(reinterpret_cast<const int*>(src) + threadIdx.x);
+    if (threadIdx.x < 20) reinterpret_cast<int*>(dst)[threadIdx.x] = __ldg(reinterpret_cast<const int*>(src) + threadIdx.x);
 }
 
 // RT1 element mass row values of one cell (unsigned-basis metric form, see edge_pass in kernels.cuh)

@@ -588,6 +588,8 @@ std::string Layout::build_ring2(int kind, Ring2& R) const {
                 R.ell_ioff.push_back((uint32_t)(ibase + ioff));
                 R.ell_woff.push_back((uint32_t)(wbase + woff));
             }
+            H.ell_i0 = (int32_t)(uint32_t)ibase; H.ell_in = (int32_t)ioff;
+            H.ell_w0 = (int32_t)(uint32_t)wbase; H.ell_wn = (int32_t)woff;
             // shared memory of vertex_ell_pass2 (doubles): offsets | x_k [nl] | x_{k+1} [nr] | b [n0] | weights + ids of the D0 slices
             auto ev2 = [](int64_t x) { return (x + 1) & ~(int64_t)1; };
             const int64_t need = ((nslice + 3) & ~1) + ev2(nl) + ev2(nr) + ev2(H.d_cnt) + (int64_t)woff0 + (int64_t)(ioff0 + 3) / 4 + 2;

@@ -49,8 +49,12 @@ struct Ring2Hdr {
     int32_t g_off, g1_cnt, g2_cnt;     // ghost list [G1 | G2] (new ids, each part ascending); first-sweep rows = [D0 | G1]
     int32_t row_off;                   // first row of this patch in the per-row arrays (replicated pinv, edge adjacency)
     int32_t vs_off, adj_off, adj_cnt;  // vertex kind: sliced-ELL adjacency of the rows [D0 | G1]
-    int32_t group, pad[3];
+    int32_t group;
+    int32_t ell_i0, ell_in;            // vertex kind: ELL mass rows of [D0 | G1]: first id code / number of codes in ell_ids,
+    int32_t ell_w0, ell_wn;            // first weight / number of weights in ell_w (two contiguous, 16-byte aligned blocks)
+    int32_t pad[3];
 };
+static_assert(sizeof(Ring2Hdr) == 80, "Ring2Hdr is loaded as 20 ints");
 struct Ring2 {
     std::vector<Ring2Hdr> hdr;
     std::vector<int32_t> pcell_user;   // [npc] user cell id of every patch cell

@@ -569,6 +569,7 @@ struct phw_solver_s {
     size_t smem_pq = 0, smem_pp = 0;
     bool pipe_en = false; EnergyPipeArgs pe{}; size_t smem_pe = 0;   // fused pipelined H_wave reduction (flags bit 11)
     bool pipe2_q = false; Mq2PipeArgs pq2{}; size_t smem_pq2 = 0;     // pipelined two-sweep M_q solve (experimental, flags bit 13)
+    bool pipe2_p = false; Ell2PipeArgs pp2{}; size_t smem_pp2 = 0;    // pipelined two-sweep M_p solve (experimental, flags bit 14)
     bool pipe_rhs = false; RhsPipeArgs pre{}, prv{}; size_t smem_pre = 0, smem_prv = 0;   // pipelined right-hand sides (flags bit 12)
     int64_t kernel_paths = 0;              // PHW_PATH_* bits of the solve kernels launched since the last phw_run began
     int *d_cells_user = nullptr; double* d_vtx_user = nullptr; unsigned long long* d_mm = nullptr;
@@ -1023,6 +1024,44 @@ int launch_mq_pipe2(phw_solver_s* s) {
     return 0;
 }
 
+// pipelined two-sweep M_p solve (kernels_pipe2.cuh; experimental)
+template <int NT, int MINB>
+int launch_ell_pipe2_cfg(phw_solver_s* s) {
+    void* kern = (void*)solve2_ell_pipe_k<NT, MINB>;
+    CU(cudaMemsetAsync(&s->ctl->gbar[0], 0, sizeof(unsigned int), s->stream));
+    static bool configured = false;
+    if (!configured) { CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048)); configured = true; }
+    int occ = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, s->smem_pp2));
+    if (occ < 1) return fail(PHW_ECUDA, "pipelined two-sweep M_p solve kernel does not fit on an SM");
+    const int grid = std::max(1, std::min(s->npatch, std::min(occ, MINB) * s->sm_count));
+    Ell2PipeArgs a = s->pp2;
+    a.m = s->r2[0];
+    for (int i = 0; i < 4; ++i) a.buf[i] = s->tp.b[i];
+    a.b = s->bp;
+    a.cheb_d = s->cheb_d[0]; a.cheb_c = s->cheb_c[0];
+    a.tol2 = s->prm.tol * s->prm.tol;
+    a.max_iter = s->prm.max_iter; a.which = 0; a.partials = s->partials; a.ctl = s->ctl;
+    void* args[] = {(void*)&a};
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    const bool prof = (s->prm.flags & 4) && s->prof_ev.size() < 2 * 8192;
+    if (prof) {
+        CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+        CU(cudaEventRecord(e0, s->stream));
+    }
+    CU(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(NT), args, s->smem_pp2, s->stream));
+    if (prof) {
+        CU(cudaEventRecord(e1, s->stream));
+        s->prof_ev.push_back(e0); s->prof_ev.push_back(e1); s->prof_which.push_back(0);
+    }
+    s->launches++;
+    s->kernel_paths |= PHW_PATH_PIPE2_P;
+    return 0;
+}
+int launch_ell_pipe2(phw_solver_s* s) {
+    return (2 * (s->smem_pp2 + 2560) <= 227 * 1024) ? launch_ell_pipe2_cfg<512, 2>(s) : launch_ell_pipe2_cfg<1024, 1>(s);
+}
+
 int solve_begin(phw_solver_s* s, int which) {
     solve_begin_k<<<1, 1, 0, s->stream>>>(s->ctl, which);
     s->launches++;
@@ -1053,6 +1092,7 @@ int solve_mass(phw_solver_s* s, int which, int n_launch) {
         return 0;
     }
     if (which == PHW_Q && s->pipe2_q && s->coop && s->pc.world <= 1) return launch_mq_pipe2(s);
+    if (which == PHW_P && s->pipe2_p && s->coop && s->pc.world <= 1) return launch_ell_pipe2(s);
     if (s->two_sweep) return which == PHW_P ? launch_coop2<0>(s) : launch_coop2<1>(s);
     RowArgs a = base_args(s);
     a.which = which; a.use_cheb_input = 1; a.finalize = 1; a.cM = 1.0; a.counter_id = which;
@@ -1614,6 +1654,7 @@ int phw_mesh_get_patch_counts(phw_mesh_t m, int32_t* counts) {
 }
 
 static size_t pipe2_carve(const Ring2& R, Mq2PipeArgs& c);
+static size_t pipe2_carve_p(const Ring2& R, Ell2PipeArgs& c);
 static void pipe_carve(const Layout& L, MqPipeArgs& cq, EllPipeArgs& cp, size_t& smem_pq, size_t& smem_pp, EnergyPipeArgs* ce = nullptr, size_t* smem_pe = nullptr,
                        RhsPipeArgs* re = nullptr, size_t* smem_re = nullptr, RhsPipeArgs* rv = nullptr, size_t* smem_rv = nullptr);
 int phw_mesh_pipe_smem(phw_mesh_t m, int64_t* bytes6) {
@@ -1625,6 +1666,14 @@ int phw_mesh_pipe_smem(phw_mesh_t m, int64_t* bytes6) {
     bytes6[5] = 0;
     Ring2 R;
     if (m->L.n_groups == 1 && m->L.build_ring2(1, R).empty()) { Mq2PipeArgs c2{}; bytes6[5] = (int64_t)pipe2_carve(R, c2); }
+    return PHW_OK;
+}
+int phw_mesh_pipe2_smem(phw_mesh_t m, int64_t* bytes2) {
+    if (!m || !bytes2) return fail(PHW_EINVAL, "mesh or bytes2 is NULL");
+    bytes2[0] = bytes2[1] = 0;
+    if (m->L.n_groups != 1) return PHW_OK;
+    { Ring2 R; if (m->L.build_ring2(0, R).empty()) { Ell2PipeArgs c{}; bytes2[0] = (int64_t)pipe2_carve_p(R, c); } }
+    { Ring2 R; if (m->L.build_ring2(1, R).empty()) { Mq2PipeArgs c{}; bytes2[1] = (int64_t)pipe2_carve(R, c); } }
     return PHW_OK;
 }
 
@@ -1872,6 +1921,25 @@ static size_t pipe2_carve(const Ring2& R, Mq2PipeArgs& c) {
     return (size_t)c.off_gidx + 2 * c.gidx_bytes;
 }
 
+static size_t pipe2_carve_p(const Ring2& R, Ell2PipeArgs& c) {
+    int max_ng = 0, max_in = 0, max_wn = 0;
+    for (const Ring2Hdr& h : R.hdr) { max_ng = std::max(max_ng, h.g1_cnt + h.g2_cnt); max_in = std::max(max_in, h.ell_in); max_wn = std::max(max_wn, h.ell_wn); }
+    auto r16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
+    const size_t nslw = r16(((size_t)(R.max_rows + 31) / 32 + 2) * 4), rowd = r16(((size_t)R.max_rows + 2) * 8);
+    size_t o = nslw;
+    c.off_wo = (uint32_t)o; o += nslw;
+    c.off_x = (uint32_t)o; o += r16(((size_t)R.max_ld + 2) * 8);
+    c.off_b = (uint32_t)o; o += rowd;
+    c.off_xprev = (uint32_t)o; o += rowd;
+    c.off_w = (uint32_t)o; o += r16((size_t)max_wn * 8);
+    c.off_ids = (uint32_t)o; o += r16((size_t)max_in * 2);
+    c.stage_bytes = (uint32_t)((o + 127) & ~(size_t)127);
+    c.off_x1 = 2 * c.stage_bytes;
+    c.off_gidx = c.off_x1 + (uint32_t)rowd;
+    c.gidx_bytes = (uint32_t)r16(((size_t)max_ng + 8) * 4);
+    return (size_t)c.off_gidx + 2 * c.gidx_bytes;
+}
+
 static int setup_solver(phw_solver_s* s) {
     const Layout& L = s->mesh->L;
     const phw_params& P = s->prm;
@@ -2036,10 +2104,17 @@ static int setup_solver(phw_solver_s* s) {
     const bool ring2_ok = s->coop && !P.strong && !implicit && L.nv_owned == L.nv && L.ne_owned == L.ne;
     s->two_sweep = ring2_ok && (P.flags & 16);
     bool want_pipe2 = ring2_ok && (P.flags & 8192) && L.n_groups == 1;
-    for (int kind = 0; kind < 2 && (s->two_sweep || want_pipe2); ++kind) {
-        if (!s->two_sweep && kind == 0) continue;                               // the pipelined two-sweep solve exists for M_q only
+    bool want_pipe2p = ring2_ok && (P.flags & 16384) && L.n_groups == 1 && s->ell_p;
+    for (int kind = 0; kind < 2 && (s->two_sweep || want_pipe2 || want_pipe2p); ++kind) {
+        if (!s->two_sweep && !(kind == 0 ? want_pipe2p : want_pipe2)) continue;  // ring-2 patches of this kind are not needed
         Ring2 R;
-        if (!L.build_ring2(kind, R).empty()) { s->two_sweep = false; want_pipe2 = false; break; }   // patches too large for one more ring
+        if (!L.build_ring2(kind, R).empty()) { s->two_sweep = false; want_pipe2 = false; want_pipe2p = false; break; }   // patches too large for one more ring
+        if (kind == 0 && want_pipe2p) {
+            s->smem_pp2 = pipe2_carve_p(R, s->pp2);
+            if (s->smem_pp2 > PIPE_SMEM_LIMIT - 1024)
+                return fail(PHW_EINVAL, "pipelined two-sweep M_p solve (flags bit 14): two stages of the largest ring-2 patch exceed the shared memory of an SM; reduce patch_cells");
+            s->pipe2_p = true;
+        }
         if (kind == 1 && want_pipe2) {   // shared-memory carve-up of solve2_mq_pipe_k for the largest ring-2 patch
             s->smem_pq2 = pipe2_carve(R, s->pq2);
             if (s->smem_pq2 > PIPE_SMEM_LIMIT - 1024)   // this kernel has 1.2 KB of static shared memory
@@ -2049,7 +2124,7 @@ static int setup_solver(phw_solver_s* s) {
         const size_t soff2 = ((size_t)(R.max_rows + 31) / 32 + 4) / 2 + 1;
         s->smem2[kind] = (kind == 0) ? (size_t)R.max_smem_ell * 8 : (ev(R.max_ld) + 3 * (size_t)R.max_c2) * 8;
         (void)soff2;
-        if (s->smem2[kind] > 200 * 1024) { s->two_sweep = false; if (!s->pipe2_q) break; }
+        if (s->smem2[kind] > 200 * 1024) { s->two_sweep = false; if (!s->pipe2_q && !s->pipe2_p && !want_pipe2) break; }
         Ring2Dev& d = s->r2[kind];
         d.npatch = s->npatch;
         Ring2Hdr* d_h; uint32_t* d_rec; int *d_gh, *d_pcu2, *d_rg; double* d_pinv2;
@@ -2282,7 +2357,7 @@ int phw_comm_setup(phw_solver_t s, int32_t rank, int32_t world, const void* hand
     }
     CU(cudaStreamSynchronize(s->stream));
     s->pc = pc;
-    if (world > 1) { s->two_sweep = false; s->pipe2_q = false; }   // the peer exchange is fused into the one-sweep kernels
+    if (world > 1) { s->two_sweep = false; s->pipe2_q = false; s->pipe2_p = false; }   // the peer exchange is fused into the one-sweep kernels
     return PHW_OK;
 }
 

@@ -102,6 +102,12 @@ class Mesh:
         _lib.check(self.lib.phw_mesh_pipe_smem(self.handle, b))
         return tuple(int(x) for x in b)
 
+    def pipe2_smem(self):
+        """dynamic shared memory (bytes) of the experimental pipelined two-sweep (M_p, M_q) solves (flags bits 14 / 13)"""
+        b = (ctypes.c_int64 * 2)()
+        _lib.check(self.lib.phw_mesh_pipe2_smem(self.handle, b))
+        return int(b[0]), int(b[1])
+
     def close(self):
         if getattr(self, 'handle', None):
             self.lib.phw_mesh_destroy(self.handle)
