@@ -622,6 +622,9 @@ std::string Layout::self_check() const {
     for (int32_t p = 0; p < npatch; ++p) {
         const PatchHdr& H = hdr[p];
         if (H.v_start != vsum || H.e_start != esum) return err("owned ranges are not contiguous", p, 0);
+        // blocks the pipelined kernels fetch with one bulk copy each must be 16-byte aligned in address and size
+        if ((H.ell_i0 % 8) != 0 || (H.ell_in % 8) != 0 || (H.ell_w0 % 2) != 0 || (H.ell_wn % 2) != 0 || (H.adj_off % 8) != 0 || (H.adj_cnt % 8) != 0)
+            return err("ELL / adjacency block of a patch is not 16-byte aligned", p, 0);
         vsum += H.v_cnt; esum += H.e_cnt;
     }
     if (vsum != nv_owned || esum != ne_owned) return "owned ranges do not cover the owned dofs";
@@ -678,6 +681,14 @@ std::string Layout::self_check() const {
             const int32_t nr = H.d_cnt + H.g1_cnt, nl = nr + H.g2_cnt;
             auto gid_of = [&](int32_t l) { return l < H.d_cnt ? H.d_start + l : R.ghost[H.g_off + l - H.d_cnt]; };
             if (H.n_c1 > H.n_c2) return err("ring-2: C1 is not a prefix of C2", p, kind);
+            if (kind == 0) {   // ELL block bounds carried by the header (bulk-copied as two contiguous, 16-byte aligned blocks)
+                const int32_t nsl = (nr + 31) / 32;
+                if ((uint32_t)H.ell_i0 != R.ell_ioff[H.vs_off] || (uint32_t)(H.ell_i0 + H.ell_in) != R.ell_ioff[H.vs_off + nsl] ||
+                    (uint32_t)H.ell_w0 != R.ell_woff[H.vs_off] || (uint32_t)(H.ell_w0 + H.ell_wn) != R.ell_woff[H.vs_off + nsl])
+                    return err("ring-2: ELL block bounds of the header do not match the slice offsets", p, 0);
+                if ((H.ell_i0 % 8) != 0 || (H.ell_in % 8) != 0 || (H.ell_w0 % 2) != 0 || (H.ell_wn % 2) != 0)
+                    return err("ring-2: ELL blocks are not 16-byte aligned", p, 0);
+            }
             for (int32_t k = 0; k < H.n_c2; ++k) {
                 const int32_t c = R.pcell_user[H.cell_off + k];
                 const uint32_t l[3] = {R.rec[2 * (size_t)(H.cell_off + k)] & 0xFFFFu, R.rec[2 * (size_t)(H.cell_off + k)] >> 16, R.rec[2 * (size_t)(H.cell_off + k) + 1] & 0xFFFFu};
