@@ -92,25 +92,32 @@ def test_structured_slab_shortcut_matches_general_partition():
                 assert len(g.recv[nb][kind]) == len(s.recv[nb][kind])
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, how='slab'):
     import torch.distributed as dist
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
     dist.init_process_group('gloo', rank=rank, world_size=world)
     try:
         import torch
-        v, c = rectangle_delaunay(20, 5, seed=4)
-        cr = pt.slab_cell_ranks(v, c, world)
+        if how == 'rcb_s1c':
+            from porthamiltonian_fem_b200.mesh import square_one_channel
+            v, c = square_one_channel(20)
+            cr = pt.rcb_cell_ranks(v, c, world)
+            shape, xL, yL = 'S_1C', 1.0, 0.1
+        else:
+            v, c = rectangle_delaunay(20, 5, seed=4)
+            cr = pt.slab_cell_ranks(v, c, world)
+            shape, xL, yL = 'R', 1.0, 0.25
         part = pt.build_local_part(v, c, cr, rank)
         gt = fem.Topology(v, c)
-        gops = fem.assemble_wave_operators(gt, fem.tag_boundary(gt, 'R', 1.0, 0.25))
+        gops = fem.assemble_wave_operators(gt, fem.tag_boundary(gt, shape, xL, yL))
         rng = np.random.default_rng(0)
         P = rng.standard_normal(gt.n_vertices)
         Q = rng.standard_normal(gt.n_edges)
         lt = fem.Topology(part.vertices, part.cells)
         assert np.array_equal(lt.edges, part.edges)
         # local operators; artificial cut edges carry tag 4 (no boundary term)
-        lops = fem.assemble_wave_operators(lt, fem.tag_boundary(lt, 'R', 1.0, 0.25))
+        lops = fem.assemble_wave_operators(lt, fem.tag_boundary(lt, shape, xL, yL))
         # local vectors: owned entries from the global vector, external entries filled by the exchange
         p_loc = np.where(part.vertex_owner == rank, P[part.vertex_gid], np.nan)
         q_loc = np.where(part.edge_owner == rank, Q[part.edge_gid], np.nan)
@@ -150,7 +157,8 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-def test_gloo_world2_partitioned_operators_match_global():
+@pytest.mark.parametrize('how,world', [('slab', 2), ('rcb_s1c', 3)])
+def test_gloo_world2_partitioned_operators_match_global(how, world):
     import torch.multiprocessing as mp
     s = socket.socket()
     s.bind(('127.0.0.1', 0))
@@ -158,7 +166,7 @@ def test_gloo_world2_partitioned_operators_match_global():
     s.close()
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, how)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=120) for _ in procs]
