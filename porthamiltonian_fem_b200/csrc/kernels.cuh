@@ -128,11 +128,18 @@ struct PeerComm {
     long long timeout_cycles;
 };
 
+// PHW_HOST_EMU: the kernels of this directory also compile for the host-side SPMD emulator of tests/emu (fibers for threads,
+// OS threads for CTAs, deferred asynchronous copies) - a CPU check of indexing, staging protocol and arithmetic.  The emulator
+// replaces the few inline-PTX helpers; nothing else differs.
+#ifdef PHW_HOST_EMU
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) { return *(const volatile unsigned long long*)p; }
+#else
 __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
     unsigned long long v;
     asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
     return v;
 }
+#endif
 
 // all-reduce (sum, rank order => identical bits on every rank) of n <= 4 doubles through the peer mailboxes.
 // Called by ONE thread per rank.  Every rank calls it the same number of times (seq is the call count).
@@ -260,6 +267,11 @@ __device__ __forceinline__ void load_hdr_smem(PatchHdr* dst, const PatchHdr* src
 
 // asynchronous global -> shared copies (LDGSTS): the data of a whole patch is put in flight at once without holding
 // registers; completion is awaited with cp_async_wait_all() before the block-wide barrier
+#ifdef PHW_HOST_EMU
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) { phw_emu::ldgsts(smem_dst, gmem_src, 16); }
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) { phw_emu::ldgsts(smem_dst, gmem_src, 8); }
+__device__ __forceinline__ void cp_async_wait_all() { phw_emu::ldgsts_wait_all(); }
+#else
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
 }
@@ -269,6 +281,7 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) 
 __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // vertex rows: all patches of this block

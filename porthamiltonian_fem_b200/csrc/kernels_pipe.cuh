@@ -19,8 +19,21 @@
 #pragma once
 #include "kernels.cuh"
 
+// the dynamic shared memory of a pipelined kernel (the emulator hands out a guarded host buffer instead)
+#ifdef PHW_HOST_EMU
+#define PHW_DYN_SMEM(name) unsigned char* name = phw_emu::dyn_smem()
+#else
+#define PHW_DYN_SMEM(name) extern __shared__ __align__(128) unsigned char name[]
+#endif
+
 namespace phw {
 
+#ifdef PHW_HOST_EMU
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) { phw_emu::mbar_init(bar, count); }
+__device__ __forceinline__ void mbar_fence_init() {}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, uint32_t bytes) { phw_emu::mbar_arrive_expect_tx(bar, bytes); }
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, uint32_t parity) { return phw_emu::mbar_try_wait(bar, parity); }
+#else
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
@@ -46,6 +59,7 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, uint32_t 
         : "memory");
     return ok != 0;
 }
+#endif
 // wait for the phase with the given parity; false if the stage did not arrive.  A wait that exceeds ~5 s (never seen; a stage
 // lands within microseconds) marks the run as failed in the high word of ctl->nonconv, which phw_run / phw_mass_solve report
 // as an error, and every later wait of the run gives up at once.  The callers then skip the patch (pipe_alive), so that a
@@ -71,6 +85,11 @@ __device__ __forceinline__ bool pipe_stage_ready(unsigned long long* bar, uint32
     __syncthreads();
     return *s_dead == 0;
 }
+#ifdef PHW_HOST_EMU
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, unsigned long long* bar) { phw_emu::bulk_g2s(smem_dst, gmem_src, bytes, bar); }
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) { phw_emu::ldgsts(smem_dst, gmem_src, 4); }
+__device__ __forceinline__ void fence_proxy_async() {}
+#else
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, unsigned long long* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
@@ -80,6 +99,7 @@ __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) 
 }
 // orders generic-proxy accesses (ld/st) against the async-proxy accesses of the bulk copies, both ways
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+#endif
 
 // ---- streams of doubles: element i of the range [start, start + n) lives at s[(start & 1) + i]
 __device__ __forceinline__ uint32_t f64s_bytes(int start, int n) {
@@ -199,7 +219,7 @@ __device__ __forceinline__ void mq_issue(const MqPipeArgs& a, unsigned char* sta
 // range, so only the ghost gathers (ordinary LDGSTS loads, behind the barrier's fence) read what the peers wrote.
 template <int NT, bool DIAG, bool MULTI>
 __global__ void __launch_bounds__(NT, 1) solve_mq_pipe_k(const __grid_constant__ MqPipeArgs a, const __grid_constant__ PeerComm pc) {
-    extern __shared__ __align__(128) unsigned char smraw[];
+    PHW_DYN_SMEM(smraw);
     __shared__ double red[64];
     __shared__ double bc[2];
     __shared__ PatchHdr s_hdr[4];
@@ -376,7 +396,7 @@ __device__ __forceinline__ void ell_issue(const EllPipeArgs& a, unsigned char* s
 
 template <int NT, int MINB, bool MULTI>
 __global__ void __launch_bounds__(NT, MINB) solve_ell_pipe_k(const __grid_constant__ EllPipeArgs a, const __grid_constant__ PeerComm pc) {
-    extern __shared__ __align__(128) unsigned char smraw[];
+    PHW_DYN_SMEM(smraw);
     __shared__ double red[64];
     __shared__ double bc[2];
     __shared__ PatchHdr s_hdr[4];
@@ -553,7 +573,7 @@ __device__ __forceinline__ void en_issue(const EnergyPipeArgs& a, unsigned char*
 
 template <int NT>
 __global__ void __launch_bounds__(NT, 1) energy_pipe_k(const __grid_constant__ EnergyPipeArgs a) {
-    extern __shared__ __align__(128) unsigned char smraw[];
+    PHW_DYN_SMEM(smraw);
     __shared__ double red[64];
     __shared__ PatchHdr s_hdr[4];
     __shared__ __align__(8) unsigned long long full[2];
@@ -675,7 +695,7 @@ __device__ __forceinline__ void rhs_e_issue(const RhsPipeArgs& a, unsigned char*
 
 template <int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) rhs_edge_pipe_k(const __grid_constant__ RhsPipeArgs a) {
-    extern __shared__ __align__(128) unsigned char smraw[];
+    PHW_DYN_SMEM(smraw);
     __shared__ PatchHdr s_hdr[4];
     __shared__ __align__(8) unsigned long long full[2];
     __shared__ int s_dead;       // a stage did not arrive (see mbar_wait): the CTA stops touching the stages
@@ -764,7 +784,7 @@ __device__ __forceinline__ void rhs_v_issue(const RhsPipeArgs& a, unsigned char*
 
 template <int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) rhs_vertex_pipe_k(const __grid_constant__ RhsPipeArgs a) {
-    extern __shared__ __align__(128) unsigned char smraw[];
+    PHW_DYN_SMEM(smraw);
     __shared__ PatchHdr s_hdr[4];
     __shared__ __align__(8) unsigned long long full[2];
     __shared__ int s_dead;       // a stage did not arrive (see mbar_wait): the CTA stops touching the stages

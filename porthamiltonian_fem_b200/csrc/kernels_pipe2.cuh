@@ -109,7 +109,7 @@ __device__ __forceinline__ void rt1_cell_s(const uint2 re, const double g0, cons
 
 template <int NT>
 __global__ void __launch_bounds__(NT, 1) solve2_mq_pipe_k(const __grid_constant__ Mq2PipeArgs a) {
-    extern __shared__ __align__(128) unsigned char smraw[];
+    PHW_DYN_SMEM(smraw);
     __shared__ double red[96];
     __shared__ double bc[3];
     __shared__ Ring2Hdr s_hdr[4];
@@ -323,7 +323,7 @@ __device__ __forceinline__ void ell_row_s(const uint4* sid4, const double* sw, u
 
 template <int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) solve2_ell_pipe_k(const __grid_constant__ Ell2PipeArgs a) {
-    extern __shared__ __align__(128) unsigned char smraw[];
+    PHW_DYN_SMEM(smraw);
     __shared__ double red[96];
     __shared__ double bc[3];
     __shared__ Ring2Hdr s_hdr[4];

@@ -18,6 +18,7 @@
 #include "kernels2.cuh"
 #include "kernels_pipe.cuh"
 #include "kernels_pipe2.cuh"
+#include "pipe_carve.hpp"
 #include "layout.hpp"
 
 using namespace phw;
@@ -1653,10 +1654,6 @@ int phw_mesh_get_patch_counts(phw_mesh_t m, int32_t* counts) {
     return PHW_OK;
 }
 
-static size_t pipe2_carve(const Ring2& R, Mq2PipeArgs& c);
-static size_t pipe2_carve_p(const Ring2& R, Ell2PipeArgs& c);
-static void pipe_carve(const Layout& L, MqPipeArgs& cq, EllPipeArgs& cp, size_t& smem_pq, size_t& smem_pp, EnergyPipeArgs* ce = nullptr, size_t* smem_pe = nullptr,
-                       RhsPipeArgs* re = nullptr, size_t* smem_re = nullptr, RhsPipeArgs* rv = nullptr, size_t* smem_rv = nullptr);
 int phw_mesh_pipe_smem(phw_mesh_t m, int64_t* bytes6) {
     if (!m || !bytes6) return fail(PHW_EINVAL, "mesh or bytes6 is NULL");
     MqPipeArgs cq{}; EllPipeArgs cp{}; EnergyPipeArgs ce{}; RhsPipeArgs re{}, rv{};
@@ -1820,124 +1817,6 @@ static int setup_scalars(phw_solver_s* s) {
     RC(s->upload(&s->d_sp, s->h_sp));
     return 0;
 #undef RC
-}
-
-// shared-memory carve-up of the bulk-copy pipelined mass solves (kernels_pipe.cuh) for the largest patch of a layout:
-// offsets inside a stage, stage size, and the dynamic shared memory each kernel needs (two stages + scratch)
-constexpr size_t PIPE_SMEM_LIMIT = 227 * 1024 - 1024;   // 227 KB per CTA minus the kernels' static shared memory
-static void pipe_carve(const Layout& L, MqPipeArgs& cq, EllPipeArgs& cp, size_t& smem_pq, size_t& smem_pp, EnergyPipeArgs* ce, size_t* smem_pe,
-                       RhsPipeArgs* re, size_t* smem_re, RhsPipeArgs* rv, size_t* smem_rv) {
-    int max_ec = 0, max_ecells = 0, max_ge = 0, max_vc = 0, max_gv = 0, max_wn = 0, max_in = 0, max_own = 0, max_adj = 0;
-    for (const PatchHdr& h : L.hdr) {
-        max_ec = std::max(max_ec, h.e_cnt); max_ecells = std::max(max_ecells, h.n_ecells); max_ge = std::max(max_ge, h.ge_cnt);
-        max_vc = std::max(max_vc, h.v_cnt); max_gv = std::max(max_gv, h.gv_cnt); max_wn = std::max(max_wn, h.ell_wn); max_in = std::max(max_in, h.ell_in);
-        max_own = std::max(max_own, h.n_own); max_adj = std::max(max_adj, h.adj_cnt);
-    }
-    auto r16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
-    {   // M_q: stage = [x_k local | cell records | b | pinv | x_{k-1} | eadj], then the cell contributions and two ghost lists
-        size_t o = r16(((size_t)L.max_le + 2) * 8);
-        cq.off_cells = (uint32_t)o; o += (size_t)max_ecells * 32;
-        cq.off_b = (uint32_t)o; o += r16(((size_t)max_ec + 2) * 8);
-        cq.off_pinv = (uint32_t)o; o += r16(((size_t)max_ec + 2) * 8);
-        cq.off_xprev = (uint32_t)o; o += r16(((size_t)max_ec + 2) * 8);
-        cq.off_eadj = (uint32_t)o; o += r16(((size_t)max_ec + 8) * 4);
-        cq.stage_bytes = (uint32_t)((o + 127) & ~(size_t)127);
-        cq.off_sc3 = 2 * cq.stage_bytes;
-        cq.off_gidx = cq.off_sc3 + (uint32_t)r16((size_t)max_ecells * 24);
-        cq.gidx_bytes = (uint32_t)r16(((size_t)max_ge + 8) * 4);
-        smem_pq = (size_t)cq.off_gidx + 2 * cq.gidx_bytes;
-    }
-    {   // M_p: stage = [slice offsets ids | slice offsets weights | x_k local | b | x_{k-1} | weights | ids], then two ghost lists
-        const size_t nslw = r16(((size_t)(max_vc + 31) / 32 + 2) * 4);
-        size_t o = nslw;
-        cp.off_wo = (uint32_t)o; o += nslw;
-        cp.off_x = (uint32_t)o; o += r16(((size_t)L.max_lv + 2) * 8);
-        cp.off_b = (uint32_t)o; o += r16(((size_t)max_vc + 2) * 8);
-        cp.off_xprev = (uint32_t)o; o += r16(((size_t)max_vc + 2) * 8);
-        cp.off_w = (uint32_t)o; o += r16((size_t)max_wn * 8);
-        cp.off_ids = (uint32_t)o; o += r16((size_t)max_in * 2);
-        cp.stage_bytes = (uint32_t)((o + 127) & ~(size_t)127);
-        cp.off_gidx = 2 * cp.stage_bytes;
-        cp.gidx_bytes = (uint32_t)r16(((size_t)max_gv + 8) * 4);
-        smem_pp = (size_t)cp.off_gidx + 2 * cp.gidx_bytes;
-    }
-    if (ce && smem_pe) {   // fused energy: stage = [p local | q local | vertex-id records | areas | edge records], two ghost lists per field
-        size_t o = r16(((size_t)L.max_lv + 2) * 8);
-        ce->off_q = (uint32_t)o; o += r16(((size_t)L.max_le + 2) * 8);
-        ce->off_recv = (uint32_t)o; o += r16(((size_t)max_own + 2) * 8);
-        ce->off_area = (uint32_t)o; o += r16(((size_t)max_own + 2) * 8);
-        ce->off_cells = (uint32_t)o; o += (size_t)max_own * 32;
-        ce->stage_bytes = (uint32_t)((o + 127) & ~(size_t)127);
-        ce->off_gv = 2 * ce->stage_bytes;
-        ce->gv_bytes = (uint32_t)r16(((size_t)max_gv + 8) * 4);
-        ce->off_ge = ce->off_gv + 2 * ce->gv_bytes;
-        ce->ge_bytes = (uint32_t)r16(((size_t)max_ge + 8) * 4);
-        *smem_pe = (size_t)ce->off_ge + 2 * ce->ge_bytes;
-    }
-    if (re && smem_re) {   // edge-row right-hand side: stage = [x_p local | vertex-id records | edge-id records | eadj], then contributions, ghost lists
-        size_t o = r16(((size_t)L.max_lv + 2) * 8);
-        re->off_a = (uint32_t)o; o += r16(((size_t)max_ecells + 2) * 8);
-        re->off_b = (uint32_t)o; o += r16(((size_t)max_ecells + 2) * 8);
-        re->off_c = (uint32_t)o; o += r16(((size_t)max_ec + 8) * 4);
-        re->stage_bytes = (uint32_t)((o + 127) & ~(size_t)127);
-        re->off_sc3 = 2 * re->stage_bytes;
-        re->off_gidx = re->off_sc3 + (uint32_t)r16((size_t)max_ecells * 24);
-        re->gidx_bytes = (uint32_t)r16(((size_t)max_gv + 8) * 4);
-        *smem_re = (size_t)re->off_gidx + 2 * re->gidx_bytes;
-    }
-    if (rv && smem_rv) {   // vertex-row right-hand side: stage = [slice offsets | x_q local | edge-id records | adjacency codes]
-        size_t o = r16(((size_t)(max_vc + 31) / 32 + 2) * 4);
-        rv->off_a = (uint32_t)o; o += r16(((size_t)L.max_le + 2) * 8);
-        rv->off_b = (uint32_t)o; o += r16(((size_t)L.max_cells + 2) * 8);
-        rv->off_c = (uint32_t)o; o += r16((size_t)max_adj * 2);
-        rv->stage_bytes = (uint32_t)((o + 127) & ~(size_t)127);
-        rv->off_sc3 = 2 * rv->stage_bytes;
-        rv->off_gidx = rv->off_sc3 + (uint32_t)r16((size_t)L.max_cells * 24);
-        rv->gidx_bytes = (uint32_t)r16(((size_t)max_ge + 8) * 4);
-        *smem_rv = (size_t)rv->off_gidx + 2 * rv->gidx_bytes;
-    }
-}
-
-// shared-memory carve-up of the pipelined two-sweep M_q solve (kernels_pipe2.cuh) for the largest ring-2 patch
-static size_t pipe2_carve(const Ring2& R, Mq2PipeArgs& c) {
-    int max_ng = 0, max_n0 = 0;
-    for (const Ring2Hdr& h : R.hdr) { max_ng = std::max(max_ng, h.g1_cnt + h.g2_cnt); max_n0 = std::max(max_n0, h.d_cnt); }
-    auto r16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
-    const size_t rowd = r16(((size_t)R.max_rows + 2) * 8), celld = r16(((size_t)R.max_c2 + 2) * 8);
-    size_t o = r16(((size_t)R.max_ld + 2) * 8);
-    c.off_xprev = (uint32_t)o; o += rowd;
-    c.off_b = (uint32_t)o; o += rowd;
-    c.off_pinv = (uint32_t)o; o += rowd;
-    c.off_eadj = (uint32_t)o; o += r16(((size_t)R.max_rows + 8) * 4);
-    c.off_rec = (uint32_t)o; o += celld;
-    c.off_g0 = (uint32_t)o; o += celld;
-    c.off_g1 = (uint32_t)o; o += celld;
-    c.off_g2 = (uint32_t)o; o += celld;
-    c.stage_bytes = (uint32_t)((o + 127) & ~(size_t)127);
-    c.off_sc3 = 2 * c.stage_bytes;
-    c.off_xk0 = c.off_sc3 + (uint32_t)r16((size_t)R.max_c2 * 24);
-    c.off_gidx = c.off_xk0 + (uint32_t)r16((size_t)max_n0 * 8);
-    c.gidx_bytes = (uint32_t)r16(((size_t)max_ng + 8) * 4);
-    return (size_t)c.off_gidx + 2 * c.gidx_bytes;
-}
-
-static size_t pipe2_carve_p(const Ring2& R, Ell2PipeArgs& c) {
-    int max_ng = 0, max_in = 0, max_wn = 0;
-    for (const Ring2Hdr& h : R.hdr) { max_ng = std::max(max_ng, h.g1_cnt + h.g2_cnt); max_in = std::max(max_in, h.ell_in); max_wn = std::max(max_wn, h.ell_wn); }
-    auto r16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
-    const size_t nslw = r16(((size_t)(R.max_rows + 31) / 32 + 2) * 4), rowd = r16(((size_t)R.max_rows + 2) * 8);
-    size_t o = nslw;
-    c.off_wo = (uint32_t)o; o += nslw;
-    c.off_x = (uint32_t)o; o += r16(((size_t)R.max_ld + 2) * 8);
-    c.off_b = (uint32_t)o; o += rowd;
-    c.off_xprev = (uint32_t)o; o += rowd;
-    c.off_w = (uint32_t)o; o += r16((size_t)max_wn * 8);
-    c.off_ids = (uint32_t)o; o += r16((size_t)max_in * 2);
-    c.stage_bytes = (uint32_t)((o + 127) & ~(size_t)127);
-    c.off_x1 = 2 * c.stage_bytes;
-    c.off_gidx = c.off_x1 + (uint32_t)rowd;
-    c.gidx_bytes = (uint32_t)r16(((size_t)max_ng + 8) * 4);
-    return (size_t)c.off_gidx + 2 * c.gidx_bytes;
 }
 
 static int setup_solver(phw_solver_s* s) {

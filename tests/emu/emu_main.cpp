@@ -1,0 +1,270 @@
+// emu_main.cpp - runs the pipelined kernels of porthamiltonian_fem_b200/csrc on the CPU inside the SPMD emulator (emu_rt.hpp).
+// Test infrastructure (tests/test_emu_cpu.py): checks indexing, shared-memory carve-ups, the staging protocol (waits before
+// use, expected byte counts, 16-byte rules, nothing in flight at exit) and the arithmetic against the CPU oracle - everything
+// except real asynchrony and performance.  The device arrays are set up here the way phwave.cu does it on the GPU (geometry,
+// packed cell records, ELL weights, Jacobi weights), from the same host-side Layout.
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "cuda_runtime.h"
+#include "kernels_pipe2.cuh"
+#include "pipe_carve.hpp"
+#include "layout.hpp"
+
+using namespace phw;
+
+namespace {
+
+struct Arena {
+    std::vector<phw_emu::Guarded> all;
+    template <class T> T* get(size_t n) {
+        phw_emu::Guarded g = phw_emu::guarded_alloc(std::max<size_t>(n, 1) * sizeof(T));
+        std::memset(g.ptr, 0, (std::max<size_t>(n, 1) * sizeof(T) + 15) & ~(size_t)15);
+        all.push_back(g);
+        return (T*)g.ptr;
+    }
+    template <class T> T* put(const std::vector<T>& v) {
+        T* p = get<T>(v.size());
+        if (!v.empty()) std::memcpy(p, v.data(), v.size() * sizeof(T));
+        return p;
+    }
+    ~Arena() { for (auto& g : all) phw_emu::guarded_free(g); }
+};
+
+void cell_geometry(const Layout& L, int32_t c, double& A, double& G0, double& G1, double& G2) {   // geom_k of phwave.cu
+    const int a = L.cells[3 * (int64_t)c], b = L.cells[3 * (int64_t)c + 1], d = L.cells[3 * (int64_t)c + 2];
+    const double ax = L.vtx[2 * a], ay = L.vtx[2 * a + 1], bx = L.vtx[2 * b], by = L.vtx[2 * b + 1], dx = L.vtx[2 * d], dy = L.vtx[2 * d + 1];
+    A = 0.5 * std::fabs((bx - ax) * (dy - ay) - (by - ay) * (dx - ax));
+    const double l0 = (dx - bx) * (dx - bx) + (dy - by) * (dy - by);
+    const double l1 = (ax - dx) * (ax - dx) + (ay - dy) * (ay - dy);
+    const double l2 = (bx - ax) * (bx - ax) + (by - ay) * (by - ay);
+    const double inv = 1.0 / (48.0 * A);
+    G0 = l0 * inv; G1 = l1 * inv; G2 = l2 * inv;
+}
+
+uint4 pack_a(uint2 r, double a) { uint64_t u; std::memcpy(&u, &a, 8); return make_uint4(r.x, r.y, (unsigned)(u & 0xFFFFFFFFu), (unsigned)(u >> 32)); }
+uint4 pack_b(double b, double c) {
+    uint64_t u, v; std::memcpy(&u, &b, 8); std::memcpy(&v, &c, 8);
+    return make_uint4((unsigned)(u & 0xFFFFFFFFu), (unsigned)(u >> 32), (unsigned)(v & 0xFFFFFFFFu), (unsigned)(v >> 32));
+}
+
+int fail(char* err, int errlen, const std::string& m) { std::snprintf(err, (size_t)errlen, "%s", m.c_str()); return -1; }
+
+}  // namespace
+
+// what: "mq1" | "mp1" (one-sweep pipelined solves), "mq2" | "mp2" (two-sweep pipelined solves), "mq_lean" | "mp_lean",
+//       "energy" (out[0] = p^T M_p p, out[1] = q^T M_q q; in1 = p, in2 = q), "rhs_e" (out = D in1), "rhs_v" (out = D^T in1)
+// btags: tag of every boundary edge in the order of the layout's boundary list (nullptr: all "none"); user numbering everywhere.
+extern "C" int emu_run(const char* what_c, int64_t nv, const double* vtx, int64_t nc, const int32_t* cells, int32_t patch_cells, int32_t grid,
+                       const int32_t* btags, const double* in1, const double* in2, double* out, int32_t* iters, double tol,
+                       char* err, int errlen) {
+    const std::string what(what_c);
+    constexpr int NT = 128;
+    Layout L;
+    std::string e = L.build(nv, vtx, nc, cells, patch_cells);
+    if (!e.empty()) return fail(err, errlen, e);
+    if (btags) for (int64_t k = 0; k < L.nb; ++k) L.btag[k] = btags[k];
+    L.boundary_set = true;
+    std::vector<CellRec> rec;
+    L.make_records(false, false, rec);
+    const int npatch = L.npatch, npc = (int)L.pcell_user.size();
+    grid = std::max(1, std::min(grid, npatch));
+    Arena A;
+    PatchHdr* d_hdr = A.put(L.hdr);
+    std::vector<uint2> hv(rec.size()), he(rec.size());
+    for (size_t k = 0; k < rec.size(); ++k) { hv[k] = make_uint2(rec[k].x, rec[k].y); he[k] = make_uint2(rec[k].z, rec[k].w); }
+    uint2* d_recv = A.put(hv); uint2* d_rece = A.put(he);
+    std::vector<double> area(npc), g0(npc), g1(npc), g2(npc);
+    for (int k = 0; k < npc; ++k) cell_geometry(L, L.pcell_user[k], area[k], g0[k], g1[k], g2[k]);
+    double* d_area = A.put(area);
+    std::vector<uint4> cq(2 * (size_t)npc);
+    for (int k = 0; k < npc; ++k) { cq[2 * (size_t)k] = pack_a(he[k], g0[k]); cq[2 * (size_t)k + 1] = pack_b(g1[k], g2[k]); }
+    uint4* d_cellq = A.put(cq);
+    int* d_gv = A.put(L.ghost_v); int* d_ge = A.put(L.ghost_e);
+    uint32_t* d_eadj = A.put(L.eadj); uint32_t* d_voff = A.put(L.vslice_off); uint16_t* d_vadj = A.put(L.vadj);
+    uint32_t* d_io = A.put(L.ell_ioff); uint32_t* d_wo = A.put(L.ell_woff); uint16_t* d_ids = A.put(L.ell_ids);
+    std::vector<double> ellw(L.ell_pair.size(), 0.0);
+    for (int p = 0; p < npatch; ++p) {
+        const PatchHdr& h = L.hdr[p];
+        const int nsl = (h.v_cnt + 31) >> 5;
+        for (uint32_t k = L.ell_woff[h.vs_off]; k < L.ell_woff[h.vs_off + nsl]; ++k) {
+            const uint32_t pr = L.ell_pair[k];
+            if (pr == 0xFFFFFFFFu) continue;
+            double v = area[h.cell_off + (pr & 0xFFFFu)];
+            if ((pr >> 16) != 0xFFFFu) v += area[h.cell_off + (pr >> 16)];
+            ellw[k] = v * (1.0 / 12.0);
+        }
+    }
+    double* d_ellw = A.put(ellw);
+    // Jacobi weights of M_q: diag_e = sum over the (<= 2) cells of 3 S - 4 g_slot
+    std::vector<double> pinvq(L.ne, 0.0);
+    for (int p = 0; p < npatch; ++p) {
+        const PatchHdr& h = L.hdr[p];
+        for (int le = 0; le < h.e_cnt; ++le) {
+            const uint32_t adj = L.eadj[h.e_start + le];
+            double dg = 0.0;
+            for (uint32_t code : {adj & 0xFFFFu, adj >> 16}) {
+                if (code == 0xFFFFu) continue;
+                const int k = h.cell_off + (int)(code >> 2);
+                const double S = g0[k] + g1[k] + g2[k], gs = (code & 3u) == 0 ? g0[k] : ((code & 3u) == 1 ? g1[k] : g2[k]);
+                dg += 3.0 * S - 4.0 * gs;
+            }
+            pinvq[h.e_start + le] = 1.0 / dg;
+        }
+    }
+    double* d_pinvq = A.put(pinvq);
+    Ctl* ctl = A.get<Ctl>(1);
+    double* partials = A.get<double>(16384);
+    PeerComm pc{};
+    pc.world = 1;
+    // user <-> internal numbering
+    auto to_new = [&](const double* user, const std::vector<int32_t>& new2old) {
+        std::vector<double> v(new2old.size());
+        for (size_t i = 0; i < new2old.size(); ++i) v[i] = user[new2old[i]];
+        return v;
+    };
+    auto to_user = [&](const double* internal, const std::vector<int32_t>& new2old, double* user) {
+        for (size_t i = 0; i < new2old.size(); ++i) user[new2old[i]] = internal[i];
+    };
+    MqPipeArgs cfg_q{}; EllPipeArgs cfg_p{}; EnergyPipeArgs cfg_e{}; RhsPipeArgs cfg_re{}, cfg_rv{};
+    size_t sm_q = 0, sm_p = 0, sm_e = 0, sm_re = 0, sm_rv = 0;
+    pipe_carve(L, cfg_q, cfg_p, sm_q, sm_p, &cfg_e, &sm_e, &cfg_re, &sm_re, &cfg_rv, &sm_rv);
+    const bool is_q = what.rfind("mq", 0) == 0, is_p = what.rfind("mp", 0) == 0;
+    if (is_q || is_p) {
+        const std::vector<int32_t>& n2o = is_q ? L.e_new2old : L.v_new2old;
+        const size_t n = n2o.size();
+        double* d_b = A.put(to_new(in1, n2o));
+        double* buf[4];
+        for (auto& bptr : buf) bptr = A.get<double>(n);
+        const double cheb_d = is_q ? 1.0 : 1.25, cheb_c = is_q ? 0.0 : 0.75;   // M_q: interval set below
+        double lam_lo = 1e300, lam_hi = 0.0;
+        if (is_q) {   // element-wise bounds of the Jacobi-scaled RT1 mass spectrum (what geom_k reduces on the GPU)
+            for (int k = 0; k < npc; ++k) {
+                const double S = g0[k] + g1[k] + g2[k];
+                const double m00 = 3 * S - 4 * g0[k], m11 = 3 * S - 4 * g1[k], m22 = 3 * S - 4 * g2[k];
+                const double m01 = S - 4 * g2[k], m02 = S - 4 * g1[k], m12 = S - 4 * g0[k];
+                const double ea = m01 / std::sqrt(m00 * m11), eb = m02 / std::sqrt(m00 * m22), ec = m12 / std::sqrt(m11 * m22);
+                const double pp = ea * ea + eb * eb + ec * ec, qq = 2.0 * ea * eb * ec;
+                double lmin = 1.0, lmax = 1.0;
+                if (pp > 1e-30) {
+                    double arg = 0.5 * qq * std::pow(3.0 / pp, 1.5);
+                    arg = std::min(1.0, std::max(-1.0, arg));
+                    const double phi = std::acos(arg) / 3.0, amp = 2.0 * std::sqrt(pp / 3.0);
+                    lmax = 1.0 + amp * std::cos(phi); lmin = 1.0 + amp * std::cos(phi + 2.0943951023931953);
+                }
+                lam_lo = std::min(lam_lo, lmin); lam_hi = std::max(lam_hi, lmax);
+            }
+        }
+        const double cd = is_q ? 0.5 * (lam_lo + lam_hi) : cheb_d, cc = is_q ? 0.5 * (lam_hi - lam_lo) : cheb_c;
+        if (what == "mq1") {
+            MqPipeArgs a = cfg_q;
+            a.npatch = npatch; a.hdr = d_hdr; a.cellq = d_cellq; a.ghost_e = d_ge; a.eadj = d_eadj; a.b = d_b; a.pinv = d_pinvq;
+            for (int i = 0; i < 3; ++i) a.buf[i] = buf[i];
+            a.cheb_d = cd; a.cheb_c = cc; a.tol2 = tol * tol; a.max_iter = 200; a.which = 1; a.partials = partials; a.ctl = ctl;
+            phw_emu::launch(grid, NT, sm_q, [&] { solve_mq_pipe_k<NT, false, false>(a, pc); });
+        } else if (what == "mq_lean") {
+            MqSolveArgs a{};
+            a.npatch = npatch; a.hdr = d_hdr; a.cellq = d_cellq; a.ghost_e = d_ge; a.eadj = d_eadj; a.b = d_b; a.pinv = d_pinvq;
+            for (int i = 0; i < 3; ++i) a.buf[i] = buf[i];
+            a.cheb_d = cd; a.cheb_c = cc; a.tol2 = tol * tol; a.max_iter = 200; a.which = 1; a.partials = partials; a.ctl = ctl;
+            const size_t sm = ((size_t)((L.max_le + 1) & ~1) + 3 * (size_t)L.max_cells) * 8;
+            phw_emu::launch(grid, NT, sm, [&] { solve_mq_coop_k<NT, 1, 2, 2, false>(a, pc); });
+        } else if (what == "mp1") {
+            EllPipeArgs a = cfg_p;
+            a.npatch = npatch; a.hdr = d_hdr; a.ell_ioff = d_io; a.ell_woff = d_wo; a.ell_ids = d_ids; a.ell_w = d_ellw; a.ghost_v = d_gv; a.b = d_b;
+            for (int i = 0; i < 3; ++i) a.buf[i] = buf[i];
+            a.cheb_d = cd; a.cheb_c = cc; a.tol2 = tol * tol; a.max_iter = 200; a.which = 0; a.partials = partials; a.ctl = ctl;
+            phw_emu::launch(grid, NT, sm_p, [&] { solve_ell_pipe_k<NT, 1, false>(a, pc); });
+        } else if (what == "mp_lean") {
+            EllSolveArgs a{};
+            a.npatch = npatch; a.hdr = d_hdr; a.ell_ioff = d_io; a.ell_woff = d_wo; a.ell_ids = d_ids; a.ell_w = d_ellw; a.ghost_v = d_gv; a.b = d_b;
+            for (int i = 0; i < 3; ++i) a.buf[i] = buf[i];
+            a.cheb_d = cd; a.cheb_c = cc; a.tol2 = tol * tol; a.max_iter = 200; a.which = 0; a.partials = partials; a.ctl = ctl;
+            const size_t sm = ((size_t)(L.max_lv + 31) / 32 + 4 + (size_t)((L.max_lv + 1) & ~1)) * 8;
+            phw_emu::launch(grid, NT, sm, [&] { solve_ell_coop_k<NT, 1, false>(a, pc); });
+        } else if (what == "mq2" || what == "mp2") {
+            Ring2 R;
+            e = L.build_ring2(is_q ? 1 : 0, R);
+            if (!e.empty()) return fail(err, errlen, "ring-2 patches: " + e);
+            const int npc2 = (int)R.pcell_user.size(), nrows = (int)R.row_gid.size();
+            std::vector<double> a2(npc2), h0(npc2), h1(npc2), h2(npc2);
+            for (int k = 0; k < npc2; ++k) cell_geometry(L, R.pcell_user[k], a2[k], h0[k], h1[k], h2[k]);
+            Ring2Dev d{};
+            d.npatch = npatch;
+            d.hdr = A.put(R.hdr);
+            d.rec = reinterpret_cast<const uint2*>(A.put(R.rec));
+            d.ghost = A.put(R.ghost);
+            if (is_q) {
+                d.g0 = A.put(h0); d.g1 = A.put(h1); d.g2 = A.put(h2);
+                std::vector<double> pr(nrows);
+                for (int r = 0; r < nrows; ++r) pr[r] = pinvq[R.row_gid[r]];
+                d.pinv = A.put(pr);
+                d.eadj = A.put(R.eadj);
+                Mq2PipeArgs a{};
+                const size_t sm = pipe2_carve(R, a);
+                a.m = d;
+                for (int i = 0; i < 4; ++i) a.buf[i] = buf[i];
+                a.b = d_b; a.cheb_d = cd; a.cheb_c = cc; a.tol2 = tol * tol; a.max_iter = 200; a.which = 1; a.partials = partials; a.ctl = ctl;
+                phw_emu::launch(grid, NT, sm, [&] { solve2_mq_pipe_k<NT>(a); });
+            } else {
+                d.g0 = A.put(a2);
+                d.ell_ioff = A.put(R.ell_ioff); d.ell_woff = A.put(R.ell_woff); d.ell_ids = A.put(R.ell_ids);
+                std::vector<double> w2(R.ell_pair.size(), 0.0);
+                for (int p = 0; p < npatch; ++p) {
+                    const Ring2Hdr& h = R.hdr[p];
+                    const int nsl = (h.d_cnt + h.g1_cnt + 31) >> 5;
+                    for (uint32_t k = R.ell_woff[h.vs_off]; k < R.ell_woff[h.vs_off + nsl]; ++k) {
+                        const uint32_t prr = R.ell_pair[k];
+                        if (prr == 0xFFFFFFFFu) continue;
+                        double v = a2[h.cell_off + (prr & 0xFFFFu)];
+                        if ((prr >> 16) != 0xFFFFu) v += a2[h.cell_off + (prr >> 16)];
+                        w2[k] = v * (1.0 / 12.0);
+                    }
+                }
+                d.ell_w = A.put(w2);
+                Ell2PipeArgs a{};
+                const size_t sm = pipe2_carve_p(R, a);
+                a.m = d;
+                for (int i = 0; i < 4; ++i) a.buf[i] = buf[i];
+                a.b = d_b; a.cheb_d = cd; a.cheb_c = cc; a.tol2 = tol * tol; a.max_iter = 200; a.which = 0; a.partials = partials; a.ctl = ctl;
+                phw_emu::launch(grid, NT, sm, [&] { solve2_ell_pipe_k<NT, 1>(a); });
+            }
+        } else return fail(err, errlen, "unknown kernel " + what);
+        const SolveCtl& sc = ctl->sc[is_q ? 1 : 0];
+        if ((ctl->nonconv >> 32) != 0) return fail(err, errlen, "a stage did not arrive");
+        if (ctl->nonconv != 0) return fail(err, errlen, "solve did not converge");
+        to_user(buf[sc.cur & 3], n2o, out);
+        if (iters) *iters = (int32_t)sc.iters;
+        return 0;
+    }
+    if (what == "energy") {
+        double* d_p = A.put(to_new(in1, L.v_new2old));
+        double* d_q = A.put(to_new(in2, L.e_new2old));
+        EnergyPipeArgs a = cfg_e;
+        a.npatch = npatch; a.hdr = d_hdr; a.recv = d_recv; a.area = d_area; a.cellq = d_cellq; a.ghost_v = d_gv; a.ghost_e = d_ge;
+        a.p = d_p; a.q = d_q; a.scale_p = 1.0 / 12.0; a.scale_q = 1.0; a.counter_id = 4; a.partials = partials; a.ctl = ctl;
+        phw_emu::launch(grid, NT, sm_e, [&] { energy_pipe_k<NT>(a); });
+        if ((ctl->nonconv >> 32) != 0) return fail(err, errlen, "a stage did not arrive");
+        out[0] = ctl->red[0]; out[1] = ctl->red[1];
+        return 0;
+    }
+    if (what == "rhs_e" || what == "rhs_v") {
+        const bool vertex = what == "rhs_v";
+        double* d_x = A.put(to_new(in1, vertex ? L.e_new2old : L.v_new2old));
+        double* d_y = A.get<double>(vertex ? L.nv : L.ne);
+        RhsPipeArgs a = vertex ? cfg_rv : cfg_re;
+        a.npatch = npatch; a.hdr = d_hdr; a.recv = d_recv; a.rece = d_rece; a.ghost = vertex ? d_ge : d_gv; a.eadj = d_eadj;
+        a.vslice_off = d_voff; a.vadj = d_vadj; a.x = d_x; a.y = d_y; a.cD = 1.0; a.ctl = ctl;
+        if (vertex) phw_emu::launch(grid, NT, sm_rv, [&] { rhs_vertex_pipe_k<NT, 1>(a); });
+        else phw_emu::launch(grid, NT, sm_re, [&] { rhs_edge_pipe_k<NT, 1>(a); });
+        if ((ctl->nonconv >> 32) != 0) return fail(err, errlen, "a stage did not arrive");
+        to_user(d_y, vertex ? L.v_new2old : L.e_new2old, out);
+        return 0;
+    }
+    return fail(err, errlen, "unknown kernel " + what);
+}

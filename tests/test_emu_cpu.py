@@ -1,0 +1,116 @@
+"""CPU check of the bulk-copy pipelined kernels (csrc/kernels_pipe.cuh, csrc/kernels_pipe2.cuh) inside a host-side SPMD emulator
+(tests/emu: one OS thread per CTA, one fiber per CUDA thread, asynchronous copies deferred until they are waited for, guard pages
+behind every array and behind the dynamic shared memory).  The SAME kernel sources are compiled with g++; only the handful of
+inline-PTX helpers is replaced (PHW_HOST_EMU).  What this covers without a GPU: indexing and shared-memory carve-ups, the staging
+protocol (every stage is waited for before it is read, expected byte counts match, 16-byte rules of the bulk copies, nothing in
+flight at exit), the Chebyshev control flow and the arithmetic - against the oracle's assembled operators and sparse direct
+solves.  What it does not cover: real asynchrony, memory-model effects, performance (the `-m gpu` suite and bench.py do that).
+In particular the experimental two-sweep kernels (flags bits 13 / 14), which have not run on a GPU yet, are exercised here."""
+import ctypes
+import os
+import sys
+
+import numpy as np
+import pytest
+import scipy.sparse.linalg as spla
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, 'emu'))
+
+from oracle import fem
+from porthamiltonian_fem_b200.mesh import rectangle_structured, rectangle_delaunay, square_one_channel
+from porthamiltonian_fem_b200.solver import Mesh, tag_boundary_edges
+
+
+@pytest.fixture(scope='module')
+def emu():
+    from build_emu import build
+    return ctypes.CDLL(build())
+
+
+def run(lib, what, v, c, pc, grid, in1, in2=None, nout=None, tags=None, tol=1e-13):
+    v = np.ascontiguousarray(v, dtype=np.float64)
+    c = np.ascontiguousarray(c, dtype=np.int32)
+    out = np.zeros(nout)
+    it = ctypes.c_int32(0)
+    err = ctypes.create_string_buffer(512)
+    in1 = np.ascontiguousarray(in1, dtype=np.float64)
+    p2 = pt = None
+    if in2 is not None:
+        in2 = np.ascontiguousarray(in2, dtype=np.float64)
+        p2 = in2.ctypes.data_as(ctypes.c_void_p)
+    if tags is not None:
+        tags = np.ascontiguousarray(tags, dtype=np.int32)
+        pt = tags.ctypes.data_as(ctypes.c_void_p)
+    rc = lib.emu_run(what.encode(), ctypes.c_int64(len(v)), v.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(len(c)),
+                     c.ctypes.data_as(ctypes.c_void_p), ctypes.c_int32(pc), ctypes.c_int32(grid), pt,
+                     in1.ctypes.data_as(ctypes.c_void_p), p2, out.ctypes.data_as(ctypes.c_void_p), ctypes.byref(it),
+                     ctypes.c_double(tol), err, 512)
+    if rc:
+        raise RuntimeError(err.value.decode())
+    return out, it.value
+
+
+def rel(a, b):
+    return np.linalg.norm(a - b) / np.linalg.norm(b)
+
+
+MESHES = [
+    # name, mesh, shape, xL, yL, patch_cells, CTAs: several patches per CTA, odd / even starts of the owned ranges, one patch, two cells
+    ('delaunay_60x15_pc48_g4', lambda: rectangle_delaunay(60, 15, seed=5), 'R', 1.0, 0.25, 48, 4),
+    ('structured_40x10_pc64_g3', lambda: rectangle_structured(40, 10), 'R', 1.0, 0.25, 64, 3),
+    ('s1c_20_pc40_g5', lambda: square_one_channel(20), 'S_1C', 1.0, 0.1, 40, 5),
+    ('single_patch', lambda: rectangle_structured(10, 4), 'R', 1.0, 0.25, 4096, 2),
+    ('tiny_2x1', lambda: rectangle_structured(2, 1), 'R', 1.0, 0.25, 16, 2),
+]
+
+
+@pytest.mark.parametrize('name,make,shape,xL,yL,pc,grid', MESHES)
+def test_emulated_mass_solves_match_direct_solves(emu, name, make, shape, xL, yL, pc, grid):
+    v, c = make()
+    topo = fem.Topology(v, c)
+    ops = fem.assemble_wave_operators(topo, fem.tag_boundary(topo, shape, xL, yL))
+    rng = np.random.default_rng(2)
+    bq = rng.standard_normal(topo.n_edges)
+    bp = rng.standard_normal(topo.n_vertices)
+    xq = spla.spsolve(ops['M_q'].tocsc(), bq)
+    xp = spla.spsolve(ops['M_p'].tocsc(), bp)
+    its = {}
+    for what, b, ref in [('mq_lean', bq, xq), ('mq1', bq, xq), ('mq2', bq, xq), ('mp_lean', bp, xp), ('mp1', bp, xp), ('mp2', bp, xp)]:
+        x, its[what] = run(emu, what, v, c, pc, grid, b, nout=len(b))
+        assert rel(x, ref) < 1e-11, (what, rel(x, ref))
+    # the lean, pipelined and pipelined two-sweep kernels run the same iteration (the stop test may differ by one step)
+    assert abs(its['mq1'] - its['mq_lean']) <= 1 and abs(its['mq2'] - its['mq_lean']) <= 1
+    assert abs(its['mp1'] - its['mp_lean']) <= 1 and abs(its['mp2'] - its['mp_lean']) <= 1
+
+
+@pytest.mark.parametrize('name,make,shape,xL,yL,pc,grid', MESHES)
+def test_emulated_energy_and_right_hand_sides_match_oracle(emu, name, make, shape, xL, yL, pc, grid):
+    v, c = make()
+    topo = fem.Topology(v, c)
+    ops = fem.assemble_wave_operators(topo, fem.tag_boundary(topo, shape, xL, yL))
+    m = Mesh(v, c, patch_cells=pc)
+    tags = tag_boundary_edges(m, shape, xL, yL)
+    m.close()
+    rng = np.random.default_rng(3)
+    p = rng.standard_normal(topo.n_vertices)
+    q = rng.standard_normal(topo.n_edges)
+    en, _ = run(emu, 'energy', v, c, pc, grid, p, q, nout=2)
+    assert abs(en[0] - p @ (ops['M_p'] @ p)) < 1e-13 * abs(en[0]) and abs(en[1] - q @ (ops['M_q'] @ q)) < 1e-13 * abs(en[1])
+    y, _ = run(emu, 'rhs_e', v, c, pc, grid, p, nout=topo.n_edges, tags=tags)
+    assert rel(y, ops['D'] @ p) < 1e-14
+    y, _ = run(emu, 'rhs_v', v, c, pc, grid, q, nout=topo.n_vertices, tags=tags)
+    assert rel(y, ops['D'].T @ q) < 1e-14
+
+
+def test_emulated_solves_with_zero_right_hand_side_and_loose_tolerance(emu):
+    v, c = rectangle_delaunay(30, 8, seed=7)
+    topo = fem.Topology(v, c)
+    for what, n in [('mq1', topo.n_edges), ('mq2', topo.n_edges), ('mp1', topo.n_vertices), ('mp2', topo.n_vertices)]:
+        x, it = run(emu, what, v, c, 40, 3, np.zeros(n), nout=n)
+        assert np.all(x == 0.0) and it <= 2
+    ops = fem.assemble_wave_operators(topo, fem.tag_boundary(topo, 'R', 1.0, 0.25))
+    b = np.random.default_rng(4).standard_normal(topo.n_edges)
+    x6, it6 = run(emu, 'mq2', v, c, 40, 3, b, nout=len(b), tol=1e-6)
+    x13, it13 = run(emu, 'mq2', v, c, 40, 3, b, nout=len(b), tol=1e-13)
+    assert it6 < it13 and rel(x6, spla.spsolve(ops['M_q'].tocsc(), b)) < 1e-5
