@@ -18,11 +18,18 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <string>
 #include <thread>
 #include <unordered_map>
 #include <vector>
 
 namespace phw_emu {
+
+// PHW_EMU_MODE: "late" (default) - asynchronous copies land as late as the programming model allows (a stage that is read before
+// it was waited for is still poison); "early" - they land at issue time (a stage that is refilled while somebody still needs its
+// old content is clobbered).  PHW_EMU_SEED != 0: the fibers of a CTA are scheduled in random order between rendezvous points.
+inline bool mode_early() { static const bool e = [] { const char* m = std::getenv("PHW_EMU_MODE"); return m && std::string(m) == "early"; }(); return e; }
+inline unsigned long long sched_seed() { static const unsigned long long v = [] { const char* m = std::getenv("PHW_EMU_SEED"); return m ? std::strtoull(m, nullptr, 10) : 0ull; }(); return v; }
 
 struct dim3e { unsigned int x = 1, y = 1, z = 1; };
 inline thread_local dim3e threadIdx, blockIdx, blockDim, gridDim;
@@ -76,7 +83,10 @@ inline double shfl_xor(double v, int lane_mask) {
 }
 
 // ---- asynchronous copies
-inline void ldgsts(void* dst, const void* src, size_t bytes) { g_cta->ldgsts[threadIdx.x].push_back(Copy{dst, src, bytes, nullptr}); }
+inline void ldgsts(void* dst, const void* src, size_t bytes) {
+    if (mode_early()) { std::memcpy(dst, src, bytes); return; }
+    g_cta->ldgsts[threadIdx.x].push_back(Copy{dst, src, bytes, nullptr});
+}
 inline void ldgsts_wait_all() {
     auto& q = g_cta->ldgsts[threadIdx.x];
     for (const Copy& k : q) std::memcpy(k.dst, k.src, k.bytes);
@@ -89,6 +99,7 @@ inline void bulk_g2s(void* dst, const void* src, unsigned bytes, const void* bar
         std::fprintf(stderr, "emu: bulk copy violates the 16-byte rule (dst %p src %p bytes %u)\n", dst, src, bytes);
         std::abort();
     }
+    if (mode_early()) { std::memcpy(dst, src, bytes); g_cta->bars.at(bar).tx -= (long long)bytes; return; }
     g_cta->bulk.push_back(Copy{dst, src, bytes, bar});
 }
 inline bool mbar_try_wait(const void* bar, unsigned parity) {
@@ -161,12 +172,22 @@ inline void run_cta(int bid, int grid, int nt, size_t smem, const std::function<
         cta.ctx[t].uc_link = &cta.sched;
         makecontext(&cta.ctx[t], (void (*)())fiber_entry, 0);
     }
-    while (cta.alive > 0)
-        for (int t = 0; t < nt; ++t) {
-            if (cta.done[t]) continue;
+    unsigned long long rng = sched_seed() ? sched_seed() * 0x9E3779B97F4A7C15ull + (unsigned long long)bid * 0xD1B54A32D192ED03ull + 1ull : 0ull;
+    while (cta.alive > 0) {
+        if (rng == 0) {
+            for (int t = 0; t < nt; ++t) {
+                if (cta.done[t]) continue;
+                cta.cur = t; threadIdx.x = (unsigned)t;
+                swapcontext(&cta.sched, &cta.ctx[t]);
+            }
+        } else {   // random runnable fiber (xorshift)
+            rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17;
+            int t = (int)(rng % (unsigned long long)nt);
+            while (cta.done[t]) t = (t + 1) % nt;
             cta.cur = t; threadIdx.x = (unsigned)t;
             swapcontext(&cta.sched, &cta.ctx[t]);
         }
+    }
     if (!cta.bulk.empty()) { std::fprintf(stderr, "emu: CTA %d exits with %zu bulk copies in flight\n", bid, cta.bulk.size()); std::abort(); }
     for (int t = 0; t < nt; ++t) {
         if (!cta.ldgsts[t].empty()) { std::fprintf(stderr, "emu: CTA %d thread %d exits with LDGSTS copies in flight\n", bid, t); std::abort(); }
