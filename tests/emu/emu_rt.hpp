@@ -51,7 +51,7 @@ struct Cta {
     std::unordered_map<const void*, MBar> bars;
     unsigned char* dyn = nullptr;
     const std::function<void()>* body = nullptr;
-    long long ticks = 0;
+    long long ticks = 0, bulk_issued = 0;
 };
 inline thread_local Cta* g_cta = nullptr;
 
@@ -60,7 +60,10 @@ inline void yield() {
     const int me = c->cur;
     swapcontext(&c->ctx[me], &c->sched);
 }
-inline long long clock() { return ++g_cta->ticks; }
+// fault injection (tests of the failure path): PHW_EMU_DROP=n drops the n-th bulk copy of CTA 0 (its bytes never arrive);
+// the emulated clock then advances fast enough for the kernels' wait limit to expire
+inline long long drop_nth() { static const long long v = [] { const char* m = std::getenv("PHW_EMU_DROP"); return m ? std::atoll(m) : 0ll; }(); return v; }
+inline long long clock() { g_cta->ticks += drop_nth() ? 50000000LL : 1LL; return g_cta->ticks; }
 
 inline void syncthreads() {
     Cta* c = g_cta;
@@ -99,6 +102,7 @@ inline void bulk_g2s(void* dst, const void* src, unsigned bytes, const void* bar
         std::fprintf(stderr, "emu: bulk copy violates the 16-byte rule (dst %p src %p bytes %u)\n", dst, src, bytes);
         std::abort();
     }
+    if (drop_nth() && blockIdx.x == 0 && ++g_cta->bulk_issued == drop_nth()) return;      // injected fault: this copy is lost
     if (mode_early()) { std::memcpy(dst, src, bytes); g_cta->bars.at(bar).tx -= (long long)bytes; return; }
     g_cta->bulk.push_back(Copy{dst, src, bytes, bar});
 }
@@ -117,7 +121,7 @@ inline bool mbar_try_wait(const void* bar, unsigned parity) {
     const bool ok = (b.phases & 1u) != parity;
     if (ok) b.idle_polls = 0;
     else {
-        if (++b.idle_polls > 20000000LL) {
+        if (++b.idle_polls > 20000000LL && !drop_nth()) {
             std::fprintf(stderr, "emu: an mbarrier phase never completes (pending arrivals %d, outstanding bytes %lld)\n", b.pending, b.tx);
             std::abort();
         }
@@ -188,9 +192,9 @@ inline void run_cta(int bid, int grid, int nt, size_t smem, const std::function<
             swapcontext(&cta.sched, &cta.ctx[t]);
         }
     }
-    if (!cta.bulk.empty()) { std::fprintf(stderr, "emu: CTA %d exits with %zu bulk copies in flight\n", bid, cta.bulk.size()); std::abort(); }
+    if (!cta.bulk.empty() && !drop_nth()) { std::fprintf(stderr, "emu: CTA %d exits with %zu bulk copies in flight\n", bid, cta.bulk.size()); std::abort(); }
     for (int t = 0; t < nt; ++t) {
-        if (!cta.ldgsts[t].empty()) { std::fprintf(stderr, "emu: CTA %d thread %d exits with LDGSTS copies in flight\n", bid, t); std::abort(); }
+        if (!cta.ldgsts[t].empty() && !drop_nth()) { std::fprintf(stderr, "emu: CTA %d thread %d exits with LDGSTS copies in flight\n", bid, t); std::abort(); }
         std::free(cta.stacks[t]);
     }
     guarded_free(dyn);

@@ -114,3 +114,30 @@ def test_emulated_solves_with_zero_right_hand_side_and_loose_tolerance(emu):
     x6, it6 = run(emu, 'mq2', v, c, 40, 3, b, nout=len(b), tol=1e-6)
     x13, it13 = run(emu, 'mq2', v, c, 40, 3, b, nout=len(b), tol=1e-13)
     assert it6 < it13 and rel(x6, spla.spsolve(ops['M_q'].tocsc(), b)) < 1e-5
+
+
+@pytest.mark.parametrize('what', ['mq1', 'mp1', 'mq2', 'mp2', 'energy', 'rhs_e'])
+def test_a_stage_that_never_arrives_ends_in_a_clean_error(what):
+    """failure path of the pipelined kernels (pipe_stage_ready): a lost bulk copy must end in an error code - all CTAs leave the
+    kernel (no hang at the grid barrier), nobody computes on the stage that did not arrive.  Runs in a child process because the
+    fault injection of the emulator is switched on by an environment variable read once."""
+    import subprocess, textwrap
+    code = textwrap.dedent('''
+        import sys, ctypes, numpy as np
+        sys.path.insert(0, {tests!r}); sys.path.insert(0, {emu!r}); sys.path.insert(0, {root!r})
+        from test_emu_cpu import run
+        from build_emu import build
+        from porthamiltonian_fem_b200.mesh import rectangle_delaunay
+        lib = ctypes.CDLL(build())
+        v, c = rectangle_delaunay(40, 10, seed=1)
+        big = np.ones(10 ** 5)                      # longer than any dof vector of this mesh: the harness reads what it needs
+        try:
+            run(lib, {what!r}, v, c, 40, 3, big, big if {what!r} == 'energy' else None, nout=10 ** 5)
+            print('NO ERROR')
+        except RuntimeError as ex:
+            print('ERROR:', ex)
+    ''').format(tests=HERE, emu=os.path.join(HERE, 'emu'), root=os.path.dirname(HERE), what=what)
+    env = dict(os.environ, PHW_EMU_DROP='7')
+    r = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert 'ERROR: a stage did not arrive' in r.stdout, r.stdout + r.stderr
