@@ -268,3 +268,171 @@ extern "C" int emu_run(const char* what_c, int64_t nv, const double* vtx, int64_
     }
     return fail(err, errlen, "unknown kernel " + what);
 }
+
+// ------------------------------------------------------------------------------------------------
+// two ranks in one process (partitioned run): each rank has its own layout (external dofs numbered after the owned
+// ones), iterate buffers, control block and mailbox; the PeerComm of a rank points at the other rank's buffers, exactly as
+// phw_comm_setup wires them through CUDA IPC on the GPU.  Both ranks' kernels run concurrently (two grids of OS threads).
+// what: "mq1" | "mp1" (pipelined solves with the exchange), "mq_lean" | "mp_lean".
+// Per rank r: local mesh, external flags (vertices by local id, edges by canonical local edge id), right-hand side on all local
+// dofs, send lists: n_send[r] owned dofs (local user ids send_loc[r]) and the ids the other rank uses for them (send_rem[r]).
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct Rank {
+    Layout L;
+    Arena A;
+    std::vector<double> g0, g1, g2, area, pinvq;
+    PatchHdr* d_hdr; uint4* d_cellq; int *d_gv, *d_ge; uint32_t *d_eadj, *d_io, *d_wo; uint16_t* d_ids; double *d_ellw, *d_pinvq, *d_b;
+    double* buf[3];
+    Ctl* ctl; double* partials; Mailbox* mbox;
+    int *d_sloc, *d_srem; int n_send;
+    PeerComm pc{};
+    double lam_lo = 1e300, lam_hi = 0.0;
+};
+}  // namespace
+
+extern "C" int emu_run2(const char* what_c, int32_t patch_cells, int32_t grid,
+                        const int64_t* nv, const double* const* vtx, const int64_t* nc, const int32_t* const* cells,
+                        const uint8_t* const* v_ext, const int64_t* ne, const uint8_t* const* e_ext,
+                        const double* const* b_user, double* const* out_user,
+                        const int32_t* n_send, const int32_t* const* send_loc, const int32_t* const* send_rem,
+                        int32_t* iters, double tol, char* err, int errlen) {
+    const std::string what(what_c);
+    constexpr int NT = 128;
+    const bool is_q = what.rfind("mq", 0) == 0;
+    Rank R[2];
+    for (int r = 0; r < 2; ++r) {
+        Rank& k = R[r];
+        std::string e = k.L.build(nv[r], vtx[r], nc[r], cells[r], patch_cells, v_ext[r], ne[r], e_ext[r]);
+        if (!e.empty()) return fail(err, errlen, "rank " + std::to_string(r) + ": " + e);
+        k.L.boundary_set = true;
+        std::vector<CellRec> rec;
+        k.L.make_records(false, false, rec);
+        const Layout& L = k.L;
+        const int npc = (int)L.pcell_user.size();
+        k.area.resize(npc); k.g0.resize(npc); k.g1.resize(npc); k.g2.resize(npc);
+        for (int c = 0; c < npc; ++c) cell_geometry(L, L.pcell_user[c], k.area[c], k.g0[c], k.g1[c], k.g2[c]);
+        std::vector<uint4> cq(2 * (size_t)npc);
+        for (int c = 0; c < npc; ++c) { cq[2 * (size_t)c] = pack_a(make_uint2(rec[c].z, rec[c].w), k.g0[c]); cq[2 * (size_t)c + 1] = pack_b(k.g1[c], k.g2[c]); }
+        k.d_hdr = k.A.put(L.hdr); k.d_cellq = k.A.put(cq); k.d_gv = k.A.put(L.ghost_v); k.d_ge = k.A.put(L.ghost_e);
+        k.d_eadj = k.A.put(L.eadj); k.d_io = k.A.put(L.ell_ioff); k.d_wo = k.A.put(L.ell_woff); k.d_ids = k.A.put(L.ell_ids);
+        std::vector<double> ellw(L.ell_pair.size(), 0.0);
+        k.pinvq.assign(L.ne, 0.0);
+        for (int p = 0; p < L.npatch; ++p) {
+            const PatchHdr& h = L.hdr[p];
+            const int nsl = (h.v_cnt + 31) >> 5;
+            for (uint32_t j = L.ell_woff[h.vs_off]; j < L.ell_woff[h.vs_off + nsl]; ++j) {
+                const uint32_t pr = L.ell_pair[j];
+                if (pr == 0xFFFFFFFFu) continue;
+                double v = k.area[h.cell_off + (pr & 0xFFFFu)];
+                if ((pr >> 16) != 0xFFFFu) v += k.area[h.cell_off + (pr >> 16)];
+                ellw[j] = v * (1.0 / 12.0);
+            }
+            for (int le = 0; le < h.e_cnt; ++le) {
+                const uint32_t adj = L.eadj[h.e_start + le];
+                double dg = 0.0;
+                for (uint32_t code : {adj & 0xFFFFu, adj >> 16}) {
+                    if (code == 0xFFFFu) continue;
+                    const int c = h.cell_off + (int)(code >> 2);
+                    const double S = k.g0[c] + k.g1[c] + k.g2[c], gs = (code & 3u) == 0 ? k.g0[c] : ((code & 3u) == 1 ? k.g1[c] : k.g2[c]);
+                    dg += 3.0 * S - 4.0 * gs;
+                }
+                k.pinvq[h.e_start + le] = 1.0 / dg;
+            }
+        }
+        k.d_ellw = k.A.put(ellw); k.d_pinvq = k.A.put(k.pinvq);
+        for (int c = 0; c < npc; ++c) {   // element bounds of the Jacobi-scaled RT1 mass spectrum
+            const double S = k.g0[c] + k.g1[c] + k.g2[c];
+            const double m00 = 3 * S - 4 * k.g0[c], m11 = 3 * S - 4 * k.g1[c], m22 = 3 * S - 4 * k.g2[c];
+            const double m01 = S - 4 * k.g2[c], m02 = S - 4 * k.g1[c], m12 = S - 4 * k.g0[c];
+            const double ea = m01 / std::sqrt(m00 * m11), eb = m02 / std::sqrt(m00 * m22), ec = m12 / std::sqrt(m11 * m22);
+            const double pp = ea * ea + eb * eb + ec * ec, qq = 2.0 * ea * eb * ec;
+            if (pp > 1e-30) {
+                double arg = 0.5 * qq * std::pow(3.0 / pp, 1.5);
+                arg = std::min(1.0, std::max(-1.0, arg));
+                const double phi = std::acos(arg) / 3.0, amp = 2.0 * std::sqrt(pp / 3.0);
+                k.lam_hi = std::max(k.lam_hi, 1.0 + amp * std::cos(phi)); k.lam_lo = std::min(k.lam_lo, 1.0 + amp * std::cos(phi + 2.0943951023931953));
+            }
+        }
+        const std::vector<int32_t>& n2o = is_q ? L.e_new2old : L.v_new2old;
+        std::vector<double> bn(n2o.size());
+        for (size_t i = 0; i < n2o.size(); ++i) bn[i] = b_user[r][n2o[i]];
+        k.d_b = k.A.put(bn);
+        for (auto& bp : k.buf) bp = k.A.get<double>(n2o.size());
+        k.ctl = k.A.get<Ctl>(1); k.partials = k.A.get<double>(16384); k.mbox = k.A.get<Mailbox>(1);
+        const std::vector<int32_t>& o2n = is_q ? L.e_old2new : L.v_old2new;
+        std::vector<int> sl(n_send[r]);
+        for (int i = 0; i < n_send[r]; ++i) sl[i] = o2n[send_loc[r][i]];
+        k.d_sloc = k.A.put(sl); k.n_send = n_send[r];
+    }
+    for (int r = 0; r < 2; ++r) {   // what phw_comm_setup does: neighbour buffers, remote positions, mailboxes
+        Rank& k = R[r]; Rank& o = R[1 - r];
+        const std::vector<int32_t>& o2n_other = is_q ? o.L.e_old2new : o.L.v_old2new;
+        std::vector<int> sr(n_send[r]);
+        for (int i = 0; i < n_send[r]; ++i) sr[i] = o2n_other[send_rem[r][i]];
+        k.d_srem = k.A.put(sr);
+        PeerComm& pc = k.pc;
+        pc.rank = r; pc.world = 2; pc.n_nb = 1; pc.nb_rank[0] = 1 - r;
+        for (int i = 0; i < 3; ++i) { pc.nb_tp[0][i] = is_q ? nullptr : o.buf[i]; pc.nb_tq[0][i] = is_q ? o.buf[i] : nullptr; }
+        if (is_q) { pc.send_e_loc[0] = k.d_sloc; pc.send_e_rem[0] = k.d_srem; pc.n_send_e[0] = k.n_send; }
+        else { pc.send_v_loc[0] = k.d_sloc; pc.send_v_rem[0] = k.d_srem; pc.n_send_v[0] = k.n_send; }
+        pc.mbox[0] = R[0].mbox; pc.mbox[1] = R[1].mbox;
+        pc.timeout_cycles = (long long)4e18;
+    }
+    const double lam_lo = std::min(R[0].lam_lo, R[1].lam_lo), lam_hi = std::max(R[0].lam_hi, R[1].lam_hi);
+    const double cd = is_q ? 0.5 * (lam_lo + lam_hi) : 1.25, cc = is_q ? 0.5 * (lam_hi - lam_lo) : 0.75;
+    auto run_rank = [&](int r) {
+        Rank& k = R[r];
+        const Layout& L = k.L;
+        const int g = std::max(1, std::min((int)grid, L.npatch));
+        MqPipeArgs cfg_q{}; EllPipeArgs cfg_p{};
+        size_t sm_q = 0, sm_p = 0;
+        pipe_carve(L, cfg_q, cfg_p, sm_q, sm_p);
+        if (what == "mq1" || what == "mq_lean") {
+            if (what == "mq1") {
+                MqPipeArgs a = cfg_q;
+                a.npatch = L.npatch; a.hdr = k.d_hdr; a.cellq = k.d_cellq; a.ghost_e = k.d_ge; a.eadj = k.d_eadj; a.b = k.d_b; a.pinv = k.d_pinvq;
+                for (int i = 0; i < 3; ++i) a.buf[i] = k.buf[i];
+                a.cheb_d = cd; a.cheb_c = cc; a.tol2 = tol * tol; a.max_iter = 200; a.which = 1; a.partials = k.partials; a.ctl = k.ctl;
+                phw_emu::launch(g, NT, sm_q, [&] { solve_mq_pipe_k<NT, false, true>(a, k.pc); });
+            } else {
+                MqSolveArgs a{};
+                a.npatch = L.npatch; a.hdr = k.d_hdr; a.cellq = k.d_cellq; a.ghost_e = k.d_ge; a.eadj = k.d_eadj; a.b = k.d_b; a.pinv = k.d_pinvq;
+                for (int i = 0; i < 3; ++i) a.buf[i] = k.buf[i];
+                a.cheb_d = cd; a.cheb_c = cc; a.tol2 = tol * tol; a.max_iter = 200; a.which = 1; a.partials = k.partials; a.ctl = k.ctl;
+                const size_t sm = ((size_t)((L.max_le + 1) & ~1) + 3 * (size_t)L.max_cells) * 8;
+                phw_emu::launch(g, NT, sm, [&] { solve_mq_coop_k<NT, 1, 2, 2, true>(a, k.pc); });
+            }
+        } else {
+            if (what == "mp1") {
+                EllPipeArgs a = cfg_p;
+                a.npatch = L.npatch; a.hdr = k.d_hdr; a.ell_ioff = k.d_io; a.ell_woff = k.d_wo; a.ell_ids = k.d_ids; a.ell_w = k.d_ellw; a.ghost_v = k.d_gv; a.b = k.d_b;
+                for (int i = 0; i < 3; ++i) a.buf[i] = k.buf[i];
+                a.cheb_d = cd; a.cheb_c = cc; a.tol2 = tol * tol; a.max_iter = 200; a.which = 0; a.partials = k.partials; a.ctl = k.ctl;
+                phw_emu::launch(g, NT, sm_p, [&] { solve_ell_pipe_k<NT, 1, true>(a, k.pc); });
+            } else {
+                EllSolveArgs a{};
+                a.npatch = L.npatch; a.hdr = k.d_hdr; a.ell_ioff = k.d_io; a.ell_woff = k.d_wo; a.ell_ids = k.d_ids; a.ell_w = k.d_ellw; a.ghost_v = k.d_gv; a.b = k.d_b;
+                for (int i = 0; i < 3; ++i) a.buf[i] = k.buf[i];
+                a.cheb_d = cd; a.cheb_c = cc; a.tol2 = tol * tol; a.max_iter = 200; a.which = 0; a.partials = k.partials; a.ctl = k.ctl;
+                const size_t sm = ((size_t)(L.max_lv + 31) / 32 + 4 + (size_t)((L.max_lv + 1) & ~1)) * 8;
+                phw_emu::launch(g, NT, sm, [&] { solve_ell_coop_k<NT, 1, true>(a, k.pc); });
+            }
+        }
+    };
+    if (what != "mq1" && what != "mq_lean" && what != "mp1" && what != "mp_lean") return fail(err, errlen, "unknown kernel " + what);
+    std::thread t1(run_rank, 1);
+    run_rank(0);
+    t1.join();
+    for (int r = 0; r < 2; ++r) {
+        Rank& k = R[r];
+        if (k.ctl->comm_dead) return fail(err, errlen, "exchange timed out");
+        if ((k.ctl->nonconv >> 32) != 0) return fail(err, errlen, "a stage did not arrive");
+        if (k.ctl->nonconv != 0) return fail(err, errlen, "solve did not converge");
+        const SolveCtl& sc = k.ctl->sc[is_q ? 1 : 0];
+        const std::vector<int32_t>& n2o = is_q ? k.L.e_new2old : k.L.v_new2old;
+        for (size_t i = 0; i < n2o.size(); ++i) out_user[r][n2o[i]] = k.buf[sc.cur][i];
+        if (iters) iters[r] = (int32_t)sc.iters;
+    }
+    return 0;
+}

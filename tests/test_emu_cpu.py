@@ -141,3 +141,70 @@ def test_a_stage_that_never_arrives_ends_in_a_clean_error(what):
     r = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     assert 'ERROR: a stage did not arrive' in r.stdout, r.stdout + r.stderr
+
+
+def _run2(lib, what, v, c, pc, grid, b_global, kind, tol=1e-13):
+    """two ranks in one process: x-slab partition, peer exchange through each other's buffers and mailboxes (emu_run2)"""
+    from porthamiltonian_fem_b200 import partition as pt
+    cr = pt.slab_cell_ranks(v, c, 2)
+    parts = [pt.build_local_part(v, c, cr, r) for r in range(2)]
+    keep = []
+
+    def A(x, dt):
+        x = np.ascontiguousarray(x, dtype=dt)
+        keep.append(x)
+        return x
+
+    def ptrs(arrs):
+        return (ctypes.c_void_p * len(arrs))(*[a.ctypes.data_as(ctypes.c_void_p) for a in arrs])
+    vtx = [A(p.vertices, np.float64) for p in parts]
+    cells = [A(p.cells, np.int32) for p in parts]
+    vext = [A(p.vertex_external, np.uint8) for p in parts]
+    eext = [A(p.edge_external, np.uint8) for p in parts]
+    gid = [(p.edge_gid if kind == 'e' else p.vertex_gid) for p in parts]
+    b = [A(b_global[g], np.float64) for g in gid]
+    out = [A(np.zeros(len(g)), np.float64) for g in gid]
+    sloc, srem = [], []
+    for r in range(2):      # rank r pushes what the other rank lists in its recv[r]: my local ids / the other's local ids, same order
+        lst = parts[1 - r].recv.get(r, {}).get(kind, np.zeros(0, np.int32))
+        g = (parts[1 - r].edge_gid if kind == 'e' else parts[1 - r].vertex_gid)[lst]
+        sloc.append(A(pt.needed_by(g, parts[r], kind), np.int32))
+        srem.append(A(lst, np.int32))
+    nv = (ctypes.c_int64 * 2)(*[len(p.vertices) for p in parts])
+    nc = (ctypes.c_int64 * 2)(*[len(p.cells) for p in parts])
+    ne = (ctypes.c_int64 * 2)(*[len(p.edge_gid) for p in parts])
+    ns = (ctypes.c_int32 * 2)(*[len(x) for x in sloc])
+    it = (ctypes.c_int32 * 2)()
+    err = ctypes.create_string_buffer(512)
+    rc = lib.emu_run2(what.encode(), ctypes.c_int32(pc), ctypes.c_int32(grid), nv, ptrs(vtx), nc, ptrs(cells), ptrs(vext), ne, ptrs(eext),
+                      ptrs(b), ptrs(out), ns, ptrs(sloc), ptrs(srem), it, ctypes.c_double(tol), err, 512)
+    if rc:
+        raise RuntimeError(err.value.decode())
+    x = np.full(len(b_global), np.nan)
+    for r, p in enumerate(parts):
+        own = (p.edge_owner if kind == 'e' else p.vertex_owner) == r
+        x[gid[r][own]] = out[r][own]
+    ext_off = max(np.abs(out[r] - x[gid[r]]).max() for r in range(2))
+    return x, list(it), ext_off
+
+
+@pytest.mark.parametrize('mesh', ['delaunay', 'structured'])
+def test_emulated_two_rank_solves_with_peer_exchange(emu, mesh):
+    """partitioned run of the pipelined solves with the inter-GPU exchange (PHW_PIPE_MULTI; not yet run on 2 GPUs) next
+    to the lean kernels that carry the same exchange on the GPU: owned parts reproduce the global solve, both ranks take the same
+    stop decision, and the external copies equal their owners' values"""
+    v, c = rectangle_delaunay(40, 10, seed=3) if mesh == 'delaunay' else rectangle_structured(36, 9)
+    topo = fem.Topology(v, c)
+    ops = fem.assemble_wave_operators(topo, fem.tag_boundary(topo, 'R', 1.0, 0.25))
+    rng = np.random.default_rng(1)
+    bq = rng.standard_normal(topo.n_edges)
+    bp = rng.standard_normal(topo.n_vertices)
+    xq = spla.spsolve(ops['M_q'].tocsc(), bq)
+    xp = spla.spsolve(ops['M_p'].tocsc(), bp)
+    its = {}
+    for what, b, ref, kind in [('mq_lean', bq, xq, 'e'), ('mq1', bq, xq, 'e'), ('mp_lean', bp, xp, 'v'), ('mp1', bp, xp, 'v')]:
+        x, it, ext_off = _run2(emu, what, v, c, 40, 3, b, kind)
+        assert not np.isnan(x).any() and rel(x, ref) < 1e-11, (what, rel(x, ref))
+        assert it[0] == it[1] and ext_off == 0.0, (what, it, ext_off)
+        its[what] = it[0]
+    assert abs(its['mq1'] - its['mq_lean']) <= 1 and abs(its['mp1'] - its['mp_lean']) <= 1
