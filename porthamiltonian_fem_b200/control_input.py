@@ -1,29 +1,40 @@
-"""Host-side mirror of the reference's passivity controller (control_input.py:3-20).
+"""Host-side mirror of the reference's passivity controller (reference control_input.py:3-20).
 
-In the reference this is a dolfin ``UserExpression`` evaluated in Python at every quadrature point of the
-port boundary.  Here the controller is a scalar function evaluated on the device inside the step loop
-(``input_value`` in csrc/phwave.cu, PHW_IN_PASSIVITY); this class only carries the parameters and offers
-the same ``eval`` law for host-side checks."""
+In the reference the controller is a dolfin ``UserExpression`` that Python evaluates at every quadrature point of the
+port boundary.  Here the law is a scalar evaluated on the device inside the step loop (``input_value`` in
+csrc/phwave.cu, PHW_IN_PASSIVITY).  This module keeps the reference's class name and call surface for host-side
+checks and for user code that constructs the controller object; the law itself lives in ``passivity_input``."""
 import math
 
+EXCITATION_AMPLITUDE = 10.0          # u(t) = 10 sin(8 pi t) while t < input_stop_t
+EXCITATION_OMEGA = 8.0 * math.pi
+DAMPING_GAIN = 100.0                 # u = -100 h_1 once t >= control_start_t (h_1: previous step's first lumped state)
 
-class Passive_control_input(object):
-    def __init__(self, t, h_1, input_stop_t, control_start_t, **kwargs):
-        self.t = t
-        self.h_1 = h_1
-        self.input_stop_t = input_stop_t
-        self.control_start_t = control_start_t
-        self.eps = 0.001
+
+def passivity_input(t, h_1, input_stop_t, control_start_t):
+    """Three regimes: excitation, free evolution, damping injection (same constants as the device code)."""
+    if t >= control_start_t and t >= input_stop_t:
+        return -DAMPING_GAIN * h_1
+    if t >= input_stop_t:
+        return 0.0
+    return EXCITATION_AMPLITUDE * math.sin(EXCITATION_OMEGA * t)
+
+
+class Passive_control_input:
+    """Carries (t, h_1, input_stop_t, control_start_t) like the reference object; ``t`` and ``h_1`` are updated by the caller."""
+    __slots__ = ('t', 'h_1', 'input_stop_t', 'control_start_t', 'eps')
+
+    def __init__(self, t, h_1, input_stop_t, control_start_t, **_ignored):
+        self.t, self.h_1 = t, h_1
+        self.input_stop_t, self.control_start_t = input_stop_t, control_start_t
+        self.eps = 1e-3
 
     def value(self):
-        if self.t < self.input_stop_t:
-            return 10 * math.sin(8 * math.pi * self.t)
-        elif self.t < self.control_start_t:
-            return 0.0
-        return -100.0 * self.h_1
+        return passivity_input(self.t, self.h_1, self.input_stop_t, self.control_start_t)
 
-    def eval_cell(self, value, x, ufc_cell):
+    def eval_cell(self, value, x=None, ufc_cell=None):
         value[0] = self.value()
 
-    def value_shape(self):
+    @staticmethod
+    def value_shape():
         return ()
