@@ -104,7 +104,7 @@ def wave_2D_solve(tFinal, numSteps, outputDir,
     prm.casimir = 1 if controlType == 'casimir' else 0
     prm.analytical = 1 if analytical else 0
     prm.dt, prm.K_wave, prm.rho = dt_value, float(K_wave), float(rho)
-    prm.tol, prm.max_iter, prm.flags, prm.extrap_order = float(tol), 200, int(solver_flags), int(extrap_order)
+    prm.tol, prm.max_iter, prm.flags, prm.extrap_order = float(tol), 2000, int(solver_flags), int(extrap_order)   # cap only: see DESIGN.md section 2 (stretched cells)
     lp = dict(_DEFAULT_LUMPED)
     if lumped:
         lp.update(lumped)
