@@ -58,6 +58,7 @@ int fail(char* err, int errlen, const std::string& m) { std::snprintf(err, (size
 }  // namespace
 
 // what: "mq1" | "mp1" (one-sweep pipelined solves), "mq2" | "mp2" (two-sweep pipelined solves), "mq_lean" | "mp_lean",
+//       "mq2_lean" | "mp2_lean" (lean two-sweep solves of kernels2.cuh),
 //       "energy" (out[0] = p^T M_p p, out[1] = q^T M_q q; in1 = p, in2 = q), "rhs_e" (out = D in1), "rhs_v" (out = D^T in1)
 // btags: tag of every boundary edge in the order of the layout's boundary list (nullptr: all "none"); user numbering everywhere.
 extern "C" int emu_run(const char* what_c, int64_t nv, const double* vtx, int64_t nc, const int32_t* cells, int32_t patch_cells, int32_t grid,
@@ -187,7 +188,8 @@ extern "C" int emu_run(const char* what_c, int64_t nv, const double* vtx, int64_
             a.cheb_d = cd; a.cheb_c = cc; a.tol2 = tol * tol; a.max_iter = 200; a.which = 0; a.partials = partials; a.ctl = ctl;
             const size_t sm = ((size_t)(L.max_lv + 31) / 32 + 4 + (size_t)((L.max_lv + 1) & ~1)) * 8;
             phw_emu::launch(grid, NT, sm, [&] { solve_ell_coop_k<NT, 1, false>(a, pc); });
-        } else if (what == "mq2" || what == "mp2") {
+        } else if (what == "mq2" || what == "mp2" || what == "mq2_lean" || what == "mp2_lean") {
+            const bool lean2 = what.size() > 3;
             Ring2 R;
             e = L.build_ring2(is_q ? 1 : 0, R);
             if (!e.empty()) return fail(err, errlen, "ring-2 patches: " + e);
@@ -205,12 +207,21 @@ extern "C" int emu_run(const char* what_c, int64_t nv, const double* vtx, int64_
                 for (int r = 0; r < nrows; ++r) pr[r] = pinvq[R.row_gid[r]];
                 d.pinv = A.put(pr);
                 d.eadj = A.put(R.eadj);
-                Mq2PipeArgs a{};
-                const size_t sm = pipe2_carve(R, a);
-                a.m = d;
-                for (int i = 0; i < 4; ++i) a.buf[i] = buf[i];
-                a.b = d_b; a.cheb_d = cd; a.cheb_c = cc; a.tol2 = tol * tol; a.max_iter = 200; a.which = 1; a.partials = partials; a.ctl = ctl;
-                phw_emu::launch(grid, NT, sm, [&] { solve2_mq_pipe_k<NT>(a); });
+                if (lean2) {   // the lean two-sweep kernel of kernels2.cuh with the custom grid barrier (flags bits 4 + 10)
+                    Solve2Args a{};
+                    a.m = d;
+                    for (int i = 0; i < 4; ++i) a.buf[i] = buf[i];
+                    a.b = d_b; a.cheb_d = cd; a.cheb_c = cc; a.tol2 = tol * tol; a.max_iter = 200; a.which = 1; a.partials = partials; a.ctl = ctl; a.gbar = 1;
+                    const size_t sm = ((size_t)((R.max_ld + 1) & ~1) + 3 * (size_t)R.max_c2) * 8;
+                    phw_emu::launch(grid, NT, sm, [&] { solve2_coop_k<1, NT, 1>(a); });
+                } else {
+                    Mq2PipeArgs a{};
+                    const size_t sm = pipe2_carve(R, a);
+                    a.m = d;
+                    for (int i = 0; i < 4; ++i) a.buf[i] = buf[i];
+                    a.b = d_b; a.cheb_d = cd; a.cheb_c = cc; a.tol2 = tol * tol; a.max_iter = 200; a.which = 1; a.partials = partials; a.ctl = ctl;
+                    phw_emu::launch(grid, NT, sm, [&] { solve2_mq_pipe_k<NT>(a); });
+                }
             } else {
                 d.g0 = A.put(a2);
                 d.ell_ioff = A.put(R.ell_ioff); d.ell_woff = A.put(R.ell_woff); d.ell_ids = A.put(R.ell_ids);
@@ -227,12 +238,20 @@ extern "C" int emu_run(const char* what_c, int64_t nv, const double* vtx, int64_
                     }
                 }
                 d.ell_w = A.put(w2);
-                Ell2PipeArgs a{};
-                const size_t sm = pipe2_carve_p(R, a);
-                a.m = d;
-                for (int i = 0; i < 4; ++i) a.buf[i] = buf[i];
-                a.b = d_b; a.cheb_d = cd; a.cheb_c = cc; a.tol2 = tol * tol; a.max_iter = 200; a.which = 0; a.partials = partials; a.ctl = ctl;
-                phw_emu::launch(grid, NT, sm, [&] { solve2_ell_pipe_k<NT, 1>(a); });
+                if (lean2) {
+                    Solve2Args a{};
+                    a.m = d;
+                    for (int i = 0; i < 4; ++i) a.buf[i] = buf[i];
+                    a.b = d_b; a.cheb_d = cd; a.cheb_c = cc; a.tol2 = tol * tol; a.max_iter = 200; a.which = 0; a.partials = partials; a.ctl = ctl; a.gbar = 1;
+                    phw_emu::launch(grid, NT, (size_t)R.max_smem_ell * 8, [&] { solve2_coop_k<0, NT, 1>(a); });
+                } else {
+                    Ell2PipeArgs a{};
+                    const size_t sm = pipe2_carve_p(R, a);
+                    a.m = d;
+                    for (int i = 0; i < 4; ++i) a.buf[i] = buf[i];
+                    a.b = d_b; a.cheb_d = cd; a.cheb_c = cc; a.tol2 = tol * tol; a.max_iter = 200; a.which = 0; a.partials = partials; a.ctl = ctl;
+                    phw_emu::launch(grid, NT, sm, [&] { solve2_ell_pipe_k<NT, 1>(a); });
+                }
             }
         } else return fail(err, errlen, "unknown kernel " + what);
         const SolveCtl& sc = ctl->sc[is_q ? 1 : 0];

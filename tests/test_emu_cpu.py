@@ -76,12 +76,13 @@ def test_emulated_mass_solves_match_direct_solves(emu, name, make, shape, xL, yL
     xq = spla.spsolve(ops['M_q'].tocsc(), bq)
     xp = spla.spsolve(ops['M_p'].tocsc(), bp)
     its = {}
-    for what, b, ref in [('mq_lean', bq, xq), ('mq1', bq, xq), ('mq2', bq, xq), ('mp_lean', bp, xp), ('mp1', bp, xp), ('mp2', bp, xp)]:
+    for what, b, ref in [('mq_lean', bq, xq), ('mq1', bq, xq), ('mq2', bq, xq), ('mq2_lean', bq, xq),
+                         ('mp_lean', bp, xp), ('mp1', bp, xp), ('mp2', bp, xp), ('mp2_lean', bp, xp)]:
         x, its[what] = run(emu, what, v, c, pc, grid, b, nout=len(b))
         assert rel(x, ref) < 1e-11, (what, rel(x, ref))
     # the lean, pipelined and pipelined two-sweep kernels run the same iteration (the stop test may differ by one step)
-    assert abs(its['mq1'] - its['mq_lean']) <= 1 and abs(its['mq2'] - its['mq_lean']) <= 1
-    assert abs(its['mp1'] - its['mp_lean']) <= 1 and abs(its['mp2'] - its['mp_lean']) <= 1
+    assert abs(its['mq1'] - its['mq_lean']) <= 1 and abs(its['mq2'] - its['mq_lean']) <= 1 and abs(its['mq2_lean'] - its['mq2']) <= 1
+    assert abs(its['mp1'] - its['mp_lean']) <= 1 and abs(its['mp2'] - its['mp_lean']) <= 1 and abs(its['mp2_lean'] - its['mp2']) <= 1
 
 
 @pytest.mark.parametrize('name,make,shape,xL,yL,pc,grid', MESHES)
