@@ -399,6 +399,9 @@ def run_bench():
             'clocks': summarize_clocks(samples),
             'roofline': {'bound': 'hbm', 'kernel': dom['kernel'], 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                          'frac': dom['frac'], 'traffic': dom['traffic'], 'peak_source': peak_src,
+                         'traffic_source': 'dram__bytes_read.sum + dram__bytes_write.sum per cell and iteration of the committed ncu --set full capture '
+                                           'of the lean solve kernels (profiles/r1b_ncu_full_lean_solves.txt: 48 / 99 B), scaled to this launch' +
+                                           ('; the pipelined kernels read the same streams, no capture of their own yet' if paths & 12 else ''),
                          'bytes_per_launch': dom['bytes_per_launch'], 'ms_per_launch': dom['ms_per_launch'],
                          'kernel_share_of_step': dom['share_of_step'], 'second_kernel': oth,
                          'whole_loop_model_gbs': st['bytes_model'] / dev_s / 1e9, 'whole_loop_model_frac': st['bytes_model'] / dev_s / 1e9 / peak,
