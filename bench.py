@@ -3,14 +3,19 @@
 
 Workload (BASELINE.json configs[3], fits one B200): refined synthetic rectangle 1.0 x 0.25, Nx x Ny quads split
 in two -> 25.0 M cells, 50.0 M dofs (P1 vertices + RT1 edges), weak form, symplectic Euler, K=3, rho=2,
-dt=2e-5, input g(t) = 10 sin(8 pi t).  One "step" = one time step of the loop wave_2D.py:787-982.
-metric = dof-updates/s = N_dof * steps / seconds.
+dt=2e-5, on the exact standing wave of the reference's analytical case (wave_2D.py:375-377,734) with its left datum
+(--from-rest: the reference's default input g(t) = 10 sin(8 pi t) from a zero state, wave_2D.py:384).
+One "step" = one time step of the loop wave_2D.py:787-982.  metric = dof-updates/s = N_dof * steps / seconds.
 
   value : device-timed (CUDA events on the solver's stream inside phw_run, state resident in HBM)
   e2e   : same K steps through the host-buffer C-ABI path (phw_set_state from pinned host memory ->
           phw_run -> H_array rows + phw_get_state back to the host), wall clock
-  roofline : Chebyshev M_q solve kernel (the dominant kernel), algorithmic bytes / its CUDA-event time
-  cpu_baseline : the CPU oracle (oracle/, scipy splu factor-once) on a down-scaled mesh of the same family
+  roofline : the dominant Chebyshev solve kernel: algorithmic bytes / its CUDA-event time; `traffic` = DRAM bytes per launch
+          from the committed ncu --set full capture of THAT kernel (profiles/ncu_dram_bytes.json)
+  cpu_baseline : the CPU oracle (oracle/, scipy SuperLU factor-once) on a down-scaled mesh of the same family, one
+          independent oracle rank per host core (the communication-free upper bound of an MPI run)
+  N > 1 : weak scaling (one 50 M-dof slab per GPU) is the headline; the same line carries config.strong = the ONE
+          50 M-dof mesh cut into N x-slabs (BASELINE configs[3] as stated), measured in the same run
 """
 import argparse
 import json
@@ -28,6 +33,7 @@ sys.path.insert(0, ROOT)
 K_WAVE, RHO = 3.0, 2.0
 FULL_NX, FULL_NY = 7072, 1768
 DT_FULL = 2e-5
+METRIC = 'dof-updates/sec (fp64, device-timed)'
 
 
 def clocks_sampler(stop, out, dev):
@@ -57,41 +63,67 @@ def summarize_clocks(samples):
     return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons}
 
 
-def cpu_oracle_rate(nx, ny, steps, refactor):
-    """dof-updates/s of the CPU oracle (SE, weak, wave only) on an nx x ny x 2 mesh of the same family."""
+# ---- CPU arms (the only places that execute oracle/) ---------------------------------------------------------------
+def cpu_oracle_rate(nx, ny, steps, refactor, scheme='SE'):
+    """dof-updates/s of the CPU oracle (weak, wave only) on an nx x ny x 2 mesh of the same family."""
     from oracle.wave_2D_oracle import wave_2D_solve_oracle
     from porthamiltonian_fem_b200.mesh import rectangle_structured
     mesh = rectangle_structured(nx, ny, 1.0, 0.25)
     dt = DT_FULL * FULL_NX / nx                       # same CFL ratio as the full-size run
     timing = {}
-    wave_2D_solve_oracle(dt * steps, steps, mesh, 1.0, 0.25, timeIntScheme='SE', K_wave=K_WAVE, rho=RHO,
+    wave_2D_solve_oracle(dt * steps, steps, mesh, 1.0, 0.25, timeIntScheme=scheme, K_wave=K_WAVE, rho=RHO,
                          refactor_every_solve=refactor, timing=timing)
     n_dof = timing['n_dof']
     return n_dof * steps / timing['loop_seconds'], n_dof, timing['loop_seconds']
 
 
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_oracle_rate_all_cores(nx, ny, steps, refactor, scheme='SE', max_procs=128):
+    """One independent oracle process per host core, each on its own nx x ny x 2 sample mesh (SuperLU is single-threaded, so
+    this is how the reference uses a multi-core host: `mpirun -n <cores>`, run_main_wave_2D_mpi.sh:1 - here without any
+    communication, i.e. an upper bound).  Aggregate rate = all dof-updates / the slowest process's loop time."""
+    n = max(1, min(host_cores(), max_procs))
+    env = dict(os.environ, OMP_NUM_THREADS='1', OPENBLAS_NUM_THREADS='1', MKL_NUM_THREADS='1', CUDA_VISIBLE_DEVICES='')
+    cmd = [sys.executable, os.path.abspath(__file__), '--cpu-worker', '{},{},{},{},{}'.format(nx, ny, steps, int(refactor), scheme)]
+    procs = [subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, env=env) for _ in range(n)]
+    res = []
+    for p in procs:
+        out, _ = p.communicate()
+        for ln in out.splitlines():
+            if ln.startswith('{'):
+                res.append(json.loads(ln))
+    if not res:
+        raise RuntimeError('no CPU worker finished')
+    secs = max(r['loop_seconds'] for r in res)
+    return sum(r['n_dof'] for r in res) * steps / secs, res[0]['n_dof'], secs, len(res)
+
+
 def run_reference_arm(args):
     """--impl reference: the reference's CPU algorithm (oracle port, re-factorising at every solve call the way
-    dolfin's solve(A, x, b) does) on a bounded sample of the workload, timed on the host cores."""
+    dolfin's solve(A, x, b) does) on a bounded sample of the workload, on all host cores (one oracle rank per core)."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     nx, ny = 221, 55
     steps = max(1, args.steps)
     t0 = time.time()
-    for _ in range(min(args.warmup, 1)):
-        cpu_oracle_rate(nx, ny, 1, True)
-    rate, n_dof, secs = cpu_oracle_rate(nx, ny, steps, True)
+    rate, n_dof, secs, cores = cpu_oracle_rate_all_cores(nx, ny, steps, True, args.scheme)
     line = {
-        'metric': 'dof-updates/sec (fp64, device-timed)', 'value': rate, 'unit': 'dof-updates/s', 'impl': 'reference', 'n_gpus': args.gpus,
+        'metric': METRIC, 'value': rate, 'unit': 'dof-updates/s', 'impl': 'reference', 'n_gpus': args.gpus,
         'steps': steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * secs / steps, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': 'SE weak P1/RT1 wave on a structured rectangle; CPU sample {}x{}x2 cells ({} dofs) of the '
-                               '7072x1768x2 workload, same CFL ratio; timed with the host clock around the step loop (this arm has '
-                               'no device)'.format(nx, ny, n_dof)},
-        'cpu_baseline': {'value': rate, 'unit': 'dof-updates/s', 'cores': 1, 'kind': 'port',
-                         'sample': '{} steps on {}x{}x2 cells, scipy SuperLU re-factorised at every solve (dolfin solve(A,x,b) '
-                                   'behaviour); the real dolfin/PETSc stack is not installable here'.format(steps, nx, ny)},
+        'config': {'workload': '{} weak P1/RT1 wave on a structured rectangle; CPU sample: {} independent oracle ranks (one per host core), each '
+                               '{}x{}x2 cells ({} dofs) of the 7072x1768x2 workload at the same CFL ratio; timed with the host clock around the step '
+                               'loop (this arm has no device); the bench arm runs the full 50 M-dof mesh per GPU'.format(args.scheme, cores, nx, ny, n_dof)},
+        'cpu_baseline': {'value': rate, 'unit': 'dof-updates/s', 'cores': cores, 'kind': 'port',
+                         'sample': '{} steps on {} x ({}x{}x2 cells), scipy SuperLU re-factorised at every solve (dolfin solve(A,x,b) '
+                                   'behaviour); the real dolfin/PETSc stack is not installable here'.format(steps, cores, nx, ny)},
         'e2e': {'value': rate, 'unit': 'dof-updates/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'wall_s': time.time() - t0,
     }
@@ -117,7 +149,7 @@ def run_sweep_bench(args):
     cases = sweep_cases(n_cases * world)[rank * n_cases:(rank + 1) * n_cases]
     dt = 1e-3
     t0 = time.time()
-    H, nc, solver = wave_sweep_solve(dt * args.warmup, args.warmup, 0, 1.0, 0.25, cases, mesh=mesh, patch_cells=args.patch_cells,
+    H, nc, solver = wave_sweep_solve(dt * args.warmup, args.warmup, 0, 1.0, 0.25, cases, mesh=mesh, patch_cells=args.patch_cells if args.patch_cells > 0 else None,
                                      extrap_order=args.extrap, return_solver=True)
     setup_s = time.time() - t0
     torch.cuda.synchronize()
@@ -131,7 +163,7 @@ def run_sweep_bench(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dev_s = float(tt.item())
     if rank == 0:
-        print(json.dumps({'metric': 'dof-updates/sec (fp64, device-timed)', 'value': world * n_cases * n_dof_case * args.steps / dev_s,
+        print(json.dumps({'metric': METRIC, 'value': world * n_cases * n_dof_case * args.steps / dev_s,
                           'unit': 'dof-updates/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
                           'ms_per_step': 1e3 * dev_s / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
                           'dtype': 'f64', 'data': 'synthetic',
@@ -144,122 +176,54 @@ def run_sweep_bench(args):
         dist.destroy_process_group()
 
 
-# DRAM bytes per cell and Chebyshev iteration of the two solve kernels, from the committed `ncu --set full` captures
-# (profiles/r1b_ncu_full_lean_solves.txt: dram__bytes_read.sum + dram__bytes_write.sum of one launch / cells / iterations)
-P_NCU_BYTES, Q_NCU_BYTES = 48.0, 99.0
+def ncu_dram_bytes():
+    """DRAM bytes per cell and Chebyshev iteration of the solve kernels, from the committed `ncu --set full` captures
+    (profiles/ncu_dram_bytes.json, written by profiles/ncu_extract.py from the .ncu-rep of the capture)."""
+    try:
+        return json.load(open(os.path.join(ROOT, 'profiles', 'ncu_dram_bytes.json')))
+    except Exception:
+        return {}
 
 
 def main():
-    """Runs the benchmark.  If the pipelined configuration fails on one GPU, it is tried once more in a fresh process (a CUDA error
-    poisons the process it happened in); if that fails too, the lean configuration is measured instead.  The JSON line says which of
-    the three it is (config.fallback is absent for a clean first run)."""
-    try:
-        return run_bench()
-    except SystemExit:
-        raise
-    except Exception as ex:
-        def argval(name, default):
-            return sys.argv[sys.argv.index(name) + 1] if name in sys.argv and sys.argv.index(name) + 1 < len(sys.argv) else default
-        if argval('--pipe', 'auto') == 'none' or int(os.environ.get('WORLD_SIZE', '1')) != 1 or argval('--impl', 'b200') != 'b200' \
-                or argval('--workload', 'mesh50m') != 'mesh50m' or os.environ.get('PHW_BENCH_NO_FALLBACK'):
-            raise
-        argv = [a for a in sys.argv[1:]]
-        env = dict(os.environ)
-        if not os.environ.get('PHW_BENCH_RETRIED'):
-            note = 'first pipelined attempt failed ({}); this is the second attempt in a fresh process'.format(str(ex)[:160])
-            env['PHW_BENCH_RETRIED'] = '1'
-        else:
-            note = 'pipelined runs failed twice ({}); lean configuration measured instead'.format(str(ex)[:160])
-            if '--pipe' in argv:
-                i = argv.index('--pipe'); del argv[i:i + 2]
-            argv += ['--pipe', 'none']
-        sys.stderr.write('bench.py: {}\n'.format(note))
-        r = subprocess.run([sys.executable, os.path.abspath(__file__)] + argv, capture_output=True, text=True, env=env)
-        sys.stderr.write(r.stderr[-2000:])
-        for ln in r.stdout.splitlines():
-            if ln.startswith('{'):
-                d = json.loads(ln)
-                cfg = d.setdefault('config', {})
-                cfg['fallback'] = note if 'fallback' not in cfg else note + ' | ' + cfg['fallback']
-                print(json.dumps(d))
-            elif ln.strip():
-                print(ln)
-        return r.returncode
+    """Runs the benchmark.  A failure of the pipelined configuration is an error: there is no silent fall-back to other kernels
+    (round 1 had one; the default path has since run 12 000 + 20 000 full-size steps without a fault)."""
+    return run_bench()
 
 
-def run_bench():
-    ap = argparse.ArgumentParser()
-    ap.add_argument('--workload', default='mesh50m', choices=['mesh50m', 'sweep'])
-    ap.add_argument('--cases', type=int, default=1024)
-    ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
-    ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--impl', default='b200')
-    ap.add_argument('--nx', type=int, default=FULL_NX)
-    ap.add_argument('--ny', type=int, default=FULL_NY)
-    ap.add_argument('--scheme', default='SE')
-    ap.add_argument('--patch-cells', type=int, default=0, help='cells per patch (0: 2048, or 1024 with --pipe so that two stages fit in shared memory)')
-    ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--tol', type=float, default=1e-13)
-    ap.add_argument('--extrap', type=int, default=3)
-    ap.add_argument('--extrap-q', type=int, default=0, help='extrapolation order of the q solves (0: same as --extrap)')
-    ap.add_argument('--phase', type=float, default=0.25, help='phase omega*t0 / pi of the standing wave the run starts from (0: the t = 0 state of wave_2D.py:734)')
-    ap.add_argument('--two-sweep', action='store_true', help='two Chebyshev iterations per pass in the mass solves (csrc/kernels2.cuh; A/B)')
-    ap.add_argument('--ell-staged', action='store_true', help='ELL rows of the M_p solve staged in shared memory by cp.async (A/B)')
-    ap.add_argument('--cell-rows', action='store_true', help='cell-based instead of assembled (ELL) rows in the M_p solve (A/B)')
-    ap.add_argument('--pipe', default='auto', help="'auto' (default): 'pqer' on one GPU, 'none' on several (the pipelined kernels carry no inter-GPU exchange yet); 'none': lean kernels; " +
-                    "bulk-copy pipelined kernels (csrc/kernels_pipe.cuh; A/B): any of 'p' (M_p solve), 'q' (M_q solve), 'e' (fused H_wave reduction), 'r' (right-hand sides), 'Q' / 'P' (EXPERIMENTAL pipelined two-sweep M_q / M_p solves, 768-cell patches)")
-    ap.add_argument('--stream-probe', action='store_true', help='print the bandwidth of a pure streaming pass over the ELL M_p data (diagnostics)')
-    ap.add_argument('--debug-residuals', action='store_true', help='print the residual history of the last M_p / M_q solve to stderr')
-    args = ap.parse_args()
-    if args.pipe == 'auto':
-        args.pipe = 'pqer' if int(os.environ.get('WORLD_SIZE', '1')) == 1 else 'none'
-    if args.pipe == 'none':
-        args.pipe = ''
-    if args.patch_cells <= 0:
-        args.patch_cells = 768 if ('Q' in args.pipe or 'P' in args.pipe) else (1024 if 'q' in args.pipe else 2048)
-    if args.impl == 'reference':
-        return run_reference_arm(args)
-    if args.workload == 'sweep':
-        return run_sweep_bench(args)
+def pipe_flags(pipe):
+    return (256 if 'q' in pipe else 0) | (512 if 'p' in pipe else 0) | (2048 if 'e' in pipe else 0) | (4096 if 'r' in pipe else 0)
 
-    import torch
-    import torch.distributed as dist
-    rank = int(os.environ.get('RANK', '0'))
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
-    if not torch.cuda.is_available():
-        raise SystemExit('bench.py needs a CUDA device (no CPU fallback)')
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
-    from porthamiltonian_fem_b200 import _lib
-    from porthamiltonian_fem_b200.mesh import rectangle_structured
-    from porthamiltonian_fem_b200.solver import Mesh, Solver, tag_boundary_edges
 
-    # ---- setup (not timed): mesh, layout, device SoA.  Weak scaling: every rank owns one slab of nx x ny quads of a
-    # global rectangle (world x 1.0) x 0.25 partitioned into x-slabs; halo values travel as peer-memory stores.
+def build_case(args, torch, dist, rank, world, local_rank, nx_local, x_per_rank):
+    """setup (not timed): slab `rank` of a global rectangle (world * x_per_rank) x 0.25, nx_local x ny quads per slab; layout, device
+    SoA, peer exchange, state = exact standing wave at phase args.phase (or rest + the reference's default input)."""
+    from porthamiltonian_fem_b200 import _lib, partition as pt
+    from porthamiltonian_fem_b200.solver import Mesh, Solver, tag_boundary_edges, port_weights, setup_peer_exchange
     t_setup = time.time()
-    from porthamiltonian_fem_b200 import partition as pt
-    from porthamiltonian_fem_b200.solver import port_weights, setup_peer_exchange
-    part = pt.structured_slab_part(args.nx, args.ny, world, rank, 1.0, 0.25)
+    part = pt.structured_slab_part(nx_local, args.ny, world, rank, x_per_rank, 0.25)
     vertices = part.vertices
     if world > 1:
         m = Mesh(part.vertices, part.cells, patch_cells=args.patch_cells, vertex_external=part.vertex_external,
-                 edge_external=part.edge_external)
+                 edge_external=part.edge_external, cell_owned=part.cell_owned)
     else:
         m = Mesh(part.vertices, part.cells, patch_cells=args.patch_cells)
-    # state and left datum of the reference's 'analytical' case (wave_2D.py:375-377,734-738): a standing wave that
-    # populates every dof, so each step updates a fully non-trivial field
-    xL, yL = 1.0 * world, 0.25
+    xL, yL = x_per_rank * world, 0.25
     omega = np.sqrt(K_WAVE / RHO) * np.sqrt(np.pi ** 2 / (4 * xL ** 2) + 4 * np.pi ** 2 / yL ** 2)
     tags = tag_boundary_edges(m, 'R', xL, yL)
-    m.set_boundary(tags, port_weights(m, tags, lambda x, y: RHO * omega * np.sin(2 * np.pi * y / yL + np.pi / 2)))
-    dt = DT_FULL * FULL_NX / args.nx
+    if args.from_rest:
+        m.set_boundary(tags)
+    else:
+        m.set_boundary(tags, port_weights(m, tags, lambda x, y: RHO * omega * np.sin(2 * np.pi * y / yL + np.pi / 2)))
+    dt = DT_FULL * FULL_NX * x_per_rank / nx_local     # same CFL ratio as 7072 quads per unit length
     prm = _lib.PhwParams()
     prm.scheme, prm.dt, prm.K_wave, prm.rho = _lib.SCHEMES[args.scheme], dt, K_WAVE, RHO
-    prm.input_kind, prm.in_amp, prm.in_omega = _lib.IN_COSINE, 1.0, omega
-    prm.tol, prm.max_iter, prm.flags, prm.extrap_order = args.tol, 200, 4 | (16 if args.two_sweep else 0) | (32 if args.cell_rows else 0) | (64 if args.ell_staged else 0) | (256 if 'q' in args.pipe else 0) | (512 if 'p' in args.pipe else 0) | (2048 if 'e' in args.pipe else 0) | (4096 if 'r' in args.pipe else 0) | (8192 if 'Q' in args.pipe else 0) | (16384 if 'P' in args.pipe else 0), args.extrap
+    if args.from_rest:
+        prm.input_kind, prm.in_amp, prm.in_omega, prm.in_t_stop = _lib.IN_SINE_WINDOW, 10.0, 8 * np.pi, 0.25    # wave_2D.py:384
+    else:
+        prm.input_kind, prm.in_amp, prm.in_omega = _lib.IN_COSINE, 1.0, omega
+    prm.tol, prm.max_iter, prm.extrap_order = args.tol, 200, args.extrap
+    prm.flags = 4 | (32 if args.cell_rows else 0) | (64 if args.ell_staged else 0) | pipe_flags(args.pipe)
     prm.extrap_order_q = args.extrap_q
     solver = Solver(m, prm, device=local_rank)
     n_dof_local = int((part.vertex_owner == rank).sum() + (part.edge_owner == rank).sum())
@@ -275,25 +239,92 @@ def run_bench():
     # edge fluxes (3-point Gauss on every edge).  At w t0 = 0 this is the reference's initial state (q = 0); the default pi/4 is
     # a generic instant of the run, where both fields and both velocities are O(1) of their amplitudes.
     phase = np.pi * args.phase
-    p0 = RHO * omega * np.cos(np.pi * vertices[:, 0] / (2 * xL)) * np.cos(2 * np.pi * vertices[:, 1] / yL) * np.cos(phase)
-    q0 = np.zeros(m.n_edges)
-    if args.phase != 0.0:
-        edges = m.edges()[0]
-        a, b = vertices[edges[:, 0]], vertices[edges[:, 1]]
-        tx, ty = b[:, 0] - a[:, 0], b[:, 1] - a[:, 1]
-        kx, ky = np.pi / (2 * xL), 2 * np.pi / yL
-        for gp, gw in zip((0.5 - np.sqrt(0.15), 0.5, 0.5 + np.sqrt(0.15)), (5.0 / 18, 8.0 / 18, 5.0 / 18)):
-            x, y = a[:, 0] + gp * tx, a[:, 1] + gp * ty
-            qx = kx * np.sin(kx * x) * np.cos(ky * y)
-            qy = ky * np.cos(kx * x) * np.sin(ky * y)
-            q0 += gw * (qx * ty - qy * tx)              # q . (|e| n_e), n_e = tangent (lo -> hi) rotated by -90 degrees
-        q0 *= np.sin(phase)
-        del edges, a, b, tx, ty, x, y, qx, qy
-    solver.set_state(p=p0, q=q0, x3=np.zeros(3))
-    solver.set_time(phase / omega)
-    del p0, q0
-    setup_s = time.time() - t_setup
-    del vertices
+    kx, ky = np.pi / (2 * xL), 2 * np.pi / yL
+    pshape = RHO * omega * np.cos(kx * vertices[:, 0]) * np.cos(ky * vertices[:, 1])      # spatial factor of the exact p at the vertices
+    if args.from_rest:
+        solver.set_state(p=np.zeros(m.n_vertices), q=np.zeros(m.n_edges), x3=np.zeros(3))
+        t0_sim = 0.0
+    else:
+        q0 = np.zeros(m.n_edges)
+        if args.phase != 0.0:
+            edges = m.edges()[0]
+            a, b = vertices[edges[:, 0]], vertices[edges[:, 1]]
+            tx, ty = b[:, 0] - a[:, 0], b[:, 1] - a[:, 1]
+            for gp, gw in zip((0.5 - np.sqrt(0.15), 0.5, 0.5 + np.sqrt(0.15)), (5.0 / 18, 8.0 / 18, 5.0 / 18)):
+                x, y = a[:, 0] + gp * tx, a[:, 1] + gp * ty
+                qx = kx * np.sin(kx * x) * np.cos(ky * y)
+                qy = ky * np.cos(kx * x) * np.sin(ky * y)
+                q0 += gw * (qx * ty - qy * tx)              # q . (|e| n_e), n_e = tangent (lo -> hi) rotated by -90 degrees
+            q0 *= np.sin(phase)
+            del edges, a, b, tx, ty, x, y, qx, qy
+        solver.set_state(p=pshape * np.cos(phase), q=q0, x3=np.zeros(3))
+        t0_sim = phase / omega
+        solver.set_time(t0_sim)
+        del q0
+    return dict(solver=solver, m=m, part=part, n_dof_local=n_dof_local, n_cells_local=n_cells_local, n_dof=n_dof,
+                n_cells_total=n_cells_total, omega=omega, dt=dt, t0=t0_sim, pshape=pshape, nx_local=nx_local, x_per_rank=x_per_rank,
+                setup_s=time.time() - t_setup, steps_done=0)
+
+
+def run_bench():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--workload', default='mesh50m', choices=['mesh50m', 'sweep', 'paper'])
+    ap.add_argument('--cases', type=int, default=1024)
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200')
+    ap.add_argument('--nx', type=int, default=FULL_NX)
+    ap.add_argument('--ny', type=int, default=FULL_NY)
+    ap.add_argument('--scheme', default='SE')
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'], help="N > 1: 'weak' (default) one nx x ny slab per GPU as the headline and the "
+                    "strong-scaling run of ONE nx x ny mesh in config.strong; 'strong': the strong-scaling run is the headline (value, ms_per_step)")
+    ap.add_argument('--no-strong', action='store_true', help='N > 1: skip the strong-scaling part')
+    ap.add_argument('--from-rest', action='store_true', help="zero initial state and the reference's default input g(t) = 10 sin(8 pi t), t < 0.25 (wave_2D.py:384)")
+    ap.add_argument('--patch-cells', type=int, default=0, help='cells per patch (0: 1024 with the pipelined M_q solve so that two stages fit in shared memory, else 2048)')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--tol', type=float, default=1e-13)
+    ap.add_argument('--extrap', type=int, default=3)
+    ap.add_argument('--extrap-q', type=int, default=0, help='extrapolation order of the q solves (0: same as --extrap)')
+    ap.add_argument('--phase', type=float, default=0.25, help='phase omega*t0 / pi of the standing wave the run starts from (0: the t = 0 state of wave_2D.py:734)')
+    ap.add_argument('--ell-staged', action='store_true', help='ELL rows of the M_p solve staged in shared memory by cp.async (A/B)')
+    ap.add_argument('--cell-rows', action='store_true', help='cell-based instead of assembled (ELL) rows in the M_p solve (A/B)')
+    ap.add_argument('--pipe', default='auto', help="'auto' (default) = 'pqer': all bulk-copy pipelined kernels (csrc/kernels_pipe.cuh), on one GPU and in partitioned runs; "
+                    "'none': lean kernels; or any of 'p' (M_p solve), 'q' (M_q solve), 'e' (fused H_wave reduction), 'r' (right-hand sides)")
+    ap.add_argument('--stream-probe', action='store_true', help='print the bandwidth of a pure streaming pass over the ELL M_p data (diagnostics)')
+    ap.add_argument('--debug-residuals', action='store_true', help='print the residual history of the last M_p / M_q solve to stderr')
+    ap.add_argument('--cpu-worker', default=None, help=argparse.SUPPRESS)
+    args = ap.parse_args()
+    if args.cpu_worker:      # one oracle rank of the CPU arms (see cpu_oracle_rate_all_cores)
+        nx, ny, steps, refactor, scheme = args.cpu_worker.split(',')
+        rate, n_dof, secs = cpu_oracle_rate(int(nx), int(ny), int(steps), bool(int(refactor)), scheme)
+        print(json.dumps({'rate': rate, 'n_dof': n_dof, 'loop_seconds': secs}))
+        return
+    if args.pipe == 'auto':
+        args.pipe = 'pqer'
+    if args.pipe == 'none':
+        args.pipe = ''
+    if args.patch_cells <= 0 and args.workload == 'mesh50m':
+        args.patch_cells = 1024 if 'q' in args.pipe else 2048
+    if args.impl == 'reference':
+        return run_reference_arm(args)
+    if args.workload == 'sweep':
+        return run_sweep_bench(args)
+    if args.workload == 'paper':
+        from profiles.paper_cases import run_paper_bench
+        return run_paper_bench(args)
+
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device (no CPU fallback)')
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    from porthamiltonian_fem_b200 import _lib
 
     def barrier():
         torch.cuda.synchronize()
@@ -301,34 +332,57 @@ def run_bench():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up
-    barrier()
-    solver.run(args.warmup)
-    barrier()
-    # ---- timed region: K steps, device events inside phw_run on the solver's stream
-    samples, stop = [], threading.Event()
-    th = threading.Thread(target=clocks_sampler, args=(stop, samples, local_rank), daemon=True)
-    th.start()
-    barrier()
-    t0 = time.perf_counter()
-    H = solver.run(args.steps)
-    barrier()
-    wall = time.perf_counter() - t0
-    stop.set()
-    th.join(timeout=2)
-    st = solver.stats()
+    def allmax(x):
+        if world == 1:
+            return x
+        tt = torch.tensor([x], dtype=torch.float64, device='cuda')
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    def allsum(xs):
+        if world == 1:
+            return list(xs)
+        tt = torch.tensor(list(xs), dtype=torch.float64, device='cuda')
+        dist.all_reduce(tt)
+        return [float(v) for v in tt.tolist()]
+
+    def measure(case, steps, warmup, sample_clocks):
+        """W warm-up steps, then EXACTLY `steps` steps bracketed by barrier + synchronize; device time = CUDA events inside
+        phw_run on the solver's stream, max over ranks"""
+        solver = case['solver']
+        barrier()
+        solver.run(warmup)
+        barrier()
+        samples, stop = [], threading.Event()
+        th = None
+        if sample_clocks:
+            th = threading.Thread(target=clocks_sampler, args=(stop, samples, local_rank), daemon=True)
+            th.start()
+        barrier()
+        t0 = time.perf_counter()
+        solver.run(steps)
+        barrier()
+        wall = time.perf_counter() - t0
+        stop.set()
+        if th:
+            th.join(timeout=2)
+        st = solver.stats()
+        case['steps_done'] += warmup + steps
+        return dict(dev_s=allmax(st['device_ms'] * 1e-3), st=st, samples=samples, wall=wall)
+
+    # ---- weak configuration (headline): every rank owns one slab of nx x ny quads of a (world x 1.0) x 0.25 rectangle
+    weak = build_case(args, torch, dist, rank, world, local_rank, args.nx, 1.0)
+    solver, m = weak['solver'], weak['m']
+    r = measure(weak, args.steps, args.warmup, True)
+    st, dev_s, samples, wall = r['st'], r['dev_s'], r['samples'], r['wall']
     if args.stream_probe and rank == 0:
         for nt, occ in ((256, 8), (256, 4), (512, 4), (1024, 2), (128, 16), (256, 2)):
             ms, nb = solver.stream_probe(nt, occ, 10)
             sys.stderr.write('stream probe {} threads x {} CTAs/SM: {:.4f} ms per pass, {:.3f} GB, {:.0f} GB/s\n'.format(nt, occ, ms, nb / 1e9, nb / ms / 1e6))
     if args.debug_residuals and rank == 0:
         for w, nm in ((0, 'M_p'), (1, 'M_q')):
-            sys.stderr.write('residual history {}: {}\n'.format(nm, ' '.join('%.1e' % r for r in solver.residual_history(w))))
-    dev_s = st['device_ms'] * 1e-3
-    if world > 1:
-        tt = torch.tensor([dev_s], dtype=torch.float64, device='cuda')
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dev_s = float(tt.item())
+            sys.stderr.write('residual history {}: {}\n'.format(nm, ' '.join('%.1e' % r_ for r_ in solver.residual_history(w))))
+    n_dof = weak['n_dof']
     value = n_dof * args.steps / dev_s
 
     # ---- end-to-end through host buffers (pinned), copies inside the timed region
@@ -345,16 +399,50 @@ def run_bench():
     _lib.check(lib.phw_run(solver.handle, args.steps, H_host.numpy().ctypes.data))
     _lib.check(lib.phw_get_state(solver.handle, p_np.ctypes.data, q_np.ctypes.data, x_host.ctypes.data))
     barrier()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        tt = torch.tensor([e2e_s], dtype=torch.float64, device='cuda')
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_s = float(tt.item())
-    st2 = solver.stats()
+    e2e_s = allmax(time.perf_counter() - t0)
+    weak['steps_done'] += args.steps
     e2e_value = n_dof * args.steps / e2e_s
     nloc = m.n_vertices + m.n_edges
     h2d = world * (nloc * 8 + 24) / args.steps
     d2h = world * (nloc * 8 + 24 + args.steps * 8 * 8) / args.steps
+    # ---- correctness at bench size: the state just read back against the exact standing wave at the simulated time (nodal values
+    # of p on this rank's vertices; first-order scheme, so the expected level is O(omega dt) for SE and O((omega dt)^2) for SV)
+    exact = None
+    if not args.from_rest:
+        t_end = weak['t0'] + weak['steps_done'] * weak['dt']
+        pe = weak['pshape'] * np.cos(weak['omega'] * t_end)
+        d = p_np - pe
+        s2, e2, finite = allsum([float(d @ d), float(pe @ pe), float(np.isfinite(p_np).all() and np.isfinite(q_np).all())])
+        emax, pmax = allmax(float(np.abs(d).max())), allmax(float(np.abs(pe).max()))
+        exact = {'p_nodal_rel_l2': float(np.sqrt(s2 / e2)), 'p_nodal_max_over_amplitude': emax / pmax, 'all_finite': finite == world,
+                 'steps_from_exact_start': weak['steps_done'], 'omega_dt': weak['omega'] * weak['dt'],
+                 'note': 'exact p = rho w cos(pi x / 2 xL) cos(2 pi y / yL) cos(w t) (wave_2D.py:734-741); the scheme is O(w dt) (SE) / O((w dt)^2) (SV) accurate'}
+        del pe, d
+    del p_host, q_host, p_np, q_np
+
+    # ---- strong scaling of ONE nx x ny mesh over the N GPUs (BASELINE configs[3] as stated; role of run_main_wave_2D_mpi.sh:1)
+    strong = None
+    if world > 1 and not args.no_strong and args.nx % (2 * world) == 0:
+        sc = build_case(args, torch, dist, rank, world, local_rank, args.nx // world, 1.0 / world)
+        rs = measure(sc, args.steps, max(args.warmup, 5), False)
+        ms1, ms1_src = None, None
+        try:     # the 1-GPU time of the same mesh: the last committed 1-GPU line of this bench
+            ref = json.load(open(os.path.join(ROOT, 'profiles', 'bench_1gpu_reference.json')))
+            if ref.get('config', {}).get('dofs_total') == sc['n_dof'] and ref.get('steps'):
+                ms1, ms1_src = float(ref['ms_per_step']), 'profiles/bench_1gpu_reference.json (committed 1-GPU line of this bench, same mesh)'
+        except Exception:
+            pass
+        ms_strong = 1e3 * rs['dev_s'] / args.steps
+        ms_weak = 1e3 * dev_s / args.steps
+        strong = {'dofs_total': sc['n_dof'], 'dofs_per_gpu': sc['n_dof_local'], 'ms_per_step': ms_strong, 'value': sc['n_dof'] * args.steps / rs['dev_s'],
+                  'iters_per_solve_p': rs['st']['iters_p'] / max(1, rs['st']['solves_p']), 'iters_per_solve_q': rs['st']['iters_q'] / max(1, rs['st']['solves_q']),
+                  'ms_per_iter_p': rs['st']['ms_solve_p'] / max(1, rs['st']['iters_p']), 'ms_per_iter_q': rs['st']['ms_solve_q'] / max(1, rs['st']['iters_q']),
+                  'max_rel_residual': rs['st']['max_rel_residual'], 'setup_seconds': sc['setup_s'],
+                  'efficiency_vs_weak_slab': ms_weak / (world * ms_strong),
+                  'efficiency_vs_weak_slab_note': 'T(one 50 M-dof slab per GPU, this run, exchange included) / (N x T(50 M dofs over N GPUs))',
+                  'ms_per_step_1gpu': ms1, 'ms_per_step_1gpu_source': ms1_src, 'efficiency': (ms1 / (world * ms_strong)) if ms1 else None}
+        sc['solver'].close()
+        sc['m'].close()
 
     if rank == 0:
         peaks = {}
@@ -366,58 +454,62 @@ def run_bench():
         peak_src = 'measured (MEASURED_PEAKS.json hbm_gbs)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s (B200_PROFILING.md)'
         # the two solve kernels take ~85 % of the step; the one with the larger share of the timed region is reported as
         # the dominant kernel.  Algorithmic bytes per cell and Chebyshev iteration: 40 (M_p), 96 (M_q).
-        # traffic = DRAM bytes of one launch from the committed ncu --set full capture (profiles/r1_ncu_full_solve_kernels.txt:
-        # P_NCU_BYTES (M_p) and Q_NCU_BYTES (M_q) per cell and iteration), scaled to this run's iterations per launch.
-        nc = n_cells_local
+        nc = weak['n_cells_local']
         paths = int(st.get('kernel_paths', 0))      # phw_path bits: 1 lean M_p, 2 lean M_q, 4 pipelined M_p, 8 pipelined M_q
+        ncu = ncu_dram_bytes()
         kern = {}
-        for key, name, alg, ncu_b, it, ms, solves in (
-                ('p', ('solve2_ell_pipe_k' if paths & 128 else 'solve_ell_pipe_k' if paths & 4 else 'solve_ell_coop_k' if paths & 1 else 'solve2_coop_k<0>' if args.two_sweep else 'solve_coop_k<0>') +
-                 ' (Chebyshev M_p solve, all iterations in one cooperative launch)', 40.0, P_NCU_BYTES, st['iters_p'], st['ms_solve_p'], st['solves_p']),
-                ('q', ('solve2_mq_pipe_k' if paths & 64 else 'solve_mq_pipe_k' if paths & 8 else 'solve_mq_coop_k' if paths & 2 else 'solve2_coop_k<1>' if args.two_sweep else 'solve_coop_k<1>') +
-                 ' (Chebyshev M_q solve, all iterations in one cooperative launch)', 96.0, Q_NCU_BYTES, st['iters_q'], st['ms_solve_q'], st['solves_q'])):
+        for key, short, alg, it, ms, solves in (
+                ('p', 'solve_ell_pipe_k' if paths & 4 else 'solve_ell_coop_k' if paths & 1 else 'solve_coop_k<0>', 40.0, st['iters_p'], st['ms_solve_p'], st['solves_p']),
+                ('q', 'solve_mq_pipe_k' if paths & 8 else 'solve_mq_coop_k' if paths & 2 else 'solve_coop_k<1>', 96.0, st['iters_q'], st['ms_solve_q'], st['solves_q'])):
             ach = alg * nc * it / (ms * 1e-3) / 1e9 if ms > 0 else None
-            kern[key] = {'kernel': name, 'achieved': ach, 'frac': (ach / peak) if ach else None, 'share_of_step': ms / st['device_ms'],
+            nb = ncu.get(short, {})
+            kern[key] = {'kernel': short + ' (Chebyshev M_{} solve, all iterations in one cooperative launch)'.format(key), 'achieved': ach,
+                         'frac': (ach / peak) if ach else None, 'share_of_step': ms / st['device_ms'],
                          'bytes_per_launch': alg * nc * it / max(1, solves), 'ms_per_launch': ms / max(1, solves),
-                         'ms_per_iteration': ms / max(1, it), 'traffic': ncu_b * nc * it / max(1, solves)}
+                         'ms_per_iteration': ms / max(1, it),
+                         'traffic': (nb['dram_bytes_per_cell_iteration'] * nc * it / max(1, solves)) if nb else None,
+                         'traffic_source': nb.get('source') if nb else None}
         dom = kern['p'] if kern['p']['share_of_step'] >= kern['q']['share_of_step'] else kern['q']
         oth = kern['q'] if dom is kern['p'] else kern['p']
-        achieved = dom['achieved']
         line = {
-            'metric': 'dof-updates/sec (fp64, device-timed)', 'value': value, 'unit': 'dof-updates/s',
+            'metric': METRIC, 'value': value, 'unit': 'dof-updates/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dev_s / args.steps,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': '{} weak P1/RT1 wave, exact standing wave of the analytical case at phase w*t0 = {:.3g} pi with its left datum (wave_2D.py:375-377,734), structured rectangle {}x{}x2 = {} cells and {} dofs per GPU ({} dofs in total, x-slab partition, peer-memory halo exchange), dt={:g}; '
-                                   'state vectors ({:.0f} MB each) exceed L2, no flush needed'.format(
-                                       args.scheme, args.phase, args.nx, args.ny, nc, n_dof_local, n_dof, dt, 8e-6 * m.n_edges),
-                       'dofs_per_gpu': n_dof_local, 'dofs_total': n_dof, 'patch_cells': args.patch_cells, 'phase_over_pi': args.phase, 'two_sweep': bool(args.two_sweep), 'pipe': args.pipe, 'tol': args.tol, 'extrap_order': args.extrap,
+            'config': {'workload': '{} weak P1/RT1 wave, {}, structured rectangle {}x{}x2 = {} cells and {} dofs per GPU ({} dofs in total, x-slab partition, peer-memory halo exchange '
+                                   'fused into the solve kernels), dt={:g}; state vectors ({:.0f} MB each) exceed L2, no flush needed'.format(
+                                       args.scheme,
+                                       "zero state + the reference's default input 10 sin(8 pi t) (wave_2D.py:384)" if args.from_rest else
+                                       'exact standing wave of the analytical case at phase w*t0 = {:.3g} pi with its left datum (wave_2D.py:375-377,734)'.format(args.phase),
+                                       args.nx, args.ny, nc, weak['n_dof_local'], n_dof, weak['dt'], 8e-6 * m.n_edges),
+                       'dofs_per_gpu': weak['n_dof_local'], 'dofs_total': n_dof, 'patch_cells': args.patch_cells, 'phase_over_pi': args.phase, 'pipe': args.pipe, 'tol': args.tol, 'extrap_order': args.extrap,
                        'iters_per_solve_p': st['iters_p'] / max(1, st['solves_p']), 'iters_per_solve_q': st['iters_q'] / max(1, st['solves_q']),
-                       'max_rel_residual': st['max_rel_residual'], 'setup_seconds': setup_s},
+                       'max_rel_residual': st['max_rel_residual'], 'setup_seconds': weak['setup_s'], 'exact_error': exact, 'strong': strong},
             'e2e': {'value': e2e_value, 'unit': 'dof-updates/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'seconds': e2e_s},
             'gpu_launches': int(st['kernel_launches']),
             'clocks': summarize_clocks(samples),
-            'roofline': {'bound': 'hbm', 'kernel': dom['kernel'], 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                         'frac': dom['frac'], 'traffic': dom['traffic'], 'peak_source': peak_src,
-                         'traffic_source': 'dram__bytes_read.sum + dram__bytes_write.sum per cell and iteration of the committed ncu --set full capture '
-                                           'of the lean solve kernels (profiles/r1b_ncu_full_lean_solves.txt: 48 / 99 B), scaled to this launch' +
-                                           ('; the pipelined kernels read the same streams, no capture of their own yet' if paths & 12 else ''),
+            'roofline': {'bound': 'hbm', 'kernel': dom['kernel'], 'achieved': dom['achieved'], 'peak': peak, 'unit': 'GB/s',
+                         'frac': dom['frac'], 'traffic': dom['traffic'], 'peak_source': peak_src, 'traffic_source': dom['traffic_source'],
                          'bytes_per_launch': dom['bytes_per_launch'], 'ms_per_launch': dom['ms_per_launch'],
                          'kernel_share_of_step': dom['share_of_step'], 'second_kernel': oth,
-                         'whole_loop_model_gbs': st['bytes_model'] / dev_s / 1e9, 'whole_loop_model_frac': st['bytes_model'] / dev_s / 1e9 / peak,
+                         'whole_loop_model_gbs': st['bytes_model'] / (st['device_ms'] * 1e-3) / 1e9, 'whole_loop_model_frac': st['bytes_model'] / (st['device_ms'] * 1e-3) / 1e9 / peak,
                          'ms_per_iter_q': kern['q']['ms_per_iteration'], 'ms_per_iter_p': kern['p']['ms_per_iteration']},
             'wall_s_timed_region': wall,
         }
+        if args.scaling == 'strong' and strong:
+            line.update({'value': strong['value'], 'ms_per_step': strong['ms_per_step'], 'scaling': 'strong'})
+            line['config']['weak'] = {'value': value, 'ms_per_step': 1e3 * dev_s / args.steps}
+            line['config']['dofs_total'], line['config']['dofs_per_gpu'] = strong['dofs_total'], strong['dofs_per_gpu']
         if not args.no_cpu_baseline:
             try:
                 t_cpu = time.time()
-                rate, nd, secs = cpu_oracle_rate(442, 110, 40, False)
-                line['cpu_baseline'] = {'value': rate, 'unit': 'dof-updates/s', 'cores': 1, 'kind': 'port',
-                                        'sample': '40 SE steps on a 442x110x2-cell mesh ({} dofs) of the same family, CPU oracle '
-                                                  '(scipy SuperLU, factor once: {:.1f} s in the step loop, {:.1f} s with assembly and '
-                                                  'factorisation)'.format(nd, secs, time.time() - t_cpu)}
+                rate, nd, secs, cores = cpu_oracle_rate_all_cores(442, 110, 40, False, args.scheme)
+                line['cpu_baseline'] = {'value': rate, 'unit': 'dof-updates/s', 'cores': cores, 'kind': 'port',
+                                        'sample': '40 {} steps on {} x (442x110x2-cell mesh, {} dofs) of the same family: one CPU-oracle rank per host core '
+                                                  '(scipy SuperLU is single-threaded; factor once: {:.1f} s in the slowest step loop, {:.1f} s with assembly and '
+                                                  'factorisation); one core alone: {:.3g} dof-updates/s'.format(args.scheme, cores, nd, secs, time.time() - t_cpu, rate / cores)}
             except Exception as ex:   # the bench line must still be printed
-                line['cpu_baseline'] = {'value': None, 'unit': 'dof-updates/s', 'cores': 1, 'kind': 'port', 'sample': 'failed: %r' % (ex,)}
+                line['cpu_baseline'] = {'value': None, 'unit': 'dof-updates/s', 'cores': host_cores(), 'kind': 'port', 'sample': 'failed: %r' % (ex,)}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -52,13 +52,12 @@ typedef struct phw_params {
     double H_init;           /* wave_2D.py:746,769,771 (computed by the caller with phw_energy) */
     double an_omega, an_xLength, an_yLength, an_xPoint, an_yPoint;  /* analytical case constants */
     double tol;              /* relative residual of the mass / block solves (default 1e-13) */
-    int32_t max_iter;        /* iteration cap per solve (default 200) */
+    int32_t max_iter;        /* iteration cap per solve (0: 200; wave_2D_solve passes 2000 - stretched cells need more than 200) */
     int32_t extrap_order;    /* initial guess of each solve = polynomial extrapolation of that solve's previous
                                 solutions: 0 last solution, 1 linear, 2 quadratic (default choice of the host code), 3 cubic ... 5 */
     int32_t flags;           /* bit0: disable first-same-as-last reuse in SV; bit1: synchronous error checks;
                                 bit2: CUDA-event timing of every solve kernel; bit3: force the multi-launch solve path;
-                                bit4: two-sweep mass solves (two Chebyshev iterations per pass over the data, csrc/kernels2.cuh;
-                                single GPU, weak form, explicit schemes; default off - see DESIGN.md section 10);
+                                bit4: (unused; was the two-sweep mass solves, removed in round 2: measured slower);
                                 bit5: cell-based instead of assembled (ELL) rows in the M_p solve;
                                 bit6: ELL rows of the M_p solve staged in shared memory by cp.async (whole patch in flight;
                                 A/B: slower than the direct loads);
@@ -68,14 +67,11 @@ typedef struct phw_params {
                                 one GPU; needs patches of <= ~1000 cells so that two stages fit - phw_solver_create fails otherwise);
                                 bit9: the same for the ELL M_p solve;
                                 bit10: the generic cooperative kernels (block solve of IE/SM/casimir, strong form, partitioned and
-                                higher-order CSR solves, two-sweep solves) synchronise the grid with the one-atomic-per-CTA barrier
+                                higher-order CSR solves) synchronise the grid with the one-atomic-per-CTA barrier
                                 of the lean kernels instead of cooperative-groups grid syncs;
                                 bit11: H_wave (both quadratic forms) in one bulk-copy pipelined pass over the own cells of every
                                 patch (64 instead of 88 B per cell; one GPU, unbatched runs);
-                                bit12: bulk-copy pipelined right-hand sides D p / D^T q (one GPU, unbatched, no casimir terms);
-                                bit13: EXPERIMENTAL - pipelined two-sweep M_q solve (csrc/kernels_pipe2.cuh: two iterations per
-                                pass over a ring-2 patch staged by bulk copies; patches of <= ~768 cells; not yet run on a GPU);
-                                bit14: EXPERIMENTAL - the same for the ELL M_p solve */
+                                bit12: bulk-copy pipelined right-hand sides D p / D^T q (one GPU, unbatched, no casimir terms); */
     int32_t extrap_order_q;  /* extrapolation order of the q (and block) solves; 0: same as extrap_order.  Orders up to 5 */
 } phw_params;
 
@@ -89,10 +85,13 @@ typedef struct phw_stats {
     double  ms_solve_p, ms_solve_q, ms_solve_block;   /* summed CUDA-event time of the solve kernels (flags bit2) */
     int64_t kernel_paths;       /* phw_path bits: which variants of the mass-solve kernels the last phw_run launched */
 } phw_stats;
-enum phw_path { PHW_PATH_LEAN_P = 1, PHW_PATH_LEAN_Q = 2, PHW_PATH_PIPE_P = 4, PHW_PATH_PIPE_Q = 8, PHW_PATH_PIPE_ENERGY = 16, PHW_PATH_PIPE_RHS = 32, PHW_PATH_PIPE2_Q = 64, PHW_PATH_PIPE2_P = 128 };
+enum phw_path { PHW_PATH_LEAN_P = 1, PHW_PATH_LEAN_Q = 2, PHW_PATH_PIPE_P = 4, PHW_PATH_PIPE_Q = 8, PHW_PATH_PIPE_ENERGY = 16, PHW_PATH_PIPE_RHS = 32 };
 
 const char* phw_last_error(void);
 int phw_version(void);
+/* sizeof(phw_params) (what = 0) / sizeof(phw_stats) (what = 1) as compiled into the library: lets a binding verify its struct
+ * layouts at load time */
+int phw_sizeof(int what);
 
 /* ---- mesh connectivity + patch layout: replaces mesh.topology / FunctionSpace dofmaps / MeshFunction
  *      markers (wave_2D.py:126,168-220,266-285).  Host-only, no GPU needed. ---- */
@@ -104,6 +103,10 @@ int phw_mesh_create(int64_t n_vertices, const double* vertices_xy, int64_t n_cel
 int phw_mesh_create_partitioned(int64_t n_vertices, const double* vertices_xy, int64_t n_cells, const int32_t* cells,
                                 int32_t patch_cells, const uint8_t* vertex_external, int64_t n_edges,
                                 const uint8_t* edge_external, phw_mesh_t* out);
+/* partitioned run, optional: cell_owned[n_cells] = 1 for the cells the partitioner gave to this rank, 0 for the halo cells of the
+ * local mesh (owned by a neighbour).  Needed by cell-based reductions (the fused H_wave pass, flags bit 11), which must count every
+ * cell of the global mesh exactly once; without it a partitioned run takes the row-based reductions. */
+int phw_mesh_set_cell_owned(phw_mesh_t m, const uint8_t* cell_owned);
 /* batched parameter sweep (BASELINE.json configs[4]; the reference runs its cases one after the other,
  * main_wave_2D.py:144): the mesh holds n_groups disjoint copies of one domain, cell_group[n_cells] names the copy
  * (= case) of every cell.  All cases advance in the same kernels; per-case physics via
@@ -126,13 +129,11 @@ int phw_mesh_get_numbering(phw_mesh_t m, int32_t* vertex_new2old, int32_t* edge_
 /* per-patch counts [n_patches,6]: own cells, edge-op cells, vertex-op cells, owned vertices, owned edges, ghosts(v+e) */
 int phw_mesh_get_patch_counts(phw_mesh_t m, int32_t* counts);
 /* dynamic shared memory (bytes) the bulk-copy pipelined kernels need for this layout: bytes6 = {M_p solve, M_q solve, fused
- * energy reduction, edge-row right-hand side, vertex-row right-hand side, two-sweep M_q solve (0: no ring-2 patches)}
+ * energy reduction, edge-row right-hand side, vertex-row right-hand side, 0 (reserved)}
  * (phw_params.flags bits 9, 8, 11, 12, 12, 13; a variant is available when its figure is <= 227 KB - 1 KB (- 2 KB for the
  * last one)).  Host-only. */
 int phw_mesh_pipe_smem(phw_mesh_t m, int64_t* bytes6);
-/* the same for the experimental pipelined two-sweep solves: bytes2 = {M_p (flags bit 14), M_q (bit 13)}; 0: no ring-2 patches */
-int phw_mesh_pipe2_smem(phw_mesh_t m, int64_t* bytes2);
-/* host-only structural invariants of the patch layout, the assembled (ELL) mass rows and the two-sweep patches
+/* host-only structural invariants of the patch layout, and the assembled (ELL) mass rows
  * (tests; small meshes) */
 int phw_mesh_self_check(phw_mesh_t m);
 int phw_mesh_destroy(phw_mesh_t m);

@@ -15,9 +15,20 @@ K_wave = 3.0   # main_wave_2D.py:19
 rho = 2.0      # main_wave_2D.py:21
 
 CASES = {
-    # main_wave_2D.py:104-114 (the active block of the reference) - P3/RT3 needs the higher-order pair (next item)
-    'analytical_t1_5_timeVariation': [['R', 'SV', 'weak', 80, 'analytical', 1.5, 3000, 'Mem', (1, 1)],
-                                      ['R', 'SE', 'weak', 80, 'analytical', 1.5, 3000, 'noMem', (1, 1)]],
+    # main_wave_2D.py:104-114 (the active block of the reference: P3/RT3, SV and SE, five step counts each)
+    'analytical_t1_5_timeVariation': [['R', 'SV', 'weak', 80, 'analytical', 1.5, 3000, 'Mem', (3, 3)],
+                                      ['R', 'SV', 'weak', 80, 'analytical', 1.5, 4250, 'noMem', (3, 3)],
+                                      ['R', 'SV', 'weak', 80, 'analytical', 1.5, 3500, 'noMem', (3, 3)],
+                                      ['R', 'SV', 'weak', 80, 'analytical', 1.5, 5000, 'noMem', (3, 3)],
+                                      ['R', 'SV', 'weak', 80, 'analytical', 1.5, 6000, 'noMem', (3, 3)],
+                                      ['R', 'SE', 'weak', 80, 'analytical', 1.5, 3000, 'noMem', (3, 3)],
+                                      ['R', 'SE', 'weak', 80, 'analytical', 1.5, 3500, 'noMem', (3, 3)],
+                                      ['R', 'SE', 'weak', 80, 'analytical', 1.5, 4250, 'noMem', (3, 3)],
+                                      ['R', 'SE', 'weak', 80, 'analytical', 1.5, 5000, 'noMem', (3, 3)],
+                                      ['R', 'SE', 'weak', 80, 'analytical', 1.5, 6000, 'noMem', (3, 3)]],
+    # the same block at lowest order (P1/RT1)
+    'analytical_t1_5_P1_RT1': [['R', 'SV', 'weak', 80, 'analytical', 1.5, 3000, 'Mem', (1, 1)],
+                               ['R', 'SE', 'weak', 80, 'analytical', 1.5, 3000, 'noMem', (1, 1)]],
     # main_wave_2D.py:24-36
     'strong_and_weak_method_variation': [['R', s, 'weak', 80, 'wave', 1.5, 3000, 'Mem'] for s in ('IE', 'EE', 'SE', 'EH', 'SV', 'SM')],
     # main_wave_2D.py:92-102
@@ -69,6 +80,6 @@ def run_cases(caseName, caseArray, outputRoot='output', **solver_kwargs):
 if __name__ == '__main__':
     print('starting script and timer')
     tic = time.time()
-    caseName = sys.argv[1] if len(sys.argv) > 1 else 'IC_t4_5_timeVariation'
+    caseName = sys.argv[1] if len(sys.argv) > 1 else 'analytical_t1_5_timeVariation'   # main_wave_2D.py:104
     run_cases(caseName, CASES[caseName])
     print('All Simulations finished in {} seconds'.format(time.time() - tic))

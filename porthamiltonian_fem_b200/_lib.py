@@ -16,6 +16,7 @@ PHW_OK, PHW_EINVAL, PHW_ECUDA, PHW_ENOMEM, PHW_ESTATE, PHW_ENOCONV = 0, -1, -2, 
 SCHEMES = {'EE': 0, 'IE': 1, 'SE': 2, 'SM': 3, 'EH': 4, 'SV': 5}
 IN_SINE_WINDOW, IN_SINE, IN_COSINE, IN_PASSIVITY = 0, 1, 2, 3
 PHW_P, PHW_Q = 0, 1
+ABI_VERSION = 200          # phw_version() of the library this binding was written against
 
 
 class PhwParams(ctypes.Structure):
@@ -54,8 +55,10 @@ class PhwStats(ctypes.Structure):
 SIGNATURES = {
     'phw_last_error': (ctypes.c_char_p, []),
     'phw_version': (ctypes.c_int, []),
+    'phw_sizeof': (ctypes.c_int, [ctypes.c_int]),
     'phw_mesh_create': (ctypes.c_int, [ctypes.c_int64, c_f64p, ctypes.c_int64, c_i32p, ctypes.c_int32, ctypes.POINTER(ctypes.c_void_p)]),
     'phw_mesh_create_partitioned': (ctypes.c_int, [ctypes.c_int64, c_f64p, ctypes.c_int64, c_i32p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]),
+    'phw_mesh_set_cell_owned': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     'phw_mesh_create_grouped': (ctypes.c_int, [ctypes.c_int64, c_f64p, ctypes.c_int64, c_i32p, ctypes.c_int32, c_i32p, ctypes.c_int32, ctypes.POINTER(ctypes.c_void_p)]),
     'phw_mesh_sizes': (ctypes.c_int, [ctypes.c_void_p, c_i64p, c_i64p, c_i64p, c_i64p, c_i64p]),
     'phw_mesh_get_edges': (ctypes.c_int, [ctypes.c_void_p, c_i32p, c_i32p, c_i8p]),
@@ -66,7 +69,6 @@ SIGNATURES = {
     'phw_mesh_self_check': (ctypes.c_int, [ctypes.c_void_p]),
     'phw_mesh_get_patch_counts': (ctypes.c_int, [ctypes.c_void_p, c_i32p]),
     'phw_mesh_pipe_smem': (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64)]),
-    'phw_mesh_pipe2_smem': (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64)]),
     'phw_mesh_destroy': (ctypes.c_int, [ctypes.c_void_p]),
     'phw_solver_create': (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(PhwParams), ctypes.c_int32, ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]),
     'phw_solver_destroy': (ctypes.c_int, [ctypes.c_void_p]),
@@ -117,16 +119,18 @@ def load(rebuild_if_stale=True):
         return _lib
     path = os.environ.get('PHW_LIB', _build.LIB)     # tuning variants of the same sources (profiles/), default: the in-tree build
     if path == _build.LIB and rebuild_if_stale and (not os.path.exists(path) or _build.needs_build()):
-        try:
-            _build.build()
-        except Exception:
-            if not os.path.exists(path):
-                raise
+        # a failed rebuild is an error even when an older binary is lying around: stale kernels (and stale struct layouts)
+        # must never run silently
+        _build.build()
     lib = ctypes.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
+    if lib.phw_version() < ABI_VERSION or lib.phw_sizeof(0) != ctypes.sizeof(PhwParams) or lib.phw_sizeof(1) != ctypes.sizeof(PhwStats):
+        raise RuntimeError('libphwave.so at {} does not match this binding (version {}, phw_params {} / {} bytes, phw_stats {} / {} bytes): '
+                           'rebuild it (python -m porthamiltonian_fem_b200.build --force)'.format(
+                               path, lib.phw_version(), lib.phw_sizeof(0), ctypes.sizeof(PhwParams), lib.phw_sizeof(1), ctypes.sizeof(PhwStats)))
     _lib = lib
     return lib
 

@@ -12,12 +12,14 @@ DAMPING_GAIN = 100.0                 # u = -100 h_1 once t >= control_start_t (h
 
 
 def passivity_input(t, h_1, input_stop_t, control_start_t):
-    """Three regimes: excitation, free evolution, damping injection (same constants as the device code)."""
-    if t >= control_start_t and t >= input_stop_t:
-        return -DAMPING_GAIN * h_1
-    if t >= input_stop_t:
+    """Three regimes in the reference's order (control_input.py:12-18; same constants and order as `input_value`,
+    PHW_IN_PASSIVITY, in csrc/phwave.cu): excitation, free evolution, damping injection."""
+    if t < input_stop_t:
+        return EXCITATION_AMPLITUDE * math.sin(EXCITATION_OMEGA * t)
+    elif t < control_start_t:
         return 0.0
-    return EXCITATION_AMPLITUDE * math.sin(EXCITATION_OMEGA * t)
+    else:
+        return -DAMPING_GAIN * h_1
 
 
 class Passive_control_input:

@@ -606,7 +606,8 @@ __global__ void __launch_bounds__(NT, 1) energy_pipe_k(const __grid_constant__ E
             const uint2 rv = srv[lc];
             const double p0 = sp[rv.x & 0xFFFFu], p1 = sp[rv.x >> 16], p2 = sp[rv.y & 0xFFFFu];
             const double ps = p0 + p1 + p2;
-            accp += sar[lc] * (p0 * p0 + p1 * p1 + p2 * p2 + ps * ps);
+            const double wgt = (rv.y & 0x400000u) ? 0.0 : 1.0;      // halo cell of another rank (partitioned run): counted there
+            accp += wgt * sar[lc] * (p0 * p0 + p1 * p1 + p2 * p2 + ps * ps);
             const uint4 qa = scell[2 * lc], qb = scell[2 * lc + 1];
             const uint32_t e0 = qa.x & 0xFFFFu, e1 = qa.x >> 16, e2 = qa.y & 0xFFFFu;
             const double g0 = __hiloint2double((int)qa.w, (int)qa.z);
@@ -615,9 +616,9 @@ __global__ void __launch_bounds__(NT, 1) energy_pipe_k(const __grid_constant__ E
             const double s0 = (e0 & 0x8000u) ? -1.0 : 1.0, s1 = (e1 & 0x8000u) ? -1.0 : 1.0, s2 = (e2 & 0x8000u) ? -1.0 : 1.0;
             const double t0 = s0 * sq[e0 & 0x3FFFu], t1 = s1 * sq[e1 & 0x3FFFu], t2 = s2 * sq[e2 & 0x3FFFu];
             const double ST = S * (t0 + t1 + t2);
-            accq += t0 * (ST + 2.0 * S * t0 - 4.0 * (g0 * t0 + g2 * t1 + g1 * t2))
-                  + t1 * (ST + 2.0 * S * t1 - 4.0 * (g2 * t0 + g1 * t1 + g0 * t2))
-                  + t2 * (ST + 2.0 * S * t2 - 4.0 * (g1 * t0 + g0 * t1 + g2 * t2));
+            accq += wgt * (t0 * (ST + 2.0 * S * t0 - 4.0 * (g0 * t0 + g2 * t1 + g1 * t2))
+                         + t1 * (ST + 2.0 * S * t1 - 4.0 * (g2 * t0 + g1 * t1 + g0 * t2))
+                         + t2 * (ST + 2.0 * S * t2 - 4.0 * (g1 * t0 + g0 * t1 + g2 * t2)));
         }
     }
     __syncthreads();

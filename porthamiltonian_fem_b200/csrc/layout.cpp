@@ -434,187 +434,6 @@ std::string Layout::build(int64_t nv_, const double* vxy, int64_t nc_, const int
     return "";
 }
 
-std::string Layout::build_ring2(int kind, Ring2& R) const {
-    const bool vk = (kind == 0);
-    const int64_t nd = vk ? nv : ne;
-    const std::vector<int32_t>& cd = vk ? cells : cell_edges;          // [nc,3] dofs of a cell (user numbering)
-    const std::vector<int32_t>& old2new = vk ? v_old2new : e_old2new;
-    const std::vector<int32_t>& new2old = vk ? v_new2old : e_new2old;
-    const uint32_t id_limit = vk ? 65535u : 32767u;
-    // dof -> cells, each list ascending in the user cell id: every patch sums the contributions of a row in this
-    // order, so a row recomputed by a neighbouring patch (G1 rows) gets bit-identical values
-    std::vector<int64_t> off(nd + 1, 0);
-    for (int64_t h = 0; h < 3 * nc; ++h) off[cd[h] + 1]++;
-    for (int64_t d = 0; d < nd; ++d) off[d + 1] += off[d];
-    std::vector<int32_t> d2c(3 * nc);
-    {
-        std::vector<int64_t> pos(off.begin(), off.end() - 1);
-        for (int64_t c = 0; c < nc; ++c)
-            for (int i = 0; i < 3; ++i) d2c[pos[cd[3 * c + i]]++] = (int32_t)c;
-    }
-    R = Ring2{};
-    R.hdr.assign(npatch, Ring2Hdr{});
-    R.slice_off.push_back(0);
-    R.ell_ioff.push_back(0); R.ell_woff.push_back(0);
-    std::vector<int32_t> mark_c(nc, -1), lc_of(nc, 0), mark_d(nd, -1), lid(nd, 0);
-    std::vector<int32_t> cl, g1, g2;
-    std::vector<uint32_t> deg;
-    for (int32_t p = 0; p < npatch; ++p) {
-        const PatchHdr& H0 = hdr[p];
-        Ring2Hdr& H = R.hdr[p];
-        H.group = H0.group;
-        H.d_start = vk ? H0.v_start : H0.e_start;
-        H.d_cnt = vk ? H0.v_cnt : H0.e_cnt;
-        auto owned = [&](int32_t nw) { return nw >= H.d_start && nw < H.d_start + H.d_cnt; };
-        cl.clear(); g1.clear(); g2.clear();
-        for (int32_t r = 0; r < H.d_cnt; ++r) {
-            const int32_t d = new2old[H.d_start + r];
-            for (int64_t k = off[d]; k < off[d + 1]; ++k) {
-                const int32_t c = d2c[k];
-                if (mark_c[c] != p) { mark_c[c] = p; lc_of[c] = (int32_t)cl.size(); cl.push_back(c); }
-            }
-        }
-        H.n_c1 = (int32_t)cl.size();
-        for (int32_t k = 0; k < H.n_c1; ++k)
-            for (int i = 0; i < 3; ++i) {
-                const int32_t d = cd[3 * (int64_t)cl[k] + i], nw = old2new[d];
-                if (!owned(nw) && mark_d[d] != p) { mark_d[d] = p; g1.push_back(nw); }
-            }
-        std::sort(g1.begin(), g1.end());
-        for (int32_t g : g1) {
-            const int32_t d = new2old[g];
-            for (int64_t k = off[d]; k < off[d + 1]; ++k) {
-                const int32_t c = d2c[k];
-                if (mark_c[c] != p) { mark_c[c] = p; lc_of[c] = (int32_t)cl.size(); cl.push_back(c); }
-            }
-        }
-        H.n_c2 = (int32_t)cl.size();
-        for (int32_t k = H.n_c1; k < H.n_c2; ++k)
-            for (int i = 0; i < 3; ++i) {
-                const int32_t d = cd[3 * (int64_t)cl[k] + i], nw = old2new[d];
-                if (!owned(nw) && mark_d[d] != p) { mark_d[d] = p; g2.push_back(nw); }
-            }
-        std::sort(g2.begin(), g2.end());
-        H.g_off = (int32_t)R.ghost.size(); H.g1_cnt = (int32_t)g1.size(); H.g2_cnt = (int32_t)g2.size();
-        for (size_t k = 0; k < g1.size(); ++k) { lid[new2old[g1[k]]] = H.d_cnt + (int32_t)k; R.ghost.push_back(g1[k]); }
-        for (size_t k = 0; k < g2.size(); ++k) { lid[new2old[g2[k]]] = H.d_cnt + H.g1_cnt + (int32_t)k; R.ghost.push_back(g2[k]); }
-        const int32_t nr = H.d_cnt + H.g1_cnt, nl = nr + H.g2_cnt;
-        if ((uint32_t)nl >= id_limit || H.n_c2 >= 16383) return "two-sweep patch too large for 16-bit local indices; reduce patch_cells";
-        R.max_ld = std::max(R.max_ld, nl); R.max_rows = std::max(R.max_rows, nr); R.max_c2 = std::max(R.max_c2, H.n_c2);
-        // cell records
-        H.cell_off = (int32_t)R.pcell_user.size();
-        for (int32_t k = 0; k < H.n_c2; ++k) {
-            const int64_t c = cl[k];
-            R.pcell_user.push_back((int32_t)c);
-            uint32_t l[3];
-            for (int i = 0; i < 3; ++i) {
-                const int32_t d = cd[3 * c + i], nw = old2new[d];
-                l[i] = (uint32_t)(owned(nw) ? nw - H.d_start : lid[d]);
-                if (!vk && cell_sign[3 * c + i] < 0) l[i] |= 0x8000u;
-            }
-            R.rec.push_back(l[0] | (l[1] << 16));
-            R.rec.push_back(l[2]);
-        }
-        // rows [D0 | G1] and their adjacency
-        H.row_off = (int32_t)R.row_gid.size();
-        for (int32_t r = 0; r < nr; ++r) R.row_gid.push_back(r < H.d_cnt ? H.d_start + r : g1[r - H.d_cnt]);
-        auto slot_of = [&](int32_t c, int32_t d) { for (int i = 0; i < 3; ++i) if (cd[3 * (int64_t)c + i] == d) return i; return 0; };
-        if (vk) {
-            H.vs_off = (int32_t)(R.slice_off.size() - 1);
-            const int32_t nslice = (nr + 31) / 32;
-            const size_t base = R.adj.size();
-            std::vector<size_t> sbase(nslice + 1, 0);
-            deg.assign(nr, 0);
-            for (int32_t r = 0; r < nr; ++r) { const int32_t d = new2old[R.row_gid[H.row_off + r]]; deg[r] = (uint32_t)(off[d + 1] - off[d]); }
-            for (int32_t sl = 0; sl < nslice; ++sl) {
-                uint32_t w = 0;
-                for (int32_t k = 32 * sl; k < std::min(32 * (sl + 1), nr); ++k) w = std::max(w, deg[k]);
-                w = (w + 7u) & ~7u;
-                sbase[sl + 1] = sbase[sl] + (size_t)w * 32;
-                R.slice_off.push_back((uint32_t)(base + sbase[sl + 1]));
-            }
-            R.adj.resize(base + sbase[nslice], (uint16_t)0xFFFFu);
-            H.adj_off = (int32_t)(uint32_t)base; H.adj_cnt = (int32_t)sbase[nslice];
-            for (int32_t r = 0; r < nr; ++r) {
-                const int32_t d = new2old[R.row_gid[H.row_off + r]];
-                uint32_t j = 0;
-                for (int64_t k = off[d]; k < off[d + 1]; ++k, ++j) {
-                    const int32_t c = d2c[k];
-                    R.adj[base + sbase[r / 32] + ((size_t)(j / 8) * 32 + (r % 32)) * 8 + (j % 8)] = (uint16_t)(lc_of[c] * 4 + slot_of(c, d));
-                }
-            }
-            // assembled mass rows (ELL) of [D0 | G1]
-            std::vector<uint16_t> nid((size_t)nr * 16);
-            std::vector<uint32_t> npair((size_t)nr * 16), ncnt(nr, 0);
-            for (int32_t r = 0; r < nr; ++r) {
-                const int32_t d = new2old[R.row_gid[H.row_off + r]];
-                uint32_t cnt = 0;
-                for (int64_t k = off[d]; k < off[d + 1]; ++k) {
-                    const int32_t c = d2c[k];
-                    const int i = slot_of(c, d);
-                    for (int t = 1; t <= 2; ++t) {
-                        const int32_t o_old = cd[3 * (int64_t)c + (i + t) % 3], o_new = old2new[o_old];
-                        const uint16_t o = (uint16_t)(owned(o_new) ? o_new - H.d_start : lid[o_old]);
-                        uint32_t j = 0;
-                        while (j < cnt && nid[(size_t)r * 16 + j] != o) ++j;
-                        if (j < cnt) npair[(size_t)r * 16 + j] = (npair[(size_t)r * 16 + j] & 0xFFFFu) | ((uint32_t)lc_of[c] << 16);
-                        else {
-                            if (cnt >= 16) return "vertex with more than 16 neighbours: not supported by the ELL mass rows";
-                            nid[(size_t)r * 16 + cnt] = o; npair[(size_t)r * 16 + cnt] = (uint32_t)lc_of[c] | 0xFFFF0000u; ++cnt;
-                        }
-                    }
-                }
-                ncnt[r] = cnt;
-            }
-            const size_t ibase = R.ell_ids.size(), wbase = R.ell_pair.size();
-            size_t ioff = 0, woff = 0, ioff0 = 0, woff0 = 0;
-            const int32_t nslice0 = (H.d_cnt + 31) / 32;
-            for (int32_t sl = 0; sl < nslice; ++sl) {
-                uint32_t w = 0;
-                for (int32_t k = 32 * sl; k < std::min(32 * (sl + 1), nr); ++k) w = std::max(w, ncnt[k]);
-                const uint32_t nch = (w + 7u) / 8u;
-                R.ell_ids.resize(ibase + ioff + (size_t)nch * 256, 0);
-                R.ell_pair.resize(wbase + woff + (size_t)w * 32, 0xFFFFFFFFu);
-                for (int32_t k = 32 * sl; k < 32 * (sl + 1); ++k) {
-                    const int lane = k % 32;
-                    for (uint32_t j = 0; j < nch * 8; ++j) {
-                        const bool valid = k < nr && j < ncnt[k];
-                        R.ell_ids[ibase + ioff + ((size_t)(j / 8) * 32 + lane) * 8 + (j % 8)] = valid ? nid[(size_t)k * 16 + j] : (uint16_t)(k < nr ? k : 0);
-                        if (j < w && valid) R.ell_pair[wbase + woff + (size_t)j * 32 + lane] = npair[(size_t)k * 16 + j];
-                    }
-                }
-                ioff += (size_t)nch * 256; woff += (size_t)w * 32;
-                if (sl + 1 == nslice0) { ioff0 = ioff; woff0 = woff; }
-                R.ell_ioff.push_back((uint32_t)(ibase + ioff));
-                R.ell_woff.push_back((uint32_t)(wbase + woff));
-            }
-            H.ell_i0 = (int32_t)(uint32_t)ibase; H.ell_in = (int32_t)ioff;
-            H.ell_w0 = (int32_t)(uint32_t)wbase; H.ell_wn = (int32_t)woff;
-            // shared memory of vertex_ell_pass2 (doubles): offsets | x_k [nl] | x_{k+1} [nr] | b [n0] | weights + ids of the D0 slices
-            auto ev2 = [](int64_t x) { return (x + 1) & ~(int64_t)1; };
-            const int64_t need = ((nslice + 3) & ~1) + ev2(nl) + ev2(nr) + ev2(H.d_cnt) + (int64_t)woff0 + (int64_t)(ioff0 + 3) / 4 + 2;
-            R.max_smem_ell = std::max(R.max_smem_ell, need);
-        } else {
-            for (int32_t r = 0; r < nr; ++r) {
-                const int32_t d = new2old[R.row_gid[H.row_off + r]];
-                uint32_t a = 0xFFFFFFFFu;
-                int j = 0;
-                for (int64_t k = off[d]; k < off[d + 1]; ++k, ++j) {
-                    const int32_t c = d2c[k];
-                    const uint32_t code = (uint32_t)(lc_of[c] * 4 + slot_of(c, d));
-                    if (j == 0) a = (a & 0xFFFF0000u) | code;
-                    else if (j == 1) a = (a & 0xFFFFu) | (code << 16);
-                    else return "internal: edge with more than two cells";
-                }
-                R.eadj.push_back(a);
-            }
-        }
-    }
-    if (R.adj.size() >= ((size_t)1 << 32) || R.pcell_user.size() >= ((size_t)1 << 31) || R.ell_ids.size() >= ((size_t)1 << 32) ||
-        R.ell_pair.size() >= ((size_t)1 << 32)) return "two-sweep layout exceeds 32-bit offsets";
-    return "";
-}
-
 std::string Layout::self_check() const {
     auto err = [](const std::string& what, int64_t p, int64_t i) { return what + " (patch " + std::to_string(p) + ", item " + std::to_string(i) + ")"; };
     // ---- every dof is a row of exactly one patch; owned ranges tile the numbering
@@ -668,95 +487,6 @@ std::string Layout::self_check() const {
         }
         (void)nsl;
     }
-    // ---- two-sweep patches of both kinds
-    for (int kind = 0; kind < 2; ++kind) {
-        Ring2 R;
-        const std::string e = build_ring2(kind, R);
-        if (!e.empty()) continue;                    // too large for one more ring: the solver falls back, nothing to check
-        const std::vector<int32_t>& cd = kind == 0 ? cells : cell_edges;
-        const std::vector<int32_t>& new2old = kind == 0 ? v_new2old : e_new2old;
-        const uint32_t mask = kind == 0 ? 0xFFFFu : 0x7FFFu;
-        for (int32_t p = 0; p < npatch; ++p) {
-            const Ring2Hdr& H = R.hdr[p];
-            const int32_t nr = H.d_cnt + H.g1_cnt, nl = nr + H.g2_cnt;
-            auto gid_of = [&](int32_t l) { return l < H.d_cnt ? H.d_start + l : R.ghost[H.g_off + l - H.d_cnt]; };
-            if (H.n_c1 > H.n_c2) return err("ring-2: C1 is not a prefix of C2", p, kind);
-            if (kind == 0) {   // ELL block bounds carried by the header (bulk-copied as two contiguous, 16-byte aligned blocks)
-                const int32_t nsl = (nr + 31) / 32;
-                if ((uint32_t)H.ell_i0 != R.ell_ioff[H.vs_off] || (uint32_t)(H.ell_i0 + H.ell_in) != R.ell_ioff[H.vs_off + nsl] ||
-                    (uint32_t)H.ell_w0 != R.ell_woff[H.vs_off] || (uint32_t)(H.ell_w0 + H.ell_wn) != R.ell_woff[H.vs_off + nsl])
-                    return err("ring-2: ELL block bounds of the header do not match the slice offsets", p, 0);
-                if ((H.ell_i0 % 8) != 0 || (H.ell_in % 8) != 0 || (H.ell_w0 % 2) != 0 || (H.ell_wn % 2) != 0)
-                    return err("ring-2: ELL blocks are not 16-byte aligned", p, 0);
-            }
-            for (int32_t k = 0; k < H.n_c2; ++k) {
-                const int32_t c = R.pcell_user[H.cell_off + k];
-                const uint32_t l[3] = {R.rec[2 * (size_t)(H.cell_off + k)] & 0xFFFFu, R.rec[2 * (size_t)(H.cell_off + k)] >> 16, R.rec[2 * (size_t)(H.cell_off + k) + 1] & 0xFFFFu};
-                for (int i = 0; i < 3; ++i) {
-                    const int32_t li = (int32_t)(l[i] & mask);
-                    if (li >= nl) return err("ring-2: local id out of range", p, k);
-                    if (k < H.n_c1 && li >= nr) return err("ring-2: a C1 cell uses a dof outside D0+G1", p, k);
-                    if (new2old[gid_of(li)] != cd[3 * (int64_t)c + i]) return err("ring-2: cell record does not match the mesh", p, k);
-                    if (kind == 1 && ((l[i] & 0x8000u) != 0) != (cell_sign[3 * (int64_t)c + i] < 0)) return err("ring-2: orientation sign", p, k);
-                }
-            }
-            // rows [D0 | G1]: the adjacency lists exactly the cells of the mesh that contain the dof, all inside C2 (C1 for D0)
-            for (int32_t r = 0; r < nr; ++r) {
-                const int32_t d_old = new2old[R.row_gid[H.row_off + r]];
-                if (R.row_gid[H.row_off + r] != gid_of(r)) return err("ring-2: row numbering", p, r);
-                std::vector<uint32_t> codes;
-                if (kind == 0) {
-                    const uint32_t o0 = R.slice_off[H.vs_off + r / 32], o1 = R.slice_off[H.vs_off + r / 32 + 1];
-                    for (uint32_t j = 0; j < (o1 - o0) / 32; ++j) {
-                        const uint16_t c = R.adj[o0 + ((size_t)(j / 8) * 32 + (r % 32)) * 8 + (j % 8)];
-                        if (c != 0xFFFFu) codes.push_back(c);
-                    }
-                } else {
-                    const uint32_t a = R.eadj[H.row_off + r];
-                    if ((a & 0xFFFFu) != 0xFFFFu) codes.push_back(a & 0xFFFFu);
-                    if ((a >> 16) != 0xFFFFu) codes.push_back(a >> 16);
-                }
-                if (kind == 0) {   // assembled mass row: neighbours = the other vertices of the row's cells; pair cells contain both
-                    const int32_t sl = r / 32, lane = r % 32;
-                    const uint32_t io0 = R.ell_ioff[H.vs_off + sl], wo0 = R.ell_woff[H.vs_off + sl];
-                    const uint32_t W = (R.ell_woff[H.vs_off + sl + 1] - wo0) / 32;
-                    std::vector<int32_t> expect, got;
-                    for (int64_t c = 0; c < nc; ++c)
-                        for (int i = 0; i < 3; ++i)
-                            if (cd[3 * c + i] == d_old) { expect.push_back(cd[3 * c + (i + 1) % 3]); expect.push_back(cd[3 * c + (i + 2) % 3]); }
-                    std::sort(expect.begin(), expect.end());
-                    expect.erase(std::unique(expect.begin(), expect.end()), expect.end());
-                    for (uint32_t k = 0; k < W; ++k) {
-                        const uint32_t pr = R.ell_pair[wo0 + k * 32 + lane];
-                        const uint16_t id = R.ell_ids[io0 + ((size_t)(k / 8) * 32 + lane) * 8 + (k % 8)];
-                        if (pr == 0xFFFFFFFFu) { if (id != r) return err("ring-2 ELL padding", p, r); continue; }
-                        if ((int32_t)id >= nl || (r < H.d_cnt && (int32_t)id >= nr)) return err("ring-2 ELL neighbour outside its sweep", p, r);
-                        const int32_t w_old = new2old[gid_of(id)];
-                        got.push_back(w_old);
-                        for (int hh = 0; hh < 2; ++hh) {
-                            const uint32_t lc = hh == 0 ? (pr & 0xFFFFu) : (pr >> 16);
-                            if (lc == 0xFFFFu) continue;
-                            if ((int32_t)lc >= H.n_c2) return err("ring-2 ELL cell out of range", p, r);
-                            const int32_t c = R.pcell_user[H.cell_off + lc];
-                            int hit = 0;
-                            for (int i = 0; i < 3; ++i) hit += (cd[3 * (int64_t)c + i] == d_old) + 2 * (cd[3 * (int64_t)c + i] == w_old);
-                            if (hit != 3) return err("ring-2 ELL cell does not contain both vertices", p, r);
-                        }
-                    }
-                    std::sort(got.begin(), got.end());
-                    if (got != expect) return err("ring-2 ELL neighbours differ from the mesh", p, r);
-                }
-                int64_t in_mesh = 0;
-                for (int64_t h = 0; h < 3 * nc; ++h) in_mesh += (cd[h] == d_old);   // small test meshes only
-                if ((int64_t)codes.size() != in_mesh) return err("ring-2: a row misses cells", p, r);
-                for (uint32_t c : codes) {
-                    const int32_t lc = (int32_t)(c >> 2);
-                    if (lc >= H.n_c2 || (r < H.d_cnt && lc >= H.n_c1)) return err("ring-2: row cell outside its sweep", p, r);
-                    if (cd[3 * (int64_t)R.pcell_user[H.cell_off + lc] + (c & 3u)] != d_old) return err("ring-2: adjacency slot", p, r);
-                }
-            }
-        }
-    }
     return "";
 }
 
@@ -782,6 +512,7 @@ void Layout::make_records(bool strong, bool casimir, std::vector<CellRec>& rec) 
                 if (casimir && t == 2) flags |= (1u << (3 + i));
             }
         }
+        if (!cell_foreign.empty() && cell_foreign[c]) flags |= (1u << 6);   // cell of another rank: no weight in cell-based sums
         rec[k].x = lv[0] | (lv[1] << 16);
         rec[k].y = lv[2] | (flags << 16);
         rec[k].z = le[0] | (le[1] << 16);

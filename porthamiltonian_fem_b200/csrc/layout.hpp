@@ -20,7 +20,9 @@ namespace phw {
 // le bits: 0..13 local edge id, bit 14: "N-term" edge (zero-flux boundary side, wave_2D.py:465-472
 // ds(1), ds(3); every boundary edge in the strong form), bit 15: orientation sign is -1.
 // flags bits (y>>16): 0..2 slot i lies on the impedance top side (casimir, tag 1),
-//                     3..5 slot i lies on the impedance right side (casimir, tag 2).
+//                     3..5 slot i lies on the impedance right side (casimir, tag 2),
+//                     6 the cell belongs to another rank of a partitioned run (halo cell of the local mesh): it contributes to
+//                       the rows of this rank's dofs but carries no weight in cell-based sums (energy_pipe_k).
 struct CellRec { uint32_t x, y, z, w; };   // (x,y) = vertex half, (z,w) = edge half; stored as two uint2 arrays on the device
 
 struct PatchHdr {
@@ -39,40 +41,6 @@ struct PatchHdr {
 };
 static_assert(sizeof(PatchHdr) == 80, "PatchHdr is loaded as 20 ints");
 
-// ---- two-sweep patches (temporal blocking of the Chebyshev mass solves): for one dof kind (vertices or edges) a patch
-// holds its owned dofs D0, the cells C1 touching D0, the other dofs G1 of those cells, the further cells C2 \ C1 touching
-// G1 and their remaining dofs G2.  With x_k on D0+G1+G2 in shared memory a CTA computes x_{k+1} on D0+G1 (all cells of
-// those rows are in C2) and then x_{k+2} on D0 (cells C1) - two Chebyshev iterations per pass over the data.
-struct Ring2Hdr {
-    int32_t cell_off, n_c1, n_c2;      // patch cells [C1 | C2 \ C1] in the ring-2 cell arrays
-    int32_t d_start, d_cnt;            // owned dof range (new numbering) = rows of the second sweep
-    int32_t g_off, g1_cnt, g2_cnt;     // ghost list [G1 | G2] (new ids, each part ascending); first-sweep rows = [D0 | G1]
-    int32_t row_off;                   // first row of this patch in the per-row arrays (replicated pinv, edge adjacency)
-    int32_t vs_off, adj_off, adj_cnt;  // vertex kind: sliced-ELL adjacency of the rows [D0 | G1]
-    int32_t group;
-    int32_t ell_i0, ell_in;            // vertex kind: ELL mass rows of [D0 | G1]: first id code / number of codes in ell_ids,
-    int32_t ell_w0, ell_wn;            // first weight / number of weights in ell_w (two contiguous, 16-byte aligned blocks)
-    int32_t pad[3];
-};
-static_assert(sizeof(Ring2Hdr) == 80, "Ring2Hdr is loaded as 20 ints");
-struct Ring2 {
-    std::vector<Ring2Hdr> hdr;
-    std::vector<int32_t> pcell_user;   // [npc] user cell id of every patch cell
-    std::vector<uint32_t> rec;         // [npc,2] cell records: x = l0 | l1<<16, y = l2 (edge kind: bit 15 = orientation sign -1)
-    std::vector<int32_t> ghost;
-    std::vector<int32_t> row_gid;      // [n_rows] new global id of every first-sweep row
-    std::vector<uint32_t> slice_off;   // vertex kind (same sliced-ELL format as Layout::vadj)
-    std::vector<uint16_t> adj;
-    std::vector<uint32_t> eadj;        // edge kind: [n_rows] two (cell, slot) codes per row
-    // vertex kind: assembled P1 mass rows of [D0 | G1] as sliced ELL (same slices as slice_off; ids = ring-2 local ids,
-    // entries of a row in ascending user cell id so that recomputed halo rows are bit-identical to their owners')
-    std::vector<uint32_t> ell_ioff, ell_woff;
-    std::vector<uint16_t> ell_ids;
-    std::vector<uint32_t> ell_pair;
-    int64_t max_smem_ell = 0;          // doubles of shared memory the ELL two-sweep pass needs for the largest patch
-    int32_t max_ld = 0, max_rows = 0, max_c2 = 0;
-};
-
 struct Layout {
     int64_t nv = 0, nc = 0, ne = 0, nb = 0;
     int32_t patch_cells = 0, npatch = 0;
@@ -88,6 +56,7 @@ struct Layout {
     bool boundary_set = false;
     std::vector<int32_t> dir_vertex;   // strong Dirichlet rows (user vertex ids) and their value weights
     std::vector<double>  dir_weight;   // value = weight * g(t)  (0 for the homogeneous right side)
+    std::vector<uint8_t> cell_foreign; // partitioned runs (optional, by user cell id): 1 = cell owned by another rank
 
     std::vector<int32_t> cell_patch;   // [nc] user cell -> patch
     std::vector<int32_t> v_new2old, v_old2new, e_new2old, e_old2new;
@@ -125,9 +94,7 @@ struct Layout {
     std::vector<int32_t> cell_group_v;      // [nc] (empty when n_groups == 1)
     // cell records with boundary flag bits for the given formulation
     void make_records(bool strong, bool casimir, std::vector<CellRec>& rec) const;
-    // two-sweep patches of the vertex (kind 0) or edge (kind 1) rows; returns "" or an error message
-    std::string build_ring2(int kind, Ring2& R) const;
-    // structural invariants of the patch layout, the ELL mass rows and the two-sweep patches (host-only; tests)
+    // structural invariants of the patch layout and the ELL mass rows (host-only; tests)
     std::string self_check() const;
 };
 

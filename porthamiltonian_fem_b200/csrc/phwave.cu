@@ -9,15 +9,15 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <numeric>
+#include <set>
 #include <string>
 #include <vector>
 
 #include "../../include/phwave.h"
 #include "kernels.cuh"
-#include "kernels2.cuh"
 #include "kernels_pipe.cuh"
-#include "kernels_pipe2.cuh"
 #include "pipe_carve.hpp"
 #include "layout.hpp"
 
@@ -92,25 +92,6 @@ __global__ void ell_weights_k(int npatch, const PatchHdr* __restrict__ hdr, cons
     for (int P = blockIdx.x; P < npatch; P += gridDim.x) {
         const PatchHdr h = hdr[P];
         const int nsl = (h.v_cnt + 31) >> 5;
-        const uint32_t e0 = woff[h.vs_off], e1 = woff[h.vs_off + nsl];
-        for (uint32_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
-            const uint32_t pr = pair[e];
-            double v = 0.0;
-            if (pr != 0xFFFFFFFFu) {
-                v = area[h.cell_off + (pr & 0xFFFFu)];
-                if ((pr >> 16) != 0xFFFFu) v += area[h.cell_off + (pr >> 16)];
-                v *= (1.0 / 12.0);
-            }
-            w[e] = v;
-        }
-    }
-}
-
-__global__ void ell2_weights_k(int npatch, const Ring2Hdr* __restrict__ hdr, const uint32_t* __restrict__ woff,
-                               const uint32_t* __restrict__ pair, const double* __restrict__ area, double* __restrict__ w) {
-    for (int P = blockIdx.x; P < npatch; P += gridDim.x) {
-        const Ring2Hdr h = hdr[P];
-        const int nsl = (h.d_cnt + h.g1_cnt + 31) >> 5;
         const uint32_t e0 = woff[h.vs_off], e1 = woff[h.vs_off + nsl];
         for (uint32_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
             const uint32_t pr = pair[e];
@@ -545,6 +526,7 @@ struct phw_solver_s {
     size_t smem_v = 0, smem_v1 = 0, smem_e = 0, smem_vd = 0, smem_ed = 0;
     int grid_rows = 0, sm_count = 148;
     int64_t launches = 0;
+    size_t l2_max_win = 0, l2_max_persist = 0;
     PeerComm pc{};
     void* arena = nullptr; size_t arena_bytes = 0;
     std::vector<void*> peer_arenas;
@@ -561,20 +543,15 @@ struct phw_solver_s {
     bool ell_p = false;         // M_p solve on the assembled ELL rows (vertex_ell_pass)
     bool ell_staged = false;    // ... with all streams of a patch staged in shared memory by cp.async
     size_t smem_ell = 0, smem_ells = 0;
-    bool two_sweep = false;     // mass solves run two Chebyshev iterations per pass (kernels2.cuh)
-    Ring2Dev r2[2]{};
-    size_t smem2[2] = {0, 0};
     uint4* d_cellq = nullptr;
     bool pipe_q = false, pipe_p = false;   // bulk-copy pipelined mass solves (kernels_pipe.cuh; flags bits 8 / 9)
     MqPipeArgs pq{}; EllPipeArgs pp{};     // their shared-memory carve-ups (sized for the largest patch)
     size_t smem_pq = 0, smem_pp = 0;
     bool pipe_en = false; EnergyPipeArgs pe{}; size_t smem_pe = 0;   // fused pipelined H_wave reduction (flags bit 11)
-    bool pipe2_q = false; Mq2PipeArgs pq2{}; size_t smem_pq2 = 0;     // pipelined two-sweep M_q solve (experimental, flags bit 13)
-    bool pipe2_p = false; Ell2PipeArgs pp2{}; size_t smem_pp2 = 0;    // pipelined two-sweep M_p solve (experimental, flags bit 14)
     bool pipe_rhs = false; RhsPipeArgs pre{}, prv{}; size_t smem_pre = 0, smem_prv = 0;   // pipelined right-hand sides (flags bit 12)
     int64_t kernel_paths = 0;              // PHW_PATH_* bits of the solve kernels launched since the last phw_run began
     int *d_cells_user = nullptr; double* d_vtx_user = nullptr; unsigned long long* d_mm = nullptr;
-    std::vector<cudaEvent_t> prof_ev; std::vector<int> prof_which;
+    std::vector<cudaEvent_t> prof_ev; std::vector<int> prof_which; bool prof_truncated = false;
     bool have_vq = false;      // Stormer-Verlet first-same-as-last: v_q of the previous step is valid
     phw_stats stats{};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -599,6 +576,18 @@ struct phw_solver_s {
 namespace {
 
 inline int nblk(int n, int bs = 256) { return (n + bs - 1) / bs; }
+
+// opt-in to more than 48 KB of dynamic shared memory.  The attribute belongs to the (device, function) pair, so it is tracked per
+// device: a second solver on another device of the same process configures its own copy of every kernel.
+int ensure_dyn_smem(int device, const void* kern, int bytes) {
+    static std::mutex mu;
+    static std::set<std::pair<int, const void*>> done;
+    std::lock_guard<std::mutex> lk(mu);
+    if (done.count(std::make_pair(device, kern))) return 0;
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    done.insert(std::make_pair(device, kern));
+    return 0;
+}
 inline int vec_grid(phw_solver_s* s, int n) { return std::max(1, std::min(nblk(n), s->sm_count * 8)); }
 
 // ---- typed launchers for the row kernels -------------------------------------------------------
@@ -606,8 +595,7 @@ template <int EPI, int MODE, bool HAS_M, bool HAS_D, bool CAS>
 int launch_vertex(phw_solver_s* s, const RowArgs& a) {
     size_t sm = HAS_D ? s->smem_vd : ((HAS_M && !CAS && MODE == MODE_OP) ? s->smem_v1 : s->smem_v);
     auto kern = vertex_rows_k<EPI, MODE, HAS_M, HAS_D, CAS>;
-    static bool configured = false;
-    if (!configured) { CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); configured = true; }
+    { int rc_ = ensure_dyn_smem(s->device, (const void*)kern, 200 * 1024); if (rc_) return rc_; }
     kern<<<s->grid_rows, NT_ROWS, sm, s->stream>>>(a);
     s->launches++;
     CU(cudaGetLastError());
@@ -617,8 +605,7 @@ template <int EPI, int MODE, bool HAS_M, bool HAS_D, bool CAS>
 int launch_edge(phw_solver_s* s, const RowArgs& a) {
     size_t sm = HAS_D ? s->smem_ed : s->smem_e;
     auto kern = edge_rows_k<EPI, MODE, HAS_M, HAS_D, CAS>;
-    static bool configured = false;
-    if (!configured) { CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); configured = true; }
+    { int rc_ = ensure_dyn_smem(s->device, (const void*)kern, 200 * 1024); if (rc_) return rc_; }
     kern<<<s->grid_rows, NT_ROWS, sm, s->stream>>>(a);
     s->launches++;
     CU(cudaGetLastError());
@@ -647,6 +634,14 @@ void csr_dot(phw_solver_s* s, const Csr& A, const double* x, double scale, int s
     }
 }
 
+// partitioned runs: which pipelined kernels (when selected by phw_params.flags) run with the inter-GPU exchange.  A/B and fallback
+// knob PHW_PIPE_MULTI = bit mask (1: the two mass solves, 2: right-hand sides, 4: fused H_wave pass); default 7 = all of them,
+// 0 = the lean kernels of round 1.
+int pipe_multi_mask() {
+    static const int m = [] { const char* e = getenv("PHW_PIPE_MULTI"); return e ? atoi(e) : 7; }();
+    return m;
+}
+
 RowArgs base_args(phw_solver_s* s) {
     RowArgs a{};
     a.m = s->dm; a.tp = s->tp; a.tq = s->tq;
@@ -666,8 +661,7 @@ template <bool VERTEX, int NT, int MINB>
 int launch_rhs_pipe_cfg(phw_solver_s* s, const double* x, double cD, double* y) {
     auto kern = VERTEX ? rhs_vertex_pipe_k<NT, MINB> : rhs_edge_pipe_k<NT, MINB>;
     const size_t sm = VERTEX ? s->smem_prv : s->smem_pre;
-    static bool configured = false;
-    if (!configured) { CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024)); configured = true; }
+    { int rc_ = ensure_dyn_smem(s->device, (const void*)kern, 227 * 1024 - 1024); if (rc_) return rc_; }
     RhsPipeArgs a = VERTEX ? s->prv : s->pre;
     a.npatch = s->npatch; a.hdr = s->dm.hdr; a.recv = s->dm.recv; a.rece = s->dm.rece;
     a.ghost = VERTEX ? s->dm.ghost_e : s->dm.ghost_v; a.eadj = s->dm.eadj; a.vslice_off = s->dm.vslice_off; a.vadj = s->dm.vadj;
@@ -692,7 +686,7 @@ int op_vertex_store(phw_solver_s* s, const double* xp, const double* xq, double 
     a.gscale = gscale;
     a.xp = xp; a.xq = xq; a.cM = cM; a.cD = cD; a.cB = cB; a.y = y;
     const bool cas = s->prm.casimir && cB != 0.0;
-    if (s->pipe_rhs && s->pc.world <= 1 && cM == 0.0 && cB == 0.0 && !gscale) return launch_rhs_pipe<true>(s, xq, cD, y);
+    if (s->pipe_rhs && (s->pc.world <= 1 || (pipe_multi_mask() & 2)) && cM == 0.0 && cB == 0.0 && !gscale) return launch_rhs_pipe<true>(s, xq, cD, y);
     if (cM != 0.0 && cD == 0.0) return cas ? launch_vertex<EPI_STORE, MODE_OP, true, false, true>(s, a) : launch_vertex<EPI_STORE, MODE_OP, true, false, false>(s, a);
     if (cM == 0.0) return cas ? launch_vertex<EPI_STORE, MODE_OP, false, true, true>(s, a) : launch_vertex<EPI_STORE, MODE_OP, false, true, false>(s, a);
     return cas ? launch_vertex<EPI_STORE, MODE_OP, true, true, true>(s, a) : launch_vertex<EPI_STORE, MODE_OP, true, true, false>(s, a);
@@ -702,7 +696,7 @@ int op_edge_store(phw_solver_s* s, const double* xp, const double* xq, double cM
     a.gscale = gscale;
     a.xp = xp; a.xq = xq; a.cM = cM; a.cD = cD; a.cB = cB; a.y = y;
     const bool cas = s->prm.casimir && cB != 0.0;
-    if (s->pipe_rhs && s->pc.world <= 1 && cM == 0.0 && cB == 0.0 && !gscale) return launch_rhs_pipe<false>(s, xp, cD, y);
+    if (s->pipe_rhs && (s->pc.world <= 1 || (pipe_multi_mask() & 2)) && cM == 0.0 && cB == 0.0 && !gscale) return launch_rhs_pipe<false>(s, xp, cD, y);
     if (cM != 0.0 && cD == 0.0) return cas ? launch_edge<EPI_STORE, MODE_OP, true, false, true>(s, a) : launch_edge<EPI_STORE, MODE_OP, true, false, false>(s, a);
     if (cM == 0.0) return cas ? launch_edge<EPI_STORE, MODE_OP, false, true, true>(s, a) : launch_edge<EPI_STORE, MODE_OP, false, true, false>(s, a);
     return cas ? launch_edge<EPI_STORE, MODE_OP, true, true, true>(s, a) : launch_edge<EPI_STORE, MODE_OP, true, true, false>(s, a);
@@ -723,6 +717,14 @@ int op_edge_dot(phw_solver_s* s, const double* xq, double cM, double cB, int slo
     return launch_edge<EPI_DOT, MODE_OP, true, false, false>(s, a);
 }
 
+// CUDA-event timing of every solve launch (flags bit 2).  Beyond 2^18 launches per phw_run the timing stops and the per-kernel
+// figures of that run are reported as 0 (a partial sum against the full iteration count would overstate the bandwidth).
+inline bool prof_on(phw_solver_s* s) {
+    if (!(s->prm.flags & 4)) return false;
+    if (s->prof_ev.size() >= 2 * (size_t)262144) { s->prof_truncated = true; return false; }
+    return true;
+}
+
 // one cooperative launch = one complete Chebyshev solve
 template <int WHICH, bool CAS, int ELL = 0>
 int launch_coop(phw_solver_s* s, const RowArgs& av, const RowArgs& ae) {
@@ -730,8 +732,7 @@ int launch_coop(phw_solver_s* s, const RowArgs& av, const RowArgs& ae) {
     constexpr int MINB = (WHICH == 0) ? (ELL == 2 ? PHW_MINB_ELLS : (ELL == 1 ? PHW_MINB_ELL : PHW_MINB_P)) : PHW_MINB_Q;
     auto kern = solve_coop_k<WHICH, CAS, NT, MINB, ELL>;
     const size_t sm = (WHICH == 0) ? (ELL == 2 ? s->smem_ells : (ELL == 1 ? s->smem_ell : s->smem_v1)) : (WHICH == 1 ? s->smem_e : s->smem_vd);
-    static bool configured = false;
-    if (!configured) { CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); configured = true; }
+    { int rc_ = ensure_dyn_smem(s->device, (const void*)kern, 200 * 1024); if (rc_) return rc_; }
     int occ = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, sm));
     if (occ < 1) return fail(PHW_ECUDA, "cooperative solve kernel does not fit on an SM");
@@ -739,7 +740,7 @@ int launch_coop(phw_solver_s* s, const RowArgs& av, const RowArgs& ae) {
     void* args[] = {(void*)&av, (void*)&ae, (void*)&s->pc};
     if (av.gbar) CU(cudaMemsetAsync(&s->ctl->gbar[0], 0, sizeof(unsigned int), s->stream));
     cudaEvent_t e0 = nullptr, e1 = nullptr;
-    const bool prof = (s->prm.flags & 4) && s->prof_ev.size() < 2 * 8192;
+    const bool prof = prof_on(s);
     if (prof) {
         CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
         CU(cudaEventRecord(e0, s->stream));
@@ -753,71 +754,12 @@ int launch_coop(phw_solver_s* s, const RowArgs& av, const RowArgs& ae) {
     return 0;
 }
 
-// one cooperative launch = one complete two-sweep Chebyshev solve of M_p (KIND 0) or M_q (KIND 1)
-template <int KIND, int NT, int MINB>
-int launch_coop2_cfg(phw_solver_s* s) {
-    auto kern = solve2_coop_k<KIND, NT, MINB>;
-    const size_t sm = s->smem2[KIND];
-    static bool configured = false;
-    if (!configured) { CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); configured = true; }
-    int occ = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, sm));
-    if (occ < 1) return fail(PHW_ECUDA, "two-sweep solve kernel does not fit on an SM");
-    const int grid = std::max(1, std::min(s->npatch, occ * s->sm_count));
-    Solve2Args a{};
-    a.m = s->r2[KIND];
-    const TriBuf& tb = (KIND == 0) ? s->tp : s->tq;
-    for (int i = 0; i < 4; ++i) a.buf[i] = tb.b[i];
-    a.b = (KIND == 0) ? s->bp : s->bq;
-    a.cheb_d = s->cheb_d[KIND]; a.cheb_c = s->cheb_c[KIND];
-    a.tol2 = s->prm.tol * s->prm.tol;
-    if (s->G > 1) { const double t = std::max(s->prm.tol / std::sqrt((double)s->G), 1e-14); a.tol2 = std::min(a.tol2, t * t); }
-    a.max_iter = s->prm.max_iter; a.which = KIND; a.partials = s->partials; a.ctl = s->ctl;
-    a.gbar = (s->prm.flags & 1024) ? 1 : 0;
-    if (a.gbar) CU(cudaMemsetAsync(&s->ctl->gbar[0], 0, sizeof(unsigned int), s->stream));
-    void* args[] = {(void*)&a};
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    const bool prof = (s->prm.flags & 4) && s->prof_ev.size() < 2 * 8192;
-    if (prof) {
-        CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
-        CU(cudaEventRecord(e0, s->stream));
-    }
-    CU(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(NT), args, sm, s->stream));
-    if (prof) {
-        CU(cudaEventRecord(e1, s->stream));
-        s->prof_ev.push_back(e0); s->prof_ev.push_back(e1); s->prof_which.push_back(KIND);
-    }
-    s->launches++;
-    return 0;
-}
-template <int KIND>
-int launch_coop2(phw_solver_s* s) {
-    static const int cfg = [] { const char* e = getenv(KIND == 0 ? "PHW_P2_CFG" : "PHW_Q2_CFG"); return e ? atoi(e) : 0; }();
-    if (KIND == 0) {
-        switch (cfg) {
-            case 1: return launch_coop2_cfg<KIND, 256, 2>(s);
-            case 2: return launch_coop2_cfg<KIND, 384, 2>(s);
-            case 3: return launch_coop2_cfg<KIND, 1024, 1>(s);
-            case 4: return launch_coop2_cfg<KIND, 256, 3>(s);
-            default: return launch_coop2_cfg<KIND, 512, 2>(s);
-        }
-    }
-    switch (cfg) {
-        case 1: return launch_coop2_cfg<KIND, 512, 2>(s);
-        case 2: return launch_coop2_cfg<KIND, 256, 4>(s);
-        case 3: return launch_coop2_cfg<KIND, 1024, 1>(s);
-        case 4: return launch_coop2_cfg<KIND, 384, 3>(s);
-        default: return launch_coop2_cfg<KIND, 384, 2>(s);
-    }
-}
-
 // lean single-GPU ELL M_p solve
 template <int NT, int MINB>
 int launch_ell_lean(phw_solver_s* s) {
     void* kern = s->pc.world > 1 ? (void*)solve_ell_coop_k<NT, MINB, true> : (void*)solve_ell_coop_k<NT, MINB, false>;
     CU(cudaMemsetAsync(&s->ctl->gbar[0], 0, sizeof(unsigned int), s->stream));
-    static bool configured[2] = {false, false};
-    if (!configured[s->pc.world > 1]) { CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); configured[s->pc.world > 1] = true; }
+    { int rc_ = ensure_dyn_smem(s->device, (const void*)kern, 200 * 1024); if (rc_) return rc_; }
     int occ = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, s->smem_ell));
     if (occ < 1) return fail(PHW_ECUDA, "ELL solve kernel does not fit on an SM");
@@ -832,7 +774,7 @@ int launch_ell_lean(phw_solver_s* s) {
     a.max_iter = s->prm.max_iter; a.which = 0; a.partials = s->partials; a.ctl = s->ctl;
     void* args[] = {(void*)&a, (void*)&s->pc};
     cudaEvent_t e0 = nullptr, e1 = nullptr;
-    const bool prof = (s->prm.flags & 4) && s->prof_ev.size() < 2 * 8192;
+    const bool prof = prof_on(s);
     if (prof) {
         CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
         CU(cudaEventRecord(e0, s->stream));
@@ -851,8 +793,7 @@ template <int NT, int MINB, int UC, int UR>
 int launch_mq_lean(phw_solver_s* s) {
     void* kern = s->pc.world > 1 ? (void*)solve_mq_coop_k<NT, MINB, UC, UR, true> : (void*)solve_mq_coop_k<NT, MINB, UC, UR, false>;
     CU(cudaMemsetAsync(&s->ctl->gbar[0], 0, sizeof(unsigned int), s->stream));
-    static bool configured[2] = {false, false};
-    if (!configured[s->pc.world > 1]) { CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); configured[s->pc.world > 1] = true; }
+    { int rc_ = ensure_dyn_smem(s->device, (const void*)kern, 200 * 1024); if (rc_) return rc_; }
     int occ = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, s->smem_e));
     if (occ < 1) return fail(PHW_ECUDA, "M_q solve kernel does not fit on an SM");
@@ -867,7 +808,7 @@ int launch_mq_lean(phw_solver_s* s) {
     a.max_iter = s->prm.max_iter; a.which = 1; a.partials = s->partials; a.ctl = s->ctl;
     void* args[] = {(void*)&a, (void*)&s->pc};
     cudaEvent_t e0 = nullptr, e1 = nullptr;
-    const bool prof = (s->prm.flags & 4) && s->prof_ev.size() < 2 * 8192;
+    const bool prof = prof_on(s);
     if (prof) {
         CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
         CU(cudaEventRecord(e0, s->stream));
@@ -892,9 +833,7 @@ int launch_mq_pipe(phw_solver_s* s) {
     const bool multi = s->pc.world > 1;
     void* kern = multi ? (void*)solve_mq_pipe_k<NT, false, true> : (diag ? (void*)solve_mq_pipe_k<NT, true, false> : (void*)solve_mq_pipe_k<NT, false, false>);
     CU(cudaMemsetAsync(&s->ctl->gbar[0], 0, sizeof(unsigned int), s->stream));
-    static bool configured[3] = {false, false, false};
-    const int ci = multi ? 2 : (diag ? 1 : 0);
-    if (!configured[ci]) { CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024)); configured[ci] = true; }
+    { int rc_ = ensure_dyn_smem(s->device, (const void*)kern, 227 * 1024 - 1024); if (rc_) return rc_; }
     int occ = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, s->smem_pq));
     if (occ < 1) return fail(PHW_ECUDA, "pipelined M_q solve kernel does not fit on an SM");
@@ -909,7 +848,7 @@ int launch_mq_pipe(phw_solver_s* s) {
     a.max_iter = s->prm.max_iter; a.which = 1; a.partials = s->partials; a.ctl = s->ctl;
     void* args[] = {(void*)&a, (void*)&s->pc};
     cudaEvent_t e0 = nullptr, e1 = nullptr;
-    const bool prof = (s->prm.flags & 4) && s->prof_ev.size() < 2 * 8192;
+    const bool prof = prof_on(s);
     if (prof) {
         CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
         CU(cudaEventRecord(e0, s->stream));
@@ -930,8 +869,7 @@ int launch_ell_pipe_cfg(phw_solver_s* s) {
     const bool multi = s->pc.world > 1;
     void* kern = multi ? (void*)solve_ell_pipe_k<NT, MINB, true> : (void*)solve_ell_pipe_k<NT, MINB, false>;
     CU(cudaMemsetAsync(&s->ctl->gbar[0], 0, sizeof(unsigned int), s->stream));
-    static bool configured[2] = {false, false};
-    if (!configured[multi]) { CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024)); configured[multi] = true; }
+    { int rc_ = ensure_dyn_smem(s->device, (const void*)kern, 227 * 1024 - 1024); if (rc_) return rc_; }
     int occ = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, s->smem_pp));
     if (occ < 1) return fail(PHW_ECUDA, "pipelined M_p solve kernel does not fit on an SM");
@@ -946,7 +884,7 @@ int launch_ell_pipe_cfg(phw_solver_s* s) {
     a.max_iter = s->prm.max_iter; a.which = 0; a.partials = s->partials; a.ctl = s->ctl;
     void* args[] = {(void*)&a, (void*)&s->pc};
     cudaEvent_t e0 = nullptr, e1 = nullptr;
-    const bool prof = (s->prm.flags & 4) && s->prof_ev.size() < 2 * 8192;
+    const bool prof = prof_on(s);
     if (prof) {
         CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
         CU(cudaEventRecord(e0, s->stream));
@@ -965,7 +903,7 @@ int launch_ell_pipe_cfg(phw_solver_s* s) {
 static int l2_persist_window(phw_solver_s* s, const void* ptr, size_t bytes, bool on) {
     static const bool want = [] { const char* e = getenv("PHW_L2_PERSIST_B"); return e && atoi(e) != 0; }();
     if (!want) return 0;
-    static size_t max_win = 0, max_persist = 0;
+    size_t& max_win = s->l2_max_win; size_t& max_persist = s->l2_max_persist;   // per solver (= per device), not per process
     if (max_win == 0) {
         cudaDeviceProp prop{};
         CU(cudaGetDeviceProperties(&prop, s->device));
@@ -988,79 +926,6 @@ int launch_ell_pipe(phw_solver_s* s) {
     rc = (2 * (s->smem_pp + 2048) <= 227 * 1024) ? launch_ell_pipe_cfg<512, 2>(s) : launch_ell_pipe_cfg<1024, 1>(s);
     if (rc) return rc;
     return l2_persist_window(s, s->bp, (size_t)s->nv * sizeof(double), false);
-}
-
-// pipelined two-sweep M_q solve (kernels_pipe2.cuh; experimental)
-int launch_mq_pipe2(phw_solver_s* s) {
-    constexpr int NT = 1024;
-    void* kern = (void*)solve2_mq_pipe_k<NT>;
-    CU(cudaMemsetAsync(&s->ctl->gbar[0], 0, sizeof(unsigned int), s->stream));
-    static bool configured = false;
-    if (!configured) { CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048)); configured = true; }
-    int occ = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, s->smem_pq2));
-    if (occ < 1) return fail(PHW_ECUDA, "pipelined two-sweep M_q solve kernel does not fit on an SM");
-    const int grid = std::max(1, std::min(s->npatch, occ * s->sm_count));
-    Mq2PipeArgs a = s->pq2;
-    a.m = s->r2[1];
-    for (int i = 0; i < 4; ++i) a.buf[i] = s->tq.b[i];
-    a.b = s->bq;
-    a.cheb_d = s->cheb_d[1]; a.cheb_c = s->cheb_c[1];
-    a.tol2 = s->prm.tol * s->prm.tol;
-    a.max_iter = s->prm.max_iter; a.which = 1; a.partials = s->partials; a.ctl = s->ctl;
-    void* args[] = {(void*)&a};
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    const bool prof = (s->prm.flags & 4) && s->prof_ev.size() < 2 * 8192;
-    if (prof) {
-        CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
-        CU(cudaEventRecord(e0, s->stream));
-    }
-    CU(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(NT), args, s->smem_pq2, s->stream));
-    if (prof) {
-        CU(cudaEventRecord(e1, s->stream));
-        s->prof_ev.push_back(e0); s->prof_ev.push_back(e1); s->prof_which.push_back(1);
-    }
-    s->launches++;
-    s->kernel_paths |= PHW_PATH_PIPE2_Q;
-    return 0;
-}
-
-// pipelined two-sweep M_p solve (kernels_pipe2.cuh; experimental)
-template <int NT, int MINB>
-int launch_ell_pipe2_cfg(phw_solver_s* s) {
-    void* kern = (void*)solve2_ell_pipe_k<NT, MINB>;
-    CU(cudaMemsetAsync(&s->ctl->gbar[0], 0, sizeof(unsigned int), s->stream));
-    static bool configured = false;
-    if (!configured) { CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048)); configured = true; }
-    int occ = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, s->smem_pp2));
-    if (occ < 1) return fail(PHW_ECUDA, "pipelined two-sweep M_p solve kernel does not fit on an SM");
-    const int grid = std::max(1, std::min(s->npatch, std::min(occ, MINB) * s->sm_count));
-    Ell2PipeArgs a = s->pp2;
-    a.m = s->r2[0];
-    for (int i = 0; i < 4; ++i) a.buf[i] = s->tp.b[i];
-    a.b = s->bp;
-    a.cheb_d = s->cheb_d[0]; a.cheb_c = s->cheb_c[0];
-    a.tol2 = s->prm.tol * s->prm.tol;
-    a.max_iter = s->prm.max_iter; a.which = 0; a.partials = s->partials; a.ctl = s->ctl;
-    void* args[] = {(void*)&a};
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    const bool prof = (s->prm.flags & 4) && s->prof_ev.size() < 2 * 8192;
-    if (prof) {
-        CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
-        CU(cudaEventRecord(e0, s->stream));
-    }
-    CU(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(NT), args, s->smem_pp2, s->stream));
-    if (prof) {
-        CU(cudaEventRecord(e1, s->stream));
-        s->prof_ev.push_back(e0); s->prof_ev.push_back(e1); s->prof_which.push_back(0);
-    }
-    s->launches++;
-    s->kernel_paths |= PHW_PATH_PIPE2_P;
-    return 0;
-}
-int launch_ell_pipe2(phw_solver_s* s) {
-    return (2 * (s->smem_pp2 + 2560) <= 227 * 1024) ? launch_ell_pipe2_cfg<512, 2>(s) : launch_ell_pipe2_cfg<1024, 1>(s);
 }
 
 int solve_begin(phw_solver_s* s, int which) {
@@ -1092,9 +957,6 @@ int solve_mass(phw_solver_s* s, int which, int n_launch) {
         s->launches++;
         return 0;
     }
-    if (which == PHW_Q && s->pipe2_q && s->coop && s->pc.world <= 1) return launch_mq_pipe2(s);
-    if (which == PHW_P && s->pipe2_p && s->coop && s->pc.world <= 1) return launch_ell_pipe2(s);
-    if (s->two_sweep) return which == PHW_P ? launch_coop2<0>(s) : launch_coop2<1>(s);
     RowArgs a = base_args(s);
     a.which = which; a.use_cheb_input = 1; a.finalize = 1; a.cM = 1.0; a.counter_id = which;
     a.cheb_d = s->cheb_d[which]; a.cheb_c = s->cheb_c[which];
@@ -1102,9 +964,7 @@ int solve_mass(phw_solver_s* s, int which, int n_launch) {
     if (s->coop) {
         a.b = which == PHW_P ? s->bp : s->bq;
         a.pinv = which == PHW_P ? s->pinv_p : s->pinv_q;
-        // partitioned runs: the pipelined solves with the exchange are opt-in (PHW_PIPE_MULTI=1) until they have run on 2+ GPUs
-        static const bool pipe_multi = [] { const char* e = getenv("PHW_PIPE_MULTI"); return e && atoi(e) != 0; }();
-        const bool pipe_ok = s->pc.world <= 1 || pipe_multi;
+        const bool pipe_ok = s->pc.world <= 1 || (pipe_multi_mask() & 1);
         if (which == PHW_Q && s->pipe_q && pipe_ok) return launch_mq_pipe(s);
         if (which == PHW_P && s->pipe_p && pipe_ok && s->ell_p && a.mdiag == nullptr) return launch_ell_pipe(s);
         if (which == PHW_P && s->ell_p && a.mdiag == nullptr && !s->ell_staged) {
@@ -1270,10 +1130,9 @@ int energy(phw_solver_s* s) {
         return 0;
     }
     int rc = 0;
-    if (s->pipe_en && s->pc.world <= 1) {   // both forms in one bulk-copy pipelined pass over the own cells (kernels_pipe.cuh)
+    if (s->pipe_en && (s->pc.world <= 1 || (pipe_multi_mask() & 4))) {   // both forms in one bulk-copy pipelined pass over the own cells (kernels_pipe.cuh)
         constexpr int NT = 1024;
-        static bool conf = false;
-        if (!conf) { CU(cudaFuncSetAttribute(energy_pipe_k<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024)); conf = true; }
+        { int rc_ = ensure_dyn_smem(s->device, (const void*)energy_pipe_k<NT>, 227 * 1024 - 1024); if (rc_) return rc_; }
         EnergyPipeArgs a = s->pe;
         a.npatch = s->npatch; a.hdr = s->dm.hdr; a.recv = s->dm.recv; a.area = s->dm.area; a.cellq = s->d_cellq;
         a.ghost_v = s->dm.ghost_v; a.ghost_e = s->dm.ghost_e; a.p = s->p; a.q = s->q;
@@ -1288,12 +1147,8 @@ int energy(phw_solver_s* s) {
         a.npatch = s->npatch; a.hdr = s->dm.hdr; a.partials = s->partials + 8192; a.ctl = s->ctl;
         a.ell_ioff = s->dm.ell_ioff; a.ell_woff = s->dm.ell_woff; a.ell_ids = s->dm.ell_ids; a.ell_w = s->dm.ell_w;
         a.ghost = s->dm.ghost_v; a.x = s->p; a.scale = 0.5 / s->prm.rho; a.slot = 0; a.counter_id = 4;
-        static bool conf = false;
-        if (!conf) {
-            CU(cudaFuncSetAttribute(dot_ell_k<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            CU(cudaFuncSetAttribute(dot_mq_k<512, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            conf = true;
-        }
+        { int rc_ = ensure_dyn_smem(s->device, (const void*)dot_ell_k<256, 4>, 200 * 1024); if (rc_) return rc_; }
+        { int rc_ = ensure_dyn_smem(s->device, (const void*)dot_mq_k<512, 2, 2>, 200 * 1024); if (rc_) return rc_; }
         dot_ell_k<256, 4><<<std::max(1, std::min(s->npatch, 4 * s->sm_count)), 256, s->smem_ell, s->stream>>>(a);
         a.cellq = s->d_cellq; a.eadj = s->dm.eadj; a.ghost = s->dm.ghost_e; a.x = s->q; a.scale = 0.5 * s->prm.K_wave; a.slot = 1; a.counter_id = 5;
         a.partials = s->partials + 8192 + 2048;
@@ -1536,7 +1391,8 @@ void ellipse_for_rectangle(double alpha, double beta, double mu, double& d, doub
 extern "C" {
 
 const char* phw_last_error(void) { return g_err.c_str(); }
-int phw_version(void) { return 100; }
+int phw_version(void) { return 200; }
+int phw_sizeof(int what) { return what == 0 ? (int)sizeof(phw_params) : (what == 1 ? (int)sizeof(phw_stats) : -1); }
 
 int phw_mesh_create(int64_t n_vertices, const double* vertices_xy, int64_t n_cells, const int32_t* cells,
                     int32_t patch_cells, phw_mesh_t* out) {
@@ -1571,6 +1427,13 @@ int phw_mesh_create_partitioned(int64_t n_vertices, const double* vertices_xy, i
     }
     if (!err.empty()) { delete m; return fail(PHW_EINVAL, err); }
     *out = m;
+    return PHW_OK;
+}
+
+int phw_mesh_set_cell_owned(phw_mesh_t m, const uint8_t* cell_owned) {
+    if (!m || !cell_owned) return fail(PHW_EINVAL, "mesh or cell_owned is NULL");
+    m->L.cell_foreign.resize((size_t)m->L.nc);
+    for (int64_t c = 0; c < m->L.nc; ++c) m->L.cell_foreign[c] = cell_owned[c] ? 0 : 1;
     return PHW_OK;
 }
 
@@ -1660,20 +1523,9 @@ int phw_mesh_pipe_smem(phw_mesh_t m, int64_t* bytes6) {
     size_t sq = 0, sp = 0, se = 0, sre = 0, srv = 0;
     pipe_carve(m->L, cq, cp, sq, sp, &ce, &se, &re, &sre, &rv, &srv);
     bytes6[0] = (int64_t)sp; bytes6[1] = (int64_t)sq; bytes6[2] = (int64_t)se; bytes6[3] = (int64_t)sre; bytes6[4] = (int64_t)srv;
-    bytes6[5] = 0;
-    Ring2 R;
-    if (m->L.n_groups == 1 && m->L.build_ring2(1, R).empty()) { Mq2PipeArgs c2{}; bytes6[5] = (int64_t)pipe2_carve(R, c2); }
+    bytes6[5] = 0;   // (was: the two-sweep pipelined M_q solve, removed in round 2 - measured slower than the one-sweep kernels)
     return PHW_OK;
 }
-int phw_mesh_pipe2_smem(phw_mesh_t m, int64_t* bytes2) {
-    if (!m || !bytes2) return fail(PHW_EINVAL, "mesh or bytes2 is NULL");
-    bytes2[0] = bytes2[1] = 0;
-    if (m->L.n_groups != 1) return PHW_OK;
-    { Ring2 R; if (m->L.build_ring2(0, R).empty()) { Ell2PipeArgs c{}; bytes2[0] = (int64_t)pipe2_carve_p(R, c); } }
-    { Ring2 R; if (m->L.build_ring2(1, R).empty()) { Mq2PipeArgs c{}; bytes2[1] = (int64_t)pipe2_carve(R, c); } }
-    return PHW_OK;
-}
-
 int phw_mesh_self_check(phw_mesh_t m) {
     if (!m) return fail(PHW_EINVAL, "mesh is NULL");
     if (m->L.nc > 200000) return fail(PHW_EINVAL, "phw_mesh_self_check is quadratic in places: meshes up to 200 000 cells");
@@ -1761,14 +1613,14 @@ static int setup_vectors(phw_solver_s* s) {
     {   // exchange arena: [Mailbox | tp0 tp1 tp2 | tq0 tq1 tq2] in ONE allocation so that a single CUDA IPC handle
         // lets the neighbouring ranks write halo values and partial sums straight into it (peer memory over NVLink)
         const size_t head = 4096, nvp = (nv + 31) & ~(size_t)31, nep = (ne + 31) & ~(size_t)31;
-        s->arena_bytes = head + 4 * (nvp + nep) * sizeof(double);   // [.. | tp3 | tq3]: fourth iterate buffers of the two-sweep solves
+        s->arena_bytes = head + 3 * (nvp + nep) * sizeof(double);
         char* base = nullptr;
         RC(s->dalloc(&base, s->arena_bytes));
         s->arena = base;
         CU(cudaMemsetAsync(base, 0, s->arena_bytes, s->stream));
         double* d0 = (double*)(base + head);
         for (int i = 0; i < 3; ++i) { s->tp.b[i] = d0 + i * nvp; s->tq.b[i] = d0 + 3 * nvp + i * nep; }
-        s->tp.b[3] = d0 + 3 * (nvp + nep); s->tq.b[3] = s->tp.b[3] + nvp;
+        s->tp.b[3] = nullptr; s->tq.b[3] = nullptr;
         s->pc = PeerComm{};
         s->pc.rank = 0; s->pc.world = 1; s->pc.n_nb = 0;
         s->pc.mbox[0] = (Mailbox*)base;
@@ -1924,11 +1776,14 @@ static int setup_solver(phw_solver_s* s) {
     // ---- bulk-copy pipelined mass solves (flags bits 8 / 9): two stages holding every stream of the largest patch
     if (P.flags & (256 | 512 | 2048 | 4096)) {
         pipe_carve(L, s->pq, s->pp, s->smem_pq, s->smem_pp, &s->pe, &s->smem_pe, &s->pre, &s->smem_pre, &s->prv, &s->smem_prv);
-        if ((P.flags & 4096) && L.n_groups == 1 && !P.casimir && L.nv_owned == L.nv && L.ne_owned == L.ne) {
+        // partitioned runs: rows exist for owned dofs only and external dofs are read like any ghost, so the row kernels need nothing
+        // extra; the cell-based energy pass needs to know which cells of the local mesh are this rank's (phw_mesh_set_cell_owned)
+        const bool partitioned = L.nv_owned != L.nv || L.ne_owned != L.ne;
+        if ((P.flags & 4096) && L.n_groups == 1 && !P.casimir) {
             if (std::max(s->smem_pre, s->smem_prv) > PIPE_SMEM_LIMIT) return fail(PHW_EINVAL, "pipelined right-hand sides (flags bit 12): two stages of the largest patch exceed the shared memory of an SM; reduce patch_cells");
             s->pipe_rhs = true;
         }
-        if ((P.flags & 2048) && L.n_groups == 1 && L.nv_owned == L.nv && L.ne_owned == L.ne) {
+        if ((P.flags & 2048) && L.n_groups == 1 && (!partitioned || !L.cell_foreign.empty())) {
             if (s->smem_pe > PIPE_SMEM_LIMIT) return fail(PHW_EINVAL, "pipelined energy reduction (flags bit 11): two stages of the largest patch exceed the shared memory of an SM; reduce patch_cells");
             s->pipe_en = true;
         }
@@ -1977,62 +1832,6 @@ static int setup_solver(phw_solver_s* s) {
             zero_at_k<<<nblk(s->n_dir), 256, 0, s->stream>>>(s->n_dir, s->d_dir_idx, s->pinv_p);
             CU(cudaGetLastError());
         }
-    }
-    // ---- two-sweep patches of the mass solves (kernels2.cuh): single GPU, weak form (pinv_p is then exactly the
-    //      inverse of the P1 mass diagonal), explicit schemes
-    const bool ring2_ok = s->coop && !P.strong && !implicit && L.nv_owned == L.nv && L.ne_owned == L.ne;
-    s->two_sweep = ring2_ok && (P.flags & 16);
-    bool want_pipe2 = ring2_ok && (P.flags & 8192) && L.n_groups == 1;
-    bool want_pipe2p = ring2_ok && (P.flags & 16384) && L.n_groups == 1 && s->ell_p;
-    for (int kind = 0; kind < 2 && (s->two_sweep || want_pipe2 || want_pipe2p); ++kind) {
-        if (!s->two_sweep && !(kind == 0 ? want_pipe2p : want_pipe2)) continue;  // ring-2 patches of this kind are not needed
-        Ring2 R;
-        if (!L.build_ring2(kind, R).empty()) { s->two_sweep = false; want_pipe2 = false; want_pipe2p = false; break; }   // patches too large for one more ring
-        if (kind == 0 && want_pipe2p) {
-            s->smem_pp2 = pipe2_carve_p(R, s->pp2);
-            if (s->smem_pp2 > PIPE_SMEM_LIMIT - 1024)
-                return fail(PHW_EINVAL, "pipelined two-sweep M_p solve (flags bit 14): two stages of the largest ring-2 patch exceed the shared memory of an SM; reduce patch_cells");
-            s->pipe2_p = true;
-        }
-        if (kind == 1 && want_pipe2) {   // shared-memory carve-up of solve2_mq_pipe_k for the largest ring-2 patch
-            s->smem_pq2 = pipe2_carve(R, s->pq2);
-            if (s->smem_pq2 > PIPE_SMEM_LIMIT - 1024)   // this kernel has 1.2 KB of static shared memory
-                return fail(PHW_EINVAL, "pipelined two-sweep M_q solve (flags bit 13): two stages of the largest ring-2 patch exceed the shared memory of an SM; use patch_cells <= 768");
-            s->pipe2_q = true;
-        }
-        const size_t soff2 = ((size_t)(R.max_rows + 31) / 32 + 4) / 2 + 1;
-        s->smem2[kind] = (kind == 0) ? (size_t)R.max_smem_ell * 8 : (ev(R.max_ld) + 3 * (size_t)R.max_c2) * 8;
-        (void)soff2;
-        if (s->smem2[kind] > 200 * 1024) { s->two_sweep = false; if (!s->pipe2_q && !s->pipe2_p && !want_pipe2) break; }
-        Ring2Dev& d = s->r2[kind];
-        d.npatch = s->npatch;
-        Ring2Hdr* d_h; uint32_t* d_rec; int *d_gh, *d_pcu2, *d_rg; double* d_pinv2;
-        const int npc2 = (int)R.pcell_user.size(), nrows = (int)R.row_gid.size();
-        RC(s->upload(&d_h, R.hdr)); RC(s->upload(&d_rec, R.rec)); RC(s->upload(&d_gh, R.ghost));
-        RC(s->upload(&d_pcu2, R.pcell_user)); RC(s->upload(&d_rg, R.row_gid));
-        RC(s->dalloc(&d_pinv2, nrows));
-        d.hdr = d_h; d.rec = reinterpret_cast<const uint2*>(d_rec); d.ghost = d_gh; d.pinv = d_pinv2;
-        double *ga = nullptr, *gb = nullptr, *gc = nullptr;
-        RC(s->dalloc(&ga, npc2));
-        if (kind == 1) { RC(s->dalloc(&gb, npc2)); RC(s->dalloc(&gc, npc2)); }
-        geom_k<<<nblk(npc2), 256, 0, s->stream>>>(npc2, d_pcu2, s->d_cells_user, s->d_vtx_user, kind == 0 ? ga : nullptr,
-                                                   kind == 1 ? ga : nullptr, gb, gc, s->d_mm);
-        gather_k<<<nblk(nrows), 256, 0, s->stream>>>(nrows, d_pinv2, kind == 0 ? s->pinv_p : s->pinv_q, d_rg);
-        CU(cudaGetLastError());
-        d.g0 = ga; d.g1 = gb; d.g2 = gc;
-        if (kind == 0) {
-            uint32_t *d_io, *d_wo, *d_pair; uint16_t* d_ids; double* d_w;
-            RC(s->upload(&d_io, R.ell_ioff)); RC(s->upload(&d_wo, R.ell_woff)); RC(s->upload(&d_ids, R.ell_ids)); RC(s->upload(&d_pair, R.ell_pair));
-            RC(s->dalloc(&d_w, R.ell_pair.size()));
-            ell2_weights_k<<<std::max(1, std::min(s->npatch, 8 * s->sm_count)), 256, 0, s->stream>>>(s->npatch, d_h, d_wo, d_pair, ga, d_w);
-            CU(cudaGetLastError());
-            d.ell_ioff = d_io; d.ell_woff = d_wo; d.ell_ids = d_ids; d.ell_w = d_w;
-        } else {
-            uint32_t* d_ea;
-            RC(s->upload(&d_ea, R.eadj));
-            d.eadj = d_ea;
-        }
-        CU(cudaStreamSynchronize(s->stream));   // the host vectors of R go out of scope
     }
     // ---- Chebyshev intervals.  P1: element bound [1/2, 2] (Wathen); RT1: element bounds from geom_k.
     s->cheb_d[0] = 1.25; s->cheb_c[0] = 0.75;
@@ -2236,7 +2035,6 @@ int phw_comm_setup(phw_solver_t s, int32_t rank, int32_t world, const void* hand
     }
     CU(cudaStreamSynchronize(s->stream));
     s->pc = pc;
-    if (world > 1) { s->two_sweep = false; s->pipe2_q = false; s->pipe2_p = false; }   // the peer exchange is fused into the one-sweep kernels
     return PHW_OK;
 }
 
@@ -2377,6 +2175,7 @@ int phw_run(phw_solver_t s, int64_t n_steps, double* H_rows) {
         cudaEventDestroy(s->prof_ev[2 * i]); cudaEventDestroy(s->prof_ev[2 * i + 1]);
     }
     s->prof_ev.clear(); s->prof_which.clear();
+    if (s->prof_truncated) { st.ms_solve_p = st.ms_solve_q = st.ms_solve_block = 0.0; s->prof_truncated = false; }
     {   // algorithmic bytes: per cell 40 B skew apply, 28/60 B mass apply; per dof 8 B per vector pass
         const double nc = s->mesh ? (double)s->mesh->L.nc : 0.0, nv = s->nv, ne = s->ne;
         const double it_p = (double)st.iters_p + (double)st.iters_block, it_q = (double)st.iters_q + (double)st.iters_block;

@@ -1,4 +1,4 @@
-// pipe_carve.hpp - shared-memory carve-ups of the bulk-copy pipelined kernels (kernels_pipe.cuh, kernels_pipe2.cuh), computed on the
+// pipe_carve.hpp - shared-memory carve-ups of the bulk-copy pipelined kernels (kernels_pipe.cuh), computed on the
 // host from the largest patch of a layout.  Used by phwave.cu (solver setup, phw_mesh_pipe_smem) and by the host-side emulator of
 // tests/emu, so that both run the kernels with the same offsets.
 #pragma once
@@ -83,48 +83,6 @@ inline void pipe_carve(const Layout& L, MqPipeArgs& cq, EllPipeArgs& cp, size_t&
         rv->gidx_bytes = (uint32_t)r16(((size_t)max_ge + 8) * 4);
         *smem_rv = (size_t)rv->off_gidx + 2 * rv->gidx_bytes;
     }
-}
-
-// shared-memory carve-up of the pipelined two-sweep M_q solve (kernels_pipe2.cuh) for the largest ring-2 patch
-inline size_t pipe2_carve(const Ring2& R, Mq2PipeArgs& c) {
-    int max_ng = 0, max_n0 = 0;
-    for (const Ring2Hdr& h : R.hdr) { max_ng = std::max(max_ng, h.g1_cnt + h.g2_cnt); max_n0 = std::max(max_n0, h.d_cnt); }
-    auto r16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
-    const size_t rowd = r16(((size_t)R.max_rows + 2) * 8), celld = r16(((size_t)R.max_c2 + 2) * 8);
-    size_t o = r16(((size_t)R.max_ld + 2) * 8);
-    c.off_xprev = (uint32_t)o; o += rowd;
-    c.off_b = (uint32_t)o; o += rowd;
-    c.off_pinv = (uint32_t)o; o += rowd;
-    c.off_eadj = (uint32_t)o; o += r16(((size_t)R.max_rows + 8) * 4);
-    c.off_rec = (uint32_t)o; o += celld;
-    c.off_g0 = (uint32_t)o; o += celld;
-    c.off_g1 = (uint32_t)o; o += celld;
-    c.off_g2 = (uint32_t)o; o += celld;
-    c.stage_bytes = (uint32_t)((o + 127) & ~(size_t)127);
-    c.off_sc3 = 2 * c.stage_bytes;
-    c.off_xk0 = c.off_sc3 + (uint32_t)r16((size_t)R.max_c2 * 24);
-    c.off_gidx = c.off_xk0 + (uint32_t)r16((size_t)max_n0 * 8);
-    c.gidx_bytes = (uint32_t)r16(((size_t)max_ng + 8) * 4);
-    return (size_t)c.off_gidx + 2 * c.gidx_bytes;
-}
-
-inline size_t pipe2_carve_p(const Ring2& R, Ell2PipeArgs& c) {
-    int max_ng = 0, max_in = 0, max_wn = 0;
-    for (const Ring2Hdr& h : R.hdr) { max_ng = std::max(max_ng, h.g1_cnt + h.g2_cnt); max_in = std::max(max_in, h.ell_in); max_wn = std::max(max_wn, h.ell_wn); }
-    auto r16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
-    const size_t nslw = r16(((size_t)(R.max_rows + 31) / 32 + 2) * 4), rowd = r16(((size_t)R.max_rows + 2) * 8);
-    size_t o = nslw;
-    c.off_wo = (uint32_t)o; o += nslw;
-    c.off_x = (uint32_t)o; o += r16(((size_t)R.max_ld + 2) * 8);
-    c.off_b = (uint32_t)o; o += rowd;
-    c.off_xprev = (uint32_t)o; o += rowd;
-    c.off_w = (uint32_t)o; o += r16((size_t)max_wn * 8);
-    c.off_ids = (uint32_t)o; o += r16((size_t)max_in * 2);
-    c.stage_bytes = (uint32_t)((o + 127) & ~(size_t)127);
-    c.off_x1 = 2 * c.stage_bytes;
-    c.off_gidx = c.off_x1 + (uint32_t)rowd;
-    c.gidx_bytes = (uint32_t)r16(((size_t)max_ng + 8) * 4);
-    return (size_t)c.off_gidx + 2 * c.gidx_bytes;
 }
 
 }  // namespace phw

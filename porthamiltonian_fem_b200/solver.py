@@ -11,7 +11,8 @@ TAG_LEFT, TAG_TOP, TAG_RIGHT, TAG_GENERAL, TAG_NONE = 0, 1, 2, 3, 4
 class Mesh:
     """Connectivity + patch layout of a triangle mesh (phw_mesh_*; host only, no GPU needed)."""
 
-    def __init__(self, vertices, cells, patch_cells=2048, vertex_external=None, edge_external=None, cell_group=None, n_groups=1):
+    def __init__(self, vertices, cells, patch_cells=2048, vertex_external=None, edge_external=None, cell_group=None, n_groups=1,
+                 cell_owned=None):
         self.lib = _lib.load()
         self.vertices = np.ascontiguousarray(vertices, dtype=np.float64)
         self.cells = np.ascontiguousarray(cells, dtype=np.int32)
@@ -38,6 +39,11 @@ class Mesh:
                 self.cells.ctypes.data_as(_lib.c_i32p), int(patch_cells), ve.ctypes.data, ee.shape[0], ee.ctypes.data,
                 ctypes.byref(h)))
         self.handle = h
+        if cell_owned is not None:   # partitioned run: which cells of the local mesh are this rank's (cell-based reductions)
+            co = np.ascontiguousarray(cell_owned, dtype=np.uint8)
+            if co.shape[0] != self.cells.shape[0]:
+                raise ValueError('one ownership flag per cell expected')
+            _lib.check(self.lib.phw_mesh_set_cell_owned(h, co.ctypes.data))
         s = [ctypes.c_int64() for _ in range(5)]
         _lib.check(self.lib.phw_mesh_sizes(h, *[ctypes.byref(x) for x in s]))
         self.n_vertices, self.n_cells, self.n_edges, self.n_boundary, self.n_patches = [int(x.value) for x in s]
@@ -97,16 +103,10 @@ class Mesh:
 
     def pipe_smem(self):
         """dynamic shared memory (bytes) of the bulk-copy pipelined kernels for this layout:
-        (M_p solve, M_q solve, energy reduction, edge-row rhs, vertex-row rhs, two-sweep M_q solve) - flags bits 9, 8, 11, 12, 12, 13"""
+        (M_p solve, M_q solve, energy reduction, edge-row rhs, vertex-row rhs, reserved) - flags bits 9, 8, 11, 12, 12"""
         b = (ctypes.c_int64 * 6)()
         _lib.check(self.lib.phw_mesh_pipe_smem(self.handle, b))
         return tuple(int(x) for x in b)
-
-    def pipe2_smem(self):
-        """dynamic shared memory (bytes) of the experimental pipelined two-sweep (M_p, M_q) solves (flags bits 14 / 13)"""
-        b = (ctypes.c_int64 * 2)()
-        _lib.check(self.lib.phw_mesh_pipe2_smem(self.handle, b))
-        return int(b[0]), int(b[1])
 
     def close(self):
         if getattr(self, 'handle', None):

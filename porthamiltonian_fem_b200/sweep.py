@@ -53,6 +53,10 @@ def wave_sweep_solve(tFinal, numSteps, nx, xLength, yLength, cases, domainShape=
     prm.dt, prm.K_wave, prm.rho = tFinal / numSteps, 1.0, 1.0
     for k, v in DEFAULT_LUMPED.items():
         setattr(prm, k, v)
+    if B == 1:   # a single case (e.g. a one-case shard of a sweep split over GPUs) has no groups: its physics goes through phw_params
+        prm.K_wave, prm.rho = float(cases[0].get('K_wave', 1.0)), float(cases[0].get('rho', 1.0))
+        for k in LUMPED_KEYS:
+            setattr(prm, k, float(cases[0].get(k, DEFAULT_LUMPED[k])))
     prm.input_kind, prm.in_amp, prm.in_omega, prm.in_t_stop = _lib.IN_SINE_WINDOW, 5.0, 8 * np.pi, 0.25     # wave_2D.py:433
     prm.tol, prm.max_iter, prm.extrap_order, prm.flags = float(tol), 400, int(extrap_order), int(solver_flags)
     solver = Solver(m, prm, device=device)

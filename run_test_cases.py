@@ -1,4 +1,5 @@
-"""Regression harness: the case lists of the reference's run_test_cases.py (:23-49) on the B200 path, written to
+"""Regression harness: the case lists of the reference's run_test_cases.py (:23-49, all eleven tuples of each set, the
+higher-order analytical ones included) on the B200 path, written to
 test_output/<caseName>/..., then compared by test_case_check.check_cases against a ground truth produced by the CPU
 oracle on the same meshes (the reference's own ground-truth files were produced on mshr meshes that cannot be
 rebuilt here; they pin the oracle instead - see tests/test_oracle_golden.py).
@@ -20,6 +21,8 @@ CASE_SETS = {
                    ['R', 'EH', 'weak', 40, 'wave', 0.1, 200, 'noMem'],
                    ['R', 'SV', 'strong', 20, 'wave', 0.1, 200, 'noMem'],
                    ['R', 'SV', 'weak', 20, 'wave', 0.1, 200, 'noMem'],
+                   ['R', 'SV', 'weak', 4, 'analytical', 0.1, 200, 'noMem', (3, 3)],
+                   ['R', 'SV', 'weak', 20, 'analytical', 0.1, 200, 'noMem', (1, 2)],
                    ['R', 'SE', 'weak', 60, 'analytical', 0.1, 200, 'noMem', (1, 1)],
                    ['R', 'SV', 'weak', 60, 'IC', 0.1, 100, 'noMem'],
                    ['R', 'SM', 'weak', 60, 'IC', 0.1, 100, 'noMem'],
@@ -29,6 +32,9 @@ CASE_SETS = {
                         ['R', 'EH', 'weak', 80, 'wave', 1.5, 3000, 'noMem'],
                         ['R', 'SV', 'strong', 20, 'wave', 1.5, 3000, 'noMem'],
                         ['R', 'SV', 'weak', 20, 'wave', 1.5, 3000, 'noMem'],
+                        ['R', 'SV', 'weak', 4, 'analytical', 1.5, 3000, 'noMem', (3, 3)],
+                        ['R', 'SV', 'weak', 20, 'analytical', 1.5, 3000, 'noMem', (1, 2)],
+                        ['R', 'SE', 'weak', 80, 'analytical', 1.5, 3000, 'noMem', (3, 3)],
                         ['R', 'SV', 'weak', 120, 'IC', 4.5, 3000, 'noMem'],
                         ['R', 'SM', 'weak', 120, 'IC', 4.5, 3000, 'noMem'],
                         ['S_1C', 'SV', 'weak', 60, 'IC', 8, 16000, 'noMem']],
@@ -47,7 +53,8 @@ def make_ground_truth(caseName, caseArray):
         H, nc = wave_2D_solve_oracle(caseVec[5], caseVec[6], mesh, 1.0, yLength, domainShape=caseVec[0],
                                      timeIntScheme=caseVec[1], dirichletImp=caseVec[2], K_wave=K_wave, rho=rho,
                                      interConnection=caseVec[4] if caseVec[4].startswith('IC') else None,
-                                     analytical=caseVec[4] == 'analytical')
+                                     analytical=caseVec[4] == 'analytical',
+                                     basis_order=caseVec[8] if len(caseVec) > 8 else (1, 1))
         np.save(os.path.join(d, 'H_array.npy'), H)
         np.save(os.path.join(d, 'numCells.npy'), np.array([float(nc)]))
 

@@ -12,7 +12,7 @@
 #include <vector>
 
 #include "cuda_runtime.h"
-#include "kernels_pipe2.cuh"
+#include "kernels_pipe.cuh"
 #include "pipe_carve.hpp"
 #include "layout.hpp"
 
@@ -57,8 +57,7 @@ int fail(char* err, int errlen, const std::string& m) { std::snprintf(err, (size
 
 }  // namespace
 
-// what: "mq1" | "mp1" (one-sweep pipelined solves), "mq2" | "mp2" (two-sweep pipelined solves), "mq_lean" | "mp_lean",
-//       "mq2_lean" | "mp2_lean" (lean two-sweep solves of kernels2.cuh),
+// what: "mq1" | "mp1" (pipelined solves), "mq_lean" | "mp_lean",
 //       "energy" (out[0] = p^T M_p p, out[1] = q^T M_q q; in1 = p, in2 = q), "rhs_e" (out = D in1), "rhs_v" (out = D^T in1)
 // btags: tag of every boundary edge in the order of the layout's boundary list (nullptr: all "none"); user numbering everywhere.
 extern "C" int emu_run(const char* what_c, int64_t nv, const double* vtx, int64_t nc, const int32_t* cells, int32_t patch_cells, int32_t grid,
@@ -188,71 +187,6 @@ extern "C" int emu_run(const char* what_c, int64_t nv, const double* vtx, int64_
             a.cheb_d = cd; a.cheb_c = cc; a.tol2 = tol * tol; a.max_iter = 200; a.which = 0; a.partials = partials; a.ctl = ctl;
             const size_t sm = ((size_t)(L.max_lv + 31) / 32 + 4 + (size_t)((L.max_lv + 1) & ~1)) * 8;
             phw_emu::launch(grid, NT, sm, [&] { solve_ell_coop_k<NT, 1, false>(a, pc); });
-        } else if (what == "mq2" || what == "mp2" || what == "mq2_lean" || what == "mp2_lean") {
-            const bool lean2 = what.size() > 3;
-            Ring2 R;
-            e = L.build_ring2(is_q ? 1 : 0, R);
-            if (!e.empty()) return fail(err, errlen, "ring-2 patches: " + e);
-            const int npc2 = (int)R.pcell_user.size(), nrows = (int)R.row_gid.size();
-            std::vector<double> a2(npc2), h0(npc2), h1(npc2), h2(npc2);
-            for (int k = 0; k < npc2; ++k) cell_geometry(L, R.pcell_user[k], a2[k], h0[k], h1[k], h2[k]);
-            Ring2Dev d{};
-            d.npatch = npatch;
-            d.hdr = A.put(R.hdr);
-            d.rec = reinterpret_cast<const uint2*>(A.put(R.rec));
-            d.ghost = A.put(R.ghost);
-            if (is_q) {
-                d.g0 = A.put(h0); d.g1 = A.put(h1); d.g2 = A.put(h2);
-                std::vector<double> pr(nrows);
-                for (int r = 0; r < nrows; ++r) pr[r] = pinvq[R.row_gid[r]];
-                d.pinv = A.put(pr);
-                d.eadj = A.put(R.eadj);
-                if (lean2) {   // the lean two-sweep kernel of kernels2.cuh with the custom grid barrier (flags bits 4 + 10)
-                    Solve2Args a{};
-                    a.m = d;
-                    for (int i = 0; i < 4; ++i) a.buf[i] = buf[i];
-                    a.b = d_b; a.cheb_d = cd; a.cheb_c = cc; a.tol2 = tol * tol; a.max_iter = 200; a.which = 1; a.partials = partials; a.ctl = ctl; a.gbar = 1;
-                    const size_t sm = ((size_t)((R.max_ld + 1) & ~1) + 3 * (size_t)R.max_c2) * 8;
-                    phw_emu::launch(grid, NT, sm, [&] { solve2_coop_k<1, NT, 1>(a); });
-                } else {
-                    Mq2PipeArgs a{};
-                    const size_t sm = pipe2_carve(R, a);
-                    a.m = d;
-                    for (int i = 0; i < 4; ++i) a.buf[i] = buf[i];
-                    a.b = d_b; a.cheb_d = cd; a.cheb_c = cc; a.tol2 = tol * tol; a.max_iter = 200; a.which = 1; a.partials = partials; a.ctl = ctl;
-                    phw_emu::launch(grid, NT, sm, [&] { solve2_mq_pipe_k<NT>(a); });
-                }
-            } else {
-                d.g0 = A.put(a2);
-                d.ell_ioff = A.put(R.ell_ioff); d.ell_woff = A.put(R.ell_woff); d.ell_ids = A.put(R.ell_ids);
-                std::vector<double> w2(R.ell_pair.size(), 0.0);
-                for (int p = 0; p < npatch; ++p) {
-                    const Ring2Hdr& h = R.hdr[p];
-                    const int nsl = (h.d_cnt + h.g1_cnt + 31) >> 5;
-                    for (uint32_t k = R.ell_woff[h.vs_off]; k < R.ell_woff[h.vs_off + nsl]; ++k) {
-                        const uint32_t prr = R.ell_pair[k];
-                        if (prr == 0xFFFFFFFFu) continue;
-                        double v = a2[h.cell_off + (prr & 0xFFFFu)];
-                        if ((prr >> 16) != 0xFFFFu) v += a2[h.cell_off + (prr >> 16)];
-                        w2[k] = v * (1.0 / 12.0);
-                    }
-                }
-                d.ell_w = A.put(w2);
-                if (lean2) {
-                    Solve2Args a{};
-                    a.m = d;
-                    for (int i = 0; i < 4; ++i) a.buf[i] = buf[i];
-                    a.b = d_b; a.cheb_d = cd; a.cheb_c = cc; a.tol2 = tol * tol; a.max_iter = 200; a.which = 0; a.partials = partials; a.ctl = ctl; a.gbar = 1;
-                    phw_emu::launch(grid, NT, (size_t)R.max_smem_ell * 8, [&] { solve2_coop_k<0, NT, 1>(a); });
-                } else {
-                    Ell2PipeArgs a{};
-                    const size_t sm = pipe2_carve_p(R, a);
-                    a.m = d;
-                    for (int i = 0; i < 4; ++i) a.buf[i] = buf[i];
-                    a.b = d_b; a.cheb_d = cd; a.cheb_c = cc; a.tol2 = tol * tol; a.max_iter = 200; a.which = 0; a.partials = partials; a.ctl = ctl;
-                    phw_emu::launch(grid, NT, sm, [&] { solve2_ell_pipe_k<NT, 1>(a); });
-                }
-            }
         } else return fail(err, errlen, "unknown kernel " + what);
         const SolveCtl& sc = ctl->sc[is_q ? 1 : 0];
         if ((ctl->nonconv >> 32) != 0) return fail(err, errlen, "a stage did not arrive");
@@ -315,16 +249,23 @@ extern "C" int emu_run2(const char* what_c, int32_t patch_cells, int32_t grid,
                         const uint8_t* const* v_ext, const int64_t* ne, const uint8_t* const* e_ext,
                         const double* const* b_user, double* const* out_user,
                         const int32_t* n_send, const int32_t* const* send_loc, const int32_t* const* send_rem,
-                        int32_t* iters, double tol, char* err, int errlen) {
+                        int32_t* iters, double tol, char* err, int errlen,
+                        const uint8_t* const* cell_owned, const int32_t* const* btags, const double* const* in2_user) {
     const std::string what(what_c);
     constexpr int NT = 128;
-    const bool is_q = what.rfind("mq", 0) == 0;
+    // single-pass kernels on the partitioned layouts (no exchange inside the kernel): "energy" (b_user = p, in2_user = q on the
+    // local dofs, externals included; out_user[r][0..1] = this rank's share of p^T M_p p and q^T M_q q), "rhs_e" (out = D p on the
+    // owned edges), "rhs_v" (out = D^T q on the owned vertices)
+    const bool single = what == "energy" || what == "rhs_e" || what == "rhs_v";
+    const bool is_q = what.rfind("mq", 0) == 0 || what == "rhs_v";
     Rank R[2];
     for (int r = 0; r < 2; ++r) {
         Rank& k = R[r];
         std::string e = k.L.build(nv[r], vtx[r], nc[r], cells[r], patch_cells, v_ext[r], ne[r], e_ext[r]);
         if (!e.empty()) return fail(err, errlen, "rank " + std::to_string(r) + ": " + e);
+        if (btags && btags[r]) for (int64_t j = 0; j < k.L.nb; ++j) k.L.btag[j] = btags[r][j];
         k.L.boundary_set = true;
+        if (cell_owned && cell_owned[r]) { k.L.cell_foreign.resize((size_t)k.L.nc); for (int64_t c = 0; c < k.L.nc; ++c) k.L.cell_foreign[c] = cell_owned[r][c] ? 0 : 1; }
         std::vector<CellRec> rec;
         k.L.make_records(false, false, rec);
         const Layout& L = k.L;
@@ -439,6 +380,51 @@ extern "C" int emu_run2(const char* what_c, int32_t patch_cells, int32_t grid,
             }
         }
     };
+    if (single) {
+        for (int r = 0; r < 2; ++r) {
+            Rank& k = R[r];
+            const Layout& L = k.L;
+            const int g = std::max(1, std::min((int)grid, L.npatch));
+            MqPipeArgs cfg_q{}; EllPipeArgs cfg_p{}; EnergyPipeArgs cfg_e{}; RhsPipeArgs cfg_re{}, cfg_rv{};
+            size_t sm_q = 0, sm_p = 0, sm_e = 0, sm_re = 0, sm_rv = 0;
+            pipe_carve(L, cfg_q, cfg_p, sm_q, sm_p, &cfg_e, &sm_e, &cfg_re, &sm_re, &cfg_rv, &sm_rv);
+            std::vector<CellRec> rec;
+            L.make_records(false, false, rec);
+            std::vector<uint2> hv(rec.size()), he(rec.size());
+            for (size_t c = 0; c < rec.size(); ++c) { hv[c] = make_uint2(rec[c].x, rec[c].y); he[c] = make_uint2(rec[c].z, rec[c].w); }
+            uint2* d_recv = k.A.put(hv); uint2* d_rece = k.A.put(he);
+            auto to_new = [&](const double* user, const std::vector<int32_t>& new2old) {
+                std::vector<double> v(new2old.size());
+                for (size_t i = 0; i < new2old.size(); ++i) v[i] = user[new2old[i]];
+                return v;
+            };
+            if (what == "energy") {
+                double* d_p = k.A.put(to_new(b_user[r], L.v_new2old));
+                double* d_q = k.A.put(to_new(in2_user[r], L.e_new2old));
+                double* d_area = k.A.put(k.area);
+                EnergyPipeArgs a = cfg_e;
+                a.npatch = L.npatch; a.hdr = k.d_hdr; a.recv = d_recv; a.area = d_area; a.cellq = k.d_cellq; a.ghost_v = k.d_gv; a.ghost_e = k.d_ge;
+                a.p = d_p; a.q = d_q; a.scale_p = 1.0 / 12.0; a.scale_q = 1.0; a.counter_id = 4; a.partials = k.partials; a.ctl = k.ctl;
+                phw_emu::launch(g, NT, sm_e, [&] { energy_pipe_k<NT>(a); });
+                if ((k.ctl->nonconv >> 32) != 0) return fail(err, errlen, "a stage did not arrive");
+                out_user[r][0] = k.ctl->red[0]; out_user[r][1] = k.ctl->red[1];
+            } else {
+                const bool vertex = what == "rhs_v";
+                double* d_x = k.A.put(to_new(b_user[r], vertex ? L.e_new2old : L.v_new2old));
+                double* d_y = k.A.get<double>(vertex ? L.nv : L.ne);
+                uint32_t* d_voff = k.A.put(L.vslice_off); uint16_t* d_vadj = k.A.put(L.vadj);
+                RhsPipeArgs a = vertex ? cfg_rv : cfg_re;
+                a.npatch = L.npatch; a.hdr = k.d_hdr; a.recv = d_recv; a.rece = d_rece; a.ghost = vertex ? k.d_ge : k.d_gv; a.eadj = k.d_eadj;
+                a.vslice_off = d_voff; a.vadj = d_vadj; a.x = d_x; a.y = d_y; a.cD = 1.0; a.ctl = k.ctl;
+                if (vertex) phw_emu::launch(g, NT, sm_rv, [&] { rhs_vertex_pipe_k<NT, 1>(a); });
+                else phw_emu::launch(g, NT, sm_re, [&] { rhs_edge_pipe_k<NT, 1>(a); });
+                if ((k.ctl->nonconv >> 32) != 0) return fail(err, errlen, "a stage did not arrive");
+                const std::vector<int32_t>& n2o = vertex ? L.v_new2old : L.e_new2old;
+                for (size_t i = 0; i < n2o.size(); ++i) out_user[r][n2o[i]] = d_y[i];
+            }
+        }
+        return 0;
+    }
     if (what != "mq1" && what != "mq_lean" && what != "mp1" && what != "mp_lean") return fail(err, errlen, "unknown kernel " + what);
     std::thread t1(run_rank, 1);
     run_rank(0);

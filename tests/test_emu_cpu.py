@@ -1,11 +1,10 @@
-"""CPU check of the bulk-copy pipelined kernels (csrc/kernels_pipe.cuh, csrc/kernels_pipe2.cuh) inside a host-side SPMD emulator
+"""CPU check of the bulk-copy pipelined kernels (csrc/kernels_pipe.cuh) inside a host-side SPMD emulator
 (tests/emu: one OS thread per CTA, one fiber per CUDA thread, asynchronous copies deferred until they are waited for, guard pages
 behind every array and behind the dynamic shared memory).  The SAME kernel sources are compiled with g++; only the handful of
 inline-PTX helpers is replaced (PHW_HOST_EMU).  What this covers without a GPU: indexing and shared-memory carve-ups, the staging
 protocol (every stage is waited for before it is read, expected byte counts match, 16-byte rules of the bulk copies, nothing in
 flight at exit), the Chebyshev control flow and the arithmetic - against the oracle's assembled operators and sparse direct
-solves.  What it does not cover: real asynchrony, memory-model effects, performance (the `-m gpu` suite and bench.py do that).
-In particular the experimental two-sweep kernels (flags bits 13 / 14), which have not run on a GPU yet, are exercised here."""
+solves.  What it does not cover: real asynchrony, memory-model effects, performance (the `-m gpu` suite and bench.py do that)."""
 import ctypes
 import os
 import sys
@@ -76,13 +75,11 @@ def test_emulated_mass_solves_match_direct_solves(emu, name, make, shape, xL, yL
     xq = spla.spsolve(ops['M_q'].tocsc(), bq)
     xp = spla.spsolve(ops['M_p'].tocsc(), bp)
     its = {}
-    for what, b, ref in [('mq_lean', bq, xq), ('mq1', bq, xq), ('mq2', bq, xq), ('mq2_lean', bq, xq),
-                         ('mp_lean', bp, xp), ('mp1', bp, xp), ('mp2', bp, xp), ('mp2_lean', bp, xp)]:
+    for what, b, ref in [('mq_lean', bq, xq), ('mq1', bq, xq), ('mp_lean', bp, xp), ('mp1', bp, xp)]:
         x, its[what] = run(emu, what, v, c, pc, grid, b, nout=len(b))
         assert rel(x, ref) < 1e-11, (what, rel(x, ref))
-    # the lean, pipelined and pipelined two-sweep kernels run the same iteration (the stop test may differ by one step)
-    assert abs(its['mq1'] - its['mq_lean']) <= 1 and abs(its['mq2'] - its['mq_lean']) <= 1 and abs(its['mq2_lean'] - its['mq2']) <= 1
-    assert abs(its['mp1'] - its['mp_lean']) <= 1 and abs(its['mp2'] - its['mp_lean']) <= 1 and abs(its['mp2_lean'] - its['mp2']) <= 1
+    # the lean and the pipelined kernels run the same iteration (the stop test may differ by one step)
+    assert abs(its['mq1'] - its['mq_lean']) <= 1 and abs(its['mp1'] - its['mp_lean']) <= 1
 
 
 @pytest.mark.parametrize('name,make,shape,xL,yL,pc,grid', MESHES)
@@ -107,17 +104,17 @@ def test_emulated_energy_and_right_hand_sides_match_oracle(emu, name, make, shap
 def test_emulated_solves_with_zero_right_hand_side_and_loose_tolerance(emu):
     v, c = rectangle_delaunay(30, 8, seed=7)
     topo = fem.Topology(v, c)
-    for what, n in [('mq1', topo.n_edges), ('mq2', topo.n_edges), ('mp1', topo.n_vertices), ('mp2', topo.n_vertices)]:
+    for what, n in [('mq1', topo.n_edges), ('mp1', topo.n_vertices)]:
         x, it = run(emu, what, v, c, 40, 3, np.zeros(n), nout=n)
         assert np.all(x == 0.0) and it <= 2
     ops = fem.assemble_wave_operators(topo, fem.tag_boundary(topo, 'R', 1.0, 0.25))
     b = np.random.default_rng(4).standard_normal(topo.n_edges)
-    x6, it6 = run(emu, 'mq2', v, c, 40, 3, b, nout=len(b), tol=1e-6)
-    x13, it13 = run(emu, 'mq2', v, c, 40, 3, b, nout=len(b), tol=1e-13)
+    x6, it6 = run(emu, 'mq1', v, c, 40, 3, b, nout=len(b), tol=1e-6)
+    x13, it13 = run(emu, 'mq1', v, c, 40, 3, b, nout=len(b), tol=1e-13)
     assert it6 < it13 and rel(x6, spla.spsolve(ops['M_q'].tocsc(), b)) < 1e-5
 
 
-@pytest.mark.parametrize('what', ['mq1', 'mp1', 'mq2', 'mp2', 'energy', 'rhs_e'])
+@pytest.mark.parametrize('what', ['mq1', 'mp1', 'energy', 'rhs_e'])
 def test_a_stage_that_never_arrives_ends_in_a_clean_error(what):
     """failure path of the pipelined kernels (pipe_stage_ready): a lost bulk copy must end in an error code - all CTAs leave the
     kernel (no hang at the grid barrier), nobody computes on the stage that did not arrive.  Runs in a child process because the
@@ -178,7 +175,7 @@ def _run2(lib, what, v, c, pc, grid, b_global, kind, tol=1e-13):
     it = (ctypes.c_int32 * 2)()
     err = ctypes.create_string_buffer(512)
     rc = lib.emu_run2(what.encode(), ctypes.c_int32(pc), ctypes.c_int32(grid), nv, ptrs(vtx), nc, ptrs(cells), ptrs(vext), ne, ptrs(eext),
-                      ptrs(b), ptrs(out), ns, ptrs(sloc), ptrs(srem), it, ctypes.c_double(tol), err, 512)
+                      ptrs(b), ptrs(out), ns, ptrs(sloc), ptrs(srem), it, ctypes.c_double(tol), err, 512, None, None, None)
     if rc:
         raise RuntimeError(err.value.decode())
     x = np.full(len(b_global), np.nan)
@@ -209,3 +206,79 @@ def test_emulated_two_rank_solves_with_peer_exchange(emu, mesh):
         assert it[0] == it[1] and ext_off == 0.0, (what, it, ext_off)
         its[what] = it[0]
     assert abs(its['mq1'] - its['mq_lean']) <= 1 and abs(its['mp1'] - its['mp_lean']) <= 1
+
+
+def _run2_single(lib, what, v, c, pc, grid, p_global, q_global, shape='R', xL=1.0, yL=0.25):
+    """energy / right-hand-side kernels on the two partitioned layouts of an x-slab split (no exchange inside these kernels: the
+    external entries of the inputs are simply given their owners' values, as the solve's exchange and the local state updates
+    leave them).  Returns per-rank outputs and the parts."""
+    from porthamiltonian_fem_b200 import partition as pt
+    cr = pt.slab_cell_ranks(v, c, 2)
+    parts = [pt.build_local_part(v, c, cr, r) for r in range(2)]
+    keep = []
+
+    def A(x, dt):
+        x = np.ascontiguousarray(x, dtype=dt)
+        keep.append(x)
+        return x
+
+    def ptrs(arrs):
+        return (ctypes.c_void_p * len(arrs))(*[a.ctypes.data_as(ctypes.c_void_p) for a in arrs])
+    vtx = [A(p.vertices, np.float64) for p in parts]
+    cells = [A(p.cells, np.int32) for p in parts]
+    vext = [A(p.vertex_external, np.uint8) for p in parts]
+    eext = [A(p.edge_external, np.uint8) for p in parts]
+    owned = [A(p.cell_owned, np.uint8) for p in parts]
+    tags = []
+    for p in parts:
+        m = Mesh(p.vertices, p.cells, patch_cells=pc, vertex_external=p.vertex_external, edge_external=p.edge_external)
+        tags.append(A(tag_boundary_edges(m, shape, xL, yL), np.int32))
+        m.close()
+    if what == 'energy':
+        in1 = [A(p_global[p.vertex_gid], np.float64) for p in parts]
+        in2 = [A(q_global[p.edge_gid], np.float64) for p in parts]
+        out = [A(np.zeros(2), np.float64) for _ in parts]
+    elif what == 'rhs_e':
+        in1 = [A(p_global[p.vertex_gid], np.float64) for p in parts]
+        in2 = in1
+        out = [A(np.full(len(p.edge_gid), np.nan), np.float64) for p in parts]
+    else:
+        in1 = [A(q_global[p.edge_gid], np.float64) for p in parts]
+        in2 = in1
+        out = [A(np.full(len(p.vertex_gid), np.nan), np.float64) for p in parts]
+    empty = [A(np.zeros(1, np.int32), np.int32) for _ in parts]
+    nv = (ctypes.c_int64 * 2)(*[len(p.vertices) for p in parts])
+    nc = (ctypes.c_int64 * 2)(*[len(p.cells) for p in parts])
+    ne = (ctypes.c_int64 * 2)(*[len(p.edge_gid) for p in parts])
+    ns = (ctypes.c_int32 * 2)(0, 0)
+    it = (ctypes.c_int32 * 2)()
+    err = ctypes.create_string_buffer(512)
+    rc = lib.emu_run2(what.encode(), ctypes.c_int32(pc), ctypes.c_int32(grid), nv, ptrs(vtx), nc, ptrs(cells), ptrs(vext), ne, ptrs(eext),
+                      ptrs(in1), ptrs(out), ns, ptrs(empty), ptrs(empty), it, ctypes.c_double(1e-13), err, 512,
+                      ptrs(owned), ptrs(tags), ptrs(in2))
+    if rc:
+        raise RuntimeError(err.value.decode())
+    return out, parts
+
+
+@pytest.mark.parametrize('mesh', ['delaunay', 'structured'])
+def test_emulated_two_rank_energy_and_right_hand_sides(emu, mesh):
+    """the pipelined H_wave pass and right-hand sides on partitioned layouts (round 2: they now also run in multi-GPU runs): the two
+    ranks' energy shares add up to the global quadratic forms (every cell counted once: halo cells of the other rank carry the
+    'foreign' flag), and every owned row equals the global operator's row"""
+    v, c = rectangle_delaunay(40, 10, seed=3) if mesh == 'delaunay' else rectangle_structured(36, 9)
+    topo = fem.Topology(v, c)
+    ops = fem.assemble_wave_operators(topo, fem.tag_boundary(topo, 'R', 1.0, 0.25))
+    rng = np.random.default_rng(5)
+    p = rng.standard_normal(topo.n_vertices)
+    q = rng.standard_normal(topo.n_edges)
+    out, parts = _run2_single(emu, 'energy', v, c, 40, 3, p, q)
+    ep, eq = out[0][0] + out[1][0], out[0][1] + out[1][1]
+    assert abs(ep - p @ (ops['M_p'] @ p)) < 1e-13 * abs(ep) and abs(eq - q @ (ops['M_q'] @ q)) < 1e-13 * abs(eq)
+    assert min(out[0][0], out[1][0]) > 0.2 * ep          # both ranks hold a real share
+    for what, ref, kind in [('rhs_e', ops['D'] @ p, 'e'), ('rhs_v', ops['D'].T @ q, 'v')]:
+        out, parts = _run2_single(emu, what, v, c, 40, 3, p, q)
+        for r, part in enumerate(parts):
+            own = (part.edge_owner if kind == 'e' else part.vertex_owner) == r
+            gid = part.edge_gid if kind == 'e' else part.vertex_gid
+            assert own.sum() > 0 and rel(out[r][own], ref[gid[own]]) < 1e-14, (what, r)

@@ -21,13 +21,11 @@ def _ngpu():
         return 0
 
 
-def _worker(rank, world, port, scheme, q, flags=0):
+def _worker(rank, world, port, scheme, q, flags=0, big=False):
     import torch
     import torch.distributed as dist
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
-    if flags & 768:
-        os.environ['PHW_PIPE_MULTI'] = '1'          # pipelined solves with the inter-GPU exchange (opt-in, csrc/kernels_pipe.cuh)
     torch.cuda.set_device(rank)
     dist.init_process_group('gloo', rank=rank, world_size=world)
     try:
@@ -35,11 +33,15 @@ def _worker(rank, world, port, scheme, q, flags=0):
         from porthamiltonian_fem_b200 import _lib, partition as pt
         from porthamiltonian_fem_b200.mesh import rectangle_delaunay
         from porthamiltonian_fem_b200.solver import Mesh, Solver, tag_boundary_edges, setup_peer_exchange
-        mesh = rectangle_delaunay(48, 12, seed=9)
-        steps, tF = 40, 0.02
+        from porthamiltonian_fem_b200.mesh import rectangle_structured
+        # big: > 296 patches per rank, so that every CTA of the persistent kernels walks through several patches (stage pipeline,
+        # ghost lists arriving one patch ahead) with the exchange in the loop
+        mesh = rectangle_structured(200, 50) if big else rectangle_delaunay(48, 12, seed=9)
+        steps, tF = (20, 0.004) if big else (40, 0.02)
         Ho, _, so = wave_2D_solve_oracle(tF, steps, mesh, 1.0, 0.25, timeIntScheme=scheme, K_wave=K_WAVE, rho=RHO, return_state=True)
         part = pt.build_local_part(mesh[0], mesh[1], pt.slab_cell_ranks(mesh[0], mesh[1], world), rank)
-        m = Mesh(part.vertices, part.cells, patch_cells=96, vertex_external=part.vertex_external, edge_external=part.edge_external)
+        m = Mesh(part.vertices, part.cells, patch_cells=32 if big else 96, vertex_external=part.vertex_external,
+                 edge_external=part.edge_external, cell_owned=part.cell_owned)
         m.set_boundary(tag_boundary_edges(m, 'R', 1.0, 0.25))
         prm = _lib.PhwParams()
         prm.scheme, prm.dt, prm.K_wave, prm.rho = _lib.SCHEMES[scheme], tF / steps, K_WAVE, RHO
@@ -48,6 +50,13 @@ def _worker(rank, world, port, scheme, q, flags=0):
         s = Solver(m, prm, device=rank)
         info = setup_peer_exchange(s, part, dist, rank, world)
         H = s.run(steps)
+        paths = s.stats()['kernel_paths']
+        if flags & 768:
+            assert paths & 12 == 12, 'the pipelined solves did not run: kernel_paths = %d' % paths
+        if flags & 2048:
+            assert paths & 16, 'the pipelined H_wave pass did not run: kernel_paths = %d' % paths
+        if flags & 4096:
+            assert paths & 32, 'the pipelined right-hand sides did not run: kernel_paths = %d' % paths
         p, qv, _ = s.get_state()
         ov, oe = part.vertex_owner == rank, part.edge_owner == rank
         topo_edges = so['topo'].edges
@@ -62,12 +71,14 @@ def _worker(rank, world, port, scheme, q, flags=0):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('scheme,flags', [('SE', 0), ('SV', 0), ('SE', 768), ('SV', 768)])
-def test_two_gpu_partitioned_run_matches_oracle(scheme, flags):
+# flags: 0 lean kernels; 768 pipelined solves (bits 8, 9); 768 + 2048 + 4096 all pipelined kernels (what bench.py runs at N > 1)
+@pytest.mark.parametrize('scheme,flags,big', [('SE', 0, False), ('SV', 0, False), ('SE', 768, False), ('SV', 768, False),
+                                              ('SE', 768 + 2048 + 4096, False), ('SV', 768 + 2048 + 4096, False),
+                                              ('EH', 768 + 2048 + 4096, False),
+                                              ('SE', 0, True), ('SE', 768, True), ('SV', 768 + 2048 + 4096, True)])
+def test_two_gpu_partitioned_run_matches_oracle(scheme, flags, big):
     if _ngpu() < 2:
         pytest.skip('needs 2 GPUs')
-    if flags & 768 and not os.environ.get('PHW_TEST_PIPE_MULTI'):
-        pytest.skip('pipelined solves with the inter-GPU exchange: opt-in until they have run on 2 GPUs (set PHW_TEST_PIPE_MULTI=1)')
     import torch.multiprocessing as mp
     sck = socket.socket()
     sck.bind(('127.0.0.1', 0))
@@ -75,7 +86,7 @@ def test_two_gpu_partitioned_run_matches_oracle(scheme, flags):
     sck.close()
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, scheme, q, flags)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, scheme, q, flags, big)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=240) for _ in procs]

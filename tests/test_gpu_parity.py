@@ -222,43 +222,6 @@ def test_time_loop_parity_config1_size(scheme):
     assert np.abs(Hg[:, 1:] - Ho[:, 1:]).max() < 1e-10 * np.abs(Ho[:, 1:]).max()
 
 
-@pytest.mark.parametrize('name,make,shape,xL,yL,pc', MESHES)
-def test_two_sweep_mass_solves_match_oracle(name, make, shape, xL, yL, pc):
-    """flags bit4: two Chebyshev iterations per pass (csrc/kernels2.cuh) - same recurrence, same stop test."""
-    v, c = make()
-    m, s = make_solver(v, c, shape, xL, yL, pc, flags=16)
-    topo = fem.Topology(v, c)
-    ops = fem.assemble_wave_operators(topo, fem.tag_boundary(topo, shape, xL, yL))
-    rng = np.random.default_rng(13)
-    bp = rng.standard_normal(topo.n_vertices)
-    bq = rng.standard_normal(topo.n_edges)
-    xp, itp = s.mass_solve(_lib.PHW_P, bp)
-    xq, itq = s.mass_solve(_lib.PHW_Q, bq)
-    assert rel(xp, spla.spsolve(ops['M_p'].tocsc(), bp)) < 1e-11
-    assert rel(xq, spla.spsolve(ops['M_q'].tocsc(), bq)) < 1e-11
-    m1, s1 = make_solver(v, c, shape, xL, yL, pc)
-    _, itp1 = s1.mass_solve(_lib.PHW_P, bp)
-    _, itq1 = s1.mass_solve(_lib.PHW_Q, bq)
-    assert (itp, itq) == (itp1, itq1)                 # the two schedules run the same iteration
-    rh = s.residual_history(_lib.PHW_Q)
-    assert rh.shape[0] == itq and rh[-1] <= 1e-13 and np.all(rh[:-1] > 1e-13)
-    z, _ = s.mass_solve(_lib.PHW_P, np.zeros(topo.n_vertices))
-    assert np.all(z == 0.0)
-
-
-@pytest.mark.parametrize('scheme,ic', [('SE', None), ('SV', 'IC'), ('EH', None)])
-def test_two_sweep_time_loop_parity(scheme, ic):
-    mesh = rectangle_delaunay(60, 15, seed=7)
-    steps, tF = 80, 0.04
-    kw = dict(timeIntScheme=scheme, interConnection=ic)
-    Ho, _, so = wave_2D_solve_oracle(tF, steps, mesh, 1.0, 0.25, K_wave=K_WAVE, rho=RHO, return_state=True, **kw)
-    Hg, _, sg = wave_2D_solve(tF, steps, '/tmp', 0, 1.0, 0.25, K_wave=K_WAVE, rho=RHO, mesh=mesh, patch_cells=160,
-                              return_state=True, verbose=False, solver_flags=16, **kw)
-    assert rel(sg['p'], so['p']) < TOL_STATE and rel(sg['q'], so['q']) < TOL_STATE
-    assert np.abs(Hg[:, 1:] - Ho[:, 1:]).max() < 1e-10 * np.abs(Ho[:, 1:]).max()
-    assert sg['stats']['max_rel_residual'] <= 1e-13
-
-
 def test_edge_cases_empty_run_tiny_meshes_and_restart():
     """n_steps = 0, a two-cell mesh, a one-patch mesh with the smallest patch size, and restart through
     phw_get_state / phw_set_state / phw_set_time: two half runs reproduce one full run."""

@@ -160,7 +160,6 @@ GBAR_CASES = [
     ('SE_strong', 34, 8, 120, 0.06, dict(timeIntScheme='SE', dirichletImp='strong')),
     ('SM_strong', 34, 8, 120, 0.06, dict(timeIntScheme='SM', dirichletImp='strong')),
     ('SM_casimir', 40, 10, 100, 0.1, dict(timeIntScheme='SM', controlType='casimir')),
-    ('SV_two_sweep', 40, 10, 100, 0.05, dict(timeIntScheme='SV', solver_flags=GBAR | 16)),
     ('SE_P2RT2', 20, 5, 100, 0.03, dict(timeIntScheme='SE', basis_order=(2, 2))),
 ]
 
@@ -200,85 +199,5 @@ def test_drop_in_default_on_a_large_mesh_runs_the_pipelined_kernels():
                                return_state=True, verbose=False)
     want = PATH_PIPE_P | PATH_PIPE_Q | PATH_PIPE_ENERGY | PATH_PIPE_RHS
     assert nc == 204800 and sg['stats']['kernel_paths'] & want == want
-    assert rel(sg['p'], so['p']) < TOL_STATE and rel(sg['q'], so['q']) < TOL_STATE
-    assert np.abs(Hg[:, 1:] - Ho[:, 1:]).max() < 1e-10 * np.abs(Ho[:, 1:]).max()
-
-
-# ---- flags bit 13 (experimental): pipelined two-sweep M_q solve (csrc/kernels_pipe2.cuh).  Written without GPU access at the end
-#      of round 1: these cases run only with PHW_TEST_EXPERIMENTAL=1 until they have passed on a B200 once.
-import os
-PIPE2 = 8192
-PIPE2P = 16384
-PATH_PIPE2_Q, PATH_PIPE2_P = 64, 128
-experimental = pytest.mark.skipif(not os.environ.get('PHW_TEST_EXPERIMENTAL'), reason='experimental kernel: set PHW_TEST_EXPERIMENTAL=1')
-
-
-@experimental
-@pytest.mark.parametrize('name,make,shape,xL,yL,pc', MESHES)
-def test_pipelined_two_sweep_mq_solve_matches_oracle(name, make, shape, xL, yL, pc):
-    if pc > 768:
-        pc = 768
-    v, c = make()
-    m, s = make_solver(v, c, shape, xL, yL, pc, flags=PIPE2)
-    topo = fem.Topology(v, c)
-    ops = fem.assemble_wave_operators(topo, fem.tag_boundary(topo, shape, xL, yL))
-    bq = np.random.default_rng(31).standard_normal(topo.n_edges)
-    xq, itq = s.mass_solve(_lib.PHW_Q, bq)
-    assert s.stats()['kernel_paths'] & PATH_PIPE2_Q
-    assert rel(xq, spla.spsolve(ops['M_q'].tocsc(), bq)) < 1e-11
-    m1, s1 = make_solver(v, c, shape, xL, yL, pc, flags=16)            # the lean two-sweep solve runs the same schedule
-    xq1, itq1 = s1.mass_solve(_lib.PHW_Q, bq)
-    assert abs(itq - itq1) <= 1 and rel(xq, xq1) < 1e-12
-    for _ in range(3):
-        xq2, _ = s.mass_solve(_lib.PHW_Q, bq)
-        assert rel(xq2, xq) < 1e-12
-    z, _ = s.mass_solve(_lib.PHW_Q, np.zeros(topo.n_edges))
-    assert np.all(z == 0.0)
-
-
-@experimental
-@pytest.mark.parametrize('scheme,ic', [('SE', None), ('SV', 'IC')])
-def test_pipelined_two_sweep_time_loop_parity(scheme, ic):
-    mesh = rectangle_delaunay(120, 30, seed=5)
-    steps, tF = 60, 0.03
-    kw = dict(timeIntScheme=scheme, interConnection=ic)
-    Ho, _, so = wave_2D_solve_oracle(tF, steps, mesh, 1.0, 0.25, K_wave=K_WAVE, rho=RHO, return_state=True, **kw)
-    Hg, _, sg = wave_2D_solve(tF, steps, '/tmp', 0, 1.0, 0.25, K_wave=K_WAVE, rho=RHO, mesh=mesh, patch_cells=48,
-                              return_state=True, verbose=False, solver_flags=PIPE2 | 512 | ENERGY | RHS, **kw)
-    assert sg['stats']['kernel_paths'] & PATH_PIPE2_Q
-    assert rel(sg['p'], so['p']) < TOL_STATE and rel(sg['q'], so['q']) < TOL_STATE
-    assert np.abs(Hg[:, 1:] - Ho[:, 1:]).max() < 1e-10 * np.abs(Ho[:, 1:]).max()
-
-
-@experimental
-@pytest.mark.parametrize('name,make,shape,xL,yL,pc', MESHES)
-def test_pipelined_two_sweep_mp_solve_matches_oracle(name, make, shape, xL, yL, pc):
-    if pc > 768:
-        pc = 768
-    v, c = make()
-    m, s = make_solver(v, c, shape, xL, yL, pc, flags=PIPE2P)
-    topo = fem.Topology(v, c)
-    ops = fem.assemble_wave_operators(topo, fem.tag_boundary(topo, shape, xL, yL))
-    bp = np.random.default_rng(37).standard_normal(topo.n_vertices)
-    xp, itp = s.mass_solve(_lib.PHW_P, bp)
-    assert s.stats()['kernel_paths'] & PATH_PIPE2_P
-    assert rel(xp, spla.spsolve(ops['M_p'].tocsc(), bp)) < 1e-11
-    m1, s1 = make_solver(v, c, shape, xL, yL, pc, flags=16)
-    xp1, itp1 = s1.mass_solve(_lib.PHW_P, bp)
-    assert abs(itp - itp1) <= 1 and rel(xp, xp1) < 1e-12
-    for _ in range(3):
-        xp2, _ = s.mass_solve(_lib.PHW_P, bp)
-        assert rel(xp2, xp) < 1e-12
-
-
-@experimental
-def test_pipelined_two_sweep_both_solves_time_loop_parity():
-    mesh = rectangle_delaunay(120, 30, seed=5)
-    steps, tF = 60, 0.03
-    kw = dict(timeIntScheme='SV', interConnection='IC')
-    Ho, _, so = wave_2D_solve_oracle(tF, steps, mesh, 1.0, 0.25, K_wave=K_WAVE, rho=RHO, return_state=True, **kw)
-    Hg, _, sg = wave_2D_solve(tF, steps, '/tmp', 0, 1.0, 0.25, K_wave=K_WAVE, rho=RHO, mesh=mesh, patch_cells=48,
-                              return_state=True, verbose=False, solver_flags=PIPE2 | PIPE2P | ENERGY | RHS, **kw)
-    assert sg['stats']['kernel_paths'] & (PATH_PIPE2_Q | PATH_PIPE2_P) == (PATH_PIPE2_Q | PATH_PIPE2_P)
     assert rel(sg['p'], so['p']) < TOL_STATE and rel(sg['q'], so['q']) < TOL_STATE
     assert np.abs(Hg[:, 1:] - Ho[:, 1:]).max() < 1e-10 * np.abs(Ho[:, 1:]).max()

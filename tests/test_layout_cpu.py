@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.phw_version() >= 100
+    assert lib.phw_version() >= 200
 
 
 def test_no_cuda_means_loud_failure():
@@ -155,9 +155,8 @@ def test_xdmf_binary_writer(tmp_path):
     ('single_patch', lambda: rectangle_structured(6, 3), 4096),
     ('tiny_2x1', lambda: rectangle_structured(2, 1), 16),
 ])
-def test_layout_self_check_ell_rows_and_two_sweep_patches(name, make, pc):
-    """ELL mass rows (neighbour lists, shared cells) and ring-2 patches (C1 prefix, rows complete inside their sweep,
-    records / signs / adjacency consistent with the mesh) - the structures behind vertex_ell_pass and kernels2.cuh."""
+def test_layout_self_check_ell_rows(name, make, pc):
+    """ELL mass rows (neighbour lists, shared cells consistent with the mesh) - the structure behind vertex_ell_pass."""
     v, c = make()
     m = Mesh(v, c, patch_cells=pc)
     m.self_check()
@@ -170,7 +169,7 @@ def test_pipelined_solve_shared_memory_budget_is_host_computable():
     limit = 227 * 1024 - 1024
     m = Mesh(v, c, patch_cells=1024)
     sp, sq, se, sre, srv, sq2 = m.pipe_smem()
-    assert sq2 > sq                              # the ring-2 patches of the two-sweep solve need smaller patches
+    assert sq2 == 0                              # reserved slot (was the two-sweep solve, removed)
     assert 0 < sp <= limit // 2 and 0 < sq <= limit and 0 < se <= limit and 0 < sre <= limit // 2 and 0 < srv <= limit // 2
     assert all(x % 16 == 0 for x in (sp, sq, se, sre, srv))
     m.close()
