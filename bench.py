@@ -375,6 +375,12 @@ def run_bench():
     solver, m = weak['solver'], weak['m']
     r = measure(weak, args.steps, args.warmup, True)
     st, dev_s, samples, wall = r['st'], r['dev_s'], r['samples'], r['wall']
+    clocks = summarize_clocks(samples)
+    if world > 1:      # every rank samples its own GPU: a power-capped straggler shows up here (all ranks advance in lock-step)
+        allclk = [None] * world
+        dist.all_gather_object(allclk, clocks)
+        clocks = dict(clocks, per_rank=allclk, sm_mhz_min_over_ranks=min((c['sm_mhz'] or 0) for c in allclk),
+                      reasons=sorted(set(x for c in allclk for x in c['reasons'])))
     if args.stream_probe and rank == 0:
         for nt, occ in ((256, 8), (256, 4), (512, 4), (1024, 2), (128, 16), (256, 2)):
             ms, nb = solver.stream_probe(nt, occ, 10)
@@ -487,7 +493,7 @@ def run_bench():
             'e2e': {'value': e2e_value, 'unit': 'dof-updates/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'seconds': e2e_s},
             'gpu_launches': int(st['kernel_launches']),
-            'clocks': summarize_clocks(samples),
+            'clocks': clocks,
             'roofline': {'bound': 'hbm', 'kernel': dom['kernel'], 'achieved': dom['achieved'], 'peak': peak, 'unit': 'GB/s',
                          'frac': dom['frac'], 'traffic': dom['traffic'], 'peak_source': peak_src, 'traffic_source': dom['traffic_source'],
                          'bytes_per_launch': dom['bytes_per_launch'], 'ms_per_launch': dom['ms_per_launch'],

@@ -126,6 +126,12 @@ struct PeerComm {
     const int* send_e_loc[MAX_RANKS]; const int* send_e_rem[MAX_RANKS]; int n_send_e[MAX_RANKS];
     Mailbox* mbox[MAX_RANKS];                  // every rank's mailbox (own one included)
     long long timeout_cycles;
+    // exchange protocol of the pipelined solves (round 2): the send lists bucketed by owner patch, so that a CTA pushes the
+    // interface rows of a patch right after computing them (overlapped with the rest of the sweep) instead of after the grid barrier.
+    // psend_off[f][P] .. psend_off[f][P + 1] = entries of patch P for field f (0 vertices, 1 edges); entry = (local row id,
+    // neighbour slot, position in the neighbour's vectors, 0)
+    const int* psend_off[2];
+    const int4* psend_ent[2];
 };
 
 // PHW_HOST_EMU: the kernels of this directory also compile for the host-side SPMD emulator of tests/emu (fibers for threads,

@@ -141,12 +141,67 @@ __device__ __forceinline__ void load_hdr_smem_at(PatchHdr* dst, const PatchHdr* 
     if (t >= 0 && t < 20) reinterpret_cast<int*>(dst)[t] = __ldg(reinterpret_cast<const int*>(src) + t);
 }
 
+// partitioned runs: the send-list range of patch P (PeerComm::psend_off) travels with its header into a parallel ring
+__device__ __forceinline__ void load_snd_smem_at(int* dst2, const int* off, int P, int first_thread) {
+    const int t = (int)threadIdx.x - first_thread - 20;
+    if (t >= 0 && t < 2) dst2[t] = __ldg(off + P + t);
+}
+
 // grid-wide barrier of the pipelined kernels: grid_barrier plus the proxy fences that order the iterate written with
 // ordinary stores before the barrier against the bulk copies that read it after the barrier
 __device__ __forceinline__ void grid_barrier_px(unsigned int* bar, unsigned int& epoch) {
     fence_proxy_async();
     grid_barrier(bar, epoch);
     fence_proxy_async();
+}
+
+// ---- inter-GPU exchange of the pipelined solves (partitioned runs; protocol of round 2) -----------------------------
+// (1) peer_push_patch: right after the rows of patch P are written, the threads of the CTA copy its interface rows straight into the
+//     neighbours' iterate buffers (peer-mapped memory, NVLink stores) and fence them at system scope - while the other CTAs (and
+//     this one) go on with the sweep, so the transfer overlaps the interior work.
+// (2) peer_finish_iter: after the grid-wide reduction of the local residual norms, ONE thread publishes the rank's norms and a
+//     sequence flag in every rank's mailbox (release at system scope: everything this grid pushed before its barrier is visible to
+//     whoever acquires the flag); thread 0 of EVERY CTA then waits for all ranks' flags in its own mailbox and sums the norms in
+//     rank order - identical bits on every rank and CTA, no second grid barrier, no broadcast through global memory.
+// Per iteration this adds one NVLink one-way latency to the critical path (the round-1 protocol, peer_exchange_iter: push after the
+// barrier + system fence by every thread + two more grid barriers).
+template <int NT>
+__device__ __forceinline__ void peer_push_patch(const PeerComm& pc, int field, int b, int e, const double* xnew, int nxt) {
+    if (b >= e) return;                                    // uniform for the CTA
+    const int4* ent = pc.psend_ent[field];
+    for (int i = b + (int)threadIdx.x; i < e; i += NT) {
+        const int4 t = ent[i];
+        double* dst = field == 0 ? pc.nb_tp[t.y][nxt] : pc.nb_tq[t.y][nxt];
+        dst[t.z] = xnew[t.x];
+    }
+    __threadfence_system();
+}
+// seq: exchange number of this iteration (the same on every rank); s_x: two doubles of shared memory.  Called by all threads.
+template <int NT>
+__device__ __forceinline__ void peer_finish_iter(const PeerComm& pc, Ctl* ctl, unsigned long long seq, double* s_x, double& rr, double& bb) {
+    const int par = (int)(seq & 1ull);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (int r = 0; r < pc.world; ++r) { pc.mbox[r]->part[par][pc.rank][0] = rr; pc.mbox[r]->part[par][pc.rank][1] = bb; }
+        __threadfence_system();
+        for (int r = 0; r < pc.world; ++r) *((volatile unsigned long long*)&pc.mbox[r]->flag[pc.rank]) = seq;
+    }
+    if (threadIdx.x == 0) {
+        Mailbox* mine = pc.mbox[pc.rank];
+        bool dead = *((volatile int*)&ctl->comm_dead) != 0;
+        if (!dead) {
+            const long long t0 = clock64();
+            for (int r = 0; r < pc.world && !dead; ++r)
+                while (ld_volatile_u64(&mine->flag[r]) < seq)
+                    if (clock64() - t0 > pc.timeout_cycles) { ctl->comm_dead = 1; dead = true; break; }
+        }
+        __threadfence_system();
+        double s0 = 0.0, s1 = 0.0;
+        for (int r = 0; r < pc.world; ++r) { s0 += *((volatile double*)&mine->part[par][r][0]); s1 += *((volatile double*)&mine->part[par][r][1]); }
+        s_x[0] = s0; s_x[1] = s1;
+    }
+    __syncthreads();
+    rr = s_x[0]; bb = s_x[1];
+    __syncthreads();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -214,9 +269,10 @@ __device__ __forceinline__ void mq_issue(const MqPipeArgs& a, unsigned char* sta
 
 // DIAG: the Jacobi weight 1 / diag(M_q)_e is recomputed from the (<= 2) cell records of the edge, which are in shared memory
 // anyway (diag contribution of slot i of a cell: 3 S - 4 g_i), instead of being streamed (12 of 99 B per cell and iteration)
-// MULTI: with the inter-GPU exchange of the lean kernels after the grid-wide reduction (peer_exchange_iter: interface values pushed
-// into the neighbours' iterate buffers, residual norms all-reduced through the mailboxes).  External dofs are never part of an owned
-// range, so only the ghost gathers (ordinary LDGSTS loads, behind the barrier's fence) read what the peers wrote.
+// MULTI: with the inter-GPU exchange (peer_push_patch / peer_finish_iter above: interface rows pushed into the neighbours' iterate
+// buffers patch by patch during the sweep, residual norms all-reduced through the mailboxes).  External dofs are never part of an
+// owned range, so only the ghost gathers (ordinary LDGSTS loads, behind the acquiring fence of peer_finish_iter) read what the
+// peers wrote.
 template <int NT, bool DIAG, bool MULTI>
 __global__ void __launch_bounds__(NT, 1) solve_mq_pipe_k(const __grid_constant__ MqPipeArgs a, const __grid_constant__ PeerComm pc) {
     PHW_DYN_SMEM(smraw);
@@ -225,12 +281,14 @@ __global__ void __launch_bounds__(NT, 1) solve_mq_pipe_k(const __grid_constant__
     __shared__ PatchHdr s_hdr[4];
     __shared__ __align__(8) unsigned long long full[2];
     __shared__ int s_dead;       // a stage did not arrive (see mbar_wait): the CTA stops touching the stages
+    __shared__ int s_snd[4][2];  // MULTI: send-list range of the patches in s_hdr
     SolveCtl& sc = a.ctl->sc[a.which];
     int k = 0, cur = sc.cur;
     double rho = 0.0, rr = 0.0, bb = 0.0;
     bool conv = false;
     unsigned int epoch = 0;
     unsigned int seq = 0;       // patches this CTA has processed so far: stage = seq & 1, mbarrier parity = (seq >> 1) & 1
+    const unsigned long long xseq0 = MULTI ? a.ctl->comm_seq : 0ull;   // exchanges done before this launch (updated only at its end)
     if (threadIdx.x == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_fence_init(); s_dead = 0; }
     __syncthreads();
     double* sc3 = reinterpret_cast<double*>(smraw + a.off_sc3);
@@ -244,7 +302,11 @@ __global__ void __launch_bounds__(NT, 1) solve_mq_pipe_k(const __grid_constant__
         double* xnew = nxt == 0 ? a.buf[0] : (nxt == 1 ? a.buf[1] : a.buf[2]);
         const bool use_prev = k > 0;
         double r0 = 0.0, b0 = 0.0;
-        for (int j = 0; j < 3 && j < n_my; ++j) load_hdr_smem_at(&s_hdr[j], &a.hdr[blockIdx.x + j * gridDim.x], 32 * j);
+        for (int j = 0; j < 3 && j < n_my; ++j) {
+            load_hdr_smem_at(&s_hdr[j], &a.hdr[blockIdx.x + j * gridDim.x], 32 * j);
+            if (MULTI) load_snd_smem_at(s_snd[j], pc.psend_off[1], blockIdx.x + j * gridDim.x, 32 * j);
+        }
+        int snd_b = 0, snd_e = 0;       // MULTI: send-list range of the patch whose rows were written last
         __syncthreads();
         if (n_my > 0)
             mq_issue<NT, DIAG>(a, smraw + (seq & 1u) * a.stage_bytes, nullptr,
@@ -254,7 +316,14 @@ __global__ void __launch_bounds__(NT, 1) solve_mq_pipe_k(const __grid_constant__
             const unsigned int s = seq & 1u;
             if (!pipe_stage_ready(&full[s], (seq >> 1) & 1u, a.ctl, &s_dead)) continue;
             const PatchHdr& h = s_hdr[it & 3];
-            if (it + 3 < n_my) load_hdr_smem_at(&s_hdr[(it + 3) & 3], &a.hdr[blockIdx.x + (it + 3) * gridDim.x], 64);
+            if (MULTI) {   // the rows of the previous patch are visible to the whole CTA now: push its interface rows to the neighbours
+                peer_push_patch<NT>(pc, 1, snd_b, snd_e, xnew, nxt);
+                snd_b = s_snd[it & 3][0]; snd_e = s_snd[it & 3][1];
+            }
+            if (it + 3 < n_my) {
+                load_hdr_smem_at(&s_hdr[(it + 3) & 3], &a.hdr[blockIdx.x + (it + 3) * gridDim.x], 64);
+                if (MULTI) load_snd_smem_at(s_snd[(it + 3) & 3], pc.psend_off[1], blockIdx.x + (it + 3) * gridDim.x, 64);
+            }
             if (it + 1 < n_my)
                 mq_issue<NT, DIAG>(a, smraw + (s ^ 1u) * a.stage_bytes,
                              reinterpret_cast<const uint32_t*>(smraw + a.off_gidx + (s ^ 1u) * a.gidx_bytes),
@@ -305,6 +374,7 @@ __global__ void __launch_bounds__(NT, 1) solve_mq_pipe_k(const __grid_constant__
             }
         }
         __syncthreads();
+        if (MULTI) peer_push_patch<NT>(pc, 1, snd_b, snd_e, xnew, nxt);      // the CTA's last patch
         block_sum2(r0, b0, red);
         double* part = a.partials + (size_t)(k & 1) * 2 * gridDim.x;
         if (threadIdx.x == 0) { part[2 * blockIdx.x] = r0; part[2 * blockIdx.x + 1] = b0; }
@@ -318,7 +388,7 @@ __global__ void __launch_bounds__(NT, 1) solve_mq_pipe_k(const __grid_constant__
         __syncthreads();
         rr = bc[0]; bb = bc[1];
         __syncthreads();
-        if (MULTI) { peer_exchange_iter<NT>(pc, a.ctl, epoch, false, xnew, nxt, k, rr, bb); fence_proxy_async(); }
+        if (MULTI) { peer_finish_iter<NT>(pc, a.ctl, xseq0 + (unsigned long long)k + 1ull, bc, rr, bb); fence_proxy_async(); }
         conv = rr <= a.tol2 * bb;
         if (blockIdx.x == 0 && threadIdx.x == 0 && k < 48) a.ctl->reshist[a.which][k] = (bb > 0.0) ? rr / bb : 0.0;
         k += 1;
@@ -329,6 +399,7 @@ __global__ void __launch_bounds__(NT, 1) solve_mq_pipe_k(const __grid_constant__
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         sc.cur = cur; sc.k = k; sc.done = 1; sc.rr = rr; sc.bb = bb; sc.rho = rho;
         sc.iters += k; sc.solves += 1;
+        if (MULTI) a.ctl->comm_seq = xseq0 + (unsigned long long)k;
         if (!conv) a.ctl->nonconv += 1;
         double rel = (bb > 0.0) ? sqrt(rr / bb) : 0.0;
         if (rel > sc.maxres) sc.maxres = rel;
@@ -402,12 +473,14 @@ __global__ void __launch_bounds__(NT, MINB) solve_ell_pipe_k(const __grid_consta
     __shared__ PatchHdr s_hdr[4];
     __shared__ __align__(8) unsigned long long full[2];
     __shared__ int s_dead;       // a stage did not arrive (see mbar_wait): the CTA stops touching the stages
+    __shared__ int s_snd[4][2];  // MULTI: send-list range of the patches in s_hdr
     SolveCtl& sc = a.ctl->sc[a.which];
     int k = 0, cur = sc.cur;
     double rho = 0.0, rr = 0.0, bb = 0.0;
     bool conv = false;
     unsigned int epoch = 0;
     unsigned int seq = 0;
+    const unsigned long long xseq0 = MULTI ? a.ctl->comm_seq : 0ull;   // exchanges done before this launch (updated only at its end)
     if (threadIdx.x == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_fence_init(); s_dead = 0; }
     __syncthreads();
     const int n_my = ((int)blockIdx.x < a.npatch) ? (a.npatch - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
@@ -420,7 +493,11 @@ __global__ void __launch_bounds__(NT, MINB) solve_ell_pipe_k(const __grid_consta
         double* xnew = nxt == 0 ? a.buf[0] : (nxt == 1 ? a.buf[1] : a.buf[2]);
         const bool use_prev = k > 0;
         double r0 = 0.0, b0 = 0.0;
-        for (int j = 0; j < 3 && j < n_my; ++j) load_hdr_smem_at(&s_hdr[j], &a.hdr[blockIdx.x + j * gridDim.x], 32 * j);
+        for (int j = 0; j < 3 && j < n_my; ++j) {
+            load_hdr_smem_at(&s_hdr[j], &a.hdr[blockIdx.x + j * gridDim.x], 32 * j);
+            if (MULTI) load_snd_smem_at(s_snd[j], pc.psend_off[0], blockIdx.x + j * gridDim.x, 32 * j);
+        }
+        int snd_b = 0, snd_e = 0;       // MULTI: send-list range of the patch whose rows were written last
         __syncthreads();
         if (n_my > 0)
             ell_issue<NT>(a, smraw + (seq & 1u) * a.stage_bytes, nullptr,
@@ -430,7 +507,14 @@ __global__ void __launch_bounds__(NT, MINB) solve_ell_pipe_k(const __grid_consta
             const unsigned int s = seq & 1u;
             if (!pipe_stage_ready(&full[s], (seq >> 1) & 1u, a.ctl, &s_dead)) continue;
             const PatchHdr& h = s_hdr[it & 3];
-            if (it + 3 < n_my) load_hdr_smem_at(&s_hdr[(it + 3) & 3], &a.hdr[blockIdx.x + (it + 3) * gridDim.x], 64);
+            if (MULTI) {   // the rows of the previous patch are visible to the whole CTA now: push its interface rows to the neighbours
+                peer_push_patch<NT>(pc, 0, snd_b, snd_e, xnew, nxt);
+                snd_b = s_snd[it & 3][0]; snd_e = s_snd[it & 3][1];
+            }
+            if (it + 3 < n_my) {
+                load_hdr_smem_at(&s_hdr[(it + 3) & 3], &a.hdr[blockIdx.x + (it + 3) * gridDim.x], 64);
+                if (MULTI) load_snd_smem_at(s_snd[(it + 3) & 3], pc.psend_off[0], blockIdx.x + (it + 3) * gridDim.x, 64);
+            }
             if (it + 1 < n_my)
                 ell_issue<NT>(a, smraw + (s ^ 1u) * a.stage_bytes,
                               reinterpret_cast<const uint32_t*>(smraw + a.off_gidx + (s ^ 1u) * a.gidx_bytes),
@@ -475,6 +559,7 @@ __global__ void __launch_bounds__(NT, MINB) solve_ell_pipe_k(const __grid_consta
             }
         }
         __syncthreads();
+        if (MULTI) peer_push_patch<NT>(pc, 0, snd_b, snd_e, xnew, nxt);      // the CTA's last patch
         block_sum2(r0, b0, red);
         double* part = a.partials + (size_t)(k & 1) * 2 * gridDim.x;
         if (threadIdx.x == 0) { part[2 * blockIdx.x] = r0; part[2 * blockIdx.x + 1] = b0; }
@@ -488,7 +573,7 @@ __global__ void __launch_bounds__(NT, MINB) solve_ell_pipe_k(const __grid_consta
         __syncthreads();
         rr = bc[0]; bb = bc[1];
         __syncthreads();
-        if (MULTI) { peer_exchange_iter<NT>(pc, a.ctl, epoch, true, xnew, nxt, k, rr, bb); fence_proxy_async(); }
+        if (MULTI) { peer_finish_iter<NT>(pc, a.ctl, xseq0 + (unsigned long long)k + 1ull, bc, rr, bb); fence_proxy_async(); }
         conv = rr <= a.tol2 * bb;
         if (blockIdx.x == 0 && threadIdx.x == 0 && k < 48) a.ctl->reshist[a.which][k] = (bb > 0.0) ? rr / bb : 0.0;
         k += 1;
@@ -499,6 +584,7 @@ __global__ void __launch_bounds__(NT, MINB) solve_ell_pipe_k(const __grid_consta
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         sc.cur = cur; sc.k = k; sc.done = 1; sc.rr = rr; sc.bb = bb; sc.rho = rho;
         sc.iters += k; sc.solves += 1;
+        if (MULTI) a.ctl->comm_seq = xseq0 + (unsigned long long)k;
         if (!conv) a.ctl->nonconv += 1;
         double rel = (bb > 0.0) ? sqrt(rr / bb) : 0.0;
         if (rel > sc.maxres) sc.maxres = rel;

@@ -2033,6 +2033,24 @@ int phw_comm_setup(phw_solver_t s, int32_t rank, int32_t world, const void* hand
         rc = s->upload(&d, loc); if (rc) return rc; pc.send_e_rem[k] = d;
         pc.n_send_e[k] = (int)n_send_e[k];
     }
+    {   // the same lists bucketed by owner patch: the pipelined solves push a patch's interface rows right after computing them
+        for (int f = 0; f < 2; ++f) {
+            std::vector<std::vector<int32_t>> locs(n_nb), rems(n_nb);
+            for (int k = 0; k < n_nb; ++k) {
+                const int64_t n = f == 0 ? n_send_v[k] : n_send_e[k];
+                const int32_t* u = f == 0 ? send_v_user[k] : send_e_user[k];
+                const int32_t* r = f == 0 ? send_v_remote[k] : send_e_remote[k];
+                locs[k].resize(n); rems[k].assign(r, r + n);
+                for (int64_t i = 0; i < n; ++i) locs[k][i] = f == 0 ? L.v_old2new[u[i]] : L.e_old2new[u[i]];
+            }
+            std::vector<int32_t> off; std::vector<PatchSendEntry> ent;
+            bucket_send_lists(L.hdr, f == 0, n_nb, locs, rems, off, ent);
+            int32_t* d_off; PatchSendEntry* d_ent;
+            int rc = s->upload(&d_off, off); if (rc) return rc;
+            rc = s->upload(&d_ent, ent); if (rc) return rc;
+            pc.psend_off[f] = d_off; pc.psend_ent[f] = reinterpret_cast<const int4*>(d_ent);
+        }
+    }
     CU(cudaStreamSynchronize(s->stream));
     s->pc = pc;
     return PHW_OK;

@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cstddef>
 #include <cstdint>
+#include <vector>
 #include "layout.hpp"
 
 namespace phw {
@@ -83,6 +84,27 @@ inline void pipe_carve(const Layout& L, MqPipeArgs& cq, EllPipeArgs& cp, size_t&
         rv->gidx_bytes = (uint32_t)r16(((size_t)max_ge + 8) * 4);
         *smem_rv = (size_t)rv->off_gidx + 2 * rv->gidx_bytes;
     }
+}
+
+
+// partitioned runs: the send lists of a rank (per neighbour k: rows to push, given by their new local ids, and their positions in
+// the neighbour's vectors) bucketed by owner patch - PeerComm::psend_off / psend_ent of the pipelined solves (kernels_pipe.cuh).
+// pstart[p] = first owned row of patch p (hdr[p].v_start or e_start); rows are owned, i.e. < pstart[npatch - 1] + count.
+struct PatchSendEntry { int32_t loc, nb, rem, pad; };
+inline void bucket_send_lists(const std::vector<PatchHdr>& hdr, bool vertex, int n_nb, const std::vector<std::vector<int32_t>>& loc_new,
+                              const std::vector<std::vector<int32_t>>& rem, std::vector<int32_t>& off, std::vector<PatchSendEntry>& ent) {
+    const int np = (int)hdr.size();
+    std::vector<int32_t> start(np);
+    for (int p = 0; p < np; ++p) start[p] = vertex ? hdr[p].v_start : hdr[p].e_start;
+    auto patch_of = [&](int32_t row) { return (int)(std::upper_bound(start.begin(), start.end(), row) - start.begin()) - 1; };
+    off.assign(np + 1, 0);
+    for (int k = 0; k < n_nb; ++k)
+        for (int32_t r : loc_new[k]) off[patch_of(r) + 1]++;
+    for (int p = 0; p < np; ++p) off[p + 1] += off[p];
+    ent.assign(off[np], PatchSendEntry{0, 0, 0, 0});
+    std::vector<int32_t> pos(off.begin(), off.end() - 1);
+    for (int k = 0; k < n_nb; ++k)
+        for (size_t i = 0; i < loc_new[k].size(); ++i) ent[pos[patch_of(loc_new[k][i])]++] = PatchSendEntry{loc_new[k][i], k, rem[k][i], 0};
 }
 
 }  // namespace phw

@@ -338,6 +338,15 @@ extern "C" int emu_run2(const char* what_c, int32_t patch_cells, int32_t grid,
         else { pc.send_v_loc[0] = k.d_sloc; pc.send_v_rem[0] = k.d_srem; pc.n_send_v[0] = k.n_send; }
         pc.mbox[0] = R[0].mbox; pc.mbox[1] = R[1].mbox;
         pc.timeout_cycles = (long long)4e18;
+        {   // send lists bucketed by owner patch (what phw_comm_setup builds for the pipelined solves)
+            std::vector<std::vector<int32_t>> locs(1), rems(1);
+            locs[0].assign(k.d_sloc, k.d_sloc + k.n_send); rems[0].assign(sr.begin(), sr.end());
+            std::vector<int32_t> off; std::vector<PatchSendEntry> ent;
+            bucket_send_lists(k.L.hdr, !is_q, 1, locs, rems, off, ent);
+            const int f = is_q ? 1 : 0;
+            pc.psend_off[f] = k.A.put(off);
+            pc.psend_ent[f] = reinterpret_cast<const int4*>(k.A.put(ent));
+        }
     }
     const double lam_lo = std::min(R[0].lam_lo, R[1].lam_lo), lam_hi = std::max(R[0].lam_hi, R[1].lam_hi);
     const double cd = is_q ? 0.5 * (lam_lo + lam_hi) : 1.25, cc = is_q ? 0.5 * (lam_hi - lam_lo) : 0.75;
