@@ -71,7 +71,11 @@ typedef struct phw_params {
                                 of the lean kernels instead of cooperative-groups grid syncs;
                                 bit11: H_wave (both quadratic forms) in one bulk-copy pipelined pass over the own cells of every
                                 patch (64 instead of 88 B per cell; one GPU, unbatched runs);
-                                bit12: bulk-copy pipelined right-hand sides D p / D^T q (one GPU, unbatched, no casimir terms); */
+                                bit12: bulk-copy pipelined right-hand sides D p / D^T q (unbatched, no casimir terms);
+                                bit15: the WHOLE time loop of phw_run in one launch (csrc/kernels_loop.cuh) for cache-resident meshes: one
+                                CTA per patch for the whole run, the CTAs of a case in one thread-block cluster (1, 2, 4, 8 or 16 patches
+                                per case) or one co-resident grid; every scheme and variant except the analytical diagnostics; one GPU.
+                                Silently ignored when the layout is not eligible (phw_stats.kernel_paths tells: PHW_PATH_LOOP) */
     int32_t extrap_order_q;  /* extrapolation order of the q (and block) solves; 0: same as extrap_order.  Orders up to 5 */
 } phw_params;
 
@@ -85,7 +89,7 @@ typedef struct phw_stats {
     double  ms_solve_p, ms_solve_q, ms_solve_block;   /* summed CUDA-event time of the solve kernels (flags bit2) */
     int64_t kernel_paths;       /* phw_path bits: which variants of the mass-solve kernels the last phw_run launched */
 } phw_stats;
-enum phw_path { PHW_PATH_LEAN_P = 1, PHW_PATH_LEAN_Q = 2, PHW_PATH_PIPE_P = 4, PHW_PATH_PIPE_Q = 8, PHW_PATH_PIPE_ENERGY = 16, PHW_PATH_PIPE_RHS = 32 };
+enum phw_path { PHW_PATH_LEAN_P = 1, PHW_PATH_LEAN_Q = 2, PHW_PATH_PIPE_P = 4, PHW_PATH_PIPE_Q = 8, PHW_PATH_PIPE_ENERGY = 16, PHW_PATH_PIPE_RHS = 32, PHW_PATH_LOOP = 256 };
 
 const char* phw_last_error(void);
 int phw_version(void);

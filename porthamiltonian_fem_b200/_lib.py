@@ -36,6 +36,21 @@ class PhwParams(ctypes.Structure):
 
 # phw_params.flags: bulk-copy pipelined M_q / M_p solves, fused energy reduction, right-hand sides (include/phwave.h)
 FLAGS_PIPELINED = 256 | 512 | 2048 | 4096
+# the whole time loop in one launch (csrc/kernels_loop.cuh): cache-resident meshes, one CTA per patch, one cluster per case
+FLAGS_LOOP = 32768
+
+
+def loop_patch_cells(n_cells, max_patch_cells=3000):
+    """patch size that cuts a mesh of n_cells into 1, 2, 4, 8 or 16 patches of <= max_patch_cells (one thread-block cluster per case),
+    aiming at ~1000 cells per CTA; None if the mesh is too large for one cluster (the caller then uses 2048-cell patches: one
+    co-resident grid) or too small to be cut evenly"""
+    for cl in (1, 2, 4, 8, 16):
+        pc = max(16, -(-n_cells // cl))
+        if -(-n_cells // pc) != cl:
+            continue
+        if pc <= 1100 or (cl == 16 and pc <= max_patch_cells):
+            return pc
+    return None
 
 
 class PhwStats(ctypes.Structure):

@@ -132,6 +132,7 @@ struct PeerComm {
     // neighbour slot, position in the neighbour's vectors, 0)
     const int* psend_off[2];
     const int4* psend_ent[2];
+    int xch_dbg;                               // A/B knobs of the exchange (PHW_XCH_DEBUG; measurement only, see peer_finish_iter)
 };
 
 // PHW_HOST_EMU: the kernels of this directory also compile for the host-side SPMD emulator of tests/emu (fibers for threads,
@@ -458,7 +459,9 @@ __device__ __forceinline__ void vertex_pass(const RowArgs& a, const PassIO& io, 
 // pass (ids 16 B + weights 8 B x degree per vertex instead of cell records + areas + adjacency), but one shared-memory
 // stage instead of two: no per-cell buffer, one barrier less, about half the shared-memory wavefronts.
 // ------------------------------------------------------------------------------------------------
-template <int NT>
+// COH: the right-hand side is read with ordinary (coherent) loads - required inside the persistent whole-loop kernel
+// (kernels_loop.cuh), where b is rewritten by an earlier phase of the SAME launch, so the read-only path must not be used
+template <int NT, bool COH = false>
 __device__ __forceinline__ void vertex_ell_pass(const RowArgs& a, const PassIO& io, double* smem, double& acc0, double& acc1) {
     const DevMesh& m = a.m;
     __shared__ PatchHdr s_hdr[2];
@@ -482,7 +485,7 @@ __device__ __forceinline__ void vertex_ell_pass(const RowArgs& a, const PassIO& 
             const uint32_t io0 = s_io[sl], wo0 = s_wo[sl];
             const int W = (int)((s_wo[sl + 1] - wo0) >> 5);
             const int gid = h.v_start + lv;
-            const double bv = __ldg(&a.b[gid]);
+            const double bv = COH ? a.b[gid] : __ldg(&a.b[gid]);
             const double xpv = io.use_prev ? io.xprev[gid] : 0.0;
             const double* __restrict__ wrow = m.ell_w + wo0 + lane;
             double val = 0.0, dsum = 0.0;
@@ -606,7 +609,7 @@ __global__ void __launch_bounds__(NT) stream_probe_k(DevMesh m, const double* __
 // ------------------------------------------------------------------------------------------------
 // edge rows: all patches of this block
 // ------------------------------------------------------------------------------------------------
-template <int EPI, int MODE, bool HAS_M, bool HAS_D, bool CAS, int NT>
+template <int EPI, int MODE, bool HAS_M, bool HAS_D, bool CAS, int NT, bool COH = false>
 __device__ __forceinline__ void edge_pass(const RowArgs& a, const PassIO& io, double* smem, double& acc0, double& acc1) {
     const DevMesh& m = a.m;
     __shared__ PatchHdr s_hdr[2];
@@ -725,7 +728,7 @@ __device__ __forceinline__ void edge_pass(const RowArgs& a, const PassIO& io, do
                     const int le = base + u * NT;
                     if (le < h.e_cnt) {
                         const int gid = h.e_start + le;
-                        adjb[u] = __ldg(&m.eadj[gid]); bvb[u] = __ldg(&a.b[gid]); pvb[u] = __ldg(&a.pinv[gid]);
+                        adjb[u] = __ldg(&m.eadj[gid]); bvb[u] = COH ? a.b[gid] : __ldg(&a.b[gid]); pvb[u] = __ldg(&a.pinv[gid]);
                         xpb[u] = io.use_prev ? io.xprev[gid] : 0.0;
                     }
                 }

@@ -1,0 +1,415 @@
+// kernels_loop.cuh - the WHOLE time loop of wave_2D.py:787-982 in ONE launch, for meshes that live in the caches (the reference's
+// own workloads: main_wave_2D.py:24-36,92-102, main_wave_2D_control.py:38-39, and every case of a batched sweep).
+//
+// The multi-launch path (phwave.cu: step()) enqueues 16-21 kernels per step and every Chebyshev iteration of its cooperative solves
+// crosses a grid-wide barrier of several hundred CTAs: on a 10-40 k-dof mesh a step costs 280-470 us of pure latency.  Here one
+// CTA owns one patch for the whole run; the CTAs of a case form ONE thread-block cluster (<= 16 CTAs, hardware cluster barrier with
+// release / acquire semantics instead of global atomics) or, for larger meshes, one co-resident grid with the one-atomic-per-CTA
+// barrier.  All vectors stay in global memory, i.e. in L2; a step is the same sequence of operations as step() - right-hand sides,
+// Chebyshev solves, port flux, the lumped ODE / controller (scalar_apply), state updates, energies, H_array row - executed by the
+// same row passes (vertex_pass / edge_pass / vertex_ell_pass of kernels.cuh), separated by cluster barriers instead of kernel
+// boundaries.  The host enqueues ONE kernel for n steps.  A batched sweep runs one independent cluster per case: no barrier and no
+// reduction ever spans two cases.
+//
+// Every scheme and variant of the multi-launch path except the analytical diagnostics: EE, SE, EH, SV, IE, SM; weak and strong
+// Dirichlet; lumped model (IC); passivity and casimir control.
+#pragma once
+
+namespace phw {
+
+struct LoopArgs {
+    DevMesh m; TriBuf tp, tq;
+    double *p, *q, *bp, *bq, *tmp_p, *tmp_q;
+    const double *pinv_p, *pinv_q, *mdiag_p, *wp, *wq;
+    double* hist[2][2][6];                    // [field][site][slot]
+    int hist_head[2][2], hist_count[2][2], extrap[2], n_sites;
+    int have_vq, sv_noreuse;
+    const int *port_goff, *port_e; const double* port_bl; int nport;
+    const double *gK, *ginvrho;               // per-case factors of a batched run (nullptr: one case)
+    int n_dir; const int* dir_idx; const double* dir_w;
+    const ScalarPrm* sp; double* Hrows; long long rows_per_group;
+    Ctl* ctl; double* partials;               // partials: 4 * gridDim doubles
+    int scheme, ic, strong, casimir, ell_p, G, cl;   // cl: CTAs (= patches) per case
+    double dt, K, rho, blw, tol2, xscale;
+    int max_iter;
+    double cheb_d[3], cheb_c[3];
+    long long n_steps;
+};
+
+struct LoopCtx {
+    int g, lead, ncta;            // case of this CTA, first CTA of the case, CTAs per case
+    unsigned int epoch, nred;
+    double* red; double* bc;      // shared memory: 64 + 2 doubles
+    int v0, vn, e0, en;           // owned dof ranges of this CTA's patch
+};
+
+template <bool CLUSTER>
+__device__ __forceinline__ void loop_sync(const LoopArgs& a, LoopCtx& cx) {
+    if (CLUSTER) {
+        __threadfence();
+        asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    } else {
+        grid_barrier(&a.ctl->gbar[0], cx.epoch);
+    }
+}
+
+// sums of (x, y) over all threads of the case, identical bits in every thread; contains one loop_sync
+template <bool CLUSTER>
+__device__ __forceinline__ void loop_reduce2(const LoopArgs& a, LoopCtx& cx, double& x, double& y) {
+    block_sum2(x, y, cx.red);
+    double* part = a.partials + (size_t)(cx.nred & 1u) * 2 * gridDim.x;
+    cx.nred++;
+    if (threadIdx.x == 0) { part[2 * blockIdx.x] = x; part[2 * blockIdx.x + 1] = y; }
+    loop_sync<CLUSTER>(a, cx);
+    if (threadIdx.x < 32) {
+        double s0 = 0.0, s1 = 0.0;
+        for (int i = threadIdx.x; i < cx.ncta; i += 32) { s0 += __ldcg(&part[2 * (cx.lead + i)]); s1 += __ldcg(&part[2 * (cx.lead + i) + 1]); }
+        s0 = warp_sum(s0); s1 = warp_sum(s1);
+        if (threadIdx.x == 0) { cx.bc[0] = s0; cx.bc[1] = s1; }
+    }
+    __syncthreads();
+    x = cx.bc[0]; y = cx.bc[1];
+    __syncthreads();
+}
+
+__device__ __forceinline__ RowArgs loop_base_args(const LoopArgs& a) {
+    RowArgs r{};
+    r.m = a.m; r.tp = a.tp; r.tq = a.tq;
+    r.partials = a.partials; r.ctl = a.ctl;
+    r.tol2 = a.tol2; r.max_iter = a.max_iter; r.weight = 1.0; r.dot_scale = 1.0;
+    r.mdiag = a.mdiag_p; r.xscale = a.xscale;
+    return r;
+}
+
+// NT threads per CTA; gridDim.x == number of patches (one patch per CTA for the whole run)
+template <bool CLUSTER, int NT>
+__global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) loop_k(const __grid_constant__ LoopArgs a) {
+    extern __shared__ double smem[];
+    __shared__ double red[64];
+    __shared__ double bc[2];
+    __shared__ PatchHdr myh;
+    LoopCtx cx;
+    cx.red = red; cx.bc = bc; cx.epoch = 0; cx.nred = 0;
+    if ((int)blockIdx.x < a.m.npatch) load_hdr_smem(&myh, &a.m.hdr[blockIdx.x]);
+    __syncthreads();
+    cx.ncta = a.cl;
+    cx.g = (int)blockIdx.x / a.cl;
+    cx.lead = cx.g * a.cl;
+    cx.v0 = myh.v_start; cx.vn = myh.v_cnt; cx.e0 = myh.e_start; cx.en = myh.e_cnt;
+    const bool leader = (int)blockIdx.x == cx.lead;
+    Ctl& ctl = a.ctl[cx.g];
+    const ScalarPrm sp = a.sp[cx.g];
+    const double dt = a.dt;
+    const bool implicit = (a.scheme == PHW_IE || a.scheme == PHW_SM);
+    int cur[3] = {ctl.sc[0].cur, ctl.sc[1].cur, ctl.sc[2].cur};
+    int hh[2][2], hc[2][2];
+    for (int f = 0; f < 2; ++f) for (int s_ = 0; s_ < 2; ++s_) { hh[f][s_] = a.hist_head[f][s_]; hc[f][s_] = a.hist_count[f][s_]; }
+    bool have_vq = a.have_vq != 0;
+    long long it_p = 0, it_q = 0, it_b = 0, n_p = 0, n_q = 0, n_b = 0, nonconv = 0;
+    double maxres[3] = {0.0, 0.0, 0.0};
+    const double Kg = a.gK ? a.gK[cx.g] : a.K;
+    const double irg = a.ginvrho ? a.ginvrho[cx.g] : 1.0 / a.rho;
+
+    // ---- small helpers (all threads of all CTAs of the case call them the same number of times) -----------------------------
+    auto SYNC = [&]() { loop_sync<CLUSTER>(a, cx); };
+    auto scalar = [&](int op, double aux0) {
+        if (leader && threadIdx.x == 0) scalar_apply(ctl, sp, cx.g, op, a.Hrows, a.rows_per_group, aux0);
+    };
+    auto tbp = [&](int which) { return tb_sel(a.tp, cur[which]); };
+    auto tbq = [&](int which) { return tb_sel(a.tq, cur[which]); };
+    // b_L^T q of the case (leader CTA, fixed order)
+    auto flux = [&](const double* qs, int slot) {
+        if (leader) {
+            double s = 0.0, z = 0.0;
+            for (int i = a.port_goff[cx.g] + (int)threadIdx.x; i < a.port_goff[cx.g + 1]; i += NT) s += a.port_bl[i] * qs[a.port_e[i]];
+            block_sum2(s, z, red);
+            if (threadIdx.x == 0) ctl.flux[slot] = s;
+            __syncthreads();
+        }
+    };
+    // elementwise work on the rows this CTA owns
+    auto axpy_v = [&](double* y, double al, const double* x) { for (int i = cx.v0 + (int)threadIdx.x; i < cx.v0 + cx.vn; i += NT) y[i] += al * x[i]; };
+    auto axpy_e = [&](double* y, double al, const double* x) { for (int i = cx.e0 + (int)threadIdx.x; i < cx.e0 + cx.en; i += NT) y[i] += al * x[i]; };
+    auto waxpy_v = [&](double* w, const double* y, double al, const double* x) { for (int i = cx.v0 + (int)threadIdx.x; i < cx.v0 + cx.vn; i += NT) w[i] = y[i] + al * x[i]; };
+    auto waxpy_e = [&](double* w, const double* y, double al, const double* x) { for (int i = cx.e0 + (int)threadIdx.x; i < cx.e0 + cx.en; i += NT) w[i] = y[i] + al * x[i]; };
+    // initial guess of a solve: extrapolation through the last solutions of its site, written into the current iterate buffer
+    auto predict = [&](int field, int site, int which) {
+        const int order = a.extrap[field] + 1;
+        const int mth = hc[field][site] < order ? hc[field][site] : order;
+        if (mth <= 0 || !a.hist[field][site][0]) return;
+        double c[6]; const double* h[6];
+        double binom = 1.0;
+        for (int j = 0; j < mth; ++j) {
+            binom = binom * (double)(mth - j) / (double)(j + 1);
+            c[j] = (j % 2 == 0) ? binom : -binom;
+            h[j] = a.hist[field][site][((hh[field][site] - j) % order + order) % order];
+        }
+        double* x = field == 0 ? tbp(which) : tbq(which);
+        const int i0 = field == 0 ? cx.v0 : cx.e0, n = field == 0 ? cx.vn : cx.en;
+        for (int i = i0 + (int)threadIdx.x; i < i0 + n; i += NT) {
+            double v = c[0] * h[0][i];
+            for (int j = 1; j < mth; ++j) v += c[j] * h[j][i];
+            x[i] = v;
+        }
+    };
+    auto remember = [&](int field, int site, int which) {
+        if (!a.hist[field][site][0]) return;
+        const int order = a.extrap[field] + 1;
+        hh[field][site] = (hh[field][site] + 1) % order;
+        hc[field][site] = hc[field][site] + 1 < order ? hc[field][site] + 1 : order;
+        double* dst = a.hist[field][site][hh[field][site]];
+        const double* x = field == 0 ? tbp(which) : tbq(which);
+        const int i0 = field == 0 ? cx.v0 : cx.e0, n = field == 0 ? cx.vn : cx.en;
+        for (int i = i0 + (int)threadIdx.x; i < i0 + n; i += NT) dst[i] = x[i];
+    };
+    // strong Dirichlet rows: the velocity unknown of a constrained vertex is prescribed (dirichlet_set_k)
+    auto dirichlet_preset = [&](int which) {
+        if (!a.strong || a.n_dir == 0) return;
+        if (leader) {
+            double* x = tbp(which);
+            const double pl = *((volatile double*)&ctl.pleft);
+            for (int i = threadIdx.x; i < a.n_dir; i += NT) x[a.dir_idx[i]] = (a.dir_w[i] * pl - a.p[a.dir_idx[i]]) * (1.0 / dt);
+        }
+    };
+    // b_p = -K (D^T qsrc [+ B_top psrc])
+    auto rhs_p = [&](const double* qsrc, const double* psrc) {
+        RowArgs r = loop_base_args(a);
+        r.xp = psrc; r.xq = qsrc; r.cM = 0.0; r.cD = -Kg; r.cB = a.casimir ? -Kg : 0.0; r.y = a.bp;
+        PassIO io{}; io.xp = psrc; io.xq = qsrc;
+        double d0 = 0.0, d1 = 0.0;
+        if (a.casimir) vertex_pass<EPI_STORE, MODE_OP, false, true, true, NT>(r, io, smem, d0, d1);
+        else vertex_pass<EPI_STORE, MODE_OP, false, true, false, NT>(r, io, smem, d0, d1);
+    };
+    // b_q = (1/rho) (D psrc - b_L p_left [- B_right qsrc]); the port term is added by the leader after a barrier
+    auto rhs_q = [&](const double* psrc, const double* qsrc) {
+        RowArgs r = loop_base_args(a);
+        r.xp = psrc; r.xq = qsrc; r.cM = 0.0; r.cD = irg; r.cB = a.casimir ? -irg : 0.0; r.y = a.bq;
+        PassIO io{}; io.xp = psrc; io.xq = qsrc;
+        double d0 = 0.0, d1 = 0.0;
+        if (a.casimir) edge_pass<EPI_STORE, MODE_OP, false, true, true, NT>(r, io, smem, d0, d1);
+        else edge_pass<EPI_STORE, MODE_OP, false, true, false, NT>(r, io, smem, d0, d1);
+        if (!a.strong && a.nport > 0) {
+            SYNC();
+            if (leader) {
+                const double pl = *((volatile double*)&ctl.pleft);
+                for (int i = a.port_goff[cx.g] + (int)threadIdx.x; i < a.port_goff[cx.g + 1]; i += NT) a.bq[a.port_e[i]] -= irg * a.port_bl[i] * pl;
+            }
+        }
+    };
+    // Chebyshev solve of M_p x = bp (which 0) / M_q x = bq (which 1); warm start = iterate buffer `cur`; ends behind a barrier
+    auto solve_mass = [&](int which) {
+        RowArgs r = loop_base_args(a);
+        r.which = which; r.cM = 1.0;
+        r.b = which == 0 ? a.bp : a.bq; r.pinv = which == 0 ? a.pinv_p : a.pinv_q;
+        const bool keep_mdiag = a.strong || (a.casimir && implicit);
+        if (!keep_mdiag) r.mdiag = nullptr;
+        int k = 0; double rho = 0.0, rr = 0.0, bb = 0.0; bool conv = false;
+        int c_ = cur[which];
+        SYNC();                                    // right-hand side and initial guess of the neighbouring patches are complete
+        while (true) {
+            double c1, c2, rho_k;
+            cheb_coeffs(k, rho, a.cheb_d[which], a.cheb_c[which], c1, c2, rho_k);
+            const int nxt = (c_ + 1) % 3, prv = (c_ + 2) % 3;
+            PassIO io{};
+            io.c1 = c1; io.c2 = c2; io.use_prev = k > 0;
+            double r0 = 0.0, b0 = 0.0;
+            if (which == 0) {
+                io.xp = tb_sel(a.tp, c_); io.xprev = tb_sel(a.tp, prv); io.xnew = tb_sel(a.tp, nxt);
+                if (a.ell_p && !keep_mdiag) vertex_ell_pass<NT, true>(r, io, smem, r0, b0);
+                else vertex_pass<EPI_CHEB, MODE_OP, true, false, false, NT>(r, io, smem, r0, b0);
+            } else {
+                io.xq = tb_sel(a.tq, c_); io.xprev = tb_sel(a.tq, prv); io.xnew = tb_sel(a.tq, nxt);
+                edge_pass<EPI_CHEB, MODE_OP, true, false, false, NT, true>(r, io, smem, r0, b0);
+            }
+            loop_reduce2<CLUSTER>(a, cx, r0, b0);
+            rr = r0; bb = b0;
+            conv = rr <= a.tol2 * bb;
+            k += 1;
+            if (conv) break;                       // the verified iterate x_k (buffer c_) is the solution
+            rho = rho_k; c_ = nxt;
+            if (k >= a.max_iter) break;
+        }
+        cur[which] = c_;
+        (which == 0 ? it_p : it_q) += k; (which == 0 ? n_p : n_q) += 1;
+        if (!conv) nonconv += 1;
+        const double rel = bb > 0.0 ? sqrt(rr / bb) : 0.0;
+        if (rel > maxres[which]) maxres[which] = rel;
+    };
+    // Chebyshev (ellipse) solve of the coupled block system of IE / SM (solve_block of phwave.cu)
+    auto solve_block = [&](double theta) {
+        RowArgs av = loop_base_args(a);
+        av.which = 2; av.cM = 1.0;
+        RowArgs ae = av;
+        av.b = a.bp; av.pinv = a.pinv_p; av.cD = theta * dt * a.K; av.cB = a.casimir ? theta * dt * a.K : 0.0; av.weight = 1.0 / a.K;
+        ae.b = a.bq; ae.pinv = a.pinv_q; ae.cD = -theta * dt / a.rho; ae.cB = a.casimir ? theta * dt / a.rho : 0.0; ae.weight = a.rho;
+        int k = 0; double rho = 0.0, rr = 0.0, bb = 0.0; bool conv = false;
+        int c_ = cur[2];
+        SYNC();
+        while (true) {
+            double c1, c2, rho_k;
+            cheb_coeffs(k, rho, a.cheb_d[2], a.cheb_c[2], c1, c2, rho_k);
+            const int nxt = (c_ + 1) % 3, prv = (c_ + 2) % 3;
+            PassIO iov{}, ioe{};
+            iov.xp = tb_sel(a.tp, c_); iov.xq = tb_sel(a.tq, c_); iov.xprev = tb_sel(a.tp, prv); iov.xnew = tb_sel(a.tp, nxt);
+            ioe.xp = iov.xp; ioe.xq = iov.xq; ioe.xprev = tb_sel(a.tq, prv); ioe.xnew = tb_sel(a.tq, nxt);
+            iov.c1 = ioe.c1 = c1; iov.c2 = ioe.c2 = c2; iov.use_prev = ioe.use_prev = (k > 0);
+            double r0 = 0.0, b0 = 0.0, a0_ = 0.0, a1_ = 0.0;
+            if (a.casimir) vertex_pass<EPI_CHEB, MODE_OP, true, true, true, NT>(av, iov, smem, a0_, a1_);
+            else vertex_pass<EPI_CHEB, MODE_OP, true, true, false, NT>(av, iov, smem, a0_, a1_);
+            r0 += av.weight * a0_; b0 += av.weight * a1_;
+            a0_ = 0.0; a1_ = 0.0;
+            if (a.casimir) edge_pass<EPI_CHEB, MODE_OP, true, true, true, NT, true>(ae, ioe, smem, a0_, a1_);
+            else edge_pass<EPI_CHEB, MODE_OP, true, true, false, NT, true>(ae, ioe, smem, a0_, a1_);
+            r0 += ae.weight * a0_; b0 += ae.weight * a1_;
+            loop_reduce2<CLUSTER>(a, cx, r0, b0);
+            rr = r0; bb = b0;
+            conv = rr <= a.tol2 * bb;
+            k += 1;
+            if (conv) break;
+            rho = rho_k; c_ = nxt;
+            if (k >= a.max_iter) break;
+        }
+        cur[2] = c_;
+        it_b += k; n_b += 1;
+        if (!conv) nonconv += 1;
+        const double rel = bb > 0.0 ? sqrt(rr / bb) : 0.0;
+        if (rel > maxres[2]) maxres[2] = rel;
+    };
+    auto solve_site = [&](int which, int site) {
+        predict(which, site, which);
+        if (which == 0 && a.strong) { SYNC(); dirichlet_preset(0); }
+        solve_mass(which);
+        remember(which, site, which);
+    };
+    // H_wave = 0.5/rho p^T M_p p + 0.5 K q^T M_q q  (wave_2D.py:882,907) -> red[0], red[1]; ends behind a barrier
+    auto energy = [&]() {
+        RowArgs r = loop_base_args(a);
+        r.cM = 1.0; r.xp = a.p; r.xq = a.q;
+        PassIO io{}; io.xp = a.p; io.xq = a.q;
+        double ap = 0.0, aq = 0.0, z0 = 0.0, z1 = 0.0;
+        vertex_pass<EPI_DOT, MODE_OP, true, false, false, NT>(r, io, smem, ap, z0);
+        edge_pass<EPI_DOT, MODE_OP, true, false, false, NT>(r, io, smem, aq, z1);
+        loop_reduce2<CLUSTER>(a, cx, ap, aq);
+        if (leader && threadIdx.x == 0) { ctl.red[0] = 0.5 * irg * ap; ctl.red[1] = 0.5 * Kg * aq; }
+    };
+    // casimir: boundary quadratic forms of the midpoint averages (wave_2D.py:633-634) -> red[2], red[3]
+    auto casimir_dots = [&](const double* xp, const double* xq) {
+        RowArgs r = loop_base_args(a);
+        r.cM = 0.0; r.cB = 1.0; r.xp = xp; r.xq = xq;
+        PassIO io{}; io.xp = xp; io.xq = xq;
+        double ap = 0.0, aq = 0.0, z0 = 0.0, z1 = 0.0;
+        vertex_pass<EPI_DOT, MODE_OP, false, false, true, NT>(r, io, smem, ap, z0);
+        edge_pass<EPI_DOT, MODE_OP, false, false, true, NT>(r, io, smem, aq, z1);
+        loop_reduce2<CLUSTER>(a, cx, ap, aq);
+        if (leader && threadIdx.x == 0) { ctl.red[2] = ap; ctl.red[3] = aq; }
+    };
+
+    // ---- the time loop (same order of operations as step() of phwave.cu) -----------------------------------------------------
+    for (long long n = 0; n < a.n_steps; ++n) {
+        switch (a.scheme) {
+            case PHW_EE:
+                scalar(S_BEGIN_1SUB, 0.0);
+                flux(a.q, 0);
+                rhs_p(a.q, a.p); solve_site(0, 0);
+                rhs_q(a.p, a.q); solve_site(1, 0);
+                axpy_v(a.p, dt, tbp(0));
+                axpy_e(a.q, dt, tbq(1));
+                SYNC();
+                energy();
+                scalar(S_END_1SUB, 0.0);
+                break;
+            case PHW_SE:
+                scalar(S_BEGIN_1SUB, 0.0);
+                flux(a.q, 0);
+                rhs_p(a.q, a.p); solve_site(0, 0);
+                axpy_v(a.p, dt, tbp(0));
+                if (a.ic) scalar(S_ODE_SE, 0.0);
+                SYNC();
+                rhs_q(a.p, a.q); solve_site(1, 0);
+                axpy_e(a.q, dt, tbq(1));
+                SYNC();
+                energy();
+                scalar(S_END_1SUB, 0.0);
+                break;
+            case PHW_SV:
+                scalar(S_SV_STAGE1, 0.0);
+                if (!have_vq || a.sv_noreuse) { SYNC(); rhs_q(a.p, a.q); solve_site(1, 0); }
+                axpy_e(a.q, 0.5 * dt, tbq(1));                        // q_temp
+                SYNC();
+                flux(a.q, 0);
+                scalar(S_SV_MID, 0.0);
+                rhs_p(a.q, a.p); solve_site(0, 0);
+                axpy_v(a.p, dt, tbp(0));
+                if (a.ic) scalar(S_ODE_SV, 0.0);
+                SYNC();
+                rhs_q(a.p, a.q); solve_site(1, 0);
+                axpy_e(a.q, 0.5 * dt, tbq(1));
+                have_vq = true;
+                SYNC();
+                energy();
+                scalar(S_END_SV, 0.0);
+                break;
+            case PHW_EH:
+                scalar(S_EH_BEGIN, 0.0);
+                flux(a.q, 0);
+                rhs_p(a.q, a.p); solve_site(0, 0);
+                rhs_q(a.p, a.q); solve_site(1, 0);
+                flux(tbq(1), 1);                                       // b_L^T v_q1
+                waxpy_v(a.tmp_p, a.p, 0.5 * dt, tbp(0));               // 0.5 (p_m + p_temp)
+                waxpy_e(a.tmp_q, a.q, 0.5 * dt, tbq(1));
+                SYNC();
+                rhs_p(a.tmp_q, a.tmp_p); solve_site(0, 1);
+                rhs_q(a.tmp_p, a.tmp_q); solve_site(1, 1);
+                axpy_v(a.p, dt, tbp(0));
+                axpy_e(a.q, dt, tbq(1));
+                SYNC();
+                energy();
+                scalar(S_END_EH, 0.0);
+                break;
+            case PHW_IE:
+            case PHW_SM: {
+                const double theta = (a.scheme == PHW_IE) ? 1.0 : 0.5;
+                scalar(S_BEGIN_1SUB, 0.0);
+                flux(a.q, 0);
+                if (a.ic) scalar(S_SM_PLEFT, 0.0);
+                rhs_p(a.q, a.p);
+                rhs_q(a.p, a.q);
+                predict(0, 0, 2); predict(1, 0, 2);
+                if (a.strong) { SYNC(); dirichlet_preset(2); }
+                solve_block(theta);
+                remember(0, 0, 2); remember(1, 0, 2);
+                if (a.ic) {
+                    flux(tbq(2), 2);                                   // b_L^T vhat_q
+                    scalar(S_ODE_SM, a.blw);
+                    SYNC();
+                    const double xi1 = *((volatile double*)&ctl.xi1);
+                    axpy_v(tbp(2), xi1, a.wp);
+                    axpy_e(tbq(2), xi1, a.wq);
+                }
+                if (a.casimir) {
+                    waxpy_v(a.tmp_p, a.p, 0.5 * dt, tbp(2));
+                    waxpy_e(a.tmp_q, a.q, 0.5 * dt, tbq(2));
+                    SYNC();
+                    casimir_dots(a.tmp_p, a.tmp_q);
+                }
+                axpy_v(a.p, dt, tbp(2));
+                axpy_e(a.q, dt, tbq(2));
+                SYNC();
+                flux(a.q, 1);
+                energy();
+                scalar(S_END_1SUB, 0.0);
+            } break;
+            default: break;
+        }
+    }
+    SYNC();
+    if (leader && threadIdx.x == 0) {
+        for (int w = 0; w < 3; ++w) { ctl.sc[w].cur = cur[w]; if (maxres[w] > ctl.sc[w].maxres) ctl.sc[w].maxres = maxres[w]; }
+        ctl.sc[0].iters += it_p; ctl.sc[0].solves += n_p;
+        ctl.sc[1].iters += it_q; ctl.sc[1].solves += n_q;
+        ctl.sc[2].iters += it_b; ctl.sc[2].solves += n_b;
+        ctl.nonconv += nonconv;
+    }
+}
+
+}  // namespace phw

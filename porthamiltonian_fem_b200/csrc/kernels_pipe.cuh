@@ -157,24 +157,32 @@ __device__ __forceinline__ void grid_barrier_px(unsigned int* bar, unsigned int&
 
 // ---- inter-GPU exchange of the pipelined solves (partitioned runs; protocol of round 2) -----------------------------
 // (1) peer_push_patch: right after the rows of patch P are written, the threads of the CTA copy its interface rows straight into the
-//     neighbours' iterate buffers (peer-mapped memory, NVLink stores) and fence them at system scope - while the other CTAs (and
-//     this one) go on with the sweep, so the transfer overlaps the interior work.
+//     neighbours' iterate buffers (peer-mapped memory, NVLink stores) - while the other CTAs (and this one) go on with the sweep, so
+//     the transfer overlaps the interior work.  A CTA that pushed anything issues ONE system-scope fence (thread 0, after the
+//     block-wide barriers of the residual reduction, before it arrives at the grid barrier): the fences are what costs on this
+//     machine (measured, profiles/r2d_exchange_ab.txt: ~5 us when every pushing thread fences, ~4 us when thread 0 of every CTA
+//     fences at system scope, ~1 us for a single thread) - and barrier + fence are cumulative, so one per CTA is enough.
 // (2) peer_finish_iter: after the grid-wide reduction of the local residual norms, ONE thread publishes the rank's norms and a
-//     sequence flag in every rank's mailbox (release at system scope: everything this grid pushed before its barrier is visible to
-//     whoever acquires the flag); thread 0 of EVERY CTA then waits for all ranks' flags in its own mailbox and sums the norms in
-//     rank order - identical bits on every rank and CTA, no second grid barrier, no broadcast through global memory.
-// Per iteration this adds one NVLink one-way latency to the critical path (the round-1 protocol, peer_exchange_iter: push after the
-// barrier + system fence by every thread + two more grid barriers).
+//     sequence flag in every rank's mailbox (system-scope release: everything this grid pushed before its barrier is visible to
+//     whoever sees the flag); thread 0 of EVERY CTA then polls the flags in its OWN mailbox (local memory, volatile loads), reads the
+//     norms with volatile loads and sums them in rank order - identical bits on every rank and CTA, no second grid barrier, no
+//     broadcast through global memory.  Consumer side: the mailbox and the iterate buffers the peers write are LOCAL memory, whose
+//     point of coherence is this GPU's L2 - once the flag is visible there, so is everything the sender fenced before it; what is
+//     left to do is to drop stale L1 lines before the CTA gathers external values, which a gpu-scope fence does (PHW_XCH_DEBUG=1
+//     restores system-scope fences on both sides: the conservative reading of the memory model, ~8 us per iteration slower).
+// Per iteration this adds about one NVLink one-way latency to the critical path (the round-1 protocol, peer_exchange_iter: push
+// after the barrier + system fence by every thread + two more grid barriers).
 template <int NT>
-__device__ __forceinline__ void peer_push_patch(const PeerComm& pc, int field, int b, int e, const double* xnew, int nxt) {
-    if (b >= e) return;                                    // uniform for the CTA
+__device__ __forceinline__ bool peer_push_patch(const PeerComm& pc, int field, int b, int e, const double* xnew, int nxt) {
+    if (b >= e) return false;                              // uniform for the CTA
     const int4* ent = pc.psend_ent[field];
     for (int i = b + (int)threadIdx.x; i < e; i += NT) {
         const int4 t = ent[i];
         double* dst = field == 0 ? pc.nb_tp[t.y][nxt] : pc.nb_tq[t.y][nxt];
         dst[t.z] = xnew[t.x];
     }
-    __threadfence_system();
+    if (pc.xch_dbg & 1) __threadfence_system();
+    return true;
 }
 // seq: exchange number of this iteration (the same on every rank); s_x: two doubles of shared memory.  Called by all threads.
 template <int NT>
@@ -194,7 +202,7 @@ __device__ __forceinline__ void peer_finish_iter(const PeerComm& pc, Ctl* ctl, u
                 while (ld_volatile_u64(&mine->flag[r]) < seq)
                     if (clock64() - t0 > pc.timeout_cycles) { ctl->comm_dead = 1; dead = true; break; }
         }
-        __threadfence_system();
+        if (pc.xch_dbg & 1) __threadfence_system(); else __threadfence();
         double s0 = 0.0, s1 = 0.0;
         for (int r = 0; r < pc.world; ++r) { s0 += *((volatile double*)&mine->part[par][r][0]); s1 += *((volatile double*)&mine->part[par][r][1]); }
         s_x[0] = s0; s_x[1] = s1;
@@ -307,6 +315,7 @@ __global__ void __launch_bounds__(NT, 1) solve_mq_pipe_k(const __grid_constant__
             if (MULTI) load_snd_smem_at(s_snd[j], pc.psend_off[1], blockIdx.x + j * gridDim.x, 32 * j);
         }
         int snd_b = 0, snd_e = 0;       // MULTI: send-list range of the patch whose rows were written last
+        bool pushed = false;
         __syncthreads();
         if (n_my > 0)
             mq_issue<NT, DIAG>(a, smraw + (seq & 1u) * a.stage_bytes, nullptr,
@@ -317,7 +326,7 @@ __global__ void __launch_bounds__(NT, 1) solve_mq_pipe_k(const __grid_constant__
             if (!pipe_stage_ready(&full[s], (seq >> 1) & 1u, a.ctl, &s_dead)) continue;
             const PatchHdr& h = s_hdr[it & 3];
             if (MULTI) {   // the rows of the previous patch are visible to the whole CTA now: push its interface rows to the neighbours
-                peer_push_patch<NT>(pc, 1, snd_b, snd_e, xnew, nxt);
+                if (!(pc.xch_dbg & 32)) pushed |= peer_push_patch<NT>(pc, 1, snd_b, snd_e, xnew, nxt);
                 snd_b = s_snd[it & 3][0]; snd_e = s_snd[it & 3][1];
             }
             if (it + 3 < n_my) {
@@ -374,10 +383,13 @@ __global__ void __launch_bounds__(NT, 1) solve_mq_pipe_k(const __grid_constant__
             }
         }
         __syncthreads();
-        if (MULTI) peer_push_patch<NT>(pc, 1, snd_b, snd_e, xnew, nxt);      // the CTA's last patch
+        if (MULTI && !(pc.xch_dbg & 32)) pushed |= peer_push_patch<NT>(pc, 1, snd_b, snd_e, xnew, nxt);      // the CTA's last patch
         block_sum2(r0, b0, red);
         double* part = a.partials + (size_t)(k & 1) * 2 * gridDim.x;
-        if (threadIdx.x == 0) { part[2 * blockIdx.x] = r0; part[2 * blockIdx.x + 1] = b0; }
+        if (threadIdx.x == 0) {
+            if (MULTI && pushed) __threadfence_system();    // one fence for everything this CTA pushed (ordered before it by the barriers above)
+            part[2 * blockIdx.x] = r0; part[2 * blockIdx.x + 1] = b0;
+        }
         grid_barrier_px(&a.ctl->gbar[0], epoch);
         if (threadIdx.x < 32) {
             double s0 = 0.0, s1 = 0.0;
@@ -388,7 +400,11 @@ __global__ void __launch_bounds__(NT, 1) solve_mq_pipe_k(const __grid_constant__
         __syncthreads();
         rr = bc[0]; bb = bc[1];
         __syncthreads();
-        if (MULTI) { peer_finish_iter<NT>(pc, a.ctl, xseq0 + (unsigned long long)k + 1ull, bc, rr, bb); fence_proxy_async(); }
+        if (MULTI) {
+            if (pc.xch_dbg & 32) { peer_exchange_iter<NT>(pc, a.ctl, epoch, false, xnew, nxt, k, rr, bb); }
+            else peer_finish_iter<NT>(pc, a.ctl, xseq0 + (unsigned long long)k + 1ull, bc, rr, bb);
+            fence_proxy_async();
+        }
         conv = rr <= a.tol2 * bb;
         if (blockIdx.x == 0 && threadIdx.x == 0 && k < 48) a.ctl->reshist[a.which][k] = (bb > 0.0) ? rr / bb : 0.0;
         k += 1;
@@ -399,7 +415,7 @@ __global__ void __launch_bounds__(NT, 1) solve_mq_pipe_k(const __grid_constant__
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         sc.cur = cur; sc.k = k; sc.done = 1; sc.rr = rr; sc.bb = bb; sc.rho = rho;
         sc.iters += k; sc.solves += 1;
-        if (MULTI) a.ctl->comm_seq = xseq0 + (unsigned long long)k;
+        if (MULTI && !(pc.xch_dbg & 32)) a.ctl->comm_seq = xseq0 + (unsigned long long)k;
         if (!conv) a.ctl->nonconv += 1;
         double rel = (bb > 0.0) ? sqrt(rr / bb) : 0.0;
         if (rel > sc.maxres) sc.maxres = rel;
@@ -498,6 +514,7 @@ __global__ void __launch_bounds__(NT, MINB) solve_ell_pipe_k(const __grid_consta
             if (MULTI) load_snd_smem_at(s_snd[j], pc.psend_off[0], blockIdx.x + j * gridDim.x, 32 * j);
         }
         int snd_b = 0, snd_e = 0;       // MULTI: send-list range of the patch whose rows were written last
+        bool pushed = false;
         __syncthreads();
         if (n_my > 0)
             ell_issue<NT>(a, smraw + (seq & 1u) * a.stage_bytes, nullptr,
@@ -508,7 +525,7 @@ __global__ void __launch_bounds__(NT, MINB) solve_ell_pipe_k(const __grid_consta
             if (!pipe_stage_ready(&full[s], (seq >> 1) & 1u, a.ctl, &s_dead)) continue;
             const PatchHdr& h = s_hdr[it & 3];
             if (MULTI) {   // the rows of the previous patch are visible to the whole CTA now: push its interface rows to the neighbours
-                peer_push_patch<NT>(pc, 0, snd_b, snd_e, xnew, nxt);
+                if (!(pc.xch_dbg & 32)) pushed |= peer_push_patch<NT>(pc, 0, snd_b, snd_e, xnew, nxt);
                 snd_b = s_snd[it & 3][0]; snd_e = s_snd[it & 3][1];
             }
             if (it + 3 < n_my) {
@@ -559,10 +576,13 @@ __global__ void __launch_bounds__(NT, MINB) solve_ell_pipe_k(const __grid_consta
             }
         }
         __syncthreads();
-        if (MULTI) peer_push_patch<NT>(pc, 0, snd_b, snd_e, xnew, nxt);      // the CTA's last patch
+        if (MULTI && !(pc.xch_dbg & 32)) pushed |= peer_push_patch<NT>(pc, 0, snd_b, snd_e, xnew, nxt);      // the CTA's last patch
         block_sum2(r0, b0, red);
         double* part = a.partials + (size_t)(k & 1) * 2 * gridDim.x;
-        if (threadIdx.x == 0) { part[2 * blockIdx.x] = r0; part[2 * blockIdx.x + 1] = b0; }
+        if (threadIdx.x == 0) {
+            if (MULTI && pushed) __threadfence_system();    // one fence for everything this CTA pushed (ordered before it by the barriers above)
+            part[2 * blockIdx.x] = r0; part[2 * blockIdx.x + 1] = b0;
+        }
         grid_barrier_px(&a.ctl->gbar[0], epoch);
         if (threadIdx.x < 32) {
             double s0 = 0.0, s1 = 0.0;
@@ -573,7 +593,11 @@ __global__ void __launch_bounds__(NT, MINB) solve_ell_pipe_k(const __grid_consta
         __syncthreads();
         rr = bc[0]; bb = bc[1];
         __syncthreads();
-        if (MULTI) { peer_finish_iter<NT>(pc, a.ctl, xseq0 + (unsigned long long)k + 1ull, bc, rr, bb); fence_proxy_async(); }
+        if (MULTI) {
+            if (pc.xch_dbg & 32) { peer_exchange_iter<NT>(pc, a.ctl, epoch, true, xnew, nxt, k, rr, bb); }
+            else peer_finish_iter<NT>(pc, a.ctl, xseq0 + (unsigned long long)k + 1ull, bc, rr, bb);
+            fence_proxy_async();
+        }
         conv = rr <= a.tol2 * bb;
         if (blockIdx.x == 0 && threadIdx.x == 0 && k < 48) a.ctl->reshist[a.which][k] = (bb > 0.0) ? rr / bb : 0.0;
         k += 1;
@@ -584,7 +608,7 @@ __global__ void __launch_bounds__(NT, MINB) solve_ell_pipe_k(const __grid_consta
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         sc.cur = cur; sc.k = k; sc.done = 1; sc.rr = rr; sc.bb = bb; sc.rho = rho;
         sc.iters += k; sc.solves += 1;
-        if (MULTI) a.ctl->comm_seq = xseq0 + (unsigned long long)k;
+        if (MULTI && !(pc.xch_dbg & 32)) a.ctl->comm_seq = xseq0 + (unsigned long long)k;
         if (!conv) a.ctl->nonconv += 1;
         double rel = (bb > 0.0) ? sqrt(rr / bb) : 0.0;
         if (rel > sc.maxres) sc.maxres = rel;

@@ -382,12 +382,8 @@ enum ScalarOp {
     S_EH_BEGIN
 };
 
-__global__ void scalar_k(Ctl* ctl, const ScalarPrm* __restrict__ prms, int n_groups, int op, double* Hrows, long long rows_per_group,
-                         double aux0, double aux1) {
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= n_groups) return;
-    Ctl& c = ctl[g];
-    const ScalarPrm s = prms[g];
+// one scalar operation of the step loop on the control block of case g (called by one thread)
+__device__ void scalar_apply(Ctl& c, const ScalarPrm& s, int g, int op, double* Hrows, long long rows_per_group, double aux0) {
     const double dt = s.dt;
     switch (op) {
         case S_BEGIN_1SUB:
@@ -493,7 +489,18 @@ __global__ void scalar_k(Ctl* ctl, const ScalarPrm* __restrict__ prms, int n_gro
     }
 }
 
+__global__ void scalar_k(Ctl* ctl, const ScalarPrm* __restrict__ prms, int n_groups, int op, double* Hrows, long long rows_per_group,
+                         double aux0, double aux1) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_groups) return;
+    const ScalarPrm s = prms[g];
+    scalar_apply(ctl[g], s, g, op, Hrows, rows_per_group, aux0);
+}
+
 }  // namespace phw
+
+#include "kernels_loop.cuh"
+
 
 // ================================================================================================
 // solver object
@@ -549,6 +556,7 @@ struct phw_solver_s {
     size_t smem_pq = 0, smem_pp = 0;
     bool pipe_en = false; EnergyPipeArgs pe{}; size_t smem_pe = 0;   // fused pipelined H_wave reduction (flags bit 11)
     bool pipe_rhs = false; RhsPipeArgs pre{}, prv{}; size_t smem_pre = 0, smem_prv = 0;   // pipelined right-hand sides (flags bit 12)
+    bool loop_on = false; int loop_cl = 0, loop_nt = 512; bool loop_cluster = false; double* loop_partials = nullptr;   // whole-loop kernel (flags bit 15)
     int64_t kernel_paths = 0;              // PHW_PATH_* bits of the solve kernels launched since the last phw_run began
     int *d_cells_user = nullptr; double* d_vtx_user = nullptr; unsigned long long* d_mm = nullptr;
     std::vector<cudaEvent_t> prof_ev; std::vector<int> prof_which; bool prof_truncated = false;
@@ -1329,6 +1337,113 @@ int step(phw_solver_s* s) {
     return 0;
 }
 
+// ---- the whole time loop in one launch (kernels_loop.cuh; flags bit 15) -----------------------------------------------------------
+// eligible: matrix-free solver on one GPU, no analytical diagnostics, one patch per CTA with all CTAs co-resident; the CTAs of a case
+// form one thread-block cluster when there are 1, 2, 4, 8 or 16 of them, else (single case only) one cooperative grid
+// 512 threads per CTA for a single case (latency per pass), 256 for a batched sweep (two CTAs per SM: the cases are independent,
+// so residency - not the latency of one case - sets the throughput)
+static void* loop_kernel(bool cluster, int nt) {
+    if (cluster) return nt == 256 ? (void*)loop_k<true, 256> : (void*)loop_k<true, 512>;
+    return nt == 256 ? (void*)loop_k<false, 256> : (void*)loop_k<false, 512>;
+}
+int setup_loop(phw_solver_s* s) {
+    const int NT_LOOP = s->G > 1 ? 256 : 512;
+    s->loop_on = false;
+    if (!(s->prm.flags & 32768) || s->ho || !s->coop || s->prm.analytical || s->npatch < 1 || s->npatch % s->G != 0) return 0;
+    const int cl = s->npatch / s->G;
+    const Layout& L = s->mesh->L;
+    if (L.nv_owned != L.nv || L.ne_owned != L.ne) return 0;            // partitioned layouts take the multi-launch path
+    for (int g = 0; g < s->G; ++g) if (L.group_patch_off[g + 1] - L.group_patch_off[g] != cl) return 0;
+    const size_t sm = s->smem_vd;
+    const bool cluster = (cl == 1 || cl == 2 || cl == 4 || cl == 8 || cl == 16);
+    if (cluster) {
+        void* kern = loop_kernel(true, NT_LOOP);
+        { int rc_ = ensure_dyn_smem(s->device, kern, 200 * 1024); if (rc_) return rc_; }
+        if (cl > 8 && cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); return 0; }
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(s->npatch); cfg.blockDim = dim3(NT_LOOP); cfg.dynamicSmemBytes = sm; cfg.stream = s->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int ncl = 0;
+        if (cudaOccupancyMaxActiveClusters(&ncl, kern, &cfg) != cudaSuccess || ncl < 1) { cudaGetLastError(); return 0; }
+    } else {
+        if (s->G != 1) return 0;
+        void* kern = loop_kernel(false, NT_LOOP);
+        { int rc_ = ensure_dyn_smem(s->device, kern, 200 * 1024); if (rc_) return rc_; }
+        int occ = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT_LOOP, sm));
+        if (occ < 1 || s->npatch > occ * s->sm_count) return 0;
+    }
+    int rc = s->dalloc(&s->loop_partials, 4 * (size_t)s->npatch + 64);
+    if (rc) return rc;
+    s->loop_on = true; s->loop_cl = cl; s->loop_cluster = cluster; s->loop_nt = NT_LOOP;
+    return 0;
+}
+
+int run_loop(phw_solver_s* s, int64_t n_steps) {
+    const phw_params& P = s->prm;
+    LoopArgs a{};
+    a.m = s->dm; a.tp = s->tp; a.tq = s->tq;
+    a.p = s->p; a.q = s->q; a.bp = s->bp; a.bq = s->bq; a.tmp_p = s->tmp_p; a.tmp_q = s->tmp_q;
+    a.pinv_p = s->pinv_p; a.pinv_q = s->pinv_q; a.mdiag_p = s->mdiag_p; a.wp = s->wp; a.wq = s->wq;
+    for (int f = 0; f < 2; ++f)
+        for (int k = 0; k < 2; ++k) {
+            for (int j = 0; j < 6; ++j) a.hist[f][k][j] = s->hist[f][k].h[j];
+            a.hist_head[f][k] = s->hist[f][k].head; a.hist_count[f][k] = s->hist[f][k].count;
+        }
+    a.extrap[0] = s->extrap_f[0]; a.extrap[1] = s->extrap_f[1]; a.n_sites = s->n_sites;
+    a.have_vq = s->have_vq ? 1 : 0; a.sv_noreuse = (P.flags & 1) ? 1 : 0;
+    a.port_goff = s->d_port_goff; a.port_e = s->d_port_e; a.port_bl = s->d_port_bl; a.nport = s->nport;
+    a.gK = s->G > 1 ? s->d_gK : nullptr; a.ginvrho = s->G > 1 ? s->d_ginvrho : nullptr;
+    a.n_dir = s->n_dir; a.dir_idx = s->d_dir_idx; a.dir_w = s->d_dir_w;
+    a.sp = s->d_sp; a.Hrows = s->dH; a.rows_per_group = s->run_rows;
+    a.ctl = s->ctl; a.partials = s->loop_partials;
+    a.scheme = P.scheme; a.ic = P.interconnection; a.strong = P.strong; a.casimir = P.casimir; a.ell_p = s->ell_p ? 1 : 0;
+    a.G = s->G; a.cl = s->loop_cl;
+    a.dt = P.dt; a.K = P.K_wave; a.rho = P.rho; a.blw = s->blw;
+    a.tol2 = P.tol * P.tol; a.xscale = P.strong ? 4.0 : 0.0;
+    a.max_iter = P.max_iter;
+    for (int i = 0; i < 3; ++i) { a.cheb_d[i] = s->cheb_d[i]; a.cheb_c[i] = s->cheb_c[i]; }
+    a.n_steps = n_steps;
+    const size_t sm = s->smem_vd;
+    const int NT_LOOP = s->loop_nt;
+    if (s->loop_cluster) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(s->npatch); cfg.blockDim = dim3(NT_LOOP); cfg.dynamicSmemBytes = sm; cfg.stream = s->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = s->loop_cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        if (NT_LOOP == 256) CU(cudaLaunchKernelEx(&cfg, loop_k<true, 256>, a)); else CU(cudaLaunchKernelEx(&cfg, loop_k<true, 512>, a));
+    } else {
+        CU(cudaMemsetAsync(&s->ctl->gbar[0], 0, sizeof(unsigned int), s->stream));
+        void* args[] = {(void*)&a};
+        CU(cudaLaunchCooperativeKernel(loop_kernel(false, NT_LOOP), dim3(s->npatch), dim3(NT_LOOP), args, sm, s->stream));
+    }
+    s->launches++;
+    s->kernel_paths |= PHW_PATH_LOOP;
+    // the history ring and the first-same-as-last flag advance deterministically: one solution per (field, site) and solve
+    auto advance = [&](int f, int site, int64_t n) {
+        phw_solver_s::Hist& H = s->hist[f][site];
+        if (!H.h[0] || n <= 0) return;
+        const int order = s->extrap_f[f] + 1;
+        H.head = (int)((H.head + n) % order);
+        H.count = (int)std::min<int64_t>((int64_t)H.count + n, order);
+    };
+    if (n_steps > 0) {
+        switch (P.scheme) {
+            case PHW_SV: {
+                const int64_t first = (!s->have_vq || (P.flags & 1)) ? ((P.flags & 1) ? n_steps : 1) : 0;
+                advance(0, 0, n_steps); advance(1, 0, n_steps + first);
+                s->have_vq = true;
+            } break;
+            case PHW_EH: advance(0, 0, n_steps); advance(1, 0, n_steps); advance(0, 1, n_steps); advance(1, 1, n_steps); break;
+            default: advance(0, 0, n_steps); advance(1, 0, n_steps);
+        }
+    }
+    return 0;
+}
+
 bool is_device_ptr(const void* p) {
     cudaPointerAttributes at{};
     if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
@@ -1943,6 +2058,8 @@ int phw_solver_create(phw_mesh_t m, const phw_params* prm, int32_t device, void*
             if (rc || cudaGetLastError() != cudaSuccess) { phw_solver_destroy(s); return fail(PHW_ECUDA, "bordered-column setup solve failed"); }
         }
     }
+    rc = setup_loop(s);
+    if (rc) { std::string keep = g_err; phw_solver_destroy(s); g_err = keep; return rc; }
     CU(cudaStreamSynchronize(s->stream));
     s->launches = 0;
     *out = s;
@@ -2051,6 +2168,7 @@ int phw_comm_setup(phw_solver_t s, int32_t rank, int32_t world, const void* hand
             pc.psend_off[f] = d_off; pc.psend_ent[f] = reinterpret_cast<const int4*>(d_ent);
         }
     }
+    { const char* e = getenv("PHW_XCH_DEBUG"); pc.xch_dbg = e ? atoi(e) : 0; }
     CU(cudaStreamSynchronize(s->stream));
     s->pc = pc;
     return PHW_OK;
@@ -2160,6 +2278,10 @@ int phw_run(phw_solver_t s, int64_t n_steps, double* H_rows) {
     s->kernel_paths = 0;
     CU(cudaEventRecord(s->ev0, s->stream));
     if (s->prm.analytical && !s->an_ready) return fail(PHW_ESTATE, "analytical run: call phw_set_analytical before phw_run");
+    if (s->loop_on && s->pc.world <= 1 && n_steps > 0) {
+        int rc = run_loop(s, n_steps);
+        if (rc) return rc;
+    } else
     for (int64_t n = 0; n < n_steps; ++n) {
         s->in_step = true;
         int rc = step(s);

@@ -7,6 +7,8 @@ launches per step serves every case; only scalars differ between cases (K_wave, 
 wave_2D.py:153-158), which the kernels look up per patch / per port edge.  There is no coupling and no collective
 between cases; on several GPUs each rank simply takes a contiguous shard of the case list.
 """
+import os
+
 import numpy as np
 
 from . import _lib
@@ -44,6 +46,12 @@ def wave_sweep_solve(tFinal, numSteps, nx, xLength, yLength, cases, domainShape=
         mesh = generate_mesh(domainShape, nx, xLength, yLength)
     B = len(cases)
     V, C, group = replicate_mesh(mesh[0], mesh[1], B)
+    if patch_cells is None and not solver_flags and not os.environ.get('PHW_NO_LOOP'):
+        # one thread-block cluster per case, every case advanced through ALL its steps by its own cluster in one launch
+        # (csrc/kernels_loop.cuh): no barrier or reduction ever spans two cases, a case stays cache-resident while it runs
+        pc = _lib.loop_patch_cells(len(mesh[1]))
+        if pc:
+            patch_cells, solver_flags = pc, _lib.FLAGS_LOOP
     if patch_cells is None:
         patch_cells = max(64, min(2048, len(mesh[1])))
     m = Mesh(V, C, patch_cells=patch_cells, cell_group=group, n_groups=B)

@@ -7,7 +7,7 @@ goes to libphwave.so (C ABI, include/phwave.h) and the whole time loop runs on t
 Extra keyword arguments (defaults keep the reference behaviour): ``mesh=(vertices, cells)`` to bypass
 the built-in generator (the reference calls mshr, :93-119), ``mesh_kind``, ``device``, ``patch_cells``,
 ``tol``, ``lumped`` (dict overriding the hard-coded constants of :153-158), ``solver_flags`` (phw_params.flags; default:
-pipelined kernels for meshes of >= 200 000 cells, lean kernels below), ``return_state``, ``save_every``
+pipelined kernels for meshes of >= 200 000 cells, the single-launch whole-loop kernel below), ``return_state``, ``save_every``
 (with ``saveP``: write p every that many steps to ``<outputDir>/p.xdmf``; default ``None`` = no field output, because a
 per-step device-to-host copy would dominate the run).
 """
@@ -88,6 +88,11 @@ def wave_2D_solve(tFinal, numSteps, outputDir,
         # solve has no pipelined variant yet)
         explicit = timeIntScheme in ('EE', 'SE', 'EH', 'SV') and controlType != 'casimir'
         solver_flags = (_lib.FLAGS_PIPELINED if big and explicit and (patch_cells is None or patch_cells <= 1024) else 0)
+    # cache-resident meshes (everything the reference itself runs): the whole time loop in ONE launch (csrc/kernels_loop.cuh; flags
+    # bit 15), the mesh cut into <= 16 patches = one thread-block cluster; PHW_NO_LOOP=1 keeps the multi-launch path (A/B, tests)
+    if solver_flags == 0 and not big and not analytical and patch_cells is None and not os.environ.get('PHW_NO_LOOP'):
+        solver_flags = _lib.FLAGS_LOOP
+        patch_cells = _lib.loop_patch_cells(len(cells)) or 2048
     if patch_cells is None:
         patch_cells = (1024 if solver_flags & 256 else 2048) if big else max(64, min(2048, len(cells) // 256))
     m = Mesh(vertices, cells, patch_cells=patch_cells)
