@@ -149,7 +149,7 @@ def run_sweep_bench(args):
     cases = sweep_cases(n_cases * world)[rank * n_cases:(rank + 1) * n_cases]
     dt = 1e-3
     t0 = time.time()
-    H, nc, solver = wave_sweep_solve(dt * args.warmup, args.warmup, 0, 1.0, 0.25, cases, mesh=mesh, patch_cells=args.patch_cells if args.patch_cells > 0 else None,
+    H, nc, solver = wave_sweep_solve(dt * args.warmup, args.warmup, 0, 1.0, 0.25, cases, mesh=mesh, device=local_rank, patch_cells=args.patch_cells if args.patch_cells > 0 else None,
                                      extrap_order=args.extrap, return_solver=True)
     setup_s = time.time() - t0
     torch.cuda.synchronize()
@@ -203,18 +203,20 @@ def build_case(args, torch, dist, rank, world, local_rank, nx_local, x_per_rank)
     t_setup = time.time()
     part = pt.structured_slab_part(nx_local, args.ny, world, rank, x_per_rank, 0.25)
     vertices = part.vertices
-    if world > 1:
-        m = Mesh(part.vertices, part.cells, patch_cells=args.patch_cells, vertex_external=part.vertex_external,
-                 edge_external=part.edge_external, cell_owned=part.cell_owned)
-    else:
-        m = Mesh(part.vertices, part.cells, patch_cells=args.patch_cells)
+    def make_mesh(patch_cells):
+        if world > 1:
+            return Mesh(part.vertices, part.cells, patch_cells=patch_cells, vertex_external=part.vertex_external,
+                        edge_external=part.edge_external, cell_owned=part.cell_owned)
+        return Mesh(part.vertices, part.cells, patch_cells=patch_cells)
     xL, yL = x_per_rank * world, 0.25
     omega = np.sqrt(K_WAVE / RHO) * np.sqrt(np.pi ** 2 / (4 * xL ** 2) + 4 * np.pi ** 2 / yL ** 2)
-    tags = tag_boundary_edges(m, 'R', xL, yL)
-    if args.from_rest:
-        m.set_boundary(tags)
-    else:
-        m.set_boundary(tags, port_weights(m, tags, lambda x, y: RHO * omega * np.sin(2 * np.pi * y / yL + np.pi / 2)))
+
+    def tag(m):
+        tags = tag_boundary_edges(m, 'R', xL, yL)
+        if args.from_rest:
+            m.set_boundary(tags)
+        else:
+            m.set_boundary(tags, port_weights(m, tags, lambda x, y: RHO * omega * np.sin(2 * np.pi * y / yL + np.pi / 2)))
     dt = DT_FULL * FULL_NX * x_per_rank / nx_local     # same CFL ratio as 7072 quads per unit length
     prm = _lib.PhwParams()
     prm.scheme, prm.dt, prm.K_wave, prm.rho = _lib.SCHEMES[args.scheme], dt, K_WAVE, RHO
@@ -225,7 +227,36 @@ def build_case(args, torch, dist, rank, world, local_rank, nx_local, x_per_rank)
     prm.tol, prm.max_iter, prm.extrap_order = args.tol, 200, args.extrap
     prm.flags = 4 | (32 if args.cell_rows else 0) | (64 if args.ell_staged else 0) | pipe_flags(args.pipe)
     prm.extrap_order_q = args.extrap_q
-    solver = Solver(m, prm, device=local_rank)
+    # the two shared-memory stages of the pipelined kernels are sized by the largest patch of the rank's layout: if they do not
+    # fit on ANY rank, all ranks step down to the next smaller patch size together (the ranks must agree before the collective setup)
+    m = solver = None
+    patch_used = None
+    for pc in [args.patch_cells] + [c for c in (896, 768, 640, 512) if c < args.patch_cells]:
+        ok, err = 1, None
+        try:
+            m = make_mesh(pc)
+            tag(m)
+            solver = Solver(m, prm, device=local_rank)
+        except _lib.PhwError as ex:
+            ok, err = 0, ex
+            if 'shared memory' not in str(ex):
+                raise
+        if world > 1:
+            tt = torch.tensor([ok], dtype=torch.int64, device='cuda')
+            dist.all_reduce(tt, op=dist.ReduceOp.MIN)
+            all_ok = int(tt.item())
+        else:
+            all_ok = ok
+        if all_ok:
+            patch_used = pc
+            break
+        if solver is not None:
+            solver.close()
+        if m is not None:
+            m.close()
+        m = solver = None
+    if solver is None:
+        raise SystemExit('no patch size fits the pipelined kernels on every rank: %r' % (err,))
     n_dof_local = int((part.vertex_owner == rank).sum() + (part.edge_owner == rank).sum())
     n_cells_local = int(part.cell_owned.sum())
     if world > 1:
@@ -263,7 +294,7 @@ def build_case(args, torch, dist, rank, world, local_rank, nx_local, x_per_rank)
         del q0
     return dict(solver=solver, m=m, part=part, n_dof_local=n_dof_local, n_cells_local=n_cells_local, n_dof=n_dof,
                 n_cells_total=n_cells_total, omega=omega, dt=dt, t0=t0_sim, pshape=pshape, nx_local=nx_local, x_per_rank=x_per_rank,
-                setup_s=time.time() - t_setup, steps_done=0)
+                setup_s=time.time() - t_setup, steps_done=0, patch_cells=patch_used)
 
 
 def run_bench():
@@ -443,7 +474,7 @@ def run_bench():
         strong = {'dofs_total': sc['n_dof'], 'dofs_per_gpu': sc['n_dof_local'], 'ms_per_step': ms_strong, 'value': sc['n_dof'] * args.steps / rs['dev_s'],
                   'iters_per_solve_p': rs['st']['iters_p'] / max(1, rs['st']['solves_p']), 'iters_per_solve_q': rs['st']['iters_q'] / max(1, rs['st']['solves_q']),
                   'ms_per_iter_p': rs['st']['ms_solve_p'] / max(1, rs['st']['iters_p']), 'ms_per_iter_q': rs['st']['ms_solve_q'] / max(1, rs['st']['iters_q']),
-                  'max_rel_residual': rs['st']['max_rel_residual'], 'setup_seconds': sc['setup_s'],
+                  'max_rel_residual': rs['st']['max_rel_residual'], 'setup_seconds': sc['setup_s'], 'patch_cells': sc['patch_cells'],
                   'efficiency_vs_weak_slab': ms_weak / (world * ms_strong),
                   'efficiency_vs_weak_slab_note': 'T(one 50 M-dof slab per GPU, this run, exchange included) / (N x T(50 M dofs over N GPUs))',
                   'ms_per_step_1gpu': ms1, 'ms_per_step_1gpu_source': ms1_src, 'efficiency': (ms1 / (world * ms_strong)) if ms1 else None}
@@ -487,7 +518,7 @@ def run_bench():
                                        "zero state + the reference's default input 10 sin(8 pi t) (wave_2D.py:384)" if args.from_rest else
                                        'exact standing wave of the analytical case at phase w*t0 = {:.3g} pi with its left datum (wave_2D.py:375-377,734)'.format(args.phase),
                                        args.nx, args.ny, nc, weak['n_dof_local'], n_dof, weak['dt'], 8e-6 * m.n_edges),
-                       'dofs_per_gpu': weak['n_dof_local'], 'dofs_total': n_dof, 'patch_cells': args.patch_cells, 'phase_over_pi': args.phase, 'pipe': args.pipe, 'tol': args.tol, 'extrap_order': args.extrap,
+                       'dofs_per_gpu': weak['n_dof_local'], 'dofs_total': n_dof, 'patch_cells': weak['patch_cells'], 'phase_over_pi': args.phase, 'pipe': args.pipe, 'tol': args.tol, 'extrap_order': args.extrap,
                        'iters_per_solve_p': st['iters_p'] / max(1, st['solves_p']), 'iters_per_solve_q': st['iters_q'] / max(1, st['solves_q']),
                        'max_rel_residual': st['max_rel_residual'], 'setup_seconds': weak['setup_s'], 'exact_error': exact, 'strong': strong},
             'e2e': {'value': e2e_value, 'unit': 'dof-updates/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,

@@ -89,7 +89,7 @@ typedef struct phw_stats {
     double  ms_solve_p, ms_solve_q, ms_solve_block;   /* summed CUDA-event time of the solve kernels (flags bit2) */
     int64_t kernel_paths;       /* phw_path bits: which variants of the mass-solve kernels the last phw_run launched */
 } phw_stats;
-enum phw_path { PHW_PATH_LEAN_P = 1, PHW_PATH_LEAN_Q = 2, PHW_PATH_PIPE_P = 4, PHW_PATH_PIPE_Q = 8, PHW_PATH_PIPE_ENERGY = 16, PHW_PATH_PIPE_RHS = 32, PHW_PATH_LOOP = 256 };
+enum phw_path { PHW_PATH_LEAN_P = 1, PHW_PATH_LEAN_Q = 2, PHW_PATH_PIPE_P = 4, PHW_PATH_PIPE_Q = 8, PHW_PATH_PIPE_ENERGY = 16, PHW_PATH_PIPE_RHS = 32, PHW_PATH_LOOP = 256, PHW_PATH_LOOP_RES = 512 /* ... with the mass solves resident in shared memory */ };
 
 const char* phw_last_error(void);
 int phw_version(void);

@@ -44,11 +44,12 @@ def loop_patch_cells(n_cells, max_patch_cells=3000):
     """patch size that cuts a mesh of n_cells into 1, 2, 4, 8 or 16 patches of <= max_patch_cells (one thread-block cluster per case),
     aiming at ~1000 cells per CTA; None if the mesh is too large for one cluster (the caller then uses 2048-cell patches: one
     co-resident grid) or too small to be cut evenly"""
-    for cl in (1, 2, 4, 8, 16):
+    force = int(os.environ.get('PHW_LOOP_CL', '0'))       # measurement knob: force the cluster size
+    for cl in ((force,) if force else (1, 2, 4, 8, 16)):
         pc = max(16, -(-n_cells // cl))
         if -(-n_cells // pc) != cl:
             continue
-        if pc <= 1100 or (cl == 16 and pc <= max_patch_cells):
+        if pc <= 1100 or (cl == 16 and pc <= max_patch_cells) or force:
             return pc
     return None
 

@@ -13,9 +13,46 @@
 //
 // Every scheme and variant of the multi-launch path except the analytical diagnostics: EE, SE, EH, SV, IE, SM; weak and strong
 // Dirichlet; lumped model (IC); passivity and casimir control.
+//
+// RES (round 2, second half): the two mass solves - 85-90 % of a step - run out of SHARED MEMORY.  At the start of the launch every
+// CTA copies the matrix data of its patch (assembled ELL rows of M_p, packed 32-byte cell records + edge adjacency + Jacobi weights
+// of M_q) into its own shared memory, where it stays for all n steps.  A solve keeps the iterate (owned rows + ghost copies), the
+// previous iterate and the right-hand side in shared memory as well; x_{k+1} overwrites x_{k-1} in place.  After each iteration
+// ONE hardware cluster barrier separates "owners have written x_{k+1}" from "neighbours pull their ghost copies and the per-CTA
+// residual norms out of the owners' shared memory" (ld.shared::cluster through mapa - distributed shared memory); nothing of an
+// iteration touches L2.  Right-hand sides, energies, state updates and the extrapolation history stay in global memory (L2):
+// they run once per step, not once per iteration.
 #pragma once
 
 namespace phw {
+
+// byte offsets into the dynamic shared memory of loop_k<.., RES = true>; identical in every CTA (maxima over the patches), so that
+// a neighbour can address this CTA's buffers from its own carve-up
+struct ResCarve {
+    int xq[2], bq, cq;            // M_q solve (transient; aliases the scratch of the row passes): iterates [owned | ghosts], b, 3 per cell
+    int xp[2], bp;                // M_p solve (transient)
+    int sio, swo, ids, w;         // persistent: ELL rows of M_p (slice offsets rebased to the patch, ids, weights)
+    int cellq, eadj, pinvq;       // persistent: M_q cell records, edge -> (cell, slot) codes, Jacobi weights
+    int gsv, gse;                 // persistent: ghost sources (owner CTA rank << 16 | row inside the owner's range)
+    int part;                     // persistent: [2][2] doubles, this CTA's residual norms (double-buffered by iteration parity)
+    int total;
+};
+
+#ifndef PHW_HOST_EMU
+__device__ __forceinline__ unsigned dsmem_addr(const void* my_smem, unsigned cta_rank) {
+    unsigned ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"((unsigned)__cvta_generic_to_shared(my_smem)), "r"(cta_rank));
+    return ra;
+}
+__device__ __forceinline__ double ld_dsmem_f64(unsigned addr) {
+    double v;
+    asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void cluster_barrier() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+#endif
 
 struct LoopArgs {
     DevMesh m; TriBuf tp, tq;
@@ -34,6 +71,8 @@ struct LoopArgs {
     int max_iter;
     double cheb_d[3], cheb_c[3];
     long long n_steps;
+    const uint4* cellq;           // RES: packed M_q cell records (phwave.cu: pack_cellq_k)
+    ResCarve rc;
 };
 
 struct LoopCtx {
@@ -82,9 +121,10 @@ __device__ __forceinline__ RowArgs loop_base_args(const LoopArgs& a) {
 }
 
 // NT threads per CTA; gridDim.x == number of patches (one patch per CTA for the whole run)
-template <bool CLUSTER, int NT>
-__global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) loop_k(const __grid_constant__ LoopArgs a) {
-    extern __shared__ double smem[];
+template <bool CLUSTER, int NT, bool RES = false>
+__global__ void __launch_bounds__(NT, (NT <= 256 && !RES) ? 2 : 1) loop_k(const __grid_constant__ LoopArgs a) {
+    static_assert(!RES || CLUSTER, "the resident solves exchange through distributed shared memory");
+    extern __shared__ __align__(16) double smem[];
     __shared__ double red[64];
     __shared__ double bc[2];
     __shared__ PatchHdr myh;
@@ -109,6 +149,54 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) loop_k(const __grid_con
     double maxres[3] = {0.0, 0.0, 0.0};
     const double Kg = a.gK ? a.gK[cx.g] : a.K;
     const double irg = a.ginvrho ? a.ginvrho[cx.g] : 1.0 / a.rho;
+
+    // ---- RES: matrix data of this CTA's patch -> shared memory, once per launch --------------------------------------------------
+    char* const sbase = reinterpret_cast<char*>(smem);
+    if (RES) {
+        const PatchHdr& h = myh;
+        const int nsl = (h.v_cnt + 31) >> 5;
+        uint32_t* s_io = reinterpret_cast<uint32_t*>(sbase + a.rc.sio);
+        uint32_t* s_wo = reinterpret_cast<uint32_t*>(sbase + a.rc.swo);
+        for (int i = threadIdx.x; i <= nsl; i += NT) {
+            s_io[i] = a.m.ell_ioff[h.vs_off + i] - (uint32_t)h.ell_i0;
+            s_wo[i] = a.m.ell_woff[h.vs_off + i] - (uint32_t)h.ell_w0;
+        }
+        {
+            uint4* d = reinterpret_cast<uint4*>(sbase + a.rc.ids);
+            const uint4* g = reinterpret_cast<const uint4*>(a.m.ell_ids + (uint32_t)h.ell_i0);
+            for (uint32_t i = threadIdx.x; i < ((uint32_t)h.ell_in >> 3); i += NT) d[i] = g[i];
+        }
+        {
+            double* d = reinterpret_cast<double*>(sbase + a.rc.w);
+            const double* g = a.m.ell_w + (uint32_t)h.ell_w0;
+            for (uint32_t i = threadIdx.x; i < (uint32_t)h.ell_wn; i += NT) d[i] = g[i];
+        }
+        {
+            uint4* d = reinterpret_cast<uint4*>(sbase + a.rc.cellq);
+            const uint4* g = a.cellq + 2 * (size_t)h.cell_off;
+            for (int i = threadIdx.x; i < 2 * h.n_ecells; i += NT) d[i] = g[i];
+        }
+        {
+            uint32_t* d = reinterpret_cast<uint32_t*>(sbase + a.rc.eadj);
+            double* dp = reinterpret_cast<double*>(sbase + a.rc.pinvq);
+            for (int i = threadIdx.x; i < h.e_cnt; i += NT) { d[i] = a.m.eadj[h.e_start + i]; dp[i] = a.pinv_q[h.e_start + i]; }
+        }
+        // ghost sources: which CTA of the cluster owns the dof, and which row of its range it is
+        uint32_t* gsv = reinterpret_cast<uint32_t*>(sbase + a.rc.gsv);
+        uint32_t* gse = reinterpret_cast<uint32_t*>(sbase + a.rc.gse);
+        for (int i = threadIdx.x; i < h.gv_cnt + h.ge_cnt; i += NT) {
+            const bool isv = i < h.gv_cnt;
+            const int gid = isv ? a.m.ghost_v[h.gv_off + i] : a.m.ghost_e[h.ge_off + (i - h.gv_cnt)];
+            uint32_t code = 0xFFFFFFFFu;
+            for (int r = 0; r < cx.ncta; ++r) {
+                const PatchHdr* hr = &a.m.hdr[cx.lead + r];
+                const int st = isv ? hr->v_start : hr->e_start, cn = isv ? hr->v_cnt : hr->e_cnt;
+                if (gid >= st && gid < st + cn) { code = ((uint32_t)r << 16) | (uint32_t)(gid - st); break; }
+            }
+            if (isv) gsv[i] = code; else gse[i - h.gv_cnt] = code;
+        }
+        __syncthreads();
+    }
 
     // ---- small helpers (all threads of all CTAs of the case call them the same number of times) -----------------------------
     auto SYNC = [&]() { loop_sync<CLUSTER>(a, cx); };
@@ -235,6 +323,134 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) loop_k(const __grid_con
         const double rel = bb > 0.0 ? sqrt(rr / bb) : 0.0;
         if (rel > maxres[which]) maxres[which] = rel;
     };
+    // RES: the same Chebyshev solves with every operand of an iteration in shared memory (see the header of this file).  Same rows,
+    // same arithmetic and the same accepted iterate as solve_mass; begins and ends behind a cluster barrier.
+    auto solve_mass_res = [&](int which) {
+#ifndef PHW_HOST_EMU
+        const PatchHdr& h = myh;
+        const int n_own = which == 0 ? h.v_cnt : h.e_cnt, n_gh = which == 0 ? h.gv_cnt : h.ge_cnt;
+        const int g0_ = which == 0 ? h.v_start : h.e_start;
+        double* xb[2] = {reinterpret_cast<double*>(sbase + (which == 0 ? a.rc.xp[0] : a.rc.xq[0])),
+                         reinterpret_cast<double*>(sbase + (which == 0 ? a.rc.xp[1] : a.rc.xq[1]))};
+        double* sb = reinterpret_cast<double*>(sbase + (which == 0 ? a.rc.bp : a.rc.bq));
+        double* part = reinterpret_cast<double*>(sbase + a.rc.part);
+        const uint32_t* gsrc = reinterpret_cast<const uint32_t*>(sbase + (which == 0 ? a.rc.gsv : a.rc.gse));
+        const double* gb = which == 0 ? a.bp : a.bq;
+        double* gx = which == 0 ? tbp(which) : tbq(which);
+        SYNC();                                    // right-hand side (port term included) and initial guess are complete in global memory
+        for (int i = threadIdx.x; i < n_own; i += NT) { sb[i] = gb[g0_ + i]; xb[0][i] = gx[g0_ + i]; }
+        auto pull_ghosts = [&](double* xdst) {     // ghost copies of the iterate out of the owners' shared memory
+            for (int i = threadIdx.x; i < n_gh; i += NT) {
+                const uint32_t code = gsrc[i];
+                xdst[n_own + i] = ld_dsmem_f64(dsmem_addr(xdst + (code & 0xFFFFu), code >> 16));
+            }
+        };
+        cluster_barrier();
+        pull_ghosts(xb[0]);
+        __syncthreads();
+        int k = 0, c_ = 0; double rho = 0.0, rr = 0.0, bb = 0.0; bool conv = false;
+        while (true) {
+            double c1, c2, rho_k;
+            cheb_coeffs(k, rho, a.cheb_d[which], a.cheb_c[which], c1, c2, rho_k);
+            const double* __restrict__ xc_ = xb[c_];
+            double* __restrict__ xo_ = xb[c_ ^ 1];                    // holds x_{k-1}, receives x_{k+1}
+            double r0 = 0.0, b0 = 0.0;
+            if (which == 0) {
+                const uint32_t* s_io = reinterpret_cast<const uint32_t*>(sbase + a.rc.sio);
+                const uint32_t* s_wo = reinterpret_cast<const uint32_t*>(sbase + a.rc.swo);
+                const uint4* sid4 = reinterpret_cast<const uint4*>(sbase + a.rc.ids);
+                const double* sw = reinterpret_cast<const double*>(sbase + a.rc.w);
+                for (int lv = threadIdx.x; lv < h.v_cnt; lv += NT) {
+                    const int sl = lv >> 5, lane = lv & 31;
+                    const uint32_t io0 = s_io[sl], wo0 = s_wo[sl];
+                    const int W = (int)((s_wo[sl + 1] - wo0) >> 5);
+                    double val = 0.0, dsum = 0.0;
+                    for (int c = 0; 8 * c < W; ++c) {
+                        const uint4 cd = sid4[(io0 >> 3) + c * 32 + lane];
+                        const uint32_t w4[4] = {cd.x, cd.y, cd.z, cd.w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const double wa = (8 * c + 2 * j < W) ? sw[wo0 + (8 * c + 2 * j) * 32 + lane] : 0.0;
+                            const double wb = (8 * c + 2 * j + 1 < W) ? sw[wo0 + (8 * c + 2 * j + 1) * 32 + lane] : 0.0;
+                            val += wa * xc_[w4[j] & 0xFFFFu];
+                            val += wb * xc_[w4[j] >> 16];
+                            dsum += wa + wb;
+                        }
+                    }
+                    const double xc = xc_[lv], bv = sb[lv];
+                    const double pv = 1.0 / dsum;
+                    val += dsum * xc;
+                    const double r_ = bv - val;
+                    double xn = xc + c2 * pv * r_;
+                    if (k > 0) xn += c1 * (xc - xo_[lv]);
+                    xo_[lv] = xn;
+                    r0 += pv * r_ * r_;
+                    b0 += pv * bv * bv;
+                }
+            } else {
+                const uint4* scq = reinterpret_cast<const uint4*>(sbase + a.rc.cellq);
+                const uint32_t* sadj = reinterpret_cast<const uint32_t*>(sbase + a.rc.eadj);
+                const double* spv = reinterpret_cast<const double*>(sbase + a.rc.pinvq);
+                double* sc3 = reinterpret_cast<double*>(sbase + a.rc.cq);
+                for (int lc = threadIdx.x; lc < h.n_ecells; lc += NT) {
+                    const uint4 qa = scq[2 * lc], qb = scq[2 * lc + 1];
+                    const uint32_t e0 = qa.x & 0xFFFFu, e1 = qa.x >> 16, e2 = qa.y & 0xFFFFu;
+                    const double g0 = __hiloint2double((int)qa.w, (int)qa.z), g1 = __hiloint2double((int)qb.y, (int)qb.x), g2 = __hiloint2double((int)qb.w, (int)qb.z);
+                    const double S = g0 + g1 + g2;
+                    const double q0 = xc_[e0 & 0x3FFFu], q1 = xc_[e1 & 0x3FFFu], q2 = xc_[e2 & 0x3FFFu];
+                    const double s0 = (e0 & 0x8000u) ? -1.0 : 1.0, s1 = (e1 & 0x8000u) ? -1.0 : 1.0, s2 = (e2 & 0x8000u) ? -1.0 : 1.0;
+                    const double t0 = s0 * q0, t1 = s1 * q1, t2 = s2 * q2;
+                    const double ST = S * (t0 + t1 + t2);
+                    sc3[3 * lc] = s0 * (ST + 2.0 * S * t0 - 4.0 * (g0 * t0 + g2 * t1 + g1 * t2));
+                    sc3[3 * lc + 1] = s1 * (ST + 2.0 * S * t1 - 4.0 * (g2 * t0 + g1 * t1 + g0 * t2));
+                    sc3[3 * lc + 2] = s2 * (ST + 2.0 * S * t2 - 4.0 * (g1 * t0 + g0 * t1 + g2 * t2));
+                }
+                __syncthreads();
+                for (int le = threadIdx.x; le < h.e_cnt; le += NT) {
+                    const uint32_t adj = sadj[le];
+                    const uint32_t ca = adj & 0xFFFFu, cb = adj >> 16;
+                    double val = sc3[3 * (ca >> 2) + (ca & 3u)];
+                    if (cb != 0xFFFFu) val += sc3[3 * (cb >> 2) + (cb & 3u)];
+                    const double xc = xc_[le], bv = sb[le], pv = spv[le];
+                    const double r_ = bv - val;
+                    double xn = xc + c2 * pv * r_;
+                    if (k > 0) xn += c1 * (xc - xo_[le]);
+                    xo_[le] = xn;
+                    r0 += pv * r_ * r_;
+                    b0 += pv * bv * bv;
+                }
+            }
+            block_sum2(r0, b0, cx.red);
+            const int par = k & 1;
+            if (threadIdx.x == 0) { part[2 * par] = r0; part[2 * par + 1] = b0; }
+            cluster_barrier();                     // x_{k+1} (owned rows) and the norms of every CTA of the case are in place
+            if (threadIdx.x < 32) {
+                double s0 = 0.0, s1 = 0.0;
+                if ((int)threadIdx.x < cx.ncta) {
+                    const unsigned ra = dsmem_addr(part + 2 * par, threadIdx.x);
+                    s0 = ld_dsmem_f64(ra); s1 = ld_dsmem_f64(ra + 8);
+                }
+                s0 = warp_sum(s0); s1 = warp_sum(s1);
+                if (threadIdx.x == 0) { cx.bc[0] = s0; cx.bc[1] = s1; }
+            }
+            __syncthreads();
+            rr = cx.bc[0]; bb = cx.bc[1];
+            conv = rr <= a.tol2 * bb;
+            k += 1;
+            if (conv) break;                       // the verified iterate x_k (buffer c_) is the solution; nobody pulls from x_{k+1}
+            pull_ghosts(xo_);
+            __syncthreads();
+            rho = rho_k; c_ ^= 1;
+            if (k >= a.max_iter) break;
+        }
+        for (int i = threadIdx.x; i < n_own; i += NT) gx[g0_ + i] = xb[c_][i];
+        (which == 0 ? it_p : it_q) += k; (which == 0 ? n_p : n_q) += 1;
+        if (!conv) nonconv += 1;
+        const double rel = bb > 0.0 ? sqrt(rr / bb) : 0.0;
+        if (rel > maxres[which]) maxres[which] = rel;
+        SYNC();                                    // solution visible to every CTA of the case; all ghost pulls have finished
+#endif
+    };
     // Chebyshev (ellipse) solve of the coupled block system of IE / SM (solve_block of phwave.cu)
     auto solve_block = [&](double theta) {
         RowArgs av = loop_base_args(a);
@@ -278,7 +494,9 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) loop_k(const __grid_con
     auto solve_site = [&](int which, int site) {
         predict(which, site, which);
         if (which == 0 && a.strong) { SYNC(); dirichlet_preset(0); }
-        solve_mass(which);
+        // strong Dirichlet rows and the casimir mass diagonal need the generic vertex rows
+        if (RES && (which == 1 || (a.ell_p && !(a.strong || (a.casimir && implicit))))) solve_mass_res(which);
+        else solve_mass(which);
         remember(which, site, which);
     };
     // H_wave = 0.5/rho p^T M_p p + 0.5 K q^T M_q q  (wave_2D.py:882,907) -> red[0], red[1]; ends behind a barrier

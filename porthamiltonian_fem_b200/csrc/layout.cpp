@@ -188,13 +188,42 @@ std::string Layout::build(int64_t nv_, const double* vxy, int64_t nc_, const int
     for (int32_t p = 0; p < npatch; ++p)
         for (int64_t k = own_off[p]; k < own_off[p + 1]; ++k) cell_patch[order[k]] = p;
     // ---- 4. dof ownership = lowest adjacent patch; renumber so owned ranges are contiguous
-    v_owner.assign(nv, std::numeric_limits<int32_t>::max());
-    e_owner.assign(ne, std::numeric_limits<int32_t>::max());
-    for (int64_t c = 0; c < nc; ++c) {
-        int32_t p = cell_patch[c];
-        for (int i = 0; i < 3; ++i) {
-            int32_t& ov = v_owner[cells[3 * c + i]]; ov = std::min(ov, p);
-            int32_t& oe = e_owner[cell_edges[3 * c + i]]; oe = std::min(oe, p);
+    auto assign_owners = [&]() {
+        v_owner.assign(nv, std::numeric_limits<int32_t>::max());
+        e_owner.assign(ne, std::numeric_limits<int32_t>::max());
+        for (int64_t c = 0; c < nc; ++c) {
+            int32_t p = cell_patch[c];
+            for (int i = 0; i < 3; ++i) {
+                int32_t& ov = v_owner[cells[3 * c + i]]; ov = std::min(ov, p);
+                int32_t& oe = e_owner[cell_edges[3 * c + i]]; oe = std::min(oe, p);
+            }
+        }
+    };
+    assign_owners();
+    npatch_rows = npatch;
+    if ((v_ext || e_ext) && n_groups == 1) {
+        // partitioned runs: a patch made of halo cells only (cells of a neighbour rank: every dof is external or belongs to an
+        // earlier patch) owns no row.  Such patches move behind the others and are never processed (npatch_rows): no kernel has
+        // work for them, and their ghost lists (every dof of ~1000 cells) must not size the shared-memory stages.
+        std::vector<uint8_t> owns(npatch, 0);
+        for (int64_t v = 0; v < nv; ++v) if (!(v_ext && v_ext[v])) owns[v_owner[v]] = 1;
+        for (int64_t e = 0; e < ne; ++e) if (!(e_ext && e_ext[e])) owns[e_owner[e]] = 1;
+        int32_t n_rows = 0;
+        for (int32_t p = 0; p < npatch; ++p) n_rows += owns[p];
+        if (n_rows < npatch && n_rows > 0) {
+            std::vector<int32_t> o2; o2.reserve(nc);
+            std::vector<int64_t> off2(1, 0);
+            for (int pass = 0; pass < 2; ++pass)
+                for (int32_t p = 0; p < npatch; ++p)
+                    if ((owns[p] != 0) == (pass == 0)) {
+                        for (int64_t k = own_off[p]; k < own_off[p + 1]; ++k) o2.push_back(order[k]);
+                        off2.push_back((int64_t)o2.size());
+                    }
+            order.swap(o2); own_off.swap(off2);
+            for (int32_t p = 0; p < npatch; ++p)
+                for (int64_t k = own_off[p]; k < own_off[p + 1]; ++k) cell_patch[order[k]] = p;
+            assign_owners();      // the relative order of the patches that own rows is unchanged, so is the ownership
+            npatch_rows = n_rows;
         }
     }
     for (int64_t v = 0; v < nv; ++v)
@@ -318,7 +347,7 @@ std::string Layout::build(int64_t nv_, const double* vxy, int64_t nc_, const int
         int32_t nlv = H.v_cnt + H.gv_cnt, nle = H.e_cnt + H.ge_cnt;
         if (nlv >= 65536 || nle >= 16384 || H.n_vcells >= 16383)
             return "patch too large for 16-bit local indices; reduce patch_cells";
-        max_lv = std::max(max_lv, nlv); max_le = std::max(max_le, nle); max_cells = std::max(max_cells, H.n_vcells);
+        if (p < npatch_rows) { max_lv = std::max(max_lv, nlv); max_le = std::max(max_le, nle); max_cells = std::max(max_cells, H.n_vcells); }
         // records + adjacency
         vcnt.assign(H.v_cnt + 1, 0);
         for (size_t lc = 0; lc < cl.size(); ++lc) {
@@ -423,7 +452,7 @@ std::string Layout::build(int64_t nv_, const double* vxy, int64_t nc_, const int
             H.ell_w0 = (int32_t)(uint32_t)wbase; H.ell_wn = (int32_t)woff;
             // shared memory of the staged pass (doubles): slice offsets | x [nlv] | b, x_prev [v_cnt] | weights | ids
             auto ev2 = [](int64_t x) { return (x + 1) & ~(int64_t)1; };
-            max_smem_ell = std::max(max_smem_ell, (int64_t)((nslice + 3) & ~1) + ev2(nlv) + 2 * ev2(H.v_cnt) + (int64_t)woff + (int64_t)(ioff + 3) / 4 + 2);
+            if (p < npatch_rows) max_smem_ell = std::max(max_smem_ell, (int64_t)((nslice + 3) & ~1) + ev2(nlv) + 2 * ev2(H.v_cnt) + (int64_t)woff + (int64_t)(ioff + 3) / 4 + 2);
         }
         // reset scratch
         for (int32_t g : gv_tmp) lv_of[v_new2old[g]] = -1;

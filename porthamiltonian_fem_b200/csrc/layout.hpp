@@ -44,6 +44,7 @@ static_assert(sizeof(PatchHdr) == 80, "PatchHdr is loaded as 20 ints");
 struct Layout {
     int64_t nv = 0, nc = 0, ne = 0, nb = 0;
     int32_t patch_cells = 0, npatch = 0;
+    int32_t npatch_rows = 0;           // patches that own rows = the patches the kernels process (partitioned runs: patches of halo cells only come last)
     std::vector<double>  vtx;          // [nv,2] user order
     std::vector<int32_t> cells;        // [nc,3] user order, CCW
     std::vector<int32_t> edges;        // [ne,2] (lo,hi), canonical order

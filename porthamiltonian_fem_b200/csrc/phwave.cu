@@ -556,7 +556,8 @@ struct phw_solver_s {
     size_t smem_pq = 0, smem_pp = 0;
     bool pipe_en = false; EnergyPipeArgs pe{}; size_t smem_pe = 0;   // fused pipelined H_wave reduction (flags bit 11)
     bool pipe_rhs = false; RhsPipeArgs pre{}, prv{}; size_t smem_pre = 0, smem_prv = 0;   // pipelined right-hand sides (flags bit 12)
-    bool loop_on = false; int loop_cl = 0, loop_nt = 512; bool loop_cluster = false; double* loop_partials = nullptr;   // whole-loop kernel (flags bit 15)
+    bool loop_on = false; int loop_cl = 0, loop_nt = 512; bool loop_cluster = false; double* loop_partials = nullptr;
+    bool loop_res = false; ResCarve loop_rc{};   // mass solves of the whole-loop kernel resident in shared memory (kernels_loop.cuh, RES)   // whole-loop kernel (flags bit 15)
     int64_t kernel_paths = 0;              // PHW_PATH_* bits of the solve kernels launched since the last phw_run began
     int *d_cells_user = nullptr; double* d_vtx_user = nullptr; unsigned long long* d_mm = nullptr;
     std::vector<cudaEvent_t> prof_ev; std::vector<int> prof_which; bool prof_truncated = false;
@@ -1342,9 +1343,38 @@ int step(phw_solver_s* s) {
 // form one thread-block cluster when there are 1, 2, 4, 8 or 16 of them, else (single case only) one cooperative grid
 // 512 threads per CTA for a single case (latency per pass), 256 for a batched sweep (two CTAs per SM: the cases are independent,
 // so residency - not the latency of one case - sets the throughput)
-static void* loop_kernel(bool cluster, int nt) {
+static void* loop_kernel(bool cluster, int nt, bool res = false) {
+    if (res) return nt == 1024 ? (void*)loop_k<true, 1024, true> : (void*)loop_k<true, 512, true>;
     if (cluster) return nt == 256 ? (void*)loop_k<true, 256> : (void*)loop_k<true, 512>;
     return nt == 256 ? (void*)loop_k<false, 256> : (void*)loop_k<false, 512>;
+}
+// shared-memory carve-up of the resident solves: maxima over all patches, every block 16-byte aligned
+static ResCarve res_carve(const Layout& L, size_t scratch_bytes) {
+    int mv = 0, mlv = 0, me = 0, mle = 0, mec = 0, mids = 0, mw = 0, mg = 0;
+    for (int32_t ip = 0; ip < L.npatch_rows; ++ip) {
+        const PatchHdr& h = L.hdr[ip];
+        mv = std::max(mv, h.v_cnt); mlv = std::max(mlv, h.v_cnt + h.gv_cnt);
+        me = std::max(me, h.e_cnt); mle = std::max(mle, h.e_cnt + h.ge_cnt);
+        mec = std::max(mec, h.n_ecells); mids = std::max(mids, h.ell_in); mw = std::max(mw, h.ell_wn);
+        mg = std::max(mg, std::max(h.gv_cnt, h.ge_cnt));
+    }
+    auto al = [](size_t b) { return (int)((b + 15) & ~(size_t)15); };
+    ResCarve c{};
+    int o = 0;
+    c.xq[0] = o; o += al(8 * (size_t)mle); c.xq[1] = o; o += al(8 * (size_t)mle);
+    c.bq = o; o += al(8 * (size_t)me); c.cq = o; o += al(24 * (size_t)mec);
+    const int tq = o;
+    o = 0;
+    c.xp[0] = o; o += al(8 * (size_t)mlv); c.xp[1] = o; o += al(8 * (size_t)mlv); c.bp = o; o += al(8 * (size_t)mv);
+    o = std::max(std::max(o, tq), al(scratch_bytes));     // the transient region also serves as the scratch of the row passes
+    const int nsl = (mv + 31) / 32 + 2;
+    c.sio = o; o += al(4 * (size_t)nsl); c.swo = o; o += al(4 * (size_t)nsl);
+    c.ids = o; o += al(2 * (size_t)mids); c.w = o; o += al(8 * (size_t)mw);
+    c.cellq = o; o += al(32 * (size_t)mec); c.eadj = o; o += al(4 * (size_t)me); c.pinvq = o; o += al(8 * (size_t)me);
+    c.gsv = o; o += al(4 * (size_t)mg); c.gse = o; o += al(4 * (size_t)mg);
+    c.part = o; o += 32;
+    c.total = o;
+    return c;
 }
 int setup_loop(phw_solver_s* s) {
     const int NT_LOOP = s->G > 1 ? 256 : 512;
@@ -1354,14 +1384,22 @@ int setup_loop(phw_solver_s* s) {
     const Layout& L = s->mesh->L;
     if (L.nv_owned != L.nv || L.ne_owned != L.ne) return 0;            // partitioned layouts take the multi-launch path
     for (int g = 0; g < s->G; ++g) if (L.group_patch_off[g + 1] - L.group_patch_off[g] != cl) return 0;
-    const size_t sm = s->smem_vd;
+    size_t sm = s->smem_vd;
     const bool cluster = (cl == 1 || cl == 2 || cl == 4 || cl == 8 || cl == 16);
+    // resident solves: every operand of a Chebyshev iteration in shared memory (one CTA per SM); needs the ELL rows of M_p, local ids
+    // below 2^14 and everything of the largest patch within the 227 KB of an SM.  PHW_NO_RES=1: the L2-resident solves (A/B)
+    s->loop_res = false;
+    if (cluster && s->ell_p && s->d_cellq && !getenv("PHW_NO_RES")) {
+        const ResCarve c = res_carve(L, s->smem_vd);
+        if (c.total <= 224 * 1024) { s->loop_res = true; s->loop_rc = c; sm = (size_t)c.total; }
+    }
+    const int NT_RES = getenv("PHW_RES_NT") ? atoi(getenv("PHW_RES_NT")) : 512;
     if (cluster) {
-        void* kern = loop_kernel(true, NT_LOOP);
-        { int rc_ = ensure_dyn_smem(s->device, kern, 200 * 1024); if (rc_) return rc_; }
+        void* kern = loop_kernel(true, s->loop_res ? NT_RES : NT_LOOP, s->loop_res);
+        { int rc_ = ensure_dyn_smem(s->device, kern, s->loop_res ? 224 * 1024 : 200 * 1024); if (rc_) return rc_; }
         if (cl > 8 && cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); return 0; }
         cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(s->npatch); cfg.blockDim = dim3(NT_LOOP); cfg.dynamicSmemBytes = sm; cfg.stream = s->stream;
+        cfg.gridDim = dim3(s->npatch); cfg.blockDim = dim3(s->loop_res ? NT_RES : NT_LOOP); cfg.dynamicSmemBytes = sm; cfg.stream = s->stream;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
@@ -1377,7 +1415,8 @@ int setup_loop(phw_solver_s* s) {
     }
     int rc = s->dalloc(&s->loop_partials, 4 * (size_t)s->npatch + 64);
     if (rc) return rc;
-    s->loop_on = true; s->loop_cl = cl; s->loop_cluster = cluster; s->loop_nt = NT_LOOP;
+    s->loop_on = true; s->loop_cl = cl; s->loop_cluster = cluster; s->loop_nt = (cluster && s->loop_res) ? NT_RES : NT_LOOP;
+    if (!cluster) s->loop_res = false;
     return 0;
 }
 
@@ -1406,7 +1445,8 @@ int run_loop(phw_solver_s* s, int64_t n_steps) {
     a.max_iter = P.max_iter;
     for (int i = 0; i < 3; ++i) { a.cheb_d[i] = s->cheb_d[i]; a.cheb_c[i] = s->cheb_c[i]; }
     a.n_steps = n_steps;
-    const size_t sm = s->smem_vd;
+    a.cellq = s->d_cellq; a.rc = s->loop_rc;
+    const size_t sm = s->loop_res ? (size_t)s->loop_rc.total : s->smem_vd;
     const int NT_LOOP = s->loop_nt;
     if (s->loop_cluster) {
         cudaLaunchConfig_t cfg{};
@@ -1414,7 +1454,9 @@ int run_loop(phw_solver_s* s, int64_t n_steps) {
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = s->loop_cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        if (NT_LOOP == 256) CU(cudaLaunchKernelEx(&cfg, loop_k<true, 256>, a)); else CU(cudaLaunchKernelEx(&cfg, loop_k<true, 512>, a));
+        if (s->loop_res) { if (NT_LOOP == 1024) CU(cudaLaunchKernelEx(&cfg, loop_k<true, 1024, true>, a)); else CU(cudaLaunchKernelEx(&cfg, loop_k<true, 512, true>, a)); }
+        else if (NT_LOOP == 256) CU(cudaLaunchKernelEx(&cfg, loop_k<true, 256>, a)); else CU(cudaLaunchKernelEx(&cfg, loop_k<true, 512>, a));
+        if (s->loop_res) s->kernel_paths |= PHW_PATH_LOOP_RES;
     } else {
         CU(cudaMemsetAsync(&s->ctl->gbar[0], 0, sizeof(unsigned int), s->stream));
         void* args[] = {(void*)&a};
@@ -1789,7 +1831,7 @@ static int setup_scalars(phw_solver_s* s) {
 static int setup_solver(phw_solver_s* s) {
     const Layout& L = s->mesh->L;
     const phw_params& P = s->prm;
-    s->nv = (int)L.nv; s->ne = (int)L.ne; s->npatch = L.npatch; s->npc = (int)L.pcell_user.size();
+    s->nv = (int)L.nv; s->ne = (int)L.ne; s->npatch = L.npatch_rows; s->npc = (int)L.pcell_user.size();
     cudaDeviceProp prop{};
     CU(cudaGetDeviceProperties(&prop, s->device));
     s->sm_count = prop.multiProcessorCount;

@@ -16,7 +16,8 @@ constexpr size_t PIPE_SMEM_LIMIT = 227 * 1024 - 1024;   // 227 KB per CTA minus 
 inline void pipe_carve(const Layout& L, MqPipeArgs& cq, EllPipeArgs& cp, size_t& smem_pq, size_t& smem_pp, EnergyPipeArgs* ce = nullptr, size_t* smem_pe = nullptr,
                        RhsPipeArgs* re = nullptr, size_t* smem_re = nullptr, RhsPipeArgs* rv = nullptr, size_t* smem_rv = nullptr) {
     int max_ec = 0, max_ecells = 0, max_ge = 0, max_vc = 0, max_gv = 0, max_wn = 0, max_in = 0, max_own = 0, max_adj = 0;
-    for (const PatchHdr& h : L.hdr) {
+    for (int32_t ip = 0; ip < L.npatch_rows; ++ip) {
+        const PatchHdr& h = L.hdr[ip];
         max_ec = std::max(max_ec, h.e_cnt); max_ecells = std::max(max_ecells, h.n_ecells); max_ge = std::max(max_ge, h.ge_cnt);
         max_vc = std::max(max_vc, h.v_cnt); max_gv = std::max(max_gv, h.gv_cnt); max_wn = std::max(max_wn, h.ell_wn); max_in = std::max(max_in, h.ell_in);
         max_own = std::max(max_own, h.n_own); max_adj = std::max(max_adj, h.adj_cnt);

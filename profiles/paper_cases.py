@@ -42,7 +42,7 @@ def run_case(name, mesh, shape, xL, yL, tF, steps, kw, cpu_steps):
     out = {'case': name, 'cells': nc, 'dofs': ndof, 'steps': steps, 'patches': st['mesh'].n_patches, 'gpu_device_ms': stats['device_ms'],
            'gpu_steps_per_s': steps / (stats['device_ms'] * 1e-3), 'gpu_us_per_step': 1e3 * stats['device_ms'] / steps,
            'gpu_dof_updates_per_s': ndof * steps / (stats['device_ms'] * 1e-3),
-           'gpu_wall_s_incl_setup': wall, 'launches': stats['kernel_launches'], 'whole_loop_kernel': bool(stats['kernel_paths'] & 256),
+           'gpu_wall_s_incl_setup': wall, 'launches': stats['kernel_launches'], 'whole_loop_kernel': bool(stats['kernel_paths'] & 256), 'resident_solves': bool(stats['kernel_paths'] & 512),
            'iters_p': stats['iters_p'] / max(1, stats['solves_p']), 'iters_q': stats['iters_q'] / max(1, stats['solves_q']),
            'iters_block': stats['iters_block'] / max(1, stats['solves_block']), 'max_rel_residual': stats['max_rel_residual'],
            'max_abs_E': float(np.abs(H[:, 2]).max()), 'H_end': float(H[-1, 1])}

@@ -72,7 +72,7 @@ extern "C" int emu_run(const char* what_c, int64_t nv, const double* vtx, int64_
     L.boundary_set = true;
     std::vector<CellRec> rec;
     L.make_records(false, false, rec);
-    const int npatch = L.npatch, npc = (int)L.pcell_user.size();
+    const int npatch = L.npatch_rows, npc = (int)L.pcell_user.size();   // patches that own rows (layout.hpp)
     grid = std::max(1, std::min(grid, npatch));
     Arena A;
     PatchHdr* d_hdr = A.put(L.hdr);
