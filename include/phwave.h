@@ -153,6 +153,12 @@ int phw_set_state(phw_solver_t s, const double* p, const double* q, const double
 int phw_get_state(phw_solver_t s, double* p, double* q, double* x3);
 /* run n_steps of the loop wave_2D.py:787-982 on the device; H_rows [n_steps, 8|12] host or device */
 int phw_run(phw_solver_t s, int64_t n_steps, double* H_rows);
+/* field output (xdmfFile_p.write(out_p, t) at every step, wave_2D.py:646-651,865-866): after every `every` steps of the following
+ * phw_run calls the p field (user numbering, n_vertices values; higher-order solvers: all n_p dofs, vertices first) is copied to
+ * snaps[k][n], k = 0 .. capacity-1, counted from the start of each phw_run.  The copy goes through a ring of four device slots and a
+ * second stream, so it overlaps the steps that follow; snaps may be host (pinned for a truly asynchronous copy) or device memory and
+ * is complete when phw_run returns.  every = 0 switches snapshots off. */
+int phw_set_snapshots(phw_solver_t s, int64_t every, double* snaps, int64_t capacity);
 int phw_get_stats(phw_solver_t s, phw_stats* out);
 int phw_synchronize(phw_solver_t s);
 /* simulation clock (t of wave_2D.py:790-799,833-834; 0 after creation): restart / continue a run from a stored state */

@@ -13,6 +13,8 @@ from porthamiltonian_fem_b200 import wave_2D_solve
 
 K_wave = 3.0   # main_wave_2D.py:19
 rho = 2.0      # main_wave_2D.py:21
+# 'Mem' cases write p.xdmf (and p_exact.xdmf) at every step as the reference does (wave_2D.py:865-866,964-965); PHW_SAVE_EVERY thins it
+SAVE_KW = dict(save_every=int(os.environ.get('PHW_SAVE_EVERY', '1')))
 
 CASES = {
     # main_wave_2D.py:104-114 (the active block of the reference: P3/RT3, SV and SE, five step counts each)
@@ -68,7 +70,7 @@ def run_cases(caseName, caseArray, outputRoot='output', **solver_kwargs):
         H_array, numCells = wave_2D_solve(caseVec[5], caseVec[6], outputSubDir, nx, xLength, yLength,
                                           domainShape=caseVec[0], timeIntScheme=caseVec[1], dirichletImp=caseVec[2],
                                           K_wave=K_wave, rho=rho, interConnection=IC, analytical=ANALYTICAL_BOOL,
-                                          saveP=saveP, basis_order=basis_order, **solver_kwargs)
+                                          saveP=saveP, basis_order=basis_order, **dict(SAVE_KW if saveP else {}, **solver_kwargs))
         np.save(os.path.join(outputSubDir, 'H_array.npy'), H_array)
         numCells_save = np.zeros((1))
         numCells_save[0] = numCells

@@ -14,6 +14,7 @@ from porthamiltonian_fem_b200 import wave_2D_solve
 
 K_wave = 3.0
 rho = 2.0
+SAVE_EVERY = int(os.environ.get('PHW_SAVE_EVERY', '1'))   # 'Mem' cases: p.xdmf at every step as in the reference (wave_2D.py:865-866)
 
 if __name__ == '__main__':
     print('starting script and timer')
@@ -42,7 +43,7 @@ if __name__ == '__main__':
         H_array, numCells = wave_2D_solve(caseVec[5], caseVec[6], outputSubDir, caseVec[3], xLength, yLength,
                                           domainShape=caseVec[0], timeIntScheme=caseVec[1], dirichletImp=caseVec[2],
                                           K_wave=K_wave, rho=rho, interConnection=IC, analytical=False,
-                                          saveP=caseVec[7] != 'noMem', controlType=controlType,
+                                          saveP=caseVec[7] != 'noMem', save_every=SAVE_EVERY if caseVec[7] != 'noMem' else None, controlType=controlType,
                                           input_stop_t=input_stop_t, control_start_t=control_start_t)
         np.save(os.path.join(outputSubDir, 'H_array.npy'), H_array)
         numCells_save = np.zeros((1))

@@ -94,6 +94,7 @@ SIGNATURES = {
     'phw_get_state': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     'phw_run': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]),
     'phw_get_stats': (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(PhwStats)]),
+    'phw_set_snapshots': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64]),
     'phw_synchronize': (ctypes.c_int, [ctypes.c_void_p]),
     'phw_comm_arena_handle': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_i64p, c_i64p]),
     'phw_comm_internal_index': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, c_i32p, c_i32p]),

@@ -29,10 +29,11 @@ namespace phw {
 // byte offsets into the dynamic shared memory of loop_k<.., RES = true>; identical in every CTA (maxima over the patches), so that
 // a neighbour can address this CTA's buffers from its own carve-up
 struct ResCarve {
-    int xq[2], bq, cq;            // M_q solve (transient; aliases the scratch of the row passes): iterates [owned | ghosts], b, 3 per cell
+    int xq[2], bq;                // M_q solve (transient; aliases the scratch of the row passes): iterates [owned | ghosts], b
     int xp[2], bp;                // M_p solve (transient)
     int sio, swo, ids, w;         // persistent: ELL rows of M_p (slice offsets rebased to the patch, ids, weights)
-    int cellq, eadj, pinvq;       // persistent: M_q cell records, edge -> (cell, slot) codes, Jacobi weights
+    int wq, idq, pinvq, me;       // persistent: assembled rows of M_q, [5][me] weights (diagonal first) and [4][me] uint16 local
+                                  // ids of the four neighbour edges, built by the CTA from the cell records; Jacobi weights
     int gsv, gse;                 // persistent: ghost sources (owner CTA rank << 16 | row inside the owner's range)
     int part;                     // persistent: [2][2] doubles, this CTA's residual norms (double-buffered by iteration parity)
     int total;
@@ -171,15 +172,35 @@ __global__ void __launch_bounds__(NT, (NT <= 256 && !RES) ? 2 : 1) loop_k(const 
             const double* g = a.m.ell_w + (uint32_t)h.ell_w0;
             for (uint32_t i = threadIdx.x; i < (uint32_t)h.ell_wn; i += NT) d[i] = g[i];
         }
-        {
-            uint4* d = reinterpret_cast<uint4*>(sbase + a.rc.cellq);
-            const uint4* g = a.cellq + 2 * (size_t)h.cell_off;
-            for (int i = threadIdx.x; i < 2 * h.n_ecells; i += NT) d[i] = g[i];
-        }
-        {
-            uint32_t* d = reinterpret_cast<uint32_t*>(sbase + a.rc.eadj);
+        {   // assembled rows of M_q from the metric of the (<= 2) cells of every owned edge: m_ii = 3 S - 4 g_i, m_ij = s_i s_j (S - 4 g_k)
+            double* wq = reinterpret_cast<double*>(sbase + a.rc.wq);
+            uint16_t* idq = reinterpret_cast<uint16_t*>(sbase + a.rc.idq);
             double* dp = reinterpret_cast<double*>(sbase + a.rc.pinvq);
-            for (int i = threadIdx.x; i < h.e_cnt; i += NT) { d[i] = a.m.eadj[h.e_start + i]; dp[i] = a.pinv_q[h.e_start + i]; }
+            const int me = a.rc.me;
+            for (int le = threadIdx.x; le < h.e_cnt; le += NT) {
+                const uint32_t adj = a.m.eadj[h.e_start + le];
+                double diag = 0.0;
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    const uint32_t code = hf ? (adj >> 16) : (adj & 0xFFFFu);
+                    double w1 = 0.0, w2 = 0.0; uint32_t i1 = (uint32_t)le, i2 = (uint32_t)le;
+                    if (code != 0xFFFFu) {
+                        const uint4 qa = a.cellq[2 * (size_t)(h.cell_off + (code >> 2))], qb = a.cellq[2 * (size_t)(h.cell_off + (code >> 2)) + 1];
+                        const uint32_t e[3] = {qa.x & 0xFFFFu, qa.x >> 16, qa.y & 0xFFFFu};
+                        const double g[3] = {__hiloint2double((int)qa.w, (int)qa.z), __hiloint2double((int)qb.y, (int)qb.x), __hiloint2double((int)qb.w, (int)qb.z)};
+                        const double S = g[0] + g[1] + g[2];
+                        const int i = (int)(code & 3u), j = (i + 1) % 3, kk = (i + 2) % 3;
+                        const double si = (e[i] & 0x8000u) ? -1.0 : 1.0, sj = (e[j] & 0x8000u) ? -1.0 : 1.0, sk = (e[kk] & 0x8000u) ? -1.0 : 1.0;
+                        diag += 3.0 * S - 4.0 * g[i];
+                        w1 = si * sj * (S - 4.0 * g[kk]); i1 = e[j] & 0x3FFFu;
+                        w2 = si * sk * (S - 4.0 * g[j]); i2 = e[kk] & 0x3FFFu;
+                    }
+                    wq[(1 + 2 * hf) * me + le] = w1; idq[(2 * hf) * me + le] = (uint16_t)i1;
+                    wq[(2 + 2 * hf) * me + le] = w2; idq[(2 * hf + 1) * me + le] = (uint16_t)i2;
+                }
+                wq[le] = diag;
+                dp[le] = a.pinv_q[h.e_start + le];
+            }
         }
         // ghost sources: which CTA of the cluster owns the dof, and which row of its range it is
         uint32_t* gsv = reinterpret_cast<uint32_t*>(sbase + a.rc.gsv);
@@ -349,9 +370,18 @@ __global__ void __launch_bounds__(NT, (NT <= 256 && !RES) ? 2 : 1) loop_k(const 
         pull_ghosts(xb[0]);
         __syncthreads();
         int k = 0, c_ = 0; double rho = 0.0, rr = 0.0, bb = 0.0; bool conv = false;
+        // The residual norm only decides when to stop (the Chebyshev recurrence itself needs no inner product), and here - unlike
+        // in the bandwidth-bound kernels - its block reduction and exchange are a third of an iteration.  It is therefore measured
+        // only when the solve can be close to the tolerance: after a measurement the asymptotic rate sigma of the recurrence gives
+        // the number of iterations still needed, and the next measurement waits for 60 % of them.  An iterate is never accepted
+        // without its own measured residual.
+        const double kap_ = (a.cheb_d[which] + a.cheb_c[which]) / (a.cheb_d[which] - a.cheb_c[which]);
+        const double lsig_ = -log((sqrt(kap_) - 1.0) / (sqrt(kap_) + 1.0));      // > 0
+        int next_check = 0;
         while (true) {
             double c1, c2, rho_k;
             cheb_coeffs(k, rho, a.cheb_d[which], a.cheb_c[which], c1, c2, rho_k);
+            const bool do_norm = k >= next_check;
             const double* __restrict__ xc_ = xb[c_];
             double* __restrict__ xo_ = xb[c_ ^ 1];                    // holds x_{k-1}, receives x_{k+1}
             double r0 = 0.0, b0 = 0.0;
@@ -388,30 +418,18 @@ __global__ void __launch_bounds__(NT, (NT <= 256 && !RES) ? 2 : 1) loop_k(const 
                     b0 += pv * bv * bv;
                 }
             } else {
-                const uint4* scq = reinterpret_cast<const uint4*>(sbase + a.rc.cellq);
-                const uint32_t* sadj = reinterpret_cast<const uint32_t*>(sbase + a.rc.eadj);
+                const double* wq = reinterpret_cast<const double*>(sbase + a.rc.wq);
+                const uint16_t* idq = reinterpret_cast<const uint16_t*>(sbase + a.rc.idq);
                 const double* spv = reinterpret_cast<const double*>(sbase + a.rc.pinvq);
-                double* sc3 = reinterpret_cast<double*>(sbase + a.rc.cq);
-                for (int lc = threadIdx.x; lc < h.n_ecells; lc += NT) {
-                    const uint4 qa = scq[2 * lc], qb = scq[2 * lc + 1];
-                    const uint32_t e0 = qa.x & 0xFFFFu, e1 = qa.x >> 16, e2 = qa.y & 0xFFFFu;
-                    const double g0 = __hiloint2double((int)qa.w, (int)qa.z), g1 = __hiloint2double((int)qb.y, (int)qb.x), g2 = __hiloint2double((int)qb.w, (int)qb.z);
-                    const double S = g0 + g1 + g2;
-                    const double q0 = xc_[e0 & 0x3FFFu], q1 = xc_[e1 & 0x3FFFu], q2 = xc_[e2 & 0x3FFFu];
-                    const double s0 = (e0 & 0x8000u) ? -1.0 : 1.0, s1 = (e1 & 0x8000u) ? -1.0 : 1.0, s2 = (e2 & 0x8000u) ? -1.0 : 1.0;
-                    const double t0 = s0 * q0, t1 = s1 * q1, t2 = s2 * q2;
-                    const double ST = S * (t0 + t1 + t2);
-                    sc3[3 * lc] = s0 * (ST + 2.0 * S * t0 - 4.0 * (g0 * t0 + g2 * t1 + g1 * t2));
-                    sc3[3 * lc + 1] = s1 * (ST + 2.0 * S * t1 - 4.0 * (g2 * t0 + g1 * t1 + g0 * t2));
-                    sc3[3 * lc + 2] = s2 * (ST + 2.0 * S * t2 - 4.0 * (g1 * t0 + g0 * t1 + g2 * t2));
-                }
-                __syncthreads();
+                const int me = a.rc.me;
                 for (int le = threadIdx.x; le < h.e_cnt; le += NT) {
-                    const uint32_t adj = sadj[le];
-                    const uint32_t ca = adj & 0xFFFFu, cb = adj >> 16;
-                    double val = sc3[3 * (ca >> 2) + (ca & 3u)];
-                    if (cb != 0xFFFFu) val += sc3[3 * (cb >> 2) + (cb & 3u)];
-                    const double xc = xc_[le], bv = sb[le], pv = spv[le];
+                    const double xc = xc_[le];
+                    double val = wq[le] * xc;
+                    val += wq[me + le] * xc_[idq[le]];
+                    val += wq[2 * me + le] * xc_[idq[me + le]];
+                    val += wq[3 * me + le] * xc_[idq[2 * me + le]];
+                    val += wq[4 * me + le] * xc_[idq[3 * me + le]];
+                    const double bv = sb[le], pv = spv[le];
                     const double r_ = bv - val;
                     double xn = xc + c2 * pv * r_;
                     if (k > 0) xn += c1 * (xc - xo_[le]);
@@ -420,11 +438,14 @@ __global__ void __launch_bounds__(NT, (NT <= 256 && !RES) ? 2 : 1) loop_k(const 
                     b0 += pv * bv * bv;
                 }
             }
-            block_sum2(r0, b0, cx.red);
             const int par = k & 1;
-            if (threadIdx.x == 0) { part[2 * par] = r0; part[2 * par + 1] = b0; }
+            if (do_norm) {
+                block_sum2(r0, b0, cx.red);
+                if (threadIdx.x == 0) { part[2 * par] = r0; part[2 * par + 1] = b0; }
+            }
             cluster_barrier();                     // x_{k+1} (owned rows) and the norms of every CTA of the case are in place
-            if (threadIdx.x < 32) {
+            pull_ghosts(xo_);
+            if (do_norm && threadIdx.x < 32) {
                 double s0 = 0.0, s1 = 0.0;
                 if ((int)threadIdx.x < cx.ncta) {
                     const unsigned ra = dsmem_addr(part + 2 * par, threadIdx.x);
@@ -434,12 +455,16 @@ __global__ void __launch_bounds__(NT, (NT <= 256 && !RES) ? 2 : 1) loop_k(const 
                 if (threadIdx.x == 0) { cx.bc[0] = s0; cx.bc[1] = s1; }
             }
             __syncthreads();
-            rr = cx.bc[0]; bb = cx.bc[1];
-            conv = rr <= a.tol2 * bb;
             k += 1;
-            if (conv) break;                       // the verified iterate x_k (buffer c_) is the solution; nobody pulls from x_{k+1}
-            pull_ghosts(xo_);
-            __syncthreads();
+            if (do_norm) {
+                rr = cx.bc[0]; bb = cx.bc[1];
+                conv = rr <= a.tol2 * bb;
+                if (conv) break;                   // the verified iterate x_k (buffer c_) is the solution
+                const double need = 0.5 * log(rr / (a.tol2 * bb)) / lsig_;      // iterations the asymptotic rate still asks for
+                const int skip = need < 1e6 ? (int)(0.6 * need) : 0;
+                next_check = k + (skip > 1 ? skip - 1 : 0);
+                if (next_check > a.max_iter - 1) next_check = a.max_iter - 1;      // the last allowed iterate is always measured
+            }
             rho = rho_k; c_ ^= 1;
             if (k >= a.max_iter) break;
         }

@@ -557,6 +557,10 @@ struct phw_solver_s {
     bool pipe_en = false; EnergyPipeArgs pe{}; size_t smem_pe = 0;   // fused pipelined H_wave reduction (flags bit 11)
     bool pipe_rhs = false; RhsPipeArgs pre{}, prv{}; size_t smem_pre = 0, smem_prv = 0;   // pipelined right-hand sides (flags bit 12)
     bool loop_on = false; int loop_cl = 0, loop_nt = 512; bool loop_cluster = false; double* loop_partials = nullptr;
+    // field snapshots (phw_set_snapshots): ring of device slots in the user numbering, drained by a second stream
+    static constexpr int SNAP_SLOTS = 4;
+    int64_t snap_every = 0, snap_cap = 0, snap_taken = 0; double* snap_dst = nullptr; double* snap_ring = nullptr; void* snap_registered = nullptr;
+    cudaStream_t snap_stream = nullptr; cudaEvent_t snap_ready[SNAP_SLOTS] = {}, snap_done[SNAP_SLOTS] = {};
     bool loop_res = false; ResCarve loop_rc{};   // mass solves of the whole-loop kernel resident in shared memory (kernels_loop.cuh, RES)   // whole-loop kernel (flags bit 15)
     int64_t kernel_paths = 0;              // PHW_PATH_* bits of the solve kernels launched since the last phw_run began
     int *d_cells_user = nullptr; double* d_vtx_user = nullptr; unsigned long long* d_mm = nullptr;
@@ -1362,7 +1366,7 @@ static ResCarve res_carve(const Layout& L, size_t scratch_bytes) {
     ResCarve c{};
     int o = 0;
     c.xq[0] = o; o += al(8 * (size_t)mle); c.xq[1] = o; o += al(8 * (size_t)mle);
-    c.bq = o; o += al(8 * (size_t)me); c.cq = o; o += al(24 * (size_t)mec);
+    c.bq = o; o += al(8 * (size_t)me);
     const int tq = o;
     o = 0;
     c.xp[0] = o; o += al(8 * (size_t)mlv); c.xp[1] = o; o += al(8 * (size_t)mlv); c.bp = o; o += al(8 * (size_t)mv);
@@ -1370,7 +1374,8 @@ static ResCarve res_carve(const Layout& L, size_t scratch_bytes) {
     const int nsl = (mv + 31) / 32 + 2;
     c.sio = o; o += al(4 * (size_t)nsl); c.swo = o; o += al(4 * (size_t)nsl);
     c.ids = o; o += al(2 * (size_t)mids); c.w = o; o += al(8 * (size_t)mw);
-    c.cellq = o; o += al(32 * (size_t)mec); c.eadj = o; o += al(4 * (size_t)me); c.pinvq = o; o += al(8 * (size_t)me);
+    c.me = (me + 7) & ~7;
+    c.wq = o; o += al(40 * (size_t)c.me); c.idq = o; o += al(8 * (size_t)c.me); c.pinvq = o; o += al(8 * (size_t)me);
     c.gsv = o; o += al(4 * (size_t)mg); c.gse = o; o += al(4 * (size_t)mg);
     c.part = o; o += 32;
     c.total = o;
@@ -1483,6 +1488,27 @@ int run_loop(phw_solver_s* s, int64_t n_steps) {
             default: advance(0, 0, n_steps); advance(1, 0, n_steps);
         }
     }
+    return 0;
+}
+
+bool is_device_ptr(const void* p);
+// p of the current state -> next free slot of the snapshot ring (user numbering), then to the caller's buffer on the snapshot
+// stream while the time loop goes on; a slot is reused only after its previous copy has finished
+int take_snapshot(phw_solver_s* s) {
+    if (s->snap_taken >= s->snap_cap) return 0;
+    const int slot = (int)(s->snap_taken % phw_solver_s::SNAP_SLOTS);
+    double* ring = s->snap_ring + (size_t)slot * s->nv;
+    if (s->snap_taken >= phw_solver_s::SNAP_SLOTS) CU(cudaStreamWaitEvent(s->stream, s->snap_done[slot], 0));
+    if (s->d_v_new2old) scatter_k<<<nblk(s->nv), 256, 0, s->stream>>>(s->nv, ring, s->p, s->d_v_new2old);
+    else CU(cudaMemcpyAsync(ring, s->p, (size_t)s->nv * 8, cudaMemcpyDeviceToDevice, s->stream));
+    CU(cudaGetLastError());
+    s->launches++;
+    CU(cudaEventRecord(s->snap_ready[slot], s->stream));
+    CU(cudaStreamWaitEvent(s->snap_stream, s->snap_ready[slot], 0));
+    double* dst = s->snap_dst + (size_t)s->snap_taken * s->nv;
+    CU(cudaMemcpyAsync(dst, ring, (size_t)s->nv * 8, is_device_ptr(dst) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s->snap_stream));
+    CU(cudaEventRecord(s->snap_done[slot], s->snap_stream));
+    s->snap_taken++;
     return 0;
 }
 
@@ -1701,6 +1727,11 @@ int phw_solver_destroy(phw_solver_t s) {
     for (void* d : s->allocs) cudaFree(d);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->snap_registered) cudaHostUnregister(s->snap_registered);
+    if (s->snap_stream) {
+        cudaStreamDestroy(s->snap_stream);
+        for (int i = 0; i < phw_solver_s::SNAP_SLOTS; ++i) { cudaEventDestroy(s->snap_ready[i]); cudaEventDestroy(s->snap_done[i]); }
+    }
     delete s;
     return PHW_OK;
 }
@@ -2320,9 +2351,17 @@ int phw_run(phw_solver_t s, int64_t n_steps, double* H_rows) {
     s->kernel_paths = 0;
     CU(cudaEventRecord(s->ev0, s->stream));
     if (s->prm.analytical && !s->an_ready) return fail(PHW_ESTATE, "analytical run: call phw_set_analytical before phw_run");
+    s->snap_taken = 0;
+    const int64_t every = (s->snap_every > 0 && s->snap_dst) ? s->snap_every : 0;
     if (s->loop_on && s->pc.world <= 1 && n_steps > 0) {
-        int rc = run_loop(s, n_steps);
-        if (rc) return rc;
+        // one launch for the whole run, or one launch per snapshot interval
+        for (int64_t done = 0; done < n_steps;) {
+            const int64_t n = every ? std::min(every - done % every, n_steps - done) : n_steps;
+            int rc = run_loop(s, n);
+            if (rc) return rc;
+            done += n;
+            if (every && done % every == 0) { rc = take_snapshot(s); if (rc) return rc; }
+        }
     } else
     for (int64_t n = 0; n < n_steps; ++n) {
         s->in_step = true;
@@ -2330,8 +2369,10 @@ int phw_run(phw_solver_t s, int64_t n_steps, double* H_rows) {
         s->in_step = false;
         if (rc) return rc;
         if ((s->prm.flags & 2) && cudaStreamSynchronize(s->stream) != cudaSuccess) return fail(PHW_ECUDA, "kernel failure inside step loop");
+        if (every && (n + 1) % every == 0) { rc = take_snapshot(s); if (rc) return rc; }
     }
     CU(cudaEventRecord(s->ev1, s->stream));
+    if (s->snap_taken > 0) CU(cudaStreamSynchronize(s->snap_stream));
     if (H_rows && n_steps > 0) {
         if (is_device_ptr(H_rows)) CU(cudaMemcpyAsync(H_rows, s->dH, nrow * s->ncol * 8, cudaMemcpyDeviceToDevice, s->stream));
         else CU(cudaMemcpyAsync(H_rows, s->dH, nrow * s->ncol * 8, cudaMemcpyDeviceToHost, s->stream));
@@ -2372,6 +2413,30 @@ int phw_run(phw_solver_t s, int64_t n_steps, double* H_rows) {
         char buf[160];
         snprintf(buf, sizeof buf, "%lld solves hit max_iter without reaching tol (max relative residual %.3e)", (long long)hc.nonconv, st.max_rel_residual);
         return fail(PHW_ENOCONV, buf);
+    }
+    return PHW_OK;
+}
+
+int phw_set_snapshots(phw_solver_t s, int64_t every, double* snaps, int64_t capacity) {
+    if (!s) return fail(PHW_EINVAL, "solver is NULL");
+    if (every < 0 || capacity < 0 || (every > 0 && !snaps)) return fail(PHW_EINVAL, "bad snapshot arguments");
+    CU(cudaSetDevice(s->device));
+    if (s->snap_registered) { cudaHostUnregister(s->snap_registered); cudaGetLastError(); s->snap_registered = nullptr; }
+    s->snap_every = every; s->snap_dst = every > 0 ? snaps : nullptr; s->snap_cap = capacity;
+    if (every > 0 && capacity > 0 && !is_device_ptr(snaps)) {
+        // page-lock a pageable destination for the lifetime of the setting, so that the device-to-host copies really run beside the
+        // time loop (an already pinned buffer makes the call fail harmlessly)
+        if (cudaHostRegister(snaps, (size_t)capacity * (size_t)s->nv * 8, cudaHostRegisterDefault) == cudaSuccess) s->snap_registered = snaps;
+        else cudaGetLastError();
+    }
+    if (every > 0 && !s->snap_stream) {
+        CU(cudaStreamCreateWithFlags(&s->snap_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < phw_solver_s::SNAP_SLOTS; ++i) {
+            CU(cudaEventCreateWithFlags(&s->snap_ready[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&s->snap_done[i], cudaEventDisableTiming));
+        }
+        int rc = s->dalloc(&s->snap_ring, (size_t)phw_solver_s::SNAP_SLOTS * s->nv);
+        if (rc) return rc;
     }
     return PHW_OK;
 }

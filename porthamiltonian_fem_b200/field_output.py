@@ -17,13 +17,14 @@ class XdmfBinaryWriter:
         self.data = open(os.path.join(out_dir, name + '_values.bin'), 'wb')
         self.times = []
 
-    def write(self, values, t):
+    def write(self, values, t, flush=True):
         v = np.ascontiguousarray(values, dtype='<f8')
         if v.shape[0] != self.nv:
             raise ValueError('one value per vertex expected')
         v.tofile(self.data)
         self.times.append(float(t))
-        self._write_xml()            # keep the index file valid after every snapshot (flush_output, wave_2D.py:648)
+        if flush:
+            self._write_xml()        # keep the index file valid after every snapshot (flush_output, wave_2D.py:648)
 
     def _write_xml(self):
         self.data.flush()

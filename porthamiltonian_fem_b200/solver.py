@@ -211,6 +211,18 @@ class Solver:
         _lib.check(self.lib.phw_run(self.handle, int(n_steps), _lib.ptr(out)))
         return out
 
+    def run_with_snapshots(self, n_steps, every, n_values=None):
+        """n_steps steps; the p field after every `every` steps (user numbering) -> (H_rows, snapshots [n_steps // every, n]).
+        Device-side snapshot ring + second stream (phw_set_snapshots): replaces xdmfFile_p.write(out_p, t), wave_2D.py:865-866."""
+        n = int(n_values if n_values is not None else self.mesh.n_vertices)
+        snaps = np.zeros((int(n_steps) // int(every), n))
+        _lib.check(self.lib.phw_set_snapshots(self.handle, int(every), snaps.ctypes.data, snaps.shape[0]))
+        try:
+            H = self.run(n_steps)
+        finally:
+            _lib.check(self.lib.phw_set_snapshots(self.handle, 0, None, 0))
+        return H, snaps
+
     def stats(self):
         st = _lib.PhwStats()
         _lib.check(self.lib.phw_get_stats(self.handle, ctypes.byref(st)))

@@ -70,7 +70,7 @@ def wave_2D_solve(tFinal, numSteps, outputDir,
     if tuple(basis_order) != (1, 1):
         return _solve_high_order(tFinal, numSteps, outputDir, nx, xLength, yLength, domainShape, timeIntScheme, dirichletImp,
                                  K_wave, rho, interConnection, analytical, controlType, tuple(basis_order), mesh, mesh_kind,
-                                 device, tol, extrap_order, lumped, return_state, verbose, tic, solver_flags or 0)
+                                 device, tol, extrap_order, lumped, return_state, verbose, tic, solver_flags or 0, saveP=saveP, save_every=save_every)
     if controlType == 'casimir' and timeIntScheme != 'SM':
         raise NotImplementedError('casimir control is only defined for the SM scheme (wave_2D.py:615)')
     if controlType == 'passivity' and timeIntScheme in ['SV', 'EH']:
@@ -90,7 +90,10 @@ def wave_2D_solve(tFinal, numSteps, outputDir,
         solver_flags = (_lib.FLAGS_PIPELINED if big and explicit and (patch_cells is None or patch_cells <= 1024) else 0)
     # cache-resident meshes (everything the reference itself runs): the whole time loop in ONE launch (csrc/kernels_loop.cuh; flags
     # bit 15), the mesh cut into <= 16 patches = one thread-block cluster; PHW_NO_LOOP=1 keeps the multi-launch path (A/B, tests)
-    if solver_flags == 0 and not big and not analytical and patch_cells is None and not os.environ.get('PHW_NO_LOOP'):
+    # (measured, profiles/r2g_*: the coupled block solve of IE / SM runs its row passes from L2 and wants every SM once the mesh has
+    # more than ~12 000 cells - there the multi-launch path is faster than one 16-CTA cluster)
+    block_big = timeIntScheme in ('IE', 'SM') and len(cells) > 12000
+    if solver_flags == 0 and not big and not analytical and patch_cells is None and not block_big and not os.environ.get('PHW_NO_LOOP'):
         solver_flags = _lib.FLAGS_LOOP
         patch_cells = _lib.loop_patch_cells(len(cells)) or 2048
     if patch_cells is None:
@@ -185,20 +188,8 @@ def wave_2D_solve(tFinal, numSteps, outputDir,
                                                  float(omega), mass.ctypes.data_as(_lib.c_f64p), lam.ctypes.data_as(_lib.c_f64p),
                                                  ev.ctypes.data_as(_lib.c_f64p), pt_v.ctypes.data_as(_lib.c_i32p), pt_l.ctypes.data_as(_lib.c_f64p)))
     if saveP and save_every and outputDir:
-        # field output (the reference writes p to p.xdmf at every step, wave_2D.py:646-651,865-866).  h5py is not
-        # available, so the heavy data goes to raw little-endian binaries referenced from an XDMF file (ParaView
-        # reads Format="Binary"); the time loop runs in chunks of `save_every` steps between snapshots.
-        from .field_output import XdmfBinaryWriter
-        writer = XdmfBinaryWriter(outputDir, 'p', m.vertices, m.cells)
-        H_array = np.zeros((numSteps, solver.ncol))
-        done = 0
-        while done < numSteps:
-            n = min(int(save_every), numSteps - done)
-            H_array[done:done + n] = solver.run(n)
-            done += n
-            p_h, _, _ = solver.get_state()
-            writer.write(p_h, H_array[done - 1, 0])
-        writer.close()
+        H_array = _run_saving_fields(solver, numSteps, int(save_every), outputDir, m.vertices, m.cells, m.n_vertices,
+                                     (lambda t: p_space * np.cos(omega * t)) if analytical else None)
     else:
         H_array = solver.run(numSteps)
     stats = solver.stats()
@@ -212,6 +203,27 @@ def wave_2D_solve(tFinal, numSteps, outputDir,
     solver.close()
     m.close()
     return H_array, numCells
+
+
+def _run_saving_fields(solver, numSteps, save_every, outputDir, vertices, cells, n_vertices, exact_of_t):
+    """The time loop with field output (wave_2D.py:646-651,865-866,964-965): p.xdmf receives the nodal p field after every
+    ``save_every`` steps (the reference: every step) and, in the analytical case, p_exact.xdmf the nodal interpolant of the exact
+    solution at the same instants.  The snapshots leave the device through a ring of device slots and a second stream while
+    the loop goes on (phw_set_snapshots); h5py is not available, so the heavy data goes to raw little-endian binaries
+    referenced from the XDMF files (ParaView reads Format="Binary")."""
+    from .field_output import XdmfBinaryWriter
+    H_array, snaps = solver.run_with_snapshots(numSteps, save_every)
+    writer = XdmfBinaryWriter(outputDir, 'p', vertices, cells)
+    writer_exact = XdmfBinaryWriter(outputDir, 'p_exact', vertices, cells) if exact_of_t is not None else None
+    for k in range(snaps.shape[0]):
+        t = H_array[(k + 1) * save_every - 1, 0]
+        writer.write(snaps[k, :n_vertices], t, flush=False)
+        if writer_exact is not None:
+            writer_exact.write(exact_of_t(t), t, flush=False)
+    writer.close()
+    if writer_exact is not None:
+        writer_exact.close()
+    return H_array
 
 
 class _AnalyticalDiagnostics:
@@ -276,7 +288,7 @@ class _AnalyticalDiagnostics:
 
 def _solve_high_order(tFinal, numSteps, outputDir, nx, xLength, yLength, domainShape, timeIntScheme, dirichletImp, K_wave, rho,
                       interConnection, analytical, controlType, basis_order, mesh, mesh_kind, device, tol, extrap_order, lumped,
-                      return_state, verbose, tic, solver_flags=0):
+                      return_state, verbose, tic, solver_flags=0, saveP=False, save_every=None):
     """basis_order != (1,1) (wave_2D.py:174-175,202-203): host-assembled operators (fem_ho.py) + CSR device kernels."""
     from .fem_ho import HighOrderSpaces, LagrangeRef, tri_rule
     from .solver import HighOrderSolver
@@ -368,7 +380,12 @@ def _solve_high_order(tFinal, numSteps, outputDir, nx, xLength, yLength, domainS
                                                     arrs[1].ctypes.data_as(_lib.c_f64p), arrs[2].ctypes.data_as(_lib.c_f64p),
                                                     arrs[3].ctypes.data_as(_lib.c_f64p), arrs[4].ctypes.data_as(_lib.c_f64p),
                                                     int(pd.shape[0]), pd.ctypes.data_as(_lib.c_i32p), arrs[5].ctypes.data_as(_lib.c_f64p)))
-    H_array = solver.run(numSteps)
+    if saveP and save_every and outputDir:     # vertex values of the P_k field (the vertex dofs come first)
+        pv_space = space(S.vertices[:, 0], S.vertices[:, 1]) if analytical else None
+        H_array = _run_saving_fields(solver, numSteps, int(save_every), outputDir, S.vertices, S.cells, S.nv,
+                                     (lambda t: pv_space * np.cos(omega * t)) if analytical else None)
+    else:
+        H_array = solver.run(numSteps)
     stats = solver.stats()
     if verbose:
         print('{}, {}, {} Simulation finished in {} seconds'.format(domainShape, timeIntScheme, dirichletImp, time.time() - tic))

@@ -175,3 +175,28 @@ def test_gloo_world2_partitioned_operators_match_global(how, world):
         assert p.exitcode == 0
     for rank, err in res:
         assert err < 1e-12, (rank, err)
+
+
+def test_halo_only_patches_come_last_and_do_not_size_the_stages():
+    """A thin interior slab of an 8-rank strong-scaling run (bench.py, BASELINE configs[3]): its two halo columns form patches of
+    neighbour cells only.  They own no row, so the layout puts them behind the patches the kernels process and leaves them out of
+    the shared-memory carve-up (every dof of such a patch is a ghost: ~3 x the cells)."""
+    from porthamiltonian_fem_b200.solver import Mesh
+    part = pt.structured_slab_part(32, 256, 8, 3, 1.0 / 8, 0.25)
+    pc = 128
+    m = Mesh(part.vertices, part.cells, patch_cells=pc, vertex_external=part.vertex_external, edge_external=part.edge_external,
+             cell_owned=part.cell_owned)
+    m.self_check()
+    cnt = m.patch_counts()                       # own cells, edge-op cells, vertex-op cells, owned vertices, owned edges, ghosts
+    owns = (cnt[:, 3] + cnt[:, 4]) > 0
+    n_rows = int(owns.sum())
+    assert n_rows < len(cnt), 'the slab should have patches made of halo cells only'
+    assert owns[:n_rows].all() and not owns[n_rows:].any()
+    assert cnt[n_rows:, 5].min() > 2 * pc        # what would have sized the stages
+    assert cnt[:n_rows, 5].max() < 2 * pc
+    # the stage sizes come from the processed patches: the same as for a layout of this slab's own cells alone, up to its halo
+    used, inv = np.unique(part.cells[part.cell_owned.astype(bool)], return_inverse=True)
+    own_only = Mesh(part.vertices[used], inv.reshape(-1, 3).astype(np.int32), patch_cells=pc)
+    a, b = np.array(m.pipe_smem()), np.array(own_only.pipe_smem())
+    assert np.all(a[:5] < 1.35 * b[:5]), (a, b)
+    m.close(); own_only.close()
