@@ -133,9 +133,9 @@ int phw_mesh_get_numbering(phw_mesh_t m, int32_t* vertex_new2old, int32_t* edge_
 /* per-patch counts [n_patches,6]: own cells, edge-op cells, vertex-op cells, owned vertices, owned edges, ghosts(v+e) */
 int phw_mesh_get_patch_counts(phw_mesh_t m, int32_t* counts);
 /* dynamic shared memory (bytes) the bulk-copy pipelined kernels need for this layout: bytes6 = {M_p solve, M_q solve, fused
- * energy reduction, edge-row right-hand side, vertex-row right-hand side, 0 (reserved)}
- * (phw_params.flags bits 9, 8, 11, 12, 12, 13; a variant is available when its figure is <= 227 KB - 1 KB (- 2 KB for the
- * last one)).  Host-only. */
+ * energy reduction, edge-row right-hand side, vertex-row right-hand side, whole-loop kernel with the mass solves resident in shared
+ * memory (flags bit 15; resident when <= 224 KB)}
+ * (phw_params.flags bits 9, 8, 11, 12, 12, 15; a pipelined variant is available when its figure is <= 227 KB - 1 KB).  Host-only. */
 int phw_mesh_pipe_smem(phw_mesh_t m, int64_t* bytes6);
 /* host-only structural invariants of the patch layout, and the assembled (ELL) mass rows
  * (tests; small meshes) */

@@ -32,8 +32,9 @@ struct ResCarve {
     int xq[2], bq;                // M_q solve (transient; aliases the scratch of the row passes): iterates [owned | ghosts], b
     int xp[2], bp;                // M_p solve (transient)
     int sio, swo, ids, w;         // persistent: ELL rows of M_p (slice offsets rebased to the patch, ids, weights)
-    int wq, idq, pinvq, me;       // persistent: assembled rows of M_q, [5][me] weights (diagonal first) and [4][me] uint16 local
-                                  // ids of the four neighbour edges, built by the CTA from the cell records; Jacobi weights
+    int wq, idq, dgq, dgp, me;    // persistent: assembled rows of M_q scaled by their diagonal, [4][me] weights and [4][me] uint16
+                                  // local ids of the four neighbour edges, built by the CTA from the cell records; the diagonals
+                                  // of M_q and M_p (the rows of M_p are scaled in place as well): needed for the norms only
     int gsv, gse;                 // persistent: ghost sources (owner CTA rank << 16 | row inside the owner's range)
     int part;                     // persistent: [2][2] doubles, this CTA's residual norms (double-buffered by iteration parity)
     int total;
@@ -172,10 +173,26 @@ __global__ void __launch_bounds__(NT, (NT <= 256 && !RES) ? 2 : 1) loop_k(const 
             const double* g = a.m.ell_w + (uint32_t)h.ell_w0;
             for (uint32_t i = threadIdx.x; i < (uint32_t)h.ell_wn; i += NT) d[i] = g[i];
         }
+        __syncthreads();
+        {   // Jacobi scaling of the M_p rows in place: w_vj / d_v with d_v = sum_j w_vj (the P1 mass diagonal is the row sum of
+            // the off-diagonal entries); the iteration then needs neither the diagonal nor a division
+            double* sw = reinterpret_cast<double*>(sbase + a.rc.w);
+            double* dg = reinterpret_cast<double*>(sbase + a.rc.dgp);
+            for (int lv = threadIdx.x; lv < h.v_cnt; lv += NT) {
+                const int sl = lv >> 5, lane = lv & 31;
+                const uint32_t wo0 = s_wo[sl];
+                const int W = (int)((s_wo[sl + 1] - wo0) >> 5);
+                double dsum = 0.0;
+                for (int j = 0; j < W; ++j) dsum += sw[wo0 + j * 32 + lane];
+                const double inv = 1.0 / dsum;
+                for (int j = 0; j < W; ++j) sw[wo0 + j * 32 + lane] *= inv;
+                dg[lv] = dsum;
+            }
+        }
         {   // assembled rows of M_q from the metric of the (<= 2) cells of every owned edge: m_ii = 3 S - 4 g_i, m_ij = s_i s_j (S - 4 g_k)
             double* wq = reinterpret_cast<double*>(sbase + a.rc.wq);
             uint16_t* idq = reinterpret_cast<uint16_t*>(sbase + a.rc.idq);
-            double* dp = reinterpret_cast<double*>(sbase + a.rc.pinvq);
+            double* dgq = reinterpret_cast<double*>(sbase + a.rc.dgq);
             const int me = a.rc.me;
             for (int le = threadIdx.x; le < h.e_cnt; le += NT) {
                 const uint32_t adj = a.m.eadj[h.e_start + le];
@@ -195,11 +212,13 @@ __global__ void __launch_bounds__(NT, (NT <= 256 && !RES) ? 2 : 1) loop_k(const 
                         w1 = si * sj * (S - 4.0 * g[kk]); i1 = e[j] & 0x3FFFu;
                         w2 = si * sk * (S - 4.0 * g[j]); i2 = e[kk] & 0x3FFFu;
                     }
-                    wq[(1 + 2 * hf) * me + le] = w1; idq[(2 * hf) * me + le] = (uint16_t)i1;
-                    wq[(2 + 2 * hf) * me + le] = w2; idq[(2 * hf + 1) * me + le] = (uint16_t)i2;
+                    wq[(2 * hf) * me + le] = w1; idq[(2 * hf) * me + le] = (uint16_t)i1;
+                    wq[(2 * hf + 1) * me + le] = w2; idq[(2 * hf + 1) * me + le] = (uint16_t)i2;
                 }
-                wq[le] = diag;
-                dp[le] = a.pinv_q[h.e_start + le];
+                const double inv = 1.0 / diag;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) wq[j * me + le] *= inv;
+                dgq[le] = diag;
             }
         }
         // ghost sources: which CTA of the cluster owns the dof, and which row of its range it is
@@ -359,7 +378,8 @@ __global__ void __launch_bounds__(NT, (NT <= 256 && !RES) ? 2 : 1) loop_k(const 
         const double* gb = which == 0 ? a.bp : a.bq;
         double* gx = which == 0 ? tbp(which) : tbq(which);
         SYNC();                                    // right-hand side (port term included) and initial guess are complete in global memory
-        for (int i = threadIdx.x; i < n_own; i += NT) { sb[i] = gb[g0_ + i]; xb[0][i] = gx[g0_ + i]; }
+        const double* dg = reinterpret_cast<const double*>(sbase + (which == 0 ? a.rc.dgp : a.rc.dgq));
+        for (int i = threadIdx.x; i < n_own; i += NT) { sb[i] = gb[g0_ + i] / dg[i]; xb[0][i] = gx[g0_ + i]; }   // Jacobi-scaled right-hand side
         auto pull_ghosts = [&](double* xdst) {     // ghost copies of the iterate out of the owners' shared memory
             for (int i = threadIdx.x; i < n_gh; i += NT) {
                 const uint32_t code = gsrc[i];
@@ -394,7 +414,7 @@ __global__ void __launch_bounds__(NT, (NT <= 256 && !RES) ? 2 : 1) loop_k(const 
                     const int sl = lv >> 5, lane = lv & 31;
                     const uint32_t io0 = s_io[sl], wo0 = s_wo[sl];
                     const int W = (int)((s_wo[sl + 1] - wo0) >> 5);
-                    double val = 0.0, dsum = 0.0;
+                    double val = 0.0;
                     for (int c = 0; 8 * c < W; ++c) {
                         const uint4 cd = sid4[(io0 >> 3) + c * 32 + lane];
                         const uint32_t w4[4] = {cd.x, cd.y, cd.z, cd.w};
@@ -404,38 +424,31 @@ __global__ void __launch_bounds__(NT, (NT <= 256 && !RES) ? 2 : 1) loop_k(const 
                             const double wb = (8 * c + 2 * j + 1 < W) ? sw[wo0 + (8 * c + 2 * j + 1) * 32 + lane] : 0.0;
                             val += wa * xc_[w4[j] & 0xFFFFu];
                             val += wb * xc_[w4[j] >> 16];
-                            dsum += wa + wb;
                         }
                     }
                     const double xc = xc_[lv], bv = sb[lv];
-                    const double pv = 1.0 / dsum;
-                    val += dsum * xc;
-                    const double r_ = bv - val;
-                    double xn = xc + c2 * pv * r_;
+                    const double r_ = bv - xc - val;                  // Jacobi-scaled residual
+                    double xn = xc + c2 * r_;
                     if (k > 0) xn += c1 * (xc - xo_[lv]);
                     xo_[lv] = xn;
-                    r0 += pv * r_ * r_;
-                    b0 += pv * bv * bv;
+                    if (do_norm) { const double d_ = dg[lv]; r0 += d_ * r_ * r_; b0 += d_ * bv * bv; }
                 }
             } else {
                 const double* wq = reinterpret_cast<const double*>(sbase + a.rc.wq);
                 const uint16_t* idq = reinterpret_cast<const uint16_t*>(sbase + a.rc.idq);
-                const double* spv = reinterpret_cast<const double*>(sbase + a.rc.pinvq);
                 const int me = a.rc.me;
                 for (int le = threadIdx.x; le < h.e_cnt; le += NT) {
                     const double xc = xc_[le];
-                    double val = wq[le] * xc;
-                    val += wq[me + le] * xc_[idq[le]];
-                    val += wq[2 * me + le] * xc_[idq[me + le]];
-                    val += wq[3 * me + le] * xc_[idq[2 * me + le]];
-                    val += wq[4 * me + le] * xc_[idq[3 * me + le]];
-                    const double bv = sb[le], pv = spv[le];
-                    const double r_ = bv - val;
-                    double xn = xc + c2 * pv * r_;
+                    double val = wq[le] * xc_[idq[le]];
+                    val += wq[me + le] * xc_[idq[me + le]];
+                    val += wq[2 * me + le] * xc_[idq[2 * me + le]];
+                    val += wq[3 * me + le] * xc_[idq[3 * me + le]];
+                    const double bv = sb[le];
+                    const double r_ = bv - xc - val;
+                    double xn = xc + c2 * r_;
                     if (k > 0) xn += c1 * (xc - xo_[le]);
                     xo_[le] = xn;
-                    r0 += pv * r_ * r_;
-                    b0 += pv * bv * bv;
+                    if (do_norm) { const double d_ = dg[le]; r0 += d_ * r_ * r_; b0 += d_ * bv * bv; }
                 }
             }
             const int par = k & 1;

@@ -1375,7 +1375,7 @@ static ResCarve res_carve(const Layout& L, size_t scratch_bytes) {
     c.sio = o; o += al(4 * (size_t)nsl); c.swo = o; o += al(4 * (size_t)nsl);
     c.ids = o; o += al(2 * (size_t)mids); c.w = o; o += al(8 * (size_t)mw);
     c.me = (me + 7) & ~7;
-    c.wq = o; o += al(40 * (size_t)c.me); c.idq = o; o += al(8 * (size_t)c.me); c.pinvq = o; o += al(8 * (size_t)me);
+    c.wq = o; o += al(32 * (size_t)c.me); c.idq = o; o += al(8 * (size_t)c.me); c.dgq = o; o += al(8 * (size_t)me); c.dgp = o; o += al(8 * (size_t)mv);
     c.gsv = o; o += al(4 * (size_t)mg); c.gse = o; o += al(4 * (size_t)mg);
     c.part = o; o += 32;
     c.total = o;
@@ -1706,7 +1706,12 @@ int phw_mesh_pipe_smem(phw_mesh_t m, int64_t* bytes6) {
     size_t sq = 0, sp = 0, se = 0, sre = 0, srv = 0;
     pipe_carve(m->L, cq, cp, sq, sp, &ce, &se, &re, &sre, &rv, &srv);
     bytes6[0] = (int64_t)sp; bytes6[1] = (int64_t)sq; bytes6[2] = (int64_t)se; bytes6[3] = (int64_t)sre; bytes6[4] = (int64_t)srv;
-    bytes6[5] = 0;   // (was: the two-sweep pipelined M_q solve, removed in round 2 - measured slower than the one-sweep kernels)
+    {   // whole-loop kernel with resident solves: scratch of the row passes (smem_vd of setup_solver) + the resident carve-up
+        const Layout& L = m->L;
+        auto ev = [](int x) { return (size_t)((x + 1) & ~1); };
+        const size_t soff = ((size_t)(L.max_lv + 31) / 32 + 4) / 2 + 1;
+        bytes6[5] = (int64_t)res_carve(L, (soff + ev(L.max_lv) + ev(L.max_le) + 3 * (size_t)L.max_cells) * 8).total;
+    }
     return PHW_OK;
 }
 int phw_mesh_self_check(phw_mesh_t m) {
