@@ -149,8 +149,10 @@ def run_sweep_bench(args):
     cases = sweep_cases(n_cases * world)[rank * n_cases:(rank + 1) * n_cases]
     dt = 1e-3
     t0 = time.time()
+    # --pipe p / q / pq with --patch-cells <= 1024: the bulk-copy pipelined mass solves on the grouped mesh (A/B against the lean kernels)
+    sflags = (pipe_flags(args.pipe) & (256 | 512)) if (args.sweep_pipe and 0 < args.patch_cells <= 1024) else 0
     H, nc, solver = wave_sweep_solve(dt * args.warmup, args.warmup, 0, 1.0, 0.25, cases, mesh=mesh, device=local_rank, patch_cells=args.patch_cells if args.patch_cells > 0 else None,
-                                     extrap_order=args.extrap, return_solver=True)
+                                     extrap_order=args.extrap, return_solver=True, solver_flags=sflags)
     setup_s = time.time() - t0
     torch.cuda.synchronize()
     H = solver.run(args.steps)
@@ -169,7 +171,8 @@ def run_sweep_bench(args):
                           'dtype': 'f64', 'data': 'synthetic',
                           'config': {'workload': 'batched sweep: {} independent IC cases per GPU, SV, 104x26x2 cells ({} dofs) each, dt=1e-3'.format(n_cases, n_dof_case),
                                      'iters_per_solve_p': st['iters_p'] / max(1, st['solves_p']), 'iters_per_solve_q': st['iters_q'] / max(1, st['solves_q']),
-                                     'max_rel_residual': st['max_rel_residual'], 'setup_seconds': setup_s},
+                                     'max_rel_residual': st['max_rel_residual'], 'setup_seconds': setup_s, 'kernel_paths': int(st['kernel_paths']),
+                                     'patches': solver.mesh.n_patches},
                           'gpu_launches': int(st['kernel_launches']),
                           'energy_residual_max': float(np.abs(H[:, :, 2]).max())}))
     if world > 1:
@@ -301,6 +304,7 @@ def run_bench():
     ap = argparse.ArgumentParser()
     ap.add_argument('--workload', default='mesh50m', choices=['mesh50m', 'sweep', 'paper'])
     ap.add_argument('--cases', type=int, default=1024)
+    ap.add_argument('--sweep-pipe', action='store_true', help='--workload sweep: pipelined mass solves (needs --patch-cells <= 1024)')
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)

@@ -77,8 +77,18 @@ def _worker(rank, world, port, scheme, q, flags=0, big=False):
                                               ('EH', 768 + 2048 + 4096, False),
                                               ('SE', 0, True), ('SE', 768, True), ('SV', 768 + 2048 + 4096, True)])
 def test_two_gpu_partitioned_run_matches_oracle(scheme, flags, big):
-    if _ngpu() < 2:
-        pytest.skip('needs 2 GPUs')
+    _run_partitioned(2, scheme, flags, big)
+
+
+# four ranks: the interior slabs have two neighbours and two halo columns (patches of halo cells only at the end of the layout)
+@pytest.mark.parametrize('scheme,flags,big', [('SE', 768 + 2048 + 4096, True), ('SV', 768 + 2048 + 4096, False), ('SE', 0, False)])
+def test_four_gpu_partitioned_run_matches_oracle(scheme, flags, big):
+    _run_partitioned(4, scheme, flags, big)
+
+
+def _run_partitioned(world, scheme, flags, big):
+    if _ngpu() < world:
+        pytest.skip('needs %d GPUs' % world)
     import torch.multiprocessing as mp
     sck = socket.socket()
     sck.bind(('127.0.0.1', 0))
@@ -86,7 +96,7 @@ def test_two_gpu_partitioned_run_matches_oracle(scheme, flags, big):
     sck.close()
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, scheme, q, flags, big)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, scheme, q, flags, big)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=240) for _ in procs]
