@@ -2457,39 +2457,39 @@ int phw_get_stats(phw_solver_t s, phw_stats* out) {
 // ---- kernel-level entry points ------------------------------------------------------------------
 int phw_apply_D(phw_solver_t s, const double* p, double* y) {
     if (!s || !p || !y) return fail(PHW_EINVAL, "NULL argument");
-    if (s->ho) return fail(PHW_ESTATE, "kernel-level entry points are for the matrix-free (P1/RT1) solver");
     CU(cudaSetDevice(s->device));
     int rc = import_vec(s, p, s->io_v2, s->nv, s->d_v_new2old, s->io_v); if (rc) return rc;
-    rc = op_edge_store(s, s->io_v2, nullptr, 0.0, 1.0, 0.0, s->io_e2); if (rc) return rc;
+    if (s->ho) { csr_store(s, s->hD, s->io_v2, 1.0, s->io_e2); CU(cudaGetLastError()); }
+    else { rc = op_edge_store(s, s->io_v2, nullptr, 0.0, 1.0, 0.0, s->io_e2); if (rc) return rc; }
     return export_vec(s, s->io_e2, y, s->ne, s->d_e_new2old, s->io_e);
 }
 int phw_apply_DT(phw_solver_t s, const double* q, double* y) {
     if (!s || !q || !y) return fail(PHW_EINVAL, "NULL argument");
-    if (s->ho) return fail(PHW_ESTATE, "kernel-level entry points are for the matrix-free (P1/RT1) solver");
     CU(cudaSetDevice(s->device));
     int rc = import_vec(s, q, s->io_e2, s->ne, s->d_e_new2old, s->io_e); if (rc) return rc;
-    rc = op_vertex_store(s, nullptr, s->io_e2, 0.0, 1.0, 0.0, s->io_v2); if (rc) return rc;
+    if (s->ho) { csr_store(s, s->hDT, s->io_e2, 1.0, s->io_v2); CU(cudaGetLastError()); }
+    else { rc = op_vertex_store(s, nullptr, s->io_e2, 0.0, 1.0, 0.0, s->io_v2); if (rc) return rc; }
     return export_vec(s, s->io_v2, y, s->nv, s->d_v_new2old, s->io_v);
 }
 int phw_mass_matvec(phw_solver_t s, int32_t which, const double* x, double* y) {
     if (!s || !x || !y) return fail(PHW_EINVAL, "NULL argument");
-    if (s->ho) return fail(PHW_ESTATE, "kernel-level entry points are for the matrix-free (P1/RT1) solver");
     CU(cudaSetDevice(s->device));
     int rc;
     if (which == PHW_P) {
         rc = import_vec(s, x, s->io_v2, s->nv, s->d_v_new2old, s->io_v); if (rc) return rc;
-        rc = op_vertex_store(s, s->io_v2, nullptr, 1.0, 0.0, 0.0, s->tmp_p); if (rc) return rc;
+        if (s->ho) { csr_store(s, s->hMp, s->io_v2, 1.0, s->tmp_p); CU(cudaGetLastError()); }
+        else { rc = op_vertex_store(s, s->io_v2, nullptr, 1.0, 0.0, 0.0, s->tmp_p); if (rc) return rc; }
         return export_vec(s, s->tmp_p, y, s->nv, s->d_v_new2old, s->io_v);
     } else if (which == PHW_Q) {
         rc = import_vec(s, x, s->io_e2, s->ne, s->d_e_new2old, s->io_e); if (rc) return rc;
-        rc = op_edge_store(s, nullptr, s->io_e2, 1.0, 0.0, 0.0, s->tmp_q); if (rc) return rc;
+        if (s->ho) { csr_store(s, s->hMq, s->io_e2, 1.0, s->tmp_q); CU(cudaGetLastError()); }
+        else { rc = op_edge_store(s, nullptr, s->io_e2, 1.0, 0.0, 0.0, s->tmp_q); if (rc) return rc; }
         return export_vec(s, s->tmp_q, y, s->ne, s->d_e_new2old, s->io_e);
     }
     return fail(PHW_EINVAL, "which must be PHW_P or PHW_Q");
 }
 int phw_mass_solve(phw_solver_t s, int32_t which, const double* b, double* x, int32_t* iters) {
     if (!s || !b || !x) return fail(PHW_EINVAL, "NULL argument");
-    if (s->ho) return fail(PHW_ESTATE, "kernel-level entry points are for the matrix-free (P1/RT1) solver");
     if (which != PHW_P && which != PHW_Q) return fail(PHW_EINVAL, "which must be PHW_P or PHW_Q");
     CU(cudaSetDevice(s->device));
     const int n = which == PHW_P ? s->nv : s->ne;
