@@ -46,12 +46,18 @@ def wave_sweep_solve(tFinal, numSteps, nx, xLength, yLength, cases, domainShape=
         mesh = generate_mesh(domainShape, nx, xLength, yLength)
     B = len(cases)
     V, C, group = replicate_mesh(mesh[0], mesh[1], B)
-    if patch_cells is None and not solver_flags and not os.environ.get('PHW_NO_LOOP'):
+    auto = patch_cells is None and not solver_flags
+    if auto and os.environ.get('PHW_SWEEP_LOOP'):
         # one thread-block cluster per case, every case advanced through ALL its steps by its own cluster in one launch
-        # (csrc/kernels_loop.cuh): no barrier or reduction ever spans two cases, a case stays cache-resident while it runs
+        # (csrc/kernels_loop.cuh, solves resident in shared memory).  Measured slower than the default below on the 1024-case
+        # sweep (profiles/r2i_sweep_*: 2.35e9 against 3.15e9 dof-updates/s): the cases do not fit the caches together, so
+        # everything outside the solves streams from HBM at one CTA per SM.  Opt-in.
         pc = _lib.loop_patch_cells(len(mesh[1]))
         if pc:
             patch_cells, solver_flags = pc, _lib.FLAGS_LOOP
+    elif auto and len(mesh[1]) > 512:
+        # default: all cases side by side in the bulk-copy pipelined mass solves (flags bits 8, 9; patches of <= 1024 cells)
+        patch_cells, solver_flags = 1024, 256 | 512
     if patch_cells is None:
         patch_cells = max(64, min(2048, len(mesh[1])))
     m = Mesh(V, C, patch_cells=patch_cells, cell_group=group, n_groups=B)
@@ -67,7 +73,17 @@ def wave_sweep_solve(tFinal, numSteps, nx, xLength, yLength, cases, domainShape=
             setattr(prm, k, float(cases[0].get(k, DEFAULT_LUMPED[k])))
     prm.input_kind, prm.in_amp, prm.in_omega, prm.in_t_stop = _lib.IN_SINE_WINDOW, 5.0, 8 * np.pi, 0.25     # wave_2D.py:433
     prm.tol, prm.max_iter, prm.extrap_order, prm.flags = float(tol), 400, int(extrap_order), int(solver_flags)
-    solver = Solver(m, prm, device=device)
+    try:
+        solver = Solver(m, prm, device=device)
+    except _lib.PhwError as ex:
+        if not (auto and 'shared memory' in str(ex)):
+            raise
+        # the two stages of the pipelined solves do not fit for this mesh: lean kernels on 2048-cell patches
+        m.close()
+        m = Mesh(V, C, patch_cells=max(64, min(2048, len(mesh[1]))), cell_group=group, n_groups=B)
+        m.set_boundary(tag_boundary_edges(m, domainShape, xLength, yLength))
+        prm.flags = 0
+        solver = Solver(m, prm, device=device)
     K = np.array([c.get('K_wave', 1.0) for c in cases], dtype=np.float64)
     rho = np.array([c.get('rho', 1.0) for c in cases], dtype=np.float64)
     lum = np.array([[c.get(k, DEFAULT_LUMPED[k]) for k in LUMPED_KEYS] for c in cases], dtype=np.float64)

@@ -132,15 +132,24 @@ def test_whole_loop_kernel_matches_the_multi_launch_path():
         assert np.abs(a[0][:, 1:] - b[0][:, 1:]).max() < 1e-11 * np.abs(b[0][:, 1:]).max()
 
 
-def test_batched_sweep_runs_one_cluster_per_case():
-    """config 5 in small: every case is advanced by its own cluster inside one launch; each H_array equals what wave_2D_solve's
-    oracle gives for that case alone; a one-case sweep takes its physics from the case"""
+@pytest.mark.parametrize('loop', [True, False])
+def test_batched_sweep_runs_one_cluster_per_case(loop, monkeypatch):
+    """config 5 in small.  loop (PHW_SWEEP_LOOP=1): every case is advanced by its own cluster inside one launch; default: all
+    cases side by side in the pipelined mass solves.  Each H_array equals what wave_2D_solve's oracle gives for that case alone;
+    a one-case sweep takes its physics from the case"""
     from porthamiltonian_fem_b200.sweep import wave_sweep_solve, sweep_cases, LUMPED_KEYS, DEFAULT_LUMPED
+    if loop:
+        monkeypatch.setenv('PHW_SWEEP_LOOP', '1')
+    else:
+        monkeypatch.delenv('PHW_SWEEP_LOOP', raising=False)
     mesh = rectangle_structured(52, 13, 1.0, 0.25)             # 1352 cells -> 2 patches per case
     cases = sweep_cases(7)
     H, nc, solver = wave_sweep_solve(0.04, 40, 0, 1.0, 0.25, cases, mesh=mesh, return_solver=True)
     st = solver.stats()
-    assert st['kernel_paths'] & PATH_LOOP and st['kernel_launches'] == 1
+    if loop:
+        assert st['kernel_paths'] & PATH_LOOP and st['kernel_launches'] == 1
+    else:
+        assert st['kernel_paths'] & 12 == 12 and not st['kernel_paths'] & PATH_LOOP      # PHW_PATH_PIPE_P | PHW_PATH_PIPE_Q
     for i, c in enumerate(cases):
         lum = {k: c.get(k, DEFAULT_LUMPED[k]) for k in LUMPED_KEYS}
         Ho, _, _ = wave_2D_solve_oracle(0.04, 40, mesh, 1.0, 0.25, timeIntScheme='SV', interConnection='IC',
