@@ -420,6 +420,19 @@ def run_bench():
         for nt, occ in ((256, 8), (256, 4), (512, 4), (1024, 2), (128, 16), (256, 2)):
             ms, nb = solver.stream_probe(nt, occ, 10)
             sys.stderr.write('stream probe {} threads x {} CTAs/SM: {:.4f} ms per pass, {:.3f} GB, {:.0f} GB/s\n'.format(nt, occ, ms, nb / 1e9, nb / ms / 1e6))
+    if world > 1 and (int(os.environ.get('PHW_XCH_DEBUG', '0')) & 64):
+        # exchange timing of the last M_p / M_q solve (diagnostics): per iteration, in us, how long CTA 0 waited at the grid barrier,
+        # how late the last CTA arrived after CTA 0, the local reduction, and the wait for the other ranks' norms
+        ts = np.zeros((2, 32, 5), dtype=np.uint64)
+        _lib.check(_lib.load().phw_debug_xch_times(solver.handle, ts.ctypes.data))
+        for f, nm in ((0, 'M_p'), (1, 'M_q')):
+            t = ts[f].astype(np.float64)
+            ok = t[:, 3] > 0
+            t = t[ok][:12]
+            if len(t) > 2:
+                d = lambda a, b: ' '.join('%5.1f' % (1e-3 * x) for x in (t[:, a] - t[:, b]))
+                sys.stderr.write('rank %d %s us barrier-wait(CTA0): %s | last arrival after CTA0: %s | reduce: %s | peer wait: %s | iteration: %s\n' % (
+                    rank, nm, d(1, 0), d(4, 0), d(2, 1), d(3, 2), ' '.join('%5.1f' % (1e-3 * x) for x in np.diff(t[:, 0]))))
     if args.debug_residuals and rank == 0:
         for w, nm in ((0, 'M_p'), (1, 'M_q')):
             sys.stderr.write('residual history {}: {}\n'.format(nm, ' '.join('%.1e' % r_ for r_ in solver.residual_history(w))))

@@ -169,6 +169,10 @@ int phw_set_time(phw_solver_t s, double t);
  * `threads` per CTA and `ctas_per_sm` resident CTAs: the bandwidth the memory system delivers for this layout */
 int phw_stream_probe(phw_solver_t s, int32_t threads, int32_t ctas_per_sm, int32_t reps, double* ms_per_pass, double* bytes_per_pass);
 int phw_residual_history(phw_solver_t s, int32_t which, int32_t n, double* rel_residuals, int32_t* n_iterations);
+/* diagnostics of the inter-GPU exchange (PHW_XCH_DEBUG bit 6 set when the solver was created): globaltimer stamps [2 fields][32
+ * iterations][5] of the most recent pipelined M_p / M_q solve: CTA 0's sweep done, grid barrier passed, local norms reduced, norms of
+ * all ranks received, latest arrival of any CTA at the grid barrier (ns) */
+int phw_debug_xch_times(phw_solver_t s, uint64_t* stamps320);
 
 /* ---- multi-GPU (one process per GPU on one node).  The exchange arena of every rank (Chebyshev buffers +
  *      mailbox) is shared through CUDA IPC; halo values and residual norms then travel as peer-memory stores

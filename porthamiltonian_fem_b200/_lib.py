@@ -116,6 +116,7 @@ SIGNATURES = {
     'phw_stream_probe': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, c_f64p, c_f64p]),
     'phw_residual_history': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, c_f64p, c_i32p]),
     'phw_set_H_init': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double]),
+    'phw_debug_xch_times': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     'phw_port_flux': (ctypes.c_int, [ctypes.c_void_p, c_f64p]),
 }
 

@@ -91,7 +91,20 @@ struct Ctl {
     unsigned int counters[8];
     unsigned int gbar[4];            // arrival counter of grid_barrier (zeroed by the host before each cooperative launch)
     double reshist[3][48];           // ||r_k||^2 / ||b||^2 of the first 48 iterations of the most recent solve (diagnostics)
+    // PHW_XCH_DEBUG bit 6 (measurement only): globaltimer stamps of the first 32 iterations of the most recent pipelined M_p / M_q
+    // solve of a partitioned run, taken by CTA 0: [0] its sweep is done, [1] grid barrier passed, [2] local norms reduced,
+    // [3] norms of all ranks received; [4] = latest arrival of any CTA at the grid barrier (atomicMax)
+    unsigned long long xts[2][32][5];
 };
+#ifdef PHW_HOST_EMU
+__device__ __forceinline__ unsigned long long phw_globaltimer() { return 0ull; }
+#else
+__device__ __forceinline__ unsigned long long phw_globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#endif
 
 struct DevMesh {
     int npatch, nv, ne;

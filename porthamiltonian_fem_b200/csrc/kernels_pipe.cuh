@@ -386,11 +386,20 @@ __global__ void __launch_bounds__(NT, 1) solve_mq_pipe_k(const __grid_constant__
         if (MULTI && !(pc.xch_dbg & 32)) pushed |= peer_push_patch<NT>(pc, 1, snd_b, snd_e, xnew, nxt);      // the CTA's last patch
         block_sum2(r0, b0, red);
         double* part = a.partials + (size_t)(k & 1) * 2 * gridDim.x;
+        const bool stamp = MULTI && (pc.xch_dbg & 64) && k < 32 && threadIdx.x == 0;
         if (threadIdx.x == 0) {
             if (MULTI && pushed) __threadfence_system();    // one fence for everything this CTA pushed (ordered before it by the barriers above)
             part[2 * blockIdx.x] = r0; part[2 * blockIdx.x + 1] = b0;
+            if (stamp) {
+                const unsigned long long t_ = phw_globaltimer();
+#ifndef PHW_HOST_EMU
+                atomicMax(&a.ctl->xts[1][k][4], t_);
+#endif
+                if (blockIdx.x == 0) a.ctl->xts[1][k][0] = t_;
+            }
         }
         grid_barrier_px(&a.ctl->gbar[0], epoch);
+        if (stamp && blockIdx.x == 0) a.ctl->xts[1][k][1] = phw_globaltimer();
         if (threadIdx.x < 32) {
             double s0 = 0.0, s1 = 0.0;
             for (int i = threadIdx.x; i < (int)gridDim.x; i += 32) { s0 += __ldcg(&part[2 * i]); s1 += __ldcg(&part[2 * i + 1]); }
@@ -400,10 +409,12 @@ __global__ void __launch_bounds__(NT, 1) solve_mq_pipe_k(const __grid_constant__
         __syncthreads();
         rr = bc[0]; bb = bc[1];
         __syncthreads();
+        if (stamp && blockIdx.x == 0) a.ctl->xts[1][k][2] = phw_globaltimer();
         if (MULTI) {
             if (pc.xch_dbg & 32) { peer_exchange_iter<NT>(pc, a.ctl, epoch, false, xnew, nxt, k, rr, bb); }
             else peer_finish_iter<NT>(pc, a.ctl, xseq0 + (unsigned long long)k + 1ull, bc, rr, bb);
             fence_proxy_async();
+            if (stamp && blockIdx.x == 0) a.ctl->xts[1][k][3] = phw_globaltimer();
         }
         conv = rr <= a.tol2 * bb;
         if (blockIdx.x == 0 && threadIdx.x == 0 && k < 48) a.ctl->reshist[a.which][k] = (bb > 0.0) ? rr / bb : 0.0;
@@ -579,11 +590,20 @@ __global__ void __launch_bounds__(NT, MINB) solve_ell_pipe_k(const __grid_consta
         if (MULTI && !(pc.xch_dbg & 32)) pushed |= peer_push_patch<NT>(pc, 0, snd_b, snd_e, xnew, nxt);      // the CTA's last patch
         block_sum2(r0, b0, red);
         double* part = a.partials + (size_t)(k & 1) * 2 * gridDim.x;
+        const bool stamp = MULTI && (pc.xch_dbg & 64) && k < 32 && threadIdx.x == 0;
         if (threadIdx.x == 0) {
             if (MULTI && pushed) __threadfence_system();    // one fence for everything this CTA pushed (ordered before it by the barriers above)
             part[2 * blockIdx.x] = r0; part[2 * blockIdx.x + 1] = b0;
+            if (stamp) {
+                const unsigned long long t_ = phw_globaltimer();
+#ifndef PHW_HOST_EMU
+                atomicMax(&a.ctl->xts[0][k][4], t_);
+#endif
+                if (blockIdx.x == 0) a.ctl->xts[0][k][0] = t_;
+            }
         }
         grid_barrier_px(&a.ctl->gbar[0], epoch);
+        if (stamp && blockIdx.x == 0) a.ctl->xts[0][k][1] = phw_globaltimer();
         if (threadIdx.x < 32) {
             double s0 = 0.0, s1 = 0.0;
             for (int i = threadIdx.x; i < (int)gridDim.x; i += 32) { s0 += __ldcg(&part[2 * i]); s1 += __ldcg(&part[2 * i + 1]); }
@@ -593,10 +613,12 @@ __global__ void __launch_bounds__(NT, MINB) solve_ell_pipe_k(const __grid_consta
         __syncthreads();
         rr = bc[0]; bb = bc[1];
         __syncthreads();
+        if (stamp && blockIdx.x == 0) a.ctl->xts[0][k][2] = phw_globaltimer();
         if (MULTI) {
             if (pc.xch_dbg & 32) { peer_exchange_iter<NT>(pc, a.ctl, epoch, true, xnew, nxt, k, rr, bb); }
             else peer_finish_iter<NT>(pc, a.ctl, xseq0 + (unsigned long long)k + 1ull, bc, rr, bb);
             fence_proxy_async();
+            if (stamp && blockIdx.x == 0) a.ctl->xts[0][k][3] = phw_globaltimer();
         }
         conv = rr <= a.tol2 * bb;
         if (blockIdx.x == 0 && threadIdx.x == 0 && k < 48) a.ctl->reshist[a.which][k] = (bb > 0.0) ? rr / bb : 0.0;

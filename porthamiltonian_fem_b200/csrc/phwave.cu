@@ -2446,6 +2446,13 @@ int phw_set_snapshots(phw_solver_t s, int64_t every, double* snaps, int64_t capa
     return PHW_OK;
 }
 
+int phw_debug_xch_times(phw_solver_t s, uint64_t* out320) {
+    if (!s || !out320) return fail(PHW_EINVAL, "NULL argument");
+    CU(cudaSetDevice(s->device));
+    CU(cudaMemcpy(out320, &s->ctl->xts[0][0][0], sizeof(unsigned long long) * 2 * 32 * 5, cudaMemcpyDeviceToHost));
+    return PHW_OK;
+}
+
 int phw_get_stats(phw_solver_t s, phw_stats* out) {
     if (!s || !out) return fail(PHW_EINVAL, "NULL argument");
     s->stats.lam_min_q = s->lam_min_q; s->stats.lam_max_q = s->lam_max_q; s->stats.skew_bound = s->skew_bound;
