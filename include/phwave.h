@@ -89,7 +89,8 @@ typedef struct phw_stats {
     double  ms_solve_p, ms_solve_q, ms_solve_block;   /* summed CUDA-event time of the solve kernels (flags bit2) */
     int64_t kernel_paths;       /* phw_path bits: which variants of the mass-solve kernels the last phw_run launched */
 } phw_stats;
-enum phw_path { PHW_PATH_LEAN_P = 1, PHW_PATH_LEAN_Q = 2, PHW_PATH_PIPE_P = 4, PHW_PATH_PIPE_Q = 8, PHW_PATH_PIPE_ENERGY = 16, PHW_PATH_PIPE_RHS = 32, PHW_PATH_LOOP = 256, PHW_PATH_LOOP_RES = 512 /* ... with the mass solves resident in shared memory */ };
+enum phw_path { PHW_PATH_LEAN_P = 1, PHW_PATH_LEAN_Q = 2, PHW_PATH_PIPE_P = 4, PHW_PATH_PIPE_Q = 8, PHW_PATH_PIPE_ENERGY = 16, PHW_PATH_PIPE_RHS = 32, PHW_PATH_LOOP = 256, PHW_PATH_LOOP_RES = 512 /* ... with the mass solves resident in shared memory */,
+                PHW_PATH_HO_MF = 1024 /* matrix-free higher-order kernels (phw_ho_create_mf) */ };
 
 const char* phw_last_error(void);
 int phw_version(void);
@@ -220,6 +221,20 @@ int phw_ho_create(const phw_params* prm, int32_t device, void* cuda_stream, int6
                   const int32_t* DT_indptr, const int32_t* DT_idx, const double* DT_val,
                   const double* b_L, double lam_min_p, double lam_max_p, double lam_min_q, double lam_max_q,
                   phw_solver_t* out);
+/* The same pairs MATRIX-FREE (csrc/kernels_ho.cuh; host side porthamiltonian_fem_b200/fem_ref.py): cells with ascending vertex ids
+ * mapped from one reference triangle, so that M_p,K = |det J| Mp_hat, C_K = sign(det J) C_hat and M_q,K = G00 A00 + G01 (A01 + A10) +
+ * G11 A11 with G = J^T J / |det J|.  cell_vertices / cell_edges [n_cells][3] (edge i opposite local vertex i; edge ids = the
+ * canonical (lo, hi) numbering), geom4 [n_cells][4] = (det J, G00, G01, G11), reference matrices row-major (Mp_hat [ndp x ndp], C_hat
+ * [ndq x ndp], A00 / A01 + A10 / A11 [ndq x ndq]).  Dofs: P_k [vertices | k-1 per edge along lo -> hi | per cell], RT_k [k moments per
+ * edge | k(k-1) per cell] - derived on the device from the ids, nothing is assembled.  The boundary operator N (zero-flux sides,
+ * wave_2D.py:465-472) and its transpose come as compact CSR over the rows they touch (row ids, indptr, idx, val); b_L [n_q] as above. */
+int phw_ho_create_mf(const phw_params* prm, int32_t device, void* cuda_stream, int32_t k_p, int32_t k_q,
+                     int64_t n_vertices, int64_t n_edges, int64_t n_cells,
+                     const int32_t* cell_vertices, const int32_t* cell_edges, const double* geom4,
+                     const double* Mp_hat, const double* C_hat, const double* A00, const double* A01s, const double* A11,
+                     int64_t nN_rows, const int32_t* N_row, const int32_t* N_indptr, const int32_t* N_idx, const double* N_val,
+                     int64_t nNT_rows, const int32_t* NT_row, const int32_t* NT_indptr, const int32_t* NT_idx, const double* NT_val,
+                     const double* b_L, double lam_min_p, double lam_max_p, double lam_min_q, double lam_max_q, phw_solver_t* out);
 /* analytical diagnostics of a higher-order run (wave_2D.py:929-965): cell_dofs [n_cells x ndp], tabulation T [nn x ndp]
  * of the P_k basis at the P_{k+3} nodes, reference mass matrix [nn x nn], exact spatial factor at those nodes
  * [n_cells x nn] and at the P_k dofs [n_p], cell areas, point probe as (dof, weight) pairs */

@@ -500,6 +500,7 @@ __global__ void scalar_k(Ctl* ctl, const ScalarPrm* __restrict__ prms, int n_gro
 }  // namespace phw
 
 #include "kernels_loop.cuh"
+#include "kernels_ho.cuh"
 
 
 // ================================================================================================
@@ -542,6 +543,7 @@ struct phw_solver_s {
     int extrap = 2, n_sites = 1;
     int extrap_f[2] = {2, 2};  // extrapolation order of the p / q solves
     bool ho = false; Csr hMp{}, hMq{}, hD{}, hDT{};
+    bool ho_mf = false; HoMf hm{}; RowCsr hN{}, hNT{}; double *ho_yacc_p = nullptr, *ho_yacc_q = nullptr;   // matrix-free higher-order pairs (kernels_ho.cuh)
     int ho_nc = 0, ho_ndp = 0, ho_nn = 0, ho_nprobe = 0; double ho_omega = 0.0;
     int *ho_cell_dofs = nullptr, *ho_probe_dofs = nullptr;
     double *ho_T = nullptr, *ho_mass = nullptr, *ho_exact_nodes = nullptr, *ho_area = nullptr, *ho_exact_dofs = nullptr, *ho_probe_w = nullptr;
@@ -645,6 +647,71 @@ void csr_dot(phw_solver_s* s, const Csr& A, const double* x, double scale, int s
         case 16: csr_dot_k<16><<<g, 256, 0, s->stream>>>(A, x, scale, s->ctl, slot, part, counter); break;
         default: csr_dot_k<32><<<g, 256, 0, s->stream>>>(A, x, scale, s->ctl, slot, part, counter);
     }
+}
+
+// ---- matrix-free higher-order operators (kernels_ho.cuh): cell loops with the reference tabulations in shared memory
+inline size_t ho_smem(const HoMf& m) { return (size_t)(((m.ref_len + 1) & ~1) + HO_MAXD * HO_NT) * sizeof(double); }
+inline int ho_grid(phw_solver_s* s) { return std::max(1, std::min(nblk(s->hm.nc, HO_NT), s->sm_count * 8)); }
+// y (+)= alpha A x, A = M_p, M_q, C or C^T
+int ho_mf_apply(phw_solver_s* s, int op, const double* x, double* y, double alpha, bool zero_first) {
+    const HoMf& m = s->hm;
+    const int n_out = (op == HO_MP || op == HO_CT) ? m.n_p : m.n_q;
+    if (zero_first) CU(cudaMemsetAsync(y, 0, (size_t)n_out * sizeof(double), s->stream));
+    const int g = ho_grid(s); const size_t sm = ho_smem(m);
+    switch (op) {
+        case HO_MP: ho_apply_k<HO_MP><<<g, HO_NT, sm, s->stream>>>(m, x, y, alpha); break;
+        case HO_MQ: ho_apply_k<HO_MQ><<<g, HO_NT, sm, s->stream>>>(m, x, y, alpha); break;
+        case HO_C: ho_apply_k<HO_C><<<g, HO_NT, sm, s->stream>>>(m, x, y, alpha); break;
+        default: ho_apply_k<HO_CT><<<g, HO_NT, sm, s->stream>>>(m, x, y, alpha);
+    }
+    s->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+int ho_row_csr(phw_solver_s* s, const RowCsr& A, const double* x, double alpha, double* y) {
+    if (A.n_rows == 0) return 0;
+    row_csr_axpy_k<<<nblk(A.n_rows), 256, 0, s->stream>>>(A, x, alpha, y);
+    s->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+// y = alpha D x = alpha (C - N) x   /   y = alpha D^T x
+int ho_mf_D(phw_solver_s* s, const double* p, double alpha, double* y) {
+    int rc = ho_mf_apply(s, HO_C, p, y, alpha, true); if (rc) return rc;
+    return ho_row_csr(s, s->hN, p, -alpha, y);
+}
+int ho_mf_DT(phw_solver_s* s, const double* q, double alpha, double* y) {
+    int rc = ho_mf_apply(s, HO_CT, q, y, alpha, true); if (rc) return rc;
+    return ho_row_csr(s, s->hNT, q, -alpha, y);
+}
+int ho_mf_quad(phw_solver_s* s, int op, const double* x, double scale, int slot, int counter) {
+    const int g = ho_grid(s);
+    double* part = s->partials + 8192 + 2048 * (size_t)slot;
+    if (op == HO_MP) ho_quad_k<HO_MP><<<g, HO_NT, ho_smem(s->hm), s->stream>>>(s->hm, x, scale, s->ctl, slot, part, counter);
+    else ho_quad_k<HO_MQ><<<g, HO_NT, ho_smem(s->hm), s->stream>>>(s->hm, x, scale, s->ctl, slot, part, counter);
+    s->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+int ho_mf_solve(phw_solver_s* s, int which) {
+    HoSolveArgs a{};
+    a.m = s->hm; a.tb = which == PHW_P ? s->tp : s->tq;
+    a.b = which == PHW_P ? s->bp : s->bq; a.pinv = which == PHW_P ? s->pinv_p : s->pinv_q;
+    a.yacc = which == PHW_P ? s->ho_yacc_p : s->ho_yacc_q;
+    a.cheb_d = s->cheb_d[which]; a.cheb_c = s->cheb_c[which]; a.tol2 = s->prm.tol * s->prm.tol;
+    a.max_iter = s->prm.max_iter; a.which = which; a.n = which == PHW_P ? s->hm.n_p : s->hm.n_q;
+    a.partials = s->partials; a.ctl = s->ctl;
+    CU(cudaMemsetAsync(&s->ctl->gbar[0], 0, sizeof(unsigned int), s->stream));
+    int occ = 0;
+    const size_t sm = ho_smem(s->hm);
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (void*)ho_solve_k, HO_NT, sm));
+    if (occ < 1) return fail(PHW_ECUDA, "ho_solve_k does not fit on an SM");
+    const int grid = std::max(1, std::min(nblk(std::max(s->hm.nc, a.n), HO_NT), std::min(occ, 8) * s->sm_count));
+    void* args[] = {(void*)&a};
+    CU(cudaLaunchCooperativeKernel((void*)ho_solve_k, dim3(grid), dim3(HO_NT), args, sm, s->stream));
+    s->launches++;
+    s->kernel_paths |= PHW_PATH_HO_MF;
+    return 0;
 }
 
 // partitioned runs: which pipelined kernels (when selected by phw_params.flags) run with the inter-GPU exchange.  A/B and fallback
@@ -951,6 +1018,7 @@ int solve_begin(phw_solver_s* s, int which) {
 // Chebyshev solve of M_p x = bp (which = 0) or M_q x = bq (which = 1); warm start = tribuf[cur]
 int solve_mass(phw_solver_s* s, int which, int n_launch) {
     int rc;
+    if (s->ho_mf) return ho_mf_solve(s, which);
     if (s->ho) {
         CsrSolveArgs a{};
         a.A = which == PHW_P ? s->hMp : s->hMq; a.tb = which == PHW_P ? s->tp : s->tq;
@@ -1087,6 +1155,7 @@ int waxpy(phw_solver_s* s, int n, double* w, const double* y, double a, const do
 // b_p = -K (D^T qsrc [+ B_top psrc])          (explicit part of the p rows, velocity form)
 int rhs_p(phw_solver_s* s, const double* qsrc, const double* psrc) {
     const double K = s->prm.K_wave;
+    if (s->ho_mf) return ho_mf_DT(s, qsrc, -K, s->bp);
     if (s->ho) {
         csr_store(s, s->hDT, qsrc, -K, s->bp);
         s->launches++;
@@ -1100,7 +1169,9 @@ int rhs_p(phw_solver_s* s, const double* qsrc, const double* psrc) {
 int rhs_q(phw_solver_s* s, const double* psrc, const double* qsrc) {
     const double ir = (s->G > 1) ? 1.0 : 1.0 / s->prm.rho;
     int rc = 0;
-    if (s->ho) {
+    if (s->ho_mf) {
+        rc = ho_mf_D(s, psrc, ir, s->bq);
+    } else if (s->ho) {
         csr_store(s, s->hD, psrc, ir, s->bq);
         s->launches++;
         CU(cudaGetLastError());
@@ -1119,9 +1190,14 @@ int rhs_q(phw_solver_s* s, const double* psrc, const double* qsrc) {
 }
 int energy(phw_solver_s* s) {
     if (s->ho) {
-        csr_dot(s, s->hMp, s->p, 0.5 / s->prm.rho, 0, 6);
-        csr_dot(s, s->hMq, s->q, 0.5 * s->prm.K_wave, 1, 7);
-        s->launches += 2;
+        if (s->ho_mf) {
+            int rc_ = ho_mf_quad(s, HO_MP, s->p, 0.5 / s->prm.rho, 0, 6); if (rc_) return rc_;
+            rc_ = ho_mf_quad(s, HO_MQ, s->q, 0.5 * s->prm.K_wave, 1, 7); if (rc_) return rc_;
+        } else {
+            csr_dot(s, s->hMp, s->p, 0.5 / s->prm.rho, 0, 6);
+            csr_dot(s, s->hMq, s->q, 0.5 * s->prm.K_wave, 1, 7);
+            s->launches += 2;
+        }
         if (s->prm.analytical && s->an_ready && s->in_step) {
             const int nb = 2 * s->sm_count;
             diag_cells_ho_k<<<nb, 128, 0, s->stream>>>(s->ho_nc, s->ho_ndp, s->ho_nn, s->ho_cell_dofs, s->ho_T, s->ho_mass, s->ho_exact_nodes,
@@ -2466,7 +2542,8 @@ int phw_apply_D(phw_solver_t s, const double* p, double* y) {
     if (!s || !p || !y) return fail(PHW_EINVAL, "NULL argument");
     CU(cudaSetDevice(s->device));
     int rc = import_vec(s, p, s->io_v2, s->nv, s->d_v_new2old, s->io_v); if (rc) return rc;
-    if (s->ho) { csr_store(s, s->hD, s->io_v2, 1.0, s->io_e2); CU(cudaGetLastError()); }
+    if (s->ho_mf) { rc = ho_mf_D(s, s->io_v2, 1.0, s->io_e2); if (rc) return rc; }
+    else if (s->ho) { csr_store(s, s->hD, s->io_v2, 1.0, s->io_e2); CU(cudaGetLastError()); }
     else { rc = op_edge_store(s, s->io_v2, nullptr, 0.0, 1.0, 0.0, s->io_e2); if (rc) return rc; }
     return export_vec(s, s->io_e2, y, s->ne, s->d_e_new2old, s->io_e);
 }
@@ -2474,7 +2551,8 @@ int phw_apply_DT(phw_solver_t s, const double* q, double* y) {
     if (!s || !q || !y) return fail(PHW_EINVAL, "NULL argument");
     CU(cudaSetDevice(s->device));
     int rc = import_vec(s, q, s->io_e2, s->ne, s->d_e_new2old, s->io_e); if (rc) return rc;
-    if (s->ho) { csr_store(s, s->hDT, s->io_e2, 1.0, s->io_v2); CU(cudaGetLastError()); }
+    if (s->ho_mf) { rc = ho_mf_DT(s, s->io_e2, 1.0, s->io_v2); if (rc) return rc; }
+    else if (s->ho) { csr_store(s, s->hDT, s->io_e2, 1.0, s->io_v2); CU(cudaGetLastError()); }
     else { rc = op_vertex_store(s, nullptr, s->io_e2, 0.0, 1.0, 0.0, s->io_v2); if (rc) return rc; }
     return export_vec(s, s->io_v2, y, s->nv, s->d_v_new2old, s->io_v);
 }
@@ -2484,12 +2562,14 @@ int phw_mass_matvec(phw_solver_t s, int32_t which, const double* x, double* y) {
     int rc;
     if (which == PHW_P) {
         rc = import_vec(s, x, s->io_v2, s->nv, s->d_v_new2old, s->io_v); if (rc) return rc;
-        if (s->ho) { csr_store(s, s->hMp, s->io_v2, 1.0, s->tmp_p); CU(cudaGetLastError()); }
+        if (s->ho_mf) { rc = ho_mf_apply(s, HO_MP, s->io_v2, s->tmp_p, 1.0, true); if (rc) return rc; }
+        else if (s->ho) { csr_store(s, s->hMp, s->io_v2, 1.0, s->tmp_p); CU(cudaGetLastError()); }
         else { rc = op_vertex_store(s, s->io_v2, nullptr, 1.0, 0.0, 0.0, s->tmp_p); if (rc) return rc; }
         return export_vec(s, s->tmp_p, y, s->nv, s->d_v_new2old, s->io_v);
     } else if (which == PHW_Q) {
         rc = import_vec(s, x, s->io_e2, s->ne, s->d_e_new2old, s->io_e); if (rc) return rc;
-        if (s->ho) { csr_store(s, s->hMq, s->io_e2, 1.0, s->tmp_q); CU(cudaGetLastError()); }
+        if (s->ho_mf) { rc = ho_mf_apply(s, HO_MQ, s->io_e2, s->tmp_q, 1.0, true); if (rc) return rc; }
+        else if (s->ho) { csr_store(s, s->hMq, s->io_e2, 1.0, s->tmp_q); CU(cudaGetLastError()); }
         else { rc = op_edge_store(s, nullptr, s->io_e2, 1.0, 0.0, 0.0, s->tmp_q); if (rc) return rc; }
         return export_vec(s, s->tmp_q, y, s->ne, s->d_e_new2old, s->io_e);
     }
@@ -2581,13 +2661,10 @@ static int upload_csr(phw_solver_s* s, int64_t n_rows, const int32_t* indptr, co
     return 0;
 }
 
-int phw_ho_create(const phw_params* prm, int32_t device, void* cuda_stream, int64_t n_p, int64_t n_q,
-                  const int32_t* Mp_indptr, const int32_t* Mp_idx, const double* Mp_val,
-                  const int32_t* Mq_indptr, const int32_t* Mq_idx, const double* Mq_val,
-                  const int32_t* D_indptr, const int32_t* D_idx, const double* D_val,
-                  const int32_t* DT_indptr, const int32_t* DT_idx, const double* DT_val,
-                  const double* b_L, double lam_min_p, double lam_max_p, double lam_min_q, double lam_max_q,
-                  phw_solver_t* out) {
+// common part of the two higher-order constructors: vectors, control block, identity numbering, port list = non-zeros of b_L,
+// Chebyshev intervals.  The caller uploads its operators and fills pinv_p / pinv_q afterwards.
+static int ho_create_base(const phw_params* prm, int32_t device, void* cuda_stream, int64_t n_p, int64_t n_q, const double* b_L,
+                          double lam_min_p, double lam_max_p, double lam_min_q, double lam_max_q, phw_solver_s** out) {
     if (!prm || !out || !b_L) return fail(PHW_EINVAL, "NULL argument");
     if (prm->scheme < 0 || prm->scheme > 5) return fail(PHW_EINVAL, "unknown scheme");
     if (prm->scheme == PHW_IE || prm->scheme == PHW_SM || prm->strong || prm->casimir)
@@ -2614,16 +2691,7 @@ int phw_ho_create(const phw_params* prm, int32_t device, void* cuda_stream, int6
     int rc = setup_vectors(s); if (rc) return bail(rc);
     if (!s->coop) return bail(fail(PHW_ECUDA, "cooperative launch is required"));
     rc = setup_scalars(s); if (rc) return bail(rc);
-    rc = upload_csr(s, n_p, Mp_indptr, Mp_idx, Mp_val, &s->hMp); if (rc) return bail(rc);
-    rc = upload_csr(s, n_q, Mq_indptr, Mq_idx, Mq_val, &s->hMq); if (rc) return bail(rc);
-    rc = upload_csr(s, n_q, D_indptr, D_idx, D_val, &s->hD); if (rc) return bail(rc);
-    rc = upload_csr(s, n_p, DT_indptr, DT_idx, DT_val, &s->hDT); if (rc) return bail(rc);
-    {   // Jacobi weights from the CSR diagonals, identity numbering, port list = non-zeros of b_L
-        std::vector<double> pp(n_p, 0.0), pq(n_q, 0.0);
-        for (int64_t r = 0; r < n_p; ++r) for (int j = Mp_indptr[r]; j < Mp_indptr[r + 1]; ++j) if (Mp_idx[j] == r) pp[r] = 1.0 / Mp_val[j];
-        for (int64_t r = 0; r < n_q; ++r) for (int j = Mq_indptr[r]; j < Mq_indptr[r + 1]; ++j) if (Mq_idx[j] == r) pq[r] = 1.0 / Mq_val[j];
-        if (cudaMemcpyAsync(s->pinv_p, pp.data(), n_p * 8, cudaMemcpyHostToDevice, s->stream) != cudaSuccess ||
-            cudaMemcpyAsync(s->pinv_q, pq.data(), n_q * 8, cudaMemcpyHostToDevice, s->stream) != cudaSuccess) return bail(fail(PHW_ECUDA, "memcpy failed"));
+    {
         std::vector<int32_t> idv(n_p), ide(n_q), pe, pg, goff(2, 0), gpoff(2, 0);
         std::iota(idv.begin(), idv.end(), 0); std::iota(ide.begin(), ide.end(), 0);
         std::vector<double> bl;
@@ -2637,12 +2705,103 @@ int phw_ho_create(const phw_params* prm, int32_t device, void* cuda_stream, int6
         rc = s->upload(&s->d_port_goff, goff); if (rc) return bail(rc);
         rc = s->upload(&s->d_port_group, pg); if (rc) return bail(rc);
         rc = s->upload(&s->d_gpoff, gpoff); if (rc) return bail(rc);
-        if (cudaStreamSynchronize(s->stream) != cudaSuccess) return bail(fail(PHW_ECUDA, "sync failed"));
     }
     s->cheb_d[0] = 0.5 * (lam_min_p + lam_max_p); s->cheb_c[0] = 0.5 * (lam_max_p - lam_min_p);
     s->cheb_d[1] = 0.5 * (lam_min_q + lam_max_q); s->cheb_c[1] = 0.5 * (lam_max_q - lam_min_q);
     s->lam_min_q = lam_min_q; s->lam_max_q = lam_max_q;
     s->launches = 0;
+    *out = s;
+    return PHW_OK;
+}
+
+int phw_ho_create(const phw_params* prm, int32_t device, void* cuda_stream, int64_t n_p, int64_t n_q,
+                  const int32_t* Mp_indptr, const int32_t* Mp_idx, const double* Mp_val,
+                  const int32_t* Mq_indptr, const int32_t* Mq_idx, const double* Mq_val,
+                  const int32_t* D_indptr, const int32_t* D_idx, const double* D_val,
+                  const int32_t* DT_indptr, const int32_t* DT_idx, const double* DT_val,
+                  const double* b_L, double lam_min_p, double lam_max_p, double lam_min_q, double lam_max_q,
+                  phw_solver_t* out) {
+    phw_solver_s* s = nullptr;
+    int rc = ho_create_base(prm, device, cuda_stream, n_p, n_q, b_L, lam_min_p, lam_max_p, lam_min_q, lam_max_q, &s);
+    if (rc) return rc;
+    auto bail = [&](int rc_) { std::string keep = g_err; phw_solver_destroy(s); g_err = keep; return rc_; };
+    rc = upload_csr(s, n_p, Mp_indptr, Mp_idx, Mp_val, &s->hMp); if (rc) return bail(rc);
+    rc = upload_csr(s, n_q, Mq_indptr, Mq_idx, Mq_val, &s->hMq); if (rc) return bail(rc);
+    rc = upload_csr(s, n_q, D_indptr, D_idx, D_val, &s->hD); if (rc) return bail(rc);
+    rc = upload_csr(s, n_p, DT_indptr, DT_idx, DT_val, &s->hDT); if (rc) return bail(rc);
+    {   // Jacobi weights from the CSR diagonals
+        std::vector<double> pp(n_p, 0.0), pq(n_q, 0.0);
+        for (int64_t r = 0; r < n_p; ++r) for (int j = Mp_indptr[r]; j < Mp_indptr[r + 1]; ++j) if (Mp_idx[j] == r) pp[r] = 1.0 / Mp_val[j];
+        for (int64_t r = 0; r < n_q; ++r) for (int j = Mq_indptr[r]; j < Mq_indptr[r + 1]; ++j) if (Mq_idx[j] == r) pq[r] = 1.0 / Mq_val[j];
+        if (cudaMemcpyAsync(s->pinv_p, pp.data(), n_p * 8, cudaMemcpyHostToDevice, s->stream) != cudaSuccess ||
+            cudaMemcpyAsync(s->pinv_q, pq.data(), n_q * 8, cudaMemcpyHostToDevice, s->stream) != cudaSuccess) return bail(fail(PHW_ECUDA, "memcpy failed"));
+        if (cudaStreamSynchronize(s->stream) != cudaSuccess) return bail(fail(PHW_ECUDA, "sync failed"));
+    }
+    *out = s;
+    return PHW_OK;
+}
+
+int phw_ho_create_mf(const phw_params* prm, int32_t device, void* cuda_stream, int32_t k_p, int32_t k_q,
+                     int64_t n_vertices, int64_t n_edges, int64_t n_cells,
+                     const int32_t* cell_vertices, const int32_t* cell_edges, const double* geom4,
+                     const double* Mp_hat, const double* C_hat, const double* A00, const double* A01s, const double* A11,
+                     int64_t nN_rows, const int32_t* N_row, const int32_t* N_indptr, const int32_t* N_idx, const double* N_val,
+                     int64_t nNT_rows, const int32_t* NT_row, const int32_t* NT_indptr, const int32_t* NT_idx, const double* NT_val,
+                     const double* b_L, double lam_min_p, double lam_max_p, double lam_min_q, double lam_max_q, phw_solver_t* out) {
+    if (!cell_vertices || !cell_edges || !geom4 || !Mp_hat || !C_hat || !A00 || !A01s || !A11) return fail(PHW_EINVAL, "NULL argument");
+    if (k_p < 1 || k_p > 3 || k_q < 1 || k_q > 3) return fail(PHW_EINVAL, "basis orders 1..3 are supported");
+    if (nN_rows < 0 || nNT_rows < 0 || (nN_rows && (!N_row || !N_indptr || !N_idx || !N_val)) || (nNT_rows && (!NT_row || !NT_indptr || !NT_idx || !NT_val)))
+        return fail(PHW_EINVAL, "bad boundary operator");
+    const int ndp = (k_p + 1) * (k_p + 2) / 2, ndq = k_q * (k_q + 2);
+    const int64_t n_p = n_vertices + n_edges * (k_p - 1) + n_cells * ((k_p - 1) * (k_p - 2) / 2);
+    const int64_t n_q = n_edges * k_q + n_cells * (int64_t)(k_q * (k_q - 1));
+    phw_solver_s* s = nullptr;
+    int rc = ho_create_base(prm, device, cuda_stream, n_p, n_q, b_L, lam_min_p, lam_max_p, lam_min_q, lam_max_q, &s);
+    if (rc) return rc;
+    auto bail = [&](int rc_) { std::string keep = g_err; phw_solver_destroy(s); g_err = keep; return rc_; };
+    HoMf& m = s->hm;
+    m.nc = (int)n_cells; m.nv = (int)n_vertices; m.ne = (int)n_edges; m.kp = k_p; m.kq = k_q; m.ndp = ndp; m.ndq = ndq;
+    m.n_p = (int)n_p; m.n_q = (int)n_q;
+    std::vector<double> ref;
+    ref.insert(ref.end(), Mp_hat, Mp_hat + ndp * ndp);
+    m.off_C = (int)ref.size(); ref.insert(ref.end(), C_hat, C_hat + ndq * ndp);
+    m.off_A00 = (int)ref.size(); ref.insert(ref.end(), A00, A00 + ndq * ndq);
+    m.off_A01 = (int)ref.size(); ref.insert(ref.end(), A01s, A01s + ndq * ndq);
+    m.off_A11 = (int)ref.size(); ref.insert(ref.end(), A11, A11 + ndq * ndq);
+    m.ref_len = (int)ref.size();
+    {
+        int *d_cv = nullptr, *d_ce = nullptr; double *d_geom = nullptr, *d_ref = nullptr;
+        rc = s->upload(&d_cv, std::vector<int32_t>(cell_vertices, cell_vertices + 3 * n_cells)); if (rc) return bail(rc);
+        rc = s->upload(&d_ce, std::vector<int32_t>(cell_edges, cell_edges + 3 * n_cells)); if (rc) return bail(rc);
+        rc = s->upload(&d_geom, std::vector<double>(geom4, geom4 + 4 * n_cells)); if (rc) return bail(rc);
+        rc = s->upload(&d_ref, ref); if (rc) return bail(rc);
+        m.cv = d_cv; m.ce = d_ce; m.geom = d_geom; m.ref = d_ref;
+    }
+    auto up_rows = [&](int64_t nr, const int32_t* row, const int32_t* ip, const int32_t* ix, const double* va, RowCsr* A) -> int {
+        A->n_rows = (int)nr;
+        if (nr == 0) return 0;
+        int *d_row = nullptr, *d_ip = nullptr, *d_ix = nullptr; double* d_va = nullptr;
+        int r_ = s->upload(&d_row, std::vector<int32_t>(row, row + nr)); if (r_) return r_;
+        r_ = s->upload(&d_ip, std::vector<int32_t>(ip, ip + nr + 1)); if (r_) return r_;
+        r_ = s->upload(&d_ix, std::vector<int32_t>(ix, ix + ip[nr])); if (r_) return r_;
+        r_ = s->upload(&d_va, std::vector<double>(va, va + ip[nr])); if (r_) return r_;
+        A->row = d_row; A->indptr = d_ip; A->idx = d_ix; A->val = d_va;
+        return 0;
+    };
+    rc = up_rows(nN_rows, N_row, N_indptr, N_idx, N_val, &s->hN); if (rc) return bail(rc);
+    rc = up_rows(nNT_rows, NT_row, NT_indptr, NT_idx, NT_val, &s->hNT); if (rc) return bail(rc);
+    rc = s->dalloc(&s->ho_yacc_p, (size_t)n_p); if (rc) return bail(rc);
+    rc = s->dalloc(&s->ho_yacc_q, (size_t)n_q); if (rc) return bail(rc);
+    s->ho_mf = true;
+    // Jacobi weights: diagonals accumulated on the device from the reference diagonals and the cell geometry
+    if (cudaMemsetAsync(s->pinv_p, 0, n_p * 8, s->stream) != cudaSuccess || cudaMemsetAsync(s->pinv_q, 0, n_q * 8, s->stream) != cudaSuccess ||
+        cudaMemsetAsync(s->ho_yacc_p, 0, n_p * 8, s->stream) != cudaSuccess || cudaMemsetAsync(s->ho_yacc_q, 0, n_q * 8, s->stream) != cudaSuccess)
+        return bail(fail(PHW_ECUDA, "memset failed"));
+    ho_diag_k<HO_MP><<<ho_grid(s), HO_NT, ho_smem(m), s->stream>>>(m, s->pinv_p);
+    ho_diag_k<HO_MQ><<<ho_grid(s), HO_NT, ho_smem(m), s->stream>>>(m, s->pinv_q);
+    invert_k<<<nblk((int)n_p), 256, 0, s->stream>>>((int)n_p, s->pinv_p);
+    invert_k<<<nblk((int)n_q), 256, 0, s->stream>>>((int)n_q, s->pinv_q);
+    if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(s->stream) != cudaSuccess) return bail(fail(PHW_ECUDA, "matrix-free setup kernels failed"));
     *out = s;
     return PHW_OK;
 }

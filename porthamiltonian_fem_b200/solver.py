@@ -396,3 +396,48 @@ class HighOrderSolver(Solver):
                                           ctypes.byref(h)))
         self.handle = h
         self.ncol = 12 if params.analytical else 8
+
+
+class MatrixFreeHighOrderSolver(Solver):
+    """Solver for the P_k x RT_k pairs, k <= 3, with the matrix-free kernels of csrc/kernels_ho.cuh (phw_ho_create_mf): the device
+    holds 3 vertex ids + 3 edge ids + 4 doubles per cell and the reference tabulations of fem_ref.RefSpaces; nothing is assembled.
+    State vectors at this interface are in the dofs of the specification (fem_ho / oracle.fem_ho); the interior RT dofs are converted
+    to / from the reference basis the device works in."""
+
+    def __init__(self, spaces, bops, params, bounds_p, bounds_q, device=0):
+        self.lib = _lib.load()
+        self.spaces = spaces
+        self.mesh = _DofCounts(spaces.np_dofs, spaces.nq_dofs)
+        self.params = params
+        r = spaces.ref
+        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+
+        def compact(M):
+            """rows of a sparse matrix that hold entries -> (n_rows, row ids, indptr, idx, val)"""
+            M = M.tocsr()
+            M.eliminate_zeros()
+            M.sort_indices()
+            rows = np.nonzero(np.diff(M.indptr))[0]
+            ip = np.concatenate([[0], np.cumsum(np.diff(M.indptr)[rows])])
+            return int(rows.shape[0]), i32(rows), i32(ip), i32(M.indices), f64(M.data)
+        nN, N_row, N_ip, N_ix, N_va = compact(bops['N'])
+        nT, T_row, T_ip, T_ix, T_va = compact(bops['N'].T)
+        cv, ce, geom = i32(spaces.cells), i32(spaces.cell_edges), f64(spaces.geom)
+        ref = [f64(a) for a in (r.Mp_hat, r.C_hat, r.A00, r.A01s, r.A11)]
+        bL = f64(bops['b_L'])
+        P = lambda a: a.ctypes.data_as(_lib.c_i32p if a.dtype == np.int32 else _lib.c_f64p)
+        h = ctypes.c_void_p()
+        _lib.check(self.lib.phw_ho_create_mf(ctypes.byref(params), int(device), None, int(spaces.kp), int(spaces.kq),
+                                             spaces.nv, spaces.ne, spaces.nc, P(cv), P(ce), P(geom), *[P(a) for a in ref],
+                                             nN, P(N_row), P(N_ip), P(N_ix), P(N_va), nT, P(T_row), P(T_ip), P(T_ix), P(T_va),
+                                             P(bL), bounds_p[0], bounds_p[1], bounds_q[0], bounds_q[1], ctypes.byref(h)))
+        self.handle = h
+        self.ncol = 12 if params.analytical else 8
+
+    def set_state(self, p=None, q=None, x3=None):
+        super().set_state(p=p, q=None if q is None else self.spaces.from_spec(np.asarray(q, dtype=np.float64)), x3=x3)
+
+    def get_state(self):
+        p, q, x = super().get_state()
+        return p, self.spaces.to_spec(q), x

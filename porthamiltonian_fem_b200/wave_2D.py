@@ -291,12 +291,16 @@ def _solve_high_order(tFinal, numSteps, outputDir, nx, xLength, yLength, domainS
                       return_state, verbose, tic, solver_flags=0, saveP=False, save_every=None):
     """basis_order != (1,1) (wave_2D.py:174-175,202-203): host-assembled operators (fem_ho.py) + CSR device kernels."""
     from .fem_ho import HighOrderSpaces, LagrangeRef, tri_rule
-    from .solver import HighOrderSolver
+    from .fem_ref import RefSpaces
+    from .solver import HighOrderSolver, MatrixFreeHighOrderSolver
     if dirichletImp != 'weak' or controlType is not None or timeIntScheme in ('IE', 'SM'):
         raise NotImplementedError('higher-order pairs are available for the explicit weak-form schemes (EE, SE, EH, SV)')
     if mesh is None:
         mesh = generate_mesh(domainShape, nx, xLength, yLength, kind=mesh_kind)
-    S = HighOrderSpaces(mesh[0], mesh[1], basis_order[0], basis_order[1])
+    # default: matrix-free kernels on the reference-element form of the spaces (csrc/kernels_ho.cuh, fem_ref.py);
+    # PHW_HO_CSR=1: host-assembled CSR operators + generic CSR kernels (round 1; A/B and cross-check)
+    matrix_free = not os.environ.get('PHW_HO_CSR')
+    S = (RefSpaces if matrix_free else HighOrderSpaces)(mesh[0], mesh[1], basis_order[0], basis_order[1])
     if verbose:
         print('number of cells = {}'.format(S.nc))
     # facet markers (wave_2D.py:226-280) on the boundary edges
@@ -322,8 +326,13 @@ def _solve_high_order(tFinal, numSteps, outputDir, nx, xLength, yLength, domainS
     c = np.sqrt(K_wave / rho)
     omega = c * np.sqrt(np.pi ** 2 / (4 * xLength ** 2) + 4 * np.pi ** 2 / yLength ** 2)
     left_w = (lambda x, y: rho * omega * np.sin(2 * np.pi * y / yLength + np.pi / 2)) if analytical else None
-    ops = S.assemble({int(e): int(t) for e, t in zip(be, tags)}, left_weight=left_w)
-    bp, bq = S.jacobi_bounds(ops)
+    tag_of = {int(e): int(t) for e, t in zip(be, tags)}
+    if matrix_free:
+        ops = S.boundary_operators(tag_of, left_weight=left_w)
+        bp, bq = S.jacobi_bounds()
+    else:
+        ops = S.assemble(tag_of, left_weight=left_w)
+        bp, bq = S.jacobi_bounds(ops)
     prm = _lib.PhwParams()
     prm.scheme = _lib.SCHEMES[timeIntScheme]
     prm.interconnection = 1 if interConnection == 'IC' else 0
@@ -341,7 +350,7 @@ def _solve_high_order(tFinal, numSteps, outputDir, nx, xLength, yLength, domainS
         prm.input_kind, prm.in_amp, prm.in_omega, prm.in_t_stop = _lib.IN_SINE_WINDOW, 5.0, 8 * np.pi, 0.25
     else:
         prm.input_kind, prm.in_amp, prm.in_omega, prm.in_t_stop = _lib.IN_SINE_WINDOW, 10.0, 8 * np.pi, 0.25
-    solver = HighOrderSolver(S, ops, prm, bp, bq, device=device)
+    solver = (MatrixFreeHighOrderSolver if matrix_free else HighOrderSolver)(S, ops, prm, bp, bq, device=device)
     H_init = 0.0
     if analytical:
         space = lambda x, y: rho * omega * np.sin(np.pi * x / (2 * xLength) + np.pi / 2) * np.sin(2 * np.pi * y / yLength + np.pi / 2)
@@ -352,7 +361,8 @@ def _solve_high_order(tFinal, numSteps, outputDir, nx, xLength, yLength, domainS
         # errornorm tabulations: P_k -> P_{k+3} (wave_2D.py:956), probe point (0.155, 0.189) (:946-950)
         kk = S.kp + 3
         hi = LagrangeRef(kk)
-        T = S.lag.tabulate(hi.nodes_bary)                                  # [nn, ndp]
+        p_tab = (lambda bary: S.ref.tab_p(bary[:, 1], bary[:, 2])) if matrix_free else S.lag.tabulate
+        T = p_tab(hi.nodes_bary)                                           # [nn, ndp]
         bary, wq = tri_rule(8)
         tab = hi.tabulate(bary)
         mass = np.einsum('qi,qj,q->ij', tab, tab, wq)
@@ -368,7 +378,7 @@ def _solve_high_order(tFinal, numSteps, outputDir, nx, xLength, yLength, domainS
         inside = np.nonzero((l0 >= -1e-12) & (l1 >= -1e-12) & (l2 >= -1e-12))[0]
         if inside.size:
             pc = int(inside[0])
-            pw = S.lag.tabulate(np.array([[l0[pc], l1[pc], l2[pc]]]))[0]
+            pw = p_tab(np.array([[l0[pc], l1[pc], l2[pc]]]))[0]
             pd = S.cell_dofs_p[pc].astype(np.int32)
         else:
             pw, pd = np.zeros(0), np.zeros(0, dtype=np.int32)

@@ -32,7 +32,7 @@ for scheme, bo, (Nx, Ny) in [('SV', (3, 3), (136, 34)), ('SE', (3, 3), (136, 34)
     err = np.abs(H[:cpu_steps, 1:] - Ho[:, 1:]).max() / np.abs(Ho[:, 1:]).max()
     print(json.dumps({'case': 'R {} weak {}x{}x2 analytical P{}/RT{}'.format(scheme, Nx, Ny, *bo), 'cells': nc, 'dofs': ndof, 'steps': steps,
                       'gpu_device_ms': stats['device_ms'], 'gpu_steps_per_s': steps / (stats['device_ms'] * 1e-3),
-                      'gpu_wall_s_incl_setup': wall, 'launches': stats['kernel_launches'],
+                      'gpu_wall_s_incl_setup': wall, 'launches': stats['kernel_launches'], 'matrix_free': bool(stats['kernel_paths'] & 1024),
                       'iters_p': stats['iters_p'] / max(1, stats['solves_p']), 'iters_q': stats['iters_q'] / max(1, stats['solves_q']),
                       'cpu_oracle_steps_per_s': cpu_steps / timing['loop_seconds'], 'cpu_oracle_total_s_incl_factorisation': time.time() - t1,
                       'H_array_rel_diff_first_%d_steps' % cpu_steps: err, 'errL2_end': float(H[-1, 8]), 'max_abs_E': float(np.abs(H[:, 2]).max())}))

@@ -30,7 +30,18 @@ CASES = [
 
 
 @pytest.mark.parametrize('name,bo,make,steps,tF,kw', CASES)
-def test_high_order_time_loop_parity(name, bo, make, steps, tF, kw):
+def test_high_order_time_loop_parity(name, bo, make, steps, tF, kw, monkeypatch):
+    monkeypatch.delenv('PHW_HO_CSR', raising=False)          # default: the matrix-free kernels (csrc/kernels_ho.cuh)
+    _parity(name, bo, make, steps, tF, kw, matrix_free=True)
+
+
+@pytest.mark.parametrize('name,bo,make,steps,tF,kw', [CASES[0], CASES[5], CASES[8]])
+def test_high_order_time_loop_parity_assembled_csr(name, bo, make, steps, tF, kw, monkeypatch):
+    monkeypatch.setenv('PHW_HO_CSR', '1')                    # host-assembled CSR operators (round 1), kept as the cross-check
+    _parity(name, bo, make, steps, tF, kw, matrix_free=False)
+
+
+def _parity(name, bo, make, steps, tF, kw, matrix_free):
     mesh = make()
     Ho, nco, so = wave_2D_solve_oracle(tF, steps, mesh, 1.0, 0.25, K_wave=K_WAVE, rho=RHO, basis_order=bo, return_state=True, **kw)
     Hg, ncg, sg = wave_2D_solve(tF, steps, '/tmp', 0, 1.0, 0.25, K_wave=K_WAVE, rho=RHO, mesh=mesh, basis_order=bo,
@@ -45,6 +56,7 @@ def test_high_order_time_loop_parity(name, bo, make, steps, tF, kw):
     for col in range(1, Ho.shape[1]):
         assert np.abs(Hg[:, col] - Ho[:, col]).max() < 1e-10 * max(scale, np.abs(Ho[:, col]).max()), (name, col)
     assert sg['stats']['max_rel_residual'] <= 1e-13
+    assert bool(sg['stats']['kernel_paths'] & 1024) == matrix_free      # PHW_PATH_HO_MF
 
 
 def test_high_order_rejects_unimplemented_variants():
@@ -52,3 +64,36 @@ def test_high_order_rejects_unimplemented_variants():
     for kw in (dict(timeIntScheme='SM'), dict(timeIntScheme='SV', dirichletImp='strong')):
         with pytest.raises(NotImplementedError):
             wave_2D_solve(0.01, 2, '/tmp', 0, 1.0, 0.25, mesh=mesh, basis_order=(2, 2), verbose=False, **kw)
+
+
+@pytest.mark.parametrize('bo', [(2, 2), (3, 3), (1, 2)])
+def test_matrix_free_operators_match_reference_assembly(bo):
+    """kernel-level entry points on the matrix-free solver: D, D^T, M_p, M_q applied by the cell kernels against the same operators
+    assembled on the host from the reference matrices (fem_ref.RefSpaces.assemble), and the Chebyshev mass solves against sparse LU"""
+    import scipy.sparse.linalg as spla
+    from porthamiltonian_fem_b200 import _lib
+    from porthamiltonian_fem_b200.fem_ref import RefSpaces
+    from porthamiltonian_fem_b200.solver import MatrixFreeHighOrderSolver
+    try:
+        from test_fem_ref_cpu import tags_of
+    except ImportError:
+        from tests.test_fem_ref_cpu import tags_of
+    mesh = rectangle_delaunay(12, 4, seed=4)
+    S = RefSpaces(mesh[0], mesh[1], bo[0], bo[1])
+    bops = S.boundary_operators(tags_of(S))
+    ops = S.assemble(bops)
+    prm = _lib.PhwParams()
+    prm.scheme, prm.dt, prm.K_wave, prm.rho, prm.tol, prm.max_iter = _lib.SCHEMES['SE'], 1e-3, 1.0, 1.0, 1e-13, 2000
+    bp, bq = S.jacobi_bounds()
+    sol = MatrixFreeHighOrderSolver(S, bops, prm, bp, bq)
+    rng = np.random.default_rng(1)
+    p, q = rng.standard_normal(S.np_dofs), rng.standard_normal(S.nq_dofs)
+    assert rel(sol.apply_D(p), ops['D'] @ p) < 1e-13
+    assert rel(sol.apply_DT(q), ops['D'].T @ q) < 1e-13
+    assert rel(sol.mass_matvec(_lib.PHW_P, p), ops['M_p'] @ p) < 1e-13
+    assert rel(sol.mass_matvec(_lib.PHW_Q, q), ops['M_q'] @ q) < 1e-13
+    xp, itp = sol.mass_solve(_lib.PHW_P, p)
+    xq, itq = sol.mass_solve(_lib.PHW_Q, q)
+    assert rel(xp, spla.spsolve(ops['M_p'].tocsc(), p)) < 1e-11 and rel(xq, spla.spsolve(ops['M_q'].tocsc(), q)) < 1e-11
+    assert 0 < itp < 200 and 0 < itq < 300
+    sol.close()
