@@ -75,7 +75,11 @@ typedef struct phw_params {
                                 bit15: the WHOLE time loop of phw_run in one launch (csrc/kernels_loop.cuh) for cache-resident meshes: one
                                 CTA per patch for the whole run, the CTAs of a case in one thread-block cluster (1, 2, 4, 8 or 16 patches
                                 per case) or one co-resident grid; every scheme and variant except the analytical diagnostics; one GPU.
-                                Silently ignored when the layout is not eligible (phw_stats.kernel_paths tells: PHW_PATH_LOOP) */
+                                Silently ignored when the layout is not eligible (phw_stats.kernel_paths tells: PHW_PATH_LOOP);
+                                bit16: conjugate-gradient instead of Chebyshev mass solves (solve_pcg_coop_k).  Selected automatically for
+                                the M_q solve when the element-wise bound of kappa(D^-1 M_q) exceeds 10 (stretched cells, slivers),
+                                where the Chebyshev interval is pessimistic; bit17 forbids it.  One GPU, weak form, unbatched,
+                                multi-launch path; phw_stats.kernel_paths tells (PHW_PATH_PCG) */
     int32_t extrap_order_q;  /* extrapolation order of the q (and block) solves; 0: same as extrap_order.  Orders up to 5 */
 } phw_params;
 
@@ -90,7 +94,8 @@ typedef struct phw_stats {
     int64_t kernel_paths;       /* phw_path bits: which variants of the mass-solve kernels the last phw_run launched */
 } phw_stats;
 enum phw_path { PHW_PATH_LEAN_P = 1, PHW_PATH_LEAN_Q = 2, PHW_PATH_PIPE_P = 4, PHW_PATH_PIPE_Q = 8, PHW_PATH_PIPE_ENERGY = 16, PHW_PATH_PIPE_RHS = 32, PHW_PATH_LOOP = 256, PHW_PATH_LOOP_RES = 512 /* ... with the mass solves resident in shared memory */,
-                PHW_PATH_HO_MF = 1024 /* matrix-free higher-order kernels (phw_ho_create_mf) */ };
+                PHW_PATH_HO_MF = 1024 /* matrix-free higher-order kernels (phw_ho_create_mf) */,
+                PHW_PATH_PCG = 2048 /* conjugate-gradient mass solves (meshes of poor quality: element-wise kappa bound > 10) */ };
 
 const char* phw_last_error(void);
 int phw_version(void);
@@ -190,6 +195,12 @@ int phw_comm_setup(phw_solver_t s, int32_t rank, int32_t world, const void* hand
                    const int64_t* n_send_e, const int32_t* const* send_e_user, const int32_t* const* send_e_remote);
 /* global spectral bounds of the Jacobi-scaled RT1 mass matrix (all ranks must iterate with the same interval) */
 int phw_set_cheb_bounds(phw_solver_t s, double lam_min_q, double lam_max_q);
+/* implicit schemes (IE, SM) on a partitioned mesh (the reference runs every scheme under MPI: wave_2D.py:305-319,560-572 with
+ * run_main_wave_2D_mpi.sh:1).  phw_solver_create defers the set-up of the coupled block solve; after phw_comm_setup every rank
+ * calls phw_comm_finish_implicit with the SAME sigma = largest singular value of P_q^-1/2 D P_p^-1/2 of the global operator
+ * (solver.setup_peer_exchange: distributed power iteration through phw_apply_D / phw_apply_DT and phw_get_jacobi).  Collective. */
+int phw_get_jacobi(phw_solver_t s, int32_t which, double* inv_diag);     /* 1 / diag of the solved block, user numbering */
+int phw_comm_finish_implicit(phw_solver_t s, double sigma);
 
 /* ---- kernel-level entry points (parity tests, profiling) ---- */
 /* y[Ne] = D p = (C - N) p            weak coupling block of wave_2D.py:468-472,479-483,503-518 */

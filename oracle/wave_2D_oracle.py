@@ -97,7 +97,8 @@ def wave_2D_solve_oracle(tFinal, numSteps, mesh, xLength, yLength,
     high_order = tuple(basis_order) != (1, 1)
     if high_order:
         # basis_order of wave_2D.py:15-20,174-175: P_k x RT_k spaces, same forms; nv / ne below are then the numbers of
-        # P / RT dofs.  Restated for the weak form without control (the variants the reference runs at higher order:
+        # P / RT dofs.  Restated for the weak form without control, every scheme, with or without the lumped model (the reference
+        # itself runs the explicit analytical variants at higher order:
         # main_wave_2D.py:53-114, run_test_cases.py:30-31,44-46).
         if dirichletImp != 'weak' or controlType is not None:
             raise NotImplementedError('oracle: higher-order pairs are restated for the weak form without control')

@@ -101,6 +101,8 @@ SIGNATURES = {
     'phw_comm_setup': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, c_i64p, c_i64p, ctypes.c_int32, c_i32p,
                                       c_i64p, ctypes.POINTER(c_i32p), ctypes.POINTER(c_i32p), c_i64p, ctypes.POINTER(c_i32p), ctypes.POINTER(c_i32p)]),
     'phw_set_cheb_bounds': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double, ctypes.c_double]),
+    'phw_get_jacobi': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p]),
+    'phw_comm_finish_implicit': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double]),
     'phw_apply_D': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     'phw_apply_DT': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     'phw_mass_matvec': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]),

@@ -112,7 +112,8 @@ def calculate_eigen(tFinal, numSteps, outputDir, nx, xLength, yLength, domainSha
         real_part = c * np.sqrt(np.abs(lam)) * np.sin(0.5 * np.angle(lam.astype(complex)))      # Re(sqrt(-lam)) of +-i omega: 0 when lam is real positive
     elif method == 'lobpcg':
         import scipy.sparse.linalg as spla
-        k = min(num_eigs, max(1, n_p // 5))
+        # two more than asked for: the pencil has the constant pressure as a zero mode, which is dropped below
+        k = min(num_eigs + 2, max(1, n_p // 5))
         A = spla.LinearOperator((n_p, n_p), matvec=lambda x: ops.stiffness(np.asarray(x).ravel()), dtype=np.float64)
         B = spla.LinearOperator((n_p, n_p), matvec=lambda x: ops.M(_lib.PHW_P, np.asarray(x).ravel()), dtype=np.float64)
         P = spla.LinearOperator((n_p, n_p), matvec=lambda x: ops.Minv(_lib.PHW_P, np.asarray(x).ravel()), dtype=np.float64)

@@ -1556,4 +1556,180 @@ __global__ void __launch_bounds__(256) solve_coop_csr_k(const CsrSolveArgs a) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Mass solves on meshes of poor quality: Jacobi-preconditioned CONJUGATE GRADIENTS, all iterations in one cooperative launch.
+// The Chebyshev solves iterate on a rigorous element-wise spectral interval; a few stretched cells widen that interval for the
+// whole mesh although they only add a few outlying eigenvalues.  CG needs no interval and converges on the true spectrum (outliers
+// cost about one iteration each), so phw_solver_create selects it when the element-wise kappa bound exceeds 10 (phw_params.flags
+// bit 16 / PHW_PCG force it on or off).  The reference's sparse LU has no mesh-quality dependence at all (wave_2D.py:820,854); CG
+// removes the dependence on the WORST cell, not the one on uniformly stretched cells (there the Jacobi-scaled RT1 mass matrix is
+// ill-conditioned for real: aspect ratio 12, kappa = 119, ~150 iterations either way).  Same rows (vertex_pass / edge_pass, STORE epilogue), same stop test ||P^-1/2 r|| <= tol ||P^-1/2 b|| (on
+// the recursively updated residual), same deterministic reductions; four grid barriers per iteration instead of one, which is why
+// it is not the default on quality meshes.  One GPU, weak form, unbatched.
+// ------------------------------------------------------------------------------------------------
+struct PcgArgs { double *r, *u; const double* b; const double* pinv; int n; };   // search direction and A pd live in the two idle iterate buffers
+template <int WHICH, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) solve_pcg_coop_k(const __grid_constant__ RowArgs a, const __grid_constant__ PcgArgs v) {
+    extern __shared__ double smem[];
+    __shared__ double red[64];
+    __shared__ double bc[2];
+    SolveCtl& sc = a.ctl->sc[WHICH];
+    unsigned int epoch = 0, nred = 0;
+    const int cur = sc.cur;
+    double* x = tb_sel(WHICH == 0 ? a.tp : a.tq, cur);
+    double* pd = tb_sel(WHICH == 0 ? a.tp : a.tq, (cur + 1) % 3);
+    double* w = tb_sel(WHICH == 0 ? a.tp : a.tq, (cur + 2) % 3);
+    const int gtid = blockIdx.x * NT + threadIdx.x, gsz = gridDim.x * NT;
+    RowArgs am = a;
+    am.y = w; am.cM = 1.0; am.cD = 0.0; am.cB = 0.0;
+    // w = A src on the owned rows, visible grid-wide on return
+    auto matvec = [&](const double* src) {
+        PassIO io;
+        io.xp = src; io.xq = src; io.xprev = nullptr; io.xnew = nullptr; io.c1 = 0.0; io.c2 = 0.0; io.use_prev = 0;
+        double t0 = 0.0, t1 = 0.0;
+        if (WHICH == 0) vertex_pass<EPI_STORE, MODE_OP, true, false, false, NT>(am, io, smem, t0, t1);
+        else edge_pass<EPI_STORE, MODE_OP, true, false, false, NT>(am, io, smem, t0, t1);
+        grid_barrier(&a.ctl->gbar[0], epoch);
+    };
+    // grid-wide sums of (s0, s1), identical bits in every thread; contains one grid barrier
+    auto reduce2 = [&](double& s0, double& s1) {
+        block_sum2(s0, s1, red);
+        double* part = a.partials + (size_t)(nred & 1u) * 2 * gridDim.x;
+        nred++;
+        if (threadIdx.x == 0) { part[2 * blockIdx.x] = s0; part[2 * blockIdx.x + 1] = s1; }
+        grid_barrier(&a.ctl->gbar[0], epoch);
+        if (threadIdx.x < 32) {
+            double q0 = 0.0, q1 = 0.0;
+            for (int i = threadIdx.x; i < (int)gridDim.x; i += 32) { q0 += __ldcg(&part[2 * i]); q1 += __ldcg(&part[2 * i + 1]); }
+            q0 = warp_sum(q0); q1 = warp_sum(q1);
+            if (threadIdx.x == 0) { bc[0] = q0; bc[1] = q1; }
+        }
+        __syncthreads();
+        s0 = bc[0]; s1 = bc[1];
+        __syncthreads();
+    };
+    matvec(x);
+    double gam = 0.0, bb = 0.0;
+    for (int i = gtid; i < v.n; i += gsz) {
+        const double bv = v.b[i], pv = v.pinv[i];
+        const double r = bv - __ldcg(&w[i]);
+        const double u = pv * r;
+        v.r[i] = r; v.u[i] = u; pd[i] = u;
+        gam += r * u; bb += pv * bv * bv;
+    }
+    reduce2(gam, bb);                                   // the barrier inside also completes pd before the first pass reads it
+    int k = 0;
+    bool conv = gam <= a.tol2 * bb;
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.ctl->reshist[WHICH][0] = (bb > 0.0) ? gam / bb : 0.0;
+    while (!conv && k < a.max_iter) {
+        matvec(pd);
+        double del = 0.0, z0 = 0.0;
+        for (int i = gtid; i < v.n; i += gsz) del += pd[i] * __ldcg(&w[i]);
+        reduce2(del, z0);
+        const double alpha = gam / del;
+        double gn = 0.0, z1 = 0.0;
+        for (int i = gtid; i < v.n; i += gsz) {
+            x[i] += alpha * pd[i];
+            const double r = v.r[i] - alpha * __ldcg(&w[i]);
+            const double u = v.pinv[i] * r;
+            v.r[i] = r; v.u[i] = u;
+            gn += r * u;
+        }
+        reduce2(gn, z1);
+        k += 1;
+        if (blockIdx.x == 0 && threadIdx.x == 0 && k < 48) a.ctl->reshist[WHICH][k] = (bb > 0.0) ? gn / bb : 0.0;
+        conv = gn <= a.tol2 * bb;
+        const double beta = gn / gam;
+        gam = gn;
+        if (conv) break;
+        for (int i = gtid; i < v.n; i += gsz) pd[i] = v.u[i] + beta * pd[i];
+        grid_barrier(&a.ctl->gbar[0], epoch);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        sc.k = k; sc.done = 1; sc.rr = gam; sc.bb = bb;
+        sc.iters += k; sc.solves += 1;
+        if (!conv) a.ctl->nonconv += 1;
+        const double rel = (bb > 0.0) ? sqrt(gam / bb) : 0.0;
+        if (rel > sc.maxres) sc.maxres = rel;
+    }
+}
+
+// All Chebyshev (ellipse) iterations of the coupled block system of the implicit schemes (IE, SM; wave_2D.py:305-319,560-572) for the
+// higher-order pairs, on assembled CSR rows, in ONE cooperative launch:
+//     M_p v_p + cDv D^T v_q = b_p ,    M_q v_q + cDe D v_p = b_q          (cDv = theta dt K,  cDe = -theta dt / rho)
+// Both row families are updated from the same iterate (Jacobi-preconditioned, simultaneous), residual norm = wv |r_p|^2_P + we |r_q|^2_P
+// as in the P1 x RT1 block solve (solve_coop_k<2>).  Eight lanes per row for all four matrices.
+struct CsrBlockArgs {
+    Csr Mp, Mq, D, DT; TriBuf tp, tq; const double *bp, *bq, *pinv_p, *pinv_q;
+    double cDv, cDe, wv, we, cheb_d, cheb_c, tol2; int max_iter;
+    double* partials; Ctl* ctl;
+};
+__global__ void __launch_bounds__(256) solve_block_csr_k(const CsrBlockArgs a) {
+    constexpr int L = 8;
+    __shared__ double red[64];
+    __shared__ double bc[2];
+    SolveCtl& sc = a.ctl->sc[2];
+    int k = 0, cur = sc.cur;
+    double rho = 0.0, rr = 0.0, bb = 0.0;
+    bool conv = false;
+    unsigned int epoch = 0;
+    const int sub = threadIdx.x % L, g = (blockIdx.x * blockDim.x + threadIdx.x) / L, ng = gridDim.x * blockDim.x / L;
+    const int n_p = a.Mp.n_rows, n_q = a.Mq.n_rows, n_all = n_p + n_q;
+    const int nround = (n_all + ng - 1) / ng;
+    while (true) {
+        double c1, c2, rho_k;
+        cheb_coeffs(k, rho, a.cheb_d, a.cheb_c, c1, c2, rho_k);
+        const int nxt = (cur + 1) % 3, prv = (cur + 2) % 3;
+        const double* xp = tb_sel(a.tp, cur); const double* xq = tb_sel(a.tq, cur);
+        double r0 = 0.0, b0 = 0.0;
+        for (int i = 0; i < nround; ++i) {
+            const int r = g + i * ng;
+            const bool live = r < n_all;
+            const bool vertex = r < n_p;                       // uniform over the 8 lanes of a row; rows of a warp may be of both kinds
+            const int row = live ? (vertex ? r : r - n_p) : 0;
+            // operands selected by pointer, not by branch: every lane of the warp reaches the same shuffles
+            Csr A1, A2;
+            A1.indptr = vertex ? a.Mp.indptr : a.Mq.indptr; A1.idx = vertex ? a.Mp.idx : a.Mq.idx; A1.val = vertex ? a.Mp.val : a.Mq.val;
+            A2.indptr = vertex ? a.DT.indptr : a.D.indptr; A2.idx = vertex ? a.DT.idx : a.D.idx; A2.val = vertex ? a.DT.val : a.D.val;
+            const double val = csr_row_group<L>(A1, row, vertex ? xp : xq, sub) + (vertex ? a.cDv : a.cDe) * csr_row_group<L>(A2, row, vertex ? xq : xp, sub);
+            if (live && sub == 0) {
+                const double* x = vertex ? xp : xq;
+                const double bv = vertex ? a.bp[row] : a.bq[row], pv = vertex ? a.pinv_p[row] : a.pinv_q[row], w = vertex ? a.wv : a.we;
+                const double xc = x[row];
+                const double res = bv - val;
+                double v = xc + c2 * pv * res;
+                if (k > 0) v += c1 * (xc - (vertex ? tb_sel(a.tp, prv) : tb_sel(a.tq, prv))[row]);
+                (vertex ? tb_sel(a.tp, nxt) : tb_sel(a.tq, nxt))[row] = v;
+                r0 += w * pv * res * res; b0 += w * pv * bv * bv;
+            }
+        }
+        block_sum2(r0, b0, red);
+        double* part = a.partials + (size_t)(k & 1) * 2 * gridDim.x;
+        if (threadIdx.x == 0) { part[2 * blockIdx.x] = r0; part[2 * blockIdx.x + 1] = b0; }
+        grid_barrier(&a.ctl->gbar[0], epoch);
+        if (threadIdx.x < 32) {
+            double s0 = 0.0, s1 = 0.0;
+            for (int i = threadIdx.x; i < (int)gridDim.x; i += 32) { s0 += __ldcg(&part[2 * i]); s1 += __ldcg(&part[2 * i + 1]); }
+            s0 = warp_sum(s0); s1 = warp_sum(s1);
+            if (threadIdx.x == 0) { bc[0] = s0; bc[1] = s1; }
+        }
+        __syncthreads();
+        rr = bc[0]; bb = bc[1];
+        __syncthreads();
+        conv = rr <= a.tol2 * bb;
+        if (blockIdx.x == 0 && threadIdx.x == 0 && k < 48) a.ctl->reshist[2][k] = (bb > 0.0) ? rr / bb : 0.0;
+        k += 1;
+        if (conv) break;
+        rho = rho_k; cur = nxt;
+        if (k >= a.max_iter) break;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        sc.cur = cur; sc.k = k; sc.done = 1; sc.rr = rr; sc.bb = bb; sc.rho = rho;
+        sc.iters += k; sc.solves += 1;
+        if (!conv) a.ctl->nonconv += 1;
+        double rel = (bb > 0.0) ? sqrt(rr / bb) : 0.0;
+        if (rel > sc.maxres) sc.maxres = rel;
+    }
+}
+
 }  // namespace phw

@@ -6,10 +6,11 @@
 // wave_2D.py:449-526 are reference matrices times a few numbers per cell:
 //     M_p,K = |det J| Mp_hat      C_K = sign(det J) C_hat      M_q,K = G00 A00 + G01 (A01 + A10) + G11 A11,  G = J^T J / |det J|.
 // Device side: per cell 3 vertex ids + 3 edge ids + 4 doubles (56 B; the assembled CSR rows of P3 x RT3 are ~2.5 KB per cell), the
-// reference tabulations (<= 7.4 KB) in shared memory, every dof index derived from the ids.  One thread per cell: gather the local
-// vector, apply the reference matrices (shared-memory broadcast reads: all lanes of a warp read the same entry), scatter with fp64
+// reference tabulations (<= 7.4 KB) in shared memory, every dof index derived from the ids.  Sixteen lanes per cell: gather the local
+// vector (one entry per lane), form one output row per lane from the reference matrices, scatter with fp64
 // atomics (RED.ADD.F64 resolves in L2; these meshes live there).  The boundary terms (zero-flux N, left port b_L) touch the dofs of
-// boundary edges only and come as a compact CSR over those rows.
+// boundary edges only and come as a compact CSR over those rows.  (Sixteen lanes per cell since the first GPU run: one thread per
+// cell left a P3 x RT3 solve iteration at 33 us - ~900 dependent shared-memory reads per thread - behind the assembled CSR rows.)
 //
 // The element contraction is a dense batched product - (ndq x 3 ndq) reference block times the G-scaled local vectors of all cells -
 // i.e. the one place of this code base where a tensor-core formulation exists (DMMA m8n8k4).  At 3 x 15 x 15 FMAs per 56 + 240 B
@@ -31,7 +32,9 @@ struct HoMf {
 struct RowCsr { int n_rows; const int* row; const int* indptr; const int* idx; const double* val; };
 
 enum { HO_MP = 0, HO_MQ = 1, HO_C = 2, HO_CT = 3 };
-constexpr int HO_NT = 128;        // threads per CTA of the cell loops
+constexpr int HO_NT = 256;        // threads per CTA of the cell loops
+constexpr int HO_NT_SOLVE_MAX = 1024;   // the persistent solve picks its CTA size at launch (fewer, larger CTAs = cheaper grid barriers)
+constexpr int HO_LPC = 16;        // lanes per cell (>= the largest local dimension, RT_3: 15; divides the warp size)
 constexpr int HO_MAXD = 15;       // RT_3: 15 dofs per cell
 
 __device__ __forceinline__ int ho_dof_p(const HoMf& m, int c, const int* v, const int* e, int i) {
@@ -52,41 +55,51 @@ __device__ __forceinline__ void ho_load_ref(const HoMf& m, double* sref) {
     __syncthreads();
 }
 
-// y += alpha * A x over the cells first, first + stride, ...: one thread per cell.  sx: [HO_MAXD][blockDim.x] doubles of shared memory
+// y += alpha * A x over all cells: HO_LPC = 16 lanes per cell (lane i gathers local entry i, then forms output row i), so the lanes
+// of a cell share a warp and __syncwarp orders the hand-over through sx ([cells per CTA][HO_LPC] doubles of shared memory).  The
+// reference rows are read at a stride of nd <= 15 doubles: the 16 lanes of a cell hit 16 different bank pairs, the second cell of
+// the warp reads the same words (broadcast).  One pass covers gridDim.x * blockDim.x / 16 cells.
 template <int OP>
-__device__ __forceinline__ void ho_cells_apply(const HoMf& m, const double* sref, double* sx, const double* x, double* y, double alpha,
-                                               int first, int stride) {
+__device__ __forceinline__ void ho_cells_apply(const HoMf& m, const double* sref, double* sx, const double* x, double* y, double alpha) {
     const int nin = (OP == HO_MP || OP == HO_C) ? m.ndp : m.ndq;
     const int nout = (OP == HO_MP || OP == HO_CT) ? m.ndp : m.ndq;
-    const int nt = blockDim.x, t = threadIdx.x;
-    for (int c = first; c < m.nc; c += stride) {
-        int v[3], e[3];
+    const int cs = threadIdx.x / HO_LPC, l = threadIdx.x % HO_LPC, cpb = blockDim.x / HO_LPC;
+    double* sxc = sx + cs * HO_LPC;
+    for (int base = blockIdx.x * cpb; base < m.nc; base += gridDim.x * cpb) {
+        const int c = base + cs;
+        const bool ok = c < m.nc;
+        int v[3] = {0, 0, 0}, e[3] = {0, 0, 0};
+        double dj = 0.0, g00 = 0.0, g01 = 0.0, g11 = 0.0;
+        if (ok) {
 #pragma unroll
-        for (int i = 0; i < 3; ++i) { v[i] = m.cv[3 * c + i]; e[i] = m.ce[3 * c + i]; }
-        const double dj = m.geom[4 * c], g00 = m.geom[4 * c + 1], g01 = m.geom[4 * c + 2], g11 = m.geom[4 * c + 3];
-        for (int j = 0; j < nin; ++j) sx[j * nt + t] = x[(OP == HO_MP || OP == HO_C) ? ho_dof_p(m, c, v, e, j) : ho_dof_q(m, c, e, j)];
-        const double sc = OP == HO_MP ? fabs(dj) * alpha : ((OP == HO_MQ) ? alpha : (dj < 0.0 ? -alpha : alpha));
-        for (int i = 0; i < nout; ++i) {
+            for (int i = 0; i < 3; ++i) { v[i] = m.cv[3 * c + i]; e[i] = m.ce[3 * c + i]; }
+            dj = m.geom[4 * c]; g00 = m.geom[4 * c + 1]; g01 = m.geom[4 * c + 2]; g11 = m.geom[4 * c + 3];
+        }
+        __syncwarp();                                                 // the rows of the previous pass have been formed
+        if (ok && l < nin) sxc[l] = x[(OP == HO_MP || OP == HO_C) ? ho_dof_p(m, c, v, e, l) : ho_dof_q(m, c, e, l)];
+        __syncwarp();
+        if (ok && l < nout) {
+            const double sc = OP == HO_MP ? fabs(dj) * alpha : ((OP == HO_MQ) ? alpha : (dj < 0.0 ? -alpha : alpha));
             double acc;
             if (OP == HO_MP) {
-                const double* A = sref + i * m.ndp;
+                const double* A = sref + l * m.ndp;
                 acc = 0.0;
-                for (int j = 0; j < nin; ++j) acc += A[j] * sx[j * nt + t];
+                for (int j = 0; j < nin; ++j) acc += A[j] * sxc[j];
             } else if (OP == HO_MQ) {
-                const double *A0 = sref + m.off_A00 + i * m.ndq, *A1 = sref + m.off_A01 + i * m.ndq, *A2 = sref + m.off_A11 + i * m.ndq;
+                const double *A0 = sref + m.off_A00 + l * m.ndq, *A1 = sref + m.off_A01 + l * m.ndq, *A2 = sref + m.off_A11 + l * m.ndq;
                 double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-                for (int j = 0; j < nin; ++j) { const double xj = sx[j * nt + t]; s0 += A0[j] * xj; s1 += A1[j] * xj; s2 += A2[j] * xj; }
+                for (int j = 0; j < nin; ++j) { const double xj = sxc[j]; s0 += A0[j] * xj; s1 += A1[j] * xj; s2 += A2[j] * xj; }
                 acc = g00 * s0 + g01 * s1 + g11 * s2;
             } else if (OP == HO_C) {
-                const double* A = sref + m.off_C + i * m.ndp;
+                const double* A = sref + m.off_C + l * m.ndp;
                 acc = 0.0;
-                for (int j = 0; j < nin; ++j) acc += A[j] * sx[j * nt + t];
+                for (int j = 0; j < nin; ++j) acc += A[j] * sxc[j];
             } else {
-                const double* A = sref + m.off_C + i;                 // column i of C_hat
+                const double* A = sref + m.off_C + l;                 // column l of C_hat
                 acc = 0.0;
-                for (int j = 0; j < nin; ++j) acc += A[j * m.ndp] * sx[j * nt + t];
+                for (int j = 0; j < nin; ++j) acc += A[j * m.ndp] * sxc[j];
             }
-            atomicAdd(&y[(OP == HO_MP || OP == HO_CT) ? ho_dof_p(m, c, v, e, i) : ho_dof_q(m, c, e, i)], sc * acc);
+            atomicAdd(&y[(OP == HO_MP || OP == HO_CT) ? ho_dof_p(m, c, v, e, l) : ho_dof_q(m, c, e, l)], sc * acc);
         }
     }
 }
@@ -97,7 +110,7 @@ __global__ void __launch_bounds__(HO_NT) ho_apply_k(const HoMf m, const double* 
     double* sref = sm_;
     double* sx = sm_ + ((m.ref_len + 1) & ~1);
     ho_load_ref(m, sref);
-    ho_cells_apply<OP>(m, sref, sx, x, y, alpha, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+    ho_cells_apply<OP>(m, sref, sx, x, y, alpha);
 }
 
 // diagonal of M_p (OP = HO_MP) or M_q (HO_MQ), accumulated with atomics (setup: Jacobi weights)
@@ -129,32 +142,38 @@ __global__ void __launch_bounds__(HO_NT) ho_quad_k(const HoMf m, const double* x
     double* sref = sm_;
     double* sx = sm_ + ((m.ref_len + 1) & ~1);
     ho_load_ref(m, sref);
-    const int nt = blockDim.x, t = threadIdx.x;
     const int nd = OP == HO_MP ? m.ndp : m.ndq;
+    const int cs = threadIdx.x / HO_LPC, l = threadIdx.x % HO_LPC, cpb = blockDim.x / HO_LPC;
+    double* sxc = sx + cs * HO_LPC;
     double s = 0.0, z = 0.0;
-    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < m.nc; c += gridDim.x * blockDim.x) {
-        int v[3], e[3];
+    for (int base = blockIdx.x * cpb; base < m.nc; base += gridDim.x * cpb) {
+        const int c = base + cs;
+        const bool ok = c < m.nc;
+        int v[3] = {0, 0, 0}, e[3] = {0, 0, 0};
+        double dj = 0.0, g00 = 0.0, g01 = 0.0, g11 = 0.0;
+        if (ok) {
 #pragma unroll
-        for (int i = 0; i < 3; ++i) { v[i] = m.cv[3 * c + i]; e[i] = m.ce[3 * c + i]; }
-        const double dj = fabs(m.geom[4 * c]), g00 = m.geom[4 * c + 1], g01 = m.geom[4 * c + 2], g11 = m.geom[4 * c + 3];
-        for (int j = 0; j < nd; ++j) sx[j * nt + t] = x[OP == HO_MP ? ho_dof_p(m, c, v, e, j) : ho_dof_q(m, c, e, j)];
-        double q = 0.0;
-        for (int i = 0; i < nd; ++i) {
-            const double xi = sx[i * nt + t];
+            for (int i = 0; i < 3; ++i) { v[i] = m.cv[3 * c + i]; e[i] = m.ce[3 * c + i]; }
+            dj = fabs(m.geom[4 * c]); g00 = m.geom[4 * c + 1]; g01 = m.geom[4 * c + 2]; g11 = m.geom[4 * c + 3];
+        }
+        __syncwarp();
+        if (ok && l < nd) sxc[l] = x[OP == HO_MP ? ho_dof_p(m, c, v, e, l) : ho_dof_q(m, c, e, l)];
+        __syncwarp();
+        if (ok && l < nd) {                                           // lane l: x_l (A x)_l of this cell
+            const double xi = sxc[l];
             if (OP == HO_MP) {
                 double a = 0.0;
-                for (int j = 0; j < nd; ++j) a += sref[i * nd + j] * sx[j * nt + t];
-                q += dj * xi * a;
+                for (int j = 0; j < nd; ++j) a += sref[l * nd + j] * sxc[j];
+                s += dj * xi * a;
             } else {
                 double s0 = 0.0, s1 = 0.0, s2 = 0.0;
                 for (int j = 0; j < nd; ++j) {
-                    const double xj = sx[j * nt + t];
-                    s0 += sref[m.off_A00 + i * nd + j] * xj; s1 += sref[m.off_A01 + i * nd + j] * xj; s2 += sref[m.off_A11 + i * nd + j] * xj;
+                    const double xj = sxc[j];
+                    s0 += sref[m.off_A00 + l * nd + j] * xj; s1 += sref[m.off_A01 + l * nd + j] * xj; s2 += sref[m.off_A11 + l * nd + j] * xj;
                 }
-                q += xi * (g00 * s0 + g01 * s1 + g11 * s2);
+                s += xi * (g00 * s0 + g01 * s1 + g11 * s2);
             }
         }
-        s += q;
     }
     block_sum2(s, z, red);
     if (threadIdx.x == 0) {
@@ -188,7 +207,7 @@ struct HoSolveArgs {
     double cheb_d, cheb_c, tol2; int max_iter, which, n;
     double* partials; Ctl* ctl;
 };
-__global__ void __launch_bounds__(HO_NT) ho_solve_k(const __grid_constant__ HoSolveArgs a) {
+__global__ void __launch_bounds__(HO_NT_SOLVE_MAX) ho_solve_k(const __grid_constant__ HoSolveArgs a) {
     extern __shared__ double sm_[];
     __shared__ double red[64];
     __shared__ double bc[2];
@@ -206,8 +225,8 @@ __global__ void __launch_bounds__(HO_NT) ho_solve_k(const __grid_constant__ HoSo
         cheb_coeffs(k, rho, a.cheb_d, a.cheb_c, c1, c2, rho_k);
         const int nxt = (cur + 1) % 3, prv = (cur + 2) % 3;
         const double* x = tb_sel(a.tb, cur); const double* xp = tb_sel(a.tb, prv); double* xn = tb_sel(a.tb, nxt);
-        if (a.which == 0) ho_cells_apply<HO_MP>(a.m, sref, sx, x, a.yacc, 1.0, gtid, gnt);
-        else ho_cells_apply<HO_MQ>(a.m, sref, sx, x, a.yacc, 1.0, gtid, gnt);
+        if (a.which == 0) ho_cells_apply<HO_MP>(a.m, sref, sx, x, a.yacc, 1.0);
+        else ho_cells_apply<HO_MQ>(a.m, sref, sx, x, a.yacc, 1.0);
         grid_barrier(&a.ctl->gbar[0], epoch);
         double r0 = 0.0, b0 = 0.0;
         for (int i = gtid; i < a.n; i += gnt) {

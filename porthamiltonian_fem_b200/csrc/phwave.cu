@@ -542,6 +542,8 @@ struct phw_solver_s {
     Hist hist[2][2];           // [field p/q][solve site]
     int extrap = 2, n_sites = 1;
     int extrap_f[2] = {2, 2};  // extrapolation order of the p / q solves
+    bool pcg[2] = {false, false};     // conjugate-gradient mass solves (poor meshes; flags bits 16 / 17)
+    bool implicit_pending = false;    // partitioned implicit run: the ellipse / bordered column are set up by phw_comm_finish_implicit
     bool ho = false; Csr hMp{}, hMq{}, hD{}, hDT{};
     bool ho_mf = false; HoMf hm{}; RowCsr hN{}, hNT{}; double *ho_yacc_p = nullptr, *ho_yacc_q = nullptr;   // matrix-free higher-order pairs (kernels_ho.cuh)
     int ho_nc = 0, ho_ndp = 0, ho_nn = 0, ho_nprobe = 0; double ho_omega = 0.0;
@@ -650,8 +652,8 @@ void csr_dot(phw_solver_s* s, const Csr& A, const double* x, double scale, int s
 }
 
 // ---- matrix-free higher-order operators (kernels_ho.cuh): cell loops with the reference tabulations in shared memory
-inline size_t ho_smem(const HoMf& m) { return (size_t)(((m.ref_len + 1) & ~1) + HO_MAXD * HO_NT) * sizeof(double); }
-inline int ho_grid(phw_solver_s* s) { return std::max(1, std::min(nblk(s->hm.nc, HO_NT), s->sm_count * 8)); }
+inline size_t ho_smem(const HoMf& m) { return (size_t)(((m.ref_len + 1) & ~1) + HO_NT) * sizeof(double); }
+inline int ho_grid(phw_solver_s* s) { return std::max(1, std::min(nblk(s->hm.nc, HO_NT / HO_LPC), s->sm_count * 8)); }
 // y (+)= alpha A x, A = M_p, M_q, C or C^T
 int ho_mf_apply(phw_solver_s* s, int op, const double* x, double* y, double alpha, bool zero_first) {
     const HoMf& m = s->hm;
@@ -702,13 +704,21 @@ int ho_mf_solve(phw_solver_s* s, int which) {
     a.max_iter = s->prm.max_iter; a.which = which; a.n = which == PHW_P ? s->hm.n_p : s->hm.n_q;
     a.partials = s->partials; a.ctl = s->ctl;
     CU(cudaMemsetAsync(&s->ctl->gbar[0], 0, sizeof(unsigned int), s->stream));
+    // CTA size: an iteration crosses two grid barriers whose cost grows with the number of CTAs (one atomic arrival each), so the
+    // cells are spread over as few, as large CTAs as cover them in one pass (PHW_HO_NT: A/B knob)
+    static const int nt_env = [] { const char* e = getenv("PHW_HO_NT"); const int v = e ? atoi(e) : 0; return (v == 256 || v == 512 || v == 1024) ? v : 0; }();
+    int nt = nt_env;
+    if (!nt) {
+        const int need = std::max(s->hm.nc * HO_LPC, a.n);
+        nt = need <= 256 * s->sm_count ? 256 : (need <= 512 * s->sm_count ? 512 : 1024);
+    }
     int occ = 0;
-    const size_t sm = ho_smem(s->hm);
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (void*)ho_solve_k, HO_NT, sm));
+    const size_t sm = (size_t)(((s->hm.ref_len + 1) & ~1) + nt) * sizeof(double);
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (void*)ho_solve_k, nt, sm));
     if (occ < 1) return fail(PHW_ECUDA, "ho_solve_k does not fit on an SM");
-    const int grid = std::max(1, std::min(nblk(std::max(s->hm.nc, a.n), HO_NT), std::min(occ, 8) * s->sm_count));
+    const int grid = std::max(1, std::min(std::max(nblk(s->hm.nc, nt / HO_LPC), nblk(a.n, nt)), std::min(occ, 8) * s->sm_count));
     void* args[] = {(void*)&a};
-    CU(cudaLaunchCooperativeKernel((void*)ho_solve_k, dim3(grid), dim3(HO_NT), args, sm, s->stream));
+    CU(cudaLaunchCooperativeKernel((void*)ho_solve_k, dim3(grid), dim3(nt), args, sm, s->stream));
     s->launches++;
     s->kernel_paths |= PHW_PATH_HO_MF;
     return 0;
@@ -831,6 +841,41 @@ int launch_coop(phw_solver_s* s, const RowArgs& av, const RowArgs& ae) {
         s->prof_ev.push_back(e0); s->prof_ev.push_back(e1); s->prof_which.push_back(WHICH);
     }
     s->launches++;
+    return 0;
+}
+
+// conjugate-gradient mass solve (solve_pcg_coop_k): residual / preconditioned residual in the import staging vectors, search
+// direction and A pd in the two idle iterate buffers
+template <int WHICH>
+int launch_pcg(phw_solver_s* s, const RowArgs& a0) {
+    constexpr int NT = WHICH == 0 ? NT_COOP_P : NT_COOP_Q;
+    constexpr int MINB = WHICH == 0 ? PHW_MINB_P : PHW_MINB_Q;
+    auto kern = solve_pcg_coop_k<WHICH, NT, MINB>;
+    const size_t sm = WHICH == 0 ? s->smem_v1 : s->smem_e;
+    { int rc_ = ensure_dyn_smem(s->device, (const void*)kern, 200 * 1024); if (rc_) return rc_; }
+    int occ = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, sm));
+    if (occ < 1) return fail(PHW_ECUDA, "conjugate-gradient solve kernel does not fit on an SM");
+    const int grid = std::max(1, std::min(s->npatch, occ * s->sm_count));
+    RowArgs a = a0;
+    PcgArgs v{};
+    v.r = WHICH == 0 ? s->io_v : s->io_e; v.u = WHICH == 0 ? s->io_v2 : s->io_e2;
+    v.b = a.b; v.pinv = a.pinv; v.n = WHICH == 0 ? s->nv : s->ne;
+    void* args[] = {(void*)&a, (void*)&v};
+    CU(cudaMemsetAsync(&s->ctl->gbar[0], 0, sizeof(unsigned int), s->stream));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    const bool prof = prof_on(s);
+    if (prof) {
+        CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+        CU(cudaEventRecord(e0, s->stream));
+    }
+    CU(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(NT), args, sm, s->stream));
+    if (prof) {
+        CU(cudaEventRecord(e1, s->stream));
+        s->prof_ev.push_back(e0); s->prof_ev.push_back(e1); s->prof_which.push_back(WHICH);
+    }
+    s->launches++;
+    s->kernel_paths |= PHW_PATH_PCG;
     return 0;
 }
 
@@ -1045,6 +1090,7 @@ int solve_mass(phw_solver_s* s, int which, int n_launch) {
     if (s->coop) {
         a.b = which == PHW_P ? s->bp : s->bq;
         a.pinv = which == PHW_P ? s->pinv_p : s->pinv_q;
+        if (s->pcg[which] && s->pc.world <= 1 && a.mdiag == nullptr) return which == PHW_P ? launch_pcg<0>(s, a) : launch_pcg<1>(s, a);
         const bool pipe_ok = s->pc.world <= 1 || (pipe_multi_mask() & 1);
         if (which == PHW_Q && s->pipe_q && pipe_ok) return launch_mq_pipe(s);
         if (which == PHW_P && s->pipe_p && pipe_ok && s->ell_p && a.mdiag == nullptr) return launch_ell_pipe(s);
@@ -1094,6 +1140,25 @@ int solve_mass(phw_solver_s* s, int which, int n_launch) {
 int solve_block(phw_solver_s* s, double theta, int n_launch) {
     int rc;
     const double dt = s->prm.dt, K = s->prm.K_wave, rho = s->prm.rho;
+    if (s->ho) {
+        // higher-order pairs: assembled CSR rows, all iterations in one cooperative launch (solve_block_csr_k)
+        if (s->ho_mf) return fail(PHW_ESTATE, "the implicit schemes of the higher-order pairs run on the assembled operators (phw_ho_create)");
+        CsrBlockArgs a{};
+        a.Mp = s->hMp; a.Mq = s->hMq; a.D = s->hD; a.DT = s->hDT; a.tp = s->tp; a.tq = s->tq;
+        a.bp = s->bp; a.bq = s->bq; a.pinv_p = s->pinv_p; a.pinv_q = s->pinv_q;
+        a.cDv = theta * dt * K; a.cDe = -theta * dt / rho; a.wv = 1.0 / K; a.we = rho;
+        a.cheb_d = s->cheb_d[2]; a.cheb_c = s->cheb_c[2]; a.tol2 = s->prm.tol * s->prm.tol; a.max_iter = n_launch;
+        a.partials = s->partials; a.ctl = s->ctl;
+        CU(cudaMemsetAsync(&s->ctl->gbar[0], 0, sizeof(unsigned int), s->stream));
+        int occ = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (void*)solve_block_csr_k, 256, 0));
+        if (occ < 1) return fail(PHW_ECUDA, "solve_block_csr_k does not fit on an SM");
+        const int grid = std::max(1, std::min(nblk((s->nv + s->ne) * 8), std::min(occ, 4) * s->sm_count));
+        void* args[] = {(void*)&a};
+        CU(cudaLaunchCooperativeKernel((void*)solve_block_csr_k, dim3(grid), dim3(256), args, 0, s->stream));
+        s->launches++;
+        return 0;
+    }
     RowArgs a = base_args(s);
     a.which = 2; a.use_cheb_input = 1; a.coupled_from_tribuf = 1; a.cM = 1.0;
     a.cheb_d = s->cheb_d[2]; a.cheb_c = s->cheb_c[2];
@@ -1404,6 +1469,7 @@ int step(phw_solver_s* s) {
                 RC(waxpy(s, ne, s->tmp_q, s->q, 0.5 * dt, nullptr, s->tq, 2));
                 RC(op_vertex_dot(s, s->tmp_p, 0.0, 1.0, 2, 1.0, 6));
                 RC(op_edge_dot(s, s->tmp_q, 0.0, 1.0, 3, 1.0, 7));
+                RC(allreduce(s, 0, 2, 2));
             }
             RC(axpy(s, nv, s->p, dt, nullptr, s->tp, 2));
             RC(axpy(s, ne, s->q, dt, nullptr, s->tq, 2));
@@ -1464,6 +1530,7 @@ int setup_loop(phw_solver_s* s) {
     const int cl = s->npatch / s->G;
     const Layout& L = s->mesh->L;
     if (L.nv_owned != L.nv || L.ne_owned != L.ne) return 0;            // partitioned layouts take the multi-launch path
+    if (s->pcg[0] || s->pcg[1]) return 0;                              // conjugate-gradient mass solves (poor meshes): multi-launch path
     for (int g = 0; g < s->G; ++g) if (L.group_patch_off[g + 1] - L.group_patch_off[g] != cl) return 0;
     size_t sm = s->smem_vd;
     const bool cluster = (cl == 1 || cl == 2 || cl == 4 || cl == 8 || cl == 16);
@@ -2105,6 +2172,15 @@ static int setup_solver(phw_solver_s* s) {
     // ---- Chebyshev intervals.  P1: element bound [1/2, 2] (Wathen); RT1: element bounds from geom_k.
     s->cheb_d[0] = 1.25; s->cheb_c[0] = 0.75;
     s->cheb_d[1] = 0.5 * (s->lam_min_q + s->lam_max_q); s->cheb_c[1] = 0.5 * (s->lam_max_q - s->lam_min_q);
+    // meshes of poor quality: the element-wise interval of the RT1 mass matrix is pessimistic (a few stretched cells set it for the
+    // whole mesh) - conjugate gradients converge on the true spectrum
+    {
+        static const int env = [] { const char* e = getenv("PHW_PCG"); return e ? atoi(e) : -1; }();
+        const bool can = s->coop && s->G == 1 && !P.strong && !(P.flags & 131072) && env != 0;
+        const bool force = (P.flags & 65536) || env == 1;
+        s->pcg[0] = can && force;
+        s->pcg[1] = can && (force || s->lam_max_q > 10.0 * s->lam_min_q);
+    }
 #undef RC
     return 0;
 }
@@ -2125,12 +2201,18 @@ static int estimate_skew(phw_solver_s* s, double* sigma) {
         // z = P_p^-1/2 h ; y = D z ; y <- P_q^-1 y ; w = D^T y ; h' = P_p^-1/2 w
         for (int i = 0; i < nv; ++i) hp[i] = h[i] * std::sqrt(dp[i]);
         CU(cudaMemcpyAsync(s->io_v, hp.data(), nv * 8, cudaMemcpyHostToDevice, s->stream));
-        rc = op_edge_store(s, s->io_v, nullptr, 0.0, 1.0, 0.0, s->io_e); if (rc) return rc;
+        if (s->ho_mf) rc = ho_mf_D(s, s->io_v, 1.0, s->io_e);
+        else if (s->ho) { csr_store(s, s->hD, s->io_v, 1.0, s->io_e); rc = 0; }
+        else rc = op_edge_store(s, s->io_v, nullptr, 0.0, 1.0, 0.0, s->io_e);
+        if (rc) return rc;
         CU(cudaMemcpyAsync(y.data(), s->io_e, ne * 8, cudaMemcpyDeviceToHost, s->stream));
         CU(cudaStreamSynchronize(s->stream));
         for (int i = 0; i < ne; ++i) hq[i] = y[i] * dq[i];
         CU(cudaMemcpyAsync(s->io_e, hq.data(), ne * 8, cudaMemcpyHostToDevice, s->stream));
-        rc = op_vertex_store(s, nullptr, s->io_e, 0.0, 1.0, 0.0, s->io_v); if (rc) return rc;
+        if (s->ho_mf) rc = ho_mf_DT(s, s->io_e, 1.0, s->io_v);
+        else if (s->ho) { csr_store(s, s->hDT, s->io_e, 1.0, s->io_v); rc = 0; }
+        else rc = op_vertex_store(s, nullptr, s->io_e, 0.0, 1.0, 0.0, s->io_v);
+        if (rc) return rc;
         CU(cudaMemcpyAsync(hp.data(), s->io_v, nv * 8, cudaMemcpyDeviceToHost, s->stream));
         CU(cudaStreamSynchronize(s->stream));
         double nrm = 0.0;
@@ -2143,6 +2225,47 @@ static int estimate_skew(phw_solver_s* s, double* sigma) {
         for (int i = 0; i < nv; ++i) h[i] = hp[i] / nrm;
     }
     *sigma = std::sqrt(lam);
+    return 0;
+}
+
+// implicit schemes (IE, SM): ellipse of the Chebyshev iteration for the coupled block system from the spectral intervals of the two
+// Jacobi-scaled mass matrices and a power-iteration bound of the skew part; with the lumped model the constant column
+// w = B^-1 [0; b_L] of the bordered system (wave_2D.py:562-572), solved once.  bl: b_L in internal edge numbering (empty: no lumped model)
+static int setup_implicit(phw_solver_s* s, const std::vector<double>& bl, double sigma_given = -1.0) {
+    const phw_params* prm = &s->prm;
+    const double theta = (prm->scheme == PHW_IE) ? 1.0 : 0.5;
+    double sigma = sigma_given;
+    int rc = 0;
+    if (!(sigma >= 0.0)) { rc = estimate_skew(s, &sigma); if (rc) return rc; }     // partitioned runs: the caller's distributed estimate
+    s->skew_bound = 1.05 * theta * prm->dt * std::sqrt(prm->K_wave / prm->rho) * sigma;
+    const double lo = std::min(s->cheb_d[0] - s->cheb_c[0], s->lam_min_q), hi = std::max(s->cheb_d[0] + s->cheb_c[0], s->lam_max_q);
+    ellipse_for_rectangle(lo, hi, s->skew_bound, s->cheb_d[2], s->cheb_c[2]);
+    if (!prm->interconnection) return 0;
+    rc = s->dalloc(&s->wp, s->nv); if (!rc) rc = s->dalloc(&s->wq, s->ne);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(s->bq, bl.data(), (size_t)s->ne * 8, cudaMemcpyHostToDevice, s->stream));
+    CU(cudaMemsetAsync(s->bp, 0, (size_t)s->nv * 8, s->stream));
+    const double tol_keep = s->prm.tol;
+    s->prm.tol = std::min(tol_keep, 1e-14);
+    rc = solve_block(s, theta, s->prm.max_iter);
+    s->prm.tol = tol_keep;
+    if (rc) return rc;
+    copy_from_tb_k<<<vec_grid(s, s->nv), 256, 0, s->stream>>>(s->nv, s->wp, s->tp, s->ctl, 2);
+    copy_from_tb_k<<<vec_grid(s, s->ne), 256, 0, s->stream>>>(s->ne, s->wq, s->tq, s->ctl, 2);
+    rc = flux(s, s->wq, 2, 3);                      // b_L^T w_q, summed over the ranks in partitioned runs
+    if (rc) return rc;
+    double f3 = 0.0;
+    unsigned long long seq = 0;
+    cudaMemcpyAsync(&f3, &s->ctl->flux[3], 8, cudaMemcpyDeviceToHost, s->stream);
+    cudaMemcpyAsync(&seq, &s->ctl->comm_seq, sizeof(seq), cudaMemcpyDeviceToHost, s->stream);
+    cudaStreamSynchronize(s->stream);
+    s->blw = f3;
+    // reset warm starts and counters (the mailbox sequence number of the inter-GPU all-reduce keeps counting)
+    for (int i = 0; i < 3; ++i) { cudaMemsetAsync(s->tp.b[i], 0, (size_t)s->nv * 8, s->stream); cudaMemsetAsync(s->tq.b[i], 0, (size_t)s->ne * 8, s->stream); }
+    cudaMemsetAsync(s->ctl, 0, sizeof(Ctl), s->stream);
+    cudaMemcpyAsync(&s->ctl->comm_seq, &seq, sizeof(seq), cudaMemcpyHostToDevice, s->stream);
+    cudaStreamSynchronize(s->stream);
+    if (cudaGetLastError() != cudaSuccess) return fail(PHW_ECUDA, "bordered-column setup solve failed");
     return 0;
 }
 
@@ -2174,42 +2297,20 @@ int phw_solver_create(phw_mesh_t m, const phw_params* prm, int32_t device, void*
     if (s->prm.max_iter <= 0) s->prm.max_iter = 200;
     int rc = setup_solver(s);
     if (rc) { std::string keep = g_err; phw_solver_destroy(s); g_err = keep; return rc; }
-    const bool implicit = (prm->scheme == PHW_IE || prm->scheme == PHW_SM);
-    if (implicit) {
-        const double theta = (prm->scheme == PHW_IE) ? 1.0 : 0.5;
-        double sigma = 0.0;
-        rc = estimate_skew(s, &sigma);
-        if (rc) { std::string keep = g_err; phw_solver_destroy(s); g_err = keep; return rc; }
-        s->skew_bound = 1.05 * theta * prm->dt * std::sqrt(prm->K_wave / prm->rho) * sigma;
-        double lo = std::min(0.5, s->lam_min_q), hi = std::max(2.0, s->lam_max_q);
-        ellipse_for_rectangle(lo, hi, s->skew_bound, s->cheb_d[2], s->cheb_c[2]);
+    if (prm->scheme == PHW_IE || prm->scheme == PHW_SM) {
+        std::vector<double> bl;
         if (prm->interconnection) {
-            // w = B^-1 [0; b_L]: constant column of the bordered system (lumped x1 <-> port edges), solved once
-            rc = s->dalloc(&s->wp, s->nv); if (!rc) rc = s->dalloc(&s->wq, s->ne);
-            if (rc) { std::string keep = g_err; phw_solver_destroy(s); g_err = keep; return rc; }
-            std::vector<double> bl(s->ne, 0.0);
+            bl.assign(s->ne, 0.0);
             const Layout& L = m->L;
             for (int64_t k = 0; k < L.nb; ++k)
                 if (L.btag[k] == PHW_TAG_LEFT) bl[L.e_old2new[L.bedge[k]]] = L.bsign[k] * L.bweight[k];
-            cudaMemcpyAsync(s->bq, bl.data(), (size_t)s->ne * 8, cudaMemcpyHostToDevice, s->stream);
-            cudaMemsetAsync(s->bp, 0, (size_t)s->nv * 8, s->stream);
-            double tol_keep = s->prm.tol;
-            s->prm.tol = std::min(tol_keep, 1e-14);
-            rc = solve_block(s, theta, s->prm.max_iter);
-            s->prm.tol = tol_keep;
-            if (!rc) {
-                copy_from_tb_k<<<vec_grid(s, s->nv), 256, 0, s->stream>>>(s->nv, s->wp, s->tp, s->ctl, 2);
-                copy_from_tb_k<<<vec_grid(s, s->ne), 256, 0, s->stream>>>(s->ne, s->wq, s->tq, s->ctl, 2);
-                flux_k<<<1, 256, 0, s->stream>>>(s->d_port_goff, s->d_port_e, s->d_port_bl, s->wq, s->tq, s->ctl, 2, 3);
-                double f3 = 0.0;
-                cudaMemcpyAsync(&f3, &s->ctl->flux[3], 8, cudaMemcpyDeviceToHost, s->stream);
-                cudaStreamSynchronize(s->stream);
-                s->blw = f3;
-                // reset warm starts and counters
-                for (int i = 0; i < 3; ++i) { cudaMemsetAsync(s->tp.b[i], 0, (size_t)s->nv * 8, s->stream); cudaMemsetAsync(s->tq.b[i], 0, (size_t)s->ne * 8, s->stream); }
-                cudaMemsetAsync(s->ctl, 0, sizeof(Ctl), s->stream);
-            }
-            if (rc || cudaGetLastError() != cudaSuccess) { phw_solver_destroy(s); return fail(PHW_ECUDA, "bordered-column setup solve failed"); }
+        }
+        const Layout& L0 = m->L;
+        if (L0.nv_owned != L0.nv || L0.ne_owned != L0.ne) {
+            s->implicit_pending = true;      // the skew bound and the bordered column need the exchange: phw_comm_finish_implicit
+        } else {
+            rc = setup_implicit(s, bl);
+            if (rc) { std::string keep = g_err; phw_solver_destroy(s); g_err = keep; return rc; }
         }
     }
     rc = setup_loop(s);
@@ -2253,7 +2354,6 @@ int phw_comm_setup(phw_solver_t s, int32_t rank, int32_t world, const void* hand
         return fail(PHW_EINVAL, "rank/world/neighbour count out of range (at most 8 ranks)");
     if (s->ho) return fail(PHW_EINVAL, "partitioned runs are not available for higher-order solvers");
     if (!s->coop) return fail(PHW_ESTATE, "multi-GPU runs need the cooperative solve path");
-    if (s->prm.scheme == PHW_IE || s->prm.scheme == PHW_SM) return fail(PHW_EINVAL, "implicit schemes are not available in partitioned runs yet");
     CU(cudaSetDevice(s->device));
     PeerComm pc = s->pc;
     pc.rank = rank; pc.world = world; pc.n_nb = n_nb;
@@ -2335,6 +2435,36 @@ int phw_set_cheb_bounds(phw_solver_t s, double lam_min_q, double lam_max_q) {
     return PHW_OK;
 }
 
+// inverse Jacobi diagonals of the solved blocks in user numbering (setup helper of the distributed skew estimate)
+int phw_get_jacobi(phw_solver_t s, int32_t which, double* inv_diag) {
+    if (!s || !inv_diag || (which != PHW_P && which != PHW_Q)) return fail(PHW_EINVAL, "bad arguments");
+    CU(cudaSetDevice(s->device));
+    return which == PHW_P ? export_vec(s, s->pinv_p, inv_diag, s->nv, s->d_v_new2old, s->io_v)
+                          : export_vec(s, s->pinv_q, inv_diag, s->ne, s->d_e_new2old, s->io_e);
+}
+
+// implicit schemes in partitioned runs: after phw_comm_setup, with sigma = largest singular value of P_q^-1/2 D P_p^-1/2 of the
+// GLOBAL operator (identical on every rank; solver.py computes it by a distributed power iteration through phw_apply_D / _DT).
+// Collective: the bordered-column solve exchanges halo values and norms with the other ranks.
+int phw_comm_finish_implicit(phw_solver_t s, double sigma) {
+    if (!s || !(sigma > 0.0)) return fail(PHW_EINVAL, "bad arguments");
+    if (!s->implicit_pending) return fail(PHW_ESTATE, "no implicit set-up is pending on this solver");
+    CU(cudaSetDevice(s->device));
+    std::vector<double> bl;
+    if (s->prm.interconnection) {
+        const Layout& L = s->mesh->L;
+        bl.assign(s->ne, 0.0);
+        for (int64_t k = 0; k < L.nb; ++k)
+            if (L.btag[k] == PHW_TAG_LEFT) bl[L.e_old2new[L.bedge[k]]] = L.bsign[k] * L.bweight[k];
+    }
+    int rc = setup_implicit(s, bl, sigma);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(s->stream));
+    s->implicit_pending = false;
+    s->launches = 0;
+    return PHW_OK;
+}
+
 int phw_solver_set_group_params(phw_solver_t s, int32_t n_groups, const double* K_wave, const double* rho, const double* lumped6) {
     if (!s || !K_wave || !rho || !lumped6) return fail(PHW_EINVAL, "NULL argument");
     if (n_groups != s->G) return fail(PHW_EINVAL, "n_groups does not match the mesh");
@@ -2409,6 +2539,7 @@ int phw_get_state(phw_solver_t s, double* p, double* q, double* x3) {
 
 int phw_run(phw_solver_t s, int64_t n_steps, double* H_rows) {
     if (!s || n_steps < 0) return fail(PHW_EINVAL, "bad arguments");
+    if (s->implicit_pending) return fail(PHW_ESTATE, "implicit scheme on a partitioned mesh: call phw_comm_setup and phw_comm_finish_implicit first");
     CU(cudaSetDevice(s->device));
     const size_t nrow = (size_t)n_steps * (size_t)s->G;
     if ((int64_t)nrow > s->dH_rows) {
@@ -2667,10 +2798,9 @@ static int ho_create_base(const phw_params* prm, int32_t device, void* cuda_stre
                           double lam_min_p, double lam_max_p, double lam_min_q, double lam_max_q, phw_solver_s** out) {
     if (!prm || !out || !b_L) return fail(PHW_EINVAL, "NULL argument");
     if (prm->scheme < 0 || prm->scheme > 5) return fail(PHW_EINVAL, "unknown scheme");
-    if (prm->scheme == PHW_IE || prm->scheme == PHW_SM || prm->strong || prm->casimir)
-        return fail(PHW_EINVAL, "higher-order pairs: explicit weak-form schemes only (EE, SE, EH, SV)");
-    if (prm->interconnection && !(prm->scheme == PHW_SE || prm->scheme == PHW_SV))
+    if (prm->interconnection && !(prm->scheme == PHW_SE || prm->scheme == PHW_SV || prm->scheme == PHW_SM))
         return fail(PHW_EINVAL, "only SE, SV and SM time int schemes implemented for interconnection model");
+    if (prm->strong || prm->casimir) return fail(PHW_EINVAL, "higher-order pairs: weak boundary conditions, no casimir control");
     if (!(lam_min_p > 0) || !(lam_min_q > 0) || lam_max_p < lam_min_p || lam_max_q < lam_min_q) return fail(PHW_EINVAL, "bad spectral bounds");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(PHW_ECUDA, "no CUDA device available (libphwave has no CPU fallback)"); }
@@ -2737,6 +2867,12 @@ int phw_ho_create(const phw_params* prm, int32_t device, void* cuda_stream, int6
             cudaMemcpyAsync(s->pinv_q, pq.data(), n_q * 8, cudaMemcpyHostToDevice, s->stream) != cudaSuccess) return bail(fail(PHW_ECUDA, "memcpy failed"));
         if (cudaStreamSynchronize(s->stream) != cudaSuccess) return bail(fail(PHW_ECUDA, "sync failed"));
     }
+    if (prm->scheme == PHW_IE || prm->scheme == PHW_SM) {
+        rc = setup_implicit(s, prm->interconnection ? std::vector<double>(b_L, b_L + n_q) : std::vector<double>());
+        if (rc) return bail(rc);
+        if (cudaStreamSynchronize(s->stream) != cudaSuccess) return bail(fail(PHW_ECUDA, "sync failed"));
+        s->launches = 0;
+    }
     *out = s;
     return PHW_OK;
 }
@@ -2750,6 +2886,8 @@ int phw_ho_create_mf(const phw_params* prm, int32_t device, void* cuda_stream, i
                      const double* b_L, double lam_min_p, double lam_max_p, double lam_min_q, double lam_max_q, phw_solver_t* out) {
     if (!cell_vertices || !cell_edges || !geom4 || !Mp_hat || !C_hat || !A00 || !A01s || !A11) return fail(PHW_EINVAL, "NULL argument");
     if (k_p < 1 || k_p > 3 || k_q < 1 || k_q > 3) return fail(PHW_EINVAL, "basis orders 1..3 are supported");
+    if (prm && (prm->scheme == PHW_IE || prm->scheme == PHW_SM))
+        return fail(PHW_EINVAL, "the implicit schemes of the higher-order pairs run on the assembled operators (phw_ho_create)");
     if (nN_rows < 0 || nNT_rows < 0 || (nN_rows && (!N_row || !N_indptr || !N_idx || !N_val)) || (nNT_rows && (!NT_row || !NT_indptr || !NT_idx || !NT_val)))
         return fail(PHW_EINVAL, "bad boundary operator");
     const int ndp = (k_p + 1) * (k_p + 2) / 2, ndq = k_q * (k_q + 2);

@@ -359,7 +359,65 @@ def setup_peer_exchange(solver, part, dist, rank, world):
         nsv.ctypes.data_as(_lib.c_i64p), PtrArr(*loc_ptrs['v']) if n else PtrArr(), PtrArr(*rem_ptrs['v']) if n else PtrArr(),
         nse.ctypes.data_as(_lib.c_i64p), PtrArr(*loc_ptrs['e']) if n else PtrArr(), PtrArr(*rem_ptrs['e']) if n else PtrArr()))
     dist.barrier()
-    return dict(neighbours=nbs, send_v=n_send['v'], send_e=n_send['e'])
+    info = dict(neighbours=nbs, send_v=n_send['v'], send_e=n_send['e'])
+    if solver.params.scheme in (_lib.SCHEMES['IE'], _lib.SCHEMES['SM']):
+        # implicit schemes: the coupled block solve needs the skew bound of the GLOBAL operator and (lumped model) a bordered column
+        # solved with the exchange in place
+        send_user = {'v': {}, 'e': {}}
+        for nb in nbs:
+            for kind in ('v', 'e'):
+                asked = allneed[nb].get(rank, {})
+                if kind in asked:
+                    send_user[kind][nb] = pt.needed_by(asked[kind][0], part, kind)
+        sigma = distributed_skew_estimate(solver, part, dist, rank, world, send_user)
+        _lib.check(lib.phw_comm_finish_implicit(solver.handle, float(sigma)))
+        dist.barrier()
+        info['skew_sigma'] = float(sigma)
+    return info
+
+
+def distributed_skew_estimate(solver, part, dist, rank, world, send_user, iters=40):
+    """Largest singular value of P_q^-1/2 D P_p^-1/2 of the global operator by power iteration on D^T P_q^-1 D (the same iteration as
+    estimate_skew in phwave.cu, which sees one rank's operator only): D and D^T are applied on the device to the owned rows of
+    every rank, the halo values and the norms travel through torch.distributed object collectives (set-up only).  The start vector
+    depends on global vertex ids only, and sums run in rank order, so every rank ends with the same bits."""
+    ov, oe = part.vertex_owner == rank, part.edge_owner == rank
+
+    def halo(vec, kind):
+        out = {int(nb): vec[idx] for nb, idx in send_user[kind].items()}
+        allv = [None] * world
+        dist.all_gather_object(allv, out)
+        for nb, lists in part.recv.items():
+            if kind in lists:
+                vec[lists[kind]] = allv[nb][rank]
+
+    def gsum(x):
+        allx = [None] * world
+        dist.all_gather_object(allx, float(x))
+        return float(sum(allx))
+
+    dp, dq = np.empty(ov.shape[0]), np.empty(oe.shape[0])
+    _lib.check(solver.lib.phw_get_jacobi(solver.handle, _lib.PHW_P, dp.ctypes.data))
+    _lib.check(solver.lib.phw_get_jacobi(solver.handle, _lib.PHW_Q, dq.ctypes.data))
+    halo(dp, 'v')
+    halo(dq, 'e')
+    sp = np.sqrt(dp)
+    gid = np.asarray(part.vertex_gid, dtype=np.uint64)
+    h = ((gid * np.uint64(2654435761)) % np.uint64(2000001)).astype(np.float64) / 1e6 - 1.0
+    lam = 0.0
+    for _ in range(iters):
+        y = solver.apply_D(h * sp) * dq
+        y[~oe] = 0.0
+        halo(y, 'e')
+        w = solver.apply_DT(y) * sp
+        w[~ov] = 0.0
+        nrm = np.sqrt(gsum(w[ov] @ w[ov]))
+        if nrm == 0.0:
+            break
+        lam = nrm / np.sqrt(gsum(h[ov] @ h[ov]))
+        h = w / nrm
+        halo(h, 'v')
+    return np.sqrt(lam)
 
 
 class _DofCounts:

@@ -152,6 +152,14 @@ def wave_2D_solve(tFinal, numSteps, outputDir,
         m.set_dirichlet(np.concatenate([left_v, right_v]), np.concatenate([left_w, np.zeros(right_v.shape[0])]))
 
     solver = Solver(m, prm, device=device)
+    # mesh quality: the mass solves are iterative here (the reference's LU is not), and their cost follows the worst cell
+    st0 = solver.stats()
+    if st0['lam_max_q'] > 10.0 * st0['lam_min_q'] and rank == 0:
+        import warnings
+        warnings.warn('stretched cells in the mesh: the element-wise bound of the condition number of the Jacobi-scaled RT1 mass matrix is '
+                      '{:.0f} (quality meshes: <= 4); the M_q solves switch from Chebyshev iteration to conjugate gradients where available '
+                      '(one GPU, weak form) and need on the order of sqrt(kappa) x 15 iterations per solve'
+                      .format(st0['lam_max_q'] / st0['lam_min_q']), UserWarning, stacklevel=2)
 
     # ---- initial conditions (wave_2D.py:732-771) ----
     H_init = 0.0
@@ -289,17 +297,20 @@ class _AnalyticalDiagnostics:
 def _solve_high_order(tFinal, numSteps, outputDir, nx, xLength, yLength, domainShape, timeIntScheme, dirichletImp, K_wave, rho,
                       interConnection, analytical, controlType, basis_order, mesh, mesh_kind, device, tol, extrap_order, lumped,
                       return_state, verbose, tic, solver_flags=0, saveP=False, save_every=None):
-    """basis_order != (1,1) (wave_2D.py:174-175,202-203): host-assembled operators (fem_ho.py) + CSR device kernels."""
+    """basis_order != (1,1) (wave_2D.py:174-175,202-203): matrix-free cell kernels on the reference-element form (fem_ref.py,
+    csrc/kernels_ho.cuh) for the explicit schemes, host-assembled CSR operators (fem_ho.py) for the implicit ones."""
     from .fem_ho import HighOrderSpaces, LagrangeRef, tri_rule
     from .fem_ref import RefSpaces
     from .solver import HighOrderSolver, MatrixFreeHighOrderSolver
-    if dirichletImp != 'weak' or controlType is not None or timeIntScheme in ('IE', 'SM'):
-        raise NotImplementedError('higher-order pairs are available for the explicit weak-form schemes (EE, SE, EH, SV)')
+    if dirichletImp != 'weak' or controlType is not None:
+        raise NotImplementedError('higher-order pairs are available for the weak form without control (all six schemes, with or without the lumped model)')
+    implicit = timeIntScheme in ('IE', 'SM')
     if mesh is None:
         mesh = generate_mesh(domainShape, nx, xLength, yLength, kind=mesh_kind)
     # default: matrix-free kernels on the reference-element form of the spaces (csrc/kernels_ho.cuh, fem_ref.py);
     # PHW_HO_CSR=1: host-assembled CSR operators + generic CSR kernels (round 1; A/B and cross-check)
-    matrix_free = not os.environ.get('PHW_HO_CSR')
+    # implicit schemes (IE, SM): coupled block solve on the assembled rows (solve_block_csr_k)
+    matrix_free = not os.environ.get('PHW_HO_CSR') and not implicit
     S = (RefSpaces if matrix_free else HighOrderSpaces)(mesh[0], mesh[1], basis_order[0], basis_order[1])
     if verbose:
         print('number of cells = {}'.format(S.nc))

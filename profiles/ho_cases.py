@@ -16,7 +16,10 @@ from oracle.wave_2D_oracle import wave_2D_solve_oracle
 K, RHO = 3.0, 2.0
 steps = int(os.environ.get('HO_STEPS', '3000'))
 cpu_steps = int(os.environ.get('CPU_STEPS', '30'))
-for scheme, bo, (Nx, Ny) in [('SV', (3, 3), (136, 34)), ('SE', (3, 3), (136, 34)), ('SV', (2, 2), (136, 34)), ('SV', (1, 2), (34, 8))]:
+CASES = [('SV', (3, 3), (136, 34)), ('SE', (3, 3), (136, 34)), ('SV', (2, 2), (136, 34)), ('SV', (1, 2), (34, 8))]
+if os.environ.get('HO_ONLY'):          # one case only (ncu captures)
+    CASES = [CASES[int(os.environ['HO_ONLY'])]]
+for scheme, bo, (Nx, Ny) in CASES:
     mesh = rectangle_structured(Nx, Ny)
     tF = 1.5
     t0 = time.time()

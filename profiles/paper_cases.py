@@ -77,5 +77,11 @@ def run_paper_bench(args):
 
 if __name__ == '__main__':
     cpu_steps = int(os.environ.get('CPU_STEPS', '300'))
-    for c in cases():
+    todo = cases()
+    if os.environ.get('PAPER_ONLY'):        # one case, optionally shortened (ncu captures)
+        todo = [todo[int(os.environ['PAPER_ONLY'])]]
+    if os.environ.get('PAPER_STEPS'):
+        n = int(os.environ['PAPER_STEPS'])
+        todo = [c[:5] + (c[5] * n / c[6], n) + c[7:] for c in todo]
+    for c in todo:
         print(json.dumps(run_case(*c, cpu_steps=cpu_steps)), flush=True)

@@ -38,15 +38,23 @@ def _worker(rank, world, port, scheme, q, flags=0, big=False):
         # ghost lists arriving one patch ahead) with the exchange in the loop
         mesh = rectangle_structured(200, 50) if big else rectangle_delaunay(48, 12, seed=9)
         steps, tF = (20, 0.004) if big else (40, 0.02)
-        Ho, _, so = wave_2D_solve_oracle(tF, steps, mesh, 1.0, 0.25, timeIntScheme=scheme, K_wave=K_WAVE, rho=RHO, return_state=True)
+        ic = scheme.endswith('+IC')          # 'SM+IC': lumped electromechanical model coupled at the left port (wave_2D.py:427-446)
+        scheme = scheme.split('+')[0]
+        Ho, _, so = wave_2D_solve_oracle(tF, steps, mesh, 1.0, 0.25, timeIntScheme=scheme, K_wave=K_WAVE, rho=RHO, return_state=True,
+                                         interConnection='IC' if ic else None)
         part = pt.build_local_part(mesh[0], mesh[1], pt.slab_cell_ranks(mesh[0], mesh[1], world), rank)
         m = Mesh(part.vertices, part.cells, patch_cells=32 if big else 96, vertex_external=part.vertex_external,
                  edge_external=part.edge_external, cell_owned=part.cell_owned)
         m.set_boundary(tag_boundary_edges(m, 'R', 1.0, 0.25))
         prm = _lib.PhwParams()
         prm.scheme, prm.dt, prm.K_wave, prm.rho = _lib.SCHEMES[scheme], tF / steps, K_WAVE, RHO
-        prm.input_kind, prm.in_amp, prm.in_omega, prm.in_t_stop = _lib.IN_SINE_WINDOW, 10.0, 8 * np.pi, 0.25
-        prm.tol, prm.max_iter, prm.extrap_order, prm.flags = 1e-13, 200, 2, int(flags)
+        prm.input_kind, prm.in_amp, prm.in_omega, prm.in_t_stop = _lib.IN_SINE_WINDOW, 5.0 if ic else 10.0, 8 * np.pi, 0.25
+        prm.interconnection = 1 if ic else 0
+        if ic:
+            from porthamiltonian_fem_b200.wave_2D import _DEFAULT_LUMPED
+            for k, v in _DEFAULT_LUMPED.items():
+                setattr(prm, k, float(v))
+        prm.tol, prm.max_iter, prm.extrap_order, prm.flags = 1e-13, 400, 2, int(flags)
         s = Solver(m, prm, device=rank)
         info = setup_peer_exchange(s, part, dist, rank, world)
         H = s.run(steps)
@@ -57,7 +65,9 @@ def _worker(rank, world, port, scheme, q, flags=0, big=False):
             assert paths & 16, 'the pipelined H_wave pass did not run: kernel_paths = %d' % paths
         if flags & 4096:
             assert paths & 32, 'the pipelined right-hand sides did not run: kernel_paths = %d' % paths
-        p, qv, _ = s.get_state()
+        p, qv, x3 = s.get_state()
+        if ic:
+            assert np.abs(x3 - so['x']).max() < 1e-10 * max(1.0, np.abs(so['x']).max()), (x3, so['x'])
         ov, oe = part.vertex_owner == rank, part.edge_owner == rank
         topo_edges = so['topo'].edges
         # oracle edge ids of my local edges (through global vertex ids)
@@ -80,8 +90,15 @@ def test_two_gpu_partitioned_run_matches_oracle(scheme, flags, big):
     _run_partitioned(2, scheme, flags, big)
 
 
+# implicit schemes (coupled block solve with the exchange inside, skew bound from the distributed power iteration) and the lumped
+# model (port fluxes all-reduced; SM: bordered column solved across the ranks) on a partitioned mesh
+@pytest.mark.parametrize('scheme', ['SM', 'IE', 'SM+IC', 'SV+IC', 'SE+IC'])
+def test_two_gpu_partitioned_implicit_and_lumped_model(scheme):
+    _run_partitioned(2, scheme, 0, False)
+
+
 # four ranks: the interior slabs have two neighbours and two halo columns (patches of halo cells only at the end of the layout)
-@pytest.mark.parametrize('scheme,flags,big', [('SE', 768 + 2048 + 4096, True), ('SV', 768 + 2048 + 4096, False), ('SE', 0, False)])
+@pytest.mark.parametrize('scheme,flags,big', [('SE', 768 + 2048 + 4096, True), ('SV', 768 + 2048 + 4096, False), ('SE', 0, False), ('SM+IC', 0, False)])
 def test_four_gpu_partitioned_run_matches_oracle(scheme, flags, big):
     _run_partitioned(4, scheme, flags, big)
 

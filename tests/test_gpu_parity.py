@@ -211,6 +211,64 @@ def test_mass_solve_port_rhs_on_square_cells():
         assert rel(x, spla.spsolve(ops['M_q'].tocsc(), ops['b_L'])) < 1e-11, (Nx, Ny, it)
 
 
+def _sliver_mesh():
+    """a quality mesh with a band of stretched cells (aspect ratio ~25): three mesh columns squeezed to 4 % of their width"""
+    v, c = rectangle_structured(40, 10)
+    v = v.copy()
+    x = v[:, 0]
+    h = 1.0 / 40
+    band = (x > 0.5 - 1e-9) & (x < 0.5 + 3 * h + 1e-9)
+    v[band, 0] = 0.5 + (x[band] - 0.5) * 0.04
+    right = x > 0.5 + 3 * h + 1e-9
+    v[right, 0] = 0.5 + 3 * h * 0.04 + (x[right] - (0.5 + 3 * h)) * (0.5 - 3 * h * 0.04) / (0.5 - 3 * h)
+    return v, c
+
+
+def test_conjugate_gradient_mass_solves_on_poor_meshes():
+    """the Chebyshev interval of the RT1 mass matrix is an element-wise bound, so a band of slivers (or uniformly
+    stretched cells) makes every solve of the whole mesh slow; the reference's LU does not care (wave_2D.py:820,854).
+    phw_solver_create switches the M_q solve to conjugate gradients (solve_pcg_coop_k) when the bound of kappa exceeds 10."""
+    for name, (v, c) in (('aspect12', rectangle_structured(6, 18)), ('sliver_band', _sliver_mesh())):
+        topo = fem.Topology(v, c)
+        ops = fem.assemble_wave_operators(topo, fem.tag_boundary(topo, 'R', 1.0, 0.25))
+        rng = np.random.default_rng(5)
+        bp, bq = rng.standard_normal(topo.n_vertices), rng.standard_normal(topo.n_edges)
+        ref_p, ref_q = spla.spsolve(ops['M_p'].tocsc(), bp), spla.spsolve(ops['M_q'].tocsc(), bq)
+        its = {}
+        for label, flags in (('auto', 0), ('chebyshev', 131072), ('cg_both', 65536)):
+            m, s = make_solver(v, c, 'R', 1.0, 0.25, 64, flags=flags, max_iter=2000)
+            st = s.stats()
+            assert st['lam_max_q'] > 10 * st['lam_min_q'], name             # the element-wise bound flags the mesh
+            xq, itq = s.mass_solve(_lib.PHW_Q, bq)
+            xp, itp = s.mass_solve(_lib.PHW_P, bp)
+            assert rel(xq, ref_q) < 1e-10 and rel(xp, ref_p) < 1e-11, (name, label, rel(xq, ref_q), rel(xp, ref_p))
+            z, _ = s.mass_solve(_lib.PHW_Q, np.zeros(topo.n_edges))
+            assert np.all(z == 0.0)
+            its[label] = (itp, itq, bool(s.stats()['kernel_paths'] & 2048))
+            s.close(); m.close()
+        assert its['auto'][2] and its['cg_both'][2] and not its['chebyshev'][2], its      # PHW_PATH_PCG
+        assert its['auto'][1] == its['cg_both'][1] and its['auto'][0] == its['chebyshev'][0], its   # auto: CG for M_q only
+        # uniformly stretched cells: the Jacobi-scaled matrix IS ill-conditioned (true kappa 119 on this mesh), CG gains little;
+        # a band of slivers only adds outlying eigenvalues, which CG deflates (host CG: 103 iterations) while the Chebyshev interval
+        # is set by the worst cell
+        assert its['auto'][1] <= its['chebyshev'][1], (name, its)
+        if name == 'sliver_band':
+            assert its['auto'][1] < 0.5 * its['chebyshev'][1], its
+
+
+def test_time_loop_on_sliver_mesh_matches_oracle_and_warns():
+    mesh = _sliver_mesh()
+    steps, tF = 60, 0.03
+    for scheme, kw in (('SE', {}), ('SV', dict(interConnection='IC'))):
+        Ho, _, so = wave_2D_solve_oracle(tF, steps, mesh, 1.0, 0.25, K_wave=K_WAVE, rho=RHO, timeIntScheme=scheme, return_state=True, **kw)
+        with pytest.warns(UserWarning, match='conjugate'):
+            Hg, _, sg = wave_2D_solve(tF, steps, '/tmp', 0, 1.0, 0.25, K_wave=K_WAVE, rho=RHO, mesh=mesh, timeIntScheme=scheme,
+                                      return_state=True, verbose=False, **kw)
+        assert sg['stats']['kernel_paths'] & 2048
+        assert rel(sg['p'], so['p']) < 1e-9 and rel(sg['q'], so['q']) < 1e-9, (rel(sg['p'], so['p']), rel(sg['q'], so['q']))
+        assert np.abs(Hg[:, 1:] - Ho[:, 1:]).max() < 1e-9 * np.abs(Ho[:, 1:]).max()
+
+
 @pytest.mark.parametrize('scheme', ['SE', 'SV', 'EE'])
 def test_time_loop_parity_config1_size(scheme):
     mesh = rectangle_structured(136, 34, 1.0, 0.25)

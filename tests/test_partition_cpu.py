@@ -177,6 +177,82 @@ def test_gloo_world2_partitioned_operators_match_global(how, world):
         assert err < 1e-12, (rank, err)
 
 
+class _HostOperators:
+    """numpy stand-in for the kernel-level entry points a partitioned Solver offers (owned rows of the local operators)"""
+
+    def __init__(self, lops):
+        self.lops = lops
+        self.lib = self
+        self.handle = None
+        self._diag = [1.0 / lops['M_p'].diagonal(), 1.0 / lops['M_q'].diagonal()]
+
+    def phw_get_jacobi(self, handle, which, addr):
+        import ctypes
+        d = self._diag[which]
+        ctypes.memmove(addr, np.ascontiguousarray(d).ctypes.data, d.nbytes)
+        return 0
+
+    def apply_D(self, p):
+        return self.lops['D'] @ p
+
+    def apply_DT(self, q):
+        return self.lops['D'].T @ q
+
+
+def _skew_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from porthamiltonian_fem_b200.solver import distributed_skew_estimate
+        v, c = rectangle_delaunay(20, 5, seed=4)
+        part = pt.build_local_part(v, c, pt.slab_cell_ranks(v, c, world), rank)
+        lt = fem.Topology(part.vertices, part.cells)
+        lops = fem.assemble_wave_operators(lt, fem.tag_boundary(lt, 'R', 1.0, 0.25))
+        # the Jacobi diagonals of halo dofs are incomplete on this rank, as on the device: the estimate must fetch the owners' values
+        need = {nb: {k: (part.vertex_gid if k == 'v' else part.edge_gid)[idx] for k, idx in lists.items()} for nb, lists in part.recv.items()}
+        allneed = [None] * world
+        dist.all_gather_object(allneed, need)
+        send_user = {'v': {}, 'e': {}}
+        for other in range(world):
+            if other != rank and rank in allneed[other]:
+                for kind, gids in allneed[other][rank].items():
+                    send_user[kind][other] = pt.needed_by(gids, part, kind)
+        sigma = distributed_skew_estimate(_HostOperators(lops), part, dist, rank, world, send_user, iters=300)
+        q.put((rank, float(sigma)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2_distributed_skew_estimate_matches_global_operator():
+    """implicit schemes in partitioned runs: the power iteration that runs across the ranks (solver.distributed_skew_estimate) finds
+    the largest singular value of the GLOBAL Jacobi-scaled skew operator, identically on every rank"""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    import torch.multiprocessing as mp
+    v, c = rectangle_delaunay(20, 5, seed=4)
+    gt = fem.Topology(v, c)
+    g = fem.assemble_wave_operators(gt, fem.tag_boundary(gt, 'R', 1.0, 0.25))
+    S = sp.diags(1 / np.sqrt(g['M_q'].diagonal())) @ g['D'] @ sp.diags(1 / np.sqrt(g['M_p'].diagonal()))
+    ref = spla.svds(S, k=1, return_singular_vectors=False)[0]
+    sck = socket.socket()
+    sck.bind(('127.0.0.1', 0))
+    port = sck.getsockname()[1]
+    sck.close()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_skew_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0][1] == res[1][1]                       # same bits on both ranks
+    assert abs(res[0][1] - ref) < 2e-3 * ref, (res, ref)
+
+
 def test_halo_only_patches_come_last_and_do_not_size_the_stages():
     """A thin interior slab of an 8-rank strong-scaling run (bench.py, BASELINE configs[3]): its two halo columns form patches of
     neighbour cells only.  They own no row, so the layout puts them behind the patches the kernels process and leaves them out of
