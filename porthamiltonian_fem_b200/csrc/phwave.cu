@@ -858,6 +858,7 @@ int launch_pcg(phw_solver_s* s, const RowArgs& a0) {
     if (occ < 1) return fail(PHW_ECUDA, "conjugate-gradient solve kernel does not fit on an SM");
     const int grid = std::max(1, std::min(s->npatch, occ * s->sm_count));
     RowArgs a = a0;
+    if (WHICH == 0) a.mdiag = s->mdiag_p;      // the STORE epilogue of the pure P1 mass rows reads the diagonal (solve_mass clears it for Chebyshev)
     PcgArgs v{};
     v.r = WHICH == 0 ? s->io_v : s->io_e; v.u = WHICH == 0 ? s->io_v2 : s->io_e2;
     v.b = a.b; v.pinv = a.pinv; v.n = WHICH == 0 ? s->nv : s->ne;

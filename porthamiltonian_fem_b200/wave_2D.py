@@ -307,10 +307,19 @@ def _solve_high_order(tFinal, numSteps, outputDir, nx, xLength, yLength, domainS
     implicit = timeIntScheme in ('IE', 'SM')
     if mesh is None:
         mesh = generate_mesh(domainShape, nx, xLength, yLength, kind=mesh_kind)
-    # default: matrix-free kernels on the reference-element form of the spaces (csrc/kernels_ho.cuh, fem_ref.py);
-    # PHW_HO_CSR=1: host-assembled CSR operators + generic CSR kernels (round 1; A/B and cross-check)
-    # implicit schemes (IE, SM): coupled block solve on the assembled rows (solve_block_csr_k)
-    matrix_free = not os.environ.get('PHW_HO_CSR') and not implicit
+    # Two device paths: matrix-free cell kernels on the reference-element form of the spaces (csrc/kernels_ho.cuh,
+    # fem_ref.py) and host-assembled CSR operators + CSR kernels (fem_ho.py).  Measured (profiles/r2o_ho_cases_matrix_free_vs_csr.jsonl):
+    # an iteration costs the same on both for P2 x RT2 but the reference-element basis needs ~25 % more Chebyshev iterations there,
+    # while at order 3 the assembled rows (~2.5 KB per cell) lose by 1.4 x on the paper mesh and 2.4 x beyond the L2.  Default:
+    # matrix-free when an order is 3, assembled rows below; PHW_HO_MF=1 / PHW_HO_CSR=1 force either.
+    # Implicit schemes (IE, SM): coupled block solve on the assembled rows (solve_block_csr_k).
+    if os.environ.get('PHW_HO_CSR'):
+        matrix_free = False
+    elif os.environ.get('PHW_HO_MF'):
+        matrix_free = True
+    else:
+        matrix_free = max(basis_order) >= 3
+    matrix_free = matrix_free and not implicit
     S = (RefSpaces if matrix_free else HighOrderSpaces)(mesh[0], mesh[1], basis_order[0], basis_order[1])
     if verbose:
         print('number of cells = {}'.format(S.nc))

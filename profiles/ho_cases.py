@@ -1,4 +1,5 @@
-"""Times the reference's default caseArray (main_wave_2D.py:105-114: R, SV / SE, weak, nx80, analytical, P3/RT3) through the
+"""(PHW_HO_MF=1 / PHW_HO_CSR=1 force the matrix-free / the assembled-CSR path; default: matrix-free at order 3.)
+Times the reference's default caseArray (main_wave_2D.py:105-114: R, SV / SE, weak, nx80, analytical, P3/RT3) through the
 drop-in wave_2D_solve call on one GPU; the CPU oracle (sparse LU, factor once) beside it on a bounded number of steps.
 Run: python profiles/ho_cases.py  (prints one JSON line per case)."""
 import json

@@ -16,8 +16,8 @@ for bo, (Nx, Ny) in [((2, 2), (816, 204)), ((3, 3), (408, 102)), ((2, 2), (272, 
     mesh = rectangle_structured(Nx, Ny)
     for csr in (False, True):
         os.environ.pop('PHW_HO_CSR', None)
-        if csr:
-            os.environ['PHW_HO_CSR'] = '1'
+        os.environ.pop('PHW_HO_MF', None)
+        os.environ['PHW_HO_CSR' if csr else 'PHW_HO_MF'] = '1'
         t0 = time.time()
         H, nc, st = wave_2D_solve(1.5 * steps / 30000, steps, '/tmp', 0, 1.0, 0.25, K_wave=K, rho=RHO, mesh=mesh, timeIntScheme='SV', analytical=True,
                                   basis_order=bo, return_state=True, verbose=False)

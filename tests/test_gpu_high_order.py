@@ -31,13 +31,23 @@ CASES = [
 
 @pytest.mark.parametrize('name,bo,make,steps,tF,kw', CASES)
 def test_high_order_time_loop_parity(name, bo, make, steps, tF, kw, monkeypatch):
-    monkeypatch.delenv('PHW_HO_CSR', raising=False)          # default: the matrix-free kernels (csrc/kernels_ho.cuh)
+    monkeypatch.delenv('PHW_HO_CSR', raising=False)
+    monkeypatch.setenv('PHW_HO_MF', '1')                     # the matrix-free kernels (csrc/kernels_ho.cuh) at every order
     _parity(name, bo, make, steps, tF, kw, matrix_free=True)
+
+
+@pytest.mark.parametrize('name,bo,make,steps,tF,kw', [CASES[0], CASES[3], CASES[4]])
+def test_high_order_default_path_selection(name, bo, make, steps, tF, kw, monkeypatch):
+    """default: matrix-free when an order is 3, assembled rows below (measured: profiles/r2o_ho_cases_matrix_free_vs_csr.jsonl)"""
+    monkeypatch.delenv('PHW_HO_CSR', raising=False)
+    monkeypatch.delenv('PHW_HO_MF', raising=False)
+    _parity(name, bo, make, steps, tF, kw, matrix_free=max(bo) >= 3)
 
 
 @pytest.mark.parametrize('name,bo,make,steps,tF,kw', [CASES[0], CASES[5], CASES[8]])
 def test_high_order_time_loop_parity_assembled_csr(name, bo, make, steps, tF, kw, monkeypatch):
-    monkeypatch.setenv('PHW_HO_CSR', '1')                    # host-assembled CSR operators (round 1), kept as the cross-check
+    monkeypatch.delenv('PHW_HO_MF', raising=False)
+    monkeypatch.setenv('PHW_HO_CSR', '1')                    # host-assembled CSR operators
     _parity(name, bo, make, steps, tF, kw, matrix_free=False)
 
 
@@ -55,6 +65,7 @@ def test_high_order_implicit_schemes_parity(name, bo, make, steps, tF, kw, monke
     """IE / SM (wave_2D.py:305-319,560-572) at basis_order > 1: coupled block solve on the assembled CSR rows (solve_block_csr_k),
     with the bordered lumped rows for 'IC'"""
     monkeypatch.delenv('PHW_HO_CSR', raising=False)
+    monkeypatch.setenv('PHW_HO_MF', '1')                     # even when the matrix-free path is asked for
     _parity(name, bo, make, steps, tF, kw, matrix_free=False, tol=2e-10)
 
 
