@@ -172,7 +172,9 @@ def run_sweep_bench(args):
                           'config': {'workload': 'batched sweep: {} independent IC cases per GPU, SV, 104x26x2 cells ({} dofs) each, dt=1e-3'.format(n_cases, n_dof_case),
                                      'iters_per_solve_p': st['iters_p'] / max(1, st['solves_p']), 'iters_per_solve_q': st['iters_q'] / max(1, st['solves_q']),
                                      'max_rel_residual': st['max_rel_residual'], 'setup_seconds': setup_s, 'kernel_paths': int(st['kernel_paths']),
-                                     'patches': solver.mesh.n_patches},
+                                     'patches': int(getattr(solver.mesh, 'n_patches', 0)),
+                                     'layout': 'state [n_dof][n_cases], case index fastest, one copy of the assembled operators (csrc/kernels_sweep.cuh)' if int(st['kernel_paths']) & 4096
+                                               else 'mesh replicated per case (grouped device mesh)'},
                           'gpu_launches': int(st['kernel_launches']),
                           'energy_residual_max': float(np.abs(H[:, :, 2]).max())}))
     if world > 1:

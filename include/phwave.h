@@ -95,7 +95,8 @@ typedef struct phw_stats {
 } phw_stats;
 enum phw_path { PHW_PATH_LEAN_P = 1, PHW_PATH_LEAN_Q = 2, PHW_PATH_PIPE_P = 4, PHW_PATH_PIPE_Q = 8, PHW_PATH_PIPE_ENERGY = 16, PHW_PATH_PIPE_RHS = 32, PHW_PATH_LOOP = 256, PHW_PATH_LOOP_RES = 512 /* ... with the mass solves resident in shared memory */,
                 PHW_PATH_HO_MF = 1024 /* matrix-free higher-order kernels (phw_ho_create_mf) */,
-                PHW_PATH_PCG = 2048 /* conjugate-gradient mass solves (meshes of poor quality: element-wise kappa bound > 10) */ };
+                PHW_PATH_PCG = 2048 /* conjugate-gradient mass solves (meshes of poor quality: element-wise kappa bound > 10) */,
+                PHW_PATH_SWEEP_CSR = 4096 /* batched sweep with the case index fastest (phw_sweep_create) */ };
 
 const char* phw_last_error(void);
 int phw_version(void);
@@ -232,6 +233,19 @@ int phw_ho_create(const phw_params* prm, int32_t device, void* cuda_stream, int6
                   const int32_t* DT_indptr, const int32_t* DT_idx, const double* DT_val,
                   const double* b_L, double lam_min_p, double lam_max_p, double lam_min_q, double lam_max_q,
                   phw_solver_t* out);
+/* Batched parameter sweep with the CASE INDEX FASTEST (BASELINE configs[4]; the loop over parameter cases of main_wave_2D.py:24-50,
+ * 119-140; csrc/kernels_sweep.cuh): n_cases >= 2 independent cases advanced together on ONE set of assembled operators (same arguments
+ * as phw_ho_create; the lowest-order pair assembled by fem_ho.py for a sweep).  Every state vector is [n_dof][n_cases] (case index
+ * fastest), in phw_set_state / phw_get_state too; per-case wave speed, density and lumped constants through
+ * phw_solver_set_group_params, per-case lumped states through phw_get_group_states; phw_run fills H_rows [n_cases][n_steps][8].
+ * Explicit weak-form schemes (the sweep runs SE / SV with the lumped model). */
+int phw_sweep_create(const phw_params* prm, int32_t device, void* cuda_stream, int32_t n_cases, int64_t n_p, int64_t n_q,
+                     const int32_t* Mp_indptr, const int32_t* Mp_idx, const double* Mp_val,
+                     const int32_t* Mq_indptr, const int32_t* Mq_idx, const double* Mq_val,
+                     const int32_t* D_indptr, const int32_t* D_idx, const double* D_val,
+                     const int32_t* DT_indptr, const int32_t* DT_idx, const double* DT_val,
+                     const double* b_L, double lam_min_p, double lam_max_p, double lam_min_q, double lam_max_q,
+                     phw_solver_t* out);
 /* The same pairs MATRIX-FREE (csrc/kernels_ho.cuh; host side porthamiltonian_fem_b200/fem_ref.py): cells with ascending vertex ids
  * mapped from one reference triangle, so that M_p,K = |det J| Mp_hat, C_K = sign(det J) C_hat and M_q,K = G00 A00 + G01 (A01 + A10) +
  * G11 A11 with G = J^T J / |det J|.  cell_vertices / cell_edges [n_cells][3] (edge i opposite local vertex i; edge ids = the

@@ -112,6 +112,9 @@ SIGNATURES = {
     'phw_ho_create': (ctypes.c_int, [ctypes.POINTER(PhwParams), ctypes.c_int32, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
                                      c_i32p, c_i32p, c_f64p, c_i32p, c_i32p, c_f64p, c_i32p, c_i32p, c_f64p, c_i32p, c_i32p, c_f64p,
                                      c_f64p, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.POINTER(ctypes.c_void_p)]),
+    'phw_sweep_create': (ctypes.c_int, [ctypes.POINTER(PhwParams), ctypes.c_int32, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_int64,
+                                        c_i32p, c_i32p, c_f64p, c_i32p, c_i32p, c_f64p, c_i32p, c_i32p, c_f64p, c_i32p, c_i32p, c_f64p,
+                                        c_f64p, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.POINTER(ctypes.c_void_p)]),
     'phw_ho_create_mf': (ctypes.c_int, [ctypes.POINTER(PhwParams), ctypes.c_int32, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32,
                                         ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, c_i32p, c_i32p, c_f64p,
                                         c_f64p, c_f64p, c_f64p, c_f64p, c_f64p,

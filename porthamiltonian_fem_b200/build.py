@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libphwave.so')
 SOURCES = ['phwave.cu', 'layout.cpp']
-HEADERS = ['kernels.cuh', 'kernels_pipe.cuh', 'kernels_loop.cuh', 'kernels_ho.cuh', 'pipe_carve.hpp', 'layout.hpp', os.path.join('..', '..', 'include', 'phwave.h')]
+HEADERS = ['kernels.cuh', 'kernels_pipe.cuh', 'kernels_loop.cuh', 'kernels_ho.cuh', 'kernels_sweep.cuh', 'pipe_carve.hpp', 'layout.hpp', os.path.join('..', '..', 'include', 'phwave.h')]
 NVCC_FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
               '-Xcompiler', '-fPIC,-O3,-fopenmp', '-shared']
 

@@ -501,6 +501,7 @@ __global__ void scalar_k(Ctl* ctl, const ScalarPrm* __restrict__ prms, int n_gro
 
 #include "kernels_loop.cuh"
 #include "kernels_ho.cuh"
+#include "kernels_sweep.cuh"
 
 
 // ================================================================================================
@@ -542,6 +543,7 @@ struct phw_solver_s {
     Hist hist[2][2];           // [field p/q][solve site]
     int extrap = 2, n_sites = 1;
     int extrap_f[2] = {2, 2};  // extrapolation order of the p / q solves
+    int bcsr = 0; double* bpart = nullptr;   // batched sweep with the case index fastest (kernels_sweep.cuh): number of cases, [row block][case] partial sums
     bool pcg[2] = {false, false};     // conjugate-gradient mass solves (poor meshes; flags bits 16 / 17)
     bool implicit_pending = false;    // partitioned implicit run: the ellipse / bordered column are set up by phw_comm_finish_implicit
     bool ho = false; Csr hMp{}, hMq{}, hD{}, hDT{};
@@ -649,6 +651,69 @@ void csr_dot(phw_solver_s* s, const Csr& A, const double* x, double scale, int s
         case 16: csr_dot_k<16><<<g, 256, 0, s->stream>>>(A, x, scale, s->ctl, slot, part, counter); break;
         default: csr_dot_k<32><<<g, 256, 0, s->stream>>>(A, x, scale, s->ctl, slot, part, counter);
     }
+}
+
+// ---- batched sweep, case index fastest (kernels_sweep.cuh): one warp = 32 cases x a block of rows
+inline bool prof_on(phw_solver_s* s);
+// row mapping of the sweep kernels (kernels_sweep.cuh: SweepMap): 1 = cyclic row tiles (default), 0 = one block of rows per warp
+inline int sweep_map_mode() {
+    static const int m = [] { const char* e = getenv("PHW_SWEEP_MAP"); return e ? atoi(e) : 1; }();
+    return m == 0 ? 0 : 1;
+}
+inline int bcsr_grid(phw_solver_s* s, const Csr& A, int* n_row_groups) {
+    const int nchunk = (s->bcsr + 31) / 32;
+    const int groups = std::max(1, std::min((A.n_rows + SWEEP_WPB - 1) / SWEEP_WPB, (8 * s->sm_count) / nchunk));   // ~8 CTAs per SM
+    *n_row_groups = groups;
+    return nchunk * groups;
+}
+void bcsr_store(phw_solver_s* s, const Csr& A, const double* x, double alpha, const double* cscale, double* y) {
+    int ng = 1;
+    const int g = bcsr_grid(s, A, &ng);
+    csr_store_b_k<<<g, 256, 0, s->stream>>>(A, s->bcsr, ng, sweep_map_mode(), x, alpha, cscale, y);
+    s->launches++;
+}
+void bcsr_dot(phw_solver_s* s, const Csr& A, const double* x, double scale, const double* cscale, int slot) {
+    int ng = 1;
+    const int g = bcsr_grid(s, A, &ng);
+    csr_dot_b_k<<<g, 256, 0, s->stream>>>(A, s->bcsr, ng, sweep_map_mode(), x, s->bpart);
+    dot_b_finish_k<<<nblk(s->bcsr, 128), 128, 0, s->stream>>>(s->bcsr, ng * SWEEP_WPB, s->bpart, scale, cscale, s->ctl, slot);
+    s->launches += 2;
+}
+int bcsr_solve(phw_solver_s* s, int which) {
+    CsrSolveBArgs a{};
+    a.A = which == PHW_P ? s->hMp : s->hMq; a.B = s->bcsr; a.tb = which == PHW_P ? s->tp : s->tq;
+    a.b = which == PHW_P ? s->bp : s->bq; a.pinv = which == PHW_P ? s->pinv_p : s->pinv_q;
+    a.cheb_d = s->cheb_d[which]; a.cheb_c = s->cheb_c[which];
+    // the stop test sees the residual aggregated over all cases: tighten it so that every case of comparable amplitude meets tol
+    const double t = std::max(s->prm.tol / std::sqrt((double)s->bcsr), 1e-14);
+    a.tol2 = std::min(s->prm.tol * s->prm.tol, t * t);
+    a.max_iter = s->prm.max_iter; a.which = which; a.partials = s->partials; a.ctl = s->ctl;
+    CU(cudaMemsetAsync(&s->ctl->gbar[0], 0, sizeof(unsigned int), s->stream));
+    int occ = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (void*)solve_coop_csr_b_k, 256, 0));
+    if (occ < 1) return fail(PHW_ECUDA, "solve_coop_csr_b_k does not fit on an SM");
+    const int nchunk = (s->bcsr + 31) / 32;
+    const int max_ctas = std::min(occ, 8) * s->sm_count;
+    if (nchunk > max_ctas) return fail(PHW_EINVAL, "too many cases for one sweep solver: shard the case list");
+    a.n_row_groups = sweep_row_groups(max_ctas, s->bcsr, a.A.n_rows);
+    a.mode = sweep_map_mode();
+    const int grid = nchunk * a.n_row_groups;
+    if (2 * 2 * grid > 8192) return fail(PHW_ECUDA, "partials too small");
+    void* args[] = {(void*)&a};
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    const bool prof = prof_on(s);
+    if (prof) {
+        CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+        CU(cudaEventRecord(e0, s->stream));
+    }
+    CU(cudaLaunchCooperativeKernel((void*)solve_coop_csr_b_k, dim3(grid), dim3(256), args, 0, s->stream));
+    if (prof) {
+        CU(cudaEventRecord(e1, s->stream));
+        s->prof_ev.push_back(e0); s->prof_ev.push_back(e1); s->prof_which.push_back(which);
+    }
+    s->launches++;
+    s->kernel_paths |= PHW_PATH_SWEEP_CSR;
+    return 0;
 }
 
 // ---- matrix-free higher-order operators (kernels_ho.cuh): cell loops with the reference tabulations in shared memory
@@ -1064,6 +1129,7 @@ int solve_begin(phw_solver_s* s, int which) {
 // Chebyshev solve of M_p x = bp (which = 0) or M_q x = bq (which = 1); warm start = tribuf[cur]
 int solve_mass(phw_solver_s* s, int which, int n_launch) {
     int rc;
+    if (s->bcsr) return bcsr_solve(s, which);
     if (s->ho_mf) return ho_mf_solve(s, which);
     if (s->ho) {
         CsrSolveArgs a{};
@@ -1200,6 +1266,12 @@ int scalar(phw_solver_s* s, int op, double aux0 = 0.0, double aux1 = 0.0) {
     return 0;
 }
 int flux(phw_solver_s* s, const double* q, int which, int slot) {
+    if (s->bcsr) {
+        flux_b_k<<<nblk(s->bcsr, 128), 128, 0, s->stream>>>(s->nport, s->d_port_e, s->d_port_bl, q, s->tq, s->ctl, which, slot, s->bcsr);
+        s->launches++;
+        CU(cudaGetLastError());
+        return 0;
+    }
     flux_k<<<s->G, s->G > 1 ? 32 : 256, 0, s->stream>>>(s->d_port_goff, s->d_port_e, s->d_port_bl, q, s->tq, s->ctl, which, slot);
     s->launches++;
     CU(cudaGetLastError());
@@ -1221,6 +1293,7 @@ int waxpy(phw_solver_s* s, int n, double* w, const double* y, double a, const do
 // b_p = -K (D^T qsrc [+ B_top psrc])          (explicit part of the p rows, velocity form)
 int rhs_p(phw_solver_s* s, const double* qsrc, const double* psrc) {
     const double K = s->prm.K_wave;
+    if (s->bcsr) { bcsr_store(s, s->hDT, qsrc, -1.0, s->d_gK, s->bp); CU(cudaGetLastError()); return 0; }
     if (s->ho_mf) return ho_mf_DT(s, qsrc, -K, s->bp);
     if (s->ho) {
         csr_store(s, s->hDT, qsrc, -K, s->bp);
@@ -1235,6 +1308,16 @@ int rhs_p(phw_solver_s* s, const double* qsrc, const double* psrc) {
 int rhs_q(phw_solver_s* s, const double* psrc, const double* qsrc) {
     const double ir = (s->G > 1) ? 1.0 : 1.0 / s->prm.rho;
     int rc = 0;
+    if (s->bcsr) {
+        bcsr_store(s, s->hD, psrc, 1.0, s->d_ginvrho, s->bq);
+        if (s->nport > 0) {
+            const long long nt = (long long)s->nport * s->bcsr;
+            port_rhs_b_k<<<(unsigned)((nt + 255) / 256), 256, 0, s->stream>>>(s->nport, s->d_port_e, s->d_port_bl, s->d_ginvrho, s->bq, 1.0, s->ctl, s->bcsr);
+            s->launches++;
+        }
+        CU(cudaGetLastError());
+        return 0;
+    }
     if (s->ho_mf) {
         rc = ho_mf_D(s, psrc, ir, s->bq);
     } else if (s->ho) {
@@ -1255,6 +1338,12 @@ int rhs_q(phw_solver_s* s, const double* psrc, const double* qsrc) {
     return 0;
 }
 int energy(phw_solver_s* s) {
+    if (s->bcsr) {
+        bcsr_dot(s, s->hMp, s->p, 0.5, s->d_ginvrho, 0);
+        bcsr_dot(s, s->hMq, s->q, 0.5, s->d_gK, 1);
+        CU(cudaGetLastError());
+        return 0;
+    }
     if (s->ho) {
         if (s->ho_mf) {
             int rc_ = ho_mf_quad(s, HO_MP, s->p, 0.5 / s->prm.rho, 0, 6); if (rc_) return rc_;
@@ -2796,8 +2885,12 @@ static int upload_csr(phw_solver_s* s, int64_t n_rows, const int32_t* indptr, co
 // common part of the two higher-order constructors: vectors, control block, identity numbering, port list = non-zeros of b_L,
 // Chebyshev intervals.  The caller uploads its operators and fills pinv_p / pinv_q afterwards.
 static int ho_create_base(const phw_params* prm, int32_t device, void* cuda_stream, int64_t n_p, int64_t n_q, const double* b_L,
-                          double lam_min_p, double lam_max_p, double lam_min_q, double lam_max_q, phw_solver_s** out) {
+                          double lam_min_p, double lam_max_p, double lam_min_q, double lam_max_q, phw_solver_s** out, int32_t n_cases = 1) {
     if (!prm || !out || !b_L) return fail(PHW_EINVAL, "NULL argument");
+    if (n_cases < 1 || n_cases > 16384 || (int64_t)n_cases * std::max(n_p, n_q) > 2000000000LL)
+        return fail(PHW_EINVAL, "number of cases out of range (at most 16 384 per sweep solver and 2e9 dof x cases: shard the case list)");
+    if (n_cases > 1 && !((prm->scheme == PHW_SE || prm->scheme == PHW_SV || prm->scheme == PHW_EE || prm->scheme == PHW_EH) && !prm->analytical))
+        return fail(PHW_EINVAL, "batched runs support the explicit weak-form schemes only");
     if (prm->scheme < 0 || prm->scheme > 5) return fail(PHW_EINVAL, "unknown scheme");
     if (prm->interconnection && !(prm->scheme == PHW_SE || prm->scheme == PHW_SV || prm->scheme == PHW_SM))
         return fail(PHW_EINVAL, "only SE, SV and SM time int schemes implemented for interconnection model");
@@ -2813,7 +2906,8 @@ static int ho_create_base(const phw_params* prm, int32_t device, void* cuda_stre
     s->prm.flags |= env_flags();
     if (!(s->prm.tol > 0)) s->prm.tol = 1e-13;
     if (s->prm.max_iter <= 0) s->prm.max_iter = 1000;
-    s->nv = (int)n_p; s->ne = (int)n_q; s->npatch = 0; s->G = 1;
+    // batched sweep (n_cases > 1): every vector is [n_dof][n_cases], so the element-wise kernels simply see longer vectors
+    s->nv = (int)(n_p * n_cases); s->ne = (int)(n_q * n_cases); s->npatch = 0; s->G = n_cases; s->bcsr = n_cases > 1 ? n_cases : 0;
     auto bail = [&](int rc) { std::string keep = g_err; phw_solver_destroy(s); g_err = keep; return rc; };
     cudaDeviceProp prop{};
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail(fail(PHW_ECUDA, "cudaGetDeviceProperties failed"));
@@ -2823,7 +2917,7 @@ static int ho_create_base(const phw_params* prm, int32_t device, void* cuda_stre
     if (!s->coop) return bail(fail(PHW_ECUDA, "cooperative launch is required"));
     rc = setup_scalars(s); if (rc) return bail(rc);
     {
-        std::vector<int32_t> idv(n_p), ide(n_q), pe, pg, goff(2, 0), gpoff(2, 0);
+        std::vector<int32_t> idv(s->nv), ide(s->ne), pe, pg, goff(2, 0), gpoff(2, 0);
         std::iota(idv.begin(), idv.end(), 0); std::iota(ide.begin(), ide.end(), 0);
         std::vector<double> bl;
         for (int64_t r = 0; r < n_q; ++r) if (b_L[r] != 0.0) { pe.push_back((int32_t)r); bl.push_back(b_L[r]); pg.push_back(0); }
@@ -2837,6 +2931,12 @@ static int ho_create_base(const phw_params* prm, int32_t device, void* cuda_stre
         rc = s->upload(&s->d_port_group, pg); if (rc) return bail(rc);
         rc = s->upload(&s->d_gpoff, gpoff); if (rc) return bail(rc);
     }
+    if (s->bcsr) {
+        std::vector<double> gk(s->G, prm->K_wave), gir(s->G, 1.0 / prm->rho);
+        rc = s->upload(&s->d_gK, gk); if (rc) return bail(rc);
+        rc = s->upload(&s->d_ginvrho, gir); if (rc) return bail(rc);
+        rc = s->dalloc(&s->bpart, (size_t)8 * 8 * s->sm_count * 32 + (size_t)s->bcsr); if (rc) return bail(rc);     // [row block][case]: row blocks x cases <= 32 x warps of a launch
+    }
     s->cheb_d[0] = 0.5 * (lam_min_p + lam_max_p); s->cheb_c[0] = 0.5 * (lam_max_p - lam_min_p);
     s->cheb_d[1] = 0.5 * (lam_min_q + lam_max_q); s->cheb_c[1] = 0.5 * (lam_max_q - lam_min_q);
     s->lam_min_q = lam_min_q; s->lam_max_q = lam_max_q;
@@ -2845,15 +2945,17 @@ static int ho_create_base(const phw_params* prm, int32_t device, void* cuda_stre
     return PHW_OK;
 }
 
-int phw_ho_create(const phw_params* prm, int32_t device, void* cuda_stream, int64_t n_p, int64_t n_q,
-                  const int32_t* Mp_indptr, const int32_t* Mp_idx, const double* Mp_val,
-                  const int32_t* Mq_indptr, const int32_t* Mq_idx, const double* Mq_val,
-                  const int32_t* D_indptr, const int32_t* D_idx, const double* D_val,
-                  const int32_t* DT_indptr, const int32_t* DT_idx, const double* DT_val,
-                  const double* b_L, double lam_min_p, double lam_max_p, double lam_min_q, double lam_max_q,
-                  phw_solver_t* out) {
+static int create_csr_solver(const phw_params* prm, int32_t device, void* cuda_stream, int32_t n_cases, int64_t n_p, int64_t n_q,
+                             const int32_t* Mp_indptr, const int32_t* Mp_idx, const double* Mp_val,
+                             const int32_t* Mq_indptr, const int32_t* Mq_idx, const double* Mq_val,
+                             const int32_t* D_indptr, const int32_t* D_idx, const double* D_val,
+                             const int32_t* DT_indptr, const int32_t* DT_idx, const double* DT_val,
+                             const double* b_L, double lam_min_p, double lam_max_p, double lam_min_q, double lam_max_q,
+                             phw_solver_t* out) {
+    if (!Mp_indptr || !Mp_idx || !Mp_val || !Mq_indptr || !Mq_idx || !Mq_val || !D_indptr || !D_idx || !D_val || !DT_indptr || !DT_idx || !DT_val)
+        return fail(PHW_EINVAL, "NULL argument");
     phw_solver_s* s = nullptr;
-    int rc = ho_create_base(prm, device, cuda_stream, n_p, n_q, b_L, lam_min_p, lam_max_p, lam_min_q, lam_max_q, &s);
+    int rc = ho_create_base(prm, device, cuda_stream, n_p, n_q, b_L, lam_min_p, lam_max_p, lam_min_q, lam_max_q, &s, n_cases);
     if (rc) return rc;
     auto bail = [&](int rc_) { std::string keep = g_err; phw_solver_destroy(s); g_err = keep; return rc_; };
     rc = upload_csr(s, n_p, Mp_indptr, Mp_idx, Mp_val, &s->hMp); if (rc) return bail(rc);
@@ -2876,6 +2978,31 @@ int phw_ho_create(const phw_params* prm, int32_t device, void* cuda_stream, int6
     }
     *out = s;
     return PHW_OK;
+}
+
+int phw_ho_create(const phw_params* prm, int32_t device, void* cuda_stream, int64_t n_p, int64_t n_q,
+                  const int32_t* Mp_indptr, const int32_t* Mp_idx, const double* Mp_val,
+                  const int32_t* Mq_indptr, const int32_t* Mq_idx, const double* Mq_val,
+                  const int32_t* D_indptr, const int32_t* D_idx, const double* D_val,
+                  const int32_t* DT_indptr, const int32_t* DT_idx, const double* DT_val,
+                  const double* b_L, double lam_min_p, double lam_max_p, double lam_min_q, double lam_max_q,
+                  phw_solver_t* out) {
+    return create_csr_solver(prm, device, cuda_stream, 1, n_p, n_q, Mp_indptr, Mp_idx, Mp_val, Mq_indptr, Mq_idx, Mq_val,
+                             D_indptr, D_idx, D_val, DT_indptr, DT_idx, DT_val, b_L, lam_min_p, lam_max_p, lam_min_q, lam_max_q, out);
+}
+
+// batched parameter sweep with the case index fastest (kernels_sweep.cuh): n_cases independent cases on ONE set of assembled operators;
+// state vectors are [n_dof][n_cases]; per-case physics through phw_solver_set_group_params
+int phw_sweep_create(const phw_params* prm, int32_t device, void* cuda_stream, int32_t n_cases, int64_t n_p, int64_t n_q,
+                     const int32_t* Mp_indptr, const int32_t* Mp_idx, const double* Mp_val,
+                     const int32_t* Mq_indptr, const int32_t* Mq_idx, const double* Mq_val,
+                     const int32_t* D_indptr, const int32_t* D_idx, const double* D_val,
+                     const int32_t* DT_indptr, const int32_t* DT_idx, const double* DT_val,
+                     const double* b_L, double lam_min_p, double lam_max_p, double lam_min_q, double lam_max_q,
+                     phw_solver_t* out) {
+    if (n_cases < 2) return fail(PHW_EINVAL, "a sweep needs at least two cases (one case: phw_ho_create / phw_solver_create)");
+    return create_csr_solver(prm, device, cuda_stream, n_cases, n_p, n_q, Mp_indptr, Mp_idx, Mp_val, Mq_indptr, Mq_idx, Mq_val,
+                             D_indptr, D_idx, D_val, DT_indptr, DT_idx, DT_val, b_L, lam_min_p, lam_max_p, lam_min_q, lam_max_q, out);
 }
 
 int phw_ho_create_mf(const phw_params* prm, int32_t device, void* cuda_stream, int32_t k_p, int32_t k_q,

@@ -456,6 +456,42 @@ class HighOrderSolver(Solver):
         self.ncol = 12 if params.analytical else 8
 
 
+class BatchedSweepSolver(Solver):
+    """n_cases independent cases on ONE set of assembled operators, state vectors [n_dof][n_cases] with the case index fastest
+    (phw_sweep_create, csrc/kernels_sweep.cuh): the batched parameter sweep of BASELINE configs[4]."""
+
+    def __init__(self, spaces, ops, params, bounds_p, bounds_q, n_cases, device=0):
+        self.lib = _lib.load()
+        self.spaces = spaces
+        self.n_cases = int(n_cases)
+        self.mesh = _DofCounts(spaces.np_dofs * self.n_cases, spaces.nq_dofs * self.n_cases)
+        self.mesh.n_groups = self.n_cases
+        self.params = params
+        keep = []
+
+        def csr(M):
+            M = M.tocsr()
+            M.sort_indices()
+            ip = np.ascontiguousarray(M.indptr, dtype=np.int32)
+            ix = np.ascontiguousarray(M.indices, dtype=np.int32)
+            v = np.ascontiguousarray(M.data, dtype=np.float64)
+            keep.extend([ip, ix, v])
+            return ip.ctypes.data_as(_lib.c_i32p), ix.ctypes.data_as(_lib.c_i32p), v.ctypes.data_as(_lib.c_f64p)
+        bL = np.ascontiguousarray(ops['b_L'], dtype=np.float64)
+        h = ctypes.c_void_p()
+        _lib.check(self.lib.phw_sweep_create(ctypes.byref(params), int(device), None, self.n_cases, spaces.np_dofs, spaces.nq_dofs,
+                                             *csr(ops['M_p']), *csr(ops['M_q']), *csr(ops['D']), *csr(ops['D'].T),
+                                             bL.ctypes.data_as(_lib.c_f64p), bounds_p[0], bounds_p[1], bounds_q[0], bounds_q[1],
+                                             ctypes.byref(h)))
+        self.handle = h
+        self.ncol = 8
+
+    def get_case_states(self):
+        """(p [n_cases, n_p], q [n_cases, n_q], x [n_cases, 3]) - the device layout is [dof][case]"""
+        p, q, _ = self.get_state()
+        return (p.reshape(self.spaces.np_dofs, self.n_cases).T.copy(), q.reshape(self.spaces.nq_dofs, self.n_cases).T.copy(), self.group_states())
+
+
 class MatrixFreeHighOrderSolver(Solver):
     """Solver for the P_k x RT_k pairs, k <= 3, with the matrix-free kernels of csrc/kernels_ho.cuh (phw_ho_create_mf): the device
     holds 3 vertex ids + 3 edge ids + 4 doubles per cell and the reference tabulations of fem_ref.RefSpaces; nothing is assembled.

@@ -45,8 +45,13 @@ def wave_sweep_solve(tFinal, numSteps, nx, xLength, yLength, cases, domainShape=
     if mesh is None:
         mesh = generate_mesh(domainShape, nx, xLength, yLength)
     B = len(cases)
-    V, C, group = replicate_mesh(mesh[0], mesh[1], B)
     auto = patch_cells is None and not solver_flags
+    if auto and B >= 32 and not os.environ.get('PHW_SWEEP_GROUPED') and not os.environ.get('PHW_SWEEP_LOOP'):
+        # default for real sweeps: ONE copy of the (assembled) operators, state [n_dof][n_cases] with the case index fastest
+        # (csrc/kernels_sweep.cuh).  PHW_SWEEP_GROUPED=1 keeps the replicated-mesh layout below (A/B, cross-check).
+        return _sweep_case_fastest(tFinal, numSteps, mesh, xLength, yLength, cases, domainShape, timeIntScheme, device, tol, extrap_order,
+                                   return_solver)
+    V, C, group = replicate_mesh(mesh[0], mesh[1], B)
     if auto and os.environ.get('PHW_SWEEP_LOOP'):
         # one thread-block cluster per case, every case advanced through ALL its steps by its own cluster in one launch
         # (csrc/kernels_loop.cuh, solves resident in shared memory).  Measured slower than the default below on the 1024-case
@@ -97,4 +102,52 @@ def wave_sweep_solve(tFinal, numSteps, nx, xLength, yLength, cases, domainShape=
         return H, numCells, solver
     solver.close()
     m.close()
+    return H, numCells
+
+
+def _sweep_case_fastest(tFinal, numSteps, mesh, xLength, yLength, cases, domainShape, timeIntScheme, device, tol, extrap_order, return_solver):
+    """The sweep on ONE set of assembled P1 x RT1 operators (host assembly of fem_ho.py at order (1, 1): M_p, M_q, D = C - N, b_L and
+    the element-wise bounds of the Jacobi-scaled mass spectra), all cases side by side in [n_dof][n_cases] vectors."""
+    from .fem_ho import HighOrderSpaces
+    from .solver import BatchedSweepSolver
+    S = HighOrderSpaces(mesh[0], mesh[1], 1, 1)
+    be = S.boundary_edges
+    pa, pb = S.vertices[S.edges[be, 0]], S.vertices[S.edges[be, 1]]
+    pm = 0.5 * (pa + pb)
+    tol_g = 1e-12
+    xin = 0.0 if domainShape == 'R' else -0.10
+
+    def on(pred):
+        return pred(pa) & pred(pb) & pred(pm)
+    tags = np.full(be.shape[0], 4, dtype=np.int64)                       # facet markers of wave_2D.py:226-280
+    tags[on(lambda p: np.abs(p[:, 0] - xin) < tol_g)] = 0
+    if domainShape == 'R':
+        tags[on(lambda p: np.abs(p[:, 1] - yLength) < tol_g)] = 1
+    tags[on(lambda p: np.abs(p[:, 0] - xLength) < tol_g)] = 2
+    if domainShape == 'R':
+        tags[on(lambda p: np.abs(p[:, 1]) < tol_g)] = 3
+    else:
+        ylo, yhi = xLength / 2 - yLength / 2, xLength / 2 + yLength / 2
+        tags[on(lambda p: (np.abs(p[:, 1]) < tol_g) | (np.abs(p[:, 1] - xLength) < tol_g) | (np.abs(p[:, 1] - ylo) < tol_g) |
+                (np.abs(p[:, 1] - yhi) < tol_g) | (np.abs(p[:, 0]) < tol_g))] = 3
+    ops = S.assemble({int(e): int(t) for e, t in zip(be, tags)})
+    bp, bq = S.jacobi_bounds(ops)
+    B = len(cases)
+    prm = _lib.PhwParams()
+    prm.scheme, prm.interconnection = _lib.SCHEMES[timeIntScheme], 1
+    prm.dt, prm.K_wave, prm.rho = tFinal / numSteps, 1.0, 1.0
+    for k, v in DEFAULT_LUMPED.items():
+        setattr(prm, k, v)
+    prm.input_kind, prm.in_amp, prm.in_omega, prm.in_t_stop = _lib.IN_SINE_WINDOW, 5.0, 8 * np.pi, 0.25     # wave_2D.py:433
+    prm.tol, prm.max_iter, prm.extrap_order, prm.flags = float(tol), 400, int(extrap_order), 0
+    solver = BatchedSweepSolver(S, ops, prm, bp, bq, B, device=device)
+    K = np.array([c.get('K_wave', 1.0) for c in cases], dtype=np.float64)
+    rho = np.array([c.get('rho', 1.0) for c in cases], dtype=np.float64)
+    lum = np.array([[c.get(k, DEFAULT_LUMPED[k]) for k in LUMPED_KEYS] for c in cases], dtype=np.float64)
+    solver.set_group_params(K, rho, lum)
+    H = solver.run(numSteps)
+    numCells = len(mesh[1])
+    if return_solver:
+        return H, numCells, solver
+    solver.close()
     return H, numCells

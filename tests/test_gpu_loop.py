@@ -157,3 +157,36 @@ def test_batched_sweep_runs_one_cluster_per_case(loop, monkeypatch):
         assert np.abs(H[i][:, 1:] - Ho[:, 1:]).max() < 1e-10 * np.abs(Ho[:, 1:]).max(), i
     H1, _ = wave_sweep_solve(0.04, 40, 0, 1.0, 0.25, cases[3:4], mesh=mesh)
     assert np.abs(H1[0][:, 1:] - H[3][:, 1:]).max() < 1e-11 * np.abs(H[3][:, 1:]).max()
+
+
+@pytest.mark.parametrize('scheme,n_cases', [('SV', 40), ('SE', 33)])
+def test_sweep_with_the_case_index_fastest_matches_the_oracle_case_by_case(scheme, n_cases, monkeypatch):
+    """config 5, layout of SURVEY K9 (default for >= 32 cases): ONE copy of the assembled operators, state [n_dof][n_cases]
+    (csrc/kernels_sweep.cuh).  Every case's H_array equals what the oracle gives for that case alone; the final fields and lumped
+    states of two cases too; the replicated-mesh layout (PHW_SWEEP_GROUPED=1) gives the same traces."""
+    from porthamiltonian_fem_b200.sweep import wave_sweep_solve, sweep_cases, LUMPED_KEYS, DEFAULT_LUMPED
+    monkeypatch.delenv('PHW_SWEEP_GROUPED', raising=False)
+    monkeypatch.delenv('PHW_SWEEP_LOOP', raising=False)
+    mesh = rectangle_structured(20, 5, 1.0, 0.25)
+    cases = sweep_cases(n_cases, seed=7)
+    steps, tF = 40, 0.04
+    H, nc, solver = wave_sweep_solve(tF, steps, 0, 1.0, 0.25, cases, mesh=mesh, timeIntScheme=scheme, return_solver=True)
+    st = solver.stats()
+    assert st['kernel_paths'] & 4096 and H.shape == (n_cases, steps, 8) and nc == len(mesh[1])       # PHW_PATH_SWEEP_CSR
+    assert st['max_rel_residual'] <= 1e-13
+    P, Q, X = solver.get_case_states()
+    solver.close()
+    for i in list(range(0, n_cases, 5)) + [n_cases - 1]:
+        c = cases[i]
+        lum = {k: c.get(k, DEFAULT_LUMPED[k]) for k in LUMPED_KEYS}
+        Ho, _, so = wave_2D_solve_oracle(tF, steps, mesh, 1.0, 0.25, timeIntScheme=scheme, interConnection='IC',
+                                         K_wave=c['K_wave'], rho=c['rho'], lumped=lum, return_state=True)
+        assert np.array_equal(H[i][:, 0], Ho[:, 0])
+        assert np.abs(H[i][:, 1:] - Ho[:, 1:]).max() < 1e-10 * np.abs(Ho[:, 1:]).max(), i
+        if i in (0, n_cases - 1):
+            assert np.linalg.norm(P[i] - so['p']) < 1e-10 * np.linalg.norm(so['p'])
+            assert np.linalg.norm(Q[i] - so['q']) < 1e-10 * np.linalg.norm(so['q'])
+            assert np.abs(X[i] - so['x']).max() < 1e-10 * max(1.0, np.abs(so['x']).max())
+    monkeypatch.setenv('PHW_SWEEP_GROUPED', '1')
+    Hg, _ = wave_sweep_solve(tF, steps, 0, 1.0, 0.25, cases, mesh=mesh, timeIntScheme=scheme)
+    assert np.abs(Hg[:, :, 1:] - H[:, :, 1:]).max() < 1e-10 * np.abs(H[:, :, 1:]).max()
