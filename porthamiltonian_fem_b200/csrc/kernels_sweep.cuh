@@ -17,22 +17,23 @@
 
 namespace phw {
 
-// Row mapping.  mode 1 (cyclic): CTA -> (chunk of 32 cases, row group g of n_row_groups); its 8 warps take 8 CONSECUTIVE rows per
-// sweep step, rows of warp w: r = (step * n_row_groups + g) * 8 + w, so at any moment the CTAs of a chunk work on one window of
-// 8 * n_row_groups consecutive rows and the rows a mesh row gathers from are in flight in the same window: read from DRAM once, L2 hits
-// for everybody else (ncu: DRAM traffic = the algorithmic 4 vectors per iteration).  mode 0 (blocks): warp -> (chunk, one contiguous
-// block of rows): neighbour rows of the same block hit in L1, but rows of other blocks were touched half an iteration earlier or later -
-// beyond what the L2 retains (ncu: L2 hit rate 9 %, DRAM traffic 2.6 x the algorithmic bytes).  A/B: PHW_SWEEP_MAP.
+// Row mapping (A/B knob PHW_SWEEP_MAP).  mode 0 (blocks, default): warp -> (chunk of 32 cases, one contiguous block of rows): neighbour
+// rows of the same block hit in L1; rows of other blocks were touched half an iteration earlier or later by another warp - beyond
+// what the L2 retains (ncu: L1 hit rate 55 %, L2 9 %, DRAM traffic 2.6 x the algorithmic bytes).  mode 1 (cyclic tiles): CTA -> (chunk,
+// row group g); its 8 warps take 8 consecutive rows per sweep step, r = (step * n_row_groups + g) * 8 + w, so the CTAs of a chunk work
+// on one window of consecutive rows and neighbour rows hit in L2 (ncu: DRAM traffic = the algorithmic 4 vectors per iteration) - and
+// the kernel is no faster (3.5-4.0e9 against 4.07e9): it is bound by the load/store unit (~24 requests per row and 32 cases, 14 of
+// them the row's own indices and values), not by DRAM.
 // `wid` numbers the warps that own rows (index of their partial sums), `n_wid` = their number.
 constexpr int SWEEP_WPB = 8;      // warps per CTA (256 threads)
 #ifndef SWEEP_MINB
-#define SWEEP_MINB 6               // resident CTAs per SM the persistent solve is compiled for (the kernel waits on loads: occupancy matters)
+#define SWEEP_MINB 4               // resident CTAs per SM the persistent solve is compiled for (64 registers, no spills; 5, 6 and 8 measured: no gain)
 #endif
 struct SweepMap {
-    int c, cs, first, step, end, wid, lane; bool on, lane_ok;
+    int c, cs, first, step, end, wid; bool on, lane_ok;
     __device__ __forceinline__ SweepMap(int n_rows, int B, int n_row_groups, int mode) {
         const int nchunk = (B + 31) >> 5, w = threadIdx.x >> 5;
-        lane = threadIdx.x & 31;
+        const int lane = threadIdx.x & 31;
         int chunk;
         if (mode == 1) {
             chunk = blockIdx.x % nchunk;
@@ -60,33 +61,15 @@ __host__ __device__ __forceinline__ int sweep_row_groups(int n_ctas, int B, int 
     return g < 1 ? 1 : (g > gmax ? gmax : g);
 }
 
-// sum_j A[r][j] x[idx_j][c] for the 32 cases of a warp.  The row's indices and values are loaded ONCE per warp (lane j takes entry j:
-// one coalesced request each) and broadcast by shuffles - first version: every lane loaded every index (broadcast loads), 14 of the
-// 24 L1 requests per row carried no data and the kernel sat at 70 % of the L1 request rate; the gathers of four entries are issued
-// before their products are summed.  All 32 lanes of the warp must call it (shuffles); ip = indptr pair of the row held by lanes 0, 1.
-__device__ __forceinline__ double sweep_row_sum(const Csr& A, int ip, const double* __restrict__ x, int B, int cs, int lane) {
-    const int j0 = __shfl_sync(0xffffffffu, ip, 0), j1 = __shfl_sync(0xffffffffu, ip, 1);
+// sum_j A[r][j] x[idx_j][c] for the 32 cases of a warp: every lane reads the row's indices and values itself (warp-uniform addresses:
+// broadcast loads that hit in L1).  Tried and measured slower (profiles/r2s_*): loading them once per warp (lane j takes entry j) and
+// broadcasting by shuffles - 24 shuffles per four entries cost more than the 14 broadcast loads per row they replace (3.1e9 instead of
+// 4.0e9 dof-updates/s on the 1024-case sweep).
+__device__ __forceinline__ double sweep_row_sum(const Csr& A, int r, const double* __restrict__ x, int B, int cs) {
     double v = 0.0;
-    for (int jb = j0; jb < j1; jb += 32) {
-        const int n = min(32, j1 - jb);
-        int mi = 0; double mv = 0.0;
-        if (lane < n) { mi = __ldg(&A.idx[jb + lane]); mv = __ldg(&A.val[jb + lane]); }
-        for (int t = 0; t < n; t += 4) {
-            const int i0 = __shfl_sync(0xffffffffu, mi, t), i1 = __shfl_sync(0xffffffffu, mi, (t + 1) & 31);
-            const int i2 = __shfl_sync(0xffffffffu, mi, (t + 2) & 31), i3 = __shfl_sync(0xffffffffu, mi, (t + 3) & 31);
-            const double w0 = __shfl_sync(0xffffffffu, mv, t), w1 = __shfl_sync(0xffffffffu, mv, (t + 1) & 31);
-            const double w2 = __shfl_sync(0xffffffffu, mv, (t + 2) & 31), w3 = __shfl_sync(0xffffffffu, mv, (t + 3) & 31);
-            const double x0 = x[(size_t)i0 * B + cs];
-            const double x1 = (t + 1 < n) ? x[(size_t)i1 * B + cs] : 0.0;
-            const double x2 = (t + 2 < n) ? x[(size_t)i2 * B + cs] : 0.0;
-            const double x3 = (t + 3 < n) ? x[(size_t)i3 * B + cs] : 0.0;
-            v += w0 * x0; v += w1 * x1; v += w2 * x2; v += w3 * x3;     // fixed order: the sum does not depend on the mapping
-        }
-    }
+    const int j1 = __ldg(&A.indptr[r + 1]);
+    for (int j = __ldg(&A.indptr[r]); j < j1; ++j) v += __ldg(&A.val[j]) * x[(size_t)__ldg(&A.idx[j]) * B + cs];
     return v;
-}
-__device__ __forceinline__ int sweep_indptr(const Csr& A, int r, int n_rows, int lane) {
-    return (lane < 2 && r < n_rows) ? __ldg(&A.indptr[r + lane]) : 0;
 }
 
 // y[r][c] = alpha * cscale[c] * sum_j A[r][j] x[j][c]
@@ -95,12 +78,9 @@ __global__ void __launch_bounds__(256) csr_store_b_k(Csr A, int B, int n_row_gro
     const SweepMap mp(A.n_rows, B, n_row_groups, mode);
     if (!mp.on) return;
     const double sc = alpha * (cscale ? cscale[mp.cs] : 1.0);
-    int ip = sweep_indptr(A, mp.first, mp.end, mp.lane);
     for (int r = mp.first; r < mp.end; r += mp.step) {
-        const int ip_next = sweep_indptr(A, r + mp.step, mp.end, mp.lane);
-        const double v = sweep_row_sum(A, ip, x, B, mp.cs, mp.lane);
+        const double v = sweep_row_sum(A, r, x, B, mp.cs);
         if (mp.lane_ok) y[(size_t)r * B + mp.c] = sc * v;
-        ip = ip_next;
     }
 }
 
@@ -109,12 +89,9 @@ __global__ void __launch_bounds__(256) csr_dot_b_k(Csr A, int B, int n_row_group
     const SweepMap mp(A.n_rows, B, n_row_groups, mode);
     if (!mp.on) return;
     double s = 0.0;
-    int ip = sweep_indptr(A, mp.first, mp.end, mp.lane);
     for (int r = mp.first; r < mp.end; r += mp.step) {
-        const int ip_next = sweep_indptr(A, r + mp.step, mp.end, mp.lane);
         const double xr = x[(size_t)r * B + mp.cs];
-        s += xr * sweep_row_sum(A, ip, x, B, mp.cs, mp.lane);
-        ip = ip_next;
+        s += xr * sweep_row_sum(A, r, x, B, mp.cs);
     }
     if (mp.lane_ok) part[(size_t)mp.wid * B + mp.c] = s;
 }
@@ -170,15 +147,12 @@ __global__ void __launch_bounds__(256, SWEEP_MINB) solve_coop_csr_b_k(const __gr
         const double* x = tb_sel(a.tb, cur); const double* xp = tb_sel(a.tb, prv); double* xn = tb_sel(a.tb, nxt);
         double r0 = 0.0, b0 = 0.0;
         if (mp.on) {                                                       // uniform per warp
-            int ip = sweep_indptr(a.A, mp.first, mp.end, mp.lane);
             for (int r = mp.first; r < mp.end; r += mp.step) {
-                const int ip_next = sweep_indptr(a.A, r + mp.step, mp.end, mp.lane);
                 const size_t o = (size_t)r * B + mp.cs;
                 const double bv = a.b[o], xc = x[o];                       // streaming operands requested before the row sum
                 const double xpv = k > 0 ? xp[o] : 0.0;
                 const double pv = __ldg(&a.pinv[r]);
-                const double v = sweep_row_sum(a.A, ip, x, B, mp.cs, mp.lane);
-                ip = ip_next;
+                const double v = sweep_row_sum(a.A, r, x, B, mp.cs);
                 const double res = bv - v;
                 double w = xc + c2 * pv * res;
                 if (k > 0) w += c1 * (xc - xpv);

@@ -655,10 +655,10 @@ void csr_dot(phw_solver_s* s, const Csr& A, const double* x, double scale, int s
 
 // ---- batched sweep, case index fastest (kernels_sweep.cuh): one warp = 32 cases x a block of rows
 inline bool prof_on(phw_solver_s* s);
-// row mapping of the sweep kernels (kernels_sweep.cuh: SweepMap): 1 = cyclic row tiles (default), 0 = one block of rows per warp
+// row mapping of the sweep kernels (kernels_sweep.cuh: SweepMap): 0 = one block of rows per warp (default), 1 = cyclic row tiles
 inline int sweep_map_mode() {
-    static const int m = [] { const char* e = getenv("PHW_SWEEP_MAP"); return e ? atoi(e) : 1; }();
-    return m == 0 ? 0 : 1;
+    static const int m = [] { const char* e = getenv("PHW_SWEEP_MAP"); return e ? atoi(e) : 0; }();
+    return m == 1 ? 1 : 0;
 }
 inline int bcsr_grid(phw_solver_s* s, const Csr& A, int* n_row_groups) {
     const int nchunk = (s->bcsr + 31) / 32;
