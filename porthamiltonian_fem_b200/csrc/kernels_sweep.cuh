@@ -64,7 +64,8 @@ __host__ __device__ __forceinline__ int sweep_row_groups(int n_ctas, int B, int 
 // sum_j A[r][j] x[idx_j][c] for the 32 cases of a warp: every lane reads the row's indices and values itself (warp-uniform addresses:
 // broadcast loads that hit in L1).  Tried and measured slower (profiles/r2s_*): loading them once per warp (lane j takes entry j) and
 // broadcasting by shuffles - 24 shuffles per four entries cost more than the 14 broadcast loads per row they replace (3.1e9 instead of
-// 4.0e9 dof-updates/s on the 1024-case sweep).
+// 4.0e9 dof-updates/s on the 1024-case sweep); two rows in flight per warp (alternating gathers, 80 registers or spills): 3.1-3.4e9
+// (profiles/r2t_*).
 __device__ __forceinline__ double sweep_row_sum(const Csr& A, int r, const double* __restrict__ x, int B, int cs) {
     double v = 0.0;
     const int j1 = __ldg(&A.indptr[r + 1]);
