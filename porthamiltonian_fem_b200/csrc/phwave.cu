@@ -689,13 +689,17 @@ int bcsr_solve(phw_solver_s* s, int which) {
     a.tol2 = std::min(s->prm.tol * s->prm.tol, t * t);
     a.max_iter = s->prm.max_iter; a.which = which; a.partials = s->partials; a.ctl = s->ctl;
     CU(cudaMemsetAsync(&s->ctl->gbar[0], 0, sizeof(unsigned int), s->stream));
+    // two consecutive cases per lane (16-byte accesses) when the number of cases is even; PHW_SWEEP_CPL=1 forces one (A/B)
+    static const int cpl_env = [] { const char* e = getenv("PHW_SWEEP_CPL"); return e ? atoi(e) : 0; }();
+    const int cpl = (cpl_env == 1 || (s->bcsr % 2) != 0) ? 1 : 2;
+    void* kern = cpl == 2 ? (void*)solve_coop_csr_b2_k : (void*)solve_coop_csr_b_k;
     int occ = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (void*)solve_coop_csr_b_k, 256, 0));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0));
     if (occ < 1) return fail(PHW_ECUDA, "solve_coop_csr_b_k does not fit on an SM");
-    const int nchunk = (s->bcsr + 31) / 32;
+    const int nchunk = (s->bcsr + 32 * cpl - 1) / (32 * cpl);
     const int max_ctas = std::min(occ, 8) * s->sm_count;
     if (nchunk > max_ctas) return fail(PHW_EINVAL, "too many cases for one sweep solver: shard the case list");
-    a.n_row_groups = sweep_row_groups(max_ctas, s->bcsr, a.A.n_rows);
+    a.n_row_groups = sweep_row_groups(max_ctas, s->bcsr, a.A.n_rows, cpl);
     a.mode = sweep_map_mode();
     const int grid = nchunk * a.n_row_groups;
     if (2 * 2 * grid > 8192) return fail(PHW_ECUDA, "partials too small");
@@ -706,7 +710,7 @@ int bcsr_solve(phw_solver_s* s, int which) {
         CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
         CU(cudaEventRecord(e0, s->stream));
     }
-    CU(cudaLaunchCooperativeKernel((void*)solve_coop_csr_b_k, dim3(grid), dim3(256), args, 0, s->stream));
+    CU(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(256), args, 0, s->stream));
     if (prof) {
         CU(cudaEventRecord(e1, s->stream));
         s->prof_ev.push_back(e0); s->prof_ev.push_back(e1); s->prof_which.push_back(which);
