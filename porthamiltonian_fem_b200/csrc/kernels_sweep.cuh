@@ -61,40 +61,78 @@ __host__ __device__ __forceinline__ int sweep_row_groups(int n_ctas, int B, int 
     return g < 1 ? 1 : (g > gmax ? gmax : g);
 }
 
-// sum_j A[r][j] x[idx_j][c] for the 32 cases of a warp: every lane reads the row's indices and values itself (warp-uniform addresses:
-// broadcast loads that hit in L1).  Tried and measured slower (profiles/r2s_*): loading them once per warp (lane j takes entry j) and
-// broadcasting by shuffles - 24 shuffles per four entries cost more than the 14 broadcast loads per row they replace (3.1e9 instead of
-// 4.0e9 dof-updates/s on the 1024-case sweep); two rows in flight per warp (alternating gathers, 80 registers or spills): 3.1-3.4e9
-// (profiles/r2t_*).
-__device__ __forceinline__ double sweep_row_sum(const Csr& A, int r, const double* __restrict__ x, int B, int cs) {
-    double v = 0.0;
+// CPL consecutive cases per lane (1, 2 or 4; the number of cases must be a multiple of CPL): with 2 or 4 every vector access is a
+// 16-byte load / store, so a row's index / value requests are shared by 64 / 128 cases instead of 32 and fewer load instructions move
+// the same data - the sweep kernels are bound by the load/store unit (measured, profiles/r2w_*, r2x_*: 3.97e9 -> 5.16e9 -> 5.39e9
+// dof-updates/s from one to two to four cases per lane on 1024 cases, 6.4e9 on 4096).
+template <int CPL> struct CaseVec { double v[CPL]; };
+template <int CPL> __device__ __forceinline__ CaseVec<CPL> ld_cases(const double* p) {
+    CaseVec<CPL> r;
+    if (CPL == 1) { r.v[0] = p[0]; }
+    else {
+#pragma unroll
+        for (int i = 0; i < CPL; i += 2) { const double2 t = *reinterpret_cast<const double2*>(p + i); r.v[i] = t.x; r.v[i + 1] = t.y; }
+    }
+    return r;
+}
+template <int CPL> __device__ __forceinline__ void st_cases(double* p, const CaseVec<CPL>& r) {
+    if (CPL == 1) { p[0] = r.v[0]; }
+    else {
+#pragma unroll
+        for (int i = 0; i < CPL; i += 2) *reinterpret_cast<double2*>(p + i) = make_double2(r.v[i], r.v[i + 1]);
+    }
+}
+// sum_j A[r][j] x[idx_j][c .. c + CPL) for the cases of a lane: every lane reads the row's indices and values itself (warp-uniform
+// addresses: broadcast loads that hit in L1).  Tried and measured slower (profiles/r2s_*, r2t_*): loading them once per warp (lane j
+// takes entry j) and broadcasting by shuffles - 24 shuffles per four entries cost more than the 14 broadcast loads per row they
+// replace; two rows in flight per warp (alternating gathers, 80 registers or spills).
+template <int CPL>
+__device__ __forceinline__ CaseVec<CPL> sweep_row_sum(const Csr& A, int r, const double* __restrict__ x, int B, int cs) {
+    CaseVec<CPL> v;
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) v.v[i] = 0.0;
     const int j1 = __ldg(&A.indptr[r + 1]);
-    for (int j = __ldg(&A.indptr[r]); j < j1; ++j) v += __ldg(&A.val[j]) * x[(size_t)__ldg(&A.idx[j]) * B + cs];
+    for (int j = __ldg(&A.indptr[r]); j < j1; ++j) {
+        const double w = __ldg(&A.val[j]);
+        const CaseVec<CPL> xj = ld_cases<CPL>(x + (size_t)__ldg(&A.idx[j]) * B + cs);
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) v.v[i] += w * xj.v[i];
+    }
     return v;
 }
 
 // y[r][c] = alpha * cscale[c] * sum_j A[r][j] x[j][c]
+template <int CPL>
 __global__ void __launch_bounds__(256) csr_store_b_k(Csr A, int B, int n_row_groups, int mode, const double* __restrict__ x, double alpha,
                                                      const double* __restrict__ cscale, double* __restrict__ y) {
-    const SweepMap mp(A.n_rows, B, n_row_groups, mode);
+    const SweepMap mp(A.n_rows, B, n_row_groups, mode, CPL);
     if (!mp.on) return;
-    const double sc = alpha * (cscale ? cscale[mp.cs] : 1.0);
+    double sc[CPL];
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) sc[i] = alpha * (cscale ? cscale[mp.cs + i] : 1.0);
     for (int r = mp.first; r < mp.end; r += mp.step) {
-        const double v = sweep_row_sum(A, r, x, B, mp.cs);
-        if (mp.lane_ok) y[(size_t)r * B + mp.c] = sc * v;
+        CaseVec<CPL> v = sweep_row_sum<CPL>(A, r, x, B, mp.cs);
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) v.v[i] *= sc[i];
+        if (mp.lane_ok) st_cases<CPL>(y + (size_t)r * B + mp.c, v);
     }
 }
 
 // part[wid][c] = sum over the rows of warp wid of x[r][c] (A x)[r][c]
+template <int CPL>
 __global__ void __launch_bounds__(256) csr_dot_b_k(Csr A, int B, int n_row_groups, int mode, const double* __restrict__ x, double* __restrict__ part) {
-    const SweepMap mp(A.n_rows, B, n_row_groups, mode);
+    const SweepMap mp(A.n_rows, B, n_row_groups, mode, CPL);
     if (!mp.on) return;
-    double s = 0.0;
+    CaseVec<CPL> s;
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) s.v[i] = 0.0;
     for (int r = mp.first; r < mp.end; r += mp.step) {
-        const double xr = x[(size_t)r * B + mp.cs];
-        s += xr * sweep_row_sum(A, r, x, B, mp.cs);
+        const CaseVec<CPL> xr = ld_cases<CPL>(x + (size_t)r * B + mp.cs);
+        const CaseVec<CPL> v = sweep_row_sum<CPL>(A, r, x, B, mp.cs);
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) s.v[i] += xr.v[i] * v.v[i];
     }
-    if (mp.lane_ok) part[(size_t)mp.wid * B + mp.c] = s;
+    if (mp.lane_ok) st_cases<CPL>(part + (size_t)mp.wid * B + mp.c, s);
 }
 // ctl[c].red[slot] = scale * cscale[c] * sum_wid part[wid][c]   (fixed order; n_row_blocks = n_row_groups * 8 warps)
 __global__ void dot_b_finish_k(int B, int n_row_blocks, const double* __restrict__ part, double scale, const double* __restrict__ cscale, Ctl* ctl, int slot) {
@@ -131,7 +169,11 @@ struct CsrSolveBArgs {
     Csr A; int B, n_row_groups, mode; TriBuf tb; const double* b; const double* pinv; double cheb_d, cheb_c, tol2; int max_iter, which;
     double* partials; Ctl* ctl;
 };
-__global__ void __launch_bounds__(256, SWEEP_MINB) solve_coop_csr_b_k(const __grid_constant__ CsrSolveBArgs a) {
+#ifndef SWEEP_MINB4
+#define SWEEP_MINB4 3
+#endif
+template <int CPL>
+__global__ void __launch_bounds__(256, CPL == 4 ? SWEEP_MINB4 : SWEEP_MINB) solve_coop_csr_b_k(const __grid_constant__ CsrSolveBArgs a) {
     __shared__ double red[64];
     __shared__ double bc[2];
     SolveCtl& sc = a.ctl->sc[a.which];
@@ -139,7 +181,7 @@ __global__ void __launch_bounds__(256, SWEEP_MINB) solve_coop_csr_b_k(const __gr
     double rho = 0.0, rr = 0.0, bb = 0.0;
     bool conv = false;
     unsigned int epoch = 0;
-    const SweepMap mp(a.A.n_rows, a.B, a.n_row_groups, a.mode);
+    const SweepMap mp(a.A.n_rows, a.B, a.n_row_groups, a.mode, CPL);
     const int B = a.B;
     while (true) {
         double c1, c2, rho_k;
@@ -150,90 +192,23 @@ __global__ void __launch_bounds__(256, SWEEP_MINB) solve_coop_csr_b_k(const __gr
         if (mp.on) {                                                       // uniform per warp
             for (int r = mp.first; r < mp.end; r += mp.step) {
                 const size_t o = (size_t)r * B + mp.cs;
-                const double bv = a.b[o], xc = x[o];                       // streaming operands requested before the row sum
-                const double xpv = k > 0 ? xp[o] : 0.0;
+                const CaseVec<CPL> bv = ld_cases<CPL>(a.b + o), xc = ld_cases<CPL>(x + o);   // streaming operands requested before the row sum
+                CaseVec<CPL> xpv;
+                if (k > 0) xpv = ld_cases<CPL>(xp + o);
                 const double pv = __ldg(&a.pinv[r]);
-                const double v = sweep_row_sum(a.A, r, x, B, mp.cs);
-                const double res = bv - v;
-                double w = xc + c2 * pv * res;
-                if (k > 0) w += c1 * (xc - xpv);
-                if (mp.lane_ok) {
-                    xn[o] = w;
-                    r0 += pv * res * res; b0 += pv * bv * bv;
+                const CaseVec<CPL> v = sweep_row_sum<CPL>(a.A, r, x, B, mp.cs);
+                CaseVec<CPL> w;
+                double rs = 0.0, bs = 0.0;
+#pragma unroll
+                for (int i = 0; i < CPL; ++i) {
+                    const double res = bv.v[i] - v.v[i];
+                    w.v[i] = xc.v[i] + c2 * pv * res;
+                    if (k > 0) w.v[i] += c1 * (xc.v[i] - xpv.v[i]);
+                    rs += res * res; bs += bv.v[i] * bv.v[i];
                 }
-            }
-        }
-        block_sum2(r0, b0, red);
-        double* part = a.partials + (size_t)(k & 1) * 2 * gridDim.x;
-        if (threadIdx.x == 0) { part[2 * blockIdx.x] = r0; part[2 * blockIdx.x + 1] = b0; }
-        grid_barrier(&a.ctl->gbar[0], epoch);
-        if (threadIdx.x < 32) {
-            double s0 = 0.0, s1 = 0.0;
-            for (int i = threadIdx.x; i < (int)gridDim.x; i += 32) { s0 += __ldcg(&part[2 * i]); s1 += __ldcg(&part[2 * i + 1]); }
-            s0 = warp_sum(s0); s1 = warp_sum(s1);
-            if (threadIdx.x == 0) { bc[0] = s0; bc[1] = s1; }
-        }
-        __syncthreads();
-        rr = bc[0]; bb = bc[1];
-        __syncthreads();
-        conv = rr <= a.tol2 * bb;
-        if (blockIdx.x == 0 && threadIdx.x == 0 && k < 48) a.ctl->reshist[a.which][k] = (bb > 0.0) ? rr / bb : 0.0;
-        k += 1;
-        if (conv) break;
-        rho = rho_k; cur = nxt;
-        if (k >= a.max_iter) break;
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        sc.cur = cur; sc.k = k; sc.done = 1; sc.rr = rr; sc.bb = bb; sc.rho = rho;
-        sc.iters += k; sc.solves += 1;
-        if (!conv) a.ctl->nonconv += 1;
-        double rel = (bb > 0.0) ? sqrt(rr / bb) : 0.0;
-        if (rel > sc.maxres) sc.maxres = rel;
-    }
-}
-
-// The same solve with TWO consecutive cases per lane (B even): every vector access is a 16-byte load / store (512 B per warp request), so
-// a row's index / value requests are shared by 64 cases instead of 32 and half as many load instructions move the same data.
-#ifndef SWEEP_MINB2
-#define SWEEP_MINB2 4
-#endif
-__device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
-__global__ void __launch_bounds__(256, SWEEP_MINB2) solve_coop_csr_b2_k(const __grid_constant__ CsrSolveBArgs a) {
-    __shared__ double red[64];
-    __shared__ double bc[2];
-    SolveCtl& sc = a.ctl->sc[a.which];
-    int k = 0, cur = sc.cur;
-    double rho = 0.0, rr = 0.0, bb = 0.0;
-    bool conv = false;
-    unsigned int epoch = 0;
-    const SweepMap mp(a.A.n_rows, a.B, a.n_row_groups, a.mode, 2);
-    const int B = a.B;
-    while (true) {
-        double c1, c2, rho_k;
-        cheb_coeffs(k, rho, a.cheb_d, a.cheb_c, c1, c2, rho_k);
-        const int nxt = (cur + 1) % 3, prv = (cur + 2) % 3;
-        const double* x = tb_sel(a.tb, cur); const double* xp = tb_sel(a.tb, prv); double* xn = tb_sel(a.tb, nxt);
-        double r0 = 0.0, b0 = 0.0;
-        if (mp.on) {
-            for (int r = mp.first; r < mp.end; r += mp.step) {
-                const size_t o = (size_t)r * B + mp.cs;
-                const double2 bv = ld2(a.b + o), xc = ld2(x + o);
-                const double2 xpv = k > 0 ? ld2(xp + o) : make_double2(0.0, 0.0);
-                const double pv = __ldg(&a.pinv[r]);
-                double v0 = 0.0, v1 = 0.0;
-                const int j1 = __ldg(&a.A.indptr[r + 1]);
-                for (int j = __ldg(&a.A.indptr[r]); j < j1; ++j) {
-                    const double wj = __ldg(&a.A.val[j]);
-                    const double2 xj = ld2(x + (size_t)__ldg(&a.A.idx[j]) * B + mp.cs);
-                    v0 += wj * xj.x; v1 += wj * xj.y;
-                }
-                const double res0 = bv.x - v0, res1 = bv.y - v1;
-                double2 w = make_double2(xc.x + c2 * pv * res0, xc.y + c2 * pv * res1);
-                if (k > 0) { w.x += c1 * (xc.x - xpv.x); w.y += c1 * (xc.y - xpv.y); }
                 if (mp.lane_ok) {
-                    *reinterpret_cast<double2*>(xn + o) = w;
-                    r0 += pv * res0 * res0; b0 += pv * bv.x * bv.x;
-                    r0 += pv * res1 * res1; b0 += pv * bv.y * bv.y;
+                    st_cases<CPL>(xn + o, w);
+                    r0 += pv * rs; b0 += pv * bs;
                 }
             }
         }

@@ -543,7 +543,7 @@ struct phw_solver_s {
     Hist hist[2][2];           // [field p/q][solve site]
     int extrap = 2, n_sites = 1;
     int extrap_f[2] = {2, 2};  // extrapolation order of the p / q solves
-    int bcsr = 0; double* bpart = nullptr;   // batched sweep with the case index fastest (kernels_sweep.cuh): number of cases, [row block][case] partial sums
+    int bcsr = 0; double* bpart = nullptr; size_t bpart_cap = 0;   // batched sweep with the case index fastest (kernels_sweep.cuh): number of cases, [row block][case] partial sums
     bool pcg[2] = {false, false};     // conjugate-gradient mass solves (poor meshes; flags bits 16 / 17)
     bool implicit_pending = false;    // partitioned implicit run: the ellipse / bordered column are set up by phw_comm_finish_implicit
     bool ho = false; Csr hMp{}, hMq{}, hD{}, hDT{};
@@ -655,29 +655,44 @@ void csr_dot(phw_solver_s* s, const Csr& A, const double* x, double scale, int s
 
 // ---- batched sweep, case index fastest (kernels_sweep.cuh): one warp = 32 cases x a block of rows
 inline bool prof_on(phw_solver_s* s);
+#ifndef SWEEP_CPL_MAX
+#define SWEEP_CPL_MAX 4            // default cap of the cases per lane (PHW_SWEEP_CPL = 1, 2: A/B)
+#endif
 // row mapping of the sweep kernels (kernels_sweep.cuh: SweepMap): 0 = one block of rows per warp (default), 1 = cyclic row tiles
 inline int sweep_map_mode() {
     static const int m = [] { const char* e = getenv("PHW_SWEEP_MAP"); return e ? atoi(e) : 0; }();
     return m == 1 ? 1 : 0;
 }
-inline int bcsr_grid(phw_solver_s* s, const Csr& A, int* n_row_groups) {
-    const int nchunk = (s->bcsr + 31) / 32;
+// cases per lane of the sweep kernels (kernels_sweep.cuh): 4 / 2 / 1 by the divisibility of the number of cases; PHW_SWEEP_CPL caps it (A/B)
+inline int sweep_cpl(phw_solver_s* s) {
+    static const int cap = [] { const char* e = getenv("PHW_SWEEP_CPL"); const int v = e ? atoi(e) : 0; return (v == 1 || v == 2 || v == 4) ? v : SWEEP_CPL_MAX; }();
+    int cpl = (s->bcsr % 4 == 0) ? 4 : ((s->bcsr % 2 == 0) ? 2 : 1);
+    return std::min(cpl, cap);
+}
+inline int bcsr_grid(phw_solver_s* s, const Csr& A, int cpl, int* n_row_groups) {
+    const int nchunk = (s->bcsr + 32 * cpl - 1) / (32 * cpl);
     const int groups = std::max(1, std::min((A.n_rows + SWEEP_WPB - 1) / SWEEP_WPB, (8 * s->sm_count) / nchunk));   // ~8 CTAs per SM
     *n_row_groups = groups;
     return nchunk * groups;
 }
 void bcsr_store(phw_solver_s* s, const Csr& A, const double* x, double alpha, const double* cscale, double* y) {
     int ng = 1;
-    const int g = bcsr_grid(s, A, &ng);
-    csr_store_b_k<<<g, 256, 0, s->stream>>>(A, s->bcsr, ng, sweep_map_mode(), x, alpha, cscale, y);
+    const int cpl = sweep_cpl(s), g = bcsr_grid(s, A, cpl, &ng), m = sweep_map_mode();
+    if (cpl == 4) csr_store_b_k<4><<<g, 256, 0, s->stream>>>(A, s->bcsr, ng, m, x, alpha, cscale, y);
+    else if (cpl == 2) csr_store_b_k<2><<<g, 256, 0, s->stream>>>(A, s->bcsr, ng, m, x, alpha, cscale, y);
+    else csr_store_b_k<1><<<g, 256, 0, s->stream>>>(A, s->bcsr, ng, m, x, alpha, cscale, y);
     s->launches++;
 }
-void bcsr_dot(phw_solver_s* s, const Csr& A, const double* x, double scale, const double* cscale, int slot) {
+int bcsr_dot(phw_solver_s* s, const Csr& A, const double* x, double scale, const double* cscale, int slot) {
     int ng = 1;
-    const int g = bcsr_grid(s, A, &ng);
-    csr_dot_b_k<<<g, 256, 0, s->stream>>>(A, s->bcsr, ng, sweep_map_mode(), x, s->bpart);
+    const int cpl = sweep_cpl(s), g = bcsr_grid(s, A, cpl, &ng), m = sweep_map_mode();
+    if ((size_t)ng * SWEEP_WPB * (size_t)s->bcsr > s->bpart_cap) return fail(PHW_ECUDA, "sweep: partial-sum buffer too small");
+    if (cpl == 4) csr_dot_b_k<4><<<g, 256, 0, s->stream>>>(A, s->bcsr, ng, m, x, s->bpart);
+    else if (cpl == 2) csr_dot_b_k<2><<<g, 256, 0, s->stream>>>(A, s->bcsr, ng, m, x, s->bpart);
+    else csr_dot_b_k<1><<<g, 256, 0, s->stream>>>(A, s->bcsr, ng, m, x, s->bpart);
     dot_b_finish_k<<<nblk(s->bcsr, 128), 128, 0, s->stream>>>(s->bcsr, ng * SWEEP_WPB, s->bpart, scale, cscale, s->ctl, slot);
     s->launches += 2;
+    return 0;
 }
 int bcsr_solve(phw_solver_s* s, int which) {
     CsrSolveBArgs a{};
@@ -689,10 +704,8 @@ int bcsr_solve(phw_solver_s* s, int which) {
     a.tol2 = std::min(s->prm.tol * s->prm.tol, t * t);
     a.max_iter = s->prm.max_iter; a.which = which; a.partials = s->partials; a.ctl = s->ctl;
     CU(cudaMemsetAsync(&s->ctl->gbar[0], 0, sizeof(unsigned int), s->stream));
-    // two consecutive cases per lane (16-byte accesses) when the number of cases is even; PHW_SWEEP_CPL=1 forces one (A/B)
-    static const int cpl_env = [] { const char* e = getenv("PHW_SWEEP_CPL"); return e ? atoi(e) : 0; }();
-    const int cpl = (cpl_env == 1 || (s->bcsr % 2) != 0) ? 1 : 2;
-    void* kern = cpl == 2 ? (void*)solve_coop_csr_b2_k : (void*)solve_coop_csr_b_k;
+    const int cpl = sweep_cpl(s);
+    void* kern = cpl == 4 ? (void*)solve_coop_csr_b_k<4> : (cpl == 2 ? (void*)solve_coop_csr_b_k<2> : (void*)solve_coop_csr_b_k<1>);
     int occ = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0));
     if (occ < 1) return fail(PHW_ECUDA, "solve_coop_csr_b_k does not fit on an SM");
@@ -1343,8 +1356,8 @@ int rhs_q(phw_solver_s* s, const double* psrc, const double* qsrc) {
 }
 int energy(phw_solver_s* s) {
     if (s->bcsr) {
-        bcsr_dot(s, s->hMp, s->p, 0.5, s->d_ginvrho, 0);
-        bcsr_dot(s, s->hMq, s->q, 0.5, s->d_gK, 1);
+        int rc_ = bcsr_dot(s, s->hMp, s->p, 0.5, s->d_ginvrho, 0); if (rc_) return rc_;
+        rc_ = bcsr_dot(s, s->hMq, s->q, 0.5, s->d_gK, 1); if (rc_) return rc_;
         CU(cudaGetLastError());
         return 0;
     }
@@ -2939,7 +2952,9 @@ static int ho_create_base(const phw_params* prm, int32_t device, void* cuda_stre
         std::vector<double> gk(s->G, prm->K_wave), gir(s->G, 1.0 / prm->rho);
         rc = s->upload(&s->d_gK, gk); if (rc) return bail(rc);
         rc = s->upload(&s->d_ginvrho, gir); if (rc) return bail(rc);
-        rc = s->dalloc(&s->bpart, (size_t)8 * 8 * s->sm_count * 32 + (size_t)s->bcsr); if (rc) return bail(rc);     // [row block][case]: row blocks x cases <= 32 x warps of a launch
+        // [row-owning warp][case] partial sums of csr_dot_b_k: (warps of a launch / case chunks) x cases <= 32 x 4 (cases per lane) x warps
+        s->bpart_cap = (size_t)8 * 8 * s->sm_count * 32 * 4 + (size_t)s->bcsr;
+        rc = s->dalloc(&s->bpart, s->bpart_cap); if (rc) return bail(rc);
     }
     s->cheb_d[0] = 0.5 * (lam_min_p + lam_max_p); s->cheb_c[0] = 0.5 * (lam_max_p - lam_min_p);
     s->cheb_d[1] = 0.5 * (lam_min_q + lam_max_q); s->cheb_c[1] = 0.5 * (lam_max_q - lam_min_q);
