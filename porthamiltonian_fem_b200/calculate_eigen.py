@@ -15,7 +15,7 @@ import numpy as np
 
 from . import _lib
 from .mesh import generate_mesh
-from .solver import Mesh, Solver, tag_boundary_edges
+from .solver import Mesh, Solver, tag_boundary_edges, tag_space_boundary
 
 
 def exact_eigenvalues(c, xLength, yLength, n=None):
@@ -36,17 +36,7 @@ class _DeviceOperators:
             from .fem_ho import HighOrderSpaces
             from .solver import HighOrderSolver
             S = HighOrderSpaces(mesh[0], mesh[1], basis_order[0], basis_order[1])
-            be = S.boundary_edges
-            pa, pb = S.vertices[S.edges[be, 0]], S.vertices[S.edges[be, 1]]
-            tags = {}
-            for e, a, b in zip(be, pa, pb):
-                on = lambda f: f(a) and f(b)
-                if on(lambda p: abs(p[0]) < 1e-12):
-                    tags[int(e)] = 0
-                elif on(lambda p: abs(p[0] - xLength) < 1e-12):
-                    tags[int(e)] = 2
-                else:
-                    tags[int(e)] = 3
+            tags = tag_space_boundary(S, domainShape, xLength, yLength)
             ops = S.assemble(tags)
             bp, bq = S.jacobi_bounds(ops)
             self.solver = HighOrderSolver(S, ops, prm, bp, bq, device=device)

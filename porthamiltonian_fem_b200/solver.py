@@ -120,14 +120,10 @@ class Mesh:
             pass
 
 
-def tag_boundary_edges(mesh, domainShape, xLength, yLength):
-    """Facet markers of the reference (wave_2D.py:226-280): 0 left/port, 1 top (rectangle only), 2 right,
-    3 bottom/general, 4 unmarked.  dolfin marks a facet when its vertices and midpoint satisfy ``inside``;
+def facet_tags(pa, pb, domainShape, xLength, yLength):
+    """Facet markers of the reference (wave_2D.py:226-280) for boundary facets with end points pa, pb [n, 2]: 0 left/port, 1 top
+    (rectangle only), 2 right, 3 bottom/general, 4 unmarked.  dolfin marks a facet when its vertices and midpoint satisfy ``inside``;
     later markers override earlier ones (left, top, right, general)."""
-    ids, _ = mesh.boundary()
-    edges = mesh.edges()[0]
-    pa = mesh.vertices[edges[ids, 0]]
-    pb = mesh.vertices[edges[ids, 1]]
     pm = 0.5 * (pa + pb)
     tol = 1e-12
     xInputStart = 0.0 if domainShape == 'R' else -0.10
@@ -135,7 +131,7 @@ def tag_boundary_edges(mesh, domainShape, xLength, yLength):
     def on(pred):
         return pred(pa) & pred(pb) & pred(pm)
 
-    tags = np.full(ids.shape[0], TAG_NONE, dtype=np.int32)
+    tags = np.full(pa.shape[0], TAG_NONE, dtype=np.int32)
     tags[on(lambda p: np.abs(p[:, 0] - xInputStart) < tol)] = TAG_LEFT
     if domainShape == 'R':
         tags[on(lambda p: np.abs(p[:, 1] - yLength) < tol)] = TAG_TOP
@@ -147,6 +143,20 @@ def tag_boundary_edges(mesh, domainShape, xLength, yLength):
         tags[on(lambda p: (np.abs(p[:, 1]) < tol) | (np.abs(p[:, 1] - xLength) < tol) | (np.abs(p[:, 1] - ylo) < tol) |
                 (np.abs(p[:, 1] - yhi) < tol) | (np.abs(p[:, 0]) < tol))] = TAG_GENERAL
     return tags
+
+
+def tag_boundary_edges(mesh, domainShape, xLength, yLength):
+    """facet_tags for the boundary edges of a libphwave Mesh (order of mesh.boundary())"""
+    ids, _ = mesh.boundary()
+    edges = mesh.edges()[0]
+    return facet_tags(mesh.vertices[edges[ids, 0]], mesh.vertices[edges[ids, 1]], domainShape, xLength, yLength)
+
+
+def tag_space_boundary(spaces, domainShape, xLength, yLength):
+    """{boundary edge id: tag} for the assembled / reference-element spaces of fem_ho.py / fem_ref.py"""
+    be = spaces.boundary_edges
+    tags = facet_tags(spaces.vertices[spaces.edges[be, 0]], spaces.vertices[spaces.edges[be, 1]], domainShape, xLength, yLength)
+    return {int(e): int(t) for e, t in zip(be, tags)}
 
 
 # closed 9-point Newton-Cotes weights on [0,1]: exact integral of the degree-8 equispaced interpolant, which

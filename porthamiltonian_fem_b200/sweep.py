@@ -109,28 +109,9 @@ def _sweep_case_fastest(tFinal, numSteps, mesh, xLength, yLength, cases, domainS
     """The sweep on ONE set of assembled P1 x RT1 operators (host assembly of fem_ho.py at order (1, 1): M_p, M_q, D = C - N, b_L and
     the element-wise bounds of the Jacobi-scaled mass spectra), all cases side by side in [n_dof][n_cases] vectors."""
     from .fem_ho import HighOrderSpaces
-    from .solver import BatchedSweepSolver
+    from .solver import BatchedSweepSolver, tag_space_boundary
     S = HighOrderSpaces(mesh[0], mesh[1], 1, 1)
-    be = S.boundary_edges
-    pa, pb = S.vertices[S.edges[be, 0]], S.vertices[S.edges[be, 1]]
-    pm = 0.5 * (pa + pb)
-    tol_g = 1e-12
-    xin = 0.0 if domainShape == 'R' else -0.10
-
-    def on(pred):
-        return pred(pa) & pred(pb) & pred(pm)
-    tags = np.full(be.shape[0], 4, dtype=np.int64)                       # facet markers of wave_2D.py:226-280
-    tags[on(lambda p: np.abs(p[:, 0] - xin) < tol_g)] = 0
-    if domainShape == 'R':
-        tags[on(lambda p: np.abs(p[:, 1] - yLength) < tol_g)] = 1
-    tags[on(lambda p: np.abs(p[:, 0] - xLength) < tol_g)] = 2
-    if domainShape == 'R':
-        tags[on(lambda p: np.abs(p[:, 1]) < tol_g)] = 3
-    else:
-        ylo, yhi = xLength / 2 - yLength / 2, xLength / 2 + yLength / 2
-        tags[on(lambda p: (np.abs(p[:, 1]) < tol_g) | (np.abs(p[:, 1] - xLength) < tol_g) | (np.abs(p[:, 1] - ylo) < tol_g) |
-                (np.abs(p[:, 1] - yhi) < tol_g) | (np.abs(p[:, 0]) < tol_g))] = 3
-    ops = S.assemble({int(e): int(t) for e, t in zip(be, tags)})
+    ops = S.assemble(tag_space_boundary(S, domainShape, xLength, yLength))                 # facet markers of wave_2D.py:226-280
     bp, bq = S.jacobi_bounds(ops)
     B = len(cases)
     prm = _lib.PhwParams()

@@ -301,7 +301,7 @@ def _solve_high_order(tFinal, numSteps, outputDir, nx, xLength, yLength, domainS
     csrc/kernels_ho.cuh) for the explicit schemes, host-assembled CSR operators (fem_ho.py) for the implicit ones."""
     from .fem_ho import HighOrderSpaces, LagrangeRef, tri_rule
     from .fem_ref import RefSpaces
-    from .solver import HighOrderSolver, MatrixFreeHighOrderSolver
+    from .solver import HighOrderSolver, MatrixFreeHighOrderSolver, tag_space_boundary
     if dirichletImp != 'weak' or controlType is not None:
         raise NotImplementedError('higher-order pairs are available for the weak form without control (all six schemes, with or without the lumped model)')
     implicit = timeIntScheme in ('IE', 'SM')
@@ -323,30 +323,10 @@ def _solve_high_order(tFinal, numSteps, outputDir, nx, xLength, yLength, domainS
     S = (RefSpaces if matrix_free else HighOrderSpaces)(mesh[0], mesh[1], basis_order[0], basis_order[1])
     if verbose:
         print('number of cells = {}'.format(S.nc))
-    # facet markers (wave_2D.py:226-280) on the boundary edges
-    be = S.boundary_edges
-    pa, pb = S.vertices[S.edges[be, 0]], S.vertices[S.edges[be, 1]]
-    pm = 0.5 * (pa + pb)
-    tol_g = 1e-12
-    xin = 0.0 if domainShape == 'R' else -0.10
-
-    def on(pred):
-        return pred(pa) & pred(pb) & pred(pm)
-    tags = np.full(be.shape[0], 4, dtype=np.int64)
-    tags[on(lambda p: np.abs(p[:, 0] - xin) < tol_g)] = 0
-    if domainShape == 'R':
-        tags[on(lambda p: np.abs(p[:, 1] - yLength) < tol_g)] = 1
-    tags[on(lambda p: np.abs(p[:, 0] - xLength) < tol_g)] = 2
-    if domainShape == 'R':
-        tags[on(lambda p: np.abs(p[:, 1]) < tol_g)] = 3
-    else:
-        ylo, yhi = xLength / 2 - yLength / 2, xLength / 2 + yLength / 2
-        tags[on(lambda p: (np.abs(p[:, 1]) < tol_g) | (np.abs(p[:, 1] - xLength) < tol_g) | (np.abs(p[:, 1] - ylo) < tol_g) |
-                (np.abs(p[:, 1] - yhi) < tol_g) | (np.abs(p[:, 0]) < tol_g))] = 3
+    tag_of = tag_space_boundary(S, domainShape, xLength, yLength)       # facet markers (wave_2D.py:226-280) on the boundary edges
     c = np.sqrt(K_wave / rho)
     omega = c * np.sqrt(np.pi ** 2 / (4 * xLength ** 2) + 4 * np.pi ** 2 / yLength ** 2)
     left_w = (lambda x, y: rho * omega * np.sin(2 * np.pi * y / yLength + np.pi / 2)) if analytical else None
-    tag_of = {int(e): int(t) for e, t in zip(be, tags)}
     if matrix_free:
         ops = S.boundary_operators(tag_of, left_weight=left_w)
         bp, bq = S.jacobi_bounds()
