@@ -4,11 +4,11 @@
 // terms) and the lumped constants differ (the loop over cases of main_wave_2D.py:24-50,119-140).  Round 1 put the cases side by side
 // as B copies of the mesh inside one device mesh, which re-reads identical index / metric / weight data B times - about half of the
 // bytes of an M_q iteration.  Here every vector is an [n_dof][B] array and the operators are ONE set of assembled CSR rows
-// (5 non-zeros per RT1 row, ~7 per P1 row: a few hundred KB, cache resident): a warp owns 32 consecutive cases and a strided set of
-// rows (SweepMap below); the row's indices and values are the same for all lanes (broadcast loads) and every vector access
-// x[idx * B + c] is a fully coalesced 256-byte segment.  The rows a mesh row gathers from are worked on at the same time by the other
-// warps of the case chunk, so they hit in L1 / L2 and DRAM sees each vector once per pass: 32 B per dof, case and Chebyshev iteration (x_k, x_{k-1}, b read; x_{k+1} written) instead of 64 (M_q) and
-// 80 (M_p) in the replicated layout.  Sparse matrix x dense block: no shared-memory staging, no atomics, fixed summation order.
+// (5 non-zeros per RT1 row, ~7 per P1 row: a few hundred KB, cache resident).  A warp owns a chunk of 32 x CPL consecutive cases
+// (CPL = 1, 2 or 4 per lane) and a block of rows (SweepMap below); the row's indices and values are the same for all lanes (broadcast
+// loads) and every vector access x[idx * B + c] is a fully coalesced segment of 256 x CPL bytes.  Algorithmic traffic: 32 B per dof,
+// case and Chebyshev iteration (x_k, x_{k-1}, b read; x_{k+1} written) instead of 64 (M_q) and 80 (M_p) in the replicated layout.
+// Sparse matrix x dense block: no shared-memory staging, no atomics, fixed summation order.
 //
 // Per-case quantities (energies, port fluxes) are per-lane sums; blocks of rows are combined in a fixed order by a finishing kernel,
 // so every case's H_array is bit-reproducible.  The Chebyshev stop test uses the residual aggregated over all cases with the
@@ -50,7 +50,7 @@ struct SweepMap {
             end = on ? (int)((long long)(wid + 1) * n_rows / nblk) : first;
             step = 1;
         }
-        c = (chunk * 32 + lane) * cpl;       // cpl consecutive cases per lane (cpl = 2: B even, 16-byte accesses)
+        c = (chunk * 32 + lane) * cpl;       // cpl consecutive cases per lane (cpl = 2, 4: B a multiple of it, 16-byte accesses)
         lane_ok = c < B;
         cs = lane_ok ? c : B - cpl;          // lanes beyond the last case read valid memory and store nothing
     }
