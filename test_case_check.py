@@ -1,6 +1,12 @@
 """Same comparison as the reference's test_case_check.py (:80-126): max absolute / relative-percent difference of
 the Hamiltonian (column 1), the energy residual (column 2) and, for analytical cases, the L2 error (column 8)
-between a run and its ground truth; FAIL above 1e-5 % (1e-7 % for the analytical error)."""
+between a run and its ground truth; FAIL above 1e-5 % (1e-7 % for the analytical error).
+
+One addition.  The reference compares two runs of the SAME code, which agree bit for bit; here the ground truth comes from an
+independent implementation (the CPU oracle), and the energy residual E is a difference of O(H) energies that is zero up to
+round-off for the conservative schemes (SM + IC: |E| ~ 1e-15).  A relative test of such a quantity measures noise: with the
+reference's eps = 1e-10 in the denominator it asks for |dE| < 1e-17.  The residual column therefore also passes when its ABSOLUTE
+difference is below 1e-10 x max|H| (printed as such); the Hamiltonian and the analytical error keep the reference's thresholds."""
 import os
 
 import numpy as np
@@ -20,14 +26,17 @@ def check_cases(caseName, caseArray):
         resDiff = max(abs(data_array[:, 2] - gt_array[:, 2]))
         hamDiffPerc = 100 * max(abs((data_array[:, 1] - gt_array[:, 1]) / (abs(gt_array[:, 1]) + eps)))
         resDiffPerc = 100 * max(abs((data_array[:, 2] - gt_array[:, 2]) / (abs(gt_array[:, 2]) + eps)))
-        ok = not (hamDiffPerc > 1e-5 or resDiffPerc > 1e-5)
+        res_floor = 1e-10 * max(abs(gt_array[:, 1]))
+        res_ok = resDiffPerc <= 1e-5 or resDiff <= res_floor
+        ok = not hamDiffPerc > 1e-5 and res_ok
         if analytical:
             analyticDiff = max(abs(data_array[:, 8] - gt_array[:, 8]))
             analyticDiffPerc = 100 * max(abs((data_array[:, 8] - gt_array[:, 8]) / (abs(gt_array[:, 8]) + eps)))
             ok = ok and not analyticDiffPerc > 1e-7
         print('{} test {}'.format(subDir, 'passed' if ok else 'FAILED'))
         print('Hamiltonian max diff    : {}%'.format(hamDiffPerc))
-        print('Energy res max diff     : {}%'.format(resDiffPerc))
+        print('Energy res max diff     : {}%{}'.format(resDiffPerc, '' if resDiffPerc <= 1e-5 else
+              ' (round-off level: absolute difference {:.1e} against the floor 1e-10 x max|H| = {:.1e})'.format(resDiff, res_floor)))
         print('Hamiltonian total diff  : {}'.format(hamDiff))
         print('Energy res total diff   : {}'.format(resDiff))
         if analytical:
