@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, 'porthamiltonian_fem_b200', 'csrc')
 BUILD = os.path.join(HERE, '_build')
 LIB = os.path.join(BUILD, 'libphwemu.so')
-HEADERS = ['kernels.cuh', 'kernels_pipe.cuh', 'pipe_carve.hpp', 'layout.hpp']
+HEADERS = ['kernels.cuh', 'kernels_pipe.cuh', 'kernels_sweep.cuh', 'pipe_carve.hpp', 'layout.hpp']
 
 
 def build(verbose=False):

@@ -19,6 +19,7 @@ struct uint2 { unsigned int x, y; };
 struct uint4 { unsigned int x, y, z, w; };
 struct int4 { int x, y, z, w; };
 struct double2 { double x, y; };
+static inline double2 make_double2(double x, double y) { return double2{x, y}; }
 static inline uint2 make_uint2(unsigned int x, unsigned int y) { return uint2{x, y}; }
 static inline uint4 make_uint4(unsigned int x, unsigned int y, unsigned int z, unsigned int w) { return uint4{x, y, z, w}; }
 

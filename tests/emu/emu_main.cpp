@@ -13,6 +13,7 @@
 
 #include "cuda_runtime.h"
 #include "kernels_pipe.cuh"
+#include "kernels_sweep.cuh"
 #include "pipe_carve.hpp"
 #include "layout.hpp"
 
@@ -187,6 +188,33 @@ extern "C" int emu_run(const char* what_c, int64_t nv, const double* vtx, int64_
             a.cheb_d = cd; a.cheb_c = cc; a.tol2 = tol * tol; a.max_iter = 200; a.which = 0; a.partials = partials; a.ctl = ctl;
             const size_t sm = ((size_t)(L.max_lv + 31) / 32 + 4 + (size_t)((L.max_lv + 1) & ~1)) * 8;
             phw_emu::launch(grid, NT, sm, [&] { solve_ell_coop_k<NT, 1, false>(a, pc); });
+        } else if (what == "mq_pcg" || what == "mp_pcg") {
+            // conjugate-gradient mass solves (solve_pcg_coop_k) on the generic row passes: meshes of poor quality
+            double* d_g0 = A.put(g0); double* d_g1 = A.put(g1); double* d_g2 = A.put(g2);
+            std::vector<double> mdiag(L.nv, 0.0);               // diag of M_p: sum_K |K| / 6
+            for (int p = 0; p < npatch; ++p) {
+                const PatchHdr& h = L.hdr[p];
+                for (int lc = 0; lc < h.n_vcells; ++lc) {
+                    const uint2 rv = hv[h.cell_off + lc];
+                    for (uint32_t lv : {rv.x & 0xFFFFu, rv.x >> 16, rv.y & 0xFFFFu})
+                        if ((int)lv < h.v_cnt) mdiag[h.v_start + lv] += area[h.cell_off + lc] / 6.0;
+                }
+            }
+            std::vector<double> pinvp(L.nv);
+            for (int i = 0; i < (int)L.nv; ++i) pinvp[i] = 1.0 / mdiag[i];
+            RowArgs a{};
+            a.m.npatch = npatch; a.m.nv = (int)L.nv; a.m.ne = (int)L.ne; a.m.hdr = d_hdr; a.m.recv = d_recv; a.m.rece = d_rece; a.m.area = d_area;
+            a.m.g0 = d_g0; a.m.g1 = d_g1; a.m.g2 = d_g2; a.m.ghost_v = d_gv; a.m.ghost_e = d_ge; a.m.eadj = d_eadj; a.m.vslice_off = d_voff; a.m.vadj = d_vadj;
+            a.m.ell_ioff = d_io; a.m.ell_woff = d_wo; a.m.ell_ids = d_ids; a.m.ell_w = d_ellw;
+            for (int i = 0; i < 3; ++i) { a.tp.b[i] = buf[i]; a.tq.b[i] = buf[i]; }
+            a.b = d_b; a.pinv = is_q ? d_pinvq : A.put(pinvp); a.mdiag = is_q ? nullptr : A.put(mdiag);
+            a.partials = partials; a.ctl = ctl; a.tol2 = tol * tol; a.max_iter = 2000; a.which = is_q ? 1 : 0; a.cM = 1.0; a.weight = 1.0;
+            PcgArgs v{};
+            v.r = A.get<double>(n); v.u = A.get<double>(n); v.b = a.b; v.pinv = a.pinv; v.n = (int)n;
+            auto ev = [](int x) { return (size_t)((x + 1) & ~1); };
+            const size_t soff = ((size_t)(L.max_lv + 31) / 32 + 4) / 2 + 1;
+            if (is_q) phw_emu::launch(grid, NT, (ev(L.max_le) + 3 * (size_t)L.max_cells) * 8, [&] { solve_pcg_coop_k<1, NT, 1>(a, v); });
+            else phw_emu::launch(grid, NT, (soff + ev(L.max_lv) + (size_t)L.max_cells) * 8, [&] { solve_pcg_coop_k<0, NT, 1>(a, v); });
         } else return fail(err, errlen, "unknown kernel " + what);
         const SolveCtl& sc = ctl->sc[is_q ? 1 : 0];
         if ((ctl->nonconv >> 32) != 0) return fail(err, errlen, "a stage did not arrive");
@@ -448,5 +476,114 @@ extern "C" int emu_run2(const char* what_c, int32_t patch_cells, int32_t grid,
         for (size_t i = 0; i < n2o.size(); ++i) out_user[r][n2o[i]] = k.buf[sc.cur][i];
         if (iters) iters[r] = (int32_t)sc.iters;
     }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// batched-sweep kernels (csrc/kernels_sweep.cuh): ONE assembled CSR operator, B cases with the case index fastest, CPL = 1 / 2 / 4
+// cases per lane, both row mappings.  what: "store" (out[n_rows][B] = alpha cscale[c] A x), "dot" (out[B] = cscale[c] x^T A x per
+// case, through csr_dot_b_k + dot_b_finish_k), "solve" (out[n_rows][B] = A^-1 b by solve_coop_csr_b_k, x0 = 0; pinv = 1 / diag).
+// ------------------------------------------------------------------------------------------------
+template <int CPL>
+static int run_csr_cpl(const std::string& what, const Csr& A, int B, int mode, int n_groups, int grid, const double* d_x, const double* d_cs,
+                       double alpha, double* d_y, double* d_part, Ctl* ctl, double* partials, const double* d_pinv, double* const* buf,
+                       double lam_lo, double lam_hi, double tol) {
+    constexpr int NT = 256;
+    if (what == "store") {
+        phw_emu::launch(grid, NT, 0, [&] { csr_store_b_k<CPL>(A, B, n_groups, mode, d_x, alpha, d_cs, d_y); });
+    } else if (what == "dot") {
+        phw_emu::launch(grid, NT, 0, [&] { csr_dot_b_k<CPL>(A, B, n_groups, mode, d_x, d_part); });
+        phw_emu::launch((B + 127) / 128, 128, 0, [&] { dot_b_finish_k(B, n_groups * SWEEP_WPB, d_part, alpha, d_cs, ctl, 0); });
+    } else {
+        CsrSolveBArgs a{};
+        a.A = A; a.B = B; a.n_row_groups = n_groups; a.mode = mode;
+        for (int i = 0; i < 3; ++i) a.tb.b[i] = buf[i];
+        a.b = d_x; a.pinv = d_pinv; a.cheb_d = 0.5 * (lam_lo + lam_hi); a.cheb_c = 0.5 * (lam_hi - lam_lo);
+        a.tol2 = tol * tol; a.max_iter = 400; a.which = 1; a.partials = partials; a.ctl = ctl;
+        phw_emu::launch(grid, NT, 0, [&] { solve_coop_csr_b_k<CPL>(a); });
+    }
+    return 0;
+}
+
+extern "C" int emu_run_csr(const char* what_c, int32_t n_rows, int32_t n_cols, const int32_t* indptr, const int32_t* idx, const double* val,
+                           int32_t B, int32_t cpl, int32_t mode, int32_t n_groups, const double* x_in, const double* cscale, double alpha,
+                           double lam_lo, double lam_hi, double tol, double* out, int32_t* iters, char* err, int errlen) {
+    const std::string what(what_c);
+    if (B % cpl != 0) return fail(err, errlen, "the number of cases must be a multiple of the cases per lane");
+    Arena A;
+    const int nnz = indptr[n_rows];
+    Csr M{};
+    M.n_rows = n_rows; M.lanes = 8;
+    M.indptr = A.put(std::vector<int>(indptr, indptr + n_rows + 1));
+    M.idx = A.put(std::vector<int>(idx, idx + nnz));
+    M.val = A.put(std::vector<double>(val, val + nnz));
+    const int nchunk = (B + 32 * cpl - 1) / (32 * cpl);
+    const int grid = nchunk * n_groups;
+    const size_t n_in = what == "solve" ? (size_t)n_rows * B : (size_t)n_cols * B;
+    double* d_x = A.put(std::vector<double>(x_in, x_in + n_in));
+    double* d_cs = cscale ? A.put(std::vector<double>(cscale, cscale + B)) : nullptr;
+    double* d_y = A.get<double>((size_t)n_rows * B);
+    double* d_part = A.get<double>((size_t)n_groups * SWEEP_WPB * B);
+    Ctl* ctl = A.get<Ctl>((size_t)B);
+    double* partials = A.get<double>(4 * (size_t)grid + 16);
+    std::vector<double> pinv(n_rows, 1.0);
+    for (int r = 0; r < n_rows; ++r)
+        for (int j = indptr[r]; j < indptr[r + 1]; ++j) if (idx[j] == r) pinv[r] = 1.0 / val[j];
+    double* d_pinv = A.put(pinv);
+    double* buf[3];
+    for (auto& b : buf) b = A.get<double>((size_t)n_rows * B);
+    int rc;
+    if (cpl == 4) rc = run_csr_cpl<4>(what, M, B, mode, n_groups, grid, d_x, d_cs, alpha, d_y, d_part, ctl, partials, d_pinv, buf, lam_lo, lam_hi, tol);
+    else if (cpl == 2) rc = run_csr_cpl<2>(what, M, B, mode, n_groups, grid, d_x, d_cs, alpha, d_y, d_part, ctl, partials, d_pinv, buf, lam_lo, lam_hi, tol);
+    else rc = run_csr_cpl<1>(what, M, B, mode, n_groups, grid, d_x, d_cs, alpha, d_y, d_part, ctl, partials, d_pinv, buf, lam_lo, lam_hi, tol);
+    if (rc) return rc;
+    if (what == "store") std::memcpy(out, d_y, (size_t)n_rows * B * sizeof(double));
+    else if (what == "dot") { for (int c = 0; c < B; ++c) out[c] = ctl[c].red[0]; }
+    else {
+        if (ctl->nonconv != 0) return fail(err, errlen, "solve did not converge");
+        std::memcpy(out, buf[ctl->sc[1].cur % 3], (size_t)n_rows * B * sizeof(double));
+        if (iters) *iters = (int32_t)ctl->sc[1].iters;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// coupled block solve of the implicit schemes on assembled CSR rows (solve_block_csr_k, higher-order pairs):
+//     M_p v_p + cDv D^T v_q = b_p ,   M_q v_q + cDe D v_p = b_q ;   Jacobi weights = 1 / diag, ellipse (cheb_d, cheb_c) from the caller
+// ------------------------------------------------------------------------------------------------
+extern "C" int emu_run_block(int32_t n_p, int32_t n_q, const int32_t* const* indptr4, const int32_t* const* idx4, const double* const* val4,
+                             double cDv, double cDe, double wv, double we, double cheb_d, double cheb_c, double tol, int32_t grid,
+                             const double* bp, const double* bq, double* xp, double* xq, int32_t* iters, char* err, int errlen) {
+    Arena A;
+    Csr M[4];     // M_p [n_p], M_q [n_q], D [n_q x n_p], D^T [n_p x n_q]
+    const int rows[4] = {n_p, n_q, n_q, n_p};
+    for (int m = 0; m < 4; ++m) {
+        const int nnz = indptr4[m][rows[m]];
+        M[m].n_rows = rows[m]; M[m].lanes = 8;
+        M[m].indptr = A.put(std::vector<int>(indptr4[m], indptr4[m] + rows[m] + 1));
+        M[m].idx = A.put(std::vector<int>(idx4[m], idx4[m] + nnz));
+        M[m].val = A.put(std::vector<double>(val4[m], val4[m] + nnz));
+    }
+    auto inv_diag = [&](int m) {
+        std::vector<double> d(rows[m], 1.0);
+        for (int r = 0; r < rows[m]; ++r)
+            for (int j = indptr4[m][r]; j < indptr4[m][r + 1]; ++j) if (idx4[m][j] == r) d[r] = 1.0 / val4[m][j];
+        return d;
+    };
+    CsrBlockArgs a{};
+    a.Mp = M[0]; a.Mq = M[1]; a.D = M[2]; a.DT = M[3];
+    for (int i = 0; i < 3; ++i) { a.tp.b[i] = A.get<double>(n_p); a.tq.b[i] = A.get<double>(n_q); }
+    a.bp = A.put(std::vector<double>(bp, bp + n_p)); a.bq = A.put(std::vector<double>(bq, bq + n_q));
+    a.pinv_p = A.put(inv_diag(0)); a.pinv_q = A.put(inv_diag(1));
+    a.cDv = cDv; a.cDe = cDe; a.wv = wv; a.we = we; a.cheb_d = cheb_d; a.cheb_c = cheb_c; a.tol2 = tol * tol; a.max_iter = 2000;
+    a.partials = A.get<double>(4 * (size_t)grid + 16);
+    Ctl* ctl = A.get<Ctl>(1);
+    a.ctl = ctl;
+    phw_emu::launch(grid, 256, 0, [&] { solve_block_csr_k(a); });
+    if (ctl->nonconv != 0) return fail(err, errlen, "block solve did not converge");
+    const int cur = ctl->sc[2].cur % 3;
+    std::memcpy(xp, a.tp.b[cur], (size_t)n_p * sizeof(double));
+    std::memcpy(xq, a.tq.b[cur], (size_t)n_q * sizeof(double));
+    if (iters) *iters = (int32_t)ctl->sc[2].iters;
     return 0;
 }

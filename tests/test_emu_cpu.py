@@ -282,3 +282,156 @@ def test_emulated_two_rank_energy_and_right_hand_sides(emu, mesh):
             own = (part.edge_owner if kind == 'e' else part.vertex_owner) == r
             gid = part.edge_gid if kind == 'e' else part.vertex_gid
             assert own.sum() > 0 and rel(out[r][own], ref[gid[own]]) < 1e-14, (what, r)
+
+
+def _run_csr(lib, what, M, B, cpl, mode, n_groups, x, cscale=None, alpha=1.0, lam=(1.0, 1.0), tol=1e-13):
+    M = M.tocsr()
+    M.sort_indices()
+    ip = np.ascontiguousarray(M.indptr, dtype=np.int32)
+    ix = np.ascontiguousarray(M.indices, dtype=np.int32)
+    va = np.ascontiguousarray(M.data, dtype=np.float64)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    out = np.zeros(B if what == 'dot' else (M.shape[0], B))
+    it = ctypes.c_int32(0)
+    err = ctypes.create_string_buffer(512)
+    cs = None if cscale is None else np.ascontiguousarray(cscale, dtype=np.float64)
+    rc = lib.emu_run_csr(what.encode(), ctypes.c_int32(M.shape[0]), ctypes.c_int32(M.shape[1]), ip.ctypes.data_as(ctypes.c_void_p),
+                         ix.ctypes.data_as(ctypes.c_void_p), va.ctypes.data_as(ctypes.c_void_p), ctypes.c_int32(B), ctypes.c_int32(cpl),
+                         ctypes.c_int32(mode), ctypes.c_int32(n_groups), x.ctypes.data_as(ctypes.c_void_p),
+                         None if cs is None else cs.ctypes.data_as(ctypes.c_void_p), ctypes.c_double(alpha), ctypes.c_double(lam[0]),
+                         ctypes.c_double(lam[1]), ctypes.c_double(tol), out.ctypes.data_as(ctypes.c_void_p), ctypes.byref(it), err, 512)
+    if rc:
+        raise RuntimeError(err.value.decode())
+    return out, it.value
+
+
+@pytest.mark.parametrize('B,cpl', [(7, 1), (10, 2), (12, 4), (40, 4), (66, 2)])
+@pytest.mark.parametrize('mode', [0, 1])
+def test_emulated_sweep_kernels_case_index_fastest(emu, B, cpl, mode):
+    """csrc/kernels_sweep.cuh on the CPU: ONE assembled operator, B cases with the case index fastest, 1 / 2 / 4 cases per lane (16-byte
+    accesses), both row mappings, chunks that are not full (guard pages behind every array): right-hand sides, per-case quadratic
+    forms and the persistent Chebyshev solve against numpy / sparse LU per case"""
+    import scipy.sparse.linalg as spla
+    v, c = rectangle_structured(6, 2)
+    topo = fem.Topology(v, c)
+    ops = fem.assemble_wave_operators(topo, fem.tag_boundary(topo, 'R', 1.0, 0.25))
+    rng = np.random.default_rng(3)
+    Mq, D = ops['M_q'].tocsr(), ops['D'].tocsr()
+    ne, nv = D.shape
+    n_groups = 2
+    # right-hand side of the q rows: (1 / rho_c) D p
+    P = rng.standard_normal((nv, B))
+    cs = rng.uniform(0.5, 2.0, B)
+    Y, _ = _run_csr(emu, 'store', D, B, cpl, mode, n_groups, P, cscale=cs, alpha=-1.5)
+    assert np.abs(Y - (-1.5) * (D @ P) * cs[None, :]).max() < 1e-13 * np.abs(D @ P).max()
+    # per-case energies 0.5 K_c q^T M_q q
+    Q = rng.standard_normal((ne, B))
+    E, _ = _run_csr(emu, 'dot', Mq, B, cpl, mode, n_groups, Q, cscale=cs, alpha=0.5)
+    assert np.abs(E - 0.5 * cs * np.einsum('ic,ic->c', Q, Mq @ Q)).max() < 1e-12 * np.abs(E).max()
+    # all Chebyshev iterations of M_q X = Bm for the B cases in one launch
+    d = Mq.diagonal()
+    S = (Mq.toarray() / np.sqrt(d)[:, None]) / np.sqrt(d)[None, :]
+    ev = np.linalg.eigvalsh(S)
+    Bm = rng.standard_normal((ne, B))
+    X, its = _run_csr(emu, 'solve', Mq, B, cpl, mode, n_groups, Bm, lam=(0.98 * ev[0], 1.02 * ev[-1]))
+    ref = spla.splu(Mq.tocsc()).solve(Bm)
+    assert np.abs(X - ref).max() < 1e-11 * np.abs(ref).max()
+    assert 5 < its < 80
+
+
+def _ellipse_for_rectangle(alpha, beta, mu):
+    """Python copy of ellipse_for_rectangle (csrc/phwave.cu): Chebyshev ellipse through the corner of [alpha, beta] x i[-mu, mu]"""
+    d, delta = 0.5 * (alpha + beta), 0.5 * (beta - alpha)
+    if mu <= 0:
+        return d, delta
+    best, best_c = 1e300, delta
+    for i in range(1, 4001):
+        a = delta * (1.0 + 4.0 * i / 4000.0 * (mu / delta + 0.05))
+        t = 1.0 - delta * delta / (a * a)
+        if t <= 0 or a >= d:
+            continue
+        b = mu / np.sqrt(t)
+        c2 = a * a - b * b
+        if c2 < 0:
+            continue
+        rate = (a + b) / (d + np.sqrt(d * d - c2))
+        if rate < best:
+            best, best_c = rate, np.sqrt(c2)
+    return d, best_c
+
+
+@pytest.mark.parametrize('order,theta', [((1, 1), 0.5), ((2, 2), 0.5), ((3, 2), 1.0)])
+def test_emulated_block_solve_of_the_implicit_schemes_on_csr_rows(emu, order, theta):
+    """solve_block_csr_k (IE / SM at basis_order > 1, wave_2D.py:305-319,560-572) on the CPU: the coupled system
+    [[M_p, th dt K D^T], [-th dt/rho D, M_q]] assembled by the oracle's higher-order spaces, against a sparse direct solve"""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    from oracle import fem_ho
+    v, c = rectangle_structured(6, 2)
+    topo = fem.Topology(v, c)
+    ops = fem_ho.SpacesHO(topo, *order).assemble(fem.tag_boundary(topo, 'R', 1.0, 0.25))
+    Mp, Mq, D = ops['M_p'].tocsr(), ops['M_q'].tocsr(), ops['D'].tocsr()
+    DT = D.T.tocsr()
+    K, rho, dt = 3.0, 2.0, 2e-3
+    cDv, cDe = theta * dt * K, -theta * dt / rho
+    dp, dq = Mp.diagonal(), Mq.diagonal()
+    lam = [np.linalg.eigvalsh((M.toarray() / np.sqrt(d)[:, None]) / np.sqrt(d)[None, :]) for M, d in ((Mp, dp), (Mq, dq))]
+    sig = np.linalg.svd((D.toarray() / np.sqrt(dq)[:, None]) / np.sqrt(dp)[None, :], compute_uv=False)[0]
+    mu = 1.05 * theta * dt * np.sqrt(K / rho) * sig
+    cd, cc = _ellipse_for_rectangle(min(lam[0][0], lam[1][0]), max(lam[0][-1], lam[1][-1]), mu)
+    rng = np.random.default_rng(8)
+    bp, bq = rng.standard_normal(Mp.shape[0]), rng.standard_normal(Mq.shape[0])
+    mats = []
+    for M in (Mp, Mq, D, DT):
+        M.sort_indices()
+        mats.append((np.ascontiguousarray(M.indptr, dtype=np.int32), np.ascontiguousarray(M.indices, dtype=np.int32),
+                     np.ascontiguousarray(M.data, dtype=np.float64)))
+    P3 = ctypes.c_void_p * 4
+    xp, xq = np.zeros(Mp.shape[0]), np.zeros(Mq.shape[0])
+    it = ctypes.c_int32(0)
+    err = ctypes.create_string_buffer(512)
+    rc = emu.emu_run_block(ctypes.c_int32(Mp.shape[0]), ctypes.c_int32(Mq.shape[0]), P3(*[m[0].ctypes.data for m in mats]),
+                           P3(*[m[1].ctypes.data for m in mats]), P3(*[m[2].ctypes.data for m in mats]),
+                           ctypes.c_double(cDv), ctypes.c_double(cDe), ctypes.c_double(1.0 / K), ctypes.c_double(rho),
+                           ctypes.c_double(cd), ctypes.c_double(cc), ctypes.c_double(1e-13), ctypes.c_int32(3),
+                           bp.ctypes.data_as(ctypes.c_void_p), bq.ctypes.data_as(ctypes.c_void_p), xp.ctypes.data_as(ctypes.c_void_p),
+                           xq.ctypes.data_as(ctypes.c_void_p), ctypes.byref(it), err, 512)
+    assert rc == 0, err.value.decode()
+    Abig = sp.bmat([[Mp, cDv * DT], [cDe * D, Mq]], format='csc')
+    ref = spla.spsolve(Abig, np.concatenate([bp, bq]))
+    got = np.concatenate([xp, xq])
+    assert np.linalg.norm(got - ref) < 1e-10 * np.linalg.norm(ref), (np.linalg.norm(got - ref) / np.linalg.norm(ref), it.value)
+    assert 5 < it.value < 400
+
+
+def _sliver_mesh():
+    """a quality mesh with a band of stretched cells (aspect ratio ~25), as in tests/test_gpu_parity.py"""
+    v, c = rectangle_structured(40, 10)
+    v = v.copy()
+    x = v[:, 0].copy()
+    h = 1.0 / 40
+    band = (x > 0.5 - 1e-9) & (x < 0.5 + 3 * h + 1e-9)
+    v[band, 0] = 0.5 + (x[band] - 0.5) * 0.04
+    right = x > 0.5 + 3 * h + 1e-9
+    v[right, 0] = 0.5 + 3 * h * 0.04 + (x[right] - (0.5 + 3 * h)) * (0.5 - 3 * h * 0.04) / (0.5 - 3 * h)
+    return v, c
+
+
+@pytest.mark.parametrize('name,make,pc,grid', [('aspect12', lambda: rectangle_structured(6, 18), 64, 3), ('sliver_band', _sliver_mesh, 96, 4),
+                                               ('delaunay', lambda: rectangle_delaunay(30, 8, seed=5), 48, 4)])
+def test_emulated_conjugate_gradient_mass_solves(emu, name, make, pc, grid):
+    """solve_pcg_coop_k (meshes of poor quality) on the CPU: both mass solves against sparse LU; on the mesh with a band of slivers CG
+    needs about as many iterations as the host CG of the same matrix (103), far fewer than the element-wise Chebyshev interval implies"""
+    import scipy.sparse.linalg as spla
+    v, c = make()
+    topo = fem.Topology(v, c)
+    ops = fem.assemble_wave_operators(topo, fem.tag_boundary(topo, 'R', 1.0, 0.25))
+    rng = np.random.default_rng(5)
+    bp, bq = rng.standard_normal(topo.n_vertices), rng.standard_normal(topo.n_edges)
+    xq, itq = run(emu, 'mq_pcg', v, c, pc, grid, bq, nout=topo.n_edges)
+    xp, itp = run(emu, 'mp_pcg', v, c, pc, grid, bp, nout=topo.n_vertices)
+    assert rel(xq, spla.spsolve(ops['M_q'].tocsc(), bq)) < 1e-10, (name, itq)
+    assert rel(xp, spla.spsolve(ops['M_p'].tocsc(), bp)) < 1e-11, (name, itp)
+    assert 5 < itp < 40
+    if name == 'sliver_band':
+        assert itq < 130, itq
